@@ -1,0 +1,88 @@
+/* athena_oracle.h -- CPU restatement (plain C) of the reference's per-MeshBlock hydro/MHD update.
+ *
+ * TEST INFRASTRUCTURE ONLY: linked/loaded solely by tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline leg.  The product (athena-gamma_b200/) never includes or links it.
+ *
+ * Pinned bit-for-bit against the unmodified reference (oracle/_ref, built by
+ * oracle/build_ref.py) by tests/test_oracle_vs_reference.py and the committed fixtures in
+ * tests/golden/.
+ */
+#ifndef ATHENA_ORACLE_H_
+#define ATHENA_ORACLE_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2 };
+enum { AO_SOLVER_HLLE = 0, AO_SOLVER_HLLC = 1, AO_SOLVER_HLLD = 2, AO_SOLVER_ROE = 3 };
+enum { AO_INT_VL2 = 0, AO_INT_RK2 = 1, AO_INT_RK1 = 2, AO_INT_RK3 = 3 };
+
+typedef struct {
+  int nx1, nx2, nx3;    /* <mesh> size */
+  int bx1, bx2, bx3;    /* <meshblock> size */
+  double x1min, x1max, x2min, x2max, x3min, x3max;
+  int bc[6];            /* ix1,ox1,ix2,ox2,ix3,ox3 */
+  int ng;               /* NGHOST */
+  int mhd;              /* MAGNETIC_FIELDS_ENABLED */
+  int solver;           /* AO_SOLVER_* */
+  int xorder;           /* 1,2,3 */
+  int integrator;       /* AO_INT_* */
+  double gamma, dfloor, pfloor, cfl, tlim, start_time;
+} AoParams;
+
+typedef struct AoMesh AoMesh;
+
+AoMesh *ao_create(const AoParams *p);
+void ao_destroy(AoMesh *m);
+int ao_nblocks(const AoMesh *m);
+/* out[0..2]=lx1..3, out[3..5]=nc1..3, out[6..11]=is,ie,js,je,ks,ke */
+void ao_block_info(const AoMesh *m, int b, long *out);
+/* array access by name: u u1 w bcc b1 b2 b3 b1_1 b1_2 b1_3 flux1 flux2 flux3 e1 e2 e3
+ * wght1 wght2 wght3 e2_x1f e3_x1f e1_x2f e3_x2f e1_x3f e2_x3f x1f x2f x3f x1v x2v x3v
+ * dx1f dx2f dx3f ; returns pointer, *n = number of doubles */
+double *ao_array(AoMesh *m, int b, const char *name, long *n);
+
+/* Mesh::Initialize after the problem generator filled u (and b): ghost exchange,
+ * ConservedToPrimitive, physical boundaries, NewBlockTimeStep + NewTimeStep */
+void ao_initialize(AoMesh *m);
+/* one full cycle (all stages) + time/dt update; returns the dt that was used */
+double ao_cycle(AoMesh *m);
+double ao_time(const AoMesh *m);
+double ao_dt(const AoMesh *m);
+void ao_set_time_dt(AoMesh *m, double time, double dt);
+int ao_ncycle(const AoMesh *m);
+
+/* task-level entry points (same granularity as the reference's task bodies) */
+void ao_calc_fluxes(AoMesh *m, int b, int order);
+void ao_corner_e(AoMesh *m, int b);
+void ao_emf_exchange(AoMesh *m);           /* SendFluxCorrection + ReceiveFluxCorrection */
+void ao_weighted_ave_cc(AoMesh *m, int b, int out_reg, int in1_reg, const double w[5]);
+void ao_weighted_ave_fc(AoMesh *m, int b, int out_reg, int in1_reg, const double w[5]);
+void ao_swap_cc(AoMesh *m, int b);          /* u <-> u1 */
+void ao_swap_fc(AoMesh *m, int b);          /* b <-> b1 */
+void ao_zero_reg1(AoMesh *m, int b);        /* u1.ZeroClear, b1.ZeroClear */
+void ao_add_flux_div(AoMesh *m, int b, double wght);
+void ao_ct(AoMesh *m, int b, double wght);
+void ao_exchange_cc(AoMesh *m);             /* Send/Receive/SetBoundaries for u */
+void ao_exchange_fc(AoMesh *m);             /* same for b */
+void ao_cons2prim(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int ku);
+void ao_prim2cons(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int ku);
+void ao_primitives(AoMesh *m, int b);       /* Primitives task: range from neighbours */
+void ao_physical_bcs(AoMesh *m, int b);
+double ao_new_block_dt(AoMesh *m, int b);
+
+/* point-wise kernels on n independent interfaces / cells (structure-of-arrays, stride n) */
+void ao_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
+                const double *bx, double gamma, double dt, double dx,
+                double *flx, double *wct);
+void ao_plm(long n, int nvar, const double *qm1, const double *q, const double *qp1,
+            double wp, double wm, double *ql_plus, double *qr_minus);
+void ao_ppm(long n, int nvar, const double *qm2, const double *qm1, const double *q,
+            const double *qp1, const double *qp2, double dfloor, double pfloor,
+            double *ql_plus, double *qr_minus);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

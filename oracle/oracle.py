@@ -1,0 +1,242 @@
+"""ctypes wrapper of the CPU oracle (oracle/libathena_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg -- never by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+BC = {"periodic": 0, "outflow": 1, "reflecting": 2}
+SOLVER = {"hlle": 0, "hllc": 1, "hlld": 2, "roe": 3}
+INTEGRATOR = {"vl2": 0, "rk2": 1, "rk1": 2, "rk3": 3}
+DEFAULT_FLOOR = float(np.sqrt(1024 * float(np.finfo(np.float32).tiny)))  # eos ctor
+
+
+class AoParams(C.Structure):
+    _fields_ = [("nx1", C.c_int), ("nx2", C.c_int), ("nx3", C.c_int),
+                ("bx1", C.c_int), ("bx2", C.c_int), ("bx3", C.c_int),
+                ("x1min", C.c_double), ("x1max", C.c_double),
+                ("x2min", C.c_double), ("x2max", C.c_double),
+                ("x3min", C.c_double), ("x3max", C.c_double),
+                ("bc", C.c_int * 6), ("ng", C.c_int), ("mhd", C.c_int),
+                ("solver", C.c_int), ("xorder", C.c_int), ("integrator", C.c_int),
+                ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
+                ("cfl", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double)]
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", HERE], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(HERE, "libathena_oracle.so")
+        srcs = [os.path.join(HERE, f) for f in
+                ("oracle_physics.c", "oracle_mesh.c", "oracle_internal.h", "athena_oracle.h")]
+        if (not os.path.exists(so)
+                or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)):
+            build()
+        L = C.CDLL(so)
+        L.ao_create.restype = C.c_void_p
+        L.ao_create.argtypes = [C.POINTER(AoParams)]
+        L.ao_destroy.argtypes = [C.c_void_p]
+        L.ao_nblocks.argtypes = [C.c_void_p]
+        L.ao_block_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_long)]
+        L.ao_array.restype = C.POINTER(C.c_double)
+        L.ao_array.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_long)]
+        for f in ("ao_initialize", "ao_emf_exchange", "ao_exchange_cc", "ao_exchange_fc"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.ao_cycle.restype = C.c_double
+        L.ao_cycle.argtypes = [C.c_void_p]
+        L.ao_time.restype = C.c_double
+        L.ao_time.argtypes = [C.c_void_p]
+        L.ao_dt.restype = C.c_double
+        L.ao_dt.argtypes = [C.c_void_p]
+        L.ao_ncycle.argtypes = [C.c_void_p]
+        L.ao_set_time_dt.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.ao_calc_fluxes.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        for f in ("ao_corner_e", "ao_swap_cc", "ao_swap_fc", "ao_zero_reg1", "ao_primitives",
+                  "ao_physical_bcs"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int]
+        for f in ("ao_weighted_ave_cc", "ao_weighted_ave_fc"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_double)]
+        L.ao_add_flux_div.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.ao_ct.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        for f in ("ao_cons2prim", "ao_prim2cons"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 6
+        L.ao_new_block_dt.restype = C.c_double
+        L.ao_new_block_dt.argtypes = [C.c_void_p, C.c_int]
+        dp = C.POINTER(C.c_double)
+        L.ao_riemann.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_double,
+                                 C.c_double, C.c_double, dp, dp]
+        L.ao_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
+        L.ao_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, C.c_double, C.c_double,
+                             dp, dp]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def params_from_athinput(par, mhd, solver, ng=None):
+    """par: dict of blocks (oracle/ref_run.parse_athinput or the product's ParameterInput)."""
+    mesh, t = par["mesh"], par["time"]
+    mb = par.get("meshblock", {})
+    xorder = int(str(t.get("xorder", "2")).rstrip("c"))
+    p = AoParams()
+    p.nx1, p.nx2, p.nx3 = int(mesh["nx1"]), int(mesh.get("nx2", 1)), int(mesh.get("nx3", 1))
+    p.bx1 = int(mb.get("nx1", p.nx1))
+    p.bx2 = int(mb.get("nx2", p.nx2))
+    p.bx3 = int(mb.get("nx3", p.nx3))
+    p.x1min, p.x1max = float(mesh["x1min"]), float(mesh["x1max"])
+    p.x2min, p.x2max = float(mesh.get("x2min", -0.5)), float(mesh.get("x2max", 0.5))
+    p.x3min, p.x3max = float(mesh.get("x3min", -0.5)), float(mesh.get("x3max", 0.5))
+    for i, k in enumerate(("ix1_bc", "ox1_bc", "ix2_bc", "ox2_bc", "ix3_bc", "ox3_bc")):
+        p.bc[i] = BC[mesh.get(k, "periodic")]
+    p.ng = ng if ng is not None else (3 if xorder == 3 else 2)
+    p.mhd = int(bool(mhd))
+    p.solver = SOLVER[solver]
+    p.xorder = xorder
+    p.integrator = INTEGRATOR[t.get("integrator", "vl2")]
+    h = par.get("hydro", {})
+    p.gamma = float(h["gamma"])
+    p.dfloor = float(h.get("dfloor", DEFAULT_FLOOR))
+    p.pfloor = float(h.get("pfloor", DEFAULT_FLOOR))
+    p.cfl = float(t["cfl_number"])
+    p.tlim = float(t["tlim"])
+    p.start_time = float(t.get("start_time", 0.0))
+    return p
+
+
+class OracleMesh:
+    def __init__(self, params):
+        self.L = lib()
+        self.p = params
+        self.h = self.L.ao_create(C.byref(params))
+        self.nb = self.L.ao_nblocks(self.h)
+        self.info = []
+        for b in range(self.nb):
+            out = (C.c_long * 12)()
+            self.L.ao_block_info(self.h, b, out)
+            self.info.append(dict(zip(("lx1", "lx2", "lx3", "nc1", "nc2", "nc3", "is", "ie",
+                                       "js", "je", "ks", "ke"), list(out))))
+
+    def __del__(self):
+        try:
+            self.L.ao_destroy(self.h)
+        except Exception:
+            pass
+
+    def shape(self, b, name):
+        i = self.info[b]
+        n1, n2, n3 = i["nc1"], i["nc2"], i["nc3"]
+        if name in ("u", "u1", "w"):
+            return (5, n3, n2, n1)
+        if name in ("bcc", "cc_e"):
+            return (3, n3, n2, n1)
+        if name in ("b1", "b1_1", "wght1", "e2_x1f", "e3_x1f"):
+            return (n3, n2, n1 + 1)
+        if name in ("b2", "b1_2", "wght2", "e1_x2f", "e3_x2f"):
+            return (n3, n2 + 1, n1)
+        if name in ("b3", "b1_3", "wght3", "e1_x3f", "e2_x3f"):
+            return (n3 + 1, n2, n1)
+        if name == "flux1":
+            return (5, n3, n2, n1 + 1)
+        if name == "flux2":
+            return (5, n3, n2 + 1, n1)
+        if name == "flux3":
+            return (5, n3 + 1, n2, n1)
+        if name == "e1":
+            return (n3 + 1, n2 + 1, n1)
+        if name == "e2":
+            return (n3 + 1, n2, n1 + 1)
+        if name == "e3":
+            return (n3, n2 + 1, n1 + 1)
+        return None
+
+    def array(self, b, name):
+        """numpy VIEW of the oracle's array (re-fetch after swaps: pointers move)."""
+        n = C.c_long()
+        ptr = self.L.ao_array(self.h, b, name.encode(), C.byref(n))
+        if not ptr or n.value == 0:
+            return None
+        a = np.ctypeslib.as_array(ptr, shape=(n.value,))
+        shp = self.shape(b, name)
+        return a.reshape(shp) if shp else a
+
+    def block_of(self, lx1, lx2, lx3):
+        for b, i in enumerate(self.info):
+            if (i["lx1"], i["lx2"], i["lx3"]) == (lx1, lx2, lx3):
+                return b
+        raise KeyError((lx1, lx2, lx3))
+
+    def load_rst(self, rst):
+        """Fill u / b of every block from a parsed reference restart dump (ref_run.read_rst)."""
+        for blk in rst["blocks"]:
+            b = self.block_of(*blk["loc"][:3])
+            self.array(b, "u")[...] = blk["u"]
+            if self.p.mhd:
+                for nm in ("b1", "b2", "b3"):
+                    self.array(b, nm)[...] = blk[nm]
+
+    def initialize(self):
+        self.L.ao_initialize(self.h)
+
+    def cycle(self):
+        return self.L.ao_cycle(self.h)
+
+    @property
+    def time(self):
+        return self.L.ao_time(self.h)
+
+    @property
+    def dt(self):
+        return self.L.ao_dt(self.h)
+
+    def set_time_dt(self, t, dt):
+        self.L.ao_set_time_dt(self.h, t, dt)
+
+
+def riemann(solver, mhd, wl, wr, bx, gamma, dt=0.0, dx=1.0):
+    """wl, wr: (nwave, n) sweep-ordered primitives. Returns flux (nwave, n), wct (n)."""
+    L = lib()
+    wl = np.ascontiguousarray(wl, dtype=np.float64)
+    wr = np.ascontiguousarray(wr, dtype=np.float64)
+    n = wl.shape[1]
+    bx = np.ascontiguousarray(bx if bx is not None else np.zeros(n), dtype=np.float64)
+    flx = np.zeros_like(wl)
+    wct = np.zeros(n)
+    L.ao_riemann(SOLVER[solver], int(mhd), n, _dp(wl), _dp(wr), _dp(bx), gamma, dt, dx,
+                 _dp(flx), _dp(wct))
+    return flx, wct
+
+
+def plm(qm1, q, qp1, wp=0.5, wm=0.5):
+    L = lib()
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    nv, n = q.shape
+    ql, qr = np.zeros_like(q), np.zeros_like(q)
+    L.ao_plm(n, nv, _dp(np.ascontiguousarray(qm1)), _dp(q), _dp(np.ascontiguousarray(qp1)),
+             wp, wm, _dp(ql), _dp(qr))
+    return ql, qr
+
+
+def ppm(qm2, qm1, q, qp1, qp2, dfloor=DEFAULT_FLOOR, pfloor=DEFAULT_FLOOR):
+    L = lib()
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    nv, n = q.shape
+    ql, qr = np.zeros_like(q), np.zeros_like(q)
+    L.ao_ppm(n, nv, _dp(np.ascontiguousarray(qm2)), _dp(np.ascontiguousarray(qm1)), _dp(q),
+             _dp(np.ascontiguousarray(qp1)), _dp(np.ascontiguousarray(qp2)), dfloor, pfloor,
+             _dp(ql), _dp(qr))
+    return ql, qr

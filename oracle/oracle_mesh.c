@@ -1,0 +1,1378 @@
+/* oracle_mesh.c -- MeshBlocks, ghost exchange, EMF correction, integrator glue of the
+ * reference path, restated in plain C for uniform Cartesian meshes (periodic / outflow).
+ *
+ * TEST INFRASTRUCTURE ONLY (see athena_oracle.h).  Each function cites the reference
+ * file:line it restates.  Loops are deliberately simple (one cell / face / edge at a time).
+ */
+#include <math.h>
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include "oracle_internal.h"
+
+static inline double mn(double a, double b) { return (b < a) ? b : a; }
+#define SQR(x) ((x)*(x))
+
+typedef struct {
+  int ox1, ox2, ox3, type; /* type: 0 face 1 edge 2 corner */
+  int gid, bufid, targetid, fid, eid;
+} Nb;
+
+typedef struct AoBlock {
+  int gid;
+  long lx1, lx2, lx3;
+  int nc1, nc2, nc3, is, ie, js, je, ks, ke;
+  double bx1min, bx1max, bx2min, bx2max, bx3min, bx3max;
+  int bcs[6];            /* -1: neighbour block (block/periodic), else AO_BC_* physical */
+  int nblevel[3][3][3];
+  int nnb; Nb nb[26];
+  int nedge_fine[12];
+  double *x1f, *x2f, *x3f, *x1v, *x2v, *x3v, *dx1f, *dx2f, *dx3f;
+  double *u, *u1, *w, *bcc, *flux[3];
+  double *b[3], *b1[3], *e[3], *wght[3];
+  double *e2_x1f, *e3_x1f, *e1_x2f, *e3_x2f, *e1_x3f, *e2_x3f, *cc_e;
+  double *recv[26]; long recvn[26];
+  double new_dt;
+} AoBlock;
+
+struct AoMesh {
+  AoParams p;
+  int ndim, f2, f3;
+  int nrbx1, nrbx2, nrbx3, nb;
+  AoBlock *blk;
+  int *gid_of;           /* [lx3][lx2][lx1] -> gid */
+  double time, dt;
+  int ncycle;
+  int nstages;
+  double beta[4], delta[4], g1[4], g2[4], g3[4];
+  double cfl;
+  /* canonical buffer-id table: src/bvals/bvals_base.cpp:153-256 */
+  int nni; int ni[26][3];
+};
+
+/* ---- indexing (src/athena_arrays.hpp:140-143: last index fastest) ---- */
+#define CC(B,n,k,j,i) ((((long)(n)*(B)->nc3 + (k))*(B)->nc2 + (j))*(B)->nc1 + (i))
+#define F1(B,k,j,i) (((long)(k)*(B)->nc2 + (j))*((B)->nc1+1) + (i))
+#define F2(B,k,j,i) (((long)(k)*((B)->nc2+1) + (j))*(B)->nc1 + (i))
+#define F3(B,k,j,i) (((long)(k)*(B)->nc2 + (j))*(B)->nc1 + (i))
+#define FL1(B,n,k,j,i) ((((long)(n)*(B)->nc3 + (k))*(B)->nc2 + (j))*((B)->nc1+1) + (i))
+#define FL2(B,n,k,j,i) ((((long)(n)*(B)->nc3 + (k))*((B)->nc2+1) + (j))*(B)->nc1 + (i))
+#define FL3(B,n,k,j,i) ((((long)(n)*((B)->nc3+1) + (k))*(B)->nc2 + (j))*(B)->nc1 + (i))
+/* EdgeField (src/athena.hpp:107-115) */
+#define E1(B,k,j,i) (((long)(k)*((B)->nc2+1) + (j))*(B)->nc1 + (i))
+#define E2(B,k,j,i) (((long)(k)*(B)->nc2 + (j))*((B)->nc1+1) + (i))
+#define E3(B,k,j,i) (((long)(k)*((B)->nc2+1) + (j))*((B)->nc1+1) + (i))
+
+static double *dalloc(long n) { return (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double)); }
+
+/* src/mesh/mesh.hpp:389-405 */
+static double mesh_gen_x(long index, long nrange) {
+  long noffset = index - (nrange)/2;
+  long noffset_ceil = index - (nrange+1)/2;
+  return (double)(noffset + noffset_ceil)/(2.0*nrange);
+}
+/* src/mesh/mesh.hpp:467-488 */
+static double uniform_gen(double x, double xmin, double xmax) {
+  return 0.5*(xmin + xmax) + (x*xmax - x*xmin);
+}
+
+/* Coordinates ctor, uniform branch (src/coordinates/coordinates.cpp:125-145 and twins),
+ * Cartesian x?v (src/coordinates/cartesian.cpp:25-75) */
+static void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, double mmax,
+                        double bmin, double bmax, int nc, double **xf, double **xv,
+                        double **dxf) {
+  *xf = dalloc(nc + 1); *xv = dalloc(nc); *dxf = dalloc(nc);
+  if (nc == 1) {
+    (*dxf)[0] = bmax - bmin;
+    (*xf)[0] = bmin;
+    (*xf)[1] = bmax;
+    (*xv)[0] = 0.5*((*xf)[1] + (*xf)[0]);
+    return;
+  }
+  int il = ng, iu = ng + bx - 1;
+  double dx = (bmax - bmin)/(iu - il + 1);
+  for (int i = il - ng; i <= iu + ng + 1; ++i) {
+    long noffset = (long)(i - il) + lx*bx;
+    double rx = mesh_gen_x(noffset, nx_mesh);
+    (*xf)[i] = uniform_gen(rx, mmin, mmax);
+  }
+  (*xf)[il] = bmin;
+  (*xf)[iu+1] = bmax;
+  for (int i = il - ng; i <= iu + ng; ++i) (*dxf)[i] = dx;
+  for (int i = il - ng; i <= iu + ng; ++i) (*xv)[i] = 0.5*((*xf)[i+1] + (*xf)[i]);
+}
+
+/* Mesh::SetBlockSizeAndBoundaries (src/mesh/mesh.cpp:1668-1751) for one direction */
+static void block_extent(long lx, int nrbx, double mmin, double mmax, int bc_in, int bc_out,
+                         int nx_mesh, double *bmin, double *bmax, int *bcs_in, int *bcs_out) {
+  if (nx_mesh == 1) {
+    *bmin = mmin; *bmax = mmax; *bcs_in = bc_in; *bcs_out = bc_out;
+    return;
+  }
+  if (lx == 0) { *bmin = mmin; *bcs_in = bc_in; }
+  else { *bmin = uniform_gen(mesh_gen_x(lx, nrbx), mmin, mmax); *bcs_in = -1; }
+  if (lx == nrbx - 1) { *bmax = mmax; *bcs_out = bc_out; }
+  else { *bmax = uniform_gen(mesh_gen_x(lx + 1, nrbx), mmin, mmax); *bcs_out = -1; }
+}
+
+static int find_ni(const AoMesh *m, int o1, int o2, int o3) {
+  for (int n = 0; n < m->nni; ++n)
+    if (m->ni[n][0] == o1 && m->ni[n][1] == o2 && m->ni[n][2] == o3) return n;
+  return -1;
+}
+
+static int cmp_morton(const void *a, const void *b) {
+  const unsigned long long *x = (const unsigned long long *)a, *y = (const unsigned long long *)b;
+  return (x[0] > y[0]) - (x[0] < y[0]);
+}
+
+static void set_integrator(AoMesh *m) {
+  /* src/task_list/time_integrator.cpp:104-604 */
+  double cfl_limit = 1.0;
+  for (int s = 0; s < 4; ++s) { m->g1[s] = 0; m->g2[s] = 1; m->g3[s] = 0; m->delta[s] = 0; }
+  m->delta[0] = 1.0;
+  switch (m->p.integrator) {
+    case AO_INT_VL2:
+      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0;
+      if (m->ndim >= 2) cfl_limit = 0.5;
+      break;
+    case AO_INT_RK1:
+      m->nstages = 1; m->beta[0] = 1.0;
+      break;
+    case AO_INT_RK2:
+      m->nstages = 2; m->beta[0] = 1.0; m->beta[1] = 0.5;
+      m->g1[1] = 0.5; m->g2[1] = 0.5;
+      break;
+    default: /* rk3 */
+      m->nstages = 3; m->beta[0] = 1.0; m->beta[1] = 0.25; m->beta[2] = 0.66666666666666667;
+      m->g1[1] = 0.25; m->g2[1] = 0.75;
+      m->g1[2] = 0.66666666666666667; m->g2[2] = 0.33333333333333333;
+      break;
+  }
+  m->cfl = m->p.cfl;
+  if (m->cfl > cfl_limit) m->cfl = cfl_limit;  /* time_integrator.cpp:886-894 */
+}
+
+AoMesh *ao_create(const AoParams *p) {
+  AoMesh *m = (AoMesh *)calloc(1, sizeof(AoMesh));
+  m->p = *p;
+  m->f2 = p->nx2 > 1; m->f3 = p->nx3 > 1;
+  m->ndim = m->f3 ? 3 : (m->f2 ? 2 : 1);
+  m->nrbx1 = p->nx1/p->bx1; m->nrbx2 = p->nx2/p->bx2; m->nrbx3 = p->nx3/p->bx3;
+  m->nb = m->nrbx1*m->nrbx2*m->nrbx3;
+  m->time = p->start_time; m->dt = DBL_MAX; m->ncycle = 0;
+  set_integrator(m);
+  /* canonical neighbour enumeration, uniform mesh (bvals_base.cpp:153-256) */
+  int b = 0;
+  for (int n = -1; n <= 1; n += 2) { m->ni[b][0] = n; m->ni[b][1] = 0; m->ni[b][2] = 0; b++; }
+  if (m->ndim >= 2)
+    for (int n = -1; n <= 1; n += 2) { m->ni[b][0] = 0; m->ni[b][1] = n; m->ni[b][2] = 0; b++; }
+  if (m->ndim == 3)
+    for (int n = -1; n <= 1; n += 2) { m->ni[b][0] = 0; m->ni[b][1] = 0; m->ni[b][2] = n; b++; }
+  if (m->ndim >= 2)
+    for (int mm = -1; mm <= 1; mm += 2) for (int n = -1; n <= 1; n += 2) {
+      m->ni[b][0] = n; m->ni[b][1] = mm; m->ni[b][2] = 0; b++; }
+  if (m->ndim == 3) {
+    for (int mm = -1; mm <= 1; mm += 2) for (int n = -1; n <= 1; n += 2) {
+      m->ni[b][0] = n; m->ni[b][1] = 0; m->ni[b][2] = mm; b++; }
+    for (int mm = -1; mm <= 1; mm += 2) for (int n = -1; n <= 1; n += 2) {
+      m->ni[b][0] = 0; m->ni[b][1] = n; m->ni[b][2] = mm; b++; }
+    for (int l = -1; l <= 1; l += 2) for (int mm = -1; mm <= 1; mm += 2)
+      for (int n = -1; n <= 1; n += 2) {
+        m->ni[b][0] = n; m->ni[b][1] = mm; m->ni[b][2] = l; b++; }
+  }
+  m->nni = b;
+
+  /* Z-ordered block list (src/mesh/meshblock_tree.cpp:87-110,336-352) */
+  unsigned long long (*keys)[4] = malloc(sizeof(unsigned long long[4])*(size_t)m->nb);
+  int c = 0;
+  for (int k = 0; k < m->nrbx3; ++k) for (int j = 0; j < m->nrbx2; ++j)
+    for (int i = 0; i < m->nrbx1; ++i) {
+      unsigned long long key = 0;
+      for (int bit = 0; bit < 20; ++bit)
+        key |= ((unsigned long long)((i >> bit) & 1) << (3*bit))
+             | ((unsigned long long)((j >> bit) & 1) << (3*bit + 1))
+             | ((unsigned long long)((k >> bit) & 1) << (3*bit + 2));
+      keys[c][0] = key; keys[c][1] = i; keys[c][2] = j; keys[c][3] = k; c++;
+    }
+  qsort(keys, (size_t)m->nb, sizeof(keys[0]), cmp_morton);
+  m->gid_of = (int *)malloc(sizeof(int)*(size_t)m->nb);
+  m->blk = (AoBlock *)calloc((size_t)m->nb, sizeof(AoBlock));
+  int ng = p->ng;
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    B->gid = g; B->lx1 = (long)keys[g][1]; B->lx2 = (long)keys[g][2]; B->lx3 = (long)keys[g][3];
+    m->gid_of[(B->lx3*m->nrbx2 + B->lx2)*m->nrbx1 + B->lx1] = g;
+    /* MeshBlock ctor index ranges (src/mesh/meshblock.cpp:55-80) */
+    B->is = ng; B->ie = ng + p->bx1 - 1; B->nc1 = p->bx1 + 2*ng;
+    if (m->f2) { B->js = ng; B->je = ng + p->bx2 - 1; B->nc2 = p->bx2 + 2*ng; }
+    else { B->js = B->je = 0; B->nc2 = 1; }
+    if (m->f3) { B->ks = ng; B->ke = ng + p->bx3 - 1; B->nc3 = p->bx3 + 2*ng; }
+    else { B->ks = B->ke = 0; B->nc3 = 1; }
+    block_extent(B->lx1, m->nrbx1, p->x1min, p->x1max, p->bc[0], p->bc[1], 2 /*always*/,
+                 &B->bx1min, &B->bx1max, &B->bcs[0], &B->bcs[1]);
+    block_extent(B->lx2, m->nrbx2, p->x2min, p->x2max, p->bc[2], p->bc[3], p->nx2,
+                 &B->bx2min, &B->bx2max, &B->bcs[2], &B->bcs[3]);
+    block_extent(B->lx3, m->nrbx3, p->x3min, p->x3max, p->bc[4], p->bc[5], p->nx3,
+                 &B->bx3min, &B->bx3max, &B->bcs[4], &B->bcs[5]);
+    make_coords(p->nx1, p->bx1, ng, B->lx1, p->x1min, p->x1max, B->bx1min, B->bx1max,
+                B->nc1, &B->x1f, &B->x1v, &B->dx1f);
+    make_coords(p->nx2, p->bx2, ng, B->lx2, p->x2min, p->x2max, B->bx2min, B->bx2max,
+                B->nc2, &B->x2f, &B->x2v, &B->dx2f);
+    make_coords(p->nx3, p->bx3, ng, B->lx3, p->x3min, p->x3max, B->bx3min, B->bx3max,
+                B->nc3, &B->x3f, &B->x3v, &B->dx3f);
+    long ncc = (long)B->nc1*B->nc2*B->nc3;
+    B->u = dalloc(NHYDRO*ncc); B->u1 = dalloc(NHYDRO*ncc); B->w = dalloc(NHYDRO*ncc);
+    B->flux[0] = dalloc(NHYDRO*(long)B->nc3*B->nc2*(B->nc1+1));
+    B->flux[1] = dalloc(NHYDRO*(long)B->nc3*(B->nc2+1)*B->nc1);
+    B->flux[2] = dalloc(NHYDRO*(long)(B->nc3+1)*B->nc2*B->nc1);
+    if (p->mhd) {
+      long n1 = (long)B->nc3*B->nc2*(B->nc1+1), n2 = (long)B->nc3*(B->nc2+1)*B->nc1,
+           n3 = (long)(B->nc3+1)*B->nc2*B->nc1;
+      B->b[0] = dalloc(n1); B->b[1] = dalloc(n2); B->b[2] = dalloc(n3);
+      B->b1[0] = dalloc(n1); B->b1[1] = dalloc(n2); B->b1[2] = dalloc(n3);
+      B->wght[0] = dalloc(n1); B->wght[1] = dalloc(n2); B->wght[2] = dalloc(n3);
+      B->e2_x1f = dalloc(n1); B->e3_x1f = dalloc(n1);
+      B->e1_x2f = dalloc(n2); B->e3_x2f = dalloc(n2);
+      B->e1_x3f = dalloc(n3); B->e2_x3f = dalloc(n3);
+      B->bcc = dalloc(3*ncc);
+      B->e[0] = dalloc((long)(B->nc3+1)*(B->nc2+1)*B->nc1);
+      B->e[1] = dalloc((long)(B->nc3+1)*B->nc2*(B->nc1+1));
+      B->e[2] = dalloc((long)B->nc3*(B->nc2+1)*(B->nc1+1));
+      B->cc_e = dalloc(3*ncc);
+    }
+  }
+  free(keys);
+  /* neighbours (src/bvals/bvals_base.cpp:299-480), same level only */
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i)
+      B->nblevel[k][j][i] = -1;
+    B->nblevel[1][1][1] = 0;
+    B->nnb = 0;
+    for (int n = 0; n < m->nni; ++n) {
+      int o1 = m->ni[n][0], o2 = m->ni[n][1], o3 = m->ni[n][2];
+      long l1 = B->lx1 + o1, l2 = B->lx2 + o2, l3 = B->lx3 + o3;
+      int ok = 1;
+      if (l1 < 0) { if (p->bc[0] == AO_BC_PERIODIC) l1 = m->nrbx1 - 1; else ok = 0; }
+      if (l1 >= m->nrbx1) { if (p->bc[1] == AO_BC_PERIODIC) l1 = 0; else ok = 0; }
+      if (l2 < 0) { if (p->bc[2] == AO_BC_PERIODIC) l2 = m->nrbx2 - 1; else ok = 0; }
+      if (l2 >= m->nrbx2) { if (p->bc[3] == AO_BC_PERIODIC) l2 = 0; else ok = 0; }
+      if (l3 < 0) { if (p->bc[4] == AO_BC_PERIODIC) l3 = m->nrbx3 - 1; else ok = 0; }
+      if (l3 >= m->nrbx3) { if (p->bc[5] == AO_BC_PERIODIC) l3 = 0; else ok = 0; }
+      if (!ok) continue;
+      Nb *nb = &B->nb[B->nnb++];
+      nb->ox1 = o1; nb->ox2 = o2; nb->ox3 = o3;
+      int nz = (o1 != 0) + (o2 != 0) + (o3 != 0);
+      nb->type = nz - 1;
+      nb->gid = m->gid_of[(l3*m->nrbx2 + l2)*m->nrbx1 + l1];
+      nb->bufid = n;
+      nb->targetid = find_ni(m, -o1, -o2, -o3);
+      nb->fid = -1; nb->eid = -1;
+      /* NeighborBlock::SetNeighbor (bvals_base.cpp:54-66) */
+      if (nb->type == 0) {
+        if (o1 == -1) nb->fid = 0; else if (o1 == 1) nb->fid = 1;
+        else if (o2 == -1) nb->fid = 2; else if (o2 == 1) nb->fid = 3;
+        else if (o3 == -1) nb->fid = 4; else nb->fid = 5;
+      } else if (nb->type == 1) {
+        if (o3 == 0) nb->eid = (((o1 + 1) >> 1) | ((o2 + 1) & 2));
+        else if (o2 == 0) nb->eid = (4 + (((o1 + 1) >> 1) | ((o3 + 1) & 2)));
+        else nb->eid = (8 + (((o2 + 1) >> 1) | ((o3 + 1) & 2)));
+      }
+      B->nblevel[o3+1][o2+1][o1+1] = 0;
+    }
+    /* CountFineEdges (src/bvals/fc/bvals_fc.cpp:1129-1193), single level */
+    int eid = 0;
+    for (int e = 0; e < 12; ++e) B->nedge_fine[e] = 1;
+    if (m->f2) {
+      for (int o2 = -1; o2 <= 1; o2 += 2) for (int o1 = -1; o1 <= 1; o1 += 2) {
+        int nis = (o1-1 > -1) ? o1-1 : -1, nie = (o1+1 < 1) ? o1+1 : 1;
+        int njs = (o2-1 > -1) ? o2-1 : -1, nje = (o2+1 < 1) ? o2+1 : 1;
+        int nf = 0;
+        for (int nj = njs; nj <= nje; nj++) for (int ni = nis; ni <= nie; ni++)
+          if (B->nblevel[1][nj+1][ni+1] == 0) nf++;
+        B->nedge_fine[eid++] = nf;
+      }
+    }
+    if (m->f3) {
+      for (int o3 = -1; o3 <= 1; o3 += 2) for (int o1 = -1; o1 <= 1; o1 += 2) {
+        int nis = (o1-1 > -1) ? o1-1 : -1, nie = (o1+1 < 1) ? o1+1 : 1;
+        int nks = (o3-1 > -1) ? o3-1 : -1, nke = (o3+1 < 1) ? o3+1 : 1;
+        int nf = 0;
+        for (int nk = nks; nk <= nke; nk++) for (int ni = nis; ni <= nie; ni++)
+          if (B->nblevel[nk+1][1][ni+1] == 0) nf++;
+        B->nedge_fine[eid++] = nf;
+      }
+      for (int o3 = -1; o3 <= 1; o3 += 2) for (int o2 = -1; o2 <= 1; o2 += 2) {
+        int njs = (o2-1 > -1) ? o2-1 : -1, nje = (o2+1 < 1) ? o2+1 : 1;
+        int nks = (o3-1 > -1) ? o3-1 : -1, nke = (o3+1 < 1) ? o3+1 : 1;
+        int nf = 0;
+        for (int nk = nks; nk <= nke; nk++) for (int nj = njs; nj <= nje; nj++)
+          if (B->nblevel[nk+1][nj+1][1] == 0) nf++;
+        B->nedge_fine[eid++] = nf;
+      }
+    }
+  }
+  return m;
+}
+
+void ao_destroy(AoMesh *m) {
+  if (!m) return;
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    double *ptrs[] = {B->x1f, B->x2f, B->x3f, B->x1v, B->x2v, B->x3v, B->dx1f, B->dx2f,
+      B->dx3f, B->u, B->u1, B->w, B->bcc, B->flux[0], B->flux[1], B->flux[2], B->b[0],
+      B->b[1], B->b[2], B->b1[0], B->b1[1], B->b1[2], B->e[0], B->e[1], B->e[2],
+      B->wght[0], B->wght[1], B->wght[2], B->e2_x1f, B->e3_x1f, B->e1_x2f, B->e3_x2f,
+      B->e1_x3f, B->e2_x3f, B->cc_e};
+    for (size_t i = 0; i < sizeof(ptrs)/sizeof(ptrs[0]); ++i) free(ptrs[i]);
+  }
+  free(m->blk); free(m->gid_of); free(m);
+}
+
+int ao_nblocks(const AoMesh *m) { return m->nb; }
+double ao_time(const AoMesh *m) { return m->time; }
+double ao_dt(const AoMesh *m) { return m->dt; }
+int ao_ncycle(const AoMesh *m) { return m->ncycle; }
+void ao_set_time_dt(AoMesh *m, double time, double dt) { m->time = time; m->dt = dt; }
+
+void ao_block_info(const AoMesh *m, int b, long *out) {
+  const AoBlock *B = &m->blk[b];
+  out[0] = B->lx1; out[1] = B->lx2; out[2] = B->lx3;
+  out[3] = B->nc1; out[4] = B->nc2; out[5] = B->nc3;
+  out[6] = B->is; out[7] = B->ie; out[8] = B->js; out[9] = B->je; out[10] = B->ks;
+  out[11] = B->ke;
+}
+
+double *ao_array(AoMesh *m, int b, const char *name, long *n) {
+  AoBlock *B = &m->blk[b];
+  long ncc = (long)B->nc1*B->nc2*B->nc3;
+  long n1 = (long)B->nc3*B->nc2*(B->nc1+1), n2 = (long)B->nc3*(B->nc2+1)*B->nc1,
+       n3 = (long)(B->nc3+1)*B->nc2*B->nc1;
+  long ne1 = (long)(B->nc3+1)*(B->nc2+1)*B->nc1, ne2 = (long)(B->nc3+1)*B->nc2*(B->nc1+1),
+       ne3 = (long)B->nc3*(B->nc2+1)*(B->nc1+1);
+  struct { const char *nm; double *p; long n; } t[] = {
+    {"u", B->u, NHYDRO*ncc}, {"u1", B->u1, NHYDRO*ncc}, {"w", B->w, NHYDRO*ncc},
+    {"bcc", B->bcc, 3*ncc}, {"b1", B->b[0], n1}, {"b2", B->b[1], n2}, {"b3", B->b[2], n3},
+    {"b1_1", B->b1[0], n1}, {"b1_2", B->b1[1], n2}, {"b1_3", B->b1[2], n3},
+    {"flux1", B->flux[0], NHYDRO*n1}, {"flux2", B->flux[1], NHYDRO*n2},
+    {"flux3", B->flux[2], NHYDRO*n3}, {"e1", B->e[0], ne1}, {"e2", B->e[1], ne2},
+    {"e3", B->e[2], ne3}, {"wght1", B->wght[0], n1}, {"wght2", B->wght[1], n2},
+    {"wght3", B->wght[2], n3}, {"e2_x1f", B->e2_x1f, n1}, {"e3_x1f", B->e3_x1f, n1},
+    {"e1_x2f", B->e1_x2f, n2}, {"e3_x2f", B->e3_x2f, n2}, {"e1_x3f", B->e1_x3f, n3},
+    {"e2_x3f", B->e2_x3f, n3}, {"x1f", B->x1f, B->nc1+1}, {"x2f", B->x2f, B->nc2+1},
+    {"x3f", B->x3f, B->nc3+1}, {"x1v", B->x1v, B->nc1}, {"x2v", B->x2v, B->nc2},
+    {"x3v", B->x3v, B->nc3}, {"dx1f", B->dx1f, B->nc1}, {"dx2f", B->dx2f, B->nc2},
+    {"dx3f", B->dx3f, B->nc3}, {"cc_e", B->cc_e, 3*ncc}};
+  for (size_t i = 0; i < sizeof(t)/sizeof(t[0]); ++i)
+    if (strcmp(t[i].nm, name) == 0) { *n = t[i].p ? t[i].n : 0; return t[i].p; }
+  *n = 0;
+  return NULL;
+}
+
+/* ------------------------------------------------------------------ EOS */
+
+/* Field::CalculateCellCenteredField (src/field/field.cpp:112-180, uniform weights) +
+ * EquationOfState::ConservedToPrimitive (src/eos/adiabatic_mhd.cpp:41-90 /
+ * adiabatic_hydro.cpp:39-80) */
+void ao_cons2prim(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int ku) {
+  AoBlock *B = &m->blk[b];
+  double gm1 = m->p.gamma - 1.0;
+  double dfl = m->p.dfloor, pfl = m->p.pfloor;
+  for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
+    double pb = 0.0;
+    if (m->p.mhd) {
+      double lw = 0.5, rw = 0.5;
+      double bcc1 = lw*B->b[0][F1(B,k,j,i)] + rw*B->b[0][F1(B,k,j,i+1)];
+      double bcc2 = lw*B->b[1][F2(B,k,j,i)] + rw*B->b[1][F2(B,k,j+1,i)];
+      double bcc3 = lw*B->b[2][F3(B,k,j,i)] + rw*B->b[2][F3(B,k+1,j,i)];
+      B->bcc[CC(B,IB1,k,j,i)] = bcc1;
+      B->bcc[CC(B,IB2,k,j,i)] = bcc2;
+      B->bcc[CC(B,IB3,k,j,i)] = bcc3;
+      pb = 0.5*(SQR(bcc1) + SQR(bcc2) + SQR(bcc3));
+    }
+    double *u_d = &B->u[CC(B,IDN,k,j,i)], *u_e = &B->u[CC(B,IEN,k,j,i)];
+    double u_m1 = B->u[CC(B,IM1,k,j,i)], u_m2 = B->u[CC(B,IM2,k,j,i)],
+           u_m3 = B->u[CC(B,IM3,k,j,i)];
+    *u_d = (*u_d > dfl) ? *u_d : dfl;
+    B->w[CC(B,IDN,k,j,i)] = *u_d;
+    double di = 1.0/(*u_d);
+    B->w[CC(B,IVX,k,j,i)] = u_m1*di;
+    B->w[CC(B,IVY,k,j,i)] = u_m2*di;
+    B->w[CC(B,IVZ,k,j,i)] = u_m3*di;
+    double e_k = 0.5*di*(SQR(u_m1) + SQR(u_m2) + SQR(u_m3));
+    double w_p;
+    if (m->p.mhd) {
+      w_p = gm1*(*u_e - e_k - pb);
+      *u_e = (w_p > pfl) ? *u_e : ((pfl/gm1) + e_k + pb);
+    } else {
+      w_p = gm1*(*u_e - e_k);
+      *u_e = (w_p > pfl) ? *u_e : ((pfl/gm1) + e_k);
+    }
+    w_p = (w_p > pfl) ? w_p : pfl;
+    B->w[CC(B,IPR,k,j,i)] = w_p;
+  }
+}
+
+/* cell-centred field only (used by physical BCs, bvals.cpp:466-470) */
+static void calc_bcc(AoBlock *B, int il, int iu, int jl, int ju, int kl, int ku) {
+  for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
+    B->bcc[CC(B,IB1,k,j,i)] = 0.5*B->b[0][F1(B,k,j,i)] + 0.5*B->b[0][F1(B,k,j,i+1)];
+    B->bcc[CC(B,IB2,k,j,i)] = 0.5*B->b[1][F2(B,k,j,i)] + 0.5*B->b[1][F2(B,k,j+1,i)];
+    B->bcc[CC(B,IB3,k,j,i)] = 0.5*B->b[2][F3(B,k,j,i)] + 0.5*B->b[2][F3(B,k+1,j,i)];
+  }
+}
+
+/* EquationOfState::PrimitiveToConserved (adiabatic_hydro.cpp:89-123, adiabatic_mhd.cpp:99-136) */
+void ao_prim2cons(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int ku) {
+  AoBlock *B = &m->blk[b];
+  double igm1 = 1.0/(m->p.gamma - 1.0);
+  for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
+    double w_d = B->w[CC(B,IDN,k,j,i)], w_vx = B->w[CC(B,IVX,k,j,i)],
+           w_vy = B->w[CC(B,IVY,k,j,i)], w_vz = B->w[CC(B,IVZ,k,j,i)],
+           w_p = B->w[CC(B,IPR,k,j,i)];
+    B->u[CC(B,IDN,k,j,i)] = w_d;
+    B->u[CC(B,IM1,k,j,i)] = w_vx*w_d;
+    B->u[CC(B,IM2,k,j,i)] = w_vy*w_d;
+    B->u[CC(B,IM3,k,j,i)] = w_vz*w_d;
+    if (m->p.mhd) {
+      double bcc1 = B->bcc[CC(B,IB1,k,j,i)], bcc2 = B->bcc[CC(B,IB2,k,j,i)],
+             bcc3 = B->bcc[CC(B,IB3,k,j,i)];
+      B->u[CC(B,IEN,k,j,i)] = w_p*igm1 + 0.5*(w_d*(SQR(w_vx) + SQR(w_vy) + SQR(w_vz))
+                                              + (SQR(bcc1) + SQR(bcc2) + SQR(bcc3)));
+    } else {
+      B->u[CC(B,IEN,k,j,i)] = w_p*igm1 + 0.5*w_d*(SQR(w_vx) + SQR(w_vy) + SQR(w_vz));
+    }
+  }
+}
+
+/* TimeIntegratorTaskList::Primitives range (src/task_list/time_integrator.cpp:1965-1983) */
+void ao_primitives(AoMesh *m, int b) {
+  AoBlock *B = &m->blk[b];
+  int ng = m->p.ng;
+  int il = B->is, iu = B->ie, jl = B->js, ju = B->je, kl = B->ks, ku = B->ke;
+  if (B->nblevel[1][1][0] != -1) il -= ng;
+  if (B->nblevel[1][1][2] != -1) iu += ng;
+  if (B->nblevel[1][0][1] != -1) jl -= ng;
+  if (B->nblevel[1][2][1] != -1) ju += ng;
+  if (B->nblevel[0][1][1] != -1) kl -= ng;
+  if (B->nblevel[2][1][1] != -1) ku += ng;
+  ao_cons2prim(m, b, il, iu, jl, ju, kl, ku);
+}
+
+/* ------------------------------------------------------------------ fluxes */
+
+/* gather the NWAVE sweep-ordered primitives of one cell (plm.cpp:45-58,159-172,272-285) */
+static void cell_state(const AoMesh *m, const AoBlock *B, int dir, int k, int j, int i,
+                       double *q) {
+  for (int n = 0; n < NHYDRO; ++n) q[n] = B->w[CC(B,n,k,j,i)];
+  if (m->p.mhd) {
+    int by = (dir + 1) % 3, bz = (dir + 2) % 3;
+    q[IBY] = B->bcc[CC(B,by,k,j,i)];
+    q[IBZ] = B->bcc[CC(B,bz,k,j,i)];
+  }
+}
+
+/* L/R states of cell (k,j,i) along dir: `plus` is the state at its upper face (becomes wl
+ * of face+1), `minus` at its lower face (wr of its own face).
+ * dc.cpp:24-110, plm.cpp:27-370, ppm.cpp:44-940 */
+static void recon_cell(const AoMesh *m, const AoBlock *B, int dir, int order, int k, int j,
+                       int i, double *plus, double *minus) {
+  int nw = m->p.mhd ? 7 : 5;
+  int dk = (dir == 2), dj = (dir == 1), di = (dir == 0);
+  double q[7];
+  cell_state(m, B, dir, k, j, i, q);
+  if (order == 1) {
+    for (int n = 0; n < nw; ++n) plus[n] = minus[n] = q[n];
+    return;
+  }
+  double qm1[7], qp1[7];
+  cell_state(m, B, dir, k-dk, j-dj, i-di, qm1);
+  cell_state(m, B, dir, k+dk, j+dj, i+di, qp1);
+  if (order == 2) {
+    const double *xf = dir == 0 ? B->x1f : (dir == 1 ? B->x2f : B->x3f);
+    const double *xv = dir == 0 ? B->x1v : (dir == 1 ? B->x2v : B->x3v);
+    const double *dxf = dir == 0 ? B->dx1f : (dir == 1 ? B->dx2f : B->dx3f);
+    int c = dir == 0 ? i : (dir == 1 ? j : k);
+    double wp = (xf[c+1] - xv[c])/dxf[c];
+    double wm = (xv[c] - xf[c])/dxf[c];
+    for (int n = 0; n < nw; ++n) ao_plm_point(qm1[n], q[n], qp1[n], wp, wm, &plus[n], &minus[n]);
+    return;
+  }
+  double qm2[7], qp2[7];
+  cell_state(m, B, dir, k-2*dk, j-2*dj, i-2*di, qm2);
+  cell_state(m, B, dir, k+2*dk, j+2*dj, i+2*di, qp2);
+  for (int n = 0; n < nw; ++n)
+    ao_ppm_point(qm2[n], qm1[n], q[n], qp1[n], qp2[n], &plus[n], &minus[n]);
+  /* ApplyPrimitiveFloors on both (ppm.cpp:326-332) */
+  plus[IDN] = (plus[IDN] > m->p.dfloor) ? plus[IDN] : m->p.dfloor;
+  plus[IPR] = (plus[IPR] > m->p.pfloor) ? plus[IPR] : m->p.pfloor;
+  minus[IDN] = (minus[IDN] > m->p.dfloor) ? minus[IDN] : m->p.dfloor;
+  minus[IPR] = (minus[IPR] > m->p.pfloor) ? minus[IPR] : m->p.pfloor;
+}
+
+/* one interface: face (k,j,i) of direction dir lies between cell-1 and cell */
+static void face_flux(AoMesh *m, AoBlock *B, int dir, int order, int k, int j, int i) {
+  int dk = (dir == 2), dj = (dir == 1), di = (dir == 0);
+  double wl[7], wr[7], tmp[7], wli[7], wri[7], f[7];
+  recon_cell(m, B, dir, order, k-dk, j-dj, i-di, wl, tmp);
+  recon_cell(m, B, dir, order, k, j, i, tmp, wr);
+  /* rotate velocities: ivx = IVX+dir (hlld.cpp:44-45,66-82) */
+  int ivx = IVX + dir, ivy = IVX + (dir + 1) % 3, ivz = IVX + (dir + 2) % 3;
+  wli[IDN] = wl[IDN]; wli[IVX] = wl[ivx]; wli[IVY] = wl[ivy]; wli[IVZ] = wl[ivz];
+  wli[IPR] = wl[IPR]; wli[IBY] = wl[IBY]; wli[IBZ] = wl[IBZ];
+  wri[IDN] = wr[IDN]; wri[IVX] = wr[ivx]; wri[IVY] = wr[ivy]; wri[IVZ] = wr[ivz];
+  wri[IPR] = wr[IPR]; wri[IBY] = wr[IBY]; wri[IBZ] = wr[IBZ];
+  double bxi = 0.0;
+  if (m->p.mhd)
+    bxi = dir == 0 ? B->b[0][F1(B,k,j,i)] : (dir == 1 ? B->b[1][F2(B,k,j,i)]
+                                                       : B->b[2][F3(B,k,j,i)]);
+  ao_riemann_point(m->p.solver, m->p.mhd, wli, wri, bxi, m->p.gamma, f);
+  double *flx = B->flux[dir];
+  long o[5];
+  for (int n = 0; n < 5; ++n)
+    o[n] = dir == 0 ? FL1(B,n,k,j,i) : (dir == 1 ? FL2(B,n,k,j,i) : FL3(B,n,k,j,i));
+  flx[o[IDN]] = f[IDN];
+  flx[o[ivx]] = f[IVX];
+  flx[o[ivy]] = f[IVY];
+  flx[o[ivz]] = f[IVZ];
+  flx[o[IEN]] = f[IEN];
+  if (m->p.mhd) {
+    /* ey = -F(By), ez = F(Bz); CT weight (hlld.cpp:371-379); dxw = CenterWidth = dx?f */
+    long fo = dir == 0 ? F1(B,k,j,i) : (dir == 1 ? F2(B,k,j,i) : F3(B,k,j,i));
+    double dxw = dir == 0 ? B->dx1f[i] : (dir == 1 ? B->dx2f[j] : B->dx3f[k]);
+    double *ey = dir == 0 ? B->e3_x1f : (dir == 1 ? B->e1_x2f : B->e2_x3f);
+    double *ez = dir == 0 ? B->e2_x1f : (dir == 1 ? B->e3_x2f : B->e1_x3f);
+    ey[fo] = -f[IBY];
+    ez[fo] = f[IBZ];
+    B->wght[dir][fo] = ao_weight_for_ct(f[IDN], wli[IDN], wri[IDN], dxw, m->dt);
+  }
+}
+
+/* Hydro::CalculateFluxes loop limits (src/hydro/calculate_fluxes.cpp:62-74,164-173,273-279) */
+void ao_calc_fluxes(AoMesh *m, int b, int order) {
+  AoBlock *B = &m->blk[b];
+  int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+  int il, iu, jl, ju, kl, ku;
+  jl = js; ju = je; kl = ks; ku = ke;
+  if (m->p.mhd) {
+    if (m->f2) {
+      if (!m->f3) { jl = js-1; ju = je+1; kl = ks; ku = ke; }
+      else { jl = js-1; ju = je+1; kl = ks-1; ku = ke+1; }
+    }
+  }
+  for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j)
+    for (int i = is; i <= ie+1; ++i) face_flux(m, B, 0, order, k, j, i);
+  if (m->f2) {
+    il = is-1; iu = ie+1; kl = ks; ku = ke;
+    if (m->p.mhd) { if (!m->f3) { kl = ks; ku = ke; } else { kl = ks-1; ku = ke+1; } }
+    for (int k = kl; k <= ku; ++k) for (int j = js; j <= je+1; ++j)
+      for (int i = il; i <= iu; ++i) face_flux(m, B, 1, order, k, j, i);
+  }
+  if (m->f3) {
+    il = is; iu = ie; jl = js; ju = je;
+    if (m->p.mhd) { il = is-1; iu = ie+1; jl = js-1; ju = je+1; }
+    for (int k = ks; k <= ke+1; ++k) for (int j = jl; j <= ju; ++j)
+      for (int i = il; i <= iu; ++i) face_flux(m, B, 2, order, k, j, i);
+  }
+}
+
+/* Field::ComputeCornerE (src/field/calculate_corner_e.cpp:28-236) */
+void ao_corner_e(AoMesh *m, int b) {
+  AoBlock *B = &m->blk[b];
+  int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+  double *e1 = B->e[0], *e2 = B->e[1], *e3 = B->e[2];
+  double *w_x1f = B->wght[0], *w_x2f = B->wght[1], *w_x3f = B->wght[2];
+  double *w = B->w, *bcc = B->bcc, *cc = B->cc_e;
+  if (!m->f2) {
+    for (int i = is; i <= ie+1; ++i) {
+      e2[E2(B,ks,js,i)] = B->e2_x1f[F1(B,ks,js,i)];
+      e2[E2(B,ke+1,js,i)] = B->e2_x1f[F1(B,ks,js,i)];
+      e3[E3(B,ks,js,i)] = B->e3_x1f[F1(B,ks,js,i)];
+      e3[E3(B,ks,je+1,i)] = B->e3_x1f[F1(B,ks,js,i)];
+    }
+    return;
+  }
+  if (!m->f3) {
+    /* 2-D: cc_e_ is a 3-D array (k,j,i) */
+    for (int k = ks; k <= ke; ++k) for (int j = js-1; j <= je+1; ++j)
+      for (int i = is-1; i <= ie+1; ++i)
+        cc[CC(B,0,k,j,i)] = w[CC(B,IVY,k,j,i)]*bcc[CC(B,IB1,k,j,i)]
+                          - w[CC(B,IVX,k,j,i)]*bcc[CC(B,IB2,k,j,i)];
+    for (int j = js; j <= je; ++j) for (int i = is; i <= ie+1; ++i)
+      e2[E2(B,ke+1,j,i)] = e2[E2(B,ks,j,i)] = B->e2_x1f[F1(B,ks,j,i)];
+    for (int j = js; j <= je+1; ++j) for (int i = is; i <= ie; ++i)
+      e1[E1(B,ke+1,j,i)] = e1[E1(B,ks,j,i)] = B->e1_x2f[F2(B,ks,j,i)];
+    for (int k = ks; k <= ke; ++k) for (int j = js; j <= je+1; ++j)
+      for (int i = is; i <= ie+1; ++i) {
+        const double *e3_x2f = B->e3_x2f, *e3_x1f = B->e3_x1f;
+        double de3_l2 = (1.0-w_x1f[F1(B,k,j-1,i)])*(e3_x2f[F2(B,k,j,i)] - cc[CC(B,0,k,j-1,i)]) +
+                        (    w_x1f[F1(B,k,j-1,i)])*(e3_x2f[F2(B,k,j,i-1)] - cc[CC(B,0,k,j-1,i-1)]);
+        double de3_r2 = (1.0-w_x1f[F1(B,k,j,i)])*(e3_x2f[F2(B,k,j,i)] - cc[CC(B,0,k,j,i)]) +
+                        (    w_x1f[F1(B,k,j,i)])*(e3_x2f[F2(B,k,j,i-1)] - cc[CC(B,0,k,j,i-1)]);
+        double de3_l1 = (1.0-w_x2f[F2(B,k,j,i-1)])*(e3_x1f[F1(B,k,j,i)] - cc[CC(B,0,k,j,i-1)]) +
+                        (    w_x2f[F2(B,k,j,i-1)])*(e3_x1f[F1(B,k,j-1,i)] - cc[CC(B,0,k,j-1,i-1)]);
+        double de3_r1 = (1.0-w_x2f[F2(B,k,j,i)])*(e3_x1f[F1(B,k,j,i)] - cc[CC(B,0,k,j,i)]) +
+                        (    w_x2f[F2(B,k,j,i)])*(e3_x1f[F1(B,k,j-1,i)] - cc[CC(B,0,k,j-1,i)]);
+        e3[E3(B,k,j,i)] = 0.25*(de3_l1 + de3_r1 + de3_l2 + de3_r2 + e3_x2f[F2(B,k,j,i-1)] +
+                                e3_x2f[F2(B,k,j,i)] + e3_x1f[F1(B,k,j-1,i)] + e3_x1f[F1(B,k,j,i)]);
+      }
+    return;
+  }
+  for (int k = ks-1; k <= ke+1; ++k) for (int j = js-1; j <= je+1; ++j)
+    for (int i = is-1; i <= ie+1; ++i) {
+      cc[CC(B,IB1,k,j,i)] = w[CC(B,IVZ,k,j,i)]*bcc[CC(B,IB2,k,j,i)] - w[CC(B,IVY,k,j,i)]*bcc[CC(B,IB3,k,j,i)];
+      cc[CC(B,IB2,k,j,i)] = w[CC(B,IVX,k,j,i)]*bcc[CC(B,IB3,k,j,i)] - w[CC(B,IVZ,k,j,i)]*bcc[CC(B,IB1,k,j,i)];
+      cc[CC(B,IB3,k,j,i)] = w[CC(B,IVY,k,j,i)]*bcc[CC(B,IB1,k,j,i)] - w[CC(B,IVX,k,j,i)]*bcc[CC(B,IB2,k,j,i)];
+    }
+  const double *e1_x2f = B->e1_x2f, *e1_x3f = B->e1_x3f, *e2_x1f = B->e2_x1f,
+               *e2_x3f = B->e2_x3f, *e3_x1f = B->e3_x1f, *e3_x2f = B->e3_x2f;
+  for (int k = ks; k <= ke+1; ++k) for (int j = js; j <= je+1; ++j)
+    for (int i = is; i <= ie+1; ++i) {
+      double de1_l3 = (1.0-w_x2f[F2(B,k-1,j,i)])*(e1_x3f[F3(B,k,j,i)] - cc[CC(B,IB1,k-1,j,i)]) +
+                      (    w_x2f[F2(B,k-1,j,i)])*(e1_x3f[F3(B,k,j-1,i)] - cc[CC(B,IB1,k-1,j-1,i)]);
+      double de1_r3 = (1.0-w_x2f[F2(B,k,j,i)])*(e1_x3f[F3(B,k,j,i)] - cc[CC(B,IB1,k,j,i)]) +
+                      (    w_x2f[F2(B,k,j,i)])*(e1_x3f[F3(B,k,j-1,i)] - cc[CC(B,IB1,k,j-1,i)]);
+      double de1_l2 = (1.0-w_x3f[F3(B,k,j-1,i)])*(e1_x2f[F2(B,k,j,i)] - cc[CC(B,IB1,k,j-1,i)]) +
+                      (    w_x3f[F3(B,k,j-1,i)])*(e1_x2f[F2(B,k-1,j,i)] - cc[CC(B,IB1,k-1,j-1,i)]);
+      double de1_r2 = (1.0-w_x3f[F3(B,k,j,i)])*(e1_x2f[F2(B,k,j,i)] - cc[CC(B,IB1,k,j,i)]) +
+                      (    w_x3f[F3(B,k,j,i)])*(e1_x2f[F2(B,k-1,j,i)] - cc[CC(B,IB1,k-1,j,i)]);
+      e1[E1(B,k,j,i)] = 0.25*(de1_l3 + de1_r3 + de1_l2 + de1_r2 + e1_x2f[F2(B,k-1,j,i)] +
+                              e1_x2f[F2(B,k,j,i)] + e1_x3f[F3(B,k,j-1,i)] + e1_x3f[F3(B,k,j,i)]);
+
+      double de2_l3 = (1.0-w_x1f[F1(B,k-1,j,i)])*(e2_x3f[F3(B,k,j,i)] - cc[CC(B,IB2,k-1,j,i)]) +
+                      (    w_x1f[F1(B,k-1,j,i)])*(e2_x3f[F3(B,k,j,i-1)] - cc[CC(B,IB2,k-1,j,i-1)]);
+      double de2_r3 = (1.0-w_x1f[F1(B,k,j,i)])*(e2_x3f[F3(B,k,j,i)] - cc[CC(B,IB2,k,j,i)]) +
+                      (    w_x1f[F1(B,k,j,i)])*(e2_x3f[F3(B,k,j,i-1)] - cc[CC(B,IB2,k,j,i-1)]);
+      double de2_l1 = (1.0-w_x3f[F3(B,k,j,i-1)])*(e2_x1f[F1(B,k,j,i)] - cc[CC(B,IB2,k,j,i-1)]) +
+                      (    w_x3f[F3(B,k,j,i-1)])*(e2_x1f[F1(B,k-1,j,i)] - cc[CC(B,IB2,k-1,j,i-1)]);
+      double de2_r1 = (1.0-w_x3f[F3(B,k,j,i)])*(e2_x1f[F1(B,k,j,i)] - cc[CC(B,IB2,k,j,i)]) +
+                      (    w_x3f[F3(B,k,j,i)])*(e2_x1f[F1(B,k-1,j,i)] - cc[CC(B,IB2,k-1,j,i)]);
+      e2[E2(B,k,j,i)] = 0.25*(de2_l3 + de2_r3 + de2_l1 + de2_r1 + e2_x3f[F3(B,k,j,i-1)] +
+                              e2_x3f[F3(B,k,j,i)] + e2_x1f[F1(B,k-1,j,i)] + e2_x1f[F1(B,k,j,i)]);
+
+      double de3_l2 = (1.0-w_x1f[F1(B,k,j-1,i)])*(e3_x2f[F2(B,k,j,i)] - cc[CC(B,IB3,k,j-1,i)]) +
+                      (    w_x1f[F1(B,k,j-1,i)])*(e3_x2f[F2(B,k,j,i-1)] - cc[CC(B,IB3,k,j-1,i-1)]);
+      double de3_r2 = (1.0-w_x1f[F1(B,k,j,i)])*(e3_x2f[F2(B,k,j,i)] - cc[CC(B,IB3,k,j,i)]) +
+                      (    w_x1f[F1(B,k,j,i)])*(e3_x2f[F2(B,k,j,i-1)] - cc[CC(B,IB3,k,j,i-1)]);
+      double de3_l1 = (1.0-w_x2f[F2(B,k,j,i-1)])*(e3_x1f[F1(B,k,j,i)] - cc[CC(B,IB3,k,j,i-1)]) +
+                      (    w_x2f[F2(B,k,j,i-1)])*(e3_x1f[F1(B,k,j-1,i)] - cc[CC(B,IB3,k,j-1,i-1)]);
+      double de3_r1 = (1.0-w_x2f[F2(B,k,j,i)])*(e3_x1f[F1(B,k,j,i)] - cc[CC(B,IB3,k,j,i)]) +
+                      (    w_x2f[F2(B,k,j,i)])*(e3_x1f[F1(B,k,j-1,i)] - cc[CC(B,IB3,k,j-1,i)]);
+      e3[E3(B,k,j,i)] = 0.25*(de3_l1 + de3_r1 + de3_l2 + de3_r2 + e3_x2f[F2(B,k,j,i-1)] +
+                              e3_x2f[F2(B,k,j,i)] + e3_x1f[F1(B,k,j-1,i)] + e3_x1f[F1(B,k,j,i)]);
+    }
+}
+
+/* ------------------------------------------------------------------ EMF correction */
+
+/* LoadFluxBoundaryBufferSameLevel (src/bvals/fc/flux_correction_fc.cpp:51-307) */
+static long emf_load(const AoMesh *m, const AoBlock *B, const Nb *nb, double *buf) {
+  long p = 0;
+  const double *e1 = B->e[0], *e2 = B->e[1], *e3 = B->e[2];
+  int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+  if (nb->type == 0) {
+    if (m->f3) {
+      if (nb->fid == 0 || nb->fid == 1) {
+        int i = nb->fid == 0 ? is : ie+1;
+        for (int k = ks; k <= ke+1; k++) for (int j = js; j <= je; j++) buf[p++] = e2[E2(B,k,j,i)];
+        for (int k = ks; k <= ke; k++) for (int j = js; j <= je+1; j++) buf[p++] = e3[E3(B,k,j,i)];
+      } else if (nb->fid == 2 || nb->fid == 3) {
+        int j = nb->fid == 2 ? js : je+1;
+        for (int k = ks; k <= ke+1; k++) for (int i = is; i <= ie; i++) buf[p++] = e1[E1(B,k,j,i)];
+        for (int k = ks; k <= ke; k++) for (int i = is; i <= ie+1; i++) buf[p++] = e3[E3(B,k,j,i)];
+      } else {
+        int k = nb->fid == 4 ? ks : ke+1;
+        for (int j = js; j <= je+1; j++) for (int i = is; i <= ie; i++) buf[p++] = e1[E1(B,k,j,i)];
+        for (int j = js; j <= je; j++) for (int i = is; i <= ie+1; i++) buf[p++] = e2[E2(B,k,j,i)];
+      }
+    } else if (m->f2) {
+      int k = ks;
+      if (nb->fid == 0 || nb->fid == 1) {
+        int i = nb->fid == 0 ? is : ie+1;
+        for (int j = js; j <= je; j++) buf[p++] = e2[E2(B,k,j,i)];
+        for (int j = js; j <= je+1; j++) buf[p++] = e3[E3(B,k,j,i)];
+      } else {
+        int j = nb->fid == 2 ? js : je+1;
+        for (int i = is; i <= ie; i++) buf[p++] = e1[E1(B,k,j,i)];
+        for (int i = is; i <= ie+1; i++) buf[p++] = e3[E3(B,k,j,i)];
+      }
+    } else {
+      int i = nb->fid == 0 ? is : ie+1;
+      buf[p++] = e2[E2(B,ks,js,i)];
+      buf[p++] = e3[E3(B,ks,js,i)];
+    }
+  } else if (nb->type == 1) {
+    if (nb->eid >= 0 && nb->eid < 4) {
+      int i = ((nb->eid & 1) == 0) ? is : ie+1;
+      int j = ((nb->eid & 2) == 0) ? js : je+1;
+      for (int k = ks; k <= ke; k++) buf[p++] = e3[E3(B,k,j,i)];
+    } else if (nb->eid >= 4 && nb->eid < 8) {
+      int i = ((nb->eid & 1) == 0) ? is : ie+1;
+      int k = ((nb->eid & 2) == 0) ? ks : ke+1;
+      for (int j = js; j <= je; j++) buf[p++] = e2[E2(B,k,j,i)];
+    } else {
+      int j = ((nb->eid & 1) == 0) ? js : je+1;
+      int k = ((nb->eid & 2) == 0) ? ks : ke+1;
+      for (int i = is; i <= ie; i++) buf[p++] = e1[E1(B,k,j,i)];
+    }
+  }
+  return p;
+}
+
+/* SetFluxBoundarySameLevel (flux_correction_fc.cpp:689-905): ADDS the neighbour's EMFs */
+static void emf_set(const AoMesh *m, AoBlock *B, const Nb *nb, const double *buf) {
+  long p = 0;
+  double *e1 = B->e[0], *e2 = B->e[1], *e3 = B->e[2];
+  int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+  if (nb->type == 0) {
+    if (m->f3) {
+      if (nb->fid == 0 || nb->fid == 1) {
+        int i = nb->fid == 0 ? is : ie+1;
+        for (int k = ks; k <= ke+1; k++) for (int j = js; j <= je; j++) e2[E2(B,k,j,i)] += buf[p++];
+        for (int k = ks; k <= ke; k++) for (int j = js; j <= je+1; j++) e3[E3(B,k,j,i)] += buf[p++];
+      } else if (nb->fid == 2 || nb->fid == 3) {
+        int j = nb->fid == 2 ? js : je+1;
+        for (int k = ks; k <= ke+1; k++) for (int i = is; i <= ie; i++) e1[E1(B,k,j,i)] += buf[p++];
+        for (int k = ks; k <= ke; k++) for (int i = is; i <= ie+1; i++) e3[E3(B,k,j,i)] += buf[p++];
+      } else {
+        int k = nb->fid == 4 ? ks : ke+1;
+        for (int j = js; j <= je+1; j++) for (int i = is; i <= ie; i++) e1[E1(B,k,j,i)] += buf[p++];
+        for (int j = js; j <= je; j++) for (int i = is; i <= ie+1; i++) e2[E2(B,k,j,i)] += buf[p++];
+      }
+    } else if (m->f2) {
+      int k = ks;
+      if (nb->fid == 0 || nb->fid == 1) {
+        int i = nb->fid == 0 ? is : ie+1;
+        for (int j = js; j <= je; j++) { e2[E2(B,k+1,j,i)] += buf[p]; e2[E2(B,k,j,i)] += buf[p++]; }
+        for (int j = js; j <= je+1; j++) e3[E3(B,k,j,i)] += buf[p++];
+      } else {
+        int j = nb->fid == 2 ? js : je+1;
+        for (int i = is; i <= ie; i++) { e1[E1(B,k+1,j,i)] += buf[p]; e1[E1(B,k,j,i)] += buf[p++]; }
+        for (int i = is; i <= ie+1; i++) e3[E3(B,k,j,i)] += buf[p++];
+      }
+    } else {
+      int i = nb->fid == 0 ? is : ie+1, j = js, k = ks;
+      e2[E2(B,k+1,j,i)] += buf[p];
+      e2[E2(B,k,j,i)] += buf[p++];
+      e3[E3(B,k,j+1,i)] += buf[p];
+      e3[E3(B,k,j,i)] += buf[p++];
+    }
+  } else if (nb->type == 1) {
+    if (nb->eid >= 0 && nb->eid < 4) {
+      int i = ((nb->eid & 1) == 0) ? is : ie+1;
+      int j = ((nb->eid & 2) == 0) ? js : je+1;
+      for (int k = ks; k <= ke; k++) e3[E3(B,k,j,i)] += buf[p++];
+    } else if (nb->eid >= 4 && nb->eid < 8) {
+      int i = ((nb->eid & 1) == 0) ? is : ie+1;
+      int k = ((nb->eid & 2) == 0) ? ks : ke+1;
+      for (int j = js; j <= je; j++) e2[E2(B,k,j,i)] += buf[p++];
+    } else {
+      int j = ((nb->eid & 1) == 0) ? js : je+1;
+      int k = ((nb->eid & 2) == 0) ? ks : ke+1;
+      for (int i = is; i <= ie; i++) e1[E1(B,k,j,i)] += buf[p++];
+    }
+  }
+}
+
+/* AverageFluxBoundary (flux_correction_fc.cpp:1355-1541), same-level branches */
+static void emf_average(const AoMesh *m, AoBlock *B) {
+  double *e1 = B->e[0], *e2 = B->e[1], *e3 = B->e[2];
+  int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+  int nface = 2*m->ndim;
+  for (int n = 0; n < nface; n++) {
+    if (B->bcs[n] != -1 && B->bcs[n] != AO_BC_PERIODIC) continue;
+    if (n == 0 || n == 1) {
+      int i = n == 0 ? is : ie+1;
+      double div = 0.5;
+      if (m->f3) {
+        for (int k = ks+1; k <= ke; k++) for (int j = js; j <= je; j++) e2[E2(B,k,j,i)] *= div;
+        for (int k = ks; k <= ke; k++) for (int j = js+1; j <= je; j++) e3[E3(B,k,j,i)] *= div;
+      } else if (m->f2) {
+        for (int j = js; j <= je; j++) { e2[E2(B,ks,j,i)] *= div; e2[E2(B,ks+1,j,i)] *= div; }
+        for (int j = js+1; j <= je; j++) e3[E3(B,ks,j,i)] *= div;
+      } else {
+        e2[E2(B,ks,js,i)] *= 0.5; e2[E2(B,ks+1,js,i)] *= 0.5;
+        e3[E3(B,ks,js,i)] *= 0.5; e3[E3(B,ks,js+1,i)] *= 0.5;
+      }
+    }
+    if (n == 2 || n == 3) {
+      int j = n == 2 ? js : je+1;
+      if (m->f3) {
+        for (int k = ks+1; k <= ke; k++) for (int i = is; i <= ie; i++) e1[E1(B,k,j,i)] *= 0.5;
+        for (int k = ks; k <= ke; k++) for (int i = is+1; i <= ie; i++) e3[E3(B,k,j,i)] *= 0.5;
+      } else if (m->f2) {
+        for (int i = is; i <= ie; i++) { e1[E1(B,ks,j,i)] *= 0.5; e1[E1(B,ks+1,j,i)] *= 0.5; }
+        for (int i = is+1; i <= ie; i++) e3[E3(B,ks,j,i)] *= 0.5;
+      }
+    }
+    if (n == 4 || n == 5) {
+      int k = n == 4 ? ks : ke+1;
+      for (int j = js+1; j <= je; j++) for (int i = is; i <= ie; i++) e1[E1(B,k,j,i)] *= 0.5;
+      for (int j = js; j <= je; j++) for (int i = is+1; i <= ie; i++) e2[E2(B,k,j,i)] *= 0.5;
+    }
+  }
+  int nedge = m->ndim == 3 ? 12 : (m->ndim == 2 ? 4 : 0);
+  for (int n = 0; n < nedge; n++) {
+    if (B->nedge_fine[n] == 1) continue;
+    double div = 1.0/(double)B->nedge_fine[n];
+    if (n < 4) {
+      int i = ((n & 1) == 0) ? is : ie+1;
+      int j = ((n & 2) == 0) ? js : je+1;
+      for (int k = ks; k <= ke; k++) e3[E3(B,k,j,i)] *= div;
+    } else if (n < 8) {
+      int i = ((n & 1) == 0) ? is : ie+1;
+      int k = ((n & 2) == 0) ? ks : ke+1;
+      for (int j = js; j <= je; j++) e2[E2(B,k,j,i)] *= div;
+    } else {
+      int j = ((n & 1) == 0) ? js : je+1;
+      int k = ((n & 2) == 0) ? ks : ke+1;
+      for (int i = is; i <= ie; i++) e1[E1(B,k,j,i)] *= div;
+    }
+  }
+}
+
+/* SendFluxCorrection (flux_correction_fc.cpp:623-680) on every block, then
+ * ReceiveFluxCorrection (:1610-1749): add in neighbour-list order, then average */
+void ao_emf_exchange(AoMesh *m) {
+  if (!m->p.mhd) return;
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    long maxn = 2L*((long)B->nc1+1)*((long)B->nc2+1) + 2L*((long)B->nc1+1)*((long)B->nc3+1)
+              + 2L*((long)B->nc2+1)*((long)B->nc3+1);
+    for (int n = 0; n < B->nnb; ++n) {
+      const Nb *nb = &B->nb[n];
+      if (nb->type > 1) break;
+      double *buf = dalloc(maxn);
+      long cnt = emf_load(m, B, nb, buf);
+      AoBlock *T = &m->blk[nb->gid];
+      T->recv[nb->targetid] = buf; T->recvn[nb->targetid] = cnt;
+    }
+  }
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    for (int n = 0; n < B->nnb; ++n) {
+      const Nb *nb = &B->nb[n];
+      if (nb->type > 1) break;
+      emf_set(m, B, nb, B->recv[nb->bufid]);
+      free(B->recv[nb->bufid]); B->recv[nb->bufid] = NULL;
+    }
+    emf_average(m, B);
+  }
+}
+
+/* ------------------------------------------------------------------ integration */
+
+static double *cc_reg(AoBlock *B, int r) { return r == 0 ? B->u : B->u1; }
+
+/* MeshBlock::WeightedAve, cell-centred (src/mesh/weighted_ave.cpp:33-236), registers
+ * u (0) / u1 (1); only wght[0..2] can be non-zero for the integrators restated here */
+void ao_weighted_ave_cc(AoMesh *m, int b, int out_reg, int in1_reg, const double w[5]) {
+  AoBlock *B = &m->blk[b];
+  double *uo = cc_reg(B, out_reg), *ui = cc_reg(B, in1_reg);
+  for (int n = 0; n < NHYDRO; ++n) for (int k = B->ks; k <= B->ke; ++k)
+    for (int j = B->js; j <= B->je; ++j) for (int i = B->is; i <= B->ie; ++i) {
+      long o = CC(B,n,k,j,i);
+      if (w[0] == 1.0) {
+        if (w[1] != 0.0) uo[o] += w[1]*ui[o];
+      } else if (w[0] == 0.0) {
+        if (w[1] == 1.0) uo[o] = ui[o];
+        else uo[o] = w[1]*ui[o];
+      } else {
+        if (w[1] != 0.0) uo[o] = w[0]*uo[o] + w[1]*ui[o];
+        else uo[o] *= w[0];
+      }
+    }
+}
+
+static void wave_fc_one(double *bo, const double *bi, long o, const double w[5]) {
+  if (w[0] == 1.0) {
+    if (w[1] != 0.0) bo[o] += w[1]*bi[o];
+  } else if (w[0] == 0.0) {
+    if (w[1] == 1.0) bo[o] = bi[o];
+    else bo[o] = w[1]*bi[o];
+  } else {
+    if (w[1] != 0.0) bo[o] = w[0]*bo[o] + w[1]*bi[o];
+    else bo[o] *= w[0];
+  }
+}
+
+/* MeshBlock::WeightedAve, face-centred (weighted_ave.cpp:238-...) */
+void ao_weighted_ave_fc(AoMesh *m, int b, int out_reg, int in1_reg, const double w[5]) {
+  AoBlock *B = &m->blk[b];
+  double **bo = out_reg == 0 ? B->b : B->b1, **bi = in1_reg == 0 ? B->b : B->b1;
+  int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+  for (int k = ks; k <= ke; ++k) for (int j = js; j <= je; ++j) for (int i = is; i <= ie+1; ++i)
+    wave_fc_one(bo[0], bi[0], F1(B,k,j,i), w);
+  for (int k = ks; k <= ke; ++k) for (int j = js; j <= je+1; ++j) for (int i = is; i <= ie; ++i)
+    wave_fc_one(bo[1], bi[1], F2(B,k,j,i), w);
+  for (int k = ks; k <= ke+1; ++k) for (int j = js; j <= je; ++j) for (int i = is; i <= ie; ++i)
+    wave_fc_one(bo[2], bi[2], F3(B,k,j,i), w);
+  (void)m;
+}
+
+void ao_swap_cc(AoMesh *m, int b) {
+  AoBlock *B = &m->blk[b]; double *t = B->u; B->u = B->u1; B->u1 = t;
+}
+void ao_swap_fc(AoMesh *m, int b) {
+  AoBlock *B = &m->blk[b];
+  for (int d = 0; d < 3; ++d) { double *t = B->b[d]; B->b[d] = B->b1[d]; B->b1[d] = t; }
+}
+/* StartupTaskList stage 1 (time_integrator.cpp:1386-1397) */
+void ao_zero_reg1(AoMesh *m, int b) {
+  AoBlock *B = &m->blk[b];
+  memset(B->u1, 0, sizeof(double)*NHYDRO*(size_t)B->nc1*B->nc2*B->nc3);
+  if (m->p.mhd) {
+    memset(B->b1[0], 0, sizeof(double)*(size_t)B->nc3*B->nc2*(B->nc1+1));
+    memset(B->b1[1], 0, sizeof(double)*(size_t)B->nc3*(B->nc2+1)*B->nc1);
+    memset(B->b1[2], 0, sizeof(double)*(size_t)(B->nc3+1)*B->nc2*B->nc1);
+  }
+}
+
+/* Hydro::AddFluxDivergence (src/hydro/add_flux_divergence.cpp:39-96); Cartesian areas and
+ * volume (src/coordinates/coordinates.cpp:436-533) */
+void ao_add_flux_div(AoMesh *m, int b, double wght) {
+  AoBlock *B = &m->blk[b];
+  for (int k = B->ks; k <= B->ke; ++k) for (int j = B->js; j <= B->je; ++j)
+    for (int n = 0; n < NHYDRO; ++n) for (int i = B->is; i <= B->ie; ++i) {
+      double x1area = B->dx2f[j]*B->dx3f[k];
+      double dflx = (x1area*B->flux[0][FL1(B,n,k,j,i+1)] - x1area*B->flux[0][FL1(B,n,k,j,i)]);
+      if (m->f2) {
+        double x2area = B->dx1f[i]*B->dx3f[k];
+        dflx += (x2area*B->flux[1][FL2(B,n,k,j+1,i)] - x2area*B->flux[1][FL2(B,n,k,j,i)]);
+      }
+      if (m->f3) {
+        double x3area = B->dx1f[i]*B->dx2f[j];
+        dflx += (x3area*B->flux[2][FL3(B,n,k+1,j,i)] - x3area*B->flux[2][FL3(B,n,k,j,i)]);
+      }
+      double vol = B->dx1f[i]*B->dx2f[j]*B->dx3f[k];
+      B->u[CC(B,n,k,j,i)] -= wght*dflx/vol;
+    }
+}
+
+/* Field::CT (src/field/ct.cpp:31-116) */
+void ao_ct(AoMesh *m, int b, double wght) {
+  AoBlock *B = &m->blk[b];
+  const double *e1 = B->e[0], *e2 = B->e[1], *e3 = B->e[2];
+  int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+  for (int k = ks; k <= ke; ++k) for (int j = js; j <= je; ++j) {
+    if (m->f2) {
+      for (int i = is; i <= ie+1; ++i) {
+        double area = B->dx2f[j]*B->dx3f[k];
+        double len = B->dx3f[k], len_p1 = B->dx3f[k];
+        B->b[0][F1(B,k,j,i)] -= (wght/area)*(len_p1*e3[E3(B,k,j+1,i)] - len*e3[E3(B,k,j,i)]);
+      }
+      if (m->f3) {
+        for (int i = is; i <= ie+1; ++i) {
+          double area = B->dx2f[j]*B->dx3f[k];
+          double len = B->dx2f[j], len_p1 = B->dx2f[j];
+          B->b[0][F1(B,k,j,i)] += (wght/area)*(len_p1*e2[E2(B,k+1,j,i)] - len*e2[E2(B,k,j,i)]);
+        }
+      }
+    }
+  }
+  for (int k = ks; k <= ke; ++k) for (int j = js; j <= je+1; ++j) {
+    for (int i = is; i <= ie; ++i) {
+      double area = B->dx1f[i]*B->dx3f[k];
+      double len = B->dx3f[k];
+      B->b[1][F2(B,k,j,i)] += (wght/area)*(len*e3[E3(B,k,j,i+1)] - len*e3[E3(B,k,j,i)]);
+    }
+    if (m->f3) {
+      for (int i = is; i <= ie; ++i) {
+        double area = B->dx1f[i]*B->dx3f[k];
+        double len = B->dx1f[i], len_p1 = B->dx1f[i];
+        B->b[1][F2(B,k,j,i)] -= (wght/area)*(len_p1*e1[E1(B,k+1,j,i)] - len*e1[E1(B,k,j,i)]);
+      }
+    }
+  }
+  for (int k = ks; k <= ke+1; ++k) for (int j = js; j <= je; ++j) {
+    for (int i = is; i <= ie; ++i) {
+      double area = B->dx1f[i]*B->dx2f[j];
+      double len = B->dx2f[j];
+      B->b[2][F3(B,k,j,i)] -= (wght/area)*(len*e2[E2(B,k,j,i+1)] - len*e2[E2(B,k,j,i)]);
+    }
+    if (m->f2) {
+      for (int i = is; i <= ie; ++i) {
+        double area = B->dx1f[i]*B->dx2f[j];
+        double len = B->dx1f[i], len_p1 = B->dx1f[i];
+        B->b[2][F3(B,k,j,i)] += (wght/area)*(len_p1*e1[E1(B,k,j+1,i)] - len*e1[E1(B,k,j,i)]);
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ ghost exchange */
+
+/* BufferUtility::PackData / UnpackData order n,k,j,i (src/utils/buffer_utils.cpp) */
+static long pack3(const double *a, long s2, long s1, int si, int ei, int sj, int ej, int sk,
+                  int ek, double *buf, long p) {
+  for (int k = sk; k <= ek; ++k) for (int j = sj; j <= ej; ++j) for (int i = si; i <= ei; ++i)
+    buf[p++] = a[((long)k*s2 + j)*s1 + i];
+  return p;
+}
+static long unpack3(double *a, long s2, long s1, int si, int ei, int sj, int ej, int sk,
+                    int ek, const double *buf, long p) {
+  for (int k = sk; k <= ek; ++k) for (int j = sj; j <= ej; ++j) for (int i = si; i <= ei; ++i)
+    a[((long)k*s2 + j)*s1 + i] = buf[p++];
+  return p;
+}
+
+/* CellCenteredBoundaryVariable::LoadBoundaryBufferSameLevel / SetBoundarySameLevel
+ * (src/bvals/cc/bvals_cc.cpp:201-216,300-336) */
+void ao_exchange_cc(AoMesh *m) {
+  int ng = m->p.ng;
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    for (int n = 0; n < B->nnb; ++n) {
+      const Nb *nb = &B->nb[n];
+      int si = (nb->ox1 > 0) ? (B->ie - ng + 1) : B->is, ei = (nb->ox1 < 0) ? (B->is + ng - 1) : B->ie;
+      int sj = (nb->ox2 > 0) ? (B->je - ng + 1) : B->js, ej = (nb->ox2 < 0) ? (B->js + ng - 1) : B->je;
+      int sk = (nb->ox3 > 0) ? (B->ke - ng + 1) : B->ks, ek = (nb->ox3 < 0) ? (B->ks + ng - 1) : B->ke;
+      long cnt = (long)NHYDRO*(ei-si+1)*(ej-sj+1)*(ek-sk+1);
+      double *buf = dalloc(cnt);
+      long p = 0;
+      for (int v = 0; v < NHYDRO; ++v)
+        p = pack3(B->u + (long)v*B->nc3*B->nc2*B->nc1, B->nc2, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
+      AoBlock *T = &m->blk[nb->gid];
+      T->recv[nb->targetid] = buf; T->recvn[nb->targetid] = cnt;
+    }
+  }
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    for (int n = 0; n < B->nnb; ++n) {
+      const Nb *nb = &B->nb[n];
+      int si, ei, sj, ej, sk, ek;
+      if (nb->ox1 == 0) { si = B->is; ei = B->ie; }
+      else if (nb->ox1 > 0) { si = B->ie + 1; ei = B->ie + ng; }
+      else { si = B->is - ng; ei = B->is - 1; }
+      if (nb->ox2 == 0) { sj = B->js; ej = B->je; }
+      else if (nb->ox2 > 0) { sj = B->je + 1; ej = B->je + ng; }
+      else { sj = B->js - ng; ej = B->js - 1; }
+      if (nb->ox3 == 0) { sk = B->ks; ek = B->ke; }
+      else if (nb->ox3 > 0) { sk = B->ke + 1; ek = B->ke + ng; }
+      else { sk = B->ks - ng; ek = B->ks - 1; }
+      const double *buf = B->recv[nb->bufid];
+      long p = 0;
+      for (int v = 0; v < NHYDRO; ++v)
+        p = unpack3(B->u + (long)v*B->nc3*B->nc2*B->nc1, B->nc2, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
+      free(B->recv[nb->bufid]); B->recv[nb->bufid] = NULL;
+    }
+  }
+}
+
+/* FaceCenteredBoundaryVariable::LoadBoundaryBufferSameLevel / SetBoundarySameLevel
+ * (src/bvals/fc/bvals_fc.cpp:344-397,583-684), uniform (non-multilevel) mesh */
+void ao_exchange_fc(AoMesh *m) {
+  if (!m->p.mhd) return;
+  int ng = m->p.ng;
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+    for (int n = 0; n < B->nnb; ++n) {
+      const Nb *nb = &B->nb[n];
+      int si, ei, sj, ej, sk, ek;
+      double *buf = dalloc(3L*(B->nc1+1)*(B->nc2+1)*(B->nc3+1));
+      long p = 0;
+      /* bx1 */
+      if (nb->ox1 == 0) { si = is; ei = ie + 1; }
+      else if (nb->ox1 > 0) { si = ie - ng + 1; ei = ie; }
+      else { si = is + 1; ei = is + ng; }
+      if (nb->ox2 == 0) { sj = js; ej = je; }
+      else if (nb->ox2 > 0) { sj = je - ng + 1; ej = je; }
+      else { sj = js; ej = js + ng - 1; }
+      if (nb->ox3 == 0) { sk = ks; ek = ke; }
+      else if (nb->ox3 > 0) { sk = ke - ng + 1; ek = ke; }
+      else { sk = ks; ek = ks + ng - 1; }
+      p = pack3(B->b[0], B->nc2, B->nc1+1, si, ei, sj, ej, sk, ek, buf, p);
+      /* bx2 */
+      if (nb->ox1 == 0) { si = is; ei = ie; }
+      else if (nb->ox1 > 0) { si = ie - ng + 1; ei = ie; }
+      else { si = is; ei = is + ng - 1; }
+      if (!m->f2) { sj = js; ej = je; }
+      else if (nb->ox2 == 0) { sj = js; ej = je + 1; }
+      else if (nb->ox2 > 0) { sj = je - ng + 1; ej = je; }
+      else { sj = js + 1; ej = js + ng; }
+      p = pack3(B->b[1], B->nc2+1, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
+      /* bx3 */
+      if (nb->ox2 == 0) { sj = js; ej = je; }
+      else if (nb->ox2 > 0) { sj = je - ng + 1; ej = je; }
+      else { sj = js; ej = js + ng - 1; }
+      if (!m->f3) { sk = ks; ek = ke; }
+      else if (nb->ox3 == 0) { sk = ks; ek = ke + 1; }
+      else if (nb->ox3 > 0) { sk = ke - ng + 1; ek = ke; }
+      else { sk = ks + 1; ek = ks + ng; }
+      p = pack3(B->b[2], B->nc2, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
+      AoBlock *T = &m->blk[nb->gid];
+      T->recv[nb->targetid] = buf; T->recvn[nb->targetid] = p;
+    }
+  }
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+    for (int n = 0; n < B->nnb; ++n) {
+      const Nb *nb = &B->nb[n];
+      int si, ei, sj, ej, sk, ek;
+      const double *buf = B->recv[nb->bufid];
+      long p = 0;
+      /* bx1: the shared face itself is never overwritten (si = ie+2) */
+      if (nb->ox1 == 0) { si = is; ei = ie + 1; }
+      else if (nb->ox1 > 0) { si = ie + 2; ei = ie + ng + 1; }
+      else { si = is - ng; ei = is - 1; }
+      if (nb->ox2 == 0) { sj = js; ej = je; }
+      else if (nb->ox2 > 0) { sj = je + 1; ej = je + ng; }
+      else { sj = js - ng; ej = js - 1; }
+      if (nb->ox3 == 0) { sk = ks; ek = ke; }
+      else if (nb->ox3 > 0) { sk = ke + 1; ek = ke + ng; }
+      else { sk = ks - ng; ek = ks - 1; }
+      p = unpack3(B->b[0], B->nc2, B->nc1+1, si, ei, sj, ej, sk, ek, buf, p);
+      /* bx2 */
+      if (nb->ox1 == 0) { si = is; ei = ie; }
+      else if (nb->ox1 > 0) { si = ie + 1; ei = ie + ng; }
+      else { si = is - ng; ei = is - 1; }
+      if (!m->f2) { sj = js; ej = je; }
+      else if (nb->ox2 == 0) { sj = js; ej = je + 1; }
+      else if (nb->ox2 > 0) { sj = je + 2; ej = je + ng + 1; }
+      else { sj = js - ng; ej = js - 1; }
+      p = unpack3(B->b[1], B->nc2+1, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
+      if (!m->f2) {
+        for (int i = si; i <= ei; ++i) B->b[1][F2(B,sk,sj+1,i)] = B->b[1][F2(B,sk,sj,i)];
+      }
+      /* bx3 */
+      if (nb->ox2 == 0) { sj = js; ej = je; }
+      else if (nb->ox2 > 0) { sj = je + 1; ej = je + ng; }
+      else { sj = js - ng; ej = js - 1; }
+      if (!m->f3) { sk = ks; ek = ke; }
+      else if (nb->ox3 == 0) { sk = ks; ek = ke + 1; }
+      else if (nb->ox3 > 0) { sk = ke + 2; ek = ke + ng + 1; }
+      else { sk = ks - ng; ek = ks - 1; }
+      p = unpack3(B->b[2], B->nc2, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
+      if (!m->f3) {
+        for (int j = sj; j <= ej; ++j) for (int i = si; i <= ei; ++i)
+          B->b[2][F3(B,sk+1,j,i)] = B->b[2][F3(B,sk,j,i)];
+      }
+      free(B->recv[nb->bufid]); B->recv[nb->bufid] = NULL;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ physical BCs */
+
+/* outflow on primitives + face fields (src/bvals/cc/outflow_cc.cpp, fc/outflow_fc.cpp) */
+static void outflow(AoMesh *m, AoBlock *B, int face, int il, int iu, int jl, int ju, int kl,
+                    int ku) {
+  int ng = m->p.ng, mhd = m->p.mhd;
+  int d = face/2, upper = face & 1;
+  /* cell-centred primitives */
+  for (int n = 0; n < NHYDRO; ++n) for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j)
+    for (int i = il; i <= iu; ++i) for (int g = 1; g <= ng; ++g) {
+      if (d == 0) {
+        if (i != il) continue;
+        if (!upper) B->w[CC(B,n,k,j,il-g)] = B->w[CC(B,n,k,j,il)];
+        else B->w[CC(B,n,k,j,iu+g)] = B->w[CC(B,n,k,j,iu)];
+      } else if (d == 1) {
+        if (j != jl) continue;
+        if (!upper) B->w[CC(B,n,k,jl-g,i)] = B->w[CC(B,n,k,jl,i)];
+        else B->w[CC(B,n,k,ju+g,i)] = B->w[CC(B,n,k,ju,i)];
+      } else {
+        if (k != kl) continue;
+        if (!upper) B->w[CC(B,n,kl-g,j,i)] = B->w[CC(B,n,kl,j,i)];
+        else B->w[CC(B,n,ku+g,j,i)] = B->w[CC(B,n,ku,j,i)];
+      }
+    }
+  if (!mhd) return;
+  double *b1 = B->b[0], *b2 = B->b[1], *b3 = B->b[2];
+  if (d == 0) {
+    for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) for (int g = 1; g <= ng; ++g) {
+      if (!upper) b1[F1(B,k,j,il-g)] = b1[F1(B,k,j,il)];
+      else b1[F1(B,k,j,iu+g+1)] = b1[F1(B,k,j,iu+1)];
+    }
+    for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju+1; ++j) for (int g = 1; g <= ng; ++g) {
+      if (!upper) b2[F2(B,k,j,il-g)] = b2[F2(B,k,j,il)];
+      else b2[F2(B,k,j,iu+g)] = b2[F2(B,k,j,iu)];
+    }
+    for (int k = kl; k <= ku+1; ++k) for (int j = jl; j <= ju; ++j) for (int g = 1; g <= ng; ++g) {
+      if (!upper) b3[F3(B,k,j,il-g)] = b3[F3(B,k,j,il)];
+      else b3[F3(B,k,j,iu+g)] = b3[F3(B,k,j,iu)];
+    }
+  } else if (d == 1) {
+    for (int k = kl; k <= ku; ++k) for (int g = 1; g <= ng; ++g) for (int i = il; i <= iu+1; ++i) {
+      if (!upper) b1[F1(B,k,jl-g,i)] = b1[F1(B,k,jl,i)];
+      else b1[F1(B,k,ju+g,i)] = b1[F1(B,k,ju,i)];
+    }
+    for (int k = kl; k <= ku; ++k) for (int g = 1; g <= ng; ++g) for (int i = il; i <= iu; ++i) {
+      if (!upper) b2[F2(B,k,jl-g,i)] = b2[F2(B,k,jl,i)];
+      else b2[F2(B,k,ju+g+1,i)] = b2[F2(B,k,ju+1,i)];
+    }
+    for (int k = kl; k <= ku+1; ++k) for (int g = 1; g <= ng; ++g) for (int i = il; i <= iu; ++i) {
+      if (!upper) b3[F3(B,k,jl-g,i)] = b3[F3(B,k,jl,i)];
+      else b3[F3(B,k,ju+g,i)] = b3[F3(B,k,ju,i)];
+    }
+  } else {
+    for (int g = 1; g <= ng; ++g) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu+1; ++i) {
+      if (!upper) b1[F1(B,kl-g,j,i)] = b1[F1(B,kl,j,i)];
+      else b1[F1(B,ku+g,j,i)] = b1[F1(B,ku,j,i)];
+    }
+    for (int g = 1; g <= ng; ++g) for (int j = jl; j <= ju+1; ++j) for (int i = il; i <= iu; ++i) {
+      if (!upper) b2[F2(B,kl-g,j,i)] = b2[F2(B,kl,j,i)];
+      else b2[F2(B,ku+g,j,i)] = b2[F2(B,ku,j,i)];
+    }
+    for (int g = 1; g <= ng; ++g) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
+      if (!upper) b3[F3(B,kl-g,j,i)] = b3[F3(B,kl,j,i)];
+      else b3[F3(B,ku+g+1,j,i)] = b3[F3(B,ku+1,j,i)];
+    }
+  }
+}
+
+/* BoundaryValues::ApplyPhysicalBoundaries (src/bvals/bvals.cpp:436-620) */
+void ao_physical_bcs(AoMesh *m, int b) {
+  AoBlock *B = &m->blk[b];
+  int ng = m->p.ng;
+  int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+  int bis = is - ng, bie = ie + ng, bjs = js, bje = je, bks = ks, bke = ke;
+  int app[6];
+  for (int f = 0; f < 6; ++f) app[f] = (B->bcs[f] != -1 && B->bcs[f] != AO_BC_PERIODIC);
+  if (!app[2] && m->f2) bjs = js - ng;
+  if (!app[3] && m->f2) bje = je + ng;
+  if (!app[4] && m->f3) bks = ks - ng;
+  if (!app[5] && m->f3) bke = ke + ng;
+  if (app[0]) {
+    outflow(m, B, 0, is, ie, bjs, bje, bks, bke);
+    if (m->p.mhd) calc_bcc(B, is-ng, is-1, bjs, bje, bks, bke);
+    ao_prim2cons(m, b, is-ng, is-1, bjs, bje, bks, bke);
+  }
+  if (app[1]) {
+    outflow(m, B, 1, is, ie, bjs, bje, bks, bke);
+    if (m->p.mhd) calc_bcc(B, ie+1, ie+ng, bjs, bje, bks, bke);
+    ao_prim2cons(m, b, ie+1, ie+ng, bjs, bje, bks, bke);
+  }
+  if (m->f2) {
+    if (app[2]) {
+      outflow(m, B, 2, bis, bie, js, je, bks, bke);
+      if (m->p.mhd) calc_bcc(B, bis, bie, js-ng, js-1, bks, bke);
+      ao_prim2cons(m, b, bis, bie, js-ng, js-1, bks, bke);
+    }
+    if (app[3]) {
+      outflow(m, B, 3, bis, bie, js, je, bks, bke);
+      if (m->p.mhd) calc_bcc(B, bis, bie, je+1, je+ng, bks, bke);
+      ao_prim2cons(m, b, bis, bie, je+1, je+ng, bks, bke);
+    }
+  }
+  if (m->f3) {
+    bjs = js - ng; bje = je + ng;
+    if (app[4]) {
+      outflow(m, B, 4, bis, bie, bjs, bje, ks, ke);
+      if (m->p.mhd) calc_bcc(B, bis, bie, bjs, bje, ks-ng, ks-1);
+      ao_prim2cons(m, b, bis, bie, bjs, bje, ks-ng, ks-1);
+    }
+    if (app[5]) {
+      outflow(m, B, 5, bis, bie, bjs, bje, ks, ke);
+      if (m->p.mhd) calc_bcc(B, bis, bie, bjs, bje, ke+1, ke+ng);
+      ao_prim2cons(m, b, bis, bie, bjs, bje, ke+1, ke+ng);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ time step */
+
+/* Hydro::NewBlockTimeStep (src/hydro/new_blockdt.cpp:42-190) */
+double ao_new_block_dt(AoMesh *m, int b) {
+  AoBlock *B = &m->blk[b];
+  double min_dt = DBL_MAX;
+  double gamma = m->p.gamma;
+  for (int k = B->ks; k <= B->ke; ++k) for (int j = B->js; j <= B->je; ++j)
+    for (int i = B->is; i <= B->ie; ++i) {
+      double wi[7];
+      for (int n = 0; n < NHYDRO; ++n) wi[n] = B->w[CC(B,n,k,j,i)];
+      double dt1 = B->dx1f[i], dt2 = B->dx2f[j], dt3 = B->dx3f[k];
+      if (m->p.mhd) {
+        double b1c = B->bcc[CC(B,IB1,k,j,i)], b2c = B->bcc[CC(B,IB2,k,j,i)],
+               b3c = B->bcc[CC(B,IB3,k,j,i)];
+        double bx = b1c + fabs(B->b[0][F1(B,k,j,i)] - b1c);
+        wi[IBY] = b2c; wi[IBZ] = b3c;
+        double cf = ao_fast_speed(gamma, wi, bx);
+        dt1 /= (fabs(wi[IVX]) + cf);
+        wi[IBY] = b3c; wi[IBZ] = b1c;
+        bx = b2c + fabs(B->b[1][F2(B,k,j,i)] - b2c);
+        cf = ao_fast_speed(gamma, wi, bx);
+        dt2 /= (fabs(wi[IVY]) + cf);
+        wi[IBY] = b1c; wi[IBZ] = b2c;
+        bx = b3c + fabs(B->b[2][F3(B,k,j,i)] - b3c);
+        cf = ao_fast_speed(gamma, wi, bx);
+        dt3 /= (fabs(wi[IVZ]) + cf);
+      } else {
+        double cs = ao_sound_speed(gamma, wi);
+        dt1 /= (fabs(wi[IVX]) + cs);
+        dt2 /= (fabs(wi[IVY]) + cs);
+        dt3 /= (fabs(wi[IVZ]) + cs);
+      }
+      min_dt = mn(min_dt, dt1);
+      if (m->f2) min_dt = mn(min_dt, dt2);
+      if (m->f3) min_dt = mn(min_dt, dt3);
+    }
+  min_dt *= m->cfl;
+  B->new_dt = min_dt;
+  return min_dt;
+}
+
+/* Mesh::NewTimeStep (src/mesh/mesh.cpp:1078-1119) */
+static void new_time_step(AoMesh *m) {
+  m->dt = 2.0*m->dt;
+  for (int g = 0; g < m->nb; ++g) m->dt = mn(m->dt, m->blk[g].new_dt);
+  if (m->time < m->p.tlim && (m->p.tlim - m->time) < m->dt) m->dt = m->p.tlim - m->time;
+}
+
+/* Mesh::Initialize after ProblemGenerator (src/mesh/mesh.cpp:1416-1649) */
+void ao_initialize(AoMesh *m) {
+  ao_exchange_cc(m);
+  ao_exchange_fc(m);
+  for (int g = 0; g < m->nb; ++g) {
+    ao_primitives(m, g);
+    ao_physical_bcs(m, g);
+  }
+  for (int g = 0; g < m->nb; ++g) ao_new_block_dt(m, g);
+  new_time_step(m);
+}
+
+/* one cycle = all stages of TimeIntegratorTaskList (task order of
+ * src/task_list/time_integrator.cpp:899-1098; bodies :1442-2083) then the main-loop
+ * bookkeeping of src/main.cpp:478-485 */
+double ao_cycle(AoMesh *m) {
+  double dt = m->dt;
+  for (int stage = 1; stage <= m->nstages; ++stage) {
+    int s = stage - 1;
+    for (int g = 0; g < m->nb; ++g) if (stage == 1) ao_zero_reg1(m, g);
+    int order = (m->p.integrator == AO_INT_VL2 && stage == 1) ? 1 : m->p.xorder;
+    for (int g = 0; g < m->nb; ++g) {
+      ao_calc_fluxes(m, g, order);
+      if (m->p.mhd) ao_corner_e(m, g);
+    }
+    ao_emf_exchange(m);
+    for (int g = 0; g < m->nb; ++g) {
+      double w[5] = {1.0, m->delta[s], 0.0, 0.0, 0.0};
+      ao_weighted_ave_cc(m, g, 1, 0, w);
+      double w2[5] = {m->g1[s], m->g2[s], m->g3[s], 0.0, 0.0};
+      if (w2[0] == 0.0 && w2[1] == 1.0 && w2[2] == 0.0) ao_swap_cc(m, g);
+      else ao_weighted_ave_cc(m, g, 0, 1, w2);
+      ao_add_flux_div(m, g, m->beta[s]*dt);
+      if (m->p.mhd) {
+        ao_weighted_ave_fc(m, g, 1, 0, w);
+        if (w2[0] == 0.0 && w2[1] == 1.0 && w2[2] == 0.0) ao_swap_fc(m, g);
+        else ao_weighted_ave_fc(m, g, 0, 1, w2);
+        ao_ct(m, g, m->beta[s]*dt);
+      }
+    }
+    ao_exchange_cc(m);
+    ao_exchange_fc(m);
+    for (int g = 0; g < m->nb; ++g) {
+      ao_primitives(m, g);
+      ao_physical_bcs(m, g);
+    }
+    if (stage == m->nstages)
+      for (int g = 0; g < m->nb; ++g) ao_new_block_dt(m, g);
+  }
+  m->ncycle++;
+  m->time += dt;
+  new_time_step(m);
+  return dt;
+}

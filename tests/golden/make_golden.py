@@ -1,0 +1,87 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures in tests/golden/*.npz from the UNMODIFIED reference.
+
+Run where /root/reference is mounted and oracle/_ref has been built
+(`python oracle/build_ref.py`).  For each case the reference binary is run with a restart
+dump every cycle; the fixture keeps the parameter blocks, the full dt sequence (the 17-digit
+`dt=` values of the stdout cycle lines, bit-exact as doubles), the initial dump (cycle 0,
+after Mesh::Initialize) and the final dump (u and face b of every MeshBlock, ghosts included).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_run  # noqa: E402
+
+I = os.path.join(ROOT, "inputs")
+LW = {"mesh/nx1": 16, "mesh/nx2": 8, "mesh/nx3": 8}
+BL = {"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16, "problem/radius": 0.3}
+OT = {"mesh/nx1": 32, "mesh/nx2": 32}
+KH = {"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16}
+
+
+def mb(a, b, c=1):
+    return {"meshblock/nx1": a, "meshblock/nx2": b, "meshblock/nx3": c}
+
+
+# name -> (cfg, pgen, athinput, overrides, solver, mhd, ncycles)
+CASES = {
+    "c2_linwave_hlld_plm_vl2_1blk": ("mhd_hlld_ng2", "linear_wave", "athinput.linear_wave3d",
+                                     dict(LW, **mb(16, 8, 8)), "hlld", True, 4),
+    "c2_linwave_hlld_plm_vl2_8blk": ("mhd_hlld_ng2", "linear_wave", "athinput.linear_wave3d",
+                                     dict(LW, **mb(8, 4, 4)), "hlld", True, 4),
+    "c5_blast_hlld_plm_vl2_8blk": ("mhd_hlld_ng2", "blast", "athinput.blast",
+                                   dict(BL, **mb(8, 8, 8)), "hlld", True, 6),
+    "c5_blast_hlld_plm_vl2_1blk": ("mhd_hlld_ng2", "blast", "athinput.blast",
+                                   dict(BL, **mb(16, 16, 16)), "hlld", True, 6),
+    "c3_ot_hlld_ppm_vl2_4blk": ("mhd_hlld_ng3", "orszag_tang", "athinput.orszag_tang",
+                                dict(OT, **mb(16, 16)), "hlld", True, 5),
+    "c4_kh_hllc_ppm_rk2_8blk": ("hydro_hllc_ng3", "kh", "athinput.kh",
+                                dict(KH, **mb(8, 8, 8)), "hllc", False, 5),
+    "c1_sod_hllc_plm_vl2_2blk": ("hydro_hllc_ng2", "shock_tube", "athinput.sod",
+                                 {"mesh/nx1": 64, "meshblock/nx1": 32}, "hllc", False, 8),
+    "sod_hlle_plm_vl2": ("hydro_hlle_ng2", "shock_tube", "athinput.sod",
+                         {"mesh/nx1": 64, "meshblock/nx1": 64}, "hlle", False, 8),
+    "sod_roe_plm_vl2": ("hydro_roe_ng2", "shock_tube", "athinput.sod",
+                        {"mesh/nx1": 64, "meshblock/nx1": 64}, "roe", False, 8),
+    "linwave_mhd_hlle_plm_vl2": ("mhd_hlle_ng2", "linear_wave", "athinput.linear_wave3d",
+                                 dict(LW, **mb(16, 8, 8), **{"problem/amp": 0.1}),
+                                 "hlle", True, 4),
+    "linwave_mhd_roe_plm_vl2_2blk": ("mhd_roe_ng2", "linear_wave", "athinput.linear_wave3d",
+                                     dict(LW, **mb(8, 8, 8), **{"problem/amp": 0.1}),
+                                     "roe", True, 4),
+}
+
+
+def make(name):
+    cfg, pgen, inp, ov, solver, mhd, ncyc = CASES[name]
+    ov = dict(ov)
+    ov["time/nlim"] = ncyc
+    res = ref_run.run_reference(cfg, pgen, os.path.join(I, inp), ov, rst_every_cycle=True)
+    first = ref_run.read_rst(res["rst"][0])
+    last = ref_run.read_rst(res["rst"][ncyc])
+    out = {"meta": json.dumps({"cfg": cfg, "pgen": pgen, "solver": solver, "mhd": mhd,
+                               "ncycles": ncyc, "nghost": first["nghost"],
+                               "par": first["par"]}),
+           "dts": np.array(res["dts"][:ncyc + 1]),
+           "locs": np.array([b["loc"][:3] for b in first["blocks"]], dtype=np.int64),
+           "final_time": np.array(last["time"]), "final_dt": np.array(last["dt"])}
+    for tag, r in (("init", first), ("final", last)):
+        for n, b in enumerate(r["blocks"]):
+            out["%s_u_%d" % (tag, n)] = b["u"]
+            if mhd:
+                for f in ("b1", "b2", "b3"):
+                    out["%s_%s_%d" % (tag, f, n)] = b[f]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    ref_run.cleanup(res)
+    print("wrote", name, "dts", len(res["dts"]))
+
+
+if __name__ == "__main__":
+    for nm in (sys.argv[1:] or CASES):
+        make(nm)

@@ -1,0 +1,23 @@
+"""CPU: the C oracle (oracle/) against the committed golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py).  Bar: bit-exact dt sequence and state
+(conserved variables and face fields of every MeshBlock, ghost zones included)."""
+import pytest
+
+import util
+
+
+@pytest.mark.parametrize("name", util.golden_names())
+def test_oracle_reproduces_reference_golden(name):
+    g = util.Golden(name)
+    m = util.oracle_from_golden(g)
+    # first dt comes out of Mesh::Initialize (NewBlockTimeStep + NewTimeStep)
+    assert m.dt == g.dts[0], ("dt0", m.dt, g.dts[0])
+    for c in range(g.ncycles):
+        used = m.cycle()
+        assert used == g.dts[c], ("cycle %d used dt" % c, used, g.dts[c])
+        assert m.dt == g.dts[c + 1], ("cycle %d new dt" % c, m.dt, g.dts[c + 1])
+    assert m.time == g.final_time
+    for n, loc in enumerate(g.locs):
+        b = m.block_of(*loc)
+        for f in g.fields:
+            util.assert_bitwise(m.array(b, f), g.final[n][f], "%s block %s %s" % (name, loc, f))

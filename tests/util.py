@@ -1,0 +1,61 @@
+"""Shared helpers for the parity tests (golden fixtures <-> oracle <-> CUDA path)."""
+import glob
+import json
+import os
+
+import numpy as np
+
+import oracle
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+class Golden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        self.meta = json.loads(str(z["meta"]))
+        self.par = self.meta["par"]
+        self.mhd = bool(self.meta["mhd"])
+        self.solver = self.meta["solver"]
+        self.ng = int(self.meta["nghost"])
+        self.ncycles = int(self.meta["ncycles"])
+        self.dts = z["dts"]
+        self.locs = [tuple(int(v) for v in l) for l in z["locs"]]
+        self.final_time = float(z["final_time"])
+        self.final_dt = float(z["final_dt"])
+        self.fields = ("u", "b1", "b2", "b3") if self.mhd else ("u",)
+        self.init = [{f: z["init_%s_%d" % (f, n)] for f in self.fields}
+                     for n in range(len(self.locs))]
+        self.final = [{f: z["final_%s_%d" % (f, n)] for f in self.fields}
+                      for n in range(len(self.locs))]
+
+    def as_rst(self, which="init"):
+        blocks = getattr(self, which)
+        return {"blocks": [dict(loc=self.locs[n] + (0,), **blocks[n])
+                           for n in range(len(self.locs))]}
+
+
+def oracle_from_golden(g):
+    p = oracle.params_from_athinput(g.par, g.mhd, g.solver, ng=g.ng)
+    m = oracle.OracleMesh(p)
+    m.load_rst(g.as_rst("init"))
+    m.initialize()
+    return m
+
+
+def assert_bitwise(a, b, what=""):
+    """numeric equality of every element (treats +0 == -0, NaN != NaN fails)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        i = tuple(bad[0])
+        raise AssertionError("%s: %d/%d elements differ; first at %s: %.17e vs %.17e (max |d| %.3e)"
+                             % (what, len(bad), a.size, i, a[i], b[i],
+                                np.nanmax(np.abs(a - b))))
