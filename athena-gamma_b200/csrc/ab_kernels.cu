@@ -1,0 +1,975 @@
+// ab_kernels.cu -- hand-written sm_100a kernels of the per-MeshBlock hydro/MHD update.
+//
+// All arithmetic is FP64 on the CUDA cores (nothing on this path is a dense contraction, so
+// no tensor cores); the file must be compiled with -fmad=false so that products and sums
+// round exactly like the reference's SSE2 build.  Threads map to the fastest (x1) index so
+// that every global access is coalesced; stencil neighbours are served by L1/L2.
+#include <float.h>
+#include <stdint.h>
+#include "ab_kernels.h"
+#include "ab_physics.cuh"
+
+namespace ab {
+
+// ---- AthenaArray-style indexing -------------------------------------------------------------
+#define CCI(b, n, k, j, i) ((((long)(n)*(b).nc3 + (k))*(b).nc2 + (j))*(b).nc1 + (i))
+#define F1I(b, k, j, i) (((long)(k)*(b).nc2 + (j))*((b).nc1 + 1) + (i))
+#define F2I(b, k, j, i) (((long)(k)*((b).nc2 + 1) + (j))*(b).nc1 + (i))
+#define F3I(b, k, j, i) (((long)(k)*(b).nc2 + (j))*(b).nc1 + (i))
+#define E1I(b, k, j, i) (((long)(k)*((b).nc2 + 1) + (j))*(b).nc1 + (i))
+#define E2I(b, k, j, i) (((long)(k)*(b).nc2 + (j))*((b).nc1 + 1) + (i))
+#define E3I(b, k, j, i) (((long)(k)*((b).nc2 + 1) + (j))*((b).nc1 + 1) + (i))
+
+long g_launches = 0;      // kernel launches issued (bench accounting)
+constexpr int BX = 128;  // threads along x1 per CTA
+
+static inline dim3 grid3(int ni, int nj, int nk) {
+  return dim3((unsigned)((ni + BX - 1)/BX), (unsigned)nj, (unsigned)nk);
+}
+
+// =============================================================================================
+// EquationOfState::ConservedToPrimitive (+ Field::CalculateCellCenteredField)
+// eos/adiabatic_mhd.cpp:41-90, eos/adiabatic_hydro.cpp:39-80, field/field.cpp:112-180
+// =============================================================================================
+template <bool MHD>
+__global__ void __launch_bounds__(BX) k_cons2prim(BlkDev b, Params p, int il, int iu, int jl,
+                                                  int kl) {
+  int i = il + blockIdx.x*BX + threadIdx.x;
+  if (i > iu) return;
+  int j = jl + blockIdx.y, k = kl + blockIdx.z;
+  double gm1 = p.gamma - 1.0;
+  double pb = 0.0;
+  if (MHD) {
+    double bcc1 = 0.5*b.b[0][F1I(b,k,j,i)] + 0.5*b.b[0][F1I(b,k,j,i+1)];
+    double bcc2 = 0.5*b.b[1][F2I(b,k,j,i)] + 0.5*b.b[1][F2I(b,k,j+1,i)];
+    double bcc3 = 0.5*b.b[2][F3I(b,k,j,i)] + 0.5*b.b[2][F3I(b,k+1,j,i)];
+    b.bcc[CCI(b,0,k,j,i)] = bcc1;
+    b.bcc[CCI(b,1,k,j,i)] = bcc2;
+    b.bcc[CCI(b,2,k,j,i)] = bcc3;
+    pb = 0.5*(sqr(bcc1) + sqr(bcc2) + sqr(bcc3));
+  }
+  long o = CCI(b,0,k,j,i);
+  long sv = (long)b.nc3*b.nc2*b.nc1;
+  double u_d = b.u[o], u_m1 = b.u[o+sv], u_m2 = b.u[o+2*sv], u_m3 = b.u[o+3*sv],
+         u_e = b.u[o+4*sv];
+  double u_d0 = u_d, u_e0 = u_e;
+  u_d = (u_d > p.dfloor) ? u_d : p.dfloor;
+  double di = 1.0/u_d;
+  double e_k = 0.5*di*(sqr(u_m1) + sqr(u_m2) + sqr(u_m3));
+  double w_p;
+  if (MHD) {
+    w_p = gm1*(u_e - e_k - pb);
+    u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k + pb);
+  } else {
+    w_p = gm1*(u_e - e_k);
+    u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k);
+  }
+  w_p = (w_p > p.pfloor) ? w_p : p.pfloor;
+  // floors write back into cons (the reference always stores; storing only changes is
+  // value-identical and saves two stores per cell)
+  if (u_d != u_d0) b.u[o] = u_d;
+  if (u_e != u_e0) b.u[o+4*sv] = u_e;
+  b.w[o] = u_d;
+  b.w[o+sv] = u_m1*di;
+  b.w[o+2*sv] = u_m2*di;
+  b.w[o+3*sv] = u_m3*di;
+  b.w[o+4*sv] = w_p;
+}
+
+void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
+                      int ku, cudaStream_t s) {
+  dim3 g = grid3(iu-il+1, ju-jl+1, ku-kl+1);
+  if (p.mhd) { k_cons2prim<true><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl); } else { k_cons2prim<false><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl); }
+  ++g_launches;
+}
+
+// EquationOfState::PrimitiveToConserved (adiabatic_hydro.cpp:89-123, adiabatic_mhd.cpp:99-136)
+template <bool MHD>
+__global__ void __launch_bounds__(BX) k_prim2cons(BlkDev b, Params p, int il, int iu, int jl,
+                                                  int kl) {
+  int i = il + blockIdx.x*BX + threadIdx.x;
+  if (i > iu) return;
+  int j = jl + blockIdx.y, k = kl + blockIdx.z;
+  double igm1 = 1.0/(p.gamma - 1.0);
+  long o = CCI(b,0,k,j,i);
+  long sv = (long)b.nc3*b.nc2*b.nc1;
+  double w_d = b.w[o], w_vx = b.w[o+sv], w_vy = b.w[o+2*sv], w_vz = b.w[o+3*sv],
+         w_p = b.w[o+4*sv];
+  b.u[o] = w_d;
+  b.u[o+sv] = w_vx*w_d;
+  b.u[o+2*sv] = w_vy*w_d;
+  b.u[o+3*sv] = w_vz*w_d;
+  if (MHD) {
+    double bcc1 = b.bcc[o], bcc2 = b.bcc[o+sv], bcc3 = b.bcc[o+2*sv];
+    b.u[o+4*sv] = w_p*igm1 + 0.5*(w_d*(sqr(w_vx) + sqr(w_vy) + sqr(w_vz))
+                                  + (sqr(bcc1) + sqr(bcc2) + sqr(bcc3)));
+  } else {
+    b.u[o+4*sv] = w_p*igm1 + 0.5*w_d*(sqr(w_vx) + sqr(w_vy) + sqr(w_vz));
+  }
+}
+
+void launch_prim2cons(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
+                      int ku, cudaStream_t s) {
+  dim3 g = grid3(iu-il+1, ju-jl+1, ku-kl+1);
+  if (p.mhd) { k_prim2cons<true><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl); } else { k_prim2cons<false><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl); }
+  ++g_launches;
+}
+
+__global__ void __launch_bounds__(BX) k_calc_bcc(BlkDev b, int il, int iu, int jl, int kl) {
+  int i = il + blockIdx.x*BX + threadIdx.x;
+  if (i > iu) return;
+  int j = jl + blockIdx.y, k = kl + blockIdx.z;
+  b.bcc[CCI(b,0,k,j,i)] = 0.5*b.b[0][F1I(b,k,j,i)] + 0.5*b.b[0][F1I(b,k,j,i+1)];
+  b.bcc[CCI(b,1,k,j,i)] = 0.5*b.b[1][F2I(b,k,j,i)] + 0.5*b.b[1][F2I(b,k,j+1,i)];
+  b.bcc[CCI(b,2,k,j,i)] = 0.5*b.b[2][F3I(b,k,j,i)] + 0.5*b.b[2][F3I(b,k+1,j,i)];
+}
+
+void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, int ku,
+                     cudaStream_t s) {
+  k_calc_bcc<<<grid3(iu-il+1, ju-jl+1, ku-kl+1), BX, 0, s>>>(b, il, iu, jl, kl); ++g_launches;
+}
+
+// =============================================================================================
+// Hydro::CalculateFluxes: reconstruction + Riemann solver, one thread per interface.
+// hydro/calculate_fluxes.cpp:36-378; reconstruct/{dc,plm,ppm}.cpp; hydro/rsolvers/*
+// =============================================================================================
+
+// sweep-ordered primitives of one cell: (rho, v_dir, v_dir+1, v_dir+2, p [, B_dir+1, B_dir+2])
+template <int DIR, bool MHD>
+__device__ __forceinline__ void load_cell(const BlkDev &b, long o, long sv, double *q) {
+  q[IDN] = b.w[o];
+  q[IVX] = b.w[o + (1 + DIR)*sv];
+  q[IVY] = b.w[o + (1 + (DIR+1)%3)*sv];
+  q[IVZ] = b.w[o + (1 + (DIR+2)%3)*sv];
+  q[IPR] = b.w[o + 4*sv];
+  if (MHD) {
+    q[IBY] = b.bcc[o + ((DIR+1)%3)*sv];
+    q[IBZ] = b.bcc[o + ((DIR+2)%3)*sv];
+  }
+}
+
+template <int DIR, int ORDER, int SOLVER, bool MHD>
+__global__ void __launch_bounds__(BX) k_flux(BlkDev b, ReconGeom g, Params p, int i0, int i1,
+                                             int j0, int k0, double dt_val,
+                                             const double *dt_ptr) {
+  constexpr int NW = MHD ? 7 : 5;
+  int i = i0 + blockIdx.x*BX + threadIdx.x;
+  if (i > i1) return;
+  int j = j0 + blockIdx.y, k = k0 + blockIdx.z;
+  const long sv = (long)b.nc3*b.nc2*b.nc1;
+  const long st = (DIR == 0) ? 1 : ((DIR == 1) ? (long)b.nc1 : (long)b.nc1*b.nc2);
+  const long oc = CCI(b,0,k,j,i);           // cell on the upper side of the face
+  const int c = (DIR == 0) ? i : ((DIR == 1) ? j : k);
+
+  double wl[NW], wr[NW];
+  if (ORDER == 1) {
+    // DonorCell (reconstruct/dc.cpp)
+    load_cell<DIR,MHD>(b, oc - st, sv, wl);
+    load_cell<DIR,MHD>(b, oc, sv, wr);
+  } else if (ORDER == 2) {
+    double qm2[NW], qm1[NW], q0[NW], qp1[NW];
+    load_cell<DIR,MHD>(b, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD>(b, oc - st, sv, qm1);
+    load_cell<DIR,MHD>(b, oc, sv, q0);
+    load_cell<DIR,MHD>(b, oc + st, sv, qp1);
+    const double wp_l = g.wp[DIR][c-1], wm_l = g.wm[DIR][c-1];
+    const double wp_r = g.wp[DIR][c], wm_r = g.wm[DIR][c];
+#pragma unroll
+    for (int n = 0; n < NW; ++n) {
+      double dummy;
+      plm(qm2[n], qm1[n], q0[n], wp_l, wm_l, wl[n], dummy);
+      plm(qm1[n], q0[n], qp1[n], wp_r, wm_r, dummy, wr[n]);
+    }
+  } else {
+    double qm3[NW], qm2[NW], qm1[NW], q0[NW], qp1[NW], qp2[NW];
+    load_cell<DIR,MHD>(b, oc - 3*st, sv, qm3);
+    load_cell<DIR,MHD>(b, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD>(b, oc - st, sv, qm1);
+    load_cell<DIR,MHD>(b, oc, sv, q0);
+    load_cell<DIR,MHD>(b, oc + st, sv, qp1);
+    load_cell<DIR,MHD>(b, oc + 2*st, sv, qp2);
+#pragma unroll
+    for (int n = 0; n < NW; ++n) {
+      double dummy;
+      ppm(qm3[n], qm2[n], qm1[n], q0[n], qp1[n], wl[n], dummy);
+      ppm(qm2[n], qm1[n], q0[n], qp1[n], qp2[n], dummy, wr[n]);
+    }
+    // ApplyPrimitiveFloors (ppm.cpp:326-332)
+    wl[IDN] = (wl[IDN] > p.dfloor) ? wl[IDN] : p.dfloor;
+    wl[IPR] = (wl[IPR] > p.pfloor) ? wl[IPR] : p.pfloor;
+    wr[IDN] = (wr[IDN] > p.dfloor) ? wr[IDN] : p.dfloor;
+    wr[IPR] = (wr[IPR] > p.pfloor) ? wr[IPR] : p.pfloor;
+  }
+
+  long of;   // face-array offset
+  if (DIR == 0) of = F1I(b,k,j,i); else if (DIR == 1) of = F2I(b,k,j,i); else of = F3I(b,k,j,i);
+  double bxi = 0.0;
+  if (MHD) bxi = b.b[DIR][of];
+  double f[NW];
+  riemann<SOLVER,MHD>(wl, wr, bxi, p.gamma, f);
+
+  const long sf = (DIR == 0) ? (long)b.nc3*b.nc2*(b.nc1+1)
+                : ((DIR == 1) ? (long)b.nc3*(b.nc2+1)*b.nc1 : (long)(b.nc3+1)*b.nc2*b.nc1);
+  double *flx = b.flux[DIR];
+  flx[of] = f[IDN];
+  flx[of + (1 + DIR)*sf] = f[IVX];
+  flx[of + (1 + (DIR+1)%3)*sf] = f[IVY];
+  flx[of + (1 + (DIR+2)%3)*sf] = f[IVZ];
+  flx[of + 4*sf] = f[IEN];
+  if (MHD) {
+    b.ef[DIR][0][of] = -f[IBY];
+    b.ef[DIR][1][of] = f[IBZ];
+    const double dt = dt_ptr ? *dt_ptr : dt_val;
+    const double dxw = (DIR == 0) ? b.dx1f[i] : ((DIR == 1) ? b.dx2f[j] : b.dx3f[k]);
+    b.wght[DIR][of] = weight_for_ct(f[IDN], wl[IDN], wr[IDN], dxw, dt);
+  }
+}
+
+template <int DIR, int ORDER, int SOLVER, bool MHD>
+static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, double dt_val,
+                     const double *dt_ptr, cudaStream_t s) {
+  int is = b.is, ie = b.ie, js = b.js, je = b.je, ks = b.ks, ke = b.ke;
+  int i0, i1, j0, j1, k0, k1;
+  // loop limits of calculate_fluxes.cpp:62-74,164-173,273-279
+  if (DIR == 0) {
+    i0 = is; i1 = ie+1; j0 = js; j1 = je; k0 = ks; k1 = ke;
+    if (MHD && b.f2) { j0 = js-1; j1 = je+1; if (b.f3) { k0 = ks-1; k1 = ke+1; } }
+  } else if (DIR == 1) {
+    i0 = is-1; i1 = ie+1; j0 = js; j1 = je+1; k0 = ks; k1 = ke;
+    if (MHD && b.f3) { k0 = ks-1; k1 = ke+1; }
+  } else {
+    i0 = is; i1 = ie; j0 = js; j1 = je; k0 = ks; k1 = ke+1;
+    if (MHD) { i0 = is-1; i1 = ie+1; j0 = js-1; j1 = je+1; }
+  }
+  k_flux<DIR,ORDER,SOLVER,MHD><<<grid3(i1-i0+1, j1-j0+1, k1-k0+1), BX, 0, s>>>(
+      b, g, p, i0, i1, j0, k0, dt_val, dt_ptr); ++g_launches;
+}
+
+template <int ORDER, int SOLVER, bool MHD>
+static void flux_all(const BlkDev &b, const ReconGeom &g, const Params &p, double dt_val,
+                     const double *dt_ptr, cudaStream_t s) {
+  flux_dir<0,ORDER,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+  if (b.f2) flux_dir<1,ORDER,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+  if (b.f3) flux_dir<2,ORDER,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+}
+
+template <int SOLVER, bool MHD>
+static void flux_order(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
+                       double dt_val, const double *dt_ptr, cudaStream_t s) {
+  if (order == 1) flux_all<1,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+  else if (order == 2) flux_all<2,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+  else flux_all<3,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+}
+
+void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
+                   double dt_val, const double *dt_ptr, cudaStream_t s) {
+  if (p.mhd) {
+    if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD,true>(b, g, p, order, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,true>(b, g, p, order, dt_val, dt_ptr, s);
+    else flux_order<SOLVER_ROE,true>(b, g, p, order, dt_val, dt_ptr, s);
+  } else {
+    if (p.solver == SOLVER_HLLC) flux_order<SOLVER_HLLC,false>(b, g, p, order, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,false>(b, g, p, order, dt_val, dt_ptr, s);
+    else flux_order<SOLVER_ROE,false>(b, g, p, order, dt_val, dt_ptr, s);
+  }
+}
+
+// =============================================================================================
+// Field::ComputeCornerE (field/calculate_corner_e.cpp:28-236)
+// =============================================================================================
+__global__ void __launch_bounds__(BX) k_cc_e(BlkDev b, int i0, int i1, int j0, int k0) {
+  int i = i0 + blockIdx.x*BX + threadIdx.x;
+  if (i > i1) return;
+  int j = j0 + blockIdx.y, k = k0 + blockIdx.z;
+  long o = CCI(b,0,k,j,i);
+  long sv = (long)b.nc3*b.nc2*b.nc1;
+  double vx = b.w[o+sv], vy = b.w[o+2*sv], vz = b.w[o+3*sv];
+  double b1 = b.bcc[o], b2 = b.bcc[o+sv], b3 = b.bcc[o+2*sv];
+  if (b.f3) {
+    b.cc_e[o] = vz*b2 - vy*b3;
+    b.cc_e[o+sv] = vx*b3 - vz*b1;
+    b.cc_e[o+2*sv] = vy*b1 - vx*b2;
+  } else {
+    b.cc_e[o] = vy*b1 - vx*b2;   // 2-D: single component (E3), stored in slot 0
+  }
+}
+
+// upwinded gradient term of the corner EMF (GS05/SG07), calculate_corner_e.cpp:190-196
+__device__ __forceinline__ double de_term(double wt, double ef_a, double cc_a, double ef_b,
+                                          double cc_b) {
+  return (1.0-wt)*(ef_a - cc_a) + (wt)*(ef_b - cc_b);
+}
+
+__global__ void __launch_bounds__(BX) k_corner_e3d(BlkDev b) {
+  int i = b.is + blockIdx.x*BX + threadIdx.x;
+  if (i > b.ie+1) return;
+  int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
+  const long sv = (long)b.nc3*b.nc2*b.nc1;
+  const double *cc1 = b.cc_e, *cc2 = b.cc_e + sv, *cc3 = b.cc_e + 2*sv;
+  const double *w_x1f = b.wght[0], *w_x2f = b.wght[1], *w_x3f = b.wght[2];
+  const double *e3_x1f = b.ef[0][0], *e2_x1f = b.ef[0][1];
+  const double *e1_x2f = b.ef[1][0], *e3_x2f = b.ef[1][1];
+  const double *e2_x3f = b.ef[2][0], *e1_x3f = b.ef[2][1];
+#define C3(k,j,i) CCI(b,0,k,j,i)
+  {
+    double de1_l3 = de_term(w_x2f[F2I(b,k-1,j,i)], e1_x3f[F3I(b,k,j,i)], cc1[C3(k-1,j,i)],
+                            e1_x3f[F3I(b,k,j-1,i)], cc1[C3(k-1,j-1,i)]);
+    double de1_r3 = de_term(w_x2f[F2I(b,k,j,i)], e1_x3f[F3I(b,k,j,i)], cc1[C3(k,j,i)],
+                            e1_x3f[F3I(b,k,j-1,i)], cc1[C3(k,j-1,i)]);
+    double de1_l2 = de_term(w_x3f[F3I(b,k,j-1,i)], e1_x2f[F2I(b,k,j,i)], cc1[C3(k,j-1,i)],
+                            e1_x2f[F2I(b,k-1,j,i)], cc1[C3(k-1,j-1,i)]);
+    double de1_r2 = de_term(w_x3f[F3I(b,k,j,i)], e1_x2f[F2I(b,k,j,i)], cc1[C3(k,j,i)],
+                            e1_x2f[F2I(b,k-1,j,i)], cc1[C3(k-1,j,i)]);
+    b.e[0][E1I(b,k,j,i)] = 0.25*(de1_l3 + de1_r3 + de1_l2 + de1_r2 + e1_x2f[F2I(b,k-1,j,i)] +
+                                 e1_x2f[F2I(b,k,j,i)] + e1_x3f[F3I(b,k,j-1,i)] + e1_x3f[F3I(b,k,j,i)]);
+  }
+  {
+    double de2_l3 = de_term(w_x1f[F1I(b,k-1,j,i)], e2_x3f[F3I(b,k,j,i)], cc2[C3(k-1,j,i)],
+                            e2_x3f[F3I(b,k,j,i-1)], cc2[C3(k-1,j,i-1)]);
+    double de2_r3 = de_term(w_x1f[F1I(b,k,j,i)], e2_x3f[F3I(b,k,j,i)], cc2[C3(k,j,i)],
+                            e2_x3f[F3I(b,k,j,i-1)], cc2[C3(k,j,i-1)]);
+    double de2_l1 = de_term(w_x3f[F3I(b,k,j,i-1)], e2_x1f[F1I(b,k,j,i)], cc2[C3(k,j,i-1)],
+                            e2_x1f[F1I(b,k-1,j,i)], cc2[C3(k-1,j,i-1)]);
+    double de2_r1 = de_term(w_x3f[F3I(b,k,j,i)], e2_x1f[F1I(b,k,j,i)], cc2[C3(k,j,i)],
+                            e2_x1f[F1I(b,k-1,j,i)], cc2[C3(k-1,j,i)]);
+    b.e[1][E2I(b,k,j,i)] = 0.25*(de2_l3 + de2_r3 + de2_l1 + de2_r1 + e2_x3f[F3I(b,k,j,i-1)] +
+                                 e2_x3f[F3I(b,k,j,i)] + e2_x1f[F1I(b,k-1,j,i)] + e2_x1f[F1I(b,k,j,i)]);
+  }
+  {
+    // e3 array has nc3 planes: k = ke+1 <= nc3-1 always holds in 3-D (ng >= 1)
+    double de3_l2 = de_term(w_x1f[F1I(b,k,j-1,i)], e3_x2f[F2I(b,k,j,i)], cc3[C3(k,j-1,i)],
+                            e3_x2f[F2I(b,k,j,i-1)], cc3[C3(k,j-1,i-1)]);
+    double de3_r2 = de_term(w_x1f[F1I(b,k,j,i)], e3_x2f[F2I(b,k,j,i)], cc3[C3(k,j,i)],
+                            e3_x2f[F2I(b,k,j,i-1)], cc3[C3(k,j,i-1)]);
+    double de3_l1 = de_term(w_x2f[F2I(b,k,j,i-1)], e3_x1f[F1I(b,k,j,i)], cc3[C3(k,j,i-1)],
+                            e3_x1f[F1I(b,k,j-1,i)], cc3[C3(k,j-1,i-1)]);
+    double de3_r1 = de_term(w_x2f[F2I(b,k,j,i)], e3_x1f[F1I(b,k,j,i)], cc3[C3(k,j,i)],
+                            e3_x1f[F1I(b,k,j-1,i)], cc3[C3(k,j-1,i)]);
+    b.e[2][E3I(b,k,j,i)] = 0.25*(de3_l1 + de3_r1 + de3_l2 + de3_r2 + e3_x2f[F2I(b,k,j,i-1)] +
+                                 e3_x2f[F2I(b,k,j,i)] + e3_x1f[F1I(b,k,j-1,i)] + e3_x1f[F1I(b,k,j,i)]);
+  }
+#undef C3
+}
+
+// 2-D (calculate_corner_e.cpp:50-128): grid.y covers j in [js, je+1]; k = ks
+__global__ void __launch_bounds__(BX) k_corner_e2d(BlkDev b) {
+  int i = b.is + blockIdx.x*BX + threadIdx.x;
+  if (i > b.ie+1) return;
+  int j = b.js + blockIdx.y, k = b.ks;
+  const double *cc = b.cc_e;
+  const double *w_x1f = b.wght[0], *w_x2f = b.wght[1];
+  const double *e3_x1f = b.ef[0][0], *e2_x1f = b.ef[0][1];
+  const double *e1_x2f = b.ef[1][0], *e3_x2f = b.ef[1][1];
+  if (j <= b.je) {
+    double v = e2_x1f[F1I(b,k,j,i)];
+    b.e[1][E2I(b,b.ke+1,j,i)] = v;
+    b.e[1][E2I(b,k,j,i)] = v;
+  }
+  if (i <= b.ie) {
+    double v = e1_x2f[F2I(b,k,j,i)];
+    b.e[0][E1I(b,b.ke+1,j,i)] = v;
+    b.e[0][E1I(b,k,j,i)] = v;
+  }
+#define C3(k,j,i) CCI(b,0,k,j,i)
+  double de3_l2 = de_term(w_x1f[F1I(b,k,j-1,i)], e3_x2f[F2I(b,k,j,i)], cc[C3(k,j-1,i)],
+                          e3_x2f[F2I(b,k,j,i-1)], cc[C3(k,j-1,i-1)]);
+  double de3_r2 = de_term(w_x1f[F1I(b,k,j,i)], e3_x2f[F2I(b,k,j,i)], cc[C3(k,j,i)],
+                          e3_x2f[F2I(b,k,j,i-1)], cc[C3(k,j,i-1)]);
+  double de3_l1 = de_term(w_x2f[F2I(b,k,j,i-1)], e3_x1f[F1I(b,k,j,i)], cc[C3(k,j,i-1)],
+                          e3_x1f[F1I(b,k,j-1,i)], cc[C3(k,j-1,i-1)]);
+  double de3_r1 = de_term(w_x2f[F2I(b,k,j,i)], e3_x1f[F1I(b,k,j,i)], cc[C3(k,j,i)],
+                          e3_x1f[F1I(b,k,j-1,i)], cc[C3(k,j-1,i)]);
+  b.e[2][E3I(b,k,j,i)] = 0.25*(de3_l1 + de3_r1 + de3_l2 + de3_r2 + e3_x2f[F2I(b,k,j,i-1)] +
+                               e3_x2f[F2I(b,k,j,i)] + e3_x1f[F1I(b,k,j-1,i)] + e3_x1f[F1I(b,k,j,i)]);
+#undef C3
+}
+
+// 1-D (calculate_corner_e.cpp:38-48)
+__global__ void __launch_bounds__(BX) k_corner_e1d(BlkDev b) {
+  int i = b.is + blockIdx.x*BX + threadIdx.x;
+  if (i > b.ie+1) return;
+  int ks = b.ks, js = b.js;
+  double v2 = b.ef[0][1][F1I(b,ks,js,i)], v3 = b.ef[0][0][F1I(b,ks,js,i)];
+  b.e[1][E2I(b,ks,js,i)] = v2;
+  b.e[1][E2I(b,b.ke+1,js,i)] = v2;
+  b.e[2][E3I(b,ks,js,i)] = v3;
+  b.e[2][E3I(b,ks,b.je+1,i)] = v3;
+}
+
+void launch_corner_e(const BlkDev &b, cudaStream_t s) {
+  int nx1 = b.ie - b.is + 1, nx2 = b.je - b.js + 1, nx3 = b.ke - b.ks + 1;
+  if (!b.f2) {
+    k_corner_e1d<<<grid3(nx1+1, 1, 1), BX, 0, s>>>(b); ++g_launches;
+  } else if (!b.f3) {
+    k_cc_e<<<grid3(nx1+2, nx2+2, 1), BX, 0, s>>>(b, b.is-1, b.ie+1, b.js-1, b.ks); ++g_launches;
+    k_corner_e2d<<<grid3(nx1+1, nx2+1, 1), BX, 0, s>>>(b); ++g_launches;
+  } else {
+    k_cc_e<<<grid3(nx1+2, nx2+2, nx3+2), BX, 0, s>>>(b, b.is-1, b.ie+1, b.js-1, b.ks-1); ++g_launches;
+    k_corner_e3d<<<grid3(nx1+1, nx2+1, nx3+1), BX, 0, s>>>(b); ++g_launches;
+  }
+}
+
+// =============================================================================================
+// EMF boundary consistency (bvals/fc/flux_correction_fc.cpp): pack what every face / edge
+// neighbour needs (LoadFluxBoundaryBufferSameLevel :51-307), then add the neighbours'
+// contributions in neighbour-list order and scale (SetFluxBoundarySameLevel :689-905,
+// AverageFluxBoundary :1355-1541).
+// =============================================================================================
+
+// One "slab" = the set of edge-EMF elements with one index pinned to a block face.
+// comp 0/1/2 = e1/e2/e3.  (a, b) run over the two free indices.
+struct SlabIdx { int k, j, i; };
+
+// number of elements and (k,j,i) of element t of the buffer section `sec` (0 or 1) that the
+// reference packs for face neighbour `fid` (3-D / 2-D / 1-D layouts)
+__device__ __forceinline__ long face_sec_count(const BlkDev &b, int fid, int sec) {
+  int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
+  if (b.f3) {
+    if (fid < 2) return sec == 0 ? (long)(nx3+1)*nx2 : (long)nx3*(nx2+1);   // e2 | e3
+    if (fid < 4) return sec == 0 ? (long)(nx3+1)*nx1 : (long)nx3*(nx1+1);   // e1 | e3
+    return sec == 0 ? (long)(nx2+1)*nx1 : (long)nx2*(nx1+1);                // e1 | e2
+  } else if (b.f2) {
+    if (fid < 2) return sec == 0 ? nx2 : nx2+1;                             // e2 | e3
+    return sec == 0 ? nx1 : nx1+1;                                          // e1 | e3
+  }
+  return 1;                                                                  // e2 | e3
+}
+__device__ __forceinline__ int face_sec_comp(const BlkDev &b, int fid, int sec) {
+  if (fid < 2) return sec == 0 ? 1 : 2;
+  if (fid < 4) return sec == 0 ? 0 : 2;
+  return sec == 0 ? 0 : 1;
+}
+__device__ __forceinline__ SlabIdx face_sec_index(const BlkDev &b, int fid, int sec, long t) {
+  int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1;
+  SlabIdx x;
+  if (fid < 2) {
+    x.i = (fid == 0) ? b.is : b.ie+1;
+    int nj = (sec == 0) ? nx2 : nx2+1;
+    if (!b.f2) nj = 1;
+    x.k = b.ks + (int)(t / nj); x.j = b.js + (int)(t % nj);
+  } else if (fid < 4) {
+    x.j = (fid == 2) ? b.js : b.je+1;
+    int ni = (sec == 0) ? nx1 : nx1+1;
+    x.k = b.ks + (int)(t / ni); x.i = b.is + (int)(t % ni);
+  } else {
+    x.k = (fid == 4) ? b.ks : b.ke+1;
+    int ni = (sec == 0) ? nx1 : nx1+1;
+    x.j = b.js + (int)(t / ni); x.i = b.is + (int)(t % ni);
+  }
+  return x;
+}
+__device__ __forceinline__ long e_index(const BlkDev &b, int comp, int k, int j, int i) {
+  return comp == 0 ? E1I(b,k,j,i) : (comp == 1 ? E2I(b,k,j,i) : E3I(b,k,j,i));
+}
+__device__ __forceinline__ long edge_count(const BlkDev &b, int eid) {
+  if (eid < 4) return b.ke-b.ks+1;
+  if (eid < 8) return b.je-b.js+1;
+  return b.ie-b.is+1;
+}
+__device__ __forceinline__ SlabIdx edge_index(const BlkDev &b, int eid, long t) {
+  SlabIdx x;
+  if (eid < 4) {
+    x.i = ((eid & 1) == 0) ? b.is : b.ie+1; x.j = ((eid & 2) == 0) ? b.js : b.je+1;
+    x.k = b.ks + (int)t;
+  } else if (eid < 8) {
+    x.i = ((eid & 1) == 0) ? b.is : b.ie+1; x.k = ((eid & 2) == 0) ? b.ks : b.ke+1;
+    x.j = b.js + (int)t;
+  } else {
+    x.j = ((eid & 1) == 0) ? b.js : b.je+1; x.k = ((eid & 2) == 0) ? b.ks : b.ke+1;
+    x.i = b.is + (int)t;
+  }
+  return x;
+}
+
+// grid.y = 0..5 faces, 6..17 edges
+__global__ void __launch_bounds__(256) k_emf_pack(BlkDev b, EmfPlan pl) {
+  int id = blockIdx.y;
+  long t = (long)blockIdx.x*256 + threadIdx.x;
+  if (id < 6) {
+    double *dst = pl.face_dst[id];
+    if (!dst) return;
+    long n0 = face_sec_count(b, id, 0), n1 = face_sec_count(b, id, 1);
+    if (t >= n0 + n1) return;
+    int sec = t < n0 ? 0 : 1;
+    long tt = sec ? t - n0 : t;
+    SlabIdx x = face_sec_index(b, id, sec, tt);
+    int comp = face_sec_comp(b, id, sec);
+    dst[t] = b.e[comp][e_index(b, comp, x.k, x.j, x.i)];
+  } else {
+    int eid = id - 6;
+    double *dst = pl.edge_dst[eid];
+    if (!dst) return;
+    if (t >= edge_count(b, eid)) return;
+    SlabIdx x = edge_index(b, eid, t);
+    int comp = eid < 4 ? 2 : (eid < 8 ? 1 : 0);
+    dst[t] = b.e[comp][e_index(b, comp, x.k, x.j, x.i)];
+  }
+}
+
+void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s) {
+  int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
+  long m = 2L*(nx1+1)*(nx2+1);
+  if (2L*(nx1+1)*(nx3+1) > m) m = 2L*(nx1+1)*(nx3+1);
+  if (2L*(nx2+1)*(nx3+1) > m) m = 2L*(nx2+1)*(nx3+1);
+  int nid = b.f3 ? 18 : (b.f2 ? 10 : 2);
+  k_emf_pack<<<dim3((unsigned)((m + 255)/256), nid), 256, 0, s>>>(b, pl); ++g_launches;
+}
+
+// offset of element (k,j,i) of component comp inside the buffer packed by the neighbour
+// across face `fid` (the neighbour packed its OPPOSITE face with the same (free-index) layout)
+__device__ __forceinline__ long face_buf_offset(const BlkDev &b, int fid, int comp, int k,
+                                                int j, int i) {
+  int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1;
+  int sec = (face_sec_comp(b, fid, 0) == comp) ? 0 : 1;
+  long base = sec ? face_sec_count(b, fid, 0) : 0;
+  if (fid < 2) {
+    int nj = (sec == 0) ? nx2 : nx2+1;
+    if (!b.f2) nj = 1;
+    return base + (long)(k - b.ks)*nj + (j - b.js);
+  } else if (fid < 4) {
+    int ni = (sec == 0) ? nx1 : nx1+1;
+    return base + (long)(k - b.ks)*ni + (i - b.is);
+  }
+  int ni = (sec == 0) ? nx1 : nx1+1;
+  return base + (long)(j - b.js)*ni + (i - b.is);
+}
+
+// corrected value of one boundary edge-EMF element: own value + neighbours' (faces in
+// neighbour order x1,x2,x3, then the edge neighbour) then the averaging factor.
+// lo/hi flags: -1 / +1 when the element sits on the inner / outer block face of a direction.
+__device__ __forceinline__ double emf_corrected(const BlkDev &b, const EmfPlan &pl, int comp,
+                                                int k, int j, int i) {
+  double v = b.e[comp][e_index(b, comp, k, j, i)];
+  // which block faces does this element touch?  (e1 lives on x2/x3 faces, e2 on x1/x3, e3 on x1/x2)
+  int s1 = 0, s2 = 0, s3 = 0;
+  if (comp != 0) s1 = (i == b.is) ? -1 : ((i == b.ie+1) ? 1 : 0);
+  if (comp != 1 && b.f2) s2 = (j == b.js) ? -1 : ((j == b.je+1) ? 1 : 0);
+  if (comp != 2 && b.f3) s3 = (k == b.ks) ? -1 : ((k == b.ke+1) ? 1 : 0);
+  // 2-D / 1-D: e1(k+1), e2(k+1), e3(j+1) duplicates receive the k (j) = start value's buffer
+  int kk = k, jj = j;
+  if (!b.f3 && comp != 2) kk = b.ks;
+  if (!b.f2 && comp == 2) jj = b.js;
+  int nface = 0;
+  int f1 = -1, f2 = -1, f3 = -1;
+  if (s1) { f1 = (s1 < 0) ? 0 : 1; nface++; }
+  if (s2) { f2 = (s2 < 0) ? 2 : 3; nface++; }
+  if (s3) { f3 = (s3 < 0) ? 4 : 5; nface++; }
+  if (nface == 0) return v;
+  if (f1 >= 0 && pl.face_src[f1]) v += pl.face_src[f1][face_buf_offset(b, f1, comp, kk, jj, i)];
+  if (f2 >= 0 && pl.face_src[f2]) v += pl.face_src[f2][face_buf_offset(b, f2, comp, kk, jj, i)];
+  if (f3 >= 0 && pl.face_src[f3]) v += pl.face_src[f3][face_buf_offset(b, f3, comp, kk, jj, i)];
+  if (nface == 2) {
+    int eid;
+    long t;
+    if (comp == 2) { eid = ((s1 > 0) ? 1 : 0) | ((s2 > 0) ? 2 : 0); t = k - b.ks; }
+    else if (comp == 1) { eid = 4 + (((s1 > 0) ? 1 : 0) | ((s3 > 0) ? 2 : 0)); t = j - b.js; }
+    else { eid = 8 + (((s2 > 0) ? 1 : 0) | ((s3 > 0) ? 2 : 0)); t = i - b.is; }
+    if (pl.edge_src[eid]) v += pl.edge_src[eid][t];
+    if (pl.nedge_fine[eid] != 1) v *= 1.0/(double)pl.nedge_fine[eid];
+  } else {
+    int f = f1 >= 0 ? f1 : (f2 >= 0 ? f2 : f3);
+    if (pl.face_avg[f]) v *= 0.5;
+  }
+  return v;
+}
+
+// One thread per boundary element; slabs enumerated without duplicates:
+// for each component, the two faces of its first bounding direction take their full extent,
+// the faces of its second bounding direction exclude the lines already covered.
+__global__ void __launch_bounds__(256) k_emf_apply(BlkDev b, EmfPlan pl) {
+  int slab = blockIdx.y;            // comp*4 + {0,1: first dir lo/hi ; 2,3: second dir lo/hi}
+  int comp = slab >> 2, which = slab & 3;
+  long t = (long)blockIdx.x*256 + threadIdx.x;
+  int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
+  int k, j, i;
+  // extents of the component's index space (calculate_corner_e ranges that CT reads)
+  // e1: k in [ks,ke+1], j in [js,je+1], i in [is,ie]
+  // e2: k in [ks,ke+1], j in [js,je],   i in [is,ie+1]
+  // e3: k in [ks,ke],   j in [js,je+1], i in [is,ie+1]
+  int nk = (comp == 2) ? nx3 : nx3+1, nj = (comp == 1) ? nx2 : nx2+1, ni = (comp == 0) ? nx1 : nx1+1;
+  if (comp == 0) {            // e1: first dir x2 (j pinned), second dir x3 (k pinned)
+    if (which < 2) {
+      if (!b.f2) return;
+      if (t >= (long)nk*ni) return;
+      j = which == 0 ? b.js : b.je+1; k = b.ks + (int)(t/ni); i = b.is + (int)(t%ni);
+    } else {
+      if (!b.f3) return;
+      if (t >= (long)(nj-2)*ni) return;
+      k = which == 2 ? b.ks : b.ke+1; j = b.js+1 + (int)(t/ni); i = b.is + (int)(t%ni);
+    }
+  } else if (comp == 1) {     // e2: first dir x1 (i pinned), second dir x3 (k pinned)
+    if (which < 2) {
+      if (t >= (long)nk*nj) return;
+      i = which == 0 ? b.is : b.ie+1; k = b.ks + (int)(t/nj); j = b.js + (int)(t%nj);
+    } else {
+      if (!b.f3) return;
+      if (t >= (long)nj*(ni-2)) return;
+      k = which == 2 ? b.ks : b.ke+1; j = b.js + (int)(t/(ni-2)); i = b.is+1 + (int)(t%(ni-2));
+    }
+  } else {                    // e3: first dir x1 (i pinned), second dir x2 (j pinned)
+    if (which < 2) {
+      if (t >= (long)nk*nj) return;
+      i = which == 0 ? b.is : b.ie+1; k = b.ks + (int)(t/nj); j = b.js + (int)(t%nj);
+    } else {
+      if (!b.f2) return;
+      if (t >= (long)nk*(ni-2)) return;
+      j = which == 2 ? b.js : b.je+1; k = b.ks + (int)(t/(ni-2)); i = b.is+1 + (int)(t%(ni-2));
+    }
+  }
+  double v = emf_corrected(b, pl, comp, k, j, i);
+  b.e[comp][e_index(b, comp, k, j, i)] = v;
+}
+
+void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s) {
+  int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
+  long m = (long)(nx1+1)*(nx2+1);
+  if ((long)(nx1+1)*(nx3+1) > m) m = (long)(nx1+1)*(nx3+1);
+  if ((long)(nx2+1)*(nx3+1) > m) m = (long)(nx2+1)*(nx3+1);
+  k_emf_apply<<<dim3((unsigned)((m + 255)/256), 12), 256, 0, s>>>(b, pl); ++g_launches;
+}
+
+// =============================================================================================
+// MeshBlock::WeightedAve (mesh/weighted_ave.cpp:33-236 / 238-...) restricted to two registers
+// =============================================================================================
+__device__ __forceinline__ double wave2(double out, double in, double w0, double w1) {
+  if (w0 == 1.0) {
+    if (w1 != 0.0) out += w1*in;
+  } else if (w0 == 0.0) {
+    if (w1 == 1.0) out = in; else out = w1*in;
+  } else {
+    if (w1 != 0.0) out = w0*out + w1*in; else out *= w0;
+  }
+  return out;
+}
+
+__global__ void __launch_bounds__(BX) k_wave_cc(BlkDev b, double *out, const double *in,
+                                                double w0, double w1) {
+  int i = b.is + blockIdx.x*BX + threadIdx.x;
+  if (i > b.ie) return;
+  int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
+  long sv = (long)b.nc3*b.nc2*b.nc1;
+  long o = CCI(b,0,k,j,i);
+#pragma unroll
+  for (int n = 0; n < NHYDRO; ++n) out[o+n*sv] = wave2(out[o+n*sv], in[o+n*sv], w0, w1);
+}
+
+void launch_weighted_ave_cc(const BlkDev &b, double *out, const double *in, double w0,
+                            double w1, cudaStream_t s) {
+  k_wave_cc<<<grid3(b.ie-b.is+1, b.je-b.js+1, b.ke-b.ks+1), BX, 0, s>>>(b, out, in, w0, w1); ++g_launches;
+}
+
+struct FcPtrs { double *o[3]; const double *i[3]; };
+
+__global__ void __launch_bounds__(BX) k_wave_fc(BlkDev b, FcPtrs f, double w0, double w1) {
+  int i = b.is + blockIdx.x*BX + threadIdx.x;
+  if (i > b.ie+1) return;
+  int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
+  if (j <= b.je && k <= b.ke) {
+    long o = F1I(b,k,j,i); f.o[0][o] = wave2(f.o[0][o], f.i[0][o], w0, w1);
+  }
+  if (i <= b.ie && k <= b.ke) {
+    long o = F2I(b,k,j,i); f.o[1][o] = wave2(f.o[1][o], f.i[1][o], w0, w1);
+  }
+  if (i <= b.ie && j <= b.je) {
+    long o = F3I(b,k,j,i); f.o[2][o] = wave2(f.o[2][o], f.i[2][o], w0, w1);
+  }
+}
+
+void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const in[3],
+                            double w0, double w1, cudaStream_t s) {
+  FcPtrs f;
+  for (int d = 0; d < 3; ++d) { f.o[d] = out[d]; f.i[d] = in[d]; }
+  k_wave_fc<<<grid3(b.ie-b.is+2, b.je-b.js+2, b.ke-b.ks+2), BX, 0, s>>>(b, f, w0, w1); ++g_launches;
+}
+
+// =============================================================================================
+// IntegrateHydro: register average + Hydro::AddFluxDivergence, fused
+// =============================================================================================
+__global__ void __launch_bounds__(BX) k_integrate_cc(BlkDev b, int mode, int zero_init,
+                                                     double delta, double g1, double g2,
+                                                     double beta, double dt_val,
+                                                     const double *dt_ptr) {
+  int i = b.is + blockIdx.x*BX + threadIdx.x;
+  if (i > b.ie) return;
+  int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
+  const double wght = beta*(dt_ptr ? *dt_ptr : dt_val);
+  const long sv = (long)b.nc3*b.nc2*b.nc1;
+  const long o = CCI(b,0,k,j,i);
+  const long s1 = (long)b.nc3*b.nc2*(b.nc1+1), s2 = (long)b.nc3*(b.nc2+1)*b.nc1,
+             s3 = (long)(b.nc3+1)*b.nc2*b.nc1;
+  const long o1 = F1I(b,k,j,i), o2 = F2I(b,k,j,i), o3 = F3I(b,k,j,i);
+  // Cartesian face areas / volume (coordinates/coordinates.cpp:436-533)
+  const double dx1 = b.dx1f[i], dx2 = b.dx2f[j], dx3 = b.dx3f[k];
+  const double a1 = dx2*dx3, a2 = dx1*dx3, a3 = dx1*dx2;
+  const double vol = dx1*dx2*dx3;
+#pragma unroll
+  for (int n = 0; n < NHYDRO; ++n) {
+    double uo;
+    if (mode == 0) {
+      uo = b.u[o+n*sv];
+    } else if (mode == 1) {
+      uo = zero_init ? 0.0 : b.u[o+n*sv];
+      if (delta != 0.0) uo += delta*b.u1[o+n*sv];
+    } else {
+      double u1v = zero_init ? 0.0 : b.u1[o+n*sv];
+      double un = b.u[o+n*sv];
+      if (delta != 0.0 || zero_init) {
+        if (delta != 0.0) u1v += delta*un;
+        b.u1[o+n*sv] = u1v;
+      }
+      uo = wave2(un, u1v, g1, g2);
+    }
+    double dflx = (a1*b.flux[0][o1+1+n*s1] - a1*b.flux[0][o1+n*s1]);
+    if (b.f2) dflx += (a2*b.flux[1][o2+b.nc1+n*s2] - a2*b.flux[1][o2+n*s2]);
+    if (b.f3) dflx += (a3*b.flux[2][o3+(long)b.nc1*b.nc2+n*s3] - a3*b.flux[2][o3+n*s3]);
+    b.u[o+n*sv] = uo - wght*dflx/vol;
+  }
+}
+
+void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
+                         double g2, double beta, double dt_val, const double *dt_ptr,
+                         cudaStream_t s) {
+  k_integrate_cc<<<grid3(b.ie-b.is+1, b.je-b.js+1, b.ke-b.ks+1), BX, 0, s>>>(
+      b, mode, zero_init, delta, g1, g2, beta, dt_val, dt_ptr); ++g_launches;
+}
+
+// register average of one face value (same modes as k_integrate_cc)
+__device__ __forceinline__ double fc_avg(double *bo, double *b1, long o, int mode,
+                                         int zero_init, double delta, double g1, double g2) {
+  if (mode == 0) return bo[o];
+  if (mode == 1) {
+    double v = zero_init ? 0.0 : bo[o];
+    if (delta != 0.0) v += delta*b1[o];
+    return v;
+  }
+  double b1v = zero_init ? 0.0 : b1[o];
+  double bn = bo[o];
+  if (delta != 0.0 || zero_init) {
+    if (delta != 0.0) b1v += delta*bn;
+    b1[o] = b1v;
+  }
+  return wave2(bn, b1v, g1, g2);
+}
+
+// IntegrateField: face-register average + Field::CT (field/ct.cpp:31-116), fused.
+// Thread (k,j,i) updates x1f(k,j,i) [i<=ie+1], x2f(k,j,i) [j<=je+1], x3f(k,j,i) [k<=ke+1].
+__global__ void __launch_bounds__(BX) k_integrate_fc(BlkDev b, int mode, int zero_init,
+                                                     double delta, double g1, double g2,
+                                                     double beta, double dt_val,
+                                                     const double *dt_ptr) {
+  int i = b.is + blockIdx.x*BX + threadIdx.x;
+  if (i > b.ie+1) return;
+  int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
+  const double wght = beta*(dt_ptr ? *dt_ptr : dt_val);
+  const double *e1 = b.e[0], *e2 = b.e[1], *e3 = b.e[2];
+  const double dx1 = b.dx1f[i <= b.ie ? i : b.ie], dx2 = b.dx2f[j <= b.je ? j : b.je],
+               dx3 = b.dx3f[k <= b.ke ? k : b.ke];
+  if (j <= b.je && k <= b.ke) {       // B1 (ct.cpp:40-62)
+    long o = F1I(b,k,j,i);
+    double v = fc_avg(b.b[0], b.b1[0], o, mode, zero_init, delta, g1, g2);
+    if (b.f2) {
+      double area = dx2*dx3;
+      v -= (wght/area)*(dx3*e3[E3I(b,k,j+1,i)] - dx3*e3[E3I(b,k,j,i)]);
+      if (b.f3) v += (wght/area)*(dx2*e2[E2I(b,k+1,j,i)] - dx2*e2[E2I(b,k,j,i)]);
+    }
+    b.b[0][o] = v;
+  }
+  if (i <= b.ie && k <= b.ke) {       // B2 (ct.cpp:64-92)
+    long o = F2I(b,k,j,i);
+    double v = fc_avg(b.b[1], b.b1[1], o, mode, zero_init, delta, g1, g2);
+    double area = dx1*dx3;
+    v += (wght/area)*(dx3*e3[E3I(b,k,j,i+1)] - dx3*e3[E3I(b,k,j,i)]);
+    if (b.f3) v -= (wght/area)*(dx1*e1[E1I(b,k+1,j,i)] - dx1*e1[E1I(b,k,j,i)]);
+    b.b[1][o] = v;
+  }
+  if (i <= b.ie && j <= b.je) {       // B3 (ct.cpp:94-114)
+    long o = F3I(b,k,j,i);
+    double v = fc_avg(b.b[2], b.b1[2], o, mode, zero_init, delta, g1, g2);
+    double area = dx1*dx2;
+    v -= (wght/area)*(dx2*e2[E2I(b,k,j,i+1)] - dx2*e2[E2I(b,k,j,i)]);
+    if (b.f2) v += (wght/area)*(dx1*e1[E1I(b,k,j+1,i)] - dx1*e1[E1I(b,k,j,i)]);
+    b.b[2][o] = v;
+  }
+}
+
+void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
+                         double g2, double beta, double dt_val, const double *dt_ptr,
+                         cudaStream_t s) {
+  k_integrate_fc<<<grid3(b.ie-b.is+2, b.je-b.js+2, b.ke-b.ks+2), BX, 0, s>>>(
+      b, mode, zero_init, delta, g1, g2, beta, dt_val, dt_ptr); ++g_launches;
+}
+
+// =============================================================================================
+// Ghost-zone exchange as box copies (bvals/cc/bvals_cc.cpp:201-216,300-336,
+// bvals/fc/bvals_fc.cpp:344-397,583-684; utils/buffer_utils.cpp ordering n,k,j,i)
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_copy_boxes(const CopyBox *boxes, int n) {
+  const CopyBox bx = boxes[blockIdx.y];
+  long per = (long)bx.ni*bx.nj*bx.nk;
+  long tot = per*bx.nvar;
+  for (long t = (long)blockIdx.x*256 + threadIdx.x; t < tot; t += (long)gridDim.x*256) {
+    int v = (int)(t / per);
+    long r = t - (long)v*per;
+    int i = (int)(r % bx.ni);
+    long r2 = r / bx.ni;
+    int j = (int)(r2 % bx.nj), k = (int)(r2 / bx.nj);
+    bx.dst[v*bx.dst_sv + (long)(bx.dk0+k)*bx.dst_s3 + (long)(bx.dj0+j)*bx.dst_s2 + (bx.di0+i)] =
+        bx.src[v*bx.src_sv + (long)(bx.sk0+k)*bx.src_s3 + (long)(bx.sj0+j)*bx.src_s2 + (bx.si0+i)];
+  }
+}
+
+void launch_copy_boxes(const CopyBox *boxes_dev, int n, long max_box_elems, cudaStream_t s) {
+  if (n <= 0) return;
+  long gx = (max_box_elems + 255)/256;
+  if (gx > 2048) gx = 2048;
+  if (gx < 1) gx = 1;
+  k_copy_boxes<<<dim3((unsigned)gx, (unsigned)n), 256, 0, s>>>(boxes_dev, n); ++g_launches;
+}
+
+// =============================================================================================
+// Outflow physical boundary (bvals/cc/outflow_cc.cpp, bvals/fc/outflow_fc.cpp)
+// one thread per (transverse a, transverse b); loops over the ng ghost layers
+// =============================================================================================
+__global__ void __launch_bounds__(BX) k_outflow(BlkDev b, int mhd, int face, int il, int iu,
+                                                int jl, int ju, int kl, int ku) {
+  int d = face >> 1, upper = face & 1, ng = b.ng;
+  int a = blockIdx.x*BX + threadIdx.x, c = blockIdx.y;
+  const long sv = (long)b.nc3*b.nc2*b.nc1;
+  if (d == 0) {
+    int j = jl + a, k = kl + c;
+    if (j > ju+1 || k > ku+1) return;
+    for (int g = 1; g <= ng; ++g) {
+      if (j <= ju && k <= ku) {
+        for (int n = 0; n < NHYDRO; ++n)
+          b.w[CCI(b,n,k,j,upper ? iu+g : il-g)] = b.w[CCI(b,n,k,j,upper ? iu : il)];
+        if (mhd) b.b[0][F1I(b,k,j,upper ? iu+g+1 : il-g)] = b.b[0][F1I(b,k,j,upper ? iu+1 : il)];
+      }
+      if (mhd && k <= ku) b.b[1][F2I(b,k,j,upper ? iu+g : il-g)] = b.b[1][F2I(b,k,j,upper ? iu : il)];
+      if (mhd && j <= ju) b.b[2][F3I(b,k,j,upper ? iu+g : il-g)] = b.b[2][F3I(b,k,j,upper ? iu : il)];
+    }
+  } else if (d == 1) {
+    int i = il + a, k = kl + c;
+    if (i > iu+1 || k > ku+1) return;
+    for (int g = 1; g <= ng; ++g) {
+      if (i <= iu && k <= ku) {
+        for (int n = 0; n < NHYDRO; ++n)
+          b.w[CCI(b,n,k,upper ? ju+g : jl-g,i)] = b.w[CCI(b,n,k,upper ? ju : jl,i)];
+        if (mhd) b.b[1][F2I(b,k,upper ? ju+g+1 : jl-g,i)] = b.b[1][F2I(b,k,upper ? ju+1 : jl,i)];
+      }
+      if (mhd && k <= ku) b.b[0][F1I(b,k,upper ? ju+g : jl-g,i)] = b.b[0][F1I(b,k,upper ? ju : jl,i)];
+      if (mhd && i <= iu) b.b[2][F3I(b,k,upper ? ju+g : jl-g,i)] = b.b[2][F3I(b,k,upper ? ju : jl,i)];
+    }
+  } else {
+    int i = il + a, j = jl + c;
+    if (i > iu+1 || j > ju+1) return;
+    for (int g = 1; g <= ng; ++g) {
+      if (i <= iu && j <= ju) {
+        for (int n = 0; n < NHYDRO; ++n)
+          b.w[CCI(b,n,upper ? ku+g : kl-g,j,i)] = b.w[CCI(b,n,upper ? ku : kl,j,i)];
+        if (mhd) b.b[2][F3I(b,upper ? ku+g+1 : kl-g,j,i)] = b.b[2][F3I(b,upper ? ku+1 : kl,j,i)];
+      }
+      if (mhd && j <= ju) b.b[0][F1I(b,upper ? ku+g : kl-g,j,i)] = b.b[0][F1I(b,upper ? ku : kl,j,i)];
+      if (mhd && i <= iu) b.b[1][F2I(b,upper ? ku+g : kl-g,j,i)] = b.b[1][F2I(b,upper ? ku : kl,j,i)];
+    }
+  }
+  (void)sv;
+}
+
+void launch_outflow(const BlkDev &b, int mhd, int face, int il, int iu, int jl, int ju, int kl,
+                    int ku, cudaStream_t s) {
+  int d = face >> 1;
+  int na, nc;
+  if (d == 0) { na = ju-jl+2; nc = ku-kl+2; }
+  else if (d == 1) { na = iu-il+2; nc = ku-kl+2; }
+  else { na = iu-il+2; nc = ju-jl+2; }
+  k_outflow<<<dim3((unsigned)((na + BX - 1)/BX), (unsigned)nc), BX, 0, s>>>(b, mhd, face, il, iu,
+                                                                          jl, ju, kl, ku); ++g_launches;
+}
+
+// =============================================================================================
+// Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:42-190): CFL min-reduction
+// =============================================================================================
+template <bool MHD>
+__global__ void __launch_bounds__(BX) k_new_dt(BlkDev b, Params p, unsigned long long *out) {
+  int i = b.is + blockIdx.x*BX + threadIdx.x;
+  int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
+  double m = DBL_MAX;
+  if (i <= b.ie) {
+    long sv = (long)b.nc3*b.nc2*b.nc1;
+    long o = CCI(b,0,k,j,i);
+    double d = b.w[o], vx = b.w[o+sv], vy = b.w[o+2*sv], vz = b.w[o+3*sv], pr = b.w[o+4*sv];
+    double dt1 = b.dx1f[i], dt2 = b.dx2f[j], dt3 = b.dx3f[k];
+    if (MHD) {
+      double b1c = b.bcc[o], b2c = b.bcc[o+sv], b3c = b.bcc[o+2*sv];
+      double bx = b1c + fabs(b.b[0][F1I(b,k,j,i)] - b1c);
+      double cf = fast_speed(p.gamma, d, pr, b2c, b3c, bx);
+      dt1 /= (fabs(vx) + cf);
+      bx = b2c + fabs(b.b[1][F2I(b,k,j,i)] - b2c);
+      cf = fast_speed(p.gamma, d, pr, b3c, b1c, bx);
+      dt2 /= (fabs(vy) + cf);
+      bx = b3c + fabs(b.b[2][F3I(b,k,j,i)] - b3c);
+      cf = fast_speed(p.gamma, d, pr, b1c, b2c, bx);
+      dt3 /= (fabs(vz) + cf);
+    } else {
+      double cs = sound_speed(p.gamma, d, pr);
+      dt1 /= (fabs(vx) + cs);
+      dt2 /= (fabs(vy) + cs);
+      dt3 /= (fabs(vz) + cs);
+    }
+    m = dmin(m, dt1);
+    if (b.f2) m = dmin(m, dt2);
+    if (b.f3) m = dmin(m, dt3);
+  }
+  // warp-shuffle min, then one atomic per warp (positive doubles order like their bit patterns)
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    double o2 = __shfl_xor_sync(0xffffffffu, m, s);
+    m = dmin(m, o2);
+  }
+  if ((threadIdx.x & 31) == 0) atomicMin(out, (unsigned long long)__double_as_longlong(m));
+}
+
+void launch_new_block_dt(const BlkDev &b, const Params &p, unsigned long long *out_bits,
+                         cudaStream_t s) {
+  dim3 g = grid3(b.ie-b.is+1, b.je-b.js+1, b.ke-b.ks+1);
+  if (p.mhd) { k_new_dt<true><<<g, BX, 0, s>>>(b, p, out_bits); } else { k_new_dt<false><<<g, BX, 0, s>>>(b, p, out_bits); }
+  ++g_launches;
+}
+
+__global__ void k_fill_u64(unsigned long long *p, int n, unsigned long long v) {
+  int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t < n) p[t] = v;
+}
+void launch_fill_u64(unsigned long long *p, int n, unsigned long long v, cudaStream_t s) {
+  k_fill_u64<<<(n + 127)/128, 128, 0, s>>>(p, n, v); ++g_launches;
+}
+
+// state: [0]=time [1]=dt [2]=tlim [3]=cfl [4]=min over (local or all) blocks of new_block_dt
+// [5]=ncycle.  Mesh::NewTimeStep (mesh/mesh.cpp:1078-1119) + main.cpp:478-481 bookkeeping.
+// phase 0: reduce local blocks into state[4] (times cfl, per block like new_blockdt.cpp:164)
+// phase 1: apply NewTimeStep with state[4] (after the optional cross-rank MIN all-reduce)
+__global__ void k_mesh_new_dt(double *st, const unsigned long long *blk_min, int nb, int phase,
+                              int advance_time) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (phase == 0) {
+    double m = DBL_MAX;
+    for (int n = 0; n < nb; ++n) {
+      double v = __longlong_as_double((long long)blk_min[n])*st[3];
+      m = dmin(m, v);
+    }
+    st[4] = m;
+  } else {
+    if (advance_time) { st[5] += 1.0; st[0] += st[1]; }
+    double dt = 2.0*st[1];
+    dt = dmin(dt, st[4]);
+    if (st[0] < st[2] && (st[2] - st[0]) < dt) dt = st[2] - st[0];
+    st[1] = dt;
+  }
+}
+void launch_mesh_new_dt(double *state, const unsigned long long *blk_min, int nb,
+                        int advance_time, cudaStream_t s) {
+  // advance_time: bit0 = advance, bit1 = phase
+  k_mesh_new_dt<<<1, 32, 0, s>>>(state, blk_min, nb, (advance_time >> 1) & 1, advance_time & 1); ++g_launches;
+}
+
+}  // namespace ab

@@ -1,0 +1,62 @@
+// ab_kernels.h -- launchers of the sm_100a kernels (implemented in ab_kernels.cu).
+#ifndef AB_KERNELS_H_
+#define AB_KERNELS_H_
+#include <cuda_runtime.h>
+#include "ab_types.h"
+
+namespace ab {
+
+// per-direction PLM face weights precomputed on the host with the reference's expression
+// (x?f(i+1)-x?v(i))/dx?f(i) and (x?v(i)-x?f(i))/dx?f(i)  (reconstruct/plm.cpp:114-119)
+struct ReconGeom { const double *wp[3]; const double *wm[3]; };
+
+// `dt_ptr` (device) wins over `dt_val` when non-null: the cycle loop keeps dt on the device.
+void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
+                      int ku, cudaStream_t s);
+void launch_prim2cons(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
+                      int ku, cudaStream_t s);
+void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, int ku,
+                     cudaStream_t s);
+void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
+                   double dt_val, const double *dt_ptr, cudaStream_t s);
+void launch_corner_e(const BlkDev &b, cudaStream_t s);
+void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);
+void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);
+
+// WeightedAve special-casing of the reference (mesh/weighted_ave.cpp) for out = w0*out + w1*in
+void launch_weighted_ave_cc(const BlkDev &b, double *out, const double *in, double w0,
+                            double w1, cudaStream_t s);
+void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const in[3],
+                            double w0, double w1, cudaStream_t s);
+
+// Fused IntegrateHydro on active cells (task_list/time_integrator.cpp:1563-1612 +
+// hydro/add_flux_divergence.cpp:39-96).  mode 0: u -= wght*div only.  mode 1 (registers
+// already pointer-swapped): u = (zero_init ? 0 : u) [+ delta*u1] ; u -= wght*div.
+// mode 2: u1 = (zero_init ? 0 : u1) [+ delta*u]; u = wave(u; u1; g1, g2); u -= wght*div.
+// wght = beta * dt.
+void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
+                         double g2, double beta, double dt_val, const double *dt_ptr,
+                         cudaStream_t s);
+// Same for the face field + Field::CT (field/ct.cpp:31-116)
+void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
+                         double g2, double beta, double dt_val, const double *dt_ptr,
+                         cudaStream_t s);
+
+// ghost exchange: apply `n` box copies (descriptors in device memory)
+void launch_copy_boxes(const CopyBox *boxes_dev, int n, long max_box_elems, cudaStream_t s);
+
+// outflow physical boundary on primitives and face fields for one block face
+void launch_outflow(const BlkDev &b, int mhd, int face, int il, int iu, int jl, int ju, int kl,
+                    int ku, cudaStream_t s);
+
+// NewBlockTimeStep: min over active cells of dx/(|v|+c) -> atomicMin into *out_bits
+// (out must be pre-set to DBL_MAX bits); result NOT yet multiplied by cfl.
+void launch_new_block_dt(const BlkDev &b, const Params &p, unsigned long long *out_bits,
+                         cudaStream_t s);
+// Mesh::NewTimeStep on the device: state = {time, dt, tlim, cfl}; blk_min[nb]
+void launch_mesh_new_dt(double *state, const unsigned long long *blk_min, int nb,
+                        int advance_time, cudaStream_t s);
+void launch_fill_u64(unsigned long long *p, int n, unsigned long long v, cudaStream_t s);
+
+}  // namespace ab
+#endif

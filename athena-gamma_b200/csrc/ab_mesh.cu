@@ -1,0 +1,1320 @@
+// ab_mesh.cu -- host runtime behind the C ABI (include/athena_b200.h): MeshBlock bookkeeping,
+// device memory, neighbour tables, ghost-exchange / EMF-correction plans, NCCL transport and
+// the TimeIntegratorTaskList stage loop.  All physics runs in the kernels of ab_kernels.cu;
+// nothing here computes on the host (there is no CPU fallback).
+//
+// Reference structure mirrored: Mesh ctor / MeshBlockTree Z-ordering (src/mesh/mesh.cpp,
+// meshblock_tree.cpp), Coordinates (src/coordinates), BoundaryBase::SearchAndSetNeighbors
+// (src/bvals/bvals_base.cpp), TimeIntegratorTaskList (src/task_list/time_integrator.cpp).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <array>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/athena_b200.h"
+#include "ab_kernels.h"
+
+namespace ab {
+extern long g_launches;
+}
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(AB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+// ------------------------------------------------------------------ NCCL through dlopen
+// (the library has no link-time NCCL dependency: single-GPU use needs none, and inside a
+//  torch process the already-loaded libnccl.so.2 is picked up)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl {
+  void *h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (h) return true;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+#define LD(name) name = (decltype(name))dlsym(h, "nccl" #name)
+    LD(GetUniqueId); LD(CommInitRank); LD(CommDestroy); LD(Send); LD(Recv); LD(AllReduce);
+    LD(GroupStart); LD(GroupEnd); LD(GetErrorString);
+#undef LD
+    return GetUniqueId && CommInitRank && Send && Recv && AllReduce && GroupStart && GroupEnd;
+  }
+};
+Nccl g_nccl;
+constexpr int NCCL_FLOAT64 = 8;   // ncclDouble
+constexpr int NCCL_MIN = 3;       // ncclMin
+
+#define NK(call)                                                                       \
+  do {                                                                                 \
+    int r_ = (call);                                                                   \
+    if (r_ != 0)                                                                       \
+      return fail(AB_ERR_NCCL, std::string(#call) + ": " +                            \
+                  (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error")); \
+  } while (0)
+
+// ------------------------------------------------------------------ mesh geometry helpers
+// src/mesh/mesh.hpp:389-405
+double mesh_gen_x(long index, long nrange) {
+  long noffset = index - (nrange)/2;
+  long noffset_ceil = index - (nrange+1)/2;
+  return static_cast<double>(noffset + noffset_ceil)/(2.0*nrange);
+}
+// src/mesh/mesh.hpp:467-488
+double uniform_gen(double x, double xmin, double xmax) {
+  return 0.5*(xmin + xmax) + (x*xmax - x*xmin);
+}
+
+struct Nb {
+  int ox1, ox2, ox3, type;   // 0 face, 1 edge, 2 corner
+  int gid, rank, bufid, targetid, fid, eid;
+};
+
+struct HostBlock {
+  int gid = 0, rank = 0;
+  long lx[3] = {0, 0, 0};
+  int bcs[6];                 // -1: neighbour block; otherwise the physical AB_BC_*
+  int nblevel[3][3][3];
+  std::vector<Nb> nbs;
+  int nedge_fine[12];
+  double bmin[3], bmax[3];
+};
+
+struct PeerBuf {              // staging for one peer rank and one exchange kind
+  double *send = nullptr, *recv = nullptr;
+  size_t nsend = 0, nrecv = 0;
+};
+
+struct LocalBlock {
+  HostBlock *hb = nullptr;
+  ab::BlkDev d;
+  ab::ReconGeom g;
+  ab::EmfPlan emf;
+  double *base = nullptr;                 // one allocation per block
+  size_t nbytes = 0;
+  long regsize[AB_NREG];
+  double *coord_dev[9];
+  long coord_n[9];
+  double *emf_send = nullptr;             // send buffers toward same-rank neighbours
+  long face_off[6], edge_off[12];
+  int parity = 0;                         // (u,u1) swap state
+  int parity_b = 0;                       // (b,b1) swap state
+  unsigned long long *dtmin = nullptr;    // slot in the mesh-wide array
+};
+
+}  // namespace
+
+struct AbMesh {
+  AbMeshParams p;
+  ab::Params kp;
+  int ndim = 1, f2 = 0, f3 = 0;
+  int nrb[3] = {1, 1, 1};
+  int nbtotal = 0;
+  int nc[3] = {1, 1, 1}, is = 0, ie = 0, js = 0, je = 0, ks = 0, ke = 0;
+  std::vector<HostBlock> hb;              // all blocks of the mesh (every rank knows them)
+  std::vector<int> gid_of;                // [lx3][lx2][lx1] -> gid
+  std::vector<LocalBlock> lb;             // blocks owned by this rank, in gid order
+  int gid_start = 0;
+  int nstages = 2;
+  double beta[4], delta[4], g1[4], g2[4], g3[4];
+  double cfl = 0.0;
+  cudaStream_t stream = nullptr;
+  double *state = nullptr;                // device: time, dt, tlim, cfl, min, ncycle
+  double *dt_hist = nullptr;              // device ring of per-cycle dt
+  int hist_cap = 0, hist_n = 0;
+  unsigned long long *dtmin = nullptr;    // device per-local-block min (bits)
+  double h_time = 0.0, h_dt = DBL_MAX;
+  long h_ncycle = 0;
+  int async = 0;
+  // exchange plans (two variants: register parity 0 / 1)
+  struct Plan {
+    bool built = false;
+    ab::CopyBox *pack = nullptr; int npack = 0; long maxpack = 0;     // to peer send buffers
+    ab::CopyBox *phase1 = nullptr; int n1 = 0; long max1 = 0;         // ghost fill
+    ab::CopyBox *phase2 = nullptr; int n2 = 0; long max2 = 0;         // 1-D/2-D duplicates
+  } plan[4];
+  std::map<int, PeerBuf> peer_state, peer_emf;
+  ncclComm_t comm = nullptr;
+  bool emf_built = false;
+};
+
+namespace {
+
+using ab::CopyBox;
+
+// ---- buffer box ranges (same for every block: all blocks have identical shape) ------------
+struct Box { int si, ei, sj, ej, sk, ek; long count() const {
+  return (long)(ei-si+1)*(ej-sj+1)*(ek-sk+1); } };
+
+// LoadBoundaryBufferSameLevel (bvals/cc/bvals_cc.cpp:201-216)
+Box cc_send_box(const AbMesh *m, int ox1, int ox2, int ox3) {
+  int ng = m->p.nghost;
+  Box b;
+  b.si = (ox1 > 0) ? (m->ie - ng + 1) : m->is; b.ei = (ox1 < 0) ? (m->is + ng - 1) : m->ie;
+  b.sj = (ox2 > 0) ? (m->je - ng + 1) : m->js; b.ej = (ox2 < 0) ? (m->js + ng - 1) : m->je;
+  b.sk = (ox3 > 0) ? (m->ke - ng + 1) : m->ks; b.ek = (ox3 < 0) ? (m->ks + ng - 1) : m->ke;
+  return b;
+}
+// SetBoundarySameLevel (bvals/cc/bvals_cc.cpp:300-336)
+Box cc_recv_box(const AbMesh *m, int ox1, int ox2, int ox3) {
+  int ng = m->p.nghost;
+  Box b;
+  if (ox1 == 0) { b.si = m->is; b.ei = m->ie; }
+  else if (ox1 > 0) { b.si = m->ie + 1; b.ei = m->ie + ng; }
+  else { b.si = m->is - ng; b.ei = m->is - 1; }
+  if (ox2 == 0) { b.sj = m->js; b.ej = m->je; }
+  else if (ox2 > 0) { b.sj = m->je + 1; b.ej = m->je + ng; }
+  else { b.sj = m->js - ng; b.ej = m->js - 1; }
+  if (ox3 == 0) { b.sk = m->ks; b.ek = m->ke; }
+  else if (ox3 > 0) { b.sk = m->ke + 1; b.ek = m->ke + ng; }
+  else { b.sk = m->ks - ng; b.ek = m->ks - 1; }
+  return b;
+}
+// FaceCentered LoadBoundaryBufferSameLevel (bvals/fc/bvals_fc.cpp:344-397), comp = 0,1,2
+Box fc_send_box(const AbMesh *m, int comp, int ox1, int ox2, int ox3) {
+  int ng = m->p.nghost;
+  int is = m->is, ie = m->ie, js = m->js, je = m->je, ks = m->ks, ke = m->ke;
+  Box b;
+  // i
+  if (comp == 0) {
+    if (ox1 == 0) { b.si = is; b.ei = ie + 1; }
+    else if (ox1 > 0) { b.si = ie - ng + 1; b.ei = ie; }
+    else { b.si = is + 1; b.ei = is + ng; }
+  } else {
+    if (ox1 == 0) { b.si = is; b.ei = ie; }
+    else if (ox1 > 0) { b.si = ie - ng + 1; b.ei = ie; }
+    else { b.si = is; b.ei = is + ng - 1; }
+  }
+  // j
+  if (comp == 1) {
+    if (!m->f2) { b.sj = js; b.ej = je; }
+    else if (ox2 == 0) { b.sj = js; b.ej = je + 1; }
+    else if (ox2 > 0) { b.sj = je - ng + 1; b.ej = je; }
+    else { b.sj = js + 1; b.ej = js + ng; }
+  } else {
+    if (ox2 == 0) { b.sj = js; b.ej = je; }
+    else if (ox2 > 0) { b.sj = je - ng + 1; b.ej = je; }
+    else { b.sj = js; b.ej = js + ng - 1; }
+  }
+  // k
+  if (comp == 2) {
+    if (!m->f3) { b.sk = ks; b.ek = ke; }
+    else if (ox3 == 0) { b.sk = ks; b.ek = ke + 1; }
+    else if (ox3 > 0) { b.sk = ke - ng + 1; b.ek = ke; }
+    else { b.sk = ks + 1; b.ek = ks + ng; }
+  } else {
+    if (ox3 == 0) { b.sk = ks; b.ek = ke; }
+    else if (ox3 > 0) { b.sk = ke - ng + 1; b.ek = ke; }
+    else { b.sk = ks; b.ek = ks + ng - 1; }
+  }
+  return b;
+}
+// FaceCentered SetBoundarySameLevel (bvals/fc/bvals_fc.cpp:583-684)
+Box fc_recv_box(const AbMesh *m, int comp, int ox1, int ox2, int ox3) {
+  int ng = m->p.nghost;
+  int is = m->is, ie = m->ie, js = m->js, je = m->je, ks = m->ks, ke = m->ke;
+  Box b;
+  if (comp == 0) {
+    if (ox1 == 0) { b.si = is; b.ei = ie + 1; }
+    else if (ox1 > 0) { b.si = ie + 2; b.ei = ie + ng + 1; }
+    else { b.si = is - ng; b.ei = is - 1; }
+  } else {
+    if (ox1 == 0) { b.si = is; b.ei = ie; }
+    else if (ox1 > 0) { b.si = ie + 1; b.ei = ie + ng; }
+    else { b.si = is - ng; b.ei = is - 1; }
+  }
+  if (comp == 1) {
+    if (!m->f2) { b.sj = js; b.ej = je; }
+    else if (ox2 == 0) { b.sj = js; b.ej = je + 1; }
+    else if (ox2 > 0) { b.sj = je + 2; b.ej = je + ng + 1; }
+    else { b.sj = js - ng; b.ej = js - 1; }
+  } else {
+    if (ox2 == 0) { b.sj = js; b.ej = je; }
+    else if (ox2 > 0) { b.sj = je + 1; b.ej = je + ng; }
+    else { b.sj = js - ng; b.ej = js - 1; }
+  }
+  if (comp == 2) {
+    if (!m->f3) { b.sk = ks; b.ek = ke; }
+    else if (ox3 == 0) { b.sk = ks; b.ek = ke + 1; }
+    else if (ox3 > 0) { b.sk = ke + 2; b.ek = ke + ng + 1; }
+    else { b.sk = ks - ng; b.ek = ks - 1; }
+  } else {
+    if (ox3 == 0) { b.sk = ks; b.ek = ke; }
+    else if (ox3 > 0) { b.sk = ke + 1; b.ek = ke + ng; }
+    else { b.sk = ks - ng; b.ek = ks - 1; }
+  }
+  return b;
+}
+
+// strides (k stride, j stride) of the register arrays
+void fc_strides(const AbMesh *m, int comp, long &s3, long &s2) {
+  int n1 = m->nc[0] + (comp == 0), n2 = m->nc[1] + (comp == 1);
+  s2 = n1; s3 = (long)n1*n2;
+}
+
+long state_msg_count(const AbMesh *m, int ox1, int ox2, int ox3) {
+  long n = ab::NHYDRO*cc_send_box(m, ox1, ox2, ox3).count();
+  if (m->p.mhd) for (int c = 0; c < 3; ++c) n += fc_send_box(m, c, ox1, ox2, ox3).count();
+  return n;
+}
+
+// EMF message sizes (bvals/fc/bvals_fc.cpp:304-338 / flux_correction_fc.cpp:51-307)
+long emf_face_count(const AbMesh *m, int fid) {
+  int nx1 = m->p.bx1, nx2 = m->p.bx2, nx3 = m->p.bx3;
+  if (m->f3) {
+    if (fid < 2) return (long)(nx3+1)*nx2 + (long)nx3*(nx2+1);
+    if (fid < 4) return (long)(nx3+1)*nx1 + (long)nx3*(nx1+1);
+    return (long)(nx2+1)*nx1 + (long)nx2*(nx1+1);
+  } else if (m->f2) {
+    if (fid < 2) return nx2 + nx2 + 1;
+    return nx1 + nx1 + 1;
+  }
+  return 2;
+}
+long emf_edge_count(const AbMesh *m, int eid) {
+  if (eid < 4) return m->p.bx3;
+  if (eid < 8) return m->p.bx2;
+  return m->p.bx1;
+}
+int opposite_eid(int eid) { return (eid & ~3) | ((eid & 3) ^ 3); }
+
+int owner_lid(const AbMesh *m, int gid) { return gid - m->gid_start; }
+
+// ------------------------------------------------------------------ construction
+void set_integrator(AbMesh *m) {
+  // src/task_list/time_integrator.cpp:104-604 (vl2, rk1, rk2, rk3)
+  double cfl_limit = 1.0;
+  for (int s = 0; s < 4; ++s) { m->g1[s] = 0; m->g2[s] = 1; m->g3[s] = 0; m->delta[s] = 0; m->beta[s] = 0; }
+  m->delta[0] = 1.0;
+  switch (m->p.integrator) {
+    case AB_INT_VL2:
+      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0;
+      if (m->ndim >= 2) cfl_limit = 0.5;
+      break;
+    case AB_INT_RK1:
+      m->nstages = 1; m->beta[0] = 1.0;
+      break;
+    case AB_INT_RK2:
+      m->nstages = 2; m->beta[0] = 1.0; m->beta[1] = 0.5;
+      m->g1[1] = 0.5; m->g2[1] = 0.5;
+      break;
+    default:
+      m->nstages = 3; m->beta[0] = 1.0; m->beta[1] = 0.25; m->beta[2] = 0.66666666666666667;
+      m->g1[1] = 0.25; m->g2[1] = 0.75;
+      m->g1[2] = 0.66666666666666667; m->g2[2] = 0.33333333333333333;
+      break;
+  }
+  m->cfl = m->p.cfl_number;
+  if (m->cfl > cfl_limit) m->cfl = cfl_limit;   // time_integrator.cpp:886-894
+}
+
+void build_block_list(AbMesh *m) {
+  const AbMeshParams &p = m->p;
+  m->nrb[0] = p.nx1/p.bx1; m->nrb[1] = p.nx2/p.bx2; m->nrb[2] = p.nx3/p.bx3;
+  m->nbtotal = m->nrb[0]*m->nrb[1]*m->nrb[2];
+  // Z-order = Morton order with x1 the fastest bit (meshblock_tree.cpp:87-110,336-352)
+  struct Key { unsigned long long key; int i, j, k; };
+  std::vector<Key> keys;
+  for (int k = 0; k < m->nrb[2]; ++k) for (int j = 0; j < m->nrb[1]; ++j)
+    for (int i = 0; i < m->nrb[0]; ++i) {
+      unsigned long long key = 0;
+      for (int bit = 0; bit < 20; ++bit)
+        key |= ((unsigned long long)((i >> bit) & 1) << (3*bit))
+             | ((unsigned long long)((j >> bit) & 1) << (3*bit + 1))
+             | ((unsigned long long)((k >> bit) & 1) << (3*bit + 2));
+      keys.push_back({key, i, j, k});
+    }
+  std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) { return a.key < b.key; });
+  m->hb.resize(m->nbtotal);
+  m->gid_of.assign(m->nbtotal, -1);
+  for (int g = 0; g < m->nbtotal; ++g) {
+    HostBlock &B = m->hb[g];
+    B.gid = g; B.lx[0] = keys[g].i; B.lx[1] = keys[g].j; B.lx[2] = keys[g].k;
+    m->gid_of[(B.lx[2]*m->nrb[1] + B.lx[1])*m->nrb[0] + B.lx[0]] = g;
+  }
+  // Mesh::CalculateLoadBalance with unit costs (mesh/amr_loadbalance.cpp:72-112)
+  {
+    int nranks = p.nranks;
+    double totalcost = m->nbtotal;
+    int j = nranks - 1;
+    double targetcost = totalcost/nranks, mycost = 0.0;
+    for (int i = m->nbtotal - 1; i >= 0; i--) {
+      mycost += 1.0;
+      m->hb[i].rank = j;
+      if (mycost >= targetcost && j > 0) {
+        j--;
+        totalcost -= mycost;
+        mycost = 0.0;
+        targetcost = totalcost/(j + 1);
+      }
+    }
+  }
+  // block extents + boundary flags (mesh/mesh.cpp:1668-1751)
+  const double mmin[3] = {p.x1min, p.x2min, p.x3min}, mmax[3] = {p.x1max, p.x2max, p.x3max};
+  const int nxm[3] = {p.nx1, p.nx2, p.nx3};
+  for (auto &B : m->hb) {
+    for (int d = 0; d < 3; ++d) {
+      if (d > 0 && nxm[d] == 1) {
+        B.bmin[d] = mmin[d]; B.bmax[d] = mmax[d];
+        B.bcs[2*d] = p.bc[2*d]; B.bcs[2*d+1] = p.bc[2*d+1];
+        continue;
+      }
+      if (B.lx[d] == 0) { B.bmin[d] = mmin[d]; B.bcs[2*d] = p.bc[2*d]; }
+      else { B.bmin[d] = uniform_gen(mesh_gen_x(B.lx[d], m->nrb[d]), mmin[d], mmax[d]); B.bcs[2*d] = -1; }
+      if (B.lx[d] == m->nrb[d] - 1) { B.bmax[d] = mmax[d]; B.bcs[2*d+1] = p.bc[2*d+1]; }
+      else { B.bmax[d] = uniform_gen(mesh_gen_x(B.lx[d] + 1, m->nrb[d]), mmin[d], mmax[d]); B.bcs[2*d+1] = -1; }
+    }
+  }
+  // canonical neighbour enumeration = buffer ids (bvals/bvals_base.cpp:153-256)
+  std::vector<std::array<int,3>> ni;
+  for (int n = -1; n <= 1; n += 2) ni.push_back({n, 0, 0});
+  if (m->ndim >= 2) for (int n = -1; n <= 1; n += 2) ni.push_back({0, n, 0});
+  if (m->ndim == 3) for (int n = -1; n <= 1; n += 2) ni.push_back({0, 0, n});
+  if (m->ndim >= 2)
+    for (int mm = -1; mm <= 1; mm += 2) for (int n = -1; n <= 1; n += 2) ni.push_back({n, mm, 0});
+  if (m->ndim == 3) {
+    for (int mm = -1; mm <= 1; mm += 2) for (int n = -1; n <= 1; n += 2) ni.push_back({n, 0, mm});
+    for (int mm = -1; mm <= 1; mm += 2) for (int n = -1; n <= 1; n += 2) ni.push_back({0, n, mm});
+    for (int l = -1; l <= 1; l += 2) for (int mm = -1; mm <= 1; mm += 2)
+      for (int n = -1; n <= 1; n += 2) ni.push_back({n, mm, l});
+  }
+  auto find_ni = [&](int a, int b, int c) {
+    for (size_t n = 0; n < ni.size(); ++n)
+      if (ni[n][0] == a && ni[n][1] == b && ni[n][2] == c) return (int)n;
+    return -1;
+  };
+  // SearchAndSetNeighbors, same level (bvals/bvals_base.cpp:299-480)
+  for (auto &B : m->hb) {
+    for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i)
+      B.nblevel[k][j][i] = -1;
+    B.nblevel[1][1][1] = 0;
+    for (size_t n = 0; n < ni.size(); ++n) {
+      int o[3] = {ni[n][0], ni[n][1], ni[n][2]};
+      long l[3];
+      bool ok = true;
+      for (int d = 0; d < 3; ++d) {
+        l[d] = B.lx[d] + o[d];
+        if (l[d] < 0) { if (p.bc[2*d] == AB_BC_PERIODIC) l[d] = m->nrb[d] - 1; else ok = false; }
+        if (l[d] >= m->nrb[d]) { if (p.bc[2*d+1] == AB_BC_PERIODIC) l[d] = 0; else ok = false; }
+      }
+      if (!ok) continue;
+      Nb nb;
+      nb.ox1 = o[0]; nb.ox2 = o[1]; nb.ox3 = o[2];
+      nb.type = (o[0] != 0) + (o[1] != 0) + (o[2] != 0) - 1;
+      nb.gid = m->gid_of[(l[2]*m->nrb[1] + l[1])*m->nrb[0] + l[0]];
+      nb.rank = m->hb[nb.gid].rank;
+      nb.bufid = (int)n;
+      nb.targetid = find_ni(-o[0], -o[1], -o[2]);
+      nb.fid = -1; nb.eid = -1;
+      if (nb.type == 0) {          // NeighborBlock::SetNeighbor (bvals_base.cpp:54-66)
+        if (o[0] == -1) nb.fid = 0; else if (o[0] == 1) nb.fid = 1;
+        else if (o[1] == -1) nb.fid = 2; else if (o[1] == 1) nb.fid = 3;
+        else if (o[2] == -1) nb.fid = 4; else nb.fid = 5;
+      } else if (nb.type == 1) {
+        if (o[2] == 0) nb.eid = (((o[0] + 1) >> 1) | ((o[1] + 1) & 2));
+        else if (o[1] == 0) nb.eid = (4 + (((o[0] + 1) >> 1) | ((o[2] + 1) & 2)));
+        else nb.eid = (8 + (((o[1] + 1) >> 1) | ((o[2] + 1) & 2)));
+      }
+      B.nblevel[o[2]+1][o[1]+1][o[0]+1] = 0;
+      B.nbs.push_back(nb);
+    }
+    // CountFineEdges (bvals/fc/bvals_fc.cpp:1129-1193), single level
+    for (int e = 0; e < 12; ++e) B.nedge_fine[e] = 1;
+    int eid = 0;
+    auto lo = [](int o) { return (o-1 > -1) ? o-1 : -1; };
+    auto hi = [](int o) { return (o+1 < 1) ? o+1 : 1; };
+    if (m->f2)
+      for (int o2 = -1; o2 <= 1; o2 += 2) for (int o1 = -1; o1 <= 1; o1 += 2) {
+        int nf = 0;
+        for (int nj = lo(o2); nj <= hi(o2); nj++) for (int nii = lo(o1); nii <= hi(o1); nii++)
+          if (B.nblevel[1][nj+1][nii+1] == 0) nf++;
+        B.nedge_fine[eid++] = nf;
+      }
+    if (m->f3) {
+      for (int o3 = -1; o3 <= 1; o3 += 2) for (int o1 = -1; o1 <= 1; o1 += 2) {
+        int nf = 0;
+        for (int nk = lo(o3); nk <= hi(o3); nk++) for (int nii = lo(o1); nii <= hi(o1); nii++)
+          if (B.nblevel[nk+1][1][nii+1] == 0) nf++;
+        B.nedge_fine[eid++] = nf;
+      }
+      for (int o3 = -1; o3 <= 1; o3 += 2) for (int o2 = -1; o2 <= 1; o2 += 2) {
+        int nf = 0;
+        for (int nk = lo(o3); nk <= hi(o3); nk++) for (int nj = lo(o2); nj <= hi(o2); nj++)
+          if (B.nblevel[nk+1][nj+1][1] == 0) nf++;
+        B.nedge_fine[eid++] = nf;
+      }
+    }
+  }
+}
+
+// Coordinates ctor (uniform branch, coordinates.cpp:125-145) + Cartesian x?v (cartesian.cpp:25-75)
+void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, double mmax, double bmin,
+                 double bmax, int nc, std::vector<double> &xf, std::vector<double> &xv,
+                 std::vector<double> &dxf) {
+  xf.assign(nc + 1, 0.0); xv.assign(nc, 0.0); dxf.assign(nc, 0.0);
+  if (nc == 1) {
+    dxf[0] = bmax - bmin;
+    xf[0] = bmin; xf[1] = bmax;
+    xv[0] = 0.5*(xf[1] + xf[0]);
+    return;
+  }
+  int il = ng, iu = ng + bx - 1;
+  double dx = (bmax - bmin)/(iu - il + 1);
+  for (int i = il - ng; i <= iu + ng + 1; ++i) {
+    long noffset = (long)(i - il) + lx*bx;
+    xf[i] = uniform_gen(mesh_gen_x(noffset, nx_mesh), mmin, mmax);
+  }
+  xf[il] = bmin;
+  xf[iu+1] = bmax;
+  for (int i = il - ng; i <= iu + ng; ++i) dxf[i] = dx;
+  for (int i = il - ng; i <= iu + ng; ++i) xv[i] = 0.5*(xf[i+1] + xf[i]);
+}
+
+long reg_size(const AbMesh *m, int reg) {
+  long n1 = m->nc[0], n2 = m->nc[1], n3 = m->nc[2];
+  long ncc = n1*n2*n3;
+  long nf1 = n3*n2*(n1+1), nf2 = n3*(n2+1)*n1, nf3 = (n3+1)*n2*n1;
+  switch (reg) {
+    case AB_U: case AB_U1: case AB_W: return ab::NHYDRO*ncc;
+    case AB_FLUX_X1: return ab::NHYDRO*nf1;
+    case AB_FLUX_X2: return ab::NHYDRO*nf2;
+    case AB_FLUX_X3: return ab::NHYDRO*nf3;
+    default: break;
+  }
+  if (!m->p.mhd) return 0;
+  switch (reg) {
+    case AB_BCC: return 3*ncc;
+    case AB_B_X1F: case AB_B1_X1F: case AB_WGHT_X1F: case AB_E3_X1F: case AB_E2_X1F: return nf1;
+    case AB_B_X2F: case AB_B1_X2F: case AB_WGHT_X2F: case AB_E1_X2F: case AB_E3_X2F: return nf2;
+    case AB_B_X3F: case AB_B1_X3F: case AB_WGHT_X3F: case AB_E2_X3F: case AB_E1_X3F: return nf3;
+    case AB_E_X1E: return (n3+1)*(n2+1)*n1;
+    case AB_E_X2E: return (n3+1)*n2*(n1+1);
+    case AB_E_X3E: return n3*(n2+1)*(n1+1);
+    default: return 0;
+  }
+}
+
+double **reg_slot(LocalBlock &L, int reg) {
+  ab::BlkDev &d = L.d;
+  switch (reg) {
+    case AB_U: return &d.u; case AB_U1: return &d.u1; case AB_W: return &d.w;
+    case AB_BCC: return &d.bcc;
+    case AB_B_X1F: return &d.b[0]; case AB_B_X2F: return &d.b[1]; case AB_B_X3F: return &d.b[2];
+    case AB_B1_X1F: return &d.b1[0]; case AB_B1_X2F: return &d.b1[1]; case AB_B1_X3F: return &d.b1[2];
+    case AB_FLUX_X1: return &d.flux[0]; case AB_FLUX_X2: return &d.flux[1];
+    case AB_FLUX_X3: return &d.flux[2];
+    case AB_E_X1E: return &d.e[0]; case AB_E_X2E: return &d.e[1]; case AB_E_X3E: return &d.e[2];
+    case AB_WGHT_X1F: return &d.wght[0]; case AB_WGHT_X2F: return &d.wght[1];
+    case AB_WGHT_X3F: return &d.wght[2];
+    case AB_E3_X1F: return &d.ef[0][0]; case AB_E2_X1F: return &d.ef[0][1];
+    case AB_E1_X2F: return &d.ef[1][0]; case AB_E3_X2F: return &d.ef[1][1];
+    case AB_E2_X3F: return &d.ef[2][0]; case AB_E1_X3F: return &d.ef[2][1];
+    default: return nullptr;
+  }
+}
+
+size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+int alloc_blocks(AbMesh *m) {
+  const AbMeshParams &p = m->p;
+  int ng = p.nghost;
+  m->gid_start = -1;
+  for (auto &B : m->hb) if (B.rank == p.rank) {
+    if (m->gid_start < 0) m->gid_start = B.gid;
+    LocalBlock L;
+    L.hb = &B;
+    m->lb.push_back(L);
+  }
+  if (m->lb.empty()) return fail(AB_ERR_ARG, "this rank owns no MeshBlock: use fewer ranks or smaller MeshBlocks");
+  CK(cudaMalloc(&m->dtmin, sizeof(unsigned long long)*m->lb.size()));
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    LocalBlock &L = m->lb[l];
+    HostBlock &B = *L.hb;
+    memset(&L.d, 0, sizeof(L.d));
+    ab::BlkDev &d = L.d;
+    d.nc1 = m->nc[0]; d.nc2 = m->nc[1]; d.nc3 = m->nc[2];
+    d.is = m->is; d.ie = m->ie; d.js = m->js; d.je = m->je; d.ks = m->ks; d.ke = m->ke;
+    d.ng = ng; d.f2 = m->f2; d.f3 = m->f3;
+    // sizes
+    size_t tot = 0;
+    for (int r = 0; r < AB_NREG; ++r) { L.regsize[r] = reg_size(m, r); tot += align256(L.regsize[r]*8); }
+    long ncc = (long)m->nc[0]*m->nc[1]*m->nc[2];
+    size_t cce = p.mhd ? align256(3*ncc*8) : 0;
+    tot += cce;
+    // coordinates: 9 arrays + 6 PLM weight arrays
+    std::vector<double> xf[3], xv[3], dxf[3], wp[3], wm[3];
+    const double mmin[3] = {p.x1min, p.x2min, p.x3min}, mmax[3] = {p.x1max, p.x2max, p.x3max};
+    const int nxm[3] = {p.nx1, p.nx2, p.nx3}, bxs[3] = {p.bx1, p.bx2, p.bx3};
+    for (int dd = 0; dd < 3; ++dd) {
+      make_coords(nxm[dd], bxs[dd], ng, B.lx[dd], mmin[dd], mmax[dd], B.bmin[dd], B.bmax[dd],
+                  m->nc[dd], xf[dd], xv[dd], dxf[dd]);
+      wp[dd].assign(m->nc[dd], 0.0); wm[dd].assign(m->nc[dd], 0.0);
+      for (int c = 0; c < m->nc[dd]; ++c) {   // plm.cpp:114-119 / 226-227 / 332-333
+        wp[dd][c] = (xf[dd][c+1] - xv[dd][c])/dxf[dd][c];
+        wm[dd][c] = (xv[dd][c] - xf[dd][c])/dxf[dd][c];
+      }
+    }
+    size_t coord_bytes = 0;
+    for (int dd = 0; dd < 3; ++dd)
+      coord_bytes += align256((m->nc[dd]+1)*8) + 4*align256(m->nc[dd]*8);
+    tot += coord_bytes;
+    // EMF send buffers for every face / edge (used for same-rank neighbours)
+    size_t emf_elems = 0;
+    if (p.mhd) {
+      for (int f = 0; f < 6; ++f) { L.face_off[f] = emf_elems; emf_elems += emf_face_count(m, f); }
+      for (int e = 0; e < 12; ++e) { L.edge_off[e] = emf_elems; emf_elems += emf_edge_count(m, e); }
+    }
+    tot += align256(emf_elems*8);
+    L.nbytes = tot;
+    CK(cudaMalloc(&L.base, tot));
+    CK(cudaMemsetAsync(L.base, 0, tot, m->stream));   // AthenaArray storage is zero-initialised
+    char *cur = (char *)L.base;
+    for (int r = 0; r < AB_NREG; ++r) {
+      double **slot = reg_slot(L, r);
+      if (L.regsize[r] > 0) { *slot = (double *)cur; cur += align256(L.regsize[r]*8); }
+      else *slot = nullptr;
+    }
+    if (p.mhd) { d.cc_e = (double *)cur; cur += cce; }
+    auto put = [&](const std::vector<double> &v, int idx) -> const double * {
+      double *dst = (double *)cur;
+      cur += align256(v.size()*8);
+      cudaMemcpyAsync(dst, v.data(), v.size()*8, cudaMemcpyHostToDevice, m->stream);
+      if (idx >= 0) { L.coord_dev[idx] = dst; L.coord_n[idx] = (long)v.size(); }
+      return dst;
+    };
+    d.x1f = put(xf[0], 0); d.x2f = put(xf[1], 1); d.x3f = put(xf[2], 2);
+    d.x1v = put(xv[0], 3); d.x2v = put(xv[1], 4); d.x3v = put(xv[2], 5);
+    d.dx1f = put(dxf[0], 6); d.dx2f = put(dxf[1], 7); d.dx3f = put(dxf[2], 8);
+    for (int dd = 0; dd < 3; ++dd) { L.g.wp[dd] = put(wp[dd], -1); L.g.wm[dd] = put(wm[dd], -1); }
+    CK(cudaStreamSynchronize(m->stream));   // host vectors go out of scope
+    L.emf_send = (double *)cur;
+    L.dtmin = m->dtmin + l;
+  }
+  return AB_OK;
+}
+
+// ------------------------------------------------------------------ exchange plans
+struct Msg { int peer; long key; int lid; int nbi; long count; };
+
+// ghost-exchange plan for the current register parity: box copies, pack lists, peer buffers
+int build_state_plan(AbMesh *m, int which) {
+  AbMesh::Plan &P = m->plan[which];
+  std::vector<CopyBox> pack, ph1, ph2;
+  const int mhd = m->p.mhd;
+  const long ncc = (long)m->nc[0]*m->nc[1]*m->nc[2];
+  // per-peer message lists (sorted by (dst gid, dst bufid))
+  std::map<int, std::vector<Msg>> sends, recvs;
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    HostBlock &B = *m->lb[l].hb;
+    for (size_t n = 0; n < B.nbs.size(); ++n) {
+      const Nb &nb = B.nbs[n];
+      if (nb.rank == m->p.rank) continue;
+      long cnt = state_msg_count(m, nb.ox1, nb.ox2, nb.ox3);
+      sends[nb.rank].push_back({nb.rank, (long)nb.gid*64 + nb.targetid, (int)l, (int)n, cnt});
+      recvs[nb.rank].push_back({nb.rank, (long)B.gid*64 + nb.bufid, (int)l, (int)n, cnt});
+    }
+  }
+  std::map<std::pair<int,int>, long> send_off, recv_off;   // (lid, nbi) -> element offset
+  for (auto &kv : sends) {
+    std::sort(kv.second.begin(), kv.second.end(), [](const Msg &a, const Msg &b) { return a.key < b.key; });
+    long off = 0;
+    for (auto &ms : kv.second) { send_off[{ms.lid, ms.nbi}] = off; off += ms.count; }
+    PeerBuf &pb = m->peer_state[kv.first];
+    if (!pb.send) { pb.nsend = off; CK(cudaMalloc(&pb.send, std::max<size_t>(off, 1)*8)); }
+  }
+  for (auto &kv : recvs) {
+    std::sort(kv.second.begin(), kv.second.end(), [](const Msg &a, const Msg &b) { return a.key < b.key; });
+    long off = 0;
+    for (auto &ms : kv.second) { recv_off[{ms.lid, ms.nbi}] = off; off += ms.count; }
+    PeerBuf &pb = m->peer_state[kv.first];
+    if (!pb.recv) { pb.nrecv = off; CK(cudaMalloc(&pb.recv, std::max<size_t>(off, 1)*8)); }
+  }
+  auto add_box = [](std::vector<CopyBox> &v, double *dst, long ds3, long ds2, long dsv,
+                    const double *src, long ss3, long ss2, long ssv, int nvar, const Box &db,
+                    int si0, int sj0, int sk0) {
+    CopyBox c;
+    c.dst = dst; c.src = src; c.dst_s3 = ds3; c.dst_s2 = ds2; c.src_s3 = ss3; c.src_s2 = ss2;
+    c.dst_sv = dsv; c.src_sv = ssv; c.nvar = nvar;
+    c.di0 = db.si; c.dj0 = db.sj; c.dk0 = db.sk; c.si0 = si0; c.sj0 = sj0; c.sk0 = sk0;
+    c.ni = db.ei-db.si+1; c.nj = db.ej-db.sj+1; c.nk = db.ek-db.sk+1; c.offset = 0;
+    if (c.ni > 0 && c.nj > 0 && c.nk > 0) v.push_back(c);
+  };
+  const long cs2 = m->nc[0], cs3 = (long)m->nc[0]*m->nc[1];
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    LocalBlock &L = m->lb[l];
+    HostBlock &B = *L.hb;
+    for (size_t n = 0; n < B.nbs.size(); ++n) {
+      const Nb &nb = B.nbs[n];
+      const bool local = (nb.rank == m->p.rank);
+      // ---- receiving side: fill my ghost zones from the neighbour's active zones
+      Box rb = cc_recv_box(m, nb.ox1, nb.ox2, nb.ox3);
+      Box sb = cc_send_box(m, -nb.ox1, -nb.ox2, -nb.ox3);      // what the neighbour loads
+      if (local) {
+        LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
+        add_box(ph1, L.d.u, cs3, cs2, ncc, N.d.u, cs3, cs2, ncc, ab::NHYDRO, rb, sb.si, sb.sj, sb.sk);
+      } else {
+        double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}];
+        Box z = {0, rb.ei-rb.si, 0, rb.ej-rb.sj, 0, rb.ek-rb.sk};
+        long s2 = z.ei+1, s3 = s2*(z.ej+1);
+        add_box(ph1, L.d.u, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), ab::NHYDRO, rb, 0, 0, 0);
+      }
+      long roff = ab::NHYDRO*rb.count();
+      if (mhd) {
+        for (int c = 0; c < 3; ++c) {
+          Box frb = fc_recv_box(m, c, nb.ox1, nb.ox2, nb.ox3);
+          Box fsb = fc_send_box(m, c, -nb.ox1, -nb.ox2, -nb.ox3);
+          long s3, s2;
+          fc_strides(m, c, s3, s2);
+          if (local) {
+            LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
+            add_box(ph1, L.d.b[c], s3, s2, 0, N.d.b[c], s3, s2, 0, 1, frb, fsb.si, fsb.sj, fsb.sk);
+          } else {
+            double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}] + roff;
+            long t2 = frb.ei-frb.si+1, t3 = t2*(frb.ej-frb.sj+1);
+            add_box(ph1, L.d.b[c], s3, s2, 0, src, t3, t2, 0, 1, frb, 0, 0, 0);
+            roff += frb.count();
+          }
+          // 1-D / 2-D duplicate faces (bvals_fc.cpp:641-645, 669-675)
+          if (c == 1 && !m->f2) {
+            Box dup = frb; dup.sj = frb.sj + 1; dup.ej = frb.sj + 1;
+            add_box(ph2, L.d.b[1], s3, s2, 0, L.d.b[1], s3, s2, 0, 1, dup, frb.si, frb.sj, frb.sk);
+          }
+          if (c == 2 && !m->f3) {
+            Box dup = frb; dup.sk = frb.sk + 1; dup.ek = frb.sk + 1;
+            add_box(ph2, L.d.b[2], s3, s2, 0, L.d.b[2], s3, s2, 0, 1, dup, frb.si, frb.sj, frb.sk);
+          }
+        }
+      }
+      // ---- sending side (remote only): pack my active zones into the peer buffer
+      if (!local) {
+        double *dst = m->peer_state[nb.rank].send + send_off[{(int)l, (int)n}];
+        Box lb2 = cc_send_box(m, nb.ox1, nb.ox2, nb.ox3);
+        Box z = {0, lb2.ei-lb2.si, 0, lb2.ej-lb2.sj, 0, lb2.ek-lb2.sk};
+        long s2 = z.ei+1, s3 = s2*(z.ej+1);
+        add_box(pack, dst, s3, s2, s3*(z.ek+1), L.d.u, cs3, cs2, ncc, ab::NHYDRO, z, lb2.si, lb2.sj, lb2.sk);
+        long soff = ab::NHYDRO*lb2.count();
+        if (mhd) for (int c = 0; c < 3; ++c) {
+          Box fb = fc_send_box(m, c, nb.ox1, nb.ox2, nb.ox3);
+          long fs3, fs2;
+          fc_strides(m, c, fs3, fs2);
+          Box fz = {0, fb.ei-fb.si, 0, fb.ej-fb.sj, 0, fb.ek-fb.sk};
+          long t2 = fz.ei+1, t3 = t2*(fz.ej+1);
+          add_box(pack, dst + soff, t3, t2, 0, L.d.b[c], fs3, fs2, 0, 1, fz, fb.si, fb.sj, fb.sk);
+          soff += fb.count();
+        }
+      }
+    }
+  }
+  auto upload = [&](const std::vector<CopyBox> &v, CopyBox *&dev, int &n, long &mx) -> int {
+    n = (int)v.size(); mx = 0;
+    for (auto &c : v) mx = std::max(mx, (long)c.ni*c.nj*c.nk*c.nvar);
+    if (dev) { cudaFree(dev); dev = nullptr; }
+    if (n == 0) return AB_OK;
+    CK(cudaMalloc(&dev, sizeof(CopyBox)*n));
+    CK(cudaMemcpy(dev, v.data(), sizeof(CopyBox)*n, cudaMemcpyHostToDevice));
+    return AB_OK;
+  };
+  int rc;
+  if ((rc = upload(pack, P.pack, P.npack, P.maxpack))) return rc;
+  if ((rc = upload(ph1, P.phase1, P.n1, P.max1))) return rc;
+  if ((rc = upload(ph2, P.phase2, P.n2, P.max2))) return rc;
+  P.built = true;
+  return AB_OK;
+}
+
+int build_emf_plan(AbMesh *m) {
+  if (!m->p.mhd) { m->emf_built = true; return AB_OK; }
+  std::map<int, std::vector<Msg>> sends, recvs;
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    HostBlock &B = *m->lb[l].hb;
+    for (size_t n = 0; n < B.nbs.size(); ++n) {
+      const Nb &nb = B.nbs[n];
+      if (nb.type > 1 || nb.rank == m->p.rank) continue;
+      long cnt = nb.type == 0 ? emf_face_count(m, nb.fid) : emf_edge_count(m, nb.eid);
+      sends[nb.rank].push_back({nb.rank, (long)nb.gid*64 + nb.targetid, (int)l, (int)n, cnt});
+      recvs[nb.rank].push_back({nb.rank, (long)B.gid*64 + nb.bufid, (int)l, (int)n, cnt});
+    }
+  }
+  std::map<std::pair<int,int>, long> send_off, recv_off;
+  for (auto &kv : sends) {
+    std::sort(kv.second.begin(), kv.second.end(), [](const Msg &a, const Msg &b) { return a.key < b.key; });
+    long off = 0;
+    for (auto &ms : kv.second) { send_off[{ms.lid, ms.nbi}] = off; off += ms.count; }
+    PeerBuf &pb = m->peer_emf[kv.first];
+    pb.nsend = off; CK(cudaMalloc(&pb.send, std::max<size_t>(off, 1)*8));
+  }
+  for (auto &kv : recvs) {
+    std::sort(kv.second.begin(), kv.second.end(), [](const Msg &a, const Msg &b) { return a.key < b.key; });
+    long off = 0;
+    for (auto &ms : kv.second) { recv_off[{ms.lid, ms.nbi}] = off; off += ms.count; }
+    PeerBuf &pb = m->peer_emf[kv.first];
+    pb.nrecv = off; CK(cudaMalloc(&pb.recv, std::max<size_t>(off, 1)*8));
+  }
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    LocalBlock &L = m->lb[l];
+    HostBlock &B = *L.hb;
+    ab::EmfPlan &E = L.emf;
+    memset(&E, 0, sizeof(E));
+    for (int e = 0; e < 12; ++e) E.nedge_fine[e] = B.nedge_fine[e];
+    for (int f = 0; f < 2*m->ndim; ++f)
+      E.face_avg[f] = (B.bcs[f] == -1 || B.bcs[f] == AB_BC_PERIODIC) ? 1 : 0;
+    for (size_t n = 0; n < B.nbs.size(); ++n) {
+      const Nb &nb = B.nbs[n];
+      if (nb.type > 1) continue;
+      const bool local = (nb.rank == m->p.rank);
+      if (nb.type == 0) {
+        if (local) {
+          LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
+          E.face_dst[nb.fid] = L.emf_send + L.face_off[nb.fid];
+          E.face_src[nb.fid] = N.emf_send + N.face_off[nb.fid ^ 1];
+        } else {
+          E.face_dst[nb.fid] = m->peer_emf[nb.rank].send + send_off[{(int)l, (int)n}];
+          E.face_src[nb.fid] = m->peer_emf[nb.rank].recv + recv_off[{(int)l, (int)n}];
+        }
+      } else {
+        if (local) {
+          LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
+          E.edge_dst[nb.eid] = L.emf_send + L.edge_off[nb.eid];
+          E.edge_src[nb.eid] = N.emf_send + N.edge_off[opposite_eid(nb.eid)];
+        } else {
+          E.edge_dst[nb.eid] = m->peer_emf[nb.rank].send + send_off[{(int)l, (int)n}];
+          E.edge_src[nb.eid] = m->peer_emf[nb.rank].recv + recv_off[{(int)l, (int)n}];
+        }
+      }
+    }
+  }
+  m->emf_built = true;
+  return AB_OK;
+}
+
+int peer_exchange(AbMesh *m, std::map<int, PeerBuf> &peers) {
+  if (peers.empty()) return AB_OK;
+  if (!m->comm) return fail(AB_ERR_STATE, "blocks on other ranks but ab_comm_init was not called");
+  NK(g_nccl.GroupStart());
+  for (auto &kv : peers) {
+    if (kv.second.nsend) NK(g_nccl.Send(kv.second.send, kv.second.nsend, NCCL_FLOAT64, kv.first, m->comm, m->stream));
+    if (kv.second.nrecv) NK(g_nccl.Recv(kv.second.recv, kv.second.nrecv, NCCL_FLOAT64, kv.first, m->comm, m->stream));
+  }
+  NK(g_nccl.GroupEnd());
+  return AB_OK;
+}
+
+int plan_index(AbMesh *m) {
+  // all local blocks swap registers in lockstep inside the driver; a mixed state (possible
+  // only through per-block ab_swap calls) forces a rebuild
+  int pu = m->lb[0].parity, pb = m->lb[0].parity_b;
+  for (auto &L : m->lb) if (L.parity != pu || L.parity_b != pb) return -1;
+  return pu | (pb << 1);
+}
+
+int bvals_exchange(AbMesh *m) {
+  int idx = plan_index(m);
+  int use = idx < 0 ? 0 : idx;
+  if (idx < 0) m->plan[0].built = false;
+  if (!m->plan[use].built) { int rc = build_state_plan(m, use); if (rc) return rc; }
+  if (idx < 0) m->plan[0].built = false;   // mixed state: never cache
+  AbMesh::Plan &P = m->plan[use];
+  if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream);
+  int rc = peer_exchange(m, m->peer_state);
+  if (rc) return rc;
+  ab::launch_copy_boxes(P.phase1, P.n1, P.max1, m->stream);
+  ab::launch_copy_boxes(P.phase2, P.n2, P.max2, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+
+int emf_exchange(AbMesh *m) {
+  if (!m->p.mhd) return AB_OK;
+  if (!m->emf_built) { int rc = build_emf_plan(m); if (rc) return rc; }
+  for (auto &L : m->lb) ab::launch_emf_pack(L.d, L.emf, m->stream);
+  int rc = peer_exchange(m, m->peer_emf);
+  if (rc) return rc;
+  for (auto &L : m->lb) ab::launch_emf_apply(L.d, L.emf, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+
+void primitives(AbMesh *m, LocalBlock &L) {
+  // TimeIntegratorTaskList::Primitives (time_integrator.cpp:1965-1983)
+  HostBlock &B = *L.hb;
+  int ng = m->p.nghost;
+  int il = m->is, iu = m->ie, jl = m->js, ju = m->je, kl = m->ks, ku = m->ke;
+  if (B.nblevel[1][1][0] != -1) il -= ng;
+  if (B.nblevel[1][1][2] != -1) iu += ng;
+  if (B.nblevel[1][0][1] != -1) jl -= ng;
+  if (B.nblevel[1][2][1] != -1) ju += ng;
+  if (B.nblevel[0][1][1] != -1) kl -= ng;
+  if (B.nblevel[2][1][1] != -1) ku += ng;
+  ab::launch_cons2prim(L.d, m->kp, il, iu, jl, ju, kl, ku, m->stream);
+}
+
+void physical_bcs(AbMesh *m, LocalBlock &L) {
+  // BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620), outflow only
+  HostBlock &B = *L.hb;
+  int ng = m->p.nghost, mhd = m->p.mhd;
+  int is = m->is, ie = m->ie, js = m->js, je = m->je, ks = m->ks, ke = m->ke;
+  int bis = is - ng, bie = ie + ng, bjs = js, bje = je, bks = ks, bke = ke;
+  bool app[6];
+  for (int f = 0; f < 6; ++f) app[f] = (B.bcs[f] != -1 && B.bcs[f] != AB_BC_PERIODIC);
+  if (!m->f2) app[2] = app[3] = false;
+  if (!m->f3) app[4] = app[5] = false;
+  if (!app[2] && m->f2) bjs = js - ng;
+  if (!app[3] && m->f2) bje = je + ng;
+  if (!app[4] && m->f3) bks = ks - ng;
+  if (!app[5] && m->f3) bke = ke + ng;
+  cudaStream_t s = m->stream;
+  if (app[0]) {
+    ab::launch_outflow(L.d, mhd, 0, is, ie, bjs, bje, bks, bke, s);
+    if (mhd) ab::launch_calc_bcc(L.d, is-ng, is-1, bjs, bje, bks, bke, s);
+    ab::launch_prim2cons(L.d, m->kp, is-ng, is-1, bjs, bje, bks, bke, s);
+  }
+  if (app[1]) {
+    ab::launch_outflow(L.d, mhd, 1, is, ie, bjs, bje, bks, bke, s);
+    if (mhd) ab::launch_calc_bcc(L.d, ie+1, ie+ng, bjs, bje, bks, bke, s);
+    ab::launch_prim2cons(L.d, m->kp, ie+1, ie+ng, bjs, bje, bks, bke, s);
+  }
+  if (m->f2) {
+    if (app[2]) {
+      ab::launch_outflow(L.d, mhd, 2, bis, bie, js, je, bks, bke, s);
+      if (mhd) ab::launch_calc_bcc(L.d, bis, bie, js-ng, js-1, bks, bke, s);
+      ab::launch_prim2cons(L.d, m->kp, bis, bie, js-ng, js-1, bks, bke, s);
+    }
+    if (app[3]) {
+      ab::launch_outflow(L.d, mhd, 3, bis, bie, js, je, bks, bke, s);
+      if (mhd) ab::launch_calc_bcc(L.d, bis, bie, je+1, je+ng, bks, bke, s);
+      ab::launch_prim2cons(L.d, m->kp, bis, bie, je+1, je+ng, bks, bke, s);
+    }
+  }
+  if (m->f3) {
+    bjs = js - ng; bje = je + ng;
+    if (app[4]) {
+      ab::launch_outflow(L.d, mhd, 4, bis, bie, bjs, bje, ks, ke, s);
+      if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ks-ng, ks-1, s);
+      ab::launch_prim2cons(L.d, m->kp, bis, bie, bjs, bje, ks-ng, ks-1, s);
+    }
+    if (app[5]) {
+      ab::launch_outflow(L.d, mhd, 5, bis, bie, bjs, bje, ks, ke, s);
+      if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ke+1, ke+ng, s);
+      ab::launch_prim2cons(L.d, m->kp, bis, bie, bjs, bje, ke+1, ke+ng, s);
+    }
+  }
+}
+
+int new_time_step(AbMesh *m, int advance) {
+  // NewBlockTimeStep on every block, then Mesh::NewTimeStep (mesh/mesh.cpp:1078-1119)
+  ab::launch_fill_u64(m->dtmin, (int)m->lb.size(), 0x7FEFFFFFFFFFFFFFull /* DBL_MAX */, m->stream);
+  for (auto &L : m->lb) ab::launch_new_block_dt(L.d, m->kp, L.dtmin, m->stream);
+  ab::launch_mesh_new_dt(m->state, m->dtmin, (int)m->lb.size(), 0 /*phase 0*/, m->stream);
+  if (m->p.nranks > 1) {
+    if (!m->comm) return fail(AB_ERR_STATE, "nranks > 1 but ab_comm_init was not called");
+    NK(g_nccl.AllReduce(m->state + 4, m->state + 4, 1, NCCL_FLOAT64, NCCL_MIN, m->comm, m->stream));
+  }
+  ab::launch_mesh_new_dt(m->state, m->dtmin, (int)m->lb.size(), 2 | (advance ? 1 : 0), m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+
+int read_state(AbMesh *m) {
+  double h[6];
+  CK(cudaMemcpyAsync(h, m->state, sizeof(h), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  m->h_time = h[0]; m->h_dt = h[1]; m->h_ncycle = (long)h[5];
+  return AB_OK;
+}
+
+void swap_cc(LocalBlock &L) { std::swap(L.d.u, L.d.u1); L.parity ^= 1; }
+void swap_fc(LocalBlock &L) {
+  for (int d = 0; d < 3; ++d) std::swap(L.d.b[d], L.d.b1[d]);
+  L.parity_b ^= 1;
+}
+
+int one_cycle(AbMesh *m) {
+  const double *dtp = m->state + 1;
+  for (int stage = 1; stage <= m->nstages; ++stage) {
+    const int s = stage - 1;
+    const int order = (m->p.integrator == AB_INT_VL2 && stage == 1) ? 1 : m->p.xorder;
+    for (auto &L : m->lb) {
+      ab::launch_fluxes(L.d, L.g, m->kp, order, 0.0, dtp, m->stream);
+      if (m->p.mhd) ab::launch_corner_e(L.d, m->stream);
+    }
+    int rc = emf_exchange(m);
+    if (rc) return rc;
+    const bool swap = (m->g1[s] == 0.0 && m->g2[s] == 1.0 && m->g3[s] == 0.0);
+    const int zero_init = (stage == 1);   // StartupTaskList: u1, b1 ZeroClear (:1386-1397)
+    for (auto &L : m->lb) {
+      if (swap) {
+        swap_cc(L);
+        ab::launch_integrate_cc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, m->stream);
+        if (m->p.mhd) {
+          swap_fc(L);
+          ab::launch_integrate_fc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, m->stream);
+        }
+      } else {
+        ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
+        if (m->p.mhd)
+          ab::launch_integrate_fc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
+      }
+    }
+    rc = bvals_exchange(m);
+    if (rc) return rc;
+    for (auto &L : m->lb) { primitives(m, L); physical_bcs(m, L); }
+    if (stage == m->nstages) {
+      // record the dt this cycle used, then time += dt, ncycle++, NewTimeStep
+      if (m->hist_n < m->hist_cap)
+        CK(cudaMemcpyAsync(m->dt_hist + m->hist_n, m->state + 1, 8, cudaMemcpyDeviceToDevice, m->stream));
+      m->hist_n++;
+      rc = new_time_step(m, 1);
+      if (rc) return rc;
+    }
+  }
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char *ab_last_error(void) { return g_err.c_str(); }
+
+int ab_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
+  if (!p || !out) return fail(AB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (p->bx1 <= 0 || p->nx1 % p->bx1 || p->nx2 % p->bx2 || p->nx3 % p->bx3)
+    return fail(AB_ERR_ARG, "the Mesh must be evenly divisible by the MeshBlock");
+  if (p->xorder < 1 || p->xorder > 3) return fail(AB_ERR_ARG, "time/xorder must be 1, 2 or 3");
+  if (p->xorder == 3 && p->nghost < 3)
+    return fail(AB_ERR_ARG, "xorder=3 (PPM) needs nghost >= 3 (reconstruction.cpp:90-99)");
+  if (p->nghost < 2) return fail(AB_ERR_ARG, "nghost must be >= 2");
+  if (p->mhd && p->solver == AB_SOLVER_HLLC) return fail(AB_ERR_ARG, "HLLC flux cannot be used with MHD");
+  if (!p->mhd && p->solver == AB_SOLVER_HLLD) return fail(AB_ERR_ARG, "HLLD flux can only be used with MHD");
+  for (int f = 0; f < 6; ++f)
+    if (p->bc[f] != AB_BC_PERIODIC && p->bc[f] != AB_BC_OUTFLOW)
+      return fail(AB_ERR_ARG, "unsupported boundary flag");
+  if (ab_device_count() <= 0)
+    return fail(AB_ERR_NO_DEVICE, "no CUDA device: libathena_b200 has no CPU fallback");
+  CK(cudaSetDevice(p->device));
+  AbMesh *m = new AbMesh();
+  m->p = *p;
+  m->f2 = p->nx2 > 1; m->f3 = p->nx3 > 1;
+  m->ndim = m->f3 ? 3 : (m->f2 ? 2 : 1);
+  m->kp.gamma = p->gamma; m->kp.dfloor = p->dfloor; m->kp.pfloor = p->pfloor;
+  m->kp.mhd = p->mhd; m->kp.solver = p->solver; m->kp.xorder = p->xorder;
+  int ng = p->nghost;
+  // MeshBlock index ranges (mesh/meshblock.cpp:55-80)
+  m->is = ng; m->ie = ng + p->bx1 - 1; m->nc[0] = p->bx1 + 2*ng;
+  if (m->f2) { m->js = ng; m->je = ng + p->bx2 - 1; m->nc[1] = p->bx2 + 2*ng; }
+  if (m->f3) { m->ks = ng; m->ke = ng + p->bx3 - 1; m->nc[2] = p->bx3 + 2*ng; }
+  set_integrator(m);
+  build_block_list(m);
+  CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  int rc = alloc_blocks(m);
+  if (rc) { delete m; return rc; }
+  CK(cudaMalloc(&m->state, 8*sizeof(double)));
+  m->hist_cap = 1 << 16;
+  CK(cudaMalloc(&m->dt_hist, sizeof(double)*m->hist_cap));
+  m->h_time = p->start_time; m->h_dt = DBL_MAX; m->h_ncycle = 0;
+  double h[8] = {p->start_time, DBL_MAX, p->tlim, m->cfl, DBL_MAX, 0.0, 0.0, 0.0};
+  CK(cudaMemcpy(m->state, h, sizeof(h), cudaMemcpyHostToDevice));
+  CK(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return AB_OK;
+}
+
+int ab_mesh_destroy(AbMesh *m) {
+  if (!m) return AB_OK;
+  cudaSetDevice(m->p.device);
+  cudaStreamSynchronize(m->stream);
+  for (auto &L : m->lb) cudaFree(L.base);
+  for (int i = 0; i < 4; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase2); }
+  for (auto &kv : m->peer_state) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
+  for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
+  cudaFree(m->state); cudaFree(m->dt_hist); cudaFree(m->dtmin);
+  if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  cudaStreamDestroy(m->stream);
+  delete m;
+  return AB_OK;
+}
+
+int ab_mesh_nblocks_total(const AbMesh *m) { return m ? m->nbtotal : 0; }
+int ab_mesh_nblocks_local(const AbMesh *m) { return m ? (int)m->lb.size() : 0; }
+
+#define GET_L(m, lid)                                                              \
+  if (!(m) || (lid) < 0 || (lid) >= (int)(m)->lb.size())                           \
+    return fail(AB_ERR_ARG, "bad mesh handle or block index");                     \
+  LocalBlock &L = (m)->lb[lid];                                                    \
+  (void)L
+
+int ab_block_info(const AbMesh *m, int lid, long *info) {
+  if (!m || lid < 0 || lid >= (int)m->lb.size() || !info) return fail(AB_ERR_ARG, "bad argument");
+  const HostBlock &B = *m->lb[lid].hb;
+  info[0] = B.gid; info[1] = B.lx[0]; info[2] = B.lx[1]; info[3] = B.lx[2];
+  info[4] = m->nc[0]; info[5] = m->nc[1]; info[6] = m->nc[2];
+  info[7] = m->is; info[8] = m->ie; info[9] = m->js; info[10] = m->je; info[11] = m->ks;
+  info[12] = m->ke;
+  return AB_OK;
+}
+
+long ab_reg_size(const AbMesh *m, int lid, int reg) {
+  if (!m || lid < 0 || lid >= (int)m->lb.size() || reg < 0 || reg >= AB_NREG) return -1;
+  return m->lb[lid].regsize[reg];
+}
+
+int ab_upload(AbMesh *m, int lid, int reg, const double *host) {
+  GET_L(m, lid);
+  if (reg < 0 || reg >= AB_NREG || !host) return fail(AB_ERR_ARG, "bad register");
+  double **slot = reg_slot(L, reg);
+  if (!slot || !*slot) return fail(AB_ERR_ARG, "register not allocated in this configuration");
+  CK(cudaMemcpyAsync(*slot, host, L.regsize[reg]*8, cudaMemcpyHostToDevice, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return AB_OK;
+}
+
+int ab_download(AbMesh *m, int lid, int reg, double *host) {
+  GET_L(m, lid);
+  if (reg < 0 || reg >= AB_NREG || !host) return fail(AB_ERR_ARG, "bad register");
+  double **slot = reg_slot(L, reg);
+  if (!slot || !*slot) return fail(AB_ERR_ARG, "register not allocated in this configuration");
+  CK(cudaMemcpyAsync(host, *slot, L.regsize[reg]*8, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return AB_OK;
+}
+
+int ab_download_coord(AbMesh *m, int lid, int which, double *host) {
+  GET_L(m, lid);
+  if (which < 0 || which > 8 || !host) return fail(AB_ERR_ARG, "bad coordinate id");
+  CK(cudaMemcpyAsync(host, L.coord_dev[which], L.coord_n[which]*8, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return AB_OK;
+}
+
+int ab_comm_unique_id(unsigned char id[128]) {
+  if (!g_nccl.load()) return fail(AB_ERR_NCCL, "cannot load libnccl.so.2");
+  ncclUniqueId u;
+  NK(g_nccl.GetUniqueId(&u));
+  memcpy(id, u.internal, 128);
+  return AB_OK;
+}
+
+int ab_comm_init(AbMesh *m, const unsigned char id[128]) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  if (m->p.nranks <= 1) return AB_OK;
+  if (!g_nccl.load()) return fail(AB_ERR_NCCL, "cannot load libnccl.so.2");
+  CK(cudaSetDevice(m->p.device));
+  ncclUniqueId u;
+  memcpy(u.internal, id, 128);
+  NK(g_nccl.CommInitRank(&m->comm, m->p.nranks, u, m->p.rank));
+  return AB_OK;
+}
+
+int ab_cons2prim(AbMesh *m, int lid, int il, int iu, int jl, int ju, int kl, int ku) {
+  GET_L(m, lid);
+  ab::launch_cons2prim(L.d, m->kp, il, iu, jl, ju, kl, ku, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_prim2cons(AbMesh *m, int lid, int il, int iu, int jl, int ju, int kl, int ku) {
+  GET_L(m, lid);
+  ab::launch_prim2cons(L.d, m->kp, il, iu, jl, ju, kl, ku, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_primitives(AbMesh *m, int lid) {
+  GET_L(m, lid);
+  primitives(m, L);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_calc_fluxes(AbMesh *m, int lid, int order, double dt) {
+  GET_L(m, lid);
+  if (order < 1 || order > 3) return fail(AB_ERR_ARG, "order must be 1, 2 or 3");
+  ab::launch_fluxes(L.d, L.g, m->kp, order, dt, nullptr, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_corner_e(AbMesh *m, int lid) {
+  GET_L(m, lid);
+  if (!m->p.mhd) return fail(AB_ERR_STATE, "ComputeCornerE needs MAGNETIC_FIELDS_ENABLED");
+  ab::launch_corner_e(L.d, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_weighted_ave(AbMesh *m, int lid, int out_reg, int in_reg, const double w[5]) {
+  GET_L(m, lid);
+  if (!w) return fail(AB_ERR_ARG, "null weights");
+  if (w[2] != 0.0 || w[3] != 0.0 || w[4] != 0.0)
+    return fail(AB_ERR_ARG, "only two-register averages (u,u1 / b,b1) are supported");
+  if ((out_reg == AB_U || out_reg == AB_U1) && (in_reg == AB_U || in_reg == AB_U1)) {
+    ab::launch_weighted_ave_cc(L.d, out_reg == AB_U ? L.d.u : L.d.u1,
+                               in_reg == AB_U ? L.d.u : L.d.u1, w[0], w[1], m->stream);
+  } else if ((out_reg == AB_B_X1F || out_reg == AB_B1_X1F) &&
+             (in_reg == AB_B_X1F || in_reg == AB_B1_X1F) && m->p.mhd) {
+    ab::launch_weighted_ave_fc(L.d, out_reg == AB_B_X1F ? L.d.b : L.d.b1,
+                               in_reg == AB_B_X1F ? L.d.b : L.d.b1, w[0], w[1], m->stream);
+  } else {
+    return fail(AB_ERR_ARG, "bad register pair for WeightedAve");
+  }
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_swap(AbMesh *m, int lid, int reg) {
+  GET_L(m, lid);
+  if (reg == AB_U) swap_cc(L);
+  else if (reg == AB_B_X1F && m->p.mhd) swap_fc(L);
+  else return fail(AB_ERR_ARG, "ab_swap: reg must be AB_U or AB_B_X1F");
+  return AB_OK;
+}
+int ab_zero(AbMesh *m, int lid, int reg) {
+  GET_L(m, lid);
+  if (reg == AB_U1) {
+    CK(cudaMemsetAsync(L.d.u1, 0, L.regsize[AB_U1]*8, m->stream));
+  } else if (reg == AB_B1_X1F && m->p.mhd) {
+    for (int d = 0; d < 3; ++d) CK(cudaMemsetAsync(L.d.b1[d], 0, L.regsize[AB_B1_X1F + d]*8, m->stream));
+  } else {
+    return fail(AB_ERR_ARG, "ab_zero: reg must be AB_U1 or AB_B1_X1F");
+  }
+  ab::g_launches++;
+  return AB_OK;
+}
+int ab_add_flux_div(AbMesh *m, int lid, double wght) {
+  GET_L(m, lid);
+  ab::launch_integrate_cc(L.d, 0, 0, 0.0, 0.0, 0.0, 1.0, wght, nullptr, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_ct(AbMesh *m, int lid, double wght) {
+  GET_L(m, lid);
+  if (!m->p.mhd) return fail(AB_ERR_STATE, "CT needs MAGNETIC_FIELDS_ENABLED");
+  ab::launch_integrate_fc(L.d, 0, 0, 0.0, 0.0, 0.0, 1.0, wght, nullptr, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_physical_bcs(AbMesh *m, int lid) {
+  GET_L(m, lid);
+  physical_bcs(m, L);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_new_block_dt(AbMesh *m, int lid, double *dt_out) {
+  GET_L(m, lid);
+  ab::launch_fill_u64(L.dtmin, 1, 0x7FEFFFFFFFFFFFFFull, m->stream);
+  ab::launch_new_block_dt(L.d, m->kp, L.dtmin, m->stream);
+  unsigned long long bits;
+  CK(cudaMemcpyAsync(&bits, L.dtmin, 8, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  double v;
+  memcpy(&v, &bits, 8);
+  if (dt_out) *dt_out = v*m->cfl;     // new_blockdt.cpp:164
+  return AB_OK;
+}
+
+int ab_emf_exchange(AbMesh *m) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  return emf_exchange(m);
+}
+int ab_bvals_exchange(AbMesh *m) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  return bvals_exchange(m);
+}
+
+int ab_mesh_initialize(AbMesh *m) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  CK(cudaSetDevice(m->p.device));
+  int rc = bvals_exchange(m);
+  if (rc) return rc;
+  for (auto &L : m->lb) { primitives(m, L); physical_bcs(m, L); }
+  rc = new_time_step(m, 0);
+  if (rc) return rc;
+  return read_state(m);
+}
+
+int ab_mesh_cycles(AbMesh *m, int ncycles) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  CK(cudaSetDevice(m->p.device));
+  m->hist_n = 0;
+  for (int c = 0; c < ncycles; ++c) {
+    if (!m->async && !(m->h_time < m->p.tlim)) break;       // main.cpp:430
+    int rc = one_cycle(m);
+    if (rc) return rc;
+    if (!m->async) { rc = read_state(m); if (rc) return rc; }
+  }
+  return AB_OK;
+}
+
+int ab_mesh_set_async(AbMesh *m, int async) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  m->async = async;
+  return AB_OK;
+}
+
+int ab_mesh_state(AbMesh *m, double *time, double *dt, long *ncycle) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  int rc = read_state(m);
+  if (rc) return rc;
+  if (time) *time = m->h_time;
+  if (dt) *dt = m->h_dt;
+  if (ncycle) *ncycle = m->h_ncycle;
+  return AB_OK;
+}
+
+int ab_mesh_set_time_dt(AbMesh *m, double time, double dt) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  double h[2] = {time, dt};
+  CK(cudaMemcpyAsync(m->state, h, sizeof(h), cudaMemcpyHostToDevice, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  m->h_time = time; m->h_dt = dt;
+  return AB_OK;
+}
+
+int ab_mesh_dt_history(AbMesh *m, double *out, int max_n) {
+  if (!m || !out) return fail(AB_ERR_ARG, "null argument");
+  int n = std::min(std::min(m->hist_n, m->hist_cap), max_n);
+  if (n > 0) {
+    CK(cudaMemcpyAsync(out, m->dt_hist, 8*(size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+  }
+  return n;
+}
+
+long ab_mesh_launch_count(const AbMesh *m) { (void)m; return ab::g_launches; }
+void *ab_mesh_stream(AbMesh *m) { return m ? (void *)m->stream : nullptr; }
+int ab_mesh_sync(AbMesh *m) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  CK(cudaStreamSynchronize(m->stream));
+  return AB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,877 @@
+// ab_physics.cuh -- point-wise device physics of the per-MeshBlock hydro/MHD update.
+//
+// Double precision, written for sm_100a and compiled with -fmad=false: every expression keeps
+// the reference's operation order and parenthesisation so that results are bit-identical to
+// the reference's default x86-64 (SSE2, no FMA) build.  The functions are __host__ __device__
+// so that tests can also exercise the very same arithmetic on the CPU (tests/hostcheck); the
+// product only ever calls them from CUDA kernels.
+//
+// Reference: src/eos/adiabatic_{hydro,mhd}.cpp, src/reconstruct/{dc,plm,ppm}.cpp,
+// src/hydro/rsolvers/{hydro/{hllc,hlle,roe},mhd/{hlld,hlle_mhd,roe_mhd}}.cpp,
+// src/hydro/hydro.cpp:154-158.
+#ifndef AB_PHYSICS_CUH_
+#define AB_PHYSICS_CUH_
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define AB_HD __host__ __device__ __forceinline__
+#else
+#define AB_HD static inline
+#endif
+
+namespace ab {
+
+// variable indices (src/athena.hpp:136-144)
+enum : int { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4, IVX = 1, IVY = 2, IVZ = 3, IPR = 4,
+             IBY = 5, IBZ = 6 };
+enum : int { SOLVER_HLLE = 0, SOLVER_HLLC = 1, SOLVER_HLLD = 2, SOLVER_ROE = 3 };
+
+// std::min / std::max semantics of the reference
+AB_HD double dmin(double a, double b) { return (b < a) ? b : a; }
+AB_HD double dmax(double a, double b) { return (a < b) ? b : a; }
+AB_HD double sqr(double x) { return x*x; }
+AB_HD double sgn(double x) { return (x < 0.0) ? -1.0 : 1.0; }
+
+// EquationOfState::SoundSpeed (eos/adiabatic_hydro.cpp:125)
+AB_HD double sound_speed(double gamma, double d, double p) { return sqrt(gamma*p/d); }
+
+// EquationOfState::FastMagnetosonicSpeed (eos/adiabatic_mhd.cpp:149-156)
+AB_HD double fast_speed(double gamma, double d, double p, double by, double bz, double bx) {
+  double asq = gamma*p;
+  double vaxsq = bx*bx;
+  double ct2 = (by*by + bz*bz);
+  double qsq = vaxsq + ct2 + asq;
+  double tmp = vaxsq + ct2 - asq;
+  return sqrt(0.5*(qsq + sqrt(tmp*tmp + 4.0*asq*ct2))/d);
+}
+
+// Hydro::GetWeightForCT (hydro/hydro.cpp:154-158)
+AB_HD double weight_for_ct(double dflx, double rhol, double rhor, double dx, double dt) {
+  double v_over_c = (1024.0)*dt*dflx/(dx*(rhol + rhor));
+  double tmp_min = dmin(0.5, v_over_c);
+  return 0.5 + dmax(-0.5, tmp_min);
+}
+
+// ------------------------------------------------------------------------ reconstruction
+
+// PLM, uniform Cartesian limiter (reconstruct/plm.cpp:69-77) with the coordinate face weights
+// of plm.cpp:114-119: plus = state at the cell's upper face, minus = at its lower face.
+AB_HD void plm(double qm1, double q, double qp1, double wp, double wm,
+               double &plus, double &minus) {
+  double dwl = (q - qm1);
+  double dwr = (qp1 - q);
+  double dw2 = dwl*dwr;
+  double dwm = 2.0*dw2/(dwl + dwr);
+  if (dw2 <= 0.0) dwm = 0.0;
+  plus = q + wp*dwm;
+  minus = q - wm*dwm;
+}
+
+// PPM limiter pieces (reconstruct/ppm.cpp:143-190): CD eq 84-85 extremum fix of one interface
+AB_HD double ppm_face_fix(double dph, double qlo, double qhi, double d2lo, double d2hi) {
+  const double C2 = 1.25;
+  double qa_tmp = dph - qlo;
+  double qb_tmp = qhi - dph;
+  double qa = 3.0*(qlo + qhi - 2.0*dph);
+  double qb = d2lo;
+  double qc = d2hi;
+  double qd = 0.0;
+  if (sgn(qa) == sgn(qb) && sgn(qa) == sgn(qc)) {
+    qd = sgn(qa)*dmin(C2*fabs(qb), dmin(C2*fabs(qc), fabs(qa)));
+  }
+  double dph_tmp = 0.5*(qlo + qhi) - qd/6.0;
+  if (qa_tmp*qb_tmp < 0.0) dph = dph_tmp;
+  return dph;
+}
+
+// PPM for one variable of one cell, uniform Cartesian mesh (reconstruct/ppm.cpp:111-309;
+// coefficients c1..c4=1/2, c5=1/6, c6=-1/6 from reconstruction.cpp:422-433)
+AB_HD void ppm(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,
+               double &plus, double &minus) {
+  const double C2 = 1.25;
+  const double c1 = 0.5, c2 = 0.5, c3 = 0.5, c4 = 0.5, c5 = 1.0/6.0, c6 = -1.0/6.0;
+  double qa = (q - q_im1);
+  double qb = (q_ip1 - q);
+  double dd_im1 = c1*qa + c2*(q_im1 - q_im2);
+  double dd     = c1*qb + c2*qa;
+  double dd_ip1 = c1*(q_ip2 - q_ip1) + c2*qb;
+  double dph = (c3*q_im1 + c4*q) + (c5*dd_im1 + c6*dd);
+  double dph_ip1 = (c3*q + c4*q_ip1) + (c5*dd + c6*dd_ip1);
+  double d2qc_im1 = q_im2 + q     - 2.0*q_im1;
+  double d2qc     = q_im1 + q_ip1 - 2.0*q;
+  double d2qc_ip1 = q     + q_ip2 - 2.0*q_ip1;
+  dph = ppm_face_fix(dph, q_im1, q, d2qc_im1, d2qc);
+  dph_ip1 = ppm_face_fix(dph_ip1, q, q_ip1, d2qc, d2qc_ip1);
+  double d2qf = 6.0*(dph + dph_ip1 - 2.0*q);
+  double qminus = dph;
+  double qplus = dph_ip1;
+  double dqf_minus = q - qminus;
+  double dqf_plus = qplus - q;
+  double qa_tmp = dqf_minus*dqf_plus;
+  double qb_tmp = (q_ip1 - q)*(q - q_im1);
+  double qa2 = d2qc_im1, qb2 = d2qc, qc2 = d2qc_ip1, qd = d2qf;
+  double qe = 0.0;
+  if (sgn(qa2) == sgn(qb2) && sgn(qa2) == sgn(qc2) && sgn(qa2) == sgn(qd)) {
+    qe = sgn(qd)*dmin(dmin(C2*fabs(qa2), C2*fabs(qb2)), dmin(C2*fabs(qc2), fabs(qd)));
+  }
+  qa2 = dmax(fabs(q_im1), fabs(q_im2));
+  qb2 = dmax(dmax(fabs(q), fabs(q_ip1)), fabs(q_ip2));
+  double rho = 0.0;
+  if (fabs(qd) > (1.0e-12)*dmax(qa2, qb2)) rho = qe/qd;
+  double tmp_m = q - rho*dqf_minus;
+  double tmp_p = q + rho*dqf_plus;
+  double tmp2_m = q - 2.0*dqf_plus;
+  double tmp2_p = q + 2.0*dqf_minus;
+  if ((qa_tmp <= 0.0 || qb_tmp <= 0.0)) {
+    if (rho <= (1.0 - (1.0e-12))) {
+      qminus = tmp_m;
+      qplus = tmp_p;
+    }
+  } else {
+    if (fabs(dqf_minus) >= 2.0*fabs(dqf_plus)) qminus = tmp2_m;
+    if (fabs(dqf_plus) >= 2.0*fabs(dqf_minus)) qplus = tmp2_p;
+  }
+  plus = qplus;
+  minus = qminus;
+}
+
+// ------------------------------------------------------------------------ hydro solvers
+// wl/wr: sweep-ordered primitives (IDN, vx, vy, vz, IPR); f: (IDN, mx, my, mz, IEN).
+
+// HLLC (hydro/rsolvers/hydro/hllc.cpp:32-179)
+AB_HD void hllc(const double *wli, const double *wri, double gamma, double *flxi) {
+  double gm1 = gamma - 1.0;
+  double igm1 = 1.0/gm1;
+  double cl = sound_speed(gamma, wli[IDN], wli[IPR]);
+  double cr = sound_speed(gamma, wri[IDN], wri[IPR]);
+  double el = wli[IPR]*igm1 + 0.5*wli[IDN]*(sqr(wli[IVX]) + sqr(wli[IVY]) + sqr(wli[IVZ]));
+  double er = wri[IPR]*igm1 + 0.5*wri[IDN]*(sqr(wri[IVX]) + sqr(wri[IVY]) + sqr(wri[IVZ]));
+  double rhoa = .5*(wli[IDN] + wri[IDN]);
+  double ca = .5*(cl + cr);
+  double pmid = .5*(wli[IPR] + wri[IPR] + (wli[IVX]-wri[IVX])*rhoa*ca);
+  double ql = (pmid <= wli[IPR]) ? 1.0 :
+      sqrt(1.0 + (gamma + 1)/(2*gamma)*(pmid/wli[IPR]-1.0));
+  double qr = (pmid <= wri[IPR]) ? 1.0 :
+      sqrt(1.0 + (gamma + 1)/(2*gamma)*(pmid/wri[IPR]-1.0));
+  double al = wli[IVX] - cl*ql;
+  double ar = wri[IVX] + cr*qr;
+  double bp = ar > 0.0 ? ar : (1.0e-20);
+  double bm = al < 0.0 ? al : -(1.0e-20);
+  double vxl = wli[IVX] - al;
+  double vxr = wri[IVX] - ar;
+  double tl = wli[IPR] + vxl*wli[IDN]*wli[IVX];
+  double tr = wri[IPR] + vxr*wri[IDN]*wri[IVX];
+  double ml = wli[IDN]*vxl;
+  double mr = -(wri[IDN]*vxr);
+  double am = (tl - tr)/(ml + mr);
+  double cp = (ml*tr + mr*tl)/(ml + mr);
+  cp = cp > 0.0 ? cp : 0.0;
+  vxl = wli[IVX] - bm;
+  vxr = wri[IVX] - bp;
+  double fl0 = wli[IDN]*vxl, fr0 = wri[IDN]*vxr;
+  double fl1 = wli[IDN]*wli[IVX]*vxl + wli[IPR], fr1 = wri[IDN]*wri[IVX]*vxr + wri[IPR];
+  double fl2 = wli[IDN]*wli[IVY]*vxl, fr2 = wri[IDN]*wri[IVY]*vxr;
+  double fl3 = wli[IDN]*wli[IVZ]*vxl, fr3 = wri[IDN]*wri[IVZ]*vxr;
+  double fl4 = el*vxl + wli[IPR]*wli[IVX], fr4 = er*vxr + wri[IPR]*wri[IVX];
+  double sl, sr, sm;
+  if (am >= 0.0) {
+    sl = am/(am - bm);
+    sr = 0.0;
+    sm = -bm/(am - bm);
+  } else {
+    sl = 0.0;
+    sr = -am/(bp - am);
+    sm = bp/(bp - am);
+  }
+  flxi[IDN] = sl*fl0 + sr*fr0;
+  flxi[IVX] = sl*fl1 + sr*fr1 + sm*cp;
+  flxi[IVY] = sl*fl2 + sr*fr2;
+  flxi[IVZ] = sl*fl3 + sr*fr3;
+  flxi[IEN] = sl*fl4 + sr*fr4 + sm*cp*am;
+}
+
+// HLLE, adiabatic hydro (hydro/rsolvers/hydro/hlle.cpp:38-162)
+AB_HD void hlle_hydro(const double *wli, const double *wri, double gamma, double *flxi) {
+  double gm1 = gamma - 1.0;
+  double igm1 = 1.0/gm1;
+  double sqrtdl = sqrt(wli[IDN]);
+  double sqrtdr = sqrt(wri[IDN]);
+  double isdlpdr = 1.0/(sqrtdl + sqrtdr);
+  double rvx = (sqrtdl*wli[IVX] + sqrtdr*wri[IVX])*isdlpdr;
+  double rvy = (sqrtdl*wli[IVY] + sqrtdr*wri[IVY])*isdlpdr;
+  double rvz = (sqrtdl*wli[IVZ] + sqrtdr*wri[IVZ])*isdlpdr;
+  double el = wli[IPR]*igm1 + 0.5*wli[IDN]*(sqr(wli[IVX]) + sqr(wli[IVY]) + sqr(wli[IVZ]));
+  double er = wri[IPR]*igm1 + 0.5*wri[IDN]*(sqr(wri[IVX]) + sqr(wri[IVY]) + sqr(wri[IVZ]));
+  double hroe = ((el + wli[IPR])/sqrtdl + (er + wri[IPR])/sqrtdr)*isdlpdr;
+  double cl = sound_speed(gamma, wli[IDN], wli[IPR]);
+  double cr = sound_speed(gamma, wri[IDN], wri[IPR]);
+  double q = hroe - 0.5*(sqr(rvx) + sqr(rvy) + sqr(rvz));
+  double a = (q < 0.0) ? 0.0 : sqrt(gm1*q);
+  double al = dmin((rvx - a), (wli[IVX] - cl));
+  double ar = dmax((rvx + a), (wri[IVX] + cr));
+  double bp = ar > 0.0 ? ar : 0.0;
+  double bm = al < 0.0 ? al : 0.0;
+  double vxl = wli[IVX] - bm;
+  double vxr = wri[IVX] - bp;
+  double fl[5], fr[5];
+  fl[IDN] = wli[IDN]*vxl;
+  fr[IDN] = wri[IDN]*vxr;
+  fl[IVX] = wli[IDN]*wli[IVX]*vxl;
+  fr[IVX] = wri[IDN]*wri[IVX]*vxr;
+  fl[IVY] = wli[IDN]*wli[IVY]*vxl;
+  fr[IVY] = wri[IDN]*wri[IVY]*vxr;
+  fl[IVZ] = wli[IDN]*wli[IVZ]*vxl;
+  fr[IVZ] = wri[IDN]*wri[IVZ]*vxr;
+  fl[IVX] += wli[IPR];
+  fr[IVX] += wri[IPR];
+  fl[IEN] = el*vxl + wli[IPR]*wli[IVX];
+  fr[IEN] = er*vxr + wri[IPR]*wri[IVX];
+  double tmp = 0.0;
+  if (bp != bm) tmp = 0.5*(bp + bm)/(bp - bm);
+#pragma unroll
+  for (int n = 0; n < 5; ++n) flxi[n] = 0.5*(fl[n]+fr[n]) + (fl[n]-fr[n])*tmp;
+}
+
+// Roe, adiabatic hydro (hydro/rsolvers/hydro/roe.cpp:42-352)
+AB_HD void roe_hydro(const double *wli, const double *wri, double gamma, double *flxi) {
+  double gm1 = gamma - 1.0;
+  double sqrtdl = sqrt(wli[IDN]);
+  double sqrtdr = sqrt(wri[IDN]);
+  double isdlpdr = 1.0/(sqrtdl + sqrtdr);
+  double v1 = (sqrtdl*wli[IVX] + sqrtdr*wri[IVX])*isdlpdr;
+  double v2 = (sqrtdl*wli[IVY] + sqrtdr*wri[IVY])*isdlpdr;
+  double v3 = (sqrtdl*wli[IVZ] + sqrtdr*wri[IVZ])*isdlpdr;
+  double el = wli[IPR]/gm1 + 0.5*wli[IDN]*(sqr(wli[IVX]) + sqr(wli[IVY]) + sqr(wli[IVZ]));
+  double er = wri[IPR]/gm1 + 0.5*wri[IDN]*(sqr(wri[IVX]) + sqr(wri[IVY]) + sqr(wri[IVZ]));
+  double h = ((el + wli[IPR])/sqrtdl + (er + wri[IPR])/sqrtdr)*isdlpdr;
+  double mxl = wli[IDN]*wli[IVX];
+  double mxr = wri[IDN]*wri[IVX];
+  double fl[5], fr[5], du[5], ev[5];
+  fl[IDN] = mxl;
+  fr[IDN] = mxr;
+  fl[IVX] = mxl*wli[IVX];
+  fr[IVX] = mxr*wri[IVX];
+  fl[IVY] = mxl*wli[IVY];
+  fr[IVY] = mxr*wri[IVY];
+  fl[IVZ] = mxl*wli[IVZ];
+  fr[IVZ] = mxr*wri[IVZ];
+  fl[IVX] += wli[IPR];
+  fr[IVX] += wri[IPR];
+  fl[IEN] = (el + wli[IPR])*wli[IVX];
+  fr[IEN] = (er + wri[IPR])*wri[IVX];
+  du[IDN] = wri[IDN]          - wli[IDN];
+  du[IVX] = wri[IDN]*wri[IVX] - wli[IDN]*wli[IVX];
+  du[IVY] = wri[IDN]*wri[IVY] - wli[IDN]*wli[IVY];
+  du[IVZ] = wri[IDN]*wri[IVZ] - wli[IDN]*wli[IVZ];
+  du[IEN] = er - el;
+#pragma unroll
+  for (int n = 0; n < 5; ++n) flxi[n] = 0.5*(fl[n] + fr[n]);
+  int llf_flag = 0;
+  {  // RoeFlux (roe.cpp:206-290)
+    double vsq = v1*v1 + v2*v2 + v3*v3;
+    double q = h - 0.5*vsq;
+    double cs_sq = (q < 0.0) ? (1.0e-20) : gm1*q;
+    double cs = sqrt(cs_sq);
+    ev[0] = v1 - cs;
+    ev[1] = v1;
+    ev[2] = v1;
+    ev[3] = v1;
+    ev[4] = v1 + cs;
+    double a[5];
+    double na = 0.5/cs_sq;
+    a[0]  = du[0]*(0.5*gm1*vsq + v1*cs);
+    a[0] -= du[1]*(gm1*v1 + cs);
+    a[0] -= du[2]*gm1*v2;
+    a[0] -= du[3]*gm1*v3;
+    a[0] += du[4]*gm1;
+    a[0] *= na;
+    a[1]  = du[0]*(-v2);
+    a[1] += du[2];
+    a[2]  = du[0]*(-v3);
+    a[2] += du[3];
+    double qa = gm1/cs_sq;
+    a[3]  = du[0]*(1.0 - na*gm1*vsq);
+    a[3] += du[1]*qa*v1;
+    a[3] += du[2]*qa*v2;
+    a[3] += du[3]*qa*v3;
+    a[3] -= du[4]*qa;
+    a[4]  = du[0]*(0.5*gm1*vsq - v1*cs);
+    a[4] -= du[1]*(gm1*v1 - cs);
+    a[4] -= du[2]*gm1*v2;
+    a[4] -= du[3]*gm1*v3;
+    a[4] += du[4]*gm1;
+    a[4] *= na;
+    double coeff[5];
+#pragma unroll
+    for (int n = 0; n < 5; ++n) coeff[n] = -0.5*fabs(ev[n])*a[n];
+    double dens = wli[IDN] + a[0];
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[3];
+    if (dens < 0.0) llf_flag = 1;
+    flxi[0] += coeff[0];
+    flxi[0] += coeff[3];
+    flxi[0] += coeff[4];
+    flxi[1] += coeff[0]*(v1 - cs);
+    flxi[1] += coeff[3]*v1;
+    flxi[1] += coeff[4]*(v1 + cs);
+    flxi[2] += coeff[0]*v2;
+    flxi[2] += coeff[1];
+    flxi[2] += coeff[3]*v2;
+    flxi[2] += coeff[4]*v2;
+    flxi[3] += coeff[0]*v3;
+    flxi[3] += coeff[2];
+    flxi[3] += coeff[3]*v3;
+    flxi[3] += coeff[4]*v3;
+    flxi[4] += coeff[0]*(h - v1*cs);
+    flxi[4] += coeff[1]*v2;
+    flxi[4] += coeff[2]*v3;
+    flxi[4] += coeff[3]*0.5*vsq;
+    flxi[4] += coeff[4]*(h + v1*cs);
+  }
+  if (ev[0] >= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) flxi[n] = fl[n];
+  }
+  if (ev[4] <= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) flxi[n] = fr[n];
+  }
+  if (llf_flag != 0) {
+    double cl = sound_speed(gamma, wli[IDN], wli[IPR]);
+    double cr = sound_speed(gamma, wri[IDN], wri[IPR]);
+    double a = 0.5*dmax((fabs(wli[IVX]) + cl), (fabs(wri[IVX]) + cr));
+#pragma unroll
+    for (int n = 0; n < 5; ++n) flxi[n] = 0.5*(fl[n] + fr[n]) - a*du[n];
+  }
+}
+
+// ------------------------------------------------------------------------ MHD solvers
+// wl/wr: (IDN, vx, vy, vz, IPR, By, Bz); f: (IDN, mx, my, mz, IEN, F(By), F(Bz)).
+
+struct Cons1D { double d, mx, my, mz, e, by, bz; };
+
+// HLLD (hydro/rsolvers/mhd/hlld.cpp:38-382)
+AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
+                double *flxi) {
+  const double SMALL_NUMBER = 1.0e-8;
+  Cons1D ul, ur, ulst, uldst, urdst, urst, fl, fr;
+  double spd0, spd1, spd2, spd3, spd4;
+  double igm1 = 1.0/(gamma - 1.0);
+  double bxsq = bxi*bxi;
+  double pbl = 0.5*(bxsq + (sqr(wli[IBY]) + sqr(wli[IBZ])));
+  double pbr = 0.5*(bxsq + (sqr(wri[IBY]) + sqr(wri[IBZ])));
+  double kel = 0.5*wli[IDN]*(sqr(wli[IVX]) + (sqr(wli[IVY]) + sqr(wli[IVZ])));
+  double ker = 0.5*wri[IDN]*(sqr(wri[IVX]) + (sqr(wri[IVY]) + sqr(wri[IVZ])));
+  ul.d  = wli[IDN];
+  ul.mx = wli[IVX]*ul.d;
+  ul.my = wli[IVY]*ul.d;
+  ul.mz = wli[IVZ]*ul.d;
+  ul.e  = wli[IPR]*igm1 + kel + pbl;
+  ul.by = wli[IBY];
+  ul.bz = wli[IBZ];
+  ur.d  = wri[IDN];
+  ur.mx = wri[IVX]*ur.d;
+  ur.my = wri[IVY]*ur.d;
+  ur.mz = wri[IVZ]*ur.d;
+  ur.e  = wri[IPR]*igm1 + ker + pbr;
+  ur.by = wri[IBY];
+  ur.bz = wri[IBZ];
+  double cfl = fast_speed(gamma, wli[IDN], wli[IPR], wli[IBY], wli[IBZ], bxi);
+  double cfr = fast_speed(gamma, wri[IDN], wri[IPR], wri[IBY], wri[IBZ], bxi);
+  spd0 = dmin(wli[IVX]-cfl, wri[IVX]-cfr);
+  spd4 = dmax(wli[IVX]+cfl, wri[IVX]+cfr);
+  double ptl = wli[IPR] + pbl;
+  double ptr = wri[IPR] + pbr;
+  fl.d  = ul.mx;
+  fl.mx = ul.mx*wli[IVX] + ptl - bxsq;
+  fl.my = ul.my*wli[IVX] - bxi*ul.by;
+  fl.mz = ul.mz*wli[IVX] - bxi*ul.bz;
+  fl.e  = wli[IVX]*(ul.e + ptl - bxsq) - bxi*(wli[IVY]*ul.by + wli[IVZ]*ul.bz);
+  fl.by = ul.by*wli[IVX] - bxi*wli[IVY];
+  fl.bz = ul.bz*wli[IVX] - bxi*wli[IVZ];
+  fr.d  = ur.mx;
+  fr.mx = ur.mx*wri[IVX] + ptr - bxsq;
+  fr.my = ur.my*wri[IVX] - bxi*ur.by;
+  fr.mz = ur.mz*wri[IVX] - bxi*ur.bz;
+  fr.e  = wri[IVX]*(ur.e + ptr - bxsq) - bxi*(wri[IVY]*ur.by + wri[IVZ]*ur.bz);
+  fr.by = ur.by*wri[IVX] - bxi*wri[IVY];
+  fr.bz = ur.bz*wri[IVX] - bxi*wri[IVZ];
+  double sdl = spd0 - wli[IVX];
+  double sdr = spd4 - wri[IVX];
+  spd2 = (sdr*ur.mx - sdl*ul.mx + (ptl - ptr))/(sdr*ur.d - sdl*ul.d);
+  double sdml = spd0 - spd2;
+  double sdmr = spd4 - spd2;
+  double sdml_inv = 1.0/sdml;
+  double sdmr_inv = 1.0/sdmr;
+  ulst.d = ul.d*sdl*sdml_inv;
+  urst.d = ur.d*sdr*sdmr_inv;
+  double ulst_d_inv = 1.0/ulst.d;
+  double urst_d_inv = 1.0/urst.d;
+  double sqrtdl = sqrt(ulst.d);
+  double sqrtdr = sqrt(urst.d);
+  spd1 = spd2 - fabs(bxi)/sqrtdl;
+  spd3 = spd2 + fabs(bxi)/sqrtdr;
+  double ptstl = ptl + ul.d*sdl*(spd2-wli[IVX]);
+  double ptstr = ptr + ur.d*sdr*(spd2-wri[IVX]);
+  double ptst = 0.5*(ptstr + ptstl);
+  ulst.mx = ulst.d*spd2;
+  if (fabs(ul.d*sdl*sdml-bxsq) < (SMALL_NUMBER)*ptst) {
+    ulst.my = ulst.d*wli[IVY];
+    ulst.mz = ulst.d*wli[IVZ];
+    ulst.by = ul.by;
+    ulst.bz = ul.bz;
+  } else {
+    double tmp = bxi*(sdl - sdml)/(ul.d*sdl*sdml - bxsq);
+    ulst.my = ulst.d*(wli[IVY] - ul.by*tmp);
+    ulst.mz = ulst.d*(wli[IVZ] - ul.bz*tmp);
+    tmp = (ul.d*sqr(sdl) - bxsq)/(ul.d*sdl*sdml - bxsq);
+    ulst.by = ul.by*tmp;
+    ulst.bz = ul.bz*tmp;
+  }
+  double vbstl = (ulst.mx*bxi+(ulst.my*ulst.by+ulst.mz*ulst.bz))*ulst_d_inv;
+  ulst.e = (sdl*ul.e - ptl*wli[IVX] + ptst*spd2 +
+            bxi*(wli[IVX]*bxi + (wli[IVY]*ul.by + wli[IVZ]*ul.bz) - vbstl))*sdml_inv;
+  urst.mx = urst.d*spd2;
+  if (fabs(ur.d*sdr*sdmr - bxsq) < (SMALL_NUMBER)*ptst) {
+    urst.my = urst.d*wri[IVY];
+    urst.mz = urst.d*wri[IVZ];
+    urst.by = ur.by;
+    urst.bz = ur.bz;
+  } else {
+    double tmp = bxi*(sdr - sdmr)/(ur.d*sdr*sdmr - bxsq);
+    urst.my = urst.d*(wri[IVY] - ur.by*tmp);
+    urst.mz = urst.d*(wri[IVZ] - ur.bz*tmp);
+    tmp = (ur.d*sqr(sdr) - bxsq)/(ur.d*sdr*sdmr - bxsq);
+    urst.by = ur.by*tmp;
+    urst.bz = ur.bz*tmp;
+  }
+  double vbstr = (urst.mx*bxi+(urst.my*urst.by+urst.mz*urst.bz))*urst_d_inv;
+  urst.e = (sdr*ur.e - ptr*wri[IVX] + ptst*spd2 +
+            bxi*(wri[IVX]*bxi + (wri[IVY]*ur.by + wri[IVZ]*ur.bz) - vbstr))*sdmr_inv;
+  if (0.5*bxsq < (SMALL_NUMBER)*ptst) {
+    uldst = ulst;
+    urdst = urst;
+  } else {
+    double invsumd = 1.0/(sqrtdl + sqrtdr);
+    double bxsig = (bxi > 0.0 ? 1.0 : -1.0);
+    uldst.d = ulst.d;
+    urdst.d = urst.d;
+    uldst.mx = ulst.mx;
+    urdst.mx = urst.mx;
+    double tmp = invsumd*(sqrtdl*(ulst.my*ulst_d_inv) + sqrtdr*(urst.my*urst_d_inv) +
+                          bxsig*(urst.by - ulst.by));
+    uldst.my = uldst.d*tmp;
+    urdst.my = urdst.d*tmp;
+    tmp = invsumd*(sqrtdl*(ulst.mz*ulst_d_inv) + sqrtdr*(urst.mz*urst_d_inv) +
+                   bxsig*(urst.bz - ulst.bz));
+    uldst.mz = uldst.d*tmp;
+    urdst.mz = urdst.d*tmp;
+    tmp = invsumd*(sqrtdl*urst.by + sqrtdr*ulst.by +
+                   bxsig*sqrtdl*sqrtdr*((urst.my*urst_d_inv) - (ulst.my*ulst_d_inv)));
+    uldst.by = urdst.by = tmp;
+    tmp = invsumd*(sqrtdl*urst.bz + sqrtdr*ulst.bz +
+                   bxsig*sqrtdl*sqrtdr*((urst.mz*urst_d_inv) - (ulst.mz*ulst_d_inv)));
+    uldst.bz = urdst.bz = tmp;
+    tmp = spd2*bxi + (uldst.my*uldst.by + uldst.mz*uldst.bz)/uldst.d;
+    uldst.e = ulst.e - sqrtdl*bxsig*(vbstl - tmp);
+    urdst.e = urst.e + sqrtdr*bxsig*(vbstr - tmp);
+  }
+  // Step 6 of the reference evaluates all four wave-jump terms and then selects; only the
+  // terms of the selected branch are evaluated here (same operations, same order).
+  if (spd0 >= 0.0) {
+    flxi[IDN] = fl.d; flxi[IVX] = fl.mx; flxi[IVY] = fl.my; flxi[IVZ] = fl.mz;
+    flxi[IEN] = fl.e; flxi[IBY] = fl.by; flxi[IBZ] = fl.bz;
+  } else if (spd4 <= 0.0) {
+    flxi[IDN] = fr.d; flxi[IVX] = fr.mx; flxi[IVY] = fr.my; flxi[IVZ] = fr.mz;
+    flxi[IEN] = fr.e; flxi[IBY] = fr.by; flxi[IBZ] = fr.bz;
+  } else if (spd1 >= 0.0) {
+    flxi[IDN] = fl.d  + spd0*(ulst.d - ul.d);
+    flxi[IVX] = fl.mx + spd0*(ulst.mx - ul.mx);
+    flxi[IVY] = fl.my + spd0*(ulst.my - ul.my);
+    flxi[IVZ] = fl.mz + spd0*(ulst.mz - ul.mz);
+    flxi[IEN] = fl.e  + spd0*(ulst.e - ul.e);
+    flxi[IBY] = fl.by + spd0*(ulst.by - ul.by);
+    flxi[IBZ] = fl.bz + spd0*(ulst.bz - ul.bz);
+  } else if (spd2 >= 0.0) {
+    flxi[IDN] = fl.d  + spd0*(ulst.d - ul.d) + spd1*(uldst.d - ulst.d);
+    flxi[IVX] = fl.mx + spd0*(ulst.mx - ul.mx) + spd1*(uldst.mx - ulst.mx);
+    flxi[IVY] = fl.my + spd0*(ulst.my - ul.my) + spd1*(uldst.my - ulst.my);
+    flxi[IVZ] = fl.mz + spd0*(ulst.mz - ul.mz) + spd1*(uldst.mz - ulst.mz);
+    flxi[IEN] = fl.e  + spd0*(ulst.e - ul.e) + spd1*(uldst.e - ulst.e);
+    flxi[IBY] = fl.by + spd0*(ulst.by - ul.by) + spd1*(uldst.by - ulst.by);
+    flxi[IBZ] = fl.bz + spd0*(ulst.bz - ul.bz) + spd1*(uldst.bz - ulst.bz);
+  } else if (spd3 > 0.0) {
+    flxi[IDN] = fr.d + spd4*(urst.d - ur.d) + spd3*(urdst.d - urst.d);
+    flxi[IVX] = fr.mx + spd4*(urst.mx - ur.mx) + spd3*(urdst.mx - urst.mx);
+    flxi[IVY] = fr.my + spd4*(urst.my - ur.my) + spd3*(urdst.my - urst.my);
+    flxi[IVZ] = fr.mz + spd4*(urst.mz - ur.mz) + spd3*(urdst.mz - urst.mz);
+    flxi[IEN] = fr.e + spd4*(urst.e - ur.e) + spd3*(urdst.e - urst.e);
+    flxi[IBY] = fr.by + spd4*(urst.by - ur.by) + spd3*(urdst.by - urst.by);
+    flxi[IBZ] = fr.bz + spd4*(urst.bz - ur.bz) + spd3*(urdst.bz - urst.bz);
+  } else {
+    flxi[IDN] = fr.d  + spd4*(urst.d - ur.d);
+    flxi[IVX] = fr.mx + spd4*(urst.mx - ur.mx);
+    flxi[IVY] = fr.my + spd4*(urst.my - ur.my);
+    flxi[IVZ] = fr.mz + spd4*(urst.mz - ur.mz);
+    flxi[IEN] = fr.e  + spd4*(urst.e - ur.e);
+    flxi[IBY] = fr.by + spd4*(urst.by - ur.by);
+    flxi[IBZ] = fr.bz + spd4*(urst.bz - ur.bz);
+  }
+}
+
+// Roe averages shared by hlle_mhd.cpp:64-85 and roe_mhd.cpp:92-113
+struct RoeAvgMHD { double d, v1, v2, v3, b2, b3, x, y, pbl, pbr, el, er, h; };
+
+AB_HD void roe_avg_mhd(const double *wli, const double *wri, double bxi, double gm1,
+                       RoeAvgMHD &r) {
+  double sqrtdl = sqrt(wli[IDN]);
+  double sqrtdr = sqrt(wri[IDN]);
+  double isdlpdr = 1.0/(sqrtdl + sqrtdr);
+  r.d = sqrtdl*sqrtdr;
+  r.v1 = (sqrtdl*wli[IVX] + sqrtdr*wri[IVX])*isdlpdr;
+  r.v2 = (sqrtdl*wli[IVY] + sqrtdr*wri[IVY])*isdlpdr;
+  r.v3 = (sqrtdl*wli[IVZ] + sqrtdr*wri[IVZ])*isdlpdr;
+  r.b2 = (sqrtdr*wli[IBY] + sqrtdl*wri[IBY])*isdlpdr;
+  r.b3 = (sqrtdr*wli[IBZ] + sqrtdl*wri[IBZ])*isdlpdr;
+  r.x = 0.5*(sqr(wli[IBY]-wri[IBY]) + sqr(wli[IBZ]-wri[IBZ]))/(sqr(sqrtdl+sqrtdr));
+  r.y = 0.5*(wli[IDN] + wri[IDN])/r.d;
+  r.pbl = 0.5*(bxi*bxi + sqr(wli[IBY]) + sqr(wli[IBZ]));
+  r.pbr = 0.5*(bxi*bxi + sqr(wri[IBY]) + sqr(wri[IBZ]));
+  r.el = wli[IPR]/gm1 + 0.5*wli[IDN]*(sqr(wli[IVX])+sqr(wli[IVY])+sqr(wli[IVZ])) + r.pbl;
+  r.er = wri[IPR]/gm1 + 0.5*wri[IDN]*(sqr(wri[IVX])+sqr(wri[IVY])+sqr(wri[IVZ])) + r.pbr;
+  r.h = ((r.el + wli[IPR] + r.pbl)/sqrtdl + (r.er + wri[IPR] + r.pbr)/sqrtdr)*isdlpdr;
+}
+
+// HLLE, adiabatic MHD (hydro/rsolvers/mhd/hlle_mhd.cpp:25-182)
+AB_HD void hlle_mhd(const double *wli, const double *wri, double bxi, double gamma,
+                    double *flxi) {
+  double gm1 = gamma - 1.0;
+  RoeAvgMHD r;
+  roe_avg_mhd(wli, wri, bxi, gm1, r);
+  double cl = fast_speed(gamma, wli[IDN], wli[IPR], wli[IBY], wli[IBZ], bxi);
+  double cr = fast_speed(gamma, wri[IDN], wri[IPR], wri[IBY], wri[IBZ], bxi);
+  double btsq = sqr(r.b2) + sqr(r.b3);
+  double vaxsq = bxi*bxi/r.d;
+  double bt_starsq = (gm1 - (gm1 - 1.0)*r.y)*btsq;
+  double hp = r.h - (vaxsq + btsq/r.d);
+  double vsq = sqr(r.v1) + sqr(r.v2) + sqr(r.v3);
+  double twid_asq = dmax((gm1*(hp-0.5*vsq)-(gm1-1.0)*r.x), 0.0);
+  double ct2 = bt_starsq/r.d;
+  double tsum = vaxsq + ct2 + twid_asq;
+  double tdif = vaxsq + ct2 - twid_asq;
+  double cf2_cs2 = sqrt(tdif*tdif + 4.0*twid_asq*ct2);
+  double cfsq = 0.5*(tsum + cf2_cs2);
+  double a = sqrt(cfsq);
+  double al = dmin((r.v1 - a), (wli[IVX] - cl));
+  double ar = dmax((r.v1 + a), (wri[IVX] + cr));
+  double bp = ar > 0.0 ? ar : 0.0;
+  double bm = al < 0.0 ? al : 0.0;
+  double vxl = wli[IVX] - bm;
+  double vxr = wri[IVX] - bp;
+  double fl[7], fr[7];
+  fl[IDN] = wli[IDN]*vxl;
+  fr[IDN] = wri[IDN]*vxr;
+  fl[IVX] = wli[IDN]*wli[IVX]*vxl + r.pbl - sqr(bxi);
+  fr[IVX] = wri[IDN]*wri[IVX]*vxr + r.pbr - sqr(bxi);
+  fl[IVY] = wli[IDN]*wli[IVY]*vxl - bxi*wli[IBY];
+  fr[IVY] = wri[IDN]*wri[IVY]*vxr - bxi*wri[IBY];
+  fl[IVZ] = wli[IDN]*wli[IVZ]*vxl - bxi*wli[IBZ];
+  fr[IVZ] = wri[IDN]*wri[IVZ]*vxr - bxi*wri[IBZ];
+  fl[IVX] += wli[IPR];
+  fr[IVX] += wri[IPR];
+  fl[IEN] = r.el*vxl + wli[IVX]*(wli[IPR] + r.pbl - bxi*bxi);
+  fr[IEN] = r.er*vxr + wri[IVX]*(wri[IPR] + r.pbr - bxi*bxi);
+  fl[IEN] -= bxi*(wli[IBY]*wli[IVY] + wli[IBZ]*wli[IVZ]);
+  fr[IEN] -= bxi*(wri[IBY]*wri[IVY] + wri[IBZ]*wri[IVZ]);
+  fl[IBY] = wli[IBY]*vxl - bxi*wli[IVY];
+  fr[IBY] = wri[IBY]*vxr - bxi*wri[IVY];
+  fl[IBZ] = wli[IBZ]*vxl - bxi*wli[IVZ];
+  fr[IBZ] = wri[IBZ]*vxr - bxi*wri[IVZ];
+  double tmp = 0.0;
+  if (bp != bm) tmp = 0.5*(bp + bm)/(bp - bm);
+#pragma unroll
+  for (int n = 0; n < 7; ++n) flxi[n] = 0.5*(fl[n]+fr[n]) + (fl[n]-fr[n])*tmp;
+}
+
+// RoeFlux, adiabatic MHD (hydro/rsolvers/mhd/roe_mhd.cpp:245-470)
+AB_HD void roe_flux_mhd(const RoeAvgMHD &r, double b1, const double *du, double wl_d,
+                        double gm1, double *flx, double &ev0, double &ev6, int &llf_flag) {
+  double d = r.d, v1 = r.v1, v2 = r.v2, v3 = r.v3, b2 = r.b2, b3 = r.b3, x = r.x, y = r.y;
+  double di = 1.0/d;
+  double btsq = b2*b2 + b3*b3;
+  double vaxsq = b1*b1*di;
+  double vsq = v1*v1 + v2*v2 + v3*v3;
+  double hp = r.h - (vaxsq + btsq*di);
+  double bt_starsq = (gm1 - (gm1 - 1.0)*y)*btsq;
+  double twid_csq = dmax((gm1*(hp-0.5*vsq)-(gm1-1.0)*x), 1.0e-20);
+  double ct2 = bt_starsq*di;
+  double tsum = vaxsq + ct2 + twid_csq;
+  double tdif = vaxsq + ct2 - twid_csq;
+  double cf2_cs2 = sqrt(tdif*tdif + 4.0*twid_csq*ct2);
+  double cfsq = 0.5*(tsum + cf2_cs2);
+  double cf = sqrt(cfsq);
+  double cssq = twid_csq*vaxsq/cfsq;
+  double cs = sqrt(cssq);
+  double bt = sqrt(btsq);
+  double bt_star = sqrt(bt_starsq);
+  double bet2 = 0.0;
+  double bet3 = 0.0;
+  if (bt != 0.0) {
+    bet2 = b2/bt;
+    bet3 = b3/bt;
+  }
+  double bet2_star = bet2/sqrt(gm1 - (gm1-1.0)*y);
+  double bet3_star = bet3/sqrt(gm1 - (gm1-1.0)*y);
+  double bet_starsq = bet2_star*bet2_star + bet3_star*bet3_star;
+  double vbet = v2*bet2_star + v3*bet3_star;
+  double q2_star = 0.0;
+  double q3_star = 0.0;
+  if (bet_starsq != 0.0) {
+    q2_star = bet2_star/bet_starsq;
+    q3_star = bet3_star/bet_starsq;
+  }
+  double alpha_f, alpha_s;
+  if ((cfsq - cssq) <= 0.0) {
+    alpha_f = 1.0;
+    alpha_s = 0.0;
+  } else if ((twid_csq - cssq) <= 0.0) {
+    alpha_f = 0.0;
+    alpha_s = 1.0;
+  } else if ((cfsq - twid_csq) <= 0.0) {
+    alpha_f = 1.0;
+    alpha_s = 0.0;
+  } else {
+    alpha_f = sqrt((twid_csq - cssq)/(cfsq - cssq));
+    alpha_s = sqrt((cfsq - twid_csq)/(cfsq - cssq));
+  }
+  double sqrtd = sqrt(d);
+  double isqrtd = 1.0/sqrtd;
+  double s = sgn(b1);
+  double twid_c = sqrt(twid_csq);
+  double qf = cf*alpha_f*s;
+  double qs = cs*alpha_s*s;
+  double af_prime = twid_c*alpha_f*isqrtd;
+  double as_prime = twid_c*alpha_s*isqrtd;
+  double afpbb = af_prime*bt_star*bet_starsq;
+  double aspbb = as_prime*bt_star*bet_starsq;
+  double vqstr = (v2*q2_star + v3*q3_star);
+  double vax = sqrt(vaxsq);
+  double norm = 0.5/twid_csq;
+  double cff = norm*alpha_f*cf;
+  double css = norm*alpha_s*cs;
+  double qf_hat = qf*norm;
+  double qs_hat = qs*norm;
+  double af = norm*af_prime*d;
+  double as = norm*as_prime*d;
+  double afpb = norm*af_prime*bt_star;
+  double aspb = norm*as_prime*bt_star;
+
+  double ev[7];
+  ev[0] = v1 - cf;
+  ev[1] = v1 - vax;
+  ev[2] = v1 - cs;
+  ev[3] = v1;
+  ev[4] = v1 + cs;
+  ev[5] = v1 + vax;
+  ev[6] = v1 + cf;
+  ev0 = ev[0];
+  ev6 = ev[6];
+
+  double a[7];
+  double alpha_f_bar = alpha_f*gm1*norm;
+  double alpha_s_bar = alpha_s*gm1*norm;
+  double gm1a = gm1/twid_csq;
+
+  a[0]  = du[0]*(alpha_f_bar*(vsq-hp) + cff*(cf+v1) - qs_hat*vqstr - aspb);
+  a[0] -= du[1]*(alpha_f_bar*v1 + cff);
+  a[0] -= du[2]*(alpha_f_bar*v2 - qs_hat*q2_star);
+  a[0] -= du[3]*(alpha_f_bar*v3 - qs_hat*q3_star);
+  a[0] += du[4]*alpha_f_bar;
+  a[0] += du[5]*(as*q2_star - alpha_f_bar*b2);
+  a[0] += du[6]*(as*q3_star - alpha_f_bar*b3);
+
+  a[1]  = du[0]*(v2*bet3 - v3*bet2);
+  a[1] -= du[2]*bet3;
+  a[1] += du[3]*bet2;
+  a[1] -= du[5]*sqrtd*bet3*s;
+  a[1] += du[6]*sqrtd*bet2*s;
+  a[1] *= 0.5;
+
+  a[2]  = du[0]*(alpha_s_bar*(vsq-hp) + css*(cs+v1) + qf_hat*vqstr + afpb);
+  a[2] -= du[1]*(alpha_s_bar*v1 + css);
+  a[2] -= du[2]*(alpha_s_bar*v2 + qf_hat*q2_star);
+  a[2] -= du[3]*(alpha_s_bar*v3 + qf_hat*q3_star);
+  a[2] += du[4]*alpha_s_bar;
+  a[2] -= du[5]*(af*q2_star + alpha_s_bar*b2);
+  a[2] -= du[6]*(af*q3_star + alpha_s_bar*b3);
+
+  a[3]  = du[0]*(1.0 - gm1a*(0.5*vsq - (gm1-1.0)*x/gm1));
+  a[3] += du[1]*gm1a*v1;
+  a[3] += du[2]*gm1a*v2;
+  a[3] += du[3]*gm1a*v3;
+  a[3] -= du[4]*gm1a;
+  a[3] += du[5]*gm1a*b2;
+  a[3] += du[6]*gm1a*b3;
+
+  a[4]  = du[0]*(alpha_s_bar*(vsq-hp) + css*(cs-v1) - qf_hat*vqstr + afpb);
+  a[4] -= du[1]*(alpha_s_bar*v1 - css);
+  a[4] -= du[2]*(alpha_s_bar*v2 - qf_hat*q2_star);
+  a[4] -= du[3]*(alpha_s_bar*v3 - qf_hat*q3_star);
+  a[4] += du[4]*alpha_s_bar;
+  a[4] -= du[5]*(af*q2_star + alpha_s_bar*b2);
+  a[4] -= du[6]*(af*q3_star + alpha_s_bar*b3);
+
+  a[5]  = du[0]*(v3*bet2 - v2*bet3);
+  a[5] += du[2]*bet3;
+  a[5] -= du[3]*bet2;
+  a[5] -= du[5]*sqrtd*bet3*s;
+  a[5] += du[6]*sqrtd*bet2*s;
+  a[5] *= 0.5;
+
+  a[6]  = du[0]*(alpha_f_bar*(vsq-hp) + cff*(cf-v1) + qs_hat*vqstr - aspb);
+  a[6] -= du[1]*(alpha_f_bar*v1 - cff);
+  a[6] -= du[2]*(alpha_f_bar*v2 + qs_hat*q2_star);
+  a[6] -= du[3]*(alpha_f_bar*v3 + qs_hat*q3_star);
+  a[6] += du[4]*alpha_f_bar;
+  a[6] += du[5]*(as*q2_star - alpha_f_bar*b2);
+  a[6] += du[6]*(as*q3_star - alpha_f_bar*b3);
+
+  double coeff[7];
+#pragma unroll
+  for (int n = 0; n < 7; ++n) coeff[n] = -0.5*fabs(ev[n])*a[n];
+
+  double dens = wl_d + a[0]*alpha_f;
+  if (dens < 0.0) llf_flag = 1;
+  dens += a[2]*alpha_s;
+  if (dens < 0.0) llf_flag = 1;
+  dens += a[3];
+  if (dens < 0.0) llf_flag = 1;
+  dens += a[4]*alpha_s;
+  if (dens < 0.0) llf_flag = 1;
+
+  flx[0] += coeff[0]*alpha_f;
+  flx[0] += coeff[2]*alpha_s;
+  flx[0] += coeff[3];
+  flx[0] += coeff[4]*alpha_s;
+  flx[0] += coeff[6]*alpha_f;
+
+  flx[1] += coeff[0]*(alpha_f*(v1 - cf));
+  flx[1] += coeff[2]*(alpha_s*(v1 - cs));
+  flx[1] += coeff[3]*v1;
+  flx[1] += coeff[4]*(alpha_s*(v1 + cs));
+  flx[1] += coeff[6]*(alpha_f*(v1 + cf));
+
+  flx[2] += coeff[0]*(alpha_f*v2 + qs*bet2_star);
+  flx[2] -= coeff[1]*bet3;
+  flx[2] += coeff[2]*(alpha_s*v2 - qf*bet2_star);
+  flx[2] += coeff[3]*v2;
+  flx[2] += coeff[4]*(alpha_s*v2 + qf*bet2_star);
+  flx[2] += coeff[5]*bet3;
+  flx[2] += coeff[6]*(alpha_f*v2 - qs*bet2_star);
+
+  flx[3] += coeff[0]*(alpha_f*v3 + qs*bet3_star);
+  flx[3] += coeff[1]*bet2;
+  flx[3] += coeff[2]*(alpha_s*v3 - qf*bet3_star);
+  flx[3] += coeff[3]*v3;
+  flx[3] += coeff[4]*(alpha_s*v3 + qf*bet3_star);
+  flx[3] -= coeff[5]*bet2;
+  flx[3] += coeff[6]*(alpha_f*v3 - qs*bet3_star);
+
+  flx[4] += coeff[0]*(alpha_f*(hp - v1*cf) + qs*vbet + aspbb);
+  flx[4] -= coeff[1]*(v2*bet3 - v3*bet2);
+  flx[4] += coeff[2]*(alpha_s*(hp - v1*cs) - qf*vbet - afpbb);
+  flx[4] += coeff[3]*(0.5*vsq + (gm1-1.0)*x/gm1);
+  flx[4] += coeff[4]*(alpha_s*(hp + v1*cs) + qf*vbet - afpbb);
+  flx[4] += coeff[5]*(v1*bet3 - v3*bet2);
+  flx[4] += coeff[6]*(alpha_f*(hp + v1*cf) - qs*vbet + aspbb);
+
+  flx[5] += coeff[0]*as_prime*bet2_star;
+  flx[5] -= coeff[1]*bet3*s*isqrtd;
+  flx[5] -= coeff[2]*af_prime*bet2_star;
+  flx[5] -= coeff[4]*af_prime*bet2_star;
+  flx[5] -= coeff[5]*bet3*s*isqrtd;
+  flx[5] += coeff[6]*as_prime*bet2_star;
+
+  flx[6] += coeff[0]*as_prime*bet3_star;
+  flx[6] += coeff[1]*bet2*s*isqrtd;
+  flx[6] -= coeff[2]*af_prime*bet3_star;
+  flx[6] -= coeff[4]*af_prime*bet3_star;
+  flx[6] += coeff[5]*bet2*s*isqrtd;
+  flx[6] += coeff[6]*as_prime*bet3_star;
+}
+
+// Roe, adiabatic MHD (hydro/rsolvers/mhd/roe_mhd.cpp:43-238)
+AB_HD void roe_mhd(const double *wli, const double *wri, double bxi, double gamma,
+                   double *flxi) {
+  double gm1 = gamma - 1.0;
+  RoeAvgMHD r;
+  roe_avg_mhd(wli, wri, bxi, gm1, r);
+  double fl[7], fr[7], du[7];
+  double mxl = wli[IDN]*wli[IVX];
+  double mxr = wri[IDN]*wri[IVX];
+  fl[IDN] = mxl;
+  fr[IDN] = mxr;
+  fl[IVX] = mxl*wli[IVX] + r.pbl - sqr(bxi);
+  fr[IVX] = mxr*wri[IVX] + r.pbr - sqr(bxi);
+  fl[IVY] = mxl*wli[IVY] - bxi*wli[IBY];
+  fr[IVY] = mxr*wri[IVY] - bxi*wri[IBY];
+  fl[IVZ] = mxl*wli[IVZ] - bxi*wli[IBZ];
+  fr[IVZ] = mxr*wri[IVZ] - bxi*wri[IBZ];
+  fl[IVX] += wli[IPR];
+  fr[IVX] += wri[IPR];
+  fl[IEN] = (r.el + wli[IPR] + r.pbl - bxi*bxi)*wli[IVX];
+  fr[IEN] = (r.er + wri[IPR] + r.pbr - bxi*bxi)*wri[IVX];
+  fl[IEN] -= bxi*(wli[IBY]*wli[IVY] + wli[IBZ]*wli[IVZ]);
+  fr[IEN] -= bxi*(wri[IBY]*wri[IVY] + wri[IBZ]*wri[IVZ]);
+  fl[IBY] = wli[IBY]*wli[IVX] - bxi*wli[IVY];
+  fr[IBY] = wri[IBY]*wri[IVX] - bxi*wri[IVY];
+  fl[IBZ] = wli[IBZ]*wli[IVX] - bxi*wli[IVZ];
+  fr[IBZ] = wri[IBZ]*wri[IVX] - bxi*wri[IVZ];
+  du[IDN] = wri[IDN]          - wli[IDN];
+  du[IVX] = wri[IDN]*wri[IVX] - wli[IDN]*wli[IVX];
+  du[IVY] = wri[IDN]*wri[IVY] - wli[IDN]*wli[IVY];
+  du[IVZ] = wri[IDN]*wri[IVZ] - wli[IDN]*wli[IVZ];
+  du[IEN] = r.er - r.el;
+  du[IBY] = wri[IBY] - wli[IBY];
+  du[IBZ] = wri[IBZ] - wli[IBZ];
+#pragma unroll
+  for (int n = 0; n < 7; ++n) flxi[n] = 0.5*(fl[n] + fr[n]);
+  int llf_flag = 0;
+  double ev0, ev6;
+  roe_flux_mhd(r, bxi, du, wli[IDN], gm1, flxi, ev0, ev6, llf_flag);
+  if (ev0 >= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 7; ++n) flxi[n] = fl[n];
+  }
+  if (ev6 <= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 7; ++n) flxi[n] = fr[n];
+  }
+  if (llf_flag != 0) {
+    double cfl = fast_speed(gamma, wli[IDN], wli[IPR], wli[IBY], wli[IBZ], bxi);
+    double cfr = fast_speed(gamma, wri[IDN], wri[IPR], wri[IBY], wri[IBZ], bxi);
+    double a = 0.5*dmax((fabs(wli[IVX]) + cfl), (fabs(wri[IVX]) + cfr));
+    // the reference's LLF fallback does not touch the IBY/IBZ fluxes (roe_mhd.cpp:222-232)
+#pragma unroll
+    for (int n = 0; n < 5; ++n) flxi[n] = 0.5*(fl[n] + fr[n]) - a*du[n];
+  }
+}
+
+// compile-time dispatch
+template <int SOLVER, bool MHD>
+AB_HD void riemann(const double *wli, const double *wri, double bxi, double gamma,
+                   double *flxi) {
+  if (!MHD) {
+    if (SOLVER == SOLVER_HLLC) hllc(wli, wri, gamma, flxi);
+    else if (SOLVER == SOLVER_HLLE) hlle_hydro(wli, wri, gamma, flxi);
+    else roe_hydro(wli, wri, gamma, flxi);
+  } else {
+    if (SOLVER == SOLVER_HLLD) hlld(wli, wri, bxi, gamma, flxi);
+    else if (SOLVER == SOLVER_HLLE) hlle_mhd(wli, wri, bxi, gamma, flxi);
+    else roe_mhd(wli, wri, bxi, gamma, flxi);
+  }
+}
+
+}  // namespace ab
+#endif  // AB_PHYSICS_CUH_

@@ -1,0 +1,213 @@
+"""Mesh: host mirror of the reference's Mesh / MeshBlock / TimeIntegratorTaskList surface for
+the accelerated path.  It owns no physics: every operation is a call through the C ABI
+(include/athena_b200.h) into the CUDA library; there is no CPU fallback.
+
+Reference surface mirrored: Mesh(pin) construction from <mesh>/<meshblock>/<time>/<hydro>
+(src/mesh/mesh.cpp:63-548), ProblemGenerator hook (src/pgen/default_pgen.cpp), Mesh::Initialize
+(mesh.cpp:1367-1651), the main loop (src/main.cpp:430-515) and the zone-cycle accounting
+(main.cpp:480,585-595).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib
+from .athinput import ParameterInput
+
+# EquationOfState ctor default floors: sqrt(1024*float_min) (src/eos/adiabatic_mhd.cpp:29-31)
+DEFAULT_FLOOR = float(np.sqrt(1024 * float(np.finfo(np.float32).tiny)))
+
+
+class MeshBlock:
+    """View of one local MeshBlock (index ranges as in src/mesh/meshblock.cpp:55-80)."""
+
+    def __init__(self, mesh, lid):
+        self.pmy_mesh, self.lid = mesh, lid
+        info = (C.c_long * 13)()
+        lib.check(mesh.L.ab_block_info(mesh.h, lid, info))
+        (self.gid, self.lx1, self.lx2, self.lx3, self.ncells1, self.ncells2, self.ncells3,
+         self.is_, self.ie, self.js, self.je, self.ks, self.ke) = [int(v) for v in info]
+
+    def shape(self, name):
+        n1, n2, n3 = self.ncells1, self.ncells2, self.ncells3
+        if name in ("u", "u1", "w"):
+            return (5, n3, n2, n1)
+        if name == "bcc":
+            return (3, n3, n2, n1)
+        if name in ("b1", "b1_1", "wght1", "e2_x1f", "e3_x1f"):
+            return (n3, n2, n1 + 1)
+        if name in ("b2", "b1_2", "wght2", "e1_x2f", "e3_x2f"):
+            return (n3, n2 + 1, n1)
+        if name in ("b3", "b1_3", "wght3", "e1_x3f", "e2_x3f"):
+            return (n3 + 1, n2, n1)
+        if name in ("flux1", "flux2", "flux3"):
+            d = int(name[-1]) - 1
+            s = [n3, n2, n1]
+            s[2 - d] += 1
+            return (5,) + tuple(s)
+        if name == "e1":
+            return (n3 + 1, n2 + 1, n1)
+        if name == "e2":
+            return (n3 + 1, n2, n1 + 1)
+        if name == "e3":
+            return (n3, n2 + 1, n1 + 1)
+        raise KeyError(name)
+
+    def get(self, name):
+        """Download a register (AthenaArray layout) into a new numpy array."""
+        m = self.pmy_mesh
+        a = np.empty(self.shape(name), dtype=np.float64)
+        assert a.size == m.L.ab_reg_size(m.h, self.lid, lib.REG[name]), name
+        lib.check(m.L.ab_download(m.h, self.lid, lib.REG[name],
+                                  a.ctypes.data_as(C.POINTER(C.c_double))))
+        return a
+
+    def set(self, name, a):
+        m = self.pmy_mesh
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == self.shape(name), (name, a.shape, self.shape(name))
+        lib.check(m.L.ab_upload(m.h, self.lid, lib.REG[name],
+                                a.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def coord(self, name):
+        m = self.pmy_mesh
+        n = {"x1f": self.ncells1 + 1, "x2f": self.ncells2 + 1, "x3f": self.ncells3 + 1,
+             "x1v": self.ncells1, "x2v": self.ncells2, "x3v": self.ncells3,
+             "dx1f": self.ncells1, "dx2f": self.ncells2, "dx3f": self.ncells3}[name]
+        a = np.empty(n)
+        lib.check(m.L.ab_download_coord(m.h, self.lid, lib.COORD[name],
+                                        a.ctypes.data_as(C.POINTER(C.c_double))))
+        return a
+
+
+class Mesh:
+    def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0):
+        """pin: ParameterInput (or athinput text); mhd / flux / nghost: what configure.py's
+        -b / --flux / --nghost fix at compile time in the reference."""
+        if not isinstance(pin, ParameterInput):
+            pin = ParameterInput(text=pin)
+        self.pin = pin
+        self.L = lib.load()
+        p = lib.AbMeshParams()
+        p.nx1 = pin.get_integer("mesh", "nx1")
+        p.nx2 = pin.get_or_add_integer("mesh", "nx2", 1)
+        p.nx3 = pin.get_or_add_integer("mesh", "nx3", 1)
+        has_mb = "meshblock" in pin.blocks
+        p.bx1 = pin.get_or_add_integer("meshblock", "nx1", p.nx1) if has_mb else p.nx1
+        p.bx2 = pin.get_or_add_integer("meshblock", "nx2", p.nx2) if has_mb else p.nx2
+        p.bx3 = pin.get_or_add_integer("meshblock", "nx3", p.nx3) if has_mb else p.nx3
+        p.x1min, p.x1max = pin.get_real("mesh", "x1min"), pin.get_real("mesh", "x1max")
+        p.x2min = pin.get_or_add_real("mesh", "x2min", -0.5)
+        p.x2max = pin.get_or_add_real("mesh", "x2max", 0.5)
+        p.x3min = pin.get_or_add_real("mesh", "x3min", -0.5)
+        p.x3max = pin.get_or_add_real("mesh", "x3max", 0.5)
+        for i, k in enumerate(("ix1_bc", "ox1_bc", "ix2_bc", "ox2_bc", "ix3_bc", "ox3_bc")):
+            flag = pin.get_or_add_string("mesh", k, "periodic")
+            if flag not in lib.BC:
+                raise ValueError("### FATAL ERROR in Mesh: boundary flag '%s' not supported on "
+                                 "the B200 path" % flag)
+            p.bc[i] = lib.BC[flag]
+        xo = pin.get_or_add_string("time", "xorder", "2")
+        if xo.endswith("c"):
+            raise ValueError("characteristic reconstruction (xorder=%s) is not on the B200 path" % xo)
+        p.xorder = int(xo)
+        p.nghost = nghost if nghost is not None else (3 if p.xorder == 3 else 2)
+        p.mhd = int(bool(mhd))
+        if flux == "default":
+            flux = "hlld" if mhd else "hllc"    # configure.py:299-308
+        p.solver = lib.SOLVER[flux]
+        p.integrator = lib.INTEGRATOR[pin.get_or_add_string("time", "integrator", "vl2")]
+        p.gamma = pin.get_real("hydro", "gamma")
+        p.dfloor = pin.get_or_add_real("hydro", "dfloor", DEFAULT_FLOOR)
+        p.pfloor = pin.get_or_add_real("hydro", "pfloor", DEFAULT_FLOOR)
+        p.cfl_number = pin.get_real("time", "cfl_number")
+        p.tlim = pin.get_real("time", "tlim")
+        p.start_time = pin.get_or_add_real("time", "start_time", 0.0)
+        p.rank, p.nranks, p.device = rank, nranks, device
+        self.params = p
+        self.mhd, self.flux = bool(mhd), flux
+        self.nlim = pin.get_or_add_integer("time", "nlim", -1)
+        h = C.c_void_p()
+        lib.check(self.L.ab_mesh_create(C.byref(p), C.byref(h)))
+        self.h = h
+        self.nbtotal = self.L.ab_mesh_nblocks_total(h)
+        self.nblocal = self.L.ab_mesh_nblocks_local(h)
+        self.my_blocks = [MeshBlock(self, l) for l in range(self.nblocal)]
+        self.time, self.dt, self.ncycle = p.start_time, float("inf"), 0
+        self.zones_per_block = p.bx1 * p.bx2 * p.bx3
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.ab_mesh_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- multi-process plumbing -------------------------------------------------------------
+    def init_comm(self, broadcast_bytes):
+        """broadcast_bytes(bytes|None) -> bytes: rank 0 passes the NCCL id, all ranks get it
+        (torch.distributed / MPI_Bcast in the host application)."""
+        if self.params.nranks <= 1:
+            return
+        idb = (C.c_ubyte * 128)()
+        if self.params.rank == 0:
+            lib.check(self.L.ab_comm_unique_id(idb))
+            data = broadcast_bytes(bytes(idb))
+        else:
+            data = broadcast_bytes(None)
+        idb = (C.c_ubyte * 128).from_buffer_copy(data)
+        lib.check(self.L.ab_comm_init(self.h, idb))
+
+    # ---- problem generator hook + initialisation -----------------------------------------------
+    def block_of(self, lx1, lx2, lx3):
+        for b in self.my_blocks:
+            if (b.lx1, b.lx2, b.lx3) == (lx1, lx2, lx3):
+                return b
+        return None
+
+    def problem_generator(self, pgen_fn):
+        """Calls pgen_fn(pmb, pin) -> dict(u=..., b1=..., b2=..., b3=...) per local MeshBlock
+        (the MeshBlock::ProblemGenerator hook) and uploads the AthenaArrays."""
+        for pmb in self.my_blocks:
+            out = pgen_fn(pmb, self.pin)
+            for k, v in out.items():
+                pmb.set(k, v)
+
+    def initialize(self):
+        lib.check(self.L.ab_mesh_initialize(self.h))
+        self._refresh()
+
+    def _refresh(self):
+        t, dt, n = C.c_double(), C.c_double(), C.c_long()
+        lib.check(self.L.ab_mesh_state(self.h, C.byref(t), C.byref(dt), C.byref(n)))
+        self.time, self.dt, self.ncycle = t.value, dt.value, n.value
+
+    # ---- main loop -----------------------------------------------------------------------------
+    def cycles(self, n, async_=False):
+        """Advance n cycles (or until tlim).  Returns the dt used by each executed cycle."""
+        lib.check(self.L.ab_mesh_set_async(self.h, int(async_)))
+        lib.check(self.L.ab_mesh_cycles(self.h, n))
+        out = np.empty(max(n, 1))
+        got = lib.check(self.L.ab_mesh_dt_history(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), n))
+        self._refresh()
+        return out[:got]
+
+    def run(self):
+        """main.cpp:430 loop: while (time < tlim && (nlim < 0 || ncycle < nlim))."""
+        dts = []
+        while self.time < self.params.tlim and (self.nlim < 0 or self.ncycle < self.nlim):
+            n = 64 if self.nlim < 0 else min(64, self.nlim - self.ncycle)
+            dts.extend(self.cycles(n))
+        return np.array(dts)
+
+    def sync(self):
+        lib.check(self.L.ab_mesh_sync(self.h))
+
+    @property
+    def launch_count(self):
+        return self.L.ab_mesh_launch_count(self.h)
+
+    @property
+    def cuda_stream(self):
+        return self.L.ab_mesh_stream(self.h)

@@ -1,0 +1,140 @@
+/* athena_b200.h -- C ABI of libathena_b200.so: the B200 (sm_100a) implementation of the
+ * per-MeshBlock finite-volume hydro/MHD update of Athena++ (fork pabolmasov/Athena-gamma).
+ *
+ * Plain C types only (pointers, ints, doubles); no exceptions cross this boundary: every call
+ * returns 0 on success or a negative error code, and ab_last_error() gives the message (the
+ * host shim turns that into ATHENA_ERROR, src/defs.hpp.in:119-123).
+ *
+ * The reference has no plugin layer; its "operator API" for this path is the set of member
+ * functions the task list calls (src/task_list/time_integrator.cpp:1442-2083) plus
+ * Mesh::Initialize / Mesh::NewTimeStep.  Each entry point below names the member function it
+ * replaces.  Blocks are addressed as (mesh handle, local block index `lid`) = pmb->lid.
+ * All device memory is owned by the library; host pointers are borrowed for the call only.
+ * There is no CPU fallback: every compute entry point fails with AB_ERR_NO_DEVICE when no
+ * CUDA device is usable.
+ */
+#ifndef ATHENA_B200_H_
+#define ATHENA_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { AB_OK = 0, AB_ERR_ARG = -1, AB_ERR_NO_DEVICE = -2, AB_ERR_CUDA = -3, AB_ERR_NCCL = -4,
+       AB_ERR_STATE = -5 };
+enum { AB_BC_PERIODIC = 0, AB_BC_OUTFLOW = 1 };               /* mesh/ix1_bc ... */
+enum { AB_SOLVER_HLLE = 0, AB_SOLVER_HLLC = 1, AB_SOLVER_HLLD = 2, AB_SOLVER_ROE = 3 };
+enum { AB_INT_VL2 = 0, AB_INT_RK2 = 1, AB_INT_RK1 = 2, AB_INT_RK3 = 3 };
+/* registers (Hydro::u,u1,w ; Field::b,b1,bcc,e,wght ; Hydro::flux ; face EMFs) */
+enum { AB_U = 0, AB_U1 = 1, AB_W = 2, AB_BCC = 3,
+       AB_B_X1F = 4, AB_B_X2F = 5, AB_B_X3F = 6, AB_B1_X1F = 7, AB_B1_X2F = 8, AB_B1_X3F = 9,
+       AB_FLUX_X1 = 10, AB_FLUX_X2 = 11, AB_FLUX_X3 = 12,
+       AB_E_X1E = 13, AB_E_X2E = 14, AB_E_X3E = 15,
+       AB_WGHT_X1F = 16, AB_WGHT_X2F = 17, AB_WGHT_X3F = 18,
+       AB_E3_X1F = 19, AB_E2_X1F = 20, AB_E1_X2F = 21, AB_E3_X2F = 22, AB_E2_X3F = 23,
+       AB_E1_X3F = 24, AB_NREG = 25 };
+
+/* What configure.py flags + the athinput <mesh>/<meshblock>/<time>/<hydro> blocks fix
+ * (src/defs.hpp.in:18-102, src/mesh/mesh.cpp:63-120, src/eos/adiabatic_mhd.cpp:26-31). */
+typedef struct {
+  int nx1, nx2, nx3;            /* <mesh> nx?            */
+  int bx1, bx2, bx3;            /* <meshblock> nx?       */
+  double x1min, x1max, x2min, x2max, x3min, x3max;
+  int bc[6];                    /* ix1,ox1,ix2,ox2,ix3,ox3 : AB_BC_* */
+  int nghost;                   /* NGHOST                */
+  int mhd;                      /* MAGNETIC_FIELDS_ENABLED */
+  int solver;                   /* RIEMANN_SOLVER        */
+  int xorder;                   /* time/xorder 1,2,3     */
+  int integrator;               /* time/integrator       */
+  double gamma, dfloor, pfloor; /* hydro/gamma,dfloor,pfloor */
+  double cfl_number, tlim, start_time;
+  int rank, nranks;             /* this process / number of processes (one GPU each) */
+  int device;                   /* CUDA device ordinal for this process */
+} AbMeshParams;
+
+typedef struct AbMesh AbMesh;
+
+const char *ab_last_error(void);
+int ab_device_count(void);                                /* 0 when no usable GPU */
+
+/* ---- construction: Mesh ctor + MeshBlock ctors + SearchAndSetNeighbors
+ *      (src/mesh/mesh.cpp:63-548, src/bvals/bvals_base.cpp:299-480) */
+int ab_mesh_create(const AbMeshParams *p, AbMesh **out);
+int ab_mesh_destroy(AbMesh *m);
+int ab_mesh_nblocks_total(const AbMesh *m);
+int ab_mesh_nblocks_local(const AbMesh *m);
+/* info[0]=gid, [1..3]=lx1..3, [4..6]=nc1..3 (cells incl. ghosts), [7..12]=is,ie,js,je,ks,ke */
+int ab_block_info(const AbMesh *m, int lid, long *info);
+/* number of doubles in a register of block lid */
+long ab_reg_size(const AbMesh *m, int lid, int reg);
+
+/* ---- host <-> device mirror of the AthenaArrays (same layout as AthenaArray::data()) */
+int ab_upload(AbMesh *m, int lid, int reg, const double *host);     /* after ProblemGenerator */
+int ab_download(AbMesh *m, int lid, int reg, double *host);         /* before outputs / hooks */
+int ab_download_coord(AbMesh *m, int lid, int which, double *host); /* 0..8: x1f x2f x3f x1v x2v x3v dx1f dx2f dx3f */
+
+/* ---- multi-process plumbing (replaces MPI_Init + persistent requests, bvals_cc.cpp:528-633).
+ * rank 0 calls ab_comm_unique_id and the host broadcasts the 128 bytes (MPI_Bcast /
+ * torch.distributed); then every rank calls ab_comm_init before the first exchange. */
+int ab_comm_unique_id(unsigned char id[128]);
+int ab_comm_init(AbMesh *m, const unsigned char id[128]);
+
+/* ---- task bodies, one block (src/task_list/time_integrator.cpp) -------------------------- */
+/* EquationOfState::ConservedToPrimitive (eos/adiabatic_{hydro,mhd}.cpp:39-90) */
+int ab_cons2prim(AbMesh *m, int lid, int il, int iu, int jl, int ju, int kl, int ku);
+/* EquationOfState::PrimitiveToConserved (eos/adiabatic_{hydro,mhd}.cpp:89-136) */
+int ab_prim2cons(AbMesh *m, int lid, int il, int iu, int jl, int ju, int kl, int ku);
+/* TimeIntegratorTaskList::Primitives range logic (:1965-1983) + ConservedToPrimitive */
+int ab_primitives(AbMesh *m, int lid);
+/* Hydro::CalculateFluxes(w,b,bcc,order) (hydro/calculate_fluxes.cpp:36-378); dt = pmesh->dt */
+int ab_calc_fluxes(AbMesh *m, int lid, int order, double dt);
+/* Field::ComputeCornerE (field/calculate_corner_e.cpp:28-236) */
+int ab_corner_e(AbMesh *m, int lid);
+/* MeshBlock::WeightedAve (mesh/weighted_ave.cpp): out = f(w[0]*out, w[1]*in); regs AB_U/AB_U1
+ * (cell-centred) or AB_B_X1F/AB_B1_X1F (all three face arrays of b / b1) */
+int ab_weighted_ave(AbMesh *m, int lid, int out_reg, int in_reg, const double w[5]);
+/* AthenaArray::SwapAthenaArray on (u,u1) when reg==AB_U, on (b,b1) when reg==AB_B_X1F */
+int ab_swap(AbMesh *m, int lid, int reg);
+/* AthenaArray::ZeroClear on u1 (AB_U1) or b1 (AB_B1_X1F) (time_integrator.cpp:1386-1397) */
+int ab_zero(AbMesh *m, int lid, int reg);
+/* Hydro::AddFluxDivergence(wght, u) (hydro/add_flux_divergence.cpp:39-96) */
+int ab_add_flux_div(AbMesh *m, int lid, double wght);
+/* Field::CT(wght, b) (field/ct.cpp:31-116) */
+int ab_ct(AbMesh *m, int lid, double wght);
+/* BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620), outflow faces */
+int ab_physical_bcs(AbMesh *m, int lid);
+/* Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:42-190): *dt_out = new_block_dt_ (synchronises) */
+int ab_new_block_dt(AbMesh *m, int lid, double *dt_out);
+
+/* ---- boundary communication over all local blocks (src/bvals): Send + Receive + Set.
+ * Same-device neighbours are copied device-to-device; neighbours on other ranks go through
+ * NCCL send/recv of packed buffers in the reference's buffer layout. */
+/* FaceCenteredBoundaryVariable::SendFluxCorrection + ReceiveFluxCorrection
+ * (bvals/fc/flux_correction_fc.cpp:623-680,1610-1749) */
+int ab_emf_exchange(AbMesh *m);
+/* hbvar / fbvar SendBoundaryBuffers + ReceiveBoundaryBuffers + SetBoundaries
+ * (bvals/bvals_var.cpp:212-296) for u (and b when MHD) */
+int ab_bvals_exchange(AbMesh *m);
+
+/* ---- whole-mesh driver (host side of the path): Mesh::Initialize after ProblemGenerator
+ * (mesh/mesh.cpp:1416-1649) and the main loop body (main.cpp:430-515 without outputs). */
+int ab_mesh_initialize(AbMesh *m);
+/* run ncycles cycles (all stages of TimeIntegratorTaskList + Mesh::NewTimeStep) without
+ * host synchronisation; stops early when time >= tlim.  dt stays on the device. */
+int ab_mesh_cycles(AbMesh *m, int ncycles);
+/* async=1: ab_mesh_cycles never synchronises (caller guarantees tlim is not reached) */
+int ab_mesh_set_async(AbMesh *m, int async);
+/* read back {time, dt, ncycle} (synchronises the stream) */
+int ab_mesh_state(AbMesh *m, double *time, double *dt, long *ncycle);
+int ab_mesh_set_time_dt(AbMesh *m, double time, double dt);
+/* per-cycle dt history of the last ab_mesh_cycles call (dt used by each cycle) */
+int ab_mesh_dt_history(AbMesh *m, double *out, int max_n);
+/* count of kernel launches issued by this mesh since creation (for bench accounting) */
+long ab_mesh_launch_count(const AbMesh *m);
+void *ab_mesh_stream(AbMesh *m);                          /* cudaStream_t of the compute stream */
+int ab_mesh_sync(AbMesh *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATHENA_B200_H_ */

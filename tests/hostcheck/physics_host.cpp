@@ -1,0 +1,42 @@
+// TEST-ONLY: compiles the product's device physics header (ab_physics.cuh) for the host so the
+// CPU test-suite can compare its arithmetic with the oracle without a GPU.  Not part of the
+// product; the product library contains no host execution path for these functions.
+#include "../../athena-gamma_b200/csrc/ab_physics.cuh"
+
+template <int S, bool M>
+static void run(long n, const double *wl, const double *wr, const double *bx, double gamma,
+                double dt, double dx, double *flx, double *wct) {
+  const int nw = M ? 7 : 5;
+  for (long i = 0; i < n; ++i) {
+    double a[7], b[7], f[7];
+    for (int v = 0; v < nw; ++v) { a[v] = wl[v*n+i]; b[v] = wr[v*n+i]; }
+    ab::riemann<S, M>(a, b, M ? bx[i] : 0.0, gamma, f);
+    for (int v = 0; v < nw; ++v) flx[v*n+i] = f[v];
+    if (M && wct) wct[i] = ab::weight_for_ct(f[0], a[0], b[0], dx, dt);
+  }
+}
+
+extern "C" {
+void hc_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
+                const double *bx, double gamma, double dt, double dx, double *flx,
+                double *wct) {
+  if (!mhd) {
+    if (solver == 1) run<1, false>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
+    else if (solver == 0) run<0, false>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
+    else run<3, false>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
+  } else {
+    if (solver == 2) run<2, true>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
+    else if (solver == 0) run<0, true>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
+    else run<3, true>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
+  }
+}
+void hc_plm(long n, int nvar, const double *qm1, const double *q, const double *qp1,
+            double wp, double wm, double *ql, double *qr) {
+  for (long i = 0; i < (long)nvar*n; ++i) ab::plm(qm1[i], q[i], qp1[i], wp, wm, ql[i], qr[i]);
+}
+void hc_ppm(long n, int nvar, const double *qm2, const double *qm1, const double *q,
+            const double *qp1, const double *qp2, double *ql, double *qr) {
+  for (long i = 0; i < (long)nvar*n; ++i)
+    ab::ppm(qm2[i], qm1[i], q[i], qp1[i], qp2[i], ql[i], qr[i]);
+}
+}

@@ -1,0 +1,92 @@
+"""CPU: the product's device physics header (athena-gamma_b200/csrc/ab_physics.cuh), compiled
+for the host by a test-only shim, against the C oracle on random states.  Bit-exact.
+This pins the arithmetic of the CUDA kernels before any GPU time is spent; the GPU parity
+tests (tests/test_gpu_*.py) then cover the kernels themselves."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "hostcheck", "libphysics_host.so")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    src = os.path.join(HERE, "hostcheck", "physics_host.cpp")
+    hdr = os.path.join(HERE, "..", "athena-gamma_b200", "csrc", "ab_physics.cuh")
+    if (not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src),
+                                                              os.path.getmtime(hdr))):
+        subprocess.run(["g++", "-O2", "-std=c++14", "-fPIC", "-shared", "-ffp-contract=off",
+                        "-x", "c++", src, "-o", SO], check=True)
+    L = C.CDLL(SO)
+    dp = C.POINTER(C.c_double)
+    L.hc_riemann.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_double, C.c_double,
+                             C.c_double, dp, dp]
+    L.hc_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
+    L.hc_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, dp, dp]
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def random_states(rng, n, mhd, regime):
+    nw = 7 if mhd else 5
+    w = np.zeros((nw, n))
+    w[0] = np.exp(rng.uniform(-3, 3, n))
+    vs = {"subsonic": 0.3, "supersonic": 5.0, "mixed": 2.0}[regime]
+    w[1:4] = rng.normal(0, vs, (3, n))
+    w[4] = np.exp(rng.uniform(-3, 3, n))
+    if mhd:
+        w[5:7] = rng.normal(0, 1.0, (2, n))
+    return w
+
+
+@pytest.mark.parametrize("solver,mhd", [("hllc", False), ("hlle", False), ("roe", False),
+                                        ("hlld", True), ("hlle", True), ("roe", True)])
+@pytest.mark.parametrize("regime", ["subsonic", "supersonic", "mixed"])
+def test_riemann_matches_oracle(hc, solver, mhd, regime):
+    rng = np.random.default_rng(1234)
+    n = 20000
+    wl = random_states(rng, n, mhd, regime)
+    wr = random_states(rng, n, mhd, regime)
+    # a share of near-identical states (smooth flow) and of Bx ~ 0 (degenerate HLLD branches)
+    wr[:, : n // 4] = wl[:, : n // 4] * (1 + 1e-6 * rng.normal(size=(wl.shape[0], n // 4)))
+    bx = rng.normal(0, 1.0, n)
+    bx[n // 2: n // 2 + n // 8] = 0.0
+    bx[n // 2 + n // 8: n // 2 + n // 4] *= 1e-9
+    fo, wo = oracle.riemann(solver, mhd, wl, wr, bx, 5.0 / 3.0, dt=0.01, dx=0.1)
+    fh = np.zeros_like(wl)
+    wh = np.zeros(n)
+    hc.hc_riemann(oracle.SOLVER[solver], int(mhd), n, _dp(wl), _dp(wr), _dp(bx), 5.0 / 3.0,
+                  0.01, 0.1, _dp(fh), _dp(wh))
+    util.assert_bitwise(fh, fo, "flux %s mhd=%s" % (solver, mhd))
+    if mhd:
+        util.assert_bitwise(wh, wo, "ct weight")
+
+
+def test_plm_ppm_match_oracle(hc):
+    rng = np.random.default_rng(7)
+    n = 50000
+    q = [np.ascontiguousarray(rng.normal(0, 1, (7, n)) + (rng.random((7, n)) < 0.1) * 5)
+         for _ in range(5)]
+    # sprinkle exact extrema / flat regions
+    q[2][:, :1000] = q[1][:, :1000]
+    q[3][:, 500:1500] = q[2][:, 500:1500]
+    ol, orr = oracle.plm(q[1], q[2], q[3], 0.5000000000000001, 0.4999999999999999)
+    hl, hr = np.zeros_like(q[2]), np.zeros_like(q[2])
+    hc.hc_plm(n, 7, _dp(q[1]), _dp(q[2]), _dp(q[3]), 0.5000000000000001, 0.4999999999999999,
+              _dp(hl), _dp(hr))
+    util.assert_bitwise(hl, ol, "plm plus")
+    util.assert_bitwise(hr, orr, "plm minus")
+    ol, orr = oracle.ppm(q[0], q[1], q[2], q[3], q[4], dfloor=-1e300, pfloor=-1e300)
+    hc.hc_ppm(n, 7, _dp(q[0]), _dp(q[1]), _dp(q[2]), _dp(q[3]), _dp(q[4]), _dp(hl), _dp(hr))
+    util.assert_bitwise(hl, ol, "ppm plus")
+    util.assert_bitwise(hr, orr, "ppm minus")
