@@ -246,32 +246,39 @@ static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, doubl
 }
 
 template <int ORDER, int SOLVER, bool MHD>
-static void flux_all(const BlkDev &b, const ReconGeom &g, const Params &p, double dt_val,
-                     const double *dt_ptr, cudaStream_t s) {
-  flux_dir<0,ORDER,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
-  if (b.f2) flux_dir<1,ORDER,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
-  if (b.f3) flux_dir<2,ORDER,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+static void flux_all(const BlkDev &b, const ReconGeom &g, const Params &p, int dir,
+                     double dt_val, const double *dt_ptr, cudaStream_t s) {
+  if (dir == 0) flux_dir<0,ORDER,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+  else if (dir == 1) flux_dir<1,ORDER,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+  else flux_dir<2,ORDER,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
 }
 
 template <int SOLVER, bool MHD>
-static void flux_order(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
+static void flux_order(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
                        double dt_val, const double *dt_ptr, cudaStream_t s) {
-  if (order == 1) flux_all<1,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
-  else if (order == 2) flux_all<2,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
-  else flux_all<3,SOLVER,MHD>(b, g, p, dt_val, dt_ptr, s);
+  if (order == 1) flux_all<1,SOLVER,MHD>(b, g, p, dir, dt_val, dt_ptr, s);
+  else if (order == 2) flux_all<2,SOLVER,MHD>(b, g, p, dir, dt_val, dt_ptr, s);
+  else flux_all<3,SOLVER,MHD>(b, g, p, dir, dt_val, dt_ptr, s);
+}
+
+void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
+                     double dt_val, const double *dt_ptr, cudaStream_t s) {
+  if (p.mhd) {
+    if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else flux_order<SOLVER_ROE,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
+  } else {
+    if (p.solver == SOLVER_HLLC) flux_order<SOLVER_HLLC,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else flux_order<SOLVER_ROE,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
+  }
 }
 
 void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
                    double dt_val, const double *dt_ptr, cudaStream_t s) {
-  if (p.mhd) {
-    if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD,true>(b, g, p, order, dt_val, dt_ptr, s);
-    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,true>(b, g, p, order, dt_val, dt_ptr, s);
-    else flux_order<SOLVER_ROE,true>(b, g, p, order, dt_val, dt_ptr, s);
-  } else {
-    if (p.solver == SOLVER_HLLC) flux_order<SOLVER_HLLC,false>(b, g, p, order, dt_val, dt_ptr, s);
-    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,false>(b, g, p, order, dt_val, dt_ptr, s);
-    else flux_order<SOLVER_ROE,false>(b, g, p, order, dt_val, dt_ptr, s);
-  }
+  launch_flux_dir(b, g, p, order, 0, dt_val, dt_ptr, s);
+  if (b.f2) launch_flux_dir(b, g, p, order, 1, dt_val, dt_ptr, s);
+  if (b.f3) launch_flux_dir(b, g, p, order, 2, dt_val, dt_ptr, s);
 }
 
 // =============================================================================================

@@ -19,6 +19,8 @@ void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, in
                      cudaStream_t s);
 void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
                    double dt_val, const double *dt_ptr, cudaStream_t s);
+void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
+                     double dt_val, const double *dt_ptr, cudaStream_t s);
 void launch_corner_e(const BlkDev &b, cudaStream_t s);
 void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);
 void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);

@@ -162,6 +162,12 @@ struct AbMesh {
   std::map<int, PeerBuf> peer_state, peer_emf;
   ncclComm_t comm = nullptr;
   bool emf_built = false;
+  // optional CUDA-event timing of the flux kernels (bench.py roofline): slot = dir*3+(order-1)
+  int profile = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
+  std::vector<int> prof_slot;
+  double prof_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long prof_n[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -960,7 +966,19 @@ int one_cycle(AbMesh *m) {
     const int s = stage - 1;
     const int order = (m->p.integrator == AB_INT_VL2 && stage == 1) ? 1 : m->p.xorder;
     for (auto &L : m->lb) {
-      ab::launch_fluxes(L.d, L.g, m->kp, order, 0.0, dtp, m->stream);
+      for (int dir = 0; dir < m->ndim; ++dir) {
+        if (m->profile) {
+          cudaEvent_t e0, e1;
+          cudaEventCreate(&e0); cudaEventCreate(&e1);
+          cudaEventRecord(e0, m->stream);
+          ab::launch_flux_dir(L.d, L.g, m->kp, order, dir, 0.0, dtp, m->stream);
+          cudaEventRecord(e1, m->stream);
+          m->prof_ev.push_back({e0, e1});
+          m->prof_slot.push_back(dir*3 + (order - 1));
+        } else {
+          ab::launch_flux_dir(L.d, L.g, m->kp, order, dir, 0.0, dtp, m->stream);
+        }
+      }
       if (m->p.mhd) ab::launch_corner_e(L.d, m->stream);
     }
     int rc = emf_exchange(m);
@@ -1307,6 +1325,29 @@ int ab_mesh_dt_history(AbMesh *m, double *out, int max_n) {
     CK(cudaStreamSynchronize(m->stream));
   }
   return n;
+}
+
+int ab_mesh_profile(AbMesh *m, int enable) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  m->profile = enable;
+  return AB_OK;
+}
+
+// out[0..8] = accumulated ms, out[9..17] = launch counts; slot = dir*3 + (order-1); resets
+int ab_mesh_profile_read(AbMesh *m, double *out) {
+  if (!m || !out) return fail(AB_ERR_ARG, "null argument");
+  CK(cudaStreamSynchronize(m->stream));
+  for (size_t i = 0; i < m->prof_ev.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, m->prof_ev[i].first, m->prof_ev[i].second);
+    m->prof_ms[m->prof_slot[i]] += ms;
+    m->prof_n[m->prof_slot[i]] += 1;
+    cudaEventDestroy(m->prof_ev[i].first);
+    cudaEventDestroy(m->prof_ev[i].second);
+  }
+  m->prof_ev.clear(); m->prof_slot.clear();
+  for (int i = 0; i < 9; ++i) { out[i] = m->prof_ms[i]; out[9+i] = (double)m->prof_n[i]; m->prof_ms[i] = 0; m->prof_n[i] = 0; }
+  return AB_OK;
 }
 
 long ab_mesh_launch_count(const AbMesh *m) { (void)m; return ab::g_launches; }

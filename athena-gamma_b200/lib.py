@@ -26,7 +26,8 @@ SYMBOLS = [
     "ab_weighted_ave", "ab_swap", "ab_zero", "ab_add_flux_div", "ab_ct", "ab_physical_bcs",
     "ab_new_block_dt", "ab_emf_exchange", "ab_bvals_exchange", "ab_mesh_initialize",
     "ab_mesh_cycles", "ab_mesh_set_async", "ab_mesh_state", "ab_mesh_set_time_dt",
-    "ab_mesh_dt_history", "ab_mesh_launch_count", "ab_mesh_stream", "ab_mesh_sync",
+    "ab_mesh_dt_history", "ab_mesh_profile", "ab_mesh_profile_read",
+    "ab_mesh_launch_count", "ab_mesh_stream", "ab_mesh_sync",
 ]
 
 
@@ -93,6 +94,8 @@ def load():
     L.ab_mesh_state.argtypes = [vp, dp, dp, C.POINTER(C.c_long)]
     L.ab_mesh_set_time_dt.argtypes = [vp, C.c_double, C.c_double]
     L.ab_mesh_dt_history.argtypes = [vp, dp, ip]
+    L.ab_mesh_profile.argtypes = [vp, ip]
+    L.ab_mesh_profile_read.argtypes = [vp, dp]
     L.ab_mesh_launch_count.restype = C.c_long
     L.ab_mesh_launch_count.argtypes = [vp]
     L.ab_mesh_stream.restype = vp

@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py -- zone-cycles/s of the per-MeshBlock hydro/MHD update on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3|c4] [--impl ours|reference]
+
+Default workload (N=1): BASELINE.json configs[4] / the north_star target: 3-D MHD blast wave,
+512^3 zones per GPU, HLLD + PLM + VL2 + CT, periodic, one 512^3 MeshBlock per GPU; weak-scaled
+(N x 512^3: 1024x512x512, 1024x1024x512, 1024^3) with MeshBlocks sharded over the ranks and the
+ghost / EMF exchange over NCCL.  A "step" is one cycle (all integrator stages + new dt).
+One JSON line is printed by rank 0.
+
+  value      zone-cycles/s with the state resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the C ABI with HOST buffers: every step uploads u and the face
+             fields from pinned host memory, runs Mesh::Initialize-style ghost fill + one cycle,
+             and downloads u and b again
+  roofline   the reconstruct+Riemann kernel (dominant): algorithmic bytes / CUDA-event duration
+  cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_ZONE_CYCLE = {"mhd": 320.0, "hydro": 200.0}    # B_alg
+FLUX_BYTES_PER_FACE = {"mhd": 128.0, "hydro": 80.0}      # (8 in + 8 out) / (5+5) doubles
+
+WORKLOADS = {
+    # name: (athinput, pgen, mhd, flux, nghost, per-GPU block (bx1,bx2,bx3), overrides)
+    "c5": ("athinput.blast", "blast", True, "hlld", 2, (512, 512, 512), {}),
+    "c2": ("athinput.linear_wave3d", "linear_wave", True, "hlld", 2, (128, 64, 64), {}),
+    "c4": ("athinput.kh", "kh", False, "hllc", 3, (512, 512, 512), {}),
+    "c3": ("athinput.orszag_tang", "orszag_tang", True, "hlld", 3, (2048, 2048, 1), {}),
+}
+REF_CFG = {"c5": ("mhd_hlld_ng2", "blast"), "c2": ("mhd_hlld_ng2", "linear_wave"),
+           "c4": ("hydro_hllc_ng3", "kh"), "c3": ("mhd_hlld_ng3", "orszag_tang")}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def weak_mesh(nranks, block):
+    """replicate the per-GPU block along x1, then x2, then x3 (Z-order gives one block/rank)"""
+    reps = [1, 1, 1]
+    d = 0
+    n = nranks
+    while n > 1:
+        if block[d] > 1:
+            reps[d] *= 2
+            n //= 2
+        d = (d + 1) % 3
+    return reps
+
+
+def make_pin(ab, wl, nranks, block=None):
+    inp, pgen, mhd, flux, ng, blk, ov = WORKLOADS[wl]
+    if block:
+        blk = block
+    pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", inp))
+    reps = weak_mesh(nranks, blk)
+    for d in range(3):
+        n = d + 1
+        pin.set("mesh", "nx%d" % n, blk[d]*reps[d])
+        pin.set("meshblock", "nx%d" % n, blk[d])
+        if reps[d] > 1:   # keep the zone size: stretch the domain
+            lo, hi = pin.get_real("mesh", "x%dmin" % n), pin.get_real("mesh", "x%dmax" % n)
+            pin.set("mesh", "x%dmax" % n, repr(lo + (hi - lo)*reps[d]))
+    pin.set("time", "nlim", -1)
+    pin.set("time", "tlim", 1.0e30)      # fixed cycle count; never clamp dt to tlim
+    for k, v in ov.items():
+        b, key = k.split("/")
+        pin.set(b, key, v)
+    return pin, pgen, mhd, flux, ng, blk
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference_cpu(wl, budget_s=20.0, steps=None, warmup=0):
+    """Times the UNMODIFIED reference (oracle/_ref) on the host cores with OpenMP over
+    MeshBlocks (src/task_list/task_list.cpp:71-88), on a bounded sample of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_run
+    cfg, pgen = REF_CFG[wl]
+    if not ref_run.have_ref(cfg, pgen):
+        return None
+    inp, _, mhd, flux, ng, blk, ov = WORKLOADS[wl]
+    cores = os.cpu_count() or 1
+    threads = cores
+    ndim = sum(1 for b in blk if b > 1)
+    # sample mesh: >= `threads` MeshBlocks of 32^3 (3-D) / 128^2 (2-D)
+    bs = 32 if ndim == 3 else 128
+    nb = 1
+    while nb**ndim < threads:
+        nb *= 2
+    nb = max(nb, 4 if ndim == 3 else 4)
+    n = nb*bs
+    over = {"time/tlim": 1e30, "time/ncycle_out": 0}
+    for d in range(3):
+        over["mesh/nx%d" % (d+1)] = n if blk[d] > 1 else 1
+        over["meshblock/nx%d" % (d+1)] = bs if blk[d] > 1 else 1
+    over.update(ov)
+    zones = n**ndim
+    inp_path = os.path.join(ROOT, "inputs", inp)
+    if steps is None:
+        # calibrate with 2 cycles, then fill the budget
+        over["time/nlim"] = 2
+        r = ref_run.run_reference(cfg, pgen, inp_path, over, threads=threads)
+        ref_run.cleanup(r)
+        rate = r["zcps_omp"] or r["zcps"]
+        ncyc = int(max(2, min(200, budget_s*rate/zones)))
+    else:
+        ncyc = steps + warmup
+    over["time/nlim"] = ncyc
+    r = ref_run.run_reference(cfg, pgen, inp_path, over, threads=threads)
+    ref_run.cleanup(r)
+    rate = r["zcps_omp"] or r["zcps"]
+    return {"value": rate, "unit": "zone-cycles/s", "cores": threads, "kind": "reference",
+            "sample": "%s %s mesh, %d MeshBlocks of %s, %d cycles, OpenMP %d threads, "
+                      "g++ -O3 (reference default flags)" %
+                      (pgen, "x".join(str(over["mesh/nx%d" % (d+1)]) for d in range(3)),
+                       nb**ndim, "x".join(str(over["meshblock/nx%d" % (d+1)]) for d in range(3)),
+                       ncyc, threads),
+            "ms_per_step": 1e3*zones/rate, "zones": zones, "cycles": ncyc}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--block", default=None, help="per-GPU MeshBlock, e.g. 256,256,256")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = a.workload
+    mhd = WORKLOADS[wl][2]
+    block = tuple(int(x) for x in a.block.split(",")) if a.block else None
+    cfg_desc = {"workload": "%s: %s" % (wl, {
+        "c5": "3D MHD blast wave, HLLD+PLM+VL2+CT, periodic (BASELINE configs[4])",
+        "c2": "3D MHD linear wave 128x64x64, HLLD+PLM+VL2, 1 MeshBlock (BASELINE configs[1])",
+        "c4": "3D Kelvin-Helmholtz hydro, HLLC+PPM+RK2 (BASELINE configs[3])",
+        "c3": "2D Orszag-Tang MHD, HLLD+PPM+VL2 (BASELINE configs[2])"}[wl])}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_reference_cpu(wl, steps=a.steps, warmup=a.warmup)
+        if r is None:
+            print(json.dumps({"impl": "reference",
+                              "unavailable": "oracle/_ref binary missing (build needs /root/reference)"}))
+            return 0
+        cfg_desc["sample"] = r["sample"]
+        out = {"impl": "reference", "metric": "zone-cycles/sec", "value": r["value"],
+               "unit": "zone-cycles/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg_desc,
+               "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+               "e2e": {"value": r["value"], "unit": "zone-cycles/s", "h2d_bytes_per_step": 0,
+                       "d2h_bytes_per_step": 0},
+               "gpu_launches": 0}
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import athena_gamma_b200 as ab
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank if world > 1 else 0
+    torch.cuda.set_device(device)
+    pin, pgen_name, mhd, flux, ng, blk = make_pin(ab, wl, world, block)
+    mesh = ab.Mesh(pin, mhd=mhd, flux=flux, nghost=ng, rank=rank, nranks=world, device=device)
+    if world > 1:
+        def bcast(data):
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                t.copy_(torch.tensor(list(data), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        mesh.init_comm(bcast)
+    # synthetic input: the reference's own problem generator formula, evaluated on the host
+    host_state = []
+    for pmb in mesh.my_blocks:
+        st = ab.pgen.BY_NAME[pgen_name](pmb, pin)
+        host_state.append(st)
+        for k, v in st.items():
+            pmb.set(k, v)
+    mesh.initialize()
+    zones = mesh.nbtotal*mesh.zones_per_block
+    zones_local = mesh.nblocal*mesh.zones_per_block
+
+    def barrier():
+        mesh.sync()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        mesh.sync()
+
+    # ---- device-resident throughput -----------------------------------------------------------
+    mesh.cycles(a.warmup, async_=True)
+    barrier()
+    L = mesh.L
+    L.ab_mesh_profile(mesh.h, 1)
+    stream = torch.cuda.ExternalStream(mesh.cuda_stream, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(device)
+    sampler.start()
+    launches0 = mesh.launch_count
+    barrier()
+    e0.record(stream)
+    mesh.cycles(a.steps, async_=True)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = mesh.launch_count - launches0
+    prof = (C.c_double*18)()
+    L.ab_mesh_profile_read(mesh.h, prof)
+    L.ab_mesh_profile(mesh.h, 0)
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = zones*a.steps/(ms*1e-3)
+
+    # ---- roofline of the dominant kernel (reconstruct + Riemann, full-order stage) ------------
+    peak, peak_src = load_peaks()
+    xo = mesh.params.xorder
+    nd = 1 + (mesh.params.nx2 > 1) + (mesh.params.nx3 > 1)
+    tot_ms = sum(prof[d*3 + (xo-1)] for d in range(nd))
+    tot_n = sum(prof[9 + d*3 + (xo-1)] for d in range(nd))
+    kname = "k_flux<dir,order=%d,%s,%s>" % (xo, flux, "mhd" if mhd else "hydro")
+    faces = mesh.zones_per_block      # ~ one interface per zone per direction
+    fb = FLUX_BYTES_PER_FACE["mhd" if mhd else "hydro"]
+    roof = None
+    if tot_n > 0:
+        avg_ms = tot_ms/tot_n
+        ach = fb*faces/(avg_ms*1e-3)/1e9
+        share = sum(prof[i] for i in range(9))/ms if ms > 0 else None
+        roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach/peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": avg_ms, "launches_timed": int(tot_n),
+                "algorithmic_bytes_per_launch": fb*faces,
+                "flux_kernels_share_of_step": share}
+    b_alg = BYTES_PER_ZONE_CYCLE["mhd" if mhd else "hydro"]
+    cycle_roof = {"B_alg_bytes_per_zone_cycle": b_alg,
+                  "achieved_GBs_per_gpu": b_alg*value/world/1e9,
+                  "frac_of_measured_peak": b_alg*value/world/1e9/peak,
+                  "frac_of_8TBs": b_alg*value/world/8.0e12}
+
+    # ---- end-to-end through the C ABI with host buffers ---------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        names = ["u"] + (["b1", "b2", "b3"] if mhd else [])
+        pinned = []
+        for st in host_state:
+            d = {}
+            for nm in names:
+                tsr = torch.from_numpy(st[nm]).pin_memory()
+                d[nm] = tsr
+            pinned.append(d)
+        host_state = None
+        nbytes = sum(t.numel()*8 for d in pinned for t in d.values())
+        dp = C.POINTER(C.c_double)
+
+        def e2e_step():
+            for pmb, d in zip(mesh.my_blocks, pinned):
+                for nm in names:
+                    ab.lib.check(L.ab_upload(mesh.h, pmb.lid, ab.lib.REG[nm],
+                                             C.cast(d[nm].data_ptr(), dp)))
+            ab.lib.check(L.ab_mesh_initialize(mesh.h))
+            ab.lib.check(L.ab_mesh_cycles(mesh.h, 1))
+            for pmb, d in zip(mesh.my_blocks, pinned):
+                for nm in names:
+                    ab.lib.check(L.ab_download(mesh.h, pmb.lid, ab.lib.REG[nm],
+                                               C.cast(d[nm].data_ptr(), dp)))
+        nsteps = max(1, min(a.steps, 3))
+        L.ab_mesh_set_async(mesh.h, 0)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            e2e_step()
+        barrier()
+        dt_wall = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([dt_wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_wall = float(t.item())
+        e2e = {"value": zones*nsteps/dt_wall, "unit": "zone-cycles/s",
+               "h2d_bytes_per_step": nbytes*world if world > 1 else nbytes,
+               "d2h_bytes_per_step": nbytes*world if world > 1 else nbytes,
+               "steps": nsteps,
+               "what": "per step: upload u,b (pinned host) -> ghost fill + cons2prim + dt -> "
+                       "1 cycle -> download u,b"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        try:
+            cpu = run_reference_cpu(wl)
+            if cpu:
+                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:   # the baseline must never break the product's bench line
+            cpu = {"value": None, "unit": "zone-cycles/s", "cores": os.cpu_count(),
+                   "kind": "reference", "sample": "failed: %s" % ex}
+
+    if rank == 0:
+        cfg_desc.update({"mesh": [mesh.params.nx1, mesh.params.nx2, mesh.params.nx3],
+                         "meshblock": list(blk), "meshblocks_total": mesh.nbtotal,
+                         "parallelism": "MeshBlocks sharded over %d GPU(s), NCCL halo" % world,
+                         "l2_policy": "working set (%.1f GB/GPU) >> 126 MB L2; no flush needed"
+                                      % (zones_local*8*55/1e9 if mhd else zones_local*8*35/1e9)})
+        out = {"metric": "zone-cycles/sec", "value": value, "unit": "zone-cycles/s",
+               "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms/a.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": cfg_desc, "roofline": roof,
+               "roofline_cycle": cycle_roof, "cpu_baseline": cpu, "e2e": e2e,
+               "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(out))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -129,6 +129,11 @@ int ab_mesh_state(AbMesh *m, double *time, double *dt, long *ncycle);
 int ab_mesh_set_time_dt(AbMesh *m, double time, double dt);
 /* per-cycle dt history of the last ab_mesh_cycles call (dt used by each cycle) */
 int ab_mesh_dt_history(AbMesh *m, double *out, int max_n);
+/* CUDA-event timing of the reconstruct+Riemann kernels on the compute stream (roofline
+ * evidence): enable, run cycles, then read out[0..8]=ms and out[9..17]=launches per
+ * slot = dir*3 + (order-1); reading resets the accumulators. */
+int ab_mesh_profile(AbMesh *m, int enable);
+int ab_mesh_profile_read(AbMesh *m, double *out);
 /* count of kernel launches issued by this mesh since creation (for bench accounting) */
 long ab_mesh_launch_count(const AbMesh *m);
 void *ab_mesh_stream(AbMesh *m);                          /* cudaStream_t of the compute stream */
