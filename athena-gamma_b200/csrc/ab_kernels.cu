@@ -31,55 +31,116 @@ static inline dim3 grid3(int ni, int nj, int nk) {
 // EquationOfState::ConservedToPrimitive (+ Field::CalculateCellCenteredField)
 // eos/adiabatic_mhd.cpp:41-90, eos/adiabatic_hydro.cpp:39-80, field/field.cpp:112-180
 // =============================================================================================
-template <bool MHD>
+// FLAGS bit0: also store the cell-centred EMF cc_e = -(v x B) used by ComputeCornerE
+// (field/calculate_corner_e.cpp:131-180) -- saves a pass over w and bcc;
+// bit1: also reduce Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:64-134) over the ACTIVE
+// cells of the launch (last integrator stage) -- w, bcc, b are already in registers.
+template <bool MHD, int FLAGS>
 __global__ void __launch_bounds__(BX) k_cons2prim(BlkDev b, Params p, int il, int iu, int jl,
-                                                  int kl) {
+                                                  int kl, unsigned long long *dtmin) {
   int i = il + blockIdx.x*BX + threadIdx.x;
-  if (i > iu) return;
   int j = jl + blockIdx.y, k = kl + blockIdx.z;
-  double gm1 = p.gamma - 1.0;
-  double pb = 0.0;
-  if (MHD) {
-    double bcc1 = 0.5*b.b[0][F1I(b,k,j,i)] + 0.5*b.b[0][F1I(b,k,j,i+1)];
-    double bcc2 = 0.5*b.b[1][F2I(b,k,j,i)] + 0.5*b.b[1][F2I(b,k,j+1,i)];
-    double bcc3 = 0.5*b.b[2][F3I(b,k,j,i)] + 0.5*b.b[2][F3I(b,k+1,j,i)];
-    b.bcc[CCI(b,0,k,j,i)] = bcc1;
-    b.bcc[CCI(b,1,k,j,i)] = bcc2;
-    b.bcc[CCI(b,2,k,j,i)] = bcc3;
-    pb = 0.5*(sqr(bcc1) + sqr(bcc2) + sqr(bcc3));
+  double m = DBL_MAX;
+  if (i <= iu) {
+    double gm1 = p.gamma - 1.0;
+    double pb = 0.0;
+    double bcc1 = 0.0, bcc2 = 0.0, bcc3 = 0.0, bf1 = 0.0, bf2 = 0.0, bf3 = 0.0;
+    long o = CCI(b,0,k,j,i);
+    long sv = (long)b.nc3*b.nc2*b.nc1;
+    if (MHD) {
+      bf1 = b.b[0][F1I(b,k,j,i)]; bf2 = b.b[1][F2I(b,k,j,i)]; bf3 = b.b[2][F3I(b,k,j,i)];
+      bcc1 = 0.5*bf1 + 0.5*b.b[0][F1I(b,k,j,i+1)];
+      bcc2 = 0.5*bf2 + 0.5*b.b[1][F2I(b,k,j+1,i)];
+      bcc3 = 0.5*bf3 + 0.5*b.b[2][F3I(b,k+1,j,i)];
+      b.bcc[o] = bcc1;
+      b.bcc[o+sv] = bcc2;
+      b.bcc[o+2*sv] = bcc3;
+      pb = 0.5*(sqr(bcc1) + sqr(bcc2) + sqr(bcc3));
+    }
+    double u_d = b.u[o], u_m1 = b.u[o+sv], u_m2 = b.u[o+2*sv], u_m3 = b.u[o+3*sv],
+           u_e = b.u[o+4*sv];
+    double u_d0 = u_d, u_e0 = u_e;
+    u_d = (u_d > p.dfloor) ? u_d : p.dfloor;
+    double di = 1.0/u_d;
+    double e_k = 0.5*di*(sqr(u_m1) + sqr(u_m2) + sqr(u_m3));
+    double w_p;
+    if (MHD) {
+      w_p = gm1*(u_e - e_k - pb);
+      u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k + pb);
+    } else {
+      w_p = gm1*(u_e - e_k);
+      u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k);
+    }
+    w_p = (w_p > p.pfloor) ? w_p : p.pfloor;
+    // floors write back into cons (the reference always stores; storing only changes is
+    // value-identical and saves two stores per cell)
+    if (u_d != u_d0) b.u[o] = u_d;
+    if (u_e != u_e0) b.u[o+4*sv] = u_e;
+    double vx = u_m1*di, vy = u_m2*di, vz = u_m3*di;
+    b.w[o] = u_d;
+    b.w[o+sv] = vx;
+    b.w[o+2*sv] = vy;
+    b.w[o+3*sv] = vz;
+    b.w[o+4*sv] = w_p;
+    if (MHD && (FLAGS & 1)) {
+      if (b.f3) {
+        b.cc_e[o] = vz*bcc2 - vy*bcc3;
+        b.cc_e[o+sv] = vx*bcc3 - vz*bcc1;
+        b.cc_e[o+2*sv] = vy*bcc1 - vx*bcc2;
+      } else if (b.f2) {
+        b.cc_e[o] = vy*bcc1 - vx*bcc2;
+      }
+    }
+    if ((FLAGS & 2) && i >= b.is && i <= b.ie && j >= b.js && j <= b.je && k >= b.ks &&
+        k <= b.ke) {
+      double dt1 = b.dx1f[i], dt2 = b.dx2f[j], dt3 = b.dx3f[k];
+      if (MHD) {
+        double bx = bcc1 + fabs(bf1 - bcc1);
+        double cf = fast_speed(p.gamma, u_d, w_p, bcc2, bcc3, bx);
+        dt1 /= (fabs(vx) + cf);
+        bx = bcc2 + fabs(bf2 - bcc2);
+        cf = fast_speed(p.gamma, u_d, w_p, bcc3, bcc1, bx);
+        dt2 /= (fabs(vy) + cf);
+        bx = bcc3 + fabs(bf3 - bcc3);
+        cf = fast_speed(p.gamma, u_d, w_p, bcc1, bcc2, bx);
+        dt3 /= (fabs(vz) + cf);
+      } else {
+        double cs = sound_speed(p.gamma, u_d, w_p);
+        dt1 /= (fabs(vx) + cs);
+        dt2 /= (fabs(vy) + cs);
+        dt3 /= (fabs(vz) + cs);
+      }
+      m = dmin(m, dt1);
+      if (b.f2) m = dmin(m, dt2);
+      if (b.f3) m = dmin(m, dt3);
+    }
   }
-  long o = CCI(b,0,k,j,i);
-  long sv = (long)b.nc3*b.nc2*b.nc1;
-  double u_d = b.u[o], u_m1 = b.u[o+sv], u_m2 = b.u[o+2*sv], u_m3 = b.u[o+3*sv],
-         u_e = b.u[o+4*sv];
-  double u_d0 = u_d, u_e0 = u_e;
-  u_d = (u_d > p.dfloor) ? u_d : p.dfloor;
-  double di = 1.0/u_d;
-  double e_k = 0.5*di*(sqr(u_m1) + sqr(u_m2) + sqr(u_m3));
-  double w_p;
-  if (MHD) {
-    w_p = gm1*(u_e - e_k - pb);
-    u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k + pb);
-  } else {
-    w_p = gm1*(u_e - e_k);
-    u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k);
+  if (FLAGS & 2) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      double o2 = __shfl_xor_sync(0xffffffffu, m, s);
+      m = dmin(m, o2);
+    }
+    if ((threadIdx.x & 31) == 0 && m < DBL_MAX)
+      atomicMin(dtmin, (unsigned long long)__double_as_longlong(m));
   }
-  w_p = (w_p > p.pfloor) ? w_p : p.pfloor;
-  // floors write back into cons (the reference always stores; storing only changes is
-  // value-identical and saves two stores per cell)
-  if (u_d != u_d0) b.u[o] = u_d;
-  if (u_e != u_e0) b.u[o+4*sv] = u_e;
-  b.w[o] = u_d;
-  b.w[o+sv] = u_m1*di;
-  b.w[o+2*sv] = u_m2*di;
-  b.w[o+3*sv] = u_m3*di;
-  b.w[o+4*sv] = w_p;
 }
 
 void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
-                      int ku, cudaStream_t s) {
+                      int ku, cudaStream_t s, int flags, unsigned long long *dtmin) {
   dim3 g = grid3(iu-il+1, ju-jl+1, ku-kl+1);
-  if (p.mhd) { k_cons2prim<true><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl); } else { k_cons2prim<false><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl); }
+  if (!p.mhd) flags &= ~1;
+  if (p.mhd) {
+    switch (flags & 3) {
+      case 0: k_cons2prim<true,0><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin); break;
+      case 1: k_cons2prim<true,1><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin); break;
+      case 2: k_cons2prim<true,2><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin); break;
+      default: k_cons2prim<true,3><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin); break;
+    }
+  } else {
+    if (flags & 2) k_cons2prim<false,2><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin);
+    else k_cons2prim<false,0><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin);
+  }
   ++g_launches;
 }
 
@@ -135,43 +196,60 @@ void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, in
 // =============================================================================================
 
 // sweep-ordered primitives of one cell: (rho, v_dir, v_dir+1, v_dir+2, p [, B_dir+1, B_dir+2])
+// (32-bit element offsets: the host checks that every register has < 2^31 elements)
 template <int DIR, bool MHD>
-__device__ __forceinline__ void load_cell(const BlkDev &b, long o, long sv, double *q) {
-  q[IDN] = b.w[o];
-  q[IVX] = b.w[o + (1 + DIR)*sv];
-  q[IVY] = b.w[o + (1 + (DIR+1)%3)*sv];
-  q[IVZ] = b.w[o + (1 + (DIR+2)%3)*sv];
-  q[IPR] = b.w[o + 4*sv];
+__device__ __forceinline__ void load_cell(const double *__restrict__ w,
+                                          const double *__restrict__ bcc, int o, int sv,
+                                          double *q) {
+  q[IDN] = w[o];
+  q[IVX] = w[o + (1 + DIR)*sv];
+  q[IVY] = w[o + (1 + (DIR+1)%3)*sv];
+  q[IVZ] = w[o + (1 + (DIR+2)%3)*sv];
+  q[IPR] = w[o + 4*sv];
   if (MHD) {
-    q[IBY] = b.bcc[o + ((DIR+1)%3)*sv];
-    q[IBZ] = b.bcc[o + ((DIR+2)%3)*sv];
+    q[IBY] = bcc[o + ((DIR+1)%3)*sv];
+    q[IBZ] = bcc[o + ((DIR+2)%3)*sv];
   }
 }
 
+// 5 CTAs of 128 threads per SM (96 registers, a few spills) measured best on B200:
+// MINB 3/4/5/6/8 -> 1.27/1.10/1.05/1.06/1.37 ms per 256^3 HLLD+PLM sweep (profiles/).
+#ifndef AB_FLUX_MINB
+#define AB_FLUX_MINB 5
+#endif
+
+// The face range [i0,i0+ni) x [j0,j0+nj) x [k0,k0+nk) is flattened so that every thread of a
+// CTA has work (rows of nx1+1 faces do not pad to a multiple of the CTA width).
 template <int DIR, int ORDER, int SOLVER, bool MHD>
-__global__ void __launch_bounds__(BX) k_flux(BlkDev b, ReconGeom g, Params p, int i0, int i1,
-                                             int j0, int k0, double dt_val,
-                                             const double *dt_ptr) {
+__global__ void __launch_bounds__(BX, AB_FLUX_MINB)
+k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int ntot,
+       double dt_val, const double *dt_ptr) {
   constexpr int NW = MHD ? 7 : 5;
-  int i = i0 + blockIdx.x*BX + threadIdx.x;
-  if (i > i1) return;
-  int j = j0 + blockIdx.y, k = k0 + blockIdx.z;
-  const long sv = (long)b.nc3*b.nc2*b.nc1;
-  const long st = (DIR == 0) ? 1 : ((DIR == 1) ? (long)b.nc1 : (long)b.nc1*b.nc2);
-  const long oc = CCI(b,0,k,j,i);           // cell on the upper side of the face
+  int t = blockIdx.x*BX + threadIdx.x;
+  if (t >= ntot) return;
+  int r = t / ni;
+  const int i = i0 + (t - r*ni);
+  const int kk = r / nj;
+  const int j = j0 + (r - kk*nj);
+  const int k = k0 + kk;
+  const int sv = b.nc3*b.nc2*b.nc1;
+  const int st = (DIR == 0) ? 1 : ((DIR == 1) ? b.nc1 : b.nc1*b.nc2);
+  const int oc = (k*b.nc2 + j)*b.nc1 + i;      // cell on the upper side of the face
   const int c = (DIR == 0) ? i : ((DIR == 1) ? j : k);
+  const double *__restrict__ w = b.w;
+  const double *__restrict__ bcc = b.bcc;
 
   double wl[NW], wr[NW];
   if (ORDER == 1) {
     // DonorCell (reconstruct/dc.cpp)
-    load_cell<DIR,MHD>(b, oc - st, sv, wl);
-    load_cell<DIR,MHD>(b, oc, sv, wr);
+    load_cell<DIR,MHD>(w, bcc, oc - st, sv, wl);
+    load_cell<DIR,MHD>(w, bcc, oc, sv, wr);
   } else if (ORDER == 2) {
     double qm2[NW], qm1[NW], q0[NW], qp1[NW];
-    load_cell<DIR,MHD>(b, oc - 2*st, sv, qm2);
-    load_cell<DIR,MHD>(b, oc - st, sv, qm1);
-    load_cell<DIR,MHD>(b, oc, sv, q0);
-    load_cell<DIR,MHD>(b, oc + st, sv, qp1);
+    load_cell<DIR,MHD>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD>(w, bcc, oc + st, sv, qp1);
     const double wp_l = g.wp[DIR][c-1], wm_l = g.wm[DIR][c-1];
     const double wp_r = g.wp[DIR][c], wm_r = g.wm[DIR][c];
 #pragma unroll
@@ -182,12 +260,12 @@ __global__ void __launch_bounds__(BX) k_flux(BlkDev b, ReconGeom g, Params p, in
     }
   } else {
     double qm3[NW], qm2[NW], qm1[NW], q0[NW], qp1[NW], qp2[NW];
-    load_cell<DIR,MHD>(b, oc - 3*st, sv, qm3);
-    load_cell<DIR,MHD>(b, oc - 2*st, sv, qm2);
-    load_cell<DIR,MHD>(b, oc - st, sv, qm1);
-    load_cell<DIR,MHD>(b, oc, sv, q0);
-    load_cell<DIR,MHD>(b, oc + st, sv, qp1);
-    load_cell<DIR,MHD>(b, oc + 2*st, sv, qp2);
+    load_cell<DIR,MHD>(w, bcc, oc - 3*st, sv, qm3);
+    load_cell<DIR,MHD>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD>(w, bcc, oc + st, sv, qp1);
+    load_cell<DIR,MHD>(w, bcc, oc + 2*st, sv, qp2);
 #pragma unroll
     for (int n = 0; n < NW; ++n) {
       double dummy;
@@ -201,16 +279,17 @@ __global__ void __launch_bounds__(BX) k_flux(BlkDev b, ReconGeom g, Params p, in
     wr[IPR] = (wr[IPR] > p.pfloor) ? wr[IPR] : p.pfloor;
   }
 
-  long of;   // face-array offset
-  if (DIR == 0) of = F1I(b,k,j,i); else if (DIR == 1) of = F2I(b,k,j,i); else of = F3I(b,k,j,i);
+  // face-array offset and variable stride
+  int of, sf;
+  if (DIR == 0) { of = (k*b.nc2 + j)*(b.nc1+1) + i; sf = b.nc3*b.nc2*(b.nc1+1); }
+  else if (DIR == 1) { of = (k*(b.nc2+1) + j)*b.nc1 + i; sf = b.nc3*(b.nc2+1)*b.nc1; }
+  else { of = (k*b.nc2 + j)*b.nc1 + i; sf = (b.nc3+1)*b.nc2*b.nc1; }
   double bxi = 0.0;
   if (MHD) bxi = b.b[DIR][of];
   double f[NW];
   riemann<SOLVER,MHD>(wl, wr, bxi, p.gamma, f);
 
-  const long sf = (DIR == 0) ? (long)b.nc3*b.nc2*(b.nc1+1)
-                : ((DIR == 1) ? (long)b.nc3*(b.nc2+1)*b.nc1 : (long)(b.nc3+1)*b.nc2*b.nc1);
-  double *flx = b.flux[DIR];
+  double *__restrict__ flx = b.flux[DIR];
   flx[of] = f[IDN];
   flx[of + (1 + DIR)*sf] = f[IVX];
   flx[of + (1 + (DIR+1)%3)*sf] = f[IVY];
@@ -241,8 +320,10 @@ static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, doubl
     i0 = is; i1 = ie; j0 = js; j1 = je; k0 = ks; k1 = ke+1;
     if (MHD) { i0 = is-1; i1 = ie+1; j0 = js-1; j1 = je+1; }
   }
-  k_flux<DIR,ORDER,SOLVER,MHD><<<grid3(i1-i0+1, j1-j0+1, k1-k0+1), BX, 0, s>>>(
-      b, g, p, i0, i1, j0, k0, dt_val, dt_ptr); ++g_launches;
+  int ni = i1-i0+1, nj = j1-j0+1, nk = k1-k0+1;
+  int ntot = ni*nj*nk;
+  k_flux<DIR,ORDER,SOLVER,MHD><<<(ntot + BX - 1)/BX, BX, 0, s>>>(
+      b, g, p, i0, ni, j0, nj, k0, ntot, dt_val, dt_ptr); ++g_launches;
 }
 
 template <int ORDER, int SOLVER, bool MHD>
@@ -403,15 +484,15 @@ __global__ void __launch_bounds__(BX) k_corner_e1d(BlkDev b) {
   b.e[2][E3I(b,ks,b.je+1,i)] = v3;
 }
 
-void launch_corner_e(const BlkDev &b, cudaStream_t s) {
+void launch_corner_e(const BlkDev &b, cudaStream_t s, int have_cc_e) {
   int nx1 = b.ie - b.is + 1, nx2 = b.je - b.js + 1, nx3 = b.ke - b.ks + 1;
   if (!b.f2) {
     k_corner_e1d<<<grid3(nx1+1, 1, 1), BX, 0, s>>>(b); ++g_launches;
   } else if (!b.f3) {
-    k_cc_e<<<grid3(nx1+2, nx2+2, 1), BX, 0, s>>>(b, b.is-1, b.ie+1, b.js-1, b.ks); ++g_launches;
+    if (!have_cc_e) { k_cc_e<<<grid3(nx1+2, nx2+2, 1), BX, 0, s>>>(b, b.is-1, b.ie+1, b.js-1, b.ks); ++g_launches; }
     k_corner_e2d<<<grid3(nx1+1, nx2+1, 1), BX, 0, s>>>(b); ++g_launches;
   } else {
-    k_cc_e<<<grid3(nx1+2, nx2+2, nx3+2), BX, 0, s>>>(b, b.is-1, b.ie+1, b.js-1, b.ks-1); ++g_launches;
+    if (!have_cc_e) { k_cc_e<<<grid3(nx1+2, nx2+2, nx3+2), BX, 0, s>>>(b, b.is-1, b.ie+1, b.js-1, b.ks-1); ++g_launches; }
     k_corner_e3d<<<grid3(nx1+1, nx2+1, nx3+1), BX, 0, s>>>(b); ++g_launches;
   }
 }

@@ -11,8 +11,9 @@ namespace ab {
 struct ReconGeom { const double *wp[3]; const double *wm[3]; };
 
 // `dt_ptr` (device) wins over `dt_val` when non-null: the cycle loop keeps dt on the device.
+// flags bit0: also write cc_e; bit1: also reduce NewBlockTimeStep over active cells into dtmin
 void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
-                      int ku, cudaStream_t s);
+                      int ku, cudaStream_t s, int flags = 0, unsigned long long *dtmin = nullptr);
 void launch_prim2cons(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
                       int ku, cudaStream_t s);
 void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, int ku,
@@ -21,7 +22,8 @@ void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int ord
                    double dt_val, const double *dt_ptr, cudaStream_t s);
 void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
                      double dt_val, const double *dt_ptr, cudaStream_t s);
-void launch_corner_e(const BlkDev &b, cudaStream_t s);
+// have_cc_e: cc_e was already written by cons2prim (flags bit0) over [is-1,ie+1]^dim
+void launch_corner_e(const BlkDev &b, cudaStream_t s, int have_cc_e = 0);
 void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);
 void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);
 

@@ -126,6 +126,8 @@ struct LocalBlock {
   int parity = 0;                         // (u,u1) swap state
   int parity_b = 0;                       // (b,b1) swap state
   unsigned long long *dtmin = nullptr;    // slot in the mesh-wide array
+  bool cc_e_valid = false;                // cc_e written by the fused cons2prim
+  bool has_phys_bc = false;
 };
 
 }  // namespace
@@ -621,6 +623,9 @@ int alloc_blocks(AbMesh *m) {
     CK(cudaStreamSynchronize(m->stream));   // host vectors go out of scope
     L.emf_send = (double *)cur;
     L.dtmin = m->dtmin + l;
+    L.has_phys_bc = false;
+    for (int f = 0; f < 2*m->ndim; ++f)
+      if (B.bcs[f] != -1 && B.bcs[f] != AB_BC_PERIODIC) L.has_phys_bc = true;
   }
   return AB_OK;
 }
@@ -866,7 +871,7 @@ int emf_exchange(AbMesh *m) {
   return AB_OK;
 }
 
-void primitives(AbMesh *m, LocalBlock &L) {
+void primitives(AbMesh *m, LocalBlock &L, int with_dt = 0) {
   // TimeIntegratorTaskList::Primitives (time_integrator.cpp:1965-1983)
   HostBlock &B = *L.hb;
   int ng = m->p.nghost;
@@ -877,7 +882,11 @@ void primitives(AbMesh *m, LocalBlock &L) {
   if (B.nblevel[1][2][1] != -1) ju += ng;
   if (B.nblevel[0][1][1] != -1) kl -= ng;
   if (B.nblevel[2][1][1] != -1) ku += ng;
-  ab::launch_cons2prim(L.d, m->kp, il, iu, jl, ju, kl, ku, m->stream);
+  // blocks without physical boundaries get cc_e from the same pass (all cells that
+  // ComputeCornerE reads, [is-1,ie+1]^dim, lie inside the cons2prim range)
+  int flags = (m->p.mhd && !L.has_phys_bc ? 1 : 0) | (with_dt ? 2 : 0);
+  ab::launch_cons2prim(L.d, m->kp, il, iu, jl, ju, kl, ku, m->stream, flags, L.dtmin);
+  L.cc_e_valid = (flags & 1) != 0;
 }
 
 void physical_bcs(AbMesh *m, LocalBlock &L) {
@@ -932,10 +941,13 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
   }
 }
 
-int new_time_step(AbMesh *m, int advance) {
-  // NewBlockTimeStep on every block, then Mesh::NewTimeStep (mesh/mesh.cpp:1078-1119)
-  ab::launch_fill_u64(m->dtmin, (int)m->lb.size(), 0x7FEFFFFFFFFFFFFFull /* DBL_MAX */, m->stream);
-  for (auto &L : m->lb) ab::launch_new_block_dt(L.d, m->kp, L.dtmin, m->stream);
+int new_time_step(AbMesh *m, int advance, bool blocks_done = false) {
+  // NewBlockTimeStep on every block (unless already reduced by the fused cons2prim), then
+  // Mesh::NewTimeStep (mesh/mesh.cpp:1078-1119)
+  if (!blocks_done) {
+    ab::launch_fill_u64(m->dtmin, (int)m->lb.size(), 0x7FEFFFFFFFFFFFFFull /* DBL_MAX */, m->stream);
+    for (auto &L : m->lb) ab::launch_new_block_dt(L.d, m->kp, L.dtmin, m->stream);
+  }
   ab::launch_mesh_new_dt(m->state, m->dtmin, (int)m->lb.size(), 0 /*phase 0*/, m->stream);
   if (m->p.nranks > 1) {
     if (!m->comm) return fail(AB_ERR_STATE, "nranks > 1 but ab_comm_init was not called");
@@ -979,7 +991,7 @@ int one_cycle(AbMesh *m) {
           ab::launch_flux_dir(L.d, L.g, m->kp, order, dir, 0.0, dtp, m->stream);
         }
       }
-      if (m->p.mhd) ab::launch_corner_e(L.d, m->stream);
+      if (m->p.mhd) ab::launch_corner_e(L.d, m->stream, L.cc_e_valid ? 1 : 0);
     }
     int rc = emf_exchange(m);
     if (rc) return rc;
@@ -1001,13 +1013,15 @@ int one_cycle(AbMesh *m) {
     }
     rc = bvals_exchange(m);
     if (rc) return rc;
-    for (auto &L : m->lb) { primitives(m, L); physical_bcs(m, L); }
+    const int last = (stage == m->nstages);
+    if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size(), 0x7FEFFFFFFFFFFFFFull, m->stream);
+    for (auto &L : m->lb) { primitives(m, L, last); physical_bcs(m, L); }
     if (stage == m->nstages) {
       // record the dt this cycle used, then time += dt, ncycle++, NewTimeStep
       if (m->hist_n < m->hist_cap)
         CK(cudaMemcpyAsync(m->dt_hist + m->hist_n, m->state + 1, 8, cudaMemcpyDeviceToDevice, m->stream));
       m->hist_n++;
-      rc = new_time_step(m, 1);
+      rc = new_time_step(m, 1, true);
       if (rc) return rc;
     }
   }
@@ -1042,6 +1056,13 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
   for (int f = 0; f < 6; ++f)
     if (p->bc[f] != AB_BC_PERIODIC && p->bc[f] != AB_BC_OUTFLOW)
       return fail(AB_ERR_ARG, "unsupported boundary flag");
+  {
+    long n1 = p->bx1 + 2L*p->nghost + 1, n2 = (p->nx2 > 1 ? p->bx2 + 2L*p->nghost : 1) + 1,
+         n3 = (p->nx3 > 1 ? p->bx3 + 2L*p->nghost : 1) + 1;
+    if (5*n1*n2*n3 >= (1L << 31))
+      return fail(AB_ERR_ARG, "MeshBlock too large: registers must have < 2^31 elements "
+                              "(kernels use 32-bit element offsets); use smaller MeshBlocks");
+  }
   if (ab_device_count() <= 0)
     return fail(AB_ERR_NO_DEVICE, "no CUDA device: libathena_b200 has no CPU fallback");
   CK(cudaSetDevice(p->device));
@@ -1113,6 +1134,7 @@ long ab_reg_size(const AbMesh *m, int lid, int reg) {
 
 int ab_upload(AbMesh *m, int lid, int reg, const double *host) {
   GET_L(m, lid);
+  if (reg == AB_W || reg == AB_BCC) L.cc_e_valid = false;
   if (reg < 0 || reg >= AB_NREG || !host) return fail(AB_ERR_ARG, "bad register");
   double **slot = reg_slot(L, reg);
   if (!slot || !*slot) return fail(AB_ERR_ARG, "register not allocated in this configuration");
@@ -1160,6 +1182,7 @@ int ab_comm_init(AbMesh *m, const unsigned char id[128]) {
 
 int ab_cons2prim(AbMesh *m, int lid, int il, int iu, int jl, int ju, int kl, int ku) {
   GET_L(m, lid);
+  L.cc_e_valid = false;
   ab::launch_cons2prim(L.d, m->kp, il, iu, jl, ju, kl, ku, m->stream);
   CK(cudaGetLastError());
   return AB_OK;
@@ -1186,7 +1209,7 @@ int ab_calc_fluxes(AbMesh *m, int lid, int order, double dt) {
 int ab_corner_e(AbMesh *m, int lid) {
   GET_L(m, lid);
   if (!m->p.mhd) return fail(AB_ERR_STATE, "ComputeCornerE needs MAGNETIC_FIELDS_ENABLED");
-  ab::launch_corner_e(L.d, m->stream);
+  ab::launch_corner_e(L.d, m->stream, L.cc_e_valid ? 1 : 0);
   CK(cudaGetLastError());
   return AB_OK;
 }

@@ -33,6 +33,19 @@ AB_HD double dmax(double a, double b) { return (a < b) ? b : a; }
 AB_HD double sqr(double x) { return x*x; }
 AB_HD double sgn(double x) { return (x < 0.0) ? -1.0 : 1.0; }
 
+// a/b, bit-identical to IEEE division.  The GPU's FP64 division falls into a ~100-instruction
+// slow path when the dividend is zero or tiny; exactly-zero dividends are common on this path
+// (static, uniform regions: zero mass flux, zero pressure jump), so they are answered
+// directly with the correctly signed zero.  0/0, 0/NaN still go through the division.
+AB_HD double fdiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  if (a == 0.0 && b == b && b != 0.0)
+    return __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) &
+                                (long long)0x8000000000000000ull);
+#endif
+  return a/b;
+}
+
 // EquationOfState::SoundSpeed (eos/adiabatic_hydro.cpp:125)
 AB_HD double sound_speed(double gamma, double d, double p) { return sqrt(gamma*p/d); }
 
@@ -48,7 +61,7 @@ AB_HD double fast_speed(double gamma, double d, double p, double by, double bz, 
 
 // Hydro::GetWeightForCT (hydro/hydro.cpp:154-158)
 AB_HD double weight_for_ct(double dflx, double rhol, double rhor, double dx, double dt) {
-  double v_over_c = (1024.0)*dt*dflx/(dx*(rhol + rhor));
+  double v_over_c = fdiv((1024.0)*dt*dflx, (dx*(rhol + rhor)));
   double tmp_min = dmin(0.5, v_over_c);
   return 0.5 + dmax(-0.5, tmp_min);
 }
@@ -62,8 +75,8 @@ AB_HD void plm(double qm1, double q, double qp1, double wp, double wm,
   double dwl = (q - qm1);
   double dwr = (qp1 - q);
   double dw2 = dwl*dwr;
-  double dwm = 2.0*dw2/(dwl + dwr);
-  if (dw2 <= 0.0) dwm = 0.0;
+  double dwm = 0.0;                       // reference: computed, then zeroed when dw2 <= 0
+  if (dw2 > 0.0) dwm = 2.0*dw2/(dwl + dwr);
   plus = q + wp*dwm;
   minus = q - wm*dwm;
 }
@@ -164,7 +177,7 @@ AB_HD void hllc(const double *wli, const double *wri, double gamma, double *flxi
   double tr = wri[IPR] + vxr*wri[IDN]*wri[IVX];
   double ml = wli[IDN]*vxl;
   double mr = -(wri[IDN]*vxr);
-  double am = (tl - tr)/(ml + mr);
+  double am = fdiv((tl - tr), (ml + mr));
   double cp = (ml*tr + mr*tl)/(ml + mr);
   cp = cp > 0.0 ? cp : 0.0;
   vxl = wli[IVX] - bm;
@@ -351,7 +364,11 @@ AB_HD void roe_hydro(const double *wli, const double *wri, double gamma, double 
 
 struct Cons1D { double d, mx, my, mz, e, by, bz; };
 
-// HLLD (hydro/rsolvers/mhd/hlld.cpp:38-382)
+// HLLD (hydro/rsolvers/mhd/hlld.cpp:38-382).
+// The reference evaluates every intermediate state and both L/R fluxes and then selects one
+// of six results (hlld.cpp:315-369).  Here the branch is decided first and only the terms
+// the selected flux depends on are evaluated -- the same operations in the same order on the
+// same operands, so the selected result is bit-identical.
 AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
                 double *flxi) {
   const double SMALL_NUMBER = 1.0e-8;
@@ -383,23 +400,9 @@ AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
   spd4 = dmax(wli[IVX]+cfl, wri[IVX]+cfr);
   double ptl = wli[IPR] + pbl;
   double ptr = wri[IPR] + pbr;
-  fl.d  = ul.mx;
-  fl.mx = ul.mx*wli[IVX] + ptl - bxsq;
-  fl.my = ul.my*wli[IVX] - bxi*ul.by;
-  fl.mz = ul.mz*wli[IVX] - bxi*ul.bz;
-  fl.e  = wli[IVX]*(ul.e + ptl - bxsq) - bxi*(wli[IVY]*ul.by + wli[IVZ]*ul.bz);
-  fl.by = ul.by*wli[IVX] - bxi*wli[IVY];
-  fl.bz = ul.bz*wli[IVX] - bxi*wli[IVZ];
-  fr.d  = ur.mx;
-  fr.mx = ur.mx*wri[IVX] + ptr - bxsq;
-  fr.my = ur.my*wri[IVX] - bxi*ur.by;
-  fr.mz = ur.mz*wri[IVX] - bxi*ur.bz;
-  fr.e  = wri[IVX]*(ur.e + ptr - bxsq) - bxi*(wri[IVY]*ur.by + wri[IVZ]*ur.bz);
-  fr.by = ur.by*wri[IVX] - bxi*wri[IVY];
-  fr.bz = ur.bz*wri[IVX] - bxi*wri[IVZ];
   double sdl = spd0 - wli[IVX];
   double sdr = spd4 - wri[IVX];
-  spd2 = (sdr*ur.mx - sdl*ul.mx + (ptl - ptr))/(sdr*ur.d - sdl*ul.d);
+  spd2 = fdiv((sdr*ur.mx - sdl*ul.mx + (ptl - ptr)), (sdr*ur.d - sdl*ul.d));
   double sdml = spd0 - spd2;
   double sdmr = spd4 - spd2;
   double sdml_inv = 1.0/sdml;
@@ -410,82 +413,129 @@ AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
   double urst_d_inv = 1.0/urst.d;
   double sqrtdl = sqrt(ulst.d);
   double sqrtdr = sqrt(urst.d);
-  spd1 = spd2 - fabs(bxi)/sqrtdl;
-  spd3 = spd2 + fabs(bxi)/sqrtdr;
+  spd1 = spd2 - fdiv(fabs(bxi), sqrtdl);
+  spd3 = spd2 + fdiv(fabs(bxi), sqrtdr);
+
+  // branch selection (hlld.cpp:315-369)
+  const bool sup_l = (spd0 >= 0.0);
+  const bool sup_r = !sup_l && (spd4 <= 0.0);
+  const bool br_l1 = !sup_l && !sup_r && (spd1 >= 0.0);
+  const bool br_l2 = !sup_l && !sup_r && !br_l1 && (spd2 >= 0.0);
+  const bool br_r2 = !sup_l && !sup_r && !br_l1 && !br_l2 && (spd3 > 0.0);
+  const bool br_r1 = !sup_l && !sup_r && !br_l1 && !br_l2 && !br_r2;
+  const bool left = sup_l || br_l1 || br_l2;
+  const bool star = !(sup_l || sup_r);
+
+  if (left) {
+    fl.d  = ul.mx;
+    fl.mx = ul.mx*wli[IVX] + ptl - bxsq;
+    fl.my = ul.my*wli[IVX] - bxi*ul.by;
+    fl.mz = ul.mz*wli[IVX] - bxi*ul.bz;
+    fl.e  = wli[IVX]*(ul.e + ptl - bxsq) - bxi*(wli[IVY]*ul.by + wli[IVZ]*ul.bz);
+    fl.by = ul.by*wli[IVX] - bxi*wli[IVY];
+    fl.bz = ul.bz*wli[IVX] - bxi*wli[IVZ];
+  } else {
+    fr.d  = ur.mx;
+    fr.mx = ur.mx*wri[IVX] + ptr - bxsq;
+    fr.my = ur.my*wri[IVX] - bxi*ur.by;
+    fr.mz = ur.mz*wri[IVX] - bxi*ur.bz;
+    fr.e  = wri[IVX]*(ur.e + ptr - bxsq) - bxi*(wri[IVY]*ur.by + wri[IVZ]*ur.bz);
+    fr.by = ur.by*wri[IVX] - bxi*wri[IVY];
+    fr.bz = ur.bz*wri[IVX] - bxi*wri[IVZ];
+  }
+  if (sup_l) {
+    flxi[IDN] = fl.d; flxi[IVX] = fl.mx; flxi[IVY] = fl.my; flxi[IVZ] = fl.mz;
+    flxi[IEN] = fl.e; flxi[IBY] = fl.by; flxi[IBZ] = fl.bz;
+    return;
+  }
+  if (sup_r) {
+    flxi[IDN] = fr.d; flxi[IVX] = fr.mx; flxi[IVY] = fr.my; flxi[IVZ] = fr.mz;
+    flxi[IEN] = fr.e; flxi[IBY] = fr.by; flxi[IBZ] = fr.bz;
+    return;
+  }
+  (void)star;
+
   double ptstl = ptl + ul.d*sdl*(spd2-wli[IVX]);
   double ptstr = ptr + ur.d*sdr*(spd2-wri[IVX]);
   double ptst = 0.5*(ptstr + ptstl);
-  ulst.mx = ulst.d*spd2;
-  if (fabs(ul.d*sdl*sdml-bxsq) < (SMALL_NUMBER)*ptst) {
-    ulst.my = ulst.d*wli[IVY];
-    ulst.mz = ulst.d*wli[IVZ];
-    ulst.by = ul.by;
-    ulst.bz = ul.bz;
-  } else {
-    double tmp = bxi*(sdl - sdml)/(ul.d*sdl*sdml - bxsq);
-    ulst.my = ulst.d*(wli[IVY] - ul.by*tmp);
-    ulst.mz = ulst.d*(wli[IVZ] - ul.bz*tmp);
-    tmp = (ul.d*sqr(sdl) - bxsq)/(ul.d*sdl*sdml - bxsq);
-    ulst.by = ul.by*tmp;
-    ulst.bz = ul.bz*tmp;
+  const bool dstar = br_l2 || br_r2;
+  double vbstl = 0.0, vbstr = 0.0;
+  // ul* (needed by Fl*, Fl**, and -- transverse components only -- by Fr**)
+  if (!br_r1) {
+    ulst.mx = ulst.d*spd2;
+    if (fabs(ul.d*sdl*sdml-bxsq) < (SMALL_NUMBER)*ptst) {
+      ulst.my = ulst.d*wli[IVY];
+      ulst.mz = ulst.d*wli[IVZ];
+      ulst.by = ul.by;
+      ulst.bz = ul.bz;
+    } else {
+      double tmp = fdiv(bxi*(sdl - sdml), (ul.d*sdl*sdml - bxsq));
+      ulst.my = ulst.d*(wli[IVY] - ul.by*tmp);
+      ulst.mz = ulst.d*(wli[IVZ] - ul.bz*tmp);
+      tmp = (ul.d*sqr(sdl) - bxsq)/(ul.d*sdl*sdml - bxsq);
+      ulst.by = ul.by*tmp;
+      ulst.bz = ul.bz*tmp;
+    }
+    if (left) {
+      vbstl = (ulst.mx*bxi+(ulst.my*ulst.by+ulst.mz*ulst.bz))*ulst_d_inv;
+      ulst.e = (sdl*ul.e - ptl*wli[IVX] + ptst*spd2 +
+                bxi*(wli[IVX]*bxi + (wli[IVY]*ul.by + wli[IVZ]*ul.bz) - vbstl))*sdml_inv;
+    }
   }
-  double vbstl = (ulst.mx*bxi+(ulst.my*ulst.by+ulst.mz*ulst.bz))*ulst_d_inv;
-  ulst.e = (sdl*ul.e - ptl*wli[IVX] + ptst*spd2 +
-            bxi*(wli[IVX]*bxi + (wli[IVY]*ul.by + wli[IVZ]*ul.bz) - vbstl))*sdml_inv;
-  urst.mx = urst.d*spd2;
-  if (fabs(ur.d*sdr*sdmr - bxsq) < (SMALL_NUMBER)*ptst) {
-    urst.my = urst.d*wri[IVY];
-    urst.mz = urst.d*wri[IVZ];
-    urst.by = ur.by;
-    urst.bz = ur.bz;
-  } else {
-    double tmp = bxi*(sdr - sdmr)/(ur.d*sdr*sdmr - bxsq);
-    urst.my = urst.d*(wri[IVY] - ur.by*tmp);
-    urst.mz = urst.d*(wri[IVZ] - ur.bz*tmp);
-    tmp = (ur.d*sqr(sdr) - bxsq)/(ur.d*sdr*sdmr - bxsq);
-    urst.by = ur.by*tmp;
-    urst.bz = ur.bz*tmp;
+  // ur* (needed by Fr*, Fr**, and -- transverse components only -- by Fl**)
+  if (!br_l1) {
+    urst.mx = urst.d*spd2;
+    if (fabs(ur.d*sdr*sdmr - bxsq) < (SMALL_NUMBER)*ptst) {
+      urst.my = urst.d*wri[IVY];
+      urst.mz = urst.d*wri[IVZ];
+      urst.by = ur.by;
+      urst.bz = ur.bz;
+    } else {
+      double tmp = fdiv(bxi*(sdr - sdmr), (ur.d*sdr*sdmr - bxsq));
+      urst.my = urst.d*(wri[IVY] - ur.by*tmp);
+      urst.mz = urst.d*(wri[IVZ] - ur.bz*tmp);
+      tmp = (ur.d*sqr(sdr) - bxsq)/(ur.d*sdr*sdmr - bxsq);
+      urst.by = ur.by*tmp;
+      urst.bz = ur.bz*tmp;
+    }
+    if (!left) {
+      vbstr = (urst.mx*bxi+(urst.my*urst.by+urst.mz*urst.bz))*urst_d_inv;
+      urst.e = (sdr*ur.e - ptr*wri[IVX] + ptst*spd2 +
+                bxi*(wri[IVX]*bxi + (wri[IVY]*ur.by + wri[IVZ]*ur.bz) - vbstr))*sdmr_inv;
+    }
   }
-  double vbstr = (urst.mx*bxi+(urst.my*urst.by+urst.mz*urst.bz))*urst_d_inv;
-  urst.e = (sdr*ur.e - ptr*wri[IVX] + ptst*spd2 +
-            bxi*(wri[IVX]*bxi + (wri[IVY]*ur.by + wri[IVZ]*ur.bz) - vbstr))*sdmr_inv;
-  if (0.5*bxsq < (SMALL_NUMBER)*ptst) {
-    uldst = ulst;
-    urdst = urst;
-  } else {
-    double invsumd = 1.0/(sqrtdl + sqrtdr);
-    double bxsig = (bxi > 0.0 ? 1.0 : -1.0);
-    uldst.d = ulst.d;
-    urdst.d = urst.d;
-    uldst.mx = ulst.mx;
-    urdst.mx = urst.mx;
-    double tmp = invsumd*(sqrtdl*(ulst.my*ulst_d_inv) + sqrtdr*(urst.my*urst_d_inv) +
-                          bxsig*(urst.by - ulst.by));
-    uldst.my = uldst.d*tmp;
-    urdst.my = urdst.d*tmp;
-    tmp = invsumd*(sqrtdl*(ulst.mz*ulst_d_inv) + sqrtdr*(urst.mz*urst_d_inv) +
-                   bxsig*(urst.bz - ulst.bz));
-    uldst.mz = uldst.d*tmp;
-    urdst.mz = urdst.d*tmp;
-    tmp = invsumd*(sqrtdl*urst.by + sqrtdr*ulst.by +
-                   bxsig*sqrtdl*sqrtdr*((urst.my*urst_d_inv) - (ulst.my*ulst_d_inv)));
-    uldst.by = urdst.by = tmp;
-    tmp = invsumd*(sqrtdl*urst.bz + sqrtdr*ulst.bz +
-                   bxsig*sqrtdl*sqrtdr*((urst.mz*urst_d_inv) - (ulst.mz*ulst_d_inv)));
-    uldst.bz = urdst.bz = tmp;
-    tmp = spd2*bxi + (uldst.my*uldst.by + uldst.mz*uldst.bz)/uldst.d;
-    uldst.e = ulst.e - sqrtdl*bxsig*(vbstl - tmp);
-    urdst.e = urst.e + sqrtdr*bxsig*(vbstr - tmp);
+  if (dstar) {
+    // ul** and ur** - if Bx is near zero, same as *-states (hlld.cpp:239-281)
+    if (0.5*bxsq < (SMALL_NUMBER)*ptst) {
+      uldst = ulst;
+      urdst = urst;
+    } else {
+      double invsumd = 1.0/(sqrtdl + sqrtdr);
+      double bxsig = (bxi > 0.0 ? 1.0 : -1.0);
+      uldst.d = ulst.d;
+      urdst.d = urst.d;
+      uldst.mx = ulst.mx;
+      urdst.mx = urst.mx;
+      double tmp = invsumd*(sqrtdl*(ulst.my*ulst_d_inv) + sqrtdr*(urst.my*urst_d_inv) +
+                            bxsig*(urst.by - ulst.by));
+      uldst.my = uldst.d*tmp;
+      urdst.my = urdst.d*tmp;
+      tmp = invsumd*(sqrtdl*(ulst.mz*ulst_d_inv) + sqrtdr*(urst.mz*urst_d_inv) +
+                     bxsig*(urst.bz - ulst.bz));
+      uldst.mz = uldst.d*tmp;
+      urdst.mz = urdst.d*tmp;
+      tmp = invsumd*(sqrtdl*urst.by + sqrtdr*ulst.by +
+                     bxsig*sqrtdl*sqrtdr*((urst.my*urst_d_inv) - (ulst.my*ulst_d_inv)));
+      uldst.by = urdst.by = tmp;
+      tmp = invsumd*(sqrtdl*urst.bz + sqrtdr*ulst.bz +
+                     bxsig*sqrtdl*sqrtdr*((urst.mz*urst_d_inv) - (ulst.mz*ulst_d_inv)));
+      uldst.bz = urdst.bz = tmp;
+      tmp = spd2*bxi + fdiv((uldst.my*uldst.by + uldst.mz*uldst.bz), uldst.d);
+      if (left) uldst.e = ulst.e - sqrtdl*bxsig*(vbstl - tmp);
+      else urdst.e = urst.e + sqrtdr*bxsig*(vbstr - tmp);
+    }
   }
-  // Step 6 of the reference evaluates all four wave-jump terms and then selects; only the
-  // terms of the selected branch are evaluated here (same operations, same order).
-  if (spd0 >= 0.0) {
-    flxi[IDN] = fl.d; flxi[IVX] = fl.mx; flxi[IVY] = fl.my; flxi[IVZ] = fl.mz;
-    flxi[IEN] = fl.e; flxi[IBY] = fl.by; flxi[IBZ] = fl.bz;
-  } else if (spd4 <= 0.0) {
-    flxi[IDN] = fr.d; flxi[IVX] = fr.mx; flxi[IVY] = fr.my; flxi[IVZ] = fr.mz;
-    flxi[IEN] = fr.e; flxi[IBY] = fr.by; flxi[IBZ] = fr.bz;
-  } else if (spd1 >= 0.0) {
+  if (br_l1) {
     flxi[IDN] = fl.d  + spd0*(ulst.d - ul.d);
     flxi[IVX] = fl.mx + spd0*(ulst.mx - ul.mx);
     flxi[IVY] = fl.my + spd0*(ulst.my - ul.my);
@@ -493,7 +543,7 @@ AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
     flxi[IEN] = fl.e  + spd0*(ulst.e - ul.e);
     flxi[IBY] = fl.by + spd0*(ulst.by - ul.by);
     flxi[IBZ] = fl.bz + spd0*(ulst.bz - ul.bz);
-  } else if (spd2 >= 0.0) {
+  } else if (br_l2) {
     flxi[IDN] = fl.d  + spd0*(ulst.d - ul.d) + spd1*(uldst.d - ulst.d);
     flxi[IVX] = fl.mx + spd0*(ulst.mx - ul.mx) + spd1*(uldst.mx - ulst.mx);
     flxi[IVY] = fl.my + spd0*(ulst.my - ul.my) + spd1*(uldst.my - ulst.my);
@@ -501,7 +551,7 @@ AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
     flxi[IEN] = fl.e  + spd0*(ulst.e - ul.e) + spd1*(uldst.e - ulst.e);
     flxi[IBY] = fl.by + spd0*(ulst.by - ul.by) + spd1*(uldst.by - ulst.by);
     flxi[IBZ] = fl.bz + spd0*(ulst.bz - ul.bz) + spd1*(uldst.bz - ulst.bz);
-  } else if (spd3 > 0.0) {
+  } else if (br_r2) {
     flxi[IDN] = fr.d + spd4*(urst.d - ur.d) + spd3*(urdst.d - urst.d);
     flxi[IVX] = fr.mx + spd4*(urst.mx - ur.mx) + spd3*(urdst.mx - urst.mx);
     flxi[IVY] = fr.my + spd4*(urst.my - ur.my) + spd3*(urdst.my - urst.my);

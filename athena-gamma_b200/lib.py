@@ -58,7 +58,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    so = _build.SO
+    so = os.environ.get("AB_LIB") or _build.SO     # AB_LIB: kernel-tuning builds only
     if not os.path.exists(so):
         so = _build.build()
     L = C.CDLL(so)

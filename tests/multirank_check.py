@@ -1,0 +1,66 @@
+"""Multi-process parity check (one process per GPU, launched by torch.distributed.run):
+MeshBlocks are sharded over the ranks exactly like Mesh::CalculateLoadBalance does, ghost zones
+and EMFs cross ranks through NCCL, dt through an NCCL MIN all-reduce; every rank compares its
+blocks with the reference golden after N cycles (bit-exact)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+    sys.path.insert(0, p)
+import gpu_util  # noqa: E402
+import util  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    names = sys.argv[1:] or ["c5_blast_hlld_plm_vl2_8blk", "c2_linwave_hlld_plm_vl2_8blk",
+                             "c4_kh_hllc_ppm_rk2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
+                             "c1_sod_hllc_plm_vl2_2blk"]
+    ok = True
+    for name in names:
+        g = util.Golden(name)
+        if len(g.locs) < world:
+            continue
+        m = gpu_util.mesh_from_golden(g, rank=rank, nranks=world, device=local)
+
+        def bcast(data):
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                t.copy_(torch.tensor(list(data), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        m.init_comm(bcast)
+        m.initialize()
+        good = (m.dt == g.dts[0])
+        dts = m.cycles(g.ncycles)
+        good &= list(dts) == list(g.dts[:g.ncycles]) and m.dt == g.dts[g.ncycles]
+        nbad = 0
+        for pmb in m.my_blocks:
+            n = g.locs.index((pmb.lx1, pmb.lx2, pmb.lx3))
+            for f in g.fields:
+                if not np.array_equal(pmb.get(f), g.final[n][f]):
+                    nbad += 1
+        good &= (nbad == 0)
+        print("rank %d/%d %s: blocks %d dt_ok %s bad_arrays %d -> %s" %
+              (rank, world, name, m.nblocal, list(dts) == list(g.dts[:g.ncycles]), nbad,
+               "OK" if good else "FAIL"), flush=True)
+        ok &= good
+        del m
+    t = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(t)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if int(t.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
