@@ -31,6 +31,28 @@ static inline dim3 grid3(int ni, int nj, int nk) {
 // EquationOfState::ConservedToPrimitive (+ Field::CalculateCellCenteredField)
 // eos/adiabatic_mhd.cpp:41-90, eos/adiabatic_hydro.cpp:39-80, field/field.cpp:112-180
 // =============================================================================================
+// CFL min-reduction tail: warp shuffles, one shared-memory step per CTA, then ONE atomicMin per
+// CTA spread over DT_SLOTS addresses (positive doubles order like their bit patterns).  A
+// single address would serialise ~10^5-10^6 atomics per launch in L2.
+__device__ __forceinline__ void block_min_to_slots(double m, unsigned long long *slots) {
+  __shared__ double sm[BX/32];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    double o2 = __shfl_xor_sync(0xffffffffu, m, s);
+    m = dmin(m, o2);
+  }
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < BX/32; ++w) m = dmin(m, sm[w]);
+    if (m < DBL_MAX) {
+      unsigned slot = (blockIdx.x + 7u*blockIdx.y + 13u*blockIdx.z) & (DT_SLOTS - 1);
+      atomicMin(slots + slot, (unsigned long long)__double_as_longlong(m));
+    }
+  }
+}
+
 // FLAGS bit0: also store the cell-centred EMF cc_e = -(v x B) used by ComputeCornerE
 // (field/calculate_corner_e.cpp:131-180) -- saves a pass over w and bcc;
 // bit1: also reduce Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:64-134) over the ACTIVE
@@ -115,15 +137,7 @@ __global__ void __launch_bounds__(BX) k_cons2prim(BlkDev b, Params p, int il, in
       if (b.f3) m = dmin(m, dt3);
     }
   }
-  if (FLAGS & 2) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      double o2 = __shfl_xor_sync(0xffffffffu, m, s);
-      m = dmin(m, o2);
-    }
-    if ((threadIdx.x & 31) == 0 && m < DBL_MAX)
-      atomicMin(dtmin, (unsigned long long)__double_as_longlong(m));
-  }
+  if (FLAGS & 2) block_min_to_slots(m, dtmin);
 }
 
 void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
@@ -1008,13 +1022,7 @@ __global__ void __launch_bounds__(BX) k_new_dt(BlkDev b, Params p, unsigned long
     if (b.f2) m = dmin(m, dt2);
     if (b.f3) m = dmin(m, dt3);
   }
-  // warp-shuffle min, then one atomic per warp (positive doubles order like their bit patterns)
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
-    double o2 = __shfl_xor_sync(0xffffffffu, m, s);
-    m = dmin(m, o2);
-  }
-  if ((threadIdx.x & 31) == 0) atomicMin(out, (unsigned long long)__double_as_longlong(m));
+  block_min_to_slots(m, out);
 }
 
 void launch_new_block_dt(const BlkDev &b, const Params &p, unsigned long long *out_bits,
@@ -1042,7 +1050,10 @@ __global__ void k_mesh_new_dt(double *st, const unsigned long long *blk_min, int
   if (phase == 0) {
     double m = DBL_MAX;
     for (int n = 0; n < nb; ++n) {
-      double v = __longlong_as_double((long long)blk_min[n])*st[3];
+      double v = DBL_MAX;
+      for (int q = 0; q < DT_SLOTS; ++q)
+        v = dmin(v, __longlong_as_double((long long)blk_min[(long)n*DT_SLOTS + q]));
+      v = v*st[3];
       m = dmin(m, v);
     }
     st[4] = m;

@@ -560,7 +560,7 @@ int alloc_blocks(AbMesh *m) {
     m->lb.push_back(L);
   }
   if (m->lb.empty()) return fail(AB_ERR_ARG, "this rank owns no MeshBlock: use fewer ranks or smaller MeshBlocks");
-  CK(cudaMalloc(&m->dtmin, sizeof(unsigned long long)*m->lb.size()));
+  CK(cudaMalloc(&m->dtmin, sizeof(unsigned long long)*m->lb.size()*ab::DT_SLOTS));
   for (size_t l = 0; l < m->lb.size(); ++l) {
     LocalBlock &L = m->lb[l];
     HostBlock &B = *L.hb;
@@ -622,7 +622,7 @@ int alloc_blocks(AbMesh *m) {
     for (int dd = 0; dd < 3; ++dd) { L.g.wp[dd] = put(wp[dd], -1); L.g.wm[dd] = put(wm[dd], -1); }
     CK(cudaStreamSynchronize(m->stream));   // host vectors go out of scope
     L.emf_send = (double *)cur;
-    L.dtmin = m->dtmin + l;
+    L.dtmin = m->dtmin + l*ab::DT_SLOTS;
     L.has_phys_bc = false;
     for (int f = 0; f < 2*m->ndim; ++f)
       if (B.bcs[f] != -1 && B.bcs[f] != AB_BC_PERIODIC) L.has_phys_bc = true;
@@ -945,7 +945,7 @@ int new_time_step(AbMesh *m, int advance, bool blocks_done = false) {
   // NewBlockTimeStep on every block (unless already reduced by the fused cons2prim), then
   // Mesh::NewTimeStep (mesh/mesh.cpp:1078-1119)
   if (!blocks_done) {
-    ab::launch_fill_u64(m->dtmin, (int)m->lb.size(), 0x7FEFFFFFFFFFFFFFull /* DBL_MAX */, m->stream);
+    ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull /* DBL_MAX */, m->stream);
     for (auto &L : m->lb) ab::launch_new_block_dt(L.d, m->kp, L.dtmin, m->stream);
   }
   ab::launch_mesh_new_dt(m->state, m->dtmin, (int)m->lb.size(), 0 /*phase 0*/, m->stream);
@@ -1014,7 +1014,7 @@ int one_cycle(AbMesh *m) {
     rc = bvals_exchange(m);
     if (rc) return rc;
     const int last = (stage == m->nstages);
-    if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size(), 0x7FEFFFFFFFFFFFFFull, m->stream);
+    if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
     for (auto &L : m->lb) { primitives(m, L, last); physical_bcs(m, L); }
     if (stage == m->nstages) {
       // record the dt this cycle used, then time += dt, ncycle++, NewTimeStep
@@ -1271,13 +1271,17 @@ int ab_physical_bcs(AbMesh *m, int lid) {
 }
 int ab_new_block_dt(AbMesh *m, int lid, double *dt_out) {
   GET_L(m, lid);
-  ab::launch_fill_u64(L.dtmin, 1, 0x7FEFFFFFFFFFFFFFull, m->stream);
+  ab::launch_fill_u64(L.dtmin, ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
   ab::launch_new_block_dt(L.d, m->kp, L.dtmin, m->stream);
-  unsigned long long bits;
-  CK(cudaMemcpyAsync(&bits, L.dtmin, 8, cudaMemcpyDeviceToHost, m->stream));
+  unsigned long long bits[ab::DT_SLOTS];
+  CK(cudaMemcpyAsync(bits, L.dtmin, sizeof(bits), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
-  double v;
-  memcpy(&v, &bits, 8);
+  double v = DBL_MAX;
+  for (int q = 0; q < ab::DT_SLOTS; ++q) {
+    double t;
+    memcpy(&t, &bits[q], 8);
+    if (t < v) v = t;
+  }
   if (dt_out) *dt_out = v*m->cfl;     // new_blockdt.cpp:164
   return AB_OK;
 }

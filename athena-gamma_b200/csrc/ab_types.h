@@ -6,6 +6,7 @@ namespace ab {
 
 constexpr int NHYDRO = 5;
 constexpr int MAX_NB = 26;
+constexpr int DT_SLOTS = 64;   // atomicMin targets per MeshBlock for the CFL reduction
 
 // Device view of one MeshBlock.  Array layouts are the reference's AthenaArray layouts
 // (src/athena_arrays.hpp:140-143: last index fastest; sizes src/hydro/hydro.cpp:31-47,
