@@ -9,7 +9,7 @@ fork pabolmasov/Athena-gamma, behind the reference's own surface.
   build.py         nvcc build of the extension (sm_100a, -fmad=false)
 """
 from .athinput import ParameterInput  # noqa: F401
-from .mesh import Mesh  # noqa: F401
+from .mesh import Mesh, MeshPlan  # noqa: F401
 from . import lib, pgen, build  # noqa: F401
 
-__all__ = ["ParameterInput", "Mesh", "lib", "pgen", "build"]
+__all__ = ["ParameterInput", "Mesh", "MeshPlan", "lib", "pgen", "build"]

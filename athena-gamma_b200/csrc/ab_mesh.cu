@@ -142,6 +142,8 @@ struct AbMesh {
   std::vector<HostBlock> hb;              // all blocks of the mesh (every rank knows them)
   std::vector<int> gid_of;                // [lx3][lx2][lx1] -> gid
   std::vector<LocalBlock> lb;             // blocks owned by this rank, in gid order
+  std::vector<HostBlock *> lb_hb;         // their host descriptors (also for dry plans)
+  bool dry = false;                       // host-only plan (no device resources)
   int gid_start = 0;
   int nstages = 2;
   double beta[4], delta[4], g1[4], g2[4], g3[4];
@@ -175,6 +177,8 @@ struct AbMesh {
 namespace {
 
 using ab::CopyBox;
+
+struct Msg { int peer; long key; int lid; int nbi; long count; };
 
 // ---- buffer box ranges (same for every block: all blocks have identical shape) ------------
 struct Box { int si, ei, sj, ej, sk, ek; long count() const {
@@ -552,11 +556,9 @@ size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 int alloc_blocks(AbMesh *m) {
   const AbMeshParams &p = m->p;
   int ng = p.nghost;
-  m->gid_start = -1;
-  for (auto &B : m->hb) if (B.rank == p.rank) {
-    if (m->gid_start < 0) m->gid_start = B.gid;
+  for (auto *pB : m->lb_hb) {
     LocalBlock L;
-    L.hb = &B;
+    L.hb = pB;
     m->lb.push_back(L);
   }
   if (m->lb.empty()) return fail(AB_ERR_ARG, "this rank owns no MeshBlock: use fewer ranks or smaller MeshBlocks");
@@ -631,7 +633,33 @@ int alloc_blocks(AbMesh *m) {
 }
 
 // ------------------------------------------------------------------ exchange plans
-struct Msg { int peer; long key; int lid; int nbi; long count; };
+// Messages this rank exchanges with every peer rank, per exchange kind (0: ghost zones of u
+// [and b], 1: EMF correction).  Both sides order a peer's messages by (destination gid,
+// destination buffer id), so one concatenated buffer per peer can be sent with a single
+// ncclSend and split identically by the receiver (the reference tags each message with
+// (lid, bufid), bvals_base.cpp:287; here the position in the buffer plays that role).
+void peer_messages(const AbMesh *m, int kind, std::map<int, std::vector<Msg>> &sends,
+                   std::map<int, std::vector<Msg>> &recvs) {
+  for (size_t l = 0; l < m->lb_hb.size(); ++l) {
+    const HostBlock &B = *m->lb_hb[l];
+    for (size_t n = 0; n < B.nbs.size(); ++n) {
+      const Nb &nb = B.nbs[n];
+      if (nb.rank == m->p.rank) continue;
+      long cnt;
+      if (kind == 0) {
+        cnt = state_msg_count(m, nb.ox1, nb.ox2, nb.ox3);
+      } else {
+        if (nb.type > 1) continue;
+        cnt = nb.type == 0 ? emf_face_count(m, nb.fid) : emf_edge_count(m, nb.eid);
+      }
+      sends[nb.rank].push_back({nb.rank, (long)nb.gid*64 + nb.targetid, (int)l, (int)n, cnt});
+      recvs[nb.rank].push_back({nb.rank, (long)B.gid*64 + nb.bufid, (int)l, (int)n, cnt});
+    }
+  }
+  auto by_key = [](const Msg &a, const Msg &b) { return a.key < b.key; };
+  for (auto &kv : sends) std::sort(kv.second.begin(), kv.second.end(), by_key);
+  for (auto &kv : recvs) std::sort(kv.second.begin(), kv.second.end(), by_key);
+}
 
 // ghost-exchange plan for the current register parity: box copies, pack lists, peer buffers
 int build_state_plan(AbMesh *m, int which) {
@@ -641,26 +669,15 @@ int build_state_plan(AbMesh *m, int which) {
   const long ncc = (long)m->nc[0]*m->nc[1]*m->nc[2];
   // per-peer message lists (sorted by (dst gid, dst bufid))
   std::map<int, std::vector<Msg>> sends, recvs;
-  for (size_t l = 0; l < m->lb.size(); ++l) {
-    HostBlock &B = *m->lb[l].hb;
-    for (size_t n = 0; n < B.nbs.size(); ++n) {
-      const Nb &nb = B.nbs[n];
-      if (nb.rank == m->p.rank) continue;
-      long cnt = state_msg_count(m, nb.ox1, nb.ox2, nb.ox3);
-      sends[nb.rank].push_back({nb.rank, (long)nb.gid*64 + nb.targetid, (int)l, (int)n, cnt});
-      recvs[nb.rank].push_back({nb.rank, (long)B.gid*64 + nb.bufid, (int)l, (int)n, cnt});
-    }
-  }
+  peer_messages(m, 0, sends, recvs);
   std::map<std::pair<int,int>, long> send_off, recv_off;   // (lid, nbi) -> element offset
   for (auto &kv : sends) {
-    std::sort(kv.second.begin(), kv.second.end(), [](const Msg &a, const Msg &b) { return a.key < b.key; });
     long off = 0;
     for (auto &ms : kv.second) { send_off[{ms.lid, ms.nbi}] = off; off += ms.count; }
     PeerBuf &pb = m->peer_state[kv.first];
     if (!pb.send) { pb.nsend = off; CK(cudaMalloc(&pb.send, std::max<size_t>(off, 1)*8)); }
   }
   for (auto &kv : recvs) {
-    std::sort(kv.second.begin(), kv.second.end(), [](const Msg &a, const Msg &b) { return a.key < b.key; });
     long off = 0;
     for (auto &ms : kv.second) { recv_off[{ms.lid, ms.nbi}] = off; off += ms.count; }
     PeerBuf &pb = m->peer_state[kv.first];
@@ -762,26 +779,15 @@ int build_state_plan(AbMesh *m, int which) {
 int build_emf_plan(AbMesh *m) {
   if (!m->p.mhd) { m->emf_built = true; return AB_OK; }
   std::map<int, std::vector<Msg>> sends, recvs;
-  for (size_t l = 0; l < m->lb.size(); ++l) {
-    HostBlock &B = *m->lb[l].hb;
-    for (size_t n = 0; n < B.nbs.size(); ++n) {
-      const Nb &nb = B.nbs[n];
-      if (nb.type > 1 || nb.rank == m->p.rank) continue;
-      long cnt = nb.type == 0 ? emf_face_count(m, nb.fid) : emf_edge_count(m, nb.eid);
-      sends[nb.rank].push_back({nb.rank, (long)nb.gid*64 + nb.targetid, (int)l, (int)n, cnt});
-      recvs[nb.rank].push_back({nb.rank, (long)B.gid*64 + nb.bufid, (int)l, (int)n, cnt});
-    }
-  }
+  peer_messages(m, 1, sends, recvs);
   std::map<std::pair<int,int>, long> send_off, recv_off;
   for (auto &kv : sends) {
-    std::sort(kv.second.begin(), kv.second.end(), [](const Msg &a, const Msg &b) { return a.key < b.key; });
     long off = 0;
     for (auto &ms : kv.second) { send_off[{ms.lid, ms.nbi}] = off; off += ms.count; }
     PeerBuf &pb = m->peer_emf[kv.first];
     pb.nsend = off; CK(cudaMalloc(&pb.send, std::max<size_t>(off, 1)*8));
   }
   for (auto &kv : recvs) {
-    std::sort(kv.second.begin(), kv.second.end(), [](const Msg &a, const Msg &b) { return a.key < b.key; });
     long off = 0;
     for (auto &ms : kv.second) { recv_off[{ms.lid, ms.nbi}] = off; off += ms.count; }
     PeerBuf &pb = m->peer_emf[kv.first];
@@ -1042,9 +1048,75 @@ int ab_device_count(void) {
   return n;
 }
 
+static int validate_params(const AbMeshParams *p);
+static void host_setup(AbMesh *m, const AbMeshParams *p);
+
 int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
   if (!p || !out) return fail(AB_ERR_ARG, "null argument");
   *out = nullptr;
+  int vrc = validate_params(p);
+  if (vrc) return vrc;
+  if (ab_device_count() <= 0)
+    return fail(AB_ERR_NO_DEVICE, "no CUDA device: libathena_b200 has no CPU fallback");
+  CK(cudaSetDevice(p->device));
+  AbMesh *m = new AbMesh();
+  host_setup(m, p);
+  CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  int rc = alloc_blocks(m);
+  if (rc) { delete m; return rc; }
+  CK(cudaMalloc(&m->state, 8*sizeof(double)));
+  m->hist_cap = 1 << 16;
+  CK(cudaMalloc(&m->dt_hist, sizeof(double)*m->hist_cap));
+  m->h_time = p->start_time; m->h_dt = DBL_MAX; m->h_ncycle = 0;
+  double h[8] = {p->start_time, DBL_MAX, p->tlim, m->cfl, DBL_MAX, 0.0, 0.0, 0.0};
+  CK(cudaMemcpy(m->state, h, sizeof(h), cudaMemcpyHostToDevice));
+  CK(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return AB_OK;
+}
+
+// Host-only plan of the same mesh (no device needed): used to check the cross-rank message
+// pairing on CPU-only machines (tests with the gloo backend).
+int ab_plan_create(const AbMeshParams *p, AbMesh **out) {
+  if (!p || !out) return fail(AB_ERR_ARG, "null argument");
+  *out = nullptr;
+  int vrc = validate_params(p);
+  if (vrc) return vrc;
+  AbMesh *m = new AbMesh();
+  m->dry = true;
+  host_setup(m, p);
+  *out = m;
+  return AB_OK;
+}
+
+// rows of 5 longs: {direction (0 send, 1 recv), peer rank, key = dst_gid*64 + dst_bufid,
+// element count, local block index}; kind 0 = ghost zones, 1 = EMF correction.
+// Returns the number of rows (also when out == NULL or max_rows is too small).
+int ab_plan_messages(const AbMesh *m, int kind, long *out, int max_rows) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  std::map<int, std::vector<Msg>> sends, recvs;
+  peer_messages(m, kind, sends, recvs);
+  int n = 0;
+  for (int dir = 0; dir < 2; ++dir)
+    for (auto &kv : (dir == 0 ? sends : recvs))
+      for (auto &ms : kv.second) {
+        if (out && n < max_rows) {
+          long *r = out + 5L*n;
+          r[0] = dir; r[1] = kv.first; r[2] = ms.key; r[3] = ms.count; r[4] = ms.lid;
+        }
+        n++;
+      }
+  return n;
+}
+
+// owner rank of every MeshBlock in gid order (Mesh::CalculateLoadBalance)
+int ab_plan_ranklist(const AbMesh *m, int *out, int max_n) {
+  if (!m) return fail(AB_ERR_ARG, "null mesh");
+  for (int g = 0; g < m->nbtotal && g < max_n; ++g) out[g] = m->hb[g].rank;
+  return m->nbtotal;
+}
+
+static int validate_params(const AbMeshParams *p) {
   if (p->bx1 <= 0 || p->nx1 % p->bx1 || p->nx2 % p->bx2 || p->nx3 % p->bx3)
     return fail(AB_ERR_ARG, "the Mesh must be evenly divisible by the MeshBlock");
   if (p->xorder < 1 || p->xorder > 3) return fail(AB_ERR_ARG, "time/xorder must be 1, 2 or 3");
@@ -1063,10 +1135,11 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
       return fail(AB_ERR_ARG, "MeshBlock too large: registers must have < 2^31 elements "
                               "(kernels use 32-bit element offsets); use smaller MeshBlocks");
   }
-  if (ab_device_count() <= 0)
-    return fail(AB_ERR_NO_DEVICE, "no CUDA device: libathena_b200 has no CPU fallback");
-  CK(cudaSetDevice(p->device));
-  AbMesh *m = new AbMesh();
+  if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(AB_ERR_ARG, "bad rank/nranks");
+  return AB_OK;
+}
+
+static void host_setup(AbMesh *m, const AbMeshParams *p) {
   m->p = *p;
   m->f2 = p->nx2 > 1; m->f3 = p->nx3 > 1;
   m->ndim = m->f3 ? 3 : (m->f2 ? 2 : 1);
@@ -1079,22 +1152,16 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
   if (m->f3) { m->ks = ng; m->ke = ng + p->bx3 - 1; m->nc[2] = p->bx3 + 2*ng; }
   set_integrator(m);
   build_block_list(m);
-  CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-  int rc = alloc_blocks(m);
-  if (rc) { delete m; return rc; }
-  CK(cudaMalloc(&m->state, 8*sizeof(double)));
-  m->hist_cap = 1 << 16;
-  CK(cudaMalloc(&m->dt_hist, sizeof(double)*m->hist_cap));
-  m->h_time = p->start_time; m->h_dt = DBL_MAX; m->h_ncycle = 0;
-  double h[8] = {p->start_time, DBL_MAX, p->tlim, m->cfl, DBL_MAX, 0.0, 0.0, 0.0};
-  CK(cudaMemcpy(m->state, h, sizeof(h), cudaMemcpyHostToDevice));
-  CK(cudaStreamSynchronize(m->stream));
-  *out = m;
-  return AB_OK;
+  m->gid_start = -1;
+  for (auto &B : m->hb) if (B.rank == p->rank) {
+    if (m->gid_start < 0) m->gid_start = B.gid;
+    m->lb_hb.push_back(&B);
+  }
 }
 
 int ab_mesh_destroy(AbMesh *m) {
   if (!m) return AB_OK;
+  if (m->dry) { delete m; return AB_OK; }
   cudaSetDevice(m->p.device);
   cudaStreamSynchronize(m->stream);
   for (auto &L : m->lb) cudaFree(L.base);
@@ -1109,7 +1176,7 @@ int ab_mesh_destroy(AbMesh *m) {
 }
 
 int ab_mesh_nblocks_total(const AbMesh *m) { return m ? m->nbtotal : 0; }
-int ab_mesh_nblocks_local(const AbMesh *m) { return m ? (int)m->lb.size() : 0; }
+int ab_mesh_nblocks_local(const AbMesh *m) { return m ? (int)m->lb_hb.size() : 0; }
 
 #define GET_L(m, lid)                                                              \
   if (!(m) || (lid) < 0 || (lid) >= (int)(m)->lb.size())                           \
@@ -1118,8 +1185,8 @@ int ab_mesh_nblocks_local(const AbMesh *m) { return m ? (int)m->lb.size() : 0; }
   (void)L
 
 int ab_block_info(const AbMesh *m, int lid, long *info) {
-  if (!m || lid < 0 || lid >= (int)m->lb.size() || !info) return fail(AB_ERR_ARG, "bad argument");
-  const HostBlock &B = *m->lb[lid].hb;
+  if (!m || lid < 0 || lid >= (int)m->lb_hb.size() || !info) return fail(AB_ERR_ARG, "bad argument");
+  const HostBlock &B = *m->lb_hb[lid];
   info[0] = B.gid; info[1] = B.lx[0]; info[2] = B.lx[1]; info[3] = B.lx[2];
   info[4] = m->nc[0]; info[5] = m->nc[1]; info[6] = m->nc[2];
   info[7] = m->is; info[8] = m->ie; info[9] = m->js; info[10] = m->je; info[11] = m->ks;

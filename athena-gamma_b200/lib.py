@@ -21,6 +21,7 @@ COORD = {"x1f": 0, "x2f": 1, "x3f": 2, "x1v": 3, "x2v": 4, "x3v": 5, "dx1f": 6, 
 SYMBOLS = [
     "ab_last_error", "ab_device_count", "ab_mesh_create", "ab_mesh_destroy",
     "ab_mesh_nblocks_total", "ab_mesh_nblocks_local", "ab_block_info", "ab_reg_size",
+    "ab_plan_create", "ab_plan_messages", "ab_plan_ranklist",
     "ab_upload", "ab_download", "ab_download_coord", "ab_comm_unique_id", "ab_comm_init",
     "ab_cons2prim", "ab_prim2cons", "ab_primitives", "ab_calc_fluxes", "ab_corner_e",
     "ab_weighted_ave", "ab_swap", "ab_zero", "ab_add_flux_div", "ab_ct", "ab_physical_bcs",
@@ -71,6 +72,9 @@ def load():
     L.ab_block_info.argtypes = [vp, ip, C.POINTER(C.c_long)]
     L.ab_reg_size.restype = C.c_long
     L.ab_reg_size.argtypes = [vp, ip, ip]
+    L.ab_plan_create.argtypes = [C.POINTER(AbMeshParams), C.POINTER(vp)]
+    L.ab_plan_messages.argtypes = [vp, ip, C.POINTER(C.c_long), ip]
+    L.ab_plan_ranklist.argtypes = [vp, C.POINTER(C.c_int), ip]
     L.ab_upload.argtypes = [vp, ip, ip, dp]
     L.ab_download.argtypes = [vp, ip, ip, dp]
     L.ab_download_coord.argtypes = [vp, ip, ip, dp]

@@ -81,13 +81,9 @@ class MeshBlock:
 
 
 class Mesh:
-    def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0):
-        """pin: ParameterInput (or athinput text); mhd / flux / nghost: what configure.py's
-        -b / --flux / --nghost fix at compile time in the reference."""
-        if not isinstance(pin, ParameterInput):
-            pin = ParameterInput(text=pin)
-        self.pin = pin
-        self.L = lib.load()
+    @staticmethod
+    def make_params(pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0):
+        """AbMeshParams from the athinput blocks + the configure-time choices."""
         p = lib.AbMeshParams()
         p.nx1 = pin.get_integer("mesh", "nx1")
         p.nx2 = pin.get_or_add_integer("mesh", "nx2", 1)
@@ -124,6 +120,16 @@ class Mesh:
         p.tlim = pin.get_real("time", "tlim")
         p.start_time = pin.get_or_add_real("time", "start_time", 0.0)
         p.rank, p.nranks, p.device = rank, nranks, device
+        return p, flux
+
+    def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0):
+        """pin: ParameterInput (or athinput text); mhd / flux / nghost: what configure.py's
+        -b / --flux / --nghost fix at compile time in the reference."""
+        if not isinstance(pin, ParameterInput):
+            pin = ParameterInput(text=pin)
+        self.pin = pin
+        self.L = lib.load()
+        p, flux = self.make_params(pin, mhd, flux, nghost, rank, nranks, device)
         self.params = p
         self.mhd, self.flux = bool(mhd), flux
         self.nlim = pin.get_or_add_integer("time", "nlim", -1)
@@ -211,3 +217,42 @@ class Mesh:
     @property
     def cuda_stream(self):
         return self.L.ab_mesh_stream(self.h)
+
+
+class MeshPlan:
+    """Host-only twin of Mesh (ab_plan_create): MeshBlock list, load balance and the
+    cross-rank message plan of one rank.  Needs no GPU; owns no device memory."""
+
+    def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1):
+        if not isinstance(pin, ParameterInput):
+            pin = ParameterInput(text=pin)
+        self.L = lib.load()
+        p, _ = Mesh.make_params(pin, mhd, flux, nghost, rank, nranks, 0)
+        self.params = p
+        h = C.c_void_p()
+        lib.check(self.L.ab_plan_create(C.byref(p), C.byref(h)))
+        self.h = h
+        self.nbtotal = self.L.ab_mesh_nblocks_total(h)
+        self.nblocal = self.L.ab_mesh_nblocks_local(h)
+        self.my_blocks = [MeshBlock(self, l) for l in range(self.nblocal)]
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.ab_mesh_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def ranklist(self):
+        out = (C.c_int * self.nbtotal)()
+        lib.check(self.L.ab_plan_ranklist(self.h, out, self.nbtotal))
+        return list(out)
+
+    def messages(self, kind):
+        """list of dict(dir, peer, key, count, lid) in buffer order; kind 0 ghost, 1 EMF"""
+        n = lib.check(self.L.ab_plan_messages(self.h, kind, None, 0))
+        buf = (C.c_long * (5 * max(n, 1)))()
+        lib.check(self.L.ab_plan_messages(self.h, kind, buf, n))
+        return [dict(zip(("dir", "peer", "key", "count", "lid"), buf[5 * i:5 * i + 5]))
+                for i in range(n)]

@@ -68,6 +68,15 @@ int ab_block_info(const AbMesh *m, int lid, long *info);
 /* number of doubles in a register of block lid */
 long ab_reg_size(const AbMesh *m, int lid, int reg);
 
+/* Host-only twin of ab_mesh_create (no GPU needed, owns no device memory): the MeshBlock
+ * list, load balance and cross-rank message plan of rank p->rank, for inspection / CPU tests.
+ * ab_plan_messages rows: {dir 0 send|1 recv, peer rank, key = dst_gid*64+dst_bufid, doubles,
+ * local block}; kind 0 = ghost zones of u (and b), 1 = EMF correction; returns the row count.
+ * Only ab_mesh_nblocks_*, ab_block_info, ab_plan_* and ab_mesh_destroy accept such a handle. */
+int ab_plan_create(const AbMeshParams *p, AbMesh **out);
+int ab_plan_messages(const AbMesh *m, int kind, long *out, int max_rows);
+int ab_plan_ranklist(const AbMesh *m, int *out, int max_n);
+
 /* ---- host <-> device mirror of the AthenaArrays (same layout as AthenaArray::data()) */
 int ab_upload(AbMesh *m, int lid, int reg, const double *host);     /* after ProblemGenerator */
 int ab_download(AbMesh *m, int lid, int reg, double *host);         /* before outputs / hooks */

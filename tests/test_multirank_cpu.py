@@ -1,0 +1,114 @@
+"""CPU, world_size 2 and 3, gloo: the host logic of the N>1 path.  MeshBlocks are sharded over
+ranks like Mesh::CalculateLoadBalance; every rank derives, independently, the list of messages
+it sends to / receives from each peer (ghost zones and EMF correction).  NCCL send/recv pairs
+them purely by ORDER and SIZE inside one concatenated buffer per peer, so the test checks that
+rank a's send list towards b is exactly rank b's receive list from a -- for periodic and
+outflow meshes in 1-D/2-D/3-D -- and that the id broadcast helper works over a process group."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = [
+    # athinput, overrides, mhd, flux, nghost
+    ("athinput.blast", ["mesh/nx1=64", "mesh/nx2=64", "mesh/nx3=64", "meshblock/nx1=16",
+                        "meshblock/nx2=32", "meshblock/nx3=32"], True, "hlld", 2),
+    ("athinput.orszag_tang", ["mesh/nx1=64", "mesh/nx2=64", "meshblock/nx1=16",
+                              "meshblock/nx2=32"], True, "hlld", 3),
+    ("athinput.kh", ["mesh/nx1=32", "mesh/nx2=32", "mesh/nx3=32", "meshblock/nx1=16",
+                     "meshblock/nx2=16", "meshblock/nx3=16"], False, "hllc", 3),
+    ("athinput.sod", ["mesh/nx1=64", "meshblock/nx1=8"], False, "hllc", 2),
+]
+
+
+def reference_load_balance(nb, nranks):
+    """Mesh::CalculateLoadBalance with unit costs (src/mesh/amr_loadbalance.cpp:72-112)"""
+    rlist = [0]*nb
+    total, j = float(nb), nranks - 1
+    target, mycost = total/nranks, 0.0
+    for i in range(nb - 1, -1, -1):
+        mycost += 1.0
+        rlist[i] = j
+        if mycost >= target and j > 0:
+            j -= 1
+            total -= mycost
+            mycost = 0.0
+            target = total/(j + 1)
+    return rlist
+
+
+def worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import athena_gamma_b200 as ab
+    errors = []
+    for inp, ov, mhd, flux, ng in CASES:
+        pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", inp))
+        pin.modify_from_cmdline(ov)
+        plan = ab.MeshPlan(pin, mhd, flux, nghost=ng, rank=rank, nranks=world)
+        mine = {"ranklist": plan.ranklist(), "nblocal": plan.nblocal,
+                "gids": [b.gid for b in plan.my_blocks],
+                "msgs": [plan.messages(0), plan.messages(1) if mhd else []]}
+        allp = [None]*world
+        dist.all_gather_object(allp, mine)
+        rl = allp[0]["ranklist"]
+        if any(p["ranklist"] != rl for p in allp):
+            errors.append("%s: ranks disagree on the load balance" % inp)
+        if rl != reference_load_balance(len(rl), world):
+            errors.append("%s: load balance differs from CalculateLoadBalance" % inp)
+        if sorted(g for p in allp for g in p["gids"]) != list(range(len(rl))):
+            errors.append("%s: blocks not partitioned" % inp)
+        if mine["gids"] != [g for g, r in enumerate(rl) if r == rank]:
+            errors.append("%s: local blocks are not the contiguous gid range" % inp)
+        for kind in (0, 1):
+            for a in range(world):
+                for b in range(world):
+                    if a == b:
+                        continue
+                    snd = [(m["key"], m["count"]) for m in allp[a]["msgs"][kind]
+                           if m["dir"] == 0 and m["peer"] == b]
+                    rcv = [(m["key"], m["count"]) for m in allp[b]["msgs"][kind]
+                           if m["dir"] == 1 and m["peer"] == a]
+                    if snd != rcv:
+                        errors.append("%s kind %d: send list %d->%d != recv list" % (inp, kind, a, b))
+                    if [k for k, _ in snd] != sorted(k for k, _ in snd):
+                        errors.append("%s kind %d: messages %d->%d not in key order" % (inp, kind, a, b))
+        # every message is addressed to a block the receiver owns
+        for m in mine["msgs"][0] + mine["msgs"][1]:
+            if m["dir"] == 0 and rl[m["key"]//64] != m["peer"]:
+                errors.append("%s: message to gid %d sent to the wrong rank" % (inp, m["key"]//64))
+
+    # the NCCL-id broadcast helper used by Mesh.init_comm, over this process group
+    def bcast(data):
+        t = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            t.copy_(torch.tensor(list(data), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return bytes(t.tolist())
+    payload = bytes(range(128)) if rank == 0 else None
+    if bcast(payload) != bytes(range(128)):
+        errors.append("id broadcast failed")
+    q.put((rank, errors))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_message_plans_pair_up_across_ranks(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + world
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, errors in results:
+        assert not errors, "rank %d: %s" % (rank, errors[:5])
