@@ -231,21 +231,47 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
 #ifndef AB_FLUX_MINB
 #define AB_FLUX_MINB 5
 #endif
+#ifndef AB_FLUX_MINB_O1
+#define AB_FLUX_MINB_O1 AB_FLUX_MINB
+#endif
+// x3 sweep: faces are visited strip by strip (AB_X3_STRIP rows of j, all k) so that the four
+// k-planes of the stencil stay in L2 between consecutive k (plane-major order re-read w/bcc
+// from DRAM: 19 GB instead of 8.8 GB per 512^3 sweep).
+#ifndef AB_X3_STRIP
+#define AB_X3_STRIP 32
+#endif
 
 // The face range [i0,i0+ni) x [j0,j0+nj) x [k0,k0+nk) is flattened so that every thread of a
 // CTA has work (rows of nx1+1 faces do not pad to a multiple of the CTA width).
 template <int DIR, int ORDER, int SOLVER, bool MHD>
-__global__ void __launch_bounds__(BX, AB_FLUX_MINB)
-k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int ntot,
-       double dt_val, const double *dt_ptr) {
+__global__ void __launch_bounds__(BX, (ORDER == 1 ? AB_FLUX_MINB_O1 : AB_FLUX_MINB))
+k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
+       int ntot, double dt_val, const double *dt_ptr) {
   constexpr int NW = MHD ? 7 : 5;
   int t = blockIdx.x*BX + threadIdx.x;
   if (t >= ntot) return;
-  int r = t / ni;
-  const int i = i0 + (t - r*ni);
-  const int kk = r / nj;
-  const int j = j0 + (r - kk*nj);
-  const int k = k0 + kk;
+  int i, j, k;
+  if (DIR == 2 && AB_X3_STRIP > 0) {
+    // strip-major: strip s of j-rows, then k, then j within the strip, then i
+    const int per_full = ni*AB_X3_STRIP*nk;
+    const int s = t / per_full;
+    int r = t - s*per_full;
+    int rows = nj - s*AB_X3_STRIP;
+    rows = rows < AB_X3_STRIP ? rows : AB_X3_STRIP;
+    const int per_k = ni*rows;
+    const int kk = r / per_k;
+    r -= kk*per_k;
+    const int jj = r / ni;
+    i = i0 + (r - jj*ni);
+    j = j0 + s*AB_X3_STRIP + jj;
+    k = k0 + kk;
+  } else {
+    int r = t / ni;
+    i = i0 + (t - r*ni);
+    const int kk = r / nj;
+    j = j0 + (r - kk*nj);
+    k = k0 + kk;
+  }
   const int sv = b.nc3*b.nc2*b.nc1;
   const int st = (DIR == 0) ? 1 : ((DIR == 1) ? b.nc1 : b.nc1*b.nc2);
   const int oc = (k*b.nc2 + j)*b.nc1 + i;      // cell on the upper side of the face
@@ -337,7 +363,7 @@ static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, doubl
   int ni = i1-i0+1, nj = j1-j0+1, nk = k1-k0+1;
   int ntot = ni*nj*nk;
   k_flux<DIR,ORDER,SOLVER,MHD><<<(ntot + BX - 1)/BX, BX, 0, s>>>(
-      b, g, p, i0, ni, j0, nj, k0, ntot, dt_val, dt_ptr); ++g_launches;
+      b, g, p, i0, ni, j0, nj, k0, nk, ntot, dt_val, dt_ptr); ++g_launches;
 }
 
 template <int ORDER, int SOLVER, bool MHD>

@@ -301,11 +301,24 @@ def main():
         avg_ms = tot_ms/tot_n
         ach = fb*faces/(avg_ms*1e-3)/1e9
         share = sum(prof[i] for i in range(9))/ms if ms > 0 else None
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "flux_traffic.json")))
+            key = "%s:%s" % (wl, "x".join(str(v) for v in blk))
+            if key in tj:
+                traffic = tj[key]["bytes_per_launch"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach/peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach/peak, "traffic": traffic, "peak_source": peak_src,
+                "note": "FP64-pipe co-roof binds this kernel (DESIGN.md section 4): DRAM traffic "
+                        "equals the algorithmic bytes, FP64 pipe 45-48% busy",
                 "avg_launch_ms": avg_ms, "launches_timed": int(tot_n),
                 "algorithmic_bytes_per_launch": fb*faces,
-                "flux_kernels_share_of_step": share}
+                "flux_kernels_share_of_step": share,
+                "flux_avg_ms_by_dir_order": {"x%d_o%d" % (d+1, o+1): prof[d*3+o]/prof[9+d*3+o]
+                                             for d in range(nd) for o in range(3)
+                                             if prof[9+d*3+o] > 0}}
     b_alg = BYTES_PER_ZONE_CYCLE["mhd" if mhd else "hydro"]
     cycle_roof = {"B_alg_bytes_per_zone_cycle": b_alg,
                   "achieved_GBs_per_gpu": b_alg*value/world/1e9,
