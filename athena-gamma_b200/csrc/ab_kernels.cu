@@ -326,8 +326,30 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
   else { of = (k*b.nc2 + j)*b.nc1 + i; sf = (b.nc3+1)*b.nc2*b.nc1; }
   double bxi = 0.0;
   if (MHD) bxi = b.b[DIR][of];
+  // LHLLC / LHLLD shock detector inputs: Hydro::CalculateVelocityDifferences
+  // (hydro/calculate_velocity_differences.cpp:20-90); dvt stays 0 in 1-D
+  double dvn = 0.0, dvt = 0.0;
+  if (SOLVER == SOLVER_LHLLC || SOLVER == SOLVER_LHLLD) {
+    const int ol = oc - st;                       // lower cell of the interface
+    dvn = w[oc + (1 + DIR)*sv] - w[ol + (1 + DIR)*sv];
+    if (b.f2) {
+      bool first = true;
+#pragma unroll
+      for (int t = 1; t <= 2; ++t) {
+        const int td = (DIR + t) % 3;             // transverse direction, reference order
+        if (td == 2 && !b.f3) continue;
+        const int ts = (td == 0) ? 1 : ((td == 1) ? b.nc1 : b.nc1*b.nc2);
+        const double *__restrict__ wt = w + (1 + td)*sv;
+        double dl = dmin(wt[ol + ts] - wt[ol], wt[ol] - wt[ol - ts]);
+        double dr = dmin(wt[oc + ts] - wt[oc], wt[oc] - wt[oc - ts]);
+        double v = dmin(dl, dr);
+        dvt = first ? v : dmin(dvt, v);
+        first = false;
+      }
+    }
+  }
   double f[NW];
-  riemann<SOLVER,MHD>(wl, wr, bxi, p.gamma, f);
+  riemann<SOLVER,MHD>(wl, wr, bxi, p.gamma, dvn, dvt, f);
 
   double *__restrict__ flx = b.flux[DIR];
   flx[of] = f[IDN];
@@ -386,10 +408,12 @@ void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int o
                      double dt_val, const double *dt_ptr, cudaStream_t s) {
   if (p.mhd) {
     if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_LHLLD) flux_order<SOLVER_LHLLD,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else flux_order<SOLVER_ROE,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
   } else {
     if (p.solver == SOLVER_HLLC) flux_order<SOLVER_HLLC,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_LHLLC) flux_order<SOLVER_LHLLC,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else flux_order<SOLVER_ROE,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
   }

@@ -1123,8 +1123,12 @@ static int validate_params(const AbMeshParams *p) {
   if (p->xorder == 3 && p->nghost < 3)
     return fail(AB_ERR_ARG, "xorder=3 (PPM) needs nghost >= 3 (reconstruction.cpp:90-99)");
   if (p->nghost < 2) return fail(AB_ERR_ARG, "nghost must be >= 2");
+  if (p->solver < 0 || p->solver > AB_SOLVER_LHLLD) return fail(AB_ERR_ARG, "unknown Riemann solver");
+  // configure.py:310-325
   if (p->mhd && p->solver == AB_SOLVER_HLLC) return fail(AB_ERR_ARG, "HLLC flux cannot be used with MHD");
+  if (p->mhd && p->solver == AB_SOLVER_LHLLC) return fail(AB_ERR_ARG, "LHLLC flux cannot be used with MHD");
   if (!p->mhd && p->solver == AB_SOLVER_HLLD) return fail(AB_ERR_ARG, "HLLD flux can only be used with MHD");
+  if (!p->mhd && p->solver == AB_SOLVER_LHLLD) return fail(AB_ERR_ARG, "LHLLD flux can only be used with MHD");
   for (int f = 0; f < 6; ++f)
     if (p->bc[f] != AB_BC_PERIODIC && p->bc[f] != AB_BC_OUTFLOW)
       return fail(AB_ERR_ARG, "unsupported boundary flag");

@@ -25,7 +25,8 @@ namespace ab {
 // variable indices (src/athena.hpp:136-144)
 enum : int { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4, IVX = 1, IVY = 2, IVZ = 3, IPR = 4,
              IBY = 5, IBZ = 6 };
-enum : int { SOLVER_HLLE = 0, SOLVER_HLLC = 1, SOLVER_HLLD = 2, SOLVER_ROE = 3 };
+enum : int { SOLVER_HLLE = 0, SOLVER_HLLC = 1, SOLVER_HLLD = 2, SOLVER_ROE = 3,
+             SOLVER_LHLLC = 4, SOLVER_LHLLD = 5 };
 
 // std::min / std::max semantics of the reference
 AB_HD double dmin(double a, double b) { return (b < a) ? b : a; }
@@ -152,14 +153,21 @@ AB_HD void ppm(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,
 // ------------------------------------------------------------------------ hydro solvers
 // wl/wr: sweep-ordered primitives (IDN, vx, vy, vz, IPR); f: (IDN, mx, my, mz, IEN).
 
-// HLLC (hydro/rsolvers/hydro/hllc.cpp:32-179)
-AB_HD void hllc(const double *wli, const double *wri, double gamma, double *flxi) {
+// HLLC (hydro/rsolvers/hydro/hllc.cpp:32-179) and, with LOW, the low-dissipation LHLLC of
+// Minoshima et al. 2021 (hydro/rsolvers/hydro/lhllc.cpp:26-175): shock detector th from the
+// velocity differences dvn, dvt (hydro/calculate_velocity_differences.cpp) and the chi/phi
+// pressure fix.
+template <bool LOW>
+AB_HD void hllc_t(const double *wli, const double *wri, double gamma, double dvn, double dvt,
+                  double *flxi) {
   double gm1 = gamma - 1.0;
   double igm1 = 1.0/gm1;
   double cl = sound_speed(gamma, wli[IDN], wli[IPR]);
   double cr = sound_speed(gamma, wri[IDN], wri[IPR]);
-  double el = wli[IPR]*igm1 + 0.5*wli[IDN]*(sqr(wli[IVX]) + sqr(wli[IVY]) + sqr(wli[IVZ]));
-  double er = wri[IPR]*igm1 + 0.5*wri[IDN]*(sqr(wri[IVX]) + sqr(wri[IVY]) + sqr(wri[IVZ]));
+  double vsql = sqr(wli[IVX]) + sqr(wli[IVY]) + sqr(wli[IVZ]);
+  double vsqr = sqr(wri[IVX]) + sqr(wri[IVY]) + sqr(wri[IVZ]);
+  double el = wli[IPR]*igm1 + 0.5*wli[IDN]*vsql;
+  double er = wri[IPR]*igm1 + 0.5*wri[IDN]*vsqr;
   double rhoa = .5*(wli[IDN] + wri[IDN]);
   double ca = .5*(cl + cr);
   double pmid = .5*(wli[IPR] + wri[IPR] + (wli[IVX]-wri[IVX])*rhoa*ca);
@@ -171,14 +179,29 @@ AB_HD void hllc(const double *wli, const double *wri, double gamma, double *flxi
   double ar = wri[IVX] + cr*qr;
   double bp = ar > 0.0 ? ar : (1.0e-20);
   double bm = al < 0.0 ? al : -(1.0e-20);
-  double vxl = wli[IVX] - al;
-  double vxr = wri[IVX] - ar;
-  double tl = wli[IPR] + vxl*wli[IDN]*wli[IVX];
-  double tr = wri[IPR] + vxr*wri[IDN]*wri[IVX];
-  double ml = wli[IDN]*vxl;
-  double mr = -(wri[IDN]*vxr);
-  double am = fdiv((tl - tr), (ml + mr));
-  double cp = (ml*tr + mr*tl)/(ml + mr);
+  double vxl, vxr, am, cp;
+  if (!LOW) {
+    vxl = wli[IVX] - al;
+    vxr = wri[IVX] - ar;
+    double tl = wli[IPR] + vxl*wli[IDN]*wli[IVX];
+    double tr = wri[IPR] + vxr*wri[IDN]*wri[IVX];
+    double ml = wli[IDN]*vxl;
+    double mr = -(wri[IDN]*vxr);
+    am = fdiv((tl - tr), (ml + mr));
+    cp = (ml*tr + mr*tl)/(ml + mr);
+  } else {
+    vxl = al - wli[IVX];
+    vxr = ar - wri[IVX];
+    double ml = wli[IDN]*vxl;
+    double mr = wri[IDN]*vxr;
+    double cmax = dmax(cl, cr);
+    double th1 = dmin(1.0, (cmax-dmin(dvn,0.0))/(cmax-dmin(dvt,0.0)));
+    double th = th1*th1*th1*th1;
+    am = fdiv((mr*wri[IVX] - ml*wli[IVX] - th*(wri[IPR]-wli[IPR])), (mr - ml));
+    double chi = dmin(1.0, sqrt(dmax(vsql, vsqr))/cmax);
+    double phi = chi*(2.0 - chi);
+    cp = (mr*wli[IPR] - ml*wri[IPR] + phi*mr*ml*(wri[IVX]-wli[IVX]))/(mr - ml);
+  }
   cp = cp > 0.0 ? cp : 0.0;
   vxl = wli[IVX] - bm;
   vxr = wri[IVX] - bp;
@@ -369,8 +392,10 @@ struct Cons1D { double d, mx, my, mz, e, by, bz; };
 // of six results (hlld.cpp:315-369).  Here the branch is decided first and only the terms
 // the selected flux depends on are evaluated -- the same operations in the same order on the
 // same operands, so the selected result is bit-identical.
-AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
-                double *flxi) {
+// With LOW: the low-dissipation LHLLD (hydro/rsolvers/mhd/lhlld.cpp:36-390).
+template <bool LOW>
+AB_HD void hlld_t(const double *wli, const double *wri, double bxi, double gamma, double dvn,
+                  double dvt, double *flxi) {
   const double SMALL_NUMBER = 1.0e-8;
   Cons1D ul, ur, ulst, uldst, urdst, urst, fl, fr;
   double spd0, spd1, spd2, spd3, spd4;
@@ -402,13 +427,28 @@ AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
   double ptr = wri[IPR] + pbr;
   double sdl = spd0 - wli[IVX];
   double sdr = spd4 - wri[IVX];
-  spd2 = fdiv((sdr*ur.mx - sdl*ul.mx + (ptl - ptr)), (sdr*ur.d - sdl*ul.d));
+  // LHLLD groups sdl*ul.d first (lhlld.cpp:155-173); HLLD multiplies left to right
+  const double sdld = sdl*ul.d, sdrd = sdr*ur.d;
+  double cfmax = 0.0;
+  if (!LOW) {
+    spd2 = fdiv((sdr*ur.mx - sdl*ul.mx + (ptl - ptr)), (sdr*ur.d - sdl*ul.d));
+  } else {
+    cfmax = dmax(cfl, cfr);
+    double th1 = dmin(1.0, (cfmax-dmin(dvn,0.0))/(cfmax-dmin(dvt,0.0)));
+    double th = th1*th1*th1*th1;
+    spd2 = fdiv((sdr*ur.mx - sdl*ul.mx + th*(ptl - ptr)), (sdrd - sdld));
+  }
   double sdml = spd0 - spd2;
   double sdmr = spd4 - spd2;
   double sdml_inv = 1.0/sdml;
   double sdmr_inv = 1.0/sdmr;
-  ulst.d = ul.d*sdl*sdml_inv;
-  urst.d = ur.d*sdr*sdmr_inv;
+  if (!LOW) {
+    ulst.d = ul.d*sdl*sdml_inv;
+    urst.d = ur.d*sdr*sdmr_inv;
+  } else {
+    ulst.d = sdld*sdml_inv;
+    urst.d = sdrd*sdmr_inv;
+  }
   double ulst_d_inv = 1.0/ulst.d;
   double urst_d_inv = 1.0/urst.d;
   double sqrtdl = sqrt(ulst.d);
@@ -455,24 +495,34 @@ AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
   }
   (void)star;
 
-  double ptstl = ptl + ul.d*sdl*(spd2-wli[IVX]);
-  double ptstr = ptr + ur.d*sdr*(spd2-wri[IVX]);
-  double ptst = 0.5*(ptstr + ptstl);
+  double ptst;
+  if (!LOW) {
+    double ptstl = ptl + ul.d*sdl*(spd2-wli[IVX]);
+    double ptstr = ptr + ur.d*sdr*(spd2-wri[IVX]);
+    ptst = 0.5*(ptstr + ptstl);
+  } else {
+    double clsq = ((pbl + kel) + sqrt(sqr(pbl + kel) - 2.0*kel*bxsq))/ul.d;
+    double crsq = ((pbr + ker) + sqrt(sqr(pbr + ker) - 2.0*ker*bxsq))/ur.d;
+    double chi = dmin(1.0, sqrt(dmax(clsq, crsq))/cfmax);
+    double phi = chi*(2.0 - chi);
+    ptst = (sdrd*ptl - sdld*ptr + phi*sdrd*sdld*(wri[IVX]-wli[IVX]))/(sdrd - sdld);
+  }
+  // (ul.d*sdl)*sdml is HLLD's ul.d*sdl*sdml and LHLLD's sdld*sdml alike
   const bool dstar = br_l2 || br_r2;
   double vbstl = 0.0, vbstr = 0.0;
   // ul* (needed by Fl*, Fl**, and -- transverse components only -- by Fr**)
   if (!br_r1) {
     ulst.mx = ulst.d*spd2;
-    if (fabs(ul.d*sdl*sdml-bxsq) < (SMALL_NUMBER)*ptst) {
+    if (fabs(sdld*sdml-bxsq) < (SMALL_NUMBER)*ptst) {
       ulst.my = ulst.d*wli[IVY];
       ulst.mz = ulst.d*wli[IVZ];
       ulst.by = ul.by;
       ulst.bz = ul.bz;
     } else {
-      double tmp = fdiv(bxi*(sdl - sdml), (ul.d*sdl*sdml - bxsq));
+      double tmp = fdiv(bxi*(sdl - sdml), (sdld*sdml - bxsq));
       ulst.my = ulst.d*(wli[IVY] - ul.by*tmp);
       ulst.mz = ulst.d*(wli[IVZ] - ul.bz*tmp);
-      tmp = (ul.d*sqr(sdl) - bxsq)/(ul.d*sdl*sdml - bxsq);
+      tmp = ((LOW ? sdld*sdl : ul.d*sqr(sdl)) - bxsq)/(sdld*sdml - bxsq);
       ulst.by = ul.by*tmp;
       ulst.bz = ul.bz*tmp;
     }
@@ -485,16 +535,16 @@ AB_HD void hlld(const double *wli, const double *wri, double bxi, double gamma,
   // ur* (needed by Fr*, Fr**, and -- transverse components only -- by Fl**)
   if (!br_l1) {
     urst.mx = urst.d*spd2;
-    if (fabs(ur.d*sdr*sdmr - bxsq) < (SMALL_NUMBER)*ptst) {
+    if (fabs(sdrd*sdmr - bxsq) < (SMALL_NUMBER)*ptst) {
       urst.my = urst.d*wri[IVY];
       urst.mz = urst.d*wri[IVZ];
       urst.by = ur.by;
       urst.bz = ur.bz;
     } else {
-      double tmp = fdiv(bxi*(sdr - sdmr), (ur.d*sdr*sdmr - bxsq));
+      double tmp = fdiv(bxi*(sdr - sdmr), (sdrd*sdmr - bxsq));
       urst.my = urst.d*(wri[IVY] - ur.by*tmp);
       urst.mz = urst.d*(wri[IVZ] - ur.bz*tmp);
-      tmp = (ur.d*sqr(sdr) - bxsq)/(ur.d*sdr*sdmr - bxsq);
+      tmp = ((LOW ? sdrd*sdr : ur.d*sqr(sdr)) - bxsq)/(sdrd*sdmr - bxsq);
       urst.by = ur.by*tmp;
       urst.bz = ur.bz*tmp;
     }
@@ -910,14 +960,16 @@ AB_HD void roe_mhd(const double *wli, const double *wri, double bxi, double gamm
 
 // compile-time dispatch
 template <int SOLVER, bool MHD>
-AB_HD void riemann(const double *wli, const double *wri, double bxi, double gamma,
-                   double *flxi) {
+AB_HD void riemann(const double *wli, const double *wri, double bxi, double gamma, double dvn,
+                   double dvt, double *flxi) {
   if (!MHD) {
-    if (SOLVER == SOLVER_HLLC) hllc(wli, wri, gamma, flxi);
+    if (SOLVER == SOLVER_HLLC) hllc_t<false>(wli, wri, gamma, 0.0, 0.0, flxi);
+    else if (SOLVER == SOLVER_LHLLC) hllc_t<true>(wli, wri, gamma, dvn, dvt, flxi);
     else if (SOLVER == SOLVER_HLLE) hlle_hydro(wli, wri, gamma, flxi);
     else roe_hydro(wli, wri, gamma, flxi);
   } else {
-    if (SOLVER == SOLVER_HLLD) hlld(wli, wri, bxi, gamma, flxi);
+    if (SOLVER == SOLVER_HLLD) hlld_t<false>(wli, wri, bxi, gamma, 0.0, 0.0, flxi);
+    else if (SOLVER == SOLVER_LHLLD) hlld_t<true>(wli, wri, bxi, gamma, dvn, dvt, flxi);
     else if (SOLVER == SOLVER_HLLE) hlle_mhd(wli, wri, bxi, gamma, flxi);
     else roe_mhd(wli, wri, bxi, gamma, flxi);
   }

@@ -15,7 +15,8 @@ extern "C" {
 #endif
 
 enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2 };
-enum { AO_SOLVER_HLLE = 0, AO_SOLVER_HLLC = 1, AO_SOLVER_HLLD = 2, AO_SOLVER_ROE = 3 };
+enum { AO_SOLVER_HLLE = 0, AO_SOLVER_HLLC = 1, AO_SOLVER_HLLD = 2, AO_SOLVER_ROE = 3,
+       AO_SOLVER_LHLLC = 4, AO_SOLVER_LHLLD = 5 };
 enum { AO_INT_VL2 = 0, AO_INT_RK2 = 1, AO_INT_RK1 = 2, AO_INT_RK3 = 3 };
 
 typedef struct {
@@ -76,6 +77,10 @@ double ao_new_block_dt(AoMesh *m, int b);
 void ao_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
                 const double *bx, double gamma, double dt, double dx,
                 double *flx, double *wct);
+/* same with the LHLLC/LHLLD shock-detector inputs (NULL = 0) */
+void ao_riemann_dv(int solver, int mhd, long n, const double *wl, const double *wr,
+                   const double *bx, const double *dvn, const double *dvt, double gamma,
+                   double dt, double dx, double *flx, double *wct);
 void ao_plm(long n, int nvar, const double *qm1, const double *q, const double *qp1,
             double wp, double wm, double *ql_plus, double *qr_minus);
 void ao_ppm(long n, int nvar, const double *qm2, const double *qm1, const double *q,

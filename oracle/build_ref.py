@@ -41,6 +41,9 @@ CONFIGS = {
     "mhd_hlle_ng2": (True, "hlle", 2, ["linear_wave", "shock_tube"]),
     "mhd_roe_ng2": (True, "roe", 2, ["linear_wave", "shock_tube"]),
     "mhd_hlld_ng3": (True, "hlld", 3, ["orszag_tang", "linear_wave", "blast"]),
+    # the fork's production solvers (confignotes: --flux=lhllc / --flux=lhlld)
+    "hydro_lhllc_ng2": (False, "lhllc", 2, ["blast", "shock_tube", "kh"]),
+    "mhd_lhlld_ng2": (True, "lhlld", 2, ["blast", "orszag_tang", "linear_wave"]),
 }
 
 CXXFLAGS = ["-O3", "-std=c++11", "-fopenmp"]

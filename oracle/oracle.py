@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 BC = {"periodic": 0, "outflow": 1, "reflecting": 2}
-SOLVER = {"hlle": 0, "hllc": 1, "hlld": 2, "roe": 3}
+SOLVER = {"hlle": 0, "hllc": 1, "hlld": 2, "roe": 3, "lhllc": 4, "lhlld": 5}
 INTEGRATOR = {"vl2": 0, "rk2": 1, "rk1": 2, "rk3": 3}
 DEFAULT_FLOOR = float(np.sqrt(1024 * float(np.finfo(np.float32).tiny)))  # eos ctor
 
@@ -77,6 +77,8 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.ao_riemann.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_double,
                                  C.c_double, C.c_double, dp, dp]
+        L.ao_riemann_dv.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, dp, dp, C.c_double,
+                                    C.c_double, C.c_double, dp, dp]
         L.ao_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
         L.ao_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, C.c_double, C.c_double,
                              dp, dp]
@@ -207,7 +209,7 @@ class OracleMesh:
         self.L.ao_set_time_dt(self.h, t, dt)
 
 
-def riemann(solver, mhd, wl, wr, bx, gamma, dt=0.0, dx=1.0):
+def riemann(solver, mhd, wl, wr, bx, gamma, dt=0.0, dx=1.0, dvn=None, dvt=None):
     """wl, wr: (nwave, n) sweep-ordered primitives. Returns flux (nwave, n), wct (n)."""
     L = lib()
     wl = np.ascontiguousarray(wl, dtype=np.float64)
@@ -216,8 +218,10 @@ def riemann(solver, mhd, wl, wr, bx, gamma, dt=0.0, dx=1.0):
     bx = np.ascontiguousarray(bx if bx is not None else np.zeros(n), dtype=np.float64)
     flx = np.zeros_like(wl)
     wct = np.zeros(n)
-    L.ao_riemann(SOLVER[solver], int(mhd), n, _dp(wl), _dp(wr), _dp(bx), gamma, dt, dx,
-                 _dp(flx), _dp(wct))
+    dvn = np.ascontiguousarray(dvn if dvn is not None else np.zeros(n), dtype=np.float64)
+    dvt = np.ascontiguousarray(dvt if dvt is not None else np.zeros(n), dtype=np.float64)
+    L.ao_riemann_dv(SOLVER[solver], int(mhd), n, _dp(wl), _dp(wr), _dp(bx), _dp(dvn), _dp(dvt),
+                    gamma, dt, dx, _dp(flx), _dp(wct))
     return flx, wct
 
 

@@ -13,7 +13,7 @@ double ao_sound_speed(double gamma, const double *prim);
 double ao_fast_speed(double gamma, const double *prim, double bx);
 double ao_weight_for_ct(double dflx, double rhol, double rhor, double dx, double dt);
 void ao_riemann_point(int solver, int mhd, const double *wli, const double *wri,
-                      double bxi, double gamma, double *flxi);
+                      double bxi, double gamma, double dvn, double dvt, double *flxi);
 void ao_plm_point(double qm1, double q, double qp1, double wp, double wm,
                   double *plus, double *minus);
 void ao_ppm_point(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,

@@ -512,6 +512,36 @@ static void recon_cell(const AoMesh *m, const AoBlock *B, int dir, int order, in
   minus[IPR] = (minus[IPR] > m->p.pfloor) ? minus[IPR] : m->p.pfloor;
 }
 
+/* Hydro::CalculateVelocityDifferences (src/hydro/calculate_velocity_differences.cpp:20-90):
+ * normal velocity jump dvn and the minimum transverse velocity difference dvt around the
+ * interface (LHLLC / LHLLD shock detector).  1-D leaves dvt at its zero initial value. */
+static void velocity_differences(const AoMesh *m, const AoBlock *B, int dir, int k, int j, int i,
+                                 double *dvn, double *dvt) {
+  const double *w = B->w;
+  int d[3][3] = {{0,0,1},{0,1,0},{1,0,0}};   /* (dk,dj,di) of x1,x2,x3 */
+  int ivx = IVX + dir;
+  int lk = k - d[dir][0], lj = j - d[dir][1], li = i - d[dir][2];   /* lower cell */
+  *dvn = w[CC(B,ivx,k,j,i)] - w[CC(B,ivx,lk,lj,li)];
+  *dvt = 0.0;
+  if (!m->f2) return;
+  /* transverse directions in the reference's order: (dir+1)%3 then (dir+2)%3, skipping x3 in 2-D */
+  double res = 0.0;
+  int first = 1;
+  for (int t = 1; t <= 2; ++t) {
+    int td = (dir + t) % 3;
+    if (!m->f3 && td == 2) continue;
+    int tv = IVX + td;
+    int tk = d[td][0], tj = d[td][1], ti = d[td][2];
+    double dl = mn(w[CC(B,tv,lk+tk,lj+tj,li+ti)] - w[CC(B,tv,lk,lj,li)],
+                   w[CC(B,tv,lk,lj,li)] - w[CC(B,tv,lk-tk,lj-tj,li-ti)]);
+    double dr = mn(w[CC(B,tv,k+tk,j+tj,i+ti)] - w[CC(B,tv,k,j,i)],
+                   w[CC(B,tv,k,j,i)] - w[CC(B,tv,k-tk,j-tj,i-ti)]);
+    double v = mn(dl, dr);
+    if (first) { res = v; first = 0; } else { res = mn(res, v); }
+  }
+  *dvt = res;
+}
+
 /* one interface: face (k,j,i) of direction dir lies between cell-1 and cell */
 static void face_flux(AoMesh *m, AoBlock *B, int dir, int order, int k, int j, int i) {
   int dk = (dir == 2), dj = (dir == 1), di = (dir == 0);
@@ -528,7 +558,10 @@ static void face_flux(AoMesh *m, AoBlock *B, int dir, int order, int k, int j, i
   if (m->p.mhd)
     bxi = dir == 0 ? B->b[0][F1(B,k,j,i)] : (dir == 1 ? B->b[1][F2(B,k,j,i)]
                                                        : B->b[2][F3(B,k,j,i)]);
-  ao_riemann_point(m->p.solver, m->p.mhd, wli, wri, bxi, m->p.gamma, f);
+  double dvn = 0.0, dvt = 0.0;
+  if (m->p.solver == AO_SOLVER_LHLLC || m->p.solver == AO_SOLVER_LHLLD)
+    velocity_differences(m, B, dir, k, j, i, &dvn, &dvt);
+  ao_riemann_point(m->p.solver, m->p.mhd, wli, wri, bxi, m->p.gamma, dvn, dvt, f);
   double *flx = B->flux[dir];
   long o[5];
   for (int n = 0; n < 5; ++n)

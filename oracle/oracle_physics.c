@@ -101,6 +101,75 @@ static void hllc(const double *wli, const double *wri, double gamma, double *flx
   flxi[IEN] = sl*fl[IEN] + sr*fr[IEN] + sm*cp*am;
 }
 
+/* src/hydro/rsolvers/hydro/lhllc.cpp:26-175 (Minoshima et al. 2021 low-dissipation HLLC);
+ * dvn, dvt from Hydro::CalculateVelocityDifferences */
+static void lhllc(const double *wli, const double *wri, double gamma, double dvn, double dvt,
+                  double *flxi) {
+  double fl[5], fr[5];
+  double gm1 = gamma - 1.0;
+  double igm1 = 1.0/gm1;
+  double cl = ao_sound_speed(gamma, wli);
+  double cr = ao_sound_speed(gamma, wri);
+  double vsql = SQR(wli[IVX]) + SQR(wli[IVY]) + SQR(wli[IVZ]);
+  double vsqr = SQR(wri[IVX]) + SQR(wri[IVY]) + SQR(wri[IVZ]);
+  double el = wli[IPR]*igm1 + 0.5*wli[IDN]*vsql;
+  double er = wri[IPR]*igm1 + 0.5*wri[IDN]*vsqr;
+  double rhoa = .5*(wli[IDN] + wri[IDN]);
+  double ca = .5*(cl + cr);
+  double pmid = .5*(wli[IPR] + wri[IPR] + (wli[IVX]-wri[IVX])*rhoa*ca);
+  double umid = .5*(wli[IVX] + wri[IVX] + (wli[IPR]-wri[IPR])/(rhoa*ca));
+  double rhol = wli[IDN] + (wli[IVX] - umid)*rhoa/ca;
+  double rhor = wri[IDN] + (umid - wri[IVX])*rhoa/ca;
+  (void)rhol; (void)rhor;
+  double ql = (pmid <= wli[IPR]) ? 1.0 :
+      sqrt(1.0 + (gamma + 1)/(2*gamma)*(pmid/wli[IPR]-1.0));
+  double qr = (pmid <= wri[IPR]) ? 1.0 :
+      sqrt(1.0 + (gamma + 1)/(2*gamma)*(pmid/wri[IPR]-1.0));
+  double al = wli[IVX] - cl*ql;
+  double ar = wri[IVX] + cr*qr;
+  double bp = ar > 0.0 ? ar : (TINY_NUMBER);
+  double bm = al < 0.0 ? al : -(TINY_NUMBER);
+  double vxl = al - wli[IVX];
+  double vxr = ar - wri[IVX];
+  double ml = wli[IDN]*vxl;
+  double mr = wri[IDN]*vxr;
+  double cmax = mx(cl, cr);
+  double th1 = mn(1.0, (cmax-mn(dvn,0.0))/(cmax-mn(dvt,0.0)));
+  double th = th1*th1*th1*th1;
+  double am = (mr*wri[IVX] - ml*wli[IVX] - th*(wri[IPR]-wli[IPR]))/(mr - ml);
+  double chi = mn(1.0, sqrt(mx(vsql, vsqr))/cmax);
+  double phi = chi*(2.0 - chi);
+  double cp = (mr*wli[IPR] - ml*wri[IPR] + phi*mr*ml*(wri[IVX]-wli[IVX]))/(mr - ml);
+  cp = cp > 0.0 ? cp : 0.0;
+  vxl = wli[IVX] - bm;
+  vxr = wri[IVX] - bp;
+  fl[IDN] = wli[IDN]*vxl;
+  fr[IDN] = wri[IDN]*vxr;
+  fl[IVX] = wli[IDN]*wli[IVX]*vxl + wli[IPR];
+  fr[IVX] = wri[IDN]*wri[IVX]*vxr + wri[IPR];
+  fl[IVY] = wli[IDN]*wli[IVY]*vxl;
+  fr[IVY] = wri[IDN]*wri[IVY]*vxr;
+  fl[IVZ] = wli[IDN]*wli[IVZ]*vxl;
+  fr[IVZ] = wri[IDN]*wri[IVZ]*vxr;
+  fl[IEN] = el*vxl + wli[IPR]*wli[IVX];
+  fr[IEN] = er*vxr + wri[IPR]*wri[IVX];
+  double sl, sr, sm;
+  if (am >= 0.0) {
+    sl = am/(am - bm);
+    sr = 0.0;
+    sm = -bm/(am - bm);
+  } else {
+    sl = 0.0;
+    sr = -am/(bp - am);
+    sm = bp/(bp - am);
+  }
+  flxi[IDN] = sl*fl[IDN] + sr*fr[IDN];
+  flxi[IVX] = sl*fl[IVX] + sr*fr[IVX] + sm*cp;
+  flxi[IVY] = sl*fl[IVY] + sr*fr[IVY];
+  flxi[IVZ] = sl*fl[IVZ] + sr*fr[IVZ];
+  flxi[IEN] = sl*fl[IEN] + sr*fr[IEN] + sm*cp*am;
+}
+
 /* src/hydro/rsolvers/hydro/hlle.cpp:38-162 (adiabatic branch) */
 static void hlle_hydro(const double *wli, const double *wri, double gamma, double *flxi) {
   double wroe[5], fl[5], fr[5];
@@ -353,6 +422,207 @@ static void hlld(const double *wli, const double *wri, double bxi, double gamma,
     urst.my = urst.d*(wri[IVY] - ur.by*tmp);
     urst.mz = urst.d*(wri[IVZ] - ur.bz*tmp);
     tmp = (ur.d*SQR(sdr) - bxsq)/(ur.d*sdr*sdmr - bxsq);
+    urst.by = ur.by*tmp;
+    urst.bz = ur.bz*tmp;
+  }
+  double vbstr = (urst.mx*bxi+(urst.my*urst.by+urst.mz*urst.bz))*urst_d_inv;
+  urst.e = (sdr*ur.e - ptr*wri[IVX] + ptst*spd[2] +
+            bxi*(wri[IVX]*bxi + (wri[IVY]*ur.by + wri[IVZ]*ur.bz) - vbstr))*sdmr_inv;
+  if (0.5*bxsq < (SMALL_NUMBER)*ptst) {
+    uldst = ulst;
+    urdst = urst;
+  } else {
+    double invsumd = 1.0/(sqrtdl + sqrtdr);
+    double bxsig = (bxi > 0.0 ? 1.0 : -1.0);
+    uldst.d = ulst.d;
+    urdst.d = urst.d;
+    uldst.mx = ulst.mx;
+    urdst.mx = urst.mx;
+    double tmp = invsumd*(sqrtdl*(ulst.my*ulst_d_inv) + sqrtdr*(urst.my*urst_d_inv) +
+                          bxsig*(urst.by - ulst.by));
+    uldst.my = uldst.d*tmp;
+    urdst.my = urdst.d*tmp;
+    tmp = invsumd*(sqrtdl*(ulst.mz*ulst_d_inv) + sqrtdr*(urst.mz*urst_d_inv) +
+                   bxsig*(urst.bz - ulst.bz));
+    uldst.mz = uldst.d*tmp;
+    urdst.mz = urdst.d*tmp;
+    tmp = invsumd*(sqrtdl*urst.by + sqrtdr*ulst.by +
+                   bxsig*sqrtdl*sqrtdr*((urst.my*urst_d_inv) - (ulst.my*ulst_d_inv)));
+    uldst.by = urdst.by = tmp;
+    tmp = invsumd*(sqrtdl*urst.bz + sqrtdr*ulst.bz +
+                   bxsig*sqrtdl*sqrtdr*((urst.mz*urst_d_inv) - (ulst.mz*ulst_d_inv)));
+    uldst.bz = urdst.bz = tmp;
+    tmp = spd[2]*bxi + (uldst.my*uldst.by + uldst.mz*uldst.bz)/uldst.d;
+    uldst.e = ulst.e - sqrtdl*bxsig*(vbstl - tmp);
+    urdst.e = urst.e + sqrtdr*bxsig*(vbstr - tmp);
+  }
+  uldst.d = spd[1]*(uldst.d - ulst.d);
+  uldst.mx = spd[1]*(uldst.mx - ulst.mx);
+  uldst.my = spd[1]*(uldst.my - ulst.my);
+  uldst.mz = spd[1]*(uldst.mz - ulst.mz);
+  uldst.e = spd[1]*(uldst.e - ulst.e);
+  uldst.by = spd[1]*(uldst.by - ulst.by);
+  uldst.bz = spd[1]*(uldst.bz - ulst.bz);
+  ulst.d = spd[0]*(ulst.d - ul.d);
+  ulst.mx = spd[0]*(ulst.mx - ul.mx);
+  ulst.my = spd[0]*(ulst.my - ul.my);
+  ulst.mz = spd[0]*(ulst.mz - ul.mz);
+  ulst.e = spd[0]*(ulst.e - ul.e);
+  ulst.by = spd[0]*(ulst.by - ul.by);
+  ulst.bz = spd[0]*(ulst.bz - ul.bz);
+  urdst.d = spd[3]*(urdst.d - urst.d);
+  urdst.mx = spd[3]*(urdst.mx - urst.mx);
+  urdst.my = spd[3]*(urdst.my - urst.my);
+  urdst.mz = spd[3]*(urdst.mz - urst.mz);
+  urdst.e = spd[3]*(urdst.e - urst.e);
+  urdst.by = spd[3]*(urdst.by - urst.by);
+  urdst.bz = spd[3]*(urdst.bz - urst.bz);
+  urst.d = spd[4]*(urst.d  - ur.d);
+  urst.mx = spd[4]*(urst.mx - ur.mx);
+  urst.my = spd[4]*(urst.my - ur.my);
+  urst.mz = spd[4]*(urst.mz - ur.mz);
+  urst.e = spd[4]*(urst.e - ur.e);
+  urst.by = spd[4]*(urst.by - ur.by);
+  urst.bz = spd[4]*(urst.bz - ur.bz);
+  if (spd[0] >= 0.0) {
+    flxi[IDN] = fl.d; flxi[IVX] = fl.mx; flxi[IVY] = fl.my; flxi[IVZ] = fl.mz;
+    flxi[IEN] = fl.e; flxi[IBY] = fl.by; flxi[IBZ] = fl.bz;
+  } else if (spd[4] <= 0.0) {
+    flxi[IDN] = fr.d; flxi[IVX] = fr.mx; flxi[IVY] = fr.my; flxi[IVZ] = fr.mz;
+    flxi[IEN] = fr.e; flxi[IBY] = fr.by; flxi[IBZ] = fr.bz;
+  } else if (spd[1] >= 0.0) {
+    flxi[IDN] = fl.d  + ulst.d;
+    flxi[IVX] = fl.mx + ulst.mx;
+    flxi[IVY] = fl.my + ulst.my;
+    flxi[IVZ] = fl.mz + ulst.mz;
+    flxi[IEN] = fl.e  + ulst.e;
+    flxi[IBY] = fl.by + ulst.by;
+    flxi[IBZ] = fl.bz + ulst.bz;
+  } else if (spd[2] >= 0.0) {
+    flxi[IDN] = fl.d  + ulst.d + uldst.d;
+    flxi[IVX] = fl.mx + ulst.mx + uldst.mx;
+    flxi[IVY] = fl.my + ulst.my + uldst.my;
+    flxi[IVZ] = fl.mz + ulst.mz + uldst.mz;
+    flxi[IEN] = fl.e  + ulst.e + uldst.e;
+    flxi[IBY] = fl.by + ulst.by + uldst.by;
+    flxi[IBZ] = fl.bz + ulst.bz + uldst.bz;
+  } else if (spd[3] > 0.0) {
+    flxi[IDN] = fr.d + urst.d + urdst.d;
+    flxi[IVX] = fr.mx + urst.mx + urdst.mx;
+    flxi[IVY] = fr.my + urst.my + urdst.my;
+    flxi[IVZ] = fr.mz + urst.mz + urdst.mz;
+    flxi[IEN] = fr.e + urst.e + urdst.e;
+    flxi[IBY] = fr.by + urst.by + urdst.by;
+    flxi[IBZ] = fr.bz + urst.bz + urdst.bz;
+  } else {
+    flxi[IDN] = fr.d  + urst.d;
+    flxi[IVX] = fr.mx + urst.mx;
+    flxi[IVY] = fr.my + urst.my;
+    flxi[IVZ] = fr.mz + urst.mz;
+    flxi[IEN] = fr.e  + urst.e;
+    flxi[IBY] = fr.by + urst.by;
+    flxi[IBZ] = fr.bz + urst.bz;
+  }
+}
+
+/* src/hydro/rsolvers/mhd/lhlld.cpp:36-390 (low-dissipation HLLD) */
+static void lhlld(const double *wli, const double *wri, double bxi, double gamma,
+                  double dvn, double dvt, double *flxi) {
+  double spd[5];
+  Cons1D ul, ur, ulst, uldst, urdst, urst, fl, fr;
+  double igm1 = 1.0/(gamma - 1.0);
+  double bxsq = bxi*bxi;
+  double pbl = 0.5*(bxsq + (SQR(wli[IBY]) + SQR(wli[IBZ])));
+  double pbr = 0.5*(bxsq + (SQR(wri[IBY]) + SQR(wri[IBZ])));
+  double kel = 0.5*wli[IDN]*(SQR(wli[IVX]) + (SQR(wli[IVY]) + SQR(wli[IVZ])));
+  double ker = 0.5*wri[IDN]*(SQR(wri[IVX]) + (SQR(wri[IVY]) + SQR(wri[IVZ])));
+  ul.d  = wli[IDN];
+  ul.mx = wli[IVX]*ul.d;
+  ul.my = wli[IVY]*ul.d;
+  ul.mz = wli[IVZ]*ul.d;
+  ul.e  = wli[IPR]*igm1 + kel + pbl;
+  ul.by = wli[IBY];
+  ul.bz = wli[IBZ];
+  ur.d  = wri[IDN];
+  ur.mx = wri[IVX]*ur.d;
+  ur.my = wri[IVY]*ur.d;
+  ur.mz = wri[IVZ]*ur.d;
+  ur.e  = wri[IPR]*igm1 + ker + pbr;
+  ur.by = wri[IBY];
+  ur.bz = wri[IBZ];
+  double cfl = ao_fast_speed(gamma, wli, bxi);
+  double cfr = ao_fast_speed(gamma, wri, bxi);
+  spd[0] = mn(wli[IVX]-cfl, wri[IVX]-cfr);
+  spd[4] = mx(wli[IVX]+cfl, wri[IVX]+cfr);
+  double cfmax = mx(cfl, cfr);
+  double ptl = wli[IPR] + pbl;
+  double ptr = wri[IPR] + pbr;
+  fl.d  = ul.mx;
+  fl.mx = ul.mx*wli[IVX] + ptl - bxsq;
+  fl.my = ul.my*wli[IVX] - bxi*ul.by;
+  fl.mz = ul.mz*wli[IVX] - bxi*ul.bz;
+  fl.e  = wli[IVX]*(ul.e + ptl - bxsq) - bxi*(wli[IVY]*ul.by + wli[IVZ]*ul.bz);
+  fl.by = ul.by*wli[IVX] - bxi*wli[IVY];
+  fl.bz = ul.bz*wli[IVX] - bxi*wli[IVZ];
+  fr.d  = ur.mx;
+  fr.mx = ur.mx*wri[IVX] + ptr - bxsq;
+  fr.my = ur.my*wri[IVX] - bxi*ur.by;
+  fr.mz = ur.mz*wri[IVX] - bxi*ur.bz;
+  fr.e  = wri[IVX]*(ur.e + ptr - bxsq) - bxi*(wri[IVY]*ur.by + wri[IVZ]*ur.bz);
+  fr.by = ur.by*wri[IVX] - bxi*wri[IVY];
+  fr.bz = ur.bz*wri[IVX] - bxi*wri[IVZ];
+  double sdl = spd[0] - wli[IVX];
+  double sdr = spd[4] - wri[IVX];
+  double sdld = sdl*ul.d;
+  double sdrd = sdr*ur.d;
+  double th1 = mn(1.0, (cfmax-mn(dvn,0.0))/(cfmax-mn(dvt,0.0)));
+  double th = th1*th1*th1*th1;
+  spd[2] = (sdr*ur.mx - sdl*ul.mx + th*(ptl - ptr))/(sdrd - sdld);
+  double sdml = spd[0] - spd[2];
+  double sdmr = spd[4] - spd[2];
+  double sdml_inv = 1.0/sdml;
+  double sdmr_inv = 1.0/sdmr;
+  ulst.d = sdld*sdml_inv;
+  urst.d = sdrd*sdmr_inv;
+  double ulst_d_inv = 1.0/ulst.d;
+  double urst_d_inv = 1.0/urst.d;
+  double sqrtdl = sqrt(ulst.d);
+  double sqrtdr = sqrt(urst.d);
+  spd[1] = spd[2] - fabs(bxi)/sqrtdl;
+  spd[3] = spd[2] + fabs(bxi)/sqrtdr;
+  double clsq = ((pbl + kel) + sqrt(SQR(pbl + kel) - 2.0*kel*bxsq))/ul.d;
+  double crsq = ((pbr + ker) + sqrt(SQR(pbr + ker) - 2.0*ker*bxsq))/ur.d;
+  double chi = mn(1.0, sqrt(mx(clsq, crsq))/cfmax);
+  double phi = chi*(2.0 - chi);
+  double ptst = (sdrd*ptl - sdld*ptr + phi*sdrd*sdld*(wri[IVX]-wli[IVX]))/(sdrd - sdld);
+  ulst.mx = ulst.d*spd[2];
+  if (fabs(sdld*sdml-bxsq) < (SMALL_NUMBER)*ptst) {
+    ulst.my = ulst.d*wli[IVY];
+    ulst.mz = ulst.d*wli[IVZ];
+    ulst.by = ul.by;
+    ulst.bz = ul.bz;
+  } else {
+    double tmp = bxi*(sdl - sdml)/(sdld*sdml - bxsq);
+    ulst.my = ulst.d*(wli[IVY] - ul.by*tmp);
+    ulst.mz = ulst.d*(wli[IVZ] - ul.bz*tmp);
+    tmp = (sdld*sdl - bxsq)/(sdld*sdml - bxsq);
+    ulst.by = ul.by*tmp;
+    ulst.bz = ul.bz*tmp;
+  }
+  double vbstl = (ulst.mx*bxi+(ulst.my*ulst.by+ulst.mz*ulst.bz))*ulst_d_inv;
+  ulst.e = (sdl*ul.e - ptl*wli[IVX] + ptst*spd[2] +
+            bxi*(wli[IVX]*bxi + (wli[IVY]*ul.by + wli[IVZ]*ul.bz) - vbstl))*sdml_inv;
+  urst.mx = urst.d*spd[2];
+  if (fabs(sdrd*sdmr - bxsq) < (SMALL_NUMBER)*ptst) {
+    urst.my = urst.d*wri[IVY];
+    urst.mz = urst.d*wri[IVZ];
+    urst.by = ur.by;
+    urst.bz = ur.bz;
+  } else {
+    double tmp = bxi*(sdr - sdmr)/(sdrd*sdmr - bxsq);
+    urst.my = urst.d*(wri[IVY] - ur.by*tmp);
+    urst.mz = urst.d*(wri[IVZ] - ur.bz*tmp);
+    tmp = (sdrd*sdr - bxsq)/(sdrd*sdmr - bxsq);
     urst.by = ur.by*tmp;
     urst.bz = ur.bz*tmp;
   }
@@ -790,13 +1060,15 @@ static void roe_mhd(const double *wli, const double *wri, double bxi, double gam
 
 /* One interface.  wli/wri in sweep-rotated order (IDN,ivx,ivy,ivz,IPR[,IBY,IBZ]). */
 void ao_riemann_point(int solver, int mhd, const double *wli, const double *wri,
-                      double bxi, double gamma, double *flxi) {
+                      double bxi, double gamma, double dvn, double dvt, double *flxi) {
   if (!mhd) {
-    if (solver == AO_SOLVER_HLLC) hllc(wli, wri, gamma, flxi);
+    if (solver == AO_SOLVER_LHLLC) lhllc(wli, wri, gamma, dvn, dvt, flxi);
+    else if (solver == AO_SOLVER_HLLC) hllc(wli, wri, gamma, flxi);
     else if (solver == AO_SOLVER_HLLE) hlle_hydro(wli, wri, gamma, flxi);
     else roe_hydro(wli, wri, gamma, flxi);
   } else {
-    if (solver == AO_SOLVER_HLLD) hlld(wli, wri, bxi, gamma, flxi);
+    if (solver == AO_SOLVER_LHLLD) lhlld(wli, wri, bxi, gamma, dvn, dvt, flxi);
+    else if (solver == AO_SOLVER_HLLD) hlld(wli, wri, bxi, gamma, flxi);
     else if (solver == AO_SOLVER_HLLE) hlle_mhd(wli, wri, bxi, gamma, flxi);
     else roe_mhd(wli, wri, bxi, gamma, flxi);
   }
@@ -805,11 +1077,18 @@ void ao_riemann_point(int solver, int mhd, const double *wli, const double *wri,
 void ao_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
                 const double *bx, double gamma, double dt, double dx,
                 double *flx, double *wct) {
+  ao_riemann_dv(solver, mhd, n, wl, wr, bx, 0, 0, gamma, dt, dx, flx, wct);
+}
+
+void ao_riemann_dv(int solver, int mhd, long n, const double *wl, const double *wr,
+                   const double *bx, const double *dvn, const double *dvt, double gamma,
+                   double dt, double dx, double *flx, double *wct) {
   int nw = mhd ? 7 : 5;
   for (long i = 0; i < n; ++i) {
     double wli[7], wri[7], f[7];
     for (int v = 0; v < nw; ++v) { wli[v] = wl[v*n+i]; wri[v] = wr[v*n+i]; }
-    ao_riemann_point(solver, mhd, wli, wri, mhd ? bx[i] : 0.0, gamma, f);
+    ao_riemann_point(solver, mhd, wli, wri, mhd ? bx[i] : 0.0, gamma, dvn ? dvn[i] : 0.0,
+                     dvt ? dvt[i] : 0.0, f);
     for (int v = 0; v < nw; ++v) flx[v*n+i] = f[v];
     if (mhd && wct) wct[i] = ao_weight_for_ct(f[IDN], wli[IDN], wri[IDN], dx, dt);
   }

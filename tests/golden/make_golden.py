@@ -52,6 +52,15 @@ CASES = {
     "linwave_mhd_hlle_plm_vl2": ("mhd_hlle_ng2", "linear_wave", "athinput.linear_wave3d",
                                  dict(LW, **mb(16, 8, 8), **{"problem/amp": 0.1}),
                                  "hlle", True, 4),
+    # the fork's production solvers (confignotes)
+    "blast_lhlld_plm_vl2_8blk": ("mhd_lhlld_ng2", "blast", "athinput.blast",
+                                 dict(BL, **mb(8, 8, 8)), "lhlld", True, 6),
+    "ot_lhlld_plm_vl2_4blk": ("mhd_lhlld_ng2", "orszag_tang", "athinput.orszag_tang",
+                              dict(OT, **mb(16, 16), **{"time/xorder": 2}), "lhlld", True, 5),
+    "blast_lhllc_plm_vl2_8blk": ("hydro_lhllc_ng2", "blast", "athinput.blast",
+                                 dict(BL, **mb(8, 8, 8)), "lhllc", False, 6),
+    "sod_lhllc_plm_vl2_2blk": ("hydro_lhllc_ng2", "shock_tube", "athinput.sod",
+                               {"mesh/nx1": 64, "meshblock/nx1": 32}, "lhllc", False, 8),
     "linwave_mhd_roe_plm_vl2_2blk": ("mhd_roe_ng2", "linear_wave", "athinput.linear_wave3d",
                                      dict(LW, **mb(8, 8, 8), **{"problem/amp": 0.1}),
                                      "roe", True, 4),

@@ -4,13 +4,14 @@
 #include "../../athena-gamma_b200/csrc/ab_physics.cuh"
 
 template <int S, bool M>
-static void run(long n, const double *wl, const double *wr, const double *bx, double gamma,
-                double dt, double dx, double *flx, double *wct) {
+static void run(long n, const double *wl, const double *wr, const double *bx, const double *dvn,
+                const double *dvt, double gamma, double dt, double dx, double *flx,
+                double *wct) {
   const int nw = M ? 7 : 5;
   for (long i = 0; i < n; ++i) {
     double a[7], b[7], f[7];
     for (int v = 0; v < nw; ++v) { a[v] = wl[v*n+i]; b[v] = wr[v*n+i]; }
-    ab::riemann<S, M>(a, b, M ? bx[i] : 0.0, gamma, f);
+    ab::riemann<S, M>(a, b, M ? bx[i] : 0.0, gamma, dvn ? dvn[i] : 0.0, dvt ? dvt[i] : 0.0, f);
     for (int v = 0; v < nw; ++v) flx[v*n+i] = f[v];
     if (M && wct) wct[i] = ab::weight_for_ct(f[0], a[0], b[0], dx, dt);
   }
@@ -18,17 +19,21 @@ static void run(long n, const double *wl, const double *wr, const double *bx, do
 
 extern "C" {
 void hc_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
-                const double *bx, double gamma, double dt, double dx, double *flx,
-                double *wct) {
+                const double *bx, const double *dvn, const double *dvt, double gamma, double dt,
+                double dx, double *flx, double *wct) {
+#define RUN(S, M) run<S, M>(n, wl, wr, bx, dvn, dvt, gamma, dt, dx, flx, wct)
   if (!mhd) {
-    if (solver == 1) run<1, false>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
-    else if (solver == 0) run<0, false>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
-    else run<3, false>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
+    if (solver == 1) RUN(1, false);
+    else if (solver == 0) RUN(0, false);
+    else if (solver == 4) RUN(4, false);
+    else RUN(3, false);
   } else {
-    if (solver == 2) run<2, true>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
-    else if (solver == 0) run<0, true>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
-    else run<3, true>(n, wl, wr, bx, gamma, dt, dx, flx, wct);
+    if (solver == 2) RUN(2, true);
+    else if (solver == 0) RUN(0, true);
+    else if (solver == 5) RUN(5, true);
+    else RUN(3, true);
   }
+#undef RUN
 }
 void hc_plm(long n, int nvar, const double *qm1, const double *q, const double *qp1,
             double wp, double wm, double *ql, double *qr) {

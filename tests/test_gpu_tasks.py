@@ -22,6 +22,10 @@ CASES = [
     ("linwave_mhd_hlle_plm_vl2", None, None),
     ("sod_roe_plm_vl2", None, None),
     ("sod_hlle_plm_vl2", None, None),
+    ("blast_lhlld_plm_vl2_8blk", None, None),
+    ("ot_lhlld_plm_vl2_4blk", None, None),
+    ("blast_lhllc_plm_vl2_8blk", None, None),
+    ("sod_lhllc_plm_vl2_2blk", None, None),
 ]
 
 

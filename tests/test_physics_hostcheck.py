@@ -26,8 +26,8 @@ def hc():
                         "-x", "c++", src, "-o", SO], check=True)
     L = C.CDLL(SO)
     dp = C.POINTER(C.c_double)
-    L.hc_riemann.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_double, C.c_double,
-                             C.c_double, dp, dp]
+    L.hc_riemann.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, dp, dp, C.c_double,
+                             C.c_double, C.c_double, dp, dp]
     L.hc_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
     L.hc_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, dp, dp]
     return L
@@ -50,7 +50,8 @@ def random_states(rng, n, mhd, regime):
 
 
 @pytest.mark.parametrize("solver,mhd", [("hllc", False), ("hlle", False), ("roe", False),
-                                        ("hlld", True), ("hlle", True), ("roe", True)])
+                                        ("lhllc", False), ("hlld", True), ("hlle", True),
+                                        ("roe", True), ("lhlld", True)])
 @pytest.mark.parametrize("regime", ["subsonic", "supersonic", "mixed"])
 def test_riemann_matches_oracle(hc, solver, mhd, regime):
     rng = np.random.default_rng(1234)
@@ -62,11 +63,14 @@ def test_riemann_matches_oracle(hc, solver, mhd, regime):
     bx = rng.normal(0, 1.0, n)
     bx[n // 2: n // 2 + n // 8] = 0.0
     bx[n // 2 + n // 8: n // 2 + n // 4] *= 1e-9
-    fo, wo = oracle.riemann(solver, mhd, wl, wr, bx, 5.0 / 3.0, dt=0.01, dx=0.1)
+    dvn = rng.normal(0, 1.0, n)
+    dvt = rng.normal(0, 1.0, n)
+    dvn[: n // 3] = 0.0
+    fo, wo = oracle.riemann(solver, mhd, wl, wr, bx, 5.0 / 3.0, dt=0.01, dx=0.1, dvn=dvn, dvt=dvt)
     fh = np.zeros_like(wl)
     wh = np.zeros(n)
-    hc.hc_riemann(oracle.SOLVER[solver], int(mhd), n, _dp(wl), _dp(wr), _dp(bx), 5.0 / 3.0,
-                  0.01, 0.1, _dp(fh), _dp(wh))
+    hc.hc_riemann(oracle.SOLVER[solver], int(mhd), n, _dp(wl), _dp(wr), _dp(bx), _dp(dvn),
+                  _dp(dvt), 5.0 / 3.0, 0.01, 0.1, _dp(fh), _dp(wh))
     util.assert_bitwise(fh, fo, "flux %s mhd=%s" % (solver, mhd))
     if mhd:
         util.assert_bitwise(wh, wo, "ct weight")
