@@ -886,10 +886,12 @@ void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta,
 }
 
 // register average of one face value (same modes as k_integrate_cc)
-__device__ __forceinline__ double fc_avg(double *bo, double *b1, long o, int mode,
-                                         int zero_init, double delta, double g1, double g2) {
-  if (mode == 0) return bo[o];
-  if (mode == 1) {
+template <int MODE>
+__device__ __forceinline__ double fc_avg(double *__restrict__ bo, double *__restrict__ b1,
+                                         int o, int zero_init, double delta, double g1,
+                                         double g2) {
+  if (MODE == 0) return bo[o];
+  if (MODE == 1) {
     double v = zero_init ? 0.0 : bo[o];
     if (delta != 0.0) v += delta*b1[o];
     return v;
@@ -904,42 +906,62 @@ __device__ __forceinline__ double fc_avg(double *bo, double *b1, long o, int mod
 }
 
 // IntegrateField: face-register average + Field::CT (field/ct.cpp:31-116), fused.
-// Thread (k,j,i) updates x1f(k,j,i) [i<=ie+1], x2f(k,j,i) [j<=je+1], x3f(k,j,i) [k<=ke+1].
-__global__ void __launch_bounds__(BX) k_integrate_fc(BlkDev b, int mode, int zero_init,
-                                                     double delta, double g1, double g2,
-                                                     double beta, double dt_val,
+// Thread (k,j,i) of the flattened box [ks,ke+1]x[js,je+1]x[is,ie+1] updates x1f(k,j,i)
+// [j<=je,k<=ke], x2f(k,j,i) [i<=ie,k<=ke] and x3f(k,j,i) [i<=ie,j<=je]; the nine edge EMFs it
+// needs are loaded once (e?(k,j,i) is shared by two of the three updates).
+template <int MODE>
+__global__ void __launch_bounds__(BX) k_integrate_fc(BlkDev b, int ni, int nj, int ntot,
+                                                     int zero_init, double delta, double g1,
+                                                     double g2, double beta, double dt_val,
                                                      const double *dt_ptr) {
-  int i = b.is + blockIdx.x*BX + threadIdx.x;
-  if (i > b.ie+1) return;
-  int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
+  int t = blockIdx.x*BX + threadIdx.x;
+  if (t >= ntot) return;
+  int r = t / ni;
+  const int i = b.is + (t - r*ni);
+  const int kk = r / nj;
+  const int j = b.js + (r - kk*nj);
+  const int k = b.ks + kk;
   const double wght = beta*(dt_ptr ? *dt_ptr : dt_val);
-  const double *e1 = b.e[0], *e2 = b.e[1], *e3 = b.e[2];
-  const double dx1 = b.dx1f[i <= b.ie ? i : b.ie], dx2 = b.dx2f[j <= b.je ? j : b.je],
-               dx3 = b.dx3f[k <= b.ke ? k : b.ke];
-  if (j <= b.je && k <= b.ke) {       // B1 (ct.cpp:40-62)
-    long o = F1I(b,k,j,i);
-    double v = fc_avg(b.b[0], b.b1[0], o, mode, zero_init, delta, g1, g2);
-    if (b.f2) {
-      double area = dx2*dx3;
-      v -= (wght/area)*(dx3*e3[E3I(b,k,j+1,i)] - dx3*e3[E3I(b,k,j,i)]);
-      if (b.f3) v += (wght/area)*(dx2*e2[E2I(b,k+1,j,i)] - dx2*e2[E2I(b,k,j,i)]);
+  const double *__restrict__ e1 = b.e[0];
+  const double *__restrict__ e2 = b.e[1];
+  const double *__restrict__ e3 = b.e[2];
+  const bool in_i = (i <= b.ie), in_j = (j <= b.je), in_k = (k <= b.ke);
+  const double dx1 = b.dx1f[in_i ? i : b.ie], dx2 = b.dx2f[in_j ? j : b.je],
+               dx3 = b.dx3f[in_k ? k : b.ke];
+  // edge-array offsets (EdgeField shapes, athena.hpp:107-115)
+  const int n1 = b.nc1, n2 = b.nc2;
+  const int o1 = (k*(n2+1) + j)*n1 + i;          // x1e(k,j,i)
+  const int o2 = (k*n2 + j)*(n1+1) + i;          // x2e(k,j,i)
+  const int o3 = (k*(n2+1) + j)*(n1+1) + i;      // x3e(k,j,i)
+  const bool f2 = b.f2, f3 = b.f3;
+  // loads guarded by the validity of the element inside its array
+  const double e3c = (in_k) ? e3[o3] : 0.0;
+  const double e2c = (in_j) ? e2[o2] : 0.0;
+  const double e1c = (in_i && f2) ? e1[o1] : 0.0;
+  if (in_j && in_k) {                  // B1 (ct.cpp:40-62)
+    const int o = (k*n2 + j)*(n1+1) + i;
+    double v = fc_avg<MODE>(b.b[0], b.b1[0], o, zero_init, delta, g1, g2);
+    if (f2) {
+      const double area = dx2*dx3;
+      v -= (wght/area)*(dx3*e3[o3 + (n1+1)] - dx3*e3c);
+      if (f3) v += (wght/area)*(dx2*e2[o2 + n2*(n1+1)] - dx2*e2c);
     }
     b.b[0][o] = v;
   }
-  if (i <= b.ie && k <= b.ke) {       // B2 (ct.cpp:64-92)
-    long o = F2I(b,k,j,i);
-    double v = fc_avg(b.b[1], b.b1[1], o, mode, zero_init, delta, g1, g2);
-    double area = dx1*dx3;
-    v += (wght/area)*(dx3*e3[E3I(b,k,j,i+1)] - dx3*e3[E3I(b,k,j,i)]);
-    if (b.f3) v -= (wght/area)*(dx1*e1[E1I(b,k+1,j,i)] - dx1*e1[E1I(b,k,j,i)]);
+  if (in_i && in_k) {                  // B2 (ct.cpp:64-92)
+    const int o = (k*(n2+1) + j)*n1 + i;
+    double v = fc_avg<MODE>(b.b[1], b.b1[1], o, zero_init, delta, g1, g2);
+    const double area = dx1*dx3;
+    v += (wght/area)*(dx3*e3[o3 + 1] - dx3*e3c);
+    if (f3) v -= (wght/area)*(dx1*e1[o1 + (n2+1)*n1] - dx1*e1c);
     b.b[1][o] = v;
   }
-  if (i <= b.ie && j <= b.je) {       // B3 (ct.cpp:94-114)
-    long o = F3I(b,k,j,i);
-    double v = fc_avg(b.b[2], b.b1[2], o, mode, zero_init, delta, g1, g2);
-    double area = dx1*dx2;
-    v -= (wght/area)*(dx2*e2[E2I(b,k,j,i+1)] - dx2*e2[E2I(b,k,j,i)]);
-    if (b.f2) v += (wght/area)*(dx1*e1[E1I(b,k,j+1,i)] - dx1*e1[E1I(b,k,j,i)]);
+  if (in_i && in_j) {                  // B3 (ct.cpp:94-114)
+    const int o = (k*n2 + j)*n1 + i;
+    double v = fc_avg<MODE>(b.b[2], b.b1[2], o, zero_init, delta, g1, g2);
+    const double area = dx1*dx2;
+    v -= (wght/area)*(dx2*e2[o2 + 1] - dx2*e2c);
+    if (f2) v += (wght/area)*(dx1*e1[o1 + n1] - dx1*e1c);
     b.b[2][o] = v;
   }
 }
@@ -947,8 +969,13 @@ __global__ void __launch_bounds__(BX) k_integrate_fc(BlkDev b, int mode, int zer
 void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
                          cudaStream_t s) {
-  k_integrate_fc<<<grid3(b.ie-b.is+2, b.je-b.js+2, b.ke-b.ks+2), BX, 0, s>>>(
-      b, mode, zero_init, delta, g1, g2, beta, dt_val, dt_ptr); ++g_launches;
+  const int ni = b.ie-b.is+2, nj = b.je-b.js+2, nk = b.ke-b.ks+2;
+  const int ntot = ni*nj*nk;
+  const int g = (ntot + BX - 1)/BX;
+  if (mode == 0) k_integrate_fc<0><<<g, BX, 0, s>>>(b, ni, nj, ntot, zero_init, delta, g1, g2, beta, dt_val, dt_ptr);
+  else if (mode == 1) k_integrate_fc<1><<<g, BX, 0, s>>>(b, ni, nj, ntot, zero_init, delta, g1, g2, beta, dt_val, dt_ptr);
+  else k_integrate_fc<2><<<g, BX, 0, s>>>(b, ni, nj, ntot, zero_init, delta, g1, g2, beta, dt_val, dt_ptr);
+  ++g_launches;
 }
 
 // =============================================================================================

@@ -1,0 +1,113 @@
+"""GPU: parity at BASELINE.json's full sizes.
+
+* C2 (3-D MHD linear wave 128x64x64, HLLD+PLM+VL2, one MeshBlock) at its FULL size against the
+  unmodified reference binary run live on the box's CPU (oracle/_ref travels with the repo):
+  bit-identical dt sequence and state.  Skipped when oracle/_ref is absent.
+* C5 (MHD blast) at 256^3 and 512^3 through size-independent properties: div B = 0 to
+  round-off (constrained transport), conservation of mass / momentum / energy under periodic
+  boundaries, and MeshBlock-decomposition invariance of the dt sequence.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import athena_gamma_b200 as ab
+import util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c2_full_size_bitwise_vs_reference_binary():
+    import ref_run
+    if not ref_run.have_ref("mhd_hlld_ng2", "linear_wave"):
+        pytest.skip("oracle/_ref not built")
+    ncyc = 4
+    res = ref_run.run_reference("mhd_hlld_ng2", "linear_wave",
+                                os.path.join(ROOT, "inputs", "athinput.linear_wave3d"),
+                                {"time/nlim": ncyc}, rst_every_cycle=True)
+    try:
+        first = ref_run.read_rst(res["rst"][0])
+        last = ref_run.read_rst(res["rst"][ncyc])
+    finally:
+        ref_run.cleanup(res)
+    assert first["nx"] == [128, 64, 64]
+    pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", "athinput.linear_wave3d"))
+    m = ab.Mesh(pin, mhd=True, flux="hlld")
+    pmb = m.my_blocks[0]
+    for f in ("u", "b1", "b2", "b3"):
+        pmb.set(f, first["blocks"][0][f])
+    m.initialize()
+    assert m.dt == res["dts"][0]
+    dts = m.cycles(ncyc)
+    assert list(dts) == res["dts"][:ncyc]
+    for f in ("u", "b1", "b2", "b3"):
+        util.assert_bitwise(pmb.get(f), last["blocks"][0][f], "C2 full size %s" % f)
+
+
+def blast_mesh(n, block, ncyc):
+    pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", "athinput.blast"))
+    for d in (1, 2, 3):
+        pin.set("mesh", "nx%d" % d, n)
+        pin.set("meshblock", "nx%d" % d, block)
+    pin.set("time", "tlim", 1e30)
+    m = ab.Mesh(pin, mhd=True, flux="hlld")
+    m.problem_generator(ab.pgen.blast)
+    m.initialize()
+    return m
+
+
+def totals_and_divb(m):
+    tot = np.zeros(5)
+    divb_max, bmax = 0.0, 0.0
+    for pmb in m.my_blocks:
+        K, J, I = (slice(pmb.ks, pmb.ke + 1), slice(pmb.js, pmb.je + 1),
+                   slice(pmb.is_, pmb.ie + 1))
+        K1, J1, I1 = (slice(pmb.ks + 1, pmb.ke + 2), slice(pmb.js + 1, pmb.je + 2),
+                      slice(pmb.is_ + 1, pmb.ie + 2))
+        u = pmb.get("u")
+        tot += u[:, K, J, I].reshape(5, -1).sum(axis=1, dtype=np.longdouble).astype(float)
+        del u
+        b1, b2, b3 = pmb.get("b1"), pmb.get("b2"), pmb.get("b3")
+        dx = pmb.coord("dx1f")[pmb.is_]
+        div = ((b1[K, J, I1] - b1[K, J, I]) + (b2[K, J1, I] - b2[K, J, I])
+               + (b3[K1, J, I] - b3[K, J, I]))
+        divb_max = max(divb_max, float(np.abs(div).max()))
+        bmax = max(bmax, float(np.abs(b1[K, J, I]).max()), float(np.abs(b2[K, J, I]).max()))
+        del b1, b2, b3, div, dx
+    return tot, divb_max/bmax
+
+
+@pytest.mark.parametrize("n", [256, 512])
+def test_c5_properties_at_scale(n):
+    ncyc = 6 if n == 256 else 3
+    m = blast_mesh(n, n, ncyc)
+    zones = float(n)**3
+    t0, d0 = totals_and_divb(m)
+    assert d0 < 1e-13
+    dts = m.cycles(ncyc)
+    assert len(dts) == ncyc and np.all(dts > 0.0)
+    t1, d1 = totals_and_divb(m)
+    # constrained transport keeps div B at round-off
+    assert d1 < 1e-12, d1
+    # periodic box: mass, momentum and total energy are conserved to round-off
+    assert abs(t1[0] - t0[0]) <= 1e-12*abs(t0[0])
+    assert abs(t1[4] - t0[4]) <= 1e-12*abs(t0[4])
+    for c in (1, 2, 3):
+        assert abs(t1[c] - t0[c]) <= 1e-12*zones*1e-3 + 1e-9      # zero-mean momenta
+    # the blast actually evolved
+    assert m.ncycle == ncyc and m.time > 0.0
+
+
+def test_c5_decomposition_invariance_of_dt():
+    """256^3 as one MeshBlock vs 8 MeshBlocks of 128^3: the reference's dt sequence does not
+    depend on the decomposition; neither does ours."""
+    ncyc = 5
+    m1 = blast_mesh(256, 256, ncyc)
+    d1 = list(m1.cycles(ncyc))
+    del m1
+    m8 = blast_mesh(256, 128, ncyc)
+    assert m8.nbtotal == 8
+    d8 = list(m8.cycles(ncyc))
+    assert d1 == d8
