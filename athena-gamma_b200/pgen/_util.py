@@ -6,12 +6,16 @@ def active(pmb):
     return (slice(pmb.ks, pmb.ke + 1), slice(pmb.js, pmb.je + 1), slice(pmb.is_, pmb.ie + 1))
 
 
-def empty_state(pmb, mhd):
-    out = {"u": np.zeros(pmb.shape("u"))}
-    if mhd:
-        for n in ("b1", "b2", "b3"):
-            out[n] = np.zeros(pmb.shape(n))
-    return out
+def empty_state(pmb, mhd, out=None):
+    """AthenaArray storage is zero-initialised (athena_arrays.hpp:527-538).  `out` lets the
+    caller provide the buffers (e.g. pinned host memory) instead of allocating new ones."""
+    names = ("u", "b1", "b2", "b3") if mhd else ("u",)
+    if out is not None:
+        for n in names:
+            assert out[n].shape == pmb.shape(n), (n, out[n].shape)
+            out[n][...] = 0.0
+        return out
+    return {n: np.zeros(pmb.shape(n)) for n in names}
 
 
 def coords(pmb):

@@ -5,7 +5,7 @@ import numpy as np
 from ._util import active, coords, empty_state
 
 
-def blast(pmb, pin):
+def blast(pmb, pin, out=None):
     m = pmb.pmy_mesh
     mhd = m.mhd
     rout = pin.get_real("problem", "radius")
@@ -19,7 +19,7 @@ def blast(pmb, pin):
     gm1 = pin.get_real("hydro", "gamma") - 1.0
     x0 = [pin.get_or_add_real("problem", "x%d_0" % d, 0.0) for d in (1, 2, 3)]
     c = coords(pmb)
-    out = empty_state(pmb, mhd)
+    out = empty_state(pmb, mhd, out)
     k, j, i = active(pmb)
     X = c["x1v"][i][None, None, :]
     Y = c["x2v"][j][None, :, None]

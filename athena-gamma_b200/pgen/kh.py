@@ -7,13 +7,13 @@ import numpy as np
 from ._util import active, coords, empty_state
 
 
-def kh(pmb, pin):
+def kh(pmb, pin, out=None):
     gm1 = pin.get_real("hydro", "gamma") - 1.0
     vflow = pin.get_real("problem", "vflow")
     drat = pin.get_real("problem", "drat")
     amp = pin.get_real("problem", "amp")
     c = coords(pmb)
-    out = empty_state(pmb, False)
+    out = empty_state(pmb, False, out)
     k, j, i = active(pmb)
     shape = (pmb.ke - pmb.ks + 1, pmb.je - pmb.js + 1, pmb.ie - pmb.is_ + 1)
     rng = np.random.default_rng(1 + pmb.gid)

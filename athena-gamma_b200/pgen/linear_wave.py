@@ -97,7 +97,7 @@ def setup(pin, mhd, f2, f3):
     return dict(sa2=sa2, ca2=ca2, sa3=sa3, ca3=ca3, k_par=2.0 * np.pi / lam)
 
 
-def linear_wave(pmb, pin):
+def linear_wave(pmb, pin, out=None):
     m = pmb.pmy_mesh
     mhd = m.mhd
     f2, f3 = pmb.ncells2 > 1, pmb.ncells3 > 1
@@ -117,7 +117,7 @@ def linear_wave(pmb, pin):
     else:
         rem, _ = right_eigenvector_hydro(wave, u0, 0.0, 0.0, h0, gm1)
     c = coords(pmb)
-    out = empty_state(pmb, mhd)
+    out = empty_state(pmb, mhd, out)
     k, j, i = active(pmb)
     X = c["x1v"][i][None, None, :]
     Y = c["x2v"][j][None, :, None]

@@ -6,14 +6,14 @@ import numpy as np
 from ._util import active, add_magnetic_energy, coords, empty_state
 
 
-def orszag_tang(pmb, pin):
+def orszag_tang(pmb, pin, out=None):
     gm1 = pin.get_real("hydro", "gamma") - 1.0
     B0 = 1.0 / np.sqrt(4.0 * np.pi)
     d0 = 25.0 / (36.0 * np.pi)
     v0 = 1.0
     p0 = 5.0 / (12.0 * np.pi)
     c = coords(pmb)
-    out = empty_state(pmb, True)
+    out = empty_state(pmb, True, out)
     k, j, i = active(pmb)
     x1f, x2f = c["x1f"], c["x2f"]
     az = B0 / (4.0 * np.pi) * (np.cos(4.0 * np.pi * x1f)[None, :]

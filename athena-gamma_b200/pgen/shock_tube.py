@@ -5,7 +5,7 @@ import numpy as np
 from ._util import active, coords, empty_state
 
 
-def shock_tube(pmb, pin):
+def shock_tube(pmb, pin, out=None):
     m = pmb.pmy_mesh
     mhd = m.mhd
     sd = pin.get_integer("problem", "shock_dir")
@@ -21,7 +21,7 @@ def shock_tube(pmb, pin):
 
     wl, wr = side("l"), side("r")
     c = coords(pmb)
-    out = empty_state(pmb, mhd)
+    out = empty_state(pmb, mhd, out)
     k, j, i = active(pmb)
     xv = [c["x1v"][i][None, None, :], c["x2v"][j][None, :, None], c["x3v"][k][:, None, None]]
     shape = (pmb.ke - pmb.ks + 1, pmb.je - pmb.js + 1, pmb.ie - pmb.is_ + 1)
