@@ -1006,63 +1006,71 @@ void launch_copy_boxes(const CopyBox *boxes_dev, int n, long max_box_elems, cuda
 }
 
 // =============================================================================================
-// Outflow physical boundary (bvals/cc/outflow_cc.cpp, bvals/fc/outflow_fc.cpp)
-// one thread per (transverse a, transverse b); loops over the ng ghost layers
+// Outflow / reflecting physical boundaries on primitives and face fields
+// (bvals/cc/outflow_cc.cpp, cc/hydro/reflect_hydro.cpp, fc/outflow_fc.cpp, fc/reflect_fc.cpp).
+// One thread per pair of transverse indices; loops over the ng ghost layers.  Ghost layer g
+// copies the last active cell/face (outflow) or the mirrored one with the normal velocity and
+// the normal field negated (reflect).
 // =============================================================================================
-__global__ void __launch_bounds__(BX) k_outflow(BlkDev b, int mhd, int face, int il, int iu,
-                                                int jl, int ju, int kl, int ku) {
-  int d = face >> 1, upper = face & 1, ng = b.ng;
-  int a = blockIdx.x*BX + threadIdx.x, c = blockIdx.y;
-  const long sv = (long)b.nc3*b.nc2*b.nc1;
-  if (d == 0) {
-    int j = jl + a, k = kl + c;
-    if (j > ju+1 || k > ku+1) return;
-    for (int g = 1; g <= ng; ++g) {
+__global__ void __launch_bounds__(BX) k_phys_bc(BlkDev b, int mhd, int face, int refl, int il,
+                                                int iu, int jl, int ju, int kl, int ku) {
+  const int d = face >> 1, upper = face & 1, ng = b.ng;
+  const int a = blockIdx.x*BX + threadIdx.x, c = blockIdx.y;
+  const int lo = d == 0 ? il : (d == 1 ? jl : kl), hi = d == 0 ? iu : (d == 1 ? ju : ku);
+  for (int g = 1; g <= ng; ++g) {
+    const int gc = upper ? hi + g : lo - g;
+    const int sc = refl ? (upper ? hi - g + 1 : lo + g - 1) : (upper ? hi : lo);
+    const int gn = upper ? hi + g + 1 : lo - g;
+    const int sn = refl ? (upper ? hi - g + 1 : lo + g) : (upper ? hi + 1 : lo);
+    if (d == 0) {
+      const int j = jl + a, k = kl + c;
+      if (j > ju+1 || k > ku+1) return;
       if (j <= ju && k <= ku) {
-        for (int n = 0; n < NHYDRO; ++n)
-          b.w[CCI(b,n,k,j,upper ? iu+g : il-g)] = b.w[CCI(b,n,k,j,upper ? iu : il)];
-        if (mhd) b.b[0][F1I(b,k,j,upper ? iu+g+1 : il-g)] = b.b[0][F1I(b,k,j,upper ? iu+1 : il)];
+        for (int n = 0; n < NHYDRO; ++n) {
+          double v = b.w[CCI(b,n,k,j,sc)];
+          b.w[CCI(b,n,k,j,gc)] = (refl && n == IVX) ? -v : v;
+        }
+        if (mhd) { double v = b.b[0][F1I(b,k,j,sn)]; b.b[0][F1I(b,k,j,gn)] = refl ? -v : v; }
       }
-      if (mhd && k <= ku) b.b[1][F2I(b,k,j,upper ? iu+g : il-g)] = b.b[1][F2I(b,k,j,upper ? iu : il)];
-      if (mhd && j <= ju) b.b[2][F3I(b,k,j,upper ? iu+g : il-g)] = b.b[2][F3I(b,k,j,upper ? iu : il)];
-    }
-  } else if (d == 1) {
-    int i = il + a, k = kl + c;
-    if (i > iu+1 || k > ku+1) return;
-    for (int g = 1; g <= ng; ++g) {
+      if (mhd && k <= ku) b.b[1][F2I(b,k,j,gc)] = b.b[1][F2I(b,k,j,sc)];
+      if (mhd && j <= ju) b.b[2][F3I(b,k,j,gc)] = b.b[2][F3I(b,k,j,sc)];
+    } else if (d == 1) {
+      const int i = il + a, k = kl + c;
+      if (i > iu+1 || k > ku+1) return;
       if (i <= iu && k <= ku) {
-        for (int n = 0; n < NHYDRO; ++n)
-          b.w[CCI(b,n,k,upper ? ju+g : jl-g,i)] = b.w[CCI(b,n,k,upper ? ju : jl,i)];
-        if (mhd) b.b[1][F2I(b,k,upper ? ju+g+1 : jl-g,i)] = b.b[1][F2I(b,k,upper ? ju+1 : jl,i)];
+        for (int n = 0; n < NHYDRO; ++n) {
+          double v = b.w[CCI(b,n,k,sc,i)];
+          b.w[CCI(b,n,k,gc,i)] = (refl && n == IVY) ? -v : v;
+        }
+        if (mhd) { double v = b.b[1][F2I(b,k,sn,i)]; b.b[1][F2I(b,k,gn,i)] = refl ? -v : v; }
       }
-      if (mhd && k <= ku) b.b[0][F1I(b,k,upper ? ju+g : jl-g,i)] = b.b[0][F1I(b,k,upper ? ju : jl,i)];
-      if (mhd && i <= iu) b.b[2][F3I(b,k,upper ? ju+g : jl-g,i)] = b.b[2][F3I(b,k,upper ? ju : jl,i)];
-    }
-  } else {
-    int i = il + a, j = jl + c;
-    if (i > iu+1 || j > ju+1) return;
-    for (int g = 1; g <= ng; ++g) {
+      if (mhd && k <= ku) b.b[0][F1I(b,k,gc,i)] = b.b[0][F1I(b,k,sc,i)];
+      if (mhd && i <= iu) b.b[2][F3I(b,k,gc,i)] = b.b[2][F3I(b,k,sc,i)];
+    } else {
+      const int i = il + a, j = jl + c;
+      if (i > iu+1 || j > ju+1) return;
       if (i <= iu && j <= ju) {
-        for (int n = 0; n < NHYDRO; ++n)
-          b.w[CCI(b,n,upper ? ku+g : kl-g,j,i)] = b.w[CCI(b,n,upper ? ku : kl,j,i)];
-        if (mhd) b.b[2][F3I(b,upper ? ku+g+1 : kl-g,j,i)] = b.b[2][F3I(b,upper ? ku+1 : kl,j,i)];
+        for (int n = 0; n < NHYDRO; ++n) {
+          double v = b.w[CCI(b,n,sc,j,i)];
+          b.w[CCI(b,n,gc,j,i)] = (refl && n == IVZ) ? -v : v;
+        }
+        if (mhd) { double v = b.b[2][F3I(b,sn,j,i)]; b.b[2][F3I(b,gn,j,i)] = refl ? -v : v; }
       }
-      if (mhd && j <= ju) b.b[0][F1I(b,upper ? ku+g : kl-g,j,i)] = b.b[0][F1I(b,upper ? ku : kl,j,i)];
-      if (mhd && i <= iu) b.b[1][F2I(b,upper ? ku+g : kl-g,j,i)] = b.b[1][F2I(b,upper ? ku : kl,j,i)];
+      if (mhd && j <= ju) b.b[0][F1I(b,gc,j,i)] = b.b[0][F1I(b,sc,j,i)];
+      if (mhd && i <= iu) b.b[1][F2I(b,gc,j,i)] = b.b[1][F2I(b,sc,j,i)];
     }
   }
-  (void)sv;
 }
 
-void launch_outflow(const BlkDev &b, int mhd, int face, int il, int iu, int jl, int ju, int kl,
-                    int ku, cudaStream_t s) {
+void launch_phys_bc(const BlkDev &b, int mhd, int face, int refl, int il, int iu, int jl,
+                    int ju, int kl, int ku, cudaStream_t s) {
   int d = face >> 1;
   int na, nc;
   if (d == 0) { na = ju-jl+2; nc = ku-kl+2; }
   else if (d == 1) { na = iu-il+2; nc = ku-kl+2; }
   else { na = iu-il+2; nc = ju-jl+2; }
-  k_outflow<<<dim3((unsigned)((na + BX - 1)/BX), (unsigned)nc), BX, 0, s>>>(b, mhd, face, il, iu,
-                                                                          jl, ju, kl, ku); ++g_launches;
+  k_phys_bc<<<dim3((unsigned)((na + BX - 1)/BX), (unsigned)nc), BX, 0, s>>>(b, mhd, face, refl, il,
+                                                                          iu, jl, ju, kl, ku); ++g_launches;
 }
 
 // =============================================================================================

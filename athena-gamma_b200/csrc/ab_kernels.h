@@ -49,9 +49,9 @@ void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta,
 // ghost exchange: apply `n` box copies (descriptors in device memory)
 void launch_copy_boxes(const CopyBox *boxes_dev, int n, long max_box_elems, cudaStream_t s);
 
-// outflow physical boundary on primitives and face fields for one block face
-void launch_outflow(const BlkDev &b, int mhd, int face, int il, int iu, int jl, int ju, int kl,
-                    int ku, cudaStream_t s);
+// outflow (refl=0) / reflecting (refl=1) physical boundary on primitives and face fields
+void launch_phys_bc(const BlkDev &b, int mhd, int face, int refl, int il, int iu, int jl,
+                    int ju, int kl, int ku, cudaStream_t s);
 
 // NewBlockTimeStep: min over active cells of dx/(|v|+c) -> atomicMin into *out_bits
 // (out must be pre-set to DBL_MAX bits); result NOT yet multiplied by cfl.

@@ -487,8 +487,8 @@ void build_block_list(AbMesh *m) {
 
 // Coordinates ctor (uniform branch, coordinates.cpp:125-145) + Cartesian x?v (cartesian.cpp:25-75)
 void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, double mmax, double bmin,
-                 double bmax, int nc, std::vector<double> &xf, std::vector<double> &xv,
-                 std::vector<double> &dxf) {
+                 double bmax, int nc, bool refl_in, bool refl_out, std::vector<double> &xf,
+                 std::vector<double> &xv, std::vector<double> &dxf) {
   xf.assign(nc + 1, 0.0); xv.assign(nc, 0.0); dxf.assign(nc, 0.0);
   if (nc == 1) {
     dxf[0] = bmax - bmin;
@@ -505,6 +505,15 @@ void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, double mmax,
   xf[il] = bmin;
   xf[iu+1] = bmax;
   for (int i = il - ng; i <= iu + ng; ++i) dxf[i] = dx;
+  // reflecting boundaries mirror the ghost-zone spacing (coordinates.cpp:147-160)
+  if (refl_in) for (int i = 1; i <= ng; ++i) {
+    dxf[il-i] = dxf[il+i-1];
+    xf[il-i] = xf[il-i+1] - dxf[il-i];
+  }
+  if (refl_out) for (int i = 1; i <= ng; ++i) {
+    dxf[iu+i] = dxf[iu-i+1];
+    xf[iu+i+1] = xf[iu+i] + dxf[iu+i];
+  }
   for (int i = il - ng; i <= iu + ng; ++i) xv[i] = 0.5*(xf[i+1] + xf[i]);
 }
 
@@ -583,7 +592,8 @@ int alloc_blocks(AbMesh *m) {
     const int nxm[3] = {p.nx1, p.nx2, p.nx3}, bxs[3] = {p.bx1, p.bx2, p.bx3};
     for (int dd = 0; dd < 3; ++dd) {
       make_coords(nxm[dd], bxs[dd], ng, B.lx[dd], mmin[dd], mmax[dd], B.bmin[dd], B.bmax[dd],
-                  m->nc[dd], xf[dd], xv[dd], dxf[dd]);
+                  m->nc[dd], B.bcs[2*dd] == AB_BC_REFLECT, B.bcs[2*dd+1] == AB_BC_REFLECT,
+                  xf[dd], xv[dd], dxf[dd]);
       wp[dd].assign(m->nc[dd], 0.0); wm[dd].assign(m->nc[dd], 0.0);
       for (int c = 0; c < m->nc[dd]; ++c) {   // plm.cpp:114-119 / 226-227 / 332-333
         wp[dd][c] = (xf[dd][c+1] - xv[dd][c])/dxf[dd][c];
@@ -896,7 +906,7 @@ void primitives(AbMesh *m, LocalBlock &L, int with_dt = 0) {
 }
 
 void physical_bcs(AbMesh *m, LocalBlock &L) {
-  // BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620), outflow only
+  // BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620): outflow, reflecting
   HostBlock &B = *L.hb;
   int ng = m->p.nghost, mhd = m->p.mhd;
   int is = m->is, ie = m->ie, js = m->js, je = m->je, ks = m->ks, ke = m->ke;
@@ -911,23 +921,23 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
   if (!app[5] && m->f3) bke = ke + ng;
   cudaStream_t s = m->stream;
   if (app[0]) {
-    ab::launch_outflow(L.d, mhd, 0, is, ie, bjs, bje, bks, bke, s);
+    ab::launch_phys_bc(L.d, mhd, 0, B.bcs[0] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
     if (mhd) ab::launch_calc_bcc(L.d, is-ng, is-1, bjs, bje, bks, bke, s);
     ab::launch_prim2cons(L.d, m->kp, is-ng, is-1, bjs, bje, bks, bke, s);
   }
   if (app[1]) {
-    ab::launch_outflow(L.d, mhd, 1, is, ie, bjs, bje, bks, bke, s);
+    ab::launch_phys_bc(L.d, mhd, 1, B.bcs[1] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
     if (mhd) ab::launch_calc_bcc(L.d, ie+1, ie+ng, bjs, bje, bks, bke, s);
     ab::launch_prim2cons(L.d, m->kp, ie+1, ie+ng, bjs, bje, bks, bke, s);
   }
   if (m->f2) {
     if (app[2]) {
-      ab::launch_outflow(L.d, mhd, 2, bis, bie, js, je, bks, bke, s);
+      ab::launch_phys_bc(L.d, mhd, 2, B.bcs[2] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, js-ng, js-1, bks, bke, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, js-ng, js-1, bks, bke, s);
     }
     if (app[3]) {
-      ab::launch_outflow(L.d, mhd, 3, bis, bie, js, je, bks, bke, s);
+      ab::launch_phys_bc(L.d, mhd, 3, B.bcs[3] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, je+1, je+ng, bks, bke, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, je+1, je+ng, bks, bke, s);
     }
@@ -935,12 +945,12 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
   if (m->f3) {
     bjs = js - ng; bje = je + ng;
     if (app[4]) {
-      ab::launch_outflow(L.d, mhd, 4, bis, bie, bjs, bje, ks, ke, s);
+      ab::launch_phys_bc(L.d, mhd, 4, B.bcs[4] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ks-ng, ks-1, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, bjs, bje, ks-ng, ks-1, s);
     }
     if (app[5]) {
-      ab::launch_outflow(L.d, mhd, 5, bis, bie, bjs, bje, ks, ke, s);
+      ab::launch_phys_bc(L.d, mhd, 5, B.bcs[5] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ke+1, ke+ng, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, bjs, bje, ke+1, ke+ng, s);
     }
@@ -1130,7 +1140,7 @@ static int validate_params(const AbMeshParams *p) {
   if (!p->mhd && p->solver == AB_SOLVER_HLLD) return fail(AB_ERR_ARG, "HLLD flux can only be used with MHD");
   if (!p->mhd && p->solver == AB_SOLVER_LHLLD) return fail(AB_ERR_ARG, "LHLLD flux can only be used with MHD");
   for (int f = 0; f < 6; ++f)
-    if (p->bc[f] != AB_BC_PERIODIC && p->bc[f] != AB_BC_OUTFLOW)
+    if (p->bc[f] != AB_BC_PERIODIC && p->bc[f] != AB_BC_OUTFLOW && p->bc[f] != AB_BC_REFLECT)
       return fail(AB_ERR_ARG, "unsupported boundary flag");
   {
     long n1 = p->bx1 + 2L*p->nghost + 1, n2 = (p->nx2 > 1 ? p->bx2 + 2L*p->nghost : 1) + 1,

@@ -22,7 +22,7 @@ extern "C" {
 
 enum { AB_OK = 0, AB_ERR_ARG = -1, AB_ERR_NO_DEVICE = -2, AB_ERR_CUDA = -3, AB_ERR_NCCL = -4,
        AB_ERR_STATE = -5 };
-enum { AB_BC_PERIODIC = 0, AB_BC_OUTFLOW = 1 };               /* mesh/ix1_bc ... */
+enum { AB_BC_PERIODIC = 0, AB_BC_OUTFLOW = 1, AB_BC_REFLECT = 2 };   /* mesh/ix1_bc ... */
 enum { AB_SOLVER_HLLE = 0, AB_SOLVER_HLLC = 1, AB_SOLVER_HLLD = 2, AB_SOLVER_ROE = 3,
        AB_SOLVER_LHLLC = 4, AB_SOLVER_LHLLD = 5 };   /* --flux=hlle|hllc|hlld|roe|lhllc|lhlld */
 enum { AB_INT_VL2 = 0, AB_INT_RK2 = 1, AB_INT_RK1 = 2, AB_INT_RK3 = 3 };
@@ -111,7 +111,8 @@ int ab_zero(AbMesh *m, int lid, int reg);
 int ab_add_flux_div(AbMesh *m, int lid, double wght);
 /* Field::CT(wght, b) (field/ct.cpp:31-116) */
 int ab_ct(AbMesh *m, int lid, double wght);
-/* BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620), outflow faces */
+/* BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620): outflow and reflecting
+ * faces (cc/outflow_cc.cpp, cc/hydro/reflect_hydro.cpp, fc/outflow_fc.cpp, fc/reflect_fc.cpp) */
 int ab_physical_bcs(AbMesh *m, int lid);
 /* Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:42-190): *dt_out = new_block_dt_ (synchronises) */
 int ab_new_block_dt(AbMesh *m, int lid, double *dt_out);

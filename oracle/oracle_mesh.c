@@ -80,8 +80,8 @@ static double uniform_gen(double x, double xmin, double xmax) {
 /* Coordinates ctor, uniform branch (src/coordinates/coordinates.cpp:125-145 and twins),
  * Cartesian x?v (src/coordinates/cartesian.cpp:25-75) */
 static void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, double mmax,
-                        double bmin, double bmax, int nc, double **xf, double **xv,
-                        double **dxf) {
+                        double bmin, double bmax, int nc, int refl_in, int refl_out,
+                        double **xf, double **xv, double **dxf) {
   *xf = dalloc(nc + 1); *xv = dalloc(nc); *dxf = dalloc(nc);
   if (nc == 1) {
     (*dxf)[0] = bmax - bmin;
@@ -100,6 +100,15 @@ static void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, doubl
   (*xf)[il] = bmin;
   (*xf)[iu+1] = bmax;
   for (int i = il - ng; i <= iu + ng; ++i) (*dxf)[i] = dx;
+  /* reflecting boundaries mirror the ghost spacing (coordinates.cpp:147-160) */
+  if (refl_in) for (int i = 1; i <= ng; ++i) {
+    (*dxf)[il-i] = (*dxf)[il+i-1];
+    (*xf)[il-i] = (*xf)[il-i+1] - (*dxf)[il-i];
+  }
+  if (refl_out) for (int i = 1; i <= ng; ++i) {
+    (*dxf)[iu+i] = (*dxf)[iu-i+1];
+    (*xf)[iu+i+1] = (*xf)[iu+i] + (*dxf)[iu+i];
+  }
   for (int i = il - ng; i <= iu + ng; ++i) (*xv)[i] = 0.5*((*xf)[i+1] + (*xf)[i]);
 }
 
@@ -217,11 +226,14 @@ AoMesh *ao_create(const AoParams *p) {
     block_extent(B->lx3, m->nrbx3, p->x3min, p->x3max, p->bc[4], p->bc[5], p->nx3,
                  &B->bx3min, &B->bx3max, &B->bcs[4], &B->bcs[5]);
     make_coords(p->nx1, p->bx1, ng, B->lx1, p->x1min, p->x1max, B->bx1min, B->bx1max,
-                B->nc1, &B->x1f, &B->x1v, &B->dx1f);
+                B->nc1, B->bcs[0] == AO_BC_REFLECT, B->bcs[1] == AO_BC_REFLECT,
+                &B->x1f, &B->x1v, &B->dx1f);
     make_coords(p->nx2, p->bx2, ng, B->lx2, p->x2min, p->x2max, B->bx2min, B->bx2max,
-                B->nc2, &B->x2f, &B->x2v, &B->dx2f);
+                B->nc2, B->bcs[2] == AO_BC_REFLECT, B->bcs[3] == AO_BC_REFLECT,
+                &B->x2f, &B->x2v, &B->dx2f);
     make_coords(p->nx3, p->bx3, ng, B->lx3, p->x3min, p->x3max, B->bx3min, B->bx3max,
-                B->nc3, &B->x3f, &B->x3v, &B->dx3f);
+                B->nc3, B->bcs[4] == AO_BC_REFLECT, B->bcs[5] == AO_BC_REFLECT,
+                &B->x3f, &B->x3v, &B->dx3f);
     long ncc = (long)B->nc1*B->nc2*B->nc3;
     B->u = dalloc(NHYDRO*ncc); B->u1 = dalloc(NHYDRO*ncc); B->w = dalloc(NHYDRO*ncc);
     B->flux[0] = dalloc(NHYDRO*(long)B->nc3*B->nc2*(B->nc1+1));
@@ -1191,68 +1203,59 @@ void ao_exchange_fc(AoMesh *m) {
 
 /* ------------------------------------------------------------------ physical BCs */
 
-/* outflow on primitives + face fields (src/bvals/cc/outflow_cc.cpp, fc/outflow_fc.cpp) */
-static void outflow(AoMesh *m, AoBlock *B, int face, int il, int iu, int jl, int ju, int kl,
-                    int ku) {
+/* outflow / reflecting physical boundary on primitives + face fields
+ * (src/bvals/cc/outflow_cc.cpp, cc/hydro/reflect_hydro.cpp, fc/outflow_fc.cpp, fc/reflect_fc.cpp).
+ * lo/hi = active range along the boundary's own direction; ghost layer g copies from
+ * outflow: the last active cell / face; reflect: the mirrored one, with the normal velocity
+ * and the normal field negated. */
+static void phys_bc(AoMesh *m, AoBlock *B, int face, int refl, int il, int iu, int jl, int ju,
+                    int kl, int ku) {
   int ng = m->p.ng, mhd = m->p.mhd;
   int d = face/2, upper = face & 1;
-  /* cell-centred primitives */
-  for (int n = 0; n < NHYDRO; ++n) for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j)
-    for (int i = il; i <= iu; ++i) for (int g = 1; g <= ng; ++g) {
-      if (d == 0) {
-        if (i != il) continue;
-        if (!upper) B->w[CC(B,n,k,j,il-g)] = B->w[CC(B,n,k,j,il)];
-        else B->w[CC(B,n,k,j,iu+g)] = B->w[CC(B,n,k,j,iu)];
-      } else if (d == 1) {
-        if (j != jl) continue;
-        if (!upper) B->w[CC(B,n,k,jl-g,i)] = B->w[CC(B,n,k,jl,i)];
-        else B->w[CC(B,n,k,ju+g,i)] = B->w[CC(B,n,k,ju,i)];
-      } else {
-        if (k != kl) continue;
-        if (!upper) B->w[CC(B,n,kl-g,j,i)] = B->w[CC(B,n,kl,j,i)];
-        else B->w[CC(B,n,ku+g,j,i)] = B->w[CC(B,n,ku,j,i)];
+  int lo = d == 0 ? il : (d == 1 ? jl : kl), hi = d == 0 ? iu : (d == 1 ? ju : ku);
+  /* loop bounds of the two transverse directions (a: slower, c: faster index) */
+  for (int g = 1; g <= ng; ++g) {
+    int gc = upper ? hi + g : lo - g;                       /* ghost cell / transverse face */
+    int sc = refl ? (upper ? hi - g + 1 : lo + g - 1) : (upper ? hi : lo);
+    int gn = upper ? hi + g + 1 : lo - g;                   /* ghost normal face */
+    int sn = refl ? (upper ? hi - g + 1 : lo + g) : (upper ? hi + 1 : lo);
+    double sgn_n = refl ? -1.0 : 1.0;
+    if (d == 0) {
+      for (int n = 0; n < NHYDRO; ++n) for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) {
+        double v = B->w[CC(B,n,k,j,sc)];
+        B->w[CC(B,n,k,j,gc)] = (refl && n == IVX) ? -v : v;
       }
-    }
-  if (!mhd) return;
-  double *b1 = B->b[0], *b2 = B->b[1], *b3 = B->b[2];
-  if (d == 0) {
-    for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) for (int g = 1; g <= ng; ++g) {
-      if (!upper) b1[F1(B,k,j,il-g)] = b1[F1(B,k,j,il)];
-      else b1[F1(B,k,j,iu+g+1)] = b1[F1(B,k,j,iu+1)];
-    }
-    for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju+1; ++j) for (int g = 1; g <= ng; ++g) {
-      if (!upper) b2[F2(B,k,j,il-g)] = b2[F2(B,k,j,il)];
-      else b2[F2(B,k,j,iu+g)] = b2[F2(B,k,j,iu)];
-    }
-    for (int k = kl; k <= ku+1; ++k) for (int j = jl; j <= ju; ++j) for (int g = 1; g <= ng; ++g) {
-      if (!upper) b3[F3(B,k,j,il-g)] = b3[F3(B,k,j,il)];
-      else b3[F3(B,k,j,iu+g)] = b3[F3(B,k,j,iu)];
-    }
-  } else if (d == 1) {
-    for (int k = kl; k <= ku; ++k) for (int g = 1; g <= ng; ++g) for (int i = il; i <= iu+1; ++i) {
-      if (!upper) b1[F1(B,k,jl-g,i)] = b1[F1(B,k,jl,i)];
-      else b1[F1(B,k,ju+g,i)] = b1[F1(B,k,ju,i)];
-    }
-    for (int k = kl; k <= ku; ++k) for (int g = 1; g <= ng; ++g) for (int i = il; i <= iu; ++i) {
-      if (!upper) b2[F2(B,k,jl-g,i)] = b2[F2(B,k,jl,i)];
-      else b2[F2(B,k,ju+g+1,i)] = b2[F2(B,k,ju+1,i)];
-    }
-    for (int k = kl; k <= ku+1; ++k) for (int g = 1; g <= ng; ++g) for (int i = il; i <= iu; ++i) {
-      if (!upper) b3[F3(B,k,jl-g,i)] = b3[F3(B,k,jl,i)];
-      else b3[F3(B,k,ju+g,i)] = b3[F3(B,k,ju,i)];
-    }
-  } else {
-    for (int g = 1; g <= ng; ++g) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu+1; ++i) {
-      if (!upper) b1[F1(B,kl-g,j,i)] = b1[F1(B,kl,j,i)];
-      else b1[F1(B,ku+g,j,i)] = b1[F1(B,ku,j,i)];
-    }
-    for (int g = 1; g <= ng; ++g) for (int j = jl; j <= ju+1; ++j) for (int i = il; i <= iu; ++i) {
-      if (!upper) b2[F2(B,kl-g,j,i)] = b2[F2(B,kl,j,i)];
-      else b2[F2(B,ku+g,j,i)] = b2[F2(B,ku,j,i)];
-    }
-    for (int g = 1; g <= ng; ++g) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
-      if (!upper) b3[F3(B,kl-g,j,i)] = b3[F3(B,kl,j,i)];
-      else b3[F3(B,ku+g+1,j,i)] = b3[F3(B,ku+1,j,i)];
+      if (!mhd) continue;
+      for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j)
+        B->b[0][F1(B,k,j,gn)] = sgn_n*B->b[0][F1(B,k,j,sn)];
+      for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju+1; ++j)
+        B->b[1][F2(B,k,j,gc)] = B->b[1][F2(B,k,j,sc)];
+      for (int k = kl; k <= ku+1; ++k) for (int j = jl; j <= ju; ++j)
+        B->b[2][F3(B,k,j,gc)] = B->b[2][F3(B,k,j,sc)];
+    } else if (d == 1) {
+      for (int n = 0; n < NHYDRO; ++n) for (int k = kl; k <= ku; ++k) for (int i = il; i <= iu; ++i) {
+        double v = B->w[CC(B,n,k,sc,i)];
+        B->w[CC(B,n,k,gc,i)] = (refl && n == IVY) ? -v : v;
+      }
+      if (!mhd) continue;
+      for (int k = kl; k <= ku; ++k) for (int i = il; i <= iu+1; ++i)
+        B->b[0][F1(B,k,gc,i)] = B->b[0][F1(B,k,sc,i)];
+      for (int k = kl; k <= ku; ++k) for (int i = il; i <= iu; ++i)
+        B->b[1][F2(B,k,gn,i)] = sgn_n*B->b[1][F2(B,k,sn,i)];
+      for (int k = kl; k <= ku+1; ++k) for (int i = il; i <= iu; ++i)
+        B->b[2][F3(B,k,gc,i)] = B->b[2][F3(B,k,sc,i)];
+    } else {
+      for (int n = 0; n < NHYDRO; ++n) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
+        double v = B->w[CC(B,n,sc,j,i)];
+        B->w[CC(B,n,gc,j,i)] = (refl && n == IVZ) ? -v : v;
+      }
+      if (!mhd) continue;
+      for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu+1; ++i)
+        B->b[0][F1(B,gc,j,i)] = B->b[0][F1(B,sc,j,i)];
+      for (int j = jl; j <= ju+1; ++j) for (int i = il; i <= iu; ++i)
+        B->b[1][F2(B,gc,j,i)] = B->b[1][F2(B,sc,j,i)];
+      for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i)
+        B->b[2][F3(B,gn,j,i)] = sgn_n*B->b[2][F3(B,sn,j,i)];
     }
   }
 }
@@ -1270,23 +1273,23 @@ void ao_physical_bcs(AoMesh *m, int b) {
   if (!app[4] && m->f3) bks = ks - ng;
   if (!app[5] && m->f3) bke = ke + ng;
   if (app[0]) {
-    outflow(m, B, 0, is, ie, bjs, bje, bks, bke);
+    phys_bc(m, B, 0, B->bcs[0] == AO_BC_REFLECT, is, ie, bjs, bje, bks, bke);
     if (m->p.mhd) calc_bcc(B, is-ng, is-1, bjs, bje, bks, bke);
     ao_prim2cons(m, b, is-ng, is-1, bjs, bje, bks, bke);
   }
   if (app[1]) {
-    outflow(m, B, 1, is, ie, bjs, bje, bks, bke);
+    phys_bc(m, B, 1, B->bcs[1] == AO_BC_REFLECT, is, ie, bjs, bje, bks, bke);
     if (m->p.mhd) calc_bcc(B, ie+1, ie+ng, bjs, bje, bks, bke);
     ao_prim2cons(m, b, ie+1, ie+ng, bjs, bje, bks, bke);
   }
   if (m->f2) {
     if (app[2]) {
-      outflow(m, B, 2, bis, bie, js, je, bks, bke);
+      phys_bc(m, B, 2, B->bcs[2] == AO_BC_REFLECT, bis, bie, js, je, bks, bke);
       if (m->p.mhd) calc_bcc(B, bis, bie, js-ng, js-1, bks, bke);
       ao_prim2cons(m, b, bis, bie, js-ng, js-1, bks, bke);
     }
     if (app[3]) {
-      outflow(m, B, 3, bis, bie, js, je, bks, bke);
+      phys_bc(m, B, 3, B->bcs[3] == AO_BC_REFLECT, bis, bie, js, je, bks, bke);
       if (m->p.mhd) calc_bcc(B, bis, bie, je+1, je+ng, bks, bke);
       ao_prim2cons(m, b, bis, bie, je+1, je+ng, bks, bke);
     }
@@ -1294,12 +1297,12 @@ void ao_physical_bcs(AoMesh *m, int b) {
   if (m->f3) {
     bjs = js - ng; bje = je + ng;
     if (app[4]) {
-      outflow(m, B, 4, bis, bie, bjs, bje, ks, ke);
+      phys_bc(m, B, 4, B->bcs[4] == AO_BC_REFLECT, bis, bie, bjs, bje, ks, ke);
       if (m->p.mhd) calc_bcc(B, bis, bie, bjs, bje, ks-ng, ks-1);
       ao_prim2cons(m, b, bis, bie, bjs, bje, ks-ng, ks-1);
     }
     if (app[5]) {
-      outflow(m, B, 5, bis, bie, bjs, bje, ks, ke);
+      phys_bc(m, B, 5, B->bcs[5] == AO_BC_REFLECT, bis, bie, bjs, bje, ks, ke);
       if (m->p.mhd) calc_bcc(B, bis, bie, bjs, bje, ke+1, ke+ng);
       ao_prim2cons(m, b, bis, bie, bjs, bje, ke+1, ke+ng);
     }

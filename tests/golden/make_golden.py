@@ -61,6 +61,30 @@ CASES = {
                                  dict(BL, **mb(8, 8, 8)), "lhllc", False, 6),
     "sod_lhllc_plm_vl2_2blk": ("hydro_lhllc_ng2", "shock_tube", "athinput.sod",
                                {"mesh/nx1": 64, "meshblock/nx1": 32}, "lhllc", False, 8),
+    # physical boundaries: reflecting box, and a reflect / outflow / periodic mix
+    "blast_refl_hlld_plm_vl2_8blk": ("mhd_hlld_ng2", "blast", "athinput.blast",
+                                     dict(BL, **mb(8, 8, 8), **{"problem/radius": 0.6},
+                                          **{"mesh/%s%d_bc" % (s, d): "reflecting"
+                                             for s in "io" for d in (1, 2, 3)}),
+                                     "hlld", True, 8),
+    "blast_mixedbc_hllc_plm_vl2_8blk": ("hydro_hllc_ng2", "blast", "athinput.blast",
+                                        dict(BL, **mb(8, 8, 8), **{
+                                            "problem/radius": 0.6,
+                                            "mesh/ix1_bc": "reflecting", "mesh/ox1_bc": "outflow",
+                                            "mesh/ix3_bc": "outflow", "mesh/ox3_bc": "reflecting"}),
+                                        "hllc", False, 8),
+    # other integrators / orders of the same path
+    "kh2d_hllc_plm_rk3_4blk": ("hydro_hllc_ng2", "kh", "athinput.kh",
+                               {"mesh/nx1": 32, "mesh/nx2": 32, "mesh/nx3": 1, "time/xorder": 2,
+                                "time/integrator": "rk3", **mb(16, 16, 1)}, "hllc", False, 4),
+    "ot_hlld_dc_rk1_4blk": ("mhd_hlld_ng2", "orszag_tang", "athinput.orszag_tang",
+                            dict(OT, **mb(16, 16), **{"time/xorder": 1, "time/integrator": "rk1",
+                                                      "time/cfl_number": 0.3}),
+                            "hlld", True, 5),
+    "blast_hlld_ppm_rk3_8blk": ("mhd_hlld_ng3", "blast", "athinput.blast",
+                                dict(BL, **mb(8, 8, 8), **{"time/xorder": 3,
+                                                           "time/integrator": "rk3"}),
+                                "hlld", True, 3),
     "linwave_mhd_roe_plm_vl2_2blk": ("mhd_roe_ng2", "linear_wave", "athinput.linear_wave3d",
                                      dict(LW, **mb(8, 8, 8), **{"problem/amp": 0.1}),
                                      "roe", True, 4),

@@ -26,6 +26,9 @@ CASES = [
     ("ot_lhlld_plm_vl2_4blk", None, None),
     ("blast_lhllc_plm_vl2_8blk", None, None),
     ("sod_lhllc_plm_vl2_2blk", None, None),
+    ("blast_refl_hlld_plm_vl2_8blk", None, None),
+    ("blast_mixedbc_hllc_plm_vl2_8blk", None, None),
+    ("blast_hlld_ppm_rk3_8blk", None, None),
 ]
 
 
