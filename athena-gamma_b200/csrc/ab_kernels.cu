@@ -452,55 +452,63 @@ __device__ __forceinline__ double de_term(double wt, double ef_a, double cc_a, d
   return (1.0-wt)*(ef_a - cc_a) + (wt)*(ef_b - cc_b);
 }
 
-__global__ void __launch_bounds__(BX) k_corner_e3d(BlkDev b) {
-  int i = b.is + blockIdx.x*BX + threadIdx.x;
-  if (i > b.ie+1) return;
-  int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
-  const long sv = (long)b.nc3*b.nc2*b.nc1;
-  const double *cc1 = b.cc_e, *cc2 = b.cc_e + sv, *cc3 = b.cc_e + 2*sv;
-  const double *w_x1f = b.wght[0], *w_x2f = b.wght[1], *w_x3f = b.wght[2];
-  const double *e3_x1f = b.ef[0][0], *e2_x1f = b.ef[0][1];
-  const double *e1_x2f = b.ef[1][0], *e3_x2f = b.ef[1][1];
-  const double *e2_x3f = b.ef[2][0], *e1_x3f = b.ef[2][1];
-#define C3(k,j,i) CCI(b,0,k,j,i)
+__global__ void __launch_bounds__(BX) k_corner_e3d(BlkDev b, int ni, int nj, int ntot) {
+  int t = blockIdx.x*BX + threadIdx.x;
+  if (t >= ntot) return;
+  int r = t / ni;
+  const int i = b.is + (t - r*ni);
+  const int kk = r / nj;
+  const int j = b.js + (r - kk*nj);
+  const int k = b.ks + kk;
+  const int n1 = b.nc1, n2 = b.nc2;
+  const int sv = b.nc3*n2*n1;
+  // element offsets of (k,j,i) in the cell-, x1f-, x2f-, x3f-shaped arrays and their strides
+  const int oc = (k*n2 + j)*n1 + i,      cj = n1,   ck = n1*n2;        // cell / x3f shape
+  const int o1 = (k*n2 + j)*(n1+1) + i,  j1 = n1+1, k1 = (n1+1)*n2;    // x1f shape
+  const int o2 = (k*(n2+1) + j)*n1 + i,  j2 = n1,   k2 = n1*(n2+1);    // x2f shape
+  const double *__restrict__ cc1 = b.cc_e;
+  const double *__restrict__ cc2 = b.cc_e + sv;
+  const double *__restrict__ cc3 = b.cc_e + 2*sv;
+  const double *__restrict__ w_x1f = b.wght[0];
+  const double *__restrict__ w_x2f = b.wght[1];
+  const double *__restrict__ w_x3f = b.wght[2];
+  const double *__restrict__ e3_x1f = b.ef[0][0];
+  const double *__restrict__ e2_x1f = b.ef[0][1];
+  const double *__restrict__ e1_x2f = b.ef[1][0];
+  const double *__restrict__ e3_x2f = b.ef[1][1];
+  const double *__restrict__ e2_x3f = b.ef[2][0];
+  const double *__restrict__ e1_x3f = b.ef[2][1];
   {
-    double de1_l3 = de_term(w_x2f[F2I(b,k-1,j,i)], e1_x3f[F3I(b,k,j,i)], cc1[C3(k-1,j,i)],
-                            e1_x3f[F3I(b,k,j-1,i)], cc1[C3(k-1,j-1,i)]);
-    double de1_r3 = de_term(w_x2f[F2I(b,k,j,i)], e1_x3f[F3I(b,k,j,i)], cc1[C3(k,j,i)],
-                            e1_x3f[F3I(b,k,j-1,i)], cc1[C3(k,j-1,i)]);
-    double de1_l2 = de_term(w_x3f[F3I(b,k,j-1,i)], e1_x2f[F2I(b,k,j,i)], cc1[C3(k,j-1,i)],
-                            e1_x2f[F2I(b,k-1,j,i)], cc1[C3(k-1,j-1,i)]);
-    double de1_r2 = de_term(w_x3f[F3I(b,k,j,i)], e1_x2f[F2I(b,k,j,i)], cc1[C3(k,j,i)],
-                            e1_x2f[F2I(b,k-1,j,i)], cc1[C3(k-1,j,i)]);
-    b.e[0][E1I(b,k,j,i)] = 0.25*(de1_l3 + de1_r3 + de1_l2 + de1_r2 + e1_x2f[F2I(b,k-1,j,i)] +
-                                 e1_x2f[F2I(b,k,j,i)] + e1_x3f[F3I(b,k,j-1,i)] + e1_x3f[F3I(b,k,j,i)]);
+    const double f3c = e1_x3f[oc], f3m = e1_x3f[oc-cj];       // e1_x3f(k,j,i), (k,j-1,i)
+    const double f2c = e1_x2f[o2], f2m = e1_x2f[o2-k2];       // e1_x2f(k,j,i), (k-1,j,i)
+    double de1_l3 = de_term(w_x2f[o2-k2], f3c, cc1[oc-ck], f3m, cc1[oc-ck-cj]);
+    double de1_r3 = de_term(w_x2f[o2], f3c, cc1[oc], f3m, cc1[oc-cj]);
+    double de1_l2 = de_term(w_x3f[oc-cj], f2c, cc1[oc-cj], f2m, cc1[oc-ck-cj]);
+    double de1_r2 = de_term(w_x3f[oc], f2c, cc1[oc], f2m, cc1[oc-ck]);
+    b.e[0][(k*(n2+1) + j)*n1 + i] =
+        0.25*(de1_l3 + de1_r3 + de1_l2 + de1_r2 + f2m + f2c + f3m + f3c);
   }
   {
-    double de2_l3 = de_term(w_x1f[F1I(b,k-1,j,i)], e2_x3f[F3I(b,k,j,i)], cc2[C3(k-1,j,i)],
-                            e2_x3f[F3I(b,k,j,i-1)], cc2[C3(k-1,j,i-1)]);
-    double de2_r3 = de_term(w_x1f[F1I(b,k,j,i)], e2_x3f[F3I(b,k,j,i)], cc2[C3(k,j,i)],
-                            e2_x3f[F3I(b,k,j,i-1)], cc2[C3(k,j,i-1)]);
-    double de2_l1 = de_term(w_x3f[F3I(b,k,j,i-1)], e2_x1f[F1I(b,k,j,i)], cc2[C3(k,j,i-1)],
-                            e2_x1f[F1I(b,k-1,j,i)], cc2[C3(k-1,j,i-1)]);
-    double de2_r1 = de_term(w_x3f[F3I(b,k,j,i)], e2_x1f[F1I(b,k,j,i)], cc2[C3(k,j,i)],
-                            e2_x1f[F1I(b,k-1,j,i)], cc2[C3(k-1,j,i)]);
-    b.e[1][E2I(b,k,j,i)] = 0.25*(de2_l3 + de2_r3 + de2_l1 + de2_r1 + e2_x3f[F3I(b,k,j,i-1)] +
-                                 e2_x3f[F3I(b,k,j,i)] + e2_x1f[F1I(b,k-1,j,i)] + e2_x1f[F1I(b,k,j,i)]);
+    const double f3c = e2_x3f[oc], f3m = e2_x3f[oc-1];        // e2_x3f(k,j,i), (k,j,i-1)
+    const double f1c = e2_x1f[o1], f1m = e2_x1f[o1-k1];       // e2_x1f(k,j,i), (k-1,j,i)
+    double de2_l3 = de_term(w_x1f[o1-k1], f3c, cc2[oc-ck], f3m, cc2[oc-ck-1]);
+    double de2_r3 = de_term(w_x1f[o1], f3c, cc2[oc], f3m, cc2[oc-1]);
+    double de2_l1 = de_term(w_x3f[oc-1], f1c, cc2[oc-1], f1m, cc2[oc-ck-1]);
+    double de2_r1 = de_term(w_x3f[oc], f1c, cc2[oc], f1m, cc2[oc-ck]);
+    b.e[1][(k*n2 + j)*(n1+1) + i] =
+        0.25*(de2_l3 + de2_r3 + de2_l1 + de2_r1 + f3m + f3c + f1m + f1c);
   }
   {
-    // e3 array has nc3 planes: k = ke+1 <= nc3-1 always holds in 3-D (ng >= 1)
-    double de3_l2 = de_term(w_x1f[F1I(b,k,j-1,i)], e3_x2f[F2I(b,k,j,i)], cc3[C3(k,j-1,i)],
-                            e3_x2f[F2I(b,k,j,i-1)], cc3[C3(k,j-1,i-1)]);
-    double de3_r2 = de_term(w_x1f[F1I(b,k,j,i)], e3_x2f[F2I(b,k,j,i)], cc3[C3(k,j,i)],
-                            e3_x2f[F2I(b,k,j,i-1)], cc3[C3(k,j,i-1)]);
-    double de3_l1 = de_term(w_x2f[F2I(b,k,j,i-1)], e3_x1f[F1I(b,k,j,i)], cc3[C3(k,j,i-1)],
-                            e3_x1f[F1I(b,k,j-1,i)], cc3[C3(k,j-1,i-1)]);
-    double de3_r1 = de_term(w_x2f[F2I(b,k,j,i)], e3_x1f[F1I(b,k,j,i)], cc3[C3(k,j,i)],
-                            e3_x1f[F1I(b,k,j-1,i)], cc3[C3(k,j-1,i)]);
-    b.e[2][E3I(b,k,j,i)] = 0.25*(de3_l1 + de3_r1 + de3_l2 + de3_r2 + e3_x2f[F2I(b,k,j,i-1)] +
-                                 e3_x2f[F2I(b,k,j,i)] + e3_x1f[F1I(b,k,j-1,i)] + e3_x1f[F1I(b,k,j,i)]);
+    const double f2c = e3_x2f[o2], f2m = e3_x2f[o2-1];        // e3_x2f(k,j,i), (k,j,i-1)
+    const double f1c = e3_x1f[o1], f1m = e3_x1f[o1-j1];       // e3_x1f(k,j,i), (k,j-1,i)
+    double de3_l2 = de_term(w_x1f[o1-j1], f2c, cc3[oc-cj], f2m, cc3[oc-cj-1]);
+    double de3_r2 = de_term(w_x1f[o1], f2c, cc3[oc], f2m, cc3[oc-1]);
+    double de3_l1 = de_term(w_x2f[o2-1], f1c, cc3[oc-1], f1m, cc3[oc-cj-1]);
+    double de3_r1 = de_term(w_x2f[o2], f1c, cc3[oc], f1m, cc3[oc-cj]);
+    b.e[2][(k*(n2+1) + j)*(n1+1) + i] =
+        0.25*(de3_l1 + de3_r1 + de3_l2 + de3_r2 + f2m + f2c + f1m + f1c);
   }
-#undef C3
+  (void)j2;
 }
 
 // 2-D (calculate_corner_e.cpp:50-128): grid.y covers j in [js, je+1]; k = ks
@@ -557,7 +565,8 @@ void launch_corner_e(const BlkDev &b, cudaStream_t s, int have_cc_e) {
     k_corner_e2d<<<grid3(nx1+1, nx2+1, 1), BX, 0, s>>>(b); ++g_launches;
   } else {
     if (!have_cc_e) { k_cc_e<<<grid3(nx1+2, nx2+2, nx3+2), BX, 0, s>>>(b, b.is-1, b.ie+1, b.js-1, b.ks-1); ++g_launches; }
-    k_corner_e3d<<<grid3(nx1+1, nx2+1, nx3+1), BX, 0, s>>>(b); ++g_launches;
+    const int ntot = (nx1+1)*(nx2+1)*(nx3+1);
+    k_corner_e3d<<<(ntot + BX - 1)/BX, BX, 0, s>>>(b, nx1+1, nx2+1, ntot); ++g_launches;
   }
 }
 
@@ -934,35 +943,42 @@ __global__ void __launch_bounds__(BX) k_integrate_fc(BlkDev b, int ni, int nj, i
   const int o2 = (k*n2 + j)*(n1+1) + i;          // x2e(k,j,i)
   const int o3 = (k*(n2+1) + j)*(n1+1) + i;      // x3e(k,j,i)
   const bool f2 = b.f2, f3 = b.f3;
-  // loads guarded by the validity of the element inside its array
-  const double e3c = (in_k) ? e3[o3] : 0.0;
-  const double e2c = (in_j) ? e2[o2] : 0.0;
+  const bool do1 = in_j && in_k, do2 = in_i && in_k, do3 = in_i && in_j;
+  // All loads are issued up front (memory-level parallelism): an element that a thread does
+  // not need is replaced by a harmless in-bounds re-read of x?e(k,j,i) of a valid thread.
+  const double e3c = in_k ? e3[o3] : 0.0;
+  const double e2c = in_j ? e2[o2] : 0.0;
   const double e1c = (in_i && f2) ? e1[o1] : 0.0;
-  if (in_j && in_k) {                  // B1 (ct.cpp:40-62)
-    const int o = (k*n2 + j)*(n1+1) + i;
-    double v = fc_avg<MODE>(b.b[0], b.b1[0], o, zero_init, delta, g1, g2);
+  const double e3_jp = (do1 && f2) ? e3[o3 + (n1+1)] : 0.0;          // x3e(k,j+1,i)
+  const double e2_kp = (do1 && f3) ? e2[o2 + n2*(n1+1)] : 0.0;       // x2e(k+1,j,i)
+  const double e3_ip = do2 ? e3[o3 + 1] : 0.0;                       // x3e(k,j,i+1)
+  const double e1_kp = (do2 && f3) ? e1[o1 + (n2+1)*n1] : 0.0;       // x1e(k+1,j,i)
+  const double e2_ip = do3 ? e2[o2 + 1] : 0.0;                       // x2e(k,j,i+1)
+  const double e1_jp = (do3 && f2) ? e1[o1 + n1] : 0.0;              // x1e(k,j+1,i)
+  const int ob1 = (k*n2 + j)*(n1+1) + i, ob2 = (k*(n2+1) + j)*n1 + i, ob3 = (k*n2 + j)*n1 + i;
+  double v1 = 0.0, v2 = 0.0, v3 = 0.0;
+  if (do1) v1 = fc_avg<MODE>(b.b[0], b.b1[0], ob1, zero_init, delta, g1, g2);
+  if (do2) v2 = fc_avg<MODE>(b.b[1], b.b1[1], ob2, zero_init, delta, g1, g2);
+  if (do3) v3 = fc_avg<MODE>(b.b[2], b.b1[2], ob3, zero_init, delta, g1, g2);
+  if (do1) {                           // B1 (ct.cpp:40-62)
     if (f2) {
-      const double area = dx2*dx3;
-      v -= (wght/area)*(dx3*e3[o3 + (n1+1)] - dx3*e3c);
-      if (f3) v += (wght/area)*(dx2*e2[o2 + n2*(n1+1)] - dx2*e2c);
+      const double c = wght/(dx2*dx3);        // (wght/area(i)), identical in both terms
+      v1 -= c*(dx3*e3_jp - dx3*e3c);
+      if (f3) v1 += c*(dx2*e2_kp - dx2*e2c);
     }
-    b.b[0][o] = v;
+    b.b[0][ob1] = v1;
   }
-  if (in_i && in_k) {                  // B2 (ct.cpp:64-92)
-    const int o = (k*(n2+1) + j)*n1 + i;
-    double v = fc_avg<MODE>(b.b[1], b.b1[1], o, zero_init, delta, g1, g2);
-    const double area = dx1*dx3;
-    v += (wght/area)*(dx3*e3[o3 + 1] - dx3*e3c);
-    if (f3) v -= (wght/area)*(dx1*e1[o1 + (n2+1)*n1] - dx1*e1c);
-    b.b[1][o] = v;
+  if (do2) {                           // B2 (ct.cpp:64-92)
+    const double c = wght/(dx1*dx3);
+    v2 += c*(dx3*e3_ip - dx3*e3c);
+    if (f3) v2 -= c*(dx1*e1_kp - dx1*e1c);
+    b.b[1][ob2] = v2;
   }
-  if (in_i && in_j) {                  // B3 (ct.cpp:94-114)
-    const int o = (k*n2 + j)*n1 + i;
-    double v = fc_avg<MODE>(b.b[2], b.b1[2], o, zero_init, delta, g1, g2);
-    const double area = dx1*dx2;
-    v -= (wght/area)*(dx2*e2[o2 + 1] - dx2*e2c);
-    if (f2) v += (wght/area)*(dx1*e1[o1 + n1] - dx1*e1c);
-    b.b[2][o] = v;
+  if (do3) {                           // B3 (ct.cpp:94-114)
+    const double c = wght/(dx1*dx2);
+    v3 -= c*(dx2*e2_ip - dx2*e2c);
+    if (f2) v3 += c*(dx1*e1_jp - dx1*e1c);
+    b.b[2][ob3] = v3;
   }
 }
 
