@@ -228,6 +228,9 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
 
 // 5 CTAs of 128 threads per SM (96 registers, a few spills) measured best on B200:
 // MINB 3/4/5/6/8 -> 1.27/1.10/1.05/1.06/1.37 ms per 256^3 HLLD+PLM sweep (profiles/).
+#ifndef AB_FLUX_BX
+#define AB_FLUX_BX 128
+#endif
 #ifndef AB_FLUX_MINB
 #define AB_FLUX_MINB 5
 #endif
@@ -237,6 +240,11 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
 // x3 sweep: faces are visited strip by strip (AB_X3_STRIP rows of j, all k) so that the four
 // k-planes of the stencil stay in L2 between consecutive k (plane-major order re-read w/bcc
 // from DRAM: 19 GB instead of 8.8 GB per 512^3 sweep).
+#ifdef AB_FLUX_MAXREG
+#define AB_FLUX_BOUNDS __maxnreg__(AB_FLUX_MAXREG)
+#else
+#define AB_FLUX_BOUNDS __launch_bounds__(AB_FLUX_BX, AB_FLUX_MINB)
+#endif
 #ifndef AB_X3_STRIP
 #define AB_X3_STRIP 32
 #endif
@@ -244,11 +252,11 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
 // The face range [i0,i0+ni) x [j0,j0+nj) x [k0,k0+nk) is flattened so that every thread of a
 // CTA has work (rows of nx1+1 faces do not pad to a multiple of the CTA width).
 template <int DIR, int ORDER, int SOLVER, bool MHD>
-__global__ void __launch_bounds__(BX, (ORDER == 1 ? AB_FLUX_MINB_O1 : AB_FLUX_MINB))
+__global__ void AB_FLUX_BOUNDS
 k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
        int ntot, double dt_val, const double *dt_ptr) {
   constexpr int NW = MHD ? 7 : 5;
-  int t = blockIdx.x*BX + threadIdx.x;
+  int t = blockIdx.x*AB_FLUX_BX + threadIdx.x;
   if (t >= ntot) return;
   int i, j, k;
   if (DIR == 2 && AB_X3_STRIP > 0) {
@@ -278,6 +286,20 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
   const int c = (DIR == 0) ? i : ((DIR == 1) ? j : k);
   const double *__restrict__ w = b.w;
   const double *__restrict__ bcc = b.bcc;
+  // face-array offset and variable stride
+  int of, sf;
+  if (DIR == 0) { of = (k*b.nc2 + j)*(b.nc1+1) + i; sf = b.nc3*b.nc2*(b.nc1+1); }
+  else if (DIR == 1) { of = (k*(b.nc2+1) + j)*b.nc1 + i; sf = b.nc3*(b.nc2+1)*b.nc1; }
+  else { of = (k*b.nc2 + j)*b.nc1 + i; sf = (b.nc3+1)*b.nc2*b.nc1; }
+  // Every global load of the thread is issued here, ahead of the reconstruction, so that their
+  // latencies overlap (ncu: the face field / dt / dx loads used to sit right in front of their
+  // first use inside the Riemann solver and cost 10 % of the kernel in long-scoreboard stalls).
+  double bxi = 0.0, dt = 0.0, dxw = 0.0;
+  if (MHD) {
+    bxi = b.b[DIR][of];
+    dt = dt_ptr ? *dt_ptr : dt_val;
+    dxw = (DIR == 0) ? b.dx1f[i] : ((DIR == 1) ? b.dx2f[j] : b.dx3f[k]);
+  }
 
   double wl[NW], wr[NW];
   if (ORDER == 1) {
@@ -319,13 +341,6 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
     wr[IPR] = (wr[IPR] > p.pfloor) ? wr[IPR] : p.pfloor;
   }
 
-  // face-array offset and variable stride
-  int of, sf;
-  if (DIR == 0) { of = (k*b.nc2 + j)*(b.nc1+1) + i; sf = b.nc3*b.nc2*(b.nc1+1); }
-  else if (DIR == 1) { of = (k*(b.nc2+1) + j)*b.nc1 + i; sf = b.nc3*(b.nc2+1)*b.nc1; }
-  else { of = (k*b.nc2 + j)*b.nc1 + i; sf = (b.nc3+1)*b.nc2*b.nc1; }
-  double bxi = 0.0;
-  if (MHD) bxi = b.b[DIR][of];
   // LHLLC / LHLLD shock detector inputs: Hydro::CalculateVelocityDifferences
   // (hydro/calculate_velocity_differences.cpp:20-90); dvt stays 0 in 1-D
   double dvn = 0.0, dvt = 0.0;
@@ -360,8 +375,6 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
   if (MHD) {
     b.ef[DIR][0][of] = -f[IBY];
     b.ef[DIR][1][of] = f[IBZ];
-    const double dt = dt_ptr ? *dt_ptr : dt_val;
-    const double dxw = (DIR == 0) ? b.dx1f[i] : ((DIR == 1) ? b.dx2f[j] : b.dx3f[k]);
     b.wght[DIR][of] = weight_for_ct(f[IDN], wl[IDN], wr[IDN], dxw, dt);
   }
 }
@@ -384,7 +397,7 @@ static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, doubl
   }
   int ni = i1-i0+1, nj = j1-j0+1, nk = k1-k0+1;
   int ntot = ni*nj*nk;
-  k_flux<DIR,ORDER,SOLVER,MHD><<<(ntot + BX - 1)/BX, BX, 0, s>>>(
+  k_flux<DIR,ORDER,SOLVER,MHD><<<(ntot + AB_FLUX_BX - 1)/AB_FLUX_BX, AB_FLUX_BX, 0, s>>>(
       b, g, p, i0, ni, j0, nj, k0, nk, ntot, dt_val, dt_ptr); ++g_launches;
 }
 
@@ -846,52 +859,65 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 // =============================================================================================
 // IntegrateHydro: register average + Hydro::AddFluxDivergence, fused
 // =============================================================================================
+// Flattened over the active cells of the planes [k0, k0+nk) with a grid-stride loop, so that the
+// same kernel runs either with a full grid (alone) or with a small persistent grid (AB_CC_GRID
+// CTAs) next to the FP64-bound flux kernels of another slab.
 __global__ void __launch_bounds__(BX) k_integrate_cc(BlkDev b, int mode, int zero_init,
                                                      double delta, double g1, double g2,
                                                      double beta, double dt_val,
-                                                     const double *dt_ptr) {
-  int i = b.is + blockIdx.x*BX + threadIdx.x;
-  if (i > b.ie) return;
-  int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
+                                                     const double *dt_ptr, int k0, int ni,
+                                                     int nj, int ntot) {
   const double wght = beta*(dt_ptr ? *dt_ptr : dt_val);
-  const long sv = (long)b.nc3*b.nc2*b.nc1;
-  const long o = CCI(b,0,k,j,i);
-  const long s1 = (long)b.nc3*b.nc2*(b.nc1+1), s2 = (long)b.nc3*(b.nc2+1)*b.nc1,
-             s3 = (long)(b.nc3+1)*b.nc2*b.nc1;
-  const long o1 = F1I(b,k,j,i), o2 = F2I(b,k,j,i), o3 = F3I(b,k,j,i);
-  // Cartesian face areas / volume (coordinates/coordinates.cpp:436-533)
-  const double dx1 = b.dx1f[i], dx2 = b.dx2f[j], dx3 = b.dx3f[k];
-  const double a1 = dx2*dx3, a2 = dx1*dx3, a3 = dx1*dx2;
-  const double vol = dx1*dx2*dx3;
+  const int n1 = b.nc1, n2 = b.nc2;
+  const int sv = b.nc3*n2*n1;
+  const int s1 = b.nc3*n2*(n1+1), s2 = b.nc3*(n2+1)*n1, s3 = (b.nc3+1)*n2*n1;
+  for (int t = blockIdx.x*BX + threadIdx.x; t < ntot; t += gridDim.x*BX) {
+    int r = t / ni;
+    const int i = b.is + (t - r*ni);
+    const int kk = r / nj;
+    const int j = b.js + (r - kk*nj);
+    const int k = k0 + kk;
+    const int o = (k*n2 + j)*n1 + i;
+    const int o1 = (k*n2 + j)*(n1+1) + i, o2 = (k*(n2+1) + j)*n1 + i, o3 = o;
+    // Cartesian face areas / volume (coordinates/coordinates.cpp:436-533)
+    const double dx1 = b.dx1f[i], dx2 = b.dx2f[j], dx3 = b.dx3f[k];
+    const double a1 = dx2*dx3, a2 = dx1*dx3, a3 = dx1*dx2;
+    const double vol = dx1*dx2*dx3;
 #pragma unroll
-  for (int n = 0; n < NHYDRO; ++n) {
-    double uo;
-    if (mode == 0) {
-      uo = b.u[o+n*sv];
-    } else if (mode == 1) {
-      uo = zero_init ? 0.0 : b.u[o+n*sv];
-      if (delta != 0.0) uo += delta*b.u1[o+n*sv];
-    } else {
-      double u1v = zero_init ? 0.0 : b.u1[o+n*sv];
-      double un = b.u[o+n*sv];
-      if (delta != 0.0 || zero_init) {
-        if (delta != 0.0) u1v += delta*un;
-        b.u1[o+n*sv] = u1v;
+    for (int n = 0; n < NHYDRO; ++n) {
+      double uo;
+      if (mode == 0) {
+        uo = b.u[o+n*sv];
+      } else if (mode == 1) {
+        uo = zero_init ? 0.0 : b.u[o+n*sv];
+        if (delta != 0.0) uo += delta*b.u1[o+n*sv];
+      } else {
+        double u1v = zero_init ? 0.0 : b.u1[o+n*sv];
+        double un = b.u[o+n*sv];
+        if (delta != 0.0 || zero_init) {
+          if (delta != 0.0) u1v += delta*un;
+          b.u1[o+n*sv] = u1v;
+        }
+        uo = wave2(un, u1v, g1, g2);
       }
-      uo = wave2(un, u1v, g1, g2);
+      double dflx = (a1*b.flux[0][o1+1+n*s1] - a1*b.flux[0][o1+n*s1]);
+      if (b.f2) dflx += (a2*b.flux[1][o2+n1+n*s2] - a2*b.flux[1][o2+n*s2]);
+      if (b.f3) dflx += (a3*b.flux[2][o3+n1*n2+n*s3] - a3*b.flux[2][o3+n*s3]);
+      b.u[o+n*sv] = uo - wght*dflx/vol;
     }
-    double dflx = (a1*b.flux[0][o1+1+n*s1] - a1*b.flux[0][o1+n*s1]);
-    if (b.f2) dflx += (a2*b.flux[1][o2+b.nc1+n*s2] - a2*b.flux[1][o2+n*s2]);
-    if (b.f3) dflx += (a3*b.flux[2][o3+(long)b.nc1*b.nc2+n*s3] - a3*b.flux[2][o3+n*s3]);
-    b.u[o+n*sv] = uo - wght*dflx/vol;
   }
 }
 
 void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
-                         cudaStream_t s) {
-  k_integrate_cc<<<grid3(b.ie-b.is+1, b.je-b.js+1, b.ke-b.ks+1), BX, 0, s>>>(
-      b, mode, zero_init, delta, g1, g2, beta, dt_val, dt_ptr); ++g_launches;
+                         cudaStream_t s, int kl, int ku, int grid) {
+  if (kl < 0) { kl = b.ks; ku = b.ke; }
+  const int ni = b.ie-b.is+1, nj = b.je-b.js+1, nk = ku-kl+1;
+  const int ntot = ni*nj*nk;
+  int g = (ntot + BX - 1)/BX;
+  if (grid > 0 && g > grid) g = grid;
+  k_integrate_cc<<<g, BX, 0, s>>>(b, mode, zero_init, delta, g1, g2, beta, dt_val, dt_ptr, kl,
+                                  ni, nj, ntot); ++g_launches;
 }
 
 // register average of one face value (same modes as k_integrate_cc)

@@ -38,9 +38,11 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 // already pointer-swapped): u = (zero_init ? 0 : u) [+ delta*u1] ; u -= wght*div.
 // mode 2: u1 = (zero_init ? 0 : u1) [+ delta*u]; u = wave(u; u1; g1, g2); u -= wght*div.
 // wght = beta * dt.
+// [kl,ku]: plane range (kl < 0: all active planes); grid > 0 caps the number of CTAs
+// (grid-stride loop) so that the kernel can share the SMs with a concurrent flux kernel.
 void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
-                         cudaStream_t s);
+                         cudaStream_t s, int kl = -1, int ku = -1, int grid = 0);
 // Same for the face field + Field::CT (field/ct.cpp:31-116)
 void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,

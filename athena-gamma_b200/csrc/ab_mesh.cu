@@ -1458,6 +1458,49 @@ int ab_mesh_profile_read(AbMesh *m, double *out) {
   return AB_OK;
 }
 
+// Tuning aid (not part of include/athena_b200.h): can the HBM-bound kernels hide under the
+// FP64-bound flux kernels when they share the SMs?  Times, on block 0, (0) the three flux sweeps
+// alone, (1) `nmem` full-grid k_integrate_cc passes alone, (2) the same with `grid_mem` CTAs,
+// (3) both concurrently on two streams (capped grid launched first).  beta = 0 keeps u intact.
+int ab_debug_overlap(AbMesh *m, int grid_mem, int nmem, double *out) {
+  if (!m || m->lb.empty()) return fail(AB_ERR_ARG, "ab_debug_overlap: no blocks");
+  LocalBlock &L = m->lb[0];
+  cudaStream_t sf = m->stream, sm2;
+  CK(cudaStreamCreateWithFlags(&sm2, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1, e2, e3;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+  const double *dtp = m->state + 1;
+  auto flux3 = [&]() {
+    for (int dir = 0; dir < m->ndim; ++dir)
+      ab::launch_flux_dir(L.d, L.g, m->kp, m->p.xorder, dir, 0.0, dtp, sf);
+  };
+  auto mem = [&](cudaStream_t s, int grid) {
+    for (int r = 0; r < nmem; ++r)
+      ab::launch_integrate_cc(L.d, 0, 0, 0.0, 0, 0, 0.0, 0.0, dtp, s, -1, -1, grid);
+  };
+  float ms;
+  CK(cudaStreamSynchronize(sf));
+  flux3(); CK(cudaStreamSynchronize(sf));                    // warm
+  cudaEventRecord(e0, sf); flux3(); cudaEventRecord(e1, sf);
+  CK(cudaStreamSynchronize(sf)); cudaEventElapsedTime(&ms, e0, e1); out[0] = ms;
+  cudaEventRecord(e0, sf); mem(sf, 0); cudaEventRecord(e1, sf);
+  CK(cudaStreamSynchronize(sf)); cudaEventElapsedTime(&ms, e0, e1); out[1] = ms;
+  cudaEventRecord(e0, sf); mem(sf, grid_mem); cudaEventRecord(e1, sf);
+  CK(cudaStreamSynchronize(sf)); cudaEventElapsedTime(&ms, e0, e1); out[2] = ms;
+  // concurrent
+  cudaEventRecord(e0, sf);
+  CK(cudaStreamWaitEvent(sm2, e0, 0));
+  mem(sm2, grid_mem); cudaEventRecord(e2, sm2);
+  flux3(); cudaEventRecord(e1, sf);
+  CK(cudaStreamSynchronize(sf)); CK(cudaStreamSynchronize(sm2));
+  float a, b2;
+  cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b2, e0, e2);
+  out[3] = a; out[4] = b2;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+  cudaStreamDestroy(sm2);
+  return AB_OK;
+}
+
 long ab_mesh_launch_count(const AbMesh *m) { (void)m; return ab::g_launches; }
 void *ab_mesh_stream(AbMesh *m) { return m ? (void *)m->stream : nullptr; }
 int ab_mesh_sync(AbMesh *m) {
