@@ -30,6 +30,10 @@ typedef struct {
   int xorder;           /* 1,2,3 */
   int integrator;       /* AO_INT_* */
   double gamma, dfloor, pfloor, cfl, tlim, start_time;
+  int nscalars;         /* NSCALARS (configure.py --nscalars) */
+  int eos;              /* 0 adiabatic ; 1 isothermal (configure.py --eos) */
+  double sfloor;        /* hydro/sfloor (eos ctor default sqrt(1024*FLT_MIN)) */
+  double iso_cs;        /* hydro/iso_sound_speed */
 } AoParams;
 
 typedef struct AoMesh AoMesh;
@@ -41,7 +45,8 @@ int ao_nblocks(const AoMesh *m);
 void ao_block_info(const AoMesh *m, int b, long *out);
 /* array access by name: u u1 w bcc b1 b2 b3 b1_1 b1_2 b1_3 flux1 flux2 flux3 e1 e2 e3
  * wght1 wght2 wght3 e2_x1f e3_x1f e1_x2f e3_x2f e1_x3f e2_x3f x1f x2f x3f x1v x2v x3v
- * dx1f dx2f dx3f ; returns pointer, *n = number of doubles */
+ * dx1f dx2f dx3f ; passive scalars: s s1 r sflux1 sflux2 sflux3 ;
+ * returns pointer, *n = number of doubles */
 double *ao_array(AoMesh *m, int b, const char *name, long *n);
 
 /* Mesh::Initialize after the problem generator filled u (and b): ghost exchange,
@@ -72,6 +77,12 @@ void ao_prim2cons(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int 
 void ao_primitives(AoMesh *m, int b);       /* Primitives task: range from neighbours */
 void ao_physical_bcs(AoMesh *m, int b);
 double ao_new_block_dt(AoMesh *m, int b);
+/* passive scalars (src/scalars, src/eos/eos_scalars.cpp) */
+void ao_calc_scalar_fluxes(AoMesh *m, int b, int order);   /* PassiveScalars::CalculateFluxes */
+void ao_integrate_scalars(AoMesh *m, int b, int stage);    /* IntegrateScalars task */
+void ao_exchange_scalars(AoMesh *m);                       /* Send/Receive/SetBoundaries for s */
+void ao_scalar_cons2prim(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int ku);
+void ao_scalar_prim2cons(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int ku);
 
 /* point-wise kernels on n independent interfaces / cells (structure-of-arrays, stride n) */
 void ao_riemann(int solver, int mhd, long n, const double *wl, const double *wr,

@@ -31,7 +31,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 
-# cfg name -> (mhd?, flux file stem, nghost, [pgens])
+# cfg name -> (mhd?, flux file stem, nghost, [pgens][, {"nscalars": n, "eos": "isothermal"}])
 CONFIGS = {
     "hydro_hllc_ng2": (False, "hllc", 2, ["shock_tube", "linear_wave", "blast", "kh"]),
     "hydro_hlle_ng2": (False, "hlle", 2, ["shock_tube", "linear_wave"]),
@@ -44,20 +44,38 @@ CONFIGS = {
     # the fork's production solvers (confignotes: --flux=lhllc / --flux=lhlld)
     "hydro_lhllc_ng2": (False, "lhllc", 2, ["blast", "shock_tube", "kh"]),
     "mhd_lhlld_ng2": (True, "lhlld", 2, ["blast", "orszag_tang", "linear_wave"]),
+    # passive scalars (confignotes: --nscalars=1 with lhllc) and the isothermal EOS
+    # (confignotes: --flux=hlle --eos=isothermal)
+    "hydro_lhllc_ng2_s1": (False, "lhllc", 2, ["kh", "shock_tube"], {"nscalars": 1}),
+    "hydro_hllc_ng3_s2": (False, "hllc", 3, ["kh"], {"nscalars": 2}),
+    "mhd_hlld_ng2_s1": (True, "hlld", 2, ["kh"], {"nscalars": 1}),
+    "hydro_hlle_iso_ng2": (False, "hlle", 2, ["linear_wave", "blast", "kh"],
+                           {"eos": "isothermal"}),
+    "hydro_hlle_iso_ng2_s1": (False, "hlle", 2, ["kh"], {"eos": "isothermal", "nscalars": 1}),
+    "mhd_hlld_iso_ng2": (True, "hlld", 2, ["linear_wave", "orszag_tang", "blast"],
+                         {"eos": "isothermal"}),
+    "mhd_hlle_iso_ng2": (True, "hlle", 2, ["linear_wave", "orszag_tang"], {"eos": "isothermal"}),
 }
+
+
+def cfg_tuple(cfg):
+    t = CONFIGS[cfg]
+    opt = t[4] if len(t) > 4 else {}
+    return t[0], t[1], t[2], t[3], int(opt.get("nscalars", 0)), opt.get("eos", "adiabatic")
 
 CXXFLAGS = ["-O3", "-std=c++11", "-fopenmp"]
 
 
-def defs_for(mhd, flux, nghost):
+def defs_for(mhd, flux, nghost, nscalars=0, eos="adiabatic"):
+    iso = eos == "isothermal"
     d = {
         "PROBLEM": "oracle_multi",
         "COORDINATE_SYSTEM": "cartesian",
         "RSOLVER": flux,
-        "EQUATION_OF_STATE": "adiabatic",
+        "EQUATION_OF_STATE": eos,
         "GENERAL_EOS": "0",
         "EOS_TABLE_ENABLED": "0",
-        "NON_BAROTROPIC_EOS": "1",
+        "NON_BAROTROPIC_EOS": "0" if iso else "1",
         "MAGNETIC_FIELDS_ENABLED": "1" if mhd else "0",
         "STS_ENABLED": "0",
         "SELF_GRAVITY_ENABLED": "0",
@@ -75,16 +93,17 @@ def defs_for(mhd, flux, nghost):
         "COMPILER_CHOICE": "g++",
         "COMPILER_COMMAND": "g++",
         "COMPILER_FLAGS": " ".join(CXXFLAGS),
-        "NHYDRO_VARIABLES": "5",
+        # configure.py:370-423
+        "NHYDRO_VARIABLES": "4" if iso else "5",
         "NFIELD_VARIABLES": "3" if mhd else "0",
-        "NWAVE_VALUE": "7" if mhd else "5",
-        "NUMBER_PASSIVE_SCALARS": "0",
+        "NWAVE_VALUE": ("6" if iso else "7") if mhd else ("4" if iso else "5"),
+        "NUMBER_PASSIVE_SCALARS": str(nscalars),
         "NUMBER_GHOST_CELLS": str(nghost),
     }
     return d
 
 
-def source_list(src, mhd, flux):
+def source_list(src, mhd, flux, eos="adiabatic"):
     """Same selection rule as the reference's Makefile.in:27-58 (one EOS, one solver)."""
     pats = ["*.cpp", "bvals/*.cpp", "bvals/cc/*.cpp", "bvals/cc/fft_grav/*.cpp",
             "bvals/cc/hydro/*.cpp", "bvals/cc/mg/*.cpp", "bvals/fc/*.cpp",
@@ -96,10 +115,13 @@ def source_list(src, mhd, flux):
     files = []
     for p in pats:
         files += sorted(glob.glob(os.path.join(src, p)))
-    eos = "adiabatic_mhd.cpp" if mhd else "adiabatic_hydro.cpp"
-    rs = flux + ("_mhd" if (mhd and flux in ("hlle", "llf", "roe")) else "") + ".cpp"
+    eosf = eos + ("_mhd.cpp" if mhd else "_hydro.cpp")
+    rs = flux + ("_mhd" if (mhd and flux in ("hlle", "llf", "roe")) else "")
+    if mhd and flux == "hlld" and eos == "isothermal":
+        rs += "_iso"                                    # configure.py:406-409
+    rs += ".cpp"
     files += [os.path.join(src, "eos/general/noop.cpp"),
-              os.path.join(src, "eos", eos),
+              os.path.join(src, "eos", eosf),
               os.path.join(src, "eos/eos_high_order.cpp"),
               os.path.join(src, "eos/eos_scalars.cpp"),
               os.path.join(src, "hydro/rsolvers", "mhd" if mhd else "hydro", rs),
@@ -117,7 +139,7 @@ def compile_one(args):
 
 
 def build(cfg, ref, jobs):
-    mhd, flux, ng, pgens = CONFIGS[cfg]
+    mhd, flux, ng, pgens, nscalars, eos = cfg_tuple(cfg)
     src = os.path.join(ref, "src")
     root = os.path.join(OUT, cfg)
     inc = os.path.join(root, "inc")
@@ -126,7 +148,7 @@ def build(cfg, ref, jobs):
     os.makedirs(obj, exist_ok=True)
     with open(os.path.join(src, "defs.hpp.in")) as f:
         text = f.read()
-    for k, v in defs_for(mhd, flux, ng).items():
+    for k, v in defs_for(mhd, flux, ng, nscalars, eos).items():
         text = text.replace("@" + k + "@", v)
     assert not re.search(r"@[A-Z0-9_]+@", text), "unfilled key in defs.hpp"
     dpath = os.path.join(inc, "defs.hpp")
@@ -135,7 +157,7 @@ def build(cfg, ref, jobs):
             f.write(text)
     # "defs.hpp" resolves through -I inc ; "../defs.hpp" through -I inc/sub
     incs = ["-I", inc, "-I", os.path.join(inc, "sub")]
-    files = source_list(src, mhd, flux)
+    files = source_list(src, mhd, flux, eos)
     work = []
     for s in files:
         rel = os.path.relpath(s, src).replace("/", "__")[:-4] + ".o"

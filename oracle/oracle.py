@@ -27,7 +27,9 @@ class AoParams(C.Structure):
                 ("bc", C.c_int * 6), ("ng", C.c_int), ("mhd", C.c_int),
                 ("solver", C.c_int), ("xorder", C.c_int), ("integrator", C.c_int),
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
-                ("cfl", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double)]
+                ("cfl", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double),
+                ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
+                ("iso_cs", C.c_double)]
 
 
 def build():
@@ -51,7 +53,8 @@ def lib():
         L.ao_block_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_long)]
         L.ao_array.restype = C.POINTER(C.c_double)
         L.ao_array.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_long)]
-        for f in ("ao_initialize", "ao_emf_exchange", "ao_exchange_cc", "ao_exchange_fc"):
+        for f in ("ao_initialize", "ao_emf_exchange", "ao_exchange_cc", "ao_exchange_fc",
+                  "ao_exchange_scalars"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.ao_cycle.restype = C.c_double
         L.ao_cycle.argtypes = [C.c_void_p]
@@ -62,6 +65,8 @@ def lib():
         L.ao_ncycle.argtypes = [C.c_void_p]
         L.ao_set_time_dt.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.ao_calc_fluxes.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ao_calc_scalar_fluxes.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ao_integrate_scalars.argtypes = [C.c_void_p, C.c_int, C.c_int]
         for f in ("ao_corner_e", "ao_swap_cc", "ao_swap_fc", "ao_zero_reg1", "ao_primitives",
                   "ao_physical_bcs"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int]
@@ -70,7 +75,7 @@ def lib():
                                       C.POINTER(C.c_double)]
         L.ao_add_flux_div.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.ao_ct.argtypes = [C.c_void_p, C.c_int, C.c_double]
-        for f in ("ao_cons2prim", "ao_prim2cons"):
+        for f in ("ao_cons2prim", "ao_prim2cons", "ao_scalar_cons2prim", "ao_scalar_prim2cons"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 6
         L.ao_new_block_dt.restype = C.c_double
         L.ao_new_block_dt.argtypes = [C.c_void_p, C.c_int]
@@ -90,7 +95,7 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def params_from_athinput(par, mhd, solver, ng=None):
+def params_from_athinput(par, mhd, solver, ng=None, nscalars=0, eos="adiabatic"):
     """par: dict of blocks (oracle/ref_run.parse_athinput or the product's ParameterInput)."""
     mesh, t = par["mesh"], par["time"]
     mb = par.get("meshblock", {})
@@ -111,7 +116,11 @@ def params_from_athinput(par, mhd, solver, ng=None):
     p.xorder = xorder
     p.integrator = INTEGRATOR[t.get("integrator", "vl2")]
     h = par.get("hydro", {})
-    p.gamma = float(h["gamma"])
+    p.eos = 1 if eos == "isothermal" else 0
+    p.gamma = float(h["gamma"]) if p.eos == 0 else 0.0
+    p.iso_cs = float(h.get("iso_sound_speed", 0.0))
+    p.nscalars = int(nscalars)
+    p.sfloor = float(h.get("sfloor", DEFAULT_FLOOR))
     p.dfloor = float(h.get("dfloor", DEFAULT_FLOOR))
     p.pfloor = float(h.get("pfloor", DEFAULT_FLOOR))
     p.cfl = float(t["cfl_number"])
@@ -144,6 +153,14 @@ class OracleMesh:
         n1, n2, n3 = i["nc1"], i["nc2"], i["nc3"]
         if name in ("u", "u1", "w"):
             return (5, n3, n2, n1)
+        ns = self.p.nscalars
+        if name in ("s", "s1", "r"):
+            return (ns, n3, n2, n1)
+        if name in ("sflux1", "sflux2", "sflux3"):
+            d = int(name[-1]) - 1
+            sh = [n3, n2, n1]
+            sh[2 - d] += 1
+            return (ns,) + tuple(sh)
         if name in ("bcc", "cc_e"):
             return (3, n3, n2, n1)
         if name in ("b1", "b1_1", "wght1", "e2_x1f", "e3_x1f"):
@@ -187,6 +204,8 @@ class OracleMesh:
         for blk in rst["blocks"]:
             b = self.block_of(*blk["loc"][:3])
             self.array(b, "u")[...] = blk["u"]
+            if self.p.nscalars > 0:
+                self.array(b, "s")[...] = blk["s"]
             if self.p.mhd:
                 for nm in ("b1", "b2", "b3"):
                     self.array(b, nm)[...] = blk[nm]

@@ -32,6 +32,7 @@ typedef struct AoBlock {
   double *u, *u1, *w, *bcc, *flux[3];
   double *b[3], *b1[3], *e[3], *wght[3];
   double *e2_x1f, *e3_x1f, *e1_x2f, *e3_x2f, *e1_x3f, *e2_x3f, *cc_e;
+  double *s, *s1, *r, *sflux[3];   /* PassiveScalars::s, s1, r, s_flux (scalars.hpp:40-56) */
   double *recv[26]; long recvn[26];
   double new_dt;
 } AoBlock;
@@ -239,6 +240,13 @@ AoMesh *ao_create(const AoParams *p) {
     B->flux[0] = dalloc(NHYDRO*(long)B->nc3*B->nc2*(B->nc1+1));
     B->flux[1] = dalloc(NHYDRO*(long)B->nc3*(B->nc2+1)*B->nc1);
     B->flux[2] = dalloc(NHYDRO*(long)(B->nc3+1)*B->nc2*B->nc1);
+    if (p->nscalars > 0) {   /* PassiveScalars ctor (src/scalars/scalars.cpp:31-75) */
+      int ns = p->nscalars;
+      B->s = dalloc(ns*ncc); B->s1 = dalloc(ns*ncc); B->r = dalloc(ns*ncc);
+      B->sflux[0] = dalloc(ns*(long)B->nc3*B->nc2*(B->nc1+1));
+      B->sflux[1] = dalloc(ns*(long)B->nc3*(B->nc2+1)*B->nc1);
+      B->sflux[2] = dalloc(ns*(long)(B->nc3+1)*B->nc2*B->nc1);
+    }
     if (p->mhd) {
       long n1 = (long)B->nc3*B->nc2*(B->nc1+1), n2 = (long)B->nc3*(B->nc2+1)*B->nc1,
            n3 = (long)(B->nc3+1)*B->nc2*B->nc1;
@@ -337,7 +345,8 @@ void ao_destroy(AoMesh *m) {
       B->dx3f, B->u, B->u1, B->w, B->bcc, B->flux[0], B->flux[1], B->flux[2], B->b[0],
       B->b[1], B->b[2], B->b1[0], B->b1[1], B->b1[2], B->e[0], B->e[1], B->e[2],
       B->wght[0], B->wght[1], B->wght[2], B->e2_x1f, B->e3_x1f, B->e1_x2f, B->e3_x2f,
-      B->e1_x3f, B->e2_x3f, B->cc_e};
+      B->e1_x3f, B->e2_x3f, B->cc_e, B->s, B->s1, B->r, B->sflux[0], B->sflux[1],
+      B->sflux[2]};
     for (size_t i = 0; i < sizeof(ptrs)/sizeof(ptrs[0]); ++i) free(ptrs[i]);
   }
   free(m->blk); free(m->gid_of); free(m);
@@ -376,7 +385,10 @@ double *ao_array(AoMesh *m, int b, const char *name, long *n) {
     {"e2_x3f", B->e2_x3f, n3}, {"x1f", B->x1f, B->nc1+1}, {"x2f", B->x2f, B->nc2+1},
     {"x3f", B->x3f, B->nc3+1}, {"x1v", B->x1v, B->nc1}, {"x2v", B->x2v, B->nc2},
     {"x3v", B->x3v, B->nc3}, {"dx1f", B->dx1f, B->nc1}, {"dx2f", B->dx2f, B->nc2},
-    {"dx3f", B->dx3f, B->nc3}, {"cc_e", B->cc_e, 3*ncc}};
+    {"dx3f", B->dx3f, B->nc3}, {"cc_e", B->cc_e, 3*ncc},
+    {"s", B->s, m->p.nscalars*ncc}, {"s1", B->s1, m->p.nscalars*ncc},
+    {"r", B->r, m->p.nscalars*ncc}, {"sflux1", B->sflux[0], m->p.nscalars*n1},
+    {"sflux2", B->sflux[1], m->p.nscalars*n2}, {"sflux3", B->sflux[2], m->p.nscalars*n3}};
   for (size_t i = 0; i < sizeof(t)/sizeof(t[0]); ++i)
     if (strcmp(t[i].nm, name) == 0) { *n = t[i].p ? t[i].n : 0; return t[i].p; }
   *n = 0;
@@ -471,6 +483,29 @@ void ao_primitives(AoMesh *m, int b) {
   if (B->nblevel[0][1][1] != -1) kl -= ng;
   if (B->nblevel[2][1][1] != -1) ku += ng;
   ao_cons2prim(m, b, il, iu, jl, ju, kl, ku);
+  if (m->p.nscalars > 0) ao_scalar_cons2prim(m, b, il, iu, jl, ju, kl, ku);
+}
+
+/* EquationOfState::PassiveScalarConservedToPrimitive (src/eos/eos_scalars.cpp:31-60): floor
+ * the conserved scalar at sfloor*rho (rho = the already floored u(IDN)), then r = s/rho */
+void ao_scalar_cons2prim(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int ku) {
+  AoBlock *B = &m->blk[b];
+  double sfl = m->p.sfloor;
+  for (int n = 0; n < m->p.nscalars; ++n) for (int k = kl; k <= ku; ++k)
+    for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
+      double d = B->u[CC(B,IDN,k,j,i)];
+      double *s_n = &B->s[CC(B,n,k,j,i)];
+      *s_n = (*s_n < sfl*d) ? sfl*d : *s_n;
+      B->r[CC(B,n,k,j,i)] = *s_n/d;
+    }
+}
+
+/* EquationOfState::PassiveScalarPrimitiveToConserved (src/eos/eos_scalars.cpp:133-152) */
+void ao_scalar_prim2cons(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int ku) {
+  AoBlock *B = &m->blk[b];
+  for (int n = 0; n < m->p.nscalars; ++n) for (int k = kl; k <= ku; ++k)
+    for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i)
+      B->s[CC(B,n,k,j,i)] = B->r[CC(B,n,k,j,i)]*B->u[CC(B,IDN,k,j,i)];
 }
 
 /* ------------------------------------------------------------------ fluxes */
@@ -968,6 +1003,8 @@ void ao_swap_fc(AoMesh *m, int b) {
 void ao_zero_reg1(AoMesh *m, int b) {
   AoBlock *B = &m->blk[b];
   memset(B->u1, 0, sizeof(double)*NHYDRO*(size_t)B->nc1*B->nc2*B->nc3);
+  if (m->p.nscalars > 0)
+    memset(B->s1, 0, sizeof(double)*(size_t)m->p.nscalars*B->nc1*B->nc2*B->nc3);
   if (m->p.mhd) {
     memset(B->b1[0], 0, sizeof(double)*(size_t)B->nc3*B->nc2*(B->nc1+1));
     memset(B->b1[1], 0, sizeof(double)*(size_t)B->nc3*(B->nc2+1)*B->nc1);
@@ -1065,7 +1102,7 @@ static long unpack3(double *a, long s2, long s1, int si, int ei, int sj, int ej,
 
 /* CellCenteredBoundaryVariable::LoadBoundaryBufferSameLevel / SetBoundarySameLevel
  * (src/bvals/cc/bvals_cc.cpp:201-216,300-336) */
-void ao_exchange_cc(AoMesh *m) {
+static void exchange_cc_var(AoMesh *m, int nvar, int scalars) {
   int ng = m->p.ng;
   for (int g = 0; g < m->nb; ++g) {
     AoBlock *B = &m->blk[g];
@@ -1074,11 +1111,12 @@ void ao_exchange_cc(AoMesh *m) {
       int si = (nb->ox1 > 0) ? (B->ie - ng + 1) : B->is, ei = (nb->ox1 < 0) ? (B->is + ng - 1) : B->ie;
       int sj = (nb->ox2 > 0) ? (B->je - ng + 1) : B->js, ej = (nb->ox2 < 0) ? (B->js + ng - 1) : B->je;
       int sk = (nb->ox3 > 0) ? (B->ke - ng + 1) : B->ks, ek = (nb->ox3 < 0) ? (B->ks + ng - 1) : B->ke;
-      long cnt = (long)NHYDRO*(ei-si+1)*(ej-sj+1)*(ek-sk+1);
+      long cnt = (long)nvar*(ei-si+1)*(ej-sj+1)*(ek-sk+1);
       double *buf = dalloc(cnt);
       long p = 0;
-      for (int v = 0; v < NHYDRO; ++v)
-        p = pack3(B->u + (long)v*B->nc3*B->nc2*B->nc1, B->nc2, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
+      const double *src = scalars ? B->s : B->u;
+      for (int v = 0; v < nvar; ++v)
+        p = pack3(src + (long)v*B->nc3*B->nc2*B->nc1, B->nc2, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
       AoBlock *T = &m->blk[nb->gid];
       T->recv[nb->targetid] = buf; T->recvn[nb->targetid] = cnt;
     }
@@ -1099,12 +1137,17 @@ void ao_exchange_cc(AoMesh *m) {
       else { sk = B->ks - ng; ek = B->ks - 1; }
       const double *buf = B->recv[nb->bufid];
       long p = 0;
-      for (int v = 0; v < NHYDRO; ++v)
-        p = unpack3(B->u + (long)v*B->nc3*B->nc2*B->nc1, B->nc2, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
+      double *dst = scalars ? B->s : B->u;
+      for (int v = 0; v < nvar; ++v)
+        p = unpack3(dst + (long)v*B->nc3*B->nc2*B->nc1, B->nc2, B->nc1, si, ei, sj, ej, sk, ek, buf, p);
       free(B->recv[nb->bufid]); B->recv[nb->bufid] = NULL;
     }
   }
 }
+
+void ao_exchange_cc(AoMesh *m) { exchange_cc_var(m, NHYDRO, 0); }
+/* PassiveScalars::sbvar is a CellCenteredBoundaryVariable on s (scalars.cpp:59-72): same boxes */
+void ao_exchange_scalars(AoMesh *m) { if (m->p.nscalars > 0) exchange_cc_var(m, m->p.nscalars, 1); }
 
 /* FaceCenteredBoundaryVariable::LoadBoundaryBufferSameLevel / SetBoundarySameLevel
  * (src/bvals/fc/bvals_fc.cpp:344-397,583-684), uniform (non-multilevel) mesh */
@@ -1260,6 +1303,44 @@ static void phys_bc(AoMesh *m, AoBlock *B, int face, int refl, int il, int iu, i
   }
 }
 
+/* CellCenteredBoundaryVariable outflow / reflect on the primitive scalars r
+ * (src/bvals/cc/outflow_cc.cpp, reflect_cc.cpp: a plain copy / mirror, no sign change) */
+static void phys_bc_scalars(AoMesh *m, AoBlock *B, int face, int refl, int il, int iu, int jl,
+                            int ju, int kl, int ku) {
+  int ng = m->p.ng;
+  int d = face/2, upper = face & 1;
+  int lo = d == 0 ? il : (d == 1 ? jl : kl), hi = d == 0 ? iu : (d == 1 ? ju : ku);
+  for (int g = 1; g <= ng; ++g) {
+    int gc = upper ? hi + g : lo - g;
+    int sc = refl ? (upper ? hi - g + 1 : lo + g - 1) : (upper ? hi : lo);
+    for (int n = 0; n < m->p.nscalars; ++n) {
+      if (d == 0) {
+        for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j)
+          B->r[CC(B,n,k,j,gc)] = B->r[CC(B,n,k,j,sc)];
+      } else if (d == 1) {
+        for (int k = kl; k <= ku; ++k) for (int i = il; i <= iu; ++i)
+          B->r[CC(B,n,k,gc,i)] = B->r[CC(B,n,k,sc,i)];
+      } else {
+        for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i)
+          B->r[CC(B,n,gc,j,i)] = B->r[CC(B,n,sc,j,i)];
+      }
+    }
+  }
+}
+
+/* one face of ApplyPhysicalBoundaries: boundary function on w, b (and r), then bcc and the
+ * conserved variables of the ghost slab [g*] (bvals.cpp:476-497) */
+static void bc_face(AoMesh *m, int b, int face, int il, int iu, int jl, int ju, int kl, int ku,
+                    int gil, int giu, int gjl, int gju, int gkl, int gku) {
+  AoBlock *B = &m->blk[b];
+  int refl = B->bcs[face] == AO_BC_REFLECT;
+  phys_bc(m, B, face, refl, il, iu, jl, ju, kl, ku);
+  if (m->p.nscalars > 0) phys_bc_scalars(m, B, face, refl, il, iu, jl, ju, kl, ku);
+  if (m->p.mhd) calc_bcc(B, gil, giu, gjl, gju, gkl, gku);
+  ao_prim2cons(m, b, gil, giu, gjl, gju, gkl, gku);
+  if (m->p.nscalars > 0) ao_scalar_prim2cons(m, b, gil, giu, gjl, gju, gkl, gku);
+}
+
 /* BoundaryValues::ApplyPhysicalBoundaries (src/bvals/bvals.cpp:436-620) */
 void ao_physical_bcs(AoMesh *m, int b) {
   AoBlock *B = &m->blk[b];
@@ -1272,41 +1353,121 @@ void ao_physical_bcs(AoMesh *m, int b) {
   if (!app[3] && m->f2) bje = je + ng;
   if (!app[4] && m->f3) bks = ks - ng;
   if (!app[5] && m->f3) bke = ke + ng;
-  if (app[0]) {
-    phys_bc(m, B, 0, B->bcs[0] == AO_BC_REFLECT, is, ie, bjs, bje, bks, bke);
-    if (m->p.mhd) calc_bcc(B, is-ng, is-1, bjs, bje, bks, bke);
-    ao_prim2cons(m, b, is-ng, is-1, bjs, bje, bks, bke);
-  }
-  if (app[1]) {
-    phys_bc(m, B, 1, B->bcs[1] == AO_BC_REFLECT, is, ie, bjs, bje, bks, bke);
-    if (m->p.mhd) calc_bcc(B, ie+1, ie+ng, bjs, bje, bks, bke);
-    ao_prim2cons(m, b, ie+1, ie+ng, bjs, bje, bks, bke);
-  }
+  if (app[0]) bc_face(m, b, 0, is, ie, bjs, bje, bks, bke, is-ng, is-1, bjs, bje, bks, bke);
+  if (app[1]) bc_face(m, b, 1, is, ie, bjs, bje, bks, bke, ie+1, ie+ng, bjs, bje, bks, bke);
   if (m->f2) {
-    if (app[2]) {
-      phys_bc(m, B, 2, B->bcs[2] == AO_BC_REFLECT, bis, bie, js, je, bks, bke);
-      if (m->p.mhd) calc_bcc(B, bis, bie, js-ng, js-1, bks, bke);
-      ao_prim2cons(m, b, bis, bie, js-ng, js-1, bks, bke);
-    }
-    if (app[3]) {
-      phys_bc(m, B, 3, B->bcs[3] == AO_BC_REFLECT, bis, bie, js, je, bks, bke);
-      if (m->p.mhd) calc_bcc(B, bis, bie, je+1, je+ng, bks, bke);
-      ao_prim2cons(m, b, bis, bie, je+1, je+ng, bks, bke);
-    }
+    if (app[2]) bc_face(m, b, 2, bis, bie, js, je, bks, bke, bis, bie, js-ng, js-1, bks, bke);
+    if (app[3]) bc_face(m, b, 3, bis, bie, js, je, bks, bke, bis, bie, je+1, je+ng, bks, bke);
   }
   if (m->f3) {
     bjs = js - ng; bje = je + ng;
-    if (app[4]) {
-      phys_bc(m, B, 4, B->bcs[4] == AO_BC_REFLECT, bis, bie, bjs, bje, ks, ke);
-      if (m->p.mhd) calc_bcc(B, bis, bie, bjs, bje, ks-ng, ks-1);
-      ao_prim2cons(m, b, bis, bie, bjs, bje, ks-ng, ks-1);
-    }
-    if (app[5]) {
-      phys_bc(m, B, 5, B->bcs[5] == AO_BC_REFLECT, bis, bie, bjs, bje, ks, ke);
-      if (m->p.mhd) calc_bcc(B, bis, bie, bjs, bje, ke+1, ke+ng);
-      ao_prim2cons(m, b, bis, bie, bjs, bje, ke+1, ke+ng);
-    }
+    if (app[4]) bc_face(m, b, 4, bis, bie, bjs, bje, ks, ke, bis, bie, bjs, bje, ks-ng, ks-1);
+    if (app[5]) bc_face(m, b, 5, bis, bie, bjs, bje, ks, ke, bis, bie, bjs, bje, ke+1, ke+ng);
   }
+}
+
+/* ------------------------------------------------------------------ passive scalars */
+
+/* both face states of r(n) in cell (k,j,i) along dir (dc_simple.cpp, plm_simple.cpp,
+ * ppm_simple.cpp: the same limiters as the hydro variables, no characteristic projection);
+ * xorder 3 re-applies the concentration floor (calculate_scalar_fluxes.cpp:83-92) */
+static void recon_scalar(const AoMesh *m, const AoBlock *B, int dir, int order, int n, int k,
+                         int j, int i, double *plus, double *minus) {
+  int dk = (dir == 2), dj = (dir == 1), di = (dir == 0);
+  const double *r = B->r;
+  double q = r[CC(B,n,k,j,i)];
+  if (order == 1) { *plus = *minus = q; return; }
+  double qm1 = r[CC(B,n,k-dk,j-dj,i-di)], qp1 = r[CC(B,n,k+dk,j+dj,i+di)];
+  if (order == 2) {
+    const double *xf = dir == 0 ? B->x1f : (dir == 1 ? B->x2f : B->x3f);
+    const double *xv = dir == 0 ? B->x1v : (dir == 1 ? B->x2v : B->x3v);
+    const double *dxf = dir == 0 ? B->dx1f : (dir == 1 ? B->dx2f : B->dx3f);
+    int c = dir == 0 ? i : (dir == 1 ? j : k);
+    double wp = (xf[c+1] - xv[c])/dxf[c];
+    double wm = (xv[c] - xf[c])/dxf[c];
+    ao_plm_point(qm1, q, qp1, wp, wm, plus, minus);
+    return;
+  }
+  double qm2 = r[CC(B,n,k-2*dk,j-2*dj,i-2*di)], qp2 = r[CC(B,n,k+2*dk,j+2*dj,i+2*di)];
+  ao_ppm_point(qm2, qm1, q, qp1, qp2, plus, minus);
+  /* EquationOfState::ApplyPassiveScalarFloors (eos_scalars.cpp:161-175) */
+  *plus = (*plus > m->p.sfloor) ? *plus : m->p.sfloor;
+  *minus = (*minus > m->p.sfloor) ? *minus : m->p.sfloor;
+}
+
+/* PassiveScalars::CalculateFluxes + ComputeUpwindFlux
+ * (src/scalars/calculate_scalar_fluxes.cpp:41-382): upwind the reconstructed concentration
+ * with the Riemann solver's mass flux.  The reference sweeps a widened transverse range
+ * (:64-71,159-166,261); only the faces AddFluxDivergence reads are evaluated here (the extra
+ * rows use mass fluxes that hydro runs never compute and are never read). */
+void ao_calc_scalar_fluxes(AoMesh *m, int b, int order) {
+  AoBlock *B = &m->blk[b];
+  if (m->p.nscalars <= 0) return;
+  int is = B->is, ie = B->ie, js = B->js, je = B->je, ks = B->ks, ke = B->ke;
+  for (int dir = 0; dir < m->ndim; ++dir) {
+    int dk = (dir == 2), dj = (dir == 1), di = (dir == 0);
+    for (int n = 0; n < m->p.nscalars; ++n)
+      for (int k = ks; k <= ke + dk; ++k) for (int j = js; j <= je + dj; ++j)
+        for (int i = is; i <= ie + di; ++i) {
+          double rl, rr, tmp;
+          recon_scalar(m, B, dir, order, n, k-dk, j-dj, i-di, &rl, &tmp);
+          recon_scalar(m, B, dir, order, n, k, j, i, &tmp, &rr);
+          long fo = dir == 0 ? FL1(B,IDN,k,j,i) : (dir == 1 ? FL2(B,IDN,k,j,i) : FL3(B,IDN,k,j,i));
+          long so = dir == 0 ? FL1(B,n,k,j,i) : (dir == 1 ? FL2(B,n,k,j,i) : FL3(B,n,k,j,i));
+          double fluid_flx = B->flux[dir][fo];
+          if (fluid_flx >= 0.0) B->sflux[dir][so] = fluid_flx*rl;
+          else B->sflux[dir][so] = fluid_flx*rr;
+        }
+  }
+}
+
+/* TimeIntegratorTaskList::IntegrateScalars (src/task_list/time_integrator.cpp:2141-2185):
+ * WeightedAve on (s1, s), swap or second average, PassiveScalars::AddFluxDivergence
+ * (src/scalars/add_scalar_flux_divergence.cpp:43-97) */
+void ao_integrate_scalars(AoMesh *m, int b, int stage) {
+  AoBlock *B = &m->blk[b];
+  int ns = m->p.nscalars;
+  if (ns <= 0) return;
+  int s = stage - 1;
+  double w[5] = {1.0, m->delta[s], 0.0, 0.0, 0.0};
+  double w2[5] = {m->g1[s], m->g2[s], m->g3[s], 0.0, 0.0};
+  for (int pass = 0; pass < 2; ++pass) {
+    double *uo = pass == 0 ? B->s1 : B->s, *ui = pass == 0 ? B->s : B->s1;
+    const double *ww = pass == 0 ? w : w2;
+    if (pass == 1 && w2[0] == 0.0 && w2[1] == 1.0 && w2[2] == 0.0) {
+      double *t = B->s; B->s = B->s1; B->s1 = t;
+      break;
+    }
+    for (int n = 0; n < ns; ++n) for (int k = B->ks; k <= B->ke; ++k)
+      for (int j = B->js; j <= B->je; ++j) for (int i = B->is; i <= B->ie; ++i) {
+        long o = CC(B,n,k,j,i);
+        if (ww[0] == 1.0) {
+          if (ww[1] != 0.0) uo[o] += ww[1]*ui[o];
+        } else if (ww[0] == 0.0) {
+          if (ww[1] == 1.0) uo[o] = ui[o];
+          else uo[o] = ww[1]*ui[o];
+        } else {
+          if (ww[1] != 0.0) uo[o] = ww[0]*uo[o] + ww[1]*ui[o];
+          else uo[o] *= ww[0];
+        }
+      }
+  }
+  double wght = m->beta[s]*m->dt;
+  for (int k = B->ks; k <= B->ke; ++k) for (int j = B->js; j <= B->je; ++j)
+    for (int n = 0; n < ns; ++n) for (int i = B->is; i <= B->ie; ++i) {
+      double x1area = B->dx2f[j]*B->dx3f[k];
+      double dflx = (x1area*B->sflux[0][FL1(B,n,k,j,i+1)] - x1area*B->sflux[0][FL1(B,n,k,j,i)]);
+      if (m->f2) {
+        double x2area = B->dx1f[i]*B->dx3f[k];
+        dflx += (x2area*B->sflux[1][FL2(B,n,k,j+1,i)] - x2area*B->sflux[1][FL2(B,n,k,j,i)]);
+      }
+      if (m->f3) {
+        double x3area = B->dx1f[i]*B->dx2f[j];
+        dflx += (x3area*B->sflux[2][FL3(B,n,k+1,j,i)] - x3area*B->sflux[2][FL3(B,n,k,j,i)]);
+      }
+      double vol = B->dx1f[i]*B->dx2f[j]*B->dx3f[k];
+      B->s[CC(B,n,k,j,i)] -= wght*dflx/vol;
+    }
 }
 
 /* ------------------------------------------------------------------ time step */
@@ -1362,6 +1523,7 @@ static void new_time_step(AoMesh *m) {
 void ao_initialize(AoMesh *m) {
   ao_exchange_cc(m);
   ao_exchange_fc(m);
+  ao_exchange_scalars(m);
   for (int g = 0; g < m->nb; ++g) {
     ao_primitives(m, g);
     ao_physical_bcs(m, g);
@@ -1382,6 +1544,7 @@ double ao_cycle(AoMesh *m) {
     for (int g = 0; g < m->nb; ++g) {
       ao_calc_fluxes(m, g, order);
       if (m->p.mhd) ao_corner_e(m, g);
+      ao_calc_scalar_fluxes(m, g, order);
     }
     ao_emf_exchange(m);
     for (int g = 0; g < m->nb; ++g) {
@@ -1397,9 +1560,11 @@ double ao_cycle(AoMesh *m) {
         else ao_weighted_ave_fc(m, g, 0, 1, w2);
         ao_ct(m, g, m->beta[s]*dt);
       }
+      ao_integrate_scalars(m, g, stage);
     }
     ao_exchange_cc(m);
     ao_exchange_fc(m);
+    ao_exchange_scalars(m);
     for (int g = 0; g < m->nb; ++g) {
       ao_primitives(m, g);
       ao_physical_bcs(m, g);

@@ -73,7 +73,7 @@ def apply_overrides(blocks, overrides):
 _CYCLE_RE = re.compile(r"cycle=(\d+)\s+time=([-+0-9.eE]+)\s+dt=([-+0-9.eE]+)")
 
 
-def read_rst(path, nhydro=5, mhd=None, nghost=None):
+def read_rst(path, nhydro=5, mhd=None, nghost=None, nscalars=0):
     raw = open(path, "rb").read()
     tag = b"<par_end>\n"
     pe = raw.index(tag) + len(tag)
@@ -109,7 +109,7 @@ def read_rst(path, nhydro=5, mhd=None, nghost=None):
         nfc = ((nc[0] + 1) * nc[1] * nc[2] + nc[0] * (nc[1] + 1) * nc[2]
                + nc[0] * nc[1] * (nc[2] + 1))
         for m in ((mhd,) if mhd is not None else (False, True)):
-            if nhydro * ncc + (nfc if m else 0) == ncell_u:
+            if (nhydro + nscalars) * ncc + (nfc if m else 0) == ncell_u:
                 cands.append((ng, m, nc))
     assert len(cands) == 1, "cannot infer block layout from datasize %d" % datasize
     ng, m, nc = cands[0]
@@ -127,6 +127,11 @@ def read_rst(path, nhydro=5, mhd=None, nghost=None):
                 a = np.frombuffer(raw, "<f8", s[0] * s[1] * s[2], o).reshape(s).copy()
                 o += a.nbytes
                 blk[name] = a
+        if nscalars > 0:      # outputs/restart.cpp:172-178: s follows u (and b)
+            a = np.frombuffer(raw, "<f8", nscalars * nc[2] * nc[1] * nc[0], o).reshape(
+                nscalars, nc[2], nc[1], nc[0]).copy()
+            o += a.nbytes
+            blk["s"] = a
         blocks.append(blk)
     return {"par": par, "nbtotal": nbtotal, "root_level": root_level, "region": rs,
             "time": time, "dt": dt, "ncycle": ncycle, "nghost": ng, "mhd": m,

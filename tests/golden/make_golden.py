@@ -29,7 +29,9 @@ def mb(a, b, c=1):
     return {"meshblock/nx1": a, "meshblock/nx2": b, "meshblock/nx3": c}
 
 
-# name -> (cfg, pgen, athinput, overrides, solver, mhd, ncycles)
+KS = {"mesh/nx1": 16, "mesh/nx2": 32, "mesh/nx3": 1}
+
+# name -> (cfg, pgen, athinput, overrides, solver, mhd, ncycles[, nscalars[, eos]])
 CASES = {
     "c2_linwave_hlld_plm_vl2_1blk": ("mhd_hlld_ng2", "linear_wave", "athinput.linear_wave3d",
                                      dict(LW, **mb(16, 8, 8)), "hlld", True, 4),
@@ -88,25 +90,43 @@ CASES = {
     "linwave_mhd_roe_plm_vl2_2blk": ("mhd_roe_ng2", "linear_wave", "athinput.linear_wave3d",
                                      dict(LW, **mb(8, 8, 8), **{"problem/amp": 0.1}),
                                      "roe", True, 4),
+    # passive scalars (src/scalars): the fork's production build carries one (confignotes)
+    "khs_lhllc_plm_vl2_4blk_s1": ("hydro_lhllc_ng2_s1", "kh", "athinput.kh_scalar",
+                                  dict(KS, **mb(8, 16, 1)), "lhllc", False, 6, 1),
+    "sods_lhllc_plm_vl2_2blk_s1": ("hydro_lhllc_ng2_s1", "shock_tube", "athinput.sod",
+                                   {"mesh/nx1": 64, "meshblock/nx1": 32}, "lhllc", False, 8, 1),
+    "khs3d_hllc_ppm_rk3_8blk_s2": ("hydro_hllc_ng3_s2", "kh", "athinput.kh_scalar",
+                                   dict({"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16},
+                                        **mb(8, 8, 8), **{"time/xorder": 3,
+                                                          "time/integrator": "rk3"}),
+                                   "hllc", False, 3, 2),
+    "khs3d_mhd_hlld_plm_vl2_8blk_s1": ("mhd_hlld_ng2_s1", "kh", "athinput.kh_scalar",
+                                       dict({"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16},
+                                            **mb(8, 8, 8)), "hlld", True, 4, 1),
 }
 
 
 def make(name):
-    cfg, pgen, inp, ov, solver, mhd, ncyc = CASES[name]
+    cfg, pgen, inp, ov, solver, mhd, ncyc = CASES[name][:7]
+    nscalars = CASES[name][7] if len(CASES[name]) > 7 else 0
+    eos = CASES[name][8] if len(CASES[name]) > 8 else "adiabatic"
+    nhydro = 4 if eos == "isothermal" else 5
     ov = dict(ov)
     ov["time/nlim"] = ncyc
     res = ref_run.run_reference(cfg, pgen, os.path.join(I, inp), ov, rst_every_cycle=True)
-    first = ref_run.read_rst(res["rst"][0])
-    last = ref_run.read_rst(res["rst"][ncyc])
+    first = ref_run.read_rst(res["rst"][0], nhydro=nhydro, mhd=mhd, nscalars=nscalars)
+    last = ref_run.read_rst(res["rst"][ncyc], nhydro=nhydro, mhd=mhd, nscalars=nscalars)
     out = {"meta": json.dumps({"cfg": cfg, "pgen": pgen, "solver": solver, "mhd": mhd,
                                "ncycles": ncyc, "nghost": first["nghost"],
-                               "par": first["par"]}),
+                               "nscalars": nscalars, "eos": eos, "par": first["par"]}),
            "dts": np.array(res["dts"][:ncyc + 1]),
            "locs": np.array([b["loc"][:3] for b in first["blocks"]], dtype=np.int64),
            "final_time": np.array(last["time"]), "final_dt": np.array(last["dt"])}
     for tag, r in (("init", first), ("final", last)):
         for n, b in enumerate(r["blocks"]):
             out["%s_u_%d" % (tag, n)] = b["u"]
+            if nscalars:
+                out["%s_s_%d" % (tag, n)] = b["s"]
             if mhd:
                 for f in ("b1", "b2", "b3"):
                     out["%s_%s_%d" % (tag, f, n)] = b[f]

@@ -24,11 +24,15 @@ class Golden:
         self.solver = self.meta["solver"]
         self.ng = int(self.meta["nghost"])
         self.ncycles = int(self.meta["ncycles"])
+        self.nscalars = int(self.meta.get("nscalars", 0))
+        self.eos = self.meta.get("eos", "adiabatic")
         self.dts = z["dts"]
         self.locs = [tuple(int(v) for v in l) for l in z["locs"]]
         self.final_time = float(z["final_time"])
         self.final_dt = float(z["final_dt"])
         self.fields = ("u", "b1", "b2", "b3") if self.mhd else ("u",)
+        if self.nscalars:
+            self.fields += ("s",)
         self.init = [{f: z["init_%s_%d" % (f, n)] for f in self.fields}
                      for n in range(len(self.locs))]
         self.final = [{f: z["final_%s_%d" % (f, n)] for f in self.fields}
@@ -41,7 +45,8 @@ class Golden:
 
 
 def oracle_from_golden(g):
-    p = oracle.params_from_athinput(g.par, g.mhd, g.solver, ng=g.ng)
+    p = oracle.params_from_athinput(g.par, g.mhd, g.solver, ng=g.ng, nscalars=g.nscalars,
+                                    eos=g.eos)
     m = oracle.OracleMesh(p)
     m.load_rst(g.as_rst("init"))
     m.initialize()
