@@ -440,6 +440,115 @@ void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int ord
 }
 
 // =============================================================================================
+// Passive scalars: PassiveScalars::CalculateFluxes + ComputeUpwindFlux
+// (scalars/calculate_scalar_fluxes.cpp:41-382), EquationOfState::PassiveScalar* (eos_scalars.cpp)
+// =============================================================================================
+// One thread per face and species: reconstruct the concentration r on both sides with the same
+// limiter as the hydro variables (dc_simple / plm_simple / ppm_simple.cpp) and upwind it with
+// the Riemann solver's mass flux.  Only the faces AddFluxDivergence reads are evaluated (the
+// reference also sweeps one more transverse row whose result is never used).  HBM-bound:
+// r (2S+2 values, stencil from L1/L2), mass flux in, s_flux out.
+template <int DIR, int ORDER>
+__global__ void __launch_bounds__(BX) k_scalar_flux(BlkDev b, ReconGeom g, double sfloor,
+                                                    int ni, int nj, int ntot) {
+  const int n1 = b.nc1, n2 = b.nc2;
+  const int sv = b.nc3*n2*n1;
+  const int st = (DIR == 0) ? 1 : ((DIR == 1) ? n1 : n1*n2);
+  const int sf = (DIR == 0) ? b.nc3*n2*(n1+1) : ((DIR == 1) ? b.nc3*(n2+1)*n1 : (b.nc3+1)*n2*n1);
+  const double *__restrict__ mflx = b.flux[DIR];       // IDN component = first sf entries
+  double *__restrict__ out = b.sflux[DIR];
+  for (int t = blockIdx.x*BX + threadIdx.x; t < ntot; t += gridDim.x*BX) {
+    int r = t / ni;
+    const int i = b.is + (t - r*ni);
+    const int kk = r / nj;
+    const int j = b.js + (r - kk*nj);
+    const int k = b.ks + kk;
+    const int oc = (k*n2 + j)*n1 + i;
+    const int c = (DIR == 0) ? i : ((DIR == 1) ? j : k);
+    int of;
+    if (DIR == 0) of = (k*n2 + j)*(n1+1) + i;
+    else if (DIR == 1) of = (k*(n2+1) + j)*n1 + i;
+    else of = oc;
+    const double fluid_flx = mflx[of];
+    for (int n = 0; n < b.ns; ++n) {
+      const double *__restrict__ q = b.r + n*sv + oc;
+      double rl, rr, dummy;
+      if (ORDER == 1) {
+        rl = q[-st]; rr = q[0];
+      } else if (ORDER == 2) {
+        plm(q[-2*st], q[-st], q[0], g.wp[DIR][c-1], g.wm[DIR][c-1], rl, dummy);
+        plm(q[-st], q[0], q[st], g.wp[DIR][c], g.wm[DIR][c], dummy, rr);
+      } else {
+        ppm(q[-3*st], q[-2*st], q[-st], q[0], q[st], rl, dummy);
+        ppm(q[-2*st], q[-st], q[0], q[st], q[2*st], dummy, rr);
+        // EquationOfState::ApplyPassiveScalarFloors (eos_scalars.cpp:161-175)
+        rl = (rl > sfloor) ? rl : sfloor;
+        rr = (rr > sfloor) ? rr : sfloor;
+      }
+      out[of + n*sf] = (fluid_flx >= 0.0) ? fluid_flx*rl : fluid_flx*rr;
+    }
+  }
+}
+
+void launch_scalar_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
+                          cudaStream_t s) {
+  if (b.ns <= 0) return;
+  const int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
+  for (int dir = 0; dir < 3; ++dir) {
+    if ((dir == 1 && !b.f2) || (dir == 2 && !b.f3)) continue;
+    const int ni = nx1 + (dir == 0), nj = nx2 + (dir == 1), nk = nx3 + (dir == 2);
+    const int ntot = ni*nj*nk;
+    const int grid = (ntot + BX - 1)/BX;
+#define AB_SF(D, O) k_scalar_flux<D,O><<<grid, BX, 0, s>>>(b, g, p.sfloor, ni, nj, ntot)
+    if (dir == 0) { if (order == 1) AB_SF(0,1); else if (order == 2) AB_SF(0,2); else AB_SF(0,3); }
+    else if (dir == 1) { if (order == 1) AB_SF(1,1); else if (order == 2) AB_SF(1,2); else AB_SF(1,3); }
+    else { if (order == 1) AB_SF(2,1); else if (order == 2) AB_SF(2,2); else AB_SF(2,3); }
+#undef AB_SF
+    ++g_launches;
+  }
+}
+
+// EquationOfState::PassiveScalarConservedToPrimitive (eos_scalars.cpp:31-60): floor s at
+// sfloor*rho (rho = the already floored u(IDN)), r = s/rho; and PassiveScalarPrimitiveToConserved
+// (eos_scalars.cpp:133-152) when TO_CONS.
+template <bool TO_CONS>
+__global__ void __launch_bounds__(BX) k_scalar_eos(BlkDev b, double sfloor, int il, int jl, int kl,
+                                                   int ni, int nj, int ntot) {
+  const int n1 = b.nc1, n2 = b.nc2;
+  const int sv = b.nc3*n2*n1;
+  for (int t = blockIdx.x*BX + threadIdx.x; t < ntot; t += gridDim.x*BX) {
+    int r = t / ni;
+    const int i = il + (t - r*ni);
+    const int kk = r / nj;
+    const int j = jl + (r - kk*nj);
+    const int o = ((kl + kk)*n2 + j)*n1 + i;
+    const double d = b.u[o];
+    for (int n = 0; n < b.ns; ++n) {
+      if (TO_CONS) {
+        b.s[o + n*sv] = b.r[o + n*sv]*d;
+      } else {
+        const double s0 = b.s[o + n*sv];
+        const double s_n = (s0 < sfloor*d) ? sfloor*d : s0;
+        if (s_n != s0) b.s[o + n*sv] = s_n;
+        b.r[o + n*sv] = s_n/d;
+      }
+    }
+  }
+}
+
+void launch_scalar_eos(const BlkDev &b, const Params &p, int to_cons, int il, int iu, int jl,
+                       int ju, int kl, int ku, cudaStream_t s) {
+  if (b.ns <= 0) return;
+  const int ni = iu-il+1, nj = ju-jl+1, nk = ku-kl+1;
+  const int ntot = ni*nj*nk;
+  if (ntot <= 0) return;
+  const int grid = (ntot + BX - 1)/BX;
+  if (to_cons) k_scalar_eos<true><<<grid, BX, 0, s>>>(b, p.sfloor, il, jl, kl, ni, nj, ntot);
+  else k_scalar_eos<false><<<grid, BX, 0, s>>>(b, p.sfloor, il, jl, kl, ni, nj, ntot);
+  ++g_launches;
+}
+
+// =============================================================================================
 // Field::ComputeCornerE (field/calculate_corner_e.cpp:28-236)
 // =============================================================================================
 __global__ void __launch_bounds__(BX) k_cc_e(BlkDev b, int i0, int i1, int j0, int k0) {
@@ -817,19 +926,19 @@ __device__ __forceinline__ double wave2(double out, double in, double w0, double
 }
 
 __global__ void __launch_bounds__(BX) k_wave_cc(BlkDev b, double *out, const double *in,
-                                                double w0, double w1) {
+                                                double w0, double w1, int nvar) {
   int i = b.is + blockIdx.x*BX + threadIdx.x;
   if (i > b.ie) return;
   int j = b.js + blockIdx.y, k = b.ks + blockIdx.z;
   long sv = (long)b.nc3*b.nc2*b.nc1;
   long o = CCI(b,0,k,j,i);
-#pragma unroll
-  for (int n = 0; n < NHYDRO; ++n) out[o+n*sv] = wave2(out[o+n*sv], in[o+n*sv], w0, w1);
+  for (int n = 0; n < nvar; ++n) out[o+n*sv] = wave2(out[o+n*sv], in[o+n*sv], w0, w1);
 }
 
 void launch_weighted_ave_cc(const BlkDev &b, double *out, const double *in, double w0,
-                            double w1, cudaStream_t s) {
-  k_wave_cc<<<grid3(b.ie-b.is+1, b.je-b.js+1, b.ke-b.ks+1), BX, 0, s>>>(b, out, in, w0, w1); ++g_launches;
+                            double w1, cudaStream_t s, int nvar) {
+  k_wave_cc<<<grid3(b.ie-b.is+1, b.je-b.js+1, b.ke-b.ks+1), BX, 0, s>>>(b, out, in, w0, w1,
+                                                                        nvar); ++g_launches;
 }
 
 struct FcPtrs { double *o[3]; const double *i[3]; };
@@ -862,7 +971,13 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 // Flattened over the active cells of the planes [k0, k0+nk) with a grid-stride loop, so that the
 // same kernel runs either with a full grid (alone) or with a small persistent grid (AB_CC_GRID
 // CTAs) next to the FP64-bound flux kernels of another slab.
-__global__ void __launch_bounds__(BX) k_integrate_cc(BlkDev b, int mode, int zero_init,
+// `c` selects the variable set: (u, u1, flux) with NVAR = NHYDRO for IntegrateHydro, or
+// (s, s1, s_flux) with NVAR = 0 -> c.nvar scalars for IntegrateScalars
+// (time_integrator.cpp:2141-2185, scalars/add_scalar_flux_divergence.cpp:43-97).
+struct CcSet { double *u, *u1; const double *f[3]; int nvar; };
+
+template <int NVAR>
+__global__ void __launch_bounds__(BX) k_integrate_cc(BlkDev b, CcSet c, int mode, int zero_init,
                                                      double delta, double g1, double g2,
                                                      double beta, double dt_val,
                                                      const double *dt_ptr, int k0, int ni,
@@ -883,41 +998,53 @@ __global__ void __launch_bounds__(BX) k_integrate_cc(BlkDev b, int mode, int zer
     const double dx1 = b.dx1f[i], dx2 = b.dx2f[j], dx3 = b.dx3f[k];
     const double a1 = dx2*dx3, a2 = dx1*dx3, a3 = dx1*dx2;
     const double vol = dx1*dx2*dx3;
+    const int nvar = NVAR > 0 ? NVAR : c.nvar;
 #pragma unroll
-    for (int n = 0; n < NHYDRO; ++n) {
+    for (int n = 0; n < nvar; ++n) {
       double uo;
       if (mode == 0) {
-        uo = b.u[o+n*sv];
+        uo = c.u[o+n*sv];
       } else if (mode == 1) {
-        uo = zero_init ? 0.0 : b.u[o+n*sv];
-        if (delta != 0.0) uo += delta*b.u1[o+n*sv];
+        uo = zero_init ? 0.0 : c.u[o+n*sv];
+        if (delta != 0.0) uo += delta*c.u1[o+n*sv];
       } else {
-        double u1v = zero_init ? 0.0 : b.u1[o+n*sv];
-        double un = b.u[o+n*sv];
+        double u1v = zero_init ? 0.0 : c.u1[o+n*sv];
+        double un = c.u[o+n*sv];
         if (delta != 0.0 || zero_init) {
           if (delta != 0.0) u1v += delta*un;
-          b.u1[o+n*sv] = u1v;
+          c.u1[o+n*sv] = u1v;
         }
         uo = wave2(un, u1v, g1, g2);
       }
-      double dflx = (a1*b.flux[0][o1+1+n*s1] - a1*b.flux[0][o1+n*s1]);
-      if (b.f2) dflx += (a2*b.flux[1][o2+n1+n*s2] - a2*b.flux[1][o2+n*s2]);
-      if (b.f3) dflx += (a3*b.flux[2][o3+n1*n2+n*s3] - a3*b.flux[2][o3+n*s3]);
-      b.u[o+n*sv] = uo - wght*dflx/vol;
+      double dflx = (a1*c.f[0][o1+1+n*s1] - a1*c.f[0][o1+n*s1]);
+      if (b.f2) dflx += (a2*c.f[1][o2+n1+n*s2] - a2*c.f[1][o2+n*s2]);
+      if (b.f3) dflx += (a3*c.f[2][o3+n1*n2+n*s3] - a3*c.f[2][o3+n*s3]);
+      c.u[o+n*sv] = uo - wght*dflx/vol;
     }
   }
 }
 
 void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
-                         cudaStream_t s, int kl, int ku, int grid) {
+                         cudaStream_t s, int kl, int ku, int grid, int scalars) {
   if (kl < 0) { kl = b.ks; ku = b.ke; }
   const int ni = b.ie-b.is+1, nj = b.je-b.js+1, nk = ku-kl+1;
   const int ntot = ni*nj*nk;
   int g = (ntot + BX - 1)/BX;
   if (grid > 0 && g > grid) g = grid;
-  k_integrate_cc<<<g, BX, 0, s>>>(b, mode, zero_init, delta, g1, g2, beta, dt_val, dt_ptr, kl,
-                                  ni, nj, ntot); ++g_launches;
+  CcSet c;
+  if (scalars) {
+    c.u = b.s; c.u1 = b.s1; c.nvar = b.ns;
+    for (int d = 0; d < 3; ++d) c.f[d] = b.sflux[d];
+    k_integrate_cc<0><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
+                                       dt_ptr, kl, ni, nj, ntot);
+  } else {
+    c.u = b.u; c.u1 = b.u1; c.nvar = NHYDRO;
+    for (int d = 0; d < 3; ++d) c.f[d] = b.flux[d];
+    k_integrate_cc<NHYDRO><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
+                                            dt_ptr, kl, ni, nj, ntot);
+  }
+  ++g_launches;
 }
 
 // register average of one face value (same modes as k_integrate_cc)
@@ -1073,6 +1200,8 @@ __global__ void __launch_bounds__(BX) k_phys_bc(BlkDev b, int mhd, int face, int
           b.w[CCI(b,n,k,j,gc)] = (refl && n == IVX) ? -v : v;
         }
         if (mhd) { double v = b.b[0][F1I(b,k,j,sn)]; b.b[0][F1I(b,k,j,gn)] = refl ? -v : v; }
+        // passive scalars: outflow_cc.cpp / reflect_cc.cpp on r (copy / mirror, no sign)
+        for (int n = 0; n < b.ns; ++n) b.r[CCI(b,n,k,j,gc)] = b.r[CCI(b,n,k,j,sc)];
       }
       if (mhd && k <= ku) b.b[1][F2I(b,k,j,gc)] = b.b[1][F2I(b,k,j,sc)];
       if (mhd && j <= ju) b.b[2][F3I(b,k,j,gc)] = b.b[2][F3I(b,k,j,sc)];
@@ -1085,6 +1214,7 @@ __global__ void __launch_bounds__(BX) k_phys_bc(BlkDev b, int mhd, int face, int
           b.w[CCI(b,n,k,gc,i)] = (refl && n == IVY) ? -v : v;
         }
         if (mhd) { double v = b.b[1][F2I(b,k,sn,i)]; b.b[1][F2I(b,k,gn,i)] = refl ? -v : v; }
+        for (int n = 0; n < b.ns; ++n) b.r[CCI(b,n,k,gc,i)] = b.r[CCI(b,n,k,sc,i)];
       }
       if (mhd && k <= ku) b.b[0][F1I(b,k,gc,i)] = b.b[0][F1I(b,k,sc,i)];
       if (mhd && i <= iu) b.b[2][F3I(b,k,gc,i)] = b.b[2][F3I(b,k,sc,i)];
@@ -1097,6 +1227,7 @@ __global__ void __launch_bounds__(BX) k_phys_bc(BlkDev b, int mhd, int face, int
           b.w[CCI(b,n,gc,j,i)] = (refl && n == IVZ) ? -v : v;
         }
         if (mhd) { double v = b.b[2][F3I(b,sn,j,i)]; b.b[2][F3I(b,gn,j,i)] = refl ? -v : v; }
+        for (int n = 0; n < b.ns; ++n) b.r[CCI(b,n,gc,j,i)] = b.r[CCI(b,n,sc,j,i)];
       }
       if (mhd && j <= ju) b.b[0][F1I(b,gc,j,i)] = b.b[0][F1I(b,sc,j,i)];
       if (mhd && i <= iu) b.b[1][F2I(b,gc,j,i)] = b.b[1][F2I(b,sc,j,i)];

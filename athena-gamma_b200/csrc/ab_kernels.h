@@ -29,7 +29,7 @@ void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);
 
 // WeightedAve special-casing of the reference (mesh/weighted_ave.cpp) for out = w0*out + w1*in
 void launch_weighted_ave_cc(const BlkDev &b, double *out, const double *in, double w0,
-                            double w1, cudaStream_t s);
+                            double w1, cudaStream_t s, int nvar = NHYDRO);
 void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const in[3],
                             double w0, double w1, cudaStream_t s);
 
@@ -42,7 +42,13 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 // (grid-stride loop) so that the kernel can share the SMs with a concurrent flux kernel.
 void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
-                         cudaStream_t s, int kl = -1, int ku = -1, int grid = 0);
+                         cudaStream_t s, int kl = -1, int ku = -1, int grid = 0,
+                         int scalars = 0);
+// passive scalars: s_flux from r and the hydro mass flux; r <-> s conversions on a cell range
+void launch_scalar_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
+                          cudaStream_t s);
+void launch_scalar_eos(const BlkDev &b, const Params &p, int to_cons, int il, int iu, int jl,
+                       int ju, int kl, int ku, cudaStream_t s);
 // Same for the face field + Field::CT (field/ct.cpp:31-116)
 void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,

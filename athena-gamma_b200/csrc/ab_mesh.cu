@@ -125,6 +125,7 @@ struct LocalBlock {
   long face_off[6], edge_off[12];
   int parity = 0;                         // (u,u1) swap state
   int parity_b = 0;                       // (b,b1) swap state
+  int parity_s = 0;                       // (s,s1) swap state
   unsigned long long *dtmin = nullptr;    // slot in the mesh-wide array
   bool cc_e_valid = false;                // cc_e written by the fused cons2prim
   bool has_phys_bc = false;
@@ -162,7 +163,7 @@ struct AbMesh {
     ab::CopyBox *pack = nullptr; int npack = 0; long maxpack = 0;     // to peer send buffers
     ab::CopyBox *phase1 = nullptr; int n1 = 0; long max1 = 0;         // ghost fill
     ab::CopyBox *phase2 = nullptr; int n2 = 0; long max2 = 0;         // 1-D/2-D duplicates
-  } plan[4];
+  } plan[8];
   std::map<int, PeerBuf> peer_state, peer_emf;
   ncclComm_t comm = nullptr;
   bool emf_built = false;
@@ -293,6 +294,7 @@ void fc_strides(const AbMesh *m, int comp, long &s3, long &s2) {
 long state_msg_count(const AbMesh *m, int ox1, int ox2, int ox3) {
   long n = ab::NHYDRO*cc_send_box(m, ox1, ox2, ox3).count();
   if (m->p.mhd) for (int c = 0; c < 3; ++c) n += fc_send_box(m, c, ox1, ox2, ox3).count();
+  n += m->p.nscalars*cc_send_box(m, ox1, ox2, ox3).count();   // s rides behind u and b
   return n;
 }
 
@@ -526,6 +528,10 @@ long reg_size(const AbMesh *m, int reg) {
     case AB_FLUX_X1: return ab::NHYDRO*nf1;
     case AB_FLUX_X2: return ab::NHYDRO*nf2;
     case AB_FLUX_X3: return ab::NHYDRO*nf3;
+    case AB_S: case AB_S1: case AB_R: return m->p.nscalars*ncc;
+    case AB_SFLUX_X1: return m->p.nscalars*nf1;
+    case AB_SFLUX_X2: return m->p.nscalars*nf2;
+    case AB_SFLUX_X3: return m->p.nscalars*nf3;
     default: break;
   }
   if (!m->p.mhd) return 0;
@@ -556,6 +562,9 @@ double **reg_slot(LocalBlock &L, int reg) {
     case AB_E3_X1F: return &d.ef[0][0]; case AB_E2_X1F: return &d.ef[0][1];
     case AB_E1_X2F: return &d.ef[1][0]; case AB_E3_X2F: return &d.ef[1][1];
     case AB_E2_X3F: return &d.ef[2][0]; case AB_E1_X3F: return &d.ef[2][1];
+    case AB_S: return &d.s; case AB_S1: return &d.s1; case AB_R: return &d.r;
+    case AB_SFLUX_X1: return &d.sflux[0]; case AB_SFLUX_X2: return &d.sflux[1];
+    case AB_SFLUX_X3: return &d.sflux[2];
     default: return nullptr;
   }
 }
@@ -580,6 +589,7 @@ int alloc_blocks(AbMesh *m) {
     d.nc1 = m->nc[0]; d.nc2 = m->nc[1]; d.nc3 = m->nc[2];
     d.is = m->is; d.ie = m->ie; d.js = m->js; d.je = m->je; d.ks = m->ks; d.ke = m->ke;
     d.ng = ng; d.f2 = m->f2; d.f3 = m->f3;
+    d.ns = p.nscalars;
     // sizes
     size_t tot = 0;
     for (int r = 0; r < AB_NREG; ++r) { L.regsize[r] = reg_size(m, r); tot += align256(L.regsize[r]*8); }
@@ -723,6 +733,7 @@ int build_state_plan(AbMesh *m, int which) {
         add_box(ph1, L.d.u, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), ab::NHYDRO, rb, 0, 0, 0);
       }
       long roff = ab::NHYDRO*rb.count();
+      const int ns = m->p.nscalars;
       if (mhd) {
         for (int c = 0; c < 3; ++c) {
           Box frb = fc_recv_box(m, c, nb.ox1, nb.ox2, nb.ox3);
@@ -749,6 +760,17 @@ int build_state_plan(AbMesh *m, int which) {
           }
         }
       }
+      if (ns > 0) {   // PassiveScalars::sbvar: same boxes as u (scalars.cpp:59-72)
+        if (local) {
+          LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
+          add_box(ph1, L.d.s, cs3, cs2, ncc, N.d.s, cs3, cs2, ncc, ns, rb, sb.si, sb.sj, sb.sk);
+        } else {
+          double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}] + roff;
+          Box z = {0, rb.ei-rb.si, 0, rb.ej-rb.sj, 0, rb.ek-rb.sk};
+          long s2 = z.ei+1, s3 = s2*(z.ej+1);
+          add_box(ph1, L.d.s, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), ns, rb, 0, 0, 0);
+        }
+      }
       // ---- sending side (remote only): pack my active zones into the peer buffer
       if (!local) {
         double *dst = m->peer_state[nb.rank].send + send_off[{(int)l, (int)n}];
@@ -766,6 +788,8 @@ int build_state_plan(AbMesh *m, int which) {
           add_box(pack, dst + soff, t3, t2, 0, L.d.b[c], fs3, fs2, 0, 1, fz, fb.si, fb.sj, fb.sk);
           soff += fb.count();
         }
+        if (ns > 0)
+          add_box(pack, dst + soff, s3, s2, s3*(z.ek+1), L.d.s, cs3, cs2, ncc, ns, z, lb2.si, lb2.sj, lb2.sk);
       }
     }
   }
@@ -855,9 +879,9 @@ int peer_exchange(AbMesh *m, std::map<int, PeerBuf> &peers) {
 int plan_index(AbMesh *m) {
   // all local blocks swap registers in lockstep inside the driver; a mixed state (possible
   // only through per-block ab_swap calls) forces a rebuild
-  int pu = m->lb[0].parity, pb = m->lb[0].parity_b;
-  for (auto &L : m->lb) if (L.parity != pu || L.parity_b != pb) return -1;
-  return pu | (pb << 1);
+  int pu = m->lb[0].parity, pb = m->lb[0].parity_b, ps = m->lb[0].parity_s;
+  for (auto &L : m->lb) if (L.parity != pu || L.parity_b != pb || L.parity_s != ps) return -1;
+  return pu | (pb << 1) | (ps << 2);
 }
 
 int bvals_exchange(AbMesh *m) {
@@ -902,6 +926,7 @@ void primitives(AbMesh *m, LocalBlock &L, int with_dt = 0) {
   // ComputeCornerE reads, [is-1,ie+1]^dim, lie inside the cons2prim range)
   int flags = (m->p.mhd && !L.has_phys_bc ? 1 : 0) | (with_dt ? 2 : 0);
   ab::launch_cons2prim(L.d, m->kp, il, iu, jl, ju, kl, ku, m->stream, flags, L.dtmin);
+  ab::launch_scalar_eos(L.d, m->kp, 0, il, iu, jl, ju, kl, ku, m->stream);
   L.cc_e_valid = (flags & 1) != 0;
 }
 
@@ -924,22 +949,26 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
     ab::launch_phys_bc(L.d, mhd, 0, B.bcs[0] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
     if (mhd) ab::launch_calc_bcc(L.d, is-ng, is-1, bjs, bje, bks, bke, s);
     ab::launch_prim2cons(L.d, m->kp, is-ng, is-1, bjs, bje, bks, bke, s);
+    ab::launch_scalar_eos(L.d, m->kp, 1, is-ng, is-1, bjs, bje, bks, bke, s);
   }
   if (app[1]) {
     ab::launch_phys_bc(L.d, mhd, 1, B.bcs[1] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
     if (mhd) ab::launch_calc_bcc(L.d, ie+1, ie+ng, bjs, bje, bks, bke, s);
     ab::launch_prim2cons(L.d, m->kp, ie+1, ie+ng, bjs, bje, bks, bke, s);
+    ab::launch_scalar_eos(L.d, m->kp, 1, ie+1, ie+ng, bjs, bje, bks, bke, s);
   }
   if (m->f2) {
     if (app[2]) {
       ab::launch_phys_bc(L.d, mhd, 2, B.bcs[2] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, js-ng, js-1, bks, bke, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, js-ng, js-1, bks, bke, s);
+      ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, js-ng, js-1, bks, bke, s);
     }
     if (app[3]) {
       ab::launch_phys_bc(L.d, mhd, 3, B.bcs[3] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, je+1, je+ng, bks, bke, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, je+1, je+ng, bks, bke, s);
+      ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, je+1, je+ng, bks, bke, s);
     }
   }
   if (m->f3) {
@@ -948,11 +977,13 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
       ab::launch_phys_bc(L.d, mhd, 4, B.bcs[4] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ks-ng, ks-1, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, bjs, bje, ks-ng, ks-1, s);
+      ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, bjs, bje, ks-ng, ks-1, s);
     }
     if (app[5]) {
       ab::launch_phys_bc(L.d, mhd, 5, B.bcs[5] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ke+1, ke+ng, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, bjs, bje, ke+1, ke+ng, s);
+      ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, bjs, bje, ke+1, ke+ng, s);
     }
   }
 }
@@ -988,6 +1019,8 @@ void swap_fc(LocalBlock &L) {
   L.parity_b ^= 1;
 }
 
+void swap_sc(LocalBlock &L) { std::swap(L.d.s, L.d.s1); L.parity_s ^= 1; }
+
 int one_cycle(AbMesh *m) {
   const double *dtp = m->state + 1;
   for (int stage = 1; stage <= m->nstages; ++stage) {
@@ -1008,6 +1041,7 @@ int one_cycle(AbMesh *m) {
         }
       }
       if (m->p.mhd) ab::launch_corner_e(L.d, m->stream, L.cc_e_valid ? 1 : 0);
+      ab::launch_scalar_fluxes(L.d, L.g, m->kp, order, m->stream);   // CALC_SCLRFLX
     }
     int rc = emf_exchange(m);
     if (rc) return rc;
@@ -1021,10 +1055,18 @@ int one_cycle(AbMesh *m) {
           swap_fc(L);
           ab::launch_integrate_fc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, m->stream);
         }
+        if (m->p.nscalars > 0) {   // INT_SCLR (time_integrator.cpp:2141-2185)
+          swap_sc(L);
+          ab::launch_integrate_cc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp,
+                                  m->stream, -1, -1, 0, 1);
+        }
       } else {
         ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
         if (m->p.mhd)
           ab::launch_integrate_fc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
+        if (m->p.nscalars > 0)
+          ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s],
+                                  0.0, dtp, m->stream, -1, -1, 0, 1);
       }
     }
     rc = bvals_exchange(m);
@@ -1150,6 +1192,9 @@ static int validate_params(const AbMeshParams *p) {
                               "(kernels use 32-bit element offsets); use smaller MeshBlocks");
   }
   if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(AB_ERR_ARG, "bad rank/nranks");
+  if (p->nscalars < 0 || p->nscalars > 16) return fail(AB_ERR_ARG, "nscalars must be in [0, 16]");
+  if (p->eos != AB_EOS_ADIABATIC)
+    return fail(AB_ERR_ARG, "only the adiabatic EOS is implemented on the device path");
   return AB_OK;
 }
 
@@ -1159,6 +1204,9 @@ static void host_setup(AbMesh *m, const AbMeshParams *p) {
   m->ndim = m->f3 ? 3 : (m->f2 ? 2 : 1);
   m->kp.gamma = p->gamma; m->kp.dfloor = p->dfloor; m->kp.pfloor = p->pfloor;
   m->kp.mhd = p->mhd; m->kp.solver = p->solver; m->kp.xorder = p->xorder;
+  // EquationOfState ctor: scalar_floor_ = hydro/sfloor, default sqrt(1024*FLT_MIN)
+  if (m->p.sfloor == 0.0) m->p.sfloor = std::sqrt(1024.0*(double)FLT_MIN);
+  m->kp.sfloor = m->p.sfloor;
   int ng = p->nghost;
   // MeshBlock index ranges (mesh/meshblock.cpp:55-80)
   m->is = ng; m->ie = ng + p->bx1 - 1; m->nc[0] = p->bx1 + 2*ng;
@@ -1179,7 +1227,7 @@ int ab_mesh_destroy(AbMesh *m) {
   cudaSetDevice(m->p.device);
   cudaStreamSynchronize(m->stream);
   for (auto &L : m->lb) cudaFree(L.base);
-  for (int i = 0; i < 4; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase2); }
+  for (int i = 0; i < 8; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase2); }
   for (auto &kv : m->peer_state) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   cudaFree(m->state); cudaFree(m->dt_hist); cudaFree(m->dtmin);
@@ -1302,6 +1350,11 @@ int ab_weighted_ave(AbMesh *m, int lid, int out_reg, int in_reg, const double w[
   if ((out_reg == AB_U || out_reg == AB_U1) && (in_reg == AB_U || in_reg == AB_U1)) {
     ab::launch_weighted_ave_cc(L.d, out_reg == AB_U ? L.d.u : L.d.u1,
                                in_reg == AB_U ? L.d.u : L.d.u1, w[0], w[1], m->stream);
+  } else if ((out_reg == AB_S || out_reg == AB_S1) && (in_reg == AB_S || in_reg == AB_S1) &&
+             m->p.nscalars > 0) {
+    ab::launch_weighted_ave_cc(L.d, out_reg == AB_S ? L.d.s : L.d.s1,
+                               in_reg == AB_S ? L.d.s : L.d.s1, w[0], w[1], m->stream,
+                               m->p.nscalars);
   } else if ((out_reg == AB_B_X1F || out_reg == AB_B1_X1F) &&
              (in_reg == AB_B_X1F || in_reg == AB_B1_X1F) && m->p.mhd) {
     ab::launch_weighted_ave_fc(L.d, out_reg == AB_B_X1F ? L.d.b : L.d.b1,
@@ -1316,7 +1369,8 @@ int ab_swap(AbMesh *m, int lid, int reg) {
   GET_L(m, lid);
   if (reg == AB_U) swap_cc(L);
   else if (reg == AB_B_X1F && m->p.mhd) swap_fc(L);
-  else return fail(AB_ERR_ARG, "ab_swap: reg must be AB_U or AB_B_X1F");
+  else if (reg == AB_S && m->p.nscalars > 0) swap_sc(L);
+  else return fail(AB_ERR_ARG, "ab_swap: reg must be AB_U, AB_B_X1F or AB_S");
   return AB_OK;
 }
 int ab_zero(AbMesh *m, int lid, int reg) {
@@ -1325,8 +1379,10 @@ int ab_zero(AbMesh *m, int lid, int reg) {
     CK(cudaMemsetAsync(L.d.u1, 0, L.regsize[AB_U1]*8, m->stream));
   } else if (reg == AB_B1_X1F && m->p.mhd) {
     for (int d = 0; d < 3; ++d) CK(cudaMemsetAsync(L.d.b1[d], 0, L.regsize[AB_B1_X1F + d]*8, m->stream));
+  } else if (reg == AB_S1 && m->p.nscalars > 0) {
+    CK(cudaMemsetAsync(L.d.s1, 0, L.regsize[AB_S1]*8, m->stream));
   } else {
-    return fail(AB_ERR_ARG, "ab_zero: reg must be AB_U1 or AB_B1_X1F");
+    return fail(AB_ERR_ARG, "ab_zero: reg must be AB_U1, AB_B1_X1F or AB_S1");
   }
   ab::g_launches++;
   return AB_OK;
@@ -1336,6 +1392,38 @@ int ab_add_flux_div(AbMesh *m, int lid, double wght) {
   ab::launch_integrate_cc(L.d, 0, 0, 0.0, 0.0, 0.0, 1.0, wght, nullptr, m->stream);
   CK(cudaGetLastError());
   return AB_OK;
+}
+int ab_calc_scalar_fluxes(AbMesh *m, int lid, int order) {
+  GET_L(m, lid);
+  if (m->p.nscalars <= 0) return fail(AB_ERR_STATE, "NSCALARS == 0");
+  if (order < 1 || order > 3) return fail(AB_ERR_ARG, "order must be 1, 2 or 3");
+  ab::launch_scalar_fluxes(L.d, L.g, m->kp, order, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_add_scalar_flux_div(AbMesh *m, int lid, double wght) {
+  GET_L(m, lid);
+  if (m->p.nscalars <= 0) return fail(AB_ERR_STATE, "NSCALARS == 0");
+  ab::launch_integrate_cc(L.d, 0, 0, 0.0, 0.0, 0.0, 1.0, wght, nullptr, m->stream, -1, -1, 0, 1);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+static int scalar_eos_range(AbMesh *m, int lid, int to_cons, int il, int iu, int jl, int ju,
+                            int kl, int ku) {
+  GET_L(m, lid);
+  if (m->p.nscalars <= 0) return fail(AB_ERR_STATE, "NSCALARS == 0");
+  if (il < 0 || iu >= m->nc[0] || jl < 0 || ju >= m->nc[1] || kl < 0 || ku >= m->nc[2] ||
+      il > iu || jl > ju || kl > ku)
+    return fail(AB_ERR_ARG, "cell range outside the MeshBlock");
+  ab::launch_scalar_eos(L.d, m->kp, to_cons, il, iu, jl, ju, kl, ku, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_scalar_cons2prim(AbMesh *m, int lid, int il, int iu, int jl, int ju, int kl, int ku) {
+  return scalar_eos_range(m, lid, 0, il, iu, jl, ju, kl, ku);
+}
+int ab_scalar_prim2cons(AbMesh *m, int lid, int il, int iu, int jl, int ju, int kl, int ku) {
+  return scalar_eos_range(m, lid, 1, il, iu, jl, ju, kl, ku);
 }
 int ab_ct(AbMesh *m, int lid, double wght) {
   GET_L(m, lid);

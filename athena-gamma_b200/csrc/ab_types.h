@@ -26,6 +26,9 @@ struct BlkDev {
   double *wght[3];                // CT upwind weights (face-array shapes)
   double *e[3];                   // edge EMFs: x1e (nc3+1)(nc2+1)nc1, x2e (nc3+1)nc2(nc1+1), x3e nc3(nc2+1)(nc1+1)
   double *cc_e;                   // 3 x nc3 x nc2 x nc1 cell-centred EMF
+  // passive scalars (src/scalars/scalars.hpp:40-56): ns x nc3 x nc2 x nc1; fluxes on the faces
+  int ns;
+  double *s, *s1, *r, *sflux[3];
   // 1-D geometry (src/coordinates/coordinates.cpp:125-145, cartesian.cpp:25-75)
   const double *x1f, *x2f, *x3f, *x1v, *x2v, *x3v, *dx1f, *dx2f, *dx3f;
 };
@@ -57,6 +60,7 @@ struct CopyBox {
 struct Params {
   double gamma, dfloor, pfloor;
   int mhd, solver, xorder;
+  double sfloor;                  // passive-scalar concentration floor (hydro/sfloor)
 };
 
 }  // namespace ab

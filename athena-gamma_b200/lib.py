@@ -13,7 +13,9 @@ INTEGRATOR = {"vl2": 0, "rk2": 1, "rk1": 2, "rk3": 3}
 REG = {"u": 0, "u1": 1, "w": 2, "bcc": 3, "b1": 4, "b2": 5, "b3": 6, "b1_1": 7, "b1_2": 8,
        "b1_3": 9, "flux1": 10, "flux2": 11, "flux3": 12, "e1": 13, "e2": 14, "e3": 15,
        "wght1": 16, "wght2": 17, "wght3": 18, "e3_x1f": 19, "e2_x1f": 20, "e1_x2f": 21,
-       "e3_x2f": 22, "e2_x3f": 23, "e1_x3f": 24}
+       "e3_x2f": 22, "e2_x3f": 23, "e1_x3f": 24,
+       "s": 25, "s1": 26, "r": 27, "sflux1": 28, "sflux2": 29, "sflux3": 30}
+EOS = {"adiabatic": 0, "isothermal": 1}
 COORD = {"x1f": 0, "x2f": 1, "x3f": 2, "x1v": 3, "x2v": 4, "x3v": 5, "dx1f": 6, "dx2f": 7,
          "dx3f": 8}
 
@@ -25,7 +27,8 @@ SYMBOLS = [
     "ab_upload", "ab_download", "ab_download_coord", "ab_comm_unique_id", "ab_comm_init",
     "ab_cons2prim", "ab_prim2cons", "ab_primitives", "ab_calc_fluxes", "ab_corner_e",
     "ab_weighted_ave", "ab_swap", "ab_zero", "ab_add_flux_div", "ab_ct", "ab_physical_bcs",
-    "ab_new_block_dt", "ab_emf_exchange", "ab_bvals_exchange", "ab_mesh_initialize",
+    "ab_calc_scalar_fluxes", "ab_add_scalar_flux_div", "ab_scalar_cons2prim",
+    "ab_scalar_prim2cons", "ab_new_block_dt", "ab_emf_exchange", "ab_bvals_exchange", "ab_mesh_initialize",
     "ab_mesh_cycles", "ab_mesh_set_async", "ab_mesh_state", "ab_mesh_set_time_dt",
     "ab_mesh_dt_history", "ab_mesh_profile", "ab_mesh_profile_read",
     "ab_mesh_launch_count", "ab_mesh_stream", "ab_mesh_sync",
@@ -42,7 +45,9 @@ class AbMeshParams(C.Structure):
                 ("solver", C.c_int), ("xorder", C.c_int), ("integrator", C.c_int),
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
                 ("cfl_number", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double),
-                ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int)]
+                ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
+                ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
+                ("iso_sound_speed", C.c_double)]
 
 
 class AbError(RuntimeError):
@@ -89,6 +94,10 @@ def load():
     L.ab_swap.argtypes = [vp, ip, ip]
     L.ab_zero.argtypes = [vp, ip, ip]
     L.ab_add_flux_div.argtypes = [vp, ip, C.c_double]
+    L.ab_calc_scalar_fluxes.argtypes = [vp, ip, ip]
+    L.ab_add_scalar_flux_div.argtypes = [vp, ip, C.c_double]
+    L.ab_scalar_cons2prim.argtypes = [vp, ip] + [ip] * 6
+    L.ab_scalar_prim2cons.argtypes = [vp, ip] + [ip] * 6
     L.ab_ct.argtypes = [vp, ip, C.c_double]
     L.ab_new_block_dt.argtypes = [vp, ip, dp]
     for f in ("ab_emf_exchange", "ab_bvals_exchange", "ab_mesh_initialize", "ab_mesh_sync"):

@@ -32,6 +32,14 @@ class MeshBlock:
         n1, n2, n3 = self.ncells1, self.ncells2, self.ncells3
         if name in ("u", "u1", "w"):
             return (5, n3, n2, n1)
+        if name in ("s", "s1", "r"):
+            return (self.pmy_mesh.params.nscalars, n3, n2, n1)
+        if name in ("sflux1", "sflux2", "sflux3"):
+            ns = self.pmy_mesh.params.nscalars
+            d = int(name[-1]) - 1
+            sh = [n3, n2, n1]
+            sh[2 - d] += 1
+            return (ns,) + tuple(sh)
         if name == "bcc":
             return (3, n3, n2, n1)
         if name in ("b1", "b1_1", "wght1", "e2_x1f", "e3_x1f"):
@@ -82,7 +90,8 @@ class MeshBlock:
 
 class Mesh:
     @staticmethod
-    def make_params(pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0):
+    def make_params(pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0, nscalars=0,
+                    eos="adiabatic"):
         """AbMeshParams from the athinput blocks + the configure-time choices."""
         p = lib.AbMeshParams()
         p.nx1 = pin.get_integer("mesh", "nx1")
@@ -120,16 +129,23 @@ class Mesh:
         p.tlim = pin.get_real("time", "tlim")
         p.start_time = pin.get_or_add_real("time", "start_time", 0.0)
         p.rank, p.nranks, p.device = rank, nranks, device
+        # configure.py --nscalars / --eos ; hydro/sfloor (eos ctor default like dfloor)
+        p.nscalars = int(nscalars)
+        p.eos = lib.EOS[eos]
+        p.sfloor = pin.get_or_add_real("hydro", "sfloor", DEFAULT_FLOOR)
+        p.iso_sound_speed = pin.get_or_add_real("hydro", "iso_sound_speed", 0.0)
         return p, flux
 
-    def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0):
-        """pin: ParameterInput (or athinput text); mhd / flux / nghost: what configure.py's
-        -b / --flux / --nghost fix at compile time in the reference."""
+    def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0, nscalars=0,
+                 eos="adiabatic"):
+        """pin: ParameterInput (or athinput text); mhd / flux / nghost / nscalars / eos: what
+        configure.py's -b / --flux / --nghost / --nscalars / --eos fix at compile time in the
+        reference."""
         if not isinstance(pin, ParameterInput):
             pin = ParameterInput(text=pin)
         self.pin = pin
         self.L = lib.load()
-        p, flux = self.make_params(pin, mhd, flux, nghost, rank, nranks, device)
+        p, flux = self.make_params(pin, mhd, flux, nghost, rank, nranks, device, nscalars, eos)
         self.params = p
         self.mhd, self.flux = bool(mhd), flux
         self.nlim = pin.get_or_add_integer("time", "nlim", -1)
@@ -223,11 +239,11 @@ class MeshPlan:
     """Host-only twin of Mesh (ab_plan_create): MeshBlock list, load balance and the
     cross-rank message plan of one rank.  Needs no GPU; owns no device memory."""
 
-    def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1):
+    def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1, nscalars=0):
         if not isinstance(pin, ParameterInput):
             pin = ParameterInput(text=pin)
         self.L = lib.load()
-        p, _ = Mesh.make_params(pin, mhd, flux, nghost, rank, nranks, 0)
+        p, _ = Mesh.make_params(pin, mhd, flux, nghost, rank, nranks, 0, nscalars)
         self.params = p
         h = C.c_void_p()
         lib.check(self.L.ab_plan_create(C.byref(p), C.byref(h)))

@@ -33,7 +33,11 @@ enum { AB_U = 0, AB_U1 = 1, AB_W = 2, AB_BCC = 3,
        AB_E_X1E = 13, AB_E_X2E = 14, AB_E_X3E = 15,
        AB_WGHT_X1F = 16, AB_WGHT_X2F = 17, AB_WGHT_X3F = 18,
        AB_E3_X1F = 19, AB_E2_X1F = 20, AB_E1_X2F = 21, AB_E3_X2F = 22, AB_E2_X3F = 23,
-       AB_E1_X3F = 24, AB_NREG = 25 };
+       AB_E1_X3F = 24,
+       /* PassiveScalars::s, s1, r, s_flux[3] (src/scalars/scalars.hpp:40-56) */
+       AB_S = 25, AB_S1 = 26, AB_R = 27, AB_SFLUX_X1 = 28, AB_SFLUX_X2 = 29, AB_SFLUX_X3 = 30,
+       AB_NREG = 31 };
+enum { AB_EOS_ADIABATIC = 0, AB_EOS_ISOTHERMAL = 1 };   /* configure.py --eos */
 
 /* What configure.py flags + the athinput <mesh>/<meshblock>/<time>/<hydro> blocks fix
  * (src/defs.hpp.in:18-102, src/mesh/mesh.cpp:63-120, src/eos/adiabatic_mhd.cpp:26-31). */
@@ -51,6 +55,10 @@ typedef struct {
   double cfl_number, tlim, start_time;
   int rank, nranks;             /* this process / number of processes (one GPU each) */
   int device;                   /* CUDA device ordinal for this process */
+  int nscalars;                 /* NSCALARS (configure.py --nscalars)   */
+  int eos;                      /* AB_EOS_* (configure.py --eos)        */
+  double sfloor;                /* hydro/sfloor (0 -> eos ctor default sqrt(1024*FLT_MIN)) */
+  double iso_sound_speed;       /* hydro/iso_sound_speed (isothermal EOS) */
 } AbMeshParams;
 
 typedef struct AbMesh AbMesh;
@@ -101,16 +109,29 @@ int ab_calc_fluxes(AbMesh *m, int lid, int order, double dt);
 /* Field::ComputeCornerE (field/calculate_corner_e.cpp:28-236) */
 int ab_corner_e(AbMesh *m, int lid);
 /* MeshBlock::WeightedAve (mesh/weighted_ave.cpp): out = f(w[0]*out, w[1]*in); regs AB_U/AB_U1
- * (cell-centred) or AB_B_X1F/AB_B1_X1F (all three face arrays of b / b1) */
+ * (cell-centred), AB_S/AB_S1 (passive scalars) or AB_B_X1F/AB_B1_X1F (all three face arrays
+ * of b / b1) */
 int ab_weighted_ave(AbMesh *m, int lid, int out_reg, int in_reg, const double w[5]);
-/* AthenaArray::SwapAthenaArray on (u,u1) when reg==AB_U, on (b,b1) when reg==AB_B_X1F */
+/* AthenaArray::SwapAthenaArray on (u,u1) when reg==AB_U, (b,b1) when reg==AB_B_X1F, (s,s1)
+ * when reg==AB_S */
 int ab_swap(AbMesh *m, int lid, int reg);
-/* AthenaArray::ZeroClear on u1 (AB_U1) or b1 (AB_B1_X1F) (time_integrator.cpp:1386-1397) */
+/* AthenaArray::ZeroClear on u1 (AB_U1), b1 (AB_B1_X1F) or s1 (AB_S1)
+ * (time_integrator.cpp:1386-1410) */
 int ab_zero(AbMesh *m, int lid, int reg);
 /* Hydro::AddFluxDivergence(wght, u) (hydro/add_flux_divergence.cpp:39-96) */
 int ab_add_flux_div(AbMesh *m, int lid, double wght);
 /* Field::CT(wght, b) (field/ct.cpp:31-116) */
 int ab_ct(AbMesh *m, int lid, double wght);
+/* ---- passive scalars (NSCALARS > 0), src/scalars + src/eos/eos_scalars.cpp ---------------- */
+/* PassiveScalars::CalculateFluxes(r, order) (scalars/calculate_scalar_fluxes.cpp:41-382);
+ * needs the mass flux of ab_calc_fluxes */
+int ab_calc_scalar_fluxes(AbMesh *m, int lid, int order);
+/* PassiveScalars::AddFluxDivergence(wght, s) (scalars/add_scalar_flux_divergence.cpp:43-97) */
+int ab_add_scalar_flux_div(AbMesh *m, int lid, double wght);
+/* EquationOfState::PassiveScalarConservedToPrimitive / PrimitiveToConserved
+ * (eos/eos_scalars.cpp:31-60,133-152) on a cell range (uses the current u(IDN)) */
+int ab_scalar_cons2prim(AbMesh *m, int lid, int il, int iu, int jl, int ju, int kl, int ku);
+int ab_scalar_prim2cons(AbMesh *m, int lid, int il, int iu, int jl, int ju, int kl, int ku);
 /* BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620): outflow and reflecting
  * faces (cc/outflow_cc.cpp, cc/hydro/reflect_hydro.cpp, fc/outflow_fc.cpp, fc/reflect_fc.cpp) */
 int ab_physical_bcs(AbMesh *m, int lid);
@@ -124,7 +145,7 @@ int ab_new_block_dt(AbMesh *m, int lid, double *dt_out);
  * (bvals/fc/flux_correction_fc.cpp:623-680,1610-1749) */
 int ab_emf_exchange(AbMesh *m);
 /* hbvar / fbvar SendBoundaryBuffers + ReceiveBoundaryBuffers + SetBoundaries
- * (bvals/bvals_var.cpp:212-296) for u (and b when MHD) */
+ * (bvals/bvals_var.cpp:212-296) for u (and b when MHD, s when NSCALARS > 0) */
 int ab_bvals_exchange(AbMesh *m);
 
 /* ---- whole-mesh driver (host side of the path): Mesh::Initialize after ProblemGenerator

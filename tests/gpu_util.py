@@ -15,7 +15,7 @@ def pin_from_par(par):
 
 def mesh_from_golden(g, **kw):
     pin = pin_from_par(g.par)
-    m = ab.Mesh(pin, mhd=g.mhd, flux=g.solver, nghost=g.ng, **kw)
+    m = ab.Mesh(pin, mhd=g.mhd, flux=g.solver, nghost=g.ng, nscalars=g.nscalars, eos=g.eos, **kw)
     for n, loc in enumerate(g.locs):
         pmb = m.block_of(*loc)
         if pmb is None:

@@ -24,7 +24,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     names = sys.argv[1:] or ["c5_blast_hlld_plm_vl2_8blk", "c2_linwave_hlld_plm_vl2_8blk",
                              "c4_kh_hllc_ppm_rk2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
-                             "c1_sod_hllc_plm_vl2_2blk"]
+                             "c1_sod_hllc_plm_vl2_2blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1",
+                             "khs_lhllc_plm_vl2_4blk_s1"]
     ok = True
     for name in names:
         g = util.Golden(name)

@@ -27,8 +27,11 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # 6 ints, 6 doubles, 6 ints (bc), 5 ints, 6 doubles, 3 ints
-    assert C.sizeof(ab.lib.AbMeshParams) == 6 * 4 + 6 * 8 + 6 * 4 + 5 * 4 + 4 + 6 * 8 + 3 * 4 + 4
+    # 6 ints, 6 doubles, 6 ints (bc), 5 ints (+pad), 6 doubles, 3 + 2 ints (+pad), 2 doubles;
+    # checked against gcc's sizeof / offsetof of include/athena_b200.h
+    P = ab.lib.AbMeshParams
+    assert C.sizeof(P) == 6 * 4 + 6 * 8 + 6 * 4 + 5 * 4 + 4 + 6 * 8 + 5 * 4 + 4 + 2 * 8 == 208
+    assert P.nscalars.offset == 180 and P.sfloor.offset == 192
 
 
 def test_no_cpu_fallback_without_device():

@@ -29,6 +29,12 @@ CASES = [
     ("blast_refl_hlld_plm_vl2_8blk", None, None),
     ("blast_mixedbc_hllc_plm_vl2_8blk", None, None),
     ("blast_hlld_ppm_rk3_8blk", None, None),
+    # passive scalars
+    ("khs_lhllc_plm_vl2_4blk_s1", None, None),
+    ("sods_lhllc_plm_vl2_2blk_s1", None, None),
+    ("khs3d_hllc_ppm_rk3_8blk_s2", None, None),
+    ("khs3d_mhd_hlld_plm_vl2_8blk_s1", None, None),
+    ("khs3d_mhd_hlld_plm_vl2_8blk_s1", 1, None),
 ]
 
 
@@ -48,7 +54,12 @@ def perturbed(g, seed):
         u[4][mask] = 1e-3
         nb["u"] = u
         for f in g.fields[1:]:
-            nb[f] = blk[f] + rng.normal(0, 0.3, blk[f].shape)
+            if f == "s":      # concentrations in [0, 1], a few below the floor
+                c = rng.random(blk[f].shape)
+                c[rng.random(c.shape) < 0.01] = -1e-3
+                nb[f] = c * u[0]
+            else:
+                nb[f] = blk[f] + rng.normal(0, 0.3, blk[f].shape)
         init.append(nb)
     return init
 
@@ -65,6 +76,8 @@ def test_task_by_task(name, xorder, solver):
     m.initialize()
     L, h = m.L, m.h
     names_cc = ("u", "w") + (("bcc", "b1", "b2", "b3") if g.mhd else ())
+    if g.nscalars:
+        names_cc += ("s", "r")
 
     def compare(names, what):
         for pmb in m.my_blocks:
@@ -86,6 +99,12 @@ def test_task_by_task(name, xorder, solver):
                 om.L.ao_corner_e(om.h, b)
                 ab_check(L.ab_corner_e(h, pmb.lid), L)
         compare_fluxes(m, om, g, name, order)
+        if g.nscalars:
+            for pmb in m.my_blocks:
+                b = om.block_of(pmb.lx1, pmb.lx2, pmb.lx3)
+                om.L.ao_calc_scalar_fluxes(om.h, b, order)
+                ab_check(L.ab_calc_scalar_fluxes(h, pmb.lid, order), L)
+            compare_scalar_fluxes(m, om, name, order)
         if g.mhd:
             compare_interior_emf(m, om, name, "corner_e order %d" % order)
             om.L.ao_emf_exchange(om.h)
@@ -111,11 +130,23 @@ def test_task_by_task(name, xorder, solver):
             ab_check(L.ab_weighted_ave(h, pmb.lid, 7, 4, w), L)
             ab_check(L.ab_swap(h, pmb.lid, 4), L)
             ab_check(L.ab_ct(h, pmb.lid, 0.5 * dt), L)
+    if g.nscalars:
+        # IntegrateScalars: the oracle runs the whole task (stage 1), the device task by task
+        beta0 = 0.5 if g.par["time"].get("integrator", "vl2") == "vl2" else 1.0
+        S, S1 = 25, 26
+        for pmb in m.my_blocks:
+            b = om.block_of(pmb.lx1, pmb.lx2, pmb.lx3)
+            om.L.ao_integrate_scalars(om.h, b, 1)
+            ab_check(L.ab_zero(h, pmb.lid, S1), L)
+            ab_check(L.ab_weighted_ave(h, pmb.lid, S1, S, w), L)
+            ab_check(L.ab_swap(h, pmb.lid, S), L)
+            ab_check(L.ab_add_scalar_flux_div(h, pmb.lid, beta0 * dt), L)
+        om.L.ao_exchange_scalars(om.h)
     om.L.ao_exchange_cc(om.h)
     om.L.ao_exchange_fc(om.h)
     ab_check(L.ab_bvals_exchange(h), L)
-    compare(("u", "u1") + (("b1", "b2", "b3", "b1_1", "b1_2", "b1_3") if g.mhd else ()),
-            "integrate+exchange")
+    compare(("u", "u1") + (("b1", "b2", "b3", "b1_1", "b1_2", "b1_3") if g.mhd else ())
+            + (("s", "s1") if g.nscalars else ()), "integrate+exchange")
     for pmb in m.my_blocks:
         b = om.block_of(pmb.lx1, pmb.lx2, pmb.lx3)
         om.L.ao_primitives(om.h, b)
@@ -171,6 +202,21 @@ def compare_fluxes(m, om, g, name, order):
                 for nm in names:
                     util.assert_bitwise(pmb.get(nm)[sl], np.array(om.array(b, nm))[sl],
                                         "%s: %s order %d block %d" % (name, nm, order, pmb.gid))
+
+
+def compare_scalar_fluxes(m, om, name, order):
+    """faces PassiveScalars::AddFluxDivergence reads (the only ones the product evaluates)"""
+    ndim = 1 + (m.params.nx2 > 1) + (m.params.nx3 > 1)
+    for pmb in m.my_blocks:
+        b = om.block_of(pmb.lx1, pmb.lx2, pmb.lx3)
+        for d in range(ndim):
+            hi = [pmb.ke, pmb.je, pmb.ie]
+            hi[2 - d] += 1
+            sl = (slice(None), slice(pmb.ks, hi[0] + 1), slice(pmb.js, hi[1] + 1),
+                  slice(pmb.is_, hi[2] + 1))
+            nm = "sflux%d" % (d + 1)
+            util.assert_bitwise(pmb.get(nm)[sl], np.array(om.array(b, nm))[sl],
+                                "%s: %s order %d block %d" % (name, nm, order, pmb.gid))
 
 
 def compare_interior_emf(m, om, name, what):

@@ -24,6 +24,9 @@ CASES = [
     ("athinput.kh", ["mesh/nx1=32", "mesh/nx2=32", "mesh/nx3=32", "meshblock/nx1=16",
                      "meshblock/nx2=16", "meshblock/nx3=16"], False, "hllc", 3),
     ("athinput.sod", ["mesh/nx1=64", "meshblock/nx1=8"], False, "hllc", 2),
+    # passive scalars ride behind u (and b) in the ghost-zone messages
+    ("athinput.kh_scalar", ["mesh/nx1=32", "mesh/nx2=32", "mesh/nx3=32", "meshblock/nx1=16",
+                            "meshblock/nx2=16", "meshblock/nx3=16"], True, "hlld", 2, 2),
 ]
 
 
@@ -48,10 +51,12 @@ def worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import athena_gamma_b200 as ab
     errors = []
-    for inp, ov, mhd, flux, ng in CASES:
+    for case in CASES:
+        inp, ov, mhd, flux, ng = case[:5]
+        ns = case[5] if len(case) > 5 else 0
         pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", inp))
         pin.modify_from_cmdline(ov)
-        plan = ab.MeshPlan(pin, mhd, flux, nghost=ng, rank=rank, nranks=world)
+        plan = ab.MeshPlan(pin, mhd, flux, nghost=ng, rank=rank, nranks=world, nscalars=ns)
         mine = {"ranklist": plan.ranklist(), "nblocal": plan.nblocal,
                 "gids": [b.gid for b in plan.my_blocks],
                 "msgs": [plan.messages(0), plan.messages(1) if mhd else []]}
