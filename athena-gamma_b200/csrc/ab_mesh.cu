@@ -147,8 +147,14 @@ struct AbMesh {
   bool dry = false;                       // host-only plan (no device resources)
   int gid_start = 0;
   int nstages = 2;
-  double beta[4], delta[4], g1[4], g2[4], g3[4];
+  double beta[4], delta[4], g1[4], g2[4], g3[4], ebeta[4];
   double cfl = 0.0;
+  // user-enrolled boundary functions (Mesh::BoundaryFunction_) and their host staging
+  AbBValFunc user_bc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void *user_bc_arg[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool has_user_bc = false;
+  double bc_time = 0.0, bc_dt = 0.0;      // (time, dt) of the PhysicalBoundary task
+  std::vector<double> stage_w, stage_b[3];
   cudaStream_t stream = nullptr;
   double *state = nullptr;                // device: time, dt, tlim, cfl, min, ncycle
   double *dt_hist = nullptr;              // device ring of per-cycle dt
@@ -326,9 +332,10 @@ void set_integrator(AbMesh *m) {
   double cfl_limit = 1.0;
   for (int s = 0; s < 4; ++s) { m->g1[s] = 0; m->g2[s] = 1; m->g3[s] = 0; m->delta[s] = 0; m->beta[s] = 0; }
   m->delta[0] = 1.0;
+  for (int s = 0; s < 4; ++s) m->ebeta[s] = 1.0;   // stage_wghts[].ebeta
   switch (m->p.integrator) {
     case AB_INT_VL2:
-      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0;
+      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0; m->ebeta[0] = 0.5;
       if (m->ndim >= 2) cfl_limit = 0.5;
       break;
     case AB_INT_RK1:
@@ -340,6 +347,7 @@ void set_integrator(AbMesh *m) {
       break;
     default:
       m->nstages = 3; m->beta[0] = 1.0; m->beta[1] = 0.25; m->beta[2] = 0.66666666666666667;
+      m->ebeta[1] = 0.5;
       m->g1[1] = 0.25; m->g2[1] = 0.75;
       m->g1[2] = 0.66666666666666667; m->g2[2] = 0.33333333333333333;
       break;
@@ -930,6 +938,32 @@ void primitives(AbMesh *m, LocalBlock &L, int with_dt = 0) {
   L.cc_e_valid = (flags & 1) != 0;
 }
 
+// DispatchBoundaryFunctions for a user-enrolled face (bvals.cpp:617-620): host round trip of
+// w (and b) of this block around the callback.
+int user_bc_face(AbMesh *m, LocalBlock &L, int face, int il, int iu, int jl, int ju, int kl,
+                 int ku) {
+  if (!m->user_bc[face]) return fail(AB_ERR_STATE, "user boundary function not enrolled");
+  cudaStream_t s = m->stream;
+  m->stage_w.resize(L.regsize[AB_W]);
+  CK(cudaMemcpyAsync(m->stage_w.data(), L.d.w, L.regsize[AB_W]*8, cudaMemcpyDeviceToHost, s));
+  double *bp[3] = {nullptr, nullptr, nullptr};
+  if (m->p.mhd) for (int c = 0; c < 3; ++c) {
+    m->stage_b[c].resize(L.regsize[AB_B_X1F + c]);
+    bp[c] = m->stage_b[c].data();
+    CK(cudaMemcpyAsync(bp[c], L.d.b[c], L.regsize[AB_B_X1F + c]*8, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  int lid = (int)(&L - &m->lb[0]);
+  m->user_bc[face](m->user_bc_arg[face], lid, m->stage_w.data(), bp[0], bp[1], bp[2],
+                   m->bc_time, m->bc_dt, il, iu, jl, ju, kl, ku, m->p.nghost);
+  CK(cudaMemcpyAsync(L.d.w, m->stage_w.data(), L.regsize[AB_W]*8, cudaMemcpyHostToDevice, s));
+  if (m->p.mhd) for (int c = 0; c < 3; ++c)
+    CK(cudaMemcpyAsync(L.d.b[c], bp[c], L.regsize[AB_B_X1F + c]*8, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));    // the staging vectors are reused by the next face
+  L.cc_e_valid = false;
+  return AB_OK;
+}
+
 void physical_bcs(AbMesh *m, LocalBlock &L) {
   // BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620): outflow, reflecting
   HostBlock &B = *L.hb;
@@ -946,26 +980,34 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
   if (!app[5] && m->f3) bke = ke + ng;
   cudaStream_t s = m->stream;
   if (app[0]) {
-    ab::launch_phys_bc(L.d, mhd, 0, B.bcs[0] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
+    if (B.bcs[0] == AB_BC_USER) user_bc_face(m, L, 0, is, ie, bjs, bje, bks, bke);
+
+    else ab::launch_phys_bc(L.d, mhd, 0, B.bcs[0] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
     if (mhd) ab::launch_calc_bcc(L.d, is-ng, is-1, bjs, bje, bks, bke, s);
     ab::launch_prim2cons(L.d, m->kp, is-ng, is-1, bjs, bje, bks, bke, s);
     ab::launch_scalar_eos(L.d, m->kp, 1, is-ng, is-1, bjs, bje, bks, bke, s);
   }
   if (app[1]) {
-    ab::launch_phys_bc(L.d, mhd, 1, B.bcs[1] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
+    if (B.bcs[1] == AB_BC_USER) user_bc_face(m, L, 1, is, ie, bjs, bje, bks, bke);
+
+    else ab::launch_phys_bc(L.d, mhd, 1, B.bcs[1] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
     if (mhd) ab::launch_calc_bcc(L.d, ie+1, ie+ng, bjs, bje, bks, bke, s);
     ab::launch_prim2cons(L.d, m->kp, ie+1, ie+ng, bjs, bje, bks, bke, s);
     ab::launch_scalar_eos(L.d, m->kp, 1, ie+1, ie+ng, bjs, bje, bks, bke, s);
   }
   if (m->f2) {
     if (app[2]) {
-      ab::launch_phys_bc(L.d, mhd, 2, B.bcs[2] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
+      if (B.bcs[2] == AB_BC_USER) user_bc_face(m, L, 2, bis, bie, js, je, bks, bke);
+
+      else ab::launch_phys_bc(L.d, mhd, 2, B.bcs[2] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, js-ng, js-1, bks, bke, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, js-ng, js-1, bks, bke, s);
       ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, js-ng, js-1, bks, bke, s);
     }
     if (app[3]) {
-      ab::launch_phys_bc(L.d, mhd, 3, B.bcs[3] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
+      if (B.bcs[3] == AB_BC_USER) user_bc_face(m, L, 3, bis, bie, js, je, bks, bke);
+
+      else ab::launch_phys_bc(L.d, mhd, 3, B.bcs[3] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, je+1, je+ng, bks, bke, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, je+1, je+ng, bks, bke, s);
       ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, je+1, je+ng, bks, bke, s);
@@ -974,13 +1016,17 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
   if (m->f3) {
     bjs = js - ng; bje = je + ng;
     if (app[4]) {
-      ab::launch_phys_bc(L.d, mhd, 4, B.bcs[4] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
+      if (B.bcs[4] == AB_BC_USER) user_bc_face(m, L, 4, bis, bie, bjs, bje, ks, ke);
+
+      else ab::launch_phys_bc(L.d, mhd, 4, B.bcs[4] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ks-ng, ks-1, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, bjs, bje, ks-ng, ks-1, s);
       ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, bjs, bje, ks-ng, ks-1, s);
     }
     if (app[5]) {
-      ab::launch_phys_bc(L.d, mhd, 5, B.bcs[5] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
+      if (B.bcs[5] == AB_BC_USER) user_bc_face(m, L, 5, bis, bie, bjs, bje, ks, ke);
+
+      else ab::launch_phys_bc(L.d, mhd, 5, B.bcs[5] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ke+1, ke+ng, s);
       ab::launch_prim2cons(L.d, m->kp, bis, bie, bjs, bje, ke+1, ke+ng, s);
       ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, bjs, bje, ke+1, ke+ng, s);
@@ -1023,6 +1069,7 @@ void swap_sc(LocalBlock &L) { std::swap(L.d.s, L.d.s1); L.parity_s ^= 1; }
 
 int one_cycle(AbMesh *m) {
   const double *dtp = m->state + 1;
+  if (m->has_user_bc) { int rc0 = read_state(m); if (rc0) return rc0; }   // host needs time, dt
   for (int stage = 1; stage <= m->nstages; ++stage) {
     const int s = stage - 1;
     const int order = (m->p.integrator == AB_INT_VL2 && stage == 1) ? 1 : m->p.xorder;
@@ -1071,6 +1118,10 @@ int one_cycle(AbMesh *m) {
     }
     rc = bvals_exchange(m);
     if (rc) return rc;
+    if (m->has_user_bc) {   // PhysicalBoundary: t_end_stage, beta*dt (time_integrator.cpp:2045-2062)
+      m->bc_time = m->h_time + m->ebeta[s]*m->h_dt;
+      m->bc_dt = m->beta[s]*m->h_dt;
+    }
     const int last = (stage == m->nstages);
     if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
     for (auto &L : m->lb) { primitives(m, L, last); physical_bcs(m, L); }
@@ -1182,7 +1233,8 @@ static int validate_params(const AbMeshParams *p) {
   if (!p->mhd && p->solver == AB_SOLVER_HLLD) return fail(AB_ERR_ARG, "HLLD flux can only be used with MHD");
   if (!p->mhd && p->solver == AB_SOLVER_LHLLD) return fail(AB_ERR_ARG, "LHLLD flux can only be used with MHD");
   for (int f = 0; f < 6; ++f)
-    if (p->bc[f] != AB_BC_PERIODIC && p->bc[f] != AB_BC_OUTFLOW && p->bc[f] != AB_BC_REFLECT)
+    if (p->bc[f] != AB_BC_PERIODIC && p->bc[f] != AB_BC_OUTFLOW && p->bc[f] != AB_BC_REFLECT &&
+        p->bc[f] != AB_BC_USER)
       return fail(AB_ERR_ARG, "unsupported boundary flag");
   {
     long n1 = p->bx1 + 2L*p->nghost + 1, n2 = (p->nx2 > 1 ? p->bx2 + 2L*p->nghost : 1) + 1,
@@ -1464,9 +1516,26 @@ int ab_bvals_exchange(AbMesh *m) {
   return bvals_exchange(m);
 }
 
+int ab_enroll_user_boundary_function(AbMesh *m, int face, AbBValFunc fn, void *user) {
+  if (!m || face < 0 || face > 5 || !fn) return fail(AB_ERR_ARG, "bad face or null function");
+  // Mesh::EnrollUserBoundaryFunction: the face must carry the "user" flag
+  if (m->p.bc[face] != AB_BC_USER)
+    return fail(AB_ERR_ARG, "boundary function enrolled on a face whose flag is not user");
+  m->user_bc[face] = fn; m->user_bc_arg[face] = user;
+  return AB_OK;
+}
+
 int ab_mesh_initialize(AbMesh *m) {
   if (!m) return fail(AB_ERR_ARG, "null mesh");
   CK(cudaSetDevice(m->p.device));
+  m->has_user_bc = false;
+  for (int f = 0; f < 2*m->ndim; ++f) if (m->p.bc[f] == AB_BC_USER) {
+    if (!m->user_bc[f])   // bvals.cpp:328-335
+      return fail(AB_ERR_STATE, "a user-defined boundary is specified but the actual boundary "
+                                "function is not enrolled");
+    m->has_user_bc = true;
+  }
+  m->bc_time = m->h_time; m->bc_dt = 0.0;   // ApplyPhysicalBoundaries(time, 0.0, ...) mesh.cpp:1574
   int rc = bvals_exchange(m);
   if (rc) return rc;
   for (auto &L : m->lb) { primitives(m, L); physical_bcs(m, L); }

@@ -7,7 +7,7 @@ from . import build as _build
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 AB_OK, AB_ERR_ARG, AB_ERR_NO_DEVICE, AB_ERR_CUDA, AB_ERR_NCCL, AB_ERR_STATE = 0, -1, -2, -3, -4, -5
-BC = {"periodic": 0, "outflow": 1, "reflecting": 2}
+BC = {"periodic": 0, "outflow": 1, "reflecting": 2, "user": 3}
 SOLVER = {"hlle": 0, "hllc": 1, "hlld": 2, "roe": 3, "lhllc": 4, "lhlld": 5}
 INTEGRATOR = {"vl2": 0, "rk2": 1, "rk1": 2, "rk3": 3}
 REG = {"u": 0, "u1": 1, "w": 2, "bcc": 3, "b1": 4, "b2": 5, "b3": 6, "b1_1": 7, "b1_2": 8,
@@ -24,7 +24,7 @@ SYMBOLS = [
     "ab_last_error", "ab_device_count", "ab_mesh_create", "ab_mesh_destroy",
     "ab_mesh_nblocks_total", "ab_mesh_nblocks_local", "ab_block_info", "ab_reg_size",
     "ab_plan_create", "ab_plan_messages", "ab_plan_ranklist",
-    "ab_upload", "ab_download", "ab_download_coord", "ab_comm_unique_id", "ab_comm_init",
+    "ab_enroll_user_boundary_function", "ab_upload", "ab_download", "ab_download_coord", "ab_comm_unique_id", "ab_comm_init",
     "ab_cons2prim", "ab_prim2cons", "ab_primitives", "ab_calc_fluxes", "ab_corner_e",
     "ab_weighted_ave", "ab_swap", "ab_zero", "ab_add_flux_div", "ab_ct", "ab_physical_bcs",
     "ab_calc_scalar_fluxes", "ab_add_scalar_flux_div", "ab_scalar_cons2prim",
@@ -48,6 +48,12 @@ class AbMeshParams(C.Structure):
                 ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
                 ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
                 ("iso_sound_speed", C.c_double)]
+
+
+# AbBValFunc (include/athena_b200.h): user-enrolled boundary function on host arrays
+_DP = C.POINTER(C.c_double)
+BVALFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_int, _DP, _DP, _DP, _DP, C.c_double, C.c_double,
+                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
 
 
 class AbError(RuntimeError):
@@ -80,6 +86,7 @@ def load():
     L.ab_plan_create.argtypes = [C.POINTER(AbMeshParams), C.POINTER(vp)]
     L.ab_plan_messages.argtypes = [vp, ip, C.POINTER(C.c_long), ip]
     L.ab_plan_ranklist.argtypes = [vp, C.POINTER(C.c_int), ip]
+    L.ab_enroll_user_boundary_function.argtypes = [vp, ip, BVALFUNC, vp]
     L.ab_upload.argtypes = [vp, ip, ip, dp]
     L.ab_download.argtypes = [vp, ip, ip, dp]
     L.ab_download_coord.argtypes = [vp, ip, ip, dp]

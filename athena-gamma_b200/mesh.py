@@ -188,6 +188,30 @@ class Mesh:
                 return b
         return None
 
+    def enroll_user_boundary_function(self, face, fn):
+        """Mesh::EnrollUserBoundaryFunction (src/mesh/mesh.cpp): fn has the BValFunc signature
+        (src/athena.hpp:179-182) fn(pmb, pco, prim, b, time, dt, il, iu, jl, ju, kl, ku, ngh);
+        prim and b.x1f/x2f/x3f are writable numpy views of the staged host arrays, pmb and pco
+        are the MeshBlock (index ranges, coord())."""
+        mesh = self
+
+        class _FaceField:
+            pass
+
+        def tramp(_user, lid, prim, b1, b2, b3, time, dt, il, iu, jl, ju, kl, ku, ngh):
+            pmb = mesh.my_blocks[lid]
+            w = np.ctypeslib.as_array(prim, shape=pmb.shape("w"))
+            bf = None
+            if mesh.mhd:
+                bf = _FaceField()
+                bf.x1f = np.ctypeslib.as_array(b1, shape=pmb.shape("b1"))
+                bf.x2f = np.ctypeslib.as_array(b2, shape=pmb.shape("b2"))
+                bf.x3f = np.ctypeslib.as_array(b3, shape=pmb.shape("b3"))
+            fn(pmb, pmb, w, bf, time, dt, il, iu, jl, ju, kl, ku, ngh)
+        cb = lib.BVALFUNC(tramp)
+        self._bval_keepalive = getattr(self, "_bval_keepalive", []) + [cb]
+        lib.check(self.L.ab_enroll_user_boundary_function(self.h, face, cb, None))
+
     def problem_generator(self, pgen_fn):
         """Calls pgen_fn(pmb, pin) -> dict(u=..., b1=..., b2=..., b3=...) per local MeshBlock
         (the MeshBlock::ProblemGenerator hook) and uploads the AthenaArrays."""

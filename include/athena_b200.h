@@ -22,7 +22,7 @@ extern "C" {
 
 enum { AB_OK = 0, AB_ERR_ARG = -1, AB_ERR_NO_DEVICE = -2, AB_ERR_CUDA = -3, AB_ERR_NCCL = -4,
        AB_ERR_STATE = -5 };
-enum { AB_BC_PERIODIC = 0, AB_BC_OUTFLOW = 1, AB_BC_REFLECT = 2 };   /* mesh/ix1_bc ... */
+enum { AB_BC_PERIODIC = 0, AB_BC_OUTFLOW = 1, AB_BC_REFLECT = 2, AB_BC_USER = 3 }; /* mesh/ix1_bc ... */
 enum { AB_SOLVER_HLLE = 0, AB_SOLVER_HLLC = 1, AB_SOLVER_HLLD = 2, AB_SOLVER_ROE = 3,
        AB_SOLVER_LHLLC = 4, AB_SOLVER_LHLLD = 5 };   /* --flux=hlle|hllc|hlld|roe|lhllc|lhlld */
 enum { AB_INT_VL2 = 0, AB_INT_RK2 = 1, AB_INT_RK1 = 2, AB_INT_RK3 = 3 };
@@ -85,6 +85,19 @@ long ab_reg_size(const AbMesh *m, int lid, int reg);
 int ab_plan_create(const AbMeshParams *p, AbMesh **out);
 int ab_plan_messages(const AbMesh *m, int kind, long *out, int max_rows);
 int ab_plan_ranklist(const AbMesh *m, int *out, int max_n);
+
+/* ---- user-enrolled boundary functions: Mesh::EnrollUserBoundaryFunction (src/mesh/mesh.cpp)
+ * with the BValFunc signature of src/athena.hpp:179-182 on plain arrays.  `face`: 0..5 =
+ * inner_x1, outer_x1, ..., outer_x3 of a face whose flag is AB_BC_USER ("user").  The function
+ * runs on the HOST: for every MeshBlock touching that face the library stages w (and the three
+ * face-field arrays when MHD; NULL otherwise) in host memory in AthenaArray layout, calls fn,
+ * and copies them back (host round trip per stage; time = end-of-stage time, dt = beta*dt as in
+ * time_integrator.cpp:2045-2062).  Must be enrolled before ab_mesh_initialize, which fails
+ * like bvals.cpp:328-335 otherwise. */
+typedef void (*AbBValFunc)(void *user, int lid, double *prim, double *b_x1f, double *b_x2f,
+                           double *b_x3f, double time, double dt, int il, int iu, int jl,
+                           int ju, int kl, int ku, int ngh);
+int ab_enroll_user_boundary_function(AbMesh *m, int face, AbBValFunc fn, void *user);
 
 /* ---- host <-> device mirror of the AthenaArrays (same layout as AthenaArray::data()) */
 int ab_upload(AbMesh *m, int lid, int reg, const double *host);     /* after ProblemGenerator */

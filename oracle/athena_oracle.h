@@ -14,7 +14,7 @@
 extern "C" {
 #endif
 
-enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2 };
+enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2, AO_BC_USER = 3 };
 enum { AO_SOLVER_HLLE = 0, AO_SOLVER_HLLC = 1, AO_SOLVER_HLLD = 2, AO_SOLVER_ROE = 3,
        AO_SOLVER_LHLLC = 4, AO_SOLVER_LHLLD = 5 };
 enum { AO_INT_VL2 = 0, AO_INT_RK2 = 1, AO_INT_RK1 = 2, AO_INT_RK3 = 3 };
@@ -77,6 +77,12 @@ void ao_prim2cons(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int 
 void ao_primitives(AoMesh *m, int b);       /* Primitives task: range from neighbours */
 void ao_physical_bcs(AoMesh *m, int b);
 double ao_new_block_dt(AoMesh *m, int b);
+/* Mesh::EnrollUserBoundaryFunction (src/mesh/mesh.cpp): BValFunc of athena.hpp:179-182 with
+ * plain arrays -- prim = w(NHYDRO,k,j,i), bf = {b.x1f, b.x2f, b.x3f} (NULL without MHD) */
+typedef void (*AoBValFunc)(void *user, int block, double *prim, double *b1f, double *b2f,
+                           double *b3f, double time, double dt, int il, int iu, int jl, int ju,
+                           int kl, int ku, int ngh);
+void ao_enroll_user_bc(AoMesh *m, int face, AoBValFunc fn, void *user);
 /* passive scalars (src/scalars, src/eos/eos_scalars.cpp) */
 void ao_calc_scalar_fluxes(AoMesh *m, int b, int order);   /* PassiveScalars::CalculateFluxes */
 void ao_integrate_scalars(AoMesh *m, int b, int stage);    /* IntegrateScalars task */

@@ -33,11 +33,13 @@ OUT = os.path.join(HERE, "_ref")
 
 # cfg name -> (mhd?, flux file stem, nghost, [pgens][, {"nscalars": n, "eos": "isothermal"}])
 CONFIGS = {
-    "hydro_hllc_ng2": (False, "hllc", 2, ["shock_tube", "linear_wave", "blast", "kh"]),
+    "hydro_hllc_ng2": (False, "hllc", 2, ["shock_tube", "linear_wave", "blast", "kh",
+                                          "shk_cloud"]),
     "hydro_hlle_ng2": (False, "hlle", 2, ["shock_tube", "linear_wave"]),
     "hydro_roe_ng2": (False, "roe", 2, ["shock_tube", "linear_wave"]),
     "hydro_hllc_ng3": (False, "hllc", 3, ["kh", "shock_tube", "linear_wave"]),
-    "mhd_hlld_ng2": (True, "hlld", 2, ["linear_wave", "blast", "orszag_tang", "shock_tube"]),
+    "mhd_hlld_ng2": (True, "hlld", 2, ["linear_wave", "blast", "orszag_tang", "shock_tube",
+                                       "shk_cloud"]),
     "mhd_hlle_ng2": (True, "hlle", 2, ["linear_wave", "shock_tube"]),
     "mhd_roe_ng2": (True, "roe", 2, ["linear_wave", "shock_tube"]),
     "mhd_hlld_ng3": (True, "hlld", 3, ["orszag_tang", "linear_wave", "blast"]),

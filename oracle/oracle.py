@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-BC = {"periodic": 0, "outflow": 1, "reflecting": 2}
+BC = {"periodic": 0, "outflow": 1, "reflecting": 2, "user": 3}
 SOLVER = {"hlle": 0, "hllc": 1, "hlld": 2, "roe": 3, "lhllc": 4, "lhlld": 5}
 INTEGRATOR = {"vl2": 0, "rk2": 1, "rk1": 2, "rk3": 3}
 DEFAULT_FLOOR = float(np.sqrt(1024 * float(np.finfo(np.float32).tiny)))  # eos ctor
@@ -30,6 +30,18 @@ class AoParams(C.Structure):
                 ("cfl", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double),
                 ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
                 ("iso_cs", C.c_double)]
+
+
+# AoBValFunc (athena_oracle.h): user-enrolled boundary function with plain arrays
+_DP = C.POINTER(C.c_double)
+BVALFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_int, _DP, _DP, _DP, _DP, C.c_double, C.c_double,
+                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+
+
+class FaceFieldView:
+    """FaceField (src/athena.hpp:95-105) as numpy views"""
+    def __init__(self, x1f, x2f, x3f):
+        self.x1f, self.x2f, self.x3f = x1f, x2f, x3f
 
 
 def build():
@@ -77,6 +89,7 @@ def lib():
         L.ao_ct.argtypes = [C.c_void_p, C.c_int, C.c_double]
         for f in ("ao_cons2prim", "ao_prim2cons", "ao_scalar_cons2prim", "ao_scalar_prim2cons"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 6
+        L.ao_enroll_user_bc.argtypes = [C.c_void_p, C.c_int, BVALFUNC, C.c_void_p]
         L.ao_new_block_dt.restype = C.c_double
         L.ao_new_block_dt.argtypes = [C.c_void_p, C.c_int]
         dp = C.POINTER(C.c_double)
@@ -210,6 +223,23 @@ class OracleMesh:
                 for nm in ("b1", "b2", "b3"):
                     self.array(b, nm)[...] = blk[nm]
 
+    def enroll_user_boundary_function(self, face, fn):
+        """Mesh::EnrollUserBoundaryFunction: fn(pmb, pco, prim, b, time, dt, il, iu, jl, ju,
+        kl, ku, ngh) with prim / b.x?f writable numpy views; pmb = pco = OracleBlockView."""
+        mesh = self
+
+        def tramp(_user, blk, prim, b1, b2, b3, time, dt, il, iu, jl, ju, kl, ku, ngh):
+            view = OracleBlockView(mesh, blk)
+            w = np.ctypeslib.as_array(prim, shape=mesh.shape(blk, "w"))
+            bf = None
+            if mesh.p.mhd:
+                bf = FaceFieldView(*[np.ctypeslib.as_array(p, shape=mesh.shape(blk, nm))
+                                     for p, nm in ((b1, "b1"), (b2, "b2"), (b3, "b3"))])
+            fn(view, view, w, bf, time, dt, il, iu, jl, ju, kl, ku, ngh)
+        cb = BVALFUNC(tramp)
+        self._keep = getattr(self, "_keep", []) + [cb]
+        self.L.ao_enroll_user_bc(self.h, face, cb, None)
+
     def initialize(self):
         self.L.ao_initialize(self.h)
 
@@ -226,6 +256,19 @@ class OracleMesh:
 
     def set_time_dt(self, t, dt):
         self.L.ao_set_time_dt(self.h, t, dt)
+
+
+class OracleBlockView:
+    """what a boundary function may ask of pmb / pco: index ranges and coordinates"""
+    def __init__(self, mesh, b):
+        self.mesh, self.b = mesh, b
+        i = mesh.info[b]
+        self.lx1, self.lx2, self.lx3 = i["lx1"], i["lx2"], i["lx3"]
+        self.is_, self.ie, self.js, self.je, self.ks, self.ke = (i["is"], i["ie"], i["js"],
+                                                                 i["je"], i["ks"], i["ke"])
+
+    def coord(self, name):
+        return np.array(self.mesh.array(self.b, name))
 
 
 def riemann(solver, mhd, wl, wr, bx, gamma, dt=0.0, dx=1.0, dvn=None, dvt=None):

@@ -46,8 +46,10 @@ struct AoMesh {
   double time, dt;
   int ncycle;
   int nstages;
-  double beta[4], delta[4], g1[4], g2[4], g3[4];
+  double beta[4], delta[4], g1[4], g2[4], g3[4], ebeta[4];
   double cfl;
+  AoBValFunc user_bc[6]; void *user_bc_arg[6];
+  double bc_time, bc_dt;   /* (time, dt) handed to boundary functions: end of stage, beta*dt */
   /* canonical buffer-id table: src/bvals/bvals_base.cpp:153-256 */
   int nni; int ni[26][3];
 };
@@ -142,9 +144,10 @@ static void set_integrator(AoMesh *m) {
   double cfl_limit = 1.0;
   for (int s = 0; s < 4; ++s) { m->g1[s] = 0; m->g2[s] = 1; m->g3[s] = 0; m->delta[s] = 0; }
   m->delta[0] = 1.0;
+  for (int s = 0; s < 4; ++s) m->ebeta[s] = 1.0;
   switch (m->p.integrator) {
     case AO_INT_VL2:
-      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0;
+      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0; m->ebeta[0] = 0.5;
       if (m->ndim >= 2) cfl_limit = 0.5;
       break;
     case AO_INT_RK1:
@@ -156,6 +159,7 @@ static void set_integrator(AoMesh *m) {
       break;
     default: /* rk3 */
       m->nstages = 3; m->beta[0] = 1.0; m->beta[1] = 0.25; m->beta[2] = 0.66666666666666667;
+      m->ebeta[1] = 0.5;
       m->g1[1] = 0.25; m->g2[1] = 0.75;
       m->g1[2] = 0.66666666666666667; m->g2[2] = 0.33333333333333333;
       break;
@@ -1334,8 +1338,14 @@ static void bc_face(AoMesh *m, int b, int face, int il, int iu, int jl, int ju, 
                     int gil, int giu, int gjl, int gju, int gkl, int gku) {
   AoBlock *B = &m->blk[b];
   int refl = B->bcs[face] == AO_BC_REFLECT;
-  phys_bc(m, B, face, refl, il, iu, jl, ju, kl, ku);
-  if (m->p.nscalars > 0) phys_bc_scalars(m, B, face, refl, il, iu, jl, ju, kl, ku);
+  if (B->bcs[face] == AO_BC_USER) {   /* DispatchBoundaryFunctions (bvals.cpp:617-620) */
+    if (m->user_bc[face])
+      m->user_bc[face](m->user_bc_arg[face], b, B->w, B->b[0], B->b[1], B->b[2], m->bc_time,
+                       m->bc_dt, il, iu, jl, ju, kl, ku, m->p.ng);
+  } else {
+    phys_bc(m, B, face, refl, il, iu, jl, ju, kl, ku);
+    if (m->p.nscalars > 0) phys_bc_scalars(m, B, face, refl, il, iu, jl, ju, kl, ku);
+  }
   if (m->p.mhd) calc_bcc(B, gil, giu, gjl, gju, gkl, gku);
   ao_prim2cons(m, b, gil, giu, gjl, gju, gkl, gku);
   if (m->p.nscalars > 0) ao_scalar_prim2cons(m, b, gil, giu, gjl, gju, gkl, gku);
@@ -1519,8 +1529,13 @@ static void new_time_step(AoMesh *m) {
   if (m->time < m->p.tlim && (m->p.tlim - m->time) < m->dt) m->dt = m->p.tlim - m->time;
 }
 
+void ao_enroll_user_bc(AoMesh *m, int face, AoBValFunc fn, void *user) {
+  m->user_bc[face] = fn; m->user_bc_arg[face] = user;
+}
+
 /* Mesh::Initialize after ProblemGenerator (src/mesh/mesh.cpp:1416-1649) */
 void ao_initialize(AoMesh *m) {
+  m->bc_time = m->time; m->bc_dt = 0.0;   /* ApplyPhysicalBoundaries(time, 0.0, ...) mesh.cpp:1515 */
   ao_exchange_cc(m);
   ao_exchange_fc(m);
   ao_exchange_scalars(m);
@@ -1565,6 +1580,8 @@ double ao_cycle(AoMesh *m) {
     ao_exchange_cc(m);
     ao_exchange_fc(m);
     ao_exchange_scalars(m);
+    /* PhysicalBoundary task: t_end_stage, beta*dt (time_integrator.cpp:2045-2062) */
+    m->bc_time = m->time + m->ebeta[s]*dt; m->bc_dt = m->beta[s]*dt;
     for (int g = 0; g < m->nb; ++g) {
       ao_primitives(m, g);
       ao_physical_bcs(m, g);

@@ -32,6 +32,7 @@ def mb(a, b, c=1):
 KS = {"mesh/nx1": 16, "mesh/nx2": 32, "mesh/nx3": 1}
 
 # name -> (cfg, pgen, athinput, overrides, solver, mhd, ncycles[, nscalars[, eos]])
+# fixtures named shkcloud* need the user boundary function tests/util.py:shock_cloud_inner_x1
 CASES = {
     "c2_linwave_hlld_plm_vl2_1blk": ("mhd_hlld_ng2", "linear_wave", "athinput.linear_wave3d",
                                      dict(LW, **mb(16, 8, 8)), "hlld", True, 4),
@@ -90,6 +91,13 @@ CASES = {
     "linwave_mhd_roe_plm_vl2_2blk": ("mhd_roe_ng2", "linear_wave", "athinput.linear_wave3d",
                                      dict(LW, **mb(8, 8, 8), **{"problem/amp": 0.1}),
                                      "roe", True, 4),
+    # user-enrolled boundary function (pgen/shk_cloud.cpp:ShockCloudInnerX1 on inner x1)
+    "shkcloud2d_hllc_plm_vl2_4blk": ("hydro_hllc_ng2", "shk_cloud", "athinput.shk_cloud",
+                                     {"mesh/nx1": 32, "mesh/nx2": 16, **mb(16, 8, 1)},
+                                     "hllc", False, 8),
+    "shkcloud3d_hlld_plm_vl2_8blk": ("mhd_hlld_ng2", "shk_cloud", "athinput.shk_cloud",
+                                     {"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16,
+                                      **mb(8, 8, 8)}, "hlld", True, 5),
     # passive scalars (src/scalars): the fork's production build carries one (confignotes)
     "khs_lhllc_plm_vl2_4blk_s1": ("hydro_lhllc_ng2_s1", "kh", "athinput.kh_scalar",
                                   dict(KS, **mb(8, 16, 1)), "lhllc", False, 6, 1),

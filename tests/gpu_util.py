@@ -16,6 +16,9 @@ def pin_from_par(par):
 def mesh_from_golden(g, **kw):
     pin = pin_from_par(g.par)
     m = ab.Mesh(pin, mhd=g.mhd, flux=g.solver, nghost=g.ng, nscalars=g.nscalars, eos=g.eos, **kw)
+    import util
+    for face, fn in util.user_bcs_for(g).items():
+        m.enroll_user_boundary_function(face, fn)
     for n, loc in enumerate(g.locs):
         pmb = m.block_of(*loc)
         if pmb is None:

@@ -29,6 +29,9 @@ CASES = [
     ("blast_refl_hlld_plm_vl2_8blk", None, None),
     ("blast_mixedbc_hllc_plm_vl2_8blk", None, None),
     ("blast_hlld_ppm_rk3_8blk", None, None),
+    # user-enrolled boundary function
+    ("shkcloud2d_hllc_plm_vl2_4blk", None, None),
+    ("shkcloud3d_hlld_plm_vl2_8blk", None, None),
     # passive scalars
     ("khs_lhllc_plm_vl2_4blk_s1", None, None),
     ("sods_lhllc_plm_vl2_2blk_s1", None, None),

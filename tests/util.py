@@ -44,10 +44,43 @@ class Golden:
                            for n in range(len(self.locs))]}
 
 
+def shock_cloud_inner_x1(par):
+    """The user boundary function of pgen/shk_cloud.cpp:196-210 (ShockCloudInnerX1): holds the
+    inner-x1 ghost zones at the post-shock state; constants as in ProblemGenerator :71-93."""
+    gmma = float(par["hydro"]["gamma"])
+    gmma1 = gmma - 1.0
+    mach = float(par["problem"]["Mach"])
+    dr, pr, ur = 1.0, 1.0/gmma, 0.0
+    jump1 = (gmma + 1.0)/(gmma1 + 2.0/(mach*mach))
+    jump2 = (2.0*gmma*mach*mach - gmma1)/(gmma + 1.0)
+    jump3 = 2.0*(1.0 - 1.0/(mach*mach))/(gmma + 1.0)
+    dl = dr*jump1
+    pl = pr*jump2
+    ul = ur + jump3*mach*float(np.sqrt(gmma*pr/dr))
+
+    def fn(pmb, pco, prim, b, time, dt, il, iu, jl, ju, kl, ku, ngh):
+        for i in range(1, ngh + 1):
+            prim[0, kl:ku+1, jl:ju+1, il-i] = dl
+            prim[1, kl:ku+1, jl:ju+1, il-i] = ul
+            prim[2, kl:ku+1, jl:ju+1, il-i] = 0.0
+            prim[3, kl:ku+1, jl:ju+1, il-i] = 0.0
+            prim[4, kl:ku+1, jl:ju+1, il-i] = pl
+    return fn
+
+
+def user_bcs_for(g):
+    """{face: boundary function} a fixture needs (BoundaryFace numbering ix1=0 ... ox3=5)"""
+    if g.name.startswith("shkcloud"):
+        return {0: shock_cloud_inner_x1(g.par)}
+    return {}
+
+
 def oracle_from_golden(g):
     p = oracle.params_from_athinput(g.par, g.mhd, g.solver, ng=g.ng, nscalars=g.nscalars,
                                     eos=g.eos)
     m = oracle.OracleMesh(p)
+    for face, fn in user_bcs_for(g).items():
+        m.enroll_user_boundary_function(face, fn)
     m.load_rst(g.as_rst("init"))
     m.initialize()
     return m
