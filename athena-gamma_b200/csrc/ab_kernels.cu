@@ -1290,6 +1290,88 @@ void launch_new_block_dt(const BlkDev &b, const Params &p, unsigned long long *o
   ++g_launches;
 }
 
+// =============================================================================================
+// HistoryOutput sums (outputs/history.cpp:69-169): volume-weighted sums over the active cells.
+// Two deterministic levels (fixed grid, fixed order): per-CTA partials, then one thread per
+// quantity adds the partials in CTA order onto the running total of the mesh.
+// =============================================================================================
+constexpr int HIST_T = 256;
+constexpr int HIST_MAXQ = 32;
+
+__global__ void __launch_bounds__(HIST_T) k_history(BlkDev b, int mhd, int nq, int ni, int nj,
+                                                    int ntot, double *partial) {
+  const int n1 = b.nc1, n2 = b.nc2;
+  const int sv = b.nc3*n2*n1;
+  const int nme = mhd ? 3 : 0;
+  double acc[HIST_MAXQ];
+#pragma unroll
+  for (int q = 0; q < HIST_MAXQ; ++q) acc[q] = 0.0;
+  for (int t = blockIdx.x*HIST_T + threadIdx.x; t < ntot; t += gridDim.x*HIST_T) {
+    int r = t / ni;
+    const int i = b.is + (t - r*ni);
+    const int kk = r / nj;
+    const int j = b.js + (r - kk*nj);
+    const int k = b.ks + kk;
+    const int o = (k*n2 + j)*n1 + i;
+    const double vol = b.dx1f[i]*b.dx2f[j]*b.dx3f[k];
+    const double u_d = b.u[o], u_mx = b.u[o+sv], u_my = b.u[o+2*sv], u_mz = b.u[o+3*sv];
+    acc[0] += vol*u_d;
+    acc[1] += vol*u_mx;
+    acc[2] += vol*u_my;
+    acc[3] += vol*u_mz;
+    acc[4] += vol*0.5*sqr(u_mx)/u_d;
+    acc[5] += vol*0.5*sqr(u_my)/u_d;
+    acc[6] += vol*0.5*sqr(u_mz)/u_d;
+    acc[7] += vol*b.u[o+4*sv];
+    if (mhd) {
+      const double bcc1 = b.bcc[o], bcc2 = b.bcc[o+sv], bcc3 = b.bcc[o+2*sv];
+      acc[8] += vol*0.5*bcc1*bcc1;
+      acc[9] += vol*0.5*bcc2*bcc2;
+      acc[10] += vol*0.5*bcc3*bcc3;
+    }
+#pragma unroll
+    for (int n = 0; n < 16; ++n)
+      if (n < b.ns) acc[8 + nme + n] += vol*b.s[o + n*sv];
+  }
+  __shared__ double sm[HIST_T/32][HIST_MAXQ];
+#pragma unroll
+  for (int q = 0; q < HIST_MAXQ; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < nq) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < HIST_T/32; ++w) v += sm[w][threadIdx.x];
+    partial[blockIdx.x*HIST_MAXQ + threadIdx.x] = v;
+  }
+}
+
+__global__ void k_history_final(const double *partial, int ncta, int nq, int first,
+                                double *out) {
+  const int q = threadIdx.x;
+  if (q >= nq) return;
+  double v = first ? 0.0 : out[q];
+  for (int c = 0; c < ncta; ++c) v += partial[c*HIST_MAXQ + q];
+  out[q] = v;
+}
+
+int history_grid() { return 148*2; }
+
+// partial: device scratch of history_grid()*32 doubles; out: device totals (nq doubles)
+void launch_history(const BlkDev &b, int mhd, int nq, int first, double *partial, double *out,
+                    cudaStream_t s) {
+  const int ni = b.ie-b.is+1, nj = b.je-b.js+1, nk = b.ke-b.ks+1;
+  const int ntot = ni*nj*nk;
+  int g = (ntot + HIST_T - 1)/HIST_T;
+  if (g > history_grid()) g = history_grid();
+  k_history<<<g, HIST_T, 0, s>>>(b, mhd, nq, ni, nj, ntot, partial); ++g_launches;
+  k_history_final<<<1, 32, 0, s>>>(partial, g, nq, first, out); ++g_launches;
+}
+
 __global__ void k_fill_u64(unsigned long long *p, int n, unsigned long long v) {
   int t = blockIdx.x*blockDim.x + threadIdx.x;
   if (t < n) p[t] = v;

@@ -68,6 +68,11 @@ void launch_new_block_dt(const BlkDev &b, const Params &p, unsigned long long *o
 // Mesh::NewTimeStep on the device: state = {time, dt, tlim, cfl}; blk_min[nb]
 void launch_mesh_new_dt(double *state, const unsigned long long *blk_min, int nb,
                         int advance_time, cudaStream_t s);
+// HistoryOutput sums of one block added onto `out` (first != 0: start from zero); `partial` is
+// device scratch of history_grid()*32 doubles
+int history_grid();
+void launch_history(const BlkDev &b, int mhd, int nq, int first, double *partial, double *out,
+                    cudaStream_t s);
 void launch_fill_u64(unsigned long long *p, int n, unsigned long long v, cudaStream_t s);
 
 }  // namespace ab

@@ -70,6 +70,7 @@ struct Nccl {
 Nccl g_nccl;
 constexpr int NCCL_FLOAT64 = 8;   // ncclDouble
 constexpr int NCCL_MIN = 3;       // ncclMin
+constexpr int NCCL_SUM = 0;       // ncclSum
 
 #define NK(call)                                                                       \
   do {                                                                                 \
@@ -160,6 +161,7 @@ struct AbMesh {
   double *dt_hist = nullptr;              // device ring of per-cycle dt
   int hist_cap = 0, hist_n = 0;
   unsigned long long *dtmin = nullptr;    // device per-local-block min (bits)
+  double *hist_partial = nullptr, *hist_out = nullptr;   // HistoryOutput reduction scratch
   double h_time = 0.0, h_dt = DBL_MAX;
   long h_ncycle = 0;
   int async = 0;
@@ -1283,6 +1285,7 @@ int ab_mesh_destroy(AbMesh *m) {
   for (auto &kv : m->peer_state) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   cudaFree(m->state); cudaFree(m->dt_hist); cudaFree(m->dtmin);
+  cudaFree(m->hist_partial); cudaFree(m->hist_out);
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
   cudaStreamDestroy(m->stream);
   delete m;
@@ -1580,6 +1583,31 @@ int ab_mesh_set_time_dt(AbMesh *m, double time, double dt) {
   CK(cudaStreamSynchronize(m->stream));
   m->h_time = time; m->h_dt = dt;
   return AB_OK;
+}
+
+int ab_history(AbMesh *m, double *out, int max_n) {
+  if (!m || !out) return fail(AB_ERR_ARG, "null argument");
+  if (m->dry) return fail(AB_ERR_STATE, "host-only plan");
+  CK(cudaSetDevice(m->p.device));
+  const int nq = ab::NHYDRO + 3 + (m->p.mhd ? 3 : 0) + m->p.nscalars;
+  if (max_n < nq) return fail(AB_ERR_ARG, "ab_history: output array too small");
+  if (!m->hist_partial) {
+    CK(cudaMalloc(&m->hist_partial, sizeof(double)*32*ab::history_grid()));
+    CK(cudaMalloc(&m->hist_out, sizeof(double)*32));
+  }
+  int first = 1;
+  for (auto &L : m->lb) {
+    ab::launch_history(L.d, m->p.mhd, nq, first, m->hist_partial, m->hist_out, m->stream);
+    first = 0;
+  }
+  CK(cudaGetLastError());
+  if (m->p.nranks > 1) {   // MPI_Reduce(MPI_SUM) of history.cpp:203-211
+    if (!m->comm) return fail(AB_ERR_STATE, "nranks > 1 but ab_comm_init was not called");
+    NK(g_nccl.AllReduce(m->hist_out, m->hist_out, nq, NCCL_FLOAT64, NCCL_SUM, m->comm, m->stream));
+  }
+  CK(cudaMemcpyAsync(out, m->hist_out, sizeof(double)*nq, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  return nq;
 }
 
 int ab_mesh_dt_history(AbMesh *m, double *out, int max_n) {

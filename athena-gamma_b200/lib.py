@@ -30,7 +30,7 @@ SYMBOLS = [
     "ab_calc_scalar_fluxes", "ab_add_scalar_flux_div", "ab_scalar_cons2prim",
     "ab_scalar_prim2cons", "ab_new_block_dt", "ab_emf_exchange", "ab_bvals_exchange", "ab_mesh_initialize",
     "ab_mesh_cycles", "ab_mesh_set_async", "ab_mesh_state", "ab_mesh_set_time_dt",
-    "ab_mesh_dt_history", "ab_mesh_profile", "ab_mesh_profile_read",
+    "ab_history", "ab_mesh_dt_history", "ab_mesh_profile", "ab_mesh_profile_read",
     "ab_mesh_launch_count", "ab_mesh_stream", "ab_mesh_sync",
 ]
 
@@ -86,6 +86,7 @@ def load():
     L.ab_plan_create.argtypes = [C.POINTER(AbMeshParams), C.POINTER(vp)]
     L.ab_plan_messages.argtypes = [vp, ip, C.POINTER(C.c_long), ip]
     L.ab_plan_ranklist.argtypes = [vp, C.POINTER(C.c_int), ip]
+    L.ab_history.argtypes = [vp, dp, ip]
     L.ab_enroll_user_boundary_function.argtypes = [vp, ip, BVALFUNC, vp]
     L.ab_upload.argtypes = [vp, ip, ip, dp]
     L.ab_download.argtypes = [vp, ip, ip, dp]

@@ -247,6 +247,13 @@ class Mesh:
             dts.extend(self.cycles(n))
         return np.array(dts)
 
+    def history(self):
+        """HistoryOutput sums (outputs/history.cpp:69-169): mass, 1..3-mom, 1..3-KE, tot-E,
+        [1..3-ME], [scalars], reduced on the device over all MeshBlocks of all ranks."""
+        out = np.zeros(32)
+        n = lib.check(self.L.ab_history(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), 32))
+        return out[:n]
+
     def sync(self):
         lib.check(self.L.ab_mesh_sync(self.h))
 

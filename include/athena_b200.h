@@ -172,6 +172,13 @@ int ab_mesh_set_async(AbMesh *m, int async);
 /* read back {time, dt, ncycle} (synchronises the stream) */
 int ab_mesh_state(AbMesh *m, double *time, double *dt, long *ncycle);
 int ab_mesh_set_time_dt(AbMesh *m, double time, double dt);
+/* HistoryOutput::WriteOutputFile sums (outputs/history.cpp:69-169) reduced on the device over
+ * the active cells of all MeshBlocks of all ranks (NCCL sum when nranks > 1): mass, 1-mom,
+ * 2-mom, 3-mom, 1-KE, 2-KE, 3-KE, tot-E, [1-ME, 2-ME, 3-ME when MHD], [one per scalar].
+ * Returns the number of values written (<= max_n) or a negative error.  The summation order
+ * is fixed (reproducible run to run) but is a tree, not the reference's running sum: values
+ * agree with the reference to ~1e-15 relative to the sum of magnitudes. */
+int ab_history(AbMesh *m, double *out, int max_n);
 /* per-cycle dt history of the last ab_mesh_cycles call (dt used by each cycle) */
 int ab_mesh_dt_history(AbMesh *m, double *out, int max_n);
 /* CUDA-event timing of the reconstruct+Riemann kernels on the compute stream (roofline

@@ -83,6 +83,9 @@ typedef void (*AoBValFunc)(void *user, int block, double *prim, double *b1f, dou
                            double *b3f, double time, double dt, int il, int iu, int jl, int ju,
                            int kl, int ku, int ngh);
 void ao_enroll_user_bc(AoMesh *m, int face, AoBValFunc fn, void *user);
+/* HistoryOutput::WriteOutputFile sums (src/outputs/history.cpp:69-169): mass, 1..3-mom,
+ * 1..3-KE, tot-E, [1..3-ME], [scalars]; returns the number of values written to out */
+int ao_history(AoMesh *m, double *out);
 /* passive scalars (src/scalars, src/eos/eos_scalars.cpp) */
 void ao_calc_scalar_fluxes(AoMesh *m, int b, int order);   /* PassiveScalars::CalculateFluxes */
 void ao_integrate_scalars(AoMesh *m, int b, int stage);    /* IntegrateScalars task */

@@ -90,6 +90,7 @@ def lib():
         for f in ("ao_cons2prim", "ao_prim2cons", "ao_scalar_cons2prim", "ao_scalar_prim2cons"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 6
         L.ao_enroll_user_bc.argtypes = [C.c_void_p, C.c_int, BVALFUNC, C.c_void_p]
+        L.ao_history.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.ao_new_block_dt.restype = C.c_double
         L.ao_new_block_dt.argtypes = [C.c_void_p, C.c_int]
         dp = C.POINTER(C.c_double)
@@ -239,6 +240,12 @@ class OracleMesh:
         cb = BVALFUNC(tramp)
         self._keep = getattr(self, "_keep", []) + [cb]
         self.L.ao_enroll_user_bc(self.h, face, cb, None)
+
+    def history(self):
+        """the sums HistoryOutput writes (mass, momenta, KE, tot-E, [ME], [scalars])"""
+        out = np.zeros(32)
+        n = self.L.ao_history(self.h, _dp(out))
+        return out[:n]
 
     def initialize(self):
         self.L.ao_initialize(self.h)

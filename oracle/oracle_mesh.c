@@ -1480,6 +1480,43 @@ void ao_integrate_scalars(AoMesh *m, int b, int stage) {
     }
 }
 
+/* ------------------------------------------------------------------ history */
+
+/* HistoryOutput::WriteOutputFile (src/outputs/history.cpp:69-169): volume-weighted sums over
+ * the active cells, MeshBlocks in list order, one running accumulator per quantity */
+int ao_history(AoMesh *m, double *out) {
+  int nme = m->p.mhd ? 3 : 0;
+  int nout = NHYDRO + 3 + nme + m->p.nscalars;
+  for (int n = 0; n < nout; ++n) out[n] = 0.0;
+  for (int g = 0; g < m->nb; ++g) {
+    AoBlock *B = &m->blk[g];
+    for (int k = B->ks; k <= B->ke; ++k) for (int j = B->js; j <= B->je; ++j)
+      for (int i = B->is; i <= B->ie; ++i) {
+        double vol = B->dx1f[i]*B->dx2f[j]*B->dx3f[k];
+        double u_d = B->u[CC(B,IDN,k,j,i)], u_mx = B->u[CC(B,IM1,k,j,i)],
+               u_my = B->u[CC(B,IM2,k,j,i)], u_mz = B->u[CC(B,IM3,k,j,i)];
+        out[0] += vol*u_d;
+        out[1] += vol*u_mx;
+        out[2] += vol*u_my;
+        out[3] += vol*u_mz;
+        out[4] += vol*0.5*SQR(u_mx)/u_d;
+        out[5] += vol*0.5*SQR(u_my)/u_d;
+        out[6] += vol*0.5*SQR(u_mz)/u_d;
+        out[7] += vol*B->u[CC(B,IEN,k,j,i)];
+        if (m->p.mhd) {
+          double bcc1 = B->bcc[CC(B,IB1,k,j,i)], bcc2 = B->bcc[CC(B,IB2,k,j,i)],
+                 bcc3 = B->bcc[CC(B,IB3,k,j,i)];
+          out[NHYDRO + 3] += vol*0.5*bcc1*bcc1;
+          out[NHYDRO + 4] += vol*0.5*bcc2*bcc2;
+          out[NHYDRO + 5] += vol*0.5*bcc3*bcc3;
+        }
+        for (int n = 0; n < m->p.nscalars; ++n)
+          out[NHYDRO + 3 + nme + n] += vol*B->s[CC(B,n,k,j,i)];
+      }
+  }
+  return nout;
+}
+
 /* ------------------------------------------------------------------ time step */
 
 /* Hydro::NewBlockTimeStep (src/hydro/new_blockdt.cpp:42-190) */

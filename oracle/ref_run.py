@@ -139,7 +139,7 @@ def read_rst(path, nhydro=5, mhd=None, nghost=None, nscalars=0):
 
 
 def run_reference(cfg, pgen, athinput_path, overrides=None, rst_every_cycle=False,
-                  keep_dir=None, timeout=3600, threads=None):
+                  keep_dir=None, timeout=3600, threads=None, hst_every_cycle=False):
     """Run the reference; returns dict(dts, times, zcps, zcps_omp, rst=[paths], dir, stdout)."""
     exe = ref_binary(cfg, pgen)
     if not os.path.isfile(exe):
@@ -150,6 +150,8 @@ def run_reference(cfg, pgen, athinput_path, overrides=None, rst_every_cycle=Fals
     apply_overrides(blocks, overrides)
     if rst_every_cycle:
         blocks["output9"] = {"file_type": "rst", "dt": "1e-300"}
+    if hst_every_cycle:   # outputs/history.cpp with 17 significant digits
+        blocks["output8"] = {"file_type": "hst", "dt": "1e-300", "data_format": "%24.16e"}
     if threads is not None:
         blocks["mesh"]["num_threads"] = str(threads)
     d = keep_dir or tempfile.mkdtemp(prefix="abref_")
@@ -177,6 +179,11 @@ def run_reference(cfg, pgen, athinput_path, overrides=None, rst_every_cycle=Fals
     m = re.search(r"omp wtime used\s*= ([-+0-9.eE]+)", r.stdout)
     out["omp_wtime"] = float(m.group(1)) if m else None
     pid = blocks["job"]["problem_id"]
+    hst = os.path.join(d, pid + ".hst")
+    out["hst"] = None
+    if hst_every_cycle and os.path.exists(hst):
+        rows = [[float(x) for x in ln.split()] for ln in open(hst) if not ln.startswith("#")]
+        out["hst"] = np.array(rows)
     out["rst"] = sorted(p for p in (os.path.join(d, f) for f in os.listdir(d))
                         if re.search(re.escape(pid) + r"\.\d{5}\.rst$", p))
     return out

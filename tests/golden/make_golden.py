@@ -121,7 +121,8 @@ def make(name):
     nhydro = 4 if eos == "isothermal" else 5
     ov = dict(ov)
     ov["time/nlim"] = ncyc
-    res = ref_run.run_reference(cfg, pgen, os.path.join(I, inp), ov, rst_every_cycle=True)
+    res = ref_run.run_reference(cfg, pgen, os.path.join(I, inp), ov, rst_every_cycle=True,
+                                hst_every_cycle=True)
     first = ref_run.read_rst(res["rst"][0], nhydro=nhydro, mhd=mhd, nscalars=nscalars)
     last = ref_run.read_rst(res["rst"][ncyc], nhydro=nhydro, mhd=mhd, nscalars=nscalars)
     out = {"meta": json.dumps({"cfg": cfg, "pgen": pgen, "solver": solver, "mhd": mhd,
@@ -130,6 +131,9 @@ def make(name):
            "dts": np.array(res["dts"][:ncyc + 1]),
            "locs": np.array([b["loc"][:3] for b in first["blocks"]], dtype=np.int64),
            "final_time": np.array(last["time"]), "final_dt": np.array(last["dt"])}
+    if res["hst"] is not None:
+        # one row per cycle 0..ncyc: time, dt, then the history sums (outputs/history.cpp)
+        out["hst"] = res["hst"][:ncyc + 1]
     for tag, r in (("init", first), ("final", last)):
         for n, b in enumerate(r["blocks"]):
             out["%s_u_%d" % (tag, n)] = b["u"]

@@ -12,10 +12,19 @@ def test_oracle_reproduces_reference_golden(name):
     m = util.oracle_from_golden(g)
     # first dt comes out of Mesh::Initialize (NewBlockTimeStep + NewTimeStep)
     assert m.dt == g.dts[0], ("dt0", m.dt, g.dts[0])
+
+    def check_history(c):
+        # HistoryOutput row of cycle c: time, dt, sums printed with %24.16e (17 digits = exact)
+        if g.hst is not None:
+            assert g.hst[c, 0] == m.time and g.hst[c, 1] == m.dt
+            h = m.history()      # columns after ours: user-enrolled history outputs (pgen)
+            util.assert_bitwise(h, g.hst[c, 2:2 + len(h)], "%s history row %d" % (name, c))
+    check_history(0)
     for c in range(g.ncycles):
         used = m.cycle()
         assert used == g.dts[c], ("cycle %d used dt" % c, used, g.dts[c])
         assert m.dt == g.dts[c + 1], ("cycle %d new dt" % c, m.dt, g.dts[c + 1])
+        check_history(c + 1)
     assert m.time == g.final_time
     for n, loc in enumerate(g.locs):
         b = m.block_of(*loc)

@@ -30,6 +30,7 @@ class Golden:
         self.locs = [tuple(int(v) for v in l) for l in z["locs"]]
         self.final_time = float(z["final_time"])
         self.final_dt = float(z["final_dt"])
+        self.hst = z["hst"] if "hst" in z.files else None
         self.fields = ("u", "b1", "b2", "b3") if self.mhd else ("u",)
         if self.nscalars:
             self.fields += ("s",)
