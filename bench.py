@@ -65,15 +65,17 @@ def weak_mesh(nranks, block):
     return reps
 
 
-def make_pin(ab, wl, nranks, block=None):
+def make_pin(ab, wl, nranks, block=None, per_gpu=None):
+    """block: MeshBlock size; per_gpu: zones per GPU (default = one MeshBlock per GPU)"""
     inp, pgen, mhd, flux, ng, blk, ov = WORKLOADS[wl]
     if block:
         blk = block
+    gpu = per_gpu or blk
     pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", inp))
-    reps = weak_mesh(nranks, blk)
+    reps = weak_mesh(nranks, gpu)
     for d in range(3):
         n = d + 1
-        pin.set("mesh", "nx%d" % n, blk[d]*reps[d])
+        pin.set("mesh", "nx%d" % n, gpu[d]*reps[d])
         pin.set("meshblock", "nx%d" % n, blk[d])
         if reps[d] > 1:   # keep the zone size: stretch the domain
             lo, hi = pin.get_real("mesh", "x%dmin" % n), pin.get_real("mesh", "x%dmax" % n)
@@ -185,7 +187,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
-    ap.add_argument("--block", default=None, help="per-GPU MeshBlock, e.g. 256,256,256")
+    ap.add_argument("--block", default=None, help="MeshBlock size, e.g. 256,256,256")
+    ap.add_argument("--per-gpu", default=None,
+                    help="zones per GPU, e.g. 512,512,512 with --block 128,128,128 = 64 "
+                         "MeshBlocks per GPU (default: one MeshBlock per GPU)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -195,6 +200,7 @@ def main():
     wl = a.workload
     mhd = WORKLOADS[wl][2]
     block = tuple(int(x) for x in a.block.split(",")) if a.block else None
+    per_gpu = tuple(int(x) for x in a.per_gpu.split(",")) if a.per_gpu else None
     cfg_desc = {"workload": "%s: %s" % (wl, {
         "c5": "3D MHD blast wave, HLLD+PLM+VL2+CT, periodic (BASELINE configs[4])",
         "c2": "3D MHD linear wave 128x64x64, HLLD+PLM+VL2, 1 MeshBlock (BASELINE configs[1])",
@@ -232,7 +238,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank if world > 1 else 0
     torch.cuda.set_device(device)
-    pin, pgen_name, mhd, flux, ng, blk = make_pin(ab, wl, world, block)
+    pin, pgen_name, mhd, flux, ng, blk = make_pin(ab, wl, world, block, per_gpu)
     mesh = ab.Mesh(pin, mhd=mhd, flux=flux, nghost=ng, rank=rank, nranks=world, device=device)
     if world > 1:
         def bcast(data):
