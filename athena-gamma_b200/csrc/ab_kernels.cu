@@ -57,8 +57,23 @@ __device__ __forceinline__ void block_min_to_slots(double m, unsigned long long 
 // (field/calculate_corner_e.cpp:131-180) -- saves a pass over w and bcc;
 // bit1: also reduce Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:64-134) over the ACTIVE
 // cells of the launch (last integrator stage) -- w, bcc, b are already in registers.
+// Resident CTAs per SM asked of the compiler for the HBM-bound kernels (more loads in flight;
+// measured together on B200 at 512^3: 76.9 -> 75.1 ms per cycle, tune4.log; 16/10/16/12 spills
+// and is slower).
+#ifndef AB_C2P_MINB
+#define AB_C2P_MINB 6      // k_cons2prim with the fused CFL reduction
+#endif
+#ifndef AB_CE_MINB
+#define AB_CE_MINB 10      // k_corner_e3d
+#endif
+#ifndef AB_FC_MINB
+#define AB_FC_MINB 10      // k_integrate_fc
+#endif
+#ifndef AB_CC_MINB
+#define AB_CC_MINB 8       // k_integrate_cc
+#endif
 template <bool MHD, int FLAGS>
-__global__ void __launch_bounds__(BX) k_cons2prim(BlkDev b, Params p, int il, int iu, int jl,
+__global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2prim(BlkDev b, Params p, int il, int iu, int jl,
                                                   int kl, unsigned long long *dtmin) {
   int i = il + blockIdx.x*BX + threadIdx.x;
   int j = jl + blockIdx.y, k = kl + blockIdx.z;
@@ -574,7 +589,7 @@ __device__ __forceinline__ double de_term(double wt, double ef_a, double cc_a, d
   return (1.0-wt)*(ef_a - cc_a) + (wt)*(ef_b - cc_b);
 }
 
-__global__ void __launch_bounds__(BX) k_corner_e3d(BlkDev b, int ni, int nj, int ntot) {
+__global__ void __launch_bounds__(BX, AB_CE_MINB) k_corner_e3d(BlkDev b, int ni, int nj, int ntot) {
   int t = blockIdx.x*BX + threadIdx.x;
   if (t >= ntot) return;
   int r = t / ni;
@@ -977,7 +992,7 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 struct CcSet { double *u, *u1; const double *f[3]; int nvar; };
 
 template <int NVAR>
-__global__ void __launch_bounds__(BX) k_integrate_cc(BlkDev b, CcSet c, int mode, int zero_init,
+__global__ void __launch_bounds__(BX, AB_CC_MINB) k_integrate_cc(BlkDev b, CcSet c, int mode, int zero_init,
                                                      double delta, double g1, double g2,
                                                      double beta, double dt_val,
                                                      const double *dt_ptr, int k0, int ni,
@@ -1072,7 +1087,7 @@ __device__ __forceinline__ double fc_avg(double *__restrict__ bo, double *__rest
 // [j<=je,k<=ke], x2f(k,j,i) [i<=ie,k<=ke] and x3f(k,j,i) [i<=ie,j<=je]; the nine edge EMFs it
 // needs are loaded once (e?(k,j,i) is shared by two of the three updates).
 template <int MODE>
-__global__ void __launch_bounds__(BX) k_integrate_fc(BlkDev b, int ni, int nj, int ntot,
+__global__ void __launch_bounds__(BX, AB_FC_MINB) k_integrate_fc(BlkDev b, int ni, int nj, int ntot,
                                                      int zero_init, double delta, double g1,
                                                      double g2, double beta, double dt_val,
                                                      const double *dt_ptr) {
