@@ -165,8 +165,9 @@ class OracleMesh:
     def shape(self, b, name):
         i = self.info[b]
         n1, n2, n3 = i["nc1"], i["nc2"], i["nc3"]
+        nh = 4 if self.p.eos == 1 else 5      # NHYDRO (configure.py:374-377)
         if name in ("u", "u1", "w"):
-            return (5, n3, n2, n1)
+            return (nh, n3, n2, n1)
         ns = self.p.nscalars
         if name in ("s", "s1", "r"):
             return (ns, n3, n2, n1)
@@ -184,11 +185,11 @@ class OracleMesh:
         if name in ("b3", "b1_3", "wght3", "e1_x3f", "e2_x3f"):
             return (n3 + 1, n2, n1)
         if name == "flux1":
-            return (5, n3, n2, n1 + 1)
+            return (nh, n3, n2, n1 + 1)
         if name == "flux2":
-            return (5, n3, n2 + 1, n1)
+            return (nh, n3, n2 + 1, n1)
         if name == "flux3":
-            return (5, n3 + 1, n2, n1)
+            return (nh, n3 + 1, n2, n1)
         if name == "e1":
             return (n3 + 1, n2 + 1, n1)
         if name == "e2":

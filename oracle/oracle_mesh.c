@@ -12,6 +12,11 @@
 #include "oracle_internal.h"
 
 static inline double mn(double a, double b) { return (b < a) ? b : a; }
+/* NHYDRO is 5 (adiabatic) or 4 (isothermal, configure.py:374-377): every function below that
+ * uses it has the mesh `m` in scope */
+#undef NHYDRO
+#define NHYDRO (m->nh)
+#define ISO(m) ((m)->p.eos == 1)
 #define SQR(x) ((x)*(x))
 
 typedef struct {
@@ -39,6 +44,7 @@ typedef struct AoBlock {
 
 struct AoMesh {
   AoParams p;
+  int nh;                /* NHYDRO */
   int ndim, f2, f3;
   int nrbx1, nrbx2, nrbx3, nb;
   AoBlock *blk;
@@ -171,6 +177,7 @@ static void set_integrator(AoMesh *m) {
 AoMesh *ao_create(const AoParams *p) {
   AoMesh *m = (AoMesh *)calloc(1, sizeof(AoMesh));
   m->p = *p;
+  m->nh = (p->eos == 1) ? 4 : 5;
   m->f2 = p->nx2 > 1; m->f3 = p->nx3 > 1;
   m->ndim = m->f3 ? 3 : (m->f2 ? 2 : 1);
   m->nrbx1 = p->nx1/p->bx1; m->nrbx2 = p->nx2/p->bx2; m->nrbx3 = p->nx3/p->bx3;
@@ -420,7 +427,7 @@ void ao_cons2prim(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int 
       B->bcc[CC(B,IB3,k,j,i)] = bcc3;
       pb = 0.5*(SQR(bcc1) + SQR(bcc2) + SQR(bcc3));
     }
-    double *u_d = &B->u[CC(B,IDN,k,j,i)], *u_e = &B->u[CC(B,IEN,k,j,i)];
+    double *u_d = &B->u[CC(B,IDN,k,j,i)];
     double u_m1 = B->u[CC(B,IM1,k,j,i)], u_m2 = B->u[CC(B,IM2,k,j,i)],
            u_m3 = B->u[CC(B,IM3,k,j,i)];
     *u_d = (*u_d > dfl) ? *u_d : dfl;
@@ -429,6 +436,8 @@ void ao_cons2prim(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int 
     B->w[CC(B,IVX,k,j,i)] = u_m1*di;
     B->w[CC(B,IVY,k,j,i)] = u_m2*di;
     B->w[CC(B,IVZ,k,j,i)] = u_m3*di;
+    if (ISO(m)) continue;   /* isothermal_{hydro,mhd}.cpp: density floor and velocities only */
+    double *u_e = &B->u[CC(B,IEN,k,j,i)];
     double e_k = 0.5*di*(SQR(u_m1) + SQR(u_m2) + SQR(u_m3));
     double w_p;
     if (m->p.mhd) {
@@ -455,15 +464,16 @@ static void calc_bcc(AoBlock *B, int il, int iu, int jl, int ju, int kl, int ku)
 /* EquationOfState::PrimitiveToConserved (adiabatic_hydro.cpp:89-123, adiabatic_mhd.cpp:99-136) */
 void ao_prim2cons(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int ku) {
   AoBlock *B = &m->blk[b];
-  double igm1 = 1.0/(m->p.gamma - 1.0);
+  double igm1 = ISO(m) ? 0.0 : 1.0/(m->p.gamma - 1.0);
   for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
     double w_d = B->w[CC(B,IDN,k,j,i)], w_vx = B->w[CC(B,IVX,k,j,i)],
            w_vy = B->w[CC(B,IVY,k,j,i)], w_vz = B->w[CC(B,IVZ,k,j,i)],
-           w_p = B->w[CC(B,IPR,k,j,i)];
+           w_p = ISO(m) ? 0.0 : B->w[CC(B,IPR,k,j,i)];
     B->u[CC(B,IDN,k,j,i)] = w_d;
     B->u[CC(B,IM1,k,j,i)] = w_vx*w_d;
     B->u[CC(B,IM2,k,j,i)] = w_vy*w_d;
     B->u[CC(B,IM3,k,j,i)] = w_vz*w_d;
+    if (ISO(m)) continue;
     if (m->p.mhd) {
       double bcc1 = B->bcc[CC(B,IB1,k,j,i)], bcc2 = B->bcc[CC(B,IB2,k,j,i)],
              bcc3 = B->bcc[CC(B,IB3,k,j,i)];
@@ -518,6 +528,7 @@ void ao_scalar_prim2cons(AoMesh *m, int b, int il, int iu, int jl, int ju, int k
 static void cell_state(const AoMesh *m, const AoBlock *B, int dir, int k, int j, int i,
                        double *q) {
   for (int n = 0; n < NHYDRO; ++n) q[n] = B->w[CC(B,n,k,j,i)];
+  if (ISO(m)) q[IPR] = 0.0;    /* slot unused: the isothermal wave vector has no pressure */
   if (m->p.mhd) {
     int by = (dir + 1) % 3, bz = (dir + 2) % 3;
     q[IBY] = B->bcc[CC(B,by,k,j,i)];
@@ -558,9 +569,11 @@ static void recon_cell(const AoMesh *m, const AoBlock *B, int dir, int order, in
     ao_ppm_point(qm2[n], qm1[n], q[n], qp1[n], qp2[n], &plus[n], &minus[n]);
   /* ApplyPrimitiveFloors on both (ppm.cpp:326-332) */
   plus[IDN] = (plus[IDN] > m->p.dfloor) ? plus[IDN] : m->p.dfloor;
-  plus[IPR] = (plus[IPR] > m->p.pfloor) ? plus[IPR] : m->p.pfloor;
   minus[IDN] = (minus[IDN] > m->p.dfloor) ? minus[IDN] : m->p.dfloor;
-  minus[IPR] = (minus[IPR] > m->p.pfloor) ? minus[IPR] : m->p.pfloor;
+  if (!ISO(m)) {
+    plus[IPR] = (plus[IPR] > m->p.pfloor) ? plus[IPR] : m->p.pfloor;
+    minus[IPR] = (minus[IPR] > m->p.pfloor) ? minus[IPR] : m->p.pfloor;
+  }
 }
 
 /* Hydro::CalculateVelocityDifferences (src/hydro/calculate_velocity_differences.cpp:20-90):
@@ -612,16 +625,19 @@ static void face_flux(AoMesh *m, AoBlock *B, int dir, int order, int k, int j, i
   double dvn = 0.0, dvt = 0.0;
   if (m->p.solver == AO_SOLVER_LHLLC || m->p.solver == AO_SOLVER_LHLLD)
     velocity_differences(m, B, dir, k, j, i, &dvn, &dvt);
-  ao_riemann_point(m->p.solver, m->p.mhd, wli, wri, bxi, m->p.gamma, dvn, dvt, f);
+  if (ISO(m))
+    ao_riemann_point_iso(m->p.solver, m->p.mhd, wli, wri, bxi, m->p.iso_cs, m->p.dfloor, f);
+  else
+    ao_riemann_point(m->p.solver, m->p.mhd, wli, wri, bxi, m->p.gamma, dvn, dvt, f);
   double *flx = B->flux[dir];
   long o[5];
-  for (int n = 0; n < 5; ++n)
+  for (int n = 0; n < NHYDRO; ++n)
     o[n] = dir == 0 ? FL1(B,n,k,j,i) : (dir == 1 ? FL2(B,n,k,j,i) : FL3(B,n,k,j,i));
   flx[o[IDN]] = f[IDN];
   flx[o[ivx]] = f[IVX];
   flx[o[ivy]] = f[IVY];
   flx[o[ivz]] = f[IVZ];
-  flx[o[IEN]] = f[IEN];
+  if (!ISO(m)) flx[o[IEN]] = f[IEN];
   if (m->p.mhd) {
     /* ey = -F(By), ez = F(Bz); CT weight (hlld.cpp:371-379); dxw = CenterWidth = dx?f */
     long fo = dir == 0 ? F1(B,k,j,i) : (dir == 1 ? F2(B,k,j,i) : F3(B,k,j,i));
@@ -1502,7 +1518,7 @@ int ao_history(AoMesh *m, double *out) {
         out[4] += vol*0.5*SQR(u_mx)/u_d;
         out[5] += vol*0.5*SQR(u_my)/u_d;
         out[6] += vol*0.5*SQR(u_mz)/u_d;
-        out[7] += vol*B->u[CC(B,IEN,k,j,i)];
+        if (!ISO(m)) out[7] += vol*B->u[CC(B,IEN,k,j,i)];
         if (m->p.mhd) {
           double bcc1 = B->bcc[CC(B,IB1,k,j,i)], bcc2 = B->bcc[CC(B,IB2,k,j,i)],
                  bcc3 = B->bcc[CC(B,IB3,k,j,i)];
@@ -1534,18 +1550,18 @@ double ao_new_block_dt(AoMesh *m, int b) {
                b3c = B->bcc[CC(B,IB3,k,j,i)];
         double bx = b1c + fabs(B->b[0][F1(B,k,j,i)] - b1c);
         wi[IBY] = b2c; wi[IBZ] = b3c;
-        double cf = ao_fast_speed(gamma, wi, bx);
+        double cf = ISO(m) ? ao_fast_speed_iso(m->p.iso_cs, wi, bx) : ao_fast_speed(gamma, wi, bx);
         dt1 /= (fabs(wi[IVX]) + cf);
         wi[IBY] = b3c; wi[IBZ] = b1c;
         bx = b2c + fabs(B->b[1][F2(B,k,j,i)] - b2c);
-        cf = ao_fast_speed(gamma, wi, bx);
+        cf = ISO(m) ? ao_fast_speed_iso(m->p.iso_cs, wi, bx) : ao_fast_speed(gamma, wi, bx);
         dt2 /= (fabs(wi[IVY]) + cf);
         wi[IBY] = b1c; wi[IBZ] = b2c;
         bx = b3c + fabs(B->b[2][F3(B,k,j,i)] - b3c);
-        cf = ao_fast_speed(gamma, wi, bx);
+        cf = ISO(m) ? ao_fast_speed_iso(m->p.iso_cs, wi, bx) : ao_fast_speed(gamma, wi, bx);
         dt3 /= (fabs(wi[IVZ]) + cf);
       } else {
-        double cs = ao_sound_speed(gamma, wi);
+        double cs = ISO(m) ? m->p.iso_cs : ao_sound_speed(gamma, wi);
         dt1 /= (fabs(wi[IVX]) + cs);
         dt2 /= (fabs(wi[IVY]) + cs);
         dt3 /= (fabs(wi[IVZ]) + cs);

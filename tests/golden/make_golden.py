@@ -98,6 +98,28 @@ CASES = {
     "shkcloud3d_hlld_plm_vl2_8blk": ("mhd_hlld_ng2", "shk_cloud", "athinput.shk_cloud",
                                      {"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16,
                                       **mb(8, 8, 8)}, "hlld", True, 5),
+    # isothermal EOS (eos/isothermal_{hydro,mhd}.cpp; hlle.cpp / hlle_mhd.cpp / hlld_iso.cpp)
+    "iso_khs_hlle_plm_vl2_4blk_s1": ("hydro_hlle_iso_ng2_s1", "kh", "athinput.kh_scalar",
+                                     dict(KS, **mb(8, 16, 1)), "hlle", False, 6, 1,
+                                     "isothermal"),
+    "iso_blast_hlle_plm_vl2_8blk": ("hydro_hlle_iso_ng2", "blast", "athinput.blast",
+                                    dict(BL, **mb(8, 8, 8), **{"hydro/iso_sound_speed": 0.4082482905,
+                                                               "problem/drat": 5.0}),
+                                    "hlle", False, 6, 0, "isothermal"),
+    "iso_blast_mhd_hlld_plm_vl2_8blk": ("mhd_hlld_iso_ng2", "blast", "athinput.blast",
+                                        dict(BL, **mb(8, 8, 8),
+                                             **{"hydro/iso_sound_speed": 0.4082482905,
+                                                "problem/drat": 5.0}),
+                                        "hlld", True, 6, 0, "isothermal"),
+    "iso_ot_hlld_plm_rk2_4blk": ("mhd_hlld_iso_ng2", "orszag_tang", "athinput.orszag_tang",
+                                 dict(OT, **mb(16, 16), **{"time/xorder": 2,
+                                                           "time/integrator": "rk2",
+                                                           "hydro/iso_sound_speed": 0.7}),
+                                 "hlld", True, 5, 0, "isothermal"),
+    "iso_ot_mhd_hlle_plm_vl2_4blk": ("mhd_hlle_iso_ng2", "orszag_tang", "athinput.orszag_tang",
+                                     dict(OT, **mb(16, 16), **{"time/xorder": 2,
+                                                               "hydro/iso_sound_speed": 0.7}),
+                                     "hlle", True, 5, 0, "isothermal"),
     # passive scalars (src/scalars): the fork's production build carries one (confignotes)
     "khs_lhllc_plm_vl2_4blk_s1": ("hydro_lhllc_ng2_s1", "kh", "athinput.kh_scalar",
                                   dict(KS, **mb(8, 16, 1)), "lhllc", False, 6, 1),
