@@ -94,21 +94,25 @@ __global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2pr
       b.bcc[o+2*sv] = bcc3;
       pb = 0.5*(sqr(bcc1) + sqr(bcc2) + sqr(bcc3));
     }
-    double u_d = b.u[o], u_m1 = b.u[o+sv], u_m2 = b.u[o+2*sv], u_m3 = b.u[o+3*sv],
-           u_e = b.u[o+4*sv];
+    // isothermal EOS (eos/isothermal_{hydro,mhd}.cpp:39-75): density floor and velocities only
+    const bool iso = (p.eos != 0);
+    double u_d = b.u[o], u_m1 = b.u[o+sv], u_m2 = b.u[o+2*sv], u_m3 = b.u[o+3*sv];
+    double u_e = iso ? 0.0 : b.u[o+4*sv];
     double u_d0 = u_d, u_e0 = u_e;
     u_d = (u_d > p.dfloor) ? u_d : p.dfloor;
     double di = 1.0/u_d;
-    double e_k = 0.5*di*(sqr(u_m1) + sqr(u_m2) + sqr(u_m3));
-    double w_p;
-    if (MHD) {
-      w_p = gm1*(u_e - e_k - pb);
-      u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k + pb);
-    } else {
-      w_p = gm1*(u_e - e_k);
-      u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k);
+    double w_p = 0.0;
+    if (!iso) {
+      double e_k = 0.5*di*(sqr(u_m1) + sqr(u_m2) + sqr(u_m3));
+      if (MHD) {
+        w_p = gm1*(u_e - e_k - pb);
+        u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k + pb);
+      } else {
+        w_p = gm1*(u_e - e_k);
+        u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k);
+      }
+      w_p = (w_p > p.pfloor) ? w_p : p.pfloor;
     }
-    w_p = (w_p > p.pfloor) ? w_p : p.pfloor;
     // floors write back into cons (the reference always stores; storing only changes is
     // value-identical and saves two stores per cell)
     if (u_d != u_d0) b.u[o] = u_d;
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2pr
     b.w[o+sv] = vx;
     b.w[o+2*sv] = vy;
     b.w[o+3*sv] = vz;
-    b.w[o+4*sv] = w_p;
+    if (!iso) b.w[o+4*sv] = w_p;
     if (MHD && (FLAGS & 1)) {
       if (b.f3) {
         b.cc_e[o] = vz*bcc2 - vy*bcc3;
@@ -133,16 +137,19 @@ __global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2pr
       double dt1 = b.dx1f[i], dt2 = b.dx2f[j], dt3 = b.dx3f[k];
       if (MHD) {
         double bx = bcc1 + fabs(bf1 - bcc1);
-        double cf = fast_speed(p.gamma, u_d, w_p, bcc2, bcc3, bx);
+        double cf = iso ? fast_speed_iso(p.iso_cs, u_d, bcc2, bcc3, bx)
+                        : fast_speed(p.gamma, u_d, w_p, bcc2, bcc3, bx);
         dt1 /= (fabs(vx) + cf);
         bx = bcc2 + fabs(bf2 - bcc2);
-        cf = fast_speed(p.gamma, u_d, w_p, bcc3, bcc1, bx);
+        cf = iso ? fast_speed_iso(p.iso_cs, u_d, bcc3, bcc1, bx)
+                 : fast_speed(p.gamma, u_d, w_p, bcc3, bcc1, bx);
         dt2 /= (fabs(vy) + cf);
         bx = bcc3 + fabs(bf3 - bcc3);
-        cf = fast_speed(p.gamma, u_d, w_p, bcc1, bcc2, bx);
+        cf = iso ? fast_speed_iso(p.iso_cs, u_d, bcc1, bcc2, bx)
+                 : fast_speed(p.gamma, u_d, w_p, bcc1, bcc2, bx);
         dt3 /= (fabs(vz) + cf);
       } else {
-        double cs = sound_speed(p.gamma, u_d, w_p);
+        double cs = iso ? p.iso_cs : sound_speed(p.gamma, u_d, w_p);
         dt1 /= (fabs(vx) + cs);
         dt2 /= (fabs(vy) + cs);
         dt3 /= (fabs(vz) + cs);
@@ -180,15 +187,16 @@ __global__ void __launch_bounds__(BX) k_prim2cons(BlkDev b, Params p, int il, in
   int i = il + blockIdx.x*BX + threadIdx.x;
   if (i > iu) return;
   int j = jl + blockIdx.y, k = kl + blockIdx.z;
-  double igm1 = 1.0/(p.gamma - 1.0);
   long o = CCI(b,0,k,j,i);
   long sv = (long)b.nc3*b.nc2*b.nc1;
-  double w_d = b.w[o], w_vx = b.w[o+sv], w_vy = b.w[o+2*sv], w_vz = b.w[o+3*sv],
-         w_p = b.w[o+4*sv];
+  double w_d = b.w[o], w_vx = b.w[o+sv], w_vy = b.w[o+2*sv], w_vz = b.w[o+3*sv];
   b.u[o] = w_d;
   b.u[o+sv] = w_vx*w_d;
   b.u[o+2*sv] = w_vy*w_d;
   b.u[o+3*sv] = w_vz*w_d;
+  if (p.eos != 0) return;        // isothermal: no energy equation
+  double igm1 = 1.0/(p.gamma - 1.0);
+  double w_p = b.w[o+4*sv];
   if (MHD) {
     double bcc1 = b.bcc[o], bcc2 = b.bcc[o+sv], bcc3 = b.bcc[o+2*sv];
     b.u[o+4*sv] = w_p*igm1 + 0.5*(w_d*(sqr(w_vx) + sqr(w_vy) + sqr(w_vz))
@@ -226,7 +234,7 @@ void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, in
 
 // sweep-ordered primitives of one cell: (rho, v_dir, v_dir+1, v_dir+2, p [, B_dir+1, B_dir+2])
 // (32-bit element offsets: the host checks that every register has < 2^31 elements)
-template <int DIR, bool MHD>
+template <int DIR, bool MHD, bool ISO = false>
 __device__ __forceinline__ void load_cell(const double *__restrict__ w,
                                           const double *__restrict__ bcc, int o, int sv,
                                           double *q) {
@@ -234,7 +242,7 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
   q[IVX] = w[o + (1 + DIR)*sv];
   q[IVY] = w[o + (1 + (DIR+1)%3)*sv];
   q[IVZ] = w[o + (1 + (DIR+2)%3)*sv];
-  q[IPR] = w[o + 4*sv];
+  q[IPR] = ISO ? 0.0 : w[o + 4*sv];       // isothermal: w has 4 variables, slot unused
   if (MHD) {
     q[IBY] = bcc[o + ((DIR+1)%3)*sv];
     q[IBZ] = bcc[o + ((DIR+2)%3)*sv];
@@ -271,6 +279,7 @@ __global__ void AB_FLUX_BOUNDS
 k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
        int ntot, double dt_val, const double *dt_ptr) {
   constexpr int NW = MHD ? 7 : 5;
+  constexpr bool ISO = (SOLVER == SOLVER_HLLE_ISO || SOLVER == SOLVER_HLLD_ISO);
   int t = blockIdx.x*AB_FLUX_BX + threadIdx.x;
   if (t >= ntot) return;
   int i, j, k;
@@ -319,14 +328,14 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
   double wl[NW], wr[NW];
   if (ORDER == 1) {
     // DonorCell (reconstruct/dc.cpp)
-    load_cell<DIR,MHD>(w, bcc, oc - st, sv, wl);
-    load_cell<DIR,MHD>(w, bcc, oc, sv, wr);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, wl);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, wr);
   } else if (ORDER == 2) {
     double qm2[NW], qm1[NW], q0[NW], qp1[NW];
-    load_cell<DIR,MHD>(w, bcc, oc - 2*st, sv, qm2);
-    load_cell<DIR,MHD>(w, bcc, oc - st, sv, qm1);
-    load_cell<DIR,MHD>(w, bcc, oc, sv, q0);
-    load_cell<DIR,MHD>(w, bcc, oc + st, sv, qp1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + st, sv, qp1);
     const double wp_l = g.wp[DIR][c-1], wm_l = g.wm[DIR][c-1];
     const double wp_r = g.wp[DIR][c], wm_r = g.wm[DIR][c];
 #pragma unroll
@@ -337,12 +346,12 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
     }
   } else {
     double qm3[NW], qm2[NW], qm1[NW], q0[NW], qp1[NW], qp2[NW];
-    load_cell<DIR,MHD>(w, bcc, oc - 3*st, sv, qm3);
-    load_cell<DIR,MHD>(w, bcc, oc - 2*st, sv, qm2);
-    load_cell<DIR,MHD>(w, bcc, oc - st, sv, qm1);
-    load_cell<DIR,MHD>(w, bcc, oc, sv, q0);
-    load_cell<DIR,MHD>(w, bcc, oc + st, sv, qp1);
-    load_cell<DIR,MHD>(w, bcc, oc + 2*st, sv, qp2);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 3*st, sv, qm3);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + st, sv, qp1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + 2*st, sv, qp2);
 #pragma unroll
     for (int n = 0; n < NW; ++n) {
       double dummy;
@@ -351,9 +360,11 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
     }
     // ApplyPrimitiveFloors (ppm.cpp:326-332)
     wl[IDN] = (wl[IDN] > p.dfloor) ? wl[IDN] : p.dfloor;
-    wl[IPR] = (wl[IPR] > p.pfloor) ? wl[IPR] : p.pfloor;
     wr[IDN] = (wr[IDN] > p.dfloor) ? wr[IDN] : p.dfloor;
-    wr[IPR] = (wr[IPR] > p.pfloor) ? wr[IPR] : p.pfloor;
+    if (!ISO) {
+      wl[IPR] = (wl[IPR] > p.pfloor) ? wl[IPR] : p.pfloor;
+      wr[IPR] = (wr[IPR] > p.pfloor) ? wr[IPR] : p.pfloor;
+    }
   }
 
   // LHLLC / LHLLD shock detector inputs: Hydro::CalculateVelocityDifferences
@@ -379,14 +390,14 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
     }
   }
   double f[NW];
-  riemann<SOLVER,MHD>(wl, wr, bxi, p.gamma, dvn, dvt, f);
+  riemann<SOLVER,MHD>(wl, wr, bxi, ISO ? p.iso_cs : p.gamma, dvn, dvt, f, p.dfloor);
 
   double *__restrict__ flx = b.flux[DIR];
   flx[of] = f[IDN];
   flx[of + (1 + DIR)*sf] = f[IVX];
   flx[of + (1 + (DIR+1)%3)*sf] = f[IVY];
   flx[of + (1 + (DIR+2)%3)*sf] = f[IVZ];
-  flx[of + 4*sf] = f[IEN];
+  if (!ISO) flx[of + 4*sf] = f[IEN];
   if (MHD) {
     b.ef[DIR][0][of] = -f[IBY];
     b.ef[DIR][1][of] = f[IBZ];
@@ -434,7 +445,11 @@ static void flux_order(const BlkDev &b, const ReconGeom &g, const Params &p, int
 
 void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
                      double dt_val, const double *dt_ptr, cudaStream_t s) {
-  if (p.mhd) {
+  if (p.eos != 0) {   // isothermal: hlle (hydro), hlle / hlld (MHD) -- configure.py:299-325
+    if (!p.mhd) flux_order<SOLVER_HLLE_ISO,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD_ISO,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else flux_order<SOLVER_HLLE_ISO,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
+  } else if (p.mhd) {
     if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else if (p.solver == SOLVER_LHLLD) flux_order<SOLVER_LHLLD,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
@@ -1054,10 +1069,14 @@ void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta,
     k_integrate_cc<0><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
                                        dt_ptr, kl, ni, nj, ntot);
   } else {
-    c.u = b.u; c.u1 = b.u1; c.nvar = NHYDRO;
+    c.u = b.u; c.u1 = b.u1; c.nvar = b.nh;
     for (int d = 0; d < 3; ++d) c.f[d] = b.flux[d];
-    k_integrate_cc<NHYDRO><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
-                                            dt_ptr, kl, ni, nj, ntot);
+    if (b.nh == NHYDRO)
+      k_integrate_cc<NHYDRO><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
+                                              dt_ptr, kl, ni, nj, ntot);
+    else
+      k_integrate_cc<4><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
+                                         dt_ptr, kl, ni, nj, ntot);
   }
   ++g_launches;
 }
@@ -1210,7 +1229,7 @@ __global__ void __launch_bounds__(BX) k_phys_bc(BlkDev b, int mhd, int face, int
       const int j = jl + a, k = kl + c;
       if (j > ju+1 || k > ku+1) return;
       if (j <= ju && k <= ku) {
-        for (int n = 0; n < NHYDRO; ++n) {
+        for (int n = 0; n < b.nh; ++n) {
           double v = b.w[CCI(b,n,k,j,sc)];
           b.w[CCI(b,n,k,j,gc)] = (refl && n == IVX) ? -v : v;
         }
@@ -1224,7 +1243,7 @@ __global__ void __launch_bounds__(BX) k_phys_bc(BlkDev b, int mhd, int face, int
       const int i = il + a, k = kl + c;
       if (i > iu+1 || k > ku+1) return;
       if (i <= iu && k <= ku) {
-        for (int n = 0; n < NHYDRO; ++n) {
+        for (int n = 0; n < b.nh; ++n) {
           double v = b.w[CCI(b,n,k,sc,i)];
           b.w[CCI(b,n,k,gc,i)] = (refl && n == IVY) ? -v : v;
         }
@@ -1237,7 +1256,7 @@ __global__ void __launch_bounds__(BX) k_phys_bc(BlkDev b, int mhd, int face, int
       const int i = il + a, j = jl + c;
       if (i > iu+1 || j > ju+1) return;
       if (i <= iu && j <= ju) {
-        for (int n = 0; n < NHYDRO; ++n) {
+        for (int n = 0; n < b.nh; ++n) {
           double v = b.w[CCI(b,n,sc,j,i)];
           b.w[CCI(b,n,gc,j,i)] = (refl && n == IVZ) ? -v : v;
         }
@@ -1272,21 +1291,26 @@ __global__ void __launch_bounds__(BX) k_new_dt(BlkDev b, Params p, unsigned long
   if (i <= b.ie) {
     long sv = (long)b.nc3*b.nc2*b.nc1;
     long o = CCI(b,0,k,j,i);
-    double d = b.w[o], vx = b.w[o+sv], vy = b.w[o+2*sv], vz = b.w[o+3*sv], pr = b.w[o+4*sv];
+    const bool iso = (p.eos != 0);
+    double d = b.w[o], vx = b.w[o+sv], vy = b.w[o+2*sv], vz = b.w[o+3*sv];
+    double pr = iso ? 0.0 : b.w[o+4*sv];
     double dt1 = b.dx1f[i], dt2 = b.dx2f[j], dt3 = b.dx3f[k];
     if (MHD) {
       double b1c = b.bcc[o], b2c = b.bcc[o+sv], b3c = b.bcc[o+2*sv];
       double bx = b1c + fabs(b.b[0][F1I(b,k,j,i)] - b1c);
-      double cf = fast_speed(p.gamma, d, pr, b2c, b3c, bx);
+      double cf = iso ? fast_speed_iso(p.iso_cs, d, b2c, b3c, bx)
+                      : fast_speed(p.gamma, d, pr, b2c, b3c, bx);
       dt1 /= (fabs(vx) + cf);
       bx = b2c + fabs(b.b[1][F2I(b,k,j,i)] - b2c);
-      cf = fast_speed(p.gamma, d, pr, b3c, b1c, bx);
+      cf = iso ? fast_speed_iso(p.iso_cs, d, b3c, b1c, bx)
+               : fast_speed(p.gamma, d, pr, b3c, b1c, bx);
       dt2 /= (fabs(vy) + cf);
       bx = b3c + fabs(b.b[2][F3I(b,k,j,i)] - b3c);
-      cf = fast_speed(p.gamma, d, pr, b1c, b2c, bx);
+      cf = iso ? fast_speed_iso(p.iso_cs, d, b1c, b2c, bx)
+               : fast_speed(p.gamma, d, pr, b1c, b2c, bx);
       dt3 /= (fabs(vz) + cf);
     } else {
-      double cs = sound_speed(p.gamma, d, pr);
+      double cs = iso ? p.iso_cs : sound_speed(p.gamma, d, pr);
       dt1 /= (fabs(vx) + cs);
       dt2 /= (fabs(vy) + cs);
       dt3 /= (fabs(vz) + cs);
@@ -1313,11 +1337,12 @@ void launch_new_block_dt(const BlkDev &b, const Params &p, unsigned long long *o
 constexpr int HIST_T = 256;
 constexpr int HIST_MAXQ = 32;
 
+template <bool ISO>
 __global__ void __launch_bounds__(HIST_T) k_history(BlkDev b, int mhd, int nq, int ni, int nj,
                                                     int ntot, double *partial) {
+  constexpr int NB = ISO ? 7 : 8;    // quantities ahead of the magnetic energies (NHYDRO + 3)
   const int n1 = b.nc1, n2 = b.nc2;
   const int sv = b.nc3*n2*n1;
-  const int nme = mhd ? 3 : 0;
   double acc[HIST_MAXQ];
 #pragma unroll
   for (int q = 0; q < HIST_MAXQ; ++q) acc[q] = 0.0;
@@ -1337,16 +1362,23 @@ __global__ void __launch_bounds__(HIST_T) k_history(BlkDev b, int mhd, int nq, i
     acc[4] += vol*0.5*sqr(u_mx)/u_d;
     acc[5] += vol*0.5*sqr(u_my)/u_d;
     acc[6] += vol*0.5*sqr(u_mz)/u_d;
-    acc[7] += vol*b.u[o+4*sv];
+    if (!ISO) acc[7] += vol*b.u[o+4*sv];
     if (mhd) {
       const double bcc1 = b.bcc[o], bcc2 = b.bcc[o+sv], bcc3 = b.bcc[o+2*sv];
-      acc[8] += vol*0.5*bcc1*bcc1;
-      acc[9] += vol*0.5*bcc2*bcc2;
-      acc[10] += vol*0.5*bcc3*bcc3;
+      acc[NB] += vol*0.5*bcc1*bcc1;
+      acc[NB + 1] += vol*0.5*bcc2*bcc2;
+      acc[NB + 2] += vol*0.5*bcc3*bcc3;
     }
+    // scalars follow the magnetic energies (history.cpp:158-162)
+    if (mhd) {
 #pragma unroll
-    for (int n = 0; n < 16; ++n)
-      if (n < b.ns) acc[8 + nme + n] += vol*b.s[o + n*sv];
+      for (int n = 0; n < 16; ++n)
+        if (n < b.ns) acc[NB + 3 + n] += vol*b.s[o + n*sv];
+    } else {
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        if (n < b.ns) acc[NB + n] += vol*b.s[o + n*sv];
+    }
   }
   __shared__ double sm[HIST_T/32][HIST_MAXQ];
 #pragma unroll
@@ -1383,7 +1415,9 @@ void launch_history(const BlkDev &b, int mhd, int nq, int first, double *partial
   const int ntot = ni*nj*nk;
   int g = (ntot + HIST_T - 1)/HIST_T;
   if (g > history_grid()) g = history_grid();
-  k_history<<<g, HIST_T, 0, s>>>(b, mhd, nq, ni, nj, ntot, partial); ++g_launches;
+  if (b.nh == NHYDRO) k_history<false><<<g, HIST_T, 0, s>>>(b, mhd, nq, ni, nj, ntot, partial);
+  else k_history<true><<<g, HIST_T, 0, s>>>(b, mhd, nq, ni, nj, ntot, partial);
+  ++g_launches;
   k_history_final<<<1, 32, 0, s>>>(partial, g, nq, first, out); ++g_launches;
 }
 

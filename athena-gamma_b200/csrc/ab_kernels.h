@@ -29,7 +29,7 @@ void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);
 
 // WeightedAve special-casing of the reference (mesh/weighted_ave.cpp) for out = w0*out + w1*in
 void launch_weighted_ave_cc(const BlkDev &b, double *out, const double *in, double w0,
-                            double w1, cudaStream_t s, int nvar = NHYDRO);
+                            double w1, cudaStream_t s, int nvar);
 void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const in[3],
                             double w0, double w1, cudaStream_t s);
 

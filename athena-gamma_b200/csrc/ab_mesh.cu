@@ -138,6 +138,7 @@ struct AbMesh {
   AbMeshParams p;
   ab::Params kp;
   int ndim = 1, f2 = 0, f3 = 0;
+  int nh = 5;                             // NHYDRO: 5 adiabatic, 4 isothermal
   int nrb[3] = {1, 1, 1};
   int nbtotal = 0;
   int nc[3] = {1, 1, 1}, is = 0, ie = 0, js = 0, je = 0, ks = 0, ke = 0;
@@ -300,7 +301,7 @@ void fc_strides(const AbMesh *m, int comp, long &s3, long &s2) {
 }
 
 long state_msg_count(const AbMesh *m, int ox1, int ox2, int ox3) {
-  long n = ab::NHYDRO*cc_send_box(m, ox1, ox2, ox3).count();
+  long n = m->nh*cc_send_box(m, ox1, ox2, ox3).count();
   if (m->p.mhd) for (int c = 0; c < 3; ++c) n += fc_send_box(m, c, ox1, ox2, ox3).count();
   n += m->p.nscalars*cc_send_box(m, ox1, ox2, ox3).count();   // s rides behind u and b
   return n;
@@ -534,10 +535,10 @@ long reg_size(const AbMesh *m, int reg) {
   long ncc = n1*n2*n3;
   long nf1 = n3*n2*(n1+1), nf2 = n3*(n2+1)*n1, nf3 = (n3+1)*n2*n1;
   switch (reg) {
-    case AB_U: case AB_U1: case AB_W: return ab::NHYDRO*ncc;
-    case AB_FLUX_X1: return ab::NHYDRO*nf1;
-    case AB_FLUX_X2: return ab::NHYDRO*nf2;
-    case AB_FLUX_X3: return ab::NHYDRO*nf3;
+    case AB_U: case AB_U1: case AB_W: return m->nh*ncc;
+    case AB_FLUX_X1: return m->nh*nf1;
+    case AB_FLUX_X2: return m->nh*nf2;
+    case AB_FLUX_X3: return m->nh*nf3;
     case AB_S: case AB_S1: case AB_R: return m->p.nscalars*ncc;
     case AB_SFLUX_X1: return m->p.nscalars*nf1;
     case AB_SFLUX_X2: return m->p.nscalars*nf2;
@@ -600,6 +601,7 @@ int alloc_blocks(AbMesh *m) {
     d.is = m->is; d.ie = m->ie; d.js = m->js; d.je = m->je; d.ks = m->ks; d.ke = m->ke;
     d.ng = ng; d.f2 = m->f2; d.f3 = m->f3;
     d.ns = p.nscalars;
+    d.nh = m->nh;
     // sizes
     size_t tot = 0;
     for (int r = 0; r < AB_NREG; ++r) { L.regsize[r] = reg_size(m, r); tot += align256(L.regsize[r]*8); }
@@ -735,14 +737,14 @@ int build_state_plan(AbMesh *m, int which) {
       Box sb = cc_send_box(m, -nb.ox1, -nb.ox2, -nb.ox3);      // what the neighbour loads
       if (local) {
         LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
-        add_box(ph1, L.d.u, cs3, cs2, ncc, N.d.u, cs3, cs2, ncc, ab::NHYDRO, rb, sb.si, sb.sj, sb.sk);
+        add_box(ph1, L.d.u, cs3, cs2, ncc, N.d.u, cs3, cs2, ncc, m->nh, rb, sb.si, sb.sj, sb.sk);
       } else {
         double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}];
         Box z = {0, rb.ei-rb.si, 0, rb.ej-rb.sj, 0, rb.ek-rb.sk};
         long s2 = z.ei+1, s3 = s2*(z.ej+1);
-        add_box(ph1, L.d.u, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), ab::NHYDRO, rb, 0, 0, 0);
+        add_box(ph1, L.d.u, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), m->nh, rb, 0, 0, 0);
       }
-      long roff = ab::NHYDRO*rb.count();
+      long roff = m->nh*rb.count();
       const int ns = m->p.nscalars;
       if (mhd) {
         for (int c = 0; c < 3; ++c) {
@@ -787,8 +789,8 @@ int build_state_plan(AbMesh *m, int which) {
         Box lb2 = cc_send_box(m, nb.ox1, nb.ox2, nb.ox3);
         Box z = {0, lb2.ei-lb2.si, 0, lb2.ej-lb2.sj, 0, lb2.ek-lb2.sk};
         long s2 = z.ei+1, s3 = s2*(z.ej+1);
-        add_box(pack, dst, s3, s2, s3*(z.ek+1), L.d.u, cs3, cs2, ncc, ab::NHYDRO, z, lb2.si, lb2.sj, lb2.sk);
-        long soff = ab::NHYDRO*lb2.count();
+        add_box(pack, dst, s3, s2, s3*(z.ek+1), L.d.u, cs3, cs2, ncc, m->nh, z, lb2.si, lb2.sj, lb2.sk);
+        long soff = m->nh*lb2.count();
         if (mhd) for (int c = 0; c < 3; ++c) {
           Box fb = fc_send_box(m, c, nb.ox1, nb.ox2, nb.ox3);
           long fs3, fs2;
@@ -1247,8 +1249,15 @@ static int validate_params(const AbMeshParams *p) {
   }
   if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(AB_ERR_ARG, "bad rank/nranks");
   if (p->nscalars < 0 || p->nscalars > 16) return fail(AB_ERR_ARG, "nscalars must be in [0, 16]");
-  if (p->eos != AB_EOS_ADIABATIC)
-    return fail(AB_ERR_ARG, "only the adiabatic EOS is implemented on the device path");
+  if (p->eos != AB_EOS_ADIABATIC && p->eos != AB_EOS_ISOTHERMAL) return fail(AB_ERR_ARG, "unknown EOS");
+  if (p->eos == AB_EOS_ISOTHERMAL) {
+    // configure.py:311-322; the isothermal Roe / LLF branches are not on the device path
+    if (p->solver == AB_SOLVER_HLLC || p->solver == AB_SOLVER_LHLLC || p->solver == AB_SOLVER_LHLLD)
+      return fail(AB_ERR_ARG, "HLLC / LHLLC / LHLLD flux cannot be used with isothermal EOS");
+    if (p->solver == AB_SOLVER_ROE)
+      return fail(AB_ERR_ARG, "Roe flux with isothermal EOS is not implemented on the device path");
+    if (!(p->iso_sound_speed > 0.0)) return fail(AB_ERR_ARG, "hydro/iso_sound_speed must be set");
+  }
   return AB_OK;
 }
 
@@ -1261,6 +1270,8 @@ static void host_setup(AbMesh *m, const AbMeshParams *p) {
   // EquationOfState ctor: scalar_floor_ = hydro/sfloor, default sqrt(1024*FLT_MIN)
   if (m->p.sfloor == 0.0) m->p.sfloor = std::sqrt(1024.0*(double)FLT_MIN);
   m->kp.sfloor = m->p.sfloor;
+  m->kp.eos = p->eos; m->kp.iso_cs = p->iso_sound_speed;
+  m->nh = (p->eos == AB_EOS_ISOTHERMAL) ? 4 : 5;     // configure.py:374-377
   int ng = p->nghost;
   // MeshBlock index ranges (mesh/meshblock.cpp:55-80)
   m->is = ng; m->ie = ng + p->bx1 - 1; m->nc[0] = p->bx1 + 2*ng;
@@ -1404,7 +1415,7 @@ int ab_weighted_ave(AbMesh *m, int lid, int out_reg, int in_reg, const double w[
     return fail(AB_ERR_ARG, "only two-register averages (u,u1 / b,b1) are supported");
   if ((out_reg == AB_U || out_reg == AB_U1) && (in_reg == AB_U || in_reg == AB_U1)) {
     ab::launch_weighted_ave_cc(L.d, out_reg == AB_U ? L.d.u : L.d.u1,
-                               in_reg == AB_U ? L.d.u : L.d.u1, w[0], w[1], m->stream);
+                               in_reg == AB_U ? L.d.u : L.d.u1, w[0], w[1], m->stream, m->nh);
   } else if ((out_reg == AB_S || out_reg == AB_S1) && (in_reg == AB_S || in_reg == AB_S1) &&
              m->p.nscalars > 0) {
     ab::launch_weighted_ave_cc(L.d, out_reg == AB_S ? L.d.s : L.d.s1,
@@ -1589,7 +1600,7 @@ int ab_history(AbMesh *m, double *out, int max_n) {
   if (!m || !out) return fail(AB_ERR_ARG, "null argument");
   if (m->dry) return fail(AB_ERR_STATE, "host-only plan");
   CK(cudaSetDevice(m->p.device));
-  const int nq = ab::NHYDRO + 3 + (m->p.mhd ? 3 : 0) + m->p.nscalars;
+  const int nq = m->nh + 3 + (m->p.mhd ? 3 : 0) + m->p.nscalars;
   if (max_n < nq) return fail(AB_ERR_ARG, "ab_history: output array too small");
   if (!m->hist_partial) {
     CK(cudaMalloc(&m->hist_partial, sizeof(double)*32*ab::history_grid()));

@@ -958,11 +958,243 @@ AB_HD void roe_mhd(const double *wli, const double *wri, double bxi, double gamm
   }
 }
 
+// ------------------------------------------------------------------------ isothermal EOS
+// NON_BAROTROPIC_EOS == 0 (configure.py --eos=isothermal): NHYDRO = 4, no IPR / IEN.  The
+// sweep-ordered work arrays keep the 7-slot layout of the adiabatic code; slot 4 is unused.
+
+// src/eos/isothermal_mhd.cpp:122-129
+AB_HD double fast_speed_iso(double cs, double d, double by, double bz, double bx) {
+  double asq = (cs*cs)*d;
+  double vaxsq = bx*bx;
+  double ct2 = by*by + bz*bz;
+  double qsq = vaxsq + ct2 + asq;
+  double tmp = vaxsq + ct2 - asq;
+  return sqrt(0.5*(qsq + sqrt(tmp*tmp + 4.0*asq*ct2))/d);
+}
+AB_HD double fast_speed_iso(double cs, const double *prim, double bx) {
+  return fast_speed_iso(cs, prim[IDN], prim[IBY], prim[IBZ], bx);
+}
+
+// src/hydro/rsolvers/hydro/hlle.cpp:38-162 (isothermal branch)
+AB_HD void hlle_hydro_iso(const double *wli, const double *wri, double iso_cs, double *flxi) {
+  double wroe[5], fl[5], fr[5];
+  double sqrtdl = sqrt(wli[IDN]);
+  double sqrtdr = sqrt(wri[IDN]);
+  double isdlpdr = 1.0/(sqrtdl + sqrtdr);
+  wroe[IDN] = sqrtdl*sqrtdr;
+  wroe[IVX] = (sqrtdl*wli[IVX] + sqrtdr*wri[IVX])*isdlpdr;
+  wroe[IVY] = (sqrtdl*wli[IVY] + sqrtdr*wri[IVY])*isdlpdr;
+  wroe[IVZ] = (sqrtdl*wli[IVZ] + sqrtdr*wri[IVZ])*isdlpdr;
+  double cl = iso_cs, cr = iso_cs, a = iso_cs;
+  double al = dmin((wroe[IVX] - a), (wli[IVX] - cl));
+  double ar = dmax((wroe[IVX] + a), (wri[IVX] + cr));
+  double bp = ar > 0.0 ? ar : 0.0;
+  double bm = al < 0.0 ? al : 0.0;
+  double vxl = wli[IVX] - bm;
+  double vxr = wri[IVX] - bp;
+  fl[IDN] = wli[IDN]*vxl;
+  fr[IDN] = wri[IDN]*vxr;
+  fl[IVX] = wli[IDN]*wli[IVX]*vxl;
+  fr[IVX] = wri[IDN]*wri[IVX]*vxr;
+  fl[IVY] = wli[IDN]*wli[IVY]*vxl;
+  fr[IVY] = wri[IDN]*wri[IVY]*vxr;
+  fl[IVZ] = wli[IDN]*wli[IVZ]*vxl;
+  fr[IVZ] = wri[IDN]*wri[IVZ]*vxr;
+  fl[IVX] += (iso_cs*iso_cs)*wli[IDN];
+  fr[IVX] += (iso_cs*iso_cs)*wri[IDN];
+  double tmp = 0.0;
+  if (bp != bm) tmp = 0.5*(bp + bm)/(bp - bm);
+  for (int n = 0; n < 4; ++n)
+    flxi[n] = 0.5*(fl[n]+fr[n]) + (fl[n]-fr[n])*tmp;
+  flxi[IEN] = 0.0;
+}
+
+// src/hydro/rsolvers/mhd/hlle_mhd.cpp:25-182 (isothermal branch)
+AB_HD void hlle_mhd_iso(const double *wli, const double *wri, double bxi, double iso_cs,
+                         double *flxi) {
+  double wroe[7], fl[7], fr[7];
+  double sqrtdl = sqrt(wli[IDN]);
+  double sqrtdr = sqrt(wri[IDN]);
+  double isdlpdr = 1.0/(sqrtdl + sqrtdr);
+  wroe[IDN] = sqrtdl*sqrtdr;
+  wroe[IVX] = (sqrtdl*wli[IVX] + sqrtdr*wri[IVX])*isdlpdr;
+  wroe[IVY] = (sqrtdl*wli[IVY] + sqrtdr*wri[IVY])*isdlpdr;
+  wroe[IVZ] = (sqrtdl*wli[IVZ] + sqrtdr*wri[IVZ])*isdlpdr;
+  wroe[IBY] = (sqrtdr*wli[IBY] + sqrtdl*wri[IBY])*isdlpdr;
+  wroe[IBZ] = (sqrtdr*wli[IBZ] + sqrtdl*wri[IBZ])*isdlpdr;
+  double x = 0.5*(sqr(wli[IBY]-wri[IBY]) + sqr(wli[IBZ]-wri[IBZ]))/(sqr(sqrtdl+sqrtdr));
+  double y = 0.5*(wli[IDN] + wri[IDN])/wroe[IDN];
+  double pbl = 0.5*(bxi*bxi + sqr(wli[IBY]) + sqr(wli[IBZ]));
+  double pbr = 0.5*(bxi*bxi + sqr(wri[IBY]) + sqr(wri[IBZ]));
+  double cl = fast_speed_iso(iso_cs, wli, bxi);
+  double cr = fast_speed_iso(iso_cs, wri, bxi);
+  double btsq = sqr(wroe[IBY]) + sqr(wroe[IBZ]);
+  double vaxsq = bxi*bxi/wroe[IDN];
+  double bt_starsq = btsq*y;
+  double twid_asq = iso_cs*iso_cs + x;
+  double ct2 = bt_starsq/wroe[IDN];
+  double tsum = vaxsq + ct2 + twid_asq;
+  double tdif = vaxsq + ct2 - twid_asq;
+  double cf2_cs2 = sqrt(tdif*tdif + 4.0*twid_asq*ct2);
+  double cfsq = 0.5*(tsum + cf2_cs2);
+  double a = sqrt(cfsq);
+  double al = dmin((wroe[IVX] - a), (wli[IVX] - cl));
+  double ar = dmax((wroe[IVX] + a), (wri[IVX] + cr));
+  double bp = ar > 0.0 ? ar : 0.0;
+  double bm = al < 0.0 ? al : 0.0;
+  double vxl = wli[IVX] - bm;
+  double vxr = wri[IVX] - bp;
+  fl[IDN] = wli[IDN]*vxl;
+  fr[IDN] = wri[IDN]*vxr;
+  fl[IVX] = wli[IDN]*wli[IVX]*vxl + pbl - sqr(bxi);
+  fr[IVX] = wri[IDN]*wri[IVX]*vxr + pbr - sqr(bxi);
+  fl[IVY] = wli[IDN]*wli[IVY]*vxl - bxi*wli[IBY];
+  fr[IVY] = wri[IDN]*wri[IVY]*vxr - bxi*wri[IBY];
+  fl[IVZ] = wli[IDN]*wli[IVZ]*vxl - bxi*wli[IBZ];
+  fr[IVZ] = wri[IDN]*wri[IVZ]*vxr - bxi*wri[IBZ];
+  fl[IVX] += (iso_cs*iso_cs)*wli[IDN];
+  fr[IVX] += (iso_cs*iso_cs)*wri[IDN];
+  fl[IBY] = wli[IBY]*vxl - bxi*wli[IVY];
+  fr[IBY] = wri[IBY]*vxr - bxi*wri[IVY];
+  fl[IBZ] = wli[IBZ]*vxl - bxi*wli[IVZ];
+  fr[IBZ] = wri[IBZ]*vxr - bxi*wri[IVZ];
+  fl[IEN] = fr[IEN] = 0.0;
+  double tmp = 0.0;
+  if (bp != bm) tmp = 0.5*(bp + bm)/(bp - bm);
+  for (int n = 0; n < 7; ++n)
+    flxi[n] = 0.5*(fl[n]+fr[n]) + (fl[n]-fr[n])*tmp;
+}
+
+// src/hydro/rsolvers/mhd/hlld_iso.cpp:36-288 (Mignone 2007)
+AB_HD void hlld_iso(const double *wli, const double *wri, double bxi, double cs, double dfloor,
+                     double *flxi) {
+  Cons1D ul, ur, ulst, urst, ucst, fl, fr;
+  double spd[5];
+  ul.d  = wli[IDN];
+  ul.mx = wli[IVX]*ul.d;
+  ul.my = wli[IVY]*ul.d;
+  ul.mz = wli[IVZ]*ul.d;
+  ul.by = wli[IBY];
+  ul.bz = wli[IBZ];
+  ur.d  = wri[IDN];
+  ur.mx = wri[IVX]*ur.d;
+  ur.my = wri[IVY]*ur.d;
+  ur.mz = wri[IVZ]*ur.d;
+  ur.by = wri[IBY];
+  ur.bz = wri[IBZ];
+  double cfl = fast_speed_iso(cs, wli, bxi);
+  double cfr = fast_speed_iso(cs, wri, bxi);
+  spd[0] = dmin(wli[IVX]-cfl, wri[IVX]-cfr);
+  spd[4] = dmax(wli[IVX]+cfl, wri[IVX]+cfr);
+  double bxsq = bxi*bxi;
+  double ptl = sqr(cs)*wli[IDN] + 0.5*(bxsq + sqr(wli[IBY]) + sqr(wli[IBZ]));
+  double ptr = sqr(cs)*wri[IDN] + 0.5*(bxsq + sqr(wri[IBY]) + sqr(wri[IBZ]));
+  fl.d  = ul.mx;
+  fl.mx = ul.mx*wli[IVX] + ptl - bxsq;
+  fl.my = ul.my*wli[IVX] - bxi*ul.by;
+  fl.mz = ul.mz*wli[IVX] - bxi*ul.bz;
+  fl.by = ul.by*wli[IVX] - bxi*wli[IVY];
+  fl.bz = ul.bz*wli[IVX] - bxi*wli[IVZ];
+  fr.d  = ur.mx;
+  fr.mx = ur.mx*wri[IVX] + ptr - bxsq;
+  fr.my = ur.my*wri[IVX] - bxi*ur.by;
+  fr.mz = ur.mz*wri[IVX] - bxi*ur.bz;
+  fr.by = ur.by*wri[IVX] - bxi*wri[IVY];
+  fr.bz = ur.bz*wri[IVX] - bxi*wri[IVZ];
+  double idspd = 1.0/(spd[4]-spd[0]);
+  double dhll = (spd[4]*ur.d - spd[0]*ul.d - fr.d + fl.d)*idspd;
+  dhll = dmax(dhll, dfloor);
+  double sqrtdhll = sqrt(dhll);
+  double fdhll  = (spd[4]*fl.d  - spd[0]*fr.d  + spd[4]*spd[0]*(ur.d -ul.d ))*idspd;
+  double fmxhll = (spd[4]*fl.mx - spd[0]*fr.mx + spd[4]*spd[0]*(ur.mx-ul.mx))*idspd;
+  double ustar = fdhll/dhll;
+  double mxhll = (spd[4]*ur.mx - spd[0]*ul.mx - fr.mx + fl.mx)*idspd;
+  spd[1] = ustar - fabs(bxi)/sqrtdhll;
+  spd[3] = ustar + fabs(bxi)/sqrtdhll;
+  ulst.d  = dhll;
+  ulst.mx = mxhll;
+  double tmp = (spd[0]-spd[1])*(spd[0]-spd[3]);
+  if (fabs(spd[0]-spd[1]) < (1.0e-8)*cs) {
+    ulst.my = ul.my;
+    ulst.mz = ul.mz;
+    ulst.by = ul.by;
+    ulst.bz = ul.bz;
+  } else {
+    double mfact = bxi*(ustar-wli[IVX])/tmp;
+    double bfact = (ul.d*sqr(spd[0]-wli[IVX]) - bxsq)/(dhll*tmp);
+    ulst.my = dhll*wli[IVY] - ul.by*mfact;
+    ulst.mz = dhll*wli[IVZ] - ul.bz*mfact;
+    ulst.by = ul.by*bfact;
+    ulst.bz = ul.bz*bfact;
+  }
+  urst.d  = dhll;
+  urst.mx = mxhll;
+  tmp = (spd[4]-spd[1])*(spd[4]-spd[3]);
+  if (fabs(spd[4]-spd[3]) < (1.0e-8)*cs) {
+    urst.my = ur.my;
+    urst.mz = ur.mz;
+    urst.by = ur.by;
+    urst.bz = ur.bz;
+  } else {
+    double mfact = bxi*(ustar-wri[IVX])/tmp;
+    double bfact = (ur.d*sqr(spd[4]-wri[IVX]) - bxsq)/(dhll*tmp);
+    urst.my = dhll*wri[IVY] - ur.by*mfact;
+    urst.mz = dhll*wri[IVZ] - ur.bz*mfact;
+    urst.by = ur.by*bfact;
+    urst.bz = ur.bz*bfact;
+  }
+  double x = sqrtdhll*(bxi > 0.0 ? 1.0 : -1.0);
+  ucst.d  = dhll;
+  ucst.mx = mxhll;
+  ucst.my = 0.5*(ulst.my + urst.my + (urst.by-ulst.by)*x);
+  ucst.mz = 0.5*(ulst.mz + urst.mz + (urst.bz-ulst.bz)*x);
+  ucst.by = 0.5*(ulst.by + urst.by + (urst.my-ulst.my)/x);
+  ucst.bz = 0.5*(ulst.bz + urst.bz + (urst.mz-ulst.mz)/x);
+  if (spd[0] >= 0.0) {
+    flxi[IDN] = fl.d; flxi[IVX] = fl.mx; flxi[IVY] = fl.my; flxi[IVZ] = fl.mz;
+    flxi[IBY] = fl.by; flxi[IBZ] = fl.bz;
+  } else if (spd[4] <= 0.0) {
+    flxi[IDN] = fr.d; flxi[IVX] = fr.mx; flxi[IVY] = fr.my; flxi[IVZ] = fr.mz;
+    flxi[IBY] = fr.by; flxi[IBZ] = fr.bz;
+  } else if (spd[1] >= 0.0) {
+    flxi[IDN] = fl.d  + spd[0]*(ulst.d  - ul.d);
+    flxi[IVX] = fl.mx + spd[0]*(ulst.mx - ul.mx);
+    flxi[IVY] = fl.my + spd[0]*(ulst.my - ul.my);
+    flxi[IVZ] = fl.mz + spd[0]*(ulst.mz - ul.mz);
+    flxi[IBY] = fl.by + spd[0]*(ulst.by - ul.by);
+    flxi[IBZ] = fl.bz + spd[0]*(ulst.bz - ul.bz);
+  } else if (spd[3] <= 0.0) {
+    flxi[IDN] = fr.d  + spd[4]*(urst.d  - ur.d);
+    flxi[IVX] = fr.mx + spd[4]*(urst.mx - ur.mx);
+    flxi[IVY] = fr.my + spd[4]*(urst.my - ur.my);
+    flxi[IVZ] = fr.mz + spd[4]*(urst.mz - ur.mz);
+    flxi[IBY] = fr.by + spd[4]*(urst.by - ur.by);
+    flxi[IBZ] = fr.bz + spd[4]*(urst.bz - ur.bz);
+  } else {
+    flxi[IDN] = dhll*ustar;
+    flxi[IVX] = fmxhll;
+    flxi[IVY] = ucst.my*ustar - bxi*ucst.by;
+    flxi[IVZ] = ucst.mz*ustar - bxi*ucst.bz;
+    flxi[IBY] = ucst.by*ustar - bxi*ucst.my/ucst.d;
+    flxi[IBZ] = ucst.bz*ustar - bxi*ucst.mz/ucst.d;
+  }
+  flxi[IEN] = 0.0;
+}
+
+// internal solver ids of the isothermal variants (the ABI keeps AB_SOLVER_* + AB_EOS_*)
+enum : int { SOLVER_HLLE_ISO = 6, SOLVER_HLLD_ISO = 7 };
+
 // compile-time dispatch
+// `gamma` carries the isothermal sound speed and `dfloor` the density floor for the *_ISO ids
 template <int SOLVER, bool MHD>
 AB_HD void riemann(const double *wli, const double *wri, double bxi, double gamma, double dvn,
-                   double dvt, double *flxi) {
-  if (!MHD) {
+                   double dvt, double *flxi, double dfloor = 0.0) {
+  if (SOLVER == SOLVER_HLLE_ISO) {
+    if (MHD) hlle_mhd_iso(wli, wri, bxi, gamma, flxi);
+    else hlle_hydro_iso(wli, wri, gamma, flxi);
+  } else if (SOLVER == SOLVER_HLLD_ISO) {
+    hlld_iso(wli, wri, bxi, gamma, dfloor, flxi);
+  } else if (!MHD) {
     if (SOLVER == SOLVER_HLLC) hllc_t<false>(wli, wri, gamma, 0.0, 0.0, flxi);
     else if (SOLVER == SOLVER_LHLLC) hllc_t<true>(wli, wri, gamma, dvn, dvt, flxi);
     else if (SOLVER == SOLVER_HLLE) hlle_hydro(wli, wri, gamma, flxi);

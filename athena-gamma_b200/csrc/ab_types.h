@@ -4,7 +4,7 @@
 
 namespace ab {
 
-constexpr int NHYDRO = 5;
+constexpr int NHYDRO = 5;    // adiabatic; BlkDev::nh holds the run-time count (4 when isothermal)
 constexpr int MAX_NB = 26;
 constexpr int DT_SLOTS = 64;   // atomicMin targets per MeshBlock for the CFL reduction
 
@@ -16,6 +16,7 @@ struct BlkDev {
   int is, ie, js, je, ks, ke;     // active range
   int ng;
   int f2, f3;                     // mesh is >=2-D / 3-D
+  int nh;                         // NHYDRO of this build: 5 adiabatic, 4 isothermal
   // conserved / primitive registers: NHYDRO x nc3 x nc2 x nc1
   double *u, *u1, *w;
   // face fields: x1f nc3 x nc2 x (nc1+1); x2f nc3 x (nc2+1) x nc1; x3f (nc3+1) x nc2 x nc1
@@ -61,6 +62,8 @@ struct Params {
   double gamma, dfloor, pfloor;
   int mhd, solver, xorder;
   double sfloor;                  // passive-scalar concentration floor (hydro/sfloor)
+  int eos;                        // 0 adiabatic, 1 isothermal
+  double iso_cs;                  // hydro/iso_sound_speed
 };
 
 }  // namespace ab

@@ -30,8 +30,10 @@ class MeshBlock:
 
     def shape(self, name):
         n1, n2, n3 = self.ncells1, self.ncells2, self.ncells3
+        # NHYDRO: 5 adiabatic, 4 isothermal (configure.py:374-377)
+        nh = 4 if getattr(getattr(self.pmy_mesh, "params", None), "eos", 0) == 1 else 5
         if name in ("u", "u1", "w"):
-            return (5, n3, n2, n1)
+            return (nh, n3, n2, n1)
         if name in ("s", "s1", "r"):
             return (self.pmy_mesh.params.nscalars, n3, n2, n1)
         if name in ("sflux1", "sflux2", "sflux3"):
@@ -52,7 +54,7 @@ class MeshBlock:
             d = int(name[-1]) - 1
             s = [n3, n2, n1]
             s[2 - d] += 1
-            return (5,) + tuple(s)
+            return (nh,) + tuple(s)
         if name == "e1":
             return (n3 + 1, n2 + 1, n1)
         if name == "e2":
@@ -122,7 +124,8 @@ class Mesh:
             flux = "hlld" if mhd else "hllc"    # configure.py:299-308
         p.solver = lib.SOLVER[flux]
         p.integrator = lib.INTEGRATOR[pin.get_or_add_string("time", "integrator", "vl2")]
-        p.gamma = pin.get_real("hydro", "gamma")
+        # the isothermal EquationOfState reads hydro/iso_sound_speed instead of hydro/gamma
+        p.gamma = pin.get_real("hydro", "gamma") if eos == "adiabatic" else 0.0
         p.dfloor = pin.get_or_add_real("hydro", "dfloor", DEFAULT_FLOOR)
         p.pfloor = pin.get_or_add_real("hydro", "pfloor", DEFAULT_FLOOR)
         p.cfl_number = pin.get_real("time", "cfl_number")
@@ -133,7 +136,8 @@ class Mesh:
         p.nscalars = int(nscalars)
         p.eos = lib.EOS[eos]
         p.sfloor = pin.get_or_add_real("hydro", "sfloor", DEFAULT_FLOOR)
-        p.iso_sound_speed = pin.get_or_add_real("hydro", "iso_sound_speed", 0.0)
+        p.iso_sound_speed = (pin.get_real("hydro", "iso_sound_speed") if eos == "isothermal"
+                             else pin.get_or_add_real("hydro", "iso_sound_speed", 0.0))
         return p, flux
 
     def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0, nscalars=0,

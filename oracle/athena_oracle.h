@@ -101,6 +101,9 @@ void ao_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
 void ao_riemann_dv(int solver, int mhd, long n, const double *wl, const double *wr,
                    const double *bx, const double *dvn, const double *dvt, double gamma,
                    double dt, double dx, double *flx, double *wct);
+/* isothermal EOS: hlle (hydro), hlle / hlld (MHD); slot 4 of the 5/7-slot vectors is unused */
+void ao_riemann_iso(int solver, int mhd, long n, const double *wl, const double *wr,
+                    const double *bx, double iso_cs, double dfloor, double *flx);
 void ao_plm(long n, int nvar, const double *qm1, const double *q, const double *qp1,
             double wp, double wm, double *ql_plus, double *qr_minus);
 void ao_ppm(long n, int nvar, const double *qm2, const double *qm1, const double *q,

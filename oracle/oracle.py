@@ -98,6 +98,8 @@ def lib():
                                  C.c_double, C.c_double, dp, dp]
         L.ao_riemann_dv.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, dp, dp, C.c_double,
                                     C.c_double, C.c_double, dp, dp]
+        L.ao_riemann_iso.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_double,
+                                     C.c_double, dp]
         L.ao_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
         L.ao_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, C.c_double, C.c_double,
                              dp, dp]
@@ -293,6 +295,18 @@ def riemann(solver, mhd, wl, wr, bx, gamma, dt=0.0, dx=1.0, dvn=None, dvt=None):
     L.ao_riemann_dv(SOLVER[solver], int(mhd), n, _dp(wl), _dp(wr), _dp(bx), _dp(dvn), _dp(dvt),
                     gamma, dt, dx, _dp(flx), _dp(wct))
     return flx, wct
+
+
+def riemann_iso(solver, mhd, wl, wr, bx, iso_cs, dfloor=DEFAULT_FLOOR):
+    L = lib()
+    wl = np.ascontiguousarray(wl, dtype=np.float64)
+    wr = np.ascontiguousarray(wr, dtype=np.float64)
+    n = wl.shape[1]
+    bx = np.ascontiguousarray(bx if bx is not None else np.zeros(n), dtype=np.float64)
+    flx = np.zeros_like(wl)
+    L.ao_riemann_iso(SOLVER[solver], int(mhd), n, _dp(wl), _dp(wr), _dp(bx), iso_cs, dfloor,
+                     _dp(flx))
+    return flx
 
 
 def plm(qm1, q, qp1, wp=0.5, wm=0.5):

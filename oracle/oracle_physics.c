@@ -1303,6 +1303,17 @@ void ao_riemann_point(int solver, int mhd, const double *wli, const double *wri,
   }
 }
 
+void ao_riemann_iso(int solver, int mhd, long n, const double *wl, const double *wr,
+                    const double *bx, double iso_cs, double dfloor, double *flx) {
+  int nw = mhd ? 7 : 5;
+  for (long i = 0; i < n; ++i) {
+    double wli[7], wri[7], f[7];
+    for (int v = 0; v < nw; ++v) { wli[v] = wl[v*n+i]; wri[v] = wr[v*n+i]; }
+    ao_riemann_point_iso(solver, mhd, wli, wri, mhd ? bx[i] : 0.0, iso_cs, dfloor, f);
+    for (int v = 0; v < nw; ++v) flx[v*n+i] = f[v];
+  }
+}
+
 void ao_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
                 const double *bx, double gamma, double dt, double dx,
                 double *flx, double *wct) {

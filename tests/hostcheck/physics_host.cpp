@@ -35,6 +35,19 @@ void hc_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
   }
 #undef RUN
 }
+// isothermal solvers: solver 0 = hlle (hydro / MHD), 2 = hlld (MHD)
+void hc_riemann_iso(int solver, int mhd, long n, const double *wl, const double *wr,
+                    const double *bx, double iso_cs, double dfloor, double *flx) {
+  const int nw = mhd ? 7 : 5;
+  for (long i = 0; i < n; ++i) {
+    double a[7], b[7], f[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int v = 0; v < nw; ++v) { a[v] = wl[v*n+i]; b[v] = wr[v*n+i]; }
+    if (!mhd) ab::riemann<ab::SOLVER_HLLE_ISO, false>(a, b, 0.0, iso_cs, 0.0, 0.0, f, dfloor);
+    else if (solver == 2) ab::riemann<ab::SOLVER_HLLD_ISO, true>(a, b, bx[i], iso_cs, 0.0, 0.0, f, dfloor);
+    else ab::riemann<ab::SOLVER_HLLE_ISO, true>(a, b, bx[i], iso_cs, 0.0, 0.0, f, dfloor);
+    for (int v = 0; v < nw; ++v) flx[v*n+i] = f[v];
+  }
+}
 void hc_plm(long n, int nvar, const double *qm1, const double *q, const double *qp1,
             double wp, double wm, double *ql, double *qr) {
   for (long i = 0; i < (long)nvar*n; ++i) ab::plm(qm1[i], q[i], qp1[i], wp, wm, ql[i], qr[i]);

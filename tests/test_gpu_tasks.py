@@ -32,6 +32,13 @@ CASES = [
     # user-enrolled boundary function
     ("shkcloud2d_hllc_plm_vl2_4blk", None, None),
     ("shkcloud3d_hlld_plm_vl2_8blk", None, None),
+    # isothermal EOS
+    ("iso_khs_hlle_plm_vl2_4blk_s1", None, None),
+    ("iso_blast_hlle_plm_vl2_8blk", None, None),
+    ("iso_blast_hlle_plm_vl2_8blk", 1, None),
+    ("iso_blast_mhd_hlld_plm_vl2_8blk", None, None),
+    ("iso_ot_hlld_plm_rk2_4blk", None, None),
+    ("iso_ot_mhd_hlle_plm_vl2_4blk", None, None),
     # passive scalars
     ("khs_lhllc_plm_vl2_4blk_s1", None, None),
     ("sods_lhllc_plm_vl2_2blk_s1", None, None),
@@ -51,10 +58,13 @@ def perturbed(g, seed):
         u = blk["u"].copy()
         u[0] *= np.exp(rng.normal(0, 0.5, u[0].shape))
         u[1:4] += rng.normal(0, 0.5, u[1:4].shape) * u[0]
-        u[4] *= np.exp(rng.normal(0, 0.3, u[4].shape))
-        u[4] += 0.5 * (u[1] ** 2 + u[2] ** 2 + u[3] ** 2) / u[0]
-        mask = rng.random(u[4].shape) < 0.002
-        u[4][mask] = 1e-3
+        if u.shape[0] > 4:          # adiabatic: energy; a few cells below the pressure floor
+            u[4] *= np.exp(rng.normal(0, 0.3, u[4].shape))
+            u[4] += 0.5 * (u[1] ** 2 + u[2] ** 2 + u[3] ** 2) / u[0]
+            mask = rng.random(u[4].shape) < 0.002
+            u[4][mask] = 1e-3
+        else:                       # isothermal: a few cells below the density floor
+            u[0][rng.random(u[0].shape) < 0.002] = 1e-30
         nb["u"] = u
         for f in g.fields[1:]:
             if f == "s":      # concentrations in [0, 1], a few below the floor

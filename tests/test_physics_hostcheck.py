@@ -28,6 +28,8 @@ def hc():
     dp = C.POINTER(C.c_double)
     L.hc_riemann.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, dp, dp, C.c_double,
                              C.c_double, C.c_double, dp, dp]
+    L.hc_riemann_iso.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_double, C.c_double,
+                                 dp]
     L.hc_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
     L.hc_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, dp, dp]
     return L
@@ -74,6 +76,26 @@ def test_riemann_matches_oracle(hc, solver, mhd, regime):
     util.assert_bitwise(fh, fo, "flux %s mhd=%s" % (solver, mhd))
     if mhd:
         util.assert_bitwise(wh, wo, "ct weight")
+
+
+@pytest.mark.parametrize("solver,mhd", [("hlle", False), ("hlle", True), ("hlld", True)])
+@pytest.mark.parametrize("regime", ["subsonic", "supersonic", "mixed"])
+def test_isothermal_riemann_matches_oracle(hc, solver, mhd, regime):
+    rng = np.random.default_rng(4321)
+    n = 20000
+    wl = random_states(rng, n, mhd, regime)
+    wr = random_states(rng, n, mhd, regime)
+    wr[:, : n // 4] = wl[:, : n // 4] * (1 + 1e-6 * rng.normal(size=(wl.shape[0], n // 4)))
+    wr[:, n // 4: n // 3] = wl[:, n // 4: n // 3]          # identical states: degenerate waves
+    bx = rng.normal(0, 1.0, n)
+    bx[n // 2: n // 2 + n // 8] = 0.0
+    bx[n // 2 + n // 8: n // 2 + n // 4] *= 1e-9
+    fo = oracle.riemann_iso(solver, mhd, wl, wr, bx, 0.7)
+    fh = np.zeros_like(wl)
+    hc.hc_riemann_iso(oracle.SOLVER[solver], int(mhd), n, _dp(wl), _dp(wr), _dp(bx), 0.7,
+                      oracle.DEFAULT_FLOOR, _dp(fh))
+    keep = [0, 1, 2, 3] + ([5, 6] if mhd else [])           # slot 4 (energy) is unused
+    util.assert_bitwise(fh[keep], fo[keep], "iso flux %s mhd=%s" % (solver, mhd))
 
 
 def test_plm_ppm_match_oracle(hc):
