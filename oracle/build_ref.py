@@ -177,7 +177,7 @@ def build(cfg, ref, jobs):
     common = [w[1] for w in work]
     for p, w in zip(pgens, pg_work):
         exe = os.path.join(root, "athena_" + p)
-        cmd = ["g++"] + CXXFLAGS + ["-o", exe] + common + [w[1]]
+        cmd = ["g++"] + CXXFLAGS + ["-s", "-o", exe] + common + [w[1]]   # -s: smaller to ship
         subprocess.run(cmd, check=True)
         print("built", exe)
 
