@@ -1004,9 +1004,12 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 // `c` selects the variable set: (u, u1, flux) with NVAR = NHYDRO for IntegrateHydro, or
 // (s, s1, s_flux) with NVAR = 0 -> c.nvar scalars for IntegrateScalars
 // (time_integrator.cpp:2141-2185, scalars/add_scalar_flux_divergence.cpp:43-97).
-struct CcSet { double *u, *u1; const double *f[3]; int nvar; };
+// SRC: HydroSourceTerms::ConstantAcceleration (hydro/srcterms/constant_acc.cpp:25-77) rides in
+// the same pass (SRC_TERM follows INT_HYD with dt = beta*dt and the stage-start primitives,
+// time_integrator.cpp:1655-1678): u(IM1+d) += src_d, u(IEN) += src_1*vx, then src_2*vy, src_3*vz.
+struct CcSet { double *u, *u1; const double *f[3]; int nvar; double g[3]; };
 
-template <int NVAR>
+template <int NVAR, bool SRC>
 __global__ void __launch_bounds__(BX, AB_CC_MINB) k_integrate_cc(BlkDev b, CcSet c, int mode, int zero_init,
                                                      double delta, double g1, double g2,
                                                      double beta, double dt_val,
@@ -1049,14 +1052,26 @@ __global__ void __launch_bounds__(BX, AB_CC_MINB) k_integrate_cc(BlkDev b, CcSet
       double dflx = (a1*c.f[0][o1+1+n*s1] - a1*c.f[0][o1+n*s1]);
       if (b.f2) dflx += (a2*c.f[1][o2+n1+n*s2] - a2*c.f[1][o2+n*s2]);
       if (b.f3) dflx += (a3*c.f[2][o3+n1*n2+n*s3] - a3*c.f[2][o3+n*s3]);
-      c.u[o+n*sv] = uo - wght*dflx/vol;
+      double v = uo - wght*dflx/vol;
+      if (SRC) {
+        const double w_d = b.w[o];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          if (c.g[d] == 0.0) continue;
+          const double src = wght*w_d*c.g[d];
+          if (n == IM1 + d) v += src;
+          if (n == IEN) v += src*b.w[o + (IVX + d)*sv];
+        }
+      }
+      c.u[o+n*sv] = v;
     }
   }
 }
 
 void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
-                         cudaStream_t s, int kl, int ku, int grid, int scalars) {
+                         cudaStream_t s, int kl, int ku, int grid, int scalars,
+                         const double *gacc) {
   if (kl < 0) { kl = b.ks; ku = b.ke; }
   const int ni = b.ie-b.is+1, nj = b.je-b.js+1, nk = ku-kl+1;
   const int ntot = ni*nj*nk;
@@ -1066,19 +1081,55 @@ void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta,
   if (scalars) {
     c.u = b.s; c.u1 = b.s1; c.nvar = b.ns;
     for (int d = 0; d < 3; ++d) c.f[d] = b.sflux[d];
-    k_integrate_cc<0><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
-                                       dt_ptr, kl, ni, nj, ntot);
+    for (int d = 0; d < 3; ++d) c.g[d] = 0.0;
+    k_integrate_cc<0,false><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
+                                             dt_ptr, kl, ni, nj, ntot);
   } else {
     c.u = b.u; c.u1 = b.u1; c.nvar = b.nh;
-    for (int d = 0; d < 3; ++d) c.f[d] = b.flux[d];
-    if (b.nh == NHYDRO)
-      k_integrate_cc<NHYDRO><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
-                                              dt_ptr, kl, ni, nj, ntot);
-    else
-      k_integrate_cc<4><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, beta, dt_val,
-                                         dt_ptr, kl, ni, nj, ntot);
+    bool src = false;
+    for (int d = 0; d < 3; ++d) {
+      c.f[d] = b.flux[d];
+      c.g[d] = gacc ? gacc[d] : 0.0;
+      src = src || (c.g[d] != 0.0);
+    }
+#define AB_ICC(NV, SR) k_integrate_cc<NV,SR><<<g, BX, 0, s>>>(b, c, mode, zero_init, delta, g1, g2, \
+                                                             beta, dt_val, dt_ptr, kl, ni, nj, ntot)
+    if (b.nh == NHYDRO) { if (src) AB_ICC(NHYDRO, true); else AB_ICC(NHYDRO, false); }
+    else { if (src) AB_ICC(4, true); else AB_ICC(4, false); }
+#undef AB_ICC
   }
   ++g_launches;
+}
+
+// HydroSourceTerms::ConstantAcceleration as its own pass (task-level entry point)
+struct Acc3 { double g[3]; };
+__global__ void __launch_bounds__(BX) k_const_accel(BlkDev b, Acc3 a, double dt, int ni, int nj,
+                                                    int ntot) {
+  const int n1 = b.nc1, n2 = b.nc2;
+  const int sv = b.nc3*n2*n1;
+  for (int t = blockIdx.x*BX + threadIdx.x; t < ntot; t += gridDim.x*BX) {
+    int r = t / ni;
+    const int i = b.is + (t - r*ni);
+    const int kk = r / nj;
+    const int j = b.js + (r - kk*nj);
+    const int o = ((b.ks + kk)*n2 + j)*n1 + i;
+    const double w_d = b.w[o];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (a.g[d] == 0.0) continue;
+      const double src = dt*w_d*a.g[d];
+      b.u[o + (IM1 + d)*sv] += src;
+      if (b.nh == NHYDRO) b.u[o + IEN*sv] += src*b.w[o + (IVX + d)*sv];
+    }
+  }
+}
+
+void launch_const_accel(const BlkDev &b, const double *g, double dt, cudaStream_t s) {
+  const int ni = b.ie-b.is+1, nj = b.je-b.js+1, nk = b.ke-b.ks+1;
+  const int ntot = ni*nj*nk;
+  Acc3 a;
+  for (int d = 0; d < 3; ++d) a.g[d] = g[d];
+  k_const_accel<<<(ntot + BX - 1)/BX, BX, 0, s>>>(b, a, dt, ni, nj, ntot); ++g_launches;
 }
 
 // register average of one face value (same modes as k_integrate_cc)

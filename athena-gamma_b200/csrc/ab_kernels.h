@@ -38,17 +38,19 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 // already pointer-swapped): u = (zero_init ? 0 : u) [+ delta*u1] ; u -= wght*div.
 // mode 2: u1 = (zero_init ? 0 : u1) [+ delta*u]; u = wave(u; u1; g1, g2); u -= wght*div.
 // wght = beta * dt.
+// gacc != nullptr: constant acceleration g[3] added in the same pass (SRC_TERM task).
 // [kl,ku]: plane range (kl < 0: all active planes); grid > 0 caps the number of CTAs
 // (grid-stride loop) so that the kernel can share the SMs with a concurrent flux kernel.
 void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
                          cudaStream_t s, int kl = -1, int ku = -1, int grid = 0,
-                         int scalars = 0);
+                         int scalars = 0, const double *gacc = nullptr);
 // passive scalars: s_flux from r and the hydro mass flux; r <-> s conversions on a cell range
 void launch_scalar_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
                           cudaStream_t s);
 void launch_scalar_eos(const BlkDev &b, const Params &p, int to_cons, int il, int iu, int jl,
                        int ju, int kl, int ku, cudaStream_t s);
+void launch_const_accel(const BlkDev &b, const double *g, double dt, cudaStream_t s);
 // Same for the face field + Field::CT (field/ct.cpp:31-116)
 void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,

@@ -1101,7 +1101,8 @@ int one_cycle(AbMesh *m) {
     for (auto &L : m->lb) {
       if (swap) {
         swap_cc(L);
-        ab::launch_integrate_cc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, m->stream);
+        ab::launch_integrate_cc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp,
+                                m->stream, -1, -1, 0, 0, m->p.grav_acc);
         if (m->p.mhd) {
           swap_fc(L);
           ab::launch_integrate_fc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, m->stream);
@@ -1112,7 +1113,8 @@ int one_cycle(AbMesh *m) {
                                   m->stream, -1, -1, 0, 1);
         }
       } else {
-        ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
+        ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0,
+                                dtp, m->stream, -1, -1, 0, 0, m->p.grav_acc);
         if (m->p.mhd)
           ab::launch_integrate_fc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
         if (m->p.nscalars > 0)
@@ -1456,6 +1458,14 @@ int ab_zero(AbMesh *m, int lid, int reg) {
 int ab_add_flux_div(AbMesh *m, int lid, double wght) {
   GET_L(m, lid);
   ab::launch_integrate_cc(L.d, 0, 0, 0.0, 0.0, 0.0, 1.0, wght, nullptr, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int ab_add_source_terms(AbMesh *m, int lid, double dt) {
+  GET_L(m, lid);
+  const double *g = m->p.grav_acc;
+  if (g[0] == 0.0 && g[1] == 0.0 && g[2] == 0.0) return AB_OK;   // hydro_sourceterms_defined
+  ab::launch_const_accel(L.d, g, dt, m->stream);
   CK(cudaGetLastError());
   return AB_OK;
 }

@@ -26,7 +26,7 @@ SYMBOLS = [
     "ab_plan_create", "ab_plan_messages", "ab_plan_ranklist",
     "ab_enroll_user_boundary_function", "ab_upload", "ab_download", "ab_download_coord", "ab_comm_unique_id", "ab_comm_init",
     "ab_cons2prim", "ab_prim2cons", "ab_primitives", "ab_calc_fluxes", "ab_corner_e",
-    "ab_weighted_ave", "ab_swap", "ab_zero", "ab_add_flux_div", "ab_ct", "ab_physical_bcs",
+    "ab_weighted_ave", "ab_swap", "ab_zero", "ab_add_flux_div", "ab_add_source_terms", "ab_ct", "ab_physical_bcs",
     "ab_calc_scalar_fluxes", "ab_add_scalar_flux_div", "ab_scalar_cons2prim",
     "ab_scalar_prim2cons", "ab_new_block_dt", "ab_emf_exchange", "ab_bvals_exchange", "ab_mesh_initialize",
     "ab_mesh_cycles", "ab_mesh_set_async", "ab_mesh_state", "ab_mesh_set_time_dt",
@@ -47,7 +47,7 @@ class AbMeshParams(C.Structure):
                 ("cfl_number", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double),
                 ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
                 ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
-                ("iso_sound_speed", C.c_double)]
+                ("iso_sound_speed", C.c_double), ("grav_acc", C.c_double * 3)]
 
 
 # AbBValFunc (include/athena_b200.h): user-enrolled boundary function on host arrays
@@ -102,6 +102,7 @@ def load():
     L.ab_swap.argtypes = [vp, ip, ip]
     L.ab_zero.argtypes = [vp, ip, ip]
     L.ab_add_flux_div.argtypes = [vp, ip, C.c_double]
+    L.ab_add_source_terms.argtypes = [vp, ip, C.c_double]
     L.ab_calc_scalar_fluxes.argtypes = [vp, ip, ip]
     L.ab_add_scalar_flux_div.argtypes = [vp, ip, C.c_double]
     L.ab_scalar_cons2prim.argtypes = [vp, ip] + [ip] * 6

@@ -138,6 +138,9 @@ class Mesh:
         p.sfloor = pin.get_or_add_real("hydro", "sfloor", DEFAULT_FLOOR)
         p.iso_sound_speed = (pin.get_real("hydro", "iso_sound_speed") if eos == "isothermal"
                              else pin.get_or_add_real("hydro", "iso_sound_speed", 0.0))
+        # HydroSourceTerms ctor (hydro/srcterms/hydro_srcterms.cpp:68-75)
+        for d in range(3):
+            p.grav_acc[d] = pin.get_or_add_real("hydro", "grav_acc%d" % (d + 1), 0.0)
         return p, flux
 
     def __init__(self, pin, mhd, flux, nghost=None, rank=0, nranks=1, device=0, nscalars=0,

@@ -59,6 +59,7 @@ typedef struct {
   int eos;                      /* AB_EOS_* (configure.py --eos)        */
   double sfloor;                /* hydro/sfloor (0 -> eos ctor default sqrt(1024*FLT_MIN)) */
   double iso_sound_speed;       /* hydro/iso_sound_speed (isothermal EOS) */
+  double grav_acc[3];           /* hydro/grav_acc1..3: constant acceleration source term */
 } AbMeshParams;
 
 typedef struct AbMesh AbMesh;
@@ -133,6 +134,11 @@ int ab_swap(AbMesh *m, int lid, int reg);
 int ab_zero(AbMesh *m, int lid, int reg);
 /* Hydro::AddFluxDivergence(wght, u) (hydro/add_flux_divergence.cpp:39-96) */
 int ab_add_flux_div(AbMesh *m, int lid, double wght);
+/* HydroSourceTerms::AddSourceTerms(time, dt, ...) -- constant acceleration hydro/grav_acc1..3
+ * (hydro/srcterms/hydro_srcterms.cpp:68-75, constant_acc.cpp:25-77) on u with the current w;
+ * dt = beta*dt of the stage (time_integrator.cpp:1655-1678).  ab_mesh_cycles fuses it into the
+ * IntegrateHydro kernel. */
+int ab_add_source_terms(AbMesh *m, int lid, double dt);
 /* Field::CT(wght, b) (field/ct.cpp:31-116) */
 int ab_ct(AbMesh *m, int lid, double wght);
 /* ---- passive scalars (NSCALARS > 0), src/scalars + src/eos/eos_scalars.cpp ---------------- */

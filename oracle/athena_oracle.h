@@ -34,6 +34,7 @@ typedef struct {
   int eos;              /* 0 adiabatic ; 1 isothermal (configure.py --eos) */
   double sfloor;        /* hydro/sfloor (eos ctor default sqrt(1024*FLT_MIN)) */
   double iso_cs;        /* hydro/iso_sound_speed */
+  double grav_acc[3];   /* hydro/grav_acc1..3 (hydro/srcterms/hydro_srcterms.cpp:68-75) */
 } AoParams;
 
 typedef struct AoMesh AoMesh;
@@ -83,6 +84,8 @@ typedef void (*AoBValFunc)(void *user, int block, double *prim, double *b1f, dou
                            double *b3f, double time, double dt, int il, int iu, int jl, int ju,
                            int kl, int ku, int ngh);
 void ao_enroll_user_bc(AoMesh *m, int face, AoBValFunc fn, void *user);
+/* HydroSourceTerms::AddSourceTerms, constant acceleration (hydro/srcterms/constant_acc.cpp) */
+void ao_add_source_terms(AoMesh *m, int b, double dt);
 /* HistoryOutput::WriteOutputFile sums (src/outputs/history.cpp:69-169): mass, 1..3-mom,
  * 1..3-KE, tot-E, [1..3-ME], [scalars]; returns the number of values written to out */
 int ao_history(AoMesh *m, double *out);

@@ -29,7 +29,7 @@ class AoParams(C.Structure):
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
                 ("cfl", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double),
                 ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
-                ("iso_cs", C.c_double)]
+                ("iso_cs", C.c_double), ("grav_acc", C.c_double * 3)]
 
 
 # AoBValFunc (athena_oracle.h): user-enrolled boundary function with plain arrays
@@ -86,6 +86,7 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.POINTER(C.c_double)]
         L.ao_add_flux_div.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.ao_add_source_terms.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.ao_ct.argtypes = [C.c_void_p, C.c_int, C.c_double]
         for f in ("ao_cons2prim", "ao_prim2cons", "ao_scalar_cons2prim", "ao_scalar_prim2cons"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 6
@@ -137,6 +138,8 @@ def params_from_athinput(par, mhd, solver, ng=None, nscalars=0, eos="adiabatic")
     p.iso_cs = float(h.get("iso_sound_speed", 0.0))
     p.nscalars = int(nscalars)
     p.sfloor = float(h.get("sfloor", DEFAULT_FLOOR))
+    for d in range(3):
+        p.grav_acc[d] = float(h.get("grav_acc%d" % (d + 1), 0.0))
     p.dfloor = float(h.get("dfloor", DEFAULT_FLOOR))
     p.pfloor = float(h.get("pfloor", DEFAULT_FLOOR))
     p.cfl = float(t["cfl_number"])

@@ -1496,6 +1496,23 @@ void ao_integrate_scalars(AoMesh *m, int b, int stage) {
     }
 }
 
+/* HydroSourceTerms::ConstantAcceleration (src/hydro/srcterms/constant_acc.cpp:25-77), called
+ * from the SRC_TERM task with dt = beta*dt on the stage's u, using the stage-start primitives
+ * (time_integrator.cpp:1655-1678) */
+void ao_add_source_terms(AoMesh *m, int b, double dt) {
+  AoBlock *B = &m->blk[b];
+  for (int d = 0; d < 3; ++d) {
+    double g = m->p.grav_acc[d];
+    if (g == 0.0) continue;
+    for (int k = B->ks; k <= B->ke; ++k) for (int j = B->js; j <= B->je; ++j)
+      for (int i = B->is; i <= B->ie; ++i) {
+        double src = dt*B->w[CC(B,IDN,k,j,i)]*g;
+        B->u[CC(B,IM1+d,k,j,i)] += src;
+        if (!ISO(m)) B->u[CC(B,IEN,k,j,i)] += src*B->w[CC(B,IVX+d,k,j,i)];
+      }
+  }
+}
+
 /* ------------------------------------------------------------------ history */
 
 /* HistoryOutput::WriteOutputFile (src/outputs/history.cpp:69-169): volume-weighted sums over
@@ -1622,6 +1639,7 @@ double ao_cycle(AoMesh *m) {
       if (w2[0] == 0.0 && w2[1] == 1.0 && w2[2] == 0.0) ao_swap_cc(m, g);
       else ao_weighted_ave_cc(m, g, 0, 1, w2);
       ao_add_flux_div(m, g, m->beta[s]*dt);
+      ao_add_source_terms(m, g, m->beta[s]*dt);    /* SRC_TERM after INT_HYD */
       if (m->p.mhd) {
         ao_weighted_ave_fc(m, g, 1, 0, w);
         if (w2[0] == 0.0 && w2[1] == 1.0 && w2[2] == 0.0) ao_swap_fc(m, g);

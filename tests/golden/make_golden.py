@@ -98,6 +98,22 @@ CASES = {
     "shkcloud3d_hlld_plm_vl2_8blk": ("mhd_hlld_ng2", "shk_cloud", "athinput.shk_cloud",
                                      {"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16,
                                       **mb(8, 8, 8)}, "hlld", True, 5),
+    # constant acceleration source term (hydro/srcterms/constant_acc.cpp) in a closed box
+    "blast_grav_hllc_plm_vl2_8blk": ("hydro_hllc_ng2", "blast", "athinput.blast",
+                                     dict(BL, **mb(8, 8, 8), **{
+                                         "hydro/grav_acc1": 0.3, "hydro/grav_acc3": -1.0,
+                                         "mesh/ix3_bc": "reflecting", "mesh/ox3_bc": "reflecting"}),
+                                     "hllc", False, 6),
+    "blast_grav_hlld_plm_rk2_8blk": ("mhd_hlld_ng2", "blast", "athinput.blast",
+                                     dict(BL, **mb(8, 8, 8), **{
+                                         "hydro/grav_acc2": -0.7, "time/integrator": "rk2",
+                                         "mesh/ix2_bc": "reflecting", "mesh/ox2_bc": "reflecting"}),
+                                     "hlld", True, 5),
+    "iso_blast_grav_hlle_plm_vl2_8blk": ("hydro_hlle_iso_ng2", "blast", "athinput.blast",
+                                         dict(BL, **mb(8, 8, 8),
+                                              **{"hydro/iso_sound_speed": 0.4082482905,
+                                                 "problem/drat": 5.0, "hydro/grav_acc1": -0.5}),
+                                         "hlle", False, 5, 0, "isothermal"),
     # isothermal EOS (eos/isothermal_{hydro,mhd}.cpp; hlle.cpp / hlle_mhd.cpp / hlld_iso.cpp)
     "iso_khs_hlle_plm_vl2_4blk_s1": ("hydro_hlle_iso_ng2_s1", "kh", "athinput.kh_scalar",
                                      dict(KS, **mb(8, 16, 1)), "hlle", False, 6, 1,
