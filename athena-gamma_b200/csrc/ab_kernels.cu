@@ -48,6 +48,7 @@ __device__ __forceinline__ void block_min_to_slots(double m, unsigned long long 
     for (int w = 1; w < BX/32; ++w) m = dmin(m, sm[w]);
     if (m < DBL_MAX) {
       unsigned slot = (blockIdx.x + 7u*blockIdx.y + 13u*blockIdx.z) & (DT_SLOTS - 1);
+      slot = (slot ^ (blockIdx.x >> 6)) & (DT_SLOTS - 1);     // spreads flattened 1-D grids too
       atomicMin(slots + slot, (unsigned long long)__double_as_longlong(m));
     }
   }
@@ -73,12 +74,19 @@ __device__ __forceinline__ void block_min_to_slots(double m, unsigned long long 
 #define AB_CC_MINB 8       // k_integrate_cc
 #endif
 template <bool MHD, int FLAGS>
-__global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2prim(BlkDev b, Params p, int il, int iu, int jl,
-                                                  int kl, unsigned long long *dtmin) {
-  int i = il + blockIdx.x*BX + threadIdx.x;
-  int j = jl + blockIdx.y, k = kl + blockIdx.z;
+__global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2prim(BlkDev b, Params p, int il, int jl,
+                                                  int kl, int ni, int nj, int ntot,
+                                                  unsigned long long *dtmin) {
+  // the cell range is flattened: rows of nx1+2*NGHOST cells do not pad to the CTA width (a
+  // 132-cell row used to occupy two 128-thread CTAs)
+  const int t = blockIdx.x*BX + threadIdx.x;
+  int r = t / ni;
+  const int i = il + (t - r*ni);
+  const int kk = r / nj;
+  const int j = jl + (r - kk*nj);
+  const int k = kl + kk;
   double m = DBL_MAX;
-  if (i <= iu) {
+  if (t < ntot) {
     double gm1 = p.gamma - 1.0;
     double pb = 0.0;
     double bcc1 = 0.0, bcc2 = 0.0, bcc3 = 0.0, bf1 = 0.0, bf2 = 0.0, bf3 = 0.0;
@@ -164,18 +172,19 @@ __global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2pr
 
 void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
                       int ku, cudaStream_t s, int flags, unsigned long long *dtmin) {
-  dim3 g = grid3(iu-il+1, ju-jl+1, ku-kl+1);
+  const int ni = iu-il+1, nj = ju-jl+1, ntot = ni*nj*(ku-kl+1);
+  const int g = (ntot + BX - 1)/BX;
   if (!p.mhd) flags &= ~1;
   if (p.mhd) {
     switch (flags & 3) {
-      case 0: k_cons2prim<true,0><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin); break;
-      case 1: k_cons2prim<true,1><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin); break;
-      case 2: k_cons2prim<true,2><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin); break;
-      default: k_cons2prim<true,3><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin); break;
+      case 0: k_cons2prim<true,0><<<g, BX, 0, s>>>(b, p, il, jl, kl, ni, nj, ntot, dtmin); break;
+      case 1: k_cons2prim<true,1><<<g, BX, 0, s>>>(b, p, il, jl, kl, ni, nj, ntot, dtmin); break;
+      case 2: k_cons2prim<true,2><<<g, BX, 0, s>>>(b, p, il, jl, kl, ni, nj, ntot, dtmin); break;
+      default: k_cons2prim<true,3><<<g, BX, 0, s>>>(b, p, il, jl, kl, ni, nj, ntot, dtmin); break;
     }
   } else {
-    if (flags & 2) k_cons2prim<false,2><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin);
-    else k_cons2prim<false,0><<<g, BX, 0, s>>>(b, p, il, iu, jl, kl, dtmin);
+    if (flags & 2) k_cons2prim<false,2><<<g, BX, 0, s>>>(b, p, il, jl, kl, ni, nj, ntot, dtmin);
+    else k_cons2prim<false,0><<<g, BX, 0, s>>>(b, p, il, jl, kl, ni, nj, ntot, dtmin);
   }
   ++g_launches;
 }
@@ -998,9 +1007,7 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 // =============================================================================================
 // IntegrateHydro: register average + Hydro::AddFluxDivergence, fused
 // =============================================================================================
-// Flattened over the active cells of the planes [k0, k0+nk) with a grid-stride loop, so that the
-// same kernel runs either with a full grid (alone) or with a small persistent grid (AB_CC_GRID
-// CTAs) next to the FP64-bound flux kernels of another slab.
+// Flattened over the active cells of the planes [k0, k0+nk).
 // `c` selects the variable set: (u, u1, flux) with NVAR = NHYDRO for IntegrateHydro, or
 // (s, s1, s_flux) with NVAR = 0 -> c.nvar scalars for IntegrateScalars
 // (time_integrator.cpp:2141-2185, scalars/add_scalar_flux_divergence.cpp:43-97).
@@ -1019,7 +1026,9 @@ __global__ void __launch_bounds__(BX, AB_CC_MINB) k_integrate_cc(BlkDev b, CcSet
   const int n1 = b.nc1, n2 = b.nc2;
   const int sv = b.nc3*n2*n1;
   const int s1 = b.nc3*n2*(n1+1), s2 = b.nc3*(n2+1)*n1, s3 = (b.nc3+1)*n2*n1;
-  for (int t = blockIdx.x*BX + threadIdx.x; t < ntot; t += gridDim.x*BX) {
+  {
+    const int t = blockIdx.x*BX + threadIdx.x;
+    if (t >= ntot) return;
     int r = t / ni;
     const int i = b.is + (t - r*ni);
     const int kk = r / nj;
@@ -1075,8 +1084,8 @@ void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta,
   if (kl < 0) { kl = b.ks; ku = b.ke; }
   const int ni = b.ie-b.is+1, nj = b.je-b.js+1, nk = ku-kl+1;
   const int ntot = ni*nj*nk;
-  int g = (ntot + BX - 1)/BX;
-  if (grid > 0 && g > grid) g = grid;
+  const int g = (ntot + BX - 1)/BX;
+  (void)grid;
   CcSet c;
   if (scalars) {
     c.u = b.s; c.u1 = b.s1; c.nvar = b.ns;
@@ -1236,27 +1245,36 @@ void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta,
 // Ghost-zone exchange as box copies (bvals/cc/bvals_cc.cpp:201-216,300-336,
 // bvals/fc/bvals_fc.cpp:344-397,583-684; utils/buffer_utils.cpp ordering n,k,j,i)
 // =============================================================================================
-__global__ void __launch_bounds__(256) k_copy_boxes(const CopyBox *boxes, int n) {
-  const CopyBox bx = boxes[blockIdx.y];
-  long per = (long)bx.ni*bx.nj*bx.nk;
-  long tot = per*bx.nvar;
-  for (long t = (long)blockIdx.x*256 + threadIdx.x; t < tot; t += (long)gridDim.x*256) {
-    int v = (int)(t / per);
-    long r = t - (long)v*per;
-    int i = (int)(r % bx.ni);
-    long r2 = r / bx.ni;
-    int j = (int)(r2 % bx.nj), k = (int)(r2 / bx.nj);
+// All boxes of one exchange phase form ONE flat element list (CopyBox::offset = exclusive prefix
+// of the element counts): a thread finds its box by binary search.  A (boxes x chunks) grid
+// launched millions of empty CTAs on many-block meshes (6656 boxes of very different sizes at
+// 64 MeshBlocks: 3.3 ms per phase).
+__global__ void __launch_bounds__(256) k_copy_boxes(const CopyBox *__restrict__ boxes, int n,
+                                                    long total) {
+  for (long t = (long)blockIdx.x*256 + threadIdx.x; t < total; t += (long)gridDim.x*256) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {                       // last box with offset <= t
+      const int mid = (lo + hi + 1) >> 1;
+      if (boxes[mid].offset <= t) lo = mid; else hi = mid - 1;
+    }
+    const CopyBox &bx = boxes[lo];
+    const long e = t - bx.offset;
+    const long per = (long)bx.ni*bx.nj*bx.nk;
+    const int v = (int)(e / per);
+    const long r = e - (long)v*per;
+    const int i = (int)(r % bx.ni);
+    const long r2 = r / bx.ni;
+    const int j = (int)(r2 % bx.nj), k = (int)(r2 / bx.nj);
     bx.dst[v*bx.dst_sv + (long)(bx.dk0+k)*bx.dst_s3 + (long)(bx.dj0+j)*bx.dst_s2 + (bx.di0+i)] =
         bx.src[v*bx.src_sv + (long)(bx.sk0+k)*bx.src_s3 + (long)(bx.sj0+j)*bx.src_s2 + (bx.si0+i)];
   }
 }
 
-void launch_copy_boxes(const CopyBox *boxes_dev, int n, long max_box_elems, cudaStream_t s) {
-  if (n <= 0) return;
-  long gx = (max_box_elems + 255)/256;
-  if (gx > 2048) gx = 2048;
-  if (gx < 1) gx = 1;
-  k_copy_boxes<<<dim3((unsigned)gx, (unsigned)n), 256, 0, s>>>(boxes_dev, n); ++g_launches;
+void launch_copy_boxes(const CopyBox *boxes_dev, int n, long total_elems, cudaStream_t s) {
+  if (n <= 0 || total_elems <= 0) return;
+  long gx = (total_elems + 255)/256;
+  if (gx > 148L*64) gx = 148L*64;
+  k_copy_boxes<<<(unsigned)gx, 256, 0, s>>>(boxes_dev, n, total_elems); ++g_launches;
 }
 
 // =============================================================================================

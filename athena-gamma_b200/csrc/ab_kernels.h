@@ -56,8 +56,9 @@ void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta,
                          double g2, double beta, double dt_val, const double *dt_ptr,
                          cudaStream_t s);
 
-// ghost exchange: apply `n` box copies (descriptors in device memory)
-void launch_copy_boxes(const CopyBox *boxes_dev, int n, long max_box_elems, cudaStream_t s);
+// ghost exchange: apply `n` box copies (descriptors in device memory, CopyBox::offset = exclusive
+// prefix of the element counts, total_elems = their sum)
+void launch_copy_boxes(const CopyBox *boxes_dev, int n, long total_elems, cudaStream_t s);
 
 // outflow (refl=0) / reflecting (refl=1) physical boundary on primitives and face fields
 void launch_phys_bc(const BlkDev &b, int mhd, int face, int refl, int il, int iu, int jl,

@@ -805,9 +805,9 @@ int build_state_plan(AbMesh *m, int which) {
       }
     }
   }
-  auto upload = [&](const std::vector<CopyBox> &v, CopyBox *&dev, int &n, long &mx) -> int {
-    n = (int)v.size(); mx = 0;
-    for (auto &c : v) mx = std::max(mx, (long)c.ni*c.nj*c.nk*c.nvar);
+  auto upload = [&](std::vector<CopyBox> &v, CopyBox *&dev, int &n, long &mx) -> int {
+    n = (int)v.size(); mx = 0;     // mx = total element count; offsets = exclusive prefix
+    for (auto &c : v) { c.offset = mx; mx += (long)c.ni*c.nj*c.nk*c.nvar; }
     if (dev) { cudaFree(dev); dev = nullptr; }
     if (n == 0) return AB_OK;
     CK(cudaMalloc(&dev, sizeof(CopyBox)*n));
@@ -1661,49 +1661,6 @@ int ab_mesh_profile_read(AbMesh *m, double *out) {
   }
   m->prof_ev.clear(); m->prof_slot.clear();
   for (int i = 0; i < 9; ++i) { out[i] = m->prof_ms[i]; out[9+i] = (double)m->prof_n[i]; m->prof_ms[i] = 0; m->prof_n[i] = 0; }
-  return AB_OK;
-}
-
-// Tuning aid (not part of include/athena_b200.h): can the HBM-bound kernels hide under the
-// FP64-bound flux kernels when they share the SMs?  Times, on block 0, (0) the three flux sweeps
-// alone, (1) `nmem` full-grid k_integrate_cc passes alone, (2) the same with `grid_mem` CTAs,
-// (3) both concurrently on two streams (capped grid launched first).  beta = 0 keeps u intact.
-int ab_debug_overlap(AbMesh *m, int grid_mem, int nmem, double *out) {
-  if (!m || m->lb.empty()) return fail(AB_ERR_ARG, "ab_debug_overlap: no blocks");
-  LocalBlock &L = m->lb[0];
-  cudaStream_t sf = m->stream, sm2;
-  CK(cudaStreamCreateWithFlags(&sm2, cudaStreamNonBlocking));
-  cudaEvent_t e0, e1, e2, e3;
-  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
-  const double *dtp = m->state + 1;
-  auto flux3 = [&]() {
-    for (int dir = 0; dir < m->ndim; ++dir)
-      ab::launch_flux_dir(L.d, L.g, m->kp, m->p.xorder, dir, 0.0, dtp, sf);
-  };
-  auto mem = [&](cudaStream_t s, int grid) {
-    for (int r = 0; r < nmem; ++r)
-      ab::launch_integrate_cc(L.d, 0, 0, 0.0, 0, 0, 0.0, 0.0, dtp, s, -1, -1, grid);
-  };
-  float ms;
-  CK(cudaStreamSynchronize(sf));
-  flux3(); CK(cudaStreamSynchronize(sf));                    // warm
-  cudaEventRecord(e0, sf); flux3(); cudaEventRecord(e1, sf);
-  CK(cudaStreamSynchronize(sf)); cudaEventElapsedTime(&ms, e0, e1); out[0] = ms;
-  cudaEventRecord(e0, sf); mem(sf, 0); cudaEventRecord(e1, sf);
-  CK(cudaStreamSynchronize(sf)); cudaEventElapsedTime(&ms, e0, e1); out[1] = ms;
-  cudaEventRecord(e0, sf); mem(sf, grid_mem); cudaEventRecord(e1, sf);
-  CK(cudaStreamSynchronize(sf)); cudaEventElapsedTime(&ms, e0, e1); out[2] = ms;
-  // concurrent
-  cudaEventRecord(e0, sf);
-  CK(cudaStreamWaitEvent(sm2, e0, 0));
-  mem(sm2, grid_mem); cudaEventRecord(e2, sm2);
-  flux3(); cudaEventRecord(e1, sf);
-  CK(cudaStreamSynchronize(sf)); CK(cudaStreamSynchronize(sm2));
-  float a, b2;
-  cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b2, e0, e2);
-  out[3] = a; out[4] = b2;
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
-  cudaStreamDestroy(sm2);
   return AB_OK;
 }
 
