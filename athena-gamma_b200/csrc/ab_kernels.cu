@@ -258,13 +258,16 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
   }
 }
 
-// 5 CTAs of 128 threads per SM (96 registers, a few spills) measured best on B200:
-// MINB 3/4/5/6/8 -> 1.27/1.10/1.05/1.06/1.37 ms per 256^3 HLLD+PLM sweep (profiles/).
+// 96 registers per thread (about 180 B of spills) with 18 single-warp CTAs per SM measured best
+// on B200 (profiles/r1_tuning_log.md): at 128-thread CTAs 3/4/5/6/8 CTAs per SM give
+// 1.27/1.10/1.05/1.06/1.37 ms per 256^3 HLLD+PLM sweep and the spill-free 144-register build
+// is 20 % slower; at equal registers, smaller CTAs (the warps of an SM start and stall on
+// their loads less in lockstep) and 18 instead of 20 warps take another 5 % off the sweeps.
 #ifndef AB_FLUX_BX
-#define AB_FLUX_BX 128
+#define AB_FLUX_BX 32
 #endif
 #ifndef AB_FLUX_MINB
-#define AB_FLUX_MINB 5
+#define AB_FLUX_MINB 18
 #endif
 #ifndef AB_FLUX_MINB_O1
 #define AB_FLUX_MINB_O1 AB_FLUX_MINB
