@@ -158,6 +158,11 @@ struct AbMesh {
   double bc_time = 0.0, bc_dt = 0.0;      // (time, dt) of the PhysicalBoundary task
   std::vector<double> stage_w, stage_b[3];
   cudaStream_t stream = nullptr;
+  // overlapped schedule (nranks > 1, or AB_OVERLAP=1): NCCL transfers on comm_stream while the
+  // compute stream works on data that does not depend on them
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_pack = nullptr, ev_recv = nullptr;
+  bool overlap = false;
   double *state = nullptr;                // device: time, dt, tlim, cfl, min, ncycle
   double *dt_hist = nullptr;              // device ring of per-cycle dt
   int hist_cap = 0, hist_n = 0;
@@ -170,7 +175,8 @@ struct AbMesh {
   struct Plan {
     bool built = false;
     ab::CopyBox *pack = nullptr; int npack = 0; long maxpack = 0;     // to peer send buffers
-    ab::CopyBox *phase1 = nullptr; int n1 = 0; long max1 = 0;         // ghost fill
+    ab::CopyBox *phase1 = nullptr; int n1 = 0; long max1 = 0;         // ghost fill, local sources
+    ab::CopyBox *phase1r = nullptr; int n1r = 0; long max1r = 0;      // ghost fill from peer buffers
     ab::CopyBox *phase2 = nullptr; int n2 = 0; long max2 = 0;         // 1-D/2-D duplicates
   } plan[8];
   std::map<int, PeerBuf> peer_state, peer_emf;
@@ -696,7 +702,7 @@ void peer_messages(const AbMesh *m, int kind, std::map<int, std::vector<Msg>> &s
 // ghost-exchange plan for the current register parity: box copies, pack lists, peer buffers
 int build_state_plan(AbMesh *m, int which) {
   AbMesh::Plan &P = m->plan[which];
-  std::vector<CopyBox> pack, ph1, ph2;
+  std::vector<CopyBox> pack, ph1, ph1r, ph2;
   const int mhd = m->p.mhd;
   const long ncc = (long)m->nc[0]*m->nc[1]*m->nc[2];
   // per-peer message lists (sorted by (dst gid, dst bufid))
@@ -742,7 +748,7 @@ int build_state_plan(AbMesh *m, int which) {
         double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}];
         Box z = {0, rb.ei-rb.si, 0, rb.ej-rb.sj, 0, rb.ek-rb.sk};
         long s2 = z.ei+1, s3 = s2*(z.ej+1);
-        add_box(ph1, L.d.u, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), m->nh, rb, 0, 0, 0);
+        add_box(ph1r, L.d.u, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), m->nh, rb, 0, 0, 0);
       }
       long roff = m->nh*rb.count();
       const int ns = m->p.nscalars;
@@ -758,7 +764,7 @@ int build_state_plan(AbMesh *m, int which) {
           } else {
             double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}] + roff;
             long t2 = frb.ei-frb.si+1, t3 = t2*(frb.ej-frb.sj+1);
-            add_box(ph1, L.d.b[c], s3, s2, 0, src, t3, t2, 0, 1, frb, 0, 0, 0);
+            add_box(ph1r, L.d.b[c], s3, s2, 0, src, t3, t2, 0, 1, frb, 0, 0, 0);
             roff += frb.count();
           }
           // 1-D / 2-D duplicate faces (bvals_fc.cpp:641-645, 669-675)
@@ -780,7 +786,7 @@ int build_state_plan(AbMesh *m, int which) {
           double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}] + roff;
           Box z = {0, rb.ei-rb.si, 0, rb.ej-rb.sj, 0, rb.ek-rb.sk};
           long s2 = z.ei+1, s3 = s2*(z.ej+1);
-          add_box(ph1, L.d.s, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), ns, rb, 0, 0, 0);
+          add_box(ph1r, L.d.s, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), ns, rb, 0, 0, 0);
         }
       }
       // ---- sending side (remote only): pack my active zones into the peer buffer
@@ -817,6 +823,7 @@ int build_state_plan(AbMesh *m, int which) {
   int rc;
   if ((rc = upload(pack, P.pack, P.npack, P.maxpack))) return rc;
   if ((rc = upload(ph1, P.phase1, P.n1, P.max1))) return rc;
+  if ((rc = upload(ph1r, P.phase1r, P.n1r, P.max1r))) return rc;
   if ((rc = upload(ph2, P.phase2, P.n2, P.max2))) return rc;
   P.built = true;
   return AB_OK;
@@ -876,13 +883,14 @@ int build_emf_plan(AbMesh *m) {
   return AB_OK;
 }
 
-int peer_exchange(AbMesh *m, std::map<int, PeerBuf> &peers) {
+int peer_exchange(AbMesh *m, std::map<int, PeerBuf> &peers, cudaStream_t st = nullptr) {
+  if (!st) st = m->stream;
   if (peers.empty()) return AB_OK;
   if (!m->comm) return fail(AB_ERR_STATE, "blocks on other ranks but ab_comm_init was not called");
   NK(g_nccl.GroupStart());
   for (auto &kv : peers) {
-    if (kv.second.nsend) NK(g_nccl.Send(kv.second.send, kv.second.nsend, NCCL_FLOAT64, kv.first, m->comm, m->stream));
-    if (kv.second.nrecv) NK(g_nccl.Recv(kv.second.recv, kv.second.nrecv, NCCL_FLOAT64, kv.first, m->comm, m->stream));
+    if (kv.second.nsend) NK(g_nccl.Send(kv.second.send, kv.second.nsend, NCCL_FLOAT64, kv.first, m->comm, st));
+    if (kv.second.nrecv) NK(g_nccl.Recv(kv.second.recv, kv.second.nrecv, NCCL_FLOAT64, kv.first, m->comm, st));
   }
   NK(g_nccl.GroupEnd());
   return AB_OK;
@@ -907,7 +915,37 @@ int bvals_exchange(AbMesh *m) {
   int rc = peer_exchange(m, m->peer_state);
   if (rc) return rc;
   ab::launch_copy_boxes(P.phase1, P.n1, P.max1, m->stream);
+  ab::launch_copy_boxes(P.phase1r, P.n1r, P.max1r, m->stream);
   ab::launch_copy_boxes(P.phase2, P.n2, P.max2, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+
+// The two halves of bvals_exchange for the overlapped schedule: everything that only needs this
+// rank's data (pack, start of the NCCL transfer on the comm stream, same-rank ghost copies) and
+// everything that needs the peers' data.
+int bvals_exchange_begin(AbMesh *m) {
+  int idx = plan_index(m);
+  int use = idx < 0 ? 0 : idx;
+  if (idx < 0) m->plan[0].built = false;
+  if (!m->plan[use].built) { int rc = build_state_plan(m, use); if (rc) return rc; }
+  AbMesh::Plan &P = m->plan[use];
+  if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream);
+  CK(cudaEventRecord(m->ev_pack, m->stream));
+  CK(cudaStreamWaitEvent(m->comm_stream, m->ev_pack, 0));
+  int rc = peer_exchange(m, m->peer_state, m->comm_stream);
+  if (rc) return rc;
+  CK(cudaEventRecord(m->ev_recv, m->comm_stream));
+  ab::launch_copy_boxes(P.phase1, P.n1, P.max1, m->stream);
+  return AB_OK;
+}
+int bvals_exchange_end(AbMesh *m) {
+  int idx = plan_index(m);
+  AbMesh::Plan &P = m->plan[idx < 0 ? 0 : idx];
+  CK(cudaStreamWaitEvent(m->stream, m->ev_recv, 0));
+  ab::launch_copy_boxes(P.phase1r, P.n1r, P.max1r, m->stream);
+  ab::launch_copy_boxes(P.phase2, P.n2, P.max2, m->stream);
+  if (idx < 0) m->plan[0].built = false;   // mixed state: never cache
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -921,6 +959,54 @@ int emf_exchange(AbMesh *m) {
   for (auto &L : m->lb) ab::launch_emf_apply(L.d, L.emf, m->stream);
   CK(cudaGetLastError());
   return AB_OK;
+}
+
+int emf_exchange_begin(AbMesh *m) {
+  if (!m->p.mhd) return AB_OK;
+  if (!m->emf_built) { int rc = build_emf_plan(m); if (rc) return rc; }
+  for (auto &L : m->lb) ab::launch_emf_pack(L.d, L.emf, m->stream);
+  CK(cudaEventRecord(m->ev_pack, m->stream));
+  CK(cudaStreamWaitEvent(m->comm_stream, m->ev_pack, 0));
+  int rc = peer_exchange(m, m->peer_emf, m->comm_stream);
+  if (rc) return rc;
+  CK(cudaEventRecord(m->ev_recv, m->comm_stream));
+  return AB_OK;
+}
+int emf_exchange_end(AbMesh *m) {
+  if (!m->p.mhd) return AB_OK;
+  CK(cudaStreamWaitEvent(m->stream, m->ev_recv, 0));
+  for (auto &L : m->lb) ab::launch_emf_apply(L.d, L.emf, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+
+// Primitives task split for the overlapped schedule: part 0 = the active cells (with the fused
+// CFL reduction), part 1 = the ghost shell as up to six slabs (after the ghost zones arrived)
+void primitives_part(AbMesh *m, LocalBlock &L, int part, int with_dt) {
+  HostBlock &B = *L.hb;
+  int ng = m->p.nghost;
+  const int is = m->is, ie = m->ie, js = m->js, je = m->je, ks = m->ks, ke = m->ke;
+  int il = is, iu = ie, jl = js, ju = je, kl = ks, ku = ke;
+  if (B.nblevel[1][1][0] != -1) il -= ng;
+  if (B.nblevel[1][1][2] != -1) iu += ng;
+  if (B.nblevel[1][0][1] != -1) jl -= ng;
+  if (B.nblevel[1][2][1] != -1) ju += ng;
+  if (B.nblevel[0][1][1] != -1) kl -= ng;
+  if (B.nblevel[2][1][1] != -1) ku += ng;
+  const int cce = (m->p.mhd && !L.has_phys_bc) ? 1 : 0;
+  auto run = [&](int a0, int a1, int b0, int b1, int c0, int c1, int flags) {
+    if (a0 > a1 || b0 > b1 || c0 > c1) return;
+    ab::launch_cons2prim(L.d, m->kp, a0, a1, b0, b1, c0, c1, m->stream, flags, L.dtmin);
+    ab::launch_scalar_eos(L.d, m->kp, 0, a0, a1, b0, b1, c0, c1, m->stream);
+  };
+  if (part == 0) {
+    run(is, ie, js, je, ks, ke, cce | (with_dt ? 2 : 0));
+  } else {
+    run(il, iu, jl, ju, kl, ks-1, cce); run(il, iu, jl, ju, ke+1, ku, cce);
+    run(il, iu, jl, js-1, ks, ke, cce); run(il, iu, je+1, ju, ks, ke, cce);
+    run(il, is-1, js, je, ks, ke, cce); run(ie+1, iu, js, je, ks, ke, cce);
+    L.cc_e_valid = cce != 0;
+  }
 }
 
 void primitives(AbMesh *m, LocalBlock &L, int with_dt = 0) {
@@ -1094,20 +1180,18 @@ int one_cycle(AbMesh *m) {
       if (m->p.mhd) ab::launch_corner_e(L.d, m->stream, L.cc_e_valid ? 1 : 0);
       ab::launch_scalar_fluxes(L.d, L.g, m->kp, order, m->stream);   // CALC_SCLRFLX
     }
-    int rc = emf_exchange(m);
+    // EMF correction.  Overlapped schedule: the NCCL transfer runs on the comm stream while
+    // IntegrateHydro / IntegrateScalars (which do not read EMFs) run on the compute stream.
+    int rc = m->overlap ? emf_exchange_begin(m) : emf_exchange(m);
     if (rc) return rc;
     const bool swap = (m->g1[s] == 0.0 && m->g2[s] == 1.0 && m->g3[s] == 0.0);
     const int zero_init = (stage == 1);   // StartupTaskList: u1, b1 ZeroClear (:1386-1397)
-    for (auto &L : m->lb) {
+    for (auto &L : m->lb) {   // INT_HYD (+ SRC_TERM), INT_SCLR (time_integrator.cpp:2141-2185)
       if (swap) {
         swap_cc(L);
         ab::launch_integrate_cc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp,
                                 m->stream, -1, -1, 0, 0, m->p.grav_acc);
-        if (m->p.mhd) {
-          swap_fc(L);
-          ab::launch_integrate_fc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, m->stream);
-        }
-        if (m->p.nscalars > 0) {   // INT_SCLR (time_integrator.cpp:2141-2185)
+        if (m->p.nscalars > 0) {
           swap_sc(L);
           ab::launch_integrate_cc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp,
                                   m->stream, -1, -1, 0, 1);
@@ -1115,22 +1199,41 @@ int one_cycle(AbMesh *m) {
       } else {
         ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0,
                                 dtp, m->stream, -1, -1, 0, 0, m->p.grav_acc);
-        if (m->p.mhd)
-          ab::launch_integrate_fc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
         if (m->p.nscalars > 0)
           ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s],
                                   0.0, dtp, m->stream, -1, -1, 0, 1);
       }
     }
-    rc = bvals_exchange(m);
-    if (rc) return rc;
+    if (m->overlap) { rc = emf_exchange_end(m); if (rc) return rc; }
+    if (m->p.mhd) for (auto &L : m->lb) {   // INT_FLD
+      if (swap) {
+        swap_fc(L);
+        ab::launch_integrate_fc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, m->stream);
+      } else {
+        ab::launch_integrate_fc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
+      }
+    }
     if (m->has_user_bc) {   // PhysicalBoundary: t_end_stage, beta*dt (time_integrator.cpp:2045-2062)
       m->bc_time = m->h_time + m->ebeta[s]*m->h_dt;
       m->bc_dt = m->beta[s]*m->h_dt;
     }
     const int last = (stage == m->nstages);
-    if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
-    for (auto &L : m->lb) { primitives(m, L, last); physical_bcs(m, L); }
+    if (!m->overlap) {
+      rc = bvals_exchange(m);
+      if (rc) return rc;
+      if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
+      for (auto &L : m->lb) { primitives(m, L, last); physical_bcs(m, L); }
+    } else {
+      // ghost zones travel while ConservedToPrimitive (+ CFL reduction) covers the active cells;
+      // the ghost shell follows once they arrived
+      rc = bvals_exchange_begin(m);
+      if (rc) return rc;
+      if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
+      for (auto &L : m->lb) primitives_part(m, L, 0, last);
+      rc = bvals_exchange_end(m);
+      if (rc) return rc;
+      for (auto &L : m->lb) { primitives_part(m, L, 1, 0); physical_bcs(m, L); }
+    }
     if (stage == m->nstages) {
       // record the dt this cycle used, then time += dt, ncycle++, NewTimeStep
       if (m->hist_n < m->hist_cap)
@@ -1171,6 +1274,13 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
   AbMesh *m = new AbMesh();
   host_setup(m, p);
   CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&m->ev_pack, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&m->ev_recv, cudaEventDisableTiming));
+  {
+    const char *e = getenv("AB_OVERLAP");
+    m->overlap = e ? (e[0] == '1') : (p->nranks > 1);
+  }
   int rc = alloc_blocks(m);
   if (rc) { delete m; return rc; }
   CK(cudaMalloc(&m->state, 8*sizeof(double)));
@@ -1294,12 +1404,15 @@ int ab_mesh_destroy(AbMesh *m) {
   cudaSetDevice(m->p.device);
   cudaStreamSynchronize(m->stream);
   for (auto &L : m->lb) cudaFree(L.base);
-  for (int i = 0; i < 8; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase2); }
+  for (int i = 0; i < 8; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase1r); cudaFree(m->plan[i].phase2); }
   for (auto &kv : m->peer_state) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   cudaFree(m->state); cudaFree(m->dt_hist); cudaFree(m->dtmin);
   cudaFree(m->hist_partial); cudaFree(m->hist_out);
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  if (m->ev_pack) cudaEventDestroy(m->ev_pack);
+  if (m->ev_recv) cudaEventDestroy(m->ev_recv);
+  if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
   cudaStreamDestroy(m->stream);
   delete m;
   return AB_OK;

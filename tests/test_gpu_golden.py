@@ -47,6 +47,26 @@ def test_cuda_matches_oracle_async_cycles(name):
             util.assert_bitwise(pmb.get(f), np.array(om.array(b, f)), "%s %s" % (name, f))
 
 
+@pytest.mark.parametrize("name", ["c5_blast_hlld_plm_vl2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
+                                  "blast_refl_hlld_plm_vl2_8blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1",
+                                  "c1_sod_hllc_plm_vl2_2blk", "iso_ot_hlld_plm_rk2_4blk",
+                                  "shkcloud2d_hllc_plm_vl2_4blk"])
+def test_overlapped_schedule_is_bit_identical(name, monkeypatch):
+    """The multi-GPU schedule (EMF / ghost transfers on a second stream, ConservedToPrimitive
+    split into active cells and ghost shell) forced on one GPU with AB_OVERLAP=1."""
+    import gpu_util
+    monkeypatch.setenv("AB_OVERLAP", "1")
+    g = util.Golden(name)
+    m = gpu_util.mesh_from_golden(g)
+    m.initialize()
+    dts = m.cycles(g.ncycles, async_=(not util.user_bcs_for(g)))
+    assert list(dts) == list(g.dts[:g.ncycles])
+    for n, loc in enumerate(g.locs):
+        pmb = m.block_of(*loc)
+        for f in g.fields:
+            util.assert_bitwise(pmb.get(f), g.final[n][f], "%s block %s %s" % (name, loc, f))
+
+
 def history_close(h, ref, scale):
     """device tree sum vs the reference's running sum: |d| <= 1e-13 x sum of magnitudes"""
     assert len(h) == len(ref)
