@@ -158,8 +158,10 @@ struct AbMesh {
   double bc_time = 0.0, bc_dt = 0.0;      // (time, dt) of the PhysicalBoundary task
   std::vector<double> stage_w, stage_b[3];
   cudaStream_t stream = nullptr;
-  // overlapped schedule (nranks > 1, or AB_OVERLAP=1): NCCL transfers on comm_stream while the
-  // compute stream works on data that does not depend on them
+  // overlapped schedule (AB_OVERLAP=1): NCCL transfers on comm_stream while the compute stream
+  // works on data that does not depend on them.  Opt-in: at 2 GPUs x 512^3 it measured 1.2 %
+  // SLOWER than the in-order schedule (73.10 vs 72.21 ms per cycle, profiles/r1_tuning_log.md):
+  // over NVLink the transfers are shorter than the six extra ghost-shell launches cost.
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_pack = nullptr, ev_recv = nullptr;
   bool overlap = false;
@@ -1279,7 +1281,7 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
   CK(cudaEventCreateWithFlags(&m->ev_recv, cudaEventDisableTiming));
   {
     const char *e = getenv("AB_OVERLAP");
-    m->overlap = e ? (e[0] == '1') : (p->nranks > 1);
+    m->overlap = e && e[0] == '1';
   }
   int rc = alloc_blocks(m);
   if (rc) { delete m; return rc; }
