@@ -10,7 +10,9 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def test_two_ranks_bitwise_vs_golden():
+@pytest.mark.parametrize("overlap", ["0", "1"])
+def test_two_ranks_bitwise_vs_golden(overlap):
+    """overlap=1: the opt-in schedule with the NCCL transfers on a second stream"""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -18,6 +20,7 @@ def test_two_ranks_bitwise_vs_golden():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517",
            os.path.join(HERE, "multirank_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, AB_OVERLAP=overlap))
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0
