@@ -155,6 +155,12 @@ struct AbMesh {
   AbBValFunc user_bc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void *user_bc_arg[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool has_user_bc = false;
+  // user-enrolled explicit source function (HydroSourceTerms::UserSourceTerm)
+  AbSrcTermFunc user_src = nullptr;
+  AbSrcTermFuncDevice user_src_dev = nullptr;
+  void *user_src_arg = nullptr;
+  double sbeta[4];
+  std::vector<double> stage_u, stage_r, stage_s, stage_bcc;
   double bc_time = 0.0, bc_dt = 0.0;      // (time, dt) of the PhysicalBoundary task
   std::vector<double> stage_w, stage_b[3];
   cudaStream_t stream = nullptr;
@@ -343,22 +349,22 @@ void set_integrator(AbMesh *m) {
   double cfl_limit = 1.0;
   for (int s = 0; s < 4; ++s) { m->g1[s] = 0; m->g2[s] = 1; m->g3[s] = 0; m->delta[s] = 0; m->beta[s] = 0; }
   m->delta[0] = 1.0;
-  for (int s = 0; s < 4; ++s) m->ebeta[s] = 1.0;   // stage_wghts[].ebeta
+  for (int s = 0; s < 4; ++s) { m->ebeta[s] = 1.0; m->sbeta[s] = 0.0; }   // stage_wghts[].ebeta/sbeta
   switch (m->p.integrator) {
     case AB_INT_VL2:
-      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0; m->ebeta[0] = 0.5;
+      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0; m->ebeta[0] = 0.5; m->sbeta[1] = 0.5;
       if (m->ndim >= 2) cfl_limit = 0.5;
       break;
     case AB_INT_RK1:
       m->nstages = 1; m->beta[0] = 1.0;
       break;
     case AB_INT_RK2:
-      m->nstages = 2; m->beta[0] = 1.0; m->beta[1] = 0.5;
+      m->nstages = 2; m->beta[0] = 1.0; m->beta[1] = 0.5; m->sbeta[1] = 1.0;
       m->g1[1] = 0.5; m->g2[1] = 0.5;
       break;
     default:
       m->nstages = 3; m->beta[0] = 1.0; m->beta[1] = 0.25; m->beta[2] = 0.66666666666666667;
-      m->ebeta[1] = 0.5;
+      m->ebeta[1] = 0.5; m->sbeta[1] = 1.0; m->sbeta[2] = 0.5;
       m->g1[1] = 0.25; m->g2[1] = 0.75;
       m->g1[2] = 0.66666666666666667; m->g2[2] = 0.33333333333333333;
       break;
@@ -1056,6 +1062,33 @@ int user_bc_face(AbMesh *m, LocalBlock &L, int face, int il, int iu, int jl, int
   return AB_OK;
 }
 
+// HydroSourceTerms::UserSourceTerm (hydro_srcterms.cpp:150-153) for one block
+int user_source(AbMesh *m, LocalBlock &L, double time, double dt) {
+  int lid = (int)(&L - &m->lb[0]);
+  cudaStream_t s = m->stream;
+  if (m->user_src_dev) {
+    m->user_src_dev(m->user_src_arg, lid, time, dt, L.d.w, L.d.r, L.d.bcc, L.d.u, L.d.s, (void *)s);
+    return AB_OK;
+  }
+  auto down = [&](std::vector<double> &v, const double *src, long n) -> double * {
+    if (!src || n <= 0) return nullptr;
+    v.resize(n);
+    cudaMemcpyAsync(v.data(), src, n*8, cudaMemcpyDeviceToHost, s);
+    return v.data();
+  };
+  double *hw = down(m->stage_w, L.d.w, L.regsize[AB_W]);
+  double *hr = down(m->stage_r, L.d.r, L.regsize[AB_R]);
+  double *hb = down(m->stage_bcc, L.d.bcc, L.regsize[AB_BCC]);
+  double *hu = down(m->stage_u, L.d.u, L.regsize[AB_U]);
+  double *hs = down(m->stage_s, L.d.s, L.regsize[AB_S]);
+  CK(cudaStreamSynchronize(s));
+  m->user_src(m->user_src_arg, lid, time, dt, hw, hr, hb, hu, hs);
+  CK(cudaMemcpyAsync(L.d.u, hu, L.regsize[AB_U]*8, cudaMemcpyHostToDevice, s));
+  if (hs) CK(cudaMemcpyAsync(L.d.s, hs, L.regsize[AB_S]*8, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  return AB_OK;
+}
+
 void physical_bcs(AbMesh *m, LocalBlock &L) {
   // BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620): outflow, reflecting
   HostBlock &B = *L.hb;
@@ -1161,7 +1194,8 @@ void swap_sc(LocalBlock &L) { std::swap(L.d.s, L.d.s1); L.parity_s ^= 1; }
 
 int one_cycle(AbMesh *m) {
   const double *dtp = m->state + 1;
-  if (m->has_user_bc) { int rc0 = read_state(m); if (rc0) return rc0; }   // host needs time, dt
+  const bool user_src = (m->user_src || m->user_src_dev);
+  if (m->has_user_bc || user_src) { int rc0 = read_state(m); if (rc0) return rc0; }   // host needs time, dt
   for (int stage = 1; stage <= m->nstages; ++stage) {
     const int s = stage - 1;
     const int order = (m->p.integrator == AB_INT_VL2 && stage == 1) ? 1 : m->p.xorder;
@@ -1204,6 +1238,12 @@ int one_cycle(AbMesh *m) {
         if (m->p.nscalars > 0)
           ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s],
                                   0.0, dtp, m->stream, -1, -1, 0, 1);
+      }
+    }
+    if (user_src) {   // SRC_TERM, user part: start-of-stage time, beta*dt
+      for (auto &L : m->lb) {
+        rc = user_source(m, L, m->h_time + m->sbeta[s]*m->h_dt, m->beta[s]*m->h_dt);
+        if (rc) return rc;
       }
     }
     if (m->overlap) { rc = emf_exchange_end(m); if (rc) return rc; }
@@ -1576,12 +1616,12 @@ int ab_add_flux_div(AbMesh *m, int lid, double wght) {
   CK(cudaGetLastError());
   return AB_OK;
 }
-int ab_add_source_terms(AbMesh *m, int lid, double dt) {
+int ab_add_source_terms(AbMesh *m, int lid, double time, double dt) {
   GET_L(m, lid);
   const double *g = m->p.grav_acc;
-  if (g[0] == 0.0 && g[1] == 0.0 && g[2] == 0.0) return AB_OK;   // hydro_sourceterms_defined
-  ab::launch_const_accel(L.d, g, dt, m->stream);
+  if (g[0] != 0.0 || g[1] != 0.0 || g[2] != 0.0) ab::launch_const_accel(L.d, g, dt, m->stream);
   CK(cudaGetLastError());
+  if (m->user_src || m->user_src_dev) return user_source(m, L, time, dt);
   return AB_OK;
 }
 int ab_calc_scalar_fluxes(AbMesh *m, int lid, int order) {
@@ -1655,6 +1695,16 @@ int ab_bvals_exchange(AbMesh *m) {
   return bvals_exchange(m);
 }
 
+int ab_enroll_user_explicit_source_function(AbMesh *m, AbSrcTermFunc fn, void *user) {
+  if (!m || !fn) return fail(AB_ERR_ARG, "null mesh or function");
+  m->user_src = fn; m->user_src_dev = nullptr; m->user_src_arg = user;
+  return AB_OK;
+}
+int ab_enroll_user_explicit_source_function_device(AbMesh *m, AbSrcTermFuncDevice fn, void *user) {
+  if (!m || !fn) return fail(AB_ERR_ARG, "null mesh or function");
+  m->user_src_dev = fn; m->user_src = nullptr; m->user_src_arg = user;
+  return AB_OK;
+}
 int ab_enroll_user_boundary_function(AbMesh *m, int face, AbBValFunc fn, void *user) {
   if (!m || face < 0 || face > 5 || !fn) return fail(AB_ERR_ARG, "bad face or null function");
   // Mesh::EnrollUserBoundaryFunction: the face must carry the "user" flag

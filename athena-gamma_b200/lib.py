@@ -24,7 +24,8 @@ SYMBOLS = [
     "ab_last_error", "ab_device_count", "ab_mesh_create", "ab_mesh_destroy",
     "ab_mesh_nblocks_total", "ab_mesh_nblocks_local", "ab_block_info", "ab_reg_size",
     "ab_plan_create", "ab_plan_messages", "ab_plan_ranklist",
-    "ab_enroll_user_boundary_function", "ab_upload", "ab_download", "ab_download_coord", "ab_comm_unique_id", "ab_comm_init",
+    "ab_enroll_user_boundary_function", "ab_enroll_user_explicit_source_function",
+    "ab_enroll_user_explicit_source_function_device", "ab_upload", "ab_download", "ab_download_coord", "ab_comm_unique_id", "ab_comm_init",
     "ab_cons2prim", "ab_prim2cons", "ab_primitives", "ab_calc_fluxes", "ab_corner_e",
     "ab_weighted_ave", "ab_swap", "ab_zero", "ab_add_flux_div", "ab_add_source_terms", "ab_ct", "ab_physical_bcs",
     "ab_calc_scalar_fluxes", "ab_add_scalar_flux_div", "ab_scalar_cons2prim",
@@ -54,6 +55,12 @@ class AbMeshParams(C.Structure):
 _DP = C.POINTER(C.c_double)
 BVALFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_int, _DP, _DP, _DP, _DP, C.c_double, C.c_double,
                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+
+
+SRCTERMFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_double, C.c_double, _DP, _DP, _DP, _DP,
+                          _DP)
+SRCTERMFUNC_DEVICE = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 
 
 class AbError(RuntimeError):
@@ -87,6 +94,8 @@ def load():
     L.ab_plan_messages.argtypes = [vp, ip, C.POINTER(C.c_long), ip]
     L.ab_plan_ranklist.argtypes = [vp, C.POINTER(C.c_int), ip]
     L.ab_history.argtypes = [vp, dp, ip]
+    L.ab_enroll_user_explicit_source_function.argtypes = [vp, SRCTERMFUNC, vp]
+    L.ab_enroll_user_explicit_source_function_device.argtypes = [vp, SRCTERMFUNC_DEVICE, vp]
     L.ab_enroll_user_boundary_function.argtypes = [vp, ip, BVALFUNC, vp]
     L.ab_upload.argtypes = [vp, ip, ip, dp]
     L.ab_download.argtypes = [vp, ip, ip, dp]
@@ -102,7 +111,7 @@ def load():
     L.ab_swap.argtypes = [vp, ip, ip]
     L.ab_zero.argtypes = [vp, ip, ip]
     L.ab_add_flux_div.argtypes = [vp, ip, C.c_double]
-    L.ab_add_source_terms.argtypes = [vp, ip, C.c_double]
+    L.ab_add_source_terms.argtypes = [vp, ip, C.c_double, C.c_double]
     L.ab_calc_scalar_fluxes.argtypes = [vp, ip, ip]
     L.ab_add_scalar_flux_div.argtypes = [vp, ip, C.c_double]
     L.ab_scalar_cons2prim.argtypes = [vp, ip] + [ip] * 6

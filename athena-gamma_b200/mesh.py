@@ -219,6 +219,46 @@ class Mesh:
         self._bval_keepalive = getattr(self, "_bval_keepalive", []) + [cb]
         lib.check(self.L.ab_enroll_user_boundary_function(self.h, face, cb, None))
 
+    def enroll_user_explicit_source_function(self, fn, device=False):
+        """Mesh::EnrollUserExplicitSourceFunction: fn(pmb, time, dt, prim, prim_scalar, bcc,
+        cons, cons_scalar) (SrcTermFunc, src/athena.hpp:185-189).  device=False: numpy views of
+        host staging arrays.  device=True: fn(pmb, time, dt, prim, prim_scalar, bcc, cons,
+        cons_scalar, stream) gets objects exposing __cuda_array_interface__ over the library's
+        device registers and the raw cudaStream_t; it must only enqueue work on that stream."""
+        mesh = self
+
+        class _Dev:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8",
+                                                 "data": (int(ptr), False), "version": 2}
+
+        def wrap(ptr, pmb, name, dev):
+            if not ptr:
+                return None
+            shp = pmb.shape(name)
+            if dev:
+                return _Dev(ptr, shp)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=shp)
+
+        if device:
+            def tramp(_user, lid, time, dt, prim, prs, bcc, cons, cs, stream):
+                pmb = mesh.my_blocks[lid]
+                fn(pmb, time, dt, wrap(prim, pmb, "w", True), wrap(prs, pmb, "r", True),
+                   wrap(bcc, pmb, "bcc", True), wrap(cons, pmb, "u", True),
+                   wrap(cs, pmb, "s", True), stream)
+            cb = lib.SRCTERMFUNC_DEVICE(tramp)
+            call = self.L.ab_enroll_user_explicit_source_function_device
+        else:
+            def tramp(_user, lid, time, dt, prim, prs, bcc, cons, cs):
+                pmb = mesh.my_blocks[lid]
+                fn(pmb, time, dt, wrap(prim, pmb, "w", False), wrap(prs, pmb, "r", False),
+                   wrap(bcc, pmb, "bcc", False), wrap(cons, pmb, "u", False),
+                   wrap(cs, pmb, "s", False))
+            cb = lib.SRCTERMFUNC(tramp)
+            call = self.L.ab_enroll_user_explicit_source_function
+        self._src_keepalive = getattr(self, "_src_keepalive", []) + [cb]
+        lib.check(call(self.h, cb, None))
+
     def problem_generator(self, pgen_fn):
         """Calls pgen_fn(pmb, pin) -> dict(u=..., b1=..., b2=..., b3=...) per local MeshBlock
         (the MeshBlock::ProblemGenerator hook) and uploads the AthenaArrays."""

@@ -100,6 +100,28 @@ typedef void (*AbBValFunc)(void *user, int lid, double *prim, double *b_x1f, dou
                            int ju, int kl, int ku, int ngh);
 int ab_enroll_user_boundary_function(AbMesh *m, int face, AbBValFunc fn, void *user);
 
+/* ---- user-enrolled explicit source terms: Mesh::EnrollUserExplicitSourceFunction with the
+ * SrcTermFunc signature of src/athena.hpp:185-189 (the fork's production pgen sg_tde.cpp enrols
+ * its black-hole gravity this way).  Called last in AddSourceTerms
+ * (hydro/srcterms/hydro_srcterms.cpp:150-153) once per stage and MeshBlock after INT_HYD /
+ * INT_SCLR, with time = start-of-stage time and dt = beta*dt (time_integrator.cpp:1655-1678).
+ *   host variant:   prim, prim_scalar, bcc, cons, cons_scalar are HOST arrays in AthenaArray
+ *                   layout (NULL where the build has none); the library stages them around the
+ *                   call (download w,r,bcc,u,s; upload u,s).
+ *   device variant: the same arguments are DEVICE pointers and `stream` is the library's
+ *                   cudaStream_t; the function must only enqueue work on that stream (no copies,
+ *                   no synchronisation) -- the native way to keep a production source term on
+ *                   the GPU. */
+typedef void (*AbSrcTermFunc)(void *user, int lid, double time, double dt, const double *prim,
+                              const double *prim_scalar, const double *bcc, double *cons,
+                              double *cons_scalar);
+typedef void (*AbSrcTermFuncDevice)(void *user, int lid, double time, double dt,
+                                    const double *prim, const double *prim_scalar,
+                                    const double *bcc, double *cons, double *cons_scalar,
+                                    void *stream);
+int ab_enroll_user_explicit_source_function(AbMesh *m, AbSrcTermFunc fn, void *user);
+int ab_enroll_user_explicit_source_function_device(AbMesh *m, AbSrcTermFuncDevice fn, void *user);
+
 /* ---- host <-> device mirror of the AthenaArrays (same layout as AthenaArray::data()) */
 int ab_upload(AbMesh *m, int lid, int reg, const double *host);     /* after ProblemGenerator */
 int ab_download(AbMesh *m, int lid, int reg, double *host);         /* before outputs / hooks */
@@ -134,11 +156,12 @@ int ab_swap(AbMesh *m, int lid, int reg);
 int ab_zero(AbMesh *m, int lid, int reg);
 /* Hydro::AddFluxDivergence(wght, u) (hydro/add_flux_divergence.cpp:39-96) */
 int ab_add_flux_div(AbMesh *m, int lid, double wght);
-/* HydroSourceTerms::AddSourceTerms(time, dt, ...) -- constant acceleration hydro/grav_acc1..3
- * (hydro/srcterms/hydro_srcterms.cpp:68-75, constant_acc.cpp:25-77) on u with the current w;
- * dt = beta*dt of the stage (time_integrator.cpp:1655-1678).  ab_mesh_cycles fuses it into the
+/* HydroSourceTerms::AddSourceTerms(time, dt, ...) (hydro/srcterms/hydro_srcterms.cpp:117-156):
+ * constant acceleration hydro/grav_acc1..3 (constant_acc.cpp:25-77) on u with the current w,
+ * then the user-enrolled explicit source function; time = start-of-stage time, dt = beta*dt
+ * (time_integrator.cpp:1655-1678).  ab_mesh_cycles fuses the constant acceleration into the
  * IntegrateHydro kernel. */
-int ab_add_source_terms(AbMesh *m, int lid, double dt);
+int ab_add_source_terms(AbMesh *m, int lid, double time, double dt);
 /* Field::CT(wght, b) (field/ct.cpp:31-116) */
 int ab_ct(AbMesh *m, int lid, double wght);
 /* ---- passive scalars (NSCALARS > 0), src/scalars + src/eos/eos_scalars.cpp ---------------- */

@@ -84,8 +84,15 @@ typedef void (*AoBValFunc)(void *user, int block, double *prim, double *b1f, dou
                            double *b3f, double time, double dt, int il, int iu, int jl, int ju,
                            int kl, int ku, int ngh);
 void ao_enroll_user_bc(AoMesh *m, int face, AoBValFunc fn, void *user);
-/* HydroSourceTerms::AddSourceTerms, constant acceleration (hydro/srcterms/constant_acc.cpp) */
-void ao_add_source_terms(AoMesh *m, int b, double dt);
+/* Mesh::EnrollUserExplicitSourceFunction: SrcTermFunc (src/athena.hpp:185-189) on plain arrays;
+ * called last in AddSourceTerms with time = start-of-stage time, dt = beta*dt */
+typedef void (*AoSrcTermFunc)(void *user, int block, double time, double dt, const double *prim,
+                              const double *prim_scalar, const double *bcc, double *cons,
+                              double *cons_scalar);
+void ao_enroll_user_source(AoMesh *m, AoSrcTermFunc fn, void *user);
+/* HydroSourceTerms::AddSourceTerms: constant acceleration (hydro/srcterms/constant_acc.cpp),
+ * then the user-enrolled source function */
+void ao_add_source_terms(AoMesh *m, int b, double time, double dt);
 /* HistoryOutput::WriteOutputFile sums (src/outputs/history.cpp:69-169): mass, 1..3-mom,
  * 1..3-KE, tot-E, [1..3-ME], [scalars]; returns the number of values written to out */
 int ao_history(AoMesh *m, double *out);

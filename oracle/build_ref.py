@@ -39,7 +39,7 @@ CONFIGS = {
     "hydro_roe_ng2": (False, "roe", 2, ["shock_tube", "linear_wave"]),
     "hydro_hllc_ng3": (False, "hllc", 3, ["kh", "shock_tube", "linear_wave"]),
     "mhd_hlld_ng2": (True, "hlld", 2, ["linear_wave", "blast", "orszag_tang", "shock_tube",
-                                       "shk_cloud"]),
+                                       "shk_cloud", "local:usersrc"]),
     "mhd_hlle_ng2": (True, "hlle", 2, ["linear_wave", "shock_tube"]),
     "mhd_roe_ng2": (True, "roe", 2, ["linear_wave", "shock_tube"]),
     "mhd_hlld_ng3": (True, "hlld", 3, ["orszag_tang", "linear_wave", "blast"]),
@@ -48,10 +48,11 @@ CONFIGS = {
     "mhd_lhlld_ng2": (True, "lhlld", 2, ["blast", "orszag_tang", "linear_wave"]),
     # passive scalars (confignotes: --nscalars=1 with lhllc) and the isothermal EOS
     # (confignotes: --flux=hlle --eos=isothermal)
-    "hydro_lhllc_ng2_s1": (False, "lhllc", 2, ["kh", "shock_tube"], {"nscalars": 1}),
+    "hydro_lhllc_ng2_s1": (False, "lhllc", 2, ["kh", "shock_tube", "local:usersrc"],
+                           {"nscalars": 1}),
     "hydro_hllc_ng3_s2": (False, "hllc", 3, ["kh"], {"nscalars": 2}),
     "mhd_hlld_ng2_s1": (True, "hlld", 2, ["kh"], {"nscalars": 1}),
-    "hydro_hlle_iso_ng2": (False, "hlle", 2, ["linear_wave", "blast", "kh"],
+    "hydro_hlle_iso_ng2": (False, "hlle", 2, ["linear_wave", "blast", "kh", "local:usersrc"],
                            {"eos": "isothermal"}),
     "hydro_hlle_iso_ng2_s1": (False, "hlle", 2, ["kh"], {"eos": "isothermal", "nscalars": 1}),
     "mhd_hlld_iso_ng2": (True, "hlld", 2, ["linear_wave", "orszag_tang", "blast"],
@@ -164,8 +165,29 @@ def build(cfg, ref, jobs):
     for s in files:
         rel = os.path.relpath(s, src).replace("/", "__")[:-4] + ".o"
         work.append((s, os.path.join(obj, rel), incs))
-    pg_work = [(os.path.join(src, "pgen", p + ".cpp"),
-                os.path.join(obj, "pgen__" + p + ".o"), incs) for p in pgens]
+    # "local:<name>": a pgen of this repository (oracle/pgen/<name>.cpp, test infrastructure
+    # written against the reference's ProblemGenerator / user-hook API), compiled with the
+    # reference's pgen directory on the include path so that its "../athena.hpp" resolves
+    def pgen_src(p):
+        if p.startswith("local:"):
+            return os.path.join(HERE, "pgen", p[6:] + ".cpp")
+        return os.path.join(src, "pgen", p + ".cpp")
+    local_inc = os.path.join(inc, "localpgen")
+    os.makedirs(local_inc, exist_ok=True)
+    pg_work = []
+    for p in pgens:
+        name = p.split(":")[-1]
+        sfile = pgen_src(p)
+        if p.startswith("local:"):
+            # compile a one-line wrapper placed virtually inside src/pgen/
+            wrap = os.path.join(local_inc, name + "_wrap.cpp")
+            with open(wrap, "w") as f:
+                f.write('#include "%s"\n' % sfile)
+            # "../x.hpp" in the included file resolves relative to ITS directory first, then -I
+            pg_work.append((wrap, os.path.join(obj, "pgen__" + name + ".o"),
+                            incs + ["-I", os.path.join(src, "pgen")]))
+        else:
+            pg_work.append((sfile, os.path.join(obj, "pgen__" + name + ".o"), incs))
     failed = False
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
         for objf, rc, err in ex.map(compile_one, work + pg_work):
@@ -176,7 +198,7 @@ def build(cfg, ref, jobs):
         raise SystemExit("reference build failed for " + cfg)
     common = [w[1] for w in work]
     for p, w in zip(pgens, pg_work):
-        exe = os.path.join(root, "athena_" + p)
+        exe = os.path.join(root, "athena_" + p.split(":")[-1])
         cmd = ["g++"] + CXXFLAGS + ["-s", "-o", exe] + common + [w[1]]   # -s: smaller to ship
         subprocess.run(cmd, check=True)
         print("built", exe)

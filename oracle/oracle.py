@@ -38,6 +38,10 @@ BVALFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_int, _DP, _DP, _DP, _DP, C.c_double
                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
 
 
+SRCTERMFUNC = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_double, C.c_double, _DP, _DP, _DP, _DP,
+                          _DP)
+
+
 class FaceFieldView:
     """FaceField (src/athena.hpp:95-105) as numpy views"""
     def __init__(self, x1f, x2f, x3f):
@@ -86,10 +90,11 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.POINTER(C.c_double)]
         L.ao_add_flux_div.argtypes = [C.c_void_p, C.c_int, C.c_double]
-        L.ao_add_source_terms.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.ao_add_source_terms.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         L.ao_ct.argtypes = [C.c_void_p, C.c_int, C.c_double]
         for f in ("ao_cons2prim", "ao_prim2cons", "ao_scalar_cons2prim", "ao_scalar_prim2cons"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int] + [C.c_int] * 6
+        L.ao_enroll_user_source.argtypes = [C.c_void_p, SRCTERMFUNC, C.c_void_p]
         L.ao_enroll_user_bc.argtypes = [C.c_void_p, C.c_int, BVALFUNC, C.c_void_p]
         L.ao_history.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.ao_new_block_dt.restype = C.c_double
@@ -246,6 +251,26 @@ class OracleMesh:
         cb = BVALFUNC(tramp)
         self._keep = getattr(self, "_keep", []) + [cb]
         self.L.ao_enroll_user_bc(self.h, face, cb, None)
+
+    def enroll_user_explicit_source_function(self, fn):
+        """Mesh::EnrollUserExplicitSourceFunction: fn(pmb, time, dt, prim, prim_scalar, bcc,
+        cons, cons_scalar) with numpy views (None where the array does not exist)."""
+        mesh = self
+
+        def view(ptr, blk, name):
+            shp = mesh.shape(blk, name)
+            if not ptr or shp is None or 0 in shp:
+                return None
+            return np.ctypeslib.as_array(ptr, shape=shp)
+
+        def tramp(_user, blk, time, dt, prim, prs, bcc, cons, cs):
+            fn(OracleBlockView(mesh, blk), time, dt, view(prim, blk, "w"),
+               view(prs, blk, "r") if mesh.p.nscalars else None,
+               view(bcc, blk, "bcc") if mesh.p.mhd else None, view(cons, blk, "u"),
+               view(cs, blk, "s") if mesh.p.nscalars else None)
+        cb = SRCTERMFUNC(tramp)
+        self._keep = getattr(self, "_keep", []) + [cb]
+        self.L.ao_enroll_user_source(self.h, cb, None)
 
     def history(self):
         """the sums HistoryOutput writes (mass, momenta, KE, tot-E, [ME], [scalars])"""

@@ -55,6 +55,8 @@ struct AoMesh {
   double beta[4], delta[4], g1[4], g2[4], g3[4], ebeta[4];
   double cfl;
   AoBValFunc user_bc[6]; void *user_bc_arg[6];
+  AoSrcTermFunc user_src; void *user_src_arg;
+  double sbeta[4];
   double bc_time, bc_dt;   /* (time, dt) handed to boundary functions: end of stage, beta*dt */
   /* canonical buffer-id table: src/bvals/bvals_base.cpp:153-256 */
   int nni; int ni[26][3];
@@ -150,22 +152,22 @@ static void set_integrator(AoMesh *m) {
   double cfl_limit = 1.0;
   for (int s = 0; s < 4; ++s) { m->g1[s] = 0; m->g2[s] = 1; m->g3[s] = 0; m->delta[s] = 0; }
   m->delta[0] = 1.0;
-  for (int s = 0; s < 4; ++s) m->ebeta[s] = 1.0;
+  for (int s = 0; s < 4; ++s) { m->ebeta[s] = 1.0; m->sbeta[s] = 0.0; }
   switch (m->p.integrator) {
     case AO_INT_VL2:
-      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0; m->ebeta[0] = 0.5;
+      m->nstages = 2; m->beta[0] = 0.5; m->beta[1] = 1.0; m->ebeta[0] = 0.5; m->sbeta[1] = 0.5;
       if (m->ndim >= 2) cfl_limit = 0.5;
       break;
     case AO_INT_RK1:
       m->nstages = 1; m->beta[0] = 1.0;
       break;
     case AO_INT_RK2:
-      m->nstages = 2; m->beta[0] = 1.0; m->beta[1] = 0.5;
+      m->nstages = 2; m->beta[0] = 1.0; m->beta[1] = 0.5; m->sbeta[1] = 1.0;
       m->g1[1] = 0.5; m->g2[1] = 0.5;
       break;
     default: /* rk3 */
       m->nstages = 3; m->beta[0] = 1.0; m->beta[1] = 0.25; m->beta[2] = 0.66666666666666667;
-      m->ebeta[1] = 0.5;
+      m->ebeta[1] = 0.5; m->sbeta[1] = 1.0; m->sbeta[2] = 0.5;
       m->g1[1] = 0.25; m->g2[1] = 0.75;
       m->g1[2] = 0.66666666666666667; m->g2[2] = 0.33333333333333333;
       break;
@@ -1499,7 +1501,7 @@ void ao_integrate_scalars(AoMesh *m, int b, int stage) {
 /* HydroSourceTerms::ConstantAcceleration (src/hydro/srcterms/constant_acc.cpp:25-77), called
  * from the SRC_TERM task with dt = beta*dt on the stage's u, using the stage-start primitives
  * (time_integrator.cpp:1655-1678) */
-void ao_add_source_terms(AoMesh *m, int b, double dt) {
+static void const_accel(AoMesh *m, int b, double dt) {
   AoBlock *B = &m->blk[b];
   for (int d = 0; d < 3; ++d) {
     double g = m->p.grav_acc[d];
@@ -1511,6 +1513,14 @@ void ao_add_source_terms(AoMesh *m, int b, double dt) {
         if (!ISO(m)) B->u[CC(B,IEN,k,j,i)] += src*B->w[CC(B,IVX+d,k,j,i)];
       }
   }
+}
+
+/* HydroSourceTerms::AddSourceTerms (hydro/srcterms/hydro_srcterms.cpp:117-156) */
+void ao_add_source_terms(AoMesh *m, int b, double time, double dt) {
+  const_accel(m, b, dt);
+  if (m->user_src)
+    m->user_src(m->user_src_arg, b, time, dt, m->blk[b].w, m->blk[b].r, m->blk[b].bcc,
+                m->blk[b].u, m->blk[b].s);
 }
 
 /* ------------------------------------------------------------------ history */
@@ -1599,6 +1609,10 @@ static void new_time_step(AoMesh *m) {
   if (m->time < m->p.tlim && (m->p.tlim - m->time) < m->dt) m->dt = m->p.tlim - m->time;
 }
 
+void ao_enroll_user_source(AoMesh *m, AoSrcTermFunc fn, void *user) {
+  m->user_src = fn; m->user_src_arg = user;
+}
+
 void ao_enroll_user_bc(AoMesh *m, int face, AoBValFunc fn, void *user) {
   m->user_bc[face] = fn; m->user_bc_arg[face] = user;
 }
@@ -1639,7 +1653,7 @@ double ao_cycle(AoMesh *m) {
       if (w2[0] == 0.0 && w2[1] == 1.0 && w2[2] == 0.0) ao_swap_cc(m, g);
       else ao_weighted_ave_cc(m, g, 0, 1, w2);
       ao_add_flux_div(m, g, m->beta[s]*dt);
-      ao_add_source_terms(m, g, m->beta[s]*dt);    /* SRC_TERM after INT_HYD */
+      const_accel(m, g, m->beta[s]*dt);            /* SRC_TERM after INT_HYD */
       if (m->p.mhd) {
         ao_weighted_ave_fc(m, g, 1, 0, w);
         if (w2[0] == 0.0 && w2[1] == 1.0 && w2[2] == 0.0) ao_swap_fc(m, g);
@@ -1647,6 +1661,11 @@ double ao_cycle(AoMesh *m) {
         ao_ct(m, g, m->beta[s]*dt);
       }
       ao_integrate_scalars(m, g, stage);
+      /* user-defined source terms, last in AddSourceTerms (hydro_srcterms.cpp:150-153); the
+       * SRC_TERM task follows INT_HYD | INT_SCLR; time = start of stage */
+      if (m->user_src)
+        m->user_src(m->user_src_arg, g, m->time + m->sbeta[s]*dt, m->beta[s]*dt, m->blk[g].w,
+                    m->blk[g].r, m->blk[g].bcc, m->blk[g].u, m->blk[g].s);
     }
     ao_exchange_cc(m);
     ao_exchange_fc(m);

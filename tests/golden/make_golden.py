@@ -98,6 +98,17 @@ CASES = {
     "shkcloud3d_hlld_plm_vl2_8blk": ("mhd_hlld_ng2", "shk_cloud", "athinput.shk_cloud",
                                      {"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16,
                                       **mb(8, 8, 8)}, "hlld", True, 5),
+    # user-enrolled explicit source function (oracle/pgen/usersrc.cpp, our own test pgen built
+    # against the reference; tests/util.py:central_gravity_source restates it)
+    "usersrc_lhllc_plm_vl2_8blk_s1": ("hydro_lhllc_ng2_s1", "usersrc", "athinput.blast",
+                                      dict(BL, **mb(8, 8, 8)), "lhllc", False, 5, 1),
+    "usersrc_hlld_plm_rk3_8blk": ("mhd_hlld_ng2", "usersrc", "athinput.blast",
+                                  dict(BL, **mb(8, 8, 8), **{"time/integrator": "rk3"}),
+                                  "hlld", True, 4),
+    "usersrc_iso_hlle_plm_rk2_8blk": ("hydro_hlle_iso_ng2", "usersrc", "athinput.blast",
+                                      dict(BL, **mb(8, 8, 8), **{"time/integrator": "rk2",
+                                           "hydro/iso_sound_speed": 0.8}),
+                                      "hlle", False, 5, 0, "isothermal"),
     # constant acceleration source term (hydro/srcterms/constant_acc.cpp) in a closed box
     "blast_grav_hllc_plm_vl2_8blk": ("hydro_hllc_ng2", "blast", "athinput.blast",
                                      dict(BL, **mb(8, 8, 8), **{

@@ -67,6 +67,31 @@ def test_overlapped_schedule_is_bit_identical(name, monkeypatch):
             util.assert_bitwise(pmb.get(f), g.final[n][f], "%s block %s %s" % (name, loc, f))
 
 
+@pytest.mark.parametrize("name", ["usersrc_lhllc_plm_vl2_8blk_s1", "usersrc_hlld_plm_rk3_8blk",
+                                  "usersrc_iso_hlle_plm_rk2_8blk"])
+def test_device_side_user_source_function(name):
+    """ab_enroll_user_explicit_source_function_device: the source term stays on the GPU (here as
+    torch kernels on the library's stream over the library's registers, zero copies)."""
+    import gpu_util
+    import athena_gamma_b200 as ab
+    g = util.Golden(name)
+    pin = gpu_util.pin_from_par(g.par)
+    m = ab.Mesh(pin, mhd=g.mhd, flux=g.solver, nghost=g.ng, nscalars=g.nscalars, eos=g.eos)
+    m.enroll_user_explicit_source_function(gpu_util.central_gravity_source_torch(g.par),
+                                           device=True)
+    for n, loc in enumerate(g.locs):
+        pmb = m.block_of(*loc)
+        for f in g.fields:
+            pmb.set(f, g.init[n][f])
+    m.initialize()
+    dts = m.cycles(g.ncycles)
+    assert list(dts) == list(g.dts[:g.ncycles])
+    for n, loc in enumerate(g.locs):
+        pmb = m.block_of(*loc)
+        for f in g.fields:
+            util.assert_bitwise(pmb.get(f), g.final[n][f], "%s block %s %s" % (name, loc, f))
+
+
 def history_close(h, ref, scale):
     """device tree sum vs the reference's running sum: |d| <= 1e-13 x sum of magnitudes"""
     assert len(h) == len(ref)

@@ -32,6 +32,9 @@ CASES = [
     # user-enrolled boundary function
     ("shkcloud2d_hllc_plm_vl2_4blk", None, None),
     ("shkcloud3d_hlld_plm_vl2_8blk", None, None),
+    # user-enrolled explicit source function
+    ("usersrc_lhllc_plm_vl2_8blk_s1", None, None),
+    ("usersrc_hlld_plm_rk3_8blk", None, None),
     # constant-acceleration source term
     ("blast_grav_hllc_plm_vl2_8blk", None, None),
     ("blast_grav_hlld_plm_rk2_8blk", None, None),
@@ -139,8 +142,8 @@ def test_task_by_task(name, xorder, solver):
         ab_check(L.ab_weighted_ave(h, pmb.lid, 1, 0, w), L)
         ab_check(L.ab_swap(h, pmb.lid, 0), L)
         ab_check(L.ab_add_flux_div(h, pmb.lid, 0.5 * dt), L)
-        om.L.ao_add_source_terms(om.h, b, 0.5 * dt)       # SRC_TERM (no-op without grav_acc)
-        ab_check(L.ab_add_source_terms(h, pmb.lid, 0.5 * dt), L)
+        om.L.ao_add_source_terms(om.h, b, 0.25, 0.5 * dt)   # SRC_TERM (no-op without sources)
+        ab_check(L.ab_add_source_terms(h, pmb.lid, 0.25, 0.5 * dt), L)
         if g.mhd:
             om.L.ao_weighted_ave_fc(om.h, b, 1, 0, w)
             om.L.ao_swap_fc(om.h, b)

@@ -69,6 +69,46 @@ def shock_cloud_inner_x1(par):
     return fn
 
 
+def central_gravity_source(par):
+    """The SrcTermFunc of oracle/pgen/usersrc.cpp (CentralGravity), restated with the same
+    operation order (only + - * / sqrt, so numpy reproduces it bit for bit)."""
+    pr = par.get("problem", {})
+    gm = float(pr.get("gm", 0.5))
+    soft2 = float(pr.get("soft2", 0.01))
+    sdecay = float(pr.get("sdecay", 0.3))
+
+    def fn(pmb, time, dt, prim, prim_scalar, bcc, cons, cons_scalar):
+        amp = gm*(1.0 + 0.5*time)
+        K = slice(pmb.ks, pmb.ke + 1)
+        J = slice(pmb.js, pmb.je + 1)
+        I = slice(pmb.is_, pmb.ie + 1)
+        x = pmb.coord("x1v")[I][None, None, :]
+        y = pmb.coord("x2v")[J][None, :, None]
+        z = pmb.coord("x3v")[K][:, None, None]
+        rsq = (x*x + y*y) + (z*z + soft2)
+        r = np.sqrt(rsq)
+        fac = amp/(rsq*r)
+        den = prim[0, K, J, I]
+        s1 = (dt*den)*(fac*x)
+        s2 = (dt*den)*(fac*y)
+        s3 = (dt*den)*(fac*z)
+        cons[1, K, J, I] -= s1
+        cons[2, K, J, I] -= s2
+        cons[3, K, J, I] -= s3
+        if cons.shape[0] > 4:
+            cons[4, K, J, I] -= (s1*prim[1, K, J, I] + s2*prim[2, K, J, I]) + s3*prim[3, K, J, I]
+        if cons_scalar is not None:
+            for n in range(cons_scalar.shape[0]):
+                cons_scalar[n, K, J, I] -= (dt*sdecay)*(den*prim_scalar[n, K, J, I])
+    return fn
+
+
+def user_source_for(g):
+    if g.name.startswith("usersrc"):
+        return central_gravity_source(g.par)
+    return None
+
+
 def user_bcs_for(g):
     """{face: boundary function} a fixture needs (BoundaryFace numbering ix1=0 ... ox3=5)"""
     if g.name.startswith("shkcloud"):
@@ -82,6 +122,8 @@ def oracle_from_golden(g):
     m = oracle.OracleMesh(p)
     for face, fn in user_bcs_for(g).items():
         m.enroll_user_boundary_function(face, fn)
+    if user_source_for(g):
+        m.enroll_user_explicit_source_function(user_source_for(g))
     m.load_rst(g.as_rst("init"))
     m.initialize()
     return m
