@@ -128,6 +128,7 @@ struct LocalBlock {
   int parity_b = 0;                       // (b,b1) swap state
   int parity_s = 0;                       // (s,s1) swap state
   unsigned long long *dtmin = nullptr;    // slot in the mesh-wide array
+  std::vector<void *> debug_allocs;       // AB_DEBUG_ALLOC=1: per-array allocations
   bool cc_e_valid = false;                // cc_e written by the fused cons2prim
   bool has_phys_bc = false;
 };
@@ -648,18 +649,32 @@ int alloc_blocks(AbMesh *m) {
     }
     tot += align256(emf_elems*8);
     L.nbytes = tot;
-    CK(cudaMalloc(&L.base, tot));
-    CK(cudaMemsetAsync(L.base, 0, tot, m->stream));   // AthenaArray storage is zero-initialised
-    char *cur = (char *)L.base;
+    // AB_DEBUG_ALLOC=1: one cudaMalloc per array instead of one slab per block, so that
+    // compute-sanitizer memcheck sees every array's bounds (debug aid; same layout otherwise)
+    const char *dbg = getenv("AB_DEBUG_ALLOC");
+    const bool split_alloc = dbg && dbg[0] == '1';
+    char *cur = nullptr;
+    if (!split_alloc) {
+      CK(cudaMalloc(&L.base, tot));
+      CK(cudaMemsetAsync(L.base, 0, tot, m->stream));   // AthenaArray storage is zero-initialised
+      cur = (char *)L.base;
+    }
+    auto carve = [&](size_t bytes) -> char * {
+      if (!split_alloc) { char *q = cur; cur += align256(bytes); return q; }
+      void *q = nullptr;
+      cudaMalloc(&q, bytes ? bytes : 8);
+      cudaMemsetAsync(q, 0, bytes ? bytes : 8, m->stream);
+      L.debug_allocs.push_back(q);
+      return (char *)q;
+    };
     for (int r = 0; r < AB_NREG; ++r) {
       double **slot = reg_slot(L, r);
-      if (L.regsize[r] > 0) { *slot = (double *)cur; cur += align256(L.regsize[r]*8); }
+      if (L.regsize[r] > 0) *slot = (double *)carve(L.regsize[r]*8);
       else *slot = nullptr;
     }
-    if (p.mhd) { d.cc_e = (double *)cur; cur += cce; }
+    if (p.mhd) d.cc_e = (double *)carve(3*ncc*8);
     auto put = [&](const std::vector<double> &v, int idx) -> const double * {
-      double *dst = (double *)cur;
-      cur += align256(v.size()*8);
+      double *dst = (double *)carve(v.size()*8);
       cudaMemcpyAsync(dst, v.data(), v.size()*8, cudaMemcpyHostToDevice, m->stream);
       if (idx >= 0) { L.coord_dev[idx] = dst; L.coord_n[idx] = (long)v.size(); }
       return dst;
@@ -669,7 +684,7 @@ int alloc_blocks(AbMesh *m) {
     d.dx1f = put(dxf[0], 6); d.dx2f = put(dxf[1], 7); d.dx3f = put(dxf[2], 8);
     for (int dd = 0; dd < 3; ++dd) { L.g.wp[dd] = put(wp[dd], -1); L.g.wm[dd] = put(wm[dd], -1); }
     CK(cudaStreamSynchronize(m->stream));   // host vectors go out of scope
-    L.emf_send = (double *)cur;
+    L.emf_send = (double *)carve(emf_elems*8);
     L.dtmin = m->dtmin + l*ab::DT_SLOTS;
     L.has_phys_bc = false;
     for (int f = 0; f < 2*m->ndim; ++f)
@@ -825,7 +840,12 @@ int build_state_plan(AbMesh *m, int which) {
     if (dev) { cudaFree(dev); dev = nullptr; }
     if (n == 0) return AB_OK;
     CK(cudaMalloc(&dev, sizeof(CopyBox)*n));
-    CK(cudaMemcpy(dev, v.data(), sizeof(CopyBox)*n, cudaMemcpyHostToDevice));
+    // Stream-ordered copy + sync.  A plain cudaMemcpy from pageable memory may return before the
+    // DMA has landed and orders only against the NULL stream; the kernels that read this table run
+    // on a non-blocking stream and occasionally saw it half-written (flaky illegal address with
+    // >64 KB tables, i.e. many MeshBlocks).
+    CK(cudaMemcpyAsync(dev, v.data(), sizeof(CopyBox)*n, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
     return AB_OK;
   };
   int rc;
@@ -1192,6 +1212,22 @@ void swap_fc(LocalBlock &L) {
 
 void swap_sc(LocalBlock &L) { std::swap(L.d.s, L.d.s1); L.parity_s ^= 1; }
 
+// AB_DEBUG_SYNC=1: synchronise after every task group of the cycle and name the group that
+// faulted (debug aid; the production path never synchronises inside a cycle)
+bool debug_sync() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("AB_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+#define DBG(m, label)                                                               \
+  do {                                                                              \
+    if (debug_sync()) {                                                             \
+      cudaError_t e_ = cudaStreamSynchronize((m)->stream);                          \
+      if (e_ != cudaSuccess)                                                        \
+        return fail(AB_ERR_CUDA, std::string("after ") + (label) + ": " + cudaGetErrorString(e_)); \
+    }                                                                               \
+  } while (0)
+
 int one_cycle(AbMesh *m) {
   const double *dtp = m->state + 1;
   const bool user_src = (m->user_src || m->user_src_dev);
@@ -1212,14 +1248,18 @@ int one_cycle(AbMesh *m) {
         } else {
           ab::launch_flux_dir(L.d, L.g, m->kp, order, dir, 0.0, dtp, m->stream);
         }
+        DBG(m, "flux dir " + std::to_string(dir) + " order " + std::to_string(order));
       }
       if (m->p.mhd) ab::launch_corner_e(L.d, m->stream, L.cc_e_valid ? 1 : 0);
+      DBG(m, "corner_e");
       ab::launch_scalar_fluxes(L.d, L.g, m->kp, order, m->stream);   // CALC_SCLRFLX
+      DBG(m, "scalar fluxes");
     }
     // EMF correction.  Overlapped schedule: the NCCL transfer runs on the comm stream while
     // IntegrateHydro / IntegrateScalars (which do not read EMFs) run on the compute stream.
     int rc = m->overlap ? emf_exchange_begin(m) : emf_exchange(m);
     if (rc) return rc;
+    DBG(m, "emf exchange");
     const bool swap = (m->g1[s] == 0.0 && m->g2[s] == 1.0 && m->g3[s] == 0.0);
     const int zero_init = (stage == 1);   // StartupTaskList: u1, b1 ZeroClear (:1386-1397)
     for (auto &L : m->lb) {   // INT_HYD (+ SRC_TERM), INT_SCLR (time_integrator.cpp:2141-2185)
@@ -1240,6 +1280,7 @@ int one_cycle(AbMesh *m) {
                                   0.0, dtp, m->stream, -1, -1, 0, 1);
       }
     }
+    DBG(m, "integrate_cc");
     if (user_src) {   // SRC_TERM, user part: start-of-stage time, beta*dt
       for (auto &L : m->lb) {
         rc = user_source(m, L, m->h_time + m->sbeta[s]*m->h_dt, m->beta[s]*m->h_dt);
@@ -1255,6 +1296,7 @@ int one_cycle(AbMesh *m) {
         ab::launch_integrate_fc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
       }
     }
+    DBG(m, "integrate_fc");
     if (m->has_user_bc) {   // PhysicalBoundary: t_end_stage, beta*dt (time_integrator.cpp:2045-2062)
       m->bc_time = m->h_time + m->ebeta[s]*m->h_dt;
       m->bc_dt = m->beta[s]*m->h_dt;
@@ -1263,8 +1305,14 @@ int one_cycle(AbMesh *m) {
     if (!m->overlap) {
       rc = bvals_exchange(m);
       if (rc) return rc;
+      DBG(m, "bvals exchange");
       if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
-      for (auto &L : m->lb) { primitives(m, L, last); physical_bcs(m, L); }
+      for (auto &L : m->lb) {
+        primitives(m, L, last);
+        DBG(m, "primitives");
+        physical_bcs(m, L);
+        DBG(m, "physical bcs");
+      }
     } else {
       // ghost zones travel while ConservedToPrimitive (+ CFL reduction) covers the active cells;
       // the ghost shell follows once they arrived
@@ -1283,6 +1331,7 @@ int one_cycle(AbMesh *m) {
       m->hist_n++;
       rc = new_time_step(m, 1, true);
       if (rc) return rc;
+      DBG(m, "new_time_step");
     }
   }
   CK(cudaGetLastError());
@@ -1330,7 +1379,7 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
   CK(cudaMalloc(&m->dt_hist, sizeof(double)*m->hist_cap));
   m->h_time = p->start_time; m->h_dt = DBL_MAX; m->h_ncycle = 0;
   double h[8] = {p->start_time, DBL_MAX, p->tlim, m->cfl, DBL_MAX, 0.0, 0.0, 0.0};
-  CK(cudaMemcpy(m->state, h, sizeof(h), cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(m->state, h, sizeof(h), cudaMemcpyHostToDevice, m->stream));
   CK(cudaStreamSynchronize(m->stream));
   *out = m;
   return AB_OK;
@@ -1445,7 +1494,7 @@ int ab_mesh_destroy(AbMesh *m) {
   if (m->dry) { delete m; return AB_OK; }
   cudaSetDevice(m->p.device);
   cudaStreamSynchronize(m->stream);
-  for (auto &L : m->lb) cudaFree(L.base);
+  for (auto &L : m->lb) { cudaFree(L.base); for (void *q : L.debug_allocs) cudaFree(q); }
   for (int i = 0; i < 8; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase1r); cudaFree(m->plan[i].phase2); }
   for (auto &kv : m->peer_state) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }

@@ -63,7 +63,9 @@ def central_gravity_source_torch(par):
             z = torch.as_tensor(pmb.coord("x3v")[K], device="cuda")[:, None, None]
             rsq = (x*x + y*y) + (z*z + soft2)
             r = torch.sqrt(rsq)
-            fac = amp/(rsq*r)
+            # tensor / tensor: torch evaluates (python scalar)/tensor as scalar*reciprocal(tensor),
+            # which rounds differently from the IEEE division the C++ function performs
+            fac = torch.full_like(rsq, amp)/(rsq*r)
             den = w[0, K, J, I]
             s1 = (dt*den)*(fac*x)
             s2 = (dt*den)*(fac*y)
