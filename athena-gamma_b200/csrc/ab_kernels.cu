@@ -291,7 +291,8 @@ __global__ void AB_FLUX_BOUNDS
 k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
        int ntot, double dt_val, const double *dt_ptr) {
   constexpr int NW = MHD ? 7 : 5;
-  constexpr bool ISO = (SOLVER == SOLVER_HLLE_ISO || SOLVER == SOLVER_HLLD_ISO);
+  constexpr bool ISO = (SOLVER == SOLVER_HLLE_ISO || SOLVER == SOLVER_HLLD_ISO ||
+                        SOLVER == SOLVER_LLF_ISO);
   int t = blockIdx.x*AB_FLUX_BX + threadIdx.x;
   if (t >= ntot) return;
   int i, j, k;
@@ -457,7 +458,15 @@ static void flux_order(const BlkDev &b, const ReconGeom &g, const Params &p, int
 
 void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
                      double dt_val, const double *dt_ptr, cudaStream_t s) {
-  if (p.eos != 0) {   // isothermal: hlle (hydro), hlle / hlld (MHD) -- configure.py:299-325
+  if (p.solver == SOLVER_LLF) {   // --flux=llf, either EOS
+    if (p.eos != 0) {
+      if (p.mhd) flux_order<SOLVER_LLF_ISO,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
+      else flux_order<SOLVER_LLF_ISO,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    } else {
+      if (p.mhd) flux_order<SOLVER_LLF,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
+      else flux_order<SOLVER_LLF,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    }
+  } else if (p.eos != 0) {   // isothermal: hlle (hydro), hlle / hlld (MHD) -- configure.py:299-325
     if (!p.mhd) flux_order<SOLVER_HLLE_ISO,false>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD_ISO,true>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else flux_order<SOLVER_HLLE_ISO,true>(b, g, p, order, dir, dt_val, dt_ptr, s);

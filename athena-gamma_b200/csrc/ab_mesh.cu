@@ -1433,7 +1433,7 @@ static int validate_params(const AbMeshParams *p) {
   if (p->xorder == 3 && p->nghost < 3)
     return fail(AB_ERR_ARG, "xorder=3 (PPM) needs nghost >= 3 (reconstruction.cpp:90-99)");
   if (p->nghost < 2) return fail(AB_ERR_ARG, "nghost must be >= 2");
-  if (p->solver < 0 || p->solver > AB_SOLVER_LHLLD) return fail(AB_ERR_ARG, "unknown Riemann solver");
+  if (p->solver < 0 || p->solver > AB_SOLVER_LLF) return fail(AB_ERR_ARG, "unknown Riemann solver");
   // configure.py:310-325
   if (p->mhd && p->solver == AB_SOLVER_HLLC) return fail(AB_ERR_ARG, "HLLC flux cannot be used with MHD");
   if (p->mhd && p->solver == AB_SOLVER_LHLLC) return fail(AB_ERR_ARG, "LHLLC flux cannot be used with MHD");

@@ -26,7 +26,7 @@ namespace ab {
 enum : int { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4, IVX = 1, IVY = 2, IVZ = 3, IPR = 4,
              IBY = 5, IBZ = 6 };
 enum : int { SOLVER_HLLE = 0, SOLVER_HLLC = 1, SOLVER_HLLD = 2, SOLVER_ROE = 3,
-             SOLVER_LHLLC = 4, SOLVER_LHLLD = 5 };
+             SOLVER_LHLLC = 4, SOLVER_LHLLD = 5, SOLVER_LLF = 6 };
 
 // std::min / std::max semantics of the reference
 AB_HD double dmin(double a, double b) { return (b < a) ? b : a; }
@@ -1182,14 +1182,100 @@ AB_HD void hlld_iso(const double *wli, const double *wri, double bxi, double cs,
 }
 
 // internal solver ids of the isothermal variants (the ABI keeps AB_SOLVER_* + AB_EOS_*)
-enum : int { SOLVER_HLLE_ISO = 6, SOLVER_HLLD_ISO = 7 };
+enum : int { SOLVER_HLLE_ISO = 8, SOLVER_HLLD_ISO = 9, SOLVER_LLF_ISO = 10 };
+
+// LLF (hydro/rsolvers/hydro/llf.cpp:34-125, mhd/llf_mhd.cpp:34-170), both EOS; `ga` is gamma
+// (adiabatic) or the isothermal sound speed
+template <bool MHD, bool ISO>
+AB_HD void llf_t(const double *wli, const double *wri, double bxi, double ga, double *flxi) {
+  double fl[7], fr[7], du[7];
+  const double gm1 = ga - 1.0;
+  double cl, cr;
+  if (MHD) {
+    cl = ISO ? fast_speed_iso(ga, wli, bxi)
+             : fast_speed(ga, wli[IDN], wli[IPR], wli[IBY], wli[IBZ], bxi);
+    cr = ISO ? fast_speed_iso(ga, wri, bxi)
+             : fast_speed(ga, wri[IDN], wri[IPR], wri[IBY], wri[IBZ], bxi);
+  } else {
+    cl = ISO ? ga : sound_speed(ga, wli[IDN], wli[IPR]);
+    cr = ISO ? ga : sound_speed(ga, wri[IDN], wri[IPR]);
+  }
+  const double a = 0.5*dmax((fabs(wli[IVX]) + cl), (fabs(wri[IVX]) + cr));
+  const double mxl = wli[IDN]*wli[IVX];
+  const double mxr = wri[IDN]*wri[IVX];
+  double pbl = 0.0, pbr = 0.0;
+  fl[IDN] = mxl;
+  fr[IDN] = mxr;
+  if (MHD) {
+    pbl = 0.5*(bxi*bxi + sqr(wli[IBY]) + sqr(wli[IBZ]));
+    pbr = 0.5*(bxi*bxi + sqr(wri[IBY]) + sqr(wri[IBZ]));
+    fl[IVX] = mxl*wli[IVX] + pbl - sqr(bxi);
+    fr[IVX] = mxr*wri[IVX] + pbr - sqr(bxi);
+    fl[IVY] = mxl*wli[IVY] - bxi*wli[IBY];
+    fr[IVY] = mxr*wri[IVY] - bxi*wri[IBY];
+    fl[IVZ] = mxl*wli[IVZ] - bxi*wli[IBZ];
+    fr[IVZ] = mxr*wri[IVZ] - bxi*wri[IBZ];
+  } else {
+    fl[IVX] = mxl*wli[IVX];
+    fr[IVX] = mxr*wri[IVX];
+    fl[IVY] = mxl*wli[IVY];
+    fr[IVY] = mxr*wri[IVY];
+    fl[IVZ] = mxl*wli[IVZ];
+    fr[IVZ] = mxr*wri[IVZ];
+  }
+  double el = 0.0, er = 0.0;
+  fl[IEN] = fr[IEN] = 0.0;
+  if (!ISO) {
+    if (MHD) {
+      el = wli[IPR]/gm1 + 0.5*wli[IDN]*(sqr(wli[IVX])+sqr(wli[IVY])+sqr(wli[IVZ])) + pbl;
+      er = wri[IPR]/gm1 + 0.5*wri[IDN]*(sqr(wri[IVX])+sqr(wri[IVY])+sqr(wri[IVZ])) + pbr;
+    } else {
+      el = wli[IPR]/gm1 + 0.5*wli[IDN]*(sqr(wli[IVX]) + sqr(wli[IVY]) + sqr(wli[IVZ]));
+      er = wri[IPR]/gm1 + 0.5*wri[IDN]*(sqr(wri[IVX]) + sqr(wri[IVY]) + sqr(wri[IVZ]));
+    }
+    fl[IVX] += wli[IPR];
+    fr[IVX] += wri[IPR];
+    if (MHD) {
+      fl[IEN] = (el + wli[IPR] + pbl - bxi*bxi)*wli[IVX];
+      fr[IEN] = (er + wri[IPR] + pbr - bxi*bxi)*wri[IVX];
+      fl[IEN] -= bxi*(wli[IBY]*wli[IVY] + wli[IBZ]*wli[IVZ]);
+      fr[IEN] -= bxi*(wri[IBY]*wri[IVY] + wri[IBZ]*wri[IVZ]);
+    } else {
+      fl[IEN] = (el + wli[IPR])*wli[IVX];
+      fr[IEN] = (er + wri[IPR])*wri[IVX];
+    }
+  } else {
+    fl[IVX] += (ga*ga)*wli[IDN];
+    fr[IVX] += (ga*ga)*wri[IDN];
+  }
+  du[IDN] = wri[IDN]          - wli[IDN];
+  du[IVX] = wri[IDN]*wri[IVX] - wli[IDN]*wli[IVX];
+  du[IVY] = wri[IDN]*wri[IVY] - wli[IDN]*wli[IVY];
+  du[IVZ] = wri[IDN]*wri[IVZ] - wli[IDN]*wli[IVZ];
+  du[IEN] = ISO ? 0.0 : (er - el);
+  if (MHD) {
+    fl[IBY] = wli[IBY]*wli[IVX] - bxi*wli[IVY];
+    fr[IBY] = wri[IBY]*wri[IVX] - bxi*wri[IVY];
+    fl[IBZ] = wli[IBZ]*wli[IVX] - bxi*wli[IVZ];
+    fr[IBZ] = wri[IBZ]*wri[IVX] - bxi*wri[IVZ];
+    du[IBY] = wri[IBY] - wli[IBY];
+    du[IBZ] = wri[IBZ] - wli[IBZ];
+  }
+#pragma unroll
+  for (int n = 0; n < (MHD ? 7 : 5); ++n) flxi[n] = 0.5*(fl[n] + fr[n]) - a*du[n];
+  if (ISO) flxi[IEN] = 0.0;
+}
 
 // compile-time dispatch
 // `gamma` carries the isothermal sound speed and `dfloor` the density floor for the *_ISO ids
 template <int SOLVER, bool MHD>
 AB_HD void riemann(const double *wli, const double *wri, double bxi, double gamma, double dvn,
                    double dvt, double *flxi, double dfloor = 0.0) {
-  if (SOLVER == SOLVER_HLLE_ISO) {
+  if (SOLVER == SOLVER_LLF) {
+    llf_t<MHD,false>(wli, wri, bxi, gamma, flxi);
+  } else if (SOLVER == SOLVER_LLF_ISO) {
+    llf_t<MHD,true>(wli, wri, bxi, gamma, flxi);
+  } else if (SOLVER == SOLVER_HLLE_ISO) {
     if (MHD) hlle_mhd_iso(wli, wri, bxi, gamma, flxi);
     else hlle_hydro_iso(wli, wri, gamma, flxi);
   } else if (SOLVER == SOLVER_HLLD_ISO) {

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 AB_OK, AB_ERR_ARG, AB_ERR_NO_DEVICE, AB_ERR_CUDA, AB_ERR_NCCL, AB_ERR_STATE = 0, -1, -2, -3, -4, -5
 BC = {"periodic": 0, "outflow": 1, "reflecting": 2, "user": 3}
-SOLVER = {"hlle": 0, "hllc": 1, "hlld": 2, "roe": 3, "lhllc": 4, "lhlld": 5}
+SOLVER = {"hlle": 0, "hllc": 1, "hlld": 2, "roe": 3, "lhllc": 4, "lhlld": 5, "llf": 6}
 INTEGRATOR = {"vl2": 0, "rk2": 1, "rk1": 2, "rk3": 3}
 REG = {"u": 0, "u1": 1, "w": 2, "bcc": 3, "b1": 4, "b2": 5, "b3": 6, "b1_1": 7, "b1_2": 8,
        "b1_3": 9, "flux1": 10, "flux2": 11, "flux3": 12, "e1": 13, "e2": 14, "e3": 15,

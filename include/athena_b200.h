@@ -24,7 +24,8 @@ enum { AB_OK = 0, AB_ERR_ARG = -1, AB_ERR_NO_DEVICE = -2, AB_ERR_CUDA = -3, AB_E
        AB_ERR_STATE = -5 };
 enum { AB_BC_PERIODIC = 0, AB_BC_OUTFLOW = 1, AB_BC_REFLECT = 2, AB_BC_USER = 3 }; /* mesh/ix1_bc ... */
 enum { AB_SOLVER_HLLE = 0, AB_SOLVER_HLLC = 1, AB_SOLVER_HLLD = 2, AB_SOLVER_ROE = 3,
-       AB_SOLVER_LHLLC = 4, AB_SOLVER_LHLLD = 5 };   /* --flux=hlle|hllc|hlld|roe|lhllc|lhlld */
+       AB_SOLVER_LHLLC = 4, AB_SOLVER_LHLLD = 5, AB_SOLVER_LLF = 6 };
+       /* --flux=hlle|hllc|hlld|roe|lhllc|lhlld|llf */
 enum { AB_INT_VL2 = 0, AB_INT_RK2 = 1, AB_INT_RK1 = 2, AB_INT_RK3 = 3 };
 /* registers (Hydro::u,u1,w ; Field::b,b1,bcc,e,wght ; Hydro::flux ; face EMFs) */
 enum { AB_U = 0, AB_U1 = 1, AB_W = 2, AB_BCC = 3,

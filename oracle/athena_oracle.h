@@ -16,7 +16,7 @@ extern "C" {
 
 enum { AO_BC_PERIODIC = 0, AO_BC_OUTFLOW = 1, AO_BC_REFLECT = 2, AO_BC_USER = 3 };
 enum { AO_SOLVER_HLLE = 0, AO_SOLVER_HLLC = 1, AO_SOLVER_HLLD = 2, AO_SOLVER_ROE = 3,
-       AO_SOLVER_LHLLC = 4, AO_SOLVER_LHLLD = 5 };
+       AO_SOLVER_LHLLC = 4, AO_SOLVER_LHLLD = 5, AO_SOLVER_LLF = 6 };
 enum { AO_INT_VL2 = 0, AO_INT_RK2 = 1, AO_INT_RK1 = 2, AO_INT_RK3 = 3 };
 
 typedef struct {

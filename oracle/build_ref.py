@@ -46,6 +46,10 @@ CONFIGS = {
     # the fork's production solvers (confignotes: --flux=lhllc / --flux=lhlld)
     "hydro_lhllc_ng2": (False, "lhllc", 2, ["blast", "shock_tube", "kh"]),
     "mhd_lhlld_ng2": (True, "lhlld", 2, ["blast", "orszag_tang", "linear_wave"]),
+    # LLF (rsolvers/hydro/llf.cpp, mhd/llf_mhd.cpp)
+    "hydro_llf_ng2": (False, "llf", 2, ["blast"]),
+    "mhd_llf_ng2": (True, "llf", 2, ["blast"]),
+    "mhd_llf_iso_ng2": (True, "llf", 2, ["blast"], {"eos": "isothermal"}),
     # passive scalars (confignotes: --nscalars=1 with lhllc) and the isothermal EOS
     # (confignotes: --flux=hlle --eos=isothermal)
     "hydro_lhllc_ng2_s1": (False, "lhllc", 2, ["kh", "shock_tube", "local:usersrc"],

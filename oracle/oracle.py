@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 BC = {"periodic": 0, "outflow": 1, "reflecting": 2, "user": 3}
-SOLVER = {"hlle": 0, "hllc": 1, "hlld": 2, "roe": 3, "lhllc": 4, "lhlld": 5}
+SOLVER = {"hlle": 0, "hllc": 1, "hlld": 2, "roe": 3, "lhllc": 4, "lhlld": 5, "llf": 6}
 INTEGRATOR = {"vl2": 0, "rk2": 1, "rk1": 2, "rk3": 3}
 DEFAULT_FLOOR = float(np.sqrt(1024 * float(np.finfo(np.float32).tiny)))  # eos ctor
 

@@ -1278,11 +1278,92 @@ static void hlld_iso(const double *wli, const double *wri, double bxi, double cs
   flxi[IEN] = 0.0;
 }
 
+/* LLF: src/hydro/rsolvers/hydro/llf.cpp:34-125 and mhd/llf_mhd.cpp:34-170 (both EOS) */
+static void llf(int mhd, int iso, const double *wli, const double *wri, double bxi,
+                double gamma, double iso_cs, double *flxi) {
+  double fl[7], fr[7], du[7];
+  double gm1 = gamma - 1.0;
+  double cl, cr;
+  if (mhd) {
+    cl = iso ? ao_fast_speed_iso(iso_cs, wli, bxi) : ao_fast_speed(gamma, wli, bxi);
+    cr = iso ? ao_fast_speed_iso(iso_cs, wri, bxi) : ao_fast_speed(gamma, wri, bxi);
+  } else {
+    cl = iso ? iso_cs : ao_sound_speed(gamma, wli);
+    cr = iso ? iso_cs : ao_sound_speed(gamma, wri);
+  }
+  double a = 0.5*mx((fabs(wli[IVX]) + cl), (fabs(wri[IVX]) + cr));
+  double mxl = wli[IDN]*wli[IVX];
+  double mxr = wri[IDN]*wri[IVX];
+  double pbl = 0.0, pbr = 0.0;
+  fl[IDN] = mxl;
+  fr[IDN] = mxr;
+  if (mhd) {
+    pbl = 0.5*(bxi*bxi + SQR(wli[IBY]) + SQR(wli[IBZ]));
+    pbr = 0.5*(bxi*bxi + SQR(wri[IBY]) + SQR(wri[IBZ]));
+    fl[IVX] = mxl*wli[IVX] + pbl - SQR(bxi);
+    fr[IVX] = mxr*wri[IVX] + pbr - SQR(bxi);
+    fl[IVY] = mxl*wli[IVY] - bxi*wli[IBY];
+    fr[IVY] = mxr*wri[IVY] - bxi*wri[IBY];
+    fl[IVZ] = mxl*wli[IVZ] - bxi*wli[IBZ];
+    fr[IVZ] = mxr*wri[IVZ] - bxi*wri[IBZ];
+  } else {
+    fl[IVX] = mxl*wli[IVX];
+    fr[IVX] = mxr*wri[IVX];
+    fl[IVY] = mxl*wli[IVY];
+    fr[IVY] = mxr*wri[IVY];
+    fl[IVZ] = mxl*wli[IVZ];
+    fr[IVZ] = mxr*wri[IVZ];
+  }
+  double el = 0.0, er = 0.0;
+  fl[IEN] = fr[IEN] = 0.0;
+  if (!iso) {
+    if (mhd) {
+      el = wli[IPR]/gm1 + 0.5*wli[IDN]*(SQR(wli[IVX])+SQR(wli[IVY])+SQR(wli[IVZ])) + pbl;
+      er = wri[IPR]/gm1 + 0.5*wri[IDN]*(SQR(wri[IVX])+SQR(wri[IVY])+SQR(wri[IVZ])) + pbr;
+    } else {
+      el = wli[IPR]/gm1 + 0.5*wli[IDN]*(SQR(wli[IVX]) + SQR(wli[IVY]) + SQR(wli[IVZ]));
+      er = wri[IPR]/gm1 + 0.5*wri[IDN]*(SQR(wri[IVX]) + SQR(wri[IVY]) + SQR(wri[IVZ]));
+    }
+    fl[IVX] += wli[IPR];
+    fr[IVX] += wri[IPR];
+    if (mhd) {
+      fl[IEN] = (el + wli[IPR] + pbl - bxi*bxi)*wli[IVX];
+      fr[IEN] = (er + wri[IPR] + pbr - bxi*bxi)*wri[IVX];
+      fl[IEN] -= bxi*(wli[IBY]*wli[IVY] + wli[IBZ]*wli[IVZ]);
+      fr[IEN] -= bxi*(wri[IBY]*wri[IVY] + wri[IBZ]*wri[IVZ]);
+    } else {
+      fl[IEN] = (el + wli[IPR])*wli[IVX];
+      fr[IEN] = (er + wri[IPR])*wri[IVX];
+    }
+  } else {
+    fl[IVX] += (iso_cs*iso_cs)*wli[IDN];
+    fr[IVX] += (iso_cs*iso_cs)*wri[IDN];
+  }
+  du[IDN] = wri[IDN]          - wli[IDN];
+  du[IVX] = wri[IDN]*wri[IVX] - wli[IDN]*wli[IVX];
+  du[IVY] = wri[IDN]*wri[IVY] - wli[IDN]*wli[IVY];
+  du[IVZ] = wri[IDN]*wri[IVZ] - wli[IDN]*wli[IVZ];
+  du[IEN] = iso ? 0.0 : (er - el);
+  int nw = 5;
+  if (mhd) {
+    fl[IBY] = wli[IBY]*wli[IVX] - bxi*wli[IVY];
+    fr[IBY] = wri[IBY]*wri[IVX] - bxi*wri[IVY];
+    fl[IBZ] = wli[IBZ]*wli[IVX] - bxi*wli[IVZ];
+    fr[IBZ] = wri[IBZ]*wri[IVX] - bxi*wri[IVZ];
+    du[IBY] = wri[IBY] - wli[IBY];
+    du[IBZ] = wri[IBZ] - wli[IBZ];
+    nw = 7;
+  }
+  for (int n = 0; n < nw; ++n) flxi[n] = 0.5*(fl[n] + fr[n]) - a*du[n];
+  if (iso) flxi[IEN] = 0.0;
+}
+
 /* One interface, isothermal EOS (configure.py:299-325 allows hlle [hydro], hlle / hlld [MHD];
  * the Roe / LLF isothermal branches are not restated) */
 void ao_riemann_point_iso(int solver, int mhd, const double *wli, const double *wri,
                           double bxi, double iso_cs, double dfloor, double *flxi) {
-  if (!mhd) hlle_hydro_iso(wli, wri, iso_cs, flxi);
+  if (solver == AO_SOLVER_LLF) llf(mhd, 1, wli, wri, bxi, 0.0, iso_cs, flxi);
+  else if (!mhd) hlle_hydro_iso(wli, wri, iso_cs, flxi);
   else if (solver == AO_SOLVER_HLLD) hlld_iso(wli, wri, bxi, iso_cs, dfloor, flxi);
   else hlle_mhd_iso(wli, wri, bxi, iso_cs, flxi);
 }
@@ -1290,6 +1371,7 @@ void ao_riemann_point_iso(int solver, int mhd, const double *wli, const double *
 /* One interface.  wli/wri in sweep-rotated order (IDN,ivx,ivy,ivz,IPR[,IBY,IBZ]). */
 void ao_riemann_point(int solver, int mhd, const double *wli, const double *wri,
                       double bxi, double gamma, double dvn, double dvt, double *flxi) {
+  if (solver == AO_SOLVER_LLF) { llf(mhd, 0, wli, wri, bxi, gamma, 0.0, flxi); return; }
   if (!mhd) {
     if (solver == AO_SOLVER_LHLLC) lhllc(wli, wri, gamma, dvn, dvt, flxi);
     else if (solver == AO_SOLVER_HLLC) hllc(wli, wri, gamma, flxi);

@@ -109,6 +109,16 @@ CASES = {
                                       dict(BL, **mb(8, 8, 8), **{"time/integrator": "rk2",
                                            "hydro/iso_sound_speed": 0.8}),
                                       "hlle", False, 5, 0, "isothermal"),
+    # LLF
+    "blast_llf_plm_vl2_8blk": ("hydro_llf_ng2", "blast", "athinput.blast", dict(BL, **mb(8, 8, 8)),
+                               "llf", False, 5),
+    "blast_mhd_llf_plm_vl2_8blk": ("mhd_llf_ng2", "blast", "athinput.blast",
+                                   dict(BL, **mb(8, 8, 8)), "llf", True, 5),
+    "iso_blast_mhd_llf_plm_vl2_8blk": ("mhd_llf_iso_ng2", "blast", "athinput.blast",
+                                       dict(BL, **mb(8, 8, 8),
+                                            **{"hydro/iso_sound_speed": 0.4082482905,
+                                               "problem/drat": 5.0}),
+                                       "llf", True, 5, 0, "isothermal"),
     # constant acceleration source term (hydro/srcterms/constant_acc.cpp) in a closed box
     "blast_grav_hllc_plm_vl2_8blk": ("hydro_hllc_ng2", "blast", "athinput.blast",
                                      dict(BL, **mb(8, 8, 8), **{

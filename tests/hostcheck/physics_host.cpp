@@ -22,6 +22,7 @@ void hc_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
                 const double *bx, const double *dvn, const double *dvt, double gamma, double dt,
                 double dx, double *flx, double *wct) {
 #define RUN(S, M) run<S, M>(n, wl, wr, bx, dvn, dvt, gamma, dt, dx, flx, wct)
+  if (solver == 6) { if (mhd) RUN(6, true); else RUN(6, false); return; }
   if (!mhd) {
     if (solver == 1) RUN(1, false);
     else if (solver == 0) RUN(0, false);
@@ -42,7 +43,9 @@ void hc_riemann_iso(int solver, int mhd, long n, const double *wl, const double 
   for (long i = 0; i < n; ++i) {
     double a[7], b[7], f[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int v = 0; v < nw; ++v) { a[v] = wl[v*n+i]; b[v] = wr[v*n+i]; }
-    if (!mhd) ab::riemann<ab::SOLVER_HLLE_ISO, false>(a, b, 0.0, iso_cs, 0.0, 0.0, f, dfloor);
+    if (solver == 6 && mhd) ab::riemann<ab::SOLVER_LLF_ISO, true>(a, b, bx[i], iso_cs, 0.0, 0.0, f, dfloor);
+    else if (solver == 6) ab::riemann<ab::SOLVER_LLF_ISO, false>(a, b, 0.0, iso_cs, 0.0, 0.0, f, dfloor);
+    else if (!mhd) ab::riemann<ab::SOLVER_HLLE_ISO, false>(a, b, 0.0, iso_cs, 0.0, 0.0, f, dfloor);
     else if (solver == 2) ab::riemann<ab::SOLVER_HLLD_ISO, true>(a, b, bx[i], iso_cs, 0.0, 0.0, f, dfloor);
     else ab::riemann<ab::SOLVER_HLLE_ISO, true>(a, b, bx[i], iso_cs, 0.0, 0.0, f, dfloor);
     for (int v = 0; v < nw; ++v) flx[v*n+i] = f[v];

@@ -32,6 +32,10 @@ CASES = [
     # user-enrolled boundary function
     ("shkcloud2d_hllc_plm_vl2_4blk", None, None),
     ("shkcloud3d_hlld_plm_vl2_8blk", None, None),
+    # LLF
+    ("blast_llf_plm_vl2_8blk", None, None),
+    ("blast_mhd_llf_plm_vl2_8blk", None, None),
+    ("iso_blast_mhd_llf_plm_vl2_8blk", None, None),
     # user-enrolled explicit source function
     ("usersrc_lhllc_plm_vl2_8blk_s1", None, None),
     ("usersrc_hlld_plm_rk3_8blk", None, None),

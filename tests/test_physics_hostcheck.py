@@ -53,7 +53,8 @@ def random_states(rng, n, mhd, regime):
 
 @pytest.mark.parametrize("solver,mhd", [("hllc", False), ("hlle", False), ("roe", False),
                                         ("lhllc", False), ("hlld", True), ("hlle", True),
-                                        ("roe", True), ("lhlld", True)])
+                                        ("roe", True), ("lhlld", True), ("llf", False),
+                                        ("llf", True)])
 @pytest.mark.parametrize("regime", ["subsonic", "supersonic", "mixed"])
 def test_riemann_matches_oracle(hc, solver, mhd, regime):
     rng = np.random.default_rng(1234)
@@ -78,7 +79,8 @@ def test_riemann_matches_oracle(hc, solver, mhd, regime):
         util.assert_bitwise(wh, wo, "ct weight")
 
 
-@pytest.mark.parametrize("solver,mhd", [("hlle", False), ("hlle", True), ("hlld", True)])
+@pytest.mark.parametrize("solver,mhd", [("hlle", False), ("hlle", True), ("hlld", True),
+                                        ("llf", False), ("llf", True)])
 @pytest.mark.parametrize("regime", ["subsonic", "supersonic", "mixed"])
 def test_isothermal_riemann_matches_oracle(hc, solver, mhd, regime):
     rng = np.random.default_rng(4321)
