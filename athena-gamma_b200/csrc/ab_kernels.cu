@@ -269,9 +269,6 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
 #ifndef AB_FLUX_MINB
 #define AB_FLUX_MINB 18
 #endif
-#ifndef AB_FLUX_MINB_O1
-#define AB_FLUX_MINB_O1 AB_FLUX_MINB
-#endif
 // x3 sweep: faces are visited strip by strip (AB_X3_STRIP rows of j, all k) so that the four
 // k-planes of the stencil stay in L2 between consecutive k (plane-major order re-read w/bcc
 // from DRAM: 19 GB instead of 8.8 GB per 512^3 sweep).
