@@ -109,6 +109,21 @@ CASES = {
                                       dict(BL, **mb(8, 8, 8), **{"time/integrator": "rk2",
                                            "hydro/iso_sound_speed": 0.8}),
                                       "hlle", False, 5, 0, "isothermal"),
+    # dimensional / shape edge cases of the MHD path: 1-D (corner E and CT special cases, the
+    # duplicated x2/x3 faces), 2-D with mixed physical boundaries, non-cubic 3-D blocks
+    "bw1d_hlld_plm_vl2_2blk": ("mhd_hlld_ng2", "shock_tube", "athinput.bw",
+                               {"mesh/nx1": 64, "meshblock/nx1": 32}, "hlld", True, 8),
+    "bw2d_x2_hlld_plm_rk2_4blk": ("mhd_hlld_ng2", "shock_tube", "athinput.bw",
+                                  {"mesh/nx1": 8, "mesh/nx2": 32, "meshblock/nx1": 4,
+                                   "meshblock/nx2": 16, "problem/shock_dir": 2,
+                                   "mesh/ix1_bc": "periodic", "mesh/ox1_bc": "periodic",
+                                   "mesh/ix2_bc": "outflow", "mesh/ox2_bc": "reflecting",
+                                   "time/integrator": "rk2"}, "hlld", True, 6),
+    "blast_noncubic_hlld_ppm_rk2_6blk": ("mhd_hlld_ng3", "blast", "athinput.blast",
+                                         {"mesh/nx1": 24, "mesh/nx2": 12, "mesh/nx3": 8,
+                                          "problem/radius": 0.3, "time/xorder": 3,
+                                          "time/integrator": "rk2", **mb(12, 6, 4)},
+                                         "hlld", True, 4),
     # LLF
     "blast_llf_plm_vl2_8blk": ("hydro_llf_ng2", "blast", "athinput.blast", dict(BL, **mb(8, 8, 8)),
                                "llf", False, 5),

@@ -32,6 +32,10 @@ CASES = [
     # user-enrolled boundary function
     ("shkcloud2d_hllc_plm_vl2_4blk", None, None),
     ("shkcloud3d_hlld_plm_vl2_8blk", None, None),
+    # 1-D / 2-D / non-cubic MHD
+    ("bw1d_hlld_plm_vl2_2blk", None, None),
+    ("bw2d_x2_hlld_plm_rk2_4blk", None, None),
+    ("blast_noncubic_hlld_ppm_rk2_6blk", None, None),
     # LLF
     ("blast_llf_plm_vl2_8blk", None, None),
     ("blast_mhd_llf_plm_vl2_8blk", None, None),
