@@ -4,7 +4,7 @@ the conserved variables `u` (active cells filled, AthenaArray layout incl. ghost
 MHD, the face fields `b1,b2,b3`, exactly what the reference's pgens write into phydro->u and
 pfield->b.  They run on the host (as in the reference); Mesh.problem_generator uploads."""
 from .blast import blast  # noqa: F401
-from .linear_wave import linear_wave  # noqa: F401
+from .linear_wave import linear_wave, linear_wave_errors  # noqa: F401
 from .orszag_tang import orszag_tang  # noqa: F401
 from .kh import kh  # noqa: F401
 from .shock_tube import shock_tube  # noqa: F401

@@ -174,3 +174,74 @@ def linear_wave(pmb, pin, out=None):
         out["b3"][KF, J, I] = ((a2[KF, J, I1] - a2[KF, J, I]) / dx1
                                - (a1[KF, J1, I] - a1[KF, J, I]) / dx2)
     return out
+
+
+def linear_wave_errors(mesh, pin):
+    """Mesh::UserWorkAfterLoop of the linear-wave problem (src/pgen/linear_wave.cpp:190-428):
+    volume-weighted L1 error of the conserved variables (and of the cell-centred field) against
+    the analytic eigenmode evaluated at the cell centres, normalised by the domain volume; RMS
+    over the variables.  Host-side hook: downloads u and bcc of every local MeshBlock.
+    Returns dict(rms, l1 = [d, M1, M2, M3, E, (B1c, B2c, B3c)], max = [...])."""
+    mhd = mesh.mhd
+    first = mesh.my_blocks[0]
+    f2, f3 = first.ncells2 > 1, first.ncells3 > 1
+    g = setup(pin, mhd, f2, f3)
+    sa2, ca2, sa3, ca3, k_par = g["sa2"], g["ca2"], g["sa3"], g["ca3"], g["k_par"]
+    wave = pin.get_integer("problem", "wave_flag")
+    amp = pin.get_real("problem", "amp")
+    vflow = pin.get_or_add_real("problem", "vflow", 0.0)
+    gam = pin.get_real("hydro", "gamma")
+    gm1 = gam - 1.0
+    d0, p0, u0 = 1.0, 1.0 / gam, vflow
+    bx0, by0, bz0 = 1.0, np.sqrt(2.0), 0.5
+    h0 = ((p0 / gm1 + 0.5 * d0 * u0 * u0) + p0) / d0
+    if mhd:
+        h0 += (bx0 ** 2 + by0 ** 2 + bz0 ** 2) / d0
+        rem, _ = right_eigenvector_mhd(wave, d0, u0, 0.0, 0.0, h0, bx0, by0, bz0, gm1)
+    else:
+        rem, _ = right_eigenvector_hydro(wave, u0, 0.0, 0.0, h0, gm1)
+    nv = 8 if mhd else 5
+    l1 = np.zeros(nv)
+    mx_err = np.zeros(nv)
+    for pmb in mesh.my_blocks:
+        c = coords(pmb)
+        k, j, i = active(pmb)
+        X = c["x1v"][i][None, None, :]
+        Y = c["x2v"][j][None, :, None]
+        Z = c["x3v"][k][:, None, None]
+        x = ca2 * (X * ca3 + Y * sa3) + Z * sa2
+        sn = np.sin(k_par * x)
+        mx = d0 * vflow + amp * sn * rem[1]
+        my = amp * sn * rem[2]
+        mz = amp * sn * rem[3]
+        ana = [d0 + amp * sn * rem[0],
+               mx * ca2 * ca3 - my * sa3 - mz * sa2 * ca3,
+               mx * ca2 * sa3 + my * ca3 - mz * sa2 * sa3,
+               mx * sa2 + mz * ca2]
+        e0 = p0 / gm1 + 0.5 * d0 * u0 * u0 + amp * sn * rem[4]
+        if mhd:
+            e0 = e0 + 0.5 * (bx0 * bx0 + by0 * by0 + bz0 * bz0)
+            bx = bx0
+            by = by0 + amp * sn * rem[5]
+            bz = bz0 + amp * sn * rem[6]
+            ana_b = [bx * ca2 * ca3 - by * sa3 - bz * sa2 * ca3,
+                     bx * ca2 * sa3 + by * ca3 - bz * sa2 * sa3,
+                     bx * sa2 + bz * ca2]
+        ana.append(e0)
+        vol = (c["dx1f"][i][None, None, :] * c["dx2f"][j][None, :, None]
+               * c["dx3f"][k][:, None, None])
+        u = pmb.get("u")
+        for n in range(5):
+            d = np.abs(ana[n] - u[n][k, j, i])
+            l1[n] += float(np.sum(d * vol))
+            mx_err[n] = max(mx_err[n], float(d.max()))
+        if mhd:
+            bcc = pmb.get("bcc")
+            for n in range(3):
+                d = np.abs(ana_b[n] - bcc[n][k, j, i])
+                l1[5 + n] += float(np.sum(d * vol))
+                mx_err[5 + n] = max(mx_err[5 + n], float(d.max()))
+    p = mesh.params
+    vol_mesh = (p.x1max - p.x1min) * (p.x2max - p.x2min) * (p.x3max - p.x3min)
+    l1 /= vol_mesh
+    return {"rms": float(np.sqrt(np.sum(l1 ** 2))), "l1": l1.tolist(), "max": mx_err.tolist()}
