@@ -129,6 +129,7 @@ struct LocalBlock {
   int parity_s = 0;                       // (s,s1) swap state
   unsigned long long *dtmin = nullptr;    // slot in the mesh-wide array
   std::vector<void *> debug_allocs;       // AB_DEBUG_ALLOC=1: per-array allocations
+  cudaStream_t stream = nullptr;          // stream of this block's per-block tasks inside a cycle
   bool cc_e_valid = false;                // cc_e written by the fused cons2prim
   bool has_phys_bc = false;
 };
@@ -172,6 +173,13 @@ struct AbMesh {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_pack = nullptr, ev_recv = nullptr;
   bool overlap = false;
+  // Many MeshBlocks per GPU: the per-block tasks of a stage are spread round-robin over a few
+  // extra streams (forked from / joined into the main stream around every exchange), so that the
+  // ramp-up and tail of one block's kernels overlap the next block's (AB_BLOCK_STREAMS, default
+  // min(#blocks, 4); 0 = everything on the main stream)
+  std::vector<cudaStream_t> bstream;
+  std::vector<cudaEvent_t> ev_b;
+  cudaEvent_t ev_main = nullptr;
   double *state = nullptr;                // device: time, dt, tlim, cfl, min, ncycle
   double *dt_hist = nullptr;              // device ring of per-cycle dt
   int hist_cap = 0, hist_n = 0;
@@ -1051,8 +1059,8 @@ void primitives(AbMesh *m, LocalBlock &L, int with_dt = 0) {
   // blocks without physical boundaries get cc_e from the same pass (all cells that
   // ComputeCornerE reads, [is-1,ie+1]^dim, lie inside the cons2prim range)
   int flags = (m->p.mhd && !L.has_phys_bc ? 1 : 0) | (with_dt ? 2 : 0);
-  ab::launch_cons2prim(L.d, m->kp, il, iu, jl, ju, kl, ku, m->stream, flags, L.dtmin);
-  ab::launch_scalar_eos(L.d, m->kp, 0, il, iu, jl, ju, kl, ku, m->stream);
+  ab::launch_cons2prim(L.d, m->kp, il, iu, jl, ju, kl, ku, L.stream, flags, L.dtmin);
+  ab::launch_scalar_eos(L.d, m->kp, 0, il, iu, jl, ju, kl, ku, L.stream);
   L.cc_e_valid = (flags & 1) != 0;
 }
 
@@ -1123,7 +1131,7 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
   if (!app[3] && m->f2) bje = je + ng;
   if (!app[4] && m->f3) bks = ks - ng;
   if (!app[5] && m->f3) bke = ke + ng;
-  cudaStream_t s = m->stream;
+  cudaStream_t s = L.stream;
   if (app[0]) {
     if (B.bcs[0] == AB_BC_USER) user_bc_face(m, L, 0, is, ie, bjs, bje, bks, bke);
 
@@ -1232,29 +1240,47 @@ int one_cycle(AbMesh *m) {
   const double *dtp = m->state + 1;
   const bool user_src = (m->user_src || m->user_src_dev);
   if (m->has_user_bc || user_src) { int rc0 = read_state(m); if (rc0) return rc0; }   // host needs time, dt
+  // per-block streams (see AbMesh::bstream); host-hook modes keep everything on the main stream
+  const bool ms = !m->bstream.empty() && !m->has_user_bc && !user_src && !debug_sync();
+  for (size_t l = 0; l < m->lb.size(); ++l)
+    m->lb[l].stream = ms ? m->bstream[l % m->bstream.size()] : m->stream;
+  auto fork = [&]() {     // block streams continue after everything queued on the main stream
+    if (!ms) return;
+    cudaEventRecord(m->ev_main, m->stream);
+    for (auto st : m->bstream) cudaStreamWaitEvent(st, m->ev_main, 0);
+  };
+  auto join = [&]() {     // the main stream continues after all block streams
+    if (!ms) return;
+    for (size_t i = 0; i < m->bstream.size(); ++i) {
+      cudaEventRecord(m->ev_b[i], m->bstream[i]);
+      cudaStreamWaitEvent(m->stream, m->ev_b[i], 0);
+    }
+  };
   for (int stage = 1; stage <= m->nstages; ++stage) {
     const int s = stage - 1;
     const int order = (m->p.integrator == AB_INT_VL2 && stage == 1) ? 1 : m->p.xorder;
+    fork();
     for (auto &L : m->lb) {
       for (int dir = 0; dir < m->ndim; ++dir) {
         if (m->profile) {
           cudaEvent_t e0, e1;
           cudaEventCreate(&e0); cudaEventCreate(&e1);
-          cudaEventRecord(e0, m->stream);
-          ab::launch_flux_dir(L.d, L.g, m->kp, order, dir, 0.0, dtp, m->stream);
-          cudaEventRecord(e1, m->stream);
+          cudaEventRecord(e0, L.stream);
+          ab::launch_flux_dir(L.d, L.g, m->kp, order, dir, 0.0, dtp, L.stream);
+          cudaEventRecord(e1, L.stream);
           m->prof_ev.push_back({e0, e1});
           m->prof_slot.push_back(dir*3 + (order - 1));
         } else {
-          ab::launch_flux_dir(L.d, L.g, m->kp, order, dir, 0.0, dtp, m->stream);
+          ab::launch_flux_dir(L.d, L.g, m->kp, order, dir, 0.0, dtp, L.stream);
         }
         DBG(m, "flux dir " + std::to_string(dir) + " order " + std::to_string(order));
       }
-      if (m->p.mhd) ab::launch_corner_e(L.d, m->stream, L.cc_e_valid ? 1 : 0);
+      if (m->p.mhd) ab::launch_corner_e(L.d, L.stream, L.cc_e_valid ? 1 : 0);
       DBG(m, "corner_e");
-      ab::launch_scalar_fluxes(L.d, L.g, m->kp, order, m->stream);   // CALC_SCLRFLX
+      ab::launch_scalar_fluxes(L.d, L.g, m->kp, order, L.stream);   // CALC_SCLRFLX
       DBG(m, "scalar fluxes");
     }
+    join();
     // EMF correction.  Overlapped schedule: the NCCL transfer runs on the comm stream while
     // IntegrateHydro / IntegrateScalars (which do not read EMFs) run on the compute stream.
     int rc = m->overlap ? emf_exchange_begin(m) : emf_exchange(m);
@@ -1262,22 +1288,23 @@ int one_cycle(AbMesh *m) {
     DBG(m, "emf exchange");
     const bool swap = (m->g1[s] == 0.0 && m->g2[s] == 1.0 && m->g3[s] == 0.0);
     const int zero_init = (stage == 1);   // StartupTaskList: u1, b1 ZeroClear (:1386-1397)
+    fork();
     for (auto &L : m->lb) {   // INT_HYD (+ SRC_TERM), INT_SCLR (time_integrator.cpp:2141-2185)
       if (swap) {
         swap_cc(L);
         ab::launch_integrate_cc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp,
-                                m->stream, -1, -1, 0, 0, m->p.grav_acc);
+                                L.stream, -1, -1, 0, 0, m->p.grav_acc);
         if (m->p.nscalars > 0) {
           swap_sc(L);
           ab::launch_integrate_cc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp,
-                                  m->stream, -1, -1, 0, 1);
+                                  L.stream, -1, -1, 0, 1);
         }
       } else {
         ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0,
-                                dtp, m->stream, -1, -1, 0, 0, m->p.grav_acc);
+                                dtp, L.stream, -1, -1, 0, 0, m->p.grav_acc);
         if (m->p.nscalars > 0)
           ab::launch_integrate_cc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s],
-                                  0.0, dtp, m->stream, -1, -1, 0, 1);
+                                  0.0, dtp, L.stream, -1, -1, 0, 1);
       }
     }
     DBG(m, "integrate_cc");
@@ -1291,11 +1318,12 @@ int one_cycle(AbMesh *m) {
     if (m->p.mhd) for (auto &L : m->lb) {   // INT_FLD
       if (swap) {
         swap_fc(L);
-        ab::launch_integrate_fc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, m->stream);
+        ab::launch_integrate_fc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, L.stream);
       } else {
-        ab::launch_integrate_fc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, m->stream);
+        ab::launch_integrate_fc(L.d, 2, zero_init, m->delta[s], m->g1[s], m->g2[s], m->beta[s], 0.0, dtp, L.stream);
       }
     }
+    join();
     DBG(m, "integrate_fc");
     if (m->has_user_bc) {   // PhysicalBoundary: t_end_stage, beta*dt (time_integrator.cpp:2045-2062)
       m->bc_time = m->h_time + m->ebeta[s]*m->h_dt;
@@ -1307,12 +1335,14 @@ int one_cycle(AbMesh *m) {
       if (rc) return rc;
       DBG(m, "bvals exchange");
       if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
+      fork();
       for (auto &L : m->lb) {
         primitives(m, L, last);
         DBG(m, "primitives");
         physical_bcs(m, L);
         DBG(m, "physical bcs");
       }
+      join();
     } else {
       // ghost zones travel while ConservedToPrimitive (+ CFL reduction) covers the active cells;
       // the ghost shell follows once they arrived
@@ -1334,6 +1364,7 @@ int one_cycle(AbMesh *m) {
       DBG(m, "new_time_step");
     }
   }
+  for (auto &L : m->lb) L.stream = m->stream;   // task-level entry points run on the main stream
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -1374,6 +1405,20 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
   }
   int rc = alloc_blocks(m);
   if (rc) { delete m; return rc; }
+  {
+    int ns = (int)std::min<size_t>(m->lb.size(), 4);
+    if (const char *e = getenv("AB_BLOCK_STREAMS")) ns = std::min<int>(atoi(e), (int)m->lb.size());
+    if (m->lb.size() < 2 || ns < 2 || m->overlap) ns = 0;
+    CK(cudaEventCreateWithFlags(&m->ev_main, cudaEventDisableTiming));
+    for (int i = 0; i < ns; ++i) {
+      cudaStream_t st; cudaEvent_t ev;
+      CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      m->bstream.push_back(st); m->ev_b.push_back(ev);
+    }
+    for (size_t l = 0; l < m->lb.size(); ++l)
+      m->lb[l].stream = ns ? m->bstream[l % ns] : m->stream;
+  }
   CK(cudaMalloc(&m->state, 8*sizeof(double)));
   m->hist_cap = 1 << 16;
   CK(cudaMalloc(&m->dt_hist, sizeof(double)*m->hist_cap));
@@ -1501,6 +1546,9 @@ int ab_mesh_destroy(AbMesh *m) {
   cudaFree(m->state); cudaFree(m->dt_hist); cudaFree(m->dtmin);
   cudaFree(m->hist_partial); cudaFree(m->hist_out);
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  for (auto st : m->bstream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  for (auto ev : m->ev_b) cudaEventDestroy(ev);
+  if (m->ev_main) cudaEventDestroy(m->ev_main);
   if (m->ev_pack) cudaEventDestroy(m->ev_pack);
   if (m->ev_recv) cudaEventDestroy(m->ev_recv);
   if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
@@ -1774,6 +1822,7 @@ int ab_mesh_initialize(AbMesh *m) {
     m->has_user_bc = true;
   }
   m->bc_time = m->h_time; m->bc_dt = 0.0;   // ApplyPhysicalBoundaries(time, 0.0, ...) mesh.cpp:1574
+  for (auto &L : m->lb) L.stream = m->stream;
   int rc = bvals_exchange(m);
   if (rc) return rc;
   for (auto &L : m->lb) { primitives(m, L); physical_bcs(m, L); }
