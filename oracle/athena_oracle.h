@@ -35,6 +35,7 @@ typedef struct {
   double sfloor;        /* hydro/sfloor (eos ctor default sqrt(1024*FLT_MIN)) */
   double iso_cs;        /* hydro/iso_sound_speed */
   double grav_acc[3];   /* hydro/grav_acc1..3 (hydro/srcterms/hydro_srcterms.cpp:68-75) */
+  int char_proj;        /* time/xorder = 2c / 3c: reconstruct characteristic variables */
 } AoParams;
 
 typedef struct AoMesh AoMesh;

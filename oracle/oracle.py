@@ -29,7 +29,7 @@ class AoParams(C.Structure):
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
                 ("cfl", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double),
                 ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
-                ("iso_cs", C.c_double), ("grav_acc", C.c_double * 3)]
+                ("iso_cs", C.c_double), ("grav_acc", C.c_double * 3), ("char_proj", C.c_int)]
 
 
 # AoBValFunc (athena_oracle.h): user-enrolled boundary function with plain arrays
@@ -136,6 +136,7 @@ def params_from_athinput(par, mhd, solver, ng=None, nscalars=0, eos="adiabatic")
     p.mhd = int(bool(mhd))
     p.solver = SOLVER[solver]
     p.xorder = xorder
+    p.char_proj = int(str(t.get("xorder", "2")).endswith("c"))
     p.integrator = INTEGRATOR[t.get("integrator", "vl2")]
     h = par.get("hydro", {})
     p.eos = 1 if eos == "isothermal" else 0

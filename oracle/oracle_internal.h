@@ -17,6 +17,8 @@ void ao_riemann_point(int solver, int mhd, const double *wli, const double *wri,
 double ao_fast_speed_iso(double cs, const double *prim, double bx);
 void ao_riemann_point_iso(int solver, int mhd, const double *wli, const double *wri,
                           double bxi, double iso_cs, double dfloor, double *flxi);
+void ao_char_left(int mhd, double gamma, const double *w, double bx, double *vect);
+void ao_char_right(int mhd, double gamma, const double *w, double bx, double *vect);
 void ao_plm_point(double qm1, double q, double qp1, double wp, double wm,
                   double *plus, double *minus);
 void ao_ppm_point(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,

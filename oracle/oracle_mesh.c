@@ -541,11 +541,74 @@ static void cell_state(const AoMesh *m, const AoBlock *B, int dir, int k, int j,
 /* L/R states of cell (k,j,i) along dir: `plus` is the state at its upper face (becomes wl
  * of face+1), `minus` at its lower face (wr of its own face).
  * dc.cpp:24-110, plm.cpp:27-370, ppm.cpp:44-940 */
+/* sweep-ordered copy: velocities rotated so that slot IVX is the sweep direction */
+static void to_sweep(int dir, const double *q, double *p) {
+  int ivx = IVX + dir, ivy = IVX + (dir + 1) % 3, ivz = IVX + (dir + 2) % 3;
+  p[IDN] = q[IDN]; p[IVX] = q[ivx]; p[IVY] = q[ivy]; p[IVZ] = q[ivz]; p[IPR] = q[IPR];
+  p[IBY] = q[IBY]; p[IBZ] = q[IBZ];
+}
+static void from_sweep(int dir, const double *p, double *q) {
+  int ivx = IVX + dir, ivy = IVX + (dir + 1) % 3, ivz = IVX + (dir + 2) % 3;
+  q[IDN] = p[IDN]; q[ivx] = p[IVX]; q[ivy] = p[IVY]; q[ivz] = p[IVZ]; q[IPR] = p[IPR];
+  q[IBY] = p[IBY]; q[IBZ] = p[IBZ];
+}
+
+/* xorder = 2c / 3c: the same cell reconstruction on characteristic variables
+ * (plm.cpp:62-66,107-110,122-130; ppm.cpp:66-75,311-332; characteristic.cpp).  The
+ * eigenvectors are those of the cell itself; floors are re-applied to both face states. */
+static void recon_cell_char(const AoMesh *m, const AoBlock *B, int dir, int order, int k, int j,
+                            int i, double *plus, double *minus) {
+  int nw = m->p.mhd ? 7 : 5, mhd = m->p.mhd;
+  int dk = (dir == 2), dj = (dir == 1), di = (dir == 0);
+  double gamma = m->p.gamma;
+  double t[7], q[7], pl[7], mi[7];
+  cell_state(m, B, dir, k, j, i, t); to_sweep(dir, t, q);
+  double bx = mhd ? B->bcc[CC(B,dir,k,j,i)] : 0.0;
+  double st[5][7];     /* stencil -2..+2 in sweep order */
+  for (int o = -2; o <= 2; ++o) {
+    if (order == 2 && (o == -2 || o == 2)) continue;
+    cell_state(m, B, dir, k+o*dk, j+o*dj, i+o*di, t); to_sweep(dir, t, st[o+2]);
+  }
+  if (order == 2) {
+    const double *xf = dir == 0 ? B->x1f : (dir == 1 ? B->x2f : B->x3f);
+    const double *xv = dir == 0 ? B->x1v : (dir == 1 ? B->x2v : B->x3v);
+    const double *dxf = dir == 0 ? B->dx1f : (dir == 1 ? B->dx2f : B->dx3f);
+    int c = dir == 0 ? i : (dir == 1 ? j : k);
+    double wp = (xf[c+1] - xv[c])/dxf[c];
+    double wm = (xv[c] - xf[c])/dxf[c];
+    double dwl[7], dwr[7], dwm[7];
+    for (int n = 0; n < nw; ++n) { dwl[n] = (q[n] - st[1][n]); dwr[n] = (st[3][n] - q[n]); }
+    ao_char_left(mhd, gamma, q, bx, dwl);
+    ao_char_left(mhd, gamma, q, bx, dwr);
+    for (int n = 0; n < nw; ++n) {
+      double dw2 = dwl[n]*dwr[n];
+      dwm[n] = 2.0*dw2/(dwl[n] + dwr[n]);
+      if (dw2 <= 0.0) dwm[n] = 0.0;
+    }
+    ao_char_right(mhd, gamma, q, bx, dwm);
+    for (int n = 0; n < nw; ++n) { pl[n] = q[n] + wp*dwm[n]; mi[n] = q[n] - wm*dwm[n]; }
+  } else {
+    for (int o = 0; o < 5; ++o) ao_char_left(mhd, gamma, q, bx, st[o]);
+    for (int n = 0; n < nw; ++n)
+      ao_ppm_point(st[0][n], st[1][n], st[2][n], st[3][n], st[4][n], &pl[n], &mi[n]);
+    ao_char_right(mhd, gamma, q, bx, pl);
+    ao_char_right(mhd, gamma, q, bx, mi);
+  }
+  /* ApplyPrimitiveFloors on both states (plm.cpp:122-130, ppm.cpp:326-332) */
+  pl[IDN] = (pl[IDN] > m->p.dfloor) ? pl[IDN] : m->p.dfloor;
+  mi[IDN] = (mi[IDN] > m->p.dfloor) ? mi[IDN] : m->p.dfloor;
+  pl[IPR] = (pl[IPR] > m->p.pfloor) ? pl[IPR] : m->p.pfloor;
+  mi[IPR] = (mi[IPR] > m->p.pfloor) ? mi[IPR] : m->p.pfloor;
+  from_sweep(dir, pl, plus);
+  from_sweep(dir, mi, minus);
+}
+
 static void recon_cell(const AoMesh *m, const AoBlock *B, int dir, int order, int k, int j,
                        int i, double *plus, double *minus) {
   int nw = m->p.mhd ? 7 : 5;
   int dk = (dir == 2), dj = (dir == 1), di = (dir == 0);
   double q[7];
+  if (m->p.char_proj && order > 1) { recon_cell_char(m, B, dir, order, k, j, i, plus, minus); return; }
   cell_state(m, B, dir, k, j, i, q);
   if (order == 1) {
     for (int n = 0; n < nw; ++n) plus[n] = minus[n] = q[n];

@@ -1416,6 +1416,124 @@ void ao_riemann_dv(int solver, int mhd, long n, const double *wl, const double *
   }
 }
 
+/* ---------------------------------------------------------------- characteristic projection
+ * src/reconstruct/characteristic.cpp:36-278 (LeftEigenmatrixDotVector) and :280-520
+ * (RightEigenmatrixDotVector), adiabatic hydro and adiabatic MHD, in sweep order: w = the
+ * cell's primitives (IDN, vx, vy, vz, IPR[, By, Bz]) with vx along the sweep, bx = the
+ * cell-centred field along the sweep; vect is transformed in place. */
+#define SIGN(x) (((x) < 0.0) ? -1.0 : 1.0)
+
+typedef struct { double id, sqrtd, isqrtd, cf, cs, asq, a, bet2, bet3, alpha_f, alpha_s, s; } MhdEig;
+
+static void mhd_eig(double gamma, const double *w, double bx, MhdEig *e) {
+  e->id = 1.0/w[IDN];
+  e->sqrtd = sqrt(w[IDN]);
+  e->isqrtd = 1.0/e->sqrtd;
+  double btsq = SQR(w[IBY]) + SQR(w[IBZ]);
+  double bxsq = bx*bx;
+  double gamp = gamma*w[IPR];
+  double tdif = bxsq + btsq - gamp;
+  double cf2_cs2 = sqrt(tdif*tdif + 4.0*gamp*btsq);
+  double cfsq = 0.5*(bxsq + btsq + gamp + cf2_cs2);
+  double cssq = gamp*bxsq/cfsq;
+  cfsq *= e->id;
+  e->cf = sqrt(cfsq);
+  cssq *= e->id;
+  e->cs = sqrt(cssq);
+  e->asq = gamp*e->id;
+  e->a = sqrt(e->asq);
+  double bt = sqrt(btsq);
+  e->bet2 = 0.0; e->bet3 = 0.0;
+  if (bt != 0.0) { e->bet2 = w[IBY]/bt; e->bet3 = w[IBZ]/bt; }
+  if ((cfsq - cssq) <= 0.0) { e->alpha_f = 1.0; e->alpha_s = 0.0; }
+  else if ((e->asq - cssq) <= 0.0) { e->alpha_f = 0.0; e->alpha_s = 1.0; }
+  else if ((cfsq - e->asq) <= 0.0) { e->alpha_f = 1.0; e->alpha_s = 0.0; }
+  else {
+    e->alpha_f = sqrt((e->asq - cssq)/(cfsq - cssq));
+    e->alpha_s = sqrt((cfsq - e->asq)/(cfsq - cssq));
+  }
+  e->s = SIGN(bx);
+}
+
+void ao_char_left(int mhd, double gamma, const double *w, double bx, double *vect) {
+  if (mhd) {
+    MhdEig e;
+    mhd_eig(gamma, w, bx, &e);
+    double id = e.id, cf = e.cf, cs = e.cs, asq = e.asq, a = e.a, bet2 = e.bet2, bet3 = e.bet3;
+    double alpha_f = e.alpha_f, alpha_s = e.alpha_s, s = e.s, isqrtd = e.isqrtd, sqrtd = e.sqrtd;
+    double nf = 0.5/asq;
+    double qf = nf*cf*alpha_f*s;
+    double qs = nf*cs*alpha_s*s;
+    double af_prime = 0.5*alpha_f/(a*sqrtd);
+    double as_prime = 0.5*alpha_s/(a*sqrtd);
+    double v_0 = nf*alpha_f*(vect[IPR]*id - cf*vect[IVX]) +
+                 qs*(bet2*vect[IVY] + bet3*vect[IVZ]) +
+                 as_prime*(bet2*vect[IBY] + bet3*vect[IBZ]);
+    double v_1 = 0.5*(bet2*(vect[IBZ]*s*isqrtd + vect[IVZ]) -
+                      bet3*(vect[IBY]*s*isqrtd + vect[IVY]));
+    double v_2 = nf*alpha_s*(vect[IPR]*id - cs*vect[IVX]) -
+                 qf*(bet2*vect[IVY] + bet3*vect[IVZ]) -
+                 af_prime*(bet2*vect[IBY] + bet3*vect[IBZ]);
+    double v_3 = vect[IDN] - vect[IPR]/asq;
+    double v_4 = nf*alpha_s*(vect[IPR]*id + cs*vect[IVX]) +
+                 qf*(bet2*vect[IVY] + bet3*vect[IVZ]) -
+                 af_prime*(bet2*vect[IBY] + bet3*vect[IBZ]);
+    double v_5 = 0.5*(bet2*(vect[IBZ]*s*isqrtd - vect[IVZ]) -
+                      bet3*(vect[IBY]*s*isqrtd - vect[IVY]));
+    double v_6 = nf*alpha_f*(vect[IPR]*id + cf*vect[IVX]) -
+                 qs*(bet2*vect[IVY] + bet3*vect[IVZ]) +
+                 as_prime*(bet2*vect[IBY] + bet3*vect[IBZ]);
+    vect[0] = v_0; vect[1] = v_1; vect[2] = v_2; vect[3] = v_3; vect[4] = v_4; vect[5] = v_5;
+    vect[6] = v_6;
+  } else {
+    double asq = gamma*w[IPR]/w[IDN];
+    double a = sqrt(asq);
+    double v_0 = 0.5*(vect[IPR]/asq - w[IDN]*vect[IVX]/a);
+    double v_1 = vect[IDN] - vect[IPR]/asq;
+    double v_2 = vect[IVY];
+    double v_3 = vect[IVZ];
+    double v_4 = 0.5*(vect[IPR]/asq + w[IDN]*vect[IVX]/a);
+    vect[0] = v_0; vect[1] = v_1; vect[2] = v_2; vect[3] = v_3; vect[4] = v_4;
+  }
+}
+
+void ao_char_right(int mhd, double gamma, const double *w, double bx, double *vect) {
+  if (mhd) {
+    MhdEig e;
+    mhd_eig(gamma, w, bx, &e);
+    double cf = e.cf, cs = e.cs, asq = e.asq, a = e.a, bet2 = e.bet2, bet3 = e.bet3;
+    double alpha_f = e.alpha_f, alpha_s = e.alpha_s, s = e.s, sqrtd = e.sqrtd;
+    double qf = cf*alpha_f*s;
+    double qs = cs*alpha_s*s;
+    double af = a*alpha_f*sqrtd;
+    double as = a*alpha_s*sqrtd;
+    double v_0 = w[IDN]*(alpha_f*(vect[0] + vect[6]) +
+                         alpha_s*(vect[2] + vect[4])) + vect[3];
+    double v_1 = cf*alpha_f*(vect[6]-vect[0]) + cs*alpha_s*(vect[4]-vect[2]);
+    double v_2 = bet2*(qs*(vect[0] - vect[6]) + qf*(vect[4] - vect[2]))
+                 + bet3*(vect[5] - vect[1]);
+    double v_3 = bet3*(qs*(vect[0] - vect[6]) + qf*(vect[4] - vect[2]))
+                 + bet2*(vect[1] - vect[5]);
+    double v_4 = w[IDN]*asq*(alpha_f*(vect[0] + vect[6]) +
+                             alpha_s*(vect[2] + vect[4]));
+    double v_5 = bet2*(as*(vect[0] + vect[6]) - af*(vect[2] + vect[4]))
+                 - bet3*s*sqrtd*(vect[5] + vect[1]);
+    double v_6 = bet3*(as*(vect[0] + vect[6]) - af*(vect[2] + vect[4]))
+                 + bet2*s*sqrtd*(vect[5] + vect[1]);
+    vect[IDN] = v_0; vect[IVX] = v_1; vect[IVY] = v_2; vect[IVZ] = v_3; vect[IPR] = v_4;
+    vect[IBY] = v_5; vect[IBZ] = v_6;
+  } else {
+    double asq = gamma*w[IPR]/w[IDN];
+    double a = sqrt(asq);
+    double v_0 = vect[0] + vect[1] + vect[4];
+    double v_1 = a*(vect[4] - vect[0])/w[IDN];
+    double v_2 = vect[2];
+    double v_3 = vect[3];
+    double v_4 = asq*(vect[0] + vect[4]);
+    vect[IDN] = v_0; vect[IVX] = v_1; vect[IVY] = v_2; vect[IVZ] = v_3; vect[IPR] = v_4;
+  }
+}
+
 /* ---------------------------------------------------------------- reconstruction */
 
 /* src/reconstruct/plm.cpp:69-77,114-119 (uniform Cartesian branch), one variable of one cell */

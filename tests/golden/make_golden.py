@@ -124,6 +124,21 @@ CASES = {
                                           "problem/radius": 0.3, "time/xorder": 3,
                                           "time/integrator": "rk2", **mb(12, 6, 4)},
                                          "hlld", True, 4),
+    # characteristic reconstruction (time/xorder = 2c, 3c; reconstruct/characteristic.cpp)
+    "blast_hlld_plmc_vl2_8blk": ("mhd_hlld_ng2", "blast", "athinput.blast",
+                                 dict(BL, **mb(8, 8, 8), **{"time/xorder": "2c"}),
+                                 "hlld", True, 6),
+    "blast_hllc_plmc_vl2_8blk": ("hydro_hllc_ng2", "blast", "athinput.blast",
+                                 dict(BL, **mb(8, 8, 8), **{"time/xorder": "2c"}),
+                                 "hllc", False, 6),
+    "blast_hlld_ppmc_rk3_8blk": ("mhd_hlld_ng3", "blast", "athinput.blast",
+                                 dict(BL, **mb(8, 8, 8), **{"time/xorder": "3c",
+                                                            "time/integrator": "rk3"}),
+                                 "hlld", True, 3),
+    "ot_hlld_ppmc_vl2_4blk": ("mhd_hlld_ng3", "orszag_tang", "athinput.orszag_tang",
+                              dict(OT, **mb(16, 16), **{"time/xorder": "3c"}), "hlld", True, 5),
+    "kh_hllc_ppmc_rk2_8blk": ("hydro_hllc_ng3", "kh", "athinput.kh",
+                              dict(KH, **mb(8, 8, 8), **{"time/xorder": "3c"}), "hllc", False, 5),
     # LLF
     "blast_llf_plm_vl2_8blk": ("hydro_llf_ng2", "blast", "athinput.blast", dict(BL, **mb(8, 8, 8)),
                                "llf", False, 5),
