@@ -354,6 +354,31 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
       plm(qm2[n], qm1[n], q0[n], wp_l, wm_l, wl[n], dummy);
       plm(qm1[n], q0[n], qp1[n], wp_r, wm_r, dummy, wr[n]);
     }
+  } else if (ORDER == 4) {
+    // xorder = 2c: PLM on characteristic variables (reconstruct/characteristic.cpp); the
+    // eigenvectors need the cell-centred field along the sweep of the two cells
+    double qm2[NW], qm1[NW], q0[NW], qp1[NW], dummy[NW];
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + st, sv, qp1);
+    const double bxl = MHD ? bcc[oc - st + DIR*sv] : 0.0, bxr = MHD ? bcc[oc + DIR*sv] : 0.0;
+    plm_char<MHD>(qm2, qm1, q0, bxl, p.gamma, g.wp[DIR][c-1], g.wm[DIR][c-1], p.dfloor, p.pfloor,
+                  wl, dummy);
+    plm_char<MHD>(qm1, q0, qp1, bxr, p.gamma, g.wp[DIR][c], g.wm[DIR][c], p.dfloor, p.pfloor,
+                  dummy, wr);
+  } else if (ORDER == 5) {
+    // xorder = 3c: PPM on characteristic variables
+    double qm3[NW], qm2[NW], qm1[NW], q0[NW], qp1[NW], qp2[NW], dummy[NW];
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 3*st, sv, qm3);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + st, sv, qp1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + 2*st, sv, qp2);
+    const double bxl = MHD ? bcc[oc - st + DIR*sv] : 0.0, bxr = MHD ? bcc[oc + DIR*sv] : 0.0;
+    ppm_char<MHD>(qm3, qm2, qm1, q0, qp1, bxl, p.gamma, p.dfloor, p.pfloor, wl, dummy);
+    ppm_char<MHD>(qm2, qm1, q0, qp1, qp2, bxr, p.gamma, p.dfloor, p.pfloor, dummy, wr);
   } else {
     double qm3[NW], qm2[NW], qm1[NW], q0[NW], qp1[NW], qp2[NW];
     load_cell<DIR,MHD,ISO>(w, bcc, oc - 3*st, sv, qm3);
@@ -448,9 +473,15 @@ static void flux_all(const BlkDev &b, const ReconGeom &g, const Params &p, int d
 template <int SOLVER, bool MHD>
 static void flux_order(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
                        double dt_val, const double *dt_ptr, cudaStream_t s) {
+  // order 4 / 5 = xorder 2c / 3c (characteristic variables; adiabatic EOS only)
+  constexpr bool ISO = (SOLVER == SOLVER_HLLE_ISO || SOLVER == SOLVER_HLLD_ISO ||
+                        SOLVER == SOLVER_LLF_ISO);
+  if (order > 1 && p.char_proj && !ISO) order += 2;
   if (order == 1) flux_all<1,SOLVER,MHD>(b, g, p, dir, dt_val, dt_ptr, s);
   else if (order == 2) flux_all<2,SOLVER,MHD>(b, g, p, dir, dt_val, dt_ptr, s);
-  else flux_all<3,SOLVER,MHD>(b, g, p, dir, dt_val, dt_ptr, s);
+  else if (order == 3) flux_all<3,SOLVER,MHD>(b, g, p, dir, dt_val, dt_ptr, s);
+  else if (order == 4) flux_all<(ISO ? 2 : 4),SOLVER,MHD>(b, g, p, dir, dt_val, dt_ptr, s);
+  else flux_all<(ISO ? 3 : 5),SOLVER,MHD>(b, g, p, dir, dt_val, dt_ptr, s);
 }
 
 void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,

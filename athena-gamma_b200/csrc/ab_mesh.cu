@@ -1498,6 +1498,8 @@ static int validate_params(const AbMeshParams *p) {
   if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) return fail(AB_ERR_ARG, "bad rank/nranks");
   if (p->nscalars < 0 || p->nscalars > 16) return fail(AB_ERR_ARG, "nscalars must be in [0, 16]");
   if (p->eos != AB_EOS_ADIABATIC && p->eos != AB_EOS_ISOTHERMAL) return fail(AB_ERR_ARG, "unknown EOS");
+  if (p->char_proj && p->eos == AB_EOS_ISOTHERMAL)
+    return fail(AB_ERR_ARG, "characteristic reconstruction with isothermal EOS is not on the device path");
   if (p->eos == AB_EOS_ISOTHERMAL) {
     // configure.py:311-322; the isothermal Roe / LLF branches are not on the device path
     if (p->solver == AB_SOLVER_HLLC || p->solver == AB_SOLVER_LHLLC || p->solver == AB_SOLVER_LHLLD)
@@ -1519,6 +1521,7 @@ static void host_setup(AbMesh *m, const AbMeshParams *p) {
   if (m->p.sfloor == 0.0) m->p.sfloor = std::sqrt(1024.0*(double)FLT_MIN);
   m->kp.sfloor = m->p.sfloor;
   m->kp.eos = p->eos; m->kp.iso_cs = p->iso_sound_speed;
+  m->kp.char_proj = p->char_proj;
   m->nh = (p->eos == AB_EOS_ISOTHERMAL) ? 4 : 5;     // configure.py:374-377
   int ng = p->nghost;
   // MeshBlock index ranges (mesh/meshblock.cpp:55-80)

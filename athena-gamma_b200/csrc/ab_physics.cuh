@@ -150,6 +150,174 @@ AB_HD void ppm(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,
   minus = qminus;
 }
 
+// ------------------------------------------------------------------------ characteristic projection
+// reconstruct/characteristic.cpp:36-278 (LeftEigenmatrixDotVector) and :280-520
+// (RightEigenmatrixDotVector), adiabatic hydro and adiabatic MHD, in sweep order: w = the cell's
+// primitives (IDN, vx, vy, vz, IPR[, By, Bz]) with vx along the sweep, bx = the cell-centred
+// field along the sweep; vect is transformed in place.
+struct MhdEig { double id, sqrtd, isqrtd, cf, cs, asq, a, bet2, bet3, alpha_f, alpha_s, s; };
+
+AB_HD void mhd_eig(double gamma, const double *w, double bx, MhdEig *e) {
+  e->id = 1.0/w[IDN];
+  e->sqrtd = sqrt(w[IDN]);
+  e->isqrtd = 1.0/e->sqrtd;
+  double btsq = sqr(w[IBY]) + sqr(w[IBZ]);
+  double bxsq = bx*bx;
+  double gamp = gamma*w[IPR];
+  double tdif = bxsq + btsq - gamp;
+  double cf2_cs2 = sqrt(tdif*tdif + 4.0*gamp*btsq);
+  double cfsq = 0.5*(bxsq + btsq + gamp + cf2_cs2);
+  double cssq = gamp*bxsq/cfsq;
+  cfsq *= e->id;
+  e->cf = sqrt(cfsq);
+  cssq *= e->id;
+  e->cs = sqrt(cssq);
+  e->asq = gamp*e->id;
+  e->a = sqrt(e->asq);
+  double bt = sqrt(btsq);
+  e->bet2 = 0.0; e->bet3 = 0.0;
+  if (bt != 0.0) { e->bet2 = w[IBY]/bt; e->bet3 = w[IBZ]/bt; }
+  if ((cfsq - cssq) <= 0.0) { e->alpha_f = 1.0; e->alpha_s = 0.0; }
+  else if ((e->asq - cssq) <= 0.0) { e->alpha_f = 0.0; e->alpha_s = 1.0; }
+  else if ((cfsq - e->asq) <= 0.0) { e->alpha_f = 1.0; e->alpha_s = 0.0; }
+  else {
+    e->alpha_f = sqrt((e->asq - cssq)/(cfsq - cssq));
+    e->alpha_s = sqrt((cfsq - e->asq)/(cfsq - cssq));
+  }
+  e->s = sgn(bx);
+}
+
+template <bool MHD>
+AB_HD void char_left(double gamma, const double *w, double bx, double *vect) {
+  if (MHD) {
+    MhdEig e;
+    mhd_eig(gamma, w, bx, &e);
+    double id = e.id, cf = e.cf, cs = e.cs, asq = e.asq, a = e.a, bet2 = e.bet2, bet3 = e.bet3;
+    double alpha_f = e.alpha_f, alpha_s = e.alpha_s, s = e.s, isqrtd = e.isqrtd, sqrtd = e.sqrtd;
+    double nf = 0.5/asq;
+    double qf = nf*cf*alpha_f*s;
+    double qs = nf*cs*alpha_s*s;
+    double af_prime = 0.5*alpha_f/(a*sqrtd);
+    double as_prime = 0.5*alpha_s/(a*sqrtd);
+    double v_0 = nf*alpha_f*(vect[IPR]*id - cf*vect[IVX]) +
+                 qs*(bet2*vect[IVY] + bet3*vect[IVZ]) +
+                 as_prime*(bet2*vect[IBY] + bet3*vect[IBZ]);
+    double v_1 = 0.5*(bet2*(vect[IBZ]*s*isqrtd + vect[IVZ]) -
+                      bet3*(vect[IBY]*s*isqrtd + vect[IVY]));
+    double v_2 = nf*alpha_s*(vect[IPR]*id - cs*vect[IVX]) -
+                 qf*(bet2*vect[IVY] + bet3*vect[IVZ]) -
+                 af_prime*(bet2*vect[IBY] + bet3*vect[IBZ]);
+    double v_3 = vect[IDN] - vect[IPR]/asq;
+    double v_4 = nf*alpha_s*(vect[IPR]*id + cs*vect[IVX]) +
+                 qf*(bet2*vect[IVY] + bet3*vect[IVZ]) -
+                 af_prime*(bet2*vect[IBY] + bet3*vect[IBZ]);
+    double v_5 = 0.5*(bet2*(vect[IBZ]*s*isqrtd - vect[IVZ]) -
+                      bet3*(vect[IBY]*s*isqrtd - vect[IVY]));
+    double v_6 = nf*alpha_f*(vect[IPR]*id + cf*vect[IVX]) -
+                 qs*(bet2*vect[IVY] + bet3*vect[IVZ]) +
+                 as_prime*(bet2*vect[IBY] + bet3*vect[IBZ]);
+    vect[0] = v_0; vect[1] = v_1; vect[2] = v_2; vect[3] = v_3; vect[4] = v_4; vect[5] = v_5;
+    vect[6] = v_6;
+  } else {
+    double asq = gamma*w[IPR]/w[IDN];
+    double a = sqrt(asq);
+    double v_0 = 0.5*(vect[IPR]/asq - w[IDN]*vect[IVX]/a);
+    double v_1 = vect[IDN] - vect[IPR]/asq;
+    double v_2 = vect[IVY];
+    double v_3 = vect[IVZ];
+    double v_4 = 0.5*(vect[IPR]/asq + w[IDN]*vect[IVX]/a);
+    vect[0] = v_0; vect[1] = v_1; vect[2] = v_2; vect[3] = v_3; vect[4] = v_4;
+  }
+}
+
+template <bool MHD>
+AB_HD void char_right(double gamma, const double *w, double bx, double *vect) {
+  if (MHD) {
+    MhdEig e;
+    mhd_eig(gamma, w, bx, &e);
+    double cf = e.cf, cs = e.cs, asq = e.asq, a = e.a, bet2 = e.bet2, bet3 = e.bet3;
+    double alpha_f = e.alpha_f, alpha_s = e.alpha_s, s = e.s, sqrtd = e.sqrtd;
+    double qf = cf*alpha_f*s;
+    double qs = cs*alpha_s*s;
+    double af = a*alpha_f*sqrtd;
+    double as = a*alpha_s*sqrtd;
+    double v_0 = w[IDN]*(alpha_f*(vect[0] + vect[6]) +
+                         alpha_s*(vect[2] + vect[4])) + vect[3];
+    double v_1 = cf*alpha_f*(vect[6]-vect[0]) + cs*alpha_s*(vect[4]-vect[2]);
+    double v_2 = bet2*(qs*(vect[0] - vect[6]) + qf*(vect[4] - vect[2]))
+                 + bet3*(vect[5] - vect[1]);
+    double v_3 = bet3*(qs*(vect[0] - vect[6]) + qf*(vect[4] - vect[2]))
+                 + bet2*(vect[1] - vect[5]);
+    double v_4 = w[IDN]*asq*(alpha_f*(vect[0] + vect[6]) +
+                             alpha_s*(vect[2] + vect[4]));
+    double v_5 = bet2*(as*(vect[0] + vect[6]) - af*(vect[2] + vect[4]))
+                 - bet3*s*sqrtd*(vect[5] + vect[1]);
+    double v_6 = bet3*(as*(vect[0] + vect[6]) - af*(vect[2] + vect[4]))
+                 + bet2*s*sqrtd*(vect[5] + vect[1]);
+    vect[IDN] = v_0; vect[IVX] = v_1; vect[IVY] = v_2; vect[IVZ] = v_3; vect[IPR] = v_4;
+    vect[IBY] = v_5; vect[IBZ] = v_6;
+  } else {
+    double asq = gamma*w[IPR]/w[IDN];
+    double a = sqrt(asq);
+    double v_0 = vect[0] + vect[1] + vect[4];
+    double v_1 = a*(vect[4] - vect[0])/w[IDN];
+    double v_2 = vect[2];
+    double v_3 = vect[3];
+    double v_4 = asq*(vect[0] + vect[4]);
+    vect[IDN] = v_0; vect[IVX] = v_1; vect[IVY] = v_2; vect[IVZ] = v_3; vect[IPR] = v_4;
+  }
+}
+
+// xorder = 2c: PLM on characteristic variables for one cell (plm.cpp:62-66,107-130): both face
+// states of the cell, floors re-applied.  q* sweep-ordered, NW = 5 / 7.
+template <bool MHD>
+AB_HD void plm_char(const double *qm1, const double *q, const double *qp1, double bx,
+                    double gamma, double wp, double wm, double dfloor, double pfloor,
+                    double *plus, double *minus) {
+  constexpr int NW = MHD ? 7 : 5;
+  double dwl[7], dwr[7], dwm[7];
+  for (int n = 0; n < NW; ++n) { dwl[n] = (q[n] - qm1[n]); dwr[n] = (qp1[n] - q[n]); }
+  char_left<MHD>(gamma, q, bx, dwl);
+  char_left<MHD>(gamma, q, bx, dwr);
+  for (int n = 0; n < NW; ++n) {
+    double dw2 = dwl[n]*dwr[n];
+    dwm[n] = 0.0;
+    if (dw2 > 0.0) dwm[n] = 2.0*dw2/(dwl[n] + dwr[n]);
+  }
+  char_right<MHD>(gamma, q, bx, dwm);
+  for (int n = 0; n < NW; ++n) { plus[n] = q[n] + wp*dwm[n]; minus[n] = q[n] - wm*dwm[n]; }
+  plus[IDN] = (plus[IDN] > dfloor) ? plus[IDN] : dfloor;
+  minus[IDN] = (minus[IDN] > dfloor) ? minus[IDN] : dfloor;
+  plus[IPR] = (plus[IPR] > pfloor) ? plus[IPR] : pfloor;
+  minus[IPR] = (minus[IPR] > pfloor) ? minus[IPR] : pfloor;
+}
+
+// xorder = 3c: PPM on characteristic variables for one cell (ppm.cpp:66-75,311-332): the five
+// stencil states are projected with the cell's own eigenvectors, reconstructed, and both face
+// states projected back; floors re-applied.
+template <bool MHD>
+AB_HD void ppm_char(const double *qm2, const double *qm1, const double *q, const double *qp1,
+                    const double *qp2, double bx, double gamma, double dfloor, double pfloor,
+                    double *plus, double *minus) {
+  constexpr int NW = MHD ? 7 : 5;
+  double c0[7], c1[7], c2[7], c3[7], c4[7];
+  for (int n = 0; n < NW; ++n) {
+    c0[n] = qm2[n]; c1[n] = qm1[n]; c2[n] = q[n]; c3[n] = qp1[n]; c4[n] = qp2[n];
+  }
+  char_left<MHD>(gamma, q, bx, c0);
+  char_left<MHD>(gamma, q, bx, c1);
+  char_left<MHD>(gamma, q, bx, c2);
+  char_left<MHD>(gamma, q, bx, c3);
+  char_left<MHD>(gamma, q, bx, c4);
+  for (int n = 0; n < NW; ++n) ppm(c0[n], c1[n], c2[n], c3[n], c4[n], plus[n], minus[n]);
+  char_right<MHD>(gamma, q, bx, plus);
+  char_right<MHD>(gamma, q, bx, minus);
+  plus[IDN] = (plus[IDN] > dfloor) ? plus[IDN] : dfloor;
+  minus[IDN] = (minus[IDN] > dfloor) ? minus[IDN] : dfloor;
+  plus[IPR] = (plus[IPR] > pfloor) ? plus[IPR] : pfloor;
+  minus[IPR] = (minus[IPR] > pfloor) ? minus[IPR] : pfloor;
+}
+
 // ------------------------------------------------------------------------ hydro solvers
 // wl/wr: sweep-ordered primitives (IDN, vx, vy, vz, IPR); f: (IDN, mx, my, mz, IEN).
 

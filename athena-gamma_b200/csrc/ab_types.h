@@ -64,6 +64,7 @@ struct Params {
   double sfloor;                  // passive-scalar concentration floor (hydro/sfloor)
   int eos;                        // 0 adiabatic, 1 isothermal
   double iso_cs;                  // hydro/iso_sound_speed
+  int char_proj;                  // time/xorder = 2c / 3c
 };
 
 }  // namespace ab

@@ -48,7 +48,8 @@ class AbMeshParams(C.Structure):
                 ("cfl_number", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double),
                 ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
                 ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
-                ("iso_sound_speed", C.c_double), ("grav_acc", C.c_double * 3)]
+                ("iso_sound_speed", C.c_double), ("grav_acc", C.c_double * 3),
+                ("char_proj", C.c_int)]
 
 
 # AbBValFunc (include/athena_b200.h): user-enrolled boundary function on host arrays

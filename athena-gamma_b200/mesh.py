@@ -115,9 +115,8 @@ class Mesh:
                                  "the B200 path" % flag)
             p.bc[i] = lib.BC[flag]
         xo = pin.get_or_add_string("time", "xorder", "2")
-        if xo.endswith("c"):
-            raise ValueError("characteristic reconstruction (xorder=%s) is not on the B200 path" % xo)
-        p.xorder = int(xo)
+        p.char_proj = int(xo.endswith("c"))        # reconstruction.cpp:60-80: "2c", "3c"
+        p.xorder = int(xo.rstrip("c"))
         p.nghost = nghost if nghost is not None else (3 if p.xorder == 3 else 2)
         p.mhd = int(bool(mhd))
         if flux == "default":

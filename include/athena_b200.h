@@ -61,6 +61,7 @@ typedef struct {
   double sfloor;                /* hydro/sfloor (0 -> eos ctor default sqrt(1024*FLT_MIN)) */
   double iso_sound_speed;       /* hydro/iso_sound_speed (isothermal EOS) */
   double grav_acc[3];           /* hydro/grav_acc1..3: constant acceleration source term */
+  int char_proj;                /* time/xorder = "2c" / "3c": characteristic reconstruction */
 } AbMeshParams;
 
 typedef struct AbMesh AbMesh;

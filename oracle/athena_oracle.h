@@ -115,6 +115,11 @@ void ao_riemann_dv(int solver, int mhd, long n, const double *wl, const double *
 /* isothermal EOS: hlle (hydro), hlle / hlld (MHD); slot 4 of the 5/7-slot vectors is unused */
 void ao_riemann_iso(int solver, int mhd, long n, const double *wl, const double *wr,
                     const double *bx, double iso_cs, double dfloor, double *flx);
+/* characteristic reconstruction (xorder 2c / 3c) of n independent cells, sweep order:
+ * q[(o*7 + v)*n + i] = variable v of stencil cell o-2; plus/minus [v*n + i] */
+void ao_recon_char(int order, int mhd, long n, const double *q, const double *bx, double gamma,
+                   double wp, double wm, double dfloor, double pfloor, double *plus,
+                   double *minus);
 void ao_plm(long n, int nvar, const double *qm1, const double *q, const double *qp1,
             double wp, double wm, double *ql_plus, double *qr_minus);
 void ao_ppm(long n, int nvar, const double *qm2, const double *qm1, const double *q,

@@ -106,6 +106,8 @@ def lib():
                                     C.c_double, C.c_double, dp, dp]
         L.ao_riemann_iso.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_double,
                                      C.c_double, dp]
+        L.ao_recon_char.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, C.c_double, C.c_double,
+                                    C.c_double, C.c_double, C.c_double, dp, dp]
         L.ao_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
         L.ao_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, C.c_double, C.c_double,
                              dp, dp]

@@ -19,6 +19,9 @@ void ao_riemann_point_iso(int solver, int mhd, const double *wli, const double *
                           double bxi, double iso_cs, double dfloor, double *flxi);
 void ao_char_left(int mhd, double gamma, const double *w, double bx, double *vect);
 void ao_char_right(int mhd, double gamma, const double *w, double bx, double *vect);
+void ao_recon_char_point(int order, int mhd, double st[5][7], double bx, double gamma,
+                         double wp, double wm, double dfloor, double pfloor, double *pl,
+                         double *mi);
 void ao_plm_point(double qm1, double q, double qp1, double wp, double wm,
                   double *plus, double *minus);
 void ao_ppm_point(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,

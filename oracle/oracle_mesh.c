@@ -569,36 +569,18 @@ static void recon_cell_char(const AoMesh *m, const AoBlock *B, int dir, int orde
     if (order == 2 && (o == -2 || o == 2)) continue;
     cell_state(m, B, dir, k+o*dk, j+o*dj, i+o*di, t); to_sweep(dir, t, st[o+2]);
   }
+  double wp = 0.0, wm = 0.0;
   if (order == 2) {
     const double *xf = dir == 0 ? B->x1f : (dir == 1 ? B->x2f : B->x3f);
     const double *xv = dir == 0 ? B->x1v : (dir == 1 ? B->x2v : B->x3v);
     const double *dxf = dir == 0 ? B->dx1f : (dir == 1 ? B->dx2f : B->dx3f);
     int c = dir == 0 ? i : (dir == 1 ? j : k);
-    double wp = (xf[c+1] - xv[c])/dxf[c];
-    double wm = (xv[c] - xf[c])/dxf[c];
-    double dwl[7], dwr[7], dwm[7];
-    for (int n = 0; n < nw; ++n) { dwl[n] = (q[n] - st[1][n]); dwr[n] = (st[3][n] - q[n]); }
-    ao_char_left(mhd, gamma, q, bx, dwl);
-    ao_char_left(mhd, gamma, q, bx, dwr);
-    for (int n = 0; n < nw; ++n) {
-      double dw2 = dwl[n]*dwr[n];
-      dwm[n] = 2.0*dw2/(dwl[n] + dwr[n]);
-      if (dw2 <= 0.0) dwm[n] = 0.0;
-    }
-    ao_char_right(mhd, gamma, q, bx, dwm);
-    for (int n = 0; n < nw; ++n) { pl[n] = q[n] + wp*dwm[n]; mi[n] = q[n] - wm*dwm[n]; }
-  } else {
-    for (int o = 0; o < 5; ++o) ao_char_left(mhd, gamma, q, bx, st[o]);
-    for (int n = 0; n < nw; ++n)
-      ao_ppm_point(st[0][n], st[1][n], st[2][n], st[3][n], st[4][n], &pl[n], &mi[n]);
-    ao_char_right(mhd, gamma, q, bx, pl);
-    ao_char_right(mhd, gamma, q, bx, mi);
+    wp = (xf[c+1] - xv[c])/dxf[c];
+    wm = (xv[c] - xf[c])/dxf[c];
+    for (int n = 0; n < 7; ++n) { st[0][n] = 0.0; st[4][n] = 0.0; }
   }
-  /* ApplyPrimitiveFloors on both states (plm.cpp:122-130, ppm.cpp:326-332) */
-  pl[IDN] = (pl[IDN] > m->p.dfloor) ? pl[IDN] : m->p.dfloor;
-  mi[IDN] = (mi[IDN] > m->p.dfloor) ? mi[IDN] : m->p.dfloor;
-  pl[IPR] = (pl[IPR] > m->p.pfloor) ? pl[IPR] : m->p.pfloor;
-  mi[IPR] = (mi[IPR] > m->p.pfloor) ? mi[IPR] : m->p.pfloor;
+  (void)q; (void)nw;
+  ao_recon_char_point(order, mhd, st, bx, gamma, wp, wm, m->p.dfloor, m->p.pfloor, pl, mi);
   from_sweep(dir, pl, plus);
   from_sweep(dir, mi, minus);
 }

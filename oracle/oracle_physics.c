@@ -1650,3 +1650,55 @@ void ao_ppm(long n, int nvar, const double *qm2, const double *qm1, const double
     }
   }
 }
+
+/* ---------------------------------------------------------------- characteristic reconstruction
+ * One cell: stencil st[5][7] = cells -2..+2 in sweep order (rows 0 and 4 unused for order 2).
+ * xorder = 2c: plm.cpp:62-66,107-130; xorder = 3c: ppm.cpp:66-75,311-332.  Eigenvectors of the
+ * cell itself; floors re-applied to both face states. */
+void ao_recon_char_point(int order, int mhd, double st[5][7], double bx, double gamma,
+                         double wp, double wm, double dfloor, double pfloor, double *pl,
+                         double *mi) {
+  int nw = mhd ? 7 : 5;
+  const double *q = st[2];
+  if (order == 2) {
+    double dwl[7], dwr[7], dwm[7];
+    for (int n = 0; n < nw; ++n) { dwl[n] = (q[n] - st[1][n]); dwr[n] = (st[3][n] - q[n]); }
+    ao_char_left(mhd, gamma, q, bx, dwl);
+    ao_char_left(mhd, gamma, q, bx, dwr);
+    for (int n = 0; n < nw; ++n) {
+      double dw2 = dwl[n]*dwr[n];
+      dwm[n] = 2.0*dw2/(dwl[n] + dwr[n]);
+      if (dw2 <= 0.0) dwm[n] = 0.0;
+    }
+    ao_char_right(mhd, gamma, q, bx, dwm);
+    for (int n = 0; n < nw; ++n) { pl[n] = q[n] + wp*dwm[n]; mi[n] = q[n] - wm*dwm[n]; }
+  } else {
+    double c[5][7], w0[7];
+    for (int n = 0; n < 7; ++n) w0[n] = q[n];
+    for (int o = 0; o < 5; ++o) {
+      for (int n = 0; n < 7; ++n) c[o][n] = st[o][n];
+      ao_char_left(mhd, gamma, w0, bx, c[o]);
+    }
+    for (int n = 0; n < nw; ++n)
+      ao_ppm_point(c[0][n], c[1][n], c[2][n], c[3][n], c[4][n], &pl[n], &mi[n]);
+    ao_char_right(mhd, gamma, w0, bx, pl);
+    ao_char_right(mhd, gamma, w0, bx, mi);
+  }
+  pl[IDN] = (pl[IDN] > dfloor) ? pl[IDN] : dfloor;
+  mi[IDN] = (mi[IDN] > dfloor) ? mi[IDN] : dfloor;
+  pl[IPR] = (pl[IPR] > pfloor) ? pl[IPR] : pfloor;
+  mi[IPR] = (mi[IPR] > pfloor) ? mi[IPR] : pfloor;
+}
+
+/* batch version for tests: q[(o*7 + v)*n + i] */
+void ao_recon_char(int order, int mhd, long n, const double *q, const double *bx, double gamma,
+                   double wp, double wm, double dfloor, double pfloor, double *plus,
+                   double *minus) {
+  int nw = mhd ? 7 : 5;
+  for (long i = 0; i < n; ++i) {
+    double st[5][7], pl[7], mi[7];
+    for (int o = 0; o < 5; ++o) for (int v = 0; v < 7; ++v) st[o][v] = q[(o*7 + v)*n + i];
+    ao_recon_char_point(order, mhd, st, mhd ? bx[i] : 0.0, gamma, wp, wm, dfloor, pfloor, pl, mi);
+    for (int v = 0; v < nw; ++v) { plus[v*n + i] = pl[v]; minus[v*n + i] = mi[v]; }
+  }
+}

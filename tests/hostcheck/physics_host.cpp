@@ -51,6 +51,26 @@ void hc_riemann_iso(int solver, int mhd, long n, const double *wl, const double 
     for (int v = 0; v < nw; ++v) flx[v*n+i] = f[v];
   }
 }
+// characteristic reconstruction of one cell per column: q[5][7][n] (stencil -2..+2, sweep order),
+// bx[n]; order 2 -> plm_char, 3 -> ppm_char; out plus/minus [7][n]
+void hc_recon_char(int order, int mhd, long n, const double *q, const double *bx, double gamma,
+                   double wp, double wm, double dfloor, double pfloor, double *plus,
+                   double *minus) {
+  const int nw = mhd ? 7 : 5;
+  for (long i = 0; i < n; ++i) {
+    double st[5][7], pl[7], mi[7];
+    for (int o = 0; o < 5; ++o) for (int v = 0; v < 7; ++v) st[o][v] = q[(o*7 + v)*n + i];
+    const double b = mhd ? bx[i] : 0.0;
+    if (order == 2) {
+      if (mhd) ab::plm_char<true>(st[1], st[2], st[3], b, gamma, wp, wm, dfloor, pfloor, pl, mi);
+      else ab::plm_char<false>(st[1], st[2], st[3], b, gamma, wp, wm, dfloor, pfloor, pl, mi);
+    } else {
+      if (mhd) ab::ppm_char<true>(st[0], st[1], st[2], st[3], st[4], b, gamma, dfloor, pfloor, pl, mi);
+      else ab::ppm_char<false>(st[0], st[1], st[2], st[3], st[4], b, gamma, dfloor, pfloor, pl, mi);
+    }
+    for (int v = 0; v < nw; ++v) { plus[v*n + i] = pl[v]; minus[v*n + i] = mi[v]; }
+  }
+}
 void hc_plm(long n, int nvar, const double *qm1, const double *q, const double *qp1,
             double wp, double wm, double *ql, double *qr) {
   for (long i = 0; i < (long)nvar*n; ++i) ab::plm(qm1[i], q[i], qp1[i], wp, wm, ql[i], qr[i]);

@@ -36,6 +36,11 @@ CASES = [
     ("bw1d_hlld_plm_vl2_2blk", None, None),
     ("bw2d_x2_hlld_plm_rk2_4blk", None, None),
     ("blast_noncubic_hlld_ppm_rk2_6blk", None, None),
+    # characteristic reconstruction
+    ("blast_hlld_plmc_vl2_8blk", None, None),
+    ("blast_hllc_plmc_vl2_8blk", None, None),
+    ("blast_hlld_ppmc_rk3_8blk", None, None),
+    ("kh_hllc_ppmc_rk2_8blk", None, None),
     # LLF
     ("blast_llf_plm_vl2_8blk", None, None),
     ("blast_mhd_llf_plm_vl2_8blk", None, None),

@@ -30,6 +30,8 @@ def hc():
                              C.c_double, C.c_double, dp, dp]
     L.hc_riemann_iso.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, dp, C.c_double, C.c_double,
                                  dp]
+    L.hc_recon_char.argtypes = [C.c_int, C.c_int, C.c_long, dp, dp, C.c_double, C.c_double,
+                                C.c_double, C.c_double, C.c_double, dp, dp]
     L.hc_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
     L.hc_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, dp, dp]
     return L
@@ -98,6 +100,33 @@ def test_isothermal_riemann_matches_oracle(hc, solver, mhd, regime):
                       oracle.DEFAULT_FLOOR, _dp(fh))
     keep = [0, 1, 2, 3] + ([5, 6] if mhd else [])           # slot 4 (energy) is unused
     util.assert_bitwise(fh[keep], fo[keep], "iso flux %s mhd=%s" % (solver, mhd))
+
+
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("mhd", [False, True])
+def test_characteristic_reconstruction_matches_oracle(hc, order, mhd):
+    """xorder = 2c / 3c: eigenvector projections + limiter + back-projection of one cell"""
+    rng = np.random.default_rng(99 + order)
+    n = 20000
+    q = np.zeros((5, 7, n))
+    base = random_states(rng, n, True, "mixed")
+    for o in range(5):
+        q[o] = base*(1.0 + 0.3*rng.normal(size=base.shape))
+        q[o][0] = np.abs(q[o][0]) + 1e-3
+        q[o][4] = np.abs(q[o][4]) + 1e-3
+    q[:, :, : n // 5] = q[2:3, :, : n // 5]                 # uniform stencil
+    q[:, 5:7, n // 5: n // 4] = 0.0                         # no transverse field (bt = 0)
+    bx = rng.normal(0, 1.0, n)
+    bx[n // 2: n // 2 + n // 10] = 0.0
+    args = (order, int(mhd), n, _dp(q), _dp(bx), 5.0/3.0, 0.5, 0.5, oracle.DEFAULT_FLOOR,
+            oracle.DEFAULT_FLOOR)
+    po, mo = np.zeros((7, n)), np.zeros((7, n))
+    ph, mh = np.zeros((7, n)), np.zeros((7, n))
+    oracle.lib().ao_recon_char(*args, _dp(po), _dp(mo))
+    hc.hc_recon_char(*args, _dp(ph), _dp(mh))
+    nw = 7 if mhd else 5
+    util.assert_bitwise(ph[:nw], po[:nw], "plus")
+    util.assert_bitwise(mh[:nw], mo[:nw], "minus")
 
 
 def test_plm_ppm_match_oracle(hc):
