@@ -36,6 +36,7 @@ typedef struct {
   double iso_cs;        /* hydro/iso_sound_speed */
   double grav_acc[3];   /* hydro/grav_acc1..3 (hydro/srcterms/hydro_srcterms.cpp:68-75) */
   int char_proj;        /* time/xorder = 2c / 3c: reconstruct characteristic variables */
+  double xrat[3];       /* mesh/x1rat..x3rat (0 or 1 = uniform): geometric cell-size ratio */
 } AoParams;
 
 typedef struct AoMesh AoMesh;

@@ -29,7 +29,8 @@ class AoParams(C.Structure):
                 ("gamma", C.c_double), ("dfloor", C.c_double), ("pfloor", C.c_double),
                 ("cfl", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double),
                 ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
-                ("iso_cs", C.c_double), ("grav_acc", C.c_double * 3), ("char_proj", C.c_int)]
+                ("iso_cs", C.c_double), ("grav_acc", C.c_double * 3), ("char_proj", C.c_int),
+                ("xrat", C.c_double * 3)]
 
 
 # AoBValFunc (athena_oracle.h): user-enrolled boundary function with plain arrays
@@ -153,6 +154,8 @@ def params_from_athinput(par, mhd, solver, ng=None, nscalars=0, eos="adiabatic")
     p.cfl = float(t["cfl_number"])
     p.tlim = float(t["tlim"])
     p.start_time = float(t.get("start_time", 0.0))
+    for d in range(3):
+        p.xrat[d] = float(mesh.get("x%drat" % (d + 1), 1.0))
     return p
 
 

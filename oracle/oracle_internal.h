@@ -19,9 +19,23 @@ void ao_riemann_point_iso(int solver, int mhd, const double *wli, const double *
                           double bxi, double iso_cs, double dfloor, double *flxi);
 void ao_char_left(int mhd, double gamma, const double *w, double bx, double *vect);
 void ao_char_right(int mhd, double gamma, const double *w, double bx, double *vect);
+/* reconstruction geometry of one cell along one direction.  mode 0: uniform spacing (only
+ * wp, wm are used); 1 / 2 / 3: the nonuniform branches of the x1 / x2 / x3 routines, which
+ * differ in rounding order and (x3) in the limiter (plm.cpp:81-105,194-214,306-322);
+ * c*: PPM weights of cells i-1 (m), i, i+1 (p) (reconstruction.cpp:434-461,559-582,609-631) */
+typedef struct {
+  double wp, wm;
+  int mode;
+  double dxf, dxv, dxvm, cf, cb, dxF, dxB;
+  double c1m, c2m, c1, c2, c1p, c2p, c3, c4, c5, c6, c3p, c4p, c5p, c6p;
+} AoReconGeom;
 void ao_recon_char_point(int order, int mhd, double st[5][7], double bx, double gamma,
-                         double wp, double wm, double dfloor, double pfloor, double *pl,
+                         const AoReconGeom *g, double dfloor, double pfloor, double *pl,
                          double *mi);
+void ao_plm_point_g(double qm1, double q, double qp1, const AoReconGeom *g,
+                    double *plus, double *minus);
+void ao_ppm_point_g(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,
+                    const AoReconGeom *g, double *plus, double *minus);
 void ao_plm_point(double qm1, double q, double qp1, double wp, double wm,
                   double *plus, double *minus);
 void ao_ppm_point(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,

@@ -34,6 +34,8 @@ typedef struct AoBlock {
   int nnb; Nb nb[26];
   int nedge_fine[12];
   double *x1f, *x2f, *x3f, *x1v, *x2v, *x3v, *dx1f, *dx2f, *dx3f;
+  AoReconGeom *rg[3];    /* per-index reconstruction geometry along x1, x2, x3 */
+  double *bw[3][2];      /* CalculateCellCenteredField weights (lw, rw) per index */
   double *u, *u1, *w, *bcc, *flux[3];
   double *b[3], *b1[3], *e[3], *wght[3];
   double *e2_x1f, *e3_x1f, *e1_x2f, *e3_x2f, *e1_x3f, *e2_x3f, *cc_e;
@@ -54,6 +56,7 @@ struct AoMesh {
   int nstages;
   double beta[4], delta[4], g1[4], g2[4], g3[4], ebeta[4];
   double cfl;
+  double xrat[3];        /* mesh/x?rat with 0 read as 1 (uniform) */
   AoBValFunc user_bc[6]; void *user_bc_arg[6];
   AoSrcTermFunc user_src; void *user_src_arg;
   double sbeta[4];
@@ -88,10 +91,25 @@ static double uniform_gen(double x, double xmin, double xmax) {
   return 0.5*(xmin + xmax) + (x*xmax - x*xmin);
 }
 
-/* Coordinates ctor, uniform branch (src/coordinates/coordinates.cpp:125-145 and twins),
+/* DefaultMeshGeneratorX? (src/mesh/mesh.hpp:411-455): geometric spacing, x in [0,1] */
+static double default_gen(double x, double xmin, double xmax, double rat, int nx) {
+  double lw, rw;
+  if (rat == 1.0) {
+    rw = x; lw = 1.0 - x;
+  } else {
+    double ratn = pow(rat, nx);
+    double rnx = pow(rat, x*nx);
+    lw = (rnx - ratn)/(1.0 - ratn);
+    rw = 1.0 - lw;
+  }
+  return xmin*lw + xmax*rw;
+}
+
+/* Coordinates ctor (src/coordinates/coordinates.cpp:92-160 and twins): uniform branch, or the
+ * mesh-generator branch when x?rat != 1 (Mesh::use_uniform_meshgen_fn_, mesh.cpp:278-289);
  * Cartesian x?v (src/coordinates/cartesian.cpp:25-75) */
 static void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, double mmax,
-                        double bmin, double bmax, int nc, int refl_in, int refl_out,
+                        double bmin, double bmax, int nc, int refl_in, int refl_out, double rat,
                         double **xf, double **xv, double **dxf) {
   *xf = dalloc(nc + 1); *xv = dalloc(nc); *dxf = dalloc(nc);
   if (nc == 1) {
@@ -102,15 +120,26 @@ static void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, doubl
     return;
   }
   int il = ng, iu = ng + bx - 1;
-  double dx = (bmax - bmin)/(iu - il + 1);
-  for (int i = il - ng; i <= iu + ng + 1; ++i) {
-    long noffset = (long)(i - il) + lx*bx;
-    double rx = mesh_gen_x(noffset, nx_mesh);
-    (*xf)[i] = uniform_gen(rx, mmin, mmax);
+  if (rat != 1.0) {
+    for (int i = il - ng; i <= iu + ng + 1; ++i) {
+      long noffset = (long)(i - il) + lx*bx;
+      double rx = (double)noffset/(double)nx_mesh;   /* ComputeMeshGeneratorX, [0,1] */
+      (*xf)[i] = default_gen(rx, mmin, mmax, rat, nx_mesh);
+    }
+    (*xf)[il] = bmin;
+    (*xf)[iu+1] = bmax;
+    for (int i = il - ng; i <= iu + ng; ++i) (*dxf)[i] = (*xf)[i+1] - (*xf)[i];
+  } else {
+    double dx = (bmax - bmin)/(iu - il + 1);
+    for (int i = il - ng; i <= iu + ng + 1; ++i) {
+      long noffset = (long)(i - il) + lx*bx;
+      double rx = mesh_gen_x(noffset, nx_mesh);
+      (*xf)[i] = uniform_gen(rx, mmin, mmax);
+    }
+    (*xf)[il] = bmin;
+    (*xf)[iu+1] = bmax;
+    for (int i = il - ng; i <= iu + ng; ++i) (*dxf)[i] = dx;
   }
-  (*xf)[il] = bmin;
-  (*xf)[iu+1] = bmax;
-  for (int i = il - ng; i <= iu + ng; ++i) (*dxf)[i] = dx;
   /* reflecting boundaries mirror the ghost spacing (coordinates.cpp:147-160) */
   if (refl_in) for (int i = 1; i <= ng; ++i) {
     (*dxf)[il-i] = (*dxf)[il+i-1];
@@ -123,17 +152,85 @@ static void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, doubl
   for (int i = il - ng; i <= iu + ng; ++i) (*xv)[i] = 0.5*((*xf)[i+1] + (*xf)[i]);
 }
 
+/* Reconstruction ctor (src/reconstruct/reconstruction.cpp:196-213,422-461,549-582,599-640) and
+ * the per-index factors the PLM / CalculateCellCenteredField loops evaluate on the fly
+ * (plm.cpp:85-93,114-119,198-204,308-313; field.cpp:139-172); dx?v as cartesian.cpp:31-75.
+ * Index ranges as in the reference: the x2 / x3 weight loops start one cell later than x1's,
+ * anything outside keeps the zero of NewAthenaArray. */
+static AoReconGeom *make_recon_geom(int dir, int nonuni, int nc, int s, int e, int ng,
+                                    const double *xf, const double *xv, const double *dxf,
+                                    double *bw[2]) {
+  AoReconGeom *g = (AoReconGeom *)calloc((size_t)nc, sizeof(AoReconGeom));
+  bw[0] = dalloc(nc); bw[1] = dalloc(nc);
+  for (int i = 0; i < nc; ++i) {
+    g[i].wp = (xf[i+1] - xv[i])/dxf[i];
+    g[i].wm = (xv[i] - xf[i])/dxf[i];
+    bw[0][i] = 0.5; bw[1][i] = 0.5;
+  }
+  if (!nonuni || nc == 1) return g;
+  double *dxv = dalloc(nc);
+  for (int i = s - ng; i <= e + ng - 1; ++i) dxv[i] = xv[i+1] - xv[i];
+  double *c[6];
+  for (int n = 0; n < 6; ++n) c[n] = dalloc(nc);
+  int first = (dir == 0) ? s - ng + 1 : s - ng + 2;
+  for (int i = first; i <= e + ng - 1; ++i) {
+    double dx_im1 = dxf[i-1], dx_i = dxf[i], dx_ip1 = dxf[i+1];
+    double qe = dx_i/(dx_im1 + dx_i + dx_ip1);
+    c[0][i] = qe*(2.0*dx_im1+dx_i)/(dx_ip1 + dx_i);
+    c[1][i] = qe*(2.0*dx_ip1+dx_i)/(dx_im1 + dx_i);
+    if (i > s - ng + 1) {
+      double dx_im2 = dxf[i-2];
+      double qa = dx_im2 + dx_im1 + dx_i + dx_ip1;
+      double qb = dx_im1/(dx_im1 + dx_i);
+      double qc = (dx_im2 + dx_im1)/(2.0*dx_im1 + dx_i);
+      double qd = (dx_ip1 + dx_i)/(2.0*dx_i + dx_im1);
+      qb = qb + 2.0*dx_i*qb/qa*(qc-qd);
+      c[2][i] = 1.0 - qb;
+      c[3][i] = qb;
+      c[4][i] = dx_i/qa*qd;
+      c[5][i] = -dx_im1/qa*qc;
+    }
+  }
+  for (int i = 0; i < nc; ++i) {
+    AoReconGeom *q = &g[i];
+    q->mode = dir + 1;
+    q->dxf = dxf[i]; q->dxv = dxv[i]; q->dxvm = (i > 0) ? dxv[i-1] : 0.0;
+    q->cf = q->dxv/(xf[i+1] - xv[i]);
+    q->cb = q->dxvm/(xv[i] - xf[i]);
+    q->dxF = q->dxf/q->dxv;
+    q->dxB = q->dxf/q->dxvm;
+    q->c1 = c[0][i]; q->c2 = c[1][i]; q->c3 = c[2][i]; q->c4 = c[3][i]; q->c5 = c[4][i];
+    q->c6 = c[5][i];
+    if (i > 0) { q->c1m = c[0][i-1]; q->c2m = c[1][i-1]; }
+    if (i < nc - 1) {
+      q->c1p = c[0][i+1]; q->c2p = c[1][i+1]; q->c3p = c[2][i+1]; q->c4p = c[3][i+1];
+      q->c5p = c[4][i+1]; q->c6p = c[5][i+1];
+    }
+    bw[0][i] = (xf[i+1] - xv[i])/dxf[i];
+    bw[1][i] = (xv[i] - xf[i])/dxf[i];
+  }
+  for (int n = 0; n < 6; ++n) free(c[n]);
+  free(dxv);
+  return g;
+}
+
 /* Mesh::SetBlockSizeAndBoundaries (src/mesh/mesh.cpp:1668-1751) for one direction */
+static double block_edge(long lx, int nrbx, double mmin, double mmax, double rat, int nx_mesh) {
+  if (rat != 1.0) return default_gen((double)lx/(double)nrbx, mmin, mmax, rat, nx_mesh);
+  return uniform_gen(mesh_gen_x(lx, nrbx), mmin, mmax);
+}
+
 static void block_extent(long lx, int nrbx, double mmin, double mmax, int bc_in, int bc_out,
-                         int nx_mesh, double *bmin, double *bmax, int *bcs_in, int *bcs_out) {
+                         int nx_mesh, double rat, double *bmin, double *bmax, int *bcs_in,
+                         int *bcs_out) {
   if (nx_mesh == 1) {
     *bmin = mmin; *bmax = mmax; *bcs_in = bc_in; *bcs_out = bc_out;
     return;
   }
   if (lx == 0) { *bmin = mmin; *bcs_in = bc_in; }
-  else { *bmin = uniform_gen(mesh_gen_x(lx, nrbx), mmin, mmax); *bcs_in = -1; }
+  else { *bmin = block_edge(lx, nrbx, mmin, mmax, rat, nx_mesh); *bcs_in = -1; }
   if (lx == nrbx - 1) { *bmax = mmax; *bcs_out = bc_out; }
-  else { *bmax = uniform_gen(mesh_gen_x(lx + 1, nrbx), mmin, mmax); *bcs_out = -1; }
+  else { *bmax = block_edge(lx + 1, nrbx, mmin, mmax, rat, nx_mesh); *bcs_out = -1; }
 }
 
 static int find_ni(const AoMesh *m, int o1, int o2, int o3) {
@@ -179,6 +276,9 @@ static void set_integrator(AoMesh *m) {
 AoMesh *ao_create(const AoParams *p) {
   AoMesh *m = (AoMesh *)calloc(1, sizeof(AoMesh));
   m->p = *p;
+  for (int d = 0; d < 3; ++d) m->xrat[d] = (p->xrat[d] == 0.0) ? 1.0 : p->xrat[d];
+  if (p->nx2 == 1) m->xrat[1] = 1.0;
+  if (p->nx3 == 1) m->xrat[2] = 1.0;
   m->nh = (p->eos == 1) ? 4 : 5;
   m->f2 = p->nx2 > 1; m->f3 = p->nx3 > 1;
   m->ndim = m->f3 ? 3 : (m->f2 ? 2 : 1);
@@ -233,21 +333,28 @@ AoMesh *ao_create(const AoParams *p) {
     else { B->js = B->je = 0; B->nc2 = 1; }
     if (m->f3) { B->ks = ng; B->ke = ng + p->bx3 - 1; B->nc3 = p->bx3 + 2*ng; }
     else { B->ks = B->ke = 0; B->nc3 = 1; }
-    block_extent(B->lx1, m->nrbx1, p->x1min, p->x1max, p->bc[0], p->bc[1], 2 /*always*/,
-                 &B->bx1min, &B->bx1max, &B->bcs[0], &B->bcs[1]);
+    /* nx1 > 1 always, so the x1 extent goes through the generator even for one block */
+    block_extent(B->lx1, m->nrbx1, p->x1min, p->x1max, p->bc[0], p->bc[1], p->nx1 > 1 ? p->nx1 : 2,
+                 m->xrat[0], &B->bx1min, &B->bx1max, &B->bcs[0], &B->bcs[1]);
     block_extent(B->lx2, m->nrbx2, p->x2min, p->x2max, p->bc[2], p->bc[3], p->nx2,
-                 &B->bx2min, &B->bx2max, &B->bcs[2], &B->bcs[3]);
+                 m->xrat[1], &B->bx2min, &B->bx2max, &B->bcs[2], &B->bcs[3]);
     block_extent(B->lx3, m->nrbx3, p->x3min, p->x3max, p->bc[4], p->bc[5], p->nx3,
-                 &B->bx3min, &B->bx3max, &B->bcs[4], &B->bcs[5]);
+                 m->xrat[2], &B->bx3min, &B->bx3max, &B->bcs[4], &B->bcs[5]);
     make_coords(p->nx1, p->bx1, ng, B->lx1, p->x1min, p->x1max, B->bx1min, B->bx1max,
-                B->nc1, B->bcs[0] == AO_BC_REFLECT, B->bcs[1] == AO_BC_REFLECT,
+                B->nc1, B->bcs[0] == AO_BC_REFLECT, B->bcs[1] == AO_BC_REFLECT, m->xrat[0],
                 &B->x1f, &B->x1v, &B->dx1f);
     make_coords(p->nx2, p->bx2, ng, B->lx2, p->x2min, p->x2max, B->bx2min, B->bx2max,
-                B->nc2, B->bcs[2] == AO_BC_REFLECT, B->bcs[3] == AO_BC_REFLECT,
+                B->nc2, B->bcs[2] == AO_BC_REFLECT, B->bcs[3] == AO_BC_REFLECT, m->xrat[1],
                 &B->x2f, &B->x2v, &B->dx2f);
     make_coords(p->nx3, p->bx3, ng, B->lx3, p->x3min, p->x3max, B->bx3min, B->bx3max,
-                B->nc3, B->bcs[4] == AO_BC_REFLECT, B->bcs[5] == AO_BC_REFLECT,
+                B->nc3, B->bcs[4] == AO_BC_REFLECT, B->bcs[5] == AO_BC_REFLECT, m->xrat[2],
                 &B->x3f, &B->x3v, &B->dx3f);
+    B->rg[0] = make_recon_geom(0, m->xrat[0] != 1.0, B->nc1, B->is, B->ie, ng, B->x1f, B->x1v,
+                               B->dx1f, B->bw[0]);
+    B->rg[1] = make_recon_geom(1, m->xrat[1] != 1.0, B->nc2, B->js, B->je, ng, B->x2f, B->x2v,
+                               B->dx2f, B->bw[1]);
+    B->rg[2] = make_recon_geom(2, m->xrat[2] != 1.0, B->nc3, B->ks, B->ke, ng, B->x3f, B->x3v,
+                               B->dx3f, B->bw[2]);
     long ncc = (long)B->nc1*B->nc2*B->nc3;
     B->u = dalloc(NHYDRO*ncc); B->u1 = dalloc(NHYDRO*ncc); B->w = dalloc(NHYDRO*ncc);
     B->flux[0] = dalloc(NHYDRO*(long)B->nc3*B->nc2*(B->nc1+1));
@@ -361,6 +468,7 @@ void ao_destroy(AoMesh *m) {
       B->e1_x3f, B->e2_x3f, B->cc_e, B->s, B->s1, B->r, B->sflux[0], B->sflux[1],
       B->sflux[2]};
     for (size_t i = 0; i < sizeof(ptrs)/sizeof(ptrs[0]); ++i) free(ptrs[i]);
+    for (int d = 0; d < 3; ++d) { free(B->rg[d]); free(B->bw[d][0]); free(B->bw[d][1]); }
   }
   free(m->blk); free(m->gid_of); free(m);
 }
@@ -420,10 +528,9 @@ void ao_cons2prim(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int 
   for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
     double pb = 0.0;
     if (m->p.mhd) {
-      double lw = 0.5, rw = 0.5;
-      double bcc1 = lw*B->b[0][F1(B,k,j,i)] + rw*B->b[0][F1(B,k,j,i+1)];
-      double bcc2 = lw*B->b[1][F2(B,k,j,i)] + rw*B->b[1][F2(B,k,j+1,i)];
-      double bcc3 = lw*B->b[2][F3(B,k,j,i)] + rw*B->b[2][F3(B,k+1,j,i)];
+      double bcc1 = B->bw[0][0][i]*B->b[0][F1(B,k,j,i)] + B->bw[0][1][i]*B->b[0][F1(B,k,j,i+1)];
+      double bcc2 = B->bw[1][0][j]*B->b[1][F2(B,k,j,i)] + B->bw[1][1][j]*B->b[1][F2(B,k,j+1,i)];
+      double bcc3 = B->bw[2][0][k]*B->b[2][F3(B,k,j,i)] + B->bw[2][1][k]*B->b[2][F3(B,k+1,j,i)];
       B->bcc[CC(B,IB1,k,j,i)] = bcc1;
       B->bcc[CC(B,IB2,k,j,i)] = bcc2;
       B->bcc[CC(B,IB3,k,j,i)] = bcc3;
@@ -457,9 +564,9 @@ void ao_cons2prim(AoMesh *m, int b, int il, int iu, int jl, int ju, int kl, int 
 /* cell-centred field only (used by physical BCs, bvals.cpp:466-470) */
 static void calc_bcc(AoBlock *B, int il, int iu, int jl, int ju, int kl, int ku) {
   for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
-    B->bcc[CC(B,IB1,k,j,i)] = 0.5*B->b[0][F1(B,k,j,i)] + 0.5*B->b[0][F1(B,k,j,i+1)];
-    B->bcc[CC(B,IB2,k,j,i)] = 0.5*B->b[1][F2(B,k,j,i)] + 0.5*B->b[1][F2(B,k,j+1,i)];
-    B->bcc[CC(B,IB3,k,j,i)] = 0.5*B->b[2][F3(B,k,j,i)] + 0.5*B->b[2][F3(B,k+1,j,i)];
+    B->bcc[CC(B,IB1,k,j,i)] = B->bw[0][0][i]*B->b[0][F1(B,k,j,i)] + B->bw[0][1][i]*B->b[0][F1(B,k,j,i+1)];
+    B->bcc[CC(B,IB2,k,j,i)] = B->bw[1][0][j]*B->b[1][F2(B,k,j,i)] + B->bw[1][1][j]*B->b[1][F2(B,k,j+1,i)];
+    B->bcc[CC(B,IB3,k,j,i)] = B->bw[2][0][k]*B->b[2][F3(B,k,j,i)] + B->bw[2][1][k]*B->b[2][F3(B,k+1,j,i)];
   }
 }
 
@@ -569,18 +676,10 @@ static void recon_cell_char(const AoMesh *m, const AoBlock *B, int dir, int orde
     if (order == 2 && (o == -2 || o == 2)) continue;
     cell_state(m, B, dir, k+o*dk, j+o*dj, i+o*di, t); to_sweep(dir, t, st[o+2]);
   }
-  double wp = 0.0, wm = 0.0;
-  if (order == 2) {
-    const double *xf = dir == 0 ? B->x1f : (dir == 1 ? B->x2f : B->x3f);
-    const double *xv = dir == 0 ? B->x1v : (dir == 1 ? B->x2v : B->x3v);
-    const double *dxf = dir == 0 ? B->dx1f : (dir == 1 ? B->dx2f : B->dx3f);
-    int c = dir == 0 ? i : (dir == 1 ? j : k);
-    wp = (xf[c+1] - xv[c])/dxf[c];
-    wm = (xv[c] - xf[c])/dxf[c];
-    for (int n = 0; n < 7; ++n) { st[0][n] = 0.0; st[4][n] = 0.0; }
-  }
+  int c = dir == 0 ? i : (dir == 1 ? j : k);
+  if (order == 2) for (int n = 0; n < 7; ++n) { st[0][n] = 0.0; st[4][n] = 0.0; }
   (void)q; (void)nw;
-  ao_recon_char_point(order, mhd, st, bx, gamma, wp, wm, m->p.dfloor, m->p.pfloor, pl, mi);
+  ao_recon_char_point(order, mhd, st, bx, gamma, &B->rg[dir][c], m->p.dfloor, m->p.pfloor, pl, mi);
   from_sweep(dir, pl, plus);
   from_sweep(dir, mi, minus);
 }
@@ -599,21 +698,16 @@ static void recon_cell(const AoMesh *m, const AoBlock *B, int dir, int order, in
   double qm1[7], qp1[7];
   cell_state(m, B, dir, k-dk, j-dj, i-di, qm1);
   cell_state(m, B, dir, k+dk, j+dj, i+di, qp1);
+  const AoReconGeom *rg = &B->rg[dir][dir == 0 ? i : (dir == 1 ? j : k)];
   if (order == 2) {
-    const double *xf = dir == 0 ? B->x1f : (dir == 1 ? B->x2f : B->x3f);
-    const double *xv = dir == 0 ? B->x1v : (dir == 1 ? B->x2v : B->x3v);
-    const double *dxf = dir == 0 ? B->dx1f : (dir == 1 ? B->dx2f : B->dx3f);
-    int c = dir == 0 ? i : (dir == 1 ? j : k);
-    double wp = (xf[c+1] - xv[c])/dxf[c];
-    double wm = (xv[c] - xf[c])/dxf[c];
-    for (int n = 0; n < nw; ++n) ao_plm_point(qm1[n], q[n], qp1[n], wp, wm, &plus[n], &minus[n]);
+    for (int n = 0; n < nw; ++n) ao_plm_point_g(qm1[n], q[n], qp1[n], rg, &plus[n], &minus[n]);
     return;
   }
   double qm2[7], qp2[7];
   cell_state(m, B, dir, k-2*dk, j-2*dj, i-2*di, qm2);
   cell_state(m, B, dir, k+2*dk, j+2*dj, i+2*di, qp2);
   for (int n = 0; n < nw; ++n)
-    ao_ppm_point(qm2[n], qm1[n], q[n], qp1[n], qp2[n], &plus[n], &minus[n]);
+    ao_ppm_point_g(qm2[n], qm1[n], q[n], qp1[n], qp2[n], rg, &plus[n], &minus[n]);
   /* ApplyPrimitiveFloors on both (ppm.cpp:326-332) */
   plus[IDN] = (plus[IDN] > m->p.dfloor) ? plus[IDN] : m->p.dfloor;
   minus[IDN] = (minus[IDN] > m->p.dfloor) ? minus[IDN] : m->p.dfloor;
@@ -1451,18 +1545,13 @@ static void recon_scalar(const AoMesh *m, const AoBlock *B, int dir, int order, 
   double q = r[CC(B,n,k,j,i)];
   if (order == 1) { *plus = *minus = q; return; }
   double qm1 = r[CC(B,n,k-dk,j-dj,i-di)], qp1 = r[CC(B,n,k+dk,j+dj,i+di)];
+  const AoReconGeom *rg = &B->rg[dir][dir == 0 ? i : (dir == 1 ? j : k)];
   if (order == 2) {
-    const double *xf = dir == 0 ? B->x1f : (dir == 1 ? B->x2f : B->x3f);
-    const double *xv = dir == 0 ? B->x1v : (dir == 1 ? B->x2v : B->x3v);
-    const double *dxf = dir == 0 ? B->dx1f : (dir == 1 ? B->dx2f : B->dx3f);
-    int c = dir == 0 ? i : (dir == 1 ? j : k);
-    double wp = (xf[c+1] - xv[c])/dxf[c];
-    double wm = (xv[c] - xf[c])/dxf[c];
-    ao_plm_point(qm1, q, qp1, wp, wm, plus, minus);
+    ao_plm_point_g(qm1, q, qp1, rg, plus, minus);
     return;
   }
   double qm2 = r[CC(B,n,k-2*dk,j-2*dj,i-2*di)], qp2 = r[CC(B,n,k+2*dk,j+2*dj,i+2*di)];
-  ao_ppm_point(qm2, qm1, q, qp1, qp2, plus, minus);
+  ao_ppm_point_g(qm2, qm1, q, qp1, qp2, rg, plus, minus);
   /* EquationOfState::ApplyPassiveScalarFloors (eos_scalars.cpp:161-175) */
   *plus = (*plus > m->p.sfloor) ? *plus : m->p.sfloor;
   *minus = (*minus > m->p.sfloor) ? *minus : m->p.sfloor;

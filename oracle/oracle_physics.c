@@ -6,6 +6,7 @@
  */
 #include <math.h>
 #include <float.h>
+#include <string.h>
 #include "oracle_internal.h"
 
 /* std::min / std::max semantics: (b<a)?b:a and (a<b)?b:a */
@@ -1629,6 +1630,67 @@ void ao_ppm_point(double q_im2, double q_im1, double q, double q_ip1, double q_i
   *minus = qminus;
 }
 
+/* limited slope of one variable: uniform van Leer (plm.cpp:69-77) or the nonuniform branches.
+ * x1 (mode 1) multiplies by dx1f before dividing by dx1v (plm.cpp:85-86), x2 / x3 use the
+ * pre-divided ratios (plm.cpp:198-204,308-313); x3 keeps the original VL expression
+ * (plm.cpp:314-318), x1 / x2 the Mignone-corrected one (plm.cpp:94-96,207-209). */
+static double plm_slope_g(double dwl, double dwr, const AoReconGeom *g) {
+  double dwm;
+  if (g->mode == 0) {
+    double dw2 = dwl*dwr;
+    dwm = 2.0*dw2/(dwl + dwr);
+    if (dw2 <= 0.0) dwm = 0.0;
+    return dwm;
+  }
+  double dqF, dqB;
+  if (g->mode == 1) { dqF = dwr*g->dxf/g->dxv; dqB = dwl*g->dxf/g->dxvm; }
+  else { dqF = dwr*g->dxF; dqB = dwl*g->dxB; }
+  double dq2 = dqF*dqB;
+  if (g->mode == 3) dwm = 2.0*dq2/(dqF + dqB);
+  else dwm = (dq2*(g->cf*dqB + g->cb*dqF)/(SQR(dqB) + SQR(dqF) + dq2*(g->cf + g->cb - 2.0)));
+  if (dq2 <= 0.0) dwm = 0.0;
+  return dwm;
+}
+
+void ao_plm_point_g(double qm1, double q, double qp1, const AoReconGeom *g,
+                    double *plus, double *minus) {
+  double dwm = plm_slope_g(q - qm1, qp1 - q, g);
+  *plus = q + g->wp*dwm;
+  *minus = q - g->wm*dwm;
+}
+
+/* PPM, nonuniform Cartesian spacing: CW interface values with the per-cell weights, strict
+ * monotonicity (Mignone eq 45) and the Mignone limiter with h ratios = 2
+ * (ppm.cpp:111-129,196-207,282-300 and the x2 / x3 twins; reconstruction.cpp:412-419) */
+void ao_ppm_point_g(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,
+                    const AoReconGeom *g, double *plus, double *minus) {
+  if (g->mode == 0) { ao_ppm_point(q_im2, q_im1, q, q_ip1, q_ip2, plus, minus); return; }
+  double qa = (q - q_im1);
+  double qb = (q_ip1 - q);
+  double dd_im1 = g->c1m*qa + g->c2m*(q_im1 - q_im2);
+  double dd     = g->c1*qb + g->c2*qa;
+  double dd_ip1 = g->c1p*(q_ip2 - q_ip1) + g->c2p*qb;
+  double dph = (g->c3*q_im1 + g->c4*q) + (g->c5*dd_im1 + g->c6*dd);
+  double dph_ip1 = (g->c3p*q + g->c4p*q_ip1) + (g->c5p*dd + g->c6p*dd_ip1);
+  dph     = mn(dph, mx(q, q_im1));
+  dph_ip1 = mn(dph_ip1, mx(q, q_ip1));
+  dph     = mx(dph, mn(q, q_im1));
+  dph_ip1 = mx(dph_ip1, mn(q, q_ip1));
+  double qminus = dph, qplus = dph_ip1;
+  double dqf_minus = q - qminus;
+  double dqf_plus = qplus - q;
+  double e = dqf_minus*dqf_plus;
+  if (e <= 0.0) {
+    qminus = q;
+    qplus = q;
+  } else {
+    if (fabs(dqf_minus) >= 2.0*fabs(dqf_plus)) qminus = q - 2.0*dqf_plus;
+    if (fabs(dqf_plus) >= 2.0*fabs(dqf_minus)) qplus = q + 2.0*dqf_minus;
+  }
+  *plus = qplus;
+  *minus = qminus;
+}
+
 void ao_plm(long n, int nvar, const double *qm1, const double *q, const double *qp1,
             double wp, double wm, double *ql_plus, double *qr_minus) {
   for (long i = 0; i < (long)nvar*n; ++i)
@@ -1656,7 +1718,7 @@ void ao_ppm(long n, int nvar, const double *qm2, const double *qm1, const double
  * xorder = 2c: plm.cpp:62-66,107-130; xorder = 3c: ppm.cpp:66-75,311-332.  Eigenvectors of the
  * cell itself; floors re-applied to both face states. */
 void ao_recon_char_point(int order, int mhd, double st[5][7], double bx, double gamma,
-                         double wp, double wm, double dfloor, double pfloor, double *pl,
+                         const AoReconGeom *g, double dfloor, double pfloor, double *pl,
                          double *mi) {
   int nw = mhd ? 7 : 5;
   const double *q = st[2];
@@ -1665,13 +1727,9 @@ void ao_recon_char_point(int order, int mhd, double st[5][7], double bx, double 
     for (int n = 0; n < nw; ++n) { dwl[n] = (q[n] - st[1][n]); dwr[n] = (st[3][n] - q[n]); }
     ao_char_left(mhd, gamma, q, bx, dwl);
     ao_char_left(mhd, gamma, q, bx, dwr);
-    for (int n = 0; n < nw; ++n) {
-      double dw2 = dwl[n]*dwr[n];
-      dwm[n] = 2.0*dw2/(dwl[n] + dwr[n]);
-      if (dw2 <= 0.0) dwm[n] = 0.0;
-    }
+    for (int n = 0; n < nw; ++n) dwm[n] = plm_slope_g(dwl[n], dwr[n], g);
     ao_char_right(mhd, gamma, q, bx, dwm);
-    for (int n = 0; n < nw; ++n) { pl[n] = q[n] + wp*dwm[n]; mi[n] = q[n] - wm*dwm[n]; }
+    for (int n = 0; n < nw; ++n) { pl[n] = q[n] + g->wp*dwm[n]; mi[n] = q[n] - g->wm*dwm[n]; }
   } else {
     double c[5][7], w0[7];
     for (int n = 0; n < 7; ++n) w0[n] = q[n];
@@ -1680,7 +1738,7 @@ void ao_recon_char_point(int order, int mhd, double st[5][7], double bx, double 
       ao_char_left(mhd, gamma, w0, bx, c[o]);
     }
     for (int n = 0; n < nw; ++n)
-      ao_ppm_point(c[0][n], c[1][n], c[2][n], c[3][n], c[4][n], &pl[n], &mi[n]);
+      ao_ppm_point_g(c[0][n], c[1][n], c[2][n], c[3][n], c[4][n], g, &pl[n], &mi[n]);
     ao_char_right(mhd, gamma, w0, bx, pl);
     ao_char_right(mhd, gamma, w0, bx, mi);
   }
@@ -1698,7 +1756,10 @@ void ao_recon_char(int order, int mhd, long n, const double *q, const double *bx
   for (long i = 0; i < n; ++i) {
     double st[5][7], pl[7], mi[7];
     for (int o = 0; o < 5; ++o) for (int v = 0; v < 7; ++v) st[o][v] = q[(o*7 + v)*n + i];
-    ao_recon_char_point(order, mhd, st, mhd ? bx[i] : 0.0, gamma, wp, wm, dfloor, pfloor, pl, mi);
+    AoReconGeom g;
+    memset(&g, 0, sizeof(g));
+    g.wp = wp; g.wm = wm;
+    ao_recon_char_point(order, mhd, st, mhd ? bx[i] : 0.0, gamma, &g, dfloor, pfloor, pl, mi);
     for (int v = 0; v < nw; ++v) { plus[v*n + i] = pl[v]; minus[v*n + i] = mi[v]; }
   }
 }

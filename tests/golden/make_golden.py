@@ -200,6 +200,52 @@ CASES = {
     "khs3d_mhd_hlld_plm_vl2_8blk_s1": ("mhd_hlld_ng2_s1", "kh", "athinput.kh_scalar",
                                        dict({"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16},
                                             **mb(8, 8, 8)), "hlld", True, 4, 1),
+    # nonuniform (geometric) mesh spacing, mesh/x?rat != 1: mesh generator, dx?v, nonuniform
+    # PLM / PPM branches (plm.cpp:81-105, ppm.cpp:196-207,282-300, reconstruction.cpp:434-461)
+    # and the weighted cell-centred field (field.cpp:139-172)
+    "blast_nonuni_hlld_plm_vl2_8blk": ("mhd_hlld_ng2", "blast", "athinput.blast",
+                                       dict(BL, **mb(8, 8, 8), **{
+                                           "mesh/x1rat": 1.05, "mesh/x2rat": 0.96,
+                                           "mesh/x3rat": 1.03}), "hlld", True, 6),
+    "blast_nonuni_hlld_ppm_rk3_8blk": ("mhd_hlld_ng3", "blast", "athinput.blast",
+                                       dict(BL, **mb(8, 8, 8), **{
+                                           "mesh/x1rat": 0.95, "mesh/x2rat": 1.04,
+                                           "mesh/x3rat": 1.06, "time/xorder": 3,
+                                           "time/integrator": "rk3",
+                                           "mesh/ix1_bc": "reflecting", "mesh/ox1_bc": "outflow",
+                                           "mesh/ix3_bc": "outflow", "mesh/ox3_bc": "reflecting"}),
+                                       "hlld", True, 3),
+    "blast_nonuni_x2_hllc_plmc_vl2_8blk": ("hydro_hllc_ng2", "blast", "athinput.blast",
+                                           dict(BL, **mb(8, 8, 8), **{
+                                               "mesh/x2rat": 1.07, "time/xorder": "2c",
+                                               "mesh/ix2_bc": "outflow", "mesh/ox2_bc": "outflow"}),
+                                           "hllc", False, 6),
+    "ot_nonuni_hlld_ppmc_vl2_4blk": ("mhd_hlld_ng3", "orszag_tang", "athinput.orszag_tang",
+                                     dict(OT, **mb(16, 16), **{"time/xorder": "3c",
+                                                               "mesh/x1rat": 1.02,
+                                                               "mesh/x2rat": 0.97}),
+                                     "hlld", True, 5),
+    "sod_nonuni_hllc_plm_vl2_2blk": ("hydro_hllc_ng2", "shock_tube", "athinput.sod",
+                                     {"mesh/nx1": 64, "meshblock/nx1": 32, "mesh/x1rat": 1.03},
+                                     "hllc", False, 8),
+    "khs_nonuni_lhllc_plm_vl2_4blk_s1": ("hydro_lhllc_ng2_s1", "kh", "athinput.kh_scalar",
+                                         dict(KS, **mb(8, 16, 1), **{"mesh/x1rat": 1.04,
+                                                                     "mesh/x2rat": 0.98}),
+                                         "lhllc", False, 6, 1),
+    "khs3d_nonuni_hllc_ppm_rk3_8blk_s2": ("hydro_hllc_ng3_s2", "kh", "athinput.kh_scalar",
+                                          dict({"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16},
+                                               **mb(8, 8, 8), **{"time/xorder": 3,
+                                                                 "time/integrator": "rk3",
+                                                                 "mesh/x1rat": 1.03,
+                                                                 "mesh/x2rat": 1.05,
+                                                                 "mesh/x3rat": 0.95}),
+                                          "hllc", False, 3, 2),
+    "iso_blast_nonuni_mhd_hlld_plm_vl2_8blk": ("mhd_hlld_iso_ng2", "blast", "athinput.blast",
+                                               dict(BL, **mb(8, 8, 8),
+                                                    **{"hydro/iso_sound_speed": 0.4082482905,
+                                                       "problem/drat": 5.0, "mesh/x1rat": 1.05,
+                                                       "mesh/x3rat": 0.94}),
+                                               "hlld", True, 6, 0, "isothermal"),
 }
 
 
