@@ -8,13 +8,14 @@ import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("ab_kernels.cu", "ab_mesh.cu")]
-HDR = [os.path.join(HERE, "csrc", f) for f in ("ab_kernels.h", "ab_types.h", "ab_physics.cuh")] + \
+SRC = [os.path.join(HERE, "csrc", f) for f in ("ab_kernels.cu", "ab_flux_nu.cu", "ab_mesh.cu")]
+HDR = [os.path.join(HERE, "csrc", f) for f in ("ab_kernels.h", "ab_types.h", "ab_physics.cuh",
+                                               "ab_flux.cuh")] + \
       [os.path.join(os.path.dirname(HERE), "include", "athena_b200.h")]
 SO = os.path.join(HERE, "libathena_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-              "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]
 
 
 def needs_build():

@@ -1,0 +1,306 @@
+// ab_flux.cuh -- the Riemann-sweep kernel (Hydro::CalculateFluxes) as a template, shared by the
+// two translation units that instantiate it: ab_kernels.cu (uniform spacing, the production
+// path) and ab_flux_nu.cu (nonuniform spacing, mesh/x?rat != 1), compiled in parallel.
+#ifndef AB_FLUX_CUH_
+#define AB_FLUX_CUH_
+#include "ab_kernels.h"
+#include "ab_physics.cuh"
+
+namespace ab {
+
+extern long g_launches;
+
+// =============================================================================================
+// Hydro::CalculateFluxes: reconstruction + Riemann solver, one thread per interface.
+// hydro/calculate_fluxes.cpp:36-378; reconstruct/{dc,plm,ppm}.cpp; hydro/rsolvers/*
+// =============================================================================================
+
+// sweep-ordered primitives of one cell: (rho, v_dir, v_dir+1, v_dir+2, p [, B_dir+1, B_dir+2])
+// (32-bit element offsets: the host checks that every register has < 2^31 elements)
+template <int DIR, bool MHD, bool ISO = false>
+__device__ __forceinline__ void load_cell(const double *__restrict__ w,
+                                          const double *__restrict__ bcc, int o, int sv,
+                                          double *q) {
+  q[IDN] = w[o];
+  q[IVX] = w[o + (1 + DIR)*sv];
+  q[IVY] = w[o + (1 + (DIR+1)%3)*sv];
+  q[IVZ] = w[o + (1 + (DIR+2)%3)*sv];
+  q[IPR] = ISO ? 0.0 : w[o + 4*sv];       // isothermal: w has 4 variables, slot unused
+  if (MHD) {
+    q[IBY] = bcc[o + ((DIR+1)%3)*sv];
+    q[IBZ] = bcc[o + ((DIR+2)%3)*sv];
+  }
+}
+
+// 96 registers per thread (about 180 B of spills) with 18 single-warp CTAs per SM measured best
+// on B200 (profiles/r1_tuning_log.md): at 128-thread CTAs 3/4/5/6/8 CTAs per SM give
+// 1.27/1.10/1.05/1.06/1.37 ms per 256^3 HLLD+PLM sweep and the spill-free 144-register build
+// is 20 % slower; at equal registers, smaller CTAs (the warps of an SM start and stall on
+// their loads less in lockstep) and 18 instead of 20 warps take another 5 % off the sweeps.
+#ifndef AB_FLUX_BX
+#define AB_FLUX_BX 32
+#endif
+#ifndef AB_FLUX_MINB
+#define AB_FLUX_MINB 18
+#endif
+// x3 sweep: faces are visited strip by strip (AB_X3_STRIP rows of j, all k) so that the four
+// k-planes of the stencil stay in L2 between consecutive k (plane-major order re-read w/bcc
+// from DRAM: 19 GB instead of 8.8 GB per 512^3 sweep).
+#ifdef AB_FLUX_MAXREG
+#define AB_FLUX_BOUNDS __maxnreg__(AB_FLUX_MAXREG)
+#else
+#define AB_FLUX_BOUNDS __launch_bounds__(AB_FLUX_BX, AB_FLUX_MINB)
+#endif
+#ifndef AB_X3_STRIP
+#define AB_X3_STRIP 32
+#endif
+
+// The face range [i0,i0+ni) x [j0,j0+nj) x [k0,k0+nk) is flattened so that every thread of a
+// CTA has work (rows of nx1+1 faces do not pad to a multiple of the CTA width).
+template <int DIR, int ORDER, int SOLVER, bool MHD, bool NU>
+__global__ void AB_FLUX_BOUNDS
+k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
+       int ntot, double dt_val, const double *dt_ptr) {
+  constexpr int NW = MHD ? 7 : 5;
+  constexpr bool ISO = (SOLVER == SOLVER_HLLE_ISO || SOLVER == SOLVER_HLLD_ISO ||
+                        SOLVER == SOLVER_LLF_ISO);
+  int t = blockIdx.x*AB_FLUX_BX + threadIdx.x;
+  if (t >= ntot) return;
+  int i, j, k;
+  if (DIR == 2 && AB_X3_STRIP > 0) {
+    // strip-major: strip s of j-rows, then k, then j within the strip, then i
+    const int per_full = ni*AB_X3_STRIP*nk;
+    const int s = t / per_full;
+    int r = t - s*per_full;
+    int rows = nj - s*AB_X3_STRIP;
+    rows = rows < AB_X3_STRIP ? rows : AB_X3_STRIP;
+    const int per_k = ni*rows;
+    const int kk = r / per_k;
+    r -= kk*per_k;
+    const int jj = r / ni;
+    i = i0 + (r - jj*ni);
+    j = j0 + s*AB_X3_STRIP + jj;
+    k = k0 + kk;
+  } else {
+    int r = t / ni;
+    i = i0 + (t - r*ni);
+    const int kk = r / nj;
+    j = j0 + (r - kk*nj);
+    k = k0 + kk;
+  }
+  const int sv = b.nc3*b.nc2*b.nc1;
+  const int st = (DIR == 0) ? 1 : ((DIR == 1) ? b.nc1 : b.nc1*b.nc2);
+  const int oc = (k*b.nc2 + j)*b.nc1 + i;      // cell on the upper side of the face
+  const int c = (DIR == 0) ? i : ((DIR == 1) ? j : k);
+  const double *__restrict__ w = b.w;
+  const double *__restrict__ bcc = b.bcc;
+  // face-array offset and variable stride
+  int of, sf;
+  if (DIR == 0) { of = (k*b.nc2 + j)*(b.nc1+1) + i; sf = b.nc3*b.nc2*(b.nc1+1); }
+  else if (DIR == 1) { of = (k*(b.nc2+1) + j)*b.nc1 + i; sf = b.nc3*(b.nc2+1)*b.nc1; }
+  else { of = (k*b.nc2 + j)*b.nc1 + i; sf = (b.nc3+1)*b.nc2*b.nc1; }
+  // Every global load of the thread is issued here, ahead of the reconstruction, so that their
+  // latencies overlap (ncu: the face field / dt / dx loads used to sit right in front of their
+  // first use inside the Riemann solver and cost 10 % of the kernel in long-scoreboard stalls).
+  double bxi = 0.0, dt = 0.0, dxw = 0.0;
+  if (MHD) {
+    bxi = b.b[DIR][of];
+    dt = dt_ptr ? *dt_ptr : dt_val;
+    dxw = (DIR == 0) ? b.dx1f[i] : ((DIR == 1) ? b.dx2f[j] : b.dx3f[k]);
+  }
+
+  double wl[NW], wr[NW];
+  if (ORDER == 1) {
+    // DonorCell (reconstruct/dc.cpp)
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, wl);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, wr);
+  } else if (ORDER == 2) {
+    double qm2[NW], qm1[NW], q0[NW], qp1[NW];
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + st, sv, qp1);
+    const double wp_l = g.wp[DIR][c-1], wm_l = g.wm[DIR][c-1];
+    const double wp_r = g.wp[DIR][c], wm_r = g.wm[DIR][c];
+    const double *tl = NU ? g.nu[DIR] + (c-1)*NUG : nullptr;   // geometry rows of the two cells
+#pragma unroll
+    for (int n = 0; n < NW; ++n) {
+      double dummy;
+      if (NU) {
+        plm_nu<DIR+1>(qm2[n], qm1[n], q0[n], wp_l, wm_l, tl, wl[n], dummy);
+        plm_nu<DIR+1>(qm1[n], q0[n], qp1[n], wp_r, wm_r, tl + NUG, dummy, wr[n]);
+      } else {
+        plm(qm2[n], qm1[n], q0[n], wp_l, wm_l, wl[n], dummy);
+        plm(qm1[n], q0[n], qp1[n], wp_r, wm_r, dummy, wr[n]);
+      }
+    }
+  } else if (ORDER == 4) {
+    // xorder = 2c: PLM on characteristic variables (reconstruct/characteristic.cpp); the
+    // eigenvectors need the cell-centred field along the sweep of the two cells
+    double qm2[NW], qm1[NW], q0[NW], qp1[NW], dummy[NW];
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + st, sv, qp1);
+    const double bxl = MHD ? bcc[oc - st + DIR*sv] : 0.0, bxr = MHD ? bcc[oc + DIR*sv] : 0.0;
+    const double *tl = NU ? g.nu[DIR] + (c-1)*NUG : nullptr;
+    plm_char<MHD,(NU ? DIR+1 : 0)>(qm2, qm1, q0, bxl, p.gamma, g.wp[DIR][c-1], g.wm[DIR][c-1],
+                                   p.dfloor, p.pfloor, wl, dummy, tl);
+    plm_char<MHD,(NU ? DIR+1 : 0)>(qm1, q0, qp1, bxr, p.gamma, g.wp[DIR][c], g.wm[DIR][c],
+                                   p.dfloor, p.pfloor, dummy, wr, tl + NUG);
+  } else if (ORDER == 5) {
+    // xorder = 3c: PPM on characteristic variables
+    double qm3[NW], qm2[NW], qm1[NW], q0[NW], qp1[NW], qp2[NW], dummy[NW];
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 3*st, sv, qm3);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + st, sv, qp1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + 2*st, sv, qp2);
+    const double bxl = MHD ? bcc[oc - st + DIR*sv] : 0.0, bxr = MHD ? bcc[oc + DIR*sv] : 0.0;
+    const double *tl = NU ? g.nu[DIR] + (c-1)*NUG : nullptr;
+    ppm_char<MHD,NU>(qm3, qm2, qm1, q0, qp1, bxl, p.gamma, p.dfloor, p.pfloor, wl, dummy, tl);
+    ppm_char<MHD,NU>(qm2, qm1, q0, qp1, qp2, bxr, p.gamma, p.dfloor, p.pfloor, dummy, wr,
+                     tl + NUG);
+  } else {
+    double qm3[NW], qm2[NW], qm1[NW], q0[NW], qp1[NW], qp2[NW];
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 3*st, sv, qm3);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - 2*st, sv, qm2);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, qm1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, q0);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + st, sv, qp1);
+    load_cell<DIR,MHD,ISO>(w, bcc, oc + 2*st, sv, qp2);
+    const double *tl = NU ? g.nu[DIR] + (c-1)*NUG : nullptr;
+#pragma unroll
+    for (int n = 0; n < NW; ++n) {
+      double dummy;
+      if (NU) {
+        ppm_nu(qm3[n], qm2[n], qm1[n], q0[n], qp1[n], tl, wl[n], dummy);
+        ppm_nu(qm2[n], qm1[n], q0[n], qp1[n], qp2[n], tl + NUG, dummy, wr[n]);
+      } else {
+        ppm(qm3[n], qm2[n], qm1[n], q0[n], qp1[n], wl[n], dummy);
+        ppm(qm2[n], qm1[n], q0[n], qp1[n], qp2[n], dummy, wr[n]);
+      }
+    }
+    // ApplyPrimitiveFloors (ppm.cpp:326-332)
+    wl[IDN] = (wl[IDN] > p.dfloor) ? wl[IDN] : p.dfloor;
+    wr[IDN] = (wr[IDN] > p.dfloor) ? wr[IDN] : p.dfloor;
+    if (!ISO) {
+      wl[IPR] = (wl[IPR] > p.pfloor) ? wl[IPR] : p.pfloor;
+      wr[IPR] = (wr[IPR] > p.pfloor) ? wr[IPR] : p.pfloor;
+    }
+  }
+
+  // LHLLC / LHLLD shock detector inputs: Hydro::CalculateVelocityDifferences
+  // (hydro/calculate_velocity_differences.cpp:20-90); dvt stays 0 in 1-D
+  double dvn = 0.0, dvt = 0.0;
+  if (SOLVER == SOLVER_LHLLC || SOLVER == SOLVER_LHLLD) {
+    const int ol = oc - st;                       // lower cell of the interface
+    dvn = w[oc + (1 + DIR)*sv] - w[ol + (1 + DIR)*sv];
+    if (b.f2) {
+      bool first = true;
+#pragma unroll
+      for (int t = 1; t <= 2; ++t) {
+        const int td = (DIR + t) % 3;             // transverse direction, reference order
+        if (td == 2 && !b.f3) continue;
+        const int ts = (td == 0) ? 1 : ((td == 1) ? b.nc1 : b.nc1*b.nc2);
+        const double *__restrict__ wt = w + (1 + td)*sv;
+        double dl = dmin(wt[ol + ts] - wt[ol], wt[ol] - wt[ol - ts]);
+        double dr = dmin(wt[oc + ts] - wt[oc], wt[oc] - wt[oc - ts]);
+        double v = dmin(dl, dr);
+        dvt = first ? v : dmin(dvt, v);
+        first = false;
+      }
+    }
+  }
+  double f[NW];
+  riemann<SOLVER,MHD>(wl, wr, bxi, ISO ? p.iso_cs : p.gamma, dvn, dvt, f, p.dfloor);
+
+  double *__restrict__ flx = b.flux[DIR];
+  flx[of] = f[IDN];
+  flx[of + (1 + DIR)*sf] = f[IVX];
+  flx[of + (1 + (DIR+1)%3)*sf] = f[IVY];
+  flx[of + (1 + (DIR+2)%3)*sf] = f[IVZ];
+  if (!ISO) flx[of + 4*sf] = f[IEN];
+  if (MHD) {
+    b.ef[DIR][0][of] = -f[IBY];
+    b.ef[DIR][1][of] = f[IBZ];
+    b.wght[DIR][of] = weight_for_ct(f[IDN], wl[IDN], wr[IDN], dxw, dt);
+  }
+}
+
+template <int DIR, int ORDER, int SOLVER, bool MHD, bool NU>
+static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, double dt_val,
+                     const double *dt_ptr, cudaStream_t s) {
+  int is = b.is, ie = b.ie, js = b.js, je = b.je, ks = b.ks, ke = b.ke;
+  int i0, i1, j0, j1, k0, k1;
+  // loop limits of calculate_fluxes.cpp:62-74,164-173,273-279
+  if (DIR == 0) {
+    i0 = is; i1 = ie+1; j0 = js; j1 = je; k0 = ks; k1 = ke;
+    if (MHD && b.f2) { j0 = js-1; j1 = je+1; if (b.f3) { k0 = ks-1; k1 = ke+1; } }
+  } else if (DIR == 1) {
+    i0 = is-1; i1 = ie+1; j0 = js; j1 = je+1; k0 = ks; k1 = ke;
+    if (MHD && b.f3) { k0 = ks-1; k1 = ke+1; }
+  } else {
+    i0 = is; i1 = ie; j0 = js; j1 = je; k0 = ks; k1 = ke+1;
+    if (MHD) { i0 = is-1; i1 = ie+1; j0 = js-1; j1 = je+1; }
+  }
+  int ni = i1-i0+1, nj = j1-j0+1, nk = k1-k0+1;
+  int ntot = ni*nj*nk;
+  k_flux<DIR,ORDER,SOLVER,MHD,NU><<<(ntot + AB_FLUX_BX - 1)/AB_FLUX_BX, AB_FLUX_BX, 0, s>>>(
+      b, g, p, i0, ni, j0, nj, k0, nk, ntot, dt_val, dt_ptr); ++g_launches;
+}
+
+template <int ORDER, int SOLVER, bool MHD, bool NU>
+static void flux_all(const BlkDev &b, const ReconGeom &g, const Params &p, int dir,
+                     double dt_val, const double *dt_ptr, cudaStream_t s) {
+  if (dir == 0) flux_dir<0,ORDER,SOLVER,MHD,NU>(b, g, p, dt_val, dt_ptr, s);
+  else if (dir == 1) flux_dir<1,ORDER,SOLVER,MHD,NU>(b, g, p, dt_val, dt_ptr, s);
+  else flux_dir<2,ORDER,SOLVER,MHD,NU>(b, g, p, dt_val, dt_ptr, s);
+}
+
+template <int SOLVER, bool MHD, bool NU>
+static void flux_order(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
+                       double dt_val, const double *dt_ptr, cudaStream_t s) {
+  // order 4 / 5 = xorder 2c / 3c (characteristic variables; adiabatic EOS only)
+  constexpr bool ISO = (SOLVER == SOLVER_HLLE_ISO || SOLVER == SOLVER_HLLD_ISO ||
+                        SOLVER == SOLVER_LLF_ISO);
+  if (order > 1 && p.char_proj && !ISO) order += 2;
+  if (order == 1) {   // donor cell has no geometry: uniform instantiation only
+    if constexpr (!NU) flux_all<1,SOLVER,MHD,false>(b, g, p, dir, dt_val, dt_ptr, s);
+  } else if (order == 2) flux_all<2,SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s);
+  else if (order == 3) flux_all<3,SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s);
+  else if (order == 4) flux_all<(ISO ? 2 : 4),SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s);
+  else flux_all<(ISO ? 3 : 5),SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s);
+}
+
+template <bool NU>
+static void launch_flux_dir_t(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
+                              int dir, double dt_val, const double *dt_ptr, cudaStream_t s) {
+  if (p.solver == SOLVER_LLF) {   // --flux=llf, either EOS
+    if (p.eos != 0) {
+      if (p.mhd) flux_order<SOLVER_LLF_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+      else flux_order<SOLVER_LLF_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    } else {
+      if (p.mhd) flux_order<SOLVER_LLF,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+      else flux_order<SOLVER_LLF,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    }
+  } else if (p.eos != 0) {   // isothermal: hlle (hydro), hlle / hlld (MHD) -- configure.py:299-325
+    if (!p.mhd) flux_order<SOLVER_HLLE_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else flux_order<SOLVER_HLLE_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+  } else if (p.mhd) {
+    if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_LHLLD) flux_order<SOLVER_LHLLD,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else flux_order<SOLVER_ROE,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+  } else {
+    if (p.solver == SOLVER_HLLC) flux_order<SOLVER_HLLC,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_LHLLC) flux_order<SOLVER_LHLLC,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    else flux_order<SOLVER_ROE,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+  }
+}
+
+}  // namespace ab
+#endif

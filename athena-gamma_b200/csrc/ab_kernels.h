@@ -8,7 +8,11 @@ namespace ab {
 
 // per-direction PLM face weights precomputed on the host with the reference's expression
 // (x?f(i+1)-x?v(i))/dx?f(i) and (x?v(i)-x?f(i))/dx?f(i)  (reconstruct/plm.cpp:114-119)
-struct ReconGeom { const double *wp[3]; const double *wm[3]; };
+// nu[dir]: nullptr for uniform spacing, else the per-index table of the nonuniform PLM / PPM
+// branches (NUG doubles per cell index, ab_physics.cuh); bcw: nullptr when every direction is
+// uniform, else the CalculateCellCenteredField weights lw, rw of x1, x2, x3 back to back
+// (field/field.cpp:139-172)
+struct ReconGeom { const double *wp[3]; const double *wm[3]; const double *nu[3]; };
 
 // `dt_ptr` (device) wins over `dt_val` when non-null: the cycle loop keeps dt on the device.
 // flags bit0: also write cc_e; bit1: also reduce NewBlockTimeStep over active cells into dtmin
@@ -20,6 +24,8 @@ void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, in
                      cudaStream_t s);
 void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
                    double dt_val, const double *dt_ptr, cudaStream_t s);
+void launch_flux_dir_nu(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
+                        double dt_val, const double *dt_ptr, cudaStream_t s);
 void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
                      double dt_val, const double *dt_ptr, cudaStream_t s);
 // have_cc_e: cc_e was already written by cons2prim (flags bit0) over [is-1,ie+1]^dim

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <array>
 #include <map>
 #include <string>
@@ -92,6 +93,28 @@ double uniform_gen(double x, double xmin, double xmax) {
   return 0.5*(xmin + xmax) + (x*xmax - x*xmin);
 }
 
+// DefaultMeshGeneratorX1..3 (src/mesh/mesh.hpp:411-455): geometric spacing with cell-size ratio
+// `rat`, logical x in [0,1]; used in a direction whose mesh/x?rat != 1
+// (Mesh::use_uniform_meshgen_fn_, mesh/mesh.cpp:278-289)
+double ratio_gen(double x, double xmin, double xmax, double rat, int nx) {
+  double lw, rw;
+  if (rat == 1.0) {
+    rw = x; lw = 1.0 - x;
+  } else {
+    double ratn = std::pow(rat, nx);
+    double rnx = std::pow(rat, x*nx);
+    lw = (rnx - ratn)/(1.0 - ratn);
+    rw = 1.0 - lw;
+  }
+  return xmin*lw + xmax*rw;
+}
+// logical block / face position -> coordinate (mesh.cpp:1679-1688, coordinates.cpp:100-145)
+double gen_x(long index, long nrange, double xmin, double xmax, double rat, int nx) {
+  if (rat != 1.0)
+    return ratio_gen(static_cast<double>(index)/static_cast<double>(nrange), xmin, xmax, rat, nx);
+  return uniform_gen(mesh_gen_x(index, nrange), xmin, xmax);
+}
+
 struct Nb {
   int ox1, ox2, ox3, type;   // 0 face, 1 edge, 2 corner
   int gid, rank, bufid, targetid, fid, eid;
@@ -142,6 +165,7 @@ struct AbMesh {
   int ndim = 1, f2 = 0, f3 = 0;
   int nh = 5;                             // NHYDRO: 5 adiabatic, 4 isothermal
   int nrb[3] = {1, 1, 1};
+  double xrat[3] = {1.0, 1.0, 1.0};       // mesh/x?rat (0 read as 1; 1 in a degenerate direction)
   int nbtotal = 0;
   int nc[3] = {1, 1, 1}, is = 0, ie = 0, js = 0, je = 0, ks = 0, ke = 0;
   std::vector<HostBlock> hb;              // all blocks of the mesh (every rank knows them)
@@ -434,9 +458,9 @@ void build_block_list(AbMesh *m) {
         continue;
       }
       if (B.lx[d] == 0) { B.bmin[d] = mmin[d]; B.bcs[2*d] = p.bc[2*d]; }
-      else { B.bmin[d] = uniform_gen(mesh_gen_x(B.lx[d], m->nrb[d]), mmin[d], mmax[d]); B.bcs[2*d] = -1; }
+      else { B.bmin[d] = gen_x(B.lx[d], m->nrb[d], mmin[d], mmax[d], m->xrat[d], nxm[d]); B.bcs[2*d] = -1; }
       if (B.lx[d] == m->nrb[d] - 1) { B.bmax[d] = mmax[d]; B.bcs[2*d+1] = p.bc[2*d+1]; }
-      else { B.bmax[d] = uniform_gen(mesh_gen_x(B.lx[d] + 1, m->nrb[d]), mmin[d], mmax[d]); B.bcs[2*d+1] = -1; }
+      else { B.bmax[d] = gen_x(B.lx[d] + 1, m->nrb[d], mmin[d], mmax[d], m->xrat[d], nxm[d]); B.bcs[2*d+1] = -1; }
     }
   }
   // canonical neighbour enumeration = buffer ids (bvals/bvals_base.cpp:153-256)
@@ -521,10 +545,11 @@ void build_block_list(AbMesh *m) {
   }
 }
 
-// Coordinates ctor (uniform branch, coordinates.cpp:125-145) + Cartesian x?v (cartesian.cpp:25-75)
+// Coordinates ctor (coordinates.cpp:92-160: uniform branch, or the mesh-generator branch with
+// dx?f = face differences when x?rat != 1) + Cartesian x?v (cartesian.cpp:25-75)
 void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, double mmax, double bmin,
-                 double bmax, int nc, bool refl_in, bool refl_out, std::vector<double> &xf,
-                 std::vector<double> &xv, std::vector<double> &dxf) {
+                 double bmax, int nc, bool refl_in, bool refl_out, double rat,
+                 std::vector<double> &xf, std::vector<double> &xv, std::vector<double> &dxf) {
   xf.assign(nc + 1, 0.0); xv.assign(nc, 0.0); dxf.assign(nc, 0.0);
   if (nc == 1) {
     dxf[0] = bmax - bmin;
@@ -536,11 +561,11 @@ void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, double mmax,
   double dx = (bmax - bmin)/(iu - il + 1);
   for (int i = il - ng; i <= iu + ng + 1; ++i) {
     long noffset = (long)(i - il) + lx*bx;
-    xf[i] = uniform_gen(mesh_gen_x(noffset, nx_mesh), mmin, mmax);
+    xf[i] = gen_x(noffset, nx_mesh, mmin, mmax, rat, nx_mesh);
   }
   xf[il] = bmin;
   xf[iu+1] = bmax;
-  for (int i = il - ng; i <= iu + ng; ++i) dxf[i] = dx;
+  for (int i = il - ng; i <= iu + ng; ++i) dxf[i] = (rat != 1.0) ? xf[i+1] - xf[i] : dx;
   // reflecting boundaries mirror the ghost-zone spacing (coordinates.cpp:147-160)
   if (refl_in) for (int i = 1; i <= ng; ++i) {
     dxf[il-i] = dxf[il+i-1];
@@ -551,6 +576,52 @@ void make_coords(int nx_mesh, int bx, int ng, long lx, double mmin, double mmax,
     xf[iu+i+1] = xf[iu+i] + dxf[iu+i];
   }
   for (int i = il - ng; i <= iu + ng; ++i) xv[i] = 0.5*(xf[i+1] + xf[i]);
+}
+
+// Geometry of the nonuniform reconstruction along one direction (x?rat != 1): NUG doubles per
+// cell index (layout: ab_physics.cuh) -- the factors plm.cpp:85-93,198-204,308-313 evaluate on
+// the fly from dx?f, dx?v (= differences of x?v, cartesian.cpp:31-75) and the PPM weights of the
+// Reconstruction ctor (reconstruction.cpp:434-461; the x2 / x3 loops :559-582,609-631 start one
+// index later than x1's, entries outside keep NewAthenaArray's zero) -- and the
+// CalculateCellCenteredField weights (field.cpp:139-172).
+void make_recon_table(int dir, int nc, int s, int e, int ng, const std::vector<double> &xf,
+                      const std::vector<double> &xv, const std::vector<double> &dxf,
+                      std::vector<double> &tab, std::vector<double> &lw, std::vector<double> &rw) {
+  tab.assign((size_t)nc*ab::NUG, 0.0);
+  lw.assign(nc, 0.5); rw.assign(nc, 0.5);
+  std::vector<double> dxv(nc, 0.0);
+  for (int i = s - ng; i <= e + ng - 1; ++i) dxv[i] = xv[i+1] - xv[i];
+  for (int i = 0; i < nc; ++i) {
+    double *t = &tab[(size_t)i*ab::NUG];
+    const double dvm = (i > 0) ? dxv[i-1] : 0.0;
+    t[0] = dxf[i]; t[1] = dxv[i]; t[2] = dvm;
+    t[3] = dxv[i]/(xf[i+1] - xv[i]);         // cf (Mignone eq 33)
+    t[4] = dvm/(xv[i] - xf[i]);              // cb
+    t[5] = dxf[i]/dxv[i];
+    t[6] = dxf[i]/dvm;
+    lw[i] = (xf[i+1] - xv[i])/dxf[i];
+    rw[i] = (xv[i] - xf[i])/dxf[i];
+  }
+  const int first = (dir == 0) ? s - ng + 1 : s - ng + 2;
+  for (int i = first; i <= e + ng - 1; ++i) {
+    double *t = &tab[(size_t)i*ab::NUG];
+    const double dm1 = dxf[i-1], d0 = dxf[i], dp1 = dxf[i+1];
+    const double qe = d0/(dm1 + d0 + dp1);               // CW eq 1.7
+    t[7] = qe*(2.0*dm1+d0)/(dp1 + d0);
+    t[8] = qe*(2.0*dp1+d0)/(dm1 + d0);
+    if (i > s - ng + 1) {
+      const double dm2 = dxf[i-2];
+      const double qa = dm2 + dm1 + d0 + dp1;
+      double qb = dm1/(dm1 + d0);
+      const double qc = (dm2 + dm1)/(2.0*dm1 + d0);
+      const double qd = (dp1 + d0)/(2.0*d0 + dm1);
+      qb = qb + 2.0*d0*qb/qa*(qc-qd);
+      t[9] = 1.0 - qb;
+      t[10] = qb;
+      t[11] = d0/qa*qd;
+      t[12] = -dm1/qa*qc;
+    }
+  }
 }
 
 long reg_size(const AbMesh *m, int reg) {
@@ -631,23 +702,35 @@ int alloc_blocks(AbMesh *m) {
     long ncc = (long)m->nc[0]*m->nc[1]*m->nc[2];
     size_t cce = p.mhd ? align256(3*ncc*8) : 0;
     tot += cce;
-    // coordinates: 9 arrays + 6 PLM weight arrays
-    std::vector<double> xf[3], xv[3], dxf[3], wp[3], wm[3];
+    // coordinates: 9 arrays + 6 PLM weight arrays (+ the nonuniform-spacing tables)
+    std::vector<double> xf[3], xv[3], dxf[3], wp[3], wm[3], nutab[3], bcw;
+    bool any_nu = false;
     const double mmin[3] = {p.x1min, p.x2min, p.x3min}, mmax[3] = {p.x1max, p.x2max, p.x3max};
     const int nxm[3] = {p.nx1, p.nx2, p.nx3}, bxs[3] = {p.bx1, p.bx2, p.bx3};
     for (int dd = 0; dd < 3; ++dd) {
       make_coords(nxm[dd], bxs[dd], ng, B.lx[dd], mmin[dd], mmax[dd], B.bmin[dd], B.bmax[dd],
                   m->nc[dd], B.bcs[2*dd] == AB_BC_REFLECT, B.bcs[2*dd+1] == AB_BC_REFLECT,
-                  xf[dd], xv[dd], dxf[dd]);
+                  m->xrat[dd], xf[dd], xv[dd], dxf[dd]);
       wp[dd].assign(m->nc[dd], 0.0); wm[dd].assign(m->nc[dd], 0.0);
       for (int c = 0; c < m->nc[dd]; ++c) {   // plm.cpp:114-119 / 226-227 / 332-333
         wp[dd][c] = (xf[dd][c+1] - xv[dd][c])/dxf[dd][c];
         wm[dd][c] = (xv[dd][c] - xf[dd][c])/dxf[dd][c];
       }
+      std::vector<double> lw(m->nc[dd], 0.5), rw(m->nc[dd], 0.5);
+      if (m->xrat[dd] != 1.0) {
+        const int s0[3] = {m->is, m->js, m->ks}, e0[3] = {m->ie, m->je, m->ke};
+        make_recon_table(dd, m->nc[dd], s0[dd], e0[dd], ng, xf[dd], xv[dd], dxf[dd], nutab[dd],
+                         lw, rw);
+        any_nu = true;
+      }
+      bcw.insert(bcw.end(), lw.begin(), lw.end());
+      bcw.insert(bcw.end(), rw.begin(), rw.end());
     }
     size_t coord_bytes = 0;
     for (int dd = 0; dd < 3; ++dd)
-      coord_bytes += align256((m->nc[dd]+1)*8) + 4*align256(m->nc[dd]*8);
+      coord_bytes += align256((m->nc[dd]+1)*8) + 4*align256(m->nc[dd]*8) +
+                     align256(nutab[dd].size()*8);
+    if (any_nu) coord_bytes += align256(bcw.size()*8);
     tot += coord_bytes;
     // EMF send buffers for every face / edge (used for same-rank neighbours)
     size_t emf_elems = 0;
@@ -691,6 +774,8 @@ int alloc_blocks(AbMesh *m) {
     d.x1v = put(xv[0], 3); d.x2v = put(xv[1], 4); d.x3v = put(xv[2], 5);
     d.dx1f = put(dxf[0], 6); d.dx2f = put(dxf[1], 7); d.dx3f = put(dxf[2], 8);
     for (int dd = 0; dd < 3; ++dd) { L.g.wp[dd] = put(wp[dd], -1); L.g.wm[dd] = put(wm[dd], -1); }
+    for (int dd = 0; dd < 3; ++dd) L.g.nu[dd] = nutab[dd].empty() ? nullptr : put(nutab[dd], -1);
+    d.bcw = any_nu ? put(bcw, -1) : nullptr;
     CK(cudaStreamSynchronize(m->stream));   // host vectors go out of scope
     L.emf_send = (double *)carve(emf_elems*8);
     L.dtmin = m->dtmin + l*ab::DT_SLOTS;
@@ -1522,6 +1607,9 @@ static void host_setup(AbMesh *m, const AbMeshParams *p) {
   m->kp.sfloor = m->p.sfloor;
   m->kp.eos = p->eos; m->kp.iso_cs = p->iso_sound_speed;
   m->kp.char_proj = p->char_proj;
+  const int nxd[3] = {p->nx1, p->nx2, p->nx3};
+  for (int d = 0; d < 3; ++d)
+    m->xrat[d] = (p->xrat[d] == 0.0 || nxd[d] == 1) ? 1.0 : p->xrat[d];
   m->nh = (p->eos == AB_EOS_ISOTHERMAL) ? 4 : 5;     // configure.py:374-377
   int ng = p->nghost;
   // MeshBlock index ranges (mesh/meshblock.cpp:55-80)
@@ -1603,6 +1691,35 @@ int ab_download(AbMesh *m, int lid, int reg, double *host) {
   CK(cudaMemcpyAsync(host, *slot, L.regsize[reg]*8, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
   return AB_OK;
+}
+
+// Host-computed geometry of local block `lid` along direction dir (0..2), no device needed:
+// what 0 x?f (nc+1), 1 x?v, 2 dx?f, 3 / 4 PLM face weights wp / wm, 5 nonuniform-reconstruction
+// table (nc*13, only when x?rat != 1), 6 / 7 cell-centred-field weights lw / rw.
+// Returns the number of doubles (also when out == NULL), 0 when that array does not exist.
+int ab_plan_geometry(const AbMesh *m, int lid, int dir, int what, double *out, int max_n) {
+  if (!m || lid < 0 || lid >= (int)m->lb_hb.size() || dir < 0 || dir > 2 || what < 0 || what > 7)
+    return fail(AB_ERR_ARG, "bad argument");
+  const HostBlock &B = *m->lb_hb[lid];
+  const AbMeshParams &p = m->p;
+  const double mmin[3] = {p.x1min, p.x2min, p.x3min}, mmax[3] = {p.x1max, p.x2max, p.x3max};
+  const int nxm[3] = {p.nx1, p.nx2, p.nx3}, bxs[3] = {p.bx1, p.bx2, p.bx3};
+  const int s0[3] = {m->is, m->js, m->ks}, e0[3] = {m->ie, m->je, m->ke};
+  const int nc = m->nc[dir];
+  std::vector<double> xf, xv, dxf, tab, lw(nc, 0.5), rw(nc, 0.5), wp(nc), wm(nc);
+  make_coords(nxm[dir], bxs[dir], p.nghost, B.lx[dir], mmin[dir], mmax[dir], B.bmin[dir],
+              B.bmax[dir], nc, B.bcs[2*dir] == AB_BC_REFLECT, B.bcs[2*dir+1] == AB_BC_REFLECT,
+              m->xrat[dir], xf, xv, dxf);
+  for (int c = 0; c < nc; ++c) {
+    wp[c] = (xf[c+1] - xv[c])/dxf[c];
+    wm[c] = (xv[c] - xf[c])/dxf[c];
+  }
+  if (m->xrat[dir] != 1.0)
+    make_recon_table(dir, nc, s0[dir], e0[dir], p.nghost, xf, xv, dxf, tab, lw, rw);
+  const std::vector<double> *src[8] = {&xf, &xv, &dxf, &wp, &wm, &tab, &lw, &rw};
+  const std::vector<double> &v = *src[what];
+  if (out) for (size_t i = 0; i < v.size() && (int)i < max_n; ++i) out[i] = v[i];
+  return (int)v.size();
 }
 
 int ab_download_coord(AbMesh *m, int lid, int which, double *host) {

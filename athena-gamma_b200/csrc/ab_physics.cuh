@@ -13,6 +13,7 @@
 #define AB_PHYSICS_CUH_
 
 #include <math.h>
+#include "ab_types.h"
 
 #if defined(__CUDACC__)
 #define AB_HD __host__ __device__ __forceinline__
@@ -268,22 +269,84 @@ AB_HD void char_right(double gamma, const double *w, double bx, double *vect) {
   }
 }
 
+// ---- nonuniform (geometric, mesh/x?rat != 1) spacing -----------------------------------------
+// Row `t` of the per-index geometry table the host builds (ab_mesh.cu: make_recon_table), NUG
+// doubles per cell index along the sweep: dxf, dxv(i), dxv(i-1), cf, cb, dxf/dxv(i),
+// dxf/dxv(i-1), c1..c6.  MODE = 1 + sweep direction: the three reference routines differ in
+// rounding order (x1 multiplies by dx1f, then divides by dx1v: plm.cpp:85-86; x2 / x3 use the
+// pre-divided ratios: plm.cpp:198-204,308-313) and x3 keeps the original van Leer expression
+// (plm.cpp:314-318) where x1 / x2 use Mignone's (plm.cpp:94-96,207-209).  MODE 0 = uniform.
+template <int MODE>
+AB_HD double plm_slope(double dwl, double dwr, const double *t) {
+  double dwm = 0.0;
+  if (MODE == 0) {
+    double dw2 = dwl*dwr;
+    if (dw2 > 0.0) dwm = 2.0*dw2/(dwl + dwr);
+    return dwm;
+  }
+  double dqF, dqB;
+  if (MODE == 1) { dqF = dwr*t[0]/t[1]; dqB = dwl*t[0]/t[2]; }
+  else { dqF = dwr*t[5]; dqB = dwl*t[6]; }
+  double dq2 = dqF*dqB;
+  if (dq2 > 0.0) {
+    if (MODE == 3) dwm = 2.0*dq2/(dqF + dqB);
+    else dwm = (dq2*(t[3]*dqB + t[4]*dqF)/(sqr(dqB) + sqr(dqF) + dq2*(t[3] + t[4] - 2.0)));
+  }
+  return dwm;
+}
+
+template <int MODE>
+AB_HD void plm_nu(double qm1, double q, double qp1, double wp, double wm, const double *t,
+                  double &plus, double &minus) {
+  double dwm = plm_slope<MODE>(q - qm1, qp1 - q, t);
+  plus = q + wp*dwm;
+  minus = q - wm*dwm;
+}
+
+// PPM with nonuniform Cartesian spacing (ppm.cpp:111-129,196-207,282-300 and the x2 / x3 twins):
+// CW84 interface values with the per-cell weights of reconstruction.cpp:434-461, strict
+// monotonicity (Mignone eq 45), Mignone's parabola limiter with h ratios 2
+// (reconstruction.cpp:412-419).  t = table row of the cell; rows of i-1 / i+1 are adjacent.
+AB_HD void ppm_nu(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,
+                  const double *t, double &plus, double &minus) {
+  const double *tm = t - NUG, *tp = t + NUG;
+  double qa = (q - q_im1);
+  double qb = (q_ip1 - q);
+  double dd_im1 = tm[7]*qa + tm[8]*(q_im1 - q_im2);
+  double dd     = t[7]*qb + t[8]*qa;
+  double dd_ip1 = tp[7]*(q_ip2 - q_ip1) + tp[8]*qb;
+  double dph = (t[9]*q_im1 + t[10]*q) + (t[11]*dd_im1 + t[12]*dd);
+  double dph_ip1 = (tp[9]*q + tp[10]*q_ip1) + (tp[11]*dd + tp[12]*dd_ip1);
+  dph     = dmin(dph, dmax(q, q_im1));
+  dph_ip1 = dmin(dph_ip1, dmax(q, q_ip1));
+  dph     = dmax(dph, dmin(q, q_im1));
+  dph_ip1 = dmax(dph_ip1, dmin(q, q_ip1));
+  double dqf_minus = q - dph;
+  double dqf_plus = dph_ip1 - q;
+  double qminus = dph, qplus = dph_ip1;
+  if (dqf_minus*dqf_plus <= 0.0) {
+    qminus = q;
+    qplus = q;
+  } else {
+    if (fabs(dqf_minus) >= 2.0*fabs(dqf_plus)) qminus = q - 2.0*dqf_plus;
+    if (fabs(dqf_plus) >= 2.0*fabs(dqf_minus)) qplus = q + 2.0*dqf_minus;
+  }
+  plus = qplus;
+  minus = qminus;
+}
+
 // xorder = 2c: PLM on characteristic variables for one cell (plm.cpp:62-66,107-130): both face
 // states of the cell, floors re-applied.  q* sweep-ordered, NW = 5 / 7.
-template <bool MHD>
+template <bool MHD, int MODE = 0>
 AB_HD void plm_char(const double *qm1, const double *q, const double *qp1, double bx,
                     double gamma, double wp, double wm, double dfloor, double pfloor,
-                    double *plus, double *minus) {
+                    double *plus, double *minus, const double *t = nullptr) {
   constexpr int NW = MHD ? 7 : 5;
   double dwl[7], dwr[7], dwm[7];
   for (int n = 0; n < NW; ++n) { dwl[n] = (q[n] - qm1[n]); dwr[n] = (qp1[n] - q[n]); }
   char_left<MHD>(gamma, q, bx, dwl);
   char_left<MHD>(gamma, q, bx, dwr);
-  for (int n = 0; n < NW; ++n) {
-    double dw2 = dwl[n]*dwr[n];
-    dwm[n] = 0.0;
-    if (dw2 > 0.0) dwm[n] = 2.0*dw2/(dwl[n] + dwr[n]);
-  }
+  for (int n = 0; n < NW; ++n) dwm[n] = plm_slope<MODE>(dwl[n], dwr[n], t);
   char_right<MHD>(gamma, q, bx, dwm);
   for (int n = 0; n < NW; ++n) { plus[n] = q[n] + wp*dwm[n]; minus[n] = q[n] - wm*dwm[n]; }
   plus[IDN] = (plus[IDN] > dfloor) ? plus[IDN] : dfloor;
@@ -295,10 +358,10 @@ AB_HD void plm_char(const double *qm1, const double *q, const double *qp1, doubl
 // xorder = 3c: PPM on characteristic variables for one cell (ppm.cpp:66-75,311-332): the five
 // stencil states are projected with the cell's own eigenvectors, reconstructed, and both face
 // states projected back; floors re-applied.
-template <bool MHD>
+template <bool MHD, bool NU = false>
 AB_HD void ppm_char(const double *qm2, const double *qm1, const double *q, const double *qp1,
                     const double *qp2, double bx, double gamma, double dfloor, double pfloor,
-                    double *plus, double *minus) {
+                    double *plus, double *minus, const double *t = nullptr) {
   constexpr int NW = MHD ? 7 : 5;
   double c0[7], c1[7], c2[7], c3[7], c4[7];
   for (int n = 0; n < NW; ++n) {
@@ -309,7 +372,10 @@ AB_HD void ppm_char(const double *qm2, const double *qm1, const double *q, const
   char_left<MHD>(gamma, q, bx, c2);
   char_left<MHD>(gamma, q, bx, c3);
   char_left<MHD>(gamma, q, bx, c4);
-  for (int n = 0; n < NW; ++n) ppm(c0[n], c1[n], c2[n], c3[n], c4[n], plus[n], minus[n]);
+  for (int n = 0; n < NW; ++n) {
+    if (NU) ppm_nu(c0[n], c1[n], c2[n], c3[n], c4[n], t, plus[n], minus[n]);
+    else ppm(c0[n], c1[n], c2[n], c3[n], c4[n], plus[n], minus[n]);
+  }
   char_right<MHD>(gamma, q, bx, plus);
   char_right<MHD>(gamma, q, bx, minus);
   plus[IDN] = (plus[IDN] > dfloor) ? plus[IDN] : dfloor;

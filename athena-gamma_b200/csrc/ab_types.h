@@ -6,6 +6,7 @@ namespace ab {
 
 constexpr int NHYDRO = 5;    // adiabatic; BlkDev::nh holds the run-time count (4 when isothermal)
 constexpr int MAX_NB = 26;
+constexpr int NUG = 13;        // doubles per cell index in the nonuniform-reconstruction table (ab_physics.cuh)
 constexpr int DT_SLOTS = 64;   // atomicMin targets per MeshBlock for the CFL reduction
 
 // Device view of one MeshBlock.  Array layouts are the reference's AthenaArray layouts
@@ -32,6 +33,9 @@ struct BlkDev {
   double *s, *s1, *r, *sflux[3];
   // 1-D geometry (src/coordinates/coordinates.cpp:125-145, cartesian.cpp:25-75)
   const double *x1f, *x2f, *x3f, *x1v, *x2v, *x3v, *dx1f, *dx2f, *dx3f;
+  // nullptr when every direction is uniformly spaced; else the CalculateCellCenteredField
+  // weights (field/field.cpp:139-172): lw[nc1], rw[nc1] of x1, then x2, then x3
+  const double *bcw;
 };
 
 // EMF-correction plan of one block (src/bvals/fc/flux_correction_fc.cpp).  For every face /

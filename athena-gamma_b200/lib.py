@@ -23,7 +23,7 @@ COORD = {"x1f": 0, "x2f": 1, "x3f": 2, "x1v": 3, "x2v": 4, "x3v": 5, "dx1f": 6, 
 SYMBOLS = [
     "ab_last_error", "ab_device_count", "ab_mesh_create", "ab_mesh_destroy",
     "ab_mesh_nblocks_total", "ab_mesh_nblocks_local", "ab_block_info", "ab_reg_size",
-    "ab_plan_create", "ab_plan_messages", "ab_plan_ranklist",
+    "ab_plan_create", "ab_plan_messages", "ab_plan_ranklist", "ab_plan_geometry",
     "ab_enroll_user_boundary_function", "ab_enroll_user_explicit_source_function",
     "ab_enroll_user_explicit_source_function_device", "ab_upload", "ab_download", "ab_download_coord", "ab_comm_unique_id", "ab_comm_init",
     "ab_cons2prim", "ab_prim2cons", "ab_primitives", "ab_calc_fluxes", "ab_corner_e",
@@ -49,7 +49,7 @@ class AbMeshParams(C.Structure):
                 ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
                 ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
                 ("iso_sound_speed", C.c_double), ("grav_acc", C.c_double * 3),
-                ("char_proj", C.c_int)]
+                ("char_proj", C.c_int), ("xrat", C.c_double * 3)]
 
 
 # AbBValFunc (include/athena_b200.h): user-enrolled boundary function on host arrays
@@ -94,6 +94,7 @@ def load():
     L.ab_plan_create.argtypes = [C.POINTER(AbMeshParams), C.POINTER(vp)]
     L.ab_plan_messages.argtypes = [vp, ip, C.POINTER(C.c_long), ip]
     L.ab_plan_ranklist.argtypes = [vp, C.POINTER(C.c_int), ip]
+    L.ab_plan_geometry.argtypes = [vp, ip, ip, ip, dp, ip]
     L.ab_history.argtypes = [vp, dp, ip]
     L.ab_enroll_user_explicit_source_function.argtypes = [vp, SRCTERMFUNC, vp]
     L.ab_enroll_user_explicit_source_function_device.argtypes = [vp, SRCTERMFUNC_DEVICE, vp]

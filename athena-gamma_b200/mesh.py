@@ -114,6 +114,10 @@ class Mesh:
                 raise ValueError("### FATAL ERROR in Mesh: boundary flag '%s' not supported on "
                                  "the B200 path" % flag)
             p.bc[i] = lib.BC[flag]
+        # Mesh ctor (mesh.cpp:69-75): geometric cell-size ratios; != 1 selects the mesh-generator
+        # coordinates and the nonuniform reconstruction branches
+        for d in range(3):
+            p.xrat[d] = pin.get_or_add_real("mesh", "x%drat" % (d + 1), 1.0)
         xo = pin.get_or_add_string("time", "xorder", "2")
         p.char_proj = int(xo.endswith("c"))        # reconstruction.cpp:60-80: "2c", "3c"
         p.xorder = int(xo.rstrip("c"))

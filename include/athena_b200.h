@@ -62,6 +62,8 @@ typedef struct {
   double iso_sound_speed;       /* hydro/iso_sound_speed (isothermal EOS) */
   double grav_acc[3];           /* hydro/grav_acc1..3: constant acceleration source term */
   int char_proj;                /* time/xorder = "2c" / "3c": characteristic reconstruction */
+  double xrat[3];               /* mesh/x1rat..x3rat: geometric cell-size ratio (0 or 1 = uniform),
+                                   Mesh ctor src/mesh/mesh.cpp:69-75,278-289 */
 } AbMeshParams;
 
 typedef struct AbMesh AbMesh;
@@ -88,6 +90,12 @@ long ab_reg_size(const AbMesh *m, int lid, int reg);
 int ab_plan_create(const AbMeshParams *p, AbMesh **out);
 int ab_plan_messages(const AbMesh *m, int kind, long *out, int max_rows);
 int ab_plan_ranklist(const AbMesh *m, int *out, int max_n);
+/* Host-computed geometry of local block lid along dir 0..2 (Coordinates / Reconstruction ctors:
+ * src/coordinates/coordinates.cpp:92-160, src/reconstruct/reconstruction.cpp:196-213,434-461):
+ * what 0 x?f, 1 x?v, 2 dx?f, 3 / 4 PLM face weights, 5 nonuniform-reconstruction table (13
+ * doubles per cell index; exists only when mesh/x?rat != 1), 6 / 7 weights of
+ * Field::CalculateCellCenteredField.  Returns the number of doubles (0: no such array). */
+int ab_plan_geometry(const AbMesh *m, int lid, int dir, int what, double *out, int max_n);
 
 /* ---- user-enrolled boundary functions: Mesh::EnrollUserBoundaryFunction (src/mesh/mesh.cpp)
  * with the BValFunc signature of src/athena.hpp:179-182 on plain arrays.  `face`: 0..5 =

@@ -127,6 +127,17 @@ void ao_ppm(long n, int nvar, const double *qm2, const double *qm1, const double
             const double *qp1, const double *qp2, double dfloor, double pfloor,
             double *ql_plus, double *qr_minus);
 
+/* test entries for the reconstruction geometry of one direction (nonuni: x?rat != 1) */
+void ao_recon_line(int dir, int nonuni, int order, int nc, int s, int e, int ng, const double *xf,
+                   const double *xv, const double *dxf, int nvar, const double *q, int lo, int hi,
+                   double *plus, double *minus);
+void ao_recon_line_char(int dir, int nonuni, int order, int mhd, int nc, int s, int e, int ng,
+                        const double *xf, const double *xv, const double *dxf, const double *q,
+                        const double *bx, double gamma, double dfloor, double pfloor, int lo,
+                        int hi, double *plus, double *minus);
+void ao_bcc_weights(int dir, int nonuni, int nc, int s, int e, int ng, const double *xf,
+                    const double *xv, const double *dxf, double *lw, double *rw);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,11 @@ def lib():
         L.ao_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
         L.ao_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, C.c_double, C.c_double,
                              dp, dp]
+        ip = C.c_int
+        L.ao_recon_line.argtypes = [ip]*7 + [dp, dp, dp, ip, dp, ip, ip, dp, dp]
+        L.ao_recon_line_char.argtypes = [ip]*8 + [dp, dp, dp, dp, dp, C.c_double, C.c_double,
+                                                  C.c_double, ip, ip, dp, dp]
+        L.ao_bcc_weights.argtypes = [ip]*6 + [dp]*5
         _LIB = L
     return _LIB
 

@@ -214,6 +214,45 @@ static AoReconGeom *make_recon_geom(int dir, int nonuni, int nc, int s, int e, i
   return g;
 }
 
+/* test entries: reconstruct cells lo..hi of a 1-D line along direction dir with the geometry of
+ * (xf, xv, dxf); q[v*nc + i]; order 2 (PLM) / 3 (PPM).  Floors are not applied here. */
+void ao_recon_line(int dir, int nonuni, int order, int nc, int s, int e, int ng, const double *xf,
+                   const double *xv, const double *dxf, int nvar, const double *q, int lo, int hi,
+                   double *plus, double *minus) {
+  double *bw[2];
+  AoReconGeom *g = make_recon_geom(dir, nonuni, nc, s, e, ng, xf, xv, dxf, bw);
+  for (int v = 0; v < nvar; ++v) for (int i = lo; i <= hi; ++i) {
+    const double *c = q + (long)v*nc + i;
+    if (order == 2) ao_plm_point_g(c[-1], c[0], c[1], &g[i], &plus[(long)v*nc+i], &minus[(long)v*nc+i]);
+    else ao_ppm_point_g(c[-2], c[-1], c[0], c[1], c[2], &g[i], &plus[(long)v*nc+i], &minus[(long)v*nc+i]);
+  }
+  free(g); free(bw[0]); free(bw[1]);
+}
+/* characteristic variant: 7 sweep-ordered variable slots, bx[i]; floors applied */
+void ao_recon_line_char(int dir, int nonuni, int order, int mhd, int nc, int s, int e, int ng,
+                        const double *xf, const double *xv, const double *dxf, const double *q,
+                        const double *bx, double gamma, double dfloor, double pfloor, int lo,
+                        int hi, double *plus, double *minus) {
+  double *bw[2];
+  AoReconGeom *g = make_recon_geom(dir, nonuni, nc, s, e, ng, xf, xv, dxf, bw);
+  int nw = mhd ? 7 : 5;
+  for (int i = lo; i <= hi; ++i) {
+    double st[5][7], pl[7], mi[7];
+    for (int o = -2; o <= 2; ++o) for (int v = 0; v < 7; ++v) st[o+2][v] = q[(long)v*nc + i + o];
+    ao_recon_char_point(order, mhd, st, mhd ? bx[i] : 0.0, gamma, &g[i], dfloor, pfloor, pl, mi);
+    for (int v = 0; v < nw; ++v) { plus[(long)v*nc+i] = pl[v]; minus[(long)v*nc+i] = mi[v]; }
+  }
+  free(g); free(bw[0]); free(bw[1]);
+}
+/* CalculateCellCenteredField weights of a line (field.cpp:139-172) */
+void ao_bcc_weights(int dir, int nonuni, int nc, int s, int e, int ng, const double *xf,
+                    const double *xv, const double *dxf, double *lw, double *rw) {
+  double *bw[2];
+  AoReconGeom *g = make_recon_geom(dir, nonuni, nc, s, e, ng, xf, xv, dxf, bw);
+  for (int i = 0; i < nc; ++i) { lw[i] = bw[0][i]; rw[i] = bw[1][i]; }
+  free(g); free(bw[0]); free(bw[1]);
+}
+
 /* Mesh::SetBlockSizeAndBoundaries (src/mesh/mesh.cpp:1668-1751) for one direction */
 static double block_edge(long lx, int nrbx, double mmin, double mmax, double rat, int nx_mesh) {
   if (rat != 1.0) return default_gen((double)lx/(double)nrbx, mmin, mmax, rat, nx_mesh);

@@ -80,4 +80,59 @@ void hc_ppm(long n, int nvar, const double *qm2, const double *qm1, const double
   for (long i = 0; i < (long)nvar*n; ++i)
     ab::ppm(qm2[i], qm1[i], q[i], qp1[i], qp2[i], ql[i], qr[i]);
 }
+}  // extern "C"
+
+// nonuniform spacing: reconstruct cells lo..hi of a 1-D line with the product's geometry
+// table (ab_plan_geometry); mode = 1 + direction, 0 = uniform.  q[v*nc + i].
+template <int MODE>
+static void line_t(int order, int nc, const double *wp, const double *wm, const double *tab,
+                   int nvar, const double *q, int lo, int hi, double *plus, double *minus) {
+  for (int v = 0; v < nvar; ++v) for (int i = lo; i <= hi; ++i) {
+    const double *c = q + (long)v*nc + i;
+    const double *t = tab ? tab + (long)i*ab::NUG : nullptr;
+    double &pl = plus[(long)v*nc + i], &mi = minus[(long)v*nc + i];
+    if (order == 2) {
+      if (MODE) ab::plm_nu<MODE>(c[-1], c[0], c[1], wp[i], wm[i], t, pl, mi);
+      else ab::plm(c[-1], c[0], c[1], wp[i], wm[i], pl, mi);
+    } else {
+      if (MODE) ab::ppm_nu(c[-2], c[-1], c[0], c[1], c[2], t, pl, mi);
+      else ab::ppm(c[-2], c[-1], c[0], c[1], c[2], pl, mi);
+    }
+  }
+}
+extern "C" void hc_recon_line(int mode, int order, int nc, const double *wp, const double *wm,
+                   const double *tab, int nvar, const double *q, int lo, int hi, double *plus,
+                   double *minus) {
+  if (mode == 0) line_t<0>(order, nc, wp, wm, tab, nvar, q, lo, hi, plus, minus);
+  else if (mode == 1) line_t<1>(order, nc, wp, wm, tab, nvar, q, lo, hi, plus, minus);
+  else if (mode == 2) line_t<2>(order, nc, wp, wm, tab, nvar, q, lo, hi, plus, minus);
+  else line_t<3>(order, nc, wp, wm, tab, nvar, q, lo, hi, plus, minus);
+}
+// characteristic variant: q[v*nc + i] with 7 sweep-ordered slots, bx[i]
+template <bool MHD, int MODE>
+static void line_char_t(int order, int nc, const double *wp, const double *wm, const double *tab,
+                        const double *q, const double *bx, double gamma, double dfloor,
+                        double pfloor, int lo, int hi, double *plus, double *minus) {
+  const int nw = MHD ? 7 : 5;
+  for (int i = lo; i <= hi; ++i) {
+    double st[5][7], pl[7], mi[7];
+    for (int o = -2; o <= 2; ++o) for (int v = 0; v < 7; ++v) st[o+2][v] = q[(long)v*nc + i + o];
+    const double b = MHD ? bx[i] : 0.0;
+    const double *t = tab ? tab + (long)i*ab::NUG : nullptr;
+    if (order == 2)
+      ab::plm_char<MHD,MODE>(st[1], st[2], st[3], b, gamma, wp[i], wm[i], dfloor, pfloor, pl, mi, t);
+    else
+      ab::ppm_char<MHD,(MODE != 0)>(st[0], st[1], st[2], st[3], st[4], b, gamma, dfloor, pfloor,
+                                    pl, mi, t);
+    for (int v = 0; v < nw; ++v) { plus[(long)v*nc + i] = pl[v]; minus[(long)v*nc + i] = mi[v]; }
+  }
+}
+extern "C" void hc_recon_line_char(int mode, int order, int mhd, int nc, const double *wp, const double *wm,
+                        const double *tab, const double *q, const double *bx, double gamma,
+                        double dfloor, double pfloor, int lo, int hi, double *plus,
+                        double *minus) {
+#define LC(M, D) line_char_t<M,D>(order, nc, wp, wm, tab, q, bx, gamma, dfloor, pfloor, lo, hi, plus, minus)
+  if (mhd) { if (mode == 0) LC(true,0); else if (mode == 1) LC(true,1); else if (mode == 2) LC(true,2); else LC(true,3); }
+  else { if (mode == 0) LC(false,0); else if (mode == 1) LC(false,1); else if (mode == 2) LC(false,2); else LC(false,3); }
+#undef LC
 }

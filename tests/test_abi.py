@@ -27,11 +27,14 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # 6 ints, 6 doubles, 6 ints (bc), 5 ints (+pad), 6 doubles, 3 + 2 ints (+pad), 2 doubles;
-    # checked against gcc's sizeof / offsetof of include/athena_b200.h
+    # 6 ints, 6 doubles, 6 ints (bc), 5 ints (+pad), 6 doubles, 3 + 2 ints (+pad), 2 doubles,
+    # grav_acc[3], char_proj (+pad), xrat[3]; checked against gcc's sizeof / offsetof of
+    # include/athena_b200.h
     P = ab.lib.AbMeshParams
-    assert C.sizeof(P) == 6 * 4 + 6 * 8 + 6 * 4 + 5 * 4 + 4 + 6 * 8 + 5 * 4 + 4 + 5 * 8 + 4 + 4 == 240
+    assert C.sizeof(P) == 6 * 4 + 6 * 8 + 6 * 4 + 5 * 4 + 4 + 6 * 8 + 5 * 4 + 4 + 5 * 8 + 4 + 4 \
+        + 3 * 8 == 264
     assert P.nscalars.offset == 180 and P.sfloor.offset == 192
+    assert P.char_proj.offset == 232 and P.xrat.offset == 240
 
 
 def test_no_cpu_fallback_without_device():
