@@ -197,6 +197,19 @@ struct AbMesh {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_pack = nullptr, ev_recv = nullptr;
   bool overlap = false;
+  // Pipelined host <-> device staging (ab_stage_*): a caller that streams a new state in and
+  // the result out every step (bench.py's e2e leg) overlaps the PCIe copies of the neighbouring
+  // steps with this step's kernels.  Device staging buffers `in` / `out` hold the chosen
+  // registers of every local block; copies run on their own streams, ordered by events.
+  struct Staging {
+    std::vector<int> regs;
+    std::vector<size_t> off;              // [lid*nregs + r] -> element offset into in / out
+    size_t elems = 0;
+    double *in = nullptr, *out = nullptr;
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t in_ready = nullptr, in_free = nullptr, out_ready = nullptr, out_free = nullptr;
+    bool active = false;
+  } stg;
   // Many MeshBlocks per GPU: the per-block tasks of a stage are spread round-robin over a few
   // extra streams (forked from / joined into the main stream around every exchange), so that the
   // ramp-up and tail of one block's kernels overlap the next block's (AB_BLOCK_STREAMS, default
@@ -1636,6 +1649,13 @@ int ab_mesh_destroy(AbMesh *m) {
   for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   cudaFree(m->state); cudaFree(m->dt_hist); cudaFree(m->dtmin);
   cudaFree(m->hist_partial); cudaFree(m->hist_out);
+  if (m->stg.active) {
+    cudaStreamSynchronize(m->stg.h2d); cudaStreamSynchronize(m->stg.d2h);
+    cudaFree(m->stg.in); cudaFree(m->stg.out);
+    cudaEventDestroy(m->stg.in_ready); cudaEventDestroy(m->stg.in_free);
+    cudaEventDestroy(m->stg.out_ready); cudaEventDestroy(m->stg.out_free);
+    cudaStreamDestroy(m->stg.h2d); cudaStreamDestroy(m->stg.d2h);
+  }
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
   for (auto st : m->bstream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   for (auto ev : m->ev_b) cudaEventDestroy(ev);
@@ -1690,6 +1710,99 @@ int ab_download(AbMesh *m, int lid, int reg, double *host) {
   if (!slot || !*slot) return fail(AB_ERR_ARG, "register not allocated in this configuration");
   CK(cudaMemcpyAsync(host, *slot, L.regsize[reg]*8, cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
+  return AB_OK;
+}
+
+// ---- pipelined staging ------------------------------------------------------------------------
+int ab_stage_begin(AbMesh *m, const int *regs, int nregs) {
+  if (!m || m->dry || !regs || nregs <= 0) return fail(AB_ERR_ARG, "bad argument");
+  if (m->stg.active) return fail(AB_ERR_STATE, "staging already set up");
+  CK(cudaSetDevice(m->p.device));
+  AbMesh::Staging &S = m->stg;
+  S.regs.assign(regs, regs + nregs);
+  S.off.clear(); S.elems = 0;
+  for (auto &L : m->lb)
+    for (int r : S.regs) {
+      if (r < 0 || r >= AB_NREG || L.regsize[r] <= 0) return fail(AB_ERR_ARG, "bad register");
+      S.off.push_back(S.elems);
+      S.elems += (size_t)((L.regsize[r] + 31)/32*32);     // keep every array 256-byte aligned
+    }
+  CK(cudaMalloc(&S.in, S.elems*8));
+  CK(cudaMalloc(&S.out, S.elems*8));
+  CK(cudaStreamCreateWithFlags(&S.h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&S.d2h, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&S.in_ready, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&S.in_free, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&S.out_ready, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&S.out_free, cudaEventDisableTiming));
+  S.active = true;
+  return AB_OK;
+}
+
+// host[lid*nregs + r] (pinned) -> device staging, on the upload stream; returns at once.  The
+// copies wait until the previous ab_stage_commit has drained the staging buffer.
+int ab_stage_upload_all(AbMesh *m, const double *const *host) {
+  if (!m || !m->stg.active || !host) return fail(AB_ERR_STATE, "staging not set up");
+  AbMesh::Staging &S = m->stg;
+  CK(cudaStreamWaitEvent(S.h2d, S.in_free, 0));      // no-op before the first commit
+  const size_t nr = S.regs.size();
+  for (size_t l = 0; l < m->lb.size(); ++l)
+    for (size_t r = 0; r < nr; ++r)
+      CK(cudaMemcpyAsync(S.in + S.off[l*nr + r], host[l*nr + r], m->lb[l].regsize[S.regs[r]]*8,
+                         cudaMemcpyHostToDevice, S.h2d));
+  CK(cudaEventRecord(S.in_ready, S.h2d));
+  return AB_OK;
+}
+
+// staging -> registers on the compute stream, behind the upload; frees the staging buffer for
+// the next ab_stage_upload_all.  Does not block the host.
+int ab_stage_commit(AbMesh *m) {
+  if (!m || !m->stg.active) return fail(AB_ERR_STATE, "staging not set up");
+  AbMesh::Staging &S = m->stg;
+  CK(cudaStreamWaitEvent(m->stream, S.in_ready, 0));
+  const size_t nr = S.regs.size();
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    LocalBlock &L = m->lb[l];
+    for (size_t r = 0; r < nr; ++r) {
+      const int reg = S.regs[r];
+      if (reg == AB_W || reg == AB_BCC) L.cc_e_valid = false;
+      CK(cudaMemcpyAsync(*reg_slot(L, reg), S.in + S.off[l*nr + r], L.regsize[reg]*8,
+                         cudaMemcpyDeviceToDevice, m->stream));
+    }
+  }
+  CK(cudaEventRecord(S.in_free, m->stream));
+  return AB_OK;
+}
+
+// registers -> staging on the compute stream (behind everything enqueued so far), then
+// staging -> host[lid*nregs + r] (pinned) on the download stream.  Does not block the host;
+// ab_stage_sync waits for the copies.
+int ab_stage_download_all(AbMesh *m, double *const *host) {
+  if (!m || !m->stg.active || !host) return fail(AB_ERR_STATE, "staging not set up");
+  AbMesh::Staging &S = m->stg;
+  CK(cudaStreamWaitEvent(m->stream, S.out_free, 0));  // previous download has left the buffer
+  const size_t nr = S.regs.size();
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    LocalBlock &L = m->lb[l];
+    for (size_t r = 0; r < nr; ++r)
+      CK(cudaMemcpyAsync(S.out + S.off[l*nr + r], *reg_slot(L, S.regs[r]),
+                         L.regsize[S.regs[r]]*8, cudaMemcpyDeviceToDevice, m->stream));
+  }
+  CK(cudaEventRecord(S.out_ready, m->stream));
+  CK(cudaStreamWaitEvent(S.d2h, S.out_ready, 0));
+  for (size_t l = 0; l < m->lb.size(); ++l)
+    for (size_t r = 0; r < nr; ++r)
+      CK(cudaMemcpyAsync(host[l*nr + r], S.out + S.off[l*nr + r],
+                         m->lb[l].regsize[S.regs[r]]*8, cudaMemcpyDeviceToHost, S.d2h));
+  CK(cudaEventRecord(S.out_free, S.d2h));
+  return AB_OK;
+}
+
+int ab_stage_sync(AbMesh *m) {
+  if (!m || !m->stg.active) return fail(AB_ERR_STATE, "staging not set up");
+  CK(cudaStreamSynchronize(m->stg.h2d));
+  CK(cudaStreamSynchronize(m->stream));
+  CK(cudaStreamSynchronize(m->stg.d2h));
   return AB_OK;
 }
 

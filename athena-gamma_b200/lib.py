@@ -33,6 +33,8 @@ SYMBOLS = [
     "ab_mesh_cycles", "ab_mesh_set_async", "ab_mesh_state", "ab_mesh_set_time_dt",
     "ab_history", "ab_mesh_dt_history", "ab_mesh_profile", "ab_mesh_profile_read",
     "ab_mesh_launch_count", "ab_mesh_stream", "ab_mesh_sync",
+    "ab_stage_begin", "ab_stage_upload_all", "ab_stage_commit", "ab_stage_download_all",
+    "ab_stage_sync",
 ]
 
 
@@ -95,6 +97,11 @@ def load():
     L.ab_plan_messages.argtypes = [vp, ip, C.POINTER(C.c_long), ip]
     L.ab_plan_ranklist.argtypes = [vp, C.POINTER(C.c_int), ip]
     L.ab_plan_geometry.argtypes = [vp, ip, ip, ip, dp, ip]
+    L.ab_stage_begin.argtypes = [vp, C.POINTER(C.c_int), ip]
+    L.ab_stage_upload_all.argtypes = [vp, C.POINTER(dp)]
+    L.ab_stage_commit.argtypes = [vp]
+    L.ab_stage_download_all.argtypes = [vp, C.POINTER(dp)]
+    L.ab_stage_sync.argtypes = [vp]
     L.ab_history.argtypes = [vp, dp, ip]
     L.ab_enroll_user_explicit_source_function.argtypes = [vp, SRCTERMFUNC, vp]
     L.ab_enroll_user_explicit_source_function_device.argtypes = [vp, SRCTERMFUNC_DEVICE, vp]

@@ -137,6 +137,23 @@ int ab_upload(AbMesh *m, int lid, int reg, const double *host);     /* after Pro
 int ab_download(AbMesh *m, int lid, int reg, double *host);         /* before outputs / hooks */
 int ab_download_coord(AbMesh *m, int lid, int which, double *host); /* 0..8: x1f x2f x3f x1v x2v x3v dx1f dx2f dx3f */
 
+/* ---- pipelined staging for callers that stream a state in and a result out EVERY step (the
+ * bench's end-to-end leg; a coupled code exchanging fields with a host-side solver).  The chosen
+ * registers of all local blocks get device staging buffers; uploads and downloads run on their
+ * own copy streams ordered against the compute stream by events, so the PCIe transfers of the
+ * neighbouring steps overlap this step's kernels.  host[] = one PINNED host pointer per
+ * (local block, register), index lid*nregs + r.  Sequence per step:
+ *   ab_stage_commit            staging -> registers (waits for the upload; frees the buffer)
+ *   ab_stage_upload_all        next step's input, returns at once
+ *   ab_mesh_initialize / ab_mesh_cycles ...
+ *   ab_stage_download_all      registers -> staging -> host, returns at once
+ * and ab_stage_sync before the host touches the downloaded arrays. */
+int ab_stage_begin(AbMesh *m, const int *regs, int nregs);
+int ab_stage_upload_all(AbMesh *m, const double *const *host);
+int ab_stage_commit(AbMesh *m);
+int ab_stage_download_all(AbMesh *m, double *const *host);
+int ab_stage_sync(AbMesh *m);
+
 /* ---- multi-process plumbing (replaces MPI_Init + persistent requests, bvals_cc.cpp:528-633).
  * rank 0 calls ab_comm_unique_id and the host broadcasts the 128 bytes (MPI_Bcast /
  * torch.distributed); then every rank calls ab_comm_init before the first exchange. */
