@@ -37,6 +37,10 @@ typedef struct {
   double grav_acc[3];   /* hydro/grav_acc1..3 (hydro/srcterms/hydro_srcterms.cpp:68-75) */
   int char_proj;        /* time/xorder = 2c / 3c: reconstruct characteristic variables */
   double xrat[3];       /* mesh/x1rat..x3rat (0 or 1 = uniform): geometric cell-size ratio */
+  /* mesh/refinement = static: <refinementN> blocks (src/mesh/mesh.cpp:323-465); hydro only */
+  int nref;
+  double ref[8][6];     /* x1min,x1max,x2min,x2max,x3min,x3max of each region */
+  int ref_level[8];     /* its level (root = 0) */
 } AoParams;
 
 typedef struct AoMesh AoMesh;
@@ -44,6 +48,7 @@ typedef struct AoMesh AoMesh;
 AoMesh *ao_create(const AoParams *p);
 void ao_destroy(AoMesh *m);
 int ao_nblocks(const AoMesh *m);
+int ao_block_level(const AoMesh *m, int b);   /* LogicalLocation::level (0 on a one-level mesh) */
 /* out[0..2]=lx1..3, out[3..5]=nc1..3, out[6..11]=is,ie,js,je,ks,ke */
 void ao_block_info(const AoMesh *m, int b, long *out);
 /* array access by name: u u1 w bcc b1 b2 b3 b1_1 b1_2 b1_3 flux1 flux2 flux3 e1 e2 e3

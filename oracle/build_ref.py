@@ -38,6 +38,8 @@ CONFIGS = {
     "hydro_hlle_ng2": (False, "hlle", 2, ["shock_tube", "linear_wave"]),
     "hydro_roe_ng2": (False, "roe", 2, ["shock_tube", "linear_wave"]),
     "hydro_hllc_ng3": (False, "hllc", 3, ["kh", "shock_tube", "linear_wave"]),
+    # even NGHOST for PPM with mesh refinement (MeshRefinement ctor rejects odd NGHOST)
+    "hydro_hllc_ng4": (False, "hllc", 4, ["kh", "blast"]),
     "mhd_hlld_ng2": (True, "hlld", 2, ["linear_wave", "blast", "orszag_tang", "shock_tube",
                                        "shk_cloud", "local:usersrc"]),
     "mhd_hlle_ng2": (True, "hlle", 2, ["linear_wave", "shock_tube"]),

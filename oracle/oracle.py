@@ -30,7 +30,8 @@ class AoParams(C.Structure):
                 ("cfl", C.c_double), ("tlim", C.c_double), ("start_time", C.c_double),
                 ("nscalars", C.c_int), ("eos", C.c_int), ("sfloor", C.c_double),
                 ("iso_cs", C.c_double), ("grav_acc", C.c_double * 3), ("char_proj", C.c_int),
-                ("xrat", C.c_double * 3)]
+                ("xrat", C.c_double * 3), ("nref", C.c_int), ("ref", (C.c_double * 6) * 8),
+                ("ref_level", C.c_int * 8)]
 
 
 # AoBValFunc (athena_oracle.h): user-enrolled boundary function with plain arrays
@@ -58,7 +59,8 @@ def lib():
     if _LIB is None:
         so = os.path.join(HERE, "libathena_oracle.so")
         srcs = [os.path.join(HERE, f) for f in
-                ("oracle_physics.c", "oracle_mesh.c", "oracle_internal.h", "athena_oracle.h")]
+                ("oracle_physics.c", "oracle_mesh.c", "oracle_smr.c", "oracle_internal.h",
+                 "athena_oracle.h")]
         if (not os.path.exists(so)
                 or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)):
             build()
@@ -67,6 +69,7 @@ def lib():
         L.ao_create.argtypes = [C.POINTER(AoParams)]
         L.ao_destroy.argtypes = [C.c_void_p]
         L.ao_nblocks.argtypes = [C.c_void_p]
+        L.ao_block_level.argtypes = [C.c_void_p, C.c_int]
         L.ao_block_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_long)]
         L.ao_array.restype = C.POINTER(C.c_double)
         L.ao_array.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_long)]
@@ -161,6 +164,18 @@ def params_from_athinput(par, mhd, solver, ng=None, nscalars=0, eos="adiabatic")
     p.start_time = float(t.get("start_time", 0.0))
     for d in range(3):
         p.xrat[d] = float(mesh.get("x%drat" % (d + 1), 1.0))
+    # <refinementN> blocks in input order (Mesh ctor, src/mesh/mesh.cpp:330-465)
+    p.nref = 0
+    if mesh.get("refinement", "none") == "static":
+        lim = {"x1min": p.x1min, "x1max": p.x1max, "x2min": p.x2min, "x2max": p.x2max,
+               "x3min": p.x3min, "x3max": p.x3max}
+        for name, blk in par.items():
+            if not name.startswith("refinement"):
+                continue
+            for c, k in enumerate(("x1min", "x1max", "x2min", "x2max", "x3min", "x3max")):
+                p.ref[p.nref][c] = float(blk.get(k, lim[k]))
+            p.ref_level[p.nref] = int(blk["level"])
+            p.nref += 1
     return p
 
 
@@ -169,6 +184,9 @@ class OracleMesh:
         self.L = lib()
         self.p = params
         self.h = self.L.ao_create(C.byref(params))
+        if not self.h:
+            raise ValueError("oracle: static refinement is restated for hydro without scalars on "
+                             "uniformly spaced levels, even MeshBlock sizes and even NGHOST only")
         self.nb = self.L.ao_nblocks(self.h)
         self.info = []
         for b in range(self.nb):
@@ -176,6 +194,7 @@ class OracleMesh:
             self.L.ao_block_info(self.h, b, out)
             self.info.append(dict(zip(("lx1", "lx2", "lx3", "nc1", "nc2", "nc3", "is", "ie",
                                        "js", "je", "ks", "ke"), list(out))))
+            self.info[-1]["level"] = self.L.ao_block_level(self.h, b)
 
     def __del__(self):
         try:
@@ -229,16 +248,18 @@ class OracleMesh:
         shp = self.shape(b, name)
         return a.reshape(shp) if shp else a
 
-    def block_of(self, lx1, lx2, lx3):
+    def block_of(self, lx1, lx2, lx3, level=None):
+        """level: only needed (and only checked) on a refined mesh"""
         for b, i in enumerate(self.info):
-            if (i["lx1"], i["lx2"], i["lx3"]) == (lx1, lx2, lx3):
+            if (i["lx1"], i["lx2"], i["lx3"]) == (lx1, lx2, lx3) and (
+                    level is None or self.p.nref == 0 or i["level"] == level):
                 return b
-        raise KeyError((lx1, lx2, lx3))
+        raise KeyError((lx1, lx2, lx3, level))
 
     def load_rst(self, rst):
         """Fill u / b of every block from a parsed reference restart dump (ref_run.read_rst)."""
         for blk in rst["blocks"]:
-            b = self.block_of(*blk["loc"][:3])
+            b = self.block_of(*blk["loc"][:4])
             self.array(b, "u")[...] = blk["u"]
             if self.p.nscalars > 0:
                 self.array(b, "s")[...] = blk["s"]

@@ -22,7 +22,9 @@ static inline double mn(double a, double b) { return (b < a) ? b : a; }
 typedef struct {
   int ox1, ox2, ox3, type; /* type: 0 face 1 edge 2 corner */
   int gid, bufid, targetid, fid, eid;
+  int level, fi1, fi2;     /* multilevel meshes: neighbour's level, finer-leaf indices */
 } Nb;
+typedef struct TNode TNode;
 
 typedef struct AoBlock {
   int gid;
@@ -31,7 +33,10 @@ typedef struct AoBlock {
   double bx1min, bx1max, bx2min, bx2max, bx3min, bx3max;
   int bcs[6];            /* -1: neighbour block (block/periodic), else AO_BC_* physical */
   int nblevel[3][3][3];
-  int nnb; Nb nb[26];
+  int nnb; Nb nb[56];      /* 26 on one level; up to 56 with finer neighbours */
+  /* static mesh refinement (oracle_smr.c): level, the MeshRefinement's coarse buffers */
+  int level, cng, cis, cie, cjs, cje, cks, cke, cnc1, cnc2, cnc3;
+  double *cx1f, *cx2f, *cx3f, *cx1v, *cx2v, *cx3v, *coarse_u, *coarse_w;
   int nedge_fine[12];
   double *x1f, *x2f, *x3f, *x1v, *x2v, *x3v, *dx1f, *dx2f, *dx3f;
   AoReconGeom *rg[3];    /* per-index reconstruction geometry along x1, x2, x3 */
@@ -57,6 +62,7 @@ struct AoMesh {
   double beta[4], delta[4], g1[4], g2[4], g3[4], ebeta[4];
   double cfl;
   double xrat[3];        /* mesh/x?rat with 0 read as 1 (uniform) */
+  int multilevel, root_level; TNode *root;
   AoBValFunc user_bc[6]; void *user_bc_arg[6];
   AoSrcTermFunc user_src; void *user_src_arg;
   double sbeta[4];
@@ -272,6 +278,8 @@ static void block_extent(long lx, int nrbx, double mmin, double mmax, int bc_in,
   else { *bmax = block_edge(lx + 1, nrbx, mmin, mmax, rat, nx_mesh); *bcs_out = -1; }
 }
 
+#include "oracle_smr.c"
+
 static int find_ni(const AoMesh *m, int o1, int o2, int o3) {
   for (int n = 0; n < m->nni; ++n)
     if (m->ni[n][0] == o1 && m->ni[n][1] == o2 && m->ni[n][2] == o3) return n;
@@ -313,6 +321,13 @@ static void set_integrator(AoMesh *m) {
 }
 
 AoMesh *ao_create(const AoParams *p) {
+  /* static refinement is restated for hydro on uniformly spaced levels only (oracle_smr.c) */
+  if (p->nref > 0 && (p->mhd || p->nscalars > 0 || (p->xrat[0] != 0.0 && p->xrat[0] != 1.0)
+                      || (p->xrat[1] != 0.0 && p->xrat[1] != 1.0)
+                      || (p->xrat[2] != 0.0 && p->xrat[2] != 1.0) || p->nref > 8
+                      || p->bx1 % 2 || (p->nx2 > 1 && p->bx2 % 2) || (p->nx3 > 1 && p->bx3 % 2)
+                      || p->ng % 2))
+    return NULL;
   AoMesh *m = (AoMesh *)calloc(1, sizeof(AoMesh));
   m->p = *p;
   for (int d = 0; d < 3; ++d) m->xrat[d] = (p->xrat[d] == 0.0) ? 1.0 : p->xrat[d];
@@ -360,12 +375,32 @@ AoMesh *ao_create(const AoParams *p) {
     }
   qsort(keys, (size_t)m->nb, sizeof(keys[0]), cmp_morton);
   m->gid_of = (int *)malloc(sizeof(int)*(size_t)m->nb);
+  TNode **leaves = NULL;
+  m->multilevel = (p->nref > 0);
+  if (m->multilevel) {   /* static refinement: block list from the tree (oracle_smr.c) */
+    smr_build_tree(m);
+    int cnt = 0;
+    tree_list(m->root, NULL, &cnt);
+    leaves = (TNode **)malloc(sizeof(TNode *)*(size_t)cnt);
+    cnt = 0;
+    tree_list(m->root, leaves, &cnt);
+    m->nb = cnt;
+  }
   m->blk = (AoBlock *)calloc((size_t)m->nb, sizeof(AoBlock));
   int ng = p->ng;
   for (int g = 0; g < m->nb; ++g) {
     AoBlock *B = &m->blk[g];
+    int dl = 0;          /* level above the root grid */
+    if (m->multilevel) {
+      B->gid = g; B->lx1 = leaves[g]->lx1; B->lx2 = leaves[g]->lx2; B->lx3 = leaves[g]->lx3;
+      B->level = leaves[g]->level;
+      dl = B->level - m->root_level;
+    } else {
     B->gid = g; B->lx1 = (long)keys[g][1]; B->lx2 = (long)keys[g][2]; B->lx3 = (long)keys[g][3];
     m->gid_of[(B->lx3*m->nrbx2 + B->lx2)*m->nrbx1 + B->lx1] = g;
+    }
+    const int nr1 = m->nrbx1 << dl, nr2 = m->nrbx2 << dl, nr3 = m->nrbx3 << dl;
+    const int nm1 = p->nx1 << dl, nm2 = m->f2 ? p->nx2 << dl : 1, nm3 = m->f3 ? p->nx3 << dl : 1;
     /* MeshBlock ctor index ranges (src/mesh/meshblock.cpp:55-80) */
     B->is = ng; B->ie = ng + p->bx1 - 1; B->nc1 = p->bx1 + 2*ng;
     if (m->f2) { B->js = ng; B->je = ng + p->bx2 - 1; B->nc2 = p->bx2 + 2*ng; }
@@ -373,21 +408,42 @@ AoMesh *ao_create(const AoParams *p) {
     if (m->f3) { B->ks = ng; B->ke = ng + p->bx3 - 1; B->nc3 = p->bx3 + 2*ng; }
     else { B->ks = B->ke = 0; B->nc3 = 1; }
     /* nx1 > 1 always, so the x1 extent goes through the generator even for one block */
-    block_extent(B->lx1, m->nrbx1, p->x1min, p->x1max, p->bc[0], p->bc[1], p->nx1 > 1 ? p->nx1 : 2,
+    block_extent(B->lx1, nr1, p->x1min, p->x1max, p->bc[0], p->bc[1], p->nx1 > 1 ? p->nx1 : 2,
                  m->xrat[0], &B->bx1min, &B->bx1max, &B->bcs[0], &B->bcs[1]);
-    block_extent(B->lx2, m->nrbx2, p->x2min, p->x2max, p->bc[2], p->bc[3], p->nx2,
+    block_extent(B->lx2, nr2, p->x2min, p->x2max, p->bc[2], p->bc[3], p->nx2,
                  m->xrat[1], &B->bx2min, &B->bx2max, &B->bcs[2], &B->bcs[3]);
-    block_extent(B->lx3, m->nrbx3, p->x3min, p->x3max, p->bc[4], p->bc[5], p->nx3,
+    block_extent(B->lx3, nr3, p->x3min, p->x3max, p->bc[4], p->bc[5], p->nx3,
                  m->xrat[2], &B->bx3min, &B->bx3max, &B->bcs[4], &B->bcs[5]);
-    make_coords(p->nx1, p->bx1, ng, B->lx1, p->x1min, p->x1max, B->bx1min, B->bx1max,
+    make_coords(nm1, p->bx1, ng, B->lx1, p->x1min, p->x1max, B->bx1min, B->bx1max,
                 B->nc1, B->bcs[0] == AO_BC_REFLECT, B->bcs[1] == AO_BC_REFLECT, m->xrat[0],
                 &B->x1f, &B->x1v, &B->dx1f);
-    make_coords(p->nx2, p->bx2, ng, B->lx2, p->x2min, p->x2max, B->bx2min, B->bx2max,
+    make_coords(nm2, p->bx2, ng, B->lx2, p->x2min, p->x2max, B->bx2min, B->bx2max,
                 B->nc2, B->bcs[2] == AO_BC_REFLECT, B->bcs[3] == AO_BC_REFLECT, m->xrat[1],
                 &B->x2f, &B->x2v, &B->dx2f);
-    make_coords(p->nx3, p->bx3, ng, B->lx3, p->x3min, p->x3max, B->bx3min, B->bx3max,
+    make_coords(nm3, p->bx3, ng, B->lx3, p->x3min, p->x3max, B->bx3min, B->bx3max,
                 B->nc3, B->bcs[4] == AO_BC_REFLECT, B->bcs[5] == AO_BC_REFLECT, m->xrat[2],
                 &B->x3f, &B->x3v, &B->dx3f);
+    if (m->multilevel) {
+      /* MeshBlock ctor, multilevel branch (meshblock.cpp:82-100): cnghost = (NGHOST+1)/2 + 1 */
+      int cng = (ng + 1)/2 + 1;
+      B->cng = cng;
+      B->cis = cng; B->cie = cng + p->bx1/2 - 1; B->cnc1 = p->bx1/2 + 2*cng;
+      if (m->f2) { B->cjs = cng; B->cje = cng + p->bx2/2 - 1; B->cnc2 = p->bx2/2 + 2*cng; }
+      else { B->cjs = B->cje = 0; B->cnc2 = 1; }
+      if (m->f3) { B->cks = cng; B->cke = cng + p->bx3/2 - 1; B->cnc3 = p->bx3/2 + 2*cng; }
+      else { B->cks = B->cke = 0; B->cnc3 = 1; }
+      make_coarse_coords(nm1, p->bx1, cng, B->lx1, p->x1min, p->x1max, B->bx1min, B->bx1max,
+                         B->cnc1, B->bcs[0] == AO_BC_REFLECT, B->bcs[1] == AO_BC_REFLECT,
+                         &B->cx1f, &B->cx1v);
+      make_coarse_coords(nm2, p->bx2, cng, B->lx2, p->x2min, p->x2max, B->bx2min, B->bx2max,
+                         B->cnc2, B->bcs[2] == AO_BC_REFLECT, B->bcs[3] == AO_BC_REFLECT,
+                         &B->cx2f, &B->cx2v);
+      make_coarse_coords(nm3, p->bx3, cng, B->lx3, p->x3min, p->x3max, B->bx3min, B->bx3max,
+                         B->cnc3, B->bcs[4] == AO_BC_REFLECT, B->bcs[5] == AO_BC_REFLECT,
+                         &B->cx3f, &B->cx3v);
+      long cncc = (long)B->cnc1*B->cnc2*B->cnc3;
+      B->coarse_u = dalloc(NHYDRO*cncc); B->coarse_w = dalloc(NHYDRO*cncc);
+    }
     B->rg[0] = make_recon_geom(0, m->xrat[0] != 1.0, B->nc1, B->is, B->ie, ng, B->x1f, B->x1v,
                                B->dx1f, B->bw[0]);
     B->rg[1] = make_recon_geom(1, m->xrat[1] != 1.0, B->nc2, B->js, B->je, ng, B->x2f, B->x2v,
@@ -423,6 +479,11 @@ AoMesh *ao_create(const AoParams *p) {
     }
   }
   free(keys);
+  free(leaves);
+  if (m->multilevel) {
+    for (int g = 0; g < m->nb; ++g) smr_search_neighbors(m, &m->blk[g]);
+    return m;
+  }
   /* neighbours (src/bvals/bvals_base.cpp:299-480), same level only */
   for (int g = 0; g < m->nb; ++g) {
     AoBlock *B = &m->blk[g];
@@ -508,11 +569,15 @@ void ao_destroy(AoMesh *m) {
       B->sflux[2]};
     for (size_t i = 0; i < sizeof(ptrs)/sizeof(ptrs[0]); ++i) free(ptrs[i]);
     for (int d = 0; d < 3; ++d) { free(B->rg[d]); free(B->bw[d][0]); free(B->bw[d][1]); }
+    free(B->cx1f); free(B->cx2f); free(B->cx3f); free(B->cx1v); free(B->cx2v); free(B->cx3v);
+    free(B->coarse_u); free(B->coarse_w);
   }
+  tree_free(m->root);
   free(m->blk); free(m->gid_of); free(m);
 }
 
 int ao_nblocks(const AoMesh *m) { return m->nb; }
+int ao_block_level(const AoMesh *m, int b) { return m->blk[b].level; }
 double ao_time(const AoMesh *m) { return m->time; }
 double ao_dt(const AoMesh *m) { return m->dt; }
 int ao_ncycle(const AoMesh *m) { return m->ncycle; }
@@ -1793,10 +1858,12 @@ void ao_enroll_user_bc(AoMesh *m, int face, AoBValFunc fn, void *user) {
 /* Mesh::Initialize after ProblemGenerator (src/mesh/mesh.cpp:1416-1649) */
 void ao_initialize(AoMesh *m) {
   m->bc_time = m->time; m->bc_dt = 0.0;   /* ApplyPhysicalBoundaries(time, 0.0, ...) mesh.cpp:1515 */
+  if (m->multilevel) smr_exchange_cc(m); else
   ao_exchange_cc(m);
   ao_exchange_fc(m);
   ao_exchange_scalars(m);
   for (int g = 0; g < m->nb; ++g) {
+    if (m->multilevel) smr_prolongate_boundaries(m, g);   /* mesh.cpp:1527-1528 */
     ao_primitives(m, g);
     ao_physical_bcs(m, g);
   }
@@ -1819,6 +1886,7 @@ double ao_cycle(AoMesh *m) {
       ao_calc_scalar_fluxes(m, g, order);
     }
     ao_emf_exchange(m);
+    if (m->multilevel) smr_flux_correction(m);   /* SEND_HYDFLX / RECV_HYDFLX before INT_HYD */
     for (int g = 0; g < m->nb; ++g) {
       double w[5] = {1.0, m->delta[s], 0.0, 0.0, 0.0};
       ao_weighted_ave_cc(m, g, 1, 0, w);
@@ -1840,12 +1908,14 @@ double ao_cycle(AoMesh *m) {
         m->user_src(m->user_src_arg, g, m->time + m->sbeta[s]*dt, m->beta[s]*dt, m->blk[g].w,
                     m->blk[g].r, m->blk[g].bcc, m->blk[g].u, m->blk[g].s);
     }
+    if (m->multilevel) smr_exchange_cc(m); else
     ao_exchange_cc(m);
     ao_exchange_fc(m);
     ao_exchange_scalars(m);
     /* PhysicalBoundary task: t_end_stage, beta*dt (time_integrator.cpp:2045-2062) */
     m->bc_time = m->time + m->ebeta[s]*dt; m->bc_dt = m->beta[s]*dt;
     for (int g = 0; g < m->nb; ++g) {
+      if (m->multilevel) smr_prolongate_boundaries(m, g);   /* PROLONG: after SETB, before CONS2PRIM */
       ao_primitives(m, g);
       ao_physical_bcs(m, g);
     }

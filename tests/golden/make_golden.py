@@ -200,6 +200,55 @@ CASES = {
     "khs3d_mhd_hlld_plm_vl2_8blk_s1": ("mhd_hlld_ng2_s1", "kh", "athinput.kh_scalar",
                                        dict({"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16},
                                             **mb(8, 8, 8)), "hlld", True, 4, 1),
+    # static mesh refinement, hydro (oracle only so far; the device path rejects it): tree and
+    # Z-ordered block list, level-aware neighbours, restriction / prolongation, flux correction
+    "smr_blast2d_hllc_plm_vl2": ("hydro_hllc_ng2", "blast", "athinput.blast",
+                                 {"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 1,
+                                  "problem/radius": 0.3, **mb(4, 4, 1), "mesh/refinement": "static",
+                                  "refinement1/x1min": -0.1, "refinement1/x1max": 0.1,
+                                  "refinement1/x2min": -0.1, "refinement1/x2max": 0.1,
+                                  "refinement1/level": 1}, "hllc", False, 6),
+    "smr_blast3d_hllc_plm_vl2": ("hydro_hllc_ng2", "blast", "athinput.blast",
+                                 {"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16,
+                                  "problem/radius": 0.3, **mb(4, 4, 4), "mesh/refinement": "static",
+                                  "refinement1/x1min": -0.1, "refinement1/x1max": 0.1,
+                                  "refinement1/x2min": -0.1, "refinement1/x2max": 0.1,
+                                  "refinement1/x3min": -0.1, "refinement1/x3max": 0.1,
+                                  "refinement1/level": 1}, "hllc", False, 4),
+    "smr_sod1d_hllc_plm_vl2": ("hydro_hllc_ng2", "shock_tube", "athinput.sod",
+                               {"mesh/nx1": 64, "meshblock/nx1": 8, "mesh/refinement": "static",
+                                "refinement1/x1min": -0.1, "refinement1/x1max": 0.15,
+                                "refinement1/level": 2}, "hllc", False, 8),
+    "smr_blast2d_lvl2_bcs_hllc_plm_rk2": ("hydro_hllc_ng2", "blast", "athinput.blast",
+                                          {"mesh/nx1": 16, "mesh/nx2": 24, "mesh/nx3": 1,
+                                           "problem/radius": 0.3, **mb(4, 4, 1),
+                                           "mesh/refinement": "static",
+                                           "time/integrator": "rk2",
+                                           "mesh/ix1_bc": "reflecting", "mesh/ox1_bc": "outflow",
+                                           "mesh/ix2_bc": "outflow", "mesh/ox2_bc": "reflecting",
+                                           "refinement1/x1min": -0.5, "refinement1/x1max": -0.2,
+                                           "refinement1/x2min": -0.1, "refinement1/x2max": 0.1,
+                                           "refinement1/level": 2,
+                                           "refinement2/x1min": 0.3, "refinement2/x1max": 0.5,
+                                           "refinement2/x2min": 0.5, "refinement2/x2max": 0.75,
+                                           "refinement2/level": 1}, "hllc", False, 6),
+    "smr_blast3d_refl_lhllc_plm_rk3": ("hydro_lhllc_ng2", "blast", "athinput.blast",
+                                       {"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 8,
+                                        "problem/radius": 0.3, **mb(4, 4, 4),
+                                        "mesh/refinement": "static", "time/integrator": "rk3",
+                                        **{"mesh/%s%d_bc" % (s, d): "reflecting"
+                                           for s in "io" for d in (1, 2, 3)},
+                                        "refinement1/x1min": -0.5, "refinement1/x1max": -0.3,
+                                        "refinement1/x2min": 0.0, "refinement1/x2max": 0.2,
+                                        "refinement1/x3min": -0.5, "refinement1/x3max": -0.3,
+                                        "refinement1/level": 1}, "lhllc", False, 3),
+    "smr_kh3d_hllc_ppm_rk2_ng4": ("hydro_hllc_ng4", "kh", "athinput.kh",
+                                  dict({"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16},
+                                       **mb(4, 4, 4), **{"mesh/refinement": "static",
+                                       "refinement1/x1min": -0.1, "refinement1/x1max": 0.1,
+                                       "refinement1/x2min": -0.1, "refinement1/x2max": 0.1,
+                                       "refinement1/x3min": -0.1, "refinement1/x3max": 0.1,
+                                       "refinement1/level": 1}), "hllc", False, 3),
     # nonuniform (geometric) mesh spacing, mesh/x?rat != 1: mesh generator, dx?v, nonuniform
     # PLM / PPM branches (plm.cpp:81-105, ppm.cpp:196-207,282-300, reconstruction.cpp:434-461)
     # and the weighted cell-centred field (field.cpp:139-172)
@@ -264,7 +313,9 @@ def make(name):
                                "ncycles": ncyc, "nghost": first["nghost"],
                                "nscalars": nscalars, "eos": eos, "par": first["par"]}),
            "dts": np.array(res["dts"][:ncyc + 1]),
-           "locs": np.array([b["loc"][:3] for b in first["blocks"]], dtype=np.int64),
+           # refined meshes keep the level too (lx alone is ambiguous across levels)
+           "locs": np.array([b["loc"][:4] if name.startswith("smr_") else b["loc"][:3]
+                             for b in first["blocks"]], dtype=np.int64),
            "final_time": np.array(last["time"]), "final_dt": np.array(last["dt"])}
     if res["hst"] is not None:
         # one row per cycle 0..ncyc: time, dt, then the history sums (outputs/history.cpp)

@@ -6,7 +6,7 @@ import pytest
 import util
 
 
-@pytest.mark.parametrize("name", util.golden_names())
+@pytest.mark.parametrize("name", util.golden_names(include_smr=True))
 def test_oracle_reproduces_reference_golden(name):
     g = util.Golden(name)
     m = util.oracle_from_golden(g)
