@@ -40,6 +40,7 @@ CONFIGS = {
     "hydro_hllc_ng3": (False, "hllc", 3, ["kh", "shock_tube", "linear_wave"]),
     # even NGHOST for PPM with mesh refinement (MeshRefinement ctor rejects odd NGHOST)
     "hydro_hllc_ng4": (False, "hllc", 4, ["kh", "blast"]),
+    "hydro_hllc_ng4_s2": (False, "hllc", 4, ["kh"], {"nscalars": 2}),
     "mhd_hlld_ng2": (True, "hlld", 2, ["linear_wave", "blast", "orszag_tang", "shock_tube",
                                        "shk_cloud", "local:usersrc"]),
     "mhd_hlle_ng2": (True, "hlle", 2, ["linear_wave", "shock_tube"]),

@@ -36,7 +36,8 @@ typedef struct AoBlock {
   int nnb; Nb nb[56];      /* 26 on one level; up to 56 with finer neighbours */
   /* static mesh refinement (oracle_smr.c): level, the MeshRefinement's coarse buffers */
   int level, cng, cis, cie, cjs, cje, cks, cke, cnc1, cnc2, cnc3;
-  double *cx1f, *cx2f, *cx3f, *cx1v, *cx2v, *cx3v, *coarse_u, *coarse_w;
+  double *cx1f, *cx2f, *cx3f, *cx1v, *cx2v, *cx3v, *coarse_u, *coarse_w, *coarse_s,
+         *coarse_r;
   int nedge_fine[12];
   double *x1f, *x2f, *x3f, *x1v, *x2v, *x3v, *dx1f, *dx2f, *dx3f;
   AoReconGeom *rg[3];    /* per-index reconstruction geometry along x1, x2, x3 */
@@ -322,7 +323,7 @@ static void set_integrator(AoMesh *m) {
 
 AoMesh *ao_create(const AoParams *p) {
   /* static refinement is restated for hydro on uniformly spaced levels only (oracle_smr.c) */
-  if (p->nref > 0 && (p->mhd || p->nscalars > 0 || (p->xrat[0] != 0.0 && p->xrat[0] != 1.0)
+  if (p->nref > 0 && (p->mhd || (p->xrat[0] != 0.0 && p->xrat[0] != 1.0)
                       || (p->xrat[1] != 0.0 && p->xrat[1] != 1.0)
                       || (p->xrat[2] != 0.0 && p->xrat[2] != 1.0) || p->nref > 8
                       || p->bx1 % 2 || (p->nx2 > 1 && p->bx2 % 2) || (p->nx3 > 1 && p->bx3 % 2)
@@ -443,6 +444,7 @@ AoMesh *ao_create(const AoParams *p) {
                          &B->cx3f, &B->cx3v);
       long cncc = (long)B->cnc1*B->cnc2*B->cnc3;
       B->coarse_u = dalloc(NHYDRO*cncc); B->coarse_w = dalloc(NHYDRO*cncc);
+      if (p->nscalars > 0) { B->coarse_s = dalloc(p->nscalars*cncc); B->coarse_r = dalloc(p->nscalars*cncc); }
     }
     B->rg[0] = make_recon_geom(0, m->xrat[0] != 1.0, B->nc1, B->is, B->ie, ng, B->x1f, B->x1v,
                                B->dx1f, B->bw[0]);
@@ -570,7 +572,7 @@ void ao_destroy(AoMesh *m) {
     for (size_t i = 0; i < sizeof(ptrs)/sizeof(ptrs[0]); ++i) free(ptrs[i]);
     for (int d = 0; d < 3; ++d) { free(B->rg[d]); free(B->bw[d][0]); free(B->bw[d][1]); }
     free(B->cx1f); free(B->cx2f); free(B->cx3f); free(B->cx1v); free(B->cx2v); free(B->cx3v);
-    free(B->coarse_u); free(B->coarse_w);
+    free(B->coarse_u); free(B->coarse_w); free(B->coarse_s); free(B->coarse_r);
   }
   tree_free(m->root);
   free(m->blk); free(m->gid_of); free(m);
@@ -1858,10 +1860,11 @@ void ao_enroll_user_bc(AoMesh *m, int face, AoBValFunc fn, void *user) {
 /* Mesh::Initialize after ProblemGenerator (src/mesh/mesh.cpp:1416-1649) */
 void ao_initialize(AoMesh *m) {
   m->bc_time = m->time; m->bc_dt = 0.0;   /* ApplyPhysicalBoundaries(time, 0.0, ...) mesh.cpp:1515 */
-  if (m->multilevel) smr_exchange_cc(m); else
+  if (m->multilevel) { smr_exchange_cc(m, 0); smr_exchange_cc(m, 1); } else {
   ao_exchange_cc(m);
   ao_exchange_fc(m);
   ao_exchange_scalars(m);
+  }
   for (int g = 0; g < m->nb; ++g) {
     if (m->multilevel) smr_prolongate_boundaries(m, g);   /* mesh.cpp:1527-1528 */
     ao_primitives(m, g);
@@ -1886,7 +1889,7 @@ double ao_cycle(AoMesh *m) {
       ao_calc_scalar_fluxes(m, g, order);
     }
     ao_emf_exchange(m);
-    if (m->multilevel) smr_flux_correction(m);   /* SEND_HYDFLX / RECV_HYDFLX before INT_HYD */
+    if (m->multilevel) { smr_flux_correction(m, 0); smr_flux_correction(m, 1); }   /* SEND_HYDFLX / RECV_HYDFLX before INT_HYD */
     for (int g = 0; g < m->nb; ++g) {
       double w[5] = {1.0, m->delta[s], 0.0, 0.0, 0.0};
       ao_weighted_ave_cc(m, g, 1, 0, w);
@@ -1908,10 +1911,11 @@ double ao_cycle(AoMesh *m) {
         m->user_src(m->user_src_arg, g, m->time + m->sbeta[s]*dt, m->beta[s]*dt, m->blk[g].w,
                     m->blk[g].r, m->blk[g].bcc, m->blk[g].u, m->blk[g].s);
     }
-    if (m->multilevel) smr_exchange_cc(m); else
+    if (m->multilevel) { smr_exchange_cc(m, 0); smr_exchange_cc(m, 1); } else {
     ao_exchange_cc(m);
     ao_exchange_fc(m);
     ao_exchange_scalars(m);
+    }
     /* PhysicalBoundary task: t_end_stage, beta*dt (time_integrator.cpp:2045-2062) */
     m->bc_time = m->time + m->ebeta[s]*dt; m->bc_dt = m->beta[s]*dt;
     for (int g = 0; g < m->nb; ++g) {

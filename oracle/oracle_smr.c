@@ -430,8 +430,9 @@ static void smr_my_fi(const AoMesh *m, const AoBlock *B, int o1, int o2, int o3,
 
 /* SendBoundaryBuffers + ReceiveBoundaryBuffers + SetBoundaries of u on a multilevel mesh, from
  * the receiver's side (bvals_cc.cpp:195-470; bvals_var.cpp:212-296) */
-static void smr_exchange_cc(AoMesh *m) {
-  int ng = m->p.ng, nv = NHYDRO;
+static void smr_exchange_cc(AoMesh *m, int scalars) {
+  int ng = m->p.ng, nv = scalars ? m->p.nscalars : NHYDRO;
+  if (nv <= 0) return;
   /* Phase 1 packs every message from the sender's arrays as they are now (the reference packs
    * at send time; with MeshBlocks narrower than 2*NGHOST a restricted slab reaches into the
    * sender's own ghost zones, i.e. the previous exchange's data), phase 2 unpacks them. */
@@ -444,6 +445,8 @@ static void smr_exchange_cc(AoMesh *m) {
     for (int n = 0; n < B->nnb; ++n) {
       const Nb *nb = &B->nb[n];
       AoBlock *N = &m->blk[nb->gid];
+      double *Bf = scalars ? B->s : B->u, *Bc = scalars ? B->coarse_s : B->coarse_u;
+      double *Nf = scalars ? N->s : N->u, *Nc = scalars ? N->coarse_s : N->coarse_u;
       int o1 = nb->ox1, o2 = nb->ox2, o3 = nb->ox3;
       int si, ei, sj, ej, sk, ek;      /* destination box in B */
       int ti, tj, tk;                  /* source origin in N */
@@ -458,7 +461,7 @@ static void smr_exchange_cc(AoMesh *m) {
         ti = (-o1 > 0) ? (N->ie - ng + 1) : N->is;
         tj = (-o2 > 0) ? (N->je - ng + 1) : N->js;
         tk = (-o3 > 0) ? (N->ke - ng + 1) : N->ks;
-        smr_stage(pass, &stage[g][n], N->u, svf, N->nc2, N->nc1, ti, tj, tk, B->u, svf, B->nc2,
+        smr_stage(pass, &stage[g][n], Nf, svf, N->nc2, N->nc1, ti, tj, tk, Bf, svf, B->nc2,
                   B->nc1, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1, nv);
       } else if (nb->level < B->level) {
         /* SetBoundaryFromCoarser: destination in B's coarse buffer */
@@ -488,8 +491,8 @@ static void smr_exchange_cc(AoMesh *m) {
           else { if (fi2 == 1) e += h3; else f -= h3; }
         }
         (void)b; (void)d; (void)f;
-        smr_stage(pass, &stage[g][n], N->u, (long)N->nc3*N->nc2*N->nc1, N->nc2, N->nc1, a, c, e,
-                  B->coarse_u, svc, B->cnc2, B->cnc1, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1, nv);
+        smr_stage(pass, &stage[g][n], Nf, (long)N->nc3*N->nc2*N->nc1, N->nc2, N->nc1, a, c, e,
+                  Bc, svc, B->cnc2, B->cnc1, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1, nv);
       } else {
         /* SetBoundaryFromFiner: destination in B's fine array, data = N's restricted slab */
         int fi1 = nb->fi1, fi2 = nb->fi2;
@@ -515,10 +518,10 @@ static void smr_exchange_cc(AoMesh *m) {
         if (pass == 0) {   /* the sender restricts this slab now (RestrictCellCenteredValues) */
           int te = (-o1 < 0) ? (N->cis + cn) : N->cie, ue = (-o2 < 0) ? (N->cjs + cn) : N->cje,
               ve = (-o3 < 0) ? (N->cks + cn) : N->cke;
-          smr_restrict(m, N, N->u, N->coarse_u, nv, ti, te, tj, ue, tk, ve);
+          smr_restrict(m, N, Nf, Nc, nv, ti, te, tj, ue, tk, ve);
         }
-        smr_stage(pass, &stage[g][n], N->coarse_u, (long)N->cnc3*N->cnc2*N->cnc1, N->cnc2, N->cnc1,
-                  ti, tj, tk, B->u, svf, B->nc2, B->nc1, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1, nv);
+        smr_stage(pass, &stage[g][n], Nc, (long)N->cnc3*N->cnc2*N->cnc1, N->cnc2, N->cnc1,
+                  ti, tj, tk, Bf, svf, B->nc2, B->nc1, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1, nv);
       }
     }
   }
@@ -561,22 +564,25 @@ static void smr_coarse_phys_bc(const AoMesh *m, AoBlock *B, int face, int il, in
   int bc = B->bcs[face];
   if (bc != AO_BC_OUTFLOW && bc != AO_BC_REFLECT) return;
   int dir = face/2, outer = face & 1;
-  for (int n = 0; n < NHYDRO; ++n) {
+  for (int n = 0; n < NHYDRO + m->p.nscalars; ++n) {
     double sign = (bc == AO_BC_REFLECT && n == IVX + dir) ? -1.0 : 1.0;
+    double *cw = B->coarse_w;
+    int v = n;
+    if (n >= NHYDRO) { cw = B->coarse_r; v = n - NHYDRO; sign = 1.0; }
     if (dir == 0) {
       for (int k = kl; k <= ku; ++k) for (int j = jl; j <= ju; ++j) {
-        if (!outer) B->coarse_w[CCC(B,n,k,j,il-1)] = sign*B->coarse_w[CCC(B,n,k,j,il)];
-        else B->coarse_w[CCC(B,n,k,j,iu+1)] = sign*B->coarse_w[CCC(B,n,k,j,iu)];
+        if (!outer) cw[CCC(B,v,k,j,il-1)] = sign*cw[CCC(B,v,k,j,il)];
+        else cw[CCC(B,v,k,j,iu+1)] = sign*cw[CCC(B,v,k,j,iu)];
       }
     } else if (dir == 1) {
       for (int k = kl; k <= ku; ++k) for (int i = il; i <= iu; ++i) {
-        if (!outer) B->coarse_w[CCC(B,n,k,jl-1,i)] = sign*B->coarse_w[CCC(B,n,k,jl,i)];
-        else B->coarse_w[CCC(B,n,k,ju+1,i)] = sign*B->coarse_w[CCC(B,n,k,ju,i)];
+        if (!outer) cw[CCC(B,v,k,jl-1,i)] = sign*cw[CCC(B,v,k,jl,i)];
+        else cw[CCC(B,v,k,ju+1,i)] = sign*cw[CCC(B,v,k,ju,i)];
       }
     } else {
       for (int j = jl; j <= ju; ++j) for (int i = il; i <= iu; ++i) {
-        if (!outer) B->coarse_w[CCC(B,n,kl-1,j,i)] = sign*B->coarse_w[CCC(B,n,kl,j,i)];
-        else B->coarse_w[CCC(B,n,ku+1,j,i)] = sign*B->coarse_w[CCC(B,n,ku,j,i)];
+        if (!outer) cw[CCC(B,v,kl-1,j,i)] = sign*cw[CCC(B,v,kl,j,i)];
+        else cw[CCC(B,v,ku+1,j,i)] = sign*cw[CCC(B,v,ku,j,i)];
       }
     }
   }
@@ -585,7 +591,7 @@ static void smr_coarse_phys_bc(const AoMesh *m, AoBlock *B, int face, int il, in
 /* BoundaryValues::ProlongateBoundaries for one block (bvals_refine.cpp:96-570, hydro) */
 static void smr_prolongate_boundaries(AoMesh *m, int g) {
   AoBlock *B = &m->blk[g];
-  int nv = NHYDRO;
+  int nv = NHYDRO, ns = m->p.nscalars;
   for (int n = 0; n < B->nnb; ++n) {
     const Nb *nb = &B->nb[n];
     if (nb->level >= B->level) continue;
@@ -607,6 +613,7 @@ static void smr_prolongate_boundaries(AoMesh *m, int g) {
         if (nk == 0) { rks = B->cks; rke = B->cke; if (o3 == 1) rks = B->cke; else if (o3 == -1) rke = B->cks; }
         else if (nk == 1) { rks = B->cke + 1; rke = B->cke + 1; } else { rks = B->cks - 1; rke = B->cks - 1; }
         smr_restrict(m, B, B->u, B->coarse_u, nv, ris, rie, rjs, rje, rks, rke);
+        if (ns > 0) smr_restrict(m, B, B->s, B->coarse_s, ns, ris, rie, rjs, rje, rks, rke);
       }
     /* loop limits of the ghost zones on the coarse level */
     int cn = B->cng - 1, si, ei, sj, ej, sk, ek;
@@ -629,6 +636,14 @@ static void smr_prolongate_boundaries(AoMesh *m, int g) {
       else { f3m = 1; f3p = 1; }
     }
     smr_coarse_cons2prim(m, B, si-f1m, ei+f1p, sj-f2m, ej+f2p, sk-f3m, ek+f3p);
+    /* PassiveScalarConservedToPrimitive on the coarse buffers (eos_scalars.cpp:31-60) */
+    for (int v = 0; v < ns; ++v) for (int k = sk-f3m; k <= ek+f3p; ++k)
+      for (int j = sj-f2m; j <= ej+f2p; ++j) for (int i = si-f1m; i <= ei+f1p; ++i) {
+        double d = B->coarse_u[CCC(B,IDN,k,j,i)];
+        double *s_n = &B->coarse_s[CCC(B,v,k,j,i)];
+        *s_n = (*s_n < m->p.sfloor*d) ? m->p.sfloor*d : *s_n;
+        B->coarse_r[CCC(B,v,k,j,i)] = *s_n/d;
+      }
     if (o1 == 0) {
       if (B->bcs[0] >= 0) smr_coarse_phys_bc(m, B, 0, B->cis, B->cie, sj, ej, sk, ek);
       if (B->bcs[1] >= 0) smr_coarse_phys_bc(m, B, 1, B->cis, B->cie, sj, ej, sk, ek);
@@ -643,11 +658,13 @@ static void smr_prolongate_boundaries(AoMesh *m, int g) {
     }
     /* Step 3: ProlongateGhostCells on primitives, then PrimitiveToConserved on the fine cells */
     smr_prolongate(m, B, B->coarse_w, B->w, nv, si, ei, sj, ej, sk, ek);
+    if (ns > 0) smr_prolongate(m, B, B->coarse_r, B->r, ns, si, ei, sj, ej, sk, ek);
     int fsi = (si - B->cis)*2 + B->is, fei = (ei - B->cis)*2 + B->is + 1;
     int fsj = B->js, fej = B->je, fsk = B->ks, fek = B->ke;
     if (m->f2) { fsj = (sj - B->cjs)*2 + B->js; fej = (ej - B->cjs)*2 + B->js + 1; }
     if (m->f3) { fsk = (sk - B->cks)*2 + B->ks; fek = (ek - B->cks)*2 + B->ks + 1; }
     ao_prim2cons(m, g, fsi, fei, fsj, fej, fsk, fek);
+    if (ns > 0) ao_scalar_prim2cons(m, g, fsi, fei, fsj, fej, fsk, fek);
   }
 }
 
@@ -655,7 +672,9 @@ static void smr_prolongate_boundaries(AoMesh *m, int g) {
 
 /* SendFluxCorrection / ReceiveFluxCorrection of the hydro fluxes (flux_correction_cc.cpp:69-290):
  * the area-weighted average of the fine fluxes replaces the coarse flux on a shared face */
-static void smr_flux_correction(AoMesh *m) {
+static void smr_flux_correction(AoMesh *m, int scalars) {
+  int nvf = scalars ? m->p.nscalars : NHYDRO;
+  if (nvf <= 0) return;
   for (int g = 0; g < m->nb; ++g) {
     AoBlock *B = &m->blk[g];            /* coarse receiver */
     for (int n = 0; n < B->nnb; ++n) {
@@ -664,21 +683,21 @@ static void smr_flux_correction(AoMesh *m) {
       AoBlock *N = &m->blk[nb->gid];    /* fine sender; its face towards B is the opposite one */
       int fid = nb->fid, sfid = fid ^ 1;
       int hx1 = m->p.bx1/2, hx2 = m->f2 ? m->p.bx2/2 : 0, hx3 = m->f3 ? m->p.bx3/2 : 0;
-      for (int nn = 0; nn < NHYDRO; ++nn) {
+      for (int nn = 0; nn < nvf; ++nn) {
         if (fid < 2) {
           int i = N->is + (N->ie - N->is + 1)*sfid;
           int il = B->is + (B->ie - B->is)*fid + fid;
           int jl = B->js, kl = B->ks;
           if (nb->fi1 != 0) jl += hx2;
           if (nb->fi2 != 0) kl += hx3;
-          const double *fx = N->flux[0];
+          const double *fx = scalars ? N->sflux[0] : N->flux[0]; double *bf = scalars ? B->sflux[0] : B->flux[0];
           if (m->f3) {
             for (int k = N->ks, ck = kl; k <= N->ke; k += 2, ++ck)
               for (int j = N->js, cj = jl; j <= N->je; j += 2, ++cj) {
                 double amm = N->dx2f[j]*N->dx3f[k], amp = N->dx2f[j+1]*N->dx3f[k];
                 double apm = N->dx2f[j]*N->dx3f[k+1], app = N->dx2f[j+1]*N->dx3f[k+1];
                 double tarea = amm + amp + apm + app;
-                B->flux[0][FL1(B,nn,ck,cj,il)] =
+                bf[FL1(B,nn,ck,cj,il)] =
                     (fx[FL1(N,nn,k,j,i)]*amm + fx[FL1(N,nn,k,j+1,i)]*amp
                      + fx[FL1(N,nn,k+1,j,i)]*apm + fx[FL1(N,nn,k+1,j+1,i)]*app)/tarea;
               }
@@ -687,11 +706,11 @@ static void smr_flux_correction(AoMesh *m) {
             for (int j = N->js, cj = jl; j <= N->je; j += 2, ++cj) {
               double am = N->dx2f[j]*N->dx3f[k], ap = N->dx2f[j+1]*N->dx3f[k];
               double tarea = am + ap;
-              B->flux[0][FL1(B,nn,B->ks,cj,il)] =
+              bf[FL1(B,nn,B->ks,cj,il)] =
                   (fx[FL1(N,nn,k,j,i)]*am + fx[FL1(N,nn,k,j+1,i)]*ap)/tarea;
             }
           } else {
-            B->flux[0][FL1(B,nn,B->ks,B->js,il)] = fx[FL1(N,nn,N->ks,N->js,i)];
+            bf[FL1(B,nn,B->ks,B->js,il)] = fx[FL1(N,nn,N->ks,N->js,i)];
           }
         } else if (fid < 4) {
           int j = N->js + (N->je - N->js + 1)*(sfid & 1);
@@ -699,14 +718,14 @@ static void smr_flux_correction(AoMesh *m) {
           int il = B->is, kl = B->ks;
           if (nb->fi1 != 0) il += hx1;
           if (nb->fi2 != 0) kl += hx3;
-          const double *fx = N->flux[1];
+          const double *fx = scalars ? N->sflux[1] : N->flux[1]; double *bf = scalars ? B->sflux[1] : B->flux[1];
           if (m->f3) {
             for (int k = N->ks, ck = kl; k <= N->ke; k += 2, ++ck)
               for (int i = N->is, ci = il; i <= N->ie; i += 2, ++ci) {
                 double a00 = N->dx1f[i]*N->dx3f[k], a01 = N->dx1f[i+1]*N->dx3f[k];
                 double a10 = N->dx1f[i]*N->dx3f[k+1], a11 = N->dx1f[i+1]*N->dx3f[k+1];
                 double tarea = a00 + a01 + a10 + a11;
-                B->flux[1][FL2(B,nn,ck,jl,ci)] =
+                bf[FL2(B,nn,ck,jl,ci)] =
                     (fx[FL2(N,nn,k,j,i)]*a00 + fx[FL2(N,nn,k,j,i+1)]*a01
                      + fx[FL2(N,nn,k+1,j,i)]*a10 + fx[FL2(N,nn,k+1,j,i+1)]*a11)/tarea;
               }
@@ -715,7 +734,7 @@ static void smr_flux_correction(AoMesh *m) {
             for (int i = N->is, ci = il; i <= N->ie; i += 2, ++ci) {
               double a0 = N->dx1f[i]*N->dx3f[k], a1 = N->dx1f[i+1]*N->dx3f[k];
               double tarea = a0 + a1;
-              B->flux[1][FL2(B,nn,B->ks,jl,ci)] =
+              bf[FL2(B,nn,B->ks,jl,ci)] =
                   (fx[FL2(N,nn,k,j,i)]*a0 + fx[FL2(N,nn,k,j,i+1)]*a1)/tarea;
             }
           }
@@ -725,13 +744,13 @@ static void smr_flux_correction(AoMesh *m) {
           int il = B->is, jl = B->js;
           if (nb->fi1 != 0) il += hx1;
           if (nb->fi2 != 0) jl += hx2;
-          const double *fx = N->flux[2];
+          const double *fx = scalars ? N->sflux[2] : N->flux[2]; double *bf = scalars ? B->sflux[2] : B->flux[2];
           for (int j = N->js, cj = jl; j <= N->je; j += 2, ++cj)
             for (int i = N->is, ci = il; i <= N->ie; i += 2, ++ci) {
               double a00 = N->dx1f[i]*N->dx2f[j], a01 = N->dx1f[i+1]*N->dx2f[j];
               double a10 = N->dx1f[i]*N->dx2f[j+1], a11 = N->dx1f[i+1]*N->dx2f[j+1];
               double tarea = a00 + a01 + a10 + a11;
-              B->flux[2][FL3(B,nn,kl,cj,ci)] =
+              bf[FL3(B,nn,kl,cj,ci)] =
                   (fx[FL3(N,nn,k,j,i)]*a00 + fx[FL3(N,nn,k,j,i+1)]*a01
                    + fx[FL3(N,nn,k,j+1,i)]*a10 + fx[FL3(N,nn,k,j+1,i+1)]*a11)/tarea;
             }

@@ -215,6 +215,20 @@ CASES = {
                                   "refinement1/x2min": -0.1, "refinement1/x2max": 0.1,
                                   "refinement1/x3min": -0.1, "refinement1/x3max": 0.1,
                                   "refinement1/level": 1}, "hllc", False, 4),
+    "smr_khs2d_lhllc_plm_vl2_s1": ("hydro_lhllc_ng2_s1", "kh", "athinput.kh_scalar",
+                                   dict(KS, **mb(4, 8, 1), **{"mesh/refinement": "static",
+                                        "refinement1/x1min": -0.1, "refinement1/x1max": 0.1,
+                                        "refinement1/x2min": -0.3, "refinement1/x2max": 0.0,
+                                        "refinement1/level": 2}), "lhllc", False, 6, 1),
+    "smr_khs3d_hllc_ppm_rk3_ng4_s2": ("hydro_hllc_ng4_s2", "kh", "athinput.kh_scalar",
+                                      dict({"mesh/nx1": 16, "mesh/nx2": 16, "mesh/nx3": 16},
+                                           **mb(8, 8, 8), **{"time/xorder": 3,
+                                           "time/integrator": "rk3", "mesh/refinement": "static",
+                                           "mesh/ix2_bc": "reflecting", "mesh/ox2_bc": "reflecting",
+                                           "refinement1/x1min": -0.5, "refinement1/x1max": -0.3,
+                                           "refinement1/x2min": -0.5, "refinement1/x2max": -0.3,
+                                           "refinement1/x3min": 0.3, "refinement1/x3max": 0.5,
+                                           "refinement1/level": 1}), "hllc", False, 3, 2),
     "smr_sod1d_hllc_plm_vl2": ("hydro_hllc_ng2", "shock_tube", "athinput.sod",
                                {"mesh/nx1": 64, "meshblock/nx1": 8, "mesh/refinement": "static",
                                 "refinement1/x1min": -0.1, "refinement1/x1max": 0.15,
