@@ -35,7 +35,15 @@ SYMBOLS = [
     "ab_mesh_launch_count", "ab_mesh_stream", "ab_mesh_sync",
     "ab_stage_begin", "ab_stage_upload_all", "ab_stage_commit", "ab_stage_download_all",
     "ab_stage_sync",
+    "ab_smr_last_error", "ab_smr_plan_create", "ab_smr_plan_destroy", "ab_smr_plan_nblocks",
+    "ab_smr_plan_blocks", "ab_smr_plan_neighbors", "ab_smr_plan_transfers",
 ]
+
+
+class AbRefinementRegion(C.Structure):
+    _fields_ = [("x1min", C.c_double), ("x1max", C.c_double), ("x2min", C.c_double),
+                ("x2max", C.c_double), ("x3min", C.c_double), ("x3max", C.c_double),
+                ("level", C.c_int)]
 
 
 class AbMeshParams(C.Structure):
@@ -102,6 +110,15 @@ def load():
     L.ab_stage_commit.argtypes = [vp]
     L.ab_stage_download_all.argtypes = [vp, C.POINTER(dp)]
     L.ab_stage_sync.argtypes = [vp]
+    L.ab_smr_last_error.restype = C.c_char_p
+    L.ab_smr_plan_create.argtypes = [C.POINTER(AbMeshParams), C.POINTER(AbRefinementRegion), ip,
+                                     C.POINTER(vp)]
+    L.ab_smr_plan_destroy.argtypes = [vp]
+    L.ab_smr_plan_nblocks.argtypes = [vp]
+    L.ab_smr_plan_blocks.argtypes = [vp, C.POINTER(C.c_long), ip]
+    L.ab_smr_plan_neighbors.argtypes = [vp, ip, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ab_smr_plan_transfers.restype = C.c_long
+    L.ab_smr_plan_transfers.argtypes = [vp, C.POINTER(C.c_long), C.c_long]
     L.ab_history.argtypes = [vp, dp, ip]
     L.ab_enroll_user_explicit_source_function.argtypes = [vp, SRCTERMFUNC, vp]
     L.ab_enroll_user_explicit_source_function_device.argtypes = [vp, SRCTERMFUNC_DEVICE, vp]

@@ -97,6 +97,37 @@ int ab_plan_ranklist(const AbMesh *m, int *out, int max_n);
  * Field::CalculateCellCenteredField.  Returns the number of doubles (0: no such array). */
 int ab_plan_geometry(const AbMesh *m, int lid, int dir, int what, double *out, int max_n);
 
+/* ---- static mesh refinement, host-side planner (no GPU needed; csrc/ab_smr.cpp).  The Mesh
+ * ctor's <refinementN> handling, MeshBlockTree, CalculateLoadBalance and
+ * BoundaryBase::SearchAndSetNeighbors on a refined mesh (src/mesh/mesh.cpp:323-465,
+ * src/mesh/meshblock_tree.cpp:60-460, src/bvals/bvals_base.cpp:299-736) plus the transfer plan of
+ * the cell-centred ghost exchange between levels, ProlongateBoundaries and the flux correction
+ * (src/bvals/cc/bvals_cc.cpp:195-470, src/bvals/bvals_refine.cpp:96-570,
+ * src/bvals/cc/flux_correction_cc.cpp:69-290) as index lists.  The device kernels that execute
+ * the plan are not in this version: ab_mesh_create has no refinement input yet.
+ *   blocks:    5 longs per MeshBlock in gid (Z) order {level, lx1, lx2, lx3, rank}
+ *   neighbors: 8 ints per neighbour {ox1, ox2, ox3, type 0 face|1 edge|2 corner, gid, level,
+ *              fi1, fi2}; nblevel = 27 ints [k][j][i] (-1: none)
+ *   transfers: 12 longs per row {kind, src gid, src origin i j k, dst gid, dst origin i j k,
+ *              extent ni nj nk}; kind 0 same level (fine -> fine ghost cells), 1 to a finer block
+ *              (fine -> its coarse buffer), 2 to a coarser block (the sender's restricted slab in
+ *              coarse indices -> fine ghost cells), 10 / 11 / 12 the ProlongateBoundaries work of
+ *              one (block, coarser neighbour), 20 flux correction {fine gid, its face, -, -,
+ *              coarse gid, its face, fi1, fi2} */
+typedef struct {
+  double x1min, x1max, x2min, x2max, x3min, x3max;   /* <refinementN> x?min / x?max */
+  int level;                                          /* <refinementN> level (root grid = 0) */
+} AbRefinementRegion;
+typedef struct AbSmrPlan AbSmrPlan;
+const char *ab_smr_last_error(void);
+int ab_smr_plan_create(const AbMeshParams *p, const AbRefinementRegion *regions, int nregions,
+                       AbSmrPlan **out);
+int ab_smr_plan_destroy(AbSmrPlan *plan);
+int ab_smr_plan_nblocks(const AbSmrPlan *plan);
+int ab_smr_plan_blocks(const AbSmrPlan *plan, long *rows, int max_rows);
+int ab_smr_plan_neighbors(const AbSmrPlan *plan, int gid, int *rows, int *nblevel);
+long ab_smr_plan_transfers(const AbSmrPlan *plan, long *rows, long max_rows);
+
 /* ---- user-enrolled boundary functions: Mesh::EnrollUserBoundaryFunction (src/mesh/mesh.cpp)
  * with the BValFunc signature of src/athena.hpp:179-182 on plain arrays.  `face`: 0..5 =
  * inner_x1, outer_x1, ..., outer_x3 of a face whose flag is AB_BC_USER ("user").  The function

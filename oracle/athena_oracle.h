@@ -132,6 +132,13 @@ void ao_ppm(long n, int nvar, const double *qm2, const double *qm1, const double
             const double *qp1, const double *qp2, double dfloor, double pfloor,
             double *ql_plus, double *qr_minus);
 
+/* test hook (refined meshes): transfer list of one exchange + ProlongateBoundaries + flux
+ * correction, 12 longs per row (layout: oracle_smr.c); returns the number of rows */
+long ao_smr_transfers(AoMesh *m, long *rows, long max_rows);
+/* neighbour list of block b: rows of 8 ints {ox1, ox2, ox3, type, gid, level, fi1, fi2};
+ * nblevel (27 ints, [k][j][i]) when not NULL; returns the number of neighbours */
+int ao_neighbors(const AoMesh *m, int b, int *rows, int *nblevel);
+
 /* test entries for the reconstruction geometry of one direction (nonuni: x?rat != 1) */
 void ao_recon_line(int dir, int nonuni, int order, int nc, int s, int e, int ng, const double *xf,
                    const double *xv, const double *dxf, int nvar, const double *q, int lo, int hi,

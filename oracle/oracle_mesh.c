@@ -580,6 +580,18 @@ void ao_destroy(AoMesh *m) {
 
 int ao_nblocks(const AoMesh *m) { return m->nb; }
 int ao_block_level(const AoMesh *m, int b) { return m->blk[b].level; }
+int ao_neighbors(const AoMesh *m, int b, int *rows, int *nblevel) {
+  const AoBlock *B = &m->blk[b];
+  for (int n = 0; n < B->nnb && rows; ++n) {
+    const Nb *nb = &B->nb[n];
+    int *r = rows + 8*n;
+    r[0] = nb->ox1; r[1] = nb->ox2; r[2] = nb->ox3; r[3] = nb->type; r[4] = nb->gid;
+    r[5] = m->multilevel ? nb->level : 0; r[6] = nb->fi1; r[7] = nb->fi2;
+  }
+  if (nblevel) for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i)
+    nblevel[(k*3 + j)*3 + i] = B->nblevel[k][j][i];
+  return B->nnb;
+}
 double ao_time(const AoMesh *m) { return m->time; }
 double ao_dt(const AoMesh *m) { return m->dt; }
 int ao_ncycle(const AoMesh *m) { return m->ncycle; }

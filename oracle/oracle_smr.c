@@ -398,6 +398,19 @@ static void box_copy(const double *src, long sv_s, long s2s, long s1s, int si, i
           src[n*sv_s + ((long)(sk+k)*s2s + (sj+j))*s1s + (si+i)];
 }
 
+/* optional log of the transfers of one exchange (test hook: ao_smr_transfers) */
+static long *g_xfer_rows = NULL; static long g_xfer_n = 0, g_xfer_cap = 0;
+static void smr_log(int kind, int src, int si, int sj, int sk, int dst, int di, int dj, int dk,
+                    int ni, int nj, int nk) {
+  if (!g_xfer_rows) return;
+  if (g_xfer_n < g_xfer_cap) {
+    long *r = g_xfer_rows + 12*g_xfer_n;
+    r[0] = kind; r[1] = src; r[2] = si; r[3] = sj; r[4] = sk; r[5] = dst; r[6] = di; r[7] = dj;
+    r[8] = dk; r[9] = ni; r[10] = nj; r[11] = nk;
+  }
+  g_xfer_n++;
+}
+
 /* pass 0: pack the source box into a fresh buffer; pass 1: unpack it into the destination box */
 static void smr_stage(int pass, double **buf, const double *src, long sv_s, long s2s, long s1s,
                       int si, int sj, int sk, double *dst, long sv_d, long s2d, long s1d, int di,
@@ -461,6 +474,7 @@ static void smr_exchange_cc(AoMesh *m, int scalars) {
         ti = (-o1 > 0) ? (N->ie - ng + 1) : N->is;
         tj = (-o2 > 0) ? (N->je - ng + 1) : N->js;
         tk = (-o3 > 0) ? (N->ke - ng + 1) : N->ks;
+        if (pass == 0) smr_log(0, nb->gid, ti, tj, tk, g, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1);
         smr_stage(pass, &stage[g][n], Nf, svf, N->nc2, N->nc1, ti, tj, tk, Bf, svf, B->nc2,
                   B->nc1, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1, nv);
       } else if (nb->level < B->level) {
@@ -491,6 +505,7 @@ static void smr_exchange_cc(AoMesh *m, int scalars) {
           else { if (fi2 == 1) e += h3; else f -= h3; }
         }
         (void)b; (void)d; (void)f;
+        if (pass == 0) smr_log(1, nb->gid, a, c, e, g, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1);
         smr_stage(pass, &stage[g][n], Nf, (long)N->nc3*N->nc2*N->nc1, N->nc2, N->nc1, a, c, e,
                   Bc, svc, B->cnc2, B->cnc1, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1, nv);
       } else {
@@ -520,6 +535,7 @@ static void smr_exchange_cc(AoMesh *m, int scalars) {
               ve = (-o3 < 0) ? (N->cks + cn) : N->cke;
           smr_restrict(m, N, Nf, Nc, nv, ti, te, tj, ue, tk, ve);
         }
+        if (pass == 0) smr_log(2, nb->gid, ti, tj, tk, g, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1);
         smr_stage(pass, &stage[g][n], Nc, (long)N->cnc3*N->cnc2*N->cnc1, N->cnc2, N->cnc1,
                   ti, tj, tk, Bf, svf, B->nc2, B->nc1, si, sj, sk, ei-si+1, ej-sj+1, ek-sk+1, nv);
       }
@@ -612,6 +628,7 @@ static void smr_prolongate_boundaries(AoMesh *m, int g) {
         else if (nj == 1) { rjs = B->cje + 1; rje = B->cje + 1; } else { rjs = B->cjs - 1; rje = B->cjs - 1; }
         if (nk == 0) { rks = B->cks; rke = B->cke; if (o3 == 1) rks = B->cke; else if (o3 == -1) rke = B->cks; }
         else if (nk == 1) { rks = B->cke + 1; rke = B->cke + 1; } else { rks = B->cks - 1; rke = B->cks - 1; }
+        smr_log(12, g, ris, rjs, rks, g, o1, o2, o3, rie-ris+1, rje-rjs+1, rke-rks+1);
         smr_restrict(m, B, B->u, B->coarse_u, nv, ris, rie, rjs, rje, rks, rke);
         if (ns > 0) smr_restrict(m, B, B->s, B->coarse_s, ns, ris, rie, rjs, rje, rks, rke);
       }
@@ -656,6 +673,8 @@ static void smr_prolongate_boundaries(AoMesh *m, int g) {
       if (B->bcs[4] >= 0) smr_coarse_phys_bc(m, B, 4, si, ei, sj, ej, B->cks, B->cke);
       if (B->bcs[5] >= 0) smr_coarse_phys_bc(m, B, 5, si, ei, sj, ej, B->cks, B->cke);
     }
+    smr_log(10, g, si, sj, sk, g, si-f1m, sj-f2m, sk-f3m, ei-si+1, ej-sj+1, ek-sk+1);
+    smr_log(11, g, ei+f1p, ej+f2p, ek+f3p, g, o1, o2, o3, 0, 0, 0);
     /* Step 3: ProlongateGhostCells on primitives, then PrimitiveToConserved on the fine cells */
     smr_prolongate(m, B, B->coarse_w, B->w, nv, si, ei, sj, ej, sk, ek);
     if (ns > 0) smr_prolongate(m, B, B->coarse_r, B->r, ns, si, ei, sj, ej, sk, ek);
@@ -681,6 +700,7 @@ static void smr_flux_correction(AoMesh *m, int scalars) {
       const Nb *nb = &B->nb[n];
       if (nb->type != 0 || nb->level <= B->level) continue;
       AoBlock *N = &m->blk[nb->gid];    /* fine sender; its face towards B is the opposite one */
+      if (!scalars) smr_log(20, nb->gid, nb->fid ^ 1, 0, 0, g, nb->fid, nb->fi1, nb->fi2, 0, 0, 0);
       int fid = nb->fid, sfid = fid ^ 1;
       int hx1 = m->p.bx1/2, hx2 = m->f2 ? m->p.bx2/2 : 0, hx3 = m->f3 ? m->p.bx3/2 : 0;
       for (int nn = 0; nn < nvf; ++nn) {
@@ -758,4 +778,21 @@ static void smr_flux_correction(AoMesh *m, int scalars) {
       }
     }
   }
+}
+
+/* test hook: the transfer list of one ghost exchange + ProlongateBoundaries + flux correction
+ * (rows of 12 longs: kind, src gid, src origin i j k, dst gid, dst origin i j k, extent ni nj nk;
+ * kind 0 same level fine->fine, 1 coarser fine -> coarse buffer, 2 finer's restricted slab ->
+ * fine, 10/11 prolongation box + coarse cons2prim margins / offsets, 12 restriction of own
+ * ghost cells, 20 flux correction {fine gid, its face, -, -, coarse gid, face, fi1, fi2}).
+ * Runs on a scratch copy of nothing: it performs a real exchange on the mesh's current state. */
+long ao_smr_transfers(AoMesh *m, long *rows, long max_rows) {
+  if (!m->multilevel) return 0;
+  static long dummy[12];
+  g_xfer_rows = rows ? rows : dummy; g_xfer_n = 0; g_xfer_cap = rows ? max_rows : 0;
+  smr_exchange_cc(m, 0);
+  for (int g = 0; g < m->nb; ++g) smr_prolongate_boundaries(m, g);
+  smr_flux_correction(m, 0);
+  g_xfer_rows = NULL;
+  return g_xfer_n;
 }

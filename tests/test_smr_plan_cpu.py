@@ -1,0 +1,179 @@
+"""CPU: the product's static-mesh-refinement planner (csrc/ab_smr.cpp through ab_smr_plan_*)
+against the C oracle, whose SMR path reproduces the reference's runs bit for bit
+(tests/golden/smr_*.npz, tests/test_oracle_golden.py).
+
+Compared exactly, on the refined meshes of the golden fixtures and a few more:
+  * the Z-ordered MeshBlock list (level, logical location) -- also against the reference's own
+    block list stored in the fixtures;
+  * every block's neighbour list (offsets, type, gid, level, finer-leaf indices) and nblevel;
+  * the transfer plan of one ghost exchange (same level / to finer / to coarser boxes), the
+    ProlongateBoundaries work list and the flux-correction pairs, as sets of index rows: the
+    product derives them sender by sender like the reference, the oracle receiver by receiver.
+The load balance is checked against Mesh::CalculateLoadBalance restated in the test."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import athena_gamma_b200 as ab  # noqa: E402
+
+SMR_GOLDENS = [n for n in util.golden_names(include_smr=True) if n.startswith("smr_")]
+
+EXTRA = {
+    # three levels, periodic, 3-D, non-cubic root grid
+    "three_levels_3d": dict(nx=(24, 16, 16), bx=(4, 4, 4), ng=2, bc=["periodic"]*6, regions=[
+        (-0.2, 0.1, -0.1, 0.1, -0.1, 0.1, 2), (0.3, 0.5, 0.3, 0.5, -0.5, -0.3, 1)]),
+    # region touching non-periodic mesh boundaries in 2-D, NGHOST = 4
+    "edges_2d_ng4": dict(nx=(32, 16, 1), bx=(8, 8, 1), ng=4,
+                         bc=["outflow", "reflecting", "reflecting", "outflow", "periodic", "periodic"],
+                         regions=[(-0.5, -0.4, -0.5, -0.3, -0.5, 0.5, 2)]),
+    "one_d": dict(nx=(64, 1, 1), bx=(4, 1, 1), ng=2, bc=["outflow", "outflow"] + ["periodic"]*4,
+                  regions=[(0.1, 0.2, -0.5, 0.5, -0.5, 0.5, 3)]),
+}
+
+
+def _case_from_golden(name):
+    g = util.Golden(name)
+    mesh, mb = g.par["mesh"], g.par.get("meshblock", {})
+    nx = tuple(int(mesh.get("nx%d" % d, 1)) for d in (1, 2, 3))
+    bx = tuple(int(mb.get("nx%d" % d, nx[d - 1])) for d in (1, 2, 3))
+    lim = {k: float(mesh.get(k, dflt)) for k, dflt in (("x1min", -0.5), ("x1max", 0.5),
+           ("x2min", -0.5), ("x2max", 0.5), ("x3min", -0.5), ("x3max", 0.5))}
+    regions = []
+    for bn, blk in g.par.items():
+        if bn.startswith("refinement"):
+            regions.append(tuple(float(blk.get(k, lim[k])) for k in
+                                 ("x1min", "x1max", "x2min", "x2max", "x3min", "x3max"))
+                           + (int(blk["level"]),))
+    bc = [mesh.get(k, "periodic") for k in ("ix1_bc", "ox1_bc", "ix2_bc", "ox2_bc", "ix3_bc",
+                                            "ox3_bc")]
+    return dict(nx=nx, bx=bx, ng=g.ng, bc=bc, regions=regions, lim=lim, locs=g.locs)
+
+
+def _both(case, nranks=1):
+    lim = case.get("lim", dict(x1min=-0.5, x1max=0.5, x2min=-0.5, x2max=0.5, x3min=-0.5,
+                               x3max=0.5))
+    # product planner
+    p = ab.lib.AbMeshParams()
+    p.nx1, p.nx2, p.nx3 = case["nx"]
+    p.bx1, p.bx2, p.bx3 = case["bx"]
+    for k, v in lim.items():
+        setattr(p, k, v)
+    for i, f in enumerate(case["bc"]):
+        p.bc[i] = ab.lib.BC[f]
+    p.nghost = case["ng"]
+    p.nranks = nranks
+    regs = (ab.lib.AbRefinementRegion*len(case["regions"]))()
+    for i, r in enumerate(case["regions"]):
+        (regs[i].x1min, regs[i].x1max, regs[i].x2min, regs[i].x2max, regs[i].x3min,
+         regs[i].x3max, regs[i].level) = r
+    L = ab.lib.load()
+    h = C.c_void_p()
+    rc = L.ab_smr_plan_create(C.byref(p), regs, len(case["regions"]), C.byref(h))
+    assert rc == 0, L.ab_smr_last_error()
+    # oracle
+    q = oracle.AoParams()
+    q.nx1, q.nx2, q.nx3 = case["nx"]
+    q.bx1, q.bx2, q.bx3 = case["bx"]
+    for k, v in lim.items():
+        setattr(q, k, v)
+    for i, f in enumerate(case["bc"]):
+        q.bc[i] = oracle.BC[f]
+    q.ng = case["ng"]
+    q.solver, q.xorder, q.gamma, q.cfl, q.tlim = oracle.SOLVER["hllc"], 2, 1.4, 0.3, 1.0
+    q.dfloor = q.pfloor = q.sfloor = oracle.DEFAULT_FLOOR
+    q.nref = len(case["regions"])
+    for i, r in enumerate(case["regions"]):
+        for c in range(6):
+            q.ref[i][c] = r[c]
+        q.ref_level[i] = r[6]
+    om = oracle.OracleMesh(q)
+    return L, h, om
+
+
+def _plan_blocks(L, h):
+    n = L.ab_smr_plan_nblocks(h)
+    rows = (C.c_long*(5*n))()
+    assert L.ab_smr_plan_blocks(h, rows, n) == n
+    return np.array(rows).reshape(n, 5)
+
+
+ALL = [("golden:" + n, None) for n in SMR_GOLDENS] + [("extra:" + k, v) for k, v in EXTRA.items()]
+
+
+@pytest.mark.parametrize("name,case", ALL, ids=[a for a, _ in ALL])
+def test_block_list_neighbours_and_plan_match_oracle(name, case):
+    if case is None:
+        case = _case_from_golden(name.split(":", 1)[1])
+    L, h, om = _both(case)
+    try:
+        blocks = _plan_blocks(L, h)
+        mine = [(int(r[1]), int(r[2]), int(r[3]), int(r[0])) for r in blocks]
+        theirs = [(i["lx1"], i["lx2"], i["lx3"], i["level"]) for i in om.info]
+        assert mine == theirs
+        if "locs" in case:      # the reference's own block list (restart file of the fixture)
+            assert mine == [tuple(l) for l in case["locs"]]
+        assert len(set(r[0] for r in blocks)) >= 2, "mesh is not refined"
+        OL = oracle.lib()
+        OL.ao_neighbors.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        for g in range(len(blocks)):
+            a, b = (C.c_int*(8*56))(), (C.c_int*(8*56))()
+            la, lb = (C.c_int*27)(), (C.c_int*27)()
+            na = L.ab_smr_plan_neighbors(h, g, a, la)
+            nb = OL.ao_neighbors(om.h, g, b, lb)
+            assert na == nb, (g, na, nb)
+            assert list(a)[:8*na] == list(b)[:8*nb], "neighbour list of block %d" % g
+            assert list(la) == list(lb), "nblevel of block %d" % g
+        # transfer plan
+        n = L.ab_smr_plan_transfers(h, None, 0)
+        rows = (C.c_long*(12*n))()
+        L.ab_smr_plan_transfers(h, rows, n)
+        mine = sorted(tuple(r) for r in np.array(rows).reshape(n, 12).tolist())
+        OL.ao_smr_transfers.restype = C.c_long
+        OL.ao_smr_transfers.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.c_long]
+        m = OL.ao_smr_transfers(om.h, None, 0)
+        orows = (C.c_long*(12*m))()
+        OL.ao_smr_transfers(om.h, orows, m)
+        theirs = sorted(tuple(r) for r in np.array(orows).reshape(m, 12).tolist())
+        assert n == m and n > 0
+        kinds = set(r[0] for r in mine)
+        assert {0, 1, 2, 10, 11, 20} <= kinds
+        assert mine == theirs
+    finally:
+        L.ab_smr_plan_destroy(h)
+
+
+def test_load_balance_of_a_refined_mesh():
+    from test_multirank_cpu import reference_load_balance
+    case = EXTRA["three_levels_3d"]
+    for nranks in (1, 2, 3, 8):
+        L, h, _ = _both(case, nranks=nranks)
+        try:
+            blocks = _plan_blocks(L, h)
+            assert list(blocks[:, 4]) == reference_load_balance(len(blocks), nranks)
+        finally:
+            L.ab_smr_plan_destroy(h)
+
+
+def test_bad_refinement_is_rejected():
+    L = ab.lib.load()
+    p = ab.lib.AbMeshParams()
+    p.nx1, p.nx2, p.nx3, p.bx1, p.bx2, p.bx3 = 16, 16, 1, 4, 4, 1
+    p.x1min, p.x1max, p.x2min, p.x2max, p.x3min, p.x3max = -0.5, 0.5, -0.5, 0.5, -0.5, 0.5
+    p.nghost = 3
+    h = C.c_void_p()
+    reg = (ab.lib.AbRefinementRegion*1)()
+    reg[0].x1min, reg[0].x1max, reg[0].x2min, reg[0].x2max, reg[0].level = -0.1, 0.1, -0.1, 0.1, 1
+    assert L.ab_smr_plan_create(C.byref(p), reg, 1, C.byref(h)) == ab.lib.AB_ERR_ARG
+    assert b"even number of ghost" in L.ab_smr_last_error()
+    p.nghost = 2
+    reg[0].x1max = 0.7
+    assert L.ab_smr_plan_create(C.byref(p), reg, 1, C.byref(h)) == ab.lib.AB_ERR_ARG
+    assert b"smaller than the whole mesh" in L.ab_smr_last_error()
