@@ -65,6 +65,17 @@ void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta,
 // ghost exchange: apply `n` box copies (descriptors in device memory, CopyBox::offset = exclusive
 // prefix of the element counts, total_elems = their sum)
 void launch_copy_boxes(const CopyBox *boxes_dev, int n, long total_elems, cudaStream_t s);
+// static mesh refinement (ab_smr_kernels.cu)
+void launch_smr_restrict(const SmrGeom &g, const double *fine, double *coarse, int nvar,
+                         const SmrBox &bx, cudaStream_t s);
+void launch_smr_prolong(const SmrGeom &g, const double *coarse, double *fine, int nvar,
+                        const SmrBox &bx, cudaStream_t s);
+void launch_smr_c2p(const SmrGeom &g, const Params &p, double *cu, double *cw, int ns, double *cs,
+                    double *cr, const SmrBox &bx, cudaStream_t s);
+void launch_smr_bc(const SmrGeom &g, double *cw, int nh, double *cr, int ns, int face, int refl,
+                   int lo, int hi, const SmrBox &bx, cudaStream_t s);
+void launch_smr_flux(const SmrGeom &gf, const double *fine_flux, double *coarse_flux, int nvar,
+                     int dir, int fpos, int cpos, int a0, int b0, int na, int nb, cudaStream_t s);
 
 // outflow (refl=0) / reflecting (refl=1) physical boundary on primitives and face fields
 void launch_phys_bc(const BlkDev &b, int mhd, int face, int refl, int il, int iu, int jl,

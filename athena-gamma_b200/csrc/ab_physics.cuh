@@ -269,6 +269,56 @@ AB_HD void char_right(double gamma, const double *w, double bx, double *vect) {
   }
 }
 
+// ---- static mesh refinement: restriction and prolongation of cell-centred variables ----------
+// MeshRefinement::RestrictCellCenteredValues (mesh/mesh_refinement.cpp:106-176): volume-weighted
+// mean of the 2^ndim fine cells, with the reference's pairing of the sums.  f / v: fine values
+// and volumes in the order (k,j,i), (k,j+1,i), (k,j,i+1), (k,j+1,i+1), then the same at k+1.
+AB_HD double restrict_cc(int ndim, const double *f, const double *v) {
+  if (ndim == 3) {
+    const double tvol = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    return (((f[0]*v[0] + f[1]*v[1]) + (f[2]*v[2] + f[3]*v[3]))
+            + ((f[4]*v[4] + f[5]*v[5]) + (f[6]*v[6] + f[7]*v[7])))/tvol;
+  } else if (ndim == 2) {
+    const double tvol = (v[0] + v[1]) + (v[2] + v[3]);
+    return ((f[0]*v[0] + f[1]*v[1]) + (f[2]*v[2] + f[3]*v[3]))/tvol;
+  }
+  const double tvol = v[0] + v[2];
+  return (f[0]*v[0] + f[2]*v[2])/tvol;
+}
+
+// minmod-limited gradient of MeshRefinement::ProlongateCellCenteredValues
+// (mesh_refinement.cpp:430-445)
+AB_HD double prolong_grad(double cm, double cc, double cp, double dxm, double dxp) {
+  const double gm = (cc - cm)/dxm;
+  const double gp = (cp - cc)/dxp;
+  return 0.5*(sgn(gm) + sgn(gp))*dmin(fabs(gm), fabs(gp));
+}
+
+// the 2^ndim fine values of one coarse cell (mesh_refinement.cpp:447-456,497-501,533-534); out in
+// the order of restrict_cc; g? limited gradients, d?m / d?p distances from the coarse centre to
+// the lower / upper fine centres
+AB_HD void prolong_cc(int ndim, double cc, double g1, double g2, double g3, double d1m, double d1p,
+                      double d2m, double d2p, double d3m, double d3p, double *out) {
+  if (ndim == 3) {
+    out[0] = cc - (g1*d1m + g2*d2m + g3*d3m);
+    out[2] = cc + (g1*d1p - g2*d2m - g3*d3m);
+    out[1] = cc - (g1*d1m - g2*d2p + g3*d3m);
+    out[3] = cc + (g1*d1p + g2*d2p - g3*d3m);
+    out[4] = cc - (g1*d1m + g2*d2m - g3*d3p);
+    out[6] = cc + (g1*d1p - g2*d2m + g3*d3p);
+    out[5] = cc - (g1*d1m - g2*d2p - g3*d3p);
+    out[7] = cc + (g1*d1p + g2*d2p + g3*d3p);
+  } else if (ndim == 2) {
+    out[0] = cc - (g1*d1m + g2*d2m);
+    out[2] = cc + (g1*d1p - g2*d2m);
+    out[1] = cc - (g1*d1m - g2*d2p);
+    out[3] = cc + (g1*d1p + g2*d2p);
+  } else {
+    out[0] = cc - g1*d1m;
+    out[2] = cc + g1*d1p;
+  }
+}
+
 // ---- nonuniform (geometric, mesh/x?rat != 1) spacing -----------------------------------------
 // Row `t` of the per-index geometry table the host builds (ab_mesh.cu: make_recon_table), NUG
 // doubles per cell index along the sweep: dxf, dxv(i), dxv(i-1), cf, cb, dxf/dxv(i),

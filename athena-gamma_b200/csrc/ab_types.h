@@ -62,6 +62,15 @@ struct CopyBox {
   long offset;                            // exclusive prefix of element counts
 };
 
+// Static mesh refinement (ab_smr_kernels.cu): index geometry of a block and its coarse buffers
+// (MeshBlock::cis.. / cnghost, mesh/meshblock.cpp:82-100) with the 1-D coordinate arrays the
+// restriction / prolongation formulas read, and an inclusive index box.
+struct SmrGeom {
+  int nc1, nc2, nc3, cnc1, cnc2, cnc3, is, js, ks, cis, cjs, cks, ndim;
+  const double *dx1f, *dx2f, *dx3f, *x1v, *x2v, *x3v, *cx1v, *cx2v, *cx3v;
+};
+struct SmrBox { int si, ei, sj, ej, sk, ek; };
+
 struct Params {
   double gamma, dfloor, pfloor;
   int mhd, solver, xorder;

@@ -135,6 +135,10 @@ void ao_ppm(long n, int nvar, const double *qm2, const double *qm1, const double
 /* test hook (refined meshes): transfer list of one exchange + ProlongateBoundaries + flux
  * correction, 12 longs per row (layout: oracle_smr.c); returns the number of rows */
 long ao_smr_transfers(AoMesh *m, long *rows, long max_rows);
+/* test hooks (refined meshes): restrict u -> coarse_u / prolongate coarse_w -> w over the coarse
+ * box {si,ei,sj,ej,sk,ek} of block b; arrays by name: coarse_u coarse_w cx1v cx2v cx3v */
+void ao_smr_restrict_box(AoMesh *m, int b, const int *box);
+void ao_smr_prolong_box(AoMesh *m, int b, const int *box);
 /* neighbour list of block b: rows of 8 ints {ox1, ox2, ox3, type, gid, level, fi1, fi2};
  * nblevel (27 ints, [k][j][i]) when not NULL; returns the number of neighbours */
 int ao_neighbors(const AoMesh *m, int b, int *rows, int *nblevel);

@@ -625,6 +625,9 @@ double *ao_array(AoMesh *m, int b, const char *name, long *n) {
     {"x3f", B->x3f, B->nc3+1}, {"x1v", B->x1v, B->nc1}, {"x2v", B->x2v, B->nc2},
     {"x3v", B->x3v, B->nc3}, {"dx1f", B->dx1f, B->nc1}, {"dx2f", B->dx2f, B->nc2},
     {"dx3f", B->dx3f, B->nc3}, {"cc_e", B->cc_e, 3*ncc},
+    {"coarse_u", B->coarse_u, NHYDRO*(long)B->cnc1*B->cnc2*B->cnc3},
+    {"coarse_w", B->coarse_w, NHYDRO*(long)B->cnc1*B->cnc2*B->cnc3},
+    {"cx1v", B->cx1v, B->cnc1}, {"cx2v", B->cx2v, B->cnc2}, {"cx3v", B->cx3v, B->cnc3},
     {"s", B->s, m->p.nscalars*ncc}, {"s1", B->s1, m->p.nscalars*ncc},
     {"r", B->r, m->p.nscalars*ncc}, {"sflux1", B->sflux[0], m->p.nscalars*n1},
     {"sflux2", B->sflux[1], m->p.nscalars*n2}, {"sflux3", B->sflux[2], m->p.nscalars*n3}};

@@ -796,3 +796,14 @@ long ao_smr_transfers(AoMesh *m, long *rows, long max_rows) {
   g_xfer_rows = NULL;
   return g_xfer_n;
 }
+
+/* test hooks: restriction of u into coarse_u / prolongation of coarse_w into w over one coarse box
+ * of block b (all variables) */
+void ao_smr_restrict_box(AoMesh *m, int b, const int *box) {
+  AoBlock *B = &m->blk[b];
+  smr_restrict(m, B, B->u, B->coarse_u, NHYDRO, box[0], box[1], box[2], box[3], box[4], box[5]);
+}
+void ao_smr_prolong_box(AoMesh *m, int b, const int *box) {
+  AoBlock *B = &m->blk[b];
+  smr_prolongate(m, B, B->coarse_w, B->w, NHYDRO, box[0], box[1], box[2], box[3], box[4], box[5]);
+}

@@ -136,3 +136,58 @@ extern "C" void hc_recon_line_char(int mode, int order, int mhd, int nc, const d
   else { if (mode == 0) LC(false,0); else if (mode == 1) LC(false,1); else if (mode == 2) LC(false,2); else LC(false,3); }
 #undef LC
 }
+
+// static mesh refinement: restriction of a fine box / prolongation of a coarse box on plain arrays
+// laid out like the MeshBlock's (fine nc3 x nc2 x nc1, coarse cnc3 x cnc2 x cnc1), with the
+// product's point functions.  dims: {nc1,nc2,nc3, cnc1,cnc2,cnc3, is,js,ks, cis,cjs,cks, ndim}
+extern "C" void hc_smr_restrict(const int *dims, const double *dx1, const double *dx2,
+                                const double *dx3, const double *fine, double *coarse,
+                                const int *box) {
+  const int nc1 = dims[0], nc2 = dims[1], c1 = dims[3], c2 = dims[4];
+  const int is = dims[6], js = dims[7], ks = dims[8], cis = dims[9], cjs = dims[10], cks = dims[11];
+  const int nd = dims[12];
+  for (int ck = box[4]; ck <= box[5]; ++ck) for (int cj = box[2]; cj <= box[3]; ++cj)
+    for (int ci = box[0]; ci <= box[1]; ++ci) {
+      const int i = (ci - cis)*2 + is, j = nd > 1 ? (cj - cjs)*2 + js : 0,
+                k = nd > 2 ? (ck - cks)*2 + ks : 0;
+      double f[8] = {0}, v[8] = {0};
+      for (int dk = 0; dk < (nd > 2 ? 2 : 1); ++dk) for (int dj = 0; dj < (nd > 1 ? 2 : 1); ++dj)
+        for (int di = 0; di < 2; ++di) {
+          const int q = dk*4 + di*2 + dj;
+          f[q] = fine[((long)(k+dk)*nc2 + (j+dj))*nc1 + (i+di)];
+          v[q] = dx1[i+di]*dx2[j+dj]*dx3[k+dk];
+        }
+      coarse[((long)ck*c2 + cj)*c1 + ci] = ab::restrict_cc(nd, f, v);
+    }
+}
+extern "C" void hc_smr_prolong(const int *dims, const double *x1v, const double *x2v,
+                               const double *x3v, const double *cx1v, const double *cx2v,
+                               const double *cx3v, const double *coarse, double *fine,
+                               const int *box) {
+  const int nc1 = dims[0], nc2 = dims[1], c1 = dims[3], c2 = dims[4];
+  const int is = dims[6], js = dims[7], ks = dims[8], cis = dims[9], cjs = dims[10], cks = dims[11];
+  const int nd = dims[12];
+  for (int k = box[4]; k <= box[5]; ++k) for (int j = box[2]; j <= box[3]; ++j)
+    for (int i = box[0]; i <= box[1]; ++i) {
+      const int fi = (i - cis)*2 + is, fj = nd > 1 ? (j - cjs)*2 + js : 0,
+                fk = nd > 2 ? (k - cks)*2 + ks : 0;
+      auto C = [&](int kk, int jj, int ii) { return coarse[((long)kk*c2 + jj)*c1 + ii]; };
+      const double cc = C(k, j, i);
+      double g1, g2 = 0, g3 = 0, d2m = 0, d2p = 0, d3m = 0, d3p = 0;
+      g1 = ab::prolong_grad(C(k,j,i-1), cc, C(k,j,i+1), cx1v[i] - cx1v[i-1], cx1v[i+1] - cx1v[i]);
+      const double d1m = cx1v[i] - x1v[fi], d1p = x1v[fi+1] - cx1v[i];
+      if (nd > 1) {
+        g2 = ab::prolong_grad(C(k,j-1,i), cc, C(k,j+1,i), cx2v[j] - cx2v[j-1], cx2v[j+1] - cx2v[j]);
+        d2m = cx2v[j] - x2v[fj]; d2p = x2v[fj+1] - cx2v[j];
+      }
+      if (nd > 2) {
+        g3 = ab::prolong_grad(C(k-1,j,i), cc, C(k+1,j,i), cx3v[k] - cx3v[k-1], cx3v[k+1] - cx3v[k]);
+        d3m = cx3v[k] - x3v[fk]; d3p = x3v[fk+1] - cx3v[k];
+      }
+      double out[8];
+      ab::prolong_cc(nd, cc, g1, g2, g3, d1m, d1p, d2m, d2p, d3m, d3p, out);
+      for (int dk = 0; dk < (nd > 2 ? 2 : 1); ++dk) for (int dj = 0; dj < (nd > 1 ? 2 : 1); ++dj)
+        for (int di = 0; di < 2; ++di)
+          fine[((long)(fk+dk)*nc2 + (fj+dj))*nc1 + (fi+di)] = out[dk*4 + di*2 + dj];
+    }
+}

@@ -19,6 +19,7 @@ import pytest
 
 import oracle
 import util
+from test_physics_hostcheck import hc  # noqa: F401  (fixture)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -177,3 +178,60 @@ def test_bad_refinement_is_rejected():
     reg[0].x1max = 0.7
     assert L.ab_smr_plan_create(C.byref(p), reg, 1, C.byref(h)) == ab.lib.AB_ERR_ARG
     assert b"smaller than the whole mesh" in L.ab_smr_last_error()
+
+
+@pytest.mark.parametrize("gname", ["smr_blast3d_hllc_plm_vl2", "smr_blast2d_lvl2_bcs_hllc_plm_rk2",
+                                   "smr_sod1d_hllc_plm_vl2"])
+def test_device_restriction_and_prolongation_arithmetic(hc, gname):  # noqa: F811
+    """ab_physics.cuh restrict_cc / prolong_grad / prolong_cc (the point functions the SMR
+    kernels are built from), compiled for the host, against the oracle on a refined block."""
+    g = util.Golden(gname)
+    om = util.oracle_from_golden(g)
+    OL = oracle.lib()
+    IP, DP = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    OL.ao_smr_restrict_box.argtypes = [C.c_void_p, C.c_int, IP]
+    OL.ao_smr_prolong_box.argtypes = [C.c_void_p, C.c_int, IP]
+    hc.hc_smr_restrict.argtypes = [IP, DP, DP, DP, DP, DP, IP]
+    hc.hc_smr_prolong.argtypes = [IP, DP, DP, DP, DP, DP, DP, DP, DP, IP]
+    rng = np.random.default_rng(5)
+    b = max(range(om.nb), key=lambda n: om.info[n]["level"])     # a refined block
+    i = om.info[b]
+    ndim = 1 + (i["nc2"] > 1) + (i["nc3"] > 1)
+    cu = om.array(b, "coarse_u")
+    nh = 5
+    cnc = [len(om.array(b, "cx%dv" % d)) for d in (1, 2, 3)]
+    cng = (g.ng + 1)//2 + 1
+    cs = [cng if n > 1 else 0 for n in cnc]
+    dims = (C.c_int*13)(i["nc1"], i["nc2"], i["nc3"], cnc[0], cnc[1], cnc[2], i["is"], i["js"],
+                        i["ks"], cs[0], cs[1], cs[2], ndim)
+    dp = lambda a: np.ascontiguousarray(a).ctypes.data_as(DP)   # noqa: E731
+    # restriction over all coarse cells whose fine cells exist (active + ghosts)
+    u = om.array(b, "u")
+    u[...] = np.exp(rng.uniform(-1, 1, u.shape))
+    box = (C.c_int*6)(*sum(([c - (g.ng//2 if n > 1 else 0), (n - 1 - c) + (g.ng//2 if n > 1 else 0)]
+                            for c, n in zip(cs, cnc)), []))
+    OL.ao_smr_restrict_box(om.h, b, box)
+    want = np.array(om.array(b, "coarse_u")).reshape(nh, cnc[2], cnc[1], cnc[0])
+    dx = [np.array(om.array(b, "dx%df" % d)) for d in (1, 2, 3)]
+    for v in range(nh):
+        got = np.zeros((cnc[2], cnc[1], cnc[0]))
+        hc.hc_smr_restrict(dims, dp(dx[0]), dp(dx[1]), dp(dx[2]), dp(u[v]), dp(got), box)
+        sl = tuple(slice(box[2*d], box[2*d+1] + 1) for d in (2, 1, 0))
+        util.assert_bitwise(got[sl], want[v][sl], "restriction var %d" % v)
+    # prolongation of a coarse box that has a one-cell margin
+    cw = om.array(b, "coarse_w")
+    cw[...] = rng.normal(0, 1, cw.shape)
+    pbox = (C.c_int*6)(*sum(([c - (1 if n > 1 else 0), (n - 1 - c) + (1 if n > 1 else 0)]
+                             for c, n in zip(cs, cnc)), []))
+    w = om.array(b, "w")
+    w[...] = 0.0
+    OL.ao_smr_prolong_box(om.h, b, pbox)
+    wantw = np.array(om.array(b, "w"))
+    xv = [np.array(om.array(b, "x%dv" % d)) for d in (1, 2, 3)]
+    cxv = [np.array(om.array(b, "cx%dv" % d)) for d in (1, 2, 3)]
+    cw4 = np.array(cw).reshape(nh, cnc[2], cnc[1], cnc[0])
+    for v in range(nh):
+        got = np.zeros(w.shape[1:])
+        hc.hc_smr_prolong(dims, dp(xv[0]), dp(xv[1]), dp(xv[2]), dp(cxv[0]), dp(cxv[1]),
+                          dp(cxv[2]), dp(cw4[v]), dp(got), pbox)
+        util.assert_bitwise(got, wantw[v], "prolongation var %d" % v)
