@@ -128,6 +128,7 @@ struct HostBlock {
   std::vector<Nb> nbs;
   int nedge_fine[12];
   double bmin[3], bmax[3];
+  int level = 0, dl = 0;      // refined meshes: logical level and its height above the root grid
 };
 
 struct PeerBuf {              // staging for one peer rank and one exchange kind
@@ -197,6 +198,18 @@ struct AbMesh {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_pack = nullptr, ev_recv = nullptr;
   bool overlap = false;
+  // Static mesh refinement (ab_mesh_create_refined): one process, hydro + passive scalars.  The
+  // host planner (ab_smr.cpp) supplies the block list and the transfer rows; every block gets the
+  // MeshRefinement's coarse buffers and coarse cell centres.
+  bool smr = false;
+  AbSmrPlan *smr_plan = nullptr;
+  std::vector<std::array<long, 12>> smr_rows;
+  struct SmrBlk {
+    double *cu = nullptr, *cw = nullptr, *cs = nullptr, *cr = nullptr, *cxv[3] = {nullptr, nullptr, nullptr};
+    ab::SmrGeom g;
+  };
+  std::vector<SmrBlk> smr_blk;
+  ab::CopyBox *smr_boxes = nullptr; size_t smr_boxes_cap = 0;
   // Pipelined host <-> device staging (ab_stage_*): a caller that streams a new state in and
   // the result out every step (bench.py's e2e leg) overlaps the PCIe copies of the neighbouring
   // steps with this step's kernels.  Device staging buffers `in` / `out` hold the chosen
@@ -721,7 +734,7 @@ int alloc_blocks(AbMesh *m) {
     const double mmin[3] = {p.x1min, p.x2min, p.x3min}, mmax[3] = {p.x1max, p.x2max, p.x3max};
     const int nxm[3] = {p.nx1, p.nx2, p.nx3}, bxs[3] = {p.bx1, p.bx2, p.bx3};
     for (int dd = 0; dd < 3; ++dd) {
-      make_coords(nxm[dd], bxs[dd], ng, B.lx[dd], mmin[dd], mmax[dd], B.bmin[dd], B.bmax[dd],
+      make_coords(nxm[dd] << B.dl, bxs[dd], ng, B.lx[dd], mmin[dd], mmax[dd], B.bmin[dd], B.bmax[dd],
                   m->nc[dd], B.bcs[2*dd] == AB_BC_REFLECT, B.bcs[2*dd+1] == AB_BC_REFLECT,
                   m->xrat[dd], xf[dd], xv[dd], dxf[dd]);
       wp[dd].assign(m->nc[dd], 0.0); wm[dd].assign(m->nc[dd], 0.0);
@@ -1334,6 +1347,154 @@ bool debug_sync() {
     }                                                                               \
   } while (0)
 
+// ------------------------------------------------------------------ static mesh refinement
+// Execution of the host planner's rows on the device (ab_smr.cpp; kernels ab_smr_kernels.cu).
+// Restated tasks: SendBoundaryBuffers / SetBoundaries of u (and s) between levels
+// (bvals/cc/bvals_cc.cpp:195-470), ProlongateBoundaries (bvals/bvals_refine.cpp:96-570) and the
+// hydro / scalar flux correction (bvals/cc/flux_correction_cc.cpp:69-290).
+
+ab::SmrBox smr_box(const long *origin, const long *extent) {
+  return ab::SmrBox{(int)origin[0], (int)(origin[0] + extent[0] - 1), (int)origin[1],
+                    (int)(origin[1] + extent[1] - 1), (int)origin[2],
+                    (int)(origin[2] + extent[2] - 1)};
+}
+
+int smr_exchange(AbMesh *m) {
+  const int nh = m->nh, ns = m->p.nscalars;
+  // the senders restrict the slabs their coarser neighbours read (LoadBoundaryBufferToCoarser)
+  for (const auto &r : m->smr_rows) {
+    if (r[0] != 2) continue;
+    LocalBlock &S = m->lb[r[1]];
+    AbMesh::SmrBlk &sb = m->smr_blk[r[1]];
+    const ab::SmrBox bx = smr_box(&r[2], &r[9]);
+    ab::launch_smr_restrict(sb.g, S.d.u, sb.cu, nh, bx, m->stream);
+    ab::launch_smr_restrict(sb.g, S.d.s, sb.cs, ns, bx, m->stream);
+  }
+  // every transfer is one box copy; all of them in one launch (sources are active cells or the
+  // restricted slabs, destinations ghost cells or coarse-buffer ghost cells: disjoint because
+  // ab_mesh_create_refined requires MeshBlocks of at least 2*NGHOST cells)
+  std::vector<ab::CopyBox> v;
+  const long ncc = (long)m->nc[0]*m->nc[1]*m->nc[2];
+  const long s2f = m->nc[0], s3f = (long)m->nc[1]*m->nc[0];
+  for (const auto &r : m->smr_rows) {
+    if (r[0] < 0 || r[0] > 2) continue;
+    LocalBlock &S = m->lb[r[1]], &T = m->lb[r[5]];
+    AbMesh::SmrBlk &sb = m->smr_blk[r[1]], &tb = m->smr_blk[r[5]];
+    const long cncc_s = (long)sb.g.cnc1*sb.g.cnc2*sb.g.cnc3, cncc_t = (long)tb.g.cnc1*tb.g.cnc2*tb.g.cnc3;
+    for (int pass = 0; pass < (ns > 0 ? 2 : 1); ++pass) {
+      ab::CopyBox c;
+      memset(&c, 0, sizeof(c));
+      const double *sf = pass ? S.d.s : S.d.u, *sc = pass ? sb.cs : sb.cu;
+      double *tf = pass ? T.d.s : T.d.u, *tc = pass ? tb.cs : tb.cu;
+      if (r[0] == 0) { c.src = sf; c.src_s3 = s3f; c.src_s2 = s2f; c.src_sv = ncc;
+                       c.dst = tf; c.dst_s3 = s3f; c.dst_s2 = s2f; c.dst_sv = ncc; }
+      else if (r[0] == 1) { c.src = sf; c.src_s3 = s3f; c.src_s2 = s2f; c.src_sv = ncc;
+                            c.dst = tc; c.dst_s3 = (long)tb.g.cnc2*tb.g.cnc1; c.dst_s2 = tb.g.cnc1;
+                            c.dst_sv = cncc_t; }
+      else { c.src = sc; c.src_s3 = (long)sb.g.cnc2*sb.g.cnc1; c.src_s2 = sb.g.cnc1; c.src_sv = cncc_s;
+             c.dst = tf; c.dst_s3 = s3f; c.dst_s2 = s2f; c.dst_sv = ncc; }
+      c.nvar = pass ? ns : nh;
+      c.si0 = (int)r[2]; c.sj0 = (int)r[3]; c.sk0 = (int)r[4];
+      c.di0 = (int)r[6]; c.dj0 = (int)r[7]; c.dk0 = (int)r[8];
+      c.ni = (int)r[9]; c.nj = (int)r[10]; c.nk = (int)r[11];
+      v.push_back(c);
+    }
+  }
+  long total = 0;
+  for (auto &c : v) { c.offset = total; total += (long)c.ni*c.nj*c.nk*c.nvar; }
+  if (v.size() > m->smr_boxes_cap) {
+    if (m->smr_boxes) cudaFree(m->smr_boxes);
+    m->smr_boxes_cap = v.size();
+    CK(cudaMalloc(&m->smr_boxes, sizeof(ab::CopyBox)*m->smr_boxes_cap));
+  }
+  if (!v.empty()) {
+    // the table carries the CURRENT register pointers (u / u1 swap every stage); stream-ordered
+    // upload + sync because the source is pageable host memory (see build_state_plan)
+    CK(cudaMemcpyAsync(m->smr_boxes, v.data(), sizeof(ab::CopyBox)*v.size(), cudaMemcpyHostToDevice,
+                       m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    ab::launch_copy_boxes(m->smr_boxes, (int)v.size(), total, m->stream);
+  }
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+
+// BoundaryValues::ProlongateBoundaries of one block: rows 12 (restriction of ghost cells filled by
+// same-level neighbours), then per coarser neighbour rows 10 / 11 (coarse ConservedToPrimitive
+// box, coarse boundary functions, prolongation box, PrimitiveToConserved on the fine ghost cells)
+int smr_prolongate(AbMesh *m, int lid) {
+  LocalBlock &L = m->lb[lid];
+  HostBlock &B = *L.hb;
+  AbMesh::SmrBlk &sb = m->smr_blk[lid];
+  const int nh = m->nh, ns = m->p.nscalars;
+  cudaStream_t st = L.stream;
+  const int cs[3] = {sb.g.cis, sb.g.cjs, sb.g.cks};
+  const int ce[3] = {sb.g.cis + m->p.bx1/2 - 1, m->f2 ? sb.g.cjs + m->p.bx2/2 - 1 : 0,
+                     m->f3 ? sb.g.cks + m->p.bx3/2 - 1 : 0};
+  const bool fdim[3] = {true, (bool)m->f2, (bool)m->f3};
+  for (size_t n = 0; n < m->smr_rows.size(); ++n) {
+    const auto &r = m->smr_rows[n];
+    if (r[1] != lid) continue;
+    if (r[0] == 12) {
+      const ab::SmrBox bx = smr_box(&r[2], &r[9]);
+      ab::launch_smr_restrict(sb.g, L.d.u, sb.cu, nh, bx, st);
+      ab::launch_smr_restrict(sb.g, L.d.s, sb.cs, ns, bx, st);
+    } else if (r[0] == 10) {
+      const auto &r2 = m->smr_rows[n + 1];       // row 11 follows its row 10
+      const ab::SmrBox pbx = smr_box(&r[2], &r[9]);
+      const ab::SmrBox cbx{(int)r[6], (int)r2[2], (int)r[7], (int)r2[3], (int)r[8], (int)r2[4]};
+      const int ox[3] = {(int)r2[6], (int)r2[7], (int)r2[8]};
+      ab::launch_smr_c2p(sb.g, m->kp, sb.cu, sb.cw, ns, sb.cs, sb.cr, cbx, st);
+      for (int d = 0; d < 3; ++d) {
+        if (!fdim[d] || ox[d] != 0) continue;
+        for (int side = 0; side < 2; ++side) {
+          const int face = 2*d + side, bc = B.bcs[face];
+          if (bc != AB_BC_OUTFLOW && bc != AB_BC_REFLECT) continue;
+          // DispatchBoundaryFunctions(cis..cie along the normal, the ghost box transversally)
+          ab::SmrBox t = pbx;
+          if (d == 0) { t.si = t.ei = 0; } else if (d == 1) { t.sj = t.ej = 0; } else { t.sk = t.ek = 0; }
+          ab::launch_smr_bc(sb.g, sb.cw, nh, sb.cr, ns, face, bc == AB_BC_REFLECT, cs[d], ce[d], t, st);
+        }
+      }
+      ab::launch_smr_prolong(sb.g, sb.cw, L.d.w, nh, pbx, st);
+      ab::launch_smr_prolong(sb.g, sb.cr, L.d.r, ns, pbx, st);
+      const int fsi = (pbx.si - cs[0])*2 + m->is, fei = (pbx.ei - cs[0])*2 + m->is + 1;
+      int fsj = m->js, fej = m->je, fsk = m->ks, fek = m->ke;
+      if (m->f2) { fsj = (pbx.sj - cs[1])*2 + m->js; fej = (pbx.ej - cs[1])*2 + m->js + 1; }
+      if (m->f3) { fsk = (pbx.sk - cs[2])*2 + m->ks; fek = (pbx.ek - cs[2])*2 + m->ks + 1; }
+      ab::launch_prim2cons(L.d, m->kp, fsi, fei, fsj, fej, fsk, fek, st);
+      ab::launch_scalar_eos(L.d, m->kp, 1, fsi, fei, fsj, fej, fsk, fek, st);
+    }
+  }
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+
+// SendFluxCorrection / ReceiveFluxCorrection (hydro and scalar fluxes): rows 20
+int smr_flux_correction(AbMesh *m) {
+  const int hx[3] = {m->p.bx1/2, m->f2 ? m->p.bx2/2 : 0, m->f3 ? m->p.bx3/2 : 0};
+  const int s0[3] = {m->is, m->js, m->ks}, e0[3] = {m->ie, m->je, m->ke};
+  for (const auto &r : m->smr_rows) {
+    if (r[0] != 20) continue;
+    LocalBlock &F = m->lb[r[1]], &Cb = m->lb[r[5]];
+    const int ffid = (int)r[2], cfid = (int)r[6], fi1 = (int)r[7], fi2 = (int)r[8];
+    const int dir = ffid >> 1;
+    const int fpos = s0[dir] + (e0[dir] - s0[dir] + 1)*(ffid & 1);     // fine face index
+    const int cpos = s0[dir] + (e0[dir] - s0[dir] + 1)*(cfid & 1);     // coarse face index
+    const int da = dir == 0 ? 1 : 0, db = dir == 2 ? 1 : 2;            // transverse directions
+    const int a0 = s0[da] + (fi1 ? hx[da] : 0), b0 = s0[db] + (fi2 ? hx[db] : 0);
+    const bool fdim[3] = {true, (bool)m->f2, (bool)m->f3};
+    const int na = fdim[da] ? hx[da] : 1, nb = fdim[db] ? hx[db] : 1;
+    ab::launch_smr_flux(m->smr_blk[r[1]].g, F.d.flux[dir], Cb.d.flux[dir], m->nh, dir, fpos, cpos,
+                        a0, b0, na, nb, m->stream);
+    if (m->p.nscalars > 0)
+      ab::launch_smr_flux(m->smr_blk[r[1]].g, F.d.sflux[dir], Cb.d.sflux[dir], m->p.nscalars, dir,
+                          fpos, cpos, a0, b0, na, nb, m->stream);
+  }
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+
 int one_cycle(AbMesh *m) {
   const double *dtp = m->state + 1;
   const bool user_src = (m->user_src || m->user_src_dev);
@@ -1379,6 +1540,7 @@ int one_cycle(AbMesh *m) {
       DBG(m, "scalar fluxes");
     }
     join();
+    if (m->smr) { int rcs = smr_flux_correction(m); if (rcs) return rcs; }   // SEND/RECV_HYDFLX
     // EMF correction.  Overlapped schedule: the NCCL transfer runs on the comm stream while
     // IntegrateHydro / IntegrateScalars (which do not read EMFs) run on the compute stream.
     int rc = m->overlap ? emf_exchange_begin(m) : emf_exchange(m);
@@ -1429,12 +1591,14 @@ int one_cycle(AbMesh *m) {
     }
     const int last = (stage == m->nstages);
     if (!m->overlap) {
-      rc = bvals_exchange(m);
+      rc = m->smr ? smr_exchange(m) : bvals_exchange(m);
       if (rc) return rc;
       DBG(m, "bvals exchange");
       if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
       fork();
-      for (auto &L : m->lb) {
+      for (size_t l = 0; l < m->lb.size(); ++l) {
+        LocalBlock &L = m->lb[l];
+        if (m->smr) { rc = smr_prolongate(m, (int)l); if (rc) return rc; }   // PROLONG
         primitives(m, L, last);
         DBG(m, "primitives");
         physical_bcs(m, L);
@@ -1516,6 +1680,155 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
     }
     for (size_t l = 0; l < m->lb.size(); ++l)
       m->lb[l].stream = ns ? m->bstream[l % ns] : m->stream;
+  }
+  CK(cudaMalloc(&m->state, 8*sizeof(double)));
+  m->hist_cap = 1 << 16;
+  CK(cudaMalloc(&m->dt_hist, sizeof(double)*m->hist_cap));
+  m->h_time = p->start_time; m->h_dt = DBL_MAX; m->h_ncycle = 0;
+  double h[8] = {p->start_time, DBL_MAX, p->tlim, m->cfl, DBL_MAX, 0.0, 0.0, 0.0};
+  CK(cudaMemcpyAsync(m->state, h, sizeof(h), cudaMemcpyHostToDevice, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return AB_OK;
+}
+
+// Mesh ctor with mesh/refinement = static (src/mesh/mesh.cpp:323-548): the block list, levels,
+// boundary flags and neighbour levels come from the host planner (ab_smr.cpp); every MeshBlock
+// additionally gets the MeshRefinement's coarse buffers (src/mesh/mesh_refinement.cpp:40-100).
+// Scope of this version: one process, hydro (+ passive scalars), uniformly spaced levels,
+// MeshBlocks of at least 2*NGHOST cells, no user-enrolled boundary functions.
+int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regions, int nregions,
+                           AbMesh **out) {
+  if (!p || !out) return fail(AB_ERR_ARG, "null argument");
+  *out = nullptr;
+  int vrc = validate_params(p);
+  if (vrc) return vrc;
+  if (p->mhd) return fail(AB_ERR_ARG, "mesh refinement with MHD is not on the device path");
+  if (p->nranks != 1) return fail(AB_ERR_ARG, "mesh refinement runs on one process in this version");
+  for (int f = 0; f < 6; ++f)
+    if (p->bc[f] == AB_BC_USER) return fail(AB_ERR_ARG, "mesh refinement with user-enrolled boundaries is not on the device path");
+  for (int d = 0; d < 3; ++d)
+    if (p->xrat[d] != 0.0 && p->xrat[d] != 1.0)
+      return fail(AB_ERR_ARG, "mesh refinement needs uniformly spaced levels (x?rat = 1)");
+  if (p->bx1 < 2*p->nghost || (p->nx2 > 1 && p->bx2 < 2*p->nghost) || (p->nx3 > 1 && p->bx3 < 2*p->nghost))
+    return fail(AB_ERR_ARG, "mesh refinement on the device path needs MeshBlocks of at least 2*NGHOST cells");
+  AbSmrPlan *plan = nullptr;
+  if (ab_smr_plan_create(p, regions, nregions, &plan) != AB_OK)
+    return fail(AB_ERR_ARG, std::string("refinement: ") + ab_smr_last_error());
+  if (ab_device_count() <= 0) {
+    ab_smr_plan_destroy(plan);
+    return fail(AB_ERR_NO_DEVICE, "no CUDA device: libathena_b200 has no CPU fallback");
+  }
+  CK(cudaSetDevice(p->device));
+  AbMesh *m = new AbMesh();
+  m->smr = true; m->smr_plan = plan;
+  // host_setup without build_block_list
+  {
+    AbMeshParams q = *p;
+    q.nx1 = q.bx1; q.nx2 = q.bx2; q.nx3 = q.bx3;      // one dummy block: sets params, index ranges
+    host_setup(m, &q);
+    m->p.nx1 = p->nx1; m->p.nx2 = p->nx2; m->p.nx3 = p->nx3;
+    m->f2 = p->nx2 > 1; m->f3 = p->nx3 > 1;
+  }
+  m->hb.clear(); m->lb_hb.clear(); m->gid_of.clear();
+  m->nrb[0] = p->nx1/p->bx1; m->nrb[1] = p->nx2/p->bx2; m->nrb[2] = p->nx3/p->bx3;
+  const int nb = ab_smr_plan_nblocks(plan);
+  m->nbtotal = nb;
+  std::vector<long> rows(5*(size_t)nb);
+  ab_smr_plan_blocks(plan, rows.data(), nb);
+  int root_level = 0;
+  { int nbmax = std::max(m->nrb[0], std::max(m->nrb[1], m->nrb[2]));
+    for (root_level = 0; (1 << root_level) < nbmax; ++root_level) {} }
+  m->hb.resize(nb);
+  const double mmin[3] = {p->x1min, p->x2min, p->x3min}, mmax[3] = {p->x1max, p->x2max, p->x3max};
+  const int nxm[3] = {p->nx1, p->nx2, p->nx3};
+  for (int g = 0; g < nb; ++g) {
+    HostBlock &B = m->hb[g];
+    B.gid = g; B.rank = 0; B.level = (int)rows[5*g]; B.dl = B.level - root_level;
+    for (int d = 0; d < 3; ++d) B.lx[d] = rows[5*g + 1 + d];
+    for (int d = 0; d < 3; ++d) {      // SetBlockSizeAndBoundaries at the block's level
+      const long nrb = (long)m->nrb[d] << B.dl;
+      if (d > 0 && nxm[d] == 1) {
+        B.bmin[d] = mmin[d]; B.bmax[d] = mmax[d];
+        B.bcs[2*d] = p->bc[2*d]; B.bcs[2*d+1] = p->bc[2*d+1];
+        continue;
+      }
+      if (B.lx[d] == 0) { B.bmin[d] = mmin[d]; B.bcs[2*d] = p->bc[2*d]; }
+      else { B.bmin[d] = gen_x(B.lx[d], nrb, mmin[d], mmax[d], 1.0, nxm[d]); B.bcs[2*d] = -1; }
+      if (B.lx[d] == nrb - 1) { B.bmax[d] = mmax[d]; B.bcs[2*d+1] = p->bc[2*d+1]; }
+      else { B.bmax[d] = gen_x(B.lx[d] + 1, nrb, mmin[d], mmax[d], 1.0, nxm[d]); B.bcs[2*d+1] = -1; }
+    }
+    int nbl[27];
+    ab_smr_plan_neighbors(plan, g, nullptr, nbl);
+    for (int k = 0; k < 3; ++k) for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i)
+      B.nblevel[k][j][i] = nbl[(k*3 + j)*3 + i];
+    for (int e = 0; e < 12; ++e) B.nedge_fine[e] = 1;
+  }
+  m->gid_start = 0;
+  for (auto &B : m->hb) m->lb_hb.push_back(&B);
+  {
+    const long n = ab_smr_plan_transfers(plan, nullptr, 0);
+    std::vector<long> tr(12*(size_t)n);
+    ab_smr_plan_transfers(plan, tr.data(), n);
+    m->smr_rows.resize(n);
+    for (long i = 0; i < n; ++i) for (int c = 0; c < 12; ++c) m->smr_rows[i][c] = tr[12*i + c];
+  }
+  CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&m->ev_pack, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&m->ev_recv, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&m->ev_main, cudaEventDisableTiming));
+  m->overlap = false;
+  int rc = alloc_blocks(m);
+  if (rc) { ab_mesh_destroy(m); return rc; }
+  for (auto &L : m->lb) L.stream = m->stream;
+  // coarse buffers, coarse cell centres (coarse_flag branch of coordinates.cpp:92-160)
+  const int ng = p->nghost, cng = (ng + 1)/2 + 1;
+  const int bxs[3] = {p->bx1, p->bx2, p->bx3};
+  m->smr_blk.resize(m->lb.size());
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    LocalBlock &L = m->lb[l];
+    HostBlock &B = *L.hb;
+    AbMesh::SmrBlk &sb = m->smr_blk[l];
+    ab::SmrGeom &g = sb.g;
+    memset(&g, 0, sizeof(g));
+    g.nc1 = m->nc[0]; g.nc2 = m->nc[1]; g.nc3 = m->nc[2];
+    g.is = m->is; g.js = m->js; g.ks = m->ks; g.ndim = m->ndim;
+    g.cnc1 = bxs[0]/2 + 2*cng; g.cis = cng;
+    g.cnc2 = m->f2 ? bxs[1]/2 + 2*cng : 1; g.cjs = m->f2 ? cng : 0;
+    g.cnc3 = m->f3 ? bxs[2]/2 + 2*cng : 1; g.cks = m->f3 ? cng : 0;
+    g.dx1f = L.d.dx1f; g.dx2f = L.d.dx2f; g.dx3f = L.d.dx3f;
+    g.x1v = L.d.x1v; g.x2v = L.d.x2v; g.x3v = L.d.x3v;
+    const int cnc[3] = {g.cnc1, g.cnc2, g.cnc3};
+    for (int d = 0; d < 3; ++d) {
+      std::vector<double> xf(cnc[d] + 1, 0.0), xv(cnc[d], 0.0);
+      if (cnc[d] == 1) {
+        xf[0] = B.bmin[d]; xf[1] = B.bmax[d]; xv[0] = 0.5*(xf[1] + xf[0]);
+      } else {
+        const int il = cng, iu = cng + bxs[d]/2 - 1;
+        const long nroot = (long)nxm[d] << B.dl;
+        std::vector<double> dxf(cnc[d], (B.bmax[d] - B.bmin[d])/(iu - il + 1));
+        for (int i = il - cng; i <= iu + cng + 1; ++i)
+          xf[i] = gen_x((long)(i - il)*2 + B.lx[d]*bxs[d], nroot, mmin[d], mmax[d], 1.0, nxm[d]);
+        xf[il] = B.bmin[d]; xf[iu+1] = B.bmax[d];
+        if (B.bcs[2*d] == AB_BC_REFLECT) for (int i = 1; i <= cng; ++i) {
+          dxf[il-i] = dxf[il+i-1]; xf[il-i] = xf[il-i+1] - dxf[il-i]; }
+        if (B.bcs[2*d+1] == AB_BC_REFLECT) for (int i = 1; i <= cng; ++i) {
+          dxf[iu+i] = dxf[iu-i+1]; xf[iu+i+1] = xf[iu+i] + dxf[iu+i]; }
+        for (int i = il - cng; i <= iu + cng; ++i) xv[i] = 0.5*(xf[i+1] + xf[i]);
+      }
+      CK(cudaMalloc(&sb.cxv[d], xv.size()*8));
+      CK(cudaMemcpyAsync(sb.cxv[d], xv.data(), xv.size()*8, cudaMemcpyHostToDevice, m->stream));
+      CK(cudaStreamSynchronize(m->stream));
+    }
+    g.cx1v = sb.cxv[0]; g.cx2v = sb.cxv[1]; g.cx3v = sb.cxv[2];
+    const size_t cncc = (size_t)g.cnc1*g.cnc2*g.cnc3;
+    CK(cudaMalloc(&sb.cu, cncc*m->nh*8)); CK(cudaMemsetAsync(sb.cu, 0, cncc*m->nh*8, m->stream));
+    CK(cudaMalloc(&sb.cw, cncc*m->nh*8)); CK(cudaMemsetAsync(sb.cw, 0, cncc*m->nh*8, m->stream));
+    if (p->nscalars > 0) {
+      CK(cudaMalloc(&sb.cs, cncc*p->nscalars*8)); CK(cudaMemsetAsync(sb.cs, 0, cncc*p->nscalars*8, m->stream));
+      CK(cudaMalloc(&sb.cr, cncc*p->nscalars*8)); CK(cudaMemsetAsync(sb.cr, 0, cncc*p->nscalars*8, m->stream));
+    }
   }
   CK(cudaMalloc(&m->state, 8*sizeof(double)));
   m->hist_cap = 1 << 16;
@@ -1649,6 +1962,12 @@ int ab_mesh_destroy(AbMesh *m) {
   for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   cudaFree(m->state); cudaFree(m->dt_hist); cudaFree(m->dtmin);
   cudaFree(m->hist_partial); cudaFree(m->hist_out);
+  for (auto &sb : m->smr_blk) {
+    cudaFree(sb.cu); cudaFree(sb.cw); cudaFree(sb.cs); cudaFree(sb.cr);
+    for (int d = 0; d < 3; ++d) cudaFree(sb.cxv[d]);
+  }
+  cudaFree(m->smr_boxes);
+  if (m->smr_plan) ab_smr_plan_destroy(m->smr_plan);
   if (m->stg.active) {
     cudaStreamSynchronize(m->stg.h2d); cudaStreamSynchronize(m->stg.d2h);
     cudaFree(m->stg.in); cudaFree(m->stg.out);
@@ -1669,6 +1988,10 @@ int ab_mesh_destroy(AbMesh *m) {
 }
 
 int ab_mesh_nblocks_total(const AbMesh *m) { return m ? m->nbtotal : 0; }
+int ab_block_level(const AbMesh *m, int lid) {
+  if (!m || lid < 0 || lid >= (int)m->lb_hb.size()) return fail(AB_ERR_ARG, "bad argument");
+  return m->lb_hb[lid]->level;
+}
 int ab_mesh_nblocks_local(const AbMesh *m) { return m ? (int)m->lb_hb.size() : 0; }
 
 #define GET_L(m, lid)                                                              \
@@ -1820,7 +2143,7 @@ int ab_plan_geometry(const AbMesh *m, int lid, int dir, int what, double *out, i
   const int s0[3] = {m->is, m->js, m->ks}, e0[3] = {m->ie, m->je, m->ke};
   const int nc = m->nc[dir];
   std::vector<double> xf, xv, dxf, tab, lw(nc, 0.5), rw(nc, 0.5), wp(nc), wm(nc);
-  make_coords(nxm[dir], bxs[dir], p.nghost, B.lx[dir], mmin[dir], mmax[dir], B.bmin[dir],
+  make_coords(nxm[dir] << B.dl, bxs[dir], p.nghost, B.lx[dir], mmin[dir], mmax[dir], B.bmin[dir],
               B.bmax[dir], nc, B.bcs[2*dir] == AB_BC_REFLECT, B.bcs[2*dir+1] == AB_BC_REFLECT,
               m->xrat[dir], xf, xv, dxf);
   for (int c = 0; c < nc; ++c) {
@@ -2056,9 +2379,13 @@ int ab_mesh_initialize(AbMesh *m) {
   }
   m->bc_time = m->h_time; m->bc_dt = 0.0;   // ApplyPhysicalBoundaries(time, 0.0, ...) mesh.cpp:1574
   for (auto &L : m->lb) L.stream = m->stream;
-  int rc = bvals_exchange(m);
+  int rc = m->smr ? smr_exchange(m) : bvals_exchange(m);
   if (rc) return rc;
-  for (auto &L : m->lb) { primitives(m, L); physical_bcs(m, L); }
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    LocalBlock &L = m->lb[l];
+    if (m->smr) { rc = smr_prolongate(m, (int)l); if (rc) return rc; }   // mesh.cpp:1527-1528
+    primitives(m, L); physical_bcs(m, L);
+  }
   rc = new_time_step(m, 0);
   if (rc) return rc;
   return read_state(m);

@@ -37,6 +37,7 @@ SYMBOLS = [
     "ab_stage_sync",
     "ab_smr_last_error", "ab_smr_plan_create", "ab_smr_plan_destroy", "ab_smr_plan_nblocks",
     "ab_smr_plan_blocks", "ab_smr_plan_neighbors", "ab_smr_plan_transfers",
+    "ab_mesh_create_refined", "ab_block_level",
 ]
 
 
@@ -119,6 +120,9 @@ def load():
     L.ab_smr_plan_neighbors.argtypes = [vp, ip, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ab_smr_plan_transfers.restype = C.c_long
     L.ab_smr_plan_transfers.argtypes = [vp, C.POINTER(C.c_long), C.c_long]
+    L.ab_mesh_create_refined.argtypes = [C.POINTER(AbMeshParams), C.POINTER(AbRefinementRegion),
+                                         ip, C.POINTER(vp)]
+    L.ab_block_level.argtypes = [vp, ip]
     L.ab_history.argtypes = [vp, dp, ip]
     L.ab_enroll_user_explicit_source_function.argtypes = [vp, SRCTERMFUNC, vp]
     L.ab_enroll_user_explicit_source_function_device.argtypes = [vp, SRCTERMFUNC_DEVICE, vp]

@@ -27,6 +27,8 @@ class MeshBlock:
         lib.check(mesh.L.ab_block_info(mesh.h, lid, info))
         (self.gid, self.lx1, self.lx2, self.lx3, self.ncells1, self.ncells2, self.ncells3,
          self.is_, self.ie, self.js, self.je, self.ks, self.ke) = [int(v) for v in info]
+        self.level = int(mesh.L.ab_block_level(mesh.h, lid)) if hasattr(mesh.L, "ab_block_level") \
+            else 0
 
     def shape(self, name):
         n1, n2, n3 = self.ncells1, self.ncells2, self.ncells3
@@ -160,13 +162,39 @@ class Mesh:
         self.mhd, self.flux = bool(mhd), flux
         self.nlim = pin.get_or_add_integer("time", "nlim", -1)
         h = C.c_void_p()
-        lib.check(self.L.ab_mesh_create(C.byref(p), C.byref(h)))
+        # mesh/refinement = static: <refinementN> blocks in input order (mesh.cpp:323-465)
+        self.refinement = self.refinement_regions(pin, p)
+        if self.refinement is not None:
+            lib.check(self.L.ab_mesh_create_refined(C.byref(p), self.refinement,
+                                                    len(self.refinement), C.byref(h)))
+        else:
+            lib.check(self.L.ab_mesh_create(C.byref(p), C.byref(h)))
         self.h = h
         self.nbtotal = self.L.ab_mesh_nblocks_total(h)
         self.nblocal = self.L.ab_mesh_nblocks_local(h)
         self.my_blocks = [MeshBlock(self, l) for l in range(self.nblocal)]
         self.time, self.dt, self.ncycle = p.start_time, float("inf"), 0
         self.zones_per_block = p.bx1 * p.bx2 * p.bx3
+
+    @staticmethod
+    def refinement_regions(pin, p):
+        """AbRefinementRegion array of the <refinementN> blocks, or None without
+        mesh/refinement = static (adaptive refinement is not supported)."""
+        mode = pin.get_or_add_string("mesh", "refinement", "none")
+        if mode == "none":
+            return None
+        if mode != "static":
+            raise ValueError("### FATAL ERROR in Mesh: mesh/refinement = %s is not supported on "
+                             "the B200 path (static only)" % mode)
+        names = [b for b in pin.blocks if b.startswith("refinement")]
+        regs = (lib.AbRefinementRegion * len(names))()
+        lim = {"x1min": p.x1min, "x1max": p.x1max, "x2min": p.x2min, "x2max": p.x2max,
+               "x3min": p.x3min, "x3max": p.x3max}
+        for r, b in zip(regs, names):
+            for k in lim:
+                setattr(r, k, pin.get_real(b, k) if pin.does_parameter_exist(b, k) else lim[k])
+            r.level = pin.get_integer(b, "level")
+        return regs
 
     def __del__(self):
         try:
@@ -192,9 +220,11 @@ class Mesh:
         lib.check(self.L.ab_comm_init(self.h, idb))
 
     # ---- problem generator hook + initialisation -----------------------------------------------
-    def block_of(self, lx1, lx2, lx3):
+    def block_of(self, lx1, lx2, lx3, level=None):
+        """level: needed (and checked) on a refined mesh only"""
         for b in self.my_blocks:
-            if (b.lx1, b.lx2, b.lx3) == (lx1, lx2, lx3):
+            if (b.lx1, b.lx2, b.lx3) == (lx1, lx2, lx3) and (
+                    level is None or self.refinement is None or b.level == level):
                 return b
         return None
 

@@ -127,6 +127,13 @@ int ab_smr_plan_nblocks(const AbSmrPlan *plan);
 int ab_smr_plan_blocks(const AbSmrPlan *plan, long *rows, int max_rows);
 int ab_smr_plan_neighbors(const AbSmrPlan *plan, int gid, int *rows, int *nblevel);
 long ab_smr_plan_transfers(const AbSmrPlan *plan, long *rows, long max_rows);
+/* Mesh ctor with mesh/refinement = static: like ab_mesh_create, MeshBlocks from the planner, each
+ * with the MeshRefinement's coarse buffers; the cycle then also runs the level-aware ghost
+ * exchange, ProlongateBoundaries and the flux correction.  This version: one process, hydro
+ * (+ passive scalars), MeshBlocks of at least 2*NGHOST cells, no user-enrolled boundaries. */
+int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regions, int nregions,
+                           AbMesh **out);
+int ab_block_level(const AbMesh *m, int lid);    /* LogicalLocation::level (0 on a one-level mesh) */
 
 /* ---- user-enrolled boundary functions: Mesh::EnrollUserBoundaryFunction (src/mesh/mesh.cpp)
  * with the BValFunc signature of src/athena.hpp:179-182 on plain arrays.  `face`: 0..5 =
