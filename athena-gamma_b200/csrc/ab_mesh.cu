@@ -22,6 +22,7 @@
 
 #include "../../include/athena_b200.h"
 #include "ab_kernels.h"
+#include "ab_smr_exec.h"
 
 namespace ab {
 extern long g_launches;
@@ -203,7 +204,7 @@ struct AbMesh {
   // MeshRefinement's coarse buffers and coarse cell centres.
   bool smr = false;
   AbSmrPlan *smr_plan = nullptr;
-  std::vector<std::array<long, 12>> smr_rows;
+  std::vector<ab::SmrRow> smr_rows;
   struct SmrBlk {
     double *cu = nullptr, *cw = nullptr, *cs = nullptr, *cr = nullptr, *cxv[3] = {nullptr, nullptr, nullptr};
     ab::SmrGeom g;
@@ -1348,149 +1349,96 @@ bool debug_sync() {
   } while (0)
 
 // ------------------------------------------------------------------ static mesh refinement
-// Execution of the host planner's rows on the device (ab_smr.cpp; kernels ab_smr_kernels.cu).
-// Restated tasks: SendBoundaryBuffers / SetBoundaries of u (and s) between levels
-// (bvals/cc/bvals_cc.cpp:195-470), ProlongateBoundaries (bvals/bvals_refine.cpp:96-570) and the
-// hydro / scalar flux correction (bvals/cc/flux_correction_cc.cpp:69-290).
+// Execution of the host planner's rows on the device.  The interpretation of the rows is the
+// back-end independent code of ab_smr_exec.h (also run on the CPU by tests/hostcheck against the
+// oracle); this back end turns each piece of work into a kernel launch (ab_smr_kernels.cu).
+struct SmrDeviceOps {
+  AbMesh *m;
+  cudaStream_t st;
+  int rc = AB_OK;
+  void restrict_box(const ab::SmrGeom &g, const double *fine, double *coarse, int nvar,
+                    const ab::SmrBox &bx) { ab::launch_smr_restrict(g, fine, coarse, nvar, bx, st); }
+  void prolong_box(const ab::SmrGeom &g, const double *coarse, double *fine, int nvar,
+                   const ab::SmrBox &bx) { ab::launch_smr_prolong(g, coarse, fine, nvar, bx, st); }
+  void c2p_box(const ab::SmrGeom &g, double *cu, double *cw, int ns, double *cs, double *cr,
+               const ab::SmrBox &bx) { ab::launch_smr_c2p(g, m->kp, cu, cw, ns, cs, cr, bx, st); }
+  void bc_box(const ab::SmrGeom &g, double *cw, int nh, double *cr, int ns, int face, bool refl,
+              int lo, int hi, const ab::SmrBox &bx) {
+    ab::launch_smr_bc(g, cw, nh, cr, ns, face, refl ? 1 : 0, lo, hi, bx, st);
+  }
+  void prim2cons_box(int lid, int il, int iu, int jl, int ju, int kl, int ku) {
+    LocalBlock &L = m->lb[lid];
+    ab::launch_prim2cons(L.d, m->kp, il, iu, jl, ju, kl, ku, st);
+    ab::launch_scalar_eos(L.d, m->kp, 1, il, iu, jl, ju, kl, ku, st);
+  }
+  void flux_face(const ab::SmrGeom &g, const double *ff, double *cf, int nvar, int dir, int fpos,
+                 int cpos, int a0, int b0, int na, int nb) {
+    ab::launch_smr_flux(g, ff, cf, nvar, dir, fpos, cpos, a0, b0, na, nb, st);
+  }
+  void copy_boxes(std::vector<ab::CopyBox> &v, long total) {
+    if (v.empty()) return;
+    if (v.size() > m->smr_boxes_cap) {
+      if (m->smr_boxes) cudaFree(m->smr_boxes);
+      m->smr_boxes = nullptr;
+      m->smr_boxes_cap = v.size();
+      if (cudaMalloc(&m->smr_boxes, sizeof(ab::CopyBox)*m->smr_boxes_cap) != cudaSuccess) { rc = AB_ERR_CUDA; return; }
+    }
+    // the table carries the CURRENT register pointers (u / u1 swap every stage); stream-ordered
+    // upload + sync because the source is pageable host memory (see build_state_plan)
+    if (cudaMemcpyAsync(m->smr_boxes, v.data(), sizeof(ab::CopyBox)*v.size(), cudaMemcpyHostToDevice, st) != cudaSuccess
+        || cudaStreamSynchronize(st) != cudaSuccess) { rc = AB_ERR_CUDA; return; }
+    ab::launch_copy_boxes(m->smr_boxes, (int)v.size(), total, st);
+  }
+};
 
-ab::SmrBox smr_box(const long *origin, const long *extent) {
-  return ab::SmrBox{(int)origin[0], (int)(origin[0] + extent[0] - 1), (int)origin[1],
-                    (int)(origin[1] + extent[1] - 1), (int)origin[2],
-                    (int)(origin[2] + extent[2] - 1)};
+ab::SmrDims smr_dims(const AbMesh *m) {
+  ab::SmrDims d;
+  d.nh = m->nh; d.ns = m->p.nscalars; d.ng = m->p.nghost;
+  d.bx[0] = m->p.bx1; d.bx[1] = m->p.bx2; d.bx[2] = m->p.bx3;
+  d.s0[0] = m->is; d.s0[1] = m->js; d.s0[2] = m->ks;
+  d.e0[0] = m->ie; d.e0[1] = m->je; d.e0[2] = m->ke;
+  d.fdim[0] = true; d.fdim[1] = m->f2; d.fdim[2] = m->f3;
+  return d;
+}
+
+// views with the registers' CURRENT pointers (u <-> u1 swap by pointer every stage)
+std::vector<ab::SmrView> smr_views(AbMesh *m) {
+  std::vector<ab::SmrView> v(m->lb.size());
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    const LocalBlock &L = m->lb[l];
+    const AbMesh::SmrBlk &sb = m->smr_blk[l];
+    ab::SmrView &x = v[l];
+    x.u = L.d.u; x.s = L.d.s; x.w = L.d.w; x.r = L.d.r;
+    for (int d = 0; d < 3; ++d) { x.flux[d] = L.d.flux[d]; x.sflux[d] = L.d.sflux[d]; x.bcs[2*d] = L.hb->bcs[2*d]; x.bcs[2*d+1] = L.hb->bcs[2*d+1]; }
+    x.cu = sb.cu; x.cw = sb.cw; x.cs = sb.cs; x.cr = sb.cr;
+    x.g = sb.g;
+  }
+  return v;
 }
 
 int smr_exchange(AbMesh *m) {
-  const int nh = m->nh, ns = m->p.nscalars;
-  // the senders restrict the slabs their coarser neighbours read (LoadBoundaryBufferToCoarser)
-  for (const auto &r : m->smr_rows) {
-    if (r[0] != 2) continue;
-    LocalBlock &S = m->lb[r[1]];
-    AbMesh::SmrBlk &sb = m->smr_blk[r[1]];
-    const ab::SmrBox bx = smr_box(&r[2], &r[9]);
-    ab::launch_smr_restrict(sb.g, S.d.u, sb.cu, nh, bx, m->stream);
-    ab::launch_smr_restrict(sb.g, S.d.s, sb.cs, ns, bx, m->stream);
-  }
-  // every transfer is one box copy; all of them in one launch (sources are active cells or the
-  // restricted slabs, destinations ghost cells or coarse-buffer ghost cells: disjoint because
-  // ab_mesh_create_refined requires MeshBlocks of at least 2*NGHOST cells)
-  std::vector<ab::CopyBox> v;
-  const long ncc = (long)m->nc[0]*m->nc[1]*m->nc[2];
-  const long s2f = m->nc[0], s3f = (long)m->nc[1]*m->nc[0];
-  for (const auto &r : m->smr_rows) {
-    if (r[0] < 0 || r[0] > 2) continue;
-    LocalBlock &S = m->lb[r[1]], &T = m->lb[r[5]];
-    AbMesh::SmrBlk &sb = m->smr_blk[r[1]], &tb = m->smr_blk[r[5]];
-    const long cncc_s = (long)sb.g.cnc1*sb.g.cnc2*sb.g.cnc3, cncc_t = (long)tb.g.cnc1*tb.g.cnc2*tb.g.cnc3;
-    for (int pass = 0; pass < (ns > 0 ? 2 : 1); ++pass) {
-      ab::CopyBox c;
-      memset(&c, 0, sizeof(c));
-      const double *sf = pass ? S.d.s : S.d.u, *sc = pass ? sb.cs : sb.cu;
-      double *tf = pass ? T.d.s : T.d.u, *tc = pass ? tb.cs : tb.cu;
-      if (r[0] == 0) { c.src = sf; c.src_s3 = s3f; c.src_s2 = s2f; c.src_sv = ncc;
-                       c.dst = tf; c.dst_s3 = s3f; c.dst_s2 = s2f; c.dst_sv = ncc; }
-      else if (r[0] == 1) { c.src = sf; c.src_s3 = s3f; c.src_s2 = s2f; c.src_sv = ncc;
-                            c.dst = tc; c.dst_s3 = (long)tb.g.cnc2*tb.g.cnc1; c.dst_s2 = tb.g.cnc1;
-                            c.dst_sv = cncc_t; }
-      else { c.src = sc; c.src_s3 = (long)sb.g.cnc2*sb.g.cnc1; c.src_s2 = sb.g.cnc1; c.src_sv = cncc_s;
-             c.dst = tf; c.dst_s3 = s3f; c.dst_s2 = s2f; c.dst_sv = ncc; }
-      c.nvar = pass ? ns : nh;
-      c.si0 = (int)r[2]; c.sj0 = (int)r[3]; c.sk0 = (int)r[4];
-      c.di0 = (int)r[6]; c.dj0 = (int)r[7]; c.dk0 = (int)r[8];
-      c.ni = (int)r[9]; c.nj = (int)r[10]; c.nk = (int)r[11];
-      v.push_back(c);
-    }
-  }
-  long total = 0;
-  for (auto &c : v) { c.offset = total; total += (long)c.ni*c.nj*c.nk*c.nvar; }
-  if (v.size() > m->smr_boxes_cap) {
-    if (m->smr_boxes) cudaFree(m->smr_boxes);
-    m->smr_boxes_cap = v.size();
-    CK(cudaMalloc(&m->smr_boxes, sizeof(ab::CopyBox)*m->smr_boxes_cap));
-  }
-  if (!v.empty()) {
-    // the table carries the CURRENT register pointers (u / u1 swap every stage); stream-ordered
-    // upload + sync because the source is pageable host memory (see build_state_plan)
-    CK(cudaMemcpyAsync(m->smr_boxes, v.data(), sizeof(ab::CopyBox)*v.size(), cudaMemcpyHostToDevice,
-                       m->stream));
-    CK(cudaStreamSynchronize(m->stream));
-    ab::launch_copy_boxes(m->smr_boxes, (int)v.size(), total, m->stream);
-  }
+  // disjoint sources / destinations within the one copy launch: ab_mesh_create_refined requires
+  // MeshBlocks of at least 2*NGHOST cells, so restricted slabs stay inside the active coarse cells
+  SmrDeviceOps ops{m, m->stream};
+  std::vector<ab::SmrView> v = smr_views(m);
+  ab::smr_run_exchange(m->smr_rows, v, smr_dims(m), ops);
+  if (ops.rc) return fail(ops.rc, "SMR exchange: CUDA error");
   CK(cudaGetLastError());
   return AB_OK;
 }
 
-// BoundaryValues::ProlongateBoundaries of one block: rows 12 (restriction of ghost cells filled by
-// same-level neighbours), then per coarser neighbour rows 10 / 11 (coarse ConservedToPrimitive
-// box, coarse boundary functions, prolongation box, PrimitiveToConserved on the fine ghost cells)
 int smr_prolongate(AbMesh *m, int lid) {
-  LocalBlock &L = m->lb[lid];
-  HostBlock &B = *L.hb;
-  AbMesh::SmrBlk &sb = m->smr_blk[lid];
-  const int nh = m->nh, ns = m->p.nscalars;
-  cudaStream_t st = L.stream;
-  const int cs[3] = {sb.g.cis, sb.g.cjs, sb.g.cks};
-  const int ce[3] = {sb.g.cis + m->p.bx1/2 - 1, m->f2 ? sb.g.cjs + m->p.bx2/2 - 1 : 0,
-                     m->f3 ? sb.g.cks + m->p.bx3/2 - 1 : 0};
-  const bool fdim[3] = {true, (bool)m->f2, (bool)m->f3};
-  for (size_t n = 0; n < m->smr_rows.size(); ++n) {
-    const auto &r = m->smr_rows[n];
-    if (r[1] != lid) continue;
-    if (r[0] == 12) {
-      const ab::SmrBox bx = smr_box(&r[2], &r[9]);
-      ab::launch_smr_restrict(sb.g, L.d.u, sb.cu, nh, bx, st);
-      ab::launch_smr_restrict(sb.g, L.d.s, sb.cs, ns, bx, st);
-    } else if (r[0] == 10) {
-      const auto &r2 = m->smr_rows[n + 1];       // row 11 follows its row 10
-      const ab::SmrBox pbx = smr_box(&r[2], &r[9]);
-      const ab::SmrBox cbx{(int)r[6], (int)r2[2], (int)r[7], (int)r2[3], (int)r[8], (int)r2[4]};
-      const int ox[3] = {(int)r2[6], (int)r2[7], (int)r2[8]};
-      ab::launch_smr_c2p(sb.g, m->kp, sb.cu, sb.cw, ns, sb.cs, sb.cr, cbx, st);
-      for (int d = 0; d < 3; ++d) {
-        if (!fdim[d] || ox[d] != 0) continue;
-        for (int side = 0; side < 2; ++side) {
-          const int face = 2*d + side, bc = B.bcs[face];
-          if (bc != AB_BC_OUTFLOW && bc != AB_BC_REFLECT) continue;
-          // DispatchBoundaryFunctions(cis..cie along the normal, the ghost box transversally)
-          ab::SmrBox t = pbx;
-          if (d == 0) { t.si = t.ei = 0; } else if (d == 1) { t.sj = t.ej = 0; } else { t.sk = t.ek = 0; }
-          ab::launch_smr_bc(sb.g, sb.cw, nh, sb.cr, ns, face, bc == AB_BC_REFLECT, cs[d], ce[d], t, st);
-        }
-      }
-      ab::launch_smr_prolong(sb.g, sb.cw, L.d.w, nh, pbx, st);
-      ab::launch_smr_prolong(sb.g, sb.cr, L.d.r, ns, pbx, st);
-      const int fsi = (pbx.si - cs[0])*2 + m->is, fei = (pbx.ei - cs[0])*2 + m->is + 1;
-      int fsj = m->js, fej = m->je, fsk = m->ks, fek = m->ke;
-      if (m->f2) { fsj = (pbx.sj - cs[1])*2 + m->js; fej = (pbx.ej - cs[1])*2 + m->js + 1; }
-      if (m->f3) { fsk = (pbx.sk - cs[2])*2 + m->ks; fek = (pbx.ek - cs[2])*2 + m->ks + 1; }
-      ab::launch_prim2cons(L.d, m->kp, fsi, fei, fsj, fej, fsk, fek, st);
-      ab::launch_scalar_eos(L.d, m->kp, 1, fsi, fei, fsj, fej, fsk, fek, st);
-    }
-  }
+  SmrDeviceOps ops{m, m->lb[lid].stream};
+  std::vector<ab::SmrView> v = smr_views(m);
+  ab::smr_run_prolongate(m->smr_rows, lid, v[lid], smr_dims(m), ops);
   CK(cudaGetLastError());
   return AB_OK;
 }
 
-// SendFluxCorrection / ReceiveFluxCorrection (hydro and scalar fluxes): rows 20
 int smr_flux_correction(AbMesh *m) {
-  const int hx[3] = {m->p.bx1/2, m->f2 ? m->p.bx2/2 : 0, m->f3 ? m->p.bx3/2 : 0};
-  const int s0[3] = {m->is, m->js, m->ks}, e0[3] = {m->ie, m->je, m->ke};
-  for (const auto &r : m->smr_rows) {
-    if (r[0] != 20) continue;
-    LocalBlock &F = m->lb[r[1]], &Cb = m->lb[r[5]];
-    const int ffid = (int)r[2], cfid = (int)r[6], fi1 = (int)r[7], fi2 = (int)r[8];
-    const int dir = ffid >> 1;
-    const int fpos = s0[dir] + (e0[dir] - s0[dir] + 1)*(ffid & 1);     // fine face index
-    const int cpos = s0[dir] + (e0[dir] - s0[dir] + 1)*(cfid & 1);     // coarse face index
-    const int da = dir == 0 ? 1 : 0, db = dir == 2 ? 1 : 2;            // transverse directions
-    const int a0 = s0[da] + (fi1 ? hx[da] : 0), b0 = s0[db] + (fi2 ? hx[db] : 0);
-    const bool fdim[3] = {true, (bool)m->f2, (bool)m->f3};
-    const int na = fdim[da] ? hx[da] : 1, nb = fdim[db] ? hx[db] : 1;
-    ab::launch_smr_flux(m->smr_blk[r[1]].g, F.d.flux[dir], Cb.d.flux[dir], m->nh, dir, fpos, cpos,
-                        a0, b0, na, nb, m->stream);
-    if (m->p.nscalars > 0)
-      ab::launch_smr_flux(m->smr_blk[r[1]].g, F.d.sflux[dir], Cb.d.sflux[dir], m->p.nscalars, dir,
-                          fpos, cpos, a0, b0, na, nb, m->stream);
-  }
+  SmrDeviceOps ops{m, m->stream};
+  std::vector<ab::SmrView> v = smr_views(m);
+  ab::smr_run_flux_correction(m->smr_rows, v, smr_dims(m), ops);
   CK(cudaGetLastError());
   return AB_OK;
 }

@@ -139,6 +139,7 @@ long ao_smr_transfers(AoMesh *m, long *rows, long max_rows);
  * box {si,ei,sj,ej,sk,ek} of block b; arrays by name: coarse_u coarse_w cx1v cx2v cx3v */
 void ao_smr_restrict_box(AoMesh *m, int b, const int *box);
 void ao_smr_prolong_box(AoMesh *m, int b, const int *box);
+void ao_smr_step(AoMesh *m, int what);   /* 0 exchange, 1 ProlongateBoundaries, 2 flux correction */
 /* neighbour list of block b: rows of 8 ints {ox1, ox2, ox3, type, gid, level, fi1, fi2};
  * nblevel (27 ints, [k][j][i]) when not NULL; returns the number of neighbours */
 int ao_neighbors(const AoMesh *m, int b, int *rows, int *nblevel);

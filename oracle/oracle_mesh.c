@@ -628,6 +628,8 @@ double *ao_array(AoMesh *m, int b, const char *name, long *n) {
     {"coarse_u", B->coarse_u, NHYDRO*(long)B->cnc1*B->cnc2*B->cnc3},
     {"coarse_w", B->coarse_w, NHYDRO*(long)B->cnc1*B->cnc2*B->cnc3},
     {"cx1v", B->cx1v, B->cnc1}, {"cx2v", B->cx2v, B->cnc2}, {"cx3v", B->cx3v, B->cnc3},
+    {"coarse_s", B->coarse_s, m->p.nscalars*(long)B->cnc1*B->cnc2*B->cnc3},
+    {"coarse_r", B->coarse_r, m->p.nscalars*(long)B->cnc1*B->cnc2*B->cnc3},
     {"s", B->s, m->p.nscalars*ncc}, {"s1", B->s1, m->p.nscalars*ncc},
     {"r", B->r, m->p.nscalars*ncc}, {"sflux1", B->sflux[0], m->p.nscalars*n1},
     {"sflux2", B->sflux[1], m->p.nscalars*n2}, {"sflux3", B->sflux[2], m->p.nscalars*n3}};

@@ -807,3 +807,12 @@ void ao_smr_prolong_box(AoMesh *m, int b, const int *box) {
   AoBlock *B = &m->blk[b];
   smr_prolongate(m, B, B->coarse_w, B->w, NHYDRO, box[0], box[1], box[2], box[3], box[4], box[5]);
 }
+
+/* test hook: one SMR step on the mesh's current state: 0 ghost exchange of u and s, 1
+ * ProlongateBoundaries of every block, 2 flux correction of the hydro and scalar fluxes */
+void ao_smr_step(AoMesh *m, int what) {
+  if (!m->multilevel) return;
+  if (what == 0) { smr_exchange_cc(m, 0); smr_exchange_cc(m, 1); }
+  else if (what == 1) { for (int g = 0; g < m->nb; ++g) smr_prolongate_boundaries(m, g); }
+  else { smr_flux_correction(m, 0); smr_flux_correction(m, 1); }
+}
