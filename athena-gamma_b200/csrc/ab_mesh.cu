@@ -651,6 +651,35 @@ void make_recon_table(int dir, int nc, int s, int e, int ng, const std::vector<d
   }
 }
 
+// cell centres of the MeshRefinement's coarse Coordinates along direction d (coarse_flag branch of
+// coordinates.cpp:92-160 + cartesian.cpp:25-75): faces from the mesh generator at every second
+// fine index, block edges pinned, reflecting ghost spacing mirrored
+std::vector<double> coarse_centres(const AbMesh *m, const HostBlock &B, int d) {
+  const AbMeshParams &p = m->p;
+  const double mmin[3] = {p.x1min, p.x2min, p.x3min}, mmax[3] = {p.x1max, p.x2max, p.x3max};
+  const int nxm[3] = {p.nx1, p.nx2, p.nx3}, bxs[3] = {p.bx1, p.bx2, p.bx3};
+  const bool fdim[3] = {true, (bool)m->f2, (bool)m->f3};
+  const int cng = (p.nghost + 1)/2 + 1;
+  const int cnc = fdim[d] ? bxs[d]/2 + 2*cng : 1;
+  std::vector<double> xf(cnc + 1, 0.0), xv(cnc, 0.0);
+  if (cnc == 1) {
+    xf[0] = B.bmin[d]; xf[1] = B.bmax[d]; xv[0] = 0.5*(xf[1] + xf[0]);
+    return xv;
+  }
+  const int il = cng, iu = cng + bxs[d]/2 - 1;
+  const long nroot = (long)nxm[d] << B.dl;
+  std::vector<double> dxf(cnc, (B.bmax[d] - B.bmin[d])/(iu - il + 1));
+  for (int i = il - cng; i <= iu + cng + 1; ++i)
+    xf[i] = gen_x((long)(i - il)*2 + B.lx[d]*bxs[d], nroot, mmin[d], mmax[d], 1.0, nxm[d]);
+  xf[il] = B.bmin[d]; xf[iu+1] = B.bmax[d];
+  if (B.bcs[2*d] == AB_BC_REFLECT) for (int i = 1; i <= cng; ++i) {
+    dxf[il-i] = dxf[il+i-1]; xf[il-i] = xf[il-i+1] - dxf[il-i]; }
+  if (B.bcs[2*d+1] == AB_BC_REFLECT) for (int i = 1; i <= cng; ++i) {
+    dxf[iu+i] = dxf[iu-i+1]; xf[iu+i+1] = xf[iu+i] + dxf[iu+i]; }
+  for (int i = il - cng; i <= iu + cng; ++i) xv[i] = 0.5*(xf[i+1] + xf[i]);
+  return xv;
+}
+
 long reg_size(const AbMesh *m, int reg) {
   long n1 = m->nc[0], n2 = m->nc[1], n3 = m->nc[2];
   long ncc = n1*n2*n3;
@@ -1645,8 +1674,8 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
 // additionally gets the MeshRefinement's coarse buffers (src/mesh/mesh_refinement.cpp:40-100).
 // Scope of this version: one process, hydro (+ passive scalars), uniformly spaced levels,
 // MeshBlocks of at least 2*NGHOST cells, no user-enrolled boundary functions.
-int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regions, int nregions,
-                           AbMesh **out) {
+static int refined_host_setup(const AbMeshParams *p, const AbRefinementRegion *regions,
+                              int nregions, bool dry, AbMesh **out) {
   if (!p || !out) return fail(AB_ERR_ARG, "null argument");
   *out = nullptr;
   int vrc = validate_params(p);
@@ -1663,12 +1692,12 @@ int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regi
   AbSmrPlan *plan = nullptr;
   if (ab_smr_plan_create(p, regions, nregions, &plan) != AB_OK)
     return fail(AB_ERR_ARG, std::string("refinement: ") + ab_smr_last_error());
-  if (ab_device_count() <= 0) {
+  if (!dry && ab_device_count() <= 0) {
     ab_smr_plan_destroy(plan);
     return fail(AB_ERR_NO_DEVICE, "no CUDA device: libathena_b200 has no CPU fallback");
   }
-  CK(cudaSetDevice(p->device));
   AbMesh *m = new AbMesh();
+  m->dry = dry;
   m->smr = true; m->smr_plan = plan;
   // host_setup without build_block_list
   {
@@ -1721,6 +1750,17 @@ int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regi
     m->smr_rows.resize(n);
     for (long i = 0; i < n; ++i) for (int c = 0; c < 12; ++c) m->smr_rows[i][c] = tr[12*i + c];
   }
+  *out = m;
+  return AB_OK;
+}
+
+int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regions, int nregions,
+                           AbMesh **out) {
+  AbMesh *m = nullptr;
+  int hrc = refined_host_setup(p, regions, nregions, false, &m);
+  if (hrc) return hrc;
+  *out = nullptr;
+  CK(cudaSetDevice(p->device));
   CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&m->ev_pack, cudaEventDisableTiming));
@@ -1747,24 +1787,8 @@ int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regi
     g.cnc3 = m->f3 ? bxs[2]/2 + 2*cng : 1; g.cks = m->f3 ? cng : 0;
     g.dx1f = L.d.dx1f; g.dx2f = L.d.dx2f; g.dx3f = L.d.dx3f;
     g.x1v = L.d.x1v; g.x2v = L.d.x2v; g.x3v = L.d.x3v;
-    const int cnc[3] = {g.cnc1, g.cnc2, g.cnc3};
     for (int d = 0; d < 3; ++d) {
-      std::vector<double> xf(cnc[d] + 1, 0.0), xv(cnc[d], 0.0);
-      if (cnc[d] == 1) {
-        xf[0] = B.bmin[d]; xf[1] = B.bmax[d]; xv[0] = 0.5*(xf[1] + xf[0]);
-      } else {
-        const int il = cng, iu = cng + bxs[d]/2 - 1;
-        const long nroot = (long)nxm[d] << B.dl;
-        std::vector<double> dxf(cnc[d], (B.bmax[d] - B.bmin[d])/(iu - il + 1));
-        for (int i = il - cng; i <= iu + cng + 1; ++i)
-          xf[i] = gen_x((long)(i - il)*2 + B.lx[d]*bxs[d], nroot, mmin[d], mmax[d], 1.0, nxm[d]);
-        xf[il] = B.bmin[d]; xf[iu+1] = B.bmax[d];
-        if (B.bcs[2*d] == AB_BC_REFLECT) for (int i = 1; i <= cng; ++i) {
-          dxf[il-i] = dxf[il+i-1]; xf[il-i] = xf[il-i+1] - dxf[il-i]; }
-        if (B.bcs[2*d+1] == AB_BC_REFLECT) for (int i = 1; i <= cng; ++i) {
-          dxf[iu+i] = dxf[iu-i+1]; xf[iu+i+1] = xf[iu+i] + dxf[iu+i]; }
-        for (int i = il - cng; i <= iu + cng; ++i) xv[i] = 0.5*(xf[i+1] + xf[i]);
-      }
+      std::vector<double> xv = coarse_centres(m, B, d);
       CK(cudaMalloc(&sb.cxv[d], xv.size()*8));
       CK(cudaMemcpyAsync(sb.cxv[d], xv.data(), xv.size()*8, cudaMemcpyHostToDevice, m->stream));
       CK(cudaStreamSynchronize(m->stream));
@@ -1787,6 +1811,14 @@ int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regi
   CK(cudaStreamSynchronize(m->stream));
   *out = m;
   return AB_OK;
+}
+
+// Host-only twin of ab_mesh_create_refined (no GPU needed): block list, levels, extents, boundary
+// flags, neighbour levels; for ab_block_info / ab_block_level / ab_plan_geometry / ab_mesh_destroy.
+int ab_plan_create_refined(const AbMeshParams *p, const AbRefinementRegion *regions, int nregions,
+                           AbMesh **out) {
+  if (!p || !out) return fail(AB_ERR_ARG, "null argument");
+  return refined_host_setup(p, regions, nregions, true, out);
 }
 
 // Host-only plan of the same mesh (no device needed): used to check the cross-rank message
@@ -1901,7 +1933,11 @@ static void host_setup(AbMesh *m, const AbMeshParams *p) {
 
 int ab_mesh_destroy(AbMesh *m) {
   if (!m) return AB_OK;
-  if (m->dry) { delete m; return AB_OK; }
+  if (m->dry) {
+    if (m->smr_plan) ab_smr_plan_destroy(m->smr_plan);
+    delete m;
+    return AB_OK;
+  }
   cudaSetDevice(m->p.device);
   cudaStreamSynchronize(m->stream);
   for (auto &L : m->lb) { cudaFree(L.base); for (void *q : L.debug_allocs) cudaFree(q); }
@@ -2082,9 +2118,15 @@ int ab_stage_sync(AbMesh *m) {
 // table (nc*13, only when x?rat != 1), 6 / 7 cell-centred-field weights lw / rw.
 // Returns the number of doubles (also when out == NULL), 0 when that array does not exist.
 int ab_plan_geometry(const AbMesh *m, int lid, int dir, int what, double *out, int max_n) {
-  if (!m || lid < 0 || lid >= (int)m->lb_hb.size() || dir < 0 || dir > 2 || what < 0 || what > 7)
+  if (!m || lid < 0 || lid >= (int)m->lb_hb.size() || dir < 0 || dir > 2 || what < 0 || what > 8)
     return fail(AB_ERR_ARG, "bad argument");
   const HostBlock &B = *m->lb_hb[lid];
+  if (what == 8) {    // refined meshes: cell centres of the coarse buffers
+    if (!m->smr) return 0;
+    const std::vector<double> v = coarse_centres(m, B, dir);
+    if (out) for (size_t i = 0; i < v.size() && (int)i < max_n; ++i) out[i] = v[i];
+    return (int)v.size();
+  }
   const AbMeshParams &p = m->p;
   const double mmin[3] = {p.x1min, p.x2min, p.x3min}, mmax[3] = {p.x1max, p.x2max, p.x3max};
   const int nxm[3] = {p.nx1, p.nx2, p.nx3}, bxs[3] = {p.bx1, p.bx2, p.bx3};

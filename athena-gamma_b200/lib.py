@@ -37,7 +37,7 @@ SYMBOLS = [
     "ab_stage_sync",
     "ab_smr_last_error", "ab_smr_plan_create", "ab_smr_plan_destroy", "ab_smr_plan_nblocks",
     "ab_smr_plan_blocks", "ab_smr_plan_neighbors", "ab_smr_plan_transfers",
-    "ab_mesh_create_refined", "ab_block_level",
+    "ab_mesh_create_refined", "ab_block_level", "ab_plan_create_refined",
 ]
 
 
@@ -123,6 +123,8 @@ def load():
     L.ab_mesh_create_refined.argtypes = [C.POINTER(AbMeshParams), C.POINTER(AbRefinementRegion),
                                          ip, C.POINTER(vp)]
     L.ab_block_level.argtypes = [vp, ip]
+    L.ab_plan_create_refined.argtypes = [C.POINTER(AbMeshParams), C.POINTER(AbRefinementRegion),
+                                         ip, C.POINTER(vp)]
     L.ab_history.argtypes = [vp, dp, ip]
     L.ab_enroll_user_explicit_source_function.argtypes = [vp, SRCTERMFUNC, vp]
     L.ab_enroll_user_explicit_source_function_device.argtypes = [vp, SRCTERMFUNC_DEVICE, vp]

@@ -94,7 +94,8 @@ int ab_plan_ranklist(const AbMesh *m, int *out, int max_n);
  * src/coordinates/coordinates.cpp:92-160, src/reconstruct/reconstruction.cpp:196-213,434-461):
  * what 0 x?f, 1 x?v, 2 dx?f, 3 / 4 PLM face weights, 5 nonuniform-reconstruction table (13
  * doubles per cell index; exists only when mesh/x?rat != 1), 6 / 7 weights of
- * Field::CalculateCellCenteredField.  Returns the number of doubles (0: no such array). */
+ * Field::CalculateCellCenteredField, 8 cell centres of the MeshRefinement's coarse buffers
+ * (refined meshes only).  Returns the number of doubles (0: no such array). */
 int ab_plan_geometry(const AbMesh *m, int lid, int dir, int what, double *out, int max_n);
 
 /* ---- static mesh refinement, host-side planner (no GPU needed; csrc/ab_smr.cpp).  The Mesh
@@ -134,6 +135,10 @@ long ab_smr_plan_transfers(const AbSmrPlan *plan, long *rows, long max_rows);
 int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regions, int nregions,
                            AbMesh **out);
 int ab_block_level(const AbMesh *m, int lid);    /* LogicalLocation::level (0 on a one-level mesh) */
+/* host-only twin (no GPU needed), for ab_block_info / ab_block_level / ab_plan_geometry (what 8 =
+ * cell centres of the coarse buffers) / ab_mesh_destroy */
+int ab_plan_create_refined(const AbMeshParams *p, const AbRefinementRegion *regions, int nregions,
+                           AbMesh **out);
 
 /* ---- user-enrolled boundary functions: Mesh::EnrollUserBoundaryFunction (src/mesh/mesh.cpp)
  * with the BValFunc signature of src/athena.hpp:179-182 on plain arrays.  `face`: 0..5 =

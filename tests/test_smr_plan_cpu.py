@@ -235,3 +235,50 @@ def test_device_restriction_and_prolongation_arithmetic(hc, gname):  # noqa: F81
         hc.hc_smr_prolong(dims, dp(xv[0]), dp(xv[1]), dp(xv[2]), dp(cxv[0]), dp(cxv[1]),
                           dp(cxv[2]), dp(cw4[v]), dp(got), pbox)
         util.assert_bitwise(got, wantw[v], "prolongation var %d" % v)
+
+
+@pytest.mark.parametrize("gname", ["smr_blast3d_refl_lhllc_plm_rk3", "smr_blast2d_lvl2_bcs_hllc_plm_rk2",
+                                   "smr_sod1d_hllc_plm_vl2", "smr_khs3d_hllc_ppm_rk3_ng4_s2"])
+def test_refined_mesh_host_setup_matches_oracle(gname):
+    """ab_plan_create_refined = the host half of ab_mesh_create_refined: per-level block extents,
+    coordinates (also in the mirrored ghost zones of reflecting boundaries), the coarse buffers'
+    cell centres, levels and block order, against the oracle's arrays."""
+    g = util.Golden(gname)
+    case = _case_from_golden(gname)
+    om = util.oracle_from_golden(g)
+    p = ab.lib.AbMeshParams()
+    p.nx1, p.nx2, p.nx3 = case["nx"]
+    p.bx1, p.bx2, p.bx3 = case["bx"]
+    for k, v in case["lim"].items():
+        setattr(p, k, v)
+    for i, f in enumerate(case["bc"]):
+        p.bc[i] = ab.lib.BC[f]
+    p.nghost, p.nranks, p.xorder = case["ng"], 1, 2
+    p.solver, p.gamma, p.cfl_number, p.tlim = ab.lib.SOLVER["hllc"], 1.4, 0.3, 1.0
+    regs = (ab.lib.AbRefinementRegion*len(case["regions"]))()
+    for i, r in enumerate(case["regions"]):
+        (regs[i].x1min, regs[i].x1max, regs[i].x2min, regs[i].x2max, regs[i].x3min,
+         regs[i].x3max, regs[i].level) = r
+    L = ab.lib.load()
+    h = C.c_void_p()
+    rc = L.ab_plan_create_refined(C.byref(p), regs, len(regs), C.byref(h))
+    assert rc == 0, L.ab_last_error()
+    try:
+        nb = L.ab_mesh_nblocks_local(h)
+        assert nb == om.nb == L.ab_mesh_nblocks_total(h)
+        DP = C.POINTER(C.c_double)
+        for lid in range(nb):
+            info = (C.c_long*13)()
+            assert L.ab_block_info(h, lid, info) == 0
+            i = om.info[lid]
+            assert (info[1], info[2], info[3]) == (i["lx1"], i["lx2"], i["lx3"])
+            assert L.ab_block_level(h, lid) == i["level"]
+            for d in range(3):
+                for what, nm in ((0, "x%df"), (1, "x%dv"), (2, "dx%df"), (8, "cx%dv")):
+                    want = np.array(om.array(lid, nm % (d + 1)))
+                    n = L.ab_plan_geometry(h, lid, d, what, None, 0)
+                    got = np.zeros(n)
+                    L.ab_plan_geometry(h, lid, d, what, got.ctypes.data_as(DP), n)
+                    util.assert_bitwise(got, want, "block %d %s" % (lid, nm % (d + 1)))
+    finally:
+        L.ab_mesh_destroy(h)
