@@ -3,6 +3,9 @@
  * TEST INFRASTRUCTURE ONLY: linked/loaded solely by tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline leg.  The product (athena-gamma_b200/) never includes or links it.
  *
+ * Covers one-level meshes (hydro / MHD, all solvers, scalars, both EOS, uniform and geometric
+ * spacing) and statically refined hydro meshes (oracle_smr.c).
+ *
  * Pinned bit-for-bit against the unmodified reference (oracle/_ref, built by
  * oracle/build_ref.py) by tests/test_oracle_vs_reference.py and the committed fixtures in
  * tests/golden/.
