@@ -2335,7 +2335,7 @@ int ab_emf_exchange(AbMesh *m) {
 }
 int ab_bvals_exchange(AbMesh *m) {
   if (!m) return fail(AB_ERR_ARG, "null mesh");
-  return bvals_exchange(m);
+  return m->smr ? smr_exchange(m) : bvals_exchange(m);
 }
 
 int ab_enroll_user_explicit_source_function(AbMesh *m, AbSrcTermFunc fn, void *user) {
