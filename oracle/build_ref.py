@@ -65,6 +65,9 @@ CONFIGS = {
     "mhd_hlld_iso_ng2": (True, "hlld", 2, ["linear_wave", "orszag_tang", "blast"],
                          {"eos": "isothermal"}),
     "mhd_hlle_iso_ng2": (True, "hlle", 2, ["linear_wave", "orszag_tang"], {"eos": "isothermal"}),
+    # Roe's solver with the isothermal EOS (the NON_BAROTROPIC_EOS == 0 branches of roe*.cpp)
+    "hydro_roe_iso_ng2": (False, "roe", 2, ["blast", "kh"], {"eos": "isothermal"}),
+    "mhd_roe_iso_ng2": (True, "roe", 2, ["blast", "orszag_tang"], {"eos": "isothermal"}),
 }
 
 

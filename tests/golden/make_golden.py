@@ -187,6 +187,25 @@ CASES = {
                                      dict(OT, **mb(16, 16), **{"time/xorder": 2,
                                                                "hydro/iso_sound_speed": 0.7}),
                                      "hlle", True, 5, 0, "isothermal"),
+    # Roe's solver with the isothermal EOS (hydro and MHD)
+    "iso_blast_roe_plm_vl2_8blk": ("hydro_roe_iso_ng2", "blast", "athinput.blast",
+                                   dict(BL, **mb(8, 8, 8), **{"hydro/iso_sound_speed": 0.4082482905,
+                                                              "problem/drat": 5.0}),
+                                   "roe", False, 6, 0, "isothermal"),
+    "iso_kh2d_roe_plm_rk2_4blk": ("hydro_roe_iso_ng2", "kh", "athinput.kh",
+                                  {"mesh/nx1": 32, "mesh/nx2": 32, "mesh/nx3": 1, "time/xorder": 2,
+                                   "time/integrator": "rk2", "hydro/iso_sound_speed": 0.9,
+                                   **mb(16, 16, 1)}, "roe", False, 5, 0, "isothermal"),
+    "iso_blast_mhd_roe_plm_vl2_8blk": ("mhd_roe_iso_ng2", "blast", "athinput.blast",
+                                       dict(BL, **mb(8, 8, 8),
+                                            **{"hydro/iso_sound_speed": 0.4082482905,
+                                               "problem/drat": 5.0}),
+                                       "roe", True, 6, 0, "isothermal"),
+    "iso_ot_mhd_roe_plm_rk2_4blk": ("mhd_roe_iso_ng2", "orszag_tang", "athinput.orszag_tang",
+                                    dict(OT, **mb(16, 16), **{"time/xorder": 2,
+                                                              "time/integrator": "rk2",
+                                                              "hydro/iso_sound_speed": 0.7}),
+                                    "roe", True, 5, 0, "isothermal"),
     # passive scalars (src/scalars): the fork's production build carries one (confignotes)
     "khs_lhllc_plm_vl2_4blk_s1": ("hydro_lhllc_ng2_s1", "kh", "athinput.kh_scalar",
                                   dict(KS, **mb(8, 16, 1)), "lhllc", False, 6, 1),
