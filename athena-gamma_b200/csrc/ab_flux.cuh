@@ -62,8 +62,7 @@ __global__ void AB_FLUX_BOUNDS
 k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
        int ntot, double dt_val, const double *dt_ptr) {
   constexpr int NW = MHD ? 7 : 5;
-  constexpr bool ISO = (SOLVER == SOLVER_HLLE_ISO || SOLVER == SOLVER_HLLD_ISO ||
-                        SOLVER == SOLVER_LLF_ISO);
+  constexpr bool ISO = solver_is_iso<SOLVER>;
   int t = blockIdx.x*AB_FLUX_BX + threadIdx.x;
   if (t >= ntot) return;
   int i, j, k;
@@ -263,8 +262,7 @@ template <int SOLVER, bool MHD, bool NU>
 static void flux_order(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
                        double dt_val, const double *dt_ptr, cudaStream_t s) {
   // order 4 / 5 = xorder 2c / 3c (characteristic variables; adiabatic EOS only)
-  constexpr bool ISO = (SOLVER == SOLVER_HLLE_ISO || SOLVER == SOLVER_HLLD_ISO ||
-                        SOLVER == SOLVER_LLF_ISO);
+  constexpr bool ISO = solver_is_iso<SOLVER>;
   if (order > 1 && p.char_proj && !ISO) order += 2;
   if (order == 1) {   // donor cell has no geometry: uniform instantiation only
     if constexpr (!NU) flux_all<1,SOLVER,MHD,false>(b, g, p, dir, dt_val, dt_ptr, s);
@@ -285,8 +283,11 @@ static void launch_flux_dir_t(const BlkDev &b, const ReconGeom &g, const Params 
       if (p.mhd) flux_order<SOLVER_LLF,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
       else flux_order<SOLVER_LLF,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
     }
-  } else if (p.eos != 0) {   // isothermal: hlle (hydro), hlle / hlld (MHD) -- configure.py:299-325
-    if (!p.mhd) flux_order<SOLVER_HLLE_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+  } else if (p.eos != 0) {   // isothermal: hlle / roe (hydro), hlle / hlld / roe (MHD) -- configure.py:299-325
+    if (p.solver == SOLVER_ROE) {
+      if (p.mhd) flux_order<SOLVER_ROE_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+      else flux_order<SOLVER_ROE_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    } else if (!p.mhd) flux_order<SOLVER_HLLE_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
     else flux_order<SOLVER_HLLE_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
   } else if (p.mhd) {

@@ -1892,11 +1892,9 @@ static int validate_params(const AbMeshParams *p) {
   if (p->char_proj && p->eos == AB_EOS_ISOTHERMAL)
     return fail(AB_ERR_ARG, "characteristic reconstruction with isothermal EOS is not on the device path");
   if (p->eos == AB_EOS_ISOTHERMAL) {
-    // configure.py:311-322; the isothermal Roe / LLF branches are not on the device path
+    // configure.py:311-322
     if (p->solver == AB_SOLVER_HLLC || p->solver == AB_SOLVER_LHLLC || p->solver == AB_SOLVER_LHLLD)
       return fail(AB_ERR_ARG, "HLLC / LHLLC / LHLLD flux cannot be used with isothermal EOS");
-    if (p->solver == AB_SOLVER_ROE)
-      return fail(AB_ERR_ARG, "Roe flux with isothermal EOS is not implemented on the device path");
     if (!(p->iso_sound_speed > 0.0)) return fail(AB_ERR_ARG, "hydro/iso_sound_speed must be set");
   }
   return AB_OK;

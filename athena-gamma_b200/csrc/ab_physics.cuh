@@ -1465,8 +1465,302 @@ AB_HD void hlld_iso(const double *wli, const double *wri, double bxi, double cs,
   flxi[IEN] = 0.0;
 }
 
+// Roe, isothermal hydro (hydro/rsolvers/hydro/roe.cpp:42-352, the NON_BAROTROPIC_EOS == 0
+// branches; RoeFlux :300-349): four waves, no energy equation
+AB_HD void roe_hydro_iso(const double *wli, const double *wri, double iso_cs, double *flxi) {
+  double sqrtdl = sqrt(wli[IDN]);
+  double sqrtdr = sqrt(wri[IDN]);
+  double isdlpdr = 1.0/(sqrtdl + sqrtdr);
+  double v1 = (sqrtdl*wli[IVX] + sqrtdr*wri[IVX])*isdlpdr;
+  double v2 = (sqrtdl*wli[IVY] + sqrtdr*wri[IVY])*isdlpdr;
+  double v3 = (sqrtdl*wli[IVZ] + sqrtdr*wri[IVZ])*isdlpdr;
+  double mxl = wli[IDN]*wli[IVX];
+  double mxr = wri[IDN]*wri[IVX];
+  double fl[4], fr[4], du[4], ev[4];
+  fl[IDN] = mxl;
+  fr[IDN] = mxr;
+  fl[IVX] = mxl*wli[IVX];
+  fr[IVX] = mxr*wri[IVX];
+  fl[IVY] = mxl*wli[IVY];
+  fr[IVY] = mxr*wri[IVY];
+  fl[IVZ] = mxl*wli[IVZ];
+  fr[IVZ] = mxr*wri[IVZ];
+  fl[IVX] += (iso_cs*iso_cs)*wli[IDN];
+  fr[IVX] += (iso_cs*iso_cs)*wri[IDN];
+  du[IDN] = wri[IDN]          - wli[IDN];
+  du[IVX] = wri[IDN]*wri[IVX] - wli[IDN]*wli[IVX];
+  du[IVY] = wri[IDN]*wri[IVY] - wli[IDN]*wli[IVY];
+  du[IVZ] = wri[IDN]*wri[IVZ] - wli[IDN]*wli[IVZ];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) flxi[n] = 0.5*(fl[n] + fr[n]);
+  int llf_flag = 0;
+  {
+    ev[0] = v1 - iso_cs;
+    ev[1] = v1;
+    ev[2] = v1;
+    ev[3] = v1 + iso_cs;
+    double a[4];
+    a[0]  = du[0]*(0.5 + 0.5*v1/iso_cs);
+    a[0] -= du[1]*0.5/iso_cs;
+    a[1]  = du[0]*(-v2);
+    a[1] += du[2];
+    a[2]  = du[0]*(-v3);
+    a[2] += du[3];
+    a[3]  = du[0]*(0.5 - 0.5*v1/iso_cs);
+    a[3] += du[1]*0.5/iso_cs;
+    double coeff[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) coeff[n] = -0.5*fabs(ev[n])*a[n];
+    double dens = wli[IDN] + a[0];
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[3];
+    if (dens < 0.0) llf_flag = 1;
+    flxi[0] += coeff[0];
+    flxi[0] += coeff[3];
+    flxi[1] += coeff[0]*(v1 - iso_cs);
+    flxi[1] += coeff[3]*(v1 + iso_cs);
+    flxi[2] += coeff[0]*v2;
+    flxi[2] += coeff[1];
+    flxi[2] += coeff[3]*v2;
+    flxi[3] += coeff[0]*v3;
+    flxi[3] += coeff[2];
+    flxi[3] += coeff[3]*v3;
+  }
+  if (ev[0] >= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) flxi[n] = fl[n];
+  }
+  if (ev[3] <= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) flxi[n] = fr[n];
+  }
+  if (llf_flag != 0) {   // SoundSpeed of the isothermal EOS is the constant iso_cs
+    double a = 0.5*dmax((fabs(wli[IVX]) + iso_cs), (fabs(wri[IVX]) + iso_cs));
+#pragma unroll
+    for (int n = 0; n < 4; ++n) flxi[n] = 0.5*(fl[n] + fr[n]) - a*du[n];
+  }
+  flxi[IEN] = 0.0;
+}
+
+// Roe, isothermal MHD (hydro/rsolvers/mhd/roe_mhd.cpp:43-238 with NON_BAROTROPIC_EOS == 0;
+// RoeFlux :245-345,498-612): six waves.  wli / wri / flxi keep the 7-slot layout (slot 4 unused).
+AB_HD void roe_mhd_iso(const double *wli, const double *wri, double bxi, double iso_cs,
+                       double *flxi) {
+  double sqrtdl = sqrt(wli[IDN]);
+  double sqrtdr = sqrt(wri[IDN]);
+  double isdlpdr = 1.0/(sqrtdl + sqrtdr);
+  double d  = sqrtdl*sqrtdr;
+  double v1 = (sqrtdl*wli[IVX] + sqrtdr*wri[IVX])*isdlpdr;
+  double v2 = (sqrtdl*wli[IVY] + sqrtdr*wri[IVY])*isdlpdr;
+  double v3 = (sqrtdl*wli[IVZ] + sqrtdr*wri[IVZ])*isdlpdr;
+  double b2 = (sqrtdr*wli[IBY] + sqrtdl*wri[IBY])*isdlpdr;
+  double b3 = (sqrtdr*wli[IBZ] + sqrtdl*wri[IBZ])*isdlpdr;
+  double x = 0.5*(sqr(wli[IBY] - wri[IBY]) + sqr(wli[IBZ] - wri[IBZ]))/(sqr(sqrtdl + sqrtdr));
+  double y = 0.5*(wli[IDN] + wri[IDN])/d;
+  double pbl = 0.5*(bxi*bxi + sqr(wli[IBY]) + sqr(wli[IBZ]));
+  double pbr = 0.5*(bxi*bxi + sqr(wri[IBY]) + sqr(wri[IBZ]));
+  double mxl = wli[IDN]*wli[IVX];
+  double mxr = wri[IDN]*wri[IVX];
+  double fl[6], fr[6], du[6], ev[6], flx[6];
+  fl[0] = mxl;
+  fr[0] = mxr;
+  fl[1] = mxl*wli[IVX] + pbl - sqr(bxi);
+  fr[1] = mxr*wri[IVX] + pbr - sqr(bxi);
+  fl[2] = mxl*wli[IVY] - bxi*wli[IBY];
+  fr[2] = mxr*wri[IVY] - bxi*wri[IBY];
+  fl[3] = mxl*wli[IVZ] - bxi*wli[IBZ];
+  fr[3] = mxr*wri[IVZ] - bxi*wri[IBZ];
+  fl[1] += (iso_cs*iso_cs)*wli[IDN];
+  fr[1] += (iso_cs*iso_cs)*wri[IDN];
+  fl[4] = wli[IBY]*wli[IVX] - bxi*wli[IVY];
+  fr[4] = wri[IBY]*wri[IVX] - bxi*wri[IVY];
+  fl[5] = wli[IBZ]*wli[IVX] - bxi*wli[IVZ];
+  fr[5] = wri[IBZ]*wri[IVX] - bxi*wri[IVZ];
+  du[0] = wri[IDN]          - wli[IDN];
+  du[1] = wri[IDN]*wri[IVX] - wli[IDN]*wli[IVX];
+  du[2] = wri[IDN]*wri[IVY] - wli[IDN]*wli[IVY];
+  du[3] = wri[IDN]*wri[IVZ] - wli[IDN]*wli[IVZ];
+  du[4] = wri[IBY] - wli[IBY];
+  du[5] = wri[IBZ] - wli[IBZ];
+#pragma unroll
+  for (int n = 0; n < 6; ++n) flx[n] = 0.5*(fl[n] + fr[n]);
+  int llf_flag = 0;
+  {
+    double b1 = bxi;
+    double di = 1.0/d;
+    double btsq = b2*b2 + b3*b3;
+    double vaxsq = b1*b1*di;
+    double bt_starsq = btsq*y;
+    double twid_csq = (iso_cs*iso_cs) + x;
+    double ct2 = bt_starsq*di;
+    double tsum = vaxsq + ct2 + twid_csq;
+    double tdif = vaxsq + ct2 - twid_csq;
+    double cf2_cs2 = sqrt(tdif*tdif + 4.0*twid_csq*ct2);
+    double cfsq = 0.5*(tsum + cf2_cs2);
+    double cf = sqrt(cfsq);
+    double cssq = twid_csq*vaxsq/cfsq;
+    double cs = sqrt(cssq);
+    double bt = sqrt(btsq);
+    double bt_star = sqrt(bt_starsq);
+    double bet2 = 0.0, bet3 = 0.0;
+    if (bt != 0.0) {
+      bet2 = b2/bt;
+      bet3 = b3/bt;
+    }
+    double bet2_star = bet2/sqrt(y);
+    double bet3_star = bet3/sqrt(y);
+    double bet_starsq = bet2_star*bet2_star + bet3_star*bet3_star;
+    double q2_star = 0.0, q3_star = 0.0;
+    if (bet_starsq != 0.0) {
+      q2_star = bet2_star/bet_starsq;
+      q3_star = bet3_star/bet_starsq;
+    }
+    double alpha_f, alpha_s;
+    if ((cfsq - cssq) <= 0.0) {
+      alpha_f = 1.0;
+      alpha_s = 0.0;
+    } else if ((twid_csq - cssq) <= 0.0) {
+      alpha_f = 0.0;
+      alpha_s = 1.0;
+    } else if ((cfsq - twid_csq) <= 0.0) {
+      alpha_f = 1.0;
+      alpha_s = 0.0;
+    } else {
+      alpha_f = sqrt((twid_csq - cssq)/(cfsq - cssq));
+      alpha_s = sqrt((cfsq - twid_csq)/(cfsq - cssq));
+    }
+    double sqrtd = sqrt(d);
+    double isqrtd = 1.0/sqrtd;
+    double s = (b1 < 0.0) ? -1.0 : 1.0;
+    double twid_c = sqrt(twid_csq);
+    double qf = cf*alpha_f*s;
+    double qs = cs*alpha_s*s;
+    double af_prime = twid_c*alpha_f*isqrtd;
+    double as_prime = twid_c*alpha_s*isqrtd;
+    double vqstr = (v2*q2_star + v3*q3_star);
+    double vax = sqrt(vaxsq);
+    double norm = 0.5/twid_csq;
+    double cff = norm*alpha_f*cf;
+    double css = norm*alpha_s*cs;
+    double qf_hat = qf*norm;
+    double qs_hat = qs*norm;
+    double af = norm*af_prime*d;
+    double as = norm*as_prime*d;
+    double afpb = norm*af_prime*bt_star;
+    double aspb = norm*as_prime*bt_star;
+    ev[0] = v1 - cf;
+    ev[1] = v1 - vax;
+    ev[2] = v1 - cs;
+    ev[3] = v1 + cs;
+    ev[4] = v1 + vax;
+    ev[5] = v1 + cf;
+    double a[6];
+    a[0]  = du[0]*(cff*(cf+v1) - qs_hat*vqstr - aspb);
+    a[0] -= du[1]*cff;
+    a[0] += du[2]*qs_hat*q2_star;
+    a[0] += du[3]*qs_hat*q3_star;
+    a[0] += du[4]*as*q2_star;
+    a[0] += du[5]*as*q3_star;
+    a[1]  = du[0]*(v2*bet3 - v3*bet2);
+    a[1] -= du[2]*bet3;
+    a[1] += du[3]*bet2;
+    a[1] -= du[4]*sqrtd*bet3*s;
+    a[1] += du[5]*sqrtd*bet2*s;
+    a[1] *= 0.5;
+    a[2]  = du[0]*(css*(cs+v1) + qf_hat*vqstr + afpb);
+    a[2] -= du[1]*css;
+    a[2] -= du[2]*qf_hat*q2_star;
+    a[2] -= du[3]*qf_hat*q3_star;
+    a[2] -= du[4]*af*q2_star;
+    a[2] -= du[5]*af*q3_star;
+    a[3]  = du[0]*(css*(cs-v1) - qf_hat*vqstr + afpb);
+    a[3] += du[1]*css;
+    a[3] += du[2]*qf_hat*q2_star;
+    a[3] += du[3]*qf_hat*q3_star;
+    a[3] -= du[4]*af*q2_star;
+    a[3] -= du[5]*af*q3_star;
+    a[4]  = du[0]*(v3*bet2 - v2*bet3);
+    a[4] += du[2]*bet3;
+    a[4] -= du[3]*bet2;
+    a[4] -= du[4]*sqrtd*bet3*s;
+    a[4] += du[5]*sqrtd*bet2*s;
+    a[4] *= 0.5;
+    a[5]  = du[0]*(cff*(cf-v1) + qs_hat*vqstr - aspb);
+    a[5] += du[1]*cff;
+    a[5] -= du[2]*qs_hat*q2_star;
+    a[5] -= du[3]*qs_hat*q3_star;
+    a[5] += du[4]*as*q2_star;
+    a[5] += du[5]*as*q3_star;
+    double coeff[6];
+#pragma unroll
+    for (int n = 0; n < 6; ++n) coeff[n] = -0.5*fabs(ev[n])*a[n];
+    double dens = wli[IDN] + a[0]*alpha_f;
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[2]*alpha_s;
+    if (dens < 0.0) llf_flag = 1;
+    dens += a[3]*alpha_s;
+    if (dens < 0.0) llf_flag = 1;
+    flx[0] += coeff[0]*alpha_f;
+    flx[0] += coeff[2]*alpha_s;
+    flx[0] += coeff[3]*alpha_s;
+    flx[0] += coeff[5]*alpha_f;
+    flx[1] += coeff[0]*alpha_f*(v1 - cf);
+    flx[1] += coeff[2]*alpha_s*(v1 - cs);
+    flx[1] += coeff[3]*alpha_s*(v1 + cs);
+    flx[1] += coeff[5]*alpha_f*(v1 + cf);
+    flx[2] += coeff[0]*(alpha_f*v2 + qs*bet2_star);
+    flx[2] -= coeff[1]*bet3;
+    flx[2] += coeff[2]*(alpha_s*v2 - qf*bet2_star);
+    flx[2] += coeff[3]*(alpha_s*v2 + qf*bet2_star);
+    flx[2] += coeff[4]*bet3;
+    flx[2] += coeff[5]*(alpha_f*v2 - qs*bet2_star);
+    flx[3] += coeff[0]*(alpha_f*v3 + qs*bet3_star);
+    flx[3] += coeff[1]*bet2;
+    flx[3] += coeff[2]*(alpha_s*v3 - qf*bet3_star);
+    flx[3] += coeff[3]*(alpha_s*v3 + qf*bet3_star);
+    flx[3] -= coeff[4]*bet2;
+    flx[3] += coeff[5]*(alpha_f*v3 - qs*bet3_star);
+    flx[4] += coeff[0]*as_prime*bet2_star;
+    flx[4] -= coeff[1]*bet3*s/sqrtd;
+    flx[4] -= coeff[2]*af_prime*bet2_star;
+    flx[4] -= coeff[3]*af_prime*bet2_star;
+    flx[4] -= coeff[4]*bet3*s/sqrtd;
+    flx[4] += coeff[5]*as_prime*bet2_star;
+    flx[5] += coeff[0]*as_prime*bet3_star;
+    flx[5] += coeff[1]*bet2*s/sqrtd;
+    flx[5] -= coeff[2]*af_prime*bet3_star;
+    flx[5] -= coeff[3]*af_prime*bet3_star;
+    flx[5] += coeff[4]*bet2*s/sqrtd;
+    flx[5] += coeff[5]*as_prime*bet3_star;
+  }
+  if (ev[0] >= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) flx[n] = fl[n];
+  }
+  if (ev[5] <= 0.0) {
+#pragma unroll
+    for (int n = 0; n < 6; ++n) flx[n] = fr[n];
+  }
+  if (llf_flag != 0) {
+    double cfl = fast_speed_iso(iso_cs, wli, bxi);
+    double cfr = fast_speed_iso(iso_cs, wri, bxi);
+    double a = 0.5*dmax((fabs(wli[IVX]) + cfl), (fabs(wri[IVX]) + cfr));
+    // the fallback leaves the field fluxes untouched (roe_mhd.cpp:222-232)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) flx[n] = 0.5*(fl[n] + fr[n]) - a*du[n];
+  }
+  flxi[IDN] = flx[0];
+  flxi[IVX] = flx[1];
+  flxi[IVY] = flx[2];
+  flxi[IVZ] = flx[3];
+  flxi[IEN] = 0.0;
+  flxi[IBY] = flx[4];
+  flxi[IBZ] = flx[5];
+}
+
 // internal solver ids of the isothermal variants (the ABI keeps AB_SOLVER_* + AB_EOS_*)
-enum : int { SOLVER_HLLE_ISO = 8, SOLVER_HLLD_ISO = 9, SOLVER_LLF_ISO = 10 };
+enum : int { SOLVER_HLLE_ISO = 8, SOLVER_HLLD_ISO = 9, SOLVER_LLF_ISO = 10, SOLVER_ROE_ISO = 11 };
+template <int SOLVER> constexpr bool solver_is_iso = (SOLVER >= SOLVER_HLLE_ISO);
 
 // LLF (hydro/rsolvers/hydro/llf.cpp:34-125, mhd/llf_mhd.cpp:34-170), both EOS; `ga` is gamma
 // (adiabatic) or the isothermal sound speed
@@ -1564,6 +1858,9 @@ AB_HD void riemann(const double *wli, const double *wri, double bxi, double gamm
     else hlle_hydro_iso(wli, wri, gamma, flxi);
   } else if (SOLVER == SOLVER_HLLD_ISO) {
     hlld_iso(wli, wri, bxi, gamma, dfloor, flxi);
+  } else if (SOLVER == SOLVER_ROE_ISO) {
+    if (MHD) roe_mhd_iso(wli, wri, bxi, gamma, flxi);
+    else roe_hydro_iso(wli, wri, gamma, flxi);
   } else if (!MHD) {
     if (SOLVER == SOLVER_HLLC) hllc_t<false>(wli, wri, gamma, 0.0, 0.0, flxi);
     else if (SOLVER == SOLVER_LHLLC) hllc_t<true>(wli, wri, gamma, dvn, dvt, flxi);

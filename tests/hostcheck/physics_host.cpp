@@ -36,7 +36,7 @@ void hc_riemann(int solver, int mhd, long n, const double *wl, const double *wr,
   }
 #undef RUN
 }
-// isothermal solvers: solver 0 = hlle (hydro / MHD), 2 = hlld (MHD)
+// isothermal solvers: solver 0 = hlle (hydro / MHD), 2 = hlld (MHD), 3 = roe, 6 = llf
 void hc_riemann_iso(int solver, int mhd, long n, const double *wl, const double *wr,
                     const double *bx, double iso_cs, double dfloor, double *flx) {
   const int nw = mhd ? 7 : 5;
@@ -45,6 +45,8 @@ void hc_riemann_iso(int solver, int mhd, long n, const double *wl, const double 
     for (int v = 0; v < nw; ++v) { a[v] = wl[v*n+i]; b[v] = wr[v*n+i]; }
     if (solver == 6 && mhd) ab::riemann<ab::SOLVER_LLF_ISO, true>(a, b, bx[i], iso_cs, 0.0, 0.0, f, dfloor);
     else if (solver == 6) ab::riemann<ab::SOLVER_LLF_ISO, false>(a, b, 0.0, iso_cs, 0.0, 0.0, f, dfloor);
+    else if (solver == 3 && mhd) ab::riemann<ab::SOLVER_ROE_ISO, true>(a, b, bx[i], iso_cs, 0.0, 0.0, f, dfloor);
+    else if (solver == 3) ab::riemann<ab::SOLVER_ROE_ISO, false>(a, b, 0.0, iso_cs, 0.0, 0.0, f, dfloor);
     else if (!mhd) ab::riemann<ab::SOLVER_HLLE_ISO, false>(a, b, 0.0, iso_cs, 0.0, 0.0, f, dfloor);
     else if (solver == 2) ab::riemann<ab::SOLVER_HLLD_ISO, true>(a, b, bx[i], iso_cs, 0.0, 0.0, f, dfloor);
     else ab::riemann<ab::SOLVER_HLLE_ISO, true>(a, b, bx[i], iso_cs, 0.0, 0.0, f, dfloor);

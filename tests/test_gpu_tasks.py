@@ -59,6 +59,10 @@ CASES = [
     ("iso_blast_mhd_hlld_plm_vl2_8blk", None, None),
     ("iso_ot_hlld_plm_rk2_4blk", None, None),
     ("iso_ot_mhd_hlle_plm_vl2_4blk", None, None),
+    ("iso_blast_roe_plm_vl2_8blk", None, None),
+    ("iso_blast_mhd_roe_plm_vl2_8blk", None, None),
+    ("iso_kh2d_roe_plm_rk2_4blk", None, None),
+    ("iso_ot_mhd_roe_plm_rk2_4blk", None, None),
     # passive scalars
     ("khs_lhllc_plm_vl2_4blk_s1", None, None),
     ("sods_lhllc_plm_vl2_2blk_s1", None, None),

@@ -82,7 +82,8 @@ def test_riemann_matches_oracle(hc, solver, mhd, regime):
 
 
 @pytest.mark.parametrize("solver,mhd", [("hlle", False), ("hlle", True), ("hlld", True),
-                                        ("llf", False), ("llf", True)])
+                                        ("llf", False), ("llf", True), ("roe", False),
+                                        ("roe", True)])
 @pytest.mark.parametrize("regime", ["subsonic", "supersonic", "mixed"])
 def test_isothermal_riemann_matches_oracle(hc, solver, mhd, regime):
     rng = np.random.default_rng(4321)
