@@ -10,7 +10,7 @@ import util
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", util.golden_names())
+@pytest.mark.parametrize("name", util.gpu_params(util.golden_names()))
 def test_cuda_reproduces_reference_golden(name):
     import gpu_util
     g = util.Golden(name)
@@ -100,7 +100,8 @@ def history_close(h, ref, scale):
     assert not bad.any(), ("history", h, ref, tol)
 
 
-@pytest.mark.parametrize("name", [n for n in util.golden_names() if util.Golden(n).hst is not None])
+@pytest.mark.parametrize("name", util.gpu_params([n for n in util.golden_names()
+                                                  if util.Golden(n).hst is not None]))
 def test_history_sums_match_reference_hst(name):
     """ab_history (on-device HistoryOutput sums) against the reference's .hst rows (17 digits)
     after every cycle.  The device sums in a fixed tree order, the reference keeps a running
