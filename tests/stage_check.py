@@ -8,6 +8,12 @@ import sys
 import numpy as np
 import torch
 
+
+def _pin(t):
+    """pinned where there is a driver (the emulated library of test_emu_device_path has none)"""
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
@@ -26,8 +32,8 @@ def main():
     # step s starts from the golden initial state scaled by (1 + 0.01 s): distinct inputs per step
     inputs = []
     for s in range(nsteps):
-        inputs.append([{f: torch.from_numpy(np.ascontiguousarray(
-            g.init[n][f]*(1.0 + 0.01*s))).pin_memory() for f in names}
+        inputs.append([{f: _pin(torch.from_numpy(np.ascontiguousarray(
+            g.init[n][f]*(1.0 + 0.01*s)))) for f in names}
             for n in range(len(g.locs))])
     order = [m.block_of(*loc) for loc in g.locs]
 
@@ -52,7 +58,7 @@ def main():
     regs = (C.c_int*nreg)(*[ab.lib.REG[f] for f in names])
     ab.lib.check(L.ab_stage_begin(m.h, regs, nreg))
     by_lid = sorted(range(len(order)), key=lambda n: order[n].lid)
-    outs = [[{f: torch.zeros_like(inputs[0][n][f]).pin_memory() for f in names}
+    outs = [[{f: _pin(torch.zeros_like(inputs[0][n][f])) for f in names}
              for n in range(len(order))] for _ in range(nsteps)]
 
     def ptrs(bufs):

@@ -1,0 +1,67 @@
+"""CPU: the product's whole device path -- kernels, launch geometry, work lists, the mesh / task
+glue and the C ABI of athena-gamma_b200/csrc -- compiled for the host against a minimal CUDA
+emulation (tests/hostcheck/emu/cuda_runtime.h: grids run block by block, thread by thread; the
+runtime API synchronous, device memory NaN-filled on allocation) and driven through the same
+Python Mesh as the GPU tests, against the reference's golden vectors, bit for bit.
+
+What this covers without a GPU: every golden fixture (dt sequence + final state of every
+MeshBlock), the statically refined meshes (ab_mesh_create_refined and the SMR launch glue) and
+the ab_stage_* pipeline.  What it cannot cover: anything that depends on parallel execution
+(races between threads or streams), NCCL, and the numerics of nvcc's code generation -- those
+stay with the -m gpu tests.  The emulated library is test infrastructure only; the product
+loads libathena_b200.so and fails loudly without a CUDA device (tests/test_abi.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NCHUNK = 4
+
+
+@pytest.fixture(scope="module")
+def emu_env():
+    sys.path.insert(0, os.path.join(HERE, "hostcheck"))
+    import build_mesh_host
+    so = build_mesh_host.build()
+    env = dict(os.environ)
+    env["AB_LIB"] = so
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    return env
+
+
+def in_device_scope(name):
+    if not name.startswith("smr_"):
+        return True
+    import test_gpu_smr
+    return name in test_gpu_smr.device_smr_goldens()
+
+
+def test_every_golden_through_the_emulated_device_path(emu_env):
+    names = [n for n in util.golden_names(include_smr=True) if in_device_scope(n)]
+    assert len(names) >= 60
+    chunks = [names[c::NCHUNK] for c in range(NCHUNK)]
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "smr_check.py")] + ch,
+                              env=emu_env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for ch in chunks]
+    bad = []
+    for ch, p in zip(chunks, procs):
+        try:
+            out = p.communicate(timeout=600)[0]
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out = "TIMEOUT " + " ".join(ch)
+        if p.returncode != 0 or "smr done: 0 failed" not in out:
+            bad.append(out[-3000:])
+        else:
+            assert out.count("\nok ") + out.startswith("ok ") == len(ch)
+    assert not bad, "\n".join(bad)
+
+
+def test_staged_pipeline_through_the_emulated_device_path(emu_env):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "stage_check.py")], env=emu_env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "staging ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
