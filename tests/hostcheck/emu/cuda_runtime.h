@@ -2,7 +2,7 @@
 // product's device sources (csrc/*.cu: kernels, launch glue, C ABI) without a GPU:
 //   * __global__ functions become plain functions; a launch (rewritten from <<< >>> by
 //     tests/hostcheck/build_mesh_host.py) runs the grid block by block, thread by thread, in
-//     order -- kernels that use __syncthreads / warp shuffles are run with one fiber per thread
+//     order (or last to first with AB_EMU_ORDER=reverse) -- kernels that use __syncthreads / warp shuffles are run with one fiber per thread
 //     and every such primitive is a block-wide phase boundary;
 //   * the runtime API is synchronous and in-order: streams and events are inert handles,
 //     "device" memory is host memory (filled with NaN bit patterns on allocation so that a read
@@ -105,6 +105,14 @@ struct State {
 inline State g;
 static const size_t STACK = 256*1024;
 
+// AB_EMU_ORDER=reverse runs blocks and threads last to first: a kernel whose result depends on
+// the order in which its threads run (one thread reading what another writes) shows up as a
+// difference between the two orders
+inline bool reversed() {
+  static const int r = [] { const char *e = getenv("AB_EMU_ORDER"); return (e && e[0] == 'r') ? 1 : 0; }();
+  return r != 0;
+}
+
 inline void barrier() {
   if (!g.coop) {
     fprintf(stderr, "ab_emu: __syncthreads / shuffle in a kernel not launched cooperatively "
@@ -123,8 +131,11 @@ template <class F> inline void call_fn(void *p) { (*(F *)p)(); }
 template <class F> inline void run_block(dim3 b, F &fn, bool coop) {
   const int nt = (int)(b.x*b.y*b.z);
   if (!coop) {
-    for (unsigned tz = 0; tz < b.z; ++tz) for (unsigned ty = 0; ty < b.y; ++ty)
-      for (unsigned tx = 0; tx < b.x; ++tx) { threadIdx = {tx, ty, tz}; fn(); }
+    for (int i = 0; i < nt; ++i) {
+      const unsigned t = (unsigned)(reversed() ? nt - 1 - i : i);
+      threadIdx = {t % b.x, (t / b.x) % b.y, t / (b.x*b.y)};
+      fn();
+    }
     return;
   }
   if ((int)g.fib.size() < nt) {
@@ -147,7 +158,8 @@ template <class F> inline void run_block(dim3 b, F &fn, bool coop) {
   int live = nt;
   while (live > 0) {            // one pass = one phase between two barriers
     live = 0;
-    for (int t = 0; t < nt; ++t) {
+    for (int i = 0; i < nt; ++i) {
+      const int t = reversed() ? nt - 1 - i : i;
       if (g.fib[t].done) continue;
       g.cur = t;
       threadIdx = {(unsigned)t % b.x, ((unsigned)t / b.x) % b.y, (unsigned)t / (b.x*b.y)};
@@ -162,8 +174,12 @@ template <class F> inline void run_block(dim3 b, F &fn, bool coop) {
 template <class F> inline void launch(dim3 gr, dim3 b, bool coop, F fn) {
   gridDim = gr;
   blockDim = b;
-  for (unsigned bz = 0; bz < gr.z; ++bz) for (unsigned by = 0; by < gr.y; ++by)
-    for (unsigned bx = 0; bx < gr.x; ++bx) { blockIdx = {bx, by, bz}; run_block(b, fn, coop); }
+  const long nb = (long)gr.x*gr.y*gr.z;
+  for (long i = 0; i < nb; ++i) {
+    const long c = reversed() ? nb - 1 - i : i;
+    blockIdx = {(unsigned)(c % gr.x), (unsigned)((c / gr.x) % gr.y), (unsigned)(c / ((long)gr.x*gr.y))};
+    run_block(b, fn, coop);
+  }
 }
 }  // namespace ab_emu
 

@@ -40,7 +40,12 @@ def in_device_scope(name):
     return name in test_gpu_smr.device_smr_goldens()
 
 
-def test_every_golden_through_the_emulated_device_path(emu_env):
+@pytest.mark.parametrize("order", ["forward", "reverse"])
+def test_every_golden_through_the_emulated_device_path(emu_env, order):
+    """order = reverse runs the blocks of a grid and the threads of a block last to first: a
+    kernel in which one thread reads what another thread of the same launch writes (a race on
+    the GPU) gives a different answer in the two orders"""
+    emu_env = dict(emu_env, AB_EMU_ORDER=order)
     names = [n for n in util.golden_names(include_smr=True) if in_device_scope(n)]
     assert len(names) >= 60
     chunks = [names[c::NCHUNK] for c in range(NCHUNK)]
