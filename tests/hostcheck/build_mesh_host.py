@@ -92,7 +92,7 @@ def rewrite_launches(src):
     return out + src[pos:], n
 
 
-def needs_build():
+def needs_build(SO=SO):
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
@@ -103,8 +103,16 @@ def needs_build():
     return any(os.path.getmtime(f) > t for f in deps)
 
 
-def build(force=False):
-    if not force and not needs_build():
+def build(force=False, asan=False):
+    """asan: a second library with AddressSanitizer (out-of-bounds accesses of "device" memory
+    in any kernel / copy); load it with LD_PRELOAD=$(gcc -print-file-name=libasan.so)"""
+    if asan:
+        return _build(SO[:-3] + "_asan.so", ["-fsanitize=address", "-fno-omit-frame-pointer"], force)
+    return _build(SO, [], force)
+
+
+def _build(SO, extra, force):
+    if not force and not needs_build(SO):
         return SO
     os.makedirs(GEN, exist_ok=True)
     total = 0
@@ -124,10 +132,10 @@ def build(force=False):
     os.makedirs(inc, exist_ok=True)
     shutil.copy(os.path.join(ROOT, "include", "athena_b200.h"), inc)
     for f in SOURCES:
-        o = os.path.join(GEN, f + ".o")
+        o = os.path.join(GEN, f + (".asan.o" if extra else ".o"))
         cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-x", "c++",
                "-I", os.path.join(HERE, "emu"), "-I", GEN, "-include", "cuda_runtime.h",
-               "-DAB_HOST_EMU=1", "-Wno-unknown-pragmas", "-c", os.path.join(GEN, f), "-o", o]
+               "-DAB_HOST_EMU=1", "-Wno-unknown-pragmas"] + extra + ["-c", os.path.join(GEN, f), "-o", o]
         procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                           text=True)))
         objs.append(o)
@@ -135,9 +143,10 @@ def build(force=False):
         log = p.communicate()[0]
         if p.returncode != 0:
             raise RuntimeError("g++ failed on %s:\n%s" % (f, log[-6000:]))
-    subprocess.run(["g++", "-shared", "-o", SO] + objs + ["-ldl"], check=True)
+    subprocess.run(["g++", "-shared", "-o", SO] + extra + objs + ["-ldl"], check=True)
     return SO
 
 
 if __name__ == "__main__":
-    print(build(force=True))
+    import sys
+    print(build(force=True, asan="--asan" in sys.argv))

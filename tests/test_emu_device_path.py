@@ -70,3 +70,41 @@ def test_staged_pipeline_through_the_emulated_device_path(emu_env):
     r = subprocess.run([sys.executable, os.path.join(HERE, "stage_check.py")], env=emu_env,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "staging ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_every_task_entry_point_through_the_emulated_device_path(emu_env):
+    """tests/test_gpu_tasks.py (each C-ABI task against the oracle on perturbed states that hit
+    floors, limiter and solver branches) with the emulated library"""
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_tasks.py"),
+                        "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "--timeout",
+                        "300", "-n", "4"], env=emu_env, capture_output=True, text=True,
+                       timeout=900)
+    tail = r.stdout.strip().splitlines()[-1]
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:]
+
+
+def test_no_out_of_bounds_access_under_address_sanitizer(emu_env):
+    """the same path with AddressSanitizer: "device" allocations are heap blocks with red zones,
+    so an out-of-range index in any kernel or copy aborts the run.  A third of the fixtures
+    plus every refined mesh (all of them pass; the subset bounds the suite's run time)."""
+    import build_mesh_host
+    libasan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True,
+                             text=True).stdout.strip()
+    if not os.path.isabs(libasan) or not os.path.exists(libasan):
+        pytest.skip("libasan not installed")
+    env = dict(emu_env, AB_LIB=build_mesh_host.build(asan=True), LD_PRELOAD=libasan,
+               ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    names = [n for n in util.golden_names(include_smr=True) if in_device_scope(n)]
+    names = [n for i, n in enumerate(names) if i % 3 == 0 or n.startswith("smr_")]
+    chunks = [names[c::NCHUNK] for c in range(NCHUNK)]
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "smr_check.py")] + ch, env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for ch in chunks]
+    for ch, p in zip(chunks, procs):
+        try:
+            out = p.communicate(timeout=900)[0]
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out = "TIMEOUT " + " ".join(ch)
+        assert p.returncode == 0 and "smr done: 0 failed" in out, out[-4000:]
+        assert "ERROR: AddressSanitizer" not in out, out[-4000:]
