@@ -108,3 +108,24 @@ def test_no_out_of_bounds_access_under_address_sanitizer(emu_env):
             out = "TIMEOUT " + " ".join(ch)
         assert p.returncode == 0 and "smr done: 0 failed" in out, out[-4000:]
         assert "ERROR: AddressSanitizer" not in out, out[-4000:]
+
+
+def test_emulator_positive_controls(tmp_path):
+    """the checks above can fail: a kernel with a dependence between threads of one launch
+    differs between the two execution orders, an out-of-range store aborts under
+    AddressSanitizer, and the fibers give the right block sums for shuffles + __syncthreads"""
+    hc = os.path.join(HERE, "hostcheck")
+    exe, exe_asan = str(tmp_path / "selftest"), str(tmp_path / "selftest_asan")
+    base = ["g++", "-O1", "-std=c++17", "-I", os.path.join(hc, "emu"),
+            os.path.join(hc, "emu_selftest.cpp")]
+    subprocess.run(base + ["-o", exe], check=True)
+
+    def run(mode, order, binary=exe):
+        return subprocess.run([binary, mode], env=dict(os.environ, AB_EMU_ORDER=order),
+                              capture_output=True, text=True)
+    assert run("shift", "forward").stdout != run("shift", "reverse").stdout
+    sums = "8128 24512 40896 57280\n"
+    assert run("reduce", "forward").stdout == sums and run("reduce", "reverse").stdout == sums
+    if subprocess.run(base + ["-fsanitize=address", "-o", exe_asan]).returncode == 0:
+        r = run("oob", "forward", exe_asan)
+        assert r.returncode != 0 and "heap-buffer-overflow" in r.stderr
