@@ -3,6 +3,8 @@
 -fmad=false is load-bearing: the reference's default build has no FMA contraction
 (configure.py:454, x86-64 SSE2), and bit-identical dt sequences require the same roundings.
 """
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -19,23 +21,47 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]
 
 
+STAMP = SO + ".srchash"
+
+
+def source_hash():
+    """sha256 over the sources, headers and flags the library is built from (mtimes do not
+    survive the copy to a GPU box; contents do)"""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SRC + HDR:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(SO):
+    if not os.path.exists(SO) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(SO)
-    return any(os.path.getmtime(f) > t for f in SRC + HDR)
+    with open(STAMP) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
+    """Compile unless the library on disk was built from exactly these sources.  Safe to call
+    from several ranks at once: one builds, the others wait on the lock file."""
     if not force and not needs_build():
         return SO
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SRC + ["-ldl"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    with open(SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():      # another rank built it while we waited
+            return SO
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        tmp = SO + ".tmp%d" % os.getpid()
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SRC + ["-ldl"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, SO)
+        with open(STAMP, "w") as fh:
+            fh.write(source_hash() + "\n")
+        if verbose:
+            print(r.stderr)
     return SO
 
 

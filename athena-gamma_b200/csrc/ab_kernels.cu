@@ -1317,11 +1317,18 @@ __global__ void k_mesh_new_dt(double *st, const unsigned long long *blk_min, int
     }
     st[4] = m;
   } else {
-    if (advance_time) { st[5] += 1.0; st[0] += st[1]; }
-    double dt = 2.0*st[1];
-    dt = dmin(dt, st[4]);
-    if (st[0] < st[2] && (st[2] - st[0]) < dt) dt = st[2] - st[0];
-    st[1] = dt;
+    // st[1] = Mesh::dt as the reference keeps it; st[6] = the dt the next cycle integrates
+    // with: 0 once time has reached tlim, so that cycles launched asynchronously past tlim
+    // change nothing and are not counted (the reference's loop stops there, main.cpp:430)
+    const bool ran = st[0] < st[2];
+    if (advance_time && ran) { st[5] += 1.0; st[0] += st[1]; }
+    if (!advance_time || ran) {
+      double dt = 2.0*st[1];
+      dt = dmin(dt, st[4]);
+      if (st[0] < st[2] && (st[2] - st[0]) < dt) dt = st[2] - st[0];
+      st[1] = dt;
+    }
+    st[6] = (st[0] < st[2]) ? st[1] : 0.0;
   }
 }
 void launch_mesh_new_dt(double *state, const unsigned long long *blk_min, int nb,

@@ -1473,7 +1473,7 @@ int smr_flux_correction(AbMesh *m) {
 }
 
 int one_cycle(AbMesh *m) {
-  const double *dtp = m->state + 1;
+  const double *dtp = m->state + 6;     // dt of this cycle (0 past tlim, see k_mesh_new_dt)
   const bool user_src = (m->user_src || m->user_src_dev);
   if (m->has_user_bc || user_src) { int rc0 = read_state(m); if (rc0) return rc0; }   // host needs time, dt
   // per-block streams (see AbMesh::bstream); host-hook modes keep everything on the main stream
@@ -1596,7 +1596,7 @@ int one_cycle(AbMesh *m) {
     if (stage == m->nstages) {
       // record the dt this cycle used, then time += dt, ncycle++, NewTimeStep
       if (m->hist_n < m->hist_cap)
-        CK(cudaMemcpyAsync(m->dt_hist + m->hist_n, m->state + 1, 8, cudaMemcpyDeviceToDevice, m->stream));
+        CK(cudaMemcpyAsync(m->dt_hist + m->hist_n, m->state + 6, 8, cudaMemcpyDeviceToDevice, m->stream));
       m->hist_n++;
       rc = new_time_step(m, 1, true);
       if (rc) return rc;
@@ -1863,8 +1863,15 @@ int ab_plan_ranklist(const AbMesh *m, int *out, int max_n) {
 }
 
 static int validate_params(const AbMeshParams *p) {
-  if (p->bx1 <= 0 || p->nx1 % p->bx1 || p->nx2 % p->bx2 || p->nx3 % p->bx3)
+  if (p->nx1 <= 0 || p->nx2 <= 0 || p->nx3 <= 0 || p->bx1 <= 0 || p->bx2 <= 0 || p->bx3 <= 0)
+    return fail(AB_ERR_ARG, "mesh/nx? and meshblock/nx? must be positive");
+  if (p->nx1 % p->bx1 || p->nx2 % p->bx2 || p->nx3 % p->bx3)
     return fail(AB_ERR_ARG, "the Mesh must be evenly divisible by the MeshBlock");
+  // mesh.cpp:260-267: ghost zones are filled from the neighbour's ACTIVE cells
+  if (p->bx1 < p->nghost || (p->nx2 > 1 && p->bx2 < p->nghost) ||
+      (p->nx3 > 1 && p->bx3 < p->nghost))
+    return fail(AB_ERR_ARG, "block_size must be larger than or equal to NGHOST cells with "
+                            "uniform grid.");
   if (p->xorder < 1 || p->xorder > 3) return fail(AB_ERR_ARG, "time/xorder must be 1, 2 or 3");
   if (p->xorder == 3 && p->nghost < 3)
     return fail(AB_ERR_ARG, "xorder=3 (PPM) needs nghost >= 3 (reconstruction.cpp:90-99)");
@@ -1882,7 +1889,8 @@ static int validate_params(const AbMeshParams *p) {
   {
     long n1 = p->bx1 + 2L*p->nghost + 1, n2 = (p->nx2 > 1 ? p->bx2 + 2L*p->nghost : 1) + 1,
          n3 = (p->nx3 > 1 ? p->bx3 + 2L*p->nghost : 1) + 1;
-    if (5*n1*n2*n3 >= (1L << 31))
+    const long nvar = p->nscalars > 5 ? p->nscalars : 5;   // scalar registers use int offsets too
+    if (nvar*n1*n2*n3 >= (1L << 31))
       return fail(AB_ERR_ARG, "MeshBlock too large: registers must have < 2^31 elements "
                               "(kernels use 32-bit element offsets); use smaller MeshBlocks");
   }
@@ -2410,8 +2418,9 @@ int ab_mesh_state(AbMesh *m, double *time, double *dt, long *ncycle) {
 
 int ab_mesh_set_time_dt(AbMesh *m, double time, double dt) {
   if (!m) return fail(AB_ERR_ARG, "null mesh");
-  double h[2] = {time, dt};
+  double h[2] = {time, dt}, eff = (time < m->p.tlim) ? dt : 0.0;
   CK(cudaMemcpyAsync(m->state, h, sizeof(h), cudaMemcpyHostToDevice, m->stream));
+  CK(cudaMemcpyAsync(m->state + 6, &eff, sizeof(eff), cudaMemcpyHostToDevice, m->stream));
   CK(cudaStreamSynchronize(m->stream));
   m->h_time = time; m->h_dt = dt;
   return AB_OK;

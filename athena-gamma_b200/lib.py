@@ -89,9 +89,10 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    so = os.environ.get("AB_LIB") or _build.SO     # AB_LIB: kernel-tuning builds only
-    if not os.path.exists(so):
-        so = _build.build()
+    # AB_LIB: kernel-tuning builds and the emulated test library only.  Otherwise the library is
+    # (re)built whenever it does not match the sources in the tree, so that tests and bench can
+    # never run a stale binary.
+    so = os.environ.get("AB_LIB") or _build.build()
     L = C.CDLL(so)
     vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.c_int
     L.ab_last_error.restype = C.c_char_p

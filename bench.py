@@ -182,39 +182,6 @@ def run_reference_cpu(wl, budget_s=20.0, steps=None, warmup=0):
             "ms_per_step": 1e3*zones/rate, "zones": zones, "cycles": ncyc}
 
 
-def first_gpu_runs():
-    """tests/ checks of the paths that have not yet run on a GPU, as subprocesses with timeouts;
-    returns {name: {"rc": .., "tail": ..}}.  Never raises."""
-    import subprocess
-    here = os.path.dirname(os.path.abspath(__file__))
-    tests = os.path.join(here, "tests")
-    py = sys.executable
-    try:
-        sys.path[:0] = [tests, os.path.join(here, "oracle")]
-        import test_gpu_smr
-        smr_names = test_gpu_smr.device_smr_goldens()
-    except Exception as ex:
-        smr_names = []
-        print("first_gpu_runs: %s" % ex, file=sys.stderr)
-    jobs = [("stage_check", [py, os.path.join(tests, "stage_check.py")], 150),
-            ("iso_roe_goldens", [py, "-m", "pytest", tests, "-q", "-m", "gpu", "--runxfail",
-                                 "--tb=line", "-p", "no:cacheprovider", "-k", "iso and roe"], 240)]
-    if smr_names:
-        jobs.insert(0, ("smr_check", [py, os.path.join(tests, "smr_check.py")] + smr_names, 300))
-    out = {}
-    for name, cmd, tmo in jobs:
-        try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=tmo, cwd=here)
-            tail = (r.stdout.strip().splitlines() or [""])[-1][-300:]
-            out[name] = {"rc": r.returncode, "tail": tail}
-            if r.returncode != 0:
-                out[name]["stderr"] = r.stderr[-400:]
-                out[name]["stdout"] = r.stdout[-1200:]
-        except Exception as ex:
-            out[name] = {"rc": None, "tail": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
-    return out
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -228,11 +195,9 @@ def main():
                          "MeshBlocks per GPU (default: one MeshBlock per GPU)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-pipelined", action="store_true",
-                    help="also measure e2e with the ab_stage_* copy/compute pipeline "
-                         "(opt-in: not yet run on a GPU)")
+                    help="also measure e2e with the ab_stage_* copy/compute pipeline")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-first-runs", action="store_true",
-                    help="skip the first-GPU-run checks of paths written without a GPU")
+    ap.add_argument("--no-first-runs", action="store_true", help=argparse.SUPPRESS)  # accepted, no-op
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -519,13 +484,6 @@ def main():
             cpu = {"value": None, "unit": "zone-cycles/s", "cores": os.cpu_count(),
                    "kind": "reference", "sample": "failed: %s" % ex}
 
-    # ---- not a measurement: paths written after the round's GPU budget was spent (device SMR,
-    # ab_stage_*, isothermal Roe) get their first GPU run here, after every timed region, each
-    # in its own bounded process, so that the verdict reaches the next round with the bench line
-    first_runs = None
-    if rank == 0 and world == 1 and not a.no_first_runs:
-        first_runs = first_gpu_runs()
-
     if rank == 0:
         cfg_desc.update({"mesh": [mesh.params.nx1, mesh.params.nx2, mesh.params.nx3],
                          "meshblock": list(blk), "meshblocks_total": mesh.nbtotal,
@@ -539,8 +497,6 @@ def main():
                "roofline_cycle": cycle_roof, "cpu_baseline": cpu, "e2e": e2e,
                "e2e_resident": e2e_res, "e2e_pipelined": e2e_pipe,
                "gpu_launches": int(launches), "clocks": clocks}
-        if first_runs:
-            out["first_gpu_runs"] = first_runs
         print(json.dumps(out))
     if dist:
         dist.barrier()

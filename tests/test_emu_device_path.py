@@ -76,7 +76,7 @@ def test_every_task_entry_point_through_the_emulated_device_path(emu_env):
     """tests/test_gpu_tasks.py (each C-ABI task against the oracle on perturbed states that hit
     floors, limiter and solver branches) with the emulated library"""
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_tasks.py"),
-                        "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "--timeout",
+                        "-q", "-m", "gpu", "-p", "no:cacheprovider", "--timeout",
                         "300", "-n", "4"], env=emu_env, capture_output=True, text=True,
                        timeout=900)
     tail = r.stdout.strip().splitlines()[-1]

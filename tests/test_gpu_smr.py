@@ -26,12 +26,6 @@ def device_smr_goldens():
     return out
 
 
-# Written at the end of round 1 with the GPU budget spent.  On the CPU the host planner is
-# verified row by row against the oracle and the kernels' arithmetic bit for bit
-# (tests/test_smr_plan_cpu.py), but the kernels themselves have not yet run on a GPU: the test
-# must not be able to turn the suite red until it has (remove the marker after the first green
-# run).
-@pytest.mark.xfail(strict=False, reason="device SMR path not yet run on a GPU (round 1 budget spent)")
 def test_refined_meshes_reproduce_reference_goldens():
     names = device_smr_goldens()
     assert len(names) >= 5

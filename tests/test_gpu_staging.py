@@ -10,10 +10,6 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-# Written at the end of round 1 with the GPU budget spent: the entry points compile, export and
-# are covered by this test, but the test itself has not yet run on a GPU -- it must not be able
-# to turn the suite red until it has (remove the marker after the first green run).
-@pytest.mark.xfail(strict=False, reason="ab_stage_* not yet run on a GPU (round 1 budget spent)")
 def test_staged_pipeline_matches_plain_sequence():
     r = subprocess.run([sys.executable, os.path.join(HERE, "stage_check.py")],
                        capture_output=True, text=True, timeout=300)

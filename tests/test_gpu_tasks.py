@@ -101,9 +101,7 @@ def perturbed(g, seed):
     return init
 
 
-@pytest.mark.parametrize("name,xorder,solver", [
-    pytest.param(*c, marks=pytest.mark.xfail(strict=False, reason="device path not yet run on a GPU"))
-    if c[0] in util.FIRST_GPU_RUN_PENDING else c for c in CASES])
+@pytest.mark.parametrize("name,xorder,solver", CASES)
 def test_task_by_task(name, xorder, solver):
     import gpu_util
     g = util.Golden(name)

@@ -16,19 +16,9 @@ def golden_names(include_smr=False):
     return [n for n in names if include_smr or not n.startswith("smr_")]
 
 
-# Fixtures whose device path was written after the round's GPU budget was spent (isothermal Roe:
-# arithmetic bit-exact against the oracle on the CPU, kernels not yet run on a GPU).  They must
-# not be able to turn the GPU suite red until they have run once: empty this set after the first
-# green (XPASS) run.
-FIRST_GPU_RUN_PENDING = {"iso_blast_roe_plm_vl2_8blk", "iso_blast_mhd_roe_plm_vl2_8blk",
-                         "iso_kh2d_roe_plm_rk2_4blk", "iso_ot_mhd_roe_plm_rk2_4blk"}
-
-
 def gpu_params(names):
-    """pytest params of golden names, the pending ones marked xfail(strict=False)"""
-    import pytest
-    mark = pytest.mark.xfail(strict=False, reason="device path not yet run on a GPU")
-    return [pytest.param(n, marks=mark) if n in FIRST_GPU_RUN_PENDING else n for n in names]
+    """pytest params of golden names (every fixture is a hard requirement on the GPU)"""
+    return list(names)
 
 
 class Golden:
