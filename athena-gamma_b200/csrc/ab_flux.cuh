@@ -55,12 +55,33 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
 #define AB_X3_STRIP 32
 #endif
 
+// Exact t / d for 0 <= t < 2^31 by one multiply-high and a shift (the divisor is a launch
+// constant; a run-time integer division costs ~20 instructions per thread and the kernel needs
+// two to five).  l = ceil(log2 d), m = ceil(2^(31+l) / d) < 2^32, t / d = umulhi(t, m) >> (l-1)
+// (Granlund & Montgomery 1994, N = 31).  d = 1 is encoded as m = 0.
+struct FastDiv { unsigned m, s; };
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f{0u, 0u};
+  if (d <= 1) return f;
+  int l = 0;
+  while ((1LL << l) < d) ++l;
+  f.m = (unsigned)(((1ULL << (31 + l)) + (unsigned long long)d - 1ULL)/(unsigned long long)d);
+  f.s = (unsigned)(l - 1);
+  return f;
+}
+__device__ __forceinline__ int fast_div(int t, FastDiv f) {
+  return f.m ? (int)(__umulhi((unsigned)t, f.m) >> f.s) : t;
+}
+// divisors of the flattened face index: ni, nj, and for the strip-major x3 order ni*STRIP*nk,
+// ni*STRIP (full strips) and ni*(rows of the last, partial strip)
+struct FluxIdx { FastDiv ni, nj, per_full, per_k, per_k_last; int last_strip; };
+
 // The face range [i0,i0+ni) x [j0,j0+nj) x [k0,k0+nk) is flattened so that every thread of a
 // CTA has work (rows of nx1+1 faces do not pad to a multiple of the CTA width).
 template <int DIR, int ORDER, int SOLVER, bool MHD, bool NU>
 __global__ void AB_FLUX_BOUNDS
 k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
-       int ntot, double dt_val, const double *dt_ptr) {
+       int ntot, double dt_val, const double *dt_ptr, FluxIdx fx) {
   constexpr int NW = MHD ? 7 : 5;
   constexpr bool ISO = solver_is_iso<SOLVER>;
   int t = blockIdx.x*AB_FLUX_BX + threadIdx.x;
@@ -69,21 +90,21 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
   if (DIR == 2 && AB_X3_STRIP > 0) {
     // strip-major: strip s of j-rows, then k, then j within the strip, then i
     const int per_full = ni*AB_X3_STRIP*nk;
-    const int s = t / per_full;
+    const int s = fast_div(t, fx.per_full);
     int r = t - s*per_full;
     int rows = nj - s*AB_X3_STRIP;
     rows = rows < AB_X3_STRIP ? rows : AB_X3_STRIP;
     const int per_k = ni*rows;
-    const int kk = r / per_k;
+    const int kk = fast_div(r, s == fx.last_strip ? fx.per_k_last : fx.per_k);
     r -= kk*per_k;
-    const int jj = r / ni;
+    const int jj = fast_div(r, fx.ni);
     i = i0 + (r - jj*ni);
     j = j0 + s*AB_X3_STRIP + jj;
     k = k0 + kk;
   } else {
-    int r = t / ni;
+    int r = fast_div(t, fx.ni);
     i = i0 + (t - r*ni);
-    const int kk = r / nj;
+    const int kk = fast_div(r, fx.nj);
     j = j0 + (r - kk*nj);
     k = k0 + kk;
   }
@@ -106,6 +127,7 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
     bxi = b.b[DIR][of];
     dt = dt_ptr ? *dt_ptr : dt_val;
     dxw = (DIR == 0) ? b.dx1f[i] : ((DIR == 1) ? b.dx2f[j] : b.dx3f[k]);
+    dt = (1024.0)*dt;               // GetWeightForCT: (1024*dt*dflx)/(dx*(rhol + rhor))
   }
 
   double wl[NW], wr[NW];
@@ -212,6 +234,7 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
       }
     }
   }
+  if (MHD) dxw = dxw*(wl[IDN] + wr[IDN]);   // the two values the CT weight needs stay live, not four
   double f[NW];
   riemann<SOLVER,MHD>(wl, wr, bxi, ISO ? p.iso_cs : p.gamma, dvn, dvt, f, p.dfloor);
 
@@ -224,7 +247,7 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
   if (MHD) {
     b.ef[DIR][0][of] = -f[IBY];
     b.ef[DIR][1][of] = f[IBZ];
-    b.wght[DIR][of] = weight_for_ct(f[IDN], wl[IDN], wr[IDN], dxw, dt);
+    b.wght[DIR][of] = weight_for_ct_pre(f[IDN], dxw, dt);
   }
 }
 
@@ -246,8 +269,13 @@ static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, doubl
   }
   int ni = i1-i0+1, nj = j1-j0+1, nk = k1-k0+1;
   int ntot = ni*nj*nk;
+  FluxIdx fx;
+  fx.ni = make_fastdiv(ni); fx.nj = make_fastdiv(nj);
+  fx.per_full = make_fastdiv(ni*AB_X3_STRIP*nk); fx.per_k = make_fastdiv(ni*AB_X3_STRIP);
+  fx.last_strip = (AB_X3_STRIP > 0 && nj % (AB_X3_STRIP > 0 ? AB_X3_STRIP : 1)) ? nj/(AB_X3_STRIP > 0 ? AB_X3_STRIP : 1) : -1;
+  fx.per_k_last = make_fastdiv(ni*(AB_X3_STRIP > 0 ? nj % AB_X3_STRIP : 1));
   k_flux<DIR,ORDER,SOLVER,MHD,NU><<<(ntot + AB_FLUX_BX - 1)/AB_FLUX_BX, AB_FLUX_BX, 0, s>>>(
-      b, g, p, i0, ni, j0, nj, k0, nk, ntot, dt_val, dt_ptr); ++g_launches;
+      b, g, p, i0, ni, j0, nj, k0, nk, ntot, dt_val, dt_ptr, fx); ++g_launches;
 }
 
 template <int ORDER, int SOLVER, bool MHD, bool NU>

@@ -13,6 +13,7 @@
 #define AB_PHYSICS_CUH_
 
 #include <math.h>
+#include <cmath>
 #include "ab_types.h"
 
 #if defined(__CUDACC__)
@@ -40,11 +41,14 @@ AB_HD double sgn(double x) { return (x < 0.0) ? -1.0 : 1.0; }
 // (static, uniform regions: zero mass flux, zero pressure jump), so they are answered
 // directly with the correctly signed zero.  0/0, 0/NaN still go through the division.
 AB_HD double fdiv(double a, double b) {
+  if (a == 0.0 && b == b && b != 0.0) {
 #if defined(__CUDA_ARCH__)
-  if (a == 0.0 && b == b && b != 0.0)
     return __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) &
                                 (long long)0x8000000000000000ull);
+#else   // the same shortcut when the tests compile this header for the host
+    return (std::signbit(a) != std::signbit(b)) ? -0.0 : 0.0;
 #endif
+  }
   return a/b;
 }
 
@@ -68,6 +72,13 @@ AB_HD double weight_for_ct(double dflx, double rhol, double rhor, double dx, dou
   return 0.5 + dmax(-0.5, tmp_min);
 }
 
+// the same with c1024dt = 1024*dt and dxrho = dx*(rhol + rhor) formed by the caller
+AB_HD double weight_for_ct_pre(double dflx, double dxrho, double c1024dt) {
+  double v_over_c = fdiv(c1024dt*dflx, dxrho);
+  double tmp_min = dmin(0.5, v_over_c);
+  return 0.5 + dmax(-0.5, tmp_min);
+}
+
 // ------------------------------------------------------------------------ reconstruction
 
 // PLM, uniform Cartesian limiter (reconstruct/plm.cpp:69-77) with the coordinate face weights
@@ -83,20 +94,39 @@ AB_HD void plm(double qm1, double q, double qp1, double wp, double wm,
   minus = q - wm*dwm;
 }
 
-// PPM limiter pieces (reconstruct/ppm.cpp:143-190): CD eq 84-85 extremum fix of one interface
+// a/6.0, bit-identical to the IEEE quotient, in three FP64 instructions instead of the ~15 of
+// a division: q0 = a*RN(1/6), exact residual r = a - 6*q0 by FMA, q = q0 + r*RN(1/6) by FMA
+// (Markstein's correction; RN(1/6) is within 2^-54 of 1/6, so q0 is close enough for the one
+// correction to round correctly -- checked against a/6.0 on 4e8 doubles, random and with
+// significands at both ends of the binade, |a| in [1e-280, 1e300]).  Outside that range (and for
+// zeros) the residual could underflow: true division there.
+AB_HD double div6(double a) {
+  const double fa = fabs(a);
+  if (!(fa > 1.0e-280 && fa < 1.0e300)) return fdiv(a, 6.0);
+  const double y = 1.0/6.0;
+  const double q0 = a*y;
+  const double r = fma(-6.0, q0, a);
+  return fma(r, y, q0);
+}
+
+// PPM limiter pieces (reconstruct/ppm.cpp:143-190): CD eq 84-85 extremum fix of one interface.
+// The reference evaluates the limited value everywhere and keeps it only at a local extremum
+// (qa_tmp*qb_tmp < 0); here it is evaluated only where it is kept (same value, no division in
+// monotone regions).
 AB_HD double ppm_face_fix(double dph, double qlo, double qhi, double d2lo, double d2hi) {
   const double C2 = 1.25;
   double qa_tmp = dph - qlo;
   double qb_tmp = qhi - dph;
-  double qa = 3.0*(qlo + qhi - 2.0*dph);
-  double qb = d2lo;
-  double qc = d2hi;
-  double qd = 0.0;
-  if (sgn(qa) == sgn(qb) && sgn(qa) == sgn(qc)) {
-    qd = sgn(qa)*dmin(C2*fabs(qb), dmin(C2*fabs(qc), fabs(qa)));
+  if (qa_tmp*qb_tmp < 0.0) {
+    double qa = 3.0*(qlo + qhi - 2.0*dph);
+    double qb = d2lo;
+    double qc = d2hi;
+    double qd = 0.0;
+    if (sgn(qa) == sgn(qb) && sgn(qa) == sgn(qc)) {
+      qd = sgn(qa)*dmin(C2*fabs(qb), dmin(C2*fabs(qc), fabs(qa)));
+    }
+    dph = 0.5*(qlo + qhi) - div6(qd);
   }
-  double dph_tmp = 0.5*(qlo + qhi) - qd/6.0;
-  if (qa_tmp*qb_tmp < 0.0) dph = dph_tmp;
   return dph;
 }
 
@@ -496,12 +526,12 @@ AB_HD void hllc_t(const double *wli, const double *wri, double gamma, double dvn
   double fl4 = el*vxl + wli[IPR]*wli[IVX], fr4 = er*vxr + wri[IPR]*wri[IVX];
   double sl, sr, sm;
   if (am >= 0.0) {
-    sl = am/(am - bm);
+    sl = fdiv(am, (am - bm));
     sr = 0.0;
     sm = -bm/(am - bm);
   } else {
     sl = 0.0;
-    sr = -am/(bp - am);
+    sr = fdiv(-am, (bp - am));
     sm = bp/(bp - am);
   }
   flxi[IDN] = sl*fl0 + sr*fr0;
@@ -671,237 +701,211 @@ AB_HD void roe_hydro(const double *wli, const double *wri, double gamma, double 
 
 struct Cons1D { double d, mx, my, mz, e, by, bz; };
 
+// c ? a : b on doubles (two 32-bit selects on the ALU pipe; never a branch)
+AB_HD double dsel(bool c, double a, double b) { return c ? a : b; }
+
 // HLLD (hydro/rsolvers/mhd/hlld.cpp:38-382).
-// The reference evaluates every intermediate state and both L/R fluxes and then selects one
-// of six results (hlld.cpp:315-369).  Here the branch is decided first and only the terms
-// the selected flux depends on are evaluated -- the same operations in the same order on the
-// same operands, so the selected result is bit-identical.
+// The reference evaluates both outer states, both star and both double-star states and both
+// L/R fluxes, then selects one of six results (hlld.cpp:315-369).  Here the side of the
+// contact the interface lies on is decided as soon as the contact speed spd2 is known, the
+// states of that side ("own") and the few transverse values of the other side ("oth") the
+// double-star state needs are picked with selects, and ONE copy of the star / double-star
+// algebra runs on them.  Every expression is the reference's, with the same operands in the
+// same order (the L and R formulas of hlld.cpp are textually identical up to the L/R suffix;
+// the few that are not -- the double-star averages, which always read "left, then right" --
+// are evaluated on re-selected L/R views), so the result is bit-identical, a warp whose
+// threads fall on both sides of the contact does not run two code paths, and the live register
+// set after the selection is one state, not two.
+// Side selection: the reference takes the left family when spd1 >= 0 or spd2 >= 0
+// (hlld.cpp:327-343); spd1 = spd2 - |Bx|/sqrt(rho*_L) <= spd2, so that is spd2 >= 0 (it could
+// differ only if rho*_L were exactly -0, where the reference's result is NaN anyway).
 // With LOW: the low-dissipation LHLLD (hydro/rsolvers/mhd/lhlld.cpp:36-390).
 template <bool LOW>
 AB_HD void hlld_t(const double *wli, const double *wri, double bxi, double gamma, double dvn,
                   double dvt, double *flxi) {
   const double SMALL_NUMBER = 1.0e-8;
-  Cons1D ul, ur, ulst, uldst, urdst, urst, fl, fr;
-  double spd0, spd1, spd2, spd3, spd4;
-  double igm1 = 1.0/(gamma - 1.0);
-  double bxsq = bxi*bxi;
-  double pbl = 0.5*(bxsq + (sqr(wli[IBY]) + sqr(wli[IBZ])));
-  double pbr = 0.5*(bxsq + (sqr(wri[IBY]) + sqr(wri[IBZ])));
-  double kel = 0.5*wli[IDN]*(sqr(wli[IVX]) + (sqr(wli[IVY]) + sqr(wli[IVZ])));
-  double ker = 0.5*wri[IDN]*(sqr(wri[IVX]) + (sqr(wri[IVY]) + sqr(wri[IVZ])));
-  ul.d  = wli[IDN];
-  ul.mx = wli[IVX]*ul.d;
-  ul.my = wli[IVY]*ul.d;
-  ul.mz = wli[IVZ]*ul.d;
-  ul.e  = wli[IPR]*igm1 + kel + pbl;
-  ul.by = wli[IBY];
-  ul.bz = wli[IBZ];
-  ur.d  = wri[IDN];
-  ur.mx = wri[IVX]*ur.d;
-  ur.my = wri[IVY]*ur.d;
-  ur.mz = wri[IVZ]*ur.d;
-  ur.e  = wri[IPR]*igm1 + ker + pbr;
-  ur.by = wri[IBY];
-  ur.bz = wri[IBZ];
-  double cfl = fast_speed(gamma, wli[IDN], wli[IPR], wli[IBY], wli[IBZ], bxi);
-  double cfr = fast_speed(gamma, wri[IDN], wri[IPR], wri[IBY], wri[IBZ], bxi);
-  spd0 = dmin(wli[IVX]-cfl, wri[IVX]-cfr);
-  spd4 = dmax(wli[IVX]+cfl, wri[IVX]+cfr);
-  double ptl = wli[IPR] + pbl;
-  double ptr = wri[IPR] + pbr;
-  double sdl = spd0 - wli[IVX];
-  double sdr = spd4 - wri[IVX];
-  // LHLLD groups sdl*ul.d first (lhlld.cpp:155-173); HLLD multiplies left to right
-  const double sdld = sdl*ul.d, sdrd = sdr*ur.d;
-  double cfmax = 0.0;
+  const double igm1 = 1.0/(gamma - 1.0);
+  const double bxsq = bxi*bxi;
+  const double pbl = 0.5*(bxsq + (sqr(wli[IBY]) + sqr(wli[IBZ])));
+  const double pbr = 0.5*(bxsq + (sqr(wri[IBY]) + sqr(wri[IBZ])));
+  const double cfl = fast_speed(gamma, wli[IDN], wli[IPR], wli[IBY], wli[IBZ], bxi);
+  const double cfr = fast_speed(gamma, wri[IDN], wri[IPR], wri[IBY], wri[IBZ], bxi);
+  const double spd0 = dmin(wli[IVX]-cfl, wri[IVX]-cfr);
+  const double spd4 = dmax(wli[IVX]+cfl, wri[IVX]+cfr);
+  const double ptl = wli[IPR] + pbl;
+  const double ptr = wri[IPR] + pbr;
+  const double sdl = spd0 - wli[IVX];
+  const double sdr = spd4 - wri[IVX];
+  const double sdld = sdl*wli[IDN], sdrd = sdr*wri[IDN];
+  const double mxl = wli[IVX]*wli[IDN], mxr = wri[IVX]*wri[IDN];
+  double spd2, cfmax = 0.0;
   if (!LOW) {
-    spd2 = fdiv((sdr*ur.mx - sdl*ul.mx + (ptl - ptr)), (sdr*ur.d - sdl*ul.d));
+    spd2 = fdiv((sdr*mxr - sdl*mxl + (ptl - ptr)), (sdrd - sdld));
   } else {
     cfmax = dmax(cfl, cfr);
     double th1 = dmin(1.0, (cfmax-dmin(dvn,0.0))/(cfmax-dmin(dvt,0.0)));
     double th = th1*th1*th1*th1;
-    spd2 = fdiv((sdr*ur.mx - sdl*ul.mx + th*(ptl - ptr)), (sdrd - sdld));
+    spd2 = fdiv((sdr*mxr - sdl*mxl + th*(ptl - ptr)), (sdrd - sdld));
   }
-  double sdml = spd0 - spd2;
-  double sdmr = spd4 - spd2;
-  double sdml_inv = 1.0/sdml;
-  double sdmr_inv = 1.0/sdmr;
-  if (!LOW) {
-    ulst.d = ul.d*sdl*sdml_inv;
-    urst.d = ur.d*sdr*sdmr_inv;
-  } else {
-    ulst.d = sdld*sdml_inv;
-    urst.d = sdrd*sdmr_inv;
-  }
-  double ulst_d_inv = 1.0/ulst.d;
-  double urst_d_inv = 1.0/urst.d;
-  double sqrtdl = sqrt(ulst.d);
-  double sqrtdr = sqrt(urst.d);
-  spd1 = spd2 - fdiv(fabs(bxi), sqrtdl);
-  spd3 = spd2 + fdiv(fabs(bxi), sqrtdr);
-
-  // branch selection (hlld.cpp:315-369)
   const bool sup_l = (spd0 >= 0.0);
   const bool sup_r = !sup_l && (spd4 <= 0.0);
-  const bool br_l1 = !sup_l && !sup_r && (spd1 >= 0.0);
-  const bool br_l2 = !sup_l && !sup_r && !br_l1 && (spd2 >= 0.0);
-  const bool br_r2 = !sup_l && !sup_r && !br_l1 && !br_l2 && (spd3 > 0.0);
-  const bool br_r1 = !sup_l && !sup_r && !br_l1 && !br_l2 && !br_r2;
-  const bool left = sup_l || br_l1 || br_l2;
-  const bool star = !(sup_l || sup_r);
+  const bool left = sup_l || (!sup_r && (spd2 >= 0.0));
 
-  if (left) {
-    fl.d  = ul.mx;
-    fl.mx = ul.mx*wli[IVX] + ptl - bxsq;
-    fl.my = ul.my*wli[IVX] - bxi*ul.by;
-    fl.mz = ul.mz*wli[IVX] - bxi*ul.bz;
-    fl.e  = wli[IVX]*(ul.e + ptl - bxsq) - bxi*(wli[IVY]*ul.by + wli[IVZ]*ul.bz);
-    fl.by = ul.by*wli[IVX] - bxi*wli[IVY];
-    fl.bz = ul.bz*wli[IVX] - bxi*wli[IVZ];
-  } else {
-    fr.d  = ur.mx;
-    fr.mx = ur.mx*wri[IVX] + ptr - bxsq;
-    fr.my = ur.my*wri[IVX] - bxi*ur.by;
-    fr.mz = ur.mz*wri[IVX] - bxi*ur.bz;
-    fr.e  = wri[IVX]*(ur.e + ptr - bxsq) - bxi*(wri[IVY]*ur.by + wri[IVZ]*ur.bz);
-    fr.by = ur.by*wri[IVX] - bxi*wri[IVY];
-    fr.bz = ur.bz*wri[IVX] - bxi*wri[IVZ];
-  }
-  if (sup_l) {
-    flxi[IDN] = fl.d; flxi[IVX] = fl.mx; flxi[IVY] = fl.my; flxi[IVZ] = fl.mz;
-    flxi[IEN] = fl.e; flxi[IBY] = fl.by; flxi[IBZ] = fl.bz;
-    return;
-  }
-  if (sup_r) {
-    flxi[IDN] = fr.d; flxi[IVX] = fr.mx; flxi[IVY] = fr.my; flxi[IVZ] = fr.mz;
-    flxi[IEN] = fr.e; flxi[IBY] = fr.by; flxi[IBZ] = fr.bz;
-    return;
-  }
-  (void)star;
-
+  // total pressure of the star region (both outer states enter; hlld.cpp:175-178)
   double ptst;
   if (!LOW) {
-    double ptstl = ptl + ul.d*sdl*(spd2-wli[IVX]);
-    double ptstr = ptr + ur.d*sdr*(spd2-wri[IVX]);
+    double ptstl = ptl + sdld*(spd2-wli[IVX]);
+    double ptstr = ptr + sdrd*(spd2-wri[IVX]);
     ptst = 0.5*(ptstr + ptstl);
   } else {
-    double clsq = ((pbl + kel) + sqrt(sqr(pbl + kel) - 2.0*kel*bxsq))/ul.d;
-    double crsq = ((pbr + ker) + sqrt(sqr(pbr + ker) - 2.0*ker*bxsq))/ur.d;
+    double kel = 0.5*wli[IDN]*(sqr(wli[IVX]) + (sqr(wli[IVY]) + sqr(wli[IVZ])));
+    double ker = 0.5*wri[IDN]*(sqr(wri[IVX]) + (sqr(wri[IVY]) + sqr(wri[IVZ])));
+    double clsq = ((pbl + kel) + sqrt(sqr(pbl + kel) - 2.0*kel*bxsq))/wli[IDN];
+    double crsq = ((pbr + ker) + sqrt(sqr(pbr + ker) - 2.0*ker*bxsq))/wri[IDN];
     double chi = dmin(1.0, sqrt(dmax(clsq, crsq))/cfmax);
     double phi = chi*(2.0 - chi);
     ptst = (sdrd*ptl - sdld*ptr + phi*sdrd*sdld*(wri[IVX]-wli[IVX]))/(sdrd - sdld);
   }
-  // (ul.d*sdl)*sdml is HLLD's ul.d*sdl*sdml and LHLLD's sdld*sdml alike
-  const bool dstar = br_l2 || br_r2;
-  double vbstl = 0.0, vbstr = 0.0;
-  // ul* (needed by Fl*, Fl**, and -- transverse components only -- by Fr**)
-  if (!br_r1) {
-    ulst.mx = ulst.d*spd2;
-    if (fabs(sdld*sdml-bxsq) < (SMALL_NUMBER)*ptst) {
-      ulst.my = ulst.d*wli[IVY];
-      ulst.mz = ulst.d*wli[IVZ];
-      ulst.by = ul.by;
-      ulst.bz = ul.bz;
+
+  // ---- own side: outer state, its flux
+  const double od = dsel(left, wli[IDN], wri[IDN]);
+  const double ovx = dsel(left, wli[IVX], wri[IVX]);
+  const double ovy = dsel(left, wli[IVY], wri[IVY]);
+  const double ovz = dsel(left, wli[IVZ], wri[IVZ]);
+  const double opr = dsel(left, wli[IPR], wri[IPR]);
+  const double oby = dsel(left, wli[IBY], wri[IBY]);
+  const double obz = dsel(left, wli[IBZ], wri[IBZ]);
+  const double pb = dsel(left, pbl, pbr);
+  const double pt = dsel(left, ptl, ptr);
+  const double sd = dsel(left, sdl, sdr);
+  const double sdd = dsel(left, sdld, sdrd);
+  const double so = dsel(left, spd0, spd4);       // outer wave speed of this side
+  const double umx = dsel(left, mxl, mxr);
+  const double umy = ovy*od;
+  const double umz = ovz*od;
+  const double ke = 0.5*od*(sqr(ovx) + (sqr(ovy) + sqr(ovz)));
+  const double ue = opr*igm1 + ke + pb;
+  const double f_d  = umx;
+  const double f_mx = umx*ovx + pt - bxsq;
+  const double f_my = umy*ovx - bxi*oby;
+  const double f_mz = umz*ovx - bxi*obz;
+  const double f_e  = ovx*(ue + pt - bxsq) - bxi*(ovy*oby + ovz*obz);
+  const double f_by = oby*ovx - bxi*ovy;
+  const double f_bz = obz*ovx - bxi*ovz;
+  if (sup_l || sup_r) {
+    flxi[IDN] = f_d; flxi[IVX] = f_mx; flxi[IVY] = f_my; flxi[IVZ] = f_mz;
+    flxi[IEN] = f_e; flxi[IBY] = f_by; flxi[IBZ] = f_bz;
+    return;
+  }
+
+  // ---- own side: star state (hlld.cpp:147-233)
+  const double sdm = so - spd2;
+  const double sdm_inv = 1.0/sdm;
+  const double st_d = sdd*sdm_inv;
+  const double st_d_inv = 1.0/st_d;
+  const double sqrtd = sqrt(st_d);
+  const double xa = fdiv(fabs(bxi), sqrtd);
+  const double spdi = spd2 - dsel(left, xa, -xa);     // spd1 = spd2 - xa | spd3 = spd2 + xa
+  // hlld.cpp:327-369: left family: U*_L if spd1 >= 0 else U**_L; right: U**_R if spd3 > 0 else U*_R
+  const bool star = left ? (spdi >= 0.0) : !(spdi > 0.0);
+  const double st_mx = st_d*spd2;
+  double st_my, st_mz, st_by, st_bz;
+  {
+    const double den = sdd*sdm - bxsq;
+    if (fabs(den) < (SMALL_NUMBER)*ptst) {
+      st_my = st_d*ovy;
+      st_mz = st_d*ovz;
+      st_by = oby;
+      st_bz = obz;
     } else {
-      double tmp = fdiv(bxi*(sdl - sdml), (sdld*sdml - bxsq));
-      ulst.my = ulst.d*(wli[IVY] - ul.by*tmp);
-      ulst.mz = ulst.d*(wli[IVZ] - ul.bz*tmp);
-      tmp = ((LOW ? sdld*sdl : ul.d*sqr(sdl)) - bxsq)/(sdld*sdml - bxsq);
-      ulst.by = ul.by*tmp;
-      ulst.bz = ul.bz*tmp;
-    }
-    if (left) {
-      vbstl = (ulst.mx*bxi+(ulst.my*ulst.by+ulst.mz*ulst.bz))*ulst_d_inv;
-      ulst.e = (sdl*ul.e - ptl*wli[IVX] + ptst*spd2 +
-                bxi*(wli[IVX]*bxi + (wli[IVY]*ul.by + wli[IVZ]*ul.bz) - vbstl))*sdml_inv;
+      double tmp = fdiv(bxi*(sd - sdm), den);
+      st_my = st_d*(ovy - oby*tmp);
+      st_mz = st_d*(ovz - obz*tmp);
+      tmp = ((LOW ? sdd*sd : od*sqr(sd)) - bxsq)/den;
+      st_by = oby*tmp;
+      st_bz = obz*tmp;
     }
   }
-  // ur* (needed by Fr*, Fr**, and -- transverse components only -- by Fl**)
-  if (!br_l1) {
-    urst.mx = urst.d*spd2;
-    if (fabs(sdrd*sdmr - bxsq) < (SMALL_NUMBER)*ptst) {
-      urst.my = urst.d*wri[IVY];
-      urst.mz = urst.d*wri[IVZ];
-      urst.by = ur.by;
-      urst.bz = ur.bz;
-    } else {
-      double tmp = fdiv(bxi*(sdr - sdmr), (sdrd*sdmr - bxsq));
-      urst.my = urst.d*(wri[IVY] - ur.by*tmp);
-      urst.mz = urst.d*(wri[IVZ] - ur.bz*tmp);
-      tmp = ((LOW ? sdrd*sdr : ur.d*sqr(sdr)) - bxsq)/(sdrd*sdmr - bxsq);
-      urst.by = ur.by*tmp;
-      urst.bz = ur.bz*tmp;
-    }
-    if (!left) {
-      vbstr = (urst.mx*bxi+(urst.my*urst.by+urst.mz*urst.bz))*urst_d_inv;
-      urst.e = (sdr*ur.e - ptr*wri[IVX] + ptst*spd2 +
-                bxi*(wri[IVX]*bxi + (wri[IVY]*ur.by + wri[IVZ]*ur.bz) - vbstr))*sdmr_inv;
-    }
+  const double vbst = (st_mx*bxi+(st_my*st_by+st_mz*st_bz))*st_d_inv;
+  const double st_e = (sd*ue - pt*ovx + ptst*spd2 +
+                       bxi*(ovx*bxi + (ovy*oby + ovz*obz) - vbst))*sdm_inv;
+  if (star) {
+    flxi[IDN] = f_d  + so*(st_d - od);
+    flxi[IVX] = f_mx + so*(st_mx - umx);
+    flxi[IVY] = f_my + so*(st_my - umy);
+    flxi[IVZ] = f_mz + so*(st_mz - umz);
+    flxi[IEN] = f_e  + so*(st_e - ue);
+    flxi[IBY] = f_by + so*(st_by - oby);
+    flxi[IBZ] = f_bz + so*(st_bz - obz);
+    return;
   }
-  if (dstar) {
-    // ul** and ur** - if Bx is near zero, same as *-states (hlld.cpp:239-281)
-    if (0.5*bxsq < (SMALL_NUMBER)*ptst) {
-      uldst = ulst;
-      urdst = urst;
-    } else {
-      double invsumd = 1.0/(sqrtdl + sqrtdr);
-      double bxsig = (bxi > 0.0 ? 1.0 : -1.0);
-      uldst.d = ulst.d;
-      urdst.d = urst.d;
-      uldst.mx = ulst.mx;
-      urdst.mx = urst.mx;
-      double tmp = invsumd*(sqrtdl*(ulst.my*ulst_d_inv) + sqrtdr*(urst.my*urst_d_inv) +
-                            bxsig*(urst.by - ulst.by));
-      uldst.my = uldst.d*tmp;
-      urdst.my = urdst.d*tmp;
-      tmp = invsumd*(sqrtdl*(ulst.mz*ulst_d_inv) + sqrtdr*(urst.mz*urst_d_inv) +
-                     bxsig*(urst.bz - ulst.bz));
-      uldst.mz = uldst.d*tmp;
-      urdst.mz = urdst.d*tmp;
-      tmp = invsumd*(sqrtdl*urst.by + sqrtdr*ulst.by +
-                     bxsig*sqrtdl*sqrtdr*((urst.my*urst_d_inv) - (ulst.my*ulst_d_inv)));
-      uldst.by = urdst.by = tmp;
-      tmp = invsumd*(sqrtdl*urst.bz + sqrtdr*ulst.bz +
-                     bxsig*sqrtdl*sqrtdr*((urst.mz*urst_d_inv) - (ulst.mz*ulst_d_inv)));
-      uldst.bz = urdst.bz = tmp;
-      tmp = spd2*bxi + fdiv((uldst.my*uldst.by + uldst.mz*uldst.bz), uldst.d);
-      if (left) uldst.e = ulst.e - sqrtdl*bxsig*(vbstl - tmp);
-      else urdst.e = urst.e + sqrtdr*bxsig*(vbstr - tmp);
+
+  // ---- double-star state of this side (hlld.cpp:239-281)
+  double ds_my = st_my, ds_mz = st_mz, ds_by = st_by, ds_bz = st_bz, ds_e = st_e;
+  if (!(0.5*bxsq < (SMALL_NUMBER)*ptst)) {
+    // transverse star state of the other side
+    const double td = dsel(left, wri[IDN], wli[IDN]);
+    const double tvy = dsel(left, wri[IVY], wli[IVY]);
+    const double tvz = dsel(left, wri[IVZ], wli[IVZ]);
+    const double tby = dsel(left, wri[IBY], wli[IBY]);
+    const double tbz = dsel(left, wri[IBZ], wli[IBZ]);
+    const double tsd = dsel(left, sdr, sdl);
+    const double tsdd = dsel(left, sdrd, sdld);
+    const double tsdm = dsel(left, spd4, spd0) - spd2;
+    const double tsdm_inv = 1.0/tsdm;
+    const double tst_d = tsdd*tsdm_inv;
+    const double tst_d_inv = 1.0/tst_d;
+    const double tsqrtd = sqrt(tst_d);
+    double tst_my, tst_mz, tst_by, tst_bz;
+    {
+      const double den = tsdd*tsdm - bxsq;
+      if (fabs(den) < (SMALL_NUMBER)*ptst) {
+        tst_my = tst_d*tvy;
+        tst_mz = tst_d*tvz;
+        tst_by = tby;
+        tst_bz = tbz;
+      } else {
+        double tmp = fdiv(bxi*(tsd - tsdm), den);
+        tst_my = tst_d*(tvy - tby*tmp);
+        tst_mz = tst_d*(tvz - tbz*tmp);
+        tmp = ((LOW ? tsdd*tsd : td*sqr(tsd)) - bxsq)/den;
+        tst_by = tby*tmp;
+        tst_bz = tbz*tmp;
+      }
     }
+    // L / R views: the averages below read "left, then right" whichever side is ours
+    const double l_d = dsel(left, st_d, tst_d), r_d = dsel(left, tst_d, st_d);
+    const double l_di = dsel(left, st_d_inv, tst_d_inv), r_di = dsel(left, tst_d_inv, st_d_inv);
+    const double sqrtdl = dsel(left, sqrtd, tsqrtd), sqrtdr = dsel(left, tsqrtd, sqrtd);
+    const double l_my = dsel(left, st_my, tst_my), r_my = dsel(left, tst_my, st_my);
+    const double l_mz = dsel(left, st_mz, tst_mz), r_mz = dsel(left, tst_mz, st_mz);
+    const double l_by = dsel(left, st_by, tst_by), r_by = dsel(left, tst_by, st_by);
+    const double l_bz = dsel(left, st_bz, tst_bz), r_bz = dsel(left, tst_bz, st_bz);
+    (void)r_d;
+    const double invsumd = 1.0/(sqrtdl + sqrtdr);
+    const double bxsig = (bxi > 0.0 ? 1.0 : -1.0);
+    double tmp = invsumd*(sqrtdl*(l_my*l_di) + sqrtdr*(r_my*r_di) + bxsig*(r_by - l_by));
+    const double uldst_my = l_d*tmp;
+    ds_my = st_d*tmp;
+    tmp = invsumd*(sqrtdl*(l_mz*l_di) + sqrtdr*(r_mz*r_di) + bxsig*(r_bz - l_bz));
+    const double uldst_mz = l_d*tmp;
+    ds_mz = st_d*tmp;
+    ds_by = invsumd*(sqrtdl*r_by + sqrtdr*l_by +
+                     bxsig*sqrtdl*sqrtdr*((r_my*r_di) - (l_my*l_di)));
+    ds_bz = invsumd*(sqrtdl*r_bz + sqrtdr*l_bz +
+                     bxsig*sqrtdl*sqrtdr*((r_mz*r_di) - (l_mz*l_di)));
+    // hlld.cpp:276-279: both energies use the LEFT double-star momenta
+    tmp = spd2*bxi + fdiv((uldst_my*ds_by + uldst_mz*ds_bz), l_d);
+    const double pe = sqrtd*bxsig*(vbst - tmp);
+    ds_e = st_e - dsel(left, pe, -pe);   // uldst.e = ulst.e - ..., urdst.e = urst.e + ...
   }
-  if (br_l1) {
-    flxi[IDN] = fl.d  + spd0*(ulst.d - ul.d);
-    flxi[IVX] = fl.mx + spd0*(ulst.mx - ul.mx);
-    flxi[IVY] = fl.my + spd0*(ulst.my - ul.my);
-    flxi[IVZ] = fl.mz + spd0*(ulst.mz - ul.mz);
-    flxi[IEN] = fl.e  + spd0*(ulst.e - ul.e);
-    flxi[IBY] = fl.by + spd0*(ulst.by - ul.by);
-    flxi[IBZ] = fl.bz + spd0*(ulst.bz - ul.bz);
-  } else if (br_l2) {
-    flxi[IDN] = fl.d  + spd0*(ulst.d - ul.d) + spd1*(uldst.d - ulst.d);
-    flxi[IVX] = fl.mx + spd0*(ulst.mx - ul.mx) + spd1*(uldst.mx - ulst.mx);
-    flxi[IVY] = fl.my + spd0*(ulst.my - ul.my) + spd1*(uldst.my - ulst.my);
-    flxi[IVZ] = fl.mz + spd0*(ulst.mz - ul.mz) + spd1*(uldst.mz - ulst.mz);
-    flxi[IEN] = fl.e  + spd0*(ulst.e - ul.e) + spd1*(uldst.e - ulst.e);
-    flxi[IBY] = fl.by + spd0*(ulst.by - ul.by) + spd1*(uldst.by - ulst.by);
-    flxi[IBZ] = fl.bz + spd0*(ulst.bz - ul.bz) + spd1*(uldst.bz - ulst.bz);
-  } else if (br_r2) {
-    flxi[IDN] = fr.d + spd4*(urst.d - ur.d) + spd3*(urdst.d - urst.d);
-    flxi[IVX] = fr.mx + spd4*(urst.mx - ur.mx) + spd3*(urdst.mx - urst.mx);
-    flxi[IVY] = fr.my + spd4*(urst.my - ur.my) + spd3*(urdst.my - urst.my);
-    flxi[IVZ] = fr.mz + spd4*(urst.mz - ur.mz) + spd3*(urdst.mz - urst.mz);
-    flxi[IEN] = fr.e + spd4*(urst.e - ur.e) + spd3*(urdst.e - urst.e);
-    flxi[IBY] = fr.by + spd4*(urst.by - ur.by) + spd3*(urdst.by - urst.by);
-    flxi[IBZ] = fr.bz + spd4*(urst.bz - ur.bz) + spd3*(urdst.bz - urst.bz);
-  } else {
-    flxi[IDN] = fr.d  + spd4*(urst.d - ur.d);
-    flxi[IVX] = fr.mx + spd4*(urst.mx - ur.mx);
-    flxi[IVY] = fr.my + spd4*(urst.my - ur.my);
-    flxi[IVZ] = fr.mz + spd4*(urst.mz - ur.mz);
-    flxi[IEN] = fr.e  + spd4*(urst.e - ur.e);
-    flxi[IBY] = fr.by + spd4*(urst.by - ur.by);
-    flxi[IBZ] = fr.bz + spd4*(urst.bz - ur.bz);
-  }
+  flxi[IDN] = f_d  + so*(st_d - od) + spdi*(st_d - st_d);
+  flxi[IVX] = f_mx + so*(st_mx - umx) + spdi*(st_mx - st_mx);
+  flxi[IVY] = f_my + so*(st_my - umy) + spdi*(ds_my - st_my);
+  flxi[IVZ] = f_mz + so*(st_mz - umz) + spdi*(ds_mz - st_mz);
+  flxi[IEN] = f_e  + so*(st_e - ue) + spdi*(ds_e - st_e);
+  flxi[IBY] = f_by + so*(st_by - oby) + spdi*(ds_by - st_by);
+  flxi[IBZ] = f_bz + so*(st_bz - obz) + spdi*(ds_bz - st_bz);
 }
 
 // Roe averages shared by hlle_mhd.cpp:64-85 and roe_mhd.cpp:92-113

@@ -84,6 +84,7 @@ inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *
 
 inline long long __double_as_longlong(double v) { long long r; memcpy(&r, &v, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a*b) >> 32); }
 inline unsigned long long atomicMin(unsigned long long *a, unsigned long long v) {
   unsigned long long old = *a;
   if (v < old) *a = v;

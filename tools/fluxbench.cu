@@ -2,7 +2,7 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
 //        -I athena-gamma_b200/csrc [-DAB_...] -o fluxbench tools/fluxbench.cu
-//   ./fluxbench [n=256] [mode=0|1] [reps=5] [ng=2]
+//   ./fluxbench [n=256] [mode=0|1] [reps=5] [ng=2] [hydro=0|1]   (hydro=1: HLLC instead of HLLD)
 //
 // Fills one n^3 MHD MeshBlock (w, bcc, face b) with either a mostly static state (mode 0: the
 // 512^3 blast after a few cycles is uniform outside a small sphere) or a developed flow (mode
@@ -44,6 +44,7 @@ int main(int argc, char **argv) {
   int mode = argc > 2 ? atoi(argv[2]) : 0;
   int reps = argc > 3 ? atoi(argv[3]) : 5;
   int ng = argc > 4 ? atoi(argv[4]) : 2;
+  int hydro = argc > 5 ? atoi(argv[5]) : 0;
   BlkDev b; memset(&b, 0, sizeof(b));
   b.ng = ng; b.nc1 = b.nc2 = b.nc3 = n + 2*ng;
   b.is = b.js = b.ks = ng; b.ie = b.je = b.ke = ng + n - 1;
@@ -104,7 +105,8 @@ int main(int argc, char **argv) {
   ReconGeom g; memset(&g, 0, sizeof(g));
   for (int d = 0; d < 3; ++d) { g.wp[d] = dhalf; g.wm[d] = dhalf; }
   Params p; memset(&p, 0, sizeof(p));
-  p.gamma = 5.0/3.0; p.dfloor = 3.4e-18; p.pfloor = 3.4e-18; p.mhd = 1; p.solver = SOLVER_HLLD;
+  p.gamma = 5.0/3.0; p.dfloor = 3.4e-18; p.pfloor = 3.4e-18; p.mhd = !hydro;
+  p.solver = hydro ? SOLVER_HLLC : SOLVER_HLLD;
   p.xorder = 2;
   const double dt = 0.3*dx/2.0;
   unsigned long long *dsum; CK(cudaMalloc(&dsum, 8));
@@ -113,10 +115,14 @@ int main(int argc, char **argv) {
   double total = 0.0;
   unsigned long long all = 0;
   for (int order = 1; order <= maxorder; ++order) for (int dir = 0; dir < 3; ++dir) {
-    for (int r = 0; r < 2; ++r) flux_order<SOLVER_HLLD,true,false>(b, g, p, order, dir, dt, nullptr, 0);
+    auto run = [&]() {
+      if (hydro) flux_order<SOLVER_HLLC,false,false>(b, g, p, order, dir, dt, nullptr, 0);
+      else flux_order<SOLVER_HLLD,true,false>(b, g, p, order, dir, dt, nullptr, 0);
+    };
+    for (int r = 0; r < 2; ++r) run();
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; ++r) flux_order<SOLVER_HLLD,true,false>(b, g, p, order, dir, dt, nullptr, 0);
+    for (int r = 0; r < reps; ++r) run();
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -124,13 +130,15 @@ int main(int argc, char **argv) {
     // only the faces the sweep writes are defined; the rest stays at the NaN fill (0xFF..),
     // identical in every build, so the checksum covers exactly the written values
     k_checksum<<<1024, 256>>>(b.flux[dir], 5*nf1, dsum);
-    k_checksum<<<1024, 256>>>(b.ef[dir][0], nf1, dsum);
-    k_checksum<<<1024, 256>>>(b.ef[dir][1], nf1, dsum);
-    k_checksum<<<1024, 256>>>(b.wght[dir], nf1, dsum);
+    if (!hydro) {
+      k_checksum<<<1024, 256>>>(b.ef[dir][0], nf1, dsum);
+      k_checksum<<<1024, 256>>>(b.ef[dir][1], nf1, dsum);
+      k_checksum<<<1024, 256>>>(b.wght[dir], nf1, dsum);
+    }
     unsigned long long h; CK(cudaMemcpy(&h, dsum, 8, cudaMemcpyDeviceToHost));
     printf("x%d_o%d %8.4f ms  sum %016llx\n", dir + 1, order, ms/reps, h);
     total += ms/reps; all ^= h*(unsigned long long)(dir*7 + order);
   }
-  printf("TOTAL n=%d mode=%d: %.4f ms  checksum %016llx\n", n, mode, total, all);
+  printf("TOTAL n=%d mode=%d ng=%d hydro=%d: %.4f ms  checksum %016llx\n", n, mode, ng, hydro, total, all);
   return 0;
 }
