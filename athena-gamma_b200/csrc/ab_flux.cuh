@@ -8,7 +8,7 @@
 
 namespace ab {
 
-extern long g_launches;
+extern std::atomic<long> g_launches;
 
 // =============================================================================================
 // Hydro::CalculateFluxes: reconstruction + Riemann solver, one thread per interface.

@@ -20,7 +20,7 @@ namespace ab {
 #define E2I(b, k, j, i) (((long)(k)*(b).nc2 + (j))*((b).nc1 + 1) + (i))
 #define E3I(b, k, j, i) (((long)(k)*((b).nc2 + 1) + (j))*((b).nc1 + 1) + (i))
 
-long g_launches = 0;      // kernel launches issued (bench accounting)
+std::atomic<long> g_launches{0};      // kernel launches issued (bench accounting)
 constexpr int BX = 128;  // threads along x1 per CTA
 
 static inline dim3 grid3(int ni, int nj, int nk) {

@@ -2,6 +2,7 @@
 #ifndef AB_KERNELS_H_
 #define AB_KERNELS_H_
 #include <cuda_runtime.h>
+#include <atomic>
 #include "ab_types.h"
 
 namespace ab {

@@ -16,7 +16,9 @@
 #include <algorithm>
 #include <cmath>
 #include <array>
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -25,7 +27,7 @@
 #include "ab_smr_exec.h"
 
 namespace ab {
-extern long g_launches;
+extern std::atomic<long> g_launches;
 }
 
 namespace {
@@ -162,6 +164,10 @@ struct LocalBlock {
 }  // namespace
 
 struct AbMesh {
+  // The reference runs its task bodies from an OpenMP loop over MeshBlocks
+  // (task_list.cpp:71-88): every entry point that takes a block index locks the mesh, so calls
+  // for different blocks may come from different host threads (they only enqueue work).
+  std::recursive_mutex mu;
   AbMeshParams p;
   ab::Params kp;
   int ndim = 1, f2 = 0, f3 = 0;
@@ -248,6 +254,13 @@ struct AbMesh {
     ab::CopyBox *phase2 = nullptr; int n2 = 0; long max2 = 0;         // 1-D/2-D duplicates
   } plan[8];
   std::map<int, PeerBuf> peer_state, peer_emf;
+  // per-block boundary tasks (ab_bvals_send / recv_try / set, ab_emf_send / recv_try): how many
+  // times each local block has sent / received each variable, the number of completed NCCL
+  // rounds, and the per-(block, variable, register parity) copy plans
+  struct BlockComm { long sent[3] = {0, 0, 0}, recvd[3] = {0, 0, 0}, emf_sent = 0, emf_recvd = 0; };
+  std::vector<BlockComm> bcomm;
+  long nccl_state_round = 0, nccl_emf_round = 0;
+  std::map<long, Plan> bplan;
   ncclComm_t comm = nullptr;
   bool emf_built = false;
   // optional CUDA-event timing of the flux kernels (bench.py roofline): slot = dir*3+(order-1)
@@ -872,8 +885,10 @@ void peer_messages(const AbMesh *m, int kind, std::map<int, std::vector<Msg>> &s
 }
 
 // ghost-exchange plan for the current register parity: box copies, pack lists, peer buffers
-int build_state_plan(AbMesh *m, int which) {
-  AbMesh::Plan &P = m->plan[which];
+// lid_filter >= 0: only the ghost zones (and send buffers) of that local block; vars: bit 0 the
+// hydro registers, bit 1 the face field, bit 2 the passive scalars (the per-block, per-variable
+// plans behind ab_bvals_send / ab_bvals_set).  Buffer offsets never depend on the filters.
+int build_state_plan(AbMesh *m, AbMesh::Plan &P, int lid_filter = -1, int vars = 7) {
   std::vector<CopyBox> pack, ph1, ph1r, ph2;
   const int mhd = m->p.mhd;
   const long ncc = (long)m->nc[0]*m->nc[1]*m->nc[2];
@@ -904,7 +919,9 @@ int build_state_plan(AbMesh *m, int which) {
     if (c.ni > 0 && c.nj > 0 && c.nk > 0) v.push_back(c);
   };
   const long cs2 = m->nc[0], cs3 = (long)m->nc[0]*m->nc[1];
+  const bool v_hyd = vars & 1, v_fld = (vars & 2) && mhd, v_scl = (vars & 4) && m->p.nscalars > 0;
   for (size_t l = 0; l < m->lb.size(); ++l) {
+    if (lid_filter >= 0 && (int)l != lid_filter) continue;
     LocalBlock &L = m->lb[l];
     HostBlock &B = *L.hb;
     for (size_t n = 0; n < B.nbs.size(); ++n) {
@@ -913,7 +930,8 @@ int build_state_plan(AbMesh *m, int which) {
       // ---- receiving side: fill my ghost zones from the neighbour's active zones
       Box rb = cc_recv_box(m, nb.ox1, nb.ox2, nb.ox3);
       Box sb = cc_send_box(m, -nb.ox1, -nb.ox2, -nb.ox3);      // what the neighbour loads
-      if (local) {
+      if (!v_hyd) {
+      } else if (local) {
         LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
         add_box(ph1, L.d.u, cs3, cs2, ncc, N.d.u, cs3, cs2, ncc, m->nh, rb, sb.si, sb.sj, sb.sk);
       } else {
@@ -932,13 +950,14 @@ int build_state_plan(AbMesh *m, int which) {
           fc_strides(m, c, s3, s2);
           if (local) {
             LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
-            add_box(ph1, L.d.b[c], s3, s2, 0, N.d.b[c], s3, s2, 0, 1, frb, fsb.si, fsb.sj, fsb.sk);
+            if (v_fld) add_box(ph1, L.d.b[c], s3, s2, 0, N.d.b[c], s3, s2, 0, 1, frb, fsb.si, fsb.sj, fsb.sk);
           } else {
             double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}] + roff;
             long t2 = frb.ei-frb.si+1, t3 = t2*(frb.ej-frb.sj+1);
-            add_box(ph1r, L.d.b[c], s3, s2, 0, src, t3, t2, 0, 1, frb, 0, 0, 0);
+            if (v_fld) add_box(ph1r, L.d.b[c], s3, s2, 0, src, t3, t2, 0, 1, frb, 0, 0, 0);
             roff += frb.count();
           }
+          if (!v_fld) continue;
           // 1-D / 2-D duplicate faces (bvals_fc.cpp:641-645, 669-675)
           if (c == 1 && !m->f2) {
             Box dup = frb; dup.sj = frb.sj + 1; dup.ej = frb.sj + 1;
@@ -950,7 +969,7 @@ int build_state_plan(AbMesh *m, int which) {
           }
         }
       }
-      if (ns > 0) {   // PassiveScalars::sbvar: same boxes as u (scalars.cpp:59-72)
+      if (v_scl) {    // PassiveScalars::sbvar: same boxes as u (scalars.cpp:59-72)
         if (local) {
           LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
           add_box(ph1, L.d.s, cs3, cs2, ncc, N.d.s, cs3, cs2, ncc, ns, rb, sb.si, sb.sj, sb.sk);
@@ -967,7 +986,7 @@ int build_state_plan(AbMesh *m, int which) {
         Box lb2 = cc_send_box(m, nb.ox1, nb.ox2, nb.ox3);
         Box z = {0, lb2.ei-lb2.si, 0, lb2.ej-lb2.sj, 0, lb2.ek-lb2.sk};
         long s2 = z.ei+1, s3 = s2*(z.ej+1);
-        add_box(pack, dst, s3, s2, s3*(z.ek+1), L.d.u, cs3, cs2, ncc, m->nh, z, lb2.si, lb2.sj, lb2.sk);
+        if (v_hyd) add_box(pack, dst, s3, s2, s3*(z.ek+1), L.d.u, cs3, cs2, ncc, m->nh, z, lb2.si, lb2.sj, lb2.sk);
         long soff = m->nh*lb2.count();
         if (mhd) for (int c = 0; c < 3; ++c) {
           Box fb = fc_send_box(m, c, nb.ox1, nb.ox2, nb.ox3);
@@ -975,10 +994,10 @@ int build_state_plan(AbMesh *m, int which) {
           fc_strides(m, c, fs3, fs2);
           Box fz = {0, fb.ei-fb.si, 0, fb.ej-fb.sj, 0, fb.ek-fb.sk};
           long t2 = fz.ei+1, t3 = t2*(fz.ej+1);
-          add_box(pack, dst + soff, t3, t2, 0, L.d.b[c], fs3, fs2, 0, 1, fz, fb.si, fb.sj, fb.sk);
+          if (v_fld) add_box(pack, dst + soff, t3, t2, 0, L.d.b[c], fs3, fs2, 0, 1, fz, fb.si, fb.sj, fb.sk);
           soff += fb.count();
         }
-        if (ns > 0)
+        if (v_scl)
           add_box(pack, dst + soff, s3, s2, s3*(z.ek+1), L.d.s, cs3, cs2, ncc, ns, z, lb2.si, lb2.sj, lb2.sk);
       }
     }
@@ -1085,7 +1104,7 @@ int bvals_exchange(AbMesh *m) {
   int idx = plan_index(m);
   int use = idx < 0 ? 0 : idx;
   if (idx < 0) m->plan[0].built = false;
-  if (!m->plan[use].built) { int rc = build_state_plan(m, use); if (rc) return rc; }
+  if (!m->plan[use].built) { int rc = build_state_plan(m, m->plan[use]); if (rc) return rc; }
   if (idx < 0) m->plan[0].built = false;   // mixed state: never cache
   AbMesh::Plan &P = m->plan[use];
   if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream);
@@ -1105,7 +1124,7 @@ int bvals_exchange_begin(AbMesh *m) {
   int idx = plan_index(m);
   int use = idx < 0 ? 0 : idx;
   if (idx < 0) m->plan[0].built = false;
-  if (!m->plan[use].built) { int rc = build_state_plan(m, use); if (rc) return rc; }
+  if (!m->plan[use].built) { int rc = build_state_plan(m, m->plan[use]); if (rc) return rc; }
   AbMesh::Plan &P = m->plan[use];
   if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream);
   CK(cudaEventRecord(m->ev_pack, m->stream));
@@ -1155,6 +1174,115 @@ int emf_exchange_end(AbMesh *m) {
   for (auto &L : m->lb) ab::launch_emf_apply(L.d, L.emf, m->stream);
   CK(cudaGetLastError());
   return AB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Boundary tasks of ONE MeshBlock, for a host scheduler that polls (task_list.cpp:66-91):
+// Send never waits, ReceiveTry answers 0 ("not yet", TaskStatus::fail) until every neighbour of
+// the block has sent for the same round, Set fills the block's ghost zones
+// (bvals_var.cpp:212-296).  Same-GPU neighbours exchange nothing: Set gathers straight from the
+// neighbour's active zones, which the neighbour's Send declared final for this stage.  Blocks on
+// other ranks: Send packs into the peer buffer; the grouped NCCL send/recv of a round is issued
+// by the last local Send of that round, and ReceiveTry of a block with remote neighbours waits
+// for it.  Everything is enqueued on the mesh's stream in call order; nothing synchronises.
+// ---------------------------------------------------------------------------------------------
+int var_applies(const AbMesh *m, int var) {
+  return var == 0 || (var == 1 && m->p.mhd) || (var == 2 && m->p.nscalars > 0);
+}
+int block_plan(AbMesh *m, int lid, int var, AbMesh::Plan **out) {
+  LocalBlock &L = m->lb[lid];
+  const int par = (var == 0) ? L.parity : ((var == 1) ? L.parity_b : L.parity_s);
+  // gathers read the neighbours' registers: their swap state is part of the key
+  long key = ((long)lid*3 + var)*2 + par;
+  for (const Nb &nb : L.hb->nbs) if (nb.rank == m->p.rank) {
+    const LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
+    const int np = (var == 0) ? N.parity : ((var == 1) ? N.parity_b : N.parity_s);
+    if (np != par) return fail(AB_ERR_STATE, "neighbouring MeshBlocks are in different register "
+                                             "swap states (integrate all blocks of a stage first)");
+  }
+  AbMesh::Plan &P = m->bplan[key];
+  if (!P.built) { int rc = build_state_plan(m, P, lid, 1 << var); if (rc) return rc; }
+  *out = &P;
+  return AB_OK;
+}
+bool has_remote_nb(const AbMesh *m, const LocalBlock &L, int max_type = 2) {
+  for (const Nb &nb : L.hb->nbs) if (nb.rank != m->p.rank && nb.type <= max_type) return true;
+  return false;
+}
+int block_bvals_send(AbMesh *m, int lid, int var) {
+  if (m->bcomm.size() != m->lb.size()) m->bcomm.assign(m->lb.size(), AbMesh::BlockComm());
+  LocalBlock &L = m->lb[lid];
+  if (has_remote_nb(m, L)) {
+    AbMesh::Plan *P;
+    int rc = block_plan(m, lid, var, &P);
+    if (rc) return rc;
+    if (P->npack) ab::launch_copy_boxes(P->pack, P->npack, P->maxpack, m->stream);
+  }
+  m->bcomm[lid].sent[var]++;
+  if (!m->peer_state.empty() || m->p.nranks > 1) {
+    long lo = m->bcomm[0].sent[0];
+    for (auto &c : m->bcomm) for (int v = 0; v < 3; ++v) if (var_applies(m, v)) lo = std::min(lo, c.sent[v]);
+    if (lo > m->nccl_state_round) {          // every block has sent every variable of this round
+      int rc = peer_exchange(m, m->peer_state);
+      if (rc) return rc;
+      m->nccl_state_round = lo;
+    }
+  }
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int block_bvals_recv_try(AbMesh *m, int lid, int var) {
+  if (m->bcomm.size() != m->lb.size()) m->bcomm.assign(m->lb.size(), AbMesh::BlockComm());
+  const long need = m->bcomm[lid].recvd[var] + 1;
+  for (const Nb &nb : m->lb[lid].hb->nbs) {
+    if (nb.rank == m->p.rank) { if (m->bcomm[owner_lid(m, nb.gid)].sent[var] < need) return 0; }
+    else if (m->nccl_state_round < need) return 0;
+  }
+  m->bcomm[lid].recvd[var] = need;
+  return 1;
+}
+int block_bvals_set(AbMesh *m, int lid, int var) {
+  AbMesh::Plan *P;
+  int rc = block_plan(m, lid, var, &P);
+  if (rc) return rc;
+  ab::launch_copy_boxes(P->phase1, P->n1, P->max1, m->stream);
+  ab::launch_copy_boxes(P->phase1r, P->n1r, P->max1r, m->stream);
+  ab::launch_copy_boxes(P->phase2, P->n2, P->max2, m->stream);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int block_emf_send(AbMesh *m, int lid) {
+  if (m->bcomm.size() != m->lb.size()) m->bcomm.assign(m->lb.size(), AbMesh::BlockComm());
+  if (!m->emf_built) { int rc = build_emf_plan(m); if (rc) return rc; }
+  LocalBlock &L = m->lb[lid];
+  ab::launch_emf_pack(L.d, L.emf, m->stream);
+  m->bcomm[lid].emf_sent++;
+  if (!m->peer_emf.empty()) {
+    long lo = m->bcomm[0].emf_sent;
+    for (auto &c : m->bcomm) lo = std::min(lo, c.emf_sent);
+    if (lo > m->nccl_emf_round) {
+      int rc = peer_exchange(m, m->peer_emf);
+      if (rc) return rc;
+      m->nccl_emf_round = lo;
+    }
+  }
+  CK(cudaGetLastError());
+  return AB_OK;
+}
+int block_emf_recv_try(AbMesh *m, int lid) {
+  if (m->bcomm.size() != m->lb.size()) m->bcomm.assign(m->lb.size(), AbMesh::BlockComm());
+  LocalBlock &L = m->lb[lid];
+  const long need = m->bcomm[lid].emf_recvd + 1;
+  if (m->bcomm[lid].emf_sent < need) return 0;      // own buffers feed the averages too
+  for (const Nb &nb : L.hb->nbs) {
+    if (nb.type > 1) continue;                      // faces and edges only
+    if (nb.rank == m->p.rank) { if (m->bcomm[owner_lid(m, nb.gid)].emf_sent < need) return 0; }
+    else if (m->nccl_emf_round < need) return 0;
+  }
+  ab::launch_emf_apply(L.d, L.emf, m->stream);
+  m->bcomm[lid].emf_recvd = need;
+  CK(cudaGetLastError());
+  return 1;
 }
 
 // Primitives task split for the overlapped schedule: part 0 = the active cells (with the fused
@@ -1948,6 +2076,7 @@ int ab_mesh_destroy(AbMesh *m) {
   cudaStreamSynchronize(m->stream);
   for (auto &L : m->lb) { cudaFree(L.base); for (void *q : L.debug_allocs) cudaFree(q); }
   for (int i = 0; i < 8; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase1r); cudaFree(m->plan[i].phase2); }
+  for (auto &kv : m->bplan) { cudaFree(kv.second.pack); cudaFree(kv.second.phase1); cudaFree(kv.second.phase1r); cudaFree(kv.second.phase2); }
   for (auto &kv : m->peer_state) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   cudaFree(m->state); cudaFree(m->dt_hist); cudaFree(m->dtmin);
@@ -1987,6 +2116,7 @@ int ab_mesh_nblocks_local(const AbMesh *m) { return m ? (int)m->lb_hb.size() : 0
 #define GET_L(m, lid)                                                              \
   if (!(m) || (lid) < 0 || (lid) >= (int)(m)->lb.size())                           \
     return fail(AB_ERR_ARG, "bad mesh handle or block index");                     \
+  std::lock_guard<std::recursive_mutex> guard_((m)->mu);                           \
   LocalBlock &L = (m)->lb[lid];                                                    \
   (void)L
 
@@ -2318,6 +2448,13 @@ int ab_physical_bcs(AbMesh *m, int lid) {
   CK(cudaGetLastError());
   return AB_OK;
 }
+int ab_physical_bcs_at(AbMesh *m, int lid, double time, double dt) {
+  GET_L(m, lid);
+  m->bc_time = time; m->bc_dt = dt;      // what user-enrolled boundary functions are handed
+  physical_bcs(m, L);
+  CK(cudaGetLastError());
+  return AB_OK;
+}
 int ab_new_block_dt(AbMesh *m, int lid, double *dt_out) {
   GET_L(m, lid);
   ab::launch_fill_u64(L.dtmin, ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
@@ -2335,12 +2472,54 @@ int ab_new_block_dt(AbMesh *m, int lid, double *dt_out) {
   return AB_OK;
 }
 
+int ab_bvals_send(AbMesh *m, int lid, int var) {
+  GET_L(m, lid);
+  if (m->smr) return fail(AB_ERR_STATE, "per-block boundary tasks are not available on a refined mesh");
+  if (var < 0 || var > 2 || !var_applies(m, var)) return fail(AB_ERR_ARG, "boundary variable not in this build");
+  return block_bvals_send(m, lid, var);
+}
+int ab_bvals_recv_try(AbMesh *m, int lid, int var) {
+  GET_L(m, lid);
+  if (var < 0 || var > 2 || !var_applies(m, var)) return fail(AB_ERR_ARG, "boundary variable not in this build");
+  return block_bvals_recv_try(m, lid, var);
+}
+int ab_bvals_set(AbMesh *m, int lid, int var) {
+  GET_L(m, lid);
+  if (m->smr) return fail(AB_ERR_STATE, "per-block boundary tasks are not available on a refined mesh");
+  if (var < 0 || var > 2 || !var_applies(m, var)) return fail(AB_ERR_ARG, "boundary variable not in this build");
+  if (!m->bcomm.empty() && m->bcomm[lid].recvd[var] == 0)
+    return fail(AB_ERR_STATE, "ab_bvals_set before ab_bvals_recv_try succeeded");
+  return block_bvals_set(m, lid, var);
+}
+int ab_emf_send(AbMesh *m, int lid) {
+  GET_L(m, lid);
+  if (!m->p.mhd) return fail(AB_ERR_STATE, "EMF correction needs MAGNETIC_FIELDS_ENABLED");
+  return block_emf_send(m, lid);
+}
+int ab_emf_recv_try(AbMesh *m, int lid) {
+  GET_L(m, lid);
+  if (!m->p.mhd) return fail(AB_ERR_STATE, "EMF correction needs MAGNETIC_FIELDS_ENABLED");
+  return block_emf_recv_try(m, lid);
+}
+int ab_clear_boundary(AbMesh *m, int lid) {
+  GET_L(m, lid);
+  // nothing is pending between stages (no persistent requests to reset); a block that sent
+  // without every neighbour having received would be a scheduler error worth reporting
+  if (m->bcomm.size() == m->lb.size())
+    for (int v = 0; v < 3; ++v)
+      if (m->bcomm[lid].recvd[v] != m->bcomm[lid].sent[v])
+        return fail(AB_ERR_STATE, "ClearBoundary: a boundary variable was sent but not received");
+  return AB_OK;
+}
+
 int ab_emf_exchange(AbMesh *m) {
   if (!m) return fail(AB_ERR_ARG, "null mesh");
+  std::lock_guard<std::recursive_mutex> guard_(m->mu);
   return emf_exchange(m);
 }
 int ab_bvals_exchange(AbMesh *m) {
   if (!m) return fail(AB_ERR_ARG, "null mesh");
+  std::lock_guard<std::recursive_mutex> guard_(m->mu);
   return m->smr ? smr_exchange(m) : bvals_exchange(m);
 }
 

@@ -41,14 +41,16 @@ AB_HD double sgn(double x) { return (x < 0.0) ? -1.0 : 1.0; }
 // (static, uniform regions: zero mass flux, zero pressure jump), so they are answered
 // directly with the correctly signed zero.  0/0, 0/NaN still go through the division.
 AB_HD double fdiv(double a, double b) {
-  if (a == 0.0 && b == b && b != 0.0) {
 #if defined(__CUDA_ARCH__)
-    return __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) &
-                                (long long)0x8000000000000000ull);
-#else   // the same shortcut when the tests compile this header for the host
-    return (std::signbit(a) != std::signbit(b)) ? -0.0 : 0.0;
-#endif
+  // the common case (a != 0) costs one integer test on the ALU pipe, not FP64 compares
+  if ((__double_as_longlong(a) << 1) == 0) {
+    if (b == b && b != 0.0)
+      return __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) &
+                                  (long long)0x8000000000000000ull);
   }
+#else   // the same shortcut when the tests compile this header for the host
+  if (a == 0.0 && b == b && b != 0.0) return (std::signbit(a) != std::signbit(b)) ? -0.0 : 0.0;
+#endif
   return a/b;
 }
 

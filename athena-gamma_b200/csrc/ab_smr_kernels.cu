@@ -13,7 +13,7 @@
 
 namespace ab {
 
-extern long g_launches;
+extern std::atomic<long> g_launches;
 
 namespace {
 

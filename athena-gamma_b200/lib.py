@@ -30,6 +30,8 @@ SYMBOLS = [
     "ab_weighted_ave", "ab_swap", "ab_zero", "ab_add_flux_div", "ab_add_source_terms", "ab_ct", "ab_physical_bcs",
     "ab_calc_scalar_fluxes", "ab_add_scalar_flux_div", "ab_scalar_cons2prim",
     "ab_scalar_prim2cons", "ab_new_block_dt", "ab_emf_exchange", "ab_bvals_exchange", "ab_mesh_initialize",
+    "ab_bvals_send", "ab_bvals_recv_try", "ab_bvals_set", "ab_emf_send", "ab_emf_recv_try",
+    "ab_clear_boundary", "ab_physical_bcs_at",
     "ab_mesh_cycles", "ab_mesh_set_async", "ab_mesh_state", "ab_mesh_set_time_dt",
     "ab_history", "ab_mesh_dt_history", "ab_mesh_profile", "ab_mesh_profile_read",
     "ab_mesh_launch_count", "ab_mesh_stream", "ab_mesh_sync",
@@ -153,6 +155,11 @@ def load():
     L.ab_new_block_dt.argtypes = [vp, ip, dp]
     for f in ("ab_emf_exchange", "ab_bvals_exchange", "ab_mesh_initialize", "ab_mesh_sync"):
         getattr(L, f).argtypes = [vp]
+    for f in ("ab_bvals_send", "ab_bvals_recv_try", "ab_bvals_set"):
+        getattr(L, f).argtypes = [vp, ip, ip]
+    L.ab_physical_bcs_at.argtypes = [vp, ip, C.c_double, C.c_double]
+    for f in ("ab_emf_send", "ab_emf_recv_try", "ab_clear_boundary"):
+        getattr(L, f).argtypes = [vp, ip]
     L.ab_mesh_cycles.argtypes = [vp, ip]
     L.ab_mesh_set_async.argtypes = [vp, ip]
     L.ab_mesh_state.argtypes = [vp, dp, dp, C.POINTER(C.c_long)]

@@ -247,8 +247,36 @@ int ab_scalar_prim2cons(AbMesh *m, int lid, int il, int iu, int jl, int ju, int 
 /* BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620): outflow and reflecting
  * faces (cc/outflow_cc.cpp, cc/hydro/reflect_hydro.cpp, fc/outflow_fc.cpp, fc/reflect_fc.cpp) */
 int ab_physical_bcs(AbMesh *m, int lid);
+/* the same with the (time, dt) arguments of ApplyPhysicalBoundaries, which user-enrolled
+ * boundary functions receive: end-of-stage time and beta*dt from the PhysicalBoundary task
+ * (task_list/time_integrator.cpp:2045-2062) */
+int ab_physical_bcs_at(AbMesh *m, int lid, double time, double dt);
 /* Hydro::NewBlockTimeStep (hydro/new_blockdt.cpp:42-190): *dt_out = new_block_dt_ (synchronises) */
 int ab_new_block_dt(AbMesh *m, int lid, double *dt_out);
+
+/* ---- boundary tasks of ONE MeshBlock, for the reference's polling scheduler
+ * (TaskList::DoAllAvailableTasks, task_list/task_list.cpp:29-59: a task that answers
+ * TaskStatus::fail is retried later).  var: AB_VAR_HYDRO (hbvar), AB_VAR_FIELD (fbvar),
+ * AB_VAR_SCALARS (sbvar).  Safe to call for different blocks from different host threads
+ * (task_list.cpp:71-88 runs the block loop under OpenMP): every per-block entry point of this
+ * header locks the mesh while it enqueues. */
+enum { AB_VAR_HYDRO = 0, AB_VAR_FIELD = 1, AB_VAR_SCALARS = 2 };
+/* BoundaryVariable::SendBoundaryBuffers (bvals/bvals_var.cpp:212-236): the block's active zones
+ * are final for this stage; packs the buffers of neighbours on other ranks.  Never waits. */
+int ab_bvals_send(AbMesh *m, int lid, int var);
+/* BoundaryVariable::ReceiveBoundaryBuffers (bvals_var.cpp:242-270): 1 = every neighbour has
+ * sent (TaskStatus::success), 0 = not yet (TaskStatus::fail, poll again), < 0 = error */
+int ab_bvals_recv_try(AbMesh *m, int lid, int var);
+/* BoundaryVariable::SetBoundaries (bvals_var.cpp:276-296): fills the block's ghost zones */
+int ab_bvals_set(AbMesh *m, int lid, int var);
+/* FaceCenteredBoundaryVariable::SendFluxCorrection (bvals/fc/flux_correction_fc.cpp:623-680) */
+int ab_emf_send(AbMesh *m, int lid);
+/* FaceCenteredBoundaryVariable::ReceiveFluxCorrection (flux_correction_fc.cpp:1610-1749):
+ * 1 = all surface EMFs arrived, summed in neighbour-list order and averaged; 0 = not yet */
+int ab_emf_recv_try(AbMesh *m, int lid);
+/* BoundaryValues::ClearBoundarySubset (bvals/bvals.cpp:390-418): end of the stage's
+ * communication for this block (reports a variable that was sent but never received) */
+int ab_clear_boundary(AbMesh *m, int lid);
 
 /* ---- boundary communication over all local blocks (src/bvals): Send + Receive + Set.
  * Same-device neighbours are copied device-to-device; neighbours on other ranks go through

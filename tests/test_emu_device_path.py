@@ -72,6 +72,16 @@ def test_staged_pipeline_through_the_emulated_device_path(emu_env):
     assert r.returncode == 0 and "staging ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_polling_scheduler_through_the_emulated_device_path(emu_env):
+    """tests/sched_check.py: the per-block boundary tasks under a host scheduler that polls the
+    way TaskList::DoTaskListOneStage does, blocks drifting apart by whole tasks"""
+    import test_gpu_sched
+    r = subprocess.run([sys.executable, os.path.join(HERE, "sched_check.py"), "--seed", "3"]
+                       + test_gpu_sched.SCHED_GOLDENS, env=emu_env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "sched done: 0 failed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_every_task_entry_point_through_the_emulated_device_path(emu_env):
     """tests/test_gpu_tasks.py (each C-ABI task against the oracle on perturbed states that hit
     floors, limiter and solver branches) with the emulated library"""

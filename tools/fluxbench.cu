@@ -18,7 +18,7 @@
 #include <cuda_runtime.h>
 #include "ab_flux.cuh"
 
-namespace ab { long g_launches = 0; }
+namespace ab { std::atomic<long> g_launches{0}; }
 using namespace ab;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
