@@ -139,13 +139,20 @@ def read_rst(path, nhydro=5, mhd=None, nghost=None, nscalars=0):
 
 
 def run_reference(cfg, pgen, athinput_path, overrides=None, rst_every_cycle=False,
-                  keep_dir=None, timeout=3600, threads=None, hst_every_cycle=False):
-    """Run the reference; returns dict(dts, times, zcps, zcps_omp, rst=[paths], dir, stdout)."""
-    exe = ref_binary(cfg, pgen)
+                  keep_dir=None, timeout=3600, threads=None, hst_every_cycle=False,
+                  exe=None, env_extra=None, blocks=None):
+    """Run the reference; returns dict(dts, times, zcps, zcps_omp, rst=[paths], dir, stdout).
+    exe / env_extra: run another build of the same program instead (the reference compiled
+    with this repository's shim, tools/build_shim.py); blocks: parameter blocks instead of
+    an athinput file."""
+    exe = exe or ref_binary(cfg, pgen)
     if not os.path.isfile(exe):
         raise FileNotFoundError(exe + " (run `python oracle/build_ref.py` where "
                                 "/root/reference is mounted)")
-    blocks = parse_athinput(open(athinput_path).read())
+    if blocks is None:
+        blocks = parse_athinput(open(athinput_path).read())
+    else:
+        blocks = {b: dict(kv) for b, kv in blocks.items()}
     blocks.pop("comment", None)
     apply_overrides(blocks, overrides)
     if rst_every_cycle:
@@ -162,6 +169,7 @@ def run_reference(cfg, pgen, athinput_path, overrides=None, rst_every_cycle=Fals
     env = dict(os.environ)
     if threads is not None:
         env["OMP_NUM_THREADS"] = str(threads)
+    env.update(env_extra or {})
     r = subprocess.run([exe, "-i", inp], cwd=d, capture_output=True, text=True,
                        timeout=timeout, env=env)
     if r.returncode != 0:
