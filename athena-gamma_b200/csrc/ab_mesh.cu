@@ -1783,8 +1783,10 @@ int ab_mesh_create(const AbMeshParams *p, AbMesh **out) {
       CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       m->bstream.push_back(st); m->ev_b.push_back(ev);
     }
-    for (size_t l = 0; l < m->lb.size(); ++l)
-      m->lb[l].stream = ns ? m->bstream[l % ns] : m->stream;
+    // outside a cycle every block's work goes to the main stream: the task-level entry points
+    // (ab_primitives, ab_physical_bcs ...) enqueue there in call order; one_cycle hands the
+    // block streams out itself, between its fork and join
+    for (size_t l = 0; l < m->lb.size(); ++l) m->lb[l].stream = m->stream;
   }
   CK(cudaMalloc(&m->state, 8*sizeof(double)));
   m->hist_cap = 1 << 16;

@@ -134,31 +134,44 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def run_reference_cpu(wl, budget_s=20.0, steps=None, warmup=0):
+def reference_sample(wl, threads):
+    """mesh / MeshBlock of the bounded CPU sample of workload `wl`: the same problem at the same
+    integrator / solver / order, cut into at least `threads` MeshBlocks (the reference's OpenMP
+    parallelises over MeshBlocks only, task_list.cpp:71-88).  The GPU arm runs the SAME mesh and
+    MeshBlocks in its `same_config` leg."""
+    blk = WORKLOADS[wl][5]
+    ndim = sum(1 for b in blk if b > 1)
+    if wl == "c2":
+        mesh, bs = [128, 64, 64], [64, 32, 32]
+    elif ndim == 3:
+        mesh, bs = [256, 256, 256], [64, 64, 64]
+    else:
+        mesh, bs = [2048, 2048, 1], [256, 256, 1]
+    nb = lambda: int(np.prod([m//b for m, b in zip(mesh, bs)]))   # noqa: E731
+    while nb() < threads and min(b for b in bs if b > 1) > 16:
+        bs = [b//2 if b > 1 else 1 for b in bs]
+    return mesh, bs
+
+
+def run_reference_cpu(wl, budget_s=25.0, steps=None, warmup=0):
     """Times the UNMODIFIED reference (oracle/_ref) on the host cores with OpenMP over
-    MeshBlocks (src/task_list/task_list.cpp:71-88), on a bounded sample of the workload."""
+    MeshBlocks, on a bounded sample of the workload (reference_sample)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ref_run
     cfg, pgen = REF_CFG[wl]
     if not ref_run.have_ref(cfg, pgen):
         return None
     inp, _, mhd, flux, ng, blk, ov = WORKLOADS[wl]
-    cores = os.cpu_count() or 1
-    threads = cores
-    ndim = sum(1 for b in blk if b > 1)
-    # sample mesh: >= `threads` MeshBlocks of 32^3 (3-D) / 128^2 (2-D)
-    bs = 32 if ndim == 3 else 128
-    nb = 1
-    while nb**ndim < threads:
-        nb *= 2
-    nb = max(nb, 4 if ndim == 3 else 4)
-    n = nb*bs
+    threads = os.cpu_count() or 1
+    mesh, bs = reference_sample(wl, threads)
+    nblocks = int(np.prod([m//b for m, b in zip(mesh, bs)]))
+    threads = min(threads, nblocks)
     over = {"time/tlim": 1e30, "time/ncycle_out": 0}
     for d in range(3):
-        over["mesh/nx%d" % (d+1)] = n if blk[d] > 1 else 1
-        over["meshblock/nx%d" % (d+1)] = bs if blk[d] > 1 else 1
+        over["mesh/nx%d" % (d+1)] = mesh[d]
+        over["meshblock/nx%d" % (d+1)] = bs[d]
     over.update(ov)
-    zones = n**ndim
+    zones = int(np.prod(mesh))
     inp_path = os.path.join(ROOT, "inputs", inp)
     if steps is None:
         # calibrate with 2 cycles, then fill the budget
@@ -168,7 +181,12 @@ def run_reference_cpu(wl, budget_s=20.0, steps=None, warmup=0):
         rate = r["zcps_omp"] or r["zcps"]
         ncyc = int(max(2, min(200, budget_s*rate/zones)))
     else:
-        ncyc = steps + warmup
+        # a bounded sample: at most ~2 minutes of CPU work whatever --steps asks for
+        over["time/nlim"] = 2
+        r = ref_run.run_reference(cfg, pgen, inp_path, over, threads=threads)
+        ref_run.cleanup(r)
+        rate = r["zcps_omp"] or r["zcps"]
+        ncyc = int(max(2, min(steps + warmup, 120.0*rate/zones)))
     over["time/nlim"] = ncyc
     r = ref_run.run_reference(cfg, pgen, inp_path, over, threads=threads)
     ref_run.cleanup(r)
@@ -176,10 +194,101 @@ def run_reference_cpu(wl, budget_s=20.0, steps=None, warmup=0):
     return {"value": rate, "unit": "zone-cycles/s", "cores": threads, "kind": "reference",
             "sample": "%s %s mesh, %d MeshBlocks of %s, %d cycles, OpenMP %d threads, "
                       "g++ -O3 (reference default flags)" %
-                      (pgen, "x".join(str(over["mesh/nx%d" % (d+1)]) for d in range(3)),
-                       nb**ndim, "x".join(str(over["meshblock/nx%d" % (d+1)]) for d in range(3)),
-                       ncyc, threads),
-            "ms_per_step": 1e3*zones/rate, "zones": zones, "cycles": ncyc}
+                      (pgen, "x".join(str(v) for v in mesh), nblocks,
+                       "x".join(str(v) for v in bs), ncyc, threads),
+            "ms_per_step": 1e3*zones/rate, "zones": zones, "cycles": ncyc,
+            "mesh": mesh, "meshblock": bs}
+
+
+def build_mesh(ab, wl, world, rank, device, dist, block=None, per_gpu=None, pinned=False):
+    """Mesh of workload `wl` filled by the reference's problem-generator formula (evaluated on
+    the host, as in the reference) and initialised.  pinned: keep the host arrays in pinned
+    memory (they are the e2e legs' host-side state)."""
+    import torch
+    pin, pgen_name, mhd, flux, ng, blk = make_pin(ab, wl, world, block, per_gpu)
+    mesh = ab.Mesh(pin, mhd=mhd, flux=flux, nghost=ng, rank=rank, nranks=world, device=device)
+    if world > 1:
+        def bcast(data):
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                t.copy_(torch.tensor(list(data), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        mesh.init_comm(bcast)
+    names = ["u"] + (["b1", "b2", "b3"] if mhd else [])
+    host = []
+    for pmb in mesh.my_blocks:
+        d = {nm: torch.zeros(pmb.shape(nm), dtype=torch.float64, pin_memory=pinned)
+             for nm in names}
+        st = ab.pgen.BY_NAME[pgen_name](pmb, pin, out={nm: t.numpy() for nm, t in d.items()})
+        for k, v in st.items():
+            pmb.set(k, v)
+        host.append(d if pinned else None)
+        if not pinned:
+            del d, st
+    mesh.initialize()
+    return mesh, pin, names, host, blk
+
+
+def timed_cycles(mesh, steps, warmup, device, dist, profile=False):
+    """W untimed cycles, then exactly K cycles between CUDA events on the library's stream,
+    barrier + synchronize on both sides, max over ranks.  Returns (ms, launches, prof)."""
+    import torch
+
+    def barrier():
+        mesh.sync()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        mesh.sync()
+    mesh.cycles(warmup, async_=True)
+    barrier()
+    L = mesh.L
+    if profile:
+        L.ab_mesh_profile(mesh.h, 1)
+    stream = torch.cuda.ExternalStream(mesh.cuda_stream, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = mesh.launch_count
+    barrier()
+    e0.record(stream)
+    mesh.cycles(steps, async_=True)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = mesh.launch_count - launches0
+    prof = (C.c_double*18)()
+    if profile:
+        L.ab_mesh_profile_read(mesh.h, prof)
+        L.ab_mesh_profile(mesh.h, 0)
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, launches, prof
+
+
+def flux_profile(prof, nd, xo):
+    return {"x%d_o%d" % (d+1, o+1): prof[d*3+o]/prof[9+d*3+o]
+            for d in range(nd) for o in range(3) if prof[9+d*3+o] > 0}
+
+
+def side_workload(ab, wl, device, steps, warmup, block=None, per_gpu=None):
+    """a short device-resident run of another workload on one GPU (N=1 only): its throughput,
+    ms per cycle and the per-direction averages of its reconstruct+Riemann kernels"""
+    import gc
+    mesh, pin, names, host, blk = build_mesh(ab, wl, 1, 0, device, None, block, per_gpu)
+    ms, launches, prof = timed_cycles(mesh, steps, warmup, device, None, profile=True)
+    zones = mesh.nbtotal*mesh.zones_per_block
+    nd = 1 + (mesh.params.nx2 > 1) + (mesh.params.nx3 > 1)
+    fp = flux_profile(prof, nd, mesh.params.xorder)
+    out = {"value": zones*steps/(ms*1e-3), "unit": "zone-cycles/s", "ms_per_step": ms/steps,
+           "steps": steps, "mesh": [mesh.params.nx1, mesh.params.nx2, mesh.params.nx3],
+           "meshblock": list(blk), "meshblocks": mesh.nbtotal, "gpu_launches": int(launches),
+           "flux_avg_ms_by_dir_order": fp,
+           "flux_kernels_share_of_step": sum(prof[i] for i in range(9))/ms if ms > 0 else None}
+    del mesh
+    gc.collect()
+    return out
 
 
 def main():
@@ -194,8 +303,11 @@ def main():
                     help="zones per GPU, e.g. 512,512,512 with --block 128,128,128 = 64 "
                          "MeshBlocks per GPU (default: one MeshBlock per GPU)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-pipelined", action="store_true",
-                    help="also measure e2e with the ab_stage_* copy/compute pipeline")
+    ap.add_argument("--e2e-pipelined", action="store_true", help=argparse.SUPPRESS)  # default now
+    ap.add_argument("--no-e2e-pipelined", action="store_true",
+                    help="skip the e2e leg that overlaps the copies with the kernels (ab_stage_*)")
+    ap.add_argument("--no-side", action="store_true",
+                    help="skip the same_config and other_workloads legs (N=1 only)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-first-runs", action="store_true", help=argparse.SUPPRESS)  # accepted, no-op
     a = ap.parse_args()
@@ -221,6 +333,9 @@ def main():
                               "unavailable": "oracle/_ref binary missing (build needs /root/reference)"}))
             return 0
         cfg_desc["sample"] = r["sample"]
+        cfg_desc["mesh"], cfg_desc["meshblock"] = r["mesh"], r["meshblock"]
+        cfg_desc["note"] = ("bounded sample of the workload on the host cores; the GPU arm's "
+                            "`same_config` leg runs this exact <mesh>/<meshblock>")
         out = {"impl": "reference", "metric": "zone-cycles/sec", "value": r["value"],
                "unit": "zone-cycles/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -336,24 +451,36 @@ def main():
         avg_ms = tot_ms/tot_n
         ach = fb*faces/(avg_ms*1e-3)/1e9
         share = sum(prof[i] for i in range(9))/ms if ms > 0 else None
+        # ncu evidence of this kernel (one --set full capture per build, summarised by
+        # tools/ncu_summary.py into profiles/flux_ncu.json with the source hash of the build it
+        # was taken on): DRAM bytes per launch, FP64-pipe utilisation, DRAM fraction, local
+        # memory traffic.  Nothing here is hard-coded; without the file the keys are null.
+        ncu = None
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "flux_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "flux_ncu.json")))
             key = "%s:%s" % (wl, "x".join(str(v) for v in blk))
-            if key in tj:
-                traffic = tj[key]["bytes_per_launch"]
+            if key in tj.get("kernels", {}):
+                ncu = dict(tj["kernels"][key])
+                ncu["source"] = "profiles/flux_ncu.json"
+                ncu["captured_on_srchash"] = tj.get("srchash")
+                ncu["srchash_now"] = ab.build.source_hash()
+                traffic = ncu.get("dram_bytes_per_launch")
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
+        bound = "hbm"
+        if ncu and ncu.get("fp64_pipe_util") is not None and ncu.get("dram_fraction") is not None:
+            bound = "fp64" if ncu["fp64_pipe_util"] > ncu["dram_fraction"] else "hbm"
+        roof = {"bound": bound, "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach/peak, "traffic": traffic, "peak_source": peak_src,
-                "note": "FP64-pipe co-roof binds this kernel (DESIGN.md section 4): DRAM traffic "
-                        "equals the algorithmic bytes, FP64 pipe 45-48% busy",
+                "fp64_pipe_util": ncu.get("fp64_pipe_util") if ncu else None,
+                "dram_fraction": ncu.get("dram_fraction") if ncu else None,
+                "local_mem_bytes": ncu.get("local_mem_bytes_per_launch") if ncu else None,
+                "ncu": ncu,
                 "avg_launch_ms": avg_ms, "launches_timed": int(tot_n),
                 "algorithmic_bytes_per_launch": fb*faces,
                 "flux_kernels_share_of_step": share,
-                "flux_avg_ms_by_dir_order": {"x%d_o%d" % (d+1, o+1): prof[d*3+o]/prof[9+d*3+o]
-                                             for d in range(nd) for o in range(3)
-                                             if prof[9+d*3+o] > 0}}
+                "flux_avg_ms_by_dir_order": flux_profile(prof, nd, xo)}
     b_alg = BYTES_PER_ZONE_CYCLE["mhd" if mhd else "hydro"]
     cycle_roof = {"B_alg_bytes_per_zone_cycle": b_alg,
                   "achieved_GBs_per_gpu": b_alg*value/world/1e9,
@@ -402,7 +529,7 @@ def main():
     # Same bytes, same work per step; the result lands in its own pinned buffers because the
     # input buffers are being read by the next upload at that time.
     e2e_pipe = None
-    if do_e2e and a.e2e_pipelined:
+    if do_e2e and not a.no_e2e_pipelined:
         try:
             dp = C.POINTER(C.c_double)
             outbuf = [{nm: torch.zeros_like(d[nm]).pin_memory() for nm in names} for d in pinned]
@@ -445,6 +572,14 @@ def main():
         except Exception as ex:
             e2e_pipe = {"value": None, "error": str(ex)[:200]}
 
+    # headline e2e: the pipelined sequence when it ran (same bytes, same work per step, copies
+    # inside the timed region); the strictly serial sequence stays on the line as e2e_plain
+    e2e_plain = None
+    if e2e_pipe and e2e_pipe.get("value"):
+        e2e_plain, e2e = e2e, e2e_pipe
+    elif e2e_pipe:
+        e2e_plain = e2e_pipe       # carries the error text
+
     # ---- the drop-in's normal mode: state stays resident, the host loop calls one cycle at a
     # time and reads back what Mesh::NewTimeStep / HistoryOutput need (dt, time, history sums)
     e2e_res = None
@@ -474,19 +609,77 @@ def main():
         except Exception as ex:
             e2e_res = {"value": None, "error": str(ex)[:200]}
 
+    cpu_full = None
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
         try:
-            cpu = run_reference_cpu(wl)
-            if cpu:
-                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu_full = run_reference_cpu(wl)
+            if cpu_full:
+                cpu = {k: cpu_full[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:   # the baseline must never break the product's bench line
             cpu = {"value": None, "unit": "zone-cycles/s", "cores": os.cpu_count(),
                    "kind": "reference", "sample": "failed: %s" % ex}
 
+    # facts of the main mesh the line needs, then free its ~59 GB before the side legs
+    mesh_dims = [mesh.params.nx1, mesh.params.nx2, mesh.params.nx3]
+    nbtotal = mesh.nbtotal
+    import gc
+    del mesh, pinned
+    gc.collect()
+
+    # ---- same_config (N=1): the GPU on exactly the <mesh>/<meshblock> the CPU baseline and the
+    # `--impl reference` arm run (a bounded sample of the workload with enough MeshBlocks for the
+    # host's OpenMP threads), so that a like-for-like ratio exists beside the headline
+    same_cfg = None
+    others = None
+    if rank == 0 and world == 1 and not a.no_side:
+        try:
+            smesh, sblk = reference_sample(wl, os.cpu_count() or 1)
+            if cpu_full:
+                smesh, sblk = cpu_full["mesh"], cpu_full["meshblock"]
+            r = side_workload(ab, wl, device, max(4, min(a.steps, 10)), 3, block=tuple(sblk),
+                              per_gpu=tuple(smesh))
+            same_cfg = {"mesh": smesh, "meshblock": sblk, "meshblocks": r["meshblocks"],
+                        "value": r["value"], "unit": "zone-cycles/s",
+                        "ms_per_step": r["ms_per_step"], "gpu_launches": r["gpu_launches"],
+                        "cpu_value": cpu["value"] if cpu else None,
+                        "cpu_cores": cpu["cores"] if cpu else None}
+        except Exception as ex:
+            same_cfg = {"value": None, "error": str(ex)[:300]}
+        # ---- the other BASELINE.json configurations, short device-resident runs
+        others = {}
+        side = {"c2": (dict(), 100, 10),
+                "c3": (dict(block=(512, 512, 1), per_gpu=(2048, 2048, 1)), 20, 5),
+                "c4": (dict(block=(128, 128, 128), per_gpu=(512, 512, 512)), 4, 2)}
+        if wl != "c5":
+            side["c5"] = (dict(), 4, 2)
+        for name, (kw, st, wu) in side.items():
+            if name == wl:
+                continue
+            try:
+                others[name] = side_workload(ab, name, device, st, wu, **kw)
+            except Exception as ex:
+                others[name] = {"value": None, "error": str(ex)[:300]}
+
+    # ---- multi-rank correctness on the scaling record: the golden fixtures of the reference,
+    # MeshBlocks sharded over these ranks, NCCL ghost / EMF exchange and dt reduction, bit for
+    # bit (tests/multirank_check.py; checker only, after every timed region)
+    parity = None
+    if dist:
+        try:
+            for pth in (os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+                if pth not in sys.path:
+                    sys.path.insert(0, pth)
+            import multirank_check
+            nrun, nfail = multirank_check.check_goldens(rank, world, local_rank, verbose=False)
+            parity = {"ranks": world, "fixtures": nrun, "failed": nfail,
+                      "what": "reference goldens sharded over the ranks, state and dt bit-exact"}
+        except Exception as ex:
+            parity = {"ranks": world, "fixtures": 0, "failed": None, "error": str(ex)[:300]}
+
     if rank == 0:
-        cfg_desc.update({"mesh": [mesh.params.nx1, mesh.params.nx2, mesh.params.nx3],
-                         "meshblock": list(blk), "meshblocks_total": mesh.nbtotal,
+        cfg_desc.update({"mesh": mesh_dims,
+                         "meshblock": list(blk), "meshblocks_total": nbtotal,
                          "parallelism": "MeshBlocks sharded over %d GPU(s), NCCL halo" % world,
                          "l2_policy": "working set (%.1f GB/GPU) >> 126 MB L2; no flush needed"
                                       % (zones_local*8*55/1e9 if mhd else zones_local*8*35/1e9)})
@@ -495,7 +688,8 @@ def main():
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": cfg_desc, "roofline": roof,
                "roofline_cycle": cycle_roof, "cpu_baseline": cpu, "e2e": e2e,
-               "e2e_resident": e2e_res, "e2e_pipelined": e2e_pipe,
+               "e2e_resident": e2e_res, "e2e_plain": e2e_plain,
+               "same_config": same_cfg, "other_workloads": others, "parity": parity,
                "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(out))
     if dist:

@@ -140,7 +140,7 @@ def read_rst(path, nhydro=5, mhd=None, nghost=None, nscalars=0):
 
 def run_reference(cfg, pgen, athinput_path, overrides=None, rst_every_cycle=False,
                   keep_dir=None, timeout=3600, threads=None, hst_every_cycle=False,
-                  exe=None, env_extra=None, blocks=None):
+                  exe=None, env_extra=None, blocks=None, rst_dcycle=None):
     """Run the reference; returns dict(dts, times, zcps, zcps_omp, rst=[paths], dir, stdout).
     exe / env_extra: run another build of the same program instead (the reference compiled
     with this repository's shim, tools/build_shim.py); blocks: parameter blocks instead of
@@ -157,6 +157,8 @@ def run_reference(cfg, pgen, athinput_path, overrides=None, rst_every_cycle=Fals
     apply_overrides(blocks, overrides)
     if rst_every_cycle:
         blocks["output9"] = {"file_type": "rst", "dt": "1e-300"}
+    if rst_dcycle:        # a dump at cycle 0 and every rst_dcycle cycles (outputs.cpp:792)
+        blocks["output9"] = {"file_type": "rst", "dcycle": str(rst_dcycle)}
     if hst_every_cycle:   # outputs/history.cpp with 17 significant digits
         blocks["output8"] = {"file_type": "hst", "dt": "1e-300", "data_format": "%24.16e"}
     if threads is not None:

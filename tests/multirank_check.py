@@ -17,17 +17,19 @@ import gpu_util  # noqa: E402
 import util  # noqa: E402
 
 
-def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    names = sys.argv[1:] or ["c5_blast_hlld_plm_vl2_8blk", "c2_linwave_hlld_plm_vl2_8blk",
-                             "c4_kh_hllc_ppm_rk2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
-                             "c1_sod_hllc_plm_vl2_2blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1",
-                             "khs_lhllc_plm_vl2_4blk_s1"]
-    ok = True
-    for name in names:
+DEFAULT_NAMES = ["c5_blast_hlld_plm_vl2_8blk", "c2_linwave_hlld_plm_vl2_8blk",
+                 "c4_kh_hllc_ppm_rk2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
+                 "c1_sod_hllc_plm_vl2_2blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1",
+                 "khs_lhllc_plm_vl2_4blk_s1"]
+
+
+def check_goldens(rank, world, local, names=None, verbose=True):
+    """Every golden with at least `world` MeshBlocks, sharded over the ranks of the already
+    initialised NCCL process group; returns (fixtures run, fixtures failed on ANY rank).
+    bench.py calls this after its timed region so that the scaling record carries multi-rank
+    correctness (checker only: nothing here is timed)."""
+    nrun = nfail = 0
+    for name in (names or DEFAULT_NAMES):
         g = util.Golden(name)
         if len(g.locs) < world:
             continue
@@ -51,16 +53,27 @@ def main():
                 if not np.array_equal(pmb.get(f), g.final[n][f]):
                     nbad += 1
         good &= (nbad == 0)
-        print("rank %d/%d %s: blocks %d dt_ok %s bad_arrays %d -> %s" %
-              (rank, world, name, m.nblocal, list(dts) == list(g.dts[:g.ncycles]), nbad,
-               "OK" if good else "FAIL"), flush=True)
-        ok &= good
+        if verbose:
+            print("rank %d/%d %s: blocks %d dt_ok %s bad_arrays %d -> %s" %
+                  (rank, world, name, m.nblocal, list(dts) == list(g.dts[:g.ncycles]), nbad,
+                   "OK" if good else "FAIL"), flush=True)
+        t = torch.tensor([0 if good else 1], device="cuda")
+        dist.all_reduce(t)
+        nrun += 1
+        nfail += 1 if int(t.item()) else 0
         del m
-    t = torch.tensor([0 if ok else 1], device="cuda")
-    dist.all_reduce(t)
+    return nrun, nfail
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nrun, nfail = check_goldens(rank, world, local, sys.argv[1:] or None)
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(1 if int(t.item()) else 0)
+    sys.exit(1 if (nfail or not nrun) else 0)
 
 
 if __name__ == "__main__":

@@ -3,6 +3,10 @@
 * C2 (3-D MHD linear wave 128x64x64, HLLD+PLM+VL2, one MeshBlock) at its FULL size against the
   unmodified reference binary run live on the box's CPU (oracle/_ref travels with the repo):
   bit-identical dt sequence and state.  Skipped when oracle/_ref is absent.
+* The benchmarked configurations at (or near) their benchmark size, state and dt bit for bit
+  against the live reference binary: C5 (MHD blast, HLLD+PLM+VL2) at 256^3 in 8 MeshBlocks of
+  128^3, C3 (Orszag-Tang, HLLD+PPM) at 2048^2 in 16 MeshBlocks of 512^2, C4 (Kelvin-Helmholtz,
+  HLLC+PPM+RK2, ran2 seed per MeshBlock) at 256^3 in 8 MeshBlocks of 128^3.
 * C5 (MHD blast) at 256^3 and 512^3 through size-independent properties: div B = 0 to
   round-off (constrained transport), conservation of mass / momentum / energy under periodic
   boundaries, and MeshBlock-decomposition invariance of the dt sequence.
@@ -44,6 +48,64 @@ def test_c2_full_size_bitwise_vs_reference_binary():
     assert list(dts) == res["dts"][:ncyc]
     for f in ("u", "b1", "b2", "b3"):
         util.assert_bitwise(pmb.get(f), last["blocks"][0][f], "C2 full size %s" % f)
+
+
+def _bitwise_vs_live_reference(cfg, pgen, inp, over, mhd, flux, nghost, ncyc, what):
+    """the reference binary runs `ncyc` cycles on the host cores with a restart dump at cycle 0
+    and at the end; the device starts from the first dump and must land on the second"""
+    import ref_run
+    if not ref_run.have_ref(cfg, pgen):
+        pytest.skip("oracle/_ref not built")
+    over = dict(over)
+    over["time/nlim"] = ncyc
+    res = ref_run.run_reference(cfg, pgen, os.path.join(ROOT, "inputs", inp), over,
+                                rst_dcycle=ncyc, threads=min(os.cpu_count() or 1, 8))
+    try:
+        assert len(res["rst"]) >= 2
+        first = ref_run.read_rst(res["rst"][0], mhd=mhd, nghost=nghost)
+        last = ref_run.read_rst(res["rst"][1], mhd=mhd, nghost=nghost)
+    finally:
+        ref_run.cleanup(res)
+    assert last["ncycle"] == ncyc
+    pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", inp))
+    pin.modify_from_cmdline(["%s=%s" % kv for kv in over.items()])
+    m = ab.Mesh(pin, mhd=mhd, flux=flux, nghost=nghost)
+    fields = ("u", "b1", "b2", "b3") if mhd else ("u",)
+    assert m.nbtotal == first["nbtotal"]
+    for blk in first["blocks"]:
+        pmb = m.block_of(*blk["loc"][:3])
+        for f in fields:
+            pmb.set(f, blk[f])
+    del first
+    m.initialize()
+    assert m.dt == res["dts"][0]
+    dts = m.cycles(ncyc)
+    assert list(dts) == res["dts"][:ncyc], (list(dts), res["dts"][:ncyc])
+    assert m.time == last["time"] and m.dt == last["dt"]
+    for blk in last["blocks"]:
+        pmb = m.block_of(*blk["loc"][:3])
+        for f in fields:
+            util.assert_bitwise(pmb.get(f), blk[f], "%s %s block %s" % (what, f, blk["loc"]))
+
+
+def test_c5_blast_256cube_8blocks_bitwise_vs_reference_binary():
+    n = {"mesh/nx%d" % d: 256 for d in (1, 2, 3)}
+    n.update({"meshblock/nx%d" % d: 128 for d in (1, 2, 3)})
+    _bitwise_vs_live_reference("mhd_hlld_ng2", "blast", "athinput.blast", n, True, "hlld", 2, 3,
+                               "C5 256^3")
+
+
+def test_c3_orszag_tang_2048sq_16blocks_bitwise_vs_reference_binary():
+    n = {"mesh/nx1": 2048, "mesh/nx2": 2048, "meshblock/nx1": 512, "meshblock/nx2": 512}
+    _bitwise_vs_live_reference("mhd_hlld_ng3", "orszag_tang", "athinput.orszag_tang", n, True,
+                               "hlld", 3, 2, "C3 2048^2")
+
+
+def test_c4_kelvin_helmholtz_256cube_8blocks_bitwise_vs_reference_binary():
+    n = {"mesh/nx%d" % d: 256 for d in (1, 2, 3)}
+    n.update({"meshblock/nx%d" % d: 128 for d in (1, 2, 3)})
+    _bitwise_vs_live_reference("hydro_hllc_ng3", "kh", "athinput.kh", n, False, "hllc", 3, 2,
+                               "C4 256^3")
 
 
 def blast_mesh(n, block, ncyc):
