@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", f) for f in ("ab_kernels.cu", "ab_flux_nu.cu", "ab_mesh.cu",
                                                "ab_smr.cpp", "ab_smr_kernels.cu")]
 HDR = [os.path.join(HERE, "csrc", f) for f in ("ab_kernels.h", "ab_types.h", "ab_physics.cuh",
-                                               "ab_flux.cuh", "ab_smr_cells.cuh", "ab_smr_exec.h")] + \
+                                               "ab_flux.cuh", "ab_batch.cuh", "ab_smr_cells.cuh", "ab_smr_exec.h")] + \
       [os.path.join(os.path.dirname(HERE), "include", "athena_b200.h")]
 SO = os.path.join(HERE, "libathena_b200.so")
 

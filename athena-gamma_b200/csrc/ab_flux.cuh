@@ -54,6 +54,10 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
 #ifndef AB_X3_STRIP
 #define AB_X3_STRIP 32
 #endif
+// 1: xorder = 3 sweeps reconstruct every cell once (k_flux_ppm_*); 0: per interface (k_flux)
+#ifndef AB_PPM_SHARED
+#define AB_PPM_SHARED 1
+#endif
 
 // Exact t / d for 0 <= t < 2^31 by one multiply-high and a shift (the divisor is a launch
 // constant; a run-time integer division costs ~20 instructions per thread and the kernel needs
@@ -251,6 +255,216 @@ k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, 
   }
 }
 
+// =============================================================================================
+// PPM sweeps with the reconstruction shared between the two interfaces of a cell.
+//
+// k_flux reconstructs per interface: the thread of face c runs PPM on cell c-1 (keeping only the
+// state at its upper face) and on cell c (keeping only the lower one).  PPM is ~100 FP64
+// instructions per variable, more than the Riemann solver itself (hydro: 10 PPM evaluations per
+// interface against one HLLC), so here every cell is reconstructed ONCE and hands its upper-face
+// state to the thread of the next interface:
+//   * x1 sweep: a warp holds 32 consecutive cells of a row, the state travels one lane up by
+//     warp shuffle; lanes 1..31 own the 31 faces between them (no shared memory, no barrier);
+//   * x2 / x3 sweeps: a CTA of (AB_PPM_ROWS+1) warps holds that many consecutive cells along the
+//     sweep for 32 positions of the flattened transverse plane; the state goes through shared
+//     memory, one barrier; warps 1..AB_PPM_ROWS own the faces.
+// The values are those of ppm() / ppm_nu() exactly as k_flux calls them, so the fluxes are the
+// same bits (ppm.cpp:111-332 computes both face states of a cell in one pass as well).
+// =============================================================================================
+#ifndef AB_PPM_ROWS
+#define AB_PPM_ROWS 8
+#endif
+#ifndef AB_PPM_MINB
+#define AB_PPM_MINB 2
+#endif
+#ifndef AB_PPM_X1_MINB
+#define AB_PPM_X1_MINB 18
+#endif
+
+// both face states of cell (k,j,i) along DIR, floors applied (ppm.cpp:326-332)
+template <int DIR, bool MHD, bool ISO, bool NU>
+__device__ __forceinline__ void ppm_cell(const BlkDev &b, const ReconGeom &g, const Params &p,
+                                         int oc, int c, double *plus, double *minus) {
+  constexpr int NW = MHD ? 7 : 5;
+  const int sv = b.nc3*b.nc2*b.nc1;
+  const int st = (DIR == 0) ? 1 : ((DIR == 1) ? b.nc1 : b.nc1*b.nc2);
+  const double *__restrict__ w = b.w;
+  const double *__restrict__ bcc = b.bcc;
+  double qm2[NW], qm1[NW], q0[NW], qp1[NW], qp2[NW];
+  load_cell<DIR,MHD,ISO>(w, bcc, oc - 2*st, sv, qm2);
+  load_cell<DIR,MHD,ISO>(w, bcc, oc - st, sv, qm1);
+  load_cell<DIR,MHD,ISO>(w, bcc, oc, sv, q0);
+  load_cell<DIR,MHD,ISO>(w, bcc, oc + st, sv, qp1);
+  load_cell<DIR,MHD,ISO>(w, bcc, oc + 2*st, sv, qp2);
+  const double *tl = NU ? g.nu[DIR] + c*NUG : nullptr;
+#pragma unroll
+  for (int n = 0; n < NW; ++n) {
+    if (NU) ppm_nu(qm2[n], qm1[n], q0[n], qp1[n], qp2[n], tl, plus[n], minus[n]);
+    else ppm(qm2[n], qm1[n], q0[n], qp1[n], qp2[n], plus[n], minus[n]);
+  }
+  plus[IDN] = (plus[IDN] > p.dfloor) ? plus[IDN] : p.dfloor;
+  minus[IDN] = (minus[IDN] > p.dfloor) ? minus[IDN] : p.dfloor;
+  if (!ISO) {
+    plus[IPR] = (plus[IPR] > p.pfloor) ? plus[IPR] : p.pfloor;
+    minus[IPR] = (minus[IPR] > p.pfloor) ? minus[IPR] : p.pfloor;
+  }
+}
+
+// Riemann solve and stores of the face (k,j,i) of direction DIR from its two states -- the second
+// half of k_flux
+template <int DIR, int SOLVER, bool MHD>
+__device__ __forceinline__ void flux_face(const BlkDev &b, const Params &p, int i, int j, int k,
+                                          double *wl, double *wr, double dt_val,
+                                          const double *dt_ptr) {
+  constexpr int NW = MHD ? 7 : 5;
+  constexpr bool ISO = solver_is_iso<SOLVER>;
+  const int sv = b.nc3*b.nc2*b.nc1;
+  const int st = (DIR == 0) ? 1 : ((DIR == 1) ? b.nc1 : b.nc1*b.nc2);
+  const int oc = (k*b.nc2 + j)*b.nc1 + i;
+  const double *__restrict__ w = b.w;
+  int of, sf;
+  if (DIR == 0) { of = (k*b.nc2 + j)*(b.nc1+1) + i; sf = b.nc3*b.nc2*(b.nc1+1); }
+  else if (DIR == 1) { of = (k*(b.nc2+1) + j)*b.nc1 + i; sf = b.nc3*(b.nc2+1)*b.nc1; }
+  else { of = (k*b.nc2 + j)*b.nc1 + i; sf = (b.nc3+1)*b.nc2*b.nc1; }
+  double bxi = 0.0, dt = 0.0, dxw = 0.0;
+  if (MHD) {
+    bxi = b.b[DIR][of];
+    dt = dt_ptr ? *dt_ptr : dt_val;
+    dxw = (DIR == 0) ? b.dx1f[i] : ((DIR == 1) ? b.dx2f[j] : b.dx3f[k]);
+    dt = (1024.0)*dt;
+  }
+  double dvn = 0.0, dvt = 0.0;
+  if (SOLVER == SOLVER_LHLLC || SOLVER == SOLVER_LHLLD) {
+    const int ol = oc - st;
+    dvn = w[oc + (1 + DIR)*sv] - w[ol + (1 + DIR)*sv];
+    if (b.f2) {
+      bool first = true;
+#pragma unroll
+      for (int t = 1; t <= 2; ++t) {
+        const int td = (DIR + t) % 3;
+        if (td == 2 && !b.f3) continue;
+        const int ts = (td == 0) ? 1 : ((td == 1) ? b.nc1 : b.nc1*b.nc2);
+        const double *__restrict__ wt = w + (1 + td)*sv;
+        double dl = dmin(wt[ol + ts] - wt[ol], wt[ol] - wt[ol - ts]);
+        double dr = dmin(wt[oc + ts] - wt[oc], wt[oc] - wt[oc - ts]);
+        double v = dmin(dl, dr);
+        dvt = first ? v : dmin(dvt, v);
+        first = false;
+      }
+    }
+  }
+  if (MHD) dxw = dxw*(wl[IDN] + wr[IDN]);
+  double f[NW];
+  riemann<SOLVER,MHD>(wl, wr, bxi, ISO ? p.iso_cs : p.gamma, dvn, dvt, f, p.dfloor);
+  double *__restrict__ flx = b.flux[DIR];
+  flx[of] = f[IDN];
+  flx[of + (1 + DIR)*sf] = f[IVX];
+  flx[of + (1 + (DIR+1)%3)*sf] = f[IVY];
+  flx[of + (1 + (DIR+2)%3)*sf] = f[IVZ];
+  if (!ISO) flx[of + 4*sf] = f[IEN];
+  if (MHD) {
+    b.ef[DIR][0][of] = -f[IBY];
+    b.ef[DIR][1][of] = f[IBZ];
+    b.wght[DIR][of] = weight_for_ct_pre(f[IDN], dxw, dt);
+  }
+}
+
+// x1 sweep: one warp per 31 faces of a row.  grid.x = rows * segments (row-major)
+struct PpmIdx { FastDiv nseg, nj, ni; int nsegs, gp, nst, np; };
+
+template <int SOLVER, bool MHD, bool NU>
+__global__ void __launch_bounds__(32, AB_PPM_X1_MINB)
+k_flux_ppm_x1(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
+              double dt_val, const double *dt_ptr, PpmIdx fx) {
+  constexpr int NW = MHD ? 7 : 5;
+  constexpr bool ISO = solver_is_iso<SOLVER>;
+  const int t = blockIdx.x;
+  const int row = fast_div(t, fx.nseg);
+  const int seg = t - row*fx.nsegs;
+  const int kk = fast_div(row, fx.nj);
+  const int j = j0 + (row - kk*nj), k = k0 + kk;
+  const int lane = threadIdx.x;
+  const int i = i0 + seg*31 - 1 + lane;          // this lane's cell; its lower face is face i
+  const bool have = (i <= i0 + ni - 1);
+  double plus[NW], minus[NW];
+#pragma unroll
+  for (int n = 0; n < NW; ++n) { plus[n] = 0.0; minus[n] = 0.0; }
+  if (have) ppm_cell<0,MHD,ISO,NU>(b, g, p, (k*b.nc2 + j)*b.nc1 + i, i, plus, minus);
+  double wl[NW];
+#pragma unroll
+  for (int n = 0; n < NW; ++n) wl[n] = __shfl_up_sync(0xffffffffu, plus[n], 1);
+  if (!have || lane == 0) return;
+  flux_face<0,SOLVER,MHD>(b, p, i, j, k, wl, minus, dt_val, dt_ptr);
+}
+
+// x2 / x3 sweeps.  The transverse plane (x2 sweep: (k,i); x3 sweep: (j,i)) is flattened into np
+// positions, 32 per CTA; along the sweep a CTA covers AB_PPM_ROWS faces.  CTA order: groups of gp
+// transverse tiles, inside a group the sweep tiles one after the other (consecutive CTAs re-read
+// the 5 stencil rows they share from L2), inside a sweep tile the gp transverse tiles.
+template <int DIR, int SOLVER, bool MHD, bool NU>
+__global__ void __launch_bounds__(32*(AB_PPM_ROWS + 1), AB_PPM_MINB)
+k_flux_ppm_t(BlkDev b, ReconGeom g, Params p, int i0, int ni, int a0, int c0, int nc,
+             double dt_val, const double *dt_ptr, PpmIdx fx) {
+  constexpr int NW = MHD ? 7 : 5;
+  constexpr bool ISO = solver_is_iso<SOLVER>;
+  __shared__ double sh[AB_PPM_ROWS][NW][32];
+  const int t = blockIdx.x;
+  const int per_group = fx.gp*fx.nst;
+  const int grp = t/per_group;                    // uniform per CTA: a plain division is fine
+  const int rem = t - grp*per_group;
+  const int stile = rem/fx.gp;
+  const int ptile = grp*fx.gp + (rem - stile*fx.gp);
+  const int lane = threadIdx.x, r = threadIdx.y;
+  const int pf = ptile*32 + lane;
+  const int a = fast_div(pf, fx.ni);
+  const int i = i0 + (pf - a*ni);
+  const int c = c0 + stile*AB_PPM_ROWS - 1 + r;   // this warp's cell along the sweep
+  const bool have = (pf < fx.np) && (c <= c0 + nc - 1);
+  const int j = (DIR == 1) ? c : a0 + a, k = (DIR == 1) ? a0 + a : c;
+  double plus[NW], minus[NW];
+  if (have) {
+    ppm_cell<DIR,MHD,ISO,NU>(b, g, p, (k*b.nc2 + j)*b.nc1 + i, c, plus, minus);
+    if (r < AB_PPM_ROWS) {
+#pragma unroll
+      for (int n = 0; n < NW; ++n) sh[r][n][lane] = plus[n];
+    }
+  }
+  __syncthreads();
+  if (!have || r == 0) return;
+  double wl[NW];
+#pragma unroll
+  for (int n = 0; n < NW; ++n) wl[n] = sh[r-1][n][lane];
+  flux_face<DIR,SOLVER,MHD>(b, p, i, j, k, wl, minus, dt_val, dt_ptr);
+}
+
+template <int DIR, int SOLVER, bool MHD, bool NU>
+static void flux_dir_ppm(const BlkDev &b, const ReconGeom &g, const Params &p, int i0, int ni,
+                         int j0, int nj, int k0, int nk, double dt_val, const double *dt_ptr,
+                         cudaStream_t s) {
+  PpmIdx fx;
+  fx.ni = make_fastdiv(ni); fx.nj = make_fastdiv(nj);
+  if constexpr (DIR == 0) {
+    fx.nsegs = (ni + 30)/31; fx.nseg = make_fastdiv(fx.nsegs);
+    fx.gp = fx.nst = fx.np = 0;
+    k_flux_ppm_x1<SOLVER,MHD,NU><<<fx.nsegs*nj*nk, 32, 0, s>>>(b, g, p, i0, ni, j0, nj, k0, nk,
+                                                              dt_val, dt_ptr, fx);
+  } else {
+    const int na = (DIR == 1) ? nk : nj;           // rows of the transverse plane
+    const int nc = (DIR == 1) ? nj : nk;           // faces along the sweep
+    fx.np = ni*na;
+    const int ntile = (fx.np + 31)/32;
+    // x2: a group = the tiles of one k-plane; x3: the tiles of a strip of 32 j-rows
+    fx.gp = (DIR == 1) ? (ni + 31)/32 : ni;
+    if (fx.gp > ntile) fx.gp = ntile;
+    const int ngrp = (ntile + fx.gp - 1)/fx.gp;
+    fx.nst = (nc + AB_PPM_ROWS - 1)/AB_PPM_ROWS;
+    fx.nsegs = 0; fx.nseg = make_fastdiv(1);
+    k_flux_ppm_t<DIR,SOLVER,MHD,NU><<<ngrp*fx.gp*fx.nst, dim3(32, AB_PPM_ROWS + 1), 0, s>>>(
+        b, g, p, i0, ni, (DIR == 1) ? k0 : j0, (DIR == 1) ? j0 : k0, nc, dt_val, dt_ptr, fx);
+  }
+  ++g_launches;
+}
+
 template <int DIR, int ORDER, int SOLVER, bool MHD, bool NU>
 static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, double dt_val,
                      const double *dt_ptr, cudaStream_t s) {
@@ -268,14 +482,18 @@ static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, doubl
     if (MHD) { i0 = is-1; i1 = ie+1; j0 = js-1; j1 = je+1; }
   }
   int ni = i1-i0+1, nj = j1-j0+1, nk = k1-k0+1;
-  int ntot = ni*nj*nk;
-  FluxIdx fx;
-  fx.ni = make_fastdiv(ni); fx.nj = make_fastdiv(nj);
-  fx.per_full = make_fastdiv(ni*AB_X3_STRIP*nk); fx.per_k = make_fastdiv(ni*AB_X3_STRIP);
-  fx.last_strip = (AB_X3_STRIP > 0 && nj % (AB_X3_STRIP > 0 ? AB_X3_STRIP : 1)) ? nj/(AB_X3_STRIP > 0 ? AB_X3_STRIP : 1) : -1;
-  fx.per_k_last = make_fastdiv(ni*(AB_X3_STRIP > 0 ? nj % AB_X3_STRIP : 1));
-  k_flux<DIR,ORDER,SOLVER,MHD,NU><<<(ntot + AB_FLUX_BX - 1)/AB_FLUX_BX, AB_FLUX_BX, 0, s>>>(
-      b, g, p, i0, ni, j0, nj, k0, nk, ntot, dt_val, dt_ptr, fx); ++g_launches;
+  if constexpr (ORDER == 3 && AB_PPM_SHARED) {
+    flux_dir_ppm<DIR,SOLVER,MHD,NU>(b, g, p, i0, ni, j0, nj, k0, nk, dt_val, dt_ptr, s);
+  } else {
+    int ntot = ni*nj*nk;
+    FluxIdx fx;
+    fx.ni = make_fastdiv(ni); fx.nj = make_fastdiv(nj);
+    fx.per_full = make_fastdiv(ni*AB_X3_STRIP*nk); fx.per_k = make_fastdiv(ni*AB_X3_STRIP);
+    fx.last_strip = (AB_X3_STRIP > 0 && nj % (AB_X3_STRIP > 0 ? AB_X3_STRIP : 1)) ? nj/(AB_X3_STRIP > 0 ? AB_X3_STRIP : 1) : -1;
+    fx.per_k_last = make_fastdiv(ni*(AB_X3_STRIP > 0 ? nj % AB_X3_STRIP : 1));
+    k_flux<DIR,ORDER,SOLVER,MHD,NU><<<(ntot + AB_FLUX_BX - 1)/AB_FLUX_BX, AB_FLUX_BX, 0, s>>>(
+        b, g, p, i0, ni, j0, nj, k0, nk, ntot, dt_val, dt_ptr, fx); ++g_launches;
+  }
 }
 
 template <int ORDER, int SOLVER, bool MHD, bool NU>

@@ -36,6 +36,9 @@ struct BlkDev {
   // nullptr when every direction is uniformly spaced; else the CalculateCellCenteredField
   // weights (field/field.cpp:139-172): lw[nc1], rw[nc1] of x1, then x2, then x3
   const double *bcw;
+  // bytes between the slabs of consecutive local MeshBlocks (one launch over all blocks of a
+  // rank, ab_batch.cuh); 0 when the blocks were allocated separately (AB_DEBUG_ALLOC)
+  long bstride;
 };
 
 // EMF-correction plan of one block (src/bvals/fc/flux_correction_fc.cpp).  For every face /

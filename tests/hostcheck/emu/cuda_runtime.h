@@ -195,4 +195,14 @@ template <class T> inline T __shfl_xor_sync(unsigned, T v, int s) {
   ab_emu::barrier();
   return r;
 }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  const unsigned t = threadIdx.x + blockDim.x*(threadIdx.y + blockDim.y*threadIdx.z);
+  memcpy(&ab_emu::g.xch[t], &v, sizeof(T));
+  ab_emu::barrier();
+  T r = v;                                   // lanes below d keep their own value
+  if ((t & 31u) >= d) memcpy(&r, &ab_emu::g.xch[t - d], sizeof(T));
+  ab_emu::barrier();
+  return r;
+}
 #endif  // AB_EMU_CUDA_RUNTIME_H_
