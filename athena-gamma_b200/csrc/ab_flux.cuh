@@ -5,6 +5,7 @@
 #define AB_FLUX_CUH_
 #include "ab_kernels.h"
 #include "ab_physics.cuh"
+#include "ab_batch.cuh"
 
 namespace ab {
 
@@ -84,8 +85,10 @@ struct FluxIdx { FastDiv ni, nj, per_full, per_k, per_k_last; int last_strip; };
 // CTA has work (rows of nx1+1 faces do not pad to a multiple of the CTA width).
 template <int DIR, int ORDER, int SOLVER, bool MHD, bool NU>
 __global__ void AB_FLUX_BOUNDS
-k_flux(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
+k_flux(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
        int ntot, double dt_val, const double *dt_ptr, FluxIdx fx) {
+  const BlkDev b = blk_view(b0, blockIdx.y);      // blockIdx.y = local MeshBlock (ab_batch.cuh)
+  const ReconGeom g = geom_view(g0, b0, blockIdx.y);
   constexpr int NW = MHD ? 7 : 5;
   constexpr bool ISO = solver_is_iso<SOLVER>;
   int t = blockIdx.x*AB_FLUX_BX + threadIdx.x;
@@ -374,8 +377,10 @@ struct PpmIdx { FastDiv nseg, nj, ni; int nsegs, gp, nst, np; };
 
 template <int SOLVER, bool MHD, bool NU>
 __global__ void __launch_bounds__(32, AB_PPM_X1_MINB)
-k_flux_ppm_x1(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
+k_flux_ppm_x1(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
               double dt_val, const double *dt_ptr, PpmIdx fx) {
+  const BlkDev b = blk_view(b0, blockIdx.y);
+  const ReconGeom g = geom_view(g0, b0, blockIdx.y);
   constexpr int NW = MHD ? 7 : 5;
   constexpr bool ISO = solver_is_iso<SOLVER>;
   const int t = blockIdx.x;
@@ -403,8 +408,10 @@ k_flux_ppm_x1(BlkDev b, ReconGeom g, Params p, int i0, int ni, int j0, int nj, i
 // the 5 stencil rows they share from L2), inside a sweep tile the gp transverse tiles.
 template <int DIR, int SOLVER, bool MHD, bool NU>
 __global__ void __launch_bounds__(32*(AB_PPM_ROWS + 1), AB_PPM_MINB)
-k_flux_ppm_t(BlkDev b, ReconGeom g, Params p, int i0, int ni, int a0, int c0, int nc,
+k_flux_ppm_t(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int a0, int c0, int nc,
              double dt_val, const double *dt_ptr, PpmIdx fx) {
+  const BlkDev b = blk_view(b0, blockIdx.y);
+  const ReconGeom g = geom_view(g0, b0, blockIdx.y);
   constexpr int NW = MHD ? 7 : 5;
   constexpr bool ISO = solver_is_iso<SOLVER>;
   __shared__ double sh[AB_PPM_ROWS][NW][32];
@@ -440,13 +447,13 @@ k_flux_ppm_t(BlkDev b, ReconGeom g, Params p, int i0, int ni, int a0, int c0, in
 template <int DIR, int SOLVER, bool MHD, bool NU>
 static void flux_dir_ppm(const BlkDev &b, const ReconGeom &g, const Params &p, int i0, int ni,
                          int j0, int nj, int k0, int nk, double dt_val, const double *dt_ptr,
-                         cudaStream_t s) {
+                         cudaStream_t s, int nb) {
   PpmIdx fx;
   fx.ni = make_fastdiv(ni); fx.nj = make_fastdiv(nj);
   if constexpr (DIR == 0) {
     fx.nsegs = (ni + 30)/31; fx.nseg = make_fastdiv(fx.nsegs);
     fx.gp = fx.nst = fx.np = 0;
-    k_flux_ppm_x1<SOLVER,MHD,NU><<<fx.nsegs*nj*nk, 32, 0, s>>>(b, g, p, i0, ni, j0, nj, k0, nk,
+    k_flux_ppm_x1<SOLVER,MHD,NU><<<dim3((unsigned)(fx.nsegs*nj*nk), (unsigned)nb), 32, 0, s>>>(b, g, p, i0, ni, j0, nj, k0, nk,
                                                               dt_val, dt_ptr, fx);
   } else {
     const int na = (DIR == 1) ? nk : nj;           // rows of the transverse plane
@@ -459,7 +466,7 @@ static void flux_dir_ppm(const BlkDev &b, const ReconGeom &g, const Params &p, i
     const int ngrp = (ntile + fx.gp - 1)/fx.gp;
     fx.nst = (nc + AB_PPM_ROWS - 1)/AB_PPM_ROWS;
     fx.nsegs = 0; fx.nseg = make_fastdiv(1);
-    k_flux_ppm_t<DIR,SOLVER,MHD,NU><<<ngrp*fx.gp*fx.nst, dim3(32, AB_PPM_ROWS + 1), 0, s>>>(
+    k_flux_ppm_t<DIR,SOLVER,MHD,NU><<<dim3((unsigned)(ngrp*fx.gp*fx.nst), (unsigned)nb), dim3(32, AB_PPM_ROWS + 1), 0, s>>>(
         b, g, p, i0, ni, (DIR == 1) ? k0 : j0, (DIR == 1) ? j0 : k0, nc, dt_val, dt_ptr, fx);
   }
   ++g_launches;
@@ -467,7 +474,7 @@ static void flux_dir_ppm(const BlkDev &b, const ReconGeom &g, const Params &p, i
 
 template <int DIR, int ORDER, int SOLVER, bool MHD, bool NU>
 static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, double dt_val,
-                     const double *dt_ptr, cudaStream_t s) {
+                     const double *dt_ptr, cudaStream_t s, int nb) {
   int is = b.is, ie = b.ie, js = b.js, je = b.je, ks = b.ks, ke = b.ke;
   int i0, i1, j0, j1, k0, k1;
   // loop limits of calculate_fluxes.cpp:62-74,164-173,273-279
@@ -483,7 +490,7 @@ static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, doubl
   }
   int ni = i1-i0+1, nj = j1-j0+1, nk = k1-k0+1;
   if constexpr (ORDER == 3 && AB_PPM_SHARED) {
-    flux_dir_ppm<DIR,SOLVER,MHD,NU>(b, g, p, i0, ni, j0, nj, k0, nk, dt_val, dt_ptr, s);
+    flux_dir_ppm<DIR,SOLVER,MHD,NU>(b, g, p, i0, ni, j0, nj, k0, nk, dt_val, dt_ptr, s, nb);
   } else {
     int ntot = ni*nj*nk;
     FluxIdx fx;
@@ -491,61 +498,62 @@ static void flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, doubl
     fx.per_full = make_fastdiv(ni*AB_X3_STRIP*nk); fx.per_k = make_fastdiv(ni*AB_X3_STRIP);
     fx.last_strip = (AB_X3_STRIP > 0 && nj % (AB_X3_STRIP > 0 ? AB_X3_STRIP : 1)) ? nj/(AB_X3_STRIP > 0 ? AB_X3_STRIP : 1) : -1;
     fx.per_k_last = make_fastdiv(ni*(AB_X3_STRIP > 0 ? nj % AB_X3_STRIP : 1));
-    k_flux<DIR,ORDER,SOLVER,MHD,NU><<<(ntot + AB_FLUX_BX - 1)/AB_FLUX_BX, AB_FLUX_BX, 0, s>>>(
+    k_flux<DIR,ORDER,SOLVER,MHD,NU><<<dim3((unsigned)((ntot + AB_FLUX_BX - 1)/AB_FLUX_BX), (unsigned)nb), AB_FLUX_BX, 0, s>>>(
         b, g, p, i0, ni, j0, nj, k0, nk, ntot, dt_val, dt_ptr, fx); ++g_launches;
   }
 }
 
 template <int ORDER, int SOLVER, bool MHD, bool NU>
 static void flux_all(const BlkDev &b, const ReconGeom &g, const Params &p, int dir,
-                     double dt_val, const double *dt_ptr, cudaStream_t s) {
-  if (dir == 0) flux_dir<0,ORDER,SOLVER,MHD,NU>(b, g, p, dt_val, dt_ptr, s);
-  else if (dir == 1) flux_dir<1,ORDER,SOLVER,MHD,NU>(b, g, p, dt_val, dt_ptr, s);
-  else flux_dir<2,ORDER,SOLVER,MHD,NU>(b, g, p, dt_val, dt_ptr, s);
+                     double dt_val, const double *dt_ptr, cudaStream_t s, int nb) {
+  if (dir == 0) flux_dir<0,ORDER,SOLVER,MHD,NU>(b, g, p, dt_val, dt_ptr, s, nb);
+  else if (dir == 1) flux_dir<1,ORDER,SOLVER,MHD,NU>(b, g, p, dt_val, dt_ptr, s, nb);
+  else flux_dir<2,ORDER,SOLVER,MHD,NU>(b, g, p, dt_val, dt_ptr, s, nb);
 }
 
 template <int SOLVER, bool MHD, bool NU>
 static void flux_order(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
-                       double dt_val, const double *dt_ptr, cudaStream_t s) {
+                       double dt_val, const double *dt_ptr, cudaStream_t s, int nb = 1) {
   // order 4 / 5 = xorder 2c / 3c (characteristic variables; adiabatic EOS only)
   constexpr bool ISO = solver_is_iso<SOLVER>;
   if (order > 1 && p.char_proj && !ISO) order += 2;
   if (order == 1) {   // donor cell has no geometry: uniform instantiation only
-    if constexpr (!NU) flux_all<1,SOLVER,MHD,false>(b, g, p, dir, dt_val, dt_ptr, s);
-  } else if (order == 2) flux_all<2,SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s);
-  else if (order == 3) flux_all<3,SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s);
-  else if (order == 4) flux_all<(ISO ? 2 : 4),SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s);
-  else flux_all<(ISO ? 3 : 5),SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s);
+    if constexpr (!NU) flux_all<1,SOLVER,MHD,false>(b, g, p, dir, dt_val, dt_ptr, s, nb);
+  } else if (order == 2) flux_all<2,SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s, nb);
+  else if (order == 3) flux_all<3,SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s, nb);
+  else if (order == 4) flux_all<(ISO ? 2 : 4),SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s, nb);
+  else flux_all<(ISO ? 3 : 5),SOLVER,MHD,NU>(b, g, p, dir, dt_val, dt_ptr, s, nb);
 }
 
 template <bool NU>
 static void launch_flux_dir_t(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
-                              int dir, double dt_val, const double *dt_ptr, cudaStream_t s) {
+                              int dir, double dt_val, const double *dt_ptr, cudaStream_t s,
+                              int nb) {
   if (p.solver == SOLVER_LLF) {   // --flux=llf, either EOS
     if (p.eos != 0) {
-      if (p.mhd) flux_order<SOLVER_LLF_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-      else flux_order<SOLVER_LLF_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+      if (p.mhd) flux_order<SOLVER_LLF_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+      else flux_order<SOLVER_LLF_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
     } else {
-      if (p.mhd) flux_order<SOLVER_LLF,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-      else flux_order<SOLVER_LLF,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+      if (p.mhd) flux_order<SOLVER_LLF,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+      else flux_order<SOLVER_LLF,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
     }
   } else if (p.eos != 0) {   // isothermal: hlle / roe (hydro), hlle / hlld / roe (MHD) -- configure.py:299-325
     if (p.solver == SOLVER_ROE) {
-      if (p.mhd) flux_order<SOLVER_ROE_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-      else flux_order<SOLVER_ROE_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-    } else if (!p.mhd) flux_order<SOLVER_HLLE_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-    else if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-    else flux_order<SOLVER_HLLE_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+      if (p.mhd) flux_order<SOLVER_ROE_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+      else flux_order<SOLVER_ROE_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+    } else if (!p.mhd) flux_order<SOLVER_HLLE_ISO,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+    else if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+    else flux_order<SOLVER_HLLE_ISO,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
   } else if (p.mhd) {
-    if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-    else if (p.solver == SOLVER_LHLLD) flux_order<SOLVER_LHLLD,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-    else flux_order<SOLVER_ROE,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    if (p.solver == SOLVER_HLLD) flux_order<SOLVER_HLLD,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+    else if (p.solver == SOLVER_LHLLD) flux_order<SOLVER_LHLLD,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+    else flux_order<SOLVER_ROE,true,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
   } else {
-    if (p.solver == SOLVER_HLLC) flux_order<SOLVER_HLLC,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-    else if (p.solver == SOLVER_LHLLC) flux_order<SOLVER_LHLLC,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
-    else flux_order<SOLVER_ROE,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s);
+    if (p.solver == SOLVER_HLLC) flux_order<SOLVER_HLLC,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+    else if (p.solver == SOLVER_LHLLC) flux_order<SOLVER_LHLLC,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+    else if (p.solver == SOLVER_HLLE) flux_order<SOLVER_HLLE,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+    else flux_order<SOLVER_ROE,false,NU>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
   }
 }
 

@@ -9,8 +9,8 @@
 namespace ab {
 
 void launch_flux_dir_nu(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
-                        double dt_val, const double *dt_ptr, cudaStream_t s) {
-  launch_flux_dir_t<true>(b, g, p, order, dir, dt_val, dt_ptr, s);
+                        double dt_val, const double *dt_ptr, cudaStream_t s, int nb) {
+  launch_flux_dir_t<true>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
 }
 
 }  // namespace ab

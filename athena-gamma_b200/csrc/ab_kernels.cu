@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include "ab_kernels.h"
 #include "ab_physics.cuh"
+#include "ab_batch.cuh"
 
 namespace ab {
 
@@ -74,9 +75,10 @@ __device__ __forceinline__ void block_min_to_slots(double m, unsigned long long 
 #define AB_CC_MINB 8       // k_integrate_cc
 #endif
 template <bool MHD, int FLAGS>
-__global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2prim(BlkDev b, Params p, int il, int jl,
+__global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2prim(BlkDev b0, Params p, int il, int jl,
                                                   int kl, int ni, int nj, int ntot,
                                                   unsigned long long *dtmin) {
+  const BlkDev b = blk_view(b0, blockIdx.y);      // blockIdx.y = local MeshBlock (ab_batch.cuh)
   // the cell range is flattened: rows of nx1+2*NGHOST cells do not pad to the CTA width (a
   // 132-cell row used to occupy two 128-thread CTAs)
   const int t = blockIdx.x*BX + threadIdx.x;
@@ -174,13 +176,13 @@ __global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2pr
       if (b.f3) m = dmin(m, dt3);
     }
   }
-  if (FLAGS & 2) block_min_to_slots(m, dtmin);
+  if (FLAGS & 2) block_min_to_slots(m, dtmin + blockIdx.y*DT_SLOTS);
 }
 
 void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
-                      int ku, cudaStream_t s, int flags, unsigned long long *dtmin) {
+                      int ku, cudaStream_t s, int flags, unsigned long long *dtmin, int nb) {
   const int ni = iu-il+1, nj = ju-jl+1, ntot = ni*nj*(ku-kl+1);
-  const int g = (ntot + BX - 1)/BX;
+  const dim3 g((unsigned)((ntot + BX - 1)/BX), (unsigned)nb);
   if (!p.mhd) flags &= ~1;
   if (p.mhd) {
     switch (flags & 3) {
@@ -254,9 +256,9 @@ namespace ab {
 
 // uniform spacing: instantiated here; nonuniform (mesh/x?rat != 1) in ab_flux_nu.cu
 void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
-                     double dt_val, const double *dt_ptr, cudaStream_t s) {
-  if (g.nu[dir] && order > 1) launch_flux_dir_nu(b, g, p, order, dir, dt_val, dt_ptr, s);
-  else launch_flux_dir_t<false>(b, g, p, order, dir, dt_val, dt_ptr, s);
+                     double dt_val, const double *dt_ptr, cudaStream_t s, int nb) {
+  if (g.nu[dir] && order > 1) launch_flux_dir_nu(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
+  else launch_flux_dir_t<false>(b, g, p, order, dir, dt_val, dt_ptr, s, nb);
 }
 
 void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
@@ -276,8 +278,10 @@ void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int ord
 // reference also sweeps one more transverse row whose result is never used).  HBM-bound:
 // r (2S+2 values, stencil from L1/L2), mass flux in, s_flux out.
 template <int DIR, int ORDER>
-__global__ void __launch_bounds__(BX) k_scalar_flux(BlkDev b, ReconGeom g, double sfloor,
+__global__ void __launch_bounds__(BX) k_scalar_flux(BlkDev b0, ReconGeom g0, double sfloor,
                                                     int ni, int nj, int ntot) {
+  const BlkDev b = blk_view(b0, blockIdx.y);
+  const ReconGeom g = geom_view(g0, b0, blockIdx.y);
   const int n1 = b.nc1, n2 = b.nc2;
   const int sv = b.nc3*n2*n1;
   const int st = (DIR == 0) ? 1 : ((DIR == 1) ? n1 : n1*n2);
@@ -331,14 +335,14 @@ __global__ void __launch_bounds__(BX) k_scalar_flux(BlkDev b, ReconGeom g, doubl
 }
 
 void launch_scalar_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
-                          cudaStream_t s) {
+                          cudaStream_t s, int nb) {
   if (b.ns <= 0) return;
   const int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
   for (int dir = 0; dir < 3; ++dir) {
     if ((dir == 1 && !b.f2) || (dir == 2 && !b.f3)) continue;
     const int ni = nx1 + (dir == 0), nj = nx2 + (dir == 1), nk = nx3 + (dir == 2);
     const int ntot = ni*nj*nk;
-    const int grid = (ntot + BX - 1)/BX;
+    const dim3 grid((unsigned)((ntot + BX - 1)/BX), (unsigned)nb);
 #define AB_SF(D, O) k_scalar_flux<D,O><<<grid, BX, 0, s>>>(b, g, p.sfloor, ni, nj, ntot)
     if (dir == 0) { if (order == 1) AB_SF(0,1); else if (order == 2) AB_SF(0,2); else AB_SF(0,3); }
     else if (dir == 1) { if (order == 1) AB_SF(1,1); else if (order == 2) AB_SF(1,2); else AB_SF(1,3); }
@@ -352,8 +356,9 @@ void launch_scalar_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, 
 // sfloor*rho (rho = the already floored u(IDN)), r = s/rho; and PassiveScalarPrimitiveToConserved
 // (eos_scalars.cpp:133-152) when TO_CONS.
 template <bool TO_CONS>
-__global__ void __launch_bounds__(BX) k_scalar_eos(BlkDev b, double sfloor, int il, int jl, int kl,
+__global__ void __launch_bounds__(BX) k_scalar_eos(BlkDev b0, double sfloor, int il, int jl, int kl,
                                                    int ni, int nj, int ntot) {
+  const BlkDev b = blk_view(b0, blockIdx.y);
   const int n1 = b.nc1, n2 = b.nc2;
   const int sv = b.nc3*n2*n1;
   for (int t = blockIdx.x*BX + threadIdx.x; t < ntot; t += gridDim.x*BX) {
@@ -377,12 +382,12 @@ __global__ void __launch_bounds__(BX) k_scalar_eos(BlkDev b, double sfloor, int 
 }
 
 void launch_scalar_eos(const BlkDev &b, const Params &p, int to_cons, int il, int iu, int jl,
-                       int ju, int kl, int ku, cudaStream_t s) {
+                       int ju, int kl, int ku, cudaStream_t s, int nb) {
   if (b.ns <= 0) return;
   const int ni = iu-il+1, nj = ju-jl+1, nk = ku-kl+1;
   const int ntot = ni*nj*nk;
   if (ntot <= 0) return;
-  const int grid = (ntot + BX - 1)/BX;
+  const dim3 grid((unsigned)((ntot + BX - 1)/BX), (unsigned)nb);
   if (to_cons) k_scalar_eos<true><<<grid, BX, 0, s>>>(b, p.sfloor, il, jl, kl, ni, nj, ntot);
   else k_scalar_eos<false><<<grid, BX, 0, s>>>(b, p.sfloor, il, jl, kl, ni, nj, ntot);
   ++g_launches;
@@ -414,7 +419,8 @@ __device__ __forceinline__ double de_term(double wt, double ef_a, double cc_a, d
   return (1.0-wt)*(ef_a - cc_a) + (wt)*(ef_b - cc_b);
 }
 
-__global__ void __launch_bounds__(BX, AB_CE_MINB) k_corner_e3d(BlkDev b, int ni, int nj, int ntot) {
+__global__ void __launch_bounds__(BX, AB_CE_MINB) k_corner_e3d(BlkDev b0, int ni, int nj, int ntot) {
+  const BlkDev b = blk_view(b0, blockIdx.y);
   int t = blockIdx.x*BX + threadIdx.x;
   if (t >= ntot) return;
   int r = t / ni;
@@ -474,7 +480,8 @@ __global__ void __launch_bounds__(BX, AB_CE_MINB) k_corner_e3d(BlkDev b, int ni,
 }
 
 // 2-D (calculate_corner_e.cpp:50-128): grid.y covers j in [js, je+1]; k = ks
-__global__ void __launch_bounds__(BX) k_corner_e2d(BlkDev b) {
+__global__ void __launch_bounds__(BX) k_corner_e2d(BlkDev b0) {
+  const BlkDev b = blk_view(b0, blockIdx.z);      // grid.y counts rows here: blocks along z
   int i = b.is + blockIdx.x*BX + threadIdx.x;
   if (i > b.ie+1) return;
   int j = b.js + blockIdx.y, k = b.ks;
@@ -507,7 +514,8 @@ __global__ void __launch_bounds__(BX) k_corner_e2d(BlkDev b) {
 }
 
 // 1-D (calculate_corner_e.cpp:38-48)
-__global__ void __launch_bounds__(BX) k_corner_e1d(BlkDev b) {
+__global__ void __launch_bounds__(BX) k_corner_e1d(BlkDev b0) {
+  const BlkDev b = blk_view(b0, blockIdx.z);
   int i = b.is + blockIdx.x*BX + threadIdx.x;
   if (i > b.ie+1) return;
   int ks = b.ks, js = b.js;
@@ -518,17 +526,18 @@ __global__ void __launch_bounds__(BX) k_corner_e1d(BlkDev b) {
   b.e[2][E3I(b,ks,b.je+1,i)] = v3;
 }
 
-void launch_corner_e(const BlkDev &b, cudaStream_t s, int have_cc_e) {
+// nb > 1 (one launch over nb MeshBlocks) requires have_cc_e: k_cc_e has no free grid dimension
+void launch_corner_e(const BlkDev &b, cudaStream_t s, int have_cc_e, int nb) {
   int nx1 = b.ie - b.is + 1, nx2 = b.je - b.js + 1, nx3 = b.ke - b.ks + 1;
   if (!b.f2) {
-    k_corner_e1d<<<grid3(nx1+1, 1, 1), BX, 0, s>>>(b); ++g_launches;
+    k_corner_e1d<<<grid3(nx1+1, 1, nb), BX, 0, s>>>(b); ++g_launches;
   } else if (!b.f3) {
     if (!have_cc_e) { k_cc_e<<<grid3(nx1+2, nx2+2, 1), BX, 0, s>>>(b, b.is-1, b.ie+1, b.js-1, b.ks); ++g_launches; }
-    k_corner_e2d<<<grid3(nx1+1, nx2+1, 1), BX, 0, s>>>(b); ++g_launches;
+    k_corner_e2d<<<grid3(nx1+1, nx2+1, nb), BX, 0, s>>>(b); ++g_launches;
   } else {
     if (!have_cc_e) { k_cc_e<<<grid3(nx1+2, nx2+2, nx3+2), BX, 0, s>>>(b, b.is-1, b.ie+1, b.js-1, b.ks-1); ++g_launches; }
     const int ntot = (nx1+1)*(nx2+1)*(nx3+1);
-    k_corner_e3d<<<(ntot + BX - 1)/BX, BX, 0, s>>>(b, nx1+1, nx2+1, ntot); ++g_launches;
+    k_corner_e3d<<<dim3((unsigned)((ntot + BX - 1)/BX), (unsigned)nb), BX, 0, s>>>(b, nx1+1, nx2+1, ntot); ++g_launches;
   }
 }
 
@@ -605,7 +614,10 @@ __device__ __forceinline__ SlabIdx edge_index(const BlkDev &b, int eid, long t) 
 }
 
 // grid.y = 0..5 faces, 6..17 edges
-__global__ void __launch_bounds__(256) k_emf_pack(BlkDev b, EmfPlan pl) {
+// grid.z = local MeshBlocks: plans != nullptr is the device array of their plans
+__global__ void __launch_bounds__(256) k_emf_pack(BlkDev b0, EmfPlan pl0, const EmfPlan *plans) {
+  const BlkDev b = blk_view(b0, blockIdx.z);
+  const EmfPlan &pl = plans ? plans[blockIdx.z] : pl0;
   int id = blockIdx.y;
   long t = (long)blockIdx.x*256 + threadIdx.x;
   if (id < 6) {
@@ -629,13 +641,14 @@ __global__ void __launch_bounds__(256) k_emf_pack(BlkDev b, EmfPlan pl) {
   }
 }
 
-void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s) {
+void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s, const EmfPlan *plans_dev,
+                     int nb) {
   int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
   long m = 2L*(nx1+1)*(nx2+1);
   if (2L*(nx1+1)*(nx3+1) > m) m = 2L*(nx1+1)*(nx3+1);
   if (2L*(nx2+1)*(nx3+1) > m) m = 2L*(nx2+1)*(nx3+1);
   int nid = b.f3 ? 18 : (b.f2 ? 10 : 2);
-  k_emf_pack<<<dim3((unsigned)((m + 255)/256), nid), 256, 0, s>>>(b, pl); ++g_launches;
+  k_emf_pack<<<dim3((unsigned)((m + 255)/256), nid, plans_dev ? nb : 1), 256, 0, s>>>(b, pl, plans_dev); ++g_launches;
 }
 
 // offset of element (k,j,i) of component comp inside the buffer packed by the neighbour
@@ -699,7 +712,9 @@ __device__ __forceinline__ double emf_corrected(const BlkDev &b, const EmfPlan &
 // One thread per boundary element; slabs enumerated without duplicates:
 // for each component, the two faces of its first bounding direction take their full extent,
 // the faces of its second bounding direction exclude the lines already covered.
-__global__ void __launch_bounds__(256) k_emf_apply(BlkDev b, EmfPlan pl) {
+__global__ void __launch_bounds__(256) k_emf_apply(BlkDev b0, EmfPlan pl0, const EmfPlan *plans) {
+  const BlkDev b = blk_view(b0, blockIdx.z);
+  const EmfPlan &pl = plans ? plans[blockIdx.z] : pl0;
   int slab = blockIdx.y;            // comp*4 + {0,1: first dir lo/hi ; 2,3: second dir lo/hi}
   int comp = slab >> 2, which = slab & 3;
   long t = (long)blockIdx.x*256 + threadIdx.x;
@@ -743,12 +758,13 @@ __global__ void __launch_bounds__(256) k_emf_apply(BlkDev b, EmfPlan pl) {
   b.e[comp][e_index(b, comp, k, j, i)] = v;
 }
 
-void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s) {
+void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s, const EmfPlan *plans_dev,
+                      int nb) {
   int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
   long m = (long)(nx1+1)*(nx2+1);
   if ((long)(nx1+1)*(nx3+1) > m) m = (long)(nx1+1)*(nx3+1);
   if ((long)(nx2+1)*(nx3+1) > m) m = (long)(nx2+1)*(nx3+1);
-  k_emf_apply<<<dim3((unsigned)((m + 255)/256), 12), 256, 0, s>>>(b, pl); ++g_launches;
+  k_emf_apply<<<dim3((unsigned)((m + 255)/256), 12, plans_dev ? nb : 1), 256, 0, s>>>(b, pl, plans_dev); ++g_launches;
 }
 
 // =============================================================================================
@@ -818,11 +834,19 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 struct CcSet { double *u, *u1; const double *f[3]; int nvar; double g[3]; };
 
 template <int NVAR, bool SRC>
-__global__ void __launch_bounds__(BX, AB_CC_MINB) k_integrate_cc(BlkDev b, CcSet c, int mode, int zero_init,
+__global__ void __launch_bounds__(BX, AB_CC_MINB) k_integrate_cc(BlkDev b0, CcSet c0, int mode, int zero_init,
                                                      double delta, double g1, double g2,
                                                      double beta, double dt_val,
                                                      const double *dt_ptr, int k0, int ni,
                                                      int nj, int ntot) {
+  const BlkDev b = blk_view(b0, blockIdx.y);
+  CcSet c = c0;
+  {
+    const long off = (long)blockIdx.y*b0.bstride;
+    c.u = blk_mv(c.u, off); c.u1 = blk_mv(c.u1, off);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) c.f[d] = blk_mv(c.f[d], off);
+  }
   const double wght = beta*(dt_ptr ? *dt_ptr : dt_val);
   const int n1 = b.nc1, n2 = b.nc2;
   const int sv = b.nc3*n2*n1;
@@ -881,11 +905,11 @@ __global__ void __launch_bounds__(BX, AB_CC_MINB) k_integrate_cc(BlkDev b, CcSet
 void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
                          cudaStream_t s, int kl, int ku, int grid, int scalars,
-                         const double *gacc) {
+                         const double *gacc, int nb) {
   if (kl < 0) { kl = b.ks; ku = b.ke; }
   const int ni = b.ie-b.is+1, nj = b.je-b.js+1, nk = ku-kl+1;
   const int ntot = ni*nj*nk;
-  const int g = (ntot + BX - 1)/BX;
+  const dim3 g((unsigned)((ntot + BX - 1)/BX), (unsigned)nb);
   (void)grid;
   CcSet c;
   if (scalars) {
@@ -967,10 +991,11 @@ __device__ __forceinline__ double fc_avg(double *__restrict__ bo, double *__rest
 // [j<=je,k<=ke], x2f(k,j,i) [i<=ie,k<=ke] and x3f(k,j,i) [i<=ie,j<=je]; the nine edge EMFs it
 // needs are loaded once (e?(k,j,i) is shared by two of the three updates).
 template <int MODE>
-__global__ void __launch_bounds__(BX, AB_FC_MINB) k_integrate_fc(BlkDev b, int ni, int nj, int ntot,
+__global__ void __launch_bounds__(BX, AB_FC_MINB) k_integrate_fc(BlkDev b0, int ni, int nj, int ntot,
                                                      int zero_init, double delta, double g1,
                                                      double g2, double beta, double dt_val,
                                                      const double *dt_ptr) {
+  const BlkDev b = blk_view(b0, blockIdx.y);
   int t = blockIdx.x*BX + threadIdx.x;
   if (t >= ntot) return;
   int r = t / ni;
@@ -1032,10 +1057,10 @@ __global__ void __launch_bounds__(BX, AB_FC_MINB) k_integrate_fc(BlkDev b, int n
 
 void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
-                         cudaStream_t s) {
+                         cudaStream_t s, int nb) {
   const int ni = b.ie-b.is+2, nj = b.je-b.js+2, nk = b.ke-b.ks+2;
   const int ntot = ni*nj*nk;
-  const int g = (ntot + BX - 1)/BX;
+  const dim3 g((unsigned)((ntot + BX - 1)/BX), (unsigned)nb);
   if (mode == 0) k_integrate_fc<0><<<g, BX, 0, s>>>(b, ni, nj, ntot, zero_init, delta, g1, g2, beta, dt_val, dt_ptr);
   else if (mode == 1) k_integrate_fc<1><<<g, BX, 0, s>>>(b, ni, nj, ntot, zero_init, delta, g1, g2, beta, dt_val, dt_ptr);
   else k_integrate_fc<2><<<g, BX, 0, s>>>(b, ni, nj, ntot, zero_init, delta, g1, g2, beta, dt_val, dt_ptr);

@@ -15,10 +15,13 @@ namespace ab {
 // (field/field.cpp:139-172)
 struct ReconGeom { const double *wp[3]; const double *wm[3]; const double *nu[3]; };
 
+// nb (last argument of the per-block task launchers): one launch over nb MeshBlocks of a rank,
+// `b` / `g` being the views of the first of them (ab_batch.cuh); 1 = that block alone.
 // `dt_ptr` (device) wins over `dt_val` when non-null: the cycle loop keeps dt on the device.
 // flags bit0: also write cc_e; bit1: also reduce NewBlockTimeStep over active cells into dtmin
 void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
-                      int ku, cudaStream_t s, int flags = 0, unsigned long long *dtmin = nullptr);
+                      int ku, cudaStream_t s, int flags = 0, unsigned long long *dtmin = nullptr,
+                      int nb = 1);
 void launch_prim2cons(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
                       int ku, cudaStream_t s);
 void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, int ku,
@@ -26,13 +29,16 @@ void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, in
 void launch_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
                    double dt_val, const double *dt_ptr, cudaStream_t s);
 void launch_flux_dir_nu(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
-                        double dt_val, const double *dt_ptr, cudaStream_t s);
+                        double dt_val, const double *dt_ptr, cudaStream_t s, int nb = 1);
 void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int order, int dir,
-                     double dt_val, const double *dt_ptr, cudaStream_t s);
+                     double dt_val, const double *dt_ptr, cudaStream_t s, int nb = 1);
 // have_cc_e: cc_e was already written by cons2prim (flags bit0) over [is-1,ie+1]^dim
-void launch_corner_e(const BlkDev &b, cudaStream_t s, int have_cc_e = 0);
-void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);
-void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s);
+void launch_corner_e(const BlkDev &b, cudaStream_t s, int have_cc_e = 0, int nb = 1);
+// plans_dev != nullptr: device array of the plans of nb blocks (then `pl` is ignored)
+void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s,
+                     const EmfPlan *plans_dev = nullptr, int nb = 1);
+void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s,
+                      const EmfPlan *plans_dev = nullptr, int nb = 1);
 
 // WeightedAve special-casing of the reference (mesh/weighted_ave.cpp) for out = w0*out + w1*in
 void launch_weighted_ave_cc(const BlkDev &b, double *out, const double *in, double w0,
@@ -51,17 +57,17 @@ void launch_weighted_ave_fc(const BlkDev &b, double *const out[3], double *const
 void launch_integrate_cc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
                          cudaStream_t s, int kl = -1, int ku = -1, int grid = 0,
-                         int scalars = 0, const double *gacc = nullptr);
+                         int scalars = 0, const double *gacc = nullptr, int nb = 1);
 // passive scalars: s_flux from r and the hydro mass flux; r <-> s conversions on a cell range
 void launch_scalar_fluxes(const BlkDev &b, const ReconGeom &g, const Params &p, int order,
-                          cudaStream_t s);
+                          cudaStream_t s, int nb = 1);
 void launch_scalar_eos(const BlkDev &b, const Params &p, int to_cons, int il, int iu, int jl,
-                       int ju, int kl, int ku, cudaStream_t s);
+                       int ju, int kl, int ku, cudaStream_t s, int nb = 1);
 void launch_const_accel(const BlkDev &b, const double *g, double dt, cudaStream_t s);
 // Same for the face field + Field::CT (field/ct.cpp:31-116)
 void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta, double g1,
                          double g2, double beta, double dt_val, const double *dt_ptr,
-                         cudaStream_t s);
+                         cudaStream_t s, int nb = 1);
 
 // ghost exchange: apply `n` box copies (descriptors in device memory, CopyBox::offset = exclusive
 // prefix of the element counts, total_elems = their sum)

@@ -144,7 +144,7 @@ struct LocalBlock {
   ab::BlkDev d;
   ab::ReconGeom g;
   ab::EmfPlan emf;
-  double *base = nullptr;                 // one allocation per block
+  char *base = nullptr;                   // this block's slab inside AbMesh::slab
   size_t nbytes = 0;
   long regsize[AB_NREG];
   double *coord_dev[9];
@@ -198,6 +198,12 @@ struct AbMesh {
   double bc_time = 0.0, bc_dt = 0.0;      // (time, dt) of the PhysicalBoundary task
   std::vector<double> stage_w, stage_b[3];
   cudaStream_t stream = nullptr;
+  // all local blocks' slabs in one allocation, bstride bytes apart (0: separate allocations,
+  // AB_DEBUG_ALLOC); the EMF-correction plans of all local blocks for the batched launches
+  char *slab = nullptr;
+  long bstride = 0;
+  ab::EmfPlan *emf_plans_dev = nullptr;
+  bool batch = false;                     // inside a cycle that runs every task as one launch
   // overlapped schedule (AB_OVERLAP=1): NCCL transfers on comm_stream while the compute stream
   // works on data that does not depend on them.  Opt-in: at 2 GPUs x 512^3 it measured 1.2 %
   // SLOWER than the in-order schedule (73.10 vs 72.21 ms per cycle, profiles/r1_tuning_log.md):
@@ -815,9 +821,17 @@ int alloc_blocks(AbMesh *m) {
     const bool split_alloc = dbg && dbg[0] == '1';
     char *cur = nullptr;
     if (!split_alloc) {
-      CK(cudaMalloc(&L.base, tot));
+      // one allocation for all local blocks, slabs bstride bytes apart with identical layouts:
+      // a task can then run over every block in ONE launch (ab_batch.cuh)
+      if (l == 0) {
+        m->bstride = (long)align256(tot);
+        CK(cudaMalloc(&m->slab, (size_t)m->bstride*m->lb.size()));
+      }
+      if ((long)align256(tot) != m->bstride) return fail(AB_ERR_STATE, "MeshBlock slabs differ in size");
+      L.base = m->slab + (size_t)l*m->bstride;
       CK(cudaMemsetAsync(L.base, 0, tot, m->stream));   // AthenaArray storage is zero-initialised
       cur = (char *)L.base;
+      d.bstride = m->bstride;
     }
     auto carve = [&](size_t bytes) -> char * {
       if (!split_alloc) { char *q = cur; cur += align256(bytes); return q; }
@@ -1075,6 +1089,15 @@ int build_emf_plan(AbMesh *m) {
       }
     }
   }
+  // the plans of all local blocks in device memory, for the one-launch-over-all-blocks path
+  {
+    std::vector<ab::EmfPlan> all;
+    for (auto &L : m->lb) all.push_back(L.emf);
+    if (!m->emf_plans_dev) CK(cudaMalloc(&m->emf_plans_dev, all.size()*sizeof(ab::EmfPlan)));
+    CK(cudaMemcpyAsync(m->emf_plans_dev, all.data(), all.size()*sizeof(ab::EmfPlan),
+                       cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+  }
   m->emf_built = true;
   return AB_OK;
 }
@@ -1146,13 +1169,23 @@ int bvals_exchange_end(AbMesh *m) {
   return AB_OK;
 }
 
+// EMF pack / apply of every local block: one launch over all blocks inside a batched cycle
+void emf_pack_all(AbMesh *m) {
+  if (m->batch) ab::launch_emf_pack(m->lb[0].d, m->lb[0].emf, m->stream, m->emf_plans_dev, (int)m->lb.size());
+  else for (auto &L : m->lb) ab::launch_emf_pack(L.d, L.emf, m->stream);
+}
+void emf_apply_all(AbMesh *m) {
+  if (m->batch) ab::launch_emf_apply(m->lb[0].d, m->lb[0].emf, m->stream, m->emf_plans_dev, (int)m->lb.size());
+  else for (auto &L : m->lb) ab::launch_emf_apply(L.d, L.emf, m->stream);
+}
+
 int emf_exchange(AbMesh *m) {
   if (!m->p.mhd) return AB_OK;
   if (!m->emf_built) { int rc = build_emf_plan(m); if (rc) return rc; }
-  for (auto &L : m->lb) ab::launch_emf_pack(L.d, L.emf, m->stream);
+  emf_pack_all(m);
   int rc = peer_exchange(m, m->peer_emf);
   if (rc) return rc;
-  for (auto &L : m->lb) ab::launch_emf_apply(L.d, L.emf, m->stream);
+  emf_apply_all(m);
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -1160,7 +1193,7 @@ int emf_exchange(AbMesh *m) {
 int emf_exchange_begin(AbMesh *m) {
   if (!m->p.mhd) return AB_OK;
   if (!m->emf_built) { int rc = build_emf_plan(m); if (rc) return rc; }
-  for (auto &L : m->lb) ab::launch_emf_pack(L.d, L.emf, m->stream);
+  emf_pack_all(m);
   CK(cudaEventRecord(m->ev_pack, m->stream));
   CK(cudaStreamWaitEvent(m->comm_stream, m->ev_pack, 0));
   int rc = peer_exchange(m, m->peer_emf, m->comm_stream);
@@ -1171,7 +1204,7 @@ int emf_exchange_begin(AbMesh *m) {
 int emf_exchange_end(AbMesh *m) {
   if (!m->p.mhd) return AB_OK;
   CK(cudaStreamWaitEvent(m->stream, m->ev_recv, 0));
-  for (auto &L : m->lb) ab::launch_emf_apply(L.d, L.emf, m->stream);
+  emf_apply_all(m);
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -1331,6 +1364,38 @@ void primitives(AbMesh *m, LocalBlock &L, int with_dt = 0) {
   ab::launch_cons2prim(L.d, m->kp, il, iu, jl, ju, kl, ku, L.stream, flags, L.dtmin);
   ab::launch_scalar_eos(L.d, m->kp, 0, il, iu, jl, ju, kl, ku, L.stream);
   L.cc_e_valid = (flags & 1) != 0;
+}
+
+// Primitives of every local block in one launch when they all convert the same cell range with
+// the same flags (always on a periodic mesh); else block by block.
+void primitives_all(AbMesh *m, int with_dt) {
+  const int ng = m->p.nghost;
+  int r0[6] = {0, 0, 0, 0, 0, 0}, f0 = 0;
+  bool same = true;
+  for (size_t l = 0; l < m->lb.size(); ++l) {
+    LocalBlock &L = m->lb[l];
+    HostBlock &B = *L.hb;
+    int r[6] = {m->is, m->ie, m->js, m->je, m->ks, m->ke};
+    if (B.nblevel[1][1][0] != -1) r[0] -= ng;
+    if (B.nblevel[1][1][2] != -1) r[1] += ng;
+    if (B.nblevel[1][0][1] != -1) r[2] -= ng;
+    if (B.nblevel[1][2][1] != -1) r[3] += ng;
+    if (B.nblevel[0][1][1] != -1) r[4] -= ng;
+    if (B.nblevel[2][1][1] != -1) r[5] += ng;
+    const int flags = (m->p.mhd && !L.has_phys_bc ? 1 : 0) | (with_dt ? 2 : 0);
+    if (l == 0) { for (int q = 0; q < 6; ++q) r0[q] = r[q]; f0 = flags; }
+    else { for (int q = 0; q < 6; ++q) same = same && (r[q] == r0[q]); same = same && (flags == f0); }
+  }
+  if (!same) {
+    for (auto &L : m->lb) primitives(m, L, with_dt);
+    return;
+  }
+  const int nb = (int)m->lb.size();
+  LocalBlock &L0 = m->lb[0];
+  ab::launch_cons2prim(L0.d, m->kp, r0[0], r0[1], r0[2], r0[3], r0[4], r0[5], m->stream, f0,
+                       L0.dtmin, nb);
+  ab::launch_scalar_eos(L0.d, m->kp, 0, r0[0], r0[1], r0[2], r0[3], r0[4], r0[5], m->stream, nb);
+  for (auto &L : m->lb) L.cc_e_valid = (f0 & 1) != 0;
 }
 
 // DispatchBoundaryFunctions for a user-enrolled face (bvals.cpp:617-620): host round trip of
@@ -1605,7 +1670,19 @@ int one_cycle(AbMesh *m) {
   const bool user_src = (m->user_src || m->user_src_dev);
   if (m->has_user_bc || user_src) { int rc0 = read_state(m); if (rc0) return rc0; }   // host needs time, dt
   // per-block streams (see AbMesh::bstream); host-hook modes keep everything on the main stream
-  const bool ms = !m->bstream.empty() && !m->has_user_bc && !user_src && !debug_sync();
+  // One launch per task over all local MeshBlocks (ab_batch.cuh) whenever the blocks are in one
+  // allocation and in the same register-swap state and no host hook has to run between the tasks
+  // of a block; refined meshes keep the block-by-block order of their prolongation hooks.
+  static const bool no_batch = [] { const char *e = getenv("AB_NO_BATCH"); return e && e[0] == '1'; }();
+  const bool bt = !no_batch && m->bstride != 0 && !m->smr && !m->has_user_bc && !user_src &&
+                  !debug_sync() && plan_index(m) >= 0;
+  const int nb = (int)m->lb.size();
+  m->batch = bt;
+  struct Leave {   // also on the error returns: task-level entry points run unbatched on the main stream
+    AbMesh *m;
+    ~Leave() { m->batch = false; for (auto &L : m->lb) L.stream = m->stream; }
+  } leave{m};
+  const bool ms = !bt && !m->bstream.empty() && !m->has_user_bc && !user_src && !debug_sync();
   for (size_t l = 0; l < m->lb.size(); ++l)
     m->lb[l].stream = ms ? m->bstream[l % m->bstream.size()] : m->stream;
   auto fork = [&]() {     // block streams continue after everything queued on the main stream
@@ -1624,7 +1701,29 @@ int one_cycle(AbMesh *m) {
     const int s = stage - 1;
     const int order = (m->p.integrator == AB_INT_VL2 && stage == 1) ? 1 : m->p.xorder;
     fork();
-    for (auto &L : m->lb) {
+    if (bt) {
+      LocalBlock &L0 = m->lb[0];
+      for (int dir = 0; dir < m->ndim; ++dir) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (m->profile) {
+          cudaEventCreate(&e0); cudaEventCreate(&e1);
+          cudaEventRecord(e0, m->stream);
+        }
+        ab::launch_flux_dir(L0.d, L0.g, m->kp, order, dir, 0.0, dtp, m->stream, nb);
+        if (m->profile) {
+          cudaEventRecord(e1, m->stream);
+          m->prof_ev.push_back({e0, e1});
+          m->prof_slot.push_back(dir*3 + (order - 1));
+        }
+      }
+      if (m->p.mhd) {
+        bool all_cce = true;
+        for (auto &L : m->lb) all_cce = all_cce && L.cc_e_valid;
+        if (all_cce) ab::launch_corner_e(L0.d, m->stream, 1, nb);
+        else for (auto &L : m->lb) ab::launch_corner_e(L.d, m->stream, L.cc_e_valid ? 1 : 0);
+      }
+      ab::launch_scalar_fluxes(L0.d, L0.g, m->kp, order, m->stream, nb);   // CALC_SCLRFLX
+    } else for (auto &L : m->lb) {
       for (int dir = 0; dir < m->ndim; ++dir) {
         if (m->profile) {
           cudaEvent_t e0, e1;
@@ -1654,7 +1753,18 @@ int one_cycle(AbMesh *m) {
     const bool swap = (m->g1[s] == 0.0 && m->g2[s] == 1.0 && m->g3[s] == 0.0);
     const int zero_init = (stage == 1);   // StartupTaskList: u1, b1 ZeroClear (:1386-1397)
     fork();
-    for (auto &L : m->lb) {   // INT_HYD (+ SRC_TERM), INT_SCLR (time_integrator.cpp:2141-2185)
+    if (bt) {   // INT_HYD (+ SRC_TERM), INT_SCLR of every block: registers swap in lockstep
+      if (swap) for (auto &L : m->lb) swap_cc(L);
+      ab::launch_integrate_cc(m->lb[0].d, swap ? 1 : 2, zero_init, m->delta[s], swap ? 0 : m->g1[s],
+                              swap ? 0 : m->g2[s], m->beta[s], 0.0, dtp, m->stream, -1, -1, 0, 0,
+                              m->p.grav_acc, nb);
+      if (m->p.nscalars > 0) {
+        if (swap) for (auto &L : m->lb) swap_sc(L);
+        ab::launch_integrate_cc(m->lb[0].d, swap ? 1 : 2, zero_init, m->delta[s], swap ? 0 : m->g1[s],
+                                swap ? 0 : m->g2[s], m->beta[s], 0.0, dtp, m->stream, -1, -1, 0, 1,
+                                nullptr, nb);
+      }
+    } else for (auto &L : m->lb) {   // INT_HYD (+ SRC_TERM), INT_SCLR (time_integrator.cpp:2141-2185)
       if (swap) {
         swap_cc(L);
         ab::launch_integrate_cc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp,
@@ -1680,7 +1790,11 @@ int one_cycle(AbMesh *m) {
       }
     }
     if (m->overlap) { rc = emf_exchange_end(m); if (rc) return rc; }
-    if (m->p.mhd) for (auto &L : m->lb) {   // INT_FLD
+    if (m->p.mhd && bt) {   // INT_FLD of every block
+      if (swap) for (auto &L : m->lb) swap_fc(L);
+      ab::launch_integrate_fc(m->lb[0].d, swap ? 1 : 2, zero_init, m->delta[s], swap ? 0 : m->g1[s],
+                              swap ? 0 : m->g2[s], m->beta[s], 0.0, dtp, m->stream, nb);
+    } else if (m->p.mhd) for (auto &L : m->lb) {   // INT_FLD
       if (swap) {
         swap_fc(L);
         ab::launch_integrate_fc(L.d, 1, zero_init, m->delta[s], 0, 0, m->beta[s], 0.0, dtp, L.stream);
@@ -1701,7 +1815,10 @@ int one_cycle(AbMesh *m) {
       DBG(m, "bvals exchange");
       if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
       fork();
-      for (size_t l = 0; l < m->lb.size(); ++l) {
+      if (bt) {
+        primitives_all(m, last);
+        for (auto &L : m->lb) physical_bcs(m, L);
+      } else for (size_t l = 0; l < m->lb.size(); ++l) {
         LocalBlock &L = m->lb[l];
         if (m->smr) { rc = smr_prolongate(m, (int)l); if (rc) return rc; }   // PROLONG
         primitives(m, L, last);
@@ -1732,6 +1849,7 @@ int one_cycle(AbMesh *m) {
     }
   }
   for (auto &L : m->lb) L.stream = m->stream;   // task-level entry points run on the main stream
+  m->batch = false;
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -2076,7 +2194,9 @@ int ab_mesh_destroy(AbMesh *m) {
   }
   cudaSetDevice(m->p.device);
   cudaStreamSynchronize(m->stream);
-  for (auto &L : m->lb) { cudaFree(L.base); for (void *q : L.debug_allocs) cudaFree(q); }
+  for (auto &L : m->lb) for (void *q : L.debug_allocs) cudaFree(q);
+  cudaFree(m->slab);
+  cudaFree(m->emf_plans_dev);
   for (int i = 0; i < 8; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase1r); cudaFree(m->plan[i].phase2); }
   for (auto &kv : m->bplan) { cudaFree(kv.second.pack); cudaFree(kv.second.phase1); cudaFree(kv.second.phase1r); cudaFree(kv.second.phase2); }
   for (auto &kv : m->peer_state) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }

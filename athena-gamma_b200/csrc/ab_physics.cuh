@@ -35,6 +35,7 @@ AB_HD double dmin(double a, double b) { return (b < a) ? b : a; }
 AB_HD double dmax(double a, double b) { return (a < b) ? b : a; }
 AB_HD double sqr(double x) { return x*x; }
 AB_HD double sgn(double x) { return (x < 0.0) ? -1.0 : 1.0; }
+AB_HD bool same_sgn(double a, double b) { return (a < 0.0) == (b < 0.0); }
 
 // a/b, bit-identical to IEEE division.  The GPU's FP64 division falls into a ~100-instruction
 // slow path when the dividend is zero or tiny; exactly-zero dividends are common on this path
@@ -124,7 +125,7 @@ AB_HD double ppm_face_fix(double dph, double qlo, double qhi, double d2lo, doubl
     double qb = d2lo;
     double qc = d2hi;
     double qd = 0.0;
-    if (sgn(qa) == sgn(qb) && sgn(qa) == sgn(qc)) {
+    if (same_sgn(qa, qb) && same_sgn(qa, qc)) {
       qd = sgn(qa)*dmin(C2*fabs(qb), dmin(C2*fabs(qc), fabs(qa)));
     }
     dph = 0.5*(qlo + qhi) - div6(qd);
@@ -159,7 +160,7 @@ AB_HD void ppm(double q_im2, double q_im1, double q, double q_ip1, double q_ip2,
   double qb_tmp = (q_ip1 - q)*(q - q_im1);
   double qa2 = d2qc_im1, qb2 = d2qc, qc2 = d2qc_ip1, qd = d2qf;
   double qe = 0.0;
-  if (sgn(qa2) == sgn(qb2) && sgn(qa2) == sgn(qc2) && sgn(qa2) == sgn(qd)) {
+  if (same_sgn(qa2, qb2) && same_sgn(qa2, qc2) && same_sgn(qa2, qd)) {
     qe = sgn(qd)*dmin(dmin(C2*fabs(qa2), C2*fabs(qb2)), dmin(C2*fabs(qc2), fabs(qd)));
   }
   qa2 = dmax(fabs(q_im1), fabs(q_im2));

@@ -116,8 +116,8 @@ int main(int argc, char **argv) {
   unsigned long long all = 0;
   for (int order = 1; order <= maxorder; ++order) for (int dir = 0; dir < 3; ++dir) {
     auto run = [&]() {
-      if (hydro) flux_order<SOLVER_HLLC,false,false>(b, g, p, order, dir, dt, nullptr, 0);
-      else flux_order<SOLVER_HLLD,true,false>(b, g, p, order, dir, dt, nullptr, 0);
+      if (hydro) flux_order<SOLVER_HLLC,false,false>(b, g, p, order, dir, dt, nullptr, 0, 1);
+      else flux_order<SOLVER_HLLD,true,false>(b, g, p, order, dir, dt, nullptr, 0, 1);
     };
     for (int r = 0; r < 2; ++r) run();
     CK(cudaDeviceSynchronize());
