@@ -43,6 +43,19 @@ __device__ __forceinline__ BlkDev blk_view(const BlkDev &b0, unsigned n) {
   return b;
 }
 
+// blockIdx.y read where it is called (not hoisted to the top of the kernel): the Riemann-sweep
+// kernels shift their OUTPUT pointers with it right before the stores, so that no shifted
+// pointer stays live in registers across the solver (they run at the register limit)
+__device__ __forceinline__ unsigned late_block_y() {
+#if defined(__CUDA_ARCH__)
+  unsigned y;
+  asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(y));
+  return y;
+#else
+  return blockIdx.y;
+#endif
+}
+
 __device__ __forceinline__ ReconGeom geom_view(const ReconGeom &g0, const BlkDev &b0, unsigned n) {
   ReconGeom g = g0;
   const long off = (long)n*b0.bstride;

@@ -245,16 +245,17 @@ k_flux(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int j0, int nj, int k0
   double f[NW];
   riemann<SOLVER,MHD>(wl, wr, bxi, ISO ? p.iso_cs : p.gamma, dvn, dvt, f, p.dfloor);
 
-  double *__restrict__ flx = b.flux[DIR];
+  const long offo = (long)late_block_y()*b0.bstride;      // b0 = the launch's first block
+  double *__restrict__ flx = blk_mv(b0.flux[DIR], offo);
   flx[of] = f[IDN];
   flx[of + (1 + DIR)*sf] = f[IVX];
   flx[of + (1 + (DIR+1)%3)*sf] = f[IVY];
   flx[of + (1 + (DIR+2)%3)*sf] = f[IVZ];
   if (!ISO) flx[of + 4*sf] = f[IEN];
   if (MHD) {
-    b.ef[DIR][0][of] = -f[IBY];
-    b.ef[DIR][1][of] = f[IBZ];
-    b.wght[DIR][of] = weight_for_ct_pre(f[IDN], dxw, dt);
+    blk_mv(b0.ef[DIR][0], offo)[of] = -f[IBY];
+    blk_mv(b0.ef[DIR][1], offo)[of] = f[IBZ];
+    blk_mv(b0.wght[DIR], offo)[of] = weight_for_ct_pre(f[IDN], dxw, dt);
   }
 }
 
@@ -316,9 +317,9 @@ __device__ __forceinline__ void ppm_cell(const BlkDev &b, const ReconGeom &g, co
 // Riemann solve and stores of the face (k,j,i) of direction DIR from its two states -- the second
 // half of k_flux
 template <int DIR, int SOLVER, bool MHD>
-__device__ __forceinline__ void flux_face(const BlkDev &b, const Params &p, int i, int j, int k,
-                                          double *wl, double *wr, double dt_val,
-                                          const double *dt_ptr) {
+__device__ __forceinline__ void flux_face(const BlkDev &b, const BlkDev &b0, const Params &p,
+                                          int i, int j, int k, double *wl, double *wr,
+                                          double dt_val, const double *dt_ptr) {
   constexpr int NW = MHD ? 7 : 5;
   constexpr bool ISO = solver_is_iso<SOLVER>;
   const int sv = b.nc3*b.nc2*b.nc1;
@@ -359,16 +360,17 @@ __device__ __forceinline__ void flux_face(const BlkDev &b, const Params &p, int 
   if (MHD) dxw = dxw*(wl[IDN] + wr[IDN]);
   double f[NW];
   riemann<SOLVER,MHD>(wl, wr, bxi, ISO ? p.iso_cs : p.gamma, dvn, dvt, f, p.dfloor);
-  double *__restrict__ flx = b.flux[DIR];
+  const long offo = (long)late_block_y()*b0.bstride;      // b0 = the launch's first block
+  double *__restrict__ flx = blk_mv(b0.flux[DIR], offo);
   flx[of] = f[IDN];
   flx[of + (1 + DIR)*sf] = f[IVX];
   flx[of + (1 + (DIR+1)%3)*sf] = f[IVY];
   flx[of + (1 + (DIR+2)%3)*sf] = f[IVZ];
   if (!ISO) flx[of + 4*sf] = f[IEN];
   if (MHD) {
-    b.ef[DIR][0][of] = -f[IBY];
-    b.ef[DIR][1][of] = f[IBZ];
-    b.wght[DIR][of] = weight_for_ct_pre(f[IDN], dxw, dt);
+    blk_mv(b0.ef[DIR][0], offo)[of] = -f[IBY];
+    blk_mv(b0.ef[DIR][1], offo)[of] = f[IBZ];
+    blk_mv(b0.wght[DIR], offo)[of] = weight_for_ct_pre(f[IDN], dxw, dt);
   }
 }
 
@@ -399,7 +401,7 @@ k_flux_ppm_x1(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int j0, int nj,
 #pragma unroll
   for (int n = 0; n < NW; ++n) wl[n] = __shfl_up_sync(0xffffffffu, plus[n], 1);
   if (!have || lane == 0) return;
-  flux_face<0,SOLVER,MHD>(b, p, i, j, k, wl, minus, dt_val, dt_ptr);
+  flux_face<0,SOLVER,MHD>(b, b0, p, i, j, k, wl, minus, dt_val, dt_ptr);
 }
 
 // x2 / x3 sweeps.  The transverse plane (x2 sweep: (k,i); x3 sweep: (j,i)) is flattened into np
@@ -441,7 +443,7 @@ k_flux_ppm_t(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int a0, int c0, 
   double wl[NW];
 #pragma unroll
   for (int n = 0; n < NW; ++n) wl[n] = sh[r-1][n][lane];
-  flux_face<DIR,SOLVER,MHD>(b, p, i, j, k, wl, minus, dt_val, dt_ptr);
+  flux_face<DIR,SOLVER,MHD>(b, b0, p, i, j, k, wl, minus, dt_val, dt_ptr);
 }
 
 template <int DIR, int SOLVER, bool MHD, bool NU>

@@ -614,10 +614,14 @@ __device__ __forceinline__ SlabIdx edge_index(const BlkDev &b, int eid, long t) 
 }
 
 // grid.y = 0..5 faces, 6..17 edges
-// grid.z = local MeshBlocks: plans != nullptr is the device array of their plans
-__global__ void __launch_bounds__(256) k_emf_pack(BlkDev b0, EmfPlan pl0, const EmfPlan *plans) {
-  const BlkDev b = blk_view(b0, blockIdx.z);
-  const EmfPlan &pl = plans ? plans[blockIdx.z] : pl0;
+// grid.z = local MeshBlocks; plans = device array of their plans (a plan passed by value would
+// have to be copied to local memory by every thread to be indexed with a run-time face / edge id)
+// The edge-EMF arrays are picked with a run-time component index: `b` stays the kernel parameter
+// (indexable in the constant bank; a shifted copy would live in local memory) and the block
+// offset `off` is applied to the one pointer that is dereferenced.
+__global__ void __launch_bounds__(256) k_emf_pack(BlkDev b, const EmfPlan *__restrict__ plans) {
+  const long off = (long)blockIdx.z*b.bstride;
+  const EmfPlan &pl = plans[blockIdx.z];
   int id = blockIdx.y;
   long t = (long)blockIdx.x*256 + threadIdx.x;
   if (id < 6) {
@@ -629,7 +633,7 @@ __global__ void __launch_bounds__(256) k_emf_pack(BlkDev b0, EmfPlan pl0, const 
     long tt = sec ? t - n0 : t;
     SlabIdx x = face_sec_index(b, id, sec, tt);
     int comp = face_sec_comp(b, id, sec);
-    dst[t] = b.e[comp][e_index(b, comp, x.k, x.j, x.i)];
+    dst[t] = blk_mv(b.e[comp], off)[e_index(b, comp, x.k, x.j, x.i)];
   } else {
     int eid = id - 6;
     double *dst = pl.edge_dst[eid];
@@ -637,18 +641,17 @@ __global__ void __launch_bounds__(256) k_emf_pack(BlkDev b0, EmfPlan pl0, const 
     if (t >= edge_count(b, eid)) return;
     SlabIdx x = edge_index(b, eid, t);
     int comp = eid < 4 ? 2 : (eid < 8 ? 1 : 0);
-    dst[t] = b.e[comp][e_index(b, comp, x.k, x.j, x.i)];
+    dst[t] = blk_mv(b.e[comp], off)[e_index(b, comp, x.k, x.j, x.i)];
   }
 }
 
-void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s, const EmfPlan *plans_dev,
-                     int nb) {
+void launch_emf_pack(const BlkDev &b, const EmfPlan *plans_dev, cudaStream_t s, int nb) {
   int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
   long m = 2L*(nx1+1)*(nx2+1);
   if (2L*(nx1+1)*(nx3+1) > m) m = 2L*(nx1+1)*(nx3+1);
   if (2L*(nx2+1)*(nx3+1) > m) m = 2L*(nx2+1)*(nx3+1);
   int nid = b.f3 ? 18 : (b.f2 ? 10 : 2);
-  k_emf_pack<<<dim3((unsigned)((m + 255)/256), nid, plans_dev ? nb : 1), 256, 0, s>>>(b, pl, plans_dev); ++g_launches;
+  k_emf_pack<<<dim3((unsigned)((m + 255)/256), nid, nb), 256, 0, s>>>(b, plans_dev); ++g_launches;
 }
 
 // offset of element (k,j,i) of component comp inside the buffer packed by the neighbour
@@ -673,9 +676,9 @@ __device__ __forceinline__ long face_buf_offset(const BlkDev &b, int fid, int co
 // corrected value of one boundary edge-EMF element: own value + neighbours' (faces in
 // neighbour order x1,x2,x3, then the edge neighbour) then the averaging factor.
 // lo/hi flags: -1 / +1 when the element sits on the inner / outer block face of a direction.
-__device__ __forceinline__ double emf_corrected(const BlkDev &b, const EmfPlan &pl, int comp,
-                                                int k, int j, int i) {
-  double v = b.e[comp][e_index(b, comp, k, j, i)];
+__device__ __forceinline__ double emf_corrected(const BlkDev &b, long off, const EmfPlan &pl,
+                                                int comp, int k, int j, int i) {
+  double v = blk_mv(b.e[comp], off)[e_index(b, comp, k, j, i)];
   // which block faces does this element touch?  (e1 lives on x2/x3 faces, e2 on x1/x3, e3 on x1/x2)
   int s1 = 0, s2 = 0, s3 = 0;
   if (comp != 0) s1 = (i == b.is) ? -1 : ((i == b.ie+1) ? 1 : 0);
@@ -712,9 +715,9 @@ __device__ __forceinline__ double emf_corrected(const BlkDev &b, const EmfPlan &
 // One thread per boundary element; slabs enumerated without duplicates:
 // for each component, the two faces of its first bounding direction take their full extent,
 // the faces of its second bounding direction exclude the lines already covered.
-__global__ void __launch_bounds__(256) k_emf_apply(BlkDev b0, EmfPlan pl0, const EmfPlan *plans) {
-  const BlkDev b = blk_view(b0, blockIdx.z);
-  const EmfPlan &pl = plans ? plans[blockIdx.z] : pl0;
+__global__ void __launch_bounds__(256) k_emf_apply(BlkDev b, const EmfPlan *__restrict__ plans) {
+  const long off = (long)blockIdx.z*b.bstride;
+  const EmfPlan &pl = plans[blockIdx.z];
   int slab = blockIdx.y;            // comp*4 + {0,1: first dir lo/hi ; 2,3: second dir lo/hi}
   int comp = slab >> 2, which = slab & 3;
   long t = (long)blockIdx.x*256 + threadIdx.x;
@@ -754,17 +757,16 @@ __global__ void __launch_bounds__(256) k_emf_apply(BlkDev b0, EmfPlan pl0, const
       j = which == 2 ? b.js : b.je+1; k = b.ks + (int)(t/(ni-2)); i = b.is+1 + (int)(t%(ni-2));
     }
   }
-  double v = emf_corrected(b, pl, comp, k, j, i);
-  b.e[comp][e_index(b, comp, k, j, i)] = v;
+  double v = emf_corrected(b, off, pl, comp, k, j, i);
+  blk_mv(b.e[comp], off)[e_index(b, comp, k, j, i)] = v;
 }
 
-void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s, const EmfPlan *plans_dev,
-                      int nb) {
+void launch_emf_apply(const BlkDev &b, const EmfPlan *plans_dev, cudaStream_t s, int nb) {
   int nx1 = b.ie-b.is+1, nx2 = b.je-b.js+1, nx3 = b.ke-b.ks+1;
   long m = (long)(nx1+1)*(nx2+1);
   if ((long)(nx1+1)*(nx3+1) > m) m = (long)(nx1+1)*(nx3+1);
   if ((long)(nx2+1)*(nx3+1) > m) m = (long)(nx2+1)*(nx3+1);
-  k_emf_apply<<<dim3((unsigned)((m + 255)/256), 12, plans_dev ? nb : 1), 256, 0, s>>>(b, pl, plans_dev); ++g_launches;
+  k_emf_apply<<<dim3((unsigned)((m + 255)/256), 12, nb), 256, 0, s>>>(b, plans_dev); ++g_launches;
 }
 
 // =============================================================================================

@@ -34,11 +34,9 @@ void launch_flux_dir(const BlkDev &b, const ReconGeom &g, const Params &p, int o
                      double dt_val, const double *dt_ptr, cudaStream_t s, int nb = 1);
 // have_cc_e: cc_e was already written by cons2prim (flags bit0) over [is-1,ie+1]^dim
 void launch_corner_e(const BlkDev &b, cudaStream_t s, int have_cc_e = 0, int nb = 1);
-// plans_dev != nullptr: device array of the plans of nb blocks (then `pl` is ignored)
-void launch_emf_pack(const BlkDev &b, const EmfPlan &pl, cudaStream_t s,
-                     const EmfPlan *plans_dev = nullptr, int nb = 1);
-void launch_emf_apply(const BlkDev &b, const EmfPlan &pl, cudaStream_t s,
-                      const EmfPlan *plans_dev = nullptr, int nb = 1);
+// plans_dev: device array of the plans of the nb blocks (first element = block b's plan)
+void launch_emf_pack(const BlkDev &b, const EmfPlan *plans_dev, cudaStream_t s, int nb = 1);
+void launch_emf_apply(const BlkDev &b, const EmfPlan *plans_dev, cudaStream_t s, int nb = 1);
 
 // WeightedAve special-casing of the reference (mesh/weighted_ave.cpp) for out = w0*out + w1*in
 void launch_weighted_ave_cc(const BlkDev &b, double *out, const double *in, double w0,

@@ -1171,12 +1171,12 @@ int bvals_exchange_end(AbMesh *m) {
 
 // EMF pack / apply of every local block: one launch over all blocks inside a batched cycle
 void emf_pack_all(AbMesh *m) {
-  if (m->batch) ab::launch_emf_pack(m->lb[0].d, m->lb[0].emf, m->stream, m->emf_plans_dev, (int)m->lb.size());
-  else for (auto &L : m->lb) ab::launch_emf_pack(L.d, L.emf, m->stream);
+  if (m->batch) ab::launch_emf_pack(m->lb[0].d, m->emf_plans_dev, m->stream, (int)m->lb.size());
+  else for (size_t l = 0; l < m->lb.size(); ++l) ab::launch_emf_pack(m->lb[l].d, m->emf_plans_dev + l, m->stream);
 }
 void emf_apply_all(AbMesh *m) {
-  if (m->batch) ab::launch_emf_apply(m->lb[0].d, m->lb[0].emf, m->stream, m->emf_plans_dev, (int)m->lb.size());
-  else for (auto &L : m->lb) ab::launch_emf_apply(L.d, L.emf, m->stream);
+  if (m->batch) ab::launch_emf_apply(m->lb[0].d, m->emf_plans_dev, m->stream, (int)m->lb.size());
+  else for (size_t l = 0; l < m->lb.size(); ++l) ab::launch_emf_apply(m->lb[l].d, m->emf_plans_dev + l, m->stream);
 }
 
 int emf_exchange(AbMesh *m) {
@@ -1288,7 +1288,7 @@ int block_emf_send(AbMesh *m, int lid) {
   if (m->bcomm.size() != m->lb.size()) m->bcomm.assign(m->lb.size(), AbMesh::BlockComm());
   if (!m->emf_built) { int rc = build_emf_plan(m); if (rc) return rc; }
   LocalBlock &L = m->lb[lid];
-  ab::launch_emf_pack(L.d, L.emf, m->stream);
+  ab::launch_emf_pack(L.d, m->emf_plans_dev + lid, m->stream);
   m->bcomm[lid].emf_sent++;
   if (!m->peer_emf.empty()) {
     long lo = m->bcomm[0].emf_sent;
@@ -1312,7 +1312,7 @@ int block_emf_recv_try(AbMesh *m, int lid) {
     if (nb.rank == m->p.rank) { if (m->bcomm[owner_lid(m, nb.gid)].emf_sent < need) return 0; }
     else if (m->nccl_emf_round < need) return 0;
   }
-  ab::launch_emf_apply(L.d, L.emf, m->stream);
+  ab::launch_emf_apply(L.d, m->emf_plans_dev + lid, m->stream);
   m->bcomm[lid].emf_recvd = need;
   CK(cudaGetLastError());
   return 1;
