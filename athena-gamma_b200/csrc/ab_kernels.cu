@@ -6,6 +6,7 @@
 // that every global access is coalesced; stencil neighbours are served by L1/L2.
 #include <float.h>
 #include <stdint.h>
+#include <string.h>
 #include "ab_kernels.h"
 #include "ab_physics.cuh"
 #include "ab_batch.cuh"
@@ -74,6 +75,98 @@ __device__ __forceinline__ void block_min_to_slots(double m, unsigned long long 
 #ifndef AB_CC_MINB
 #define AB_CC_MINB 8       // k_integrate_cc
 #endif
+// one cell of ConservedToPrimitive (+ cc_e, + the cell's CFL limit folded into m)
+template <bool MHD, int FLAGS>
+__device__ __forceinline__ void c2p_cell(const BlkDev &b, const Params &p, int i, int j, int k,
+                                         double &m) {
+  double gm1 = p.gamma - 1.0;
+  double pb = 0.0;
+  double bcc1 = 0.0, bcc2 = 0.0, bcc3 = 0.0, bf1 = 0.0, bf2 = 0.0, bf3 = 0.0;
+  long o = CCI(b,0,k,j,i);
+  long sv = (long)b.nc3*b.nc2*b.nc1;
+  if (MHD) {
+    bf1 = b.b[0][F1I(b,k,j,i)]; bf2 = b.b[1][F2I(b,k,j,i)]; bf3 = b.b[2][F3I(b,k,j,i)];
+    if (b.bcw) {   // nonuniform spacing: interpolate to the volume centre (field.cpp:139-172)
+      const double *__restrict__ q1 = b.bcw, *q2 = q1 + 2*b.nc1, *q3 = q2 + 2*b.nc2;
+      bcc1 = q1[i]*bf1 + q1[b.nc1+i]*b.b[0][F1I(b,k,j,i+1)];
+      bcc2 = q2[j]*bf2 + q2[b.nc2+j]*b.b[1][F2I(b,k,j+1,i)];
+      bcc3 = q3[k]*bf3 + q3[b.nc3+k]*b.b[2][F3I(b,k+1,j,i)];
+    } else {
+      bcc1 = 0.5*bf1 + 0.5*b.b[0][F1I(b,k,j,i+1)];
+      bcc2 = 0.5*bf2 + 0.5*b.b[1][F2I(b,k,j+1,i)];
+      bcc3 = 0.5*bf3 + 0.5*b.b[2][F3I(b,k+1,j,i)];
+    }
+    b.bcc[o] = bcc1;
+    b.bcc[o+sv] = bcc2;
+    b.bcc[o+2*sv] = bcc3;
+    pb = 0.5*(sqr(bcc1) + sqr(bcc2) + sqr(bcc3));
+  }
+  // isothermal EOS (eos/isothermal_{hydro,mhd}.cpp:39-75): density floor and velocities only
+  const bool iso = (p.eos != 0);
+  double u_d = b.u[o], u_m1 = b.u[o+sv], u_m2 = b.u[o+2*sv], u_m3 = b.u[o+3*sv];
+  double u_e = iso ? 0.0 : b.u[o+4*sv];
+  double u_d0 = u_d, u_e0 = u_e;
+  u_d = (u_d > p.dfloor) ? u_d : p.dfloor;
+  double di = 1.0/u_d;
+  double w_p = 0.0;
+  if (!iso) {
+    double e_k = 0.5*di*(sqr(u_m1) + sqr(u_m2) + sqr(u_m3));
+    if (MHD) {
+      w_p = gm1*(u_e - e_k - pb);
+      u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k + pb);
+    } else {
+      w_p = gm1*(u_e - e_k);
+      u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k);
+    }
+    w_p = (w_p > p.pfloor) ? w_p : p.pfloor;
+  }
+  // floors write back into cons (the reference always stores; storing only changes is
+  // value-identical and saves two stores per cell)
+  if (u_d != u_d0) b.u[o] = u_d;
+  if (u_e != u_e0) b.u[o+4*sv] = u_e;
+  double vx = u_m1*di, vy = u_m2*di, vz = u_m3*di;
+  b.w[o] = u_d;
+  b.w[o+sv] = vx;
+  b.w[o+2*sv] = vy;
+  b.w[o+3*sv] = vz;
+  if (!iso) b.w[o+4*sv] = w_p;
+  if (MHD && (FLAGS & 1)) {
+    if (b.f3) {
+      b.cc_e[o] = vz*bcc2 - vy*bcc3;
+      b.cc_e[o+sv] = vx*bcc3 - vz*bcc1;
+      b.cc_e[o+2*sv] = vy*bcc1 - vx*bcc2;
+    } else if (b.f2) {
+      b.cc_e[o] = vy*bcc1 - vx*bcc2;
+    }
+  }
+  if ((FLAGS & 2) && i >= b.is && i <= b.ie && j >= b.js && j <= b.je && k >= b.ks &&
+      k <= b.ke) {
+    double dt1 = b.dx1f[i], dt2 = b.dx2f[j], dt3 = b.dx3f[k];
+    if (MHD) {
+      double bx = bcc1 + fabs(bf1 - bcc1);
+      double cf = iso ? fast_speed_iso(p.iso_cs, u_d, bcc2, bcc3, bx)
+                      : fast_speed(p.gamma, u_d, w_p, bcc2, bcc3, bx);
+      dt1 /= (fabs(vx) + cf);
+      bx = bcc2 + fabs(bf2 - bcc2);
+      cf = iso ? fast_speed_iso(p.iso_cs, u_d, bcc3, bcc1, bx)
+               : fast_speed(p.gamma, u_d, w_p, bcc3, bcc1, bx);
+      dt2 /= (fabs(vy) + cf);
+      bx = bcc3 + fabs(bf3 - bcc3);
+      cf = iso ? fast_speed_iso(p.iso_cs, u_d, bcc1, bcc2, bx)
+               : fast_speed(p.gamma, u_d, w_p, bcc1, bcc2, bx);
+      dt3 /= (fabs(vz) + cf);
+    } else {
+      double cs = iso ? p.iso_cs : sound_speed(p.gamma, u_d, w_p);
+      dt1 /= (fabs(vx) + cs);
+      dt2 /= (fabs(vy) + cs);
+      dt3 /= (fabs(vz) + cs);
+    }
+    m = dmin(m, dt1);
+    if (b.f2) m = dmin(m, dt2);
+    if (b.f3) m = dmin(m, dt3);
+  }
+}
+
 template <bool MHD, int FLAGS>
 __global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2prim(BlkDev b0, Params p, int il, int jl,
                                                   int kl, int ni, int nj, int ntot,
@@ -88,95 +181,30 @@ __global__ void __launch_bounds__(BX, ((FLAGS & 2) ? AB_C2P_MINB : 1)) k_cons2pr
   const int j = jl + (r - kk*nj);
   const int k = kl + kk;
   double m = DBL_MAX;
-  if (t < ntot) {
-    double gm1 = p.gamma - 1.0;
-    double pb = 0.0;
-    double bcc1 = 0.0, bcc2 = 0.0, bcc3 = 0.0, bf1 = 0.0, bf2 = 0.0, bf3 = 0.0;
-    long o = CCI(b,0,k,j,i);
-    long sv = (long)b.nc3*b.nc2*b.nc1;
-    if (MHD) {
-      bf1 = b.b[0][F1I(b,k,j,i)]; bf2 = b.b[1][F2I(b,k,j,i)]; bf3 = b.b[2][F3I(b,k,j,i)];
-      if (b.bcw) {   // nonuniform spacing: interpolate to the volume centre (field.cpp:139-172)
-        const double *__restrict__ q1 = b.bcw, *q2 = q1 + 2*b.nc1, *q3 = q2 + 2*b.nc2;
-        bcc1 = q1[i]*bf1 + q1[b.nc1+i]*b.b[0][F1I(b,k,j,i+1)];
-        bcc2 = q2[j]*bf2 + q2[b.nc2+j]*b.b[1][F2I(b,k,j+1,i)];
-        bcc3 = q3[k]*bf3 + q3[b.nc3+k]*b.b[2][F3I(b,k+1,j,i)];
-      } else {
-        bcc1 = 0.5*bf1 + 0.5*b.b[0][F1I(b,k,j,i+1)];
-        bcc2 = 0.5*bf2 + 0.5*b.b[1][F2I(b,k,j+1,i)];
-        bcc3 = 0.5*bf3 + 0.5*b.b[2][F3I(b,k+1,j,i)];
-      }
-      b.bcc[o] = bcc1;
-      b.bcc[o+sv] = bcc2;
-      b.bcc[o+2*sv] = bcc3;
-      pb = 0.5*(sqr(bcc1) + sqr(bcc2) + sqr(bcc3));
-    }
-    // isothermal EOS (eos/isothermal_{hydro,mhd}.cpp:39-75): density floor and velocities only
-    const bool iso = (p.eos != 0);
-    double u_d = b.u[o], u_m1 = b.u[o+sv], u_m2 = b.u[o+2*sv], u_m3 = b.u[o+3*sv];
-    double u_e = iso ? 0.0 : b.u[o+4*sv];
-    double u_d0 = u_d, u_e0 = u_e;
-    u_d = (u_d > p.dfloor) ? u_d : p.dfloor;
-    double di = 1.0/u_d;
-    double w_p = 0.0;
-    if (!iso) {
-      double e_k = 0.5*di*(sqr(u_m1) + sqr(u_m2) + sqr(u_m3));
-      if (MHD) {
-        w_p = gm1*(u_e - e_k - pb);
-        u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k + pb);
-      } else {
-        w_p = gm1*(u_e - e_k);
-        u_e = (w_p > p.pfloor) ? u_e : ((p.pfloor/gm1) + e_k);
-      }
-      w_p = (w_p > p.pfloor) ? w_p : p.pfloor;
-    }
-    // floors write back into cons (the reference always stores; storing only changes is
-    // value-identical and saves two stores per cell)
-    if (u_d != u_d0) b.u[o] = u_d;
-    if (u_e != u_e0) b.u[o+4*sv] = u_e;
-    double vx = u_m1*di, vy = u_m2*di, vz = u_m3*di;
-    b.w[o] = u_d;
-    b.w[o+sv] = vx;
-    b.w[o+2*sv] = vy;
-    b.w[o+3*sv] = vz;
-    if (!iso) b.w[o+4*sv] = w_p;
-    if (MHD && (FLAGS & 1)) {
-      if (b.f3) {
-        b.cc_e[o] = vz*bcc2 - vy*bcc3;
-        b.cc_e[o+sv] = vx*bcc3 - vz*bcc1;
-        b.cc_e[o+2*sv] = vy*bcc1 - vx*bcc2;
-      } else if (b.f2) {
-        b.cc_e[o] = vy*bcc1 - vx*bcc2;
-      }
-    }
-    if ((FLAGS & 2) && i >= b.is && i <= b.ie && j >= b.js && j <= b.je && k >= b.ks &&
-        k <= b.ke) {
-      double dt1 = b.dx1f[i], dt2 = b.dx2f[j], dt3 = b.dx3f[k];
-      if (MHD) {
-        double bx = bcc1 + fabs(bf1 - bcc1);
-        double cf = iso ? fast_speed_iso(p.iso_cs, u_d, bcc2, bcc3, bx)
-                        : fast_speed(p.gamma, u_d, w_p, bcc2, bcc3, bx);
-        dt1 /= (fabs(vx) + cf);
-        bx = bcc2 + fabs(bf2 - bcc2);
-        cf = iso ? fast_speed_iso(p.iso_cs, u_d, bcc3, bcc1, bx)
-                 : fast_speed(p.gamma, u_d, w_p, bcc3, bcc1, bx);
-        dt2 /= (fabs(vy) + cf);
-        bx = bcc3 + fabs(bf3 - bcc3);
-        cf = iso ? fast_speed_iso(p.iso_cs, u_d, bcc1, bcc2, bx)
-                 : fast_speed(p.gamma, u_d, w_p, bcc1, bcc2, bx);
-        dt3 /= (fabs(vz) + cf);
-      } else {
-        double cs = iso ? p.iso_cs : sound_speed(p.gamma, u_d, w_p);
-        dt1 /= (fabs(vx) + cs);
-        dt2 /= (fabs(vy) + cs);
-        dt3 /= (fabs(vz) + cs);
-      }
-      m = dmin(m, dt1);
-      if (b.f2) m = dmin(m, dt2);
-      if (b.f3) m = dmin(m, dt3);
-    }
-  }
+  if (t < ntot) c2p_cell<MHD,FLAGS>(b, p, i, j, k, m);
   if (FLAGS & 2) block_min_to_slots(m, dtmin + blockIdx.y*DT_SLOTS);
+}
+
+// The same over up to six boxes in ONE launch (the ghost shell of a block as six slabs, for the
+// schedule that converts the active cells while the ghost zones are still travelling):
+// end[q] = inclusive prefix of the boxes' cell counts, a thread finds its box by a linear scan.
+struct C2PBoxes { int n; int il[6], jl[6], kl[6], ni[6], nj[6], end[6]; };
+template <bool MHD, int FLAGS>
+__global__ void __launch_bounds__(BX) k_cons2prim_boxes(BlkDev b0, Params p, C2PBoxes bx) {
+  const BlkDev b = blk_view(b0, blockIdx.y);
+  int t = blockIdx.x*BX + threadIdx.x;
+  if (t >= bx.end[bx.n - 1]) return;
+  int q = 0;
+  while (t >= bx.end[q]) ++q;
+  if (q > 0) t -= bx.end[q - 1];
+  const int ni = bx.ni[q], nj = bx.nj[q];
+  int r = t / ni;
+  const int i = bx.il[q] + (t - r*ni);
+  const int kk = r / nj;
+  const int j = bx.jl[q] + (r - kk*nj);
+  const int k = bx.kl[q] + kk;
+  double m = DBL_MAX;
+  c2p_cell<MHD,(FLAGS & 1)>(b, p, i, j, k, m);
 }
 
 void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
@@ -194,6 +222,32 @@ void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, 
   } else {
     if (flags & 2) k_cons2prim<false,2><<<g, BX, 0, s>>>(b, p, il, jl, kl, ni, nj, ntot, dtmin);
     else k_cons2prim<false,0><<<g, BX, 0, s>>>(b, p, il, jl, kl, ni, nj, ntot, dtmin);
+  }
+  ++g_launches;
+}
+
+void launch_cons2prim_boxes(const BlkDev &b, const Params &p, int nbox, const int (*box)[6],
+                            cudaStream_t s, int flags, int nb) {
+  C2PBoxes bx;
+  memset(&bx, 0, sizeof(bx));
+  int tot = 0;
+  for (int q = 0; q < nbox; ++q) {
+    const int ni = box[q][1] - box[q][0] + 1, nj = box[q][3] - box[q][2] + 1,
+              nk = box[q][5] - box[q][4] + 1;
+    if (ni <= 0 || nj <= 0 || nk <= 0) continue;
+    const int n = bx.n++;
+    bx.il[n] = box[q][0]; bx.jl[n] = box[q][2]; bx.kl[n] = box[q][4];
+    bx.ni[n] = ni; bx.nj[n] = nj;
+    tot += ni*nj*nk;
+    bx.end[n] = tot;
+  }
+  if (bx.n == 0) return;
+  const dim3 g((unsigned)((tot + BX - 1)/BX), (unsigned)nb);
+  if (p.mhd) {
+    if (flags & 1) k_cons2prim_boxes<true,1><<<g, BX, 0, s>>>(b, p, bx);
+    else k_cons2prim_boxes<true,0><<<g, BX, 0, s>>>(b, p, bx);
+  } else {
+    k_cons2prim_boxes<false,0><<<g, BX, 0, s>>>(b, p, bx);
   }
   ++g_launches;
 }

@@ -22,6 +22,9 @@ struct ReconGeom { const double *wp[3]; const double *wm[3]; const double *nu[3]
 void launch_cons2prim(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
                       int ku, cudaStream_t s, int flags = 0, unsigned long long *dtmin = nullptr,
                       int nb = 1);
+// the same over up to six cell boxes {il,iu,jl,ju,kl,ku} in one launch (no CFL reduction)
+void launch_cons2prim_boxes(const BlkDev &b, const Params &p, int nbox, const int (*box)[6],
+                            cudaStream_t s, int flags = 0, int nb = 1);
 void launch_prim2cons(const BlkDev &b, const Params &p, int il, int iu, int jl, int ju, int kl,
                       int ku, cudaStream_t s);
 void launch_calc_bcc(const BlkDev &b, int il, int iu, int jl, int ju, int kl, int ku,

@@ -1319,8 +1319,9 @@ int block_emf_recv_try(AbMesh *m, int lid) {
 }
 
 // Primitives task split for the overlapped schedule: part 0 = the active cells (with the fused
-// CFL reduction), part 1 = the ghost shell as up to six slabs (after the ghost zones arrived)
-void primitives_part(AbMesh *m, LocalBlock &L, int part, int with_dt) {
+// CFL reduction), part 1 = the ghost shell as up to six slabs in one launch (after the ghost zones
+// arrived).  nb > 1: the same for nb blocks starting at L in one launch (same ranges, same flags).
+void primitives_part(AbMesh *m, LocalBlock &L, int part, int with_dt, int nb = 1) {
   HostBlock &B = *L.hb;
   int ng = m->p.nghost;
   const int is = m->is, ie = m->ie, js = m->js, je = m->je, ks = m->ks, ke = m->ke;
@@ -1332,19 +1333,36 @@ void primitives_part(AbMesh *m, LocalBlock &L, int part, int with_dt) {
   if (B.nblevel[0][1][1] != -1) kl -= ng;
   if (B.nblevel[2][1][1] != -1) ku += ng;
   const int cce = (m->p.mhd && !L.has_phys_bc) ? 1 : 0;
-  auto run = [&](int a0, int a1, int b0, int b1, int c0, int c1, int flags) {
-    if (a0 > a1 || b0 > b1 || c0 > c1) return;
-    ab::launch_cons2prim(L.d, m->kp, a0, a1, b0, b1, c0, c1, m->stream, flags, L.dtmin);
-    ab::launch_scalar_eos(L.d, m->kp, 0, a0, a1, b0, b1, c0, c1, m->stream);
-  };
   if (part == 0) {
-    run(is, ie, js, je, ks, ke, cce | (with_dt ? 2 : 0));
+    ab::launch_cons2prim(L.d, m->kp, is, ie, js, je, ks, ke, m->stream, cce | (with_dt ? 2 : 0),
+                         L.dtmin, nb);
+    ab::launch_scalar_eos(L.d, m->kp, 0, is, ie, js, je, ks, ke, m->stream, nb);
   } else {
-    run(il, iu, jl, ju, kl, ks-1, cce); run(il, iu, jl, ju, ke+1, ku, cce);
-    run(il, iu, jl, js-1, ks, ke, cce); run(il, iu, je+1, ju, ks, ke, cce);
-    run(il, is-1, js, je, ks, ke, cce); run(ie+1, iu, js, je, ks, ke, cce);
-    L.cc_e_valid = cce != 0;
+    const int box[6][6] = {{il, iu, jl, ju, kl, ks-1}, {il, iu, jl, ju, ke+1, ku},
+                           {il, iu, jl, js-1, ks, ke}, {il, iu, je+1, ju, ks, ke},
+                           {il, is-1, js, je, ks, ke}, {ie+1, iu, js, je, ks, ke}};
+    ab::launch_cons2prim_boxes(L.d, m->kp, 6, box, m->stream, cce, nb);
+    if (m->p.nscalars > 0) for (int q = 0; q < 6; ++q)
+      if (box[q][0] <= box[q][1] && box[q][2] <= box[q][3] && box[q][4] <= box[q][5])
+        ab::launch_scalar_eos(L.d, m->kp, 0, box[q][0], box[q][1], box[q][2], box[q][3], box[q][4],
+                              box[q][5], m->stream, nb);
+    for (int l = 0; l < nb; ++l) (&L)[l].cc_e_valid = cce != 0;
   }
+}
+
+// true when every local block converts the same cell range with the same flags (always on a
+// periodic mesh): the Primitives task can then run over all of them in one launch
+bool primitives_uniform(const AbMesh *m) {
+  for (size_t l = 1; l < m->lb.size(); ++l) {
+    const HostBlock &A = *m->lb[0].hb, &B = *m->lb[l].hb;
+    if (m->lb[0].has_phys_bc != m->lb[l].has_phys_bc) return false;
+    for (int d = 0; d < 3; ++d) for (int sgn = 0; sgn < 3; sgn += 2) {
+      const int a = (d == 0) ? A.nblevel[1][1][sgn] : ((d == 1) ? A.nblevel[1][sgn][1] : A.nblevel[sgn][1][1]);
+      const int b = (d == 0) ? B.nblevel[1][1][sgn] : ((d == 1) ? B.nblevel[1][sgn][1] : B.nblevel[sgn][1][1]);
+      if ((a != -1) != (b != -1)) return false;
+    }
+  }
+  return true;
 }
 
 void primitives(AbMesh *m, LocalBlock &L, int with_dt = 0) {
@@ -1833,10 +1851,14 @@ int one_cycle(AbMesh *m) {
       rc = bvals_exchange_begin(m);
       if (rc) return rc;
       if (last) ab::launch_fill_u64(m->dtmin, (int)m->lb.size()*ab::DT_SLOTS, 0x7FEFFFFFFFFFFFFFull, m->stream);
-      for (auto &L : m->lb) primitives_part(m, L, 0, last);
+      const bool one = bt && primitives_uniform(m);
+      if (one) primitives_part(m, m->lb[0], 0, last, nb);
+      else for (auto &L : m->lb) primitives_part(m, L, 0, last);
       rc = bvals_exchange_end(m);
       if (rc) return rc;
-      for (auto &L : m->lb) { primitives_part(m, L, 1, 0); physical_bcs(m, L); }
+      if (one) primitives_part(m, m->lb[0], 1, 0, nb);
+      else for (auto &L : m->lb) primitives_part(m, L, 1, 0);
+      for (auto &L : m->lb) physical_bcs(m, L);
     }
     if (stage == m->nstages) {
       // record the dt this cycle used, then time += dt, ncycle++, NewTimeStep
