@@ -269,21 +269,39 @@ k_flux(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int j0, int nj, int k0
 // state to the thread of the next interface:
 //   * x1 sweep: a warp holds 32 consecutive cells of a row, the state travels one lane up by
 //     warp shuffle; lanes 1..31 own the 31 faces between them (no shared memory, no barrier);
-//   * x2 / x3 sweeps: a CTA of (AB_PPM_ROWS+1) warps holds that many consecutive cells along the
+//   * x2 / x3 sweeps: a CTA of (ROWS+1) warps holds that many consecutive cells along the
 //     sweep for 32 positions of the flattened transverse plane; the state goes through shared
-//     memory, one barrier; warps 1..AB_PPM_ROWS own the faces.
+//     memory, one barrier; warps 1..ROWS own the faces.
 // The values are those of ppm() / ppm_nu() exactly as k_flux calls them, so the fluxes are the
 // same bits (ppm.cpp:111-332 computes both face states of a cell in one pass as well).
 // =============================================================================================
-#ifndef AB_PPM_ROWS
-#define AB_PPM_ROWS 8
+// Measured on B200 (256^3, developed flow, ms per x2 / x3 sweep; profiles/r2_tuning_log.md):
+// hydro (PPM+HLLC, 90 registers unconstrained): 8 rows + 3 CTAs/SM (72 registers, 27 warps)
+// 1.03 against 1.20 with 2 CTAs/SM; MHD (PPM+HLLD, at the 96-register limit either way): 7 rows
+// (8 warps) + 2 CTAs/SM 2.06 against 2.15 with 8 rows, 3 CTAs/SM spill 390 B and lose.
+#ifndef AB_PPM_ROWS_HYDRO
+#define AB_PPM_ROWS_HYDRO 8
 #endif
-#ifndef AB_PPM_MINB
-#define AB_PPM_MINB 2
+#ifndef AB_PPM_MINB_HYDRO
+#define AB_PPM_MINB_HYDRO 3
 #endif
-#ifndef AB_PPM_X1_MINB
-#define AB_PPM_X1_MINB 18
+#ifndef AB_PPM_ROWS_MHD
+#define AB_PPM_ROWS_MHD 7
 #endif
+#ifndef AB_PPM_MINB_MHD
+#define AB_PPM_MINB_MHD 2
+#endif
+#ifndef AB_PPM_X1_MINB_HYDRO
+#define AB_PPM_X1_MINB_HYDRO 28   // 72 registers: 1.16 against 1.22 ms per 256^3 sweep at 18
+#endif
+#ifndef AB_PPM_X1_MINB_MHD
+#define AB_PPM_X1_MINB_MHD 18
+#endif
+template <bool MHD> struct PpmTune {
+  static constexpr int ROWS = MHD ? AB_PPM_ROWS_MHD : AB_PPM_ROWS_HYDRO;
+  static constexpr int MINB = MHD ? AB_PPM_MINB_MHD : AB_PPM_MINB_HYDRO;
+  static constexpr int X1_MINB = MHD ? AB_PPM_X1_MINB_MHD : AB_PPM_X1_MINB_HYDRO;
+};
 
 // both face states of cell (k,j,i) along DIR, floors applied (ppm.cpp:326-332)
 template <int DIR, bool MHD, bool ISO, bool NU>
@@ -378,7 +396,7 @@ __device__ __forceinline__ void flux_face(const BlkDev &b, const BlkDev &b0, con
 struct PpmIdx { FastDiv nseg, nj, ni; int nsegs, gp, nst, np; };
 
 template <int SOLVER, bool MHD, bool NU>
-__global__ void __launch_bounds__(32, AB_PPM_X1_MINB)
+__global__ void __launch_bounds__(32, PpmTune<MHD>::X1_MINB)
 k_flux_ppm_x1(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int j0, int nj, int k0, int nk,
               double dt_val, const double *dt_ptr, PpmIdx fx) {
   const BlkDev b = blk_view(b0, blockIdx.y);
@@ -405,18 +423,19 @@ k_flux_ppm_x1(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int j0, int nj,
 }
 
 // x2 / x3 sweeps.  The transverse plane (x2 sweep: (k,i); x3 sweep: (j,i)) is flattened into np
-// positions, 32 per CTA; along the sweep a CTA covers AB_PPM_ROWS faces.  CTA order: groups of gp
+// positions, 32 per CTA; along the sweep a CTA covers PpmTune::ROWS faces.  CTA order: groups of gp
 // transverse tiles, inside a group the sweep tiles one after the other (consecutive CTAs re-read
 // the 5 stencil rows they share from L2), inside a sweep tile the gp transverse tiles.
 template <int DIR, int SOLVER, bool MHD, bool NU>
-__global__ void __launch_bounds__(32*(AB_PPM_ROWS + 1), AB_PPM_MINB)
+__global__ void __launch_bounds__(32*(PpmTune<MHD>::ROWS + 1), PpmTune<MHD>::MINB)
 k_flux_ppm_t(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int a0, int c0, int nc,
              double dt_val, const double *dt_ptr, PpmIdx fx) {
   const BlkDev b = blk_view(b0, blockIdx.y);
   const ReconGeom g = geom_view(g0, b0, blockIdx.y);
   constexpr int NW = MHD ? 7 : 5;
   constexpr bool ISO = solver_is_iso<SOLVER>;
-  __shared__ double sh[AB_PPM_ROWS][NW][32];
+  constexpr int ROWS = PpmTune<MHD>::ROWS;
+  __shared__ double sh[ROWS][NW][32];
   const int t = blockIdx.x;
   const int per_group = fx.gp*fx.nst;
   const int grp = t/per_group;                    // uniform per CTA: a plain division is fine
@@ -427,13 +446,13 @@ k_flux_ppm_t(BlkDev b0, ReconGeom g0, Params p, int i0, int ni, int a0, int c0, 
   const int pf = ptile*32 + lane;
   const int a = fast_div(pf, fx.ni);
   const int i = i0 + (pf - a*ni);
-  const int c = c0 + stile*AB_PPM_ROWS - 1 + r;   // this warp's cell along the sweep
+  const int c = c0 + stile*ROWS - 1 + r;          // this warp's cell along the sweep
   const bool have = (pf < fx.np) && (c <= c0 + nc - 1);
   const int j = (DIR == 1) ? c : a0 + a, k = (DIR == 1) ? a0 + a : c;
   double plus[NW], minus[NW];
   if (have) {
     ppm_cell<DIR,MHD,ISO,NU>(b, g, p, (k*b.nc2 + j)*b.nc1 + i, c, plus, minus);
-    if (r < AB_PPM_ROWS) {
+    if (r < ROWS) {
 #pragma unroll
       for (int n = 0; n < NW; ++n) sh[r][n][lane] = plus[n];
     }
@@ -466,9 +485,10 @@ static void flux_dir_ppm(const BlkDev &b, const ReconGeom &g, const Params &p, i
     fx.gp = (DIR == 1) ? (ni + 31)/32 : ni;
     if (fx.gp > ntile) fx.gp = ntile;
     const int ngrp = (ntile + fx.gp - 1)/fx.gp;
-    fx.nst = (nc + AB_PPM_ROWS - 1)/AB_PPM_ROWS;
+    constexpr int ROWS = PpmTune<MHD>::ROWS;
+    fx.nst = (nc + ROWS - 1)/ROWS;
     fx.nsegs = 0; fx.nseg = make_fastdiv(1);
-    k_flux_ppm_t<DIR,SOLVER,MHD,NU><<<dim3((unsigned)(ngrp*fx.gp*fx.nst), (unsigned)nb), dim3(32, AB_PPM_ROWS + 1), 0, s>>>(
+    k_flux_ppm_t<DIR,SOLVER,MHD,NU><<<dim3((unsigned)(ngrp*fx.gp*fx.nst), (unsigned)nb), dim3(32, ROWS + 1), 0, s>>>(
         b, g, p, i0, ni, (DIR == 1) ? k0 : j0, (DIR == 1) ? j0 : k0, nc, dt_val, dt_ptr, fx);
   }
   ++g_launches;
