@@ -529,7 +529,20 @@ def main():
     # Same bytes, same work per step; the result lands in its own pinned buffers because the
     # input buffers are being read by the next upload at that time.
     e2e_pipe = None
-    if do_e2e and not a.no_e2e_pipelined:
+    pipe_ok = do_e2e and not a.no_e2e_pipelined
+    if pipe_ok:
+        # the leg pins a second copy of the state (its results land in their own buffers): skip it
+        # when the ranks of this node together would take more than half of the free host memory
+        try:
+            import psutil
+            need = sum(t.numel()*8 for d in pinned for t in d.values())*max(world, 1)
+            if need > 0.5*psutil.virtual_memory().available:
+                pipe_ok = False
+                e2e_pipe = {"value": None, "error": "skipped: another %.0f GB of pinned host memory needed"
+                                                    % (need/1e9)}
+        except Exception:
+            pass
+    if pipe_ok:
         try:
             dp = C.POINTER(C.c_double)
             outbuf = [{nm: torch.zeros_like(d[nm]).pin_memory() for nm in names} for d in pinned]
@@ -660,6 +673,18 @@ def main():
                 others[name] = side_workload(ab, name, device, st, wu, **kw)
             except Exception as ex:
                 others[name] = {"value": None, "error": str(ex)[:300]}
+        # developed-flow figure for the c5 kernels (HLLD+PLM+VL2, 3-D MHD): the linear-wave
+        # problem of c2 on a 512x256x256 MeshBlock -- every interface has non-zero jumps in every
+        # variable, none of the zero-dividend shortcuts the mostly static blast state takes fires
+        try:
+            r = side_workload(ab, "c2", device, 6, 3, block=(512, 256, 256), per_gpu=(512, 256, 256))
+            r["what"] = ("c2's linear wave on one 512x256x256 MeshBlock: same kernels as c5 on a "
+                         "state with gradients everywhere; compare ms per interface with c5")
+            r["flux_ns_per_interface"] = {k: 1e6*v/(513.0*256*256) for k, v in
+                                          r["flux_avg_ms_by_dir_order"].items()}
+            others["c5_kernels_on_developed_flow"] = r
+        except Exception as ex:
+            others["c5_kernels_on_developed_flow"] = {"value": None, "error": str(ex)[:300]}
 
     # ---- multi-rank correctness on the scaling record: the golden fixtures of the reference,
     # MeshBlocks sharded over these ranks, NCCL ghost / EMF exchange and dt reduction, bit for
