@@ -12,6 +12,10 @@
 
 namespace ab {
 
+__device__ __forceinline__ int fast_div(int t, FastDiv f) {     // ab_types.h
+  return f.m ? (int)(__umulhi((unsigned)t, f.m) >> f.s) : t;
+}
+
 template <class T>
 __device__ __forceinline__ T *blk_mv(T *p, long off) {
   return (T *)((char *)p + off);

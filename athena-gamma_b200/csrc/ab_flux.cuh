@@ -60,23 +60,6 @@ __device__ __forceinline__ void load_cell(const double *__restrict__ w,
 #define AB_PPM_SHARED 1
 #endif
 
-// Exact t / d for 0 <= t < 2^31 by one multiply-high and a shift (the divisor is a launch
-// constant; a run-time integer division costs ~20 instructions per thread and the kernel needs
-// two to five).  l = ceil(log2 d), m = ceil(2^(31+l) / d) < 2^32, t / d = umulhi(t, m) >> (l-1)
-// (Granlund & Montgomery 1994, N = 31).  d = 1 is encoded as m = 0.
-struct FastDiv { unsigned m, s; };
-static inline FastDiv make_fastdiv(int d) {
-  FastDiv f{0u, 0u};
-  if (d <= 1) return f;
-  int l = 0;
-  while ((1LL << l) < d) ++l;
-  f.m = (unsigned)(((1ULL << (31 + l)) + (unsigned long long)d - 1ULL)/(unsigned long long)d);
-  f.s = (unsigned)(l - 1);
-  return f;
-}
-__device__ __forceinline__ int fast_div(int t, FastDiv f) {
-  return f.m ? (int)(__umulhi((unsigned)t, f.m) >> f.s) : t;
-}
 // divisors of the flattened face index: ni, nj, and for the strip-major x3 order ni*STRIP*nk,
 // ni*STRIP (full strips) and ni*(rows of the last, partial strip)
 struct FluxIdx { FastDiv ni, nj, per_full, per_k, per_k_last; int last_strip; };

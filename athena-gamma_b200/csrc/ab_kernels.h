@@ -72,7 +72,9 @@ void launch_integrate_fc(const BlkDev &b, int mode, int zero_init, double delta,
 
 // ghost exchange: apply `n` box copies (descriptors in device memory, CopyBox::offset = exclusive
 // prefix of the element counts, total_elems = their sum)
-void launch_copy_boxes(const CopyBox *boxes_dev, int n, long total_elems, cudaStream_t s);
+// chunked != 0: the per-256-element first-box table follows the n boxes in the same allocation
+void launch_copy_boxes(const CopyBox *boxes_dev, int n, long total_elems, cudaStream_t s,
+                       int chunked = 0);
 // static mesh refinement (ab_smr_kernels.cu)
 void launch_smr_restrict(const SmrGeom &g, const double *fine, double *coarse, int nvar,
                          const SmrBox &bx, cudaStream_t s);

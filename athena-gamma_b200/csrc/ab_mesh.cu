@@ -1018,10 +1018,22 @@ int build_state_plan(AbMesh *m, AbMesh::Plan &P, int lid_filter = -1, int vars =
   }
   auto upload = [&](std::vector<CopyBox> &v, CopyBox *&dev, int &n, long &mx) -> int {
     n = (int)v.size(); mx = 0;     // mx = total element count; offsets = exclusive prefix
-    for (auto &c : v) { c.offset = mx; mx += (long)c.ni*c.nj*c.nk*c.nvar; }
+    for (auto &c : v) { c.offset = mx; mx += (long)c.ni*c.nj*c.nk*c.nvar; ab::set_box_divisors(c); }
     if (dev) { cudaFree(dev); dev = nullptr; }
     if (n == 0) return AB_OK;
-    CK(cudaMalloc(&dev, sizeof(CopyBox)*n));
+    // behind the boxes: for every chunk of 256 consecutive elements the box of its first element
+    // (k_copy_boxes scans forward from it)
+    std::vector<int> first((size_t)((mx + 255)/256), 0);
+    {
+      int q = 0;
+      for (size_t c = 0; c < first.size(); ++c) {
+        const long t = (long)c*256;
+        while (q + 1 < n && v[q + 1].offset <= t) ++q;
+        first[c] = q;
+      }
+    }
+    CK(cudaMalloc(&dev, sizeof(CopyBox)*n + sizeof(int)*first.size()));
+    CK(cudaMemcpyAsync(dev + n, first.data(), sizeof(int)*first.size(), cudaMemcpyHostToDevice, m->stream));
     // Stream-ordered copy + sync.  A plain cudaMemcpy from pageable memory may return before the
     // DMA has landed and orders only against the NULL stream; the kernels that read this table run
     // on a non-blocking stream and occasionally saw it half-written (flaky illegal address with
@@ -1130,12 +1142,12 @@ int bvals_exchange(AbMesh *m) {
   if (!m->plan[use].built) { int rc = build_state_plan(m, m->plan[use]); if (rc) return rc; }
   if (idx < 0) m->plan[0].built = false;   // mixed state: never cache
   AbMesh::Plan &P = m->plan[use];
-  if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream);
+  if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream, 1);
   int rc = peer_exchange(m, m->peer_state);
   if (rc) return rc;
-  ab::launch_copy_boxes(P.phase1, P.n1, P.max1, m->stream);
-  ab::launch_copy_boxes(P.phase1r, P.n1r, P.max1r, m->stream);
-  ab::launch_copy_boxes(P.phase2, P.n2, P.max2, m->stream);
+  ab::launch_copy_boxes(P.phase1, P.n1, P.max1, m->stream, 1);
+  ab::launch_copy_boxes(P.phase1r, P.n1r, P.max1r, m->stream, 1);
+  ab::launch_copy_boxes(P.phase2, P.n2, P.max2, m->stream, 1);
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -1149,21 +1161,21 @@ int bvals_exchange_begin(AbMesh *m) {
   if (idx < 0) m->plan[0].built = false;
   if (!m->plan[use].built) { int rc = build_state_plan(m, m->plan[use]); if (rc) return rc; }
   AbMesh::Plan &P = m->plan[use];
-  if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream);
+  if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream, 1);
   CK(cudaEventRecord(m->ev_pack, m->stream));
   CK(cudaStreamWaitEvent(m->comm_stream, m->ev_pack, 0));
   int rc = peer_exchange(m, m->peer_state, m->comm_stream);
   if (rc) return rc;
   CK(cudaEventRecord(m->ev_recv, m->comm_stream));
-  ab::launch_copy_boxes(P.phase1, P.n1, P.max1, m->stream);
+  ab::launch_copy_boxes(P.phase1, P.n1, P.max1, m->stream, 1);
   return AB_OK;
 }
 int bvals_exchange_end(AbMesh *m) {
   int idx = plan_index(m);
   AbMesh::Plan &P = m->plan[idx < 0 ? 0 : idx];
   CK(cudaStreamWaitEvent(m->stream, m->ev_recv, 0));
-  ab::launch_copy_boxes(P.phase1r, P.n1r, P.max1r, m->stream);
-  ab::launch_copy_boxes(P.phase2, P.n2, P.max2, m->stream);
+  ab::launch_copy_boxes(P.phase1r, P.n1r, P.max1r, m->stream, 1);
+  ab::launch_copy_boxes(P.phase2, P.n2, P.max2, m->stream, 1);
   if (idx < 0) m->plan[0].built = false;   // mixed state: never cache
   CK(cudaGetLastError());
   return AB_OK;
@@ -1249,7 +1261,7 @@ int block_bvals_send(AbMesh *m, int lid, int var) {
     AbMesh::Plan *P;
     int rc = block_plan(m, lid, var, &P);
     if (rc) return rc;
-    if (P->npack) ab::launch_copy_boxes(P->pack, P->npack, P->maxpack, m->stream);
+    if (P->npack) ab::launch_copy_boxes(P->pack, P->npack, P->maxpack, m->stream, 1);
   }
   m->bcomm[lid].sent[var]++;
   if (!m->peer_state.empty() || m->p.nranks > 1) {
@@ -1278,9 +1290,9 @@ int block_bvals_set(AbMesh *m, int lid, int var) {
   AbMesh::Plan *P;
   int rc = block_plan(m, lid, var, &P);
   if (rc) return rc;
-  ab::launch_copy_boxes(P->phase1, P->n1, P->max1, m->stream);
-  ab::launch_copy_boxes(P->phase1r, P->n1r, P->max1r, m->stream);
-  ab::launch_copy_boxes(P->phase2, P->n2, P->max2, m->stream);
+  ab::launch_copy_boxes(P->phase1, P->n1, P->max1, m->stream, 1);
+  ab::launch_copy_boxes(P->phase1r, P->n1r, P->max1r, m->stream, 1);
+  ab::launch_copy_boxes(P->phase2, P->n2, P->max2, m->stream, 1);
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -1625,6 +1637,7 @@ struct SmrDeviceOps {
     }
     // the table carries the CURRENT register pointers (u / u1 swap every stage); stream-ordered
     // upload + sync because the source is pageable host memory (see build_state_plan)
+    for (auto &c : v) ab::set_box_divisors(c);
     if (cudaMemcpyAsync(m->smr_boxes, v.data(), sizeof(ab::CopyBox)*v.size(), cudaMemcpyHostToDevice, st) != cudaSuccess
         || cudaStreamSynchronize(st) != cudaSuccess) { rc = AB_ERR_CUDA; return; }
     ab::launch_copy_boxes(m->smr_boxes, (int)v.size(), total, st);

@@ -53,6 +53,21 @@ struct EmfPlan {
   int nedge_fine[12];             // divisor on the 12 (4 in 2-D) block edges
 };
 
+// Exact t / d for 0 <= t < 2^31 by one multiply-high and a shift (the divisor is a launch / plan
+// constant; a run-time integer division costs ~20 instructions, a 64-bit one ~70).
+// l = ceil(log2 d), m = ceil(2^(31+l) / d) < 2^32, t / d = umulhi(t, m) >> (l-1)
+// (Granlund & Montgomery 1994, N = 31).  d = 1 is encoded as m = 0.
+struct FastDiv { unsigned m, s; };
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f{0u, 0u};
+  if (d <= 1) return f;
+  int l = 0;
+  while ((1LL << l) < d) ++l;
+  f.m = (unsigned)(((1ULL << (31 + l)) + (unsigned long long)d - 1ULL)/(unsigned long long)d);
+  f.s = (unsigned)(l - 1);
+  return f;
+}
+
 // one box copy of the ghost exchange: dst(k,j,i) = src(k+dk, j+dj, i+di) for the box
 struct CopyBox {
   double *dst; const double *src;
@@ -63,7 +78,11 @@ struct CopyBox {
   int si0, sj0, sk0;                      // src box origin
   int ni, nj, nk;                         // box extent
   long offset;                            // exclusive prefix of element counts
+  FastDiv d_per, d_ni, d_nj;              // divisors ni*nj*nk, ni, nj (set_box_divisors)
 };
+static inline void set_box_divisors(CopyBox &c) {
+  c.d_per = make_fastdiv(c.ni*c.nj*c.nk); c.d_ni = make_fastdiv(c.ni); c.d_nj = make_fastdiv(c.nj);
+}
 
 // Static mesh refinement (ab_smr_kernels.cu): index geometry of a block and its coarse buffers
 // (MeshBlock::cis.. / cnghost, mesh/meshblock.cpp:82-100) with the 1-D coordinate arrays the
