@@ -19,7 +19,7 @@ GEN = os.path.join(HERE, "_gen", "pkg", "csrc")
 SO = os.path.join(HERE, "libathena_b200_emu.so")
 SOURCES = ["ab_kernels.cu", "ab_flux_nu.cu", "ab_mesh.cu", "ab_smr.cpp", "ab_smr_kernels.cu"]
 # kernels that use __syncthreads / warp shuffles (run with one fiber per thread)
-COOP = {"k_cons2prim", "k_new_dt", "k_history", "k_flux_ppm_x1", "k_flux_ppm_t"}
+COOP = {"k_cons2prim", "k_new_dt", "k_history", "k_flux_ppm_x1", "k_flux_ppm_t", "k_mesh_new_dt"}
 
 
 def _balanced_back(s, end, open_c, close_c):
