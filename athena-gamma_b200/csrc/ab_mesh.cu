@@ -1481,7 +1481,7 @@ int user_source(AbMesh *m, LocalBlock &L, double time, double dt) {
   return AB_OK;
 }
 
-void physical_bcs(AbMesh *m, LocalBlock &L) {
+int physical_bcs(AbMesh *m, LocalBlock &L) {
   // BoundaryValues::ApplyPhysicalBoundaries (bvals/bvals.cpp:436-620): outflow, reflecting
   HostBlock &B = *L.hb;
   int ng = m->p.nghost, mhd = m->p.mhd;
@@ -1497,7 +1497,7 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
   if (!app[5] && m->f3) bke = ke + ng;
   cudaStream_t s = L.stream;
   if (app[0]) {
-    if (B.bcs[0] == AB_BC_USER) user_bc_face(m, L, 0, is, ie, bjs, bje, bks, bke);
+    if (B.bcs[0] == AB_BC_USER) { const int rcu = user_bc_face(m, L, 0, is, ie, bjs, bje, bks, bke); if (rcu) return rcu; }
 
     else ab::launch_phys_bc(L.d, mhd, 0, B.bcs[0] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
     if (mhd) ab::launch_calc_bcc(L.d, is-ng, is-1, bjs, bje, bks, bke, s);
@@ -1505,7 +1505,7 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
     ab::launch_scalar_eos(L.d, m->kp, 1, is-ng, is-1, bjs, bje, bks, bke, s);
   }
   if (app[1]) {
-    if (B.bcs[1] == AB_BC_USER) user_bc_face(m, L, 1, is, ie, bjs, bje, bks, bke);
+    if (B.bcs[1] == AB_BC_USER) { const int rcu = user_bc_face(m, L, 1, is, ie, bjs, bje, bks, bke); if (rcu) return rcu; }
 
     else ab::launch_phys_bc(L.d, mhd, 1, B.bcs[1] == AB_BC_REFLECT, is, ie, bjs, bje, bks, bke, s);
     if (mhd) ab::launch_calc_bcc(L.d, ie+1, ie+ng, bjs, bje, bks, bke, s);
@@ -1514,7 +1514,7 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
   }
   if (m->f2) {
     if (app[2]) {
-      if (B.bcs[2] == AB_BC_USER) user_bc_face(m, L, 2, bis, bie, js, je, bks, bke);
+      if (B.bcs[2] == AB_BC_USER) { const int rcu = user_bc_face(m, L, 2, bis, bie, js, je, bks, bke); if (rcu) return rcu; }
 
       else ab::launch_phys_bc(L.d, mhd, 2, B.bcs[2] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, js-ng, js-1, bks, bke, s);
@@ -1522,7 +1522,7 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
       ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, js-ng, js-1, bks, bke, s);
     }
     if (app[3]) {
-      if (B.bcs[3] == AB_BC_USER) user_bc_face(m, L, 3, bis, bie, js, je, bks, bke);
+      if (B.bcs[3] == AB_BC_USER) { const int rcu = user_bc_face(m, L, 3, bis, bie, js, je, bks, bke); if (rcu) return rcu; }
 
       else ab::launch_phys_bc(L.d, mhd, 3, B.bcs[3] == AB_BC_REFLECT, bis, bie, js, je, bks, bke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, je+1, je+ng, bks, bke, s);
@@ -1533,7 +1533,7 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
   if (m->f3) {
     bjs = js - ng; bje = je + ng;
     if (app[4]) {
-      if (B.bcs[4] == AB_BC_USER) user_bc_face(m, L, 4, bis, bie, bjs, bje, ks, ke);
+      if (B.bcs[4] == AB_BC_USER) { const int rcu = user_bc_face(m, L, 4, bis, bie, bjs, bje, ks, ke); if (rcu) return rcu; }
 
       else ab::launch_phys_bc(L.d, mhd, 4, B.bcs[4] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ks-ng, ks-1, s);
@@ -1541,7 +1541,7 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
       ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, bjs, bje, ks-ng, ks-1, s);
     }
     if (app[5]) {
-      if (B.bcs[5] == AB_BC_USER) user_bc_face(m, L, 5, bis, bie, bjs, bje, ks, ke);
+      if (B.bcs[5] == AB_BC_USER) { const int rcu = user_bc_face(m, L, 5, bis, bie, bjs, bje, ks, ke); if (rcu) return rcu; }
 
       else ab::launch_phys_bc(L.d, mhd, 5, B.bcs[5] == AB_BC_REFLECT, bis, bie, bjs, bje, ks, ke, s);
       if (mhd) ab::launch_calc_bcc(L.d, bis, bie, bjs, bje, ke+1, ke+ng, s);
@@ -1549,6 +1549,7 @@ void physical_bcs(AbMesh *m, LocalBlock &L) {
       ab::launch_scalar_eos(L.d, m->kp, 1, bis, bie, bjs, bje, ke+1, ke+ng, s);
     }
   }
+  return AB_OK;
 }
 
 int new_time_step(AbMesh *m, int advance, bool blocks_done = false) {
@@ -1684,6 +1685,7 @@ int smr_prolongate(AbMesh *m, int lid) {
   SmrDeviceOps ops{m, m->lb[lid].stream};
   std::vector<ab::SmrView> v = smr_views(m);
   ab::smr_run_prolongate(m->smr_rows, lid, v[lid], smr_dims(m), ops);
+  if (ops.rc) return fail(ops.rc, "SMR prolongation: CUDA error");
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -1692,6 +1694,7 @@ int smr_flux_correction(AbMesh *m) {
   SmrDeviceOps ops{m, m->stream};
   std::vector<ab::SmrView> v = smr_views(m);
   ab::smr_run_flux_correction(m->smr_rows, v, smr_dims(m), ops);
+  if (ops.rc) return fail(ops.rc, "SMR flux correction: CUDA error");
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -1848,13 +1851,14 @@ int one_cycle(AbMesh *m) {
       fork();
       if (bt) {
         primitives_all(m, last);
-        for (auto &L : m->lb) physical_bcs(m, L);
+        for (auto &L : m->lb) { rc = physical_bcs(m, L); if (rc) return rc; }
       } else for (size_t l = 0; l < m->lb.size(); ++l) {
         LocalBlock &L = m->lb[l];
         if (m->smr) { rc = smr_prolongate(m, (int)l); if (rc) return rc; }   // PROLONG
         primitives(m, L, last);
         DBG(m, "primitives");
-        physical_bcs(m, L);
+        rc = physical_bcs(m, L);
+        if (rc) return rc;
         DBG(m, "physical bcs");
       }
       join();
@@ -1871,7 +1875,7 @@ int one_cycle(AbMesh *m) {
       if (rc) return rc;
       if (one) primitives_part(m, m->lb[0], 1, 0, nb);
       else for (auto &L : m->lb) primitives_part(m, L, 1, 0);
-      for (auto &L : m->lb) physical_bcs(m, L);
+      for (auto &L : m->lb) { rc = physical_bcs(m, L); if (rc) return rc; }
     }
     if (stage == m->nstages) {
       // record the dt this cycle used, then time += dt, ncycle++, NewTimeStep
@@ -2601,14 +2605,14 @@ int ab_ct(AbMesh *m, int lid, double wght) {
 }
 int ab_physical_bcs(AbMesh *m, int lid) {
   GET_L(m, lid);
-  physical_bcs(m, L);
+  { const int rcb = physical_bcs(m, L); if (rcb) return rcb; }
   CK(cudaGetLastError());
   return AB_OK;
 }
 int ab_physical_bcs_at(AbMesh *m, int lid, double time, double dt) {
   GET_L(m, lid);
   m->bc_time = time; m->bc_dt = dt;      // what user-enrolled boundary functions are handed
-  physical_bcs(m, L);
+  { const int rcb = physical_bcs(m, L); if (rcb) return rcb; }
   CK(cudaGetLastError());
   return AB_OK;
 }
@@ -2716,7 +2720,9 @@ int ab_mesh_initialize(AbMesh *m) {
   for (size_t l = 0; l < m->lb.size(); ++l) {
     LocalBlock &L = m->lb[l];
     if (m->smr) { rc = smr_prolongate(m, (int)l); if (rc) return rc; }   // mesh.cpp:1527-1528
-    primitives(m, L); physical_bcs(m, L);
+    primitives(m, L);
+    rc = physical_bcs(m, L);
+    if (rc) return rc;
   }
   rc = new_time_step(m, 0);
   if (rc) return rc;

@@ -66,6 +66,24 @@ def test_every_golden_through_the_emulated_device_path(emu_env, order):
     assert not bad, "\n".join(bad)
 
 
+SCHEDULE_GOLDENS = ["c5_blast_hlld_plm_vl2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
+                    "c4_kh_hllc_ppm_rk2_8blk", "blast_mixedbc_hllc_plm_vl2_8blk",
+                    "khs3d_mhd_hlld_plm_vl2_8blk_s1", "c1_sod_hllc_plm_vl2_2blk"]
+
+
+@pytest.mark.parametrize("knob", ["AB_NO_BATCH", "AB_OVERLAP"])
+def test_other_schedules_through_the_emulated_device_path(emu_env, knob):
+    """The cycle runs every task as ONE launch over all MeshBlocks of the rank (ab_batch.cuh) by
+    default; AB_NO_BATCH=1 launches block by block, AB_OVERLAP=1 is the multi-GPU schedule with
+    the Primitives task split into active cells and a one-launch ghost shell.  All three must
+    land on the same bits (periodic, mixed physical boundaries, scalars, 1-D / 2-D / 3-D)."""
+    env = dict(emu_env)
+    env[knob] = "1"
+    r = subprocess.run([sys.executable, os.path.join(HERE, "smr_check.py")] + SCHEDULE_GOLDENS,
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "smr done: 0 failed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_staged_pipeline_through_the_emulated_device_path(emu_env):
     r = subprocess.run([sys.executable, os.path.join(HERE, "stage_check.py")], env=emu_env,
                        capture_output=True, text=True, timeout=300)

@@ -2,10 +2,14 @@
 the unmodified reference and (b) the C oracle stepping the same input.  Bar: bit-identical dt
 sequence; conserved variables and face fields bit-identical (north_star allows 1e-12 relative;
 we hold the stricter bit-exact bar and report the max deviation on failure)."""
+import os
+
 import numpy as np
 import pytest
 
 import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 pytestmark = pytest.mark.gpu
 
@@ -65,6 +69,20 @@ def test_overlapped_schedule_is_bit_identical(name, monkeypatch):
         pmb = m.block_of(*loc)
         for f in g.fields:
             util.assert_bitwise(pmb.get(f), g.final[n][f], "%s block %s %s" % (name, loc, f))
+
+
+def test_block_by_block_launches_are_bit_identical():
+    """AB_NO_BATCH=1: one launch per task AND MeshBlock (the schedule before ab_batch.cuh, still
+    what the task-level entry points and refined meshes use) against the same goldens the default
+    one-launch-over-all-blocks cycle reproduces in test_cuda_reproduces_reference_golden."""
+    import subprocess
+    import sys
+    names = ["c5_blast_hlld_plm_vl2_8blk", "c3_ot_hlld_ppm_vl2_4blk", "c4_kh_hllc_ppm_rk2_8blk",
+             "blast_mixedbc_hllc_plm_vl2_8blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1"]
+    r = subprocess.run([sys.executable, os.path.join(HERE, "smr_check.py")] + names,
+                       env=dict(os.environ, AB_NO_BATCH="1"), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "smr done: 0 failed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("name", ["usersrc_lhllc_plm_vl2_8blk_s1", "usersrc_hlld_plm_rk3_8blk",
