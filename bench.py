@@ -12,11 +12,20 @@ One JSON line is printed by rank 0.
   value      zone-cycles/s with the state resident in HBM (CUDA events, max over ranks)
   e2e        same metric through the C ABI with HOST buffers: every step uploads u and the face
              fields from pinned host memory, runs Mesh::Initialize-style ghost fill + one cycle,
-             and downloads u and b again
+             and downloads u and b again; the copies of neighbouring steps overlap the kernels
+             (ab_stage_*).  e2e_plain: the same sequence strictly serial
   e2e_resident  (extra) the drop-in's normal mode: state resident, one ab_mesh_cycles(1) +
              ab_history per step with their host synchronisation and read-backs
-  roofline   the reconstruct+Riemann kernel (dominant): algorithmic bytes / CUDA-event duration
-  cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref) on the host cores.
+  roofline   the reconstruct+Riemann kernel (dominant): algorithmic bytes / CUDA-event duration;
+             traffic / fp64_pipe_util / dram_fraction / local_mem_bytes / bound from the ncu
+             summary of that kernel (profiles/flux_ncu.json, with the source hash it was taken on)
+  cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref) on the host cores, a
+             bounded sample of the same problem (c5: 256^3 in 64 MeshBlocks)
+  same_config   (N=1) the GPU on exactly that <mesh>/<meshblock>
+  other_workloads  (N=1) short device-resident runs of BASELINE configs C2, C3, C4 and of the c5
+             kernels on a developed flow
+  parity     (N>1) the reference goldens sharded over the ranks of this run, bit-exact, after
+             the timed regions (tests/multirank_check.py)
 """
 import argparse
 import ctypes as C
