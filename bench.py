@@ -491,10 +491,27 @@ def main():
                 "flux_kernels_share_of_step": share,
                 "flux_avg_ms_by_dir_order": flux_profile(prof, nd, xo)}
     b_alg = BYTES_PER_ZONE_CYCLE["mhd" if mhd else "hydro"]
+    # measured DRAM traffic of one whole cycle (ncu --set full over its 23 launches, summarised by
+    # tools/ncu_cycle.py into profiles/cycle_ncu.json with the source hash of that build)
+    cyc = None
+    try:
+        cj = json.load(open(os.path.join(ROOT, "profiles", "cycle_ncu.json")))
+        if cj.get("workload") == "%s:%s" % (wl, "x".join(str(v) for v in blk)):
+            cyc = cj
+    except Exception:
+        pass
     cycle_roof = {"B_alg_bytes_per_zone_cycle": b_alg,
                   "achieved_GBs_per_gpu": b_alg*value/world/1e9,
                   "frac_of_measured_peak": b_alg*value/world/1e9/peak,
                   "frac_of_8TBs": b_alg*value/world/8.0e12}
+    if cyc:
+        moved = float(cyc["dram_bytes_per_zone_cycle"])
+        cycle_roof.update({
+            "measured_dram_bytes_per_zone_cycle": moved,
+            "measured_dram_GBs_per_gpu": moved*value/world/1e9,
+            "measured_dram_frac_of_measured_peak": moved*value/world/1e9/peak,
+            "source": "profiles/cycle_ncu.json", "captured_on_srchash": cyc.get("srchash"),
+            "srchash_now": ab.build.source_hash()})
 
     # ---- end-to-end through the C ABI with host buffers ---------------------------------------
     e2e = None if e2e_skip is None else {"value": None, "skipped": e2e_skip}
