@@ -108,6 +108,79 @@ def test_c4_kelvin_helmholtz_256cube_8blocks_bitwise_vs_reference_binary():
                                "C4 256^3")
 
 
+def _assemble_single_block(dump, n, ng):
+    """the active zones of the reference's MeshBlocks (128^3 each) put together as the arrays of
+    ONE MeshBlock of n^3 zones with ghost zones left at zero (Mesh::Initialize fills them)"""
+    nc = n + 2*ng
+    out = {"u": np.zeros((5, nc, nc, nc)), "b1": np.zeros((nc, nc, nc + 1)),
+           "b2": np.zeros((nc, nc + 1, nc)), "b3": np.zeros((nc + 1, nc, nc))}
+    for blk in dump["blocks"]:
+        bx = blk["u"].shape[-1] - 2*ng
+        i0, j0, k0 = (ng + bx*blk["loc"][d] for d in range(3))
+        a = slice(ng, ng + bx)
+        f = slice(ng, ng + bx + 1)
+        out["u"][:, k0:k0+bx, j0:j0+bx, i0:i0+bx] = blk["u"][:, a, a, a]
+        out["b1"][k0:k0+bx, j0:j0+bx, i0:i0+bx+1] = blk["b1"][a, a, f]
+        out["b2"][k0:k0+bx, j0:j0+bx+1, i0:i0+bx] = blk["b2"][a, f, a]
+        out["b3"][k0:k0+bx+1, j0:j0+bx, i0:i0+bx] = blk["b3"][f, a, a]
+    return out
+
+
+def test_c5_benchmark_mesh_one_512cube_block_bitwise_vs_reference_binary():
+    """The configuration bench.py times -- the MHD blast on ONE MeshBlock of 512^3 zones -- against
+    the unmodified reference run live on the box's CPU on the same mesh cut into 64 MeshBlocks of
+    128^3 (its OpenMP needs MeshBlocks; the decomposition does not change a bit of the result):
+    dt sequence and the active zones of u and the face fields after two cycles, bit for bit.
+    The reference needs ~70 GB of host memory at 512^3 (522 B per zone, measured) and 20 GB of
+    scratch disk for its two restart dumps: 384^3 when the box has less, skipped below that."""
+    import shutil
+    import tempfile
+    import psutil
+    import ref_run
+    if not ref_run.have_ref("mhd_hlld_ng2", "blast"):
+        pytest.skip("oracle/_ref not built")
+    avail = psutil.virtual_memory().available/2**30
+    disk = shutil.disk_usage(tempfile.gettempdir()).free/2**30
+    n = 512 if (avail > 110 and disk > 40) else (384 if (avail > 50 and disk > 20) else 0)
+    if not n:
+        pytest.skip("needs > 50 GB of free host memory and > 20 GB of scratch disk")
+    ng, ncyc = 2, 2
+    over = {"mesh/nx%d" % d: n for d in (1, 2, 3)}
+    over.update({"meshblock/nx%d" % d: 128 for d in (1, 2, 3)})
+    over["time/nlim"] = ncyc
+    res = ref_run.run_reference("mhd_hlld_ng2", "blast", os.path.join(ROOT, "inputs", "athinput.blast"),
+                                over, rst_dcycle=ncyc, threads=os.cpu_count() or 1, timeout=3000)
+    try:
+        assert len(res["rst"]) >= 2
+        first = _assemble_single_block(ref_run.read_rst(res["rst"][0], mhd=True, nghost=ng), n, ng)
+        pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", "athinput.blast"))
+        pin.modify_from_cmdline(["mesh/nx%d=%d" % (d, n) for d in (1, 2, 3)] +
+                                ["meshblock/nx%d=%d" % (d, n) for d in (1, 2, 3)] +
+                                ["time/nlim=%d" % ncyc])
+        m = ab.Mesh(pin, mhd=True, flux="hlld", nghost=ng)
+        assert m.nbtotal == 1
+        pmb = m.my_blocks[0]
+        for f in ("u", "b1", "b2", "b3"):
+            pmb.set(f, first[f])
+        del first
+        m.initialize()
+        assert m.dt == res["dts"][0]
+        dts = m.cycles(ncyc)
+        assert list(dts) == res["dts"][:ncyc], (list(dts), res["dts"][:ncyc])
+        last_dump = ref_run.read_rst(res["rst"][1], mhd=True, nghost=ng)
+        assert last_dump["ncycle"] == ncyc and m.time == last_dump["time"] and m.dt == last_dump["dt"]
+        last = _assemble_single_block(last_dump, n, ng)
+        del last_dump
+    finally:
+        ref_run.cleanup(res)
+    a = slice(ng, ng + n)
+    f = slice(ng, ng + n + 1)
+    util.assert_bitwise(pmb.get("u")[:, a, a, a], last["u"][:, a, a, a], "c5 %d^3 one block u" % n)
+    util.assert_bitwise(pmb.get("b1")[a, a, f], last["b1"][a, a, f], "c5 %d^3 one block b1" % n)
+    util.assert_bitwise(pmb.get("b2")[a, f, a], last["b2"][a, f, a], "c5 %d^3 one block b2" % n)
+    util.assert_bitwise(pmb.get("b3")[f, a, a], last["b3"][f, a, a], "c5 %d^3 one block b3" % n)
+
+
 def blast_mesh(n, block, ncyc):
     pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", "athinput.blast"))
     for d in (1, 2, 3):
