@@ -108,22 +108,82 @@ def test_c4_kelvin_helmholtz_256cube_8blocks_bitwise_vs_reference_binary():
                                "C4 256^3")
 
 
-def _assemble_single_block(dump, n, ng):
-    """the active zones of the reference's MeshBlocks (128^3 each) put together as the arrays of
-    ONE MeshBlock of n^3 zones with ghost zones left at zero (Mesh::Initialize fills them)"""
-    nc = n + 2*ng
-    out = {"u": np.zeros((5, nc, nc, nc)), "b1": np.zeros((nc, nc, nc + 1)),
-           "b2": np.zeros((nc, nc + 1, nc)), "b3": np.zeros((nc + 1, nc, nc))}
+def _assemble_single_block(dump, nx, ng, mhd):
+    """the active zones of the reference's MeshBlocks put together as the arrays of ONE MeshBlock
+    of nx = (nx1, nx2, nx3) zones, ghost zones left at zero (Mesh::Initialize fills them)"""
+    g = [ng if n > 1 else 0 for n in nx]
+    nc = [n + 2*gg for n, gg in zip(nx, g)]
+    out = {"u": np.zeros((5, nc[2], nc[1], nc[0]))}
+    if mhd:
+        out.update({"b1": np.zeros((nc[2], nc[1], nc[0] + 1)), "b2": np.zeros((nc[2], nc[1] + 1, nc[0])),
+                    "b3": np.zeros((nc[2] + 1, nc[1], nc[0]))})
     for blk in dump["blocks"]:
-        bx = blk["u"].shape[-1] - 2*ng
-        i0, j0, k0 = (ng + bx*blk["loc"][d] for d in range(3))
-        a = slice(ng, ng + bx)
-        f = slice(ng, ng + bx + 1)
-        out["u"][:, k0:k0+bx, j0:j0+bx, i0:i0+bx] = blk["u"][:, a, a, a]
-        out["b1"][k0:k0+bx, j0:j0+bx, i0:i0+bx+1] = blk["b1"][a, a, f]
-        out["b2"][k0:k0+bx, j0:j0+bx+1, i0:i0+bx] = blk["b2"][a, f, a]
-        out["b3"][k0:k0+bx+1, j0:j0+bx, i0:i0+bx] = blk["b3"][f, a, a]
+        bx = [blk["u"].shape[3 - d] - 2*g[d] for d in range(3)]
+        o = [g[d] + bx[d]*blk["loc"][d] for d in range(3)]
+        a = [slice(g[d], g[d] + bx[d]) for d in range(3)]            # active cells of the block
+        f = [slice(g[d], g[d] + bx[d] + 1) for d in range(3)]        # ... faces along d
+        A = [slice(o[d], o[d] + bx[d]) for d in range(3)]            # where they go
+        F = [slice(o[d], o[d] + bx[d] + 1) for d in range(3)]
+        out["u"][:, A[2], A[1], A[0]] = blk["u"][:, a[2], a[1], a[0]]
+        if mhd:
+            out["b1"][A[2], A[1], F[0]] = blk["b1"][a[2], a[1], f[0]]
+            out["b2"][A[2], F[1], A[0]] = blk["b2"][a[2], f[1], a[0]]
+            out["b3"][F[2], A[1], A[0]] = blk["b3"][f[2], a[1], a[0]]
     return out
+
+
+def _one_block_vs_live_reference(cfg, pgen, inp, mhd, flux, ng, nx, bx, ncyc, what):
+    """the reference on mesh nx cut into MeshBlocks bx (live, all host threads) against the device
+    on the same mesh as ONE MeshBlock: dt sequence and active zones after ncyc cycles, bit for bit"""
+    import ref_run
+    if not ref_run.have_ref(cfg, pgen):
+        pytest.skip("oracle/_ref not built")
+    over = {"mesh/nx%d" % (d + 1): nx[d] for d in range(3)}
+    over.update({"meshblock/nx%d" % (d + 1): bx[d] for d in range(3)})
+    over["time/nlim"] = ncyc
+    nblocks = int(np.prod([nx[d]//bx[d] for d in range(3)]))
+    res = ref_run.run_reference(cfg, pgen, os.path.join(ROOT, "inputs", inp), over, rst_dcycle=ncyc,
+                                threads=min(os.cpu_count() or 1, nblocks), timeout=3000)
+    fields = ("u", "b1", "b2", "b3") if mhd else ("u",)
+    try:
+        assert len(res["rst"]) >= 2
+        first = _assemble_single_block(ref_run.read_rst(res["rst"][0], mhd=mhd, nghost=ng), nx, ng, mhd)
+        pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", inp))
+        pin.modify_from_cmdline(["mesh/nx%d=%d" % (d + 1, nx[d]) for d in range(3)] +
+                                ["meshblock/nx%d=%d" % (d + 1, nx[d]) for d in range(3)] +
+                                ["time/nlim=%d" % ncyc])
+        m = ab.Mesh(pin, mhd=mhd, flux=flux, nghost=ng)
+        assert m.nbtotal == 1
+        pmb = m.my_blocks[0]
+        for f in fields:
+            pmb.set(f, first[f])
+        del first
+        m.initialize()
+        assert m.dt == res["dts"][0]
+        dts = m.cycles(ncyc)
+        assert list(dts) == res["dts"][:ncyc], (list(dts), res["dts"][:ncyc])
+        last_dump = ref_run.read_rst(res["rst"][1], mhd=mhd, nghost=ng)
+        assert last_dump["ncycle"] == ncyc and m.time == last_dump["time"] and m.dt == last_dump["dt"]
+        last = _assemble_single_block(last_dump, nx, ng, mhd)
+        del last_dump
+    finally:
+        ref_run.cleanup(res)
+    g = [ng if n > 1 else 0 for n in nx]
+    a = [slice(g[d], g[d] + nx[d]) for d in range(3)]
+    f = [slice(g[d], g[d] + nx[d] + 1) for d in range(3)]
+    util.assert_bitwise(pmb.get("u")[:, a[2], a[1], a[0]], last["u"][:, a[2], a[1], a[0]], what + " u")
+    if mhd:
+        util.assert_bitwise(pmb.get("b1")[a[2], a[1], f[0]], last["b1"][a[2], a[1], f[0]], what + " b1")
+        util.assert_bitwise(pmb.get("b2")[a[2], f[1], a[0]], last["b2"][a[2], f[1], a[0]], what + " b2")
+        util.assert_bitwise(pmb.get("b3")[f[2], a[1], a[0]], last["b3"][f[2], a[1], a[0]], what + " b3")
+
+
+def _host_room():
+    import shutil
+    import tempfile
+    import psutil
+    return (psutil.virtual_memory().available/2**30,
+            shutil.disk_usage(tempfile.gettempdir()).free/2**30)
 
 
 def test_c5_benchmark_mesh_one_512cube_block_bitwise_vs_reference_binary():
@@ -133,52 +193,31 @@ def test_c5_benchmark_mesh_one_512cube_block_bitwise_vs_reference_binary():
     dt sequence and the active zones of u and the face fields after two cycles, bit for bit.
     The reference needs ~70 GB of host memory at 512^3 (522 B per zone, measured) and 20 GB of
     scratch disk for its two restart dumps: 384^3 when the box has less, skipped below that."""
-    import shutil
-    import tempfile
-    import psutil
-    import ref_run
-    if not ref_run.have_ref("mhd_hlld_ng2", "blast"):
-        pytest.skip("oracle/_ref not built")
-    avail = psutil.virtual_memory().available/2**30
-    disk = shutil.disk_usage(tempfile.gettempdir()).free/2**30
+    avail, disk = _host_room()
     n = 512 if (avail > 110 and disk > 40) else (384 if (avail > 50 and disk > 20) else 0)
     if not n:
         pytest.skip("needs > 50 GB of free host memory and > 20 GB of scratch disk")
-    ng, ncyc = 2, 2
-    over = {"mesh/nx%d" % d: n for d in (1, 2, 3)}
-    over.update({"meshblock/nx%d" % d: 128 for d in (1, 2, 3)})
-    over["time/nlim"] = ncyc
-    res = ref_run.run_reference("mhd_hlld_ng2", "blast", os.path.join(ROOT, "inputs", "athinput.blast"),
-                                over, rst_dcycle=ncyc, threads=os.cpu_count() or 1, timeout=3000)
-    try:
-        assert len(res["rst"]) >= 2
-        first = _assemble_single_block(ref_run.read_rst(res["rst"][0], mhd=True, nghost=ng), n, ng)
-        pin = ab.ParameterInput(path=os.path.join(ROOT, "inputs", "athinput.blast"))
-        pin.modify_from_cmdline(["mesh/nx%d=%d" % (d, n) for d in (1, 2, 3)] +
-                                ["meshblock/nx%d=%d" % (d, n) for d in (1, 2, 3)] +
-                                ["time/nlim=%d" % ncyc])
-        m = ab.Mesh(pin, mhd=True, flux="hlld", nghost=ng)
-        assert m.nbtotal == 1
-        pmb = m.my_blocks[0]
-        for f in ("u", "b1", "b2", "b3"):
-            pmb.set(f, first[f])
-        del first
-        m.initialize()
-        assert m.dt == res["dts"][0]
-        dts = m.cycles(ncyc)
-        assert list(dts) == res["dts"][:ncyc], (list(dts), res["dts"][:ncyc])
-        last_dump = ref_run.read_rst(res["rst"][1], mhd=True, nghost=ng)
-        assert last_dump["ncycle"] == ncyc and m.time == last_dump["time"] and m.dt == last_dump["dt"]
-        last = _assemble_single_block(last_dump, n, ng)
-        del last_dump
-    finally:
-        ref_run.cleanup(res)
-    a = slice(ng, ng + n)
-    f = slice(ng, ng + n + 1)
-    util.assert_bitwise(pmb.get("u")[:, a, a, a], last["u"][:, a, a, a], "c5 %d^3 one block u" % n)
-    util.assert_bitwise(pmb.get("b1")[a, a, f], last["b1"][a, a, f], "c5 %d^3 one block b1" % n)
-    util.assert_bitwise(pmb.get("b2")[a, f, a], last["b2"][a, f, a], "c5 %d^3 one block b2" % n)
-    util.assert_bitwise(pmb.get("b3")[f, a, a], last["b3"][f, a, a], "c5 %d^3 one block b3" % n)
+    _one_block_vs_live_reference("mhd_hlld_ng2", "blast", "athinput.blast", True, "hlld", 2,
+                                 (n, n, n), (128, 128, 128), 2, "c5 %d^3 one block" % n)
+
+
+def test_c4_benchmark_mesh_one_512cube_block_bitwise_vs_reference_binary():
+    """BASELINE configs[3] at its size: Kelvin-Helmholtz, HLLC + PPM + RK2 (the shared-memory PPM
+    sweeps) on ONE 512^3 MeshBlock against the reference on 64 MeshBlocks of 128^3, two cycles.
+    The device starts from the reference's dump of cycle 0, so the reference's per-MeshBlock
+    random seeds (pgen/kh.cpp:71) are part of the input."""
+    avail, disk = _host_room()
+    n = 512 if (avail > 70 and disk > 30) else (256 if (avail > 20 and disk > 10) else 0)
+    if not n:
+        pytest.skip("needs > 20 GB of free host memory and > 10 GB of scratch disk")
+    _one_block_vs_live_reference("hydro_hllc_ng3", "kh", "athinput.kh", False, "hllc", 3,
+                                 (n, n, n), (128, 128, 128), 2, "c4 %d^3 one block" % n)
+
+
+def test_c3_benchmark_mesh_one_2048sq_block_bitwise_vs_reference_binary():
+    """BASELINE configs[2] as ONE 2048^2 MeshBlock against the reference on 16 MeshBlocks of 512^2"""
+    _one_block_vs_live_reference("mhd_hlld_ng3", "orszag_tang", "athinput.orszag_tang", True, "hlld",
+                                 3, (2048, 2048, 1), (512, 512, 1), 2, "c3 2048^2 one block")
 
 
 def blast_mesh(n, block, ncyc):
