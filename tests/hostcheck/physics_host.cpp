@@ -2,6 +2,7 @@
 // CPU test-suite can compare its arithmetic with the oracle without a GPU.  Not part of the
 // product; the product library contains no host execution path for these functions.
 #include "../../athena-gamma_b200/csrc/ab_physics.cuh"
+#include "../../athena-gamma_b200/csrc/ab_types.h"
 
 template <int S, bool M>
 static void run(long n, const double *wl, const double *wr, const double *bx, const double *dvn,
@@ -192,4 +193,17 @@ extern "C" void hc_smr_prolong(const int *dims, const double *x1v, const double 
         for (int di = 0; di < 2; ++di)
           fine[((long)(fk+dk)*nc2 + (fj+dj))*nc1 + (fi+di)] = out[dk*4 + di*2 + dj];
     }
+}
+
+// make_fastdiv (ab_types.h) with the device's fast_div formula (ab_batch.cuh: __umulhi(t, m) >> s,
+// m = 0 meaning d = 1): number of t in [t0, t1] (stride `step`) where it differs from t / d
+extern "C" long hc_fastdiv_mismatches(int d, long t0, long t1, long step) {
+  const ab::FastDiv f = ab::make_fastdiv(d);
+  long bad = 0;
+  for (long t = t0; t <= t1; t += step) {
+    const unsigned hi = (unsigned)(((unsigned long long)(unsigned)t*f.m) >> 32);
+    const int q = f.m ? (int)(hi >> f.s) : (int)t;
+    if (q != (int)(t / d)) ++bad;
+  }
+  return bad;
 }

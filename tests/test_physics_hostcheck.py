@@ -34,7 +34,29 @@ def hc():
                                 C.c_double, C.c_double, C.c_double, dp, dp]
     L.hc_plm.argtypes = [C.c_long, C.c_int, dp, dp, dp, C.c_double, C.c_double, dp, dp]
     L.hc_ppm.argtypes = [C.c_long, C.c_int, dp, dp, dp, dp, dp, dp, dp]
+    L.hc_fastdiv_mismatches.argtypes = [C.c_int, C.c_long, C.c_long, C.c_long]
+    L.hc_fastdiv_mismatches.restype = C.c_long
     return L
+
+
+def test_multiply_high_division_is_exact(hc):
+    """FastDiv (ab_types.h): the index decode of every flattened kernel and of k_copy_boxes.
+    t / d for 0 <= t < 2^31: every t up to 2^20 and windows at the top of the range for the
+    divisors that occur (row lengths 2..600, 513/514/516/517, powers of two and their
+    neighbours), strided sweeps of the whole range for a sample of large divisors."""
+    rng = np.random.default_rng(5)
+    top = 2**31 - 1
+    small = list(range(1, 601)) + [2**k + e for k in range(10, 31) for e in (-1, 0, 1)]
+    for d in small:
+        if d > top:
+            continue
+        assert hc.hc_fastdiv_mismatches(d, 0, 2**20, 1) == 0, d
+        assert hc.hc_fastdiv_mismatches(d, top - 2**18, top, 1) == 0, d
+    for d in [int(x) for x in rng.integers(2, top, 300)] + [top, top - 1, 3, 7, 641, 65537]:
+        assert hc.hc_fastdiv_mismatches(d, 0, top, 65521) == 0, d
+        for k in (1, 2, 3, 1000):                  # around multiples of d: where a wrong constant shows
+            lo = max(0, min(top, k*d) - 40)
+            assert hc.hc_fastdiv_mismatches(d, lo, min(top, lo + 80), 1) == 0, (d, k)
 
 
 def _dp(a):
