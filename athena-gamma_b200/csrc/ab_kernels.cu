@@ -1149,7 +1149,7 @@ __global__ void __launch_bounds__(256) k_copy_boxes(const CopyBox *__restrict__ 
     const long t = t0 + threadIdx.x;
     if (t >= total) break;
     int lo;
-    if (chunked) {
+    if (chunked & 1) {
       lo = first[t0 >> 8];
       while (lo + 1 < n && boxes[lo + 1].offset <= t) ++lo;
     } else {
@@ -1171,6 +1171,11 @@ __global__ void __launch_bounds__(256) k_copy_boxes(const CopyBox *__restrict__ 
     bx.dst[v*bx.dst_sv + (long)(bx.dk0+k)*bx.dst_s3 + (long)(bx.dj0+j)*bx.dst_s2 + (bx.di0+i)] =
         bx.src[v*bx.src_sv + (long)(bx.sk0+k)*bx.src_s3 + (long)(bx.sj0+j)*bx.src_s2 + (bx.si0+i)];
   }
+  // bit 1 of `chunked`: the destinations are another GPU's memory (direct ghost-zone exchange):
+  // make the stores visible system-wide before the kernel ends
+#ifndef AB_HOST_EMU
+  if (chunked & 2) __threadfence_system();
+#endif
 }
 
 void launch_copy_boxes(const CopyBox *boxes_dev, int n, long total_elems, cudaStream_t s,

@@ -137,6 +137,12 @@ struct HostBlock {
 struct PeerBuf {              // staging for one peer rank and one exchange kind
   double *send = nullptr, *recv = nullptr;
   size_t nsend = 0, nrecv = 0;
+  // Direct exchange over NVLink peer memory (AbMesh::p2p): my receive buffers, two of them used
+  // alternately, are exported with cudaIpcGetMemHandle; p2p_send[] are the PEER's receive
+  // buffers for my messages mapped into this process -- the pack kernel stores straight into
+  // them and no ncclSend / ncclRecv moves the ghost zones.
+  double *p2p_recv[2] = {nullptr, nullptr};
+  double *p2p_send[2] = {nullptr, nullptr};
 };
 
 struct LocalBlock {
@@ -258,7 +264,7 @@ struct AbMesh {
     ab::CopyBox *phase1 = nullptr; int n1 = 0; long max1 = 0;         // ghost fill, local sources
     ab::CopyBox *phase1r = nullptr; int n1r = 0; long max1r = 0;      // ghost fill from peer buffers
     ab::CopyBox *phase2 = nullptr; int n2 = 0; long max2 = 0;         // 1-D/2-D duplicates
-  } plan[8];
+  } plan[24];                             // [0,8): NCCL path by register-swap parity; [8,24): direct exchange, parity | buffer << 3
   std::map<int, PeerBuf> peer_state, peer_emf;
   // per-block boundary tasks (ab_bvals_send / recv_try / set, ab_emf_send / recv_try): how many
   // times each local block has sent / received each variable, the number of completed NCCL
@@ -266,6 +272,11 @@ struct AbMesh {
   struct BlockComm { long sent[3] = {0, 0, 0}, recvd[3] = {0, 0, 0}, emf_sent = 0, emf_recvd = 0; };
   std::vector<BlockComm> bcomm;
   long nccl_state_round = 0, nccl_emf_round = 0;
+  // p2p: 0 off (NCCL moves the ghost zones), 1 requested (AB_P2P=1), 2 active (peer buffers
+  // mapped), -1 unavailable (cudaIpc* failed: NCCL path)
+  int p2p = 0;
+  long p2p_round = 0;                     // whole-mesh ghost exchanges done (selects the buffer)
+  double *p2p_token = nullptr;            // 1 double: operand of the barrier all-reduce
   std::map<long, Plan> bplan;
   ncclComm_t comm = nullptr;
   bool emf_built = false;
@@ -902,7 +913,7 @@ void peer_messages(const AbMesh *m, int kind, std::map<int, std::vector<Msg>> &s
 // lid_filter >= 0: only the ghost zones (and send buffers) of that local block; vars: bit 0 the
 // hydro registers, bit 1 the face field, bit 2 the passive scalars (the per-block, per-variable
 // plans behind ab_bvals_send / ab_bvals_set).  Buffer offsets never depend on the filters.
-int build_state_plan(AbMesh *m, AbMesh::Plan &P, int lid_filter = -1, int vars = 7) {
+int build_state_plan(AbMesh *m, AbMesh::Plan &P, int lid_filter = -1, int vars = 7, int p2p_buf = -1) {
   std::vector<CopyBox> pack, ph1, ph1r, ph2;
   const int mhd = m->p.mhd;
   const long ncc = (long)m->nc[0]*m->nc[1]*m->nc[2];
@@ -922,6 +933,16 @@ int build_state_plan(AbMesh *m, AbMesh::Plan &P, int lid_filter = -1, int vars =
     PeerBuf &pb = m->peer_state[kv.first];
     if (!pb.recv) { pb.nrecv = off; CK(cudaMalloc(&pb.recv, std::max<size_t>(off, 1)*8)); }
   }
+  // where a peer's messages land / are read: the NCCL staging buffers, or (direct exchange) the
+  // peer's own receive buffer of this round mapped into this process and mine
+  auto send_base = [&](int rank) -> double * {
+    PeerBuf &pb = m->peer_state[rank];
+    return p2p_buf >= 0 ? pb.p2p_send[p2p_buf] : pb.send;
+  };
+  auto recv_base = [&](int rank) -> double * {
+    PeerBuf &pb = m->peer_state[rank];
+    return p2p_buf >= 0 ? pb.p2p_recv[p2p_buf] : pb.recv;
+  };
   auto add_box = [](std::vector<CopyBox> &v, double *dst, long ds3, long ds2, long dsv,
                     const double *src, long ss3, long ss2, long ssv, int nvar, const Box &db,
                     int si0, int sj0, int sk0) {
@@ -949,7 +970,7 @@ int build_state_plan(AbMesh *m, AbMesh::Plan &P, int lid_filter = -1, int vars =
         LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
         add_box(ph1, L.d.u, cs3, cs2, ncc, N.d.u, cs3, cs2, ncc, m->nh, rb, sb.si, sb.sj, sb.sk);
       } else {
-        double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}];
+        double *src = recv_base(nb.rank) + recv_off[{(int)l, (int)n}];
         Box z = {0, rb.ei-rb.si, 0, rb.ej-rb.sj, 0, rb.ek-rb.sk};
         long s2 = z.ei+1, s3 = s2*(z.ej+1);
         add_box(ph1r, L.d.u, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), m->nh, rb, 0, 0, 0);
@@ -966,7 +987,7 @@ int build_state_plan(AbMesh *m, AbMesh::Plan &P, int lid_filter = -1, int vars =
             LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
             if (v_fld) add_box(ph1, L.d.b[c], s3, s2, 0, N.d.b[c], s3, s2, 0, 1, frb, fsb.si, fsb.sj, fsb.sk);
           } else {
-            double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}] + roff;
+            double *src = recv_base(nb.rank) + recv_off[{(int)l, (int)n}] + roff;
             long t2 = frb.ei-frb.si+1, t3 = t2*(frb.ej-frb.sj+1);
             if (v_fld) add_box(ph1r, L.d.b[c], s3, s2, 0, src, t3, t2, 0, 1, frb, 0, 0, 0);
             roff += frb.count();
@@ -988,7 +1009,7 @@ int build_state_plan(AbMesh *m, AbMesh::Plan &P, int lid_filter = -1, int vars =
           LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
           add_box(ph1, L.d.s, cs3, cs2, ncc, N.d.s, cs3, cs2, ncc, ns, rb, sb.si, sb.sj, sb.sk);
         } else {
-          double *src = m->peer_state[nb.rank].recv + recv_off[{(int)l, (int)n}] + roff;
+          double *src = recv_base(nb.rank) + recv_off[{(int)l, (int)n}] + roff;
           Box z = {0, rb.ei-rb.si, 0, rb.ej-rb.sj, 0, rb.ek-rb.sk};
           long s2 = z.ei+1, s3 = s2*(z.ej+1);
           add_box(ph1r, L.d.s, cs3, cs2, ncc, src, s3, s2, s3*(z.ek+1), ns, rb, 0, 0, 0);
@@ -996,7 +1017,7 @@ int build_state_plan(AbMesh *m, AbMesh::Plan &P, int lid_filter = -1, int vars =
       }
       // ---- sending side (remote only): pack my active zones into the peer buffer
       if (!local) {
-        double *dst = m->peer_state[nb.rank].send + send_off[{(int)l, (int)n}];
+        double *dst = send_base(nb.rank) + send_off[{(int)l, (int)n}];
         Box lb2 = cc_send_box(m, nb.ox1, nb.ox2, nb.ox3);
         Box z = {0, lb2.ei-lb2.si, 0, lb2.ej-lb2.sj, 0, lb2.ek-lb2.sk};
         long s2 = z.ei+1, s3 = s2*(z.ej+1);
@@ -1127,6 +1148,77 @@ int peer_exchange(AbMesh *m, std::map<int, PeerBuf> &peers, cudaStream_t st = nu
   return AB_OK;
 }
 
+// Direct ghost-zone exchange (AB_P2P=1): every rank exports two receive buffers per peer with
+// cudaIpcGetMemHandle, the handles travel over NCCL, the peers map them.  Collective: every rank
+// gets here in its first whole-mesh exchange.  Any failure on any rank -> all fall back to NCCL.
+int p2p_setup(AbMesh *m) {
+#ifdef AB_HOST_EMU
+  m->p2p = -1;
+  return AB_OK;
+#else
+  if (!m->comm) { m->p2p = -1; return AB_OK; }
+  std::map<int, std::vector<Msg>> sends, recvs;
+  peer_messages(m, 0, sends, recvs);
+  double ok = 1.0;
+  std::map<int, std::array<cudaIpcMemHandle_t, 2>> mine, theirs;
+  for (auto &kv : recvs) {
+    long n = 0;
+    for (auto &ms : kv.second) n += ms.count;
+    PeerBuf &pb = m->peer_state[kv.first];
+    for (int b = 0; b < 2; ++b) {
+      if (cudaMalloc(&pb.p2p_recv[b], std::max<size_t>(n, 1)*8) != cudaSuccess ||
+          cudaIpcGetMemHandle(&mine[kv.first][b], pb.p2p_recv[b]) != cudaSuccess) ok = 0.0;
+    }
+  }
+  cudaGetLastError();
+  // handles: 2 x 64 bytes per peer, moved as 16 doubles
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+  const size_t npeer = recvs.size();
+  double *stage = nullptr;
+  CK(cudaMalloc(&stage, std::max<size_t>(npeer, 1)*2*128));
+  {
+    size_t q = 0;
+    for (auto &kv : recvs) {
+      CK(cudaMemcpyAsync((char *)stage + q*256, mine[kv.first].data(), 128, cudaMemcpyHostToDevice, m->stream));
+      ++q;
+    }
+    NK(g_nccl.GroupStart());
+    q = 0;
+    for (auto &kv : recvs) {
+      NK(g_nccl.Send((char *)stage + q*256, 16, NCCL_FLOAT64, kv.first, m->comm, m->stream));
+      NK(g_nccl.Recv((char *)stage + q*256 + 128, 16, NCCL_FLOAT64, kv.first, m->comm, m->stream));
+      ++q;
+    }
+    NK(g_nccl.GroupEnd());
+    q = 0;
+    for (auto &kv : recvs) {
+      CK(cudaMemcpyAsync(theirs[kv.first].data(), (char *)stage + q*256 + 128, 128, cudaMemcpyDeviceToHost, m->stream));
+      ++q;
+    }
+    CK(cudaStreamSynchronize(m->stream));
+  }
+  cudaFree(stage);
+  if (ok != 0.0) for (auto &kv : recvs) {
+    PeerBuf &pb = m->peer_state[kv.first];
+    for (int b = 0; b < 2; ++b)
+      if (cudaIpcOpenMemHandle((void **)&pb.p2p_send[b], theirs[kv.first][b],
+                               cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0.0; pb.p2p_send[b] = nullptr; }
+  }
+  cudaGetLastError();
+  if (!m->p2p_token) CK(cudaMalloc(&m->p2p_token, 8));
+  CK(cudaMemcpyAsync(m->p2p_token, &ok, 8, cudaMemcpyHostToDevice, m->stream));
+  NK(g_nccl.AllReduce(m->p2p_token, m->p2p_token, 1, NCCL_FLOAT64, NCCL_MIN, m->comm, m->stream));
+  double all_ok = 0.0;
+  CK(cudaMemcpyAsync(&all_ok, m->p2p_token, 8, cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  m->p2p = (all_ok != 0.0) ? 2 : -1;
+  if (const char *e = getenv("AB_P2P_VERBOSE")) if (e[0] == '1')
+    fprintf(stderr, "[athena_b200] rank %d: direct ghost-zone exchange over peer memory %s (%zu peers)\n",
+            m->p.rank, m->p2p == 2 ? "ACTIVE" : "unavailable, using NCCL", npeer);
+  return AB_OK;
+#endif
+}
+
 int plan_index(AbMesh *m) {
   // all local blocks swap registers in lockstep inside the driver; a mixed state (possible
   // only through per-block ab_swap calls) forces a rebuild
@@ -1135,15 +1227,31 @@ int plan_index(AbMesh *m) {
   return pu | (pb << 1) | (ps << 2);
 }
 
+int p2p_setup(AbMesh *m);
+
 int bvals_exchange(AbMesh *m) {
   int idx = plan_index(m);
+  if (m->p2p == 1) { int rc = p2p_setup(m); if (rc) return rc; }   // first exchange: map the peers
+  // Direct exchange: the pack kernel stores into the peers' receive buffers over NVLink; one
+  // 8-byte all-reduce is the barrier between everybody's stores and everybody's unpack.  The two
+  // receive buffers alternate by round: a rank that is a whole round ahead writes the buffer its
+  // peer is not reading (it cannot be two ahead: the barrier in between needs the peer).
+  const bool direct = (m->p2p == 2);
+  const int buf = direct ? (int)(m->p2p_round & 1) : -1;
   int use = idx < 0 ? 0 : idx;
-  if (idx < 0) m->plan[0].built = false;
-  if (!m->plan[use].built) { int rc = build_state_plan(m, m->plan[use]); if (rc) return rc; }
-  if (idx < 0) m->plan[0].built = false;   // mixed state: never cache
+  if (direct) use = 8 + (use | (buf << 3));
+  if (idx < 0) m->plan[use].built = false;
+  if (!m->plan[use].built) { int rc = build_state_plan(m, m->plan[use], -1, 7, buf); if (rc) return rc; }
+  if (idx < 0) m->plan[use].built = false;   // mixed state: never cache
   AbMesh::Plan &P = m->plan[use];
-  if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream, 1);
-  int rc = peer_exchange(m, m->peer_state);
+  if (P.npack) ab::launch_copy_boxes(P.pack, P.npack, P.maxpack, m->stream, direct ? 3 : 1);
+  int rc = AB_OK;
+  if (direct) {
+    NK(g_nccl.AllReduce(m->p2p_token, m->p2p_token, 1, NCCL_FLOAT64, NCCL_MIN, m->comm, m->stream));
+    ++m->p2p_round;
+  } else {
+    rc = peer_exchange(m, m->peer_state);
+  }
   if (rc) return rc;
   ab::launch_copy_boxes(P.phase1, P.n1, P.max1, m->stream, 1);
   ab::launch_copy_boxes(P.phase1r, P.n1r, P.max1r, m->stream, 1);
@@ -2236,7 +2344,14 @@ int ab_mesh_destroy(AbMesh *m) {
   for (auto &L : m->lb) for (void *q : L.debug_allocs) cudaFree(q);
   cudaFree(m->slab);
   cudaFree(m->emf_plans_dev);
-  for (int i = 0; i < 8; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase1r); cudaFree(m->plan[i].phase2); }
+  for (int i = 0; i < 24; ++i) { cudaFree(m->plan[i].pack); cudaFree(m->plan[i].phase1); cudaFree(m->plan[i].phase1r); cudaFree(m->plan[i].phase2); }
+#ifndef AB_HOST_EMU
+  for (auto &kv : m->peer_state) for (int b = 0; b < 2; ++b) {
+    if (kv.second.p2p_send[b]) cudaIpcCloseMemHandle(kv.second.p2p_send[b]);
+    cudaFree(kv.second.p2p_recv[b]);
+  }
+#endif
+  cudaFree(m->p2p_token);
   for (auto &kv : m->bplan) { cudaFree(kv.second.pack); cudaFree(kv.second.phase1); cudaFree(kv.second.phase1r); cudaFree(kv.second.phase2); }
   for (auto &kv : m->peer_state) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
@@ -2469,6 +2584,10 @@ int ab_comm_init(AbMesh *m, const unsigned char id[128]) {
   ncclUniqueId u;
   memcpy(u.internal, id, 128);
   NK(g_nccl.CommInitRank(&m->comm, m->p.nranks, u, m->p.rank));
+  // direct ghost-zone exchange over peer memory unless AB_P2P=0 (falls back to NCCL by itself when
+  // the peers' buffers cannot be mapped); the overlapped schedule keeps its NCCL transfers
+  m->p2p = 1;
+  if (const char *e = getenv("AB_P2P")) m->p2p = (e[0] == '0') ? 0 : 1;
   return AB_OK;
 }
 

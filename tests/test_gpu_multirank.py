@@ -10,9 +10,11 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("overlap", ["0", "1"])
-def test_two_ranks_bitwise_vs_golden(overlap):
-    """overlap=1: the opt-in schedule with the NCCL transfers on a second stream"""
+@pytest.mark.parametrize("overlap,p2p", [("0", "0"), ("1", "0"), ("0", "1")])
+def test_two_ranks_bitwise_vs_golden(overlap, p2p):
+    """overlap=1: the opt-in schedule with the NCCL transfers on a second stream; p2p=1: the ghost
+    zones are stored straight into the peer's receive buffers over NVLink (cudaIpc-mapped), NCCL
+    only carries the barrier (AB_P2P_VERBOSE=1 prints whether the mapping succeeded)"""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -21,6 +23,6 @@ def test_two_ranks_bitwise_vs_golden(overlap):
            "--master-addr", "127.0.0.1", "--master-port", "29517",
            os.path.join(HERE, "multirank_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, AB_OVERLAP=overlap))
+                       env=dict(os.environ, AB_OVERLAP=overlap, AB_P2P=p2p, AB_P2P_VERBOSE="1"))
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0
