@@ -4,7 +4,7 @@ cd /root/repo
 N=${1:-8}
 O=gpurun_out/r2mg$N; mkdir -p $O
 nvidia-smi -L | wc -l; free -g | head -2
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 10 --warmup 3 ) > $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 10 --warmup 3 --no-e2e --no-cpu ) > $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err
 tail -5 $O/bench_${N}gpu.err
 python - $O/bench_${N}gpu.json <<'PY'
 import json, sys
