@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of round 2: everything that was written at the end of round 1 without a GPU.
-#   gpurun --timeout 900 -- 'bash tools/round2_first.sh'
+#   gpurun --timeout 900 -- 'bash tools/calls/round2_first.sh'
 # 1. the regular GPU suite (must stay green: the one-level path was not touched)
 # 2. the two xfail-marked tests with their output (device SMR path, ab_stage_* pipeline)
 # 3. the isothermal-Roe fixtures without their xfail marker
