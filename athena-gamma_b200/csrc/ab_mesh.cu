@@ -60,7 +60,10 @@ struct Nccl {
   const char *(*GetErrorString)(int) = nullptr;
   bool load() {
     if (h) return true;
-    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    // AB_NCCL_LIB: which NCCL to load (an absolute path; default: the libnccl.so.2 already in the
+    // process, else the system's)
+    if (const char *e = getenv("AB_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!h) return false;

@@ -18,7 +18,8 @@ One JSON line is printed by rank 0.
              ab_history per step with their host synchronisation and read-backs
   roofline   the reconstruct+Riemann kernel (dominant): algorithmic bytes / CUDA-event duration;
              traffic / fp64_pipe_util / dram_fraction / local_mem_bytes / bound from the ncu
-             summary of that kernel (profiles/flux_ncu.json, with the source hash it was taken on)
+             summary of that kernel (profiles/flux_ncu.json, with the hash of the device sources it
+             was taken on)
   cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref) on the host cores, a
              bounded sample of the same problem (c5: 256^3 in 64 MeshBlocks)
   same_config   (N=1) the GPU on exactly that <mesh>/<meshblock>
@@ -472,8 +473,8 @@ def main():
             if key in tj.get("kernels", {}):
                 ncu = dict(tj["kernels"][key])
                 ncu["source"] = "profiles/flux_ncu.json"
-                ncu["captured_on_srchash"] = tj.get("srchash")
-                ncu["srchash_now"] = ab.build.source_hash()
+                ncu["captured_on_kernel_hash"] = ncu.get("kernel_hash") or tj.get("kernel_hash")
+                ncu["kernel_hash_now"] = ab.build.kernel_hash()   # device sources + flags
                 traffic = ncu.get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -510,8 +511,9 @@ def main():
             "measured_dram_bytes_per_zone_cycle": moved,
             "measured_dram_GBs_per_gpu": moved*value/world/1e9,
             "measured_dram_frac_of_measured_peak": moved*value/world/1e9/peak,
-            "source": "profiles/cycle_ncu.json", "captured_on_srchash": cyc.get("srchash"),
-            "srchash_now": ab.build.source_hash()})
+            "source": "profiles/cycle_ncu.json",
+            "captured_on_kernel_hash": cyc.get("kernel_hash"),
+            "kernel_hash_now": ab.build.kernel_hash()})
 
     # ---- end-to-end through the C ABI with host buffers ---------------------------------------
     e2e = None if e2e_skip is None else {"value": None, "skipped": e2e_skip}

@@ -117,3 +117,62 @@ def test_message_plans_pair_up_across_ranks(world):
         p.join(timeout=60)
     for rank, errors in results:
         assert not errors, "rank %d: %s" % (rank, errors[:5])
+
+
+# ---------------------------------------------------------------------------------------------
+# The N > 1 path END TO END on the CPU: world_size processes, each running the emulated device
+# path (tests/hostcheck: the product's csrc/*.cu compiled for the host) with the MeshBlocks of a
+# golden fixture sharded over the ranks.  The NCCL entry points the library loads with dlopen are
+# served by a test-only stand-in over UNIX sockets (tests/hostcheck/nccl_emu.c, AB_NCCL_LIB), so
+# the pack / send / receive / unpack plans, the EMF correction across rank boundaries and the dt
+# all-reduce really move the data -- and must land on the reference's bits.
+EMU_CASES = [
+    (2, "0", ["c5_blast_hlld_plm_vl2_8blk", "c2_linwave_hlld_plm_vl2_8blk", "c4_kh_hllc_ppm_rk2_8blk",
+              "c3_ot_hlld_ppm_vl2_4blk", "c1_sod_hllc_plm_vl2_2blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1",
+              "blast_refl_hlld_plm_vl2_8blk", "iso_blast_hlle_plm_vl2_8blk"]),
+    (2, "1", ["c5_blast_hlld_plm_vl2_8blk", "c3_ot_hlld_ppm_vl2_4blk", "blast_mixedbc_hllc_plm_vl2_8blk"]),
+    (3, "0", ["c5_blast_hlld_plm_vl2_8blk", "c3_ot_hlld_ppm_vl2_4blk", "iso_blast_hlle_plm_vl2_8blk"]),
+    (4, "0", ["c5_blast_hlld_plm_vl2_8blk", "c4_kh_hllc_ppm_rk2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
+              "blast_mixedbc_hllc_plm_vl2_8blk"]),
+    (8, "0", ["c5_blast_hlld_plm_vl2_8blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1", "blast_hlld_ppm_rk3_8blk"]),
+]
+
+
+@pytest.fixture(scope="module")
+def emu_multirank_env(tmp_path_factory):
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "hostcheck"))
+    import build_mesh_host
+    so = build_mesh_host.build()
+    nccl = os.path.join(here, "hostcheck", "libnccl_emu.so")
+    src = os.path.join(here, "hostcheck", "nccl_emu.c")
+    if not os.path.exists(nccl) or os.path.getmtime(nccl) < os.path.getmtime(src):
+        subprocess.run(["gcc", "-O1", "-g", "-fPIC", "-shared", "-o", nccl, src], check=True)
+    env = dict(os.environ, AB_LIB=so, AB_NCCL_LIB=nccl, CUDA_VISIBLE_DEVICES="")
+    return env
+
+
+@pytest.mark.parametrize("world,overlap,names", EMU_CASES)
+def test_goldens_sharded_over_ranks_through_the_emulated_device_path(emu_multirank_env, tmp_path,
+                                                                     world, overlap, names):
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    procs = []
+    for r in range(world):
+        env = dict(emu_multirank_env, RANK=str(r), WORLD_SIZE=str(world), AB_ID_DIR=str(tmp_path),
+                   AB_OVERLAP=overlap)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(here, "multirank_emu_check.py")]
+                                      + names, env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=600)[0])
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and ("rank %d done: 0 failed" % r) in out, out[-3000:]
+        assert out.count("-> OK") == len(names), out[-3000:]

@@ -9,8 +9,9 @@ profiles/flux_ncu.json, the file bench.py reads its ncu-backed roofline keys fro
 
 Every `--key` starts a new group; the launches of the CSVs that follow whose kernel name matches
 `--match` (default: any k_flux) are averaged.  The source hash of the build the capture ran on is
-recorded (athena-gamma_b200/build.py:source_hash), so a stale summary is visible on the bench
-line (`captured_on_srchash` vs `srchash_now`).  Existing keys of the output file are kept."""
+recorded (athena-gamma_b200/build.py: kernel_hash over the device sources and flags, source_hash
+over everything), so a stale summary is visible on the bench line (`captured_on_kernel_hash` vs
+`kernel_hash_now`).  Existing keys of the output file are kept."""
 import csv
 import json
 import os
@@ -104,6 +105,7 @@ def main():
     if os.path.exists(out):
         doc = json.load(open(out))
     doc["srchash"] = ab.build.source_hash()
+    doc["kernel_hash"] = ab.build.kernel_hash()
     for key, match, files in groups:
         rx = re.compile(match)
         launches = [r for f in files for r in rows_of(f) if rx.search(r.get("Kernel Name", ""))]
@@ -114,6 +116,7 @@ def main():
         s["from"] = [os.path.relpath(os.path.abspath(f), ROOT) for f in files]
         s["match"] = match
         s["srchash"] = doc["srchash"]
+        s["kernel_hash"] = doc["kernel_hash"]
         doc["kernels"][key] = s
         print(key, json.dumps(s))
     json.dump(doc, open(out, "w"), indent=1, sort_keys=True)
