@@ -84,8 +84,10 @@ void launch_smr_c2p(const SmrGeom &g, const Params &p, double *cu, double *cw, i
                     double *cr, const SmrBox &bx, cudaStream_t s);
 void launch_smr_bc(const SmrGeom &g, double *cw, int nh, double *cr, int ns, int face, int refl,
                    int lo, int hi, const SmrBox &bx, cudaStream_t s);
+// compact != 0: coarse_flux is a message buffer, values stored as [nvar][nb][na]
 void launch_smr_flux(const SmrGeom &gf, const double *fine_flux, double *coarse_flux, int nvar,
-                     int dir, int fpos, int cpos, int a0, int b0, int na, int nb, cudaStream_t s);
+                     int dir, int fpos, int cpos, int a0, int b0, int na, int nb, cudaStream_t s,
+                     int compact = 0);
 
 // outflow (refl=0) / reflecting (refl=1) physical boundary on primitives and face fields
 void launch_phys_bc(const BlkDev &b, int mhd, int face, int refl, int il, int iu, int jl,

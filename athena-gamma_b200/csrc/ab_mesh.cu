@@ -232,6 +232,7 @@ struct AbMesh {
   };
   std::vector<SmrBlk> smr_blk;
   ab::CopyBox *smr_boxes = nullptr; size_t smr_boxes_cap = 0;
+  std::map<int, PeerBuf> peer_smr, peer_smr_flux;   // refined meshes across ranks: message buffers
   // Pipelined host <-> device staging (ab_stage_*): a caller that streams a new state in and
   // the result out every step (bench.py's e2e leg) overlaps the PCIe copies of the neighbouring
   // steps with this step's kernels.  Device staging buffers `in` / `out` hold the chosen
@@ -1730,8 +1731,8 @@ struct SmrDeviceOps {
               int lo, int hi, const ab::SmrBox &bx) {
     ab::launch_smr_bc(g, cw, nh, cr, ns, face, refl ? 1 : 0, lo, hi, bx, st);
   }
-  void prim2cons_box(int lid, int il, int iu, int jl, int ju, int kl, int ku) {
-    LocalBlock &L = m->lb[lid];
+  void prim2cons_box(int gid, int il, int iu, int jl, int ju, int kl, int ku) {
+    LocalBlock &L = m->lb[gid - m->gid_start];
     ab::launch_prim2cons(L.d, m->kp, il, iu, jl, ju, kl, ku, st);
     ab::launch_scalar_eos(L.d, m->kp, 1, il, iu, jl, ju, kl, ku, st);
   }
@@ -1766,19 +1767,50 @@ ab::SmrDims smr_dims(const AbMesh *m) {
   return d;
 }
 
-// views with the registers' CURRENT pointers (u <-> u1 swap by pointer every stage)
+// views with the registers' CURRENT pointers (u <-> u1 swap by pointer every stage), one per
+// MeshBlock of the MESH in gid order (the planner's rows name blocks by gid); the blocks of other
+// ranks carry the index geometry only (all blocks have the same shape), their pointers are null
 std::vector<ab::SmrView> smr_views(AbMesh *m) {
-  std::vector<ab::SmrView> v(m->lb.size());
-  for (size_t l = 0; l < m->lb.size(); ++l) {
+  std::vector<ab::SmrView> v(m->hb.size());
+  for (size_t g = 0; g < m->hb.size(); ++g) {
+    ab::SmrView &x = v[g];
+    const HostBlock &B = m->hb[g];
+    for (int f = 0; f < 6; ++f) x.bcs[f] = B.bcs[f];
+    x.g = m->smr_blk[0].g;                       // nc*, cnc*, is.., cis..: identical on every block
+    x.g.dx1f = x.g.dx2f = x.g.dx3f = x.g.x1v = x.g.x2v = x.g.x3v = nullptr;
+    x.g.cx1v = x.g.cx2v = x.g.cx3v = nullptr;
+    if (B.rank != m->p.rank) continue;
+    const int l = (int)g - m->gid_start;
     const LocalBlock &L = m->lb[l];
     const AbMesh::SmrBlk &sb = m->smr_blk[l];
-    ab::SmrView &x = v[l];
     x.u = L.d.u; x.s = L.d.s; x.w = L.d.w; x.r = L.d.r;
-    for (int d = 0; d < 3; ++d) { x.flux[d] = L.d.flux[d]; x.sflux[d] = L.d.sflux[d]; x.bcs[2*d] = L.hb->bcs[2*d]; x.bcs[2*d+1] = L.hb->bcs[2*d+1]; }
+    for (int d = 0; d < 3; ++d) { x.flux[d] = L.d.flux[d]; x.sflux[d] = L.d.sflux[d]; }
     x.cu = sb.cu; x.cw = sb.cw; x.cs = sb.cs; x.cr = sb.cr;
     x.g = sb.g;
   }
   return v;
+}
+
+// message buffers of one exchange kind sized for this round (grown on demand)
+int smr_peer_buffers(std::map<int, PeerBuf> &peers, const std::map<int, long> &nsend,
+                     const std::map<int, long> &nrecv) {
+  for (auto &kv : nsend) {
+    PeerBuf &pb = peers[kv.first];
+    if ((size_t)kv.second > pb.nsend || !pb.send) {
+      cudaFree(pb.send);
+      CK(cudaMalloc(&pb.send, std::max<long>(kv.second, 1)*8));
+    }
+    pb.nsend = (size_t)kv.second;
+  }
+  for (auto &kv : nrecv) {
+    PeerBuf &pb = peers[kv.first];
+    if ((size_t)kv.second > pb.nrecv || !pb.recv) {
+      cudaFree(pb.recv);
+      CK(cudaMalloc(&pb.recv, std::max<long>(kv.second, 1)*8));
+    }
+    pb.nrecv = (size_t)kv.second;
+  }
+  return AB_OK;
 }
 
 int smr_exchange(AbMesh *m) {
@@ -1786,7 +1818,65 @@ int smr_exchange(AbMesh *m) {
   // MeshBlocks of at least 2*NGHOST cells, so restricted slabs stay inside the active coarse cells
   SmrDeviceOps ops{m, m->stream};
   std::vector<ab::SmrView> v = smr_views(m);
-  ab::smr_run_exchange(m->smr_rows, v, smr_dims(m), ops);
+  const ab::SmrDims d = smr_dims(m);
+  if (m->p.nranks == 1) {
+    ab::smr_run_exchange(m->smr_rows, v, d, ops);
+    if (ops.rc) return fail(ops.rc, "SMR exchange: CUDA error");
+    CK(cudaGetLastError());
+    return AB_OK;
+  }
+  // Across ranks (bvals_cc.cpp:195-470 with MPI): every rank walks the SAME row list, so the
+  // messages of a pair of ranks are in the same order on both sides: the sender packs the box of
+  // a row (after restricting it, kind 2) into its buffer for the receiver's rank, one grouped
+  // send/recv per peer moves the buffers, the receiver unpacks in the same order.
+  const int me = m->p.rank;
+  const int npass = d.ns > 0 ? 2 : 1;
+  std::map<int, long> nsend, nrecv;
+  for (const auto &r : m->smr_rows) {
+    if (r[0] < 0 || r[0] > 2) continue;
+    const int rs = m->hb[r[1]].rank, rt = m->hb[r[5]].rank;
+    if (r[0] == 2 && rs == me) {
+      ab::SmrView &S = v[r[1]];
+      const ab::SmrBox bx = ab::smr_box(&r[2], &r[9]);
+      ops.restrict_box(S.g, S.u, S.cu, d.nh, bx);
+      if (d.ns > 0) ops.restrict_box(S.g, S.s, S.cs, d.ns, bx);
+    }
+    if (rs == rt) continue;
+    const long cnt = (long)r[9]*r[10]*r[11]*(d.nh + d.ns);
+    if (rs == me) nsend[rt] += cnt;
+    if (rt == me) nrecv[rs] += cnt;
+  }
+  { int rcb = smr_peer_buffers(m->peer_smr, nsend, nrecv); if (rcb) return rcb; }
+  std::vector<ab::CopyBox> local, pack, unpack;
+  std::map<int, long> soff, roff;
+  for (const auto &r : m->smr_rows) {
+    if (r[0] < 0 || r[0] > 2) continue;
+    const int rs = m->hb[r[1]].rank, rt = m->hb[r[5]].rank;
+    if (rs != me && rt != me) continue;
+    ab::SmrView &S = v[r[1]], &T = v[r[5]];
+    for (int pass = 0; pass < npass; ++pass) {
+      const long cnt = (long)r[9]*r[10]*r[11]*(pass ? d.ns : d.nh);
+      if (rs == me && rt == me) {
+        local.push_back(ab::smr_row_copy(r, S, T, d, pass));
+      } else if (rs == me) {
+        pack.push_back(ab::smr_row_copy_buffered(r, S, T, d, pass, m->peer_smr[rt].send + soff[rt], true));
+        soff[rt] += cnt;
+      } else {
+        unpack.push_back(ab::smr_row_copy_buffered(r, S, T, d, pass, m->peer_smr[rs].recv + roff[rs], false));
+        roff[rs] += cnt;
+      }
+    }
+  }
+  auto launch = [&](std::vector<ab::CopyBox> &b) {
+    long total = 0;
+    for (auto &c : b) { c.offset = total; total += (long)c.ni*c.nj*c.nk*c.nvar; }
+    ops.copy_boxes(b, total);
+  };
+  launch(pack);
+  if (ops.rc) return fail(ops.rc, "SMR exchange: CUDA error");
+  { int rcx = peer_exchange(m, m->peer_smr); if (rcx) return rcx; }
+  local.insert(local.end(), unpack.begin(), unpack.end());
+  launch(local);
   if (ops.rc) return fail(ops.rc, "SMR exchange: CUDA error");
   CK(cudaGetLastError());
   return AB_OK;
@@ -1795,7 +1885,8 @@ int smr_exchange(AbMesh *m) {
 int smr_prolongate(AbMesh *m, int lid) {
   SmrDeviceOps ops{m, m->lb[lid].stream};
   std::vector<ab::SmrView> v = smr_views(m);
-  ab::smr_run_prolongate(m->smr_rows, lid, v[lid], smr_dims(m), ops);
+  const int gid = m->lb[lid].hb->gid;
+  ab::smr_run_prolongate(m->smr_rows, gid, v[gid], smr_dims(m), ops);
   if (ops.rc) return fail(ops.rc, "SMR prolongation: CUDA error");
   CK(cudaGetLastError());
   return AB_OK;
@@ -1804,7 +1895,91 @@ int smr_prolongate(AbMesh *m, int lid) {
 int smr_flux_correction(AbMesh *m) {
   SmrDeviceOps ops{m, m->stream};
   std::vector<ab::SmrView> v = smr_views(m);
-  ab::smr_run_flux_correction(m->smr_rows, v, smr_dims(m), ops);
+  const ab::SmrDims d = smr_dims(m);
+  if (m->p.nranks == 1) {
+    ab::smr_run_flux_correction(m->smr_rows, v, d, ops);
+    if (ops.rc) return fail(ops.rc, "SMR flux correction: CUDA error");
+    CK(cudaGetLastError());
+    return AB_OK;
+  }
+  // Across ranks (flux_correction_cc.cpp:69-290 with MPI): the fine block's rank forms the
+  // area-weighted coarse fluxes straight into its message buffer, the coarse block's rank copies
+  // them onto its face; same row order on both sides.
+  const int me = m->p.rank;
+  struct Geo { int dir, fpos, cpos, a0, b0, na, nb; };
+  auto geo = [&](const ab::SmrRow &r) {
+    Geo q;
+    const int ffid = (int)r[2], cfid = (int)r[6], fi1 = (int)r[7], fi2 = (int)r[8];
+    q.dir = ffid >> 1;
+    q.fpos = d.s0[q.dir] + (d.e0[q.dir] - d.s0[q.dir] + 1)*(ffid & 1);
+    q.cpos = d.s0[q.dir] + (d.e0[q.dir] - d.s0[q.dir] + 1)*(cfid & 1);
+    const int da = q.dir == 0 ? 1 : 0, db = q.dir == 2 ? 1 : 2;
+    const int ha = d.fdim[da] ? d.bx[da]/2 : 0, hb = d.fdim[db] ? d.bx[db]/2 : 0;
+    q.a0 = d.s0[da] + (fi1 ? ha : 0); q.b0 = d.s0[db] + (fi2 ? hb : 0);
+    q.na = d.fdim[da] ? ha : 1; q.nb = d.fdim[db] ? hb : 1;
+    return q;
+  };
+  std::map<int, long> nsend, nrecv;
+  for (const auto &r : m->smr_rows) {
+    if (r[0] != 20) continue;
+    const int rf = m->hb[r[1]].rank, rc_ = m->hb[r[5]].rank;
+    if (rf == rc_) continue;
+    const Geo q = geo(r);
+    const long cnt = (long)q.na*q.nb*(d.nh + d.ns);
+    if (rf == me) nsend[rc_] += cnt;
+    if (rc_ == me) nrecv[rf] += cnt;
+  }
+  { int rcb = smr_peer_buffers(m->peer_smr_flux, nsend, nrecv); if (rcb) return rcb; }
+  std::vector<ab::CopyBox> unpack;
+  std::map<int, long> soff, roff;
+  const int n1 = m->nc[0], n2 = m->nc[1], n3 = m->nc[2];
+  for (const auto &r : m->smr_rows) {
+    if (r[0] != 20) continue;
+    const int rf = m->hb[r[1]].rank, rc_ = m->hb[r[5]].rank;
+    if (rf != me && rc_ != me) continue;
+    ab::SmrView &F = v[r[1]], &Cb = v[r[5]];
+    const Geo q = geo(r);
+    for (int pass = 0; pass < (d.ns > 0 ? 2 : 1); ++pass) {
+      const int nvar = pass ? d.ns : d.nh;
+      const long cnt = (long)q.na*q.nb*nvar;
+      if (rf == me && rc_ == me) {
+        ops.flux_face(F.g, pass ? F.sflux[q.dir] : F.flux[q.dir], pass ? Cb.sflux[q.dir] : Cb.flux[q.dir],
+                      nvar, q.dir, q.fpos, q.cpos, q.a0, q.b0, q.na, q.nb);
+      } else if (rf == me) {
+        ab::launch_smr_flux(F.g, pass ? F.sflux[q.dir] : F.flux[q.dir], m->peer_smr_flux[rc_].send + soff[rc_],
+                            nvar, q.dir, q.fpos, q.cpos, q.a0, q.b0, q.na, q.nb, m->stream, 1);
+        soff[rc_] += cnt;
+      } else {
+        // buffer [nvar][nb][na] -> the coarse block's face array of direction dir at (cpos, a0.., b0..)
+        ab::CopyBox c;
+        memset(&c, 0, sizeof(c));
+        c.src = m->peer_smr_flux[rf].recv + roff[rf];
+        c.dst = pass ? Cb.sflux[q.dir] : Cb.flux[q.dir];
+        c.nvar = nvar;
+        c.src_sv = (long)q.na*q.nb;
+        if (q.dir == 0) {          // x1 faces: (a, b) = (j, k)
+          c.dst_s2 = n1 + 1; c.dst_s3 = (long)n2*(n1 + 1); c.dst_sv = (long)n3*n2*(n1 + 1);
+          c.di0 = q.cpos; c.dj0 = q.a0; c.dk0 = q.b0; c.ni = 1; c.nj = q.na; c.nk = q.nb;
+          c.src_s2 = 1; c.src_s3 = q.na;
+        } else if (q.dir == 1) {   // x2 faces: (a, b) = (i, k)
+          c.dst_s2 = n1; c.dst_s3 = (long)(n2 + 1)*n1; c.dst_sv = (long)n3*(n2 + 1)*n1;
+          c.di0 = q.a0; c.dj0 = q.cpos; c.dk0 = q.b0; c.ni = q.na; c.nj = 1; c.nk = q.nb;
+          c.src_s2 = q.na; c.src_s3 = q.na;
+        } else {                   // x3 faces: (a, b) = (i, j)
+          c.dst_s2 = n1; c.dst_s3 = (long)n2*n1; c.dst_sv = (long)(n3 + 1)*n2*n1;
+          c.di0 = q.a0; c.dj0 = q.b0; c.dk0 = q.cpos; c.ni = q.na; c.nj = q.nb; c.nk = 1;
+          c.src_s2 = q.na; c.src_s3 = (long)q.na*q.nb;
+        }
+        unpack.push_back(c);
+        roff[rf] += cnt;
+      }
+    }
+  }
+  if (ops.rc) return fail(ops.rc, "SMR flux correction: CUDA error");
+  { int rcx = peer_exchange(m, m->peer_smr_flux); if (rcx) return rcx; }
+  long total = 0;
+  for (auto &c : unpack) { c.offset = total; total += (long)c.ni*c.nj*c.nk*c.nvar; }
+  ops.copy_boxes(unpack, total);
   if (ops.rc) return fail(ops.rc, "SMR flux correction: CUDA error");
   CK(cudaGetLastError());
   return AB_OK;
@@ -2079,7 +2254,6 @@ static int refined_host_setup(const AbMeshParams *p, const AbRefinementRegion *r
   int vrc = validate_params(p);
   if (vrc) return vrc;
   if (p->mhd) return fail(AB_ERR_ARG, "mesh refinement with MHD is not on the device path");
-  if (p->nranks != 1) return fail(AB_ERR_ARG, "mesh refinement runs on one process in this version");
   for (int f = 0; f < 6; ++f)
     if (p->bc[f] == AB_BC_USER) return fail(AB_ERR_ARG, "mesh refinement with user-enrolled boundaries is not on the device path");
   for (int d = 0; d < 3; ++d)
@@ -2139,8 +2313,34 @@ static int refined_host_setup(const AbMeshParams *p, const AbRefinementRegion *r
       B.nblevel[k][j][i] = nbl[(k*3 + j)*3 + i];
     for (int e = 0; e < 12; ++e) B.nedge_fine[e] = 1;
   }
-  m->gid_start = 0;
-  for (auto &B : m->hb) m->lb_hb.push_back(&B);
+  // Mesh::CalculateLoadBalance with unit costs over the Z-ordered block list of all levels
+  // (mesh/amr_loadbalance.cpp:72-112): contiguous gid ranges per rank
+  {
+    int nranks = p->nranks;
+    double totalcost = nb;
+    int j = nranks - 1;
+    double targetcost = totalcost/nranks, mycost = 0.0;
+    for (int i = nb - 1; i >= 0; i--) {
+      mycost += 1.0;
+      m->hb[i].rank = j;
+      if (mycost >= targetcost && j > 0) {
+        j--;
+        totalcost -= mycost;
+        mycost = 0.0;
+        targetcost = totalcost/(j + 1);
+      }
+    }
+  }
+  m->gid_start = -1;
+  for (auto &B : m->hb) if (B.rank == p->rank) {
+    if (m->gid_start < 0) m->gid_start = B.gid;
+    m->lb_hb.push_back(&B);
+  }
+  if (m->lb_hb.empty()) {
+    ab_smr_plan_destroy(plan);
+    delete m;
+    return fail(AB_ERR_ARG, "this rank owns no MeshBlock: use fewer ranks or smaller MeshBlocks");
+  }
   {
     const long n = ab_smr_plan_transfers(plan, nullptr, 0);
     std::vector<long> tr(12*(size_t)n);
@@ -2358,6 +2558,8 @@ int ab_mesh_destroy(AbMesh *m) {
   for (auto &kv : m->bplan) { cudaFree(kv.second.pack); cudaFree(kv.second.phase1); cudaFree(kv.second.phase1r); cudaFree(kv.second.phase2); }
   for (auto &kv : m->peer_state) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   for (auto &kv : m->peer_emf) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
+  for (auto &kv : m->peer_smr) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
+  for (auto &kv : m->peer_smr_flux) { cudaFree(kv.second.send); cudaFree(kv.second.recv); }
   cudaFree(m->state); cudaFree(m->dt_hist); cudaFree(m->dtmin);
   cudaFree(m->hist_partial); cudaFree(m->hist_out);
   for (auto &sb : m->smr_blk) {

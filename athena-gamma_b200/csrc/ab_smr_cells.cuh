@@ -114,8 +114,11 @@ AB_HD void smr_bc_cell(const SmrGeom &g, double *cw, int nh, double *cr, int ns,
 // LoadFluxBoundaryBufferToCoarser + SetFluxBoundaryFromFiner for one coarse face cell (ia, ib =
 // coarse offsets along the two transverse directions, a fastest: dir 0 -> (j,k), 1 -> (i,k),
 // 2 -> (i,j)): the area-weighted mean of the fine fluxes replaces the coarse flux
+// compact_na > 0: the coarse values go into a message buffer instead (the fine block's rank sends
+// them): element (n, ib, ia) at (n*compact_nb + ib)*compact_na + ia
 AB_HD void smr_flux_cell(const SmrGeom &gf, const double *ffl, double *cfl, int nvar, int dir,
-                         int fpos, int cpos, int a0, int b0, int ia, int ib) {
+                         int fpos, int cpos, int a0, int b0, int ia, int ib, int compact_na = 0,
+                         int compact_nb = 0) {
   const int ndim = gf.ndim;
   const int nc1 = gf.nc1, nc2 = gf.nc2, nc3 = gf.nc3;
   long sf_f, o00, sa, sb, o_c;
@@ -159,7 +162,8 @@ AB_HD void smr_flux_cell(const SmrGeom &gf, const double *ffl, double *cfl, int 
     } else {
       val = f[0];
     }
-    cfl[n*sf_f + o_c] = val;
+    if (compact_na > 0) cfl[((long)n*compact_nb + ib)*compact_na + ia] = val;
+    else cfl[n*sf_f + o_c] = val;
   }
 }
 

@@ -44,6 +44,38 @@ inline SmrBox smr_box(const long *origin, const long *extent) {
                 (int)(origin[1] + extent[1] - 1), (int)origin[2], (int)(origin[2] + extent[2] - 1)};
 }
 
+// the box copy of an exchange row (kind 0 same level, 1 into the finer block's coarse buffer, 2 from
+// the finer block's coarse buffer) for the hydro variables (pass 0) or the scalars (pass 1)
+inline CopyBox smr_row_copy(const SmrRow &r, const SmrView &S, const SmrView &T, const SmrDims &d,
+                            int pass) {
+  const long ncc_s = (long)S.g.nc1*S.g.nc2*S.g.nc3, ncc_t = (long)T.g.nc1*T.g.nc2*T.g.nc3;
+  const long cncc_s = (long)S.g.cnc1*S.g.cnc2*S.g.cnc3, cncc_t = (long)T.g.cnc1*T.g.cnc2*T.g.cnc3;
+  CopyBox c;
+  std::memset(&c, 0, sizeof(c));
+  const bool src_coarse = (r[0] == 2), dst_coarse = (r[0] == 1);
+  c.src = src_coarse ? (pass ? S.cs : S.cu) : (pass ? S.s : S.u);
+  c.dst = dst_coarse ? (pass ? T.cs : T.cu) : (pass ? T.s : T.u);
+  if (src_coarse) { c.src_s3 = (long)S.g.cnc2*S.g.cnc1; c.src_s2 = S.g.cnc1; c.src_sv = cncc_s; }
+  else { c.src_s3 = (long)S.g.nc2*S.g.nc1; c.src_s2 = S.g.nc1; c.src_sv = ncc_s; }
+  if (dst_coarse) { c.dst_s3 = (long)T.g.cnc2*T.g.cnc1; c.dst_s2 = T.g.cnc1; c.dst_sv = cncc_t; }
+  else { c.dst_s3 = (long)T.g.nc2*T.g.nc1; c.dst_s2 = T.g.nc1; c.dst_sv = ncc_t; }
+  c.nvar = pass ? d.ns : d.nh;
+  c.si0 = (int)r[2]; c.sj0 = (int)r[3]; c.sk0 = (int)r[4];
+  c.di0 = (int)r[6]; c.dj0 = (int)r[7]; c.dk0 = (int)r[8];
+  c.ni = (int)r[9]; c.nj = (int)r[10]; c.nk = (int)r[11];
+  return c;
+}
+// the same copy with one end in a message buffer (the box stored compactly, variable slowest):
+// `to_buffer`: source block -> buffer at buf; else buffer at buf -> destination block
+inline CopyBox smr_row_copy_buffered(const SmrRow &r, const SmrView &S, const SmrView &T,
+                                     const SmrDims &d, int pass, double *buf, bool to_buffer) {
+  CopyBox c = smr_row_copy(r, S, T, d, pass);
+  const long s2 = c.ni, s3 = (long)c.ni*c.nj, sv = s3*c.nk;
+  if (to_buffer) { c.dst = buf; c.dst_s2 = s2; c.dst_s3 = s3; c.dst_sv = sv; c.di0 = c.dj0 = c.dk0 = 0; }
+  else { c.src = buf; c.src_s2 = s2; c.src_s3 = s3; c.src_sv = sv; c.si0 = c.sj0 = c.sk0 = 0; }
+  return c;
+}
+
 // ghost exchange of u (and s): rows 2 first restrict the senders' slabs, then every row 0 / 1 / 2
 // is one box copy
 template <class Ops>
@@ -60,22 +92,8 @@ void smr_run_exchange(const std::vector<SmrRow> &rows, std::vector<SmrView> &v, 
   for (const auto &r : rows) {
     if (r[0] < 0 || r[0] > 2) continue;
     SmrView &S = v[r[1]], &T = v[r[5]];
-    const long ncc_s = (long)S.g.nc1*S.g.nc2*S.g.nc3, ncc_t = (long)T.g.nc1*T.g.nc2*T.g.nc3;
-    const long cncc_s = (long)S.g.cnc1*S.g.cnc2*S.g.cnc3, cncc_t = (long)T.g.cnc1*T.g.cnc2*T.g.cnc3;
     for (int pass = 0; pass < (d.ns > 0 ? 2 : 1); ++pass) {
-      CopyBox c;
-      std::memset(&c, 0, sizeof(c));
-      const bool src_coarse = (r[0] == 2), dst_coarse = (r[0] == 1);
-      c.src = src_coarse ? (pass ? S.cs : S.cu) : (pass ? S.s : S.u);
-      c.dst = dst_coarse ? (pass ? T.cs : T.cu) : (pass ? T.s : T.u);
-      if (src_coarse) { c.src_s3 = (long)S.g.cnc2*S.g.cnc1; c.src_s2 = S.g.cnc1; c.src_sv = cncc_s; }
-      else { c.src_s3 = (long)S.g.nc2*S.g.nc1; c.src_s2 = S.g.nc1; c.src_sv = ncc_s; }
-      if (dst_coarse) { c.dst_s3 = (long)T.g.cnc2*T.g.cnc1; c.dst_s2 = T.g.cnc1; c.dst_sv = cncc_t; }
-      else { c.dst_s3 = (long)T.g.nc2*T.g.nc1; c.dst_s2 = T.g.nc1; c.dst_sv = ncc_t; }
-      c.nvar = pass ? d.ns : d.nh;
-      c.si0 = (int)r[2]; c.sj0 = (int)r[3]; c.sk0 = (int)r[4];
-      c.di0 = (int)r[6]; c.dj0 = (int)r[7]; c.dk0 = (int)r[8];
-      c.ni = (int)r[9]; c.nj = (int)r[10]; c.nk = (int)r[11];
+      CopyBox c = smr_row_copy(r, S, T, d, pass);
       boxes.push_back(c);
     }
   }
@@ -84,7 +102,7 @@ void smr_run_exchange(const std::vector<SmrRow> &rows, std::vector<SmrView> &v, 
   ops.copy_boxes(boxes, total);
 }
 
-// BoundaryValues::ProlongateBoundaries of block `lid`: rows 12 (restriction of the ghost cells
+// BoundaryValues::ProlongateBoundaries of block `lid` (its gid: the rows name blocks by gid): rows 12 (restriction of the ghost cells
 // that same-level neighbours filled), then per coarser neighbour rows 10 / 11: ConservedToPrimitive
 // on the coarse box with its margins, the boundary functions of the mesh faces this block
 // touches, prolongation of the primitives, PrimitiveToConserved on the fine ghost cells

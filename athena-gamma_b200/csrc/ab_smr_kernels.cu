@@ -60,11 +60,11 @@ __global__ void __launch_bounds__(SB) k_smr_bc(SmrGeom g, double *cw, int nh, do
 __global__ void __launch_bounds__(SB) k_smr_flux(SmrGeom gf, const double *__restrict__ ffl,
                                                 double *__restrict__ cfl, int nvar, int dir,
                                                 int fpos, int cpos, int a0, int b0, int na,
-                                                int nb) {
+                                                int nb, int compact) {
   const int t = blockIdx.x*SB + threadIdx.x;
   if (t >= na*nb) return;
   const int ib = t / na, ia = t - ib*na;
-  smr_flux_cell(gf, ffl, cfl, nvar, dir, fpos, cpos, a0, b0, ia, ib);
+  smr_flux_cell(gf, ffl, cfl, nvar, dir, fpos, cpos, a0, b0, ia, ib, compact ? na : 0, nb);
 }
 
 }  // namespace
@@ -89,10 +89,10 @@ void launch_smr_bc(const SmrGeom &g, double *cw, int nh, double *cr, int ns, int
 }
 void launch_smr_flux(const SmrGeom &gf, const double *fine_flux, double *coarse_flux, int nvar,
                      int dir, int fpos, int cpos, int a0, int b0, int na, int nb,
-                     cudaStream_t s) {
+                     cudaStream_t s, int compact) {
   if (nvar <= 0 || na*nb <= 0) return;
   k_smr_flux<<<(na*nb + SB - 1)/SB, SB, 0, s>>>(gf, fine_flux, coarse_flux, nvar, dir, fpos, cpos,
-                                                a0, b0, na, nb); ++g_launches;
+                                                a0, b0, na, nb, compact); ++g_launches;
 }
 
 }  // namespace ab

@@ -130,8 +130,10 @@ int ab_smr_plan_neighbors(const AbSmrPlan *plan, int gid, int *rows, int *nbleve
 long ab_smr_plan_transfers(const AbSmrPlan *plan, long *rows, long max_rows);
 /* Mesh ctor with mesh/refinement = static: like ab_mesh_create, MeshBlocks from the planner, each
  * with the MeshRefinement's coarse buffers; the cycle then also runs the level-aware ghost
- * exchange, ProlongateBoundaries and the flux correction.  This version: one process, hydro
- * (+ passive scalars), MeshBlocks of at least 2*NGHOST cells, no user-enrolled boundaries. */
+ * exchange, ProlongateBoundaries and the flux correction.  MeshBlocks of all levels are sharded
+ * over the ranks like Mesh::CalculateLoadBalance (contiguous Z-order gid ranges, unit costs); the
+ * transfers between blocks of different ranks travel over NCCL (ab_comm_init).  This version:
+ * hydro (+ passive scalars), MeshBlocks of at least 2*NGHOST cells, no user-enrolled boundaries. */
 int ab_mesh_create_refined(const AbMeshParams *p, const AbRefinementRegion *regions, int nregions,
                            AbMesh **out);
 int ab_block_level(const AbMesh *m, int lid);    /* LogicalLocation::level (0 on a one-level mesh) */

@@ -20,7 +20,10 @@ import util  # noqa: E402
 DEFAULT_NAMES = ["c5_blast_hlld_plm_vl2_8blk", "c2_linwave_hlld_plm_vl2_8blk",
                  "c4_kh_hllc_ppm_rk2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
                  "c1_sod_hllc_plm_vl2_2blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1",
-                 "khs_lhllc_plm_vl2_4blk_s1"]
+                 "khs_lhllc_plm_vl2_4blk_s1",
+                 # statically refined meshes: levels sharded over the ranks
+                 "smr_blast3d_hllc_plm_vl2", "smr_khs2d_lhllc_plm_vl2_s1",
+                 "smr_blast2d_lvl2_bcs_hllc_plm_rk2"]
 
 
 def check_goldens(rank, world, local, names=None, verbose=True):
@@ -47,12 +50,16 @@ def check_goldens(rank, world, local, names=None, verbose=True):
         dts = m.cycles(g.ncycles)
         good &= list(dts) == list(g.dts[:g.ncycles]) and m.dt == g.dts[g.ncycles]
         nbad = 0
-        for pmb in m.my_blocks:
-            n = g.locs.index((pmb.lx1, pmb.lx2, pmb.lx3))
+        nmine = 0
+        for n, loc in enumerate(g.locs):         # loc carries the level on refined meshes
+            pmb = m.block_of(*loc)
+            if pmb is None:
+                continue
+            nmine += 1
             for f in g.fields:
                 if not np.array_equal(pmb.get(f), g.final[n][f]):
                     nbad += 1
-        good &= (nbad == 0)
+        good &= (nbad == 0) and nmine == m.nblocal
         if verbose:
             print("rank %d/%d %s: blocks %d dt_ok %s bad_arrays %d -> %s" %
                   (rank, world, name, m.nblocal, list(dts) == list(g.dts[:g.ncycles]), nbad,

@@ -48,14 +48,16 @@ def main(names):
         dts = m.cycles(g.ncycles)
         ok &= list(dts) == list(g.dts[:g.ncycles]) and m.dt == g.dts[g.ncycles]
         nbad = 0
-        for pmb in m.my_blocks:
-            n = g.locs.index((pmb.lx1, pmb.lx2, pmb.lx3))
+        nmine = 0
+        for n, loc in enumerate(g.locs):         # loc carries the level on refined meshes
+            pmb = m.block_of(*loc)
+            if pmb is None:
+                continue
+            nmine += 1
             for f in g.fields:
                 if not np.array_equal(pmb.get(f), g.final[n][f]):
                     nbad += 1
-        ok &= (nbad == 0)
-        if g.hst is not None and not util.user_bcs_for(g):
-            pass
+        ok &= (nbad == 0) and nmine == m.nblocal
         print("rank %d/%d %s: blocks %d dt_ok %s bad_arrays %d -> %s" %
               (rank, world, name, m.nblocal, list(dts) == list(g.dts[:g.ncycles]), nbad,
                "OK" if ok else "FAIL"), flush=True)

@@ -126,6 +126,9 @@ def test_message_plans_pair_up_across_ranks(world):
 # served by a test-only stand-in over UNIX sockets (tests/hostcheck/nccl_emu.c, AB_NCCL_LIB), so
 # the pack / send / receive / unpack plans, the EMF correction across rank boundaries and the dt
 # all-reduce really move the data -- and must land on the reference's bits.
+SMR_GOLDENS = ["smr_blast2d_hllc_plm_vl2", "smr_blast2d_lvl2_bcs_hllc_plm_rk2",
+               "smr_blast3d_hllc_plm_vl2", "smr_blast3d_refl_lhllc_plm_rk3",
+               "smr_khs2d_lhllc_plm_vl2_s1", "smr_khs3d_hllc_ppm_rk3_ng4_s2", "smr_sod1d_hllc_plm_vl2"]
 EMU_CASES = [
     (2, "0", ["c5_blast_hlld_plm_vl2_8blk", "c2_linwave_hlld_plm_vl2_8blk", "c4_kh_hllc_ppm_rk2_8blk",
               "c3_ot_hlld_ppm_vl2_4blk", "c1_sod_hllc_plm_vl2_2blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1",
@@ -135,6 +138,9 @@ EMU_CASES = [
     (4, "0", ["c5_blast_hlld_plm_vl2_8blk", "c4_kh_hllc_ppm_rk2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
               "blast_mixedbc_hllc_plm_vl2_8blk"]),
     (8, "0", ["c5_blast_hlld_plm_vl2_8blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1", "blast_hlld_ppm_rk3_8blk"]),
+    # statically refined meshes across ranks: ghost zones between levels (restricted slabs,
+    # coarse-buffer fills), flux correction fine -> coarse, prolongation next to rank boundaries
+    (2, "0", SMR_GOLDENS), (3, "0", SMR_GOLDENS), (4, "0", SMR_GOLDENS), (8, "0", SMR_GOLDENS),
 ]
 
 
