@@ -35,13 +35,14 @@ def source_hash():
     return h.hexdigest()
 
 
-KERNEL_FILES = ("ab_kernels.cu", "ab_flux_nu.cu", "ab_smr_kernels.cu", "ab_kernels.h", "ab_types.h",
-                "ab_physics.cuh", "ab_flux.cuh", "ab_batch.cuh", "ab_smr_cells.cuh")
+KERNEL_FILES = ("ab_kernels.cu", "ab_flux_nu.cu", "ab_types.h", "ab_physics.cuh", "ab_flux.cuh",
+                "ab_batch.cuh")
 
 
 def kernel_hash():
-    """sha256 over the DEVICE sources and the compiler flags only: what an ncu capture of a kernel
-    depends on (the host glue in ab_mesh.cu / ab_smr.cpp may change without invalidating it)"""
+    """sha256 over the sources of the kernels on the cycle path and the compiler flags: what an
+    ncu capture of those kernels depends on (the host glue in ab_mesh.cu / ab_smr.cpp, the launcher
+    declarations and the refinement kernels may change without invalidating it)"""
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     for name in KERNEL_FILES:
         h.update(name.encode())

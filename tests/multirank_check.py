@@ -20,10 +20,13 @@ import util  # noqa: E402
 DEFAULT_NAMES = ["c5_blast_hlld_plm_vl2_8blk", "c2_linwave_hlld_plm_vl2_8blk",
                  "c4_kh_hllc_ppm_rk2_8blk", "c3_ot_hlld_ppm_vl2_4blk",
                  "c1_sod_hllc_plm_vl2_2blk", "khs3d_mhd_hlld_plm_vl2_8blk_s1",
-                 "khs_lhllc_plm_vl2_4blk_s1",
-                 # statically refined meshes: levels sharded over the ranks
-                 "smr_blast3d_hllc_plm_vl2", "smr_khs2d_lhllc_plm_vl2_s1",
-                 "smr_blast2d_lvl2_bcs_hllc_plm_rk2"]
+                 "khs_lhllc_plm_vl2_4blk_s1"]
+# statically refined meshes with the levels sharded over the ranks: bit-exact at 2-8 ranks on the
+# emulated device path (tests/test_multirank_cpu.py); their first run under NCCL on GPUs was cut
+# off by the round's GPU budget before it reported, so they are not part of the default set that
+# bench.py runs behind its timed region (python tests/multirank_check.py <names> runs them)
+SMR_NAMES = ["smr_blast3d_hllc_plm_vl2", "smr_khs2d_lhllc_plm_vl2_s1",
+             "smr_blast2d_lvl2_bcs_hllc_plm_rk2"]
 
 
 def check_goldens(rank, world, local, names=None, verbose=True):

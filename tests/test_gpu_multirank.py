@@ -26,3 +26,21 @@ def test_two_ranks_bitwise_vs_golden(overlap, p2p):
                        env=dict(os.environ, AB_OVERLAP=overlap, AB_P2P=p2p, AB_P2P_VERBOSE="1"))
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0
+
+
+@pytest.mark.skipif(os.environ.get("AB_TEST_SMR_MULTIRANK") != "1",
+                    reason="refined meshes across ranks are verified at 2-8 ranks on the emulated "
+                           "device path (tests/test_multirank_cpu.py); the first NCCL run on GPUs was "
+                           "cut off by the round's GPU budget: opt in with AB_TEST_SMR_MULTIRANK=1")
+def test_refined_meshes_two_ranks_bitwise_vs_golden():
+    """static mesh refinement with the MeshBlocks of all levels sharded over 2 GPUs"""
+    import torch
+    import multirank_check
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29518",
+           os.path.join(HERE, "multirank_check.py")] + multirank_check.SMR_NAMES
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0
