@@ -33,7 +33,9 @@ typedef struct Comm {
 } Comm;
 typedef Comm *ncclComm_t;
 
-typedef struct { int send; char *p; size_t left; int peer; Comm *c; } Op;
+/* every message is preceded by its byte count: a receive that expects another size fails
+ * loudly (real NCCL would hang or corrupt memory) */
+typedef struct { int send; char *p; size_t left; int peer; Comm *c; size_t size; size_t hdr; int hleft; } Op;
 static Op g_ops[4096];
 static int g_nops = 0, g_depth = 0;
 
@@ -128,6 +130,19 @@ static int progress_all(void) {
     for (int j = 0; j < n; ++j) {
       if (!(pf[j].revents & (POLLIN | POLLOUT | POLLHUP | POLLERR))) continue;
       Op *o = &g_ops[idx[j]];
+      if (o->hleft > 0) {               /* the size header first */
+        char *h = (char *)&o->hdr + (8 - o->hleft);
+        ssize_t k = o->send ? write(pf[j].fd, h, o->hleft) : read(pf[j].fd, h, o->hleft);
+        if (k < 0) { if (errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR) continue; rc = 7; break; }
+        if (k == 0 && !o->send) { rc = 8; break; }
+        o->hleft -= (int)k;
+        if (o->hleft == 0 && !o->send && o->hdr != o->size) {
+          fprintf(stderr, "nccl_emu: rank %d expected %zu bytes from rank %d, the sender posted %zu\n",
+                  o->c->rank, o->size, o->peer, o->hdr);
+          rc = 14; break;
+        }
+        continue;
+      }
       ssize_t k = o->send ? write(pf[j].fd, o->p, o->left) : read(pf[j].fd, o->p, o->left);
       if (k < 0) { if (errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR) continue; rc = 7; break; }
       if (k == 0 && !o->send) { rc = 8; break; }
@@ -155,7 +170,9 @@ static int post(int send, void *p, size_t count, int dtype, int peer, Comm *c) {
   if (peer == c->rank || peer < 0 || peer >= c->nranks || g_nops >= 4096) return 9;
   if (count == 0) return 0;
   g_ops[g_nops].send = send; g_ops[g_nops].p = (char *)p; g_ops[g_nops].left = count*tsize(dtype);
-  g_ops[g_nops].peer = peer; g_ops[g_nops].c = c; ++g_nops;
+  g_ops[g_nops].peer = peer; g_ops[g_nops].c = c;
+  g_ops[g_nops].size = g_ops[g_nops].left; g_ops[g_nops].hdr = g_ops[g_nops].left; g_ops[g_nops].hleft = 8;
+  ++g_nops;
   return g_depth > 0 ? 0 : progress_all();
 }
 int ncclSend(const void *p, size_t count, int dtype, int peer, ncclComm_t c, void *stream) {
