@@ -1346,12 +1346,16 @@ int emf_exchange_end(AbMesh *m) {
 int var_applies(const AbMesh *m, int var) {
   return var == 0 || (var == 1 && m->p.mhd) || (var == 2 && m->p.nscalars > 0);
 }
-int block_plan(AbMesh *m, int lid, int var, AbMesh::Plan **out) {
+// for_send: the plan is used for its pack list only (Send reads nothing but the block's own
+// arrays, so the same-rank neighbours may still be a task behind, in the other swap state); the
+// gather lists of such a plan carry the neighbours' pointers of that moment and are never used --
+// Set builds its own plan, when every neighbour has sent
+int block_plan(AbMesh *m, int lid, int var, AbMesh::Plan **out, bool for_send = false) {
   LocalBlock &L = m->lb[lid];
   const int par = (var == 0) ? L.parity : ((var == 1) ? L.parity_b : L.parity_s);
   // gathers read the neighbours' registers: their swap state is part of the key
-  long key = ((long)lid*3 + var)*2 + par;
-  for (const Nb &nb : L.hb->nbs) if (nb.rank == m->p.rank) {
+  long key = (((long)lid*3 + var)*2 + par)*2 + (for_send ? 1 : 0);
+  if (!for_send) for (const Nb &nb : L.hb->nbs) if (nb.rank == m->p.rank) {
     const LocalBlock &N = m->lb[owner_lid(m, nb.gid)];
     const int np = (var == 0) ? N.parity : ((var == 1) ? N.parity_b : N.parity_s);
     if (np != par) return fail(AB_ERR_STATE, "neighbouring MeshBlocks are in different register "
@@ -1371,7 +1375,7 @@ int block_bvals_send(AbMesh *m, int lid, int var) {
   LocalBlock &L = m->lb[lid];
   if (has_remote_nb(m, L)) {
     AbMesh::Plan *P;
-    int rc = block_plan(m, lid, var, &P);
+    int rc = block_plan(m, lid, var, &P, true);
     if (rc) return rc;
     if (P->npack) ab::launch_copy_boxes(P->pack, P->npack, P->maxpack, m->stream, 1);
   }

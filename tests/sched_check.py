@@ -11,6 +11,12 @@ dt comes from ab_new_block_dt per block + Mesh::NewTimeStep on the host (mesh.cp
 Result: dt sequence and every array of every block bit-identical to the reference golden.
 
   python tests/sched_check.py [--seed N] golden [golden ...]
+
+With RANK / WORLD_SIZE / AB_ID_DIR in the environment (tests/test_multirank_cpu.py: several
+processes of the emulated device path with the socket stand-in for NCCL) the MeshBlocks are
+sharded over the ranks: every rank runs its own randomly drifting scheduler, the per-block Send /
+ReceiveTry / Set then pack, count rounds and unpack across rank boundaries, and the host's
+MPI_Allreduce(MIN) of Mesh::NewTimeStep is a file exchange in AB_ID_DIR.
 """
 import ctypes as C
 import os
@@ -66,9 +72,41 @@ def build_tasks(mhd, ns):
     return t
 
 
+RANK, WORLD = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def wait_for(path):
+    import time as _t
+    for _ in range(120000):
+        if os.path.exists(path):
+            return open(path, "rb").read()
+        _t.sleep(0.0005)
+    raise RuntimeError("timeout waiting for " + path)
+
+
+def put(path, data):
+    with open(path + ".tmp%d" % RANK, "wb") as fh:
+        fh.write(data)
+    os.replace(path + ".tmp%d" % RANK, path)
+
+
+def allreduce_min(tag, value):
+    """the host application's MPI_Allreduce(MIN) (mesh.cpp:1105-1108)"""
+    if WORLD == 1:
+        return value
+    d = os.environ["AB_ID_DIR"]
+    put(os.path.join(d, "%s_%d" % (tag, RANK)), repr(value).encode())
+    return min(float(wait_for(os.path.join(d, "%s_%d" % (tag, r))).decode()) for r in range(WORLD))
+
+
 def run_golden(name, seed):
     g = util.Golden(name)
-    m = gpu_util.mesh_from_golden(g)
+    if WORLD > 1:
+        m = gpu_util.mesh_from_golden(g, rank=RANK, nranks=WORLD, device=0)
+        idpath = os.path.join(os.environ["AB_ID_DIR"], "schedid_" + name)
+        m.init_comm(lambda data: (put(idpath, data), data)[1] if data is not None else wait_for(idpath))
+    else:
+        m = gpu_util.mesh_from_golden(g)
     m.initialize()
     L, h = m.L, m.h
     ck = ab.lib.check
@@ -76,7 +114,7 @@ def run_golden(name, seed):
     xorder = m.params.xorder
     wts = WEIGHTS[integ]
     tasks = build_tasks(g.mhd, g.nscalars)
-    rng = random.Random(seed)
+    rng = random.Random(seed + 7919*RANK)     # every rank drifts on its own
     time, dt = float(g.par["time"].get("start_time", 0.0)), m.dt
     tlim = float(g.par["time"]["tlim"])
     assert dt == g.dts[0], (dt, g.dts[0])
@@ -182,17 +220,22 @@ def run_golden(name, seed):
                                 break    # TaskStatus::success: on to the next MeshBlock
         time += dt
         # Mesh::NewTimeStep (mesh.cpp:1078-1119)
-        dt_new = min(2.0*dt, min(new_dt.values()))
+        dt_new = min(2.0*dt, allreduce_min("dt_%s_%d" % (name, len(dts)), min(new_dt.values())))
         if time < tlim and (tlim - time) < dt_new:
             dt_new = tlim - time
         dt = dt_new
         ck(L.ab_mesh_set_time_dt(h, time, dt))
     assert list(dts) == list(g.dts[:len(dts)]), "dt sequence differs: %r vs %r" % (dts, list(g.dts))
     assert dt == g.final_dt, (dt, g.final_dt)
+    nmine = 0
     for n, loc in enumerate(g.locs):
         pmb = m.block_of(*loc)
+        if pmb is None:          # a block of another rank
+            continue
+        nmine += 1
         for f in g.fields:
             util.assert_bitwise(pmb.get(f), g.final[n][f], "%s %s block %d" % (name, f, n))
+    assert nmine == m.nblocal
     return polls, fails
 
 
@@ -204,6 +247,9 @@ def main():
         args = args[2:]
     bad = 0
     for name in args:
+        if WORLD > len(util.Golden(name).locs):
+            print("ok %s (skipped: fewer MeshBlocks than ranks)" % name, flush=True)
+            continue
         try:
             polls, fails = run_golden(name, seed)
             print("ok %s (%d polls, %d answered not-yet)" % (name, polls, fails), flush=True)

@@ -182,3 +182,33 @@ def test_goldens_sharded_over_ranks_through_the_emulated_device_path(emu_multira
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and ("rank %d done: 0 failed" % r) in out, out[-3000:]
         assert out.count("-> OK") == len(names), out[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_per_block_boundary_tasks_across_ranks_under_a_polling_scheduler(emu_multirank_env, tmp_path,
+                                                                         world):
+    """tests/sched_check.py with the MeshBlocks sharded over the ranks: every rank runs its own
+    randomly drifting TaskList-style scheduler over the C ABI's per-block tasks; ab_bvals_send
+    packs for the other ranks while same-rank neighbours may still be a task behind (their
+    registers not yet swapped), the grouped NCCL exchange of a round goes out with the last local
+    Send, ab_bvals_recv_try / ab_emf_recv_try answer "not yet" until it has.  dt sequence and every
+    local array bit-identical to the reference goldens."""
+    import subprocess
+    import test_gpu_sched
+    here = os.path.dirname(os.path.abspath(__file__))
+    procs = []
+    for r in range(world):
+        env = dict(emu_multirank_env, RANK=str(r), WORLD_SIZE=str(world), AB_ID_DIR=str(tmp_path))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(here, "sched_check.py"),
+                                       "--seed", "3"] + test_gpu_sched.SCHED_GOLDENS, env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=900)[0])
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    for p, out in zip(procs, outs):
+        assert p.returncode == 0 and "sched done: 0 failed" in out, out[-3000:]
