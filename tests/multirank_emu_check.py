@@ -58,6 +58,12 @@ def main(names):
                 if not np.array_equal(pmb.get(f), g.final[n][f]):
                     nbad += 1
         ok &= (nbad == 0) and nmine == m.nblocal
+        # HistoryOutput sums over the blocks of ALL ranks (device reduction + all-reduce SUM) against
+        # the reference's .hst row of the final state; summation order differs: 1e-13 of the scale
+        if g.hst is not None:
+            h = m.history()
+            ref = g.hst[g.ncycles, 2:2 + len(h)]
+            ok &= bool(np.all(np.abs(h - ref) <= 1e-13*np.abs(ref).max()))
         print("rank %d/%d %s: blocks %d dt_ok %s bad_arrays %d -> %s" %
               (rank, world, name, m.nblocal, list(dts) == list(g.dts[:g.ncycles]), nbad,
                "OK" if ok else "FAIL"), flush=True)
