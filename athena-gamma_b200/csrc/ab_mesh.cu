@@ -1744,14 +1744,20 @@ struct SmrDeviceOps {
                  int cpos, int a0, int b0, int na, int nb) {
     ab::launch_smr_flux(g, ff, cf, nvar, dir, fpos, cpos, a0, b0, na, nb, st);
   }
+  // room for n box descriptors in the device table.  Across ranks this must happen BEFORE the
+  // round's NCCL operation is enqueued: cudaFree / cudaMalloc synchronise the device, and blocking
+  // in them while a send/recv kernel waits for its peer can deadlock with NCCL's own progress.
+  void reserve_boxes(size_t n) {
+    if (n <= m->smr_boxes_cap) return;
+    if (m->smr_boxes) cudaFree(m->smr_boxes);
+    m->smr_boxes = nullptr;
+    m->smr_boxes_cap = n;
+    if (cudaMalloc(&m->smr_boxes, sizeof(ab::CopyBox)*m->smr_boxes_cap) != cudaSuccess) rc = AB_ERR_CUDA;
+  }
   void copy_boxes(std::vector<ab::CopyBox> &v, long total) {
     if (v.empty()) return;
-    if (v.size() > m->smr_boxes_cap) {
-      if (m->smr_boxes) cudaFree(m->smr_boxes);
-      m->smr_boxes = nullptr;
-      m->smr_boxes_cap = v.size();
-      if (cudaMalloc(&m->smr_boxes, sizeof(ab::CopyBox)*m->smr_boxes_cap) != cudaSuccess) { rc = AB_ERR_CUDA; return; }
-    }
+    reserve_boxes(v.size());
+    if (rc) return;
     // the table carries the CURRENT register pointers (u / u1 swap every stage); stream-ordered
     // upload + sync because the source is pageable host memory (see build_state_plan)
     for (auto &c : v) ab::set_box_divisors(c);
@@ -1876,6 +1882,7 @@ int smr_exchange(AbMesh *m) {
     for (auto &c : b) { c.offset = total; total += (long)c.ni*c.nj*c.nk*c.nvar; }
     ops.copy_boxes(b, total);
   };
+  ops.reserve_boxes(std::max(pack.size(), local.size() + unpack.size()));   // no allocation once NCCL is in flight
   launch(pack);
   if (ops.rc) return fail(ops.rc, "SMR exchange: CUDA error");
   { int rcx = peer_exchange(m, m->peer_smr); if (rcx) return rcx; }
@@ -1979,6 +1986,7 @@ int smr_flux_correction(AbMesh *m) {
       }
     }
   }
+  ops.reserve_boxes(unpack.size());            // no allocation once NCCL is in flight
   if (ops.rc) return fail(ops.rc, "SMR flux correction: CUDA error");
   { int rcx = peer_exchange(m, m->peer_smr_flux); if (rcx) return rcx; }
   long total = 0;
