@@ -94,10 +94,14 @@ def test_polling_scheduler_through_the_emulated_device_path(emu_env):
     """tests/sched_check.py: the per-block boundary tasks under a host scheduler that polls the
     way TaskList::DoTaskListOneStage does, blocks drifting apart by whole tasks"""
     import test_gpu_sched
-    r = subprocess.run([sys.executable, os.path.join(HERE, "sched_check.py"), "--seed", "3"]
-                       + test_gpu_sched.SCHED_GOLDENS, env=emu_env, capture_output=True,
-                       text=True, timeout=900)
-    assert r.returncode == 0 and "sched done: 0 failed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    names = test_gpu_sched.SCHED_GOLDENS
+    chunks = [names[c::3] for c in range(3)]          # three processes side by side
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "sched_check.py"), "--seed", "3"]
+                              + ch, env=emu_env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for ch in chunks]
+    for p in procs:
+        out = p.communicate(timeout=900)[0]
+        assert p.returncode == 0 and "sched done: 0 failed" in out, out[-3000:]
 
 
 def test_every_task_entry_point_through_the_emulated_device_path(emu_env):
